@@ -1,0 +1,145 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of oracle/spruce_oracle.c (the CPU restatement of the
+reference's per-timestep advance).  Allowed importers: tests/, __graft_entry__.smoke(), bench.py's
+cpu_baseline leg.  The product path (spruce_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ORACLE_DIR = Path(__file__).resolve().parent
+LIB_PATH = ORACLE_DIR / "_ref" / "liboracle.so"
+
+BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3, "open_moc": 4, "open_ucnp": 5}   # plasmadomain.hpp:22-26
+TI = {"euler": 0, "rk2": 1, "rk4": 2}                                                       # plasmadomain.hpp:29-32
+VARS = ["rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y",
+        "n", "press", "thermal_energy", "v_x", "v_y", "v_z", "kinetic_energy",
+        "b_x", "b_y", "b_z", "b_mag", "b_hat_x", "b_hat_y", "b_hat_z", "dt"]                # idealmhd.hpp:19-23
+EVOLVED = ["rho", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z"]     # idealmhd.hpp:32-34
+DOMAIN = {"d_x": 0, "d_y": 1, "be_x": 2, "be_y": 3, "be_z": 4, "pos_x": 5, "pos_y": 6, "mask": 7}
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", str(ORACLE_DIR), "oracle"], check=True, stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            build()
+        L = C.CDLL(str(LIB_PATH))
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.c_int] * 7 + [C.c_double] * 8
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_plane.restype = C.POINTER(C.c_double)
+        L.oracle_plane.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_setup.argtypes = [C.c_void_p]
+        L.oracle_propagate.argtypes = [C.c_void_p]
+        L.oracle_step.restype = C.c_double
+        L.oracle_step.argtypes = [C.c_void_p]
+        L.oracle_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_time.restype = C.c_double
+        L.oracle_time.argtypes = [C.c_void_p]
+        L.oracle_subcycles.restype = C.c_int
+        L.oracle_subcycles.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_rhs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.oracle_operator.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3
+        L.oracle_set_thermal_conduction.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.oracle_set_radiative_losses.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.oracle_set_ambient_heating.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Oracle:
+    """One ideal-MHD domain evolved by the C restatement.  planes: the reference's .state planes."""
+
+    def __init__(self, planes, ion_mass, adiabatic_index, *, xb=("periodic", "periodic"), yb=("periodic", "periodic"),
+                 integrator="rk2", epsilon=0.2, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6,
+                 open_strength=1.0, open_decay=0.5, setup=True):
+        L = lib()
+        nx, ny = planes["rho"].shape
+        self.nx, self.ny = nx, ny
+        self.h = L.oracle_create(nx, ny, BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]], TI[integrator],
+                                 ion_mass, adiabatic_index, epsilon, density_min, temp_min, thermal_energy_min,
+                                 open_strength, open_decay)
+        for name, a in planes.items():
+            if name in ("mask",):
+                continue
+            self.view(name)[...] = a
+        if setup:
+            L.oracle_setup(self.h)
+
+    def view(self, name) -> np.ndarray:
+        which = DOMAIN[name] if name in DOMAIN else 100 + VARS.index(name)
+        p = lib().oracle_plane(self.h, which)
+        return np.ctypeslib.as_array(p, shape=(self.nx, self.ny))
+
+    def get(self, name) -> np.ndarray:
+        return self.view(name).copy()
+
+    def evolved(self) -> dict:
+        return {k: self.get(k) for k in EVOLVED}
+
+    def step(self) -> float:
+        return lib().oracle_step(self.h)
+
+    def run(self, nsteps) -> np.ndarray:
+        dts = np.zeros(nsteps)
+        lib().oracle_run(self.h, nsteps, _dp(dts))
+        return dts
+
+    def propagate(self):
+        lib().oracle_propagate(self.h)
+
+    def rhs(self) -> np.ndarray:
+        k = np.zeros((8, self.nx, self.ny))
+        lib().oracle_rhs(self.h, _dp(k))
+        return k
+
+    def operator(self, op, index, q, vel=None) -> np.ndarray:
+        ops = {"derivative1D": 0, "secondDerivative1D": 1, "laplacian": 2, "transportDerivative1D": 3}
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        vel = q if vel is None else np.ascontiguousarray(vel, dtype=np.float64)
+        out = np.zeros_like(q)
+        lib().oracle_operator(self.h, ops[op], index, _dp(q), _dp(vel), _dp(out))
+        return out
+
+    @property
+    def time(self) -> float:
+        return lib().oracle_time(self.h)
+
+    def subcycles(self, which) -> int:
+        return lib().oracle_subcycles(self.h, {"thermal_conduction": 1, "radiative_losses": 2}[which])
+
+    def set_thermal_conduction(self, *, flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-4, weakening_factor=1.0):
+        lib().oracle_set_thermal_conduction(self.h, int(flux_saturation), TI[integrator], epsilon, dt_subcycle_min, weakening_factor)
+
+    def set_radiative_losses(self, *, integrator="euler", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1, prevent_subcycling=False):
+        lib().oracle_set_radiative_losses(self.h, TI[integrator], cutoff_ramp, cutoff_temp, epsilon, int(prevent_subcycling))
+
+    def set_ambient_heating(self, *, heating_rate=0.0, exp_mode=False, exp_base_heating_rate=0.0, exp_scale_height=1.0,
+                            split_exp_mode=False, split_exp_scale_height=1.0, split_exp_start_height=0.0):
+        lib().oracle_set_ambient_heating(self.h, heating_rate, int(exp_mode), exp_base_heating_rate, exp_scale_height,
+                                         int(split_exp_mode), split_exp_scale_height, split_exp_start_height)
+
+    def close(self):
+        if self.h:
+            lib().oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

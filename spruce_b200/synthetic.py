@@ -1,0 +1,117 @@
+"""Synthetic inputs in the reference's .state layout (plane[i, j]: i = x index, j = y index, j contiguous).
+
+`orszag_tang` is the "OT-N" workload of SURVEY.md 8(d): a doubly periodic Orszag-Tang vortex in coronal
+CGS units on a NON-uniform rectilinear grid, analytic (no RNG).  `zfull=True` switches on non-zero
+z-components / external field / gravity so that every force term of the ideal-MHD right-hand side
+(reference: source/equationsets/idealmhd.cpp:51-86) is exercised by the parity tests.
+
+`stratified_loop` is a small stand-in for the reference's example.state: gravity-stratified atmosphere with
+a bipolar external field, used with non-periodic boundaries (fixed / reflect / open).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+K_B = 1.3807e-16      # reference source/constants.hpp:8
+M_I = 1.6726e-24
+GAMMA = 5.0 / 3.0
+
+
+def stretched_spacing(n: int, length: float, amp: float = 0.2) -> np.ndarray:
+    i = np.arange(n, dtype=np.float64)
+    d = (length / n) * (1.0 + amp * np.sin(2.0 * np.pi * (i + 0.5) / n))
+    return d * (length / d.sum())
+
+
+def centres(d: np.ndarray) -> np.ndarray:
+    # same recurrence as the reference's convertCellSizesToCellPositions (plasmadomain.cpp:169-181)
+    pos = np.empty_like(d)
+    pos[0] = 0.5 * d[0]
+    for k in range(1, d.size):
+        pos[k] = pos[k - 1] + 0.5 * d[k - 1] + 0.5 * d[k]
+    return pos
+
+
+def orszag_tang(nx: int, ny: int | None = None, *, length: float = 1.0e9, zfull: bool = False,
+                temp_mod: float = 0.0, stretch: float = 0.2) -> dict:
+    """Returns dict(planes=..., ion_mass=..., adiabatic_index=...) with all planes the reference needs
+    (7 domain grids + IdealMHD state variables)."""
+    ny = nx if ny is None else ny
+    dx = stretched_spacing(nx, length, stretch)
+    dy = stretched_spacing(ny, length, stretch)
+    px, py = centres(dx), centres(dy)
+    X = np.repeat(px[:, None], ny, axis=1)
+    Y = np.repeat(py[None, :], nx, axis=0)
+    rho0, T0 = 1.0e-15, 1.0e6
+    n0 = rho0 / M_I
+    p0 = 2.0 * n0 * K_B * T0
+    cs = np.sqrt(GAMMA * p0 / rho0)
+    v0 = cs
+    B0 = 0.6 * v0 * np.sqrt(4.0 * np.pi * rho0)
+    k = 2.0 * np.pi / length
+    rho = np.full((nx, ny), rho0)
+    temp = T0 * (1.0 + temp_mod * np.sin(k * X) * np.sin(k * Y))
+    vx = -v0 * np.sin(k * Y)
+    vy = v0 * np.sin(k * X)
+    z = np.zeros((nx, ny))
+    P = {
+        "d_x": np.repeat(dx[:, None], ny, axis=1), "d_y": np.repeat(dy[None, :], nx, axis=0),
+        "pos_x": X, "pos_y": Y,
+        "be_x": z.copy(), "be_y": z.copy(), "be_z": z.copy(),
+        "rho": rho, "temp": temp,
+        "mom_x": rho * vx, "mom_y": rho * vy, "mom_z": z.copy(),
+        "bi_x": -B0 * np.sin(k * Y), "bi_y": B0 * np.sin(2.0 * k * X), "bi_z": z.copy(),
+        "grav_x": z.copy(), "grav_y": z.copy(),
+    }
+    if zfull:
+        P["rho"] = rho0 * (1.0 + 0.3 * np.cos(k * X) * np.sin(2 * k * Y))
+        P["mom_x"] = P["rho"] * vx
+        P["mom_y"] = P["rho"] * vy
+        P["mom_z"] = P["rho"] * (0.2 * v0) * np.cos(k * X + 0.3)
+        P["bi_z"] = 0.3 * B0 * np.sin(k * X + k * Y)
+        P["be_x"] = 0.25 * B0 * (1.0 + 0.5 * np.cos(k * Y))
+        P["be_y"] = -0.15 * B0 * (1.0 + 0.5 * np.sin(k * X))
+        P["be_z"] = 0.1 * B0 * np.cos(2 * k * X) * np.cos(k * Y)
+        g0 = 0.05 * cs * cs / (length / 10.0)
+        P["grav_x"] = g0 * np.sin(k * X)
+        P["grav_y"] = -g0 * (1.0 + 0.2 * np.cos(k * Y))
+    return dict(planes=P, ion_mass=M_I, adiabatic_index=GAMMA)
+
+
+def stratified_loop(nx: int, ny: int, *, length: float = 4.0e9, zfull: bool = True, bump: float = 0.0) -> dict:
+    """Gravity-stratified isothermal atmosphere (y = height) with a bipolar external field and a velocity /
+    field perturbation; meant for non-periodic boundaries.  `bump` adds a Gaussian temperature excess."""
+    dx = stretched_spacing(nx, length, 0.15)
+    dy = stretched_spacing(ny, length, 0.10)
+    px, py = centres(dx), centres(dy)
+    X = np.repeat(px[:, None], ny, axis=1)
+    Y = np.repeat(py[None, :], nx, axis=0)
+    T0 = 1.0e6
+    g = 2.748e4
+    H = 2.0 * K_B * T0 / (M_I * g)
+    rho = 1.0e-14 * np.exp(-Y / H) + 2.0e-16
+    temp = T0 * (1.0 + bump * np.exp(-(((X - 0.5 * length) / (0.12 * length)) ** 2 + ((Y - 0.4 * length) / (0.12 * length)) ** 2)))
+    cs = np.sqrt(GAMMA * 2.0 * K_B * T0 / M_I)
+    k = 2.0 * np.pi / length
+    vx = 0.05 * cs * np.sin(k * X) * np.cos(k * Y)
+    vy = 0.04 * cs * np.cos(2 * k * X) * np.sin(k * Y)
+    B0 = 5.0
+    l = length / 4.0
+    be_x = B0 * np.cos(np.pi * (X - 0.5 * length) / (2 * l)) * np.exp(-np.pi * Y / (2 * l))
+    be_y = -B0 * np.sin(np.pi * (X - 0.5 * length) / (2 * l)) * np.exp(-np.pi * Y / (2 * l))
+    z = np.zeros((nx, ny))
+    P = {
+        "d_x": np.repeat(dx[:, None], ny, axis=1), "d_y": np.repeat(dy[None, :], nx, axis=0),
+        "pos_x": X, "pos_y": Y,
+        "be_x": be_x, "be_y": be_y, "be_z": z.copy(),
+        "rho": rho, "temp": temp,
+        "mom_x": rho * vx, "mom_y": rho * vy, "mom_z": z.copy(),
+        "bi_x": 0.02 * B0 * np.sin(k * Y), "bi_y": 0.02 * B0 * np.sin(k * X), "bi_z": z.copy(),
+        "grav_x": z.copy(), "grav_y": np.full((nx, ny), -g),
+    }
+    if zfull:
+        P["mom_z"] = rho * 0.03 * cs * np.sin(k * X + 2 * k * Y)
+        P["bi_z"] = 0.01 * B0 * np.cos(k * X) * np.sin(k * Y)
+        P["be_z"] = 0.05 * B0 * np.exp(-Y / (2 * H)) * np.cos(k * X)
+        P["grav_x"] = 0.02 * g * np.sin(k * X)
+    return dict(planes=P, ion_mass=M_I, adiabatic_index=GAMMA)

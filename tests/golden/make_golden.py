@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference binary
+(oracle/_ref/run, built from /root/reference by oracle/Makefile) on small deterministic inputs.
+
+    python tests/golden/make_golden.py [case ...]
+
+Each fixture <case>.npz holds: the exact input planes, the case description (JSON: boundary
+conditions, integrator, floors, module blocks), the per-iteration step sizes recovered from the
+lossless (write_precision = 17) `dt` output planes  -- step_k = epsilon * min(dt_k over the interior),
+reference source/mhd/evolution.cpp:62 --, and the evolved planes + dt + temp after selected iterations.
+
+Needs /root/reference only through the prebuilt binary; the fixtures themselves travel with the repo.
+"""
+from __future__ import annotations
+
+import json
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import refrun  # noqa: E402
+from spruce_b200 import synthetic  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+OUT_VARS = ["rho", "temp", "thermal_energy", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "dt"]
+NX, NY = 32, 28
+
+INACTIVE_FLOORS = dict(density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
+SOLAR_FLOORS = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+
+TC = lambda **kw: ("thermal_conduction", list(dict(dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4", output_to_file="true"), **kw).items()))
+RL = lambda **kw: ("radiative_losses", list(dict(dict(cutoff_ramp="1.0e3", cutoff_temp="3.0e4", epsilon="0.1", output_to_file="true"), **kw).items()))
+AH = lambda **kw: ("ambient_heating", list(dict(dict(heating_rate="1.0e-4"), **kw).items()))
+
+CASES = {
+    # name: (generator, gen kwargs, config kwargs, n_steps, frames to keep)
+    "ot_pp_rk2":   ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("periodic", "periodic"), **INACTIVE_FLOORS), 10, (1, 2, 10)),
+    "ot_pp_euler": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"), **INACTIVE_FLOORS), 4, (1, 4)),
+    "ot_pp_rk4":   ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="rk4", xb=("periodic", "periodic"), yb=("periodic", "periodic"), **INACTIVE_FLOORS), 4, (1, 4)),
+    "ot2d_pp_rk2_100": ("orszag_tang", dict(nx=NX, ny=NY, zfull=False), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("periodic", "periodic"), **INACTIVE_FLOORS), 100, (1, 50, 100)),
+    "loop_pf_rk2": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 10, (1, 2, 10)),
+    "loop_ro_rk2": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("reflect", "reflect"), yb=("open", "open"), **SOLAR_FLOORS), 10, (1, 2, 10)),
+    "loop_oo_rk4": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk4", xb=("open", "open"), yb=("open", "open"), **SOLAR_FLOORS), 4, (1, 4)),
+    "loop_ff_euler": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 6, (1, 6)),
+    "loop_mixed_rk2": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("fixed", "reflect"), yb=("open", "fixed"), density_min=3.0e8, temp_min=1.0e4, thermal_energy_min=1.0e-6), 8, (1, 8)),
+    "loop_ucnp_rk2": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("open_ucnp", "open_ucnp"), yb=("open_ucnp", "open_ucnp"), **SOLAR_FLOORS), 6, (1, 6)),
+    # physics modules (default.config:57-76 parameter values)
+    "loop_tc_euler": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[TC()], **SOLAR_FLOORS), 4, (1, 4)),
+    "loop_tc_sat_rk2": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[TC(flux_saturation="true", time_integrator="rk2")], **SOLAR_FLOORS), 4, (1, 4)),
+    "loop_tc_sat_rk4": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="euler", xb=("reflect", "reflect"), yb=("fixed", "open"), modules=[TC(flux_saturation="true", time_integrator="rk4")], **SOLAR_FLOORS), 3, (1, 3)),
+    "loop_rl_euler": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[RL()], **SOLAR_FLOORS), 4, (1, 4)),
+    "loop_rl_rk4": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[RL(time_integrator="rk4")], **SOLAR_FLOORS), 3, (1, 3)),
+    "loop_ah": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[AH()], **SOLAR_FLOORS), 4, (1, 4)),
+    "loop_ah_exp": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[AH(exp_mode="true", exp_base_heating_rate="3.0e-4", exp_scale_height="6.0e8")], **SOLAR_FLOORS), 3, (1, 3)),
+    "loop_solar_all": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"),
+                       modules=[TC(flux_saturation="true"), RL(time_integrator="rk2"), AH()], **SOLAR_FLOORS), 6, (1, 6)),
+    # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
+    "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
+}
+
+
+def example_state():
+    meta, planes = refrun.read_state("/root/reference/example.state")
+    z = np.zeros_like(planes["rho"])
+    for k in ("be_z", "mom_z", "bi_z"):
+        planes.setdefault(k, z.copy())
+    order = ["d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z", "rho", "temp", "mom_x", "mom_y", "mom_z",
+             "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
+    return dict(planes={k: planes[k] for k in order}, ion_mass=meta["ion_mass"], adiabatic_index=meta["adiabatic_index"])
+
+
+def interior(cfg, nx, ny):
+    xl = 0 if cfg["xb"][0] == "periodic" else 2
+    xu = nx - 1 if cfg["xb"][1] == "periodic" else nx - 3
+    yl = 0 if cfg["yb"][0] == "periodic" else 2
+    yu = ny - 1 if cfg["yb"][1] == "periodic" else ny - 3
+    return xl, xu, yl, yu
+
+
+def make(name):
+    gen, gkw, ckw, nsteps, keep = CASES[name]
+    s = example_state() if gen == "example_state" else getattr(synthetic, gen)(**gkw)
+    tmp = Path(tempfile.mkdtemp(prefix="golden_"))
+    try:
+        refrun.write_state(tmp / "in.state", s["planes"], s["ion_mass"], s["adiabatic_index"])
+        cfg = refrun.ideal_mhd_config(max_iterations=nsteps, output_flags=OUT_VARS, std_out_interval=1, **ckw)
+        _, stdout = refrun.run_reference(tmp / "in.state", cfg, tmp / "out", threads=8)
+        _, frames = refrun.read_out(tmp / "out" / "mhd.out")
+        assert len(frames) == nsteps + 1, (len(frames), nsteps)
+        nx, ny = s["planes"]["rho"].shape
+        xl, xu, yl, yu = interior(ckw, nx, ny)
+        eps = ckw.get("epsilon", 0.2)
+        steps = np.array([eps * np.nanmin(f["dt"][xl:xu + 1, yl:yu + 1]) for f in frames[:-1]])
+        times = np.array([f["t"] for f in frames])
+        out = {"in_" + k: v for k, v in s["planes"].items()}
+        out["ion_mass"] = np.float64(s["ion_mass"])
+        out["adiabatic_index"] = np.float64(s["adiabatic_index"])
+        out["steps"] = steps
+        out["times_6digits"] = times
+        for fi in keep:
+            for v in OUT_VARS:
+                out["f%d_%s" % (fi, v)] = frames[fi][v]
+            for v in frames[fi]:
+                if v not in OUT_VARS and v != "t":       # module output planes (thermal_conduction, rad, ...)
+                    out["f%d_mod_%s" % (fi, v)] = frames[fi][v]
+        desc = dict(case=name, generator=gen, gen_kwargs=gkw, n_steps=nsteps, keep=list(keep),
+                    config={k: v for k, v in ckw.items()}, config_text=cfg,
+                    subcycle_log=[ln for ln in stdout.splitlines() if "Subcycles" in ln][:nsteps])
+        out["desc"] = np.array(json.dumps(desc))
+        np.savez_compressed(HERE / (name + ".npz"), **out)
+        print("%-20s steps=%d first dt=%s  -> %s.npz" % (name, nsteps, float(steps[0]).hex(), name))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    assert refrun.have_reference(), "build the reference first: make -C oracle ref"
+    for nm in (sys.argv[1:] or list(CASES)):
+        make(nm)

@@ -1,0 +1,91 @@
+"""Shared helpers for the parity tests: load a golden fixture (tests/golden/*.npz, produced by
+tests/golden/make_golden.py from the unmodified reference binary) and describe it."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+OUT_VARS = ["rho", "temp", "thermal_energy", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "dt"]
+EVOLVED = ["rho", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z"]
+
+
+def cases(prefixes=None):
+    names = sorted(p.stem for p in GOLDEN.glob("*.npz"))
+    if prefixes:
+        names = [n for n in names if any(n.startswith(p) for p in prefixes)]
+    return names
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(GOLDEN / (name + ".npz"))
+        self.name = name
+        self.desc = json.loads(str(z["desc"]))
+        self.planes = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+        self.ion_mass = float(z["ion_mass"])
+        self.adiabatic_index = float(z["adiabatic_index"])
+        self.steps = z["steps"]
+        self.n_steps = self.desc["n_steps"]
+        self.keep = self.desc["keep"]
+        self.frames = {fi: {v: z["f%d_%s" % (fi, v)] for v in OUT_VARS} for fi in self.keep}
+        self.module_planes = {fi: {k.split("_mod_", 1)[1]: z[k] for k in z.files if k.startswith("f%d_mod_" % fi)} for fi in self.keep}
+        cfg = self.desc["config"]
+        self.cfg = cfg
+        self.kw = dict(xb=tuple(cfg["xb"]), yb=tuple(cfg["yb"]), integrator=cfg["integrator"],
+                       epsilon=cfg.get("epsilon", 0.2), density_min=cfg["density_min"], temp_min=cfg["temp_min"],
+                       thermal_energy_min=cfg["thermal_energy_min"],
+                       open_strength=cfg.get("open_strength", 1.0), open_decay=cfg.get("open_decay", 0.5))
+        self.modules = [(m[0], dict(m[1])) for m in cfg.get("modules", [])]
+
+    def subcycle_counts(self, label):
+        """Per-iteration sub-cycle counts parsed from the reference's stdout lines ('Thermal Subcycles: N')."""
+        out = []
+        for ln in self.desc["subcycle_log"]:
+            for part in ln.split("|"):
+                if part.startswith(label):
+                    out.append(int(part.split(":")[1].split()[0]))
+        return out
+
+
+def module_kwargs(name, kv):
+    """Translate a .config module block into keyword arguments shared by the oracle and the product API."""
+    b = lambda s: s == "true"
+    if name == "thermal_conduction":
+        return dict(flux_saturation=b(kv.get("flux_saturation", "false")), integrator=kv.get("time_integrator", "euler"),
+                    epsilon=float(kv["epsilon"]), dt_subcycle_min=float(kv["dt_subcycle_min"]),
+                    weakening_factor=float(kv.get("weakening_factor", "1.0")))
+    if name == "radiative_losses":
+        return dict(integrator=kv.get("time_integrator", "euler"), cutoff_ramp=float(kv["cutoff_ramp"]),
+                    cutoff_temp=float(kv["cutoff_temp"]), epsilon=float(kv["epsilon"]),
+                    prevent_subcycling=b(kv.get("prevent_subcycling", "false")))
+    if name == "ambient_heating":
+        return dict(heating_rate=float(kv.get("heating_rate", "0.0")), exp_mode=b(kv.get("exp_mode", "false")),
+                    exp_base_heating_rate=float(kv.get("exp_base_heating_rate", "0.0")),
+                    exp_scale_height=float(kv.get("exp_scale_height", "1.0")),
+                    split_exp_mode=b(kv.get("split_exp_mode", "false")),
+                    split_exp_scale_height=float(kv.get("split_exp_scale_height", "1.0")),
+                    split_exp_start_height=float(kv.get("split_exp_start_height", "0.0")))
+    raise KeyError(name)
+
+
+def same_bits(a, b):
+    """Bit-for-bit equality up to the sign of zero (and NaN == NaN)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def mismatch(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    n = int(bad.sum())
+    if n == 0:
+        return "identical"
+    with np.errstate(all="ignore"):
+        rel = np.nanmax(np.abs(a - b)) / max(np.nanmax(np.abs(b)), 1e-300)
+    idx = np.argwhere(bad)[:5].tolist()
+    return "%d/%d cells differ, rel Linf %.3e, first at %s" % (n, a.size, rel, idx)

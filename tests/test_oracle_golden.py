@@ -1,0 +1,35 @@
+"""Pins the oracle (oracle/spruce_oracle.c, the CPU restatement) against outputs of the UNMODIFIED reference
+binary: every fixture in tests/golden/ must be reproduced bit-for-bit -- the step-size history (reference
+source/mhd/evolution.cpp:62) and every evolved plane + temp + dt after the recorded iterations."""
+import numpy as np
+import pytest
+
+from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_bits
+from oracle.oracle import Oracle
+
+
+def make_oracle(g: Golden) -> Oracle:
+    o = Oracle(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
+    for name, kv in g.modules:
+        getattr(o, "set_" + name)(**module_kwargs(name, kv))
+    return o
+
+
+@pytest.mark.parametrize("name", cases())
+def test_oracle_reproduces_reference(name):
+    g = Golden(name)
+    o = make_oracle(g)
+    tc, rl = [], []
+    for it in range(1, g.n_steps + 1):
+        step = o.step()
+        tc.append(o.subcycles("thermal_conduction"))
+        rl.append(o.subcycles("radiative_losses"))
+        assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())
+        if it in g.frames:
+            for v in OUT_VARS:
+                assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
+    names = [m[0] for m in g.modules]
+    if "thermal_conduction" in names:
+        assert tc == g.subcycle_counts("Thermal Subcycles")
+    if "radiative_losses" in names:
+        assert rl == g.subcycle_counts("Radiative Subcycles")
