@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the per-timestep advance (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 4096] [--impl ours|reference]
+
+One "step" = one advanceTime of the reference (source/mhd/evolution.cpp:59-82): an RK2 step of ideal MHD over the
+whole grid.  Workload at N=1: BASELINE.json configs[3], the synthetic doubly periodic non-uniform 4096^2
+Orszag-Tang grid ("OT-4096").  N>1: the same global grid slab-decomposed along x (strong scaling).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is the same metric through the public
+API with host buffers (upload of every input plane from pinned memory + setup + K steps + download of the evolved
+planes and the step-size history inside the timed region).  `roofline` is for the fused stage kernel against the
+measured HBM copy bandwidth in MEASURED_PEAKS.json; `cpu_baseline` times the unmodified reference binary
+(oracle/_ref/run, OpenMP, all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "cell-updates/sec at 4096^2 ideal MHD (RK2, FP64)"
+UNIT = "cell-updates/s"
+ALG_BYTES_PER_CELL_STEP = 400.0      # RK2: stage 1 reads 13 planes, writes 8; stage 2 reads 21, writes 8
+FALLBACK_HBM_GBS = 6650.0            # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+KW = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator="rk2", epsilon=0.2,
+          density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_rate(size: int, n1: int, n2: int, threads: int):
+    """cell-updates/s of the unmodified reference binary: wall(n2 iterations) - wall(n1 iterations), so parsing the
+    text state and writing end.state cancel.  Test infrastructure (oracle/) is used here only as the
+    thing being timed on the CPU, never on the product path."""
+    from oracle import refrun
+    from spruce_b200 import synthetic
+    if not refrun.have_reference():
+        return None
+    s = synthetic.orszag_tang(size, size)
+    tmp = Path(tempfile.mkdtemp(prefix="spruce_ref_"))
+    try:
+        refrun.write_state(tmp / "in.state", s["planes"], s["ion_mass"], s["adiabatic_index"])
+        walls = []
+        for n_it in (n1, n2):
+            cfg = refrun.ideal_mhd_config(max_iterations=n_it, iter_output_interval=-1, output_flags=("rho",), write_interval=-1, **KW)
+            w, _ = refrun.run_reference(tmp / "in.state", cfg, tmp / ("out%d" % n_it), threads=threads)
+            walls.append(w)
+        dt = max(walls[1] - walls[0], 1e-9)
+        return dict(value=size * size * (n2 - n1) / dt, seconds_per_step=dt / (n2 - n1), walls=walls)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    size = 512
+    k = max(1, min(args.steps, 12))
+    w = max(1, min(args.warmup, 3))
+    r = reference_rate(size, w, w + k, threads)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/run is missing (build with make -C oracle ref where /root/reference exists)"}))
+        return
+    sample = "unmodified reference binary (oracle/_ref/run, g++ -O3 -fopenmp), OT-%d (same generator as the 4096^2 workload), wall(%d it) - wall(%d it), %d OpenMP threads" % (size, w + k, w, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w,
+            "ms_per_step": 1e3 * r["seconds_per_step"] * (args.size / size) ** 2, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "OT-%d ideal MHD RK2 doubly periodic non-uniform grid" % args.size, "sample_grid": size,
+                       "note": "CPU rate is grid-size independent to about 20 percent (BASELINE.md 2); ms_per_step is scaled to the %d^2 grid" % args.size},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spruce_b200 import build, synthetic
+    from spruce_b200.domain import PlasmaDomain
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    build.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.size
+    s = synthetic.orszag_tang(n, n)
+    planes = s["planes"]
+    dx, dy = np.ascontiguousarray(planes["d_x"][:, 0]), np.ascontiguousarray(planes["d_y"][0, :])
+    names = ["be_x", "be_y", "be_z", "rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
+
+    if world > 1:
+        from spruce_b200.multigpu import SlabRunner
+        runner = SlabRunner(planes, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, **KW)
+        result = runner.bench(args.steps, args.warmup)
+        if rank == 0:
+            emit(args, result, world)
+        dist.destroy_process_group()
+        return
+
+    # pinned host staging of every input plane (e2e leg)
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(planes[k])).pin_memory() for k in names}
+    host = {k: v.numpy() for k, v in pinned.items()}
+    host["d_x"], host["d_y"] = dx, dy
+    ion_mass, gamma = s["ion_mass"], s["adiabatic_index"]
+    dom = PlasmaDomain(host, ion_mass, gamma, device=local, **KW)
+    del planes, s
+    stream = torch.cuda.ExternalStream(dom.stream())
+    cells = n * n
+
+    # ---- device-resident throughput
+    dom.advance(args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = dom.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    dts = dom.advance(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = dom.launch_count() - l0
+    assert len(dts) == args.steps and np.all(dts > 0) and np.all(np.isfinite(dts))
+    value = cells * args.steps / (ms * 1e-3)
+
+    # ---- stage kernel alone (roofline numerator is per launch)
+    stage_ms = dom.time_stage_kernel(10)
+    peak, peak_src = hbm_peak()
+    n_stage = 2 * args.steps
+    avg_launch_ms = ms / n_stage                        # the two tiny bookkeeping kernels per step are < 0.1% of the step
+    alg_bytes_per_launch = 0.5 * ALG_BYTES_PER_CELL_STEP * cells
+    achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = ROOT / "profiles" / "stage_traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get(str(n))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel": "k_mhd_stage", "alg_bytes_per_launch": alg_bytes_per_launch,
+                "avg_launch_ms": avg_launch_ms, "stage1_alone_ms": stage_ms,
+                "note": "FP64-issue co-bound: exact-parity arithmetic needs ~1.1e3 DFMA-pipe instructions per cell per stage (DESIGN.md)"}
+
+    # ---- end to end through the public API with host buffers
+    dom.close()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dom = PlasmaDomain(host, ion_mass, gamma, device=local, **KW)     # uploads 13 planes from pinned memory + setup
+    dts2 = dom.advance(args.steps)
+    out = {k: dom.grid(k) for k in PlasmaDomain.EVOLVED}
+    t1 = time.perf_counter()
+    e2e_value = cells * args.steps / (t1 - t0)
+    h2d = len(names) * cells * 8
+    d2h = len(PlasmaDomain.EVOLVED) * cells * 8 + 8 * args.steps
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+           "seconds": t1 - t0, "definition": "one job = upload 13 input planes from pinned host memory + setup + K steps + download 8 evolved planes and the K step sizes (the reference's state-in / K steps / state-out pattern)"}
+    assert np.isfinite(out["rho"]).all()
+    dom.close()
+
+    # ---- CPU baseline on the host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r = reference_rate(512, 2, 10, threads)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": "unmodified reference binary (oracle/_ref/run), OT-512 (same generator), wall(10 it) - wall(2 it), %d OpenMP threads" % threads}
+    result = dict(value=value, ms=ms, launches=launches, clocks=clocks, roofline=roofline, e2e=e2e, cpu=cpu)
+    emit(args, result, 1)
+
+
+def emit(args, r, world):
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "OT-%d: synthetic doubly periodic Orszag-Tang vortex, non-uniform rectilinear %dx%d grid, ideal MHD, RK2, epsilon 0.2 (BASELINE.json configs[3])" % (args.size, args.size, args.size),
+                       "parallelism": "slab%d" % world if world > 1 else "single", "l2": "working set per step (21 planes, %.1f GB) >> 126 MB L2: inputs larger than L2" % (21 * args.size ** 2 * 8 / 1e9),
+                       "mode": "exact (bit-identical to the reference CPU build)"},
+            "clocks": r["clocks"], "gpu_launches": r["launches"], "e2e": r["e2e"], "roofline": r["roofline"]}
+    if r.get("cpu"):
+        line["cpu_baseline"] = r["cpu"]
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

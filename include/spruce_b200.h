@@ -1,0 +1,162 @@
+/* spruce_b200.h -- C ABI of the B200-native per-timestep advance for SPRUCE (gszypko/spruce).
+ *
+ * This is the drop-in boundary: plain C, opaque handle, plain pointers and sizes, int status codes
+ * (0 = ok; spruce_last_error() gives the message).  The reference has NO FFI of its own -- its
+ * plug-in surface is C++ inheritance inside one binary -- so each entry point below names the
+ * reference member function(s) whose arithmetic it replaces (file:line in the reference tree).
+ * The host-side C++ mirror of the reference classes (spruce_b200/host/) and the Python binding
+ * (spruce_b200/capi.py) call only these functions.
+ *
+ * Data layout at the boundary = the reference's Grid: row-major plane[i*ydim + j], i = x index,
+ * j = y index, j contiguous (source/mhd/grid.cpp:516-526), FP64.  With a slab decomposition a rank
+ * passes only its own rows [row0, row0+nx_local) of every plane.
+ *
+ * Threading: one host thread drives one handle; all device work is ordered on the handle's stream.
+ * There is no CPU fallback: every call fails with SPRUCE_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef SPRUCE_B200_H
+#define SPRUCE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPRUCE_ABI_VERSION 1
+
+/* status codes */
+enum {
+    SPRUCE_OK = 0,
+    SPRUCE_ERR_ARG = 1,       /* bad argument / unknown plane name (reference: assert + abort)            */
+    SPRUCE_ERR_CUDA = 2,      /* CUDA runtime failure or no device                                         */
+    SPRUCE_ERR_STATE = 3,     /* call order violated (e.g. advance before setup)                           */
+    SPRUCE_ERR_UNSUPPORTED = 4 /* feature outside the hot-path scope (open_moc, non rank-1 d_x/d_y, ...)   */
+};
+
+/* PlasmaDomain::BoundaryCondition, source/mhd/plasmadomain.hpp:22 (same order => same integer values) */
+enum { SPRUCE_BC_PERIODIC = 0, SPRUCE_BC_OPEN = 1, SPRUCE_BC_FIXED = 2, SPRUCE_BC_REFLECT = 3,
+       SPRUCE_BC_OPEN_MOC = 4, SPRUCE_BC_OPEN_UCNP = 5 };
+/* PlasmaDomain::TimeIntegrator, source/mhd/plasmadomain.hpp:29 */
+enum { SPRUCE_TI_EULER = 0, SPRUCE_TI_RK2 = 1, SPRUCE_TI_RK4 = 2 };
+/* EquationSet::m_sets, source/equationsets/equationset.hpp:22 (index in that list) */
+enum { SPRUCE_EQS_IDEAL_MHD = 0, SPRUCE_EQS_IDEAL_2F = 3 };
+
+/* Everything PlasmaDomain reads from the .config / .state headers that the device needs
+ * (source/mhd/plasmadomain.hpp:93-153, source/mhd/fileio.cpp:297-325). */
+typedef struct spruce_config {
+    int32_t abi_version;        /* = SPRUCE_ABI_VERSION */
+    int32_t equation_set;       /* SPRUCE_EQS_* */
+    int32_t xdim, ydim;         /* GLOBAL grid size (m_xdim, m_ydim) */
+    int32_t x_bound_1, x_bound_2, y_bound_1, y_bound_2;  /* SPRUCE_BC_* */
+    int32_t time_integrator;    /* SPRUCE_TI_* */
+    int32_t device;             /* CUDA device ordinal; -1 = current device */
+    /* slab decomposition along x (i): this handle owns global rows [row0, row0 + nx_local).
+     * Single GPU: row0 = 0, nx_local = xdim, n_ranks = 1. */
+    int32_t row0, nx_local, rank, n_ranks;
+    double ion_mass;            /* m_ion_mass   (.state header)  */
+    double adiabatic_index;     /* m_adiabatic_index             */
+    double epsilon;             /* CFL safety factor             */
+    double density_min, temp_min, thermal_energy_min;
+    double open_boundary_strength, open_boundary_decay_base;
+    double time;                /* m_time at start (continue mode) */
+} spruce_config;
+
+typedef struct spruce_domain spruce_domain;
+
+const char *spruce_last_error(void);
+int spruce_abi_version(void);
+
+/* PlasmaDomain::PlasmaDomain + computeIterationBounds (source/mhd/plasmadomain.cpp:13-75,138-161):
+ * allocates the SoA FP64 device arena for the equation set's variables and the domain grids. */
+int spruce_domain_create(const spruce_config *cfg, spruce_domain **out);
+void spruce_domain_destroy(spruce_domain *dom);
+
+/* Cell sizes.  The reference stores d_x, d_y as full planes (plasmadomain.hpp:35) but requires d_x to vary
+ * with i only and d_y with j only (README.md:41); the arena keeps them as 1-D tables.  d_x: xdim GLOBAL
+ * entries (every rank passes the whole array), d_y: ydim entries.  Also derives the exact-division tables
+ * used by the stencil kernels (DESIGN.md "exact division"). */
+int spruce_set_cell_sizes(spruce_domain *dom, const double *d_x, size_t n_x, const double *d_y, size_t n_y);
+
+/* Grid upload / download by the reference's variable names: domain grids "be_x","be_y","be_z","pos_x","pos_y"
+ * (plasmadomain.hpp:36) and every EquationSet variable (idealmhd.hpp:19-23 / ideal2F.hpp:23-38).
+ * host: nx_local*ydim doubles, reference layout.  Derived variables are materialised on download from the
+ * evolved state exactly as IdealMHD::recomputeDerivedVarsFromEvolvedVars / recomputeDT would have left them
+ * (source/equationsets/idealmhd.cpp:241-304).  Replaces EquationSet::grid(name) (equationset.cpp:113-121). */
+int spruce_grid_upload(spruce_domain *dom, const char *name, const double *host, size_t count);
+int spruce_grid_download(spruce_domain *dom, const char *name, double *host, size_t count);
+
+/* EquationSet::setupEquationSet -> populateVariablesFromState (source/equationsets/equationset.cpp:87-104):
+ * state variables -> evolved variables, floors, ghost zones, derived variables, dt. */
+int spruce_eqs_setup(spruce_domain *dom);
+
+/* EquationSet::propagateChanges on the primary state (source/equationsets/equationset.cpp:212-220);
+ * called by host-side modules after they edited an evolved plane through spruce_grid_upload. */
+int spruce_eqs_propagate_changes(spruce_domain *dom);
+
+/* epsilon * getDT().min(m_xl_dt, m_yl_dt, m_xu_dt, m_yu_dt) (source/mhd/evolution.cpp:62,
+ * source/mhd/grid.cpp:71-82): the step the NEXT advance will use.  With n_ranks > 1 this is the LOCAL slab
+ * minimum until spruce_set_global_dt_min() has been fed the all-reduced value. */
+int spruce_next_step_size(spruce_domain *dom, double *step);
+
+/* PlasmaDomain::advanceTime x n_steps (source/mhd/evolution.cpp:59-82) with the configured integrator
+ * (integrateEuler/RK2/RK4, :84-124) and the device-resident modules, entirely on the device: no host
+ * round trip between steps.  dt_used (may be NULL) receives the n_steps step sizes.  Stops early, like
+ * PlasmaDomain::run (:26), once time >= max_time when max_time > 0; *steps_done (may be NULL) gets the count. */
+int spruce_advance(spruce_domain *dom, int n_steps, double max_time, double *dt_used, int *steps_done);
+int spruce_get_time(spruce_domain *dom, double *time, int64_t *iter);
+
+/* One evaluation of EquationSet::computeTimeDerivatives on the primary state
+ * (source/equationsets/equationset.cpp:204-210 -> idealmhd.cpp:42-105); k_out: n_evolved planes of
+ * nx_local*ydim doubles in evolved_variables() order (idealmhd.hpp:32-34).  Test / module hook. */
+int spruce_eqs_time_derivatives(spruce_domain *dom, double *k_out, size_t count);
+
+/* PlasmaDomain differential operators on a host plane (source/mhd/derivs.cpp), so that host-side modules
+ * that are not ported keep working: op = "derivative1D" (:223), "secondDerivative1D" (:417), "laplacian" (:458),
+ * "transportDerivative1D" (:122; vel required).  index: 0 = x, 1 = y. Single-rank only. */
+int spruce_operator(spruce_domain *dom, const char *op, int index, const double *q, const double *vel, double *out, size_t count);
+
+/* ---- physics modules on the device (source/modules/...) ; call order = execution order (modulehandler.cpp:27-65) */
+/* ThermalConduction::parseModuleConfigs (solar/thermalconduction.cpp:16-30) */
+int spruce_module_thermal_conduction(spruce_domain *dom, int flux_saturation, int time_integrator, double epsilon,
+                                     double dt_subcycle_min, double weakening_factor);
+/* RadiativeLosses::parseModuleConfigs (solar/radiativelosses.cpp:17-31) */
+int spruce_module_radiative_losses(spruce_domain *dom, int time_integrator, double cutoff_ramp, double cutoff_temp,
+                                   double epsilon, int prevent_subcycling);
+/* AmbientHeating::setupModule (solar/ambientheating.cpp:28-40): heating = nx_local*ydim plane built on the host
+ * (the exp() profile is evaluated there with the host libm, as the reference does once at setup). */
+int spruce_module_ambient_heating(spruce_domain *dom, const double *heating, size_t count);
+/* curr_num_subcycles of the last advance: which = "thermal_conduction" | "radiative_losses" */
+int spruce_module_subcycles(spruce_domain *dom, const char *which, int *count);
+
+/* ---- multi-GPU (slab decomposition along x, one process per GPU; DESIGN.md "multi-GPU") */
+/* Device pointers + byte counts of the contiguous halo staging buffers of the state that the next
+ * right-hand-side evaluation reads: send_lo/send_hi = my first/last 2 rows (all evolved planes packed),
+ * recv_lo/recv_hi = where the neighbours' rows must land.  The caller moves them (NCCL send/recv). */
+int spruce_halo_buffers(spruce_domain *dom, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, size_t *bytes);
+/* Stepping split at the exchange points, for callers that own the communicator (bench.py, torch.distributed):
+ * phase 0: pack halos of the primary state; then per RK stage s: stage_begin(s) computes stage s and packs the halos
+ * of its output; the caller exchanges; stage_end(s) unpacks.  The dt minimum is exchanged with
+ * spruce_local_dt_min / spruce_set_global_dt_min (ncclAllReduce(min)). */
+int spruce_mgpu_pack(spruce_domain *dom, int which_state);
+int spruce_mgpu_unpack(spruce_domain *dom, int which_state);
+int spruce_mgpu_stage(spruce_domain *dom, int stage);
+int spruce_mgpu_n_stages(spruce_domain *dom, int *n);
+int spruce_mgpu_dt_min_ptr(spruce_domain *dom, void **device_double);   /* 1 double on the device: all-reduce(min) it in place */
+int spruce_mgpu_begin_step(spruce_domain *dom);   /* fixes `step` from the (all-reduced) dt minimum */
+int spruce_mgpu_end_step(spruce_domain *dom);     /* t += step; iter++ */
+
+/* stream on which every kernel of this handle is launched (cudaStream_t as void*), for event timing */
+int spruce_stream(spruce_domain *dom, void **stream);
+int spruce_synchronize(spruce_domain *dom);
+/* number of kernels this library has launched on the handle since creation (bench.py's gpu_launches) */
+int spruce_launch_count(spruce_domain *dom, int64_t *count);
+/* Stage kernel only: launches it `reps` times on a scratch copy and returns the mean duration in ms measured with
+ * CUDA events on the handle's stream (bench.py roofline leg). */
+int spruce_time_stage_kernel(spruce_domain *dom, int reps, float *ms_mean);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPRUCE_B200_H */

@@ -1,0 +1,574 @@
+// capi.cu -- host side of the C ABI declared in include/spruce_b200.h: device arena, geometry tables,
+// plane transfer, and the launch sequences that replace PlasmaDomain::advanceTime (source/mhd/evolution.cpp:59-124).
+// Compiled with -fmad=false (see exact_math.cuh).  No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/spruce_b200.h"
+#include "mhd_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace spruce;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(SPRUCE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CHECK_DOM(d) do { if (!(d)) return fail(SPRUCE_ERR_ARG, "null domain handle"); } while (0)
+
+namespace {
+
+struct PlaneSet { double *p[NEV] = {nullptr}; };
+
+struct HostAxis {          // 1-D tables of one axis on the host, index -TAB_APRON .. n+TAB_APRON-1 stored at [k+TAB_APRON]
+    std::vector<double> h, fs, rfs, ep, em, d, rd;
+};
+
+}  // namespace
+
+struct spruce_domain {
+    spruce_config cfg{};
+    DomainParams P{};
+    cudaStream_t stream = nullptr;
+    size_t plane_doubles = 0;      // allocation size of one plane incl. halo rows
+    size_t row_off = 0;            // offset (doubles) of local row 0 inside an allocation
+    std::vector<double *> allocs;  // every cudaMalloc, for destroy
+    PlaneSet Pset, Mset, M2set, K1set, K2set;
+    double *stat[NSTATIC] = {nullptr};
+    double *scratch_temp = nullptr, *scratch_out = nullptr;
+    double *r1strip[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *tab_dev = nullptr;     // all 1-D tables in one allocation
+    StepCtl *ctl = nullptr;
+    double *dt_hist = nullptr; size_t dt_hist_cap = 0;
+    bool have_geom = false, is_setup = false, raw_rho = true, rk4_alloc = false;
+    std::vector<double> dxg, dyg;  // global cell sizes (host copy)
+    GhostArgs ghost_proto{};
+    int64_t launches = 0;
+    bool any_ucnp = false, any_primary_ghost = false;
+    // modules
+    struct Mod { int kind; } ;
+    std::vector<int> module_order;
+    double *heating = nullptr;
+};
+
+namespace {
+
+int alloc_plane(spruce_domain *d, double **out)
+{
+    double *base = nullptr;
+    CUDA_TRY(cudaMalloc(&base, d->plane_doubles * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(base, 0, d->plane_doubles * sizeof(double), d->stream));
+    d->allocs.push_back(base);
+    *out = base + d->row_off;
+    return SPRUCE_OK;
+}
+int alloc_set(spruce_domain *d, PlaneSet &s)
+{
+    for (int v = 0; v < NEV; v++) { int rc = alloc_plane(d, &s.p[v]); if (rc) return rc; }
+    return SPRUCE_OK;
+}
+
+// computeIterationBounds, source/mhd/plasmadomain.cpp:138-161
+void iteration_bounds(const spruce_config &c, DomainParams &P)
+{
+    P.xl = (c.x_bound_1 == SPRUCE_BC_PERIODIC) ? 0 : HALO;
+    P.xu = (c.x_bound_2 == SPRUCE_BC_PERIODIC) ? c.xdim - 1 : c.xdim - HALO - 1;
+    P.yl = (c.y_bound_1 == SPRUCE_BC_PERIODIC) ? 0 : HALO;
+    P.yu = (c.y_bound_2 == SPRUCE_BC_PERIODIC) ? c.ydim - 1 : c.ydim - HALO - 1;
+}
+
+// 1-D tables for indices [lo-TAB_APRON, lo+n+TAB_APRON) of a global axis of length gn (periodic wrap when per)
+void build_axis(const std::vector<double> &dg, int gn, bool per, int lo, int n, HostAxis &A)
+{
+    const int m = n + 2 * TAB_APRON;
+    auto dval = [&](int g) -> double {          // cell size at global index g
+        if (per) { g = ((g % gn) + gn) % gn; return dg[g]; }
+        if (g < 0 || g >= gn) return 1.0;       // never used by an in-range operator
+        return dg[g];
+    };
+    auto hval = [&](int g) { return 0.5 * dval(g); };
+    A.h.resize(m); A.fs.resize(m); A.rfs.resize(m); A.ep.resize(m); A.em.resize(m); A.d.resize(m); A.rd.resize(m);
+    for (int k = 0; k < m; k++) {
+        const int g = lo + k - TAB_APRON;
+        A.d[k] = dval(g);
+        A.rd[k] = 1.0 / A.d[k];
+        A.h[k] = hval(g);
+        A.fs[k] = hval(g) + hval(g - 1);
+        A.rfs[k] = 1.0 / A.fs[k];
+        A.ep[k] = hval(g - 2) + 2.0 * hval(g - 1);
+        A.em[k] = hval(g + 1) + 2.0 * hval(g);
+    }
+}
+
+int upload_tables(spruce_domain *d)
+{
+    const spruce_config &c = d->cfg;
+    HostAxis X, Y;
+    build_axis(d->dxg, c.xdim, d->P.xper, c.row0, c.nx_local, X);
+    build_axis(d->dyg, c.ydim, d->P.yper, 0, c.ydim, Y);
+    const size_t mx = X.h.size(), my = Y.h.size();
+    std::vector<double> all;
+    all.reserve(7 * (mx + my));
+    const std::vector<double> *xs[7] = {&X.h, &X.fs, &X.rfs, &X.ep, &X.em, &X.d, &X.rd};
+    const std::vector<double> *ys[7] = {&Y.h, &Y.fs, &Y.rfs, &Y.ep, &Y.em, &Y.d, &Y.rd};
+    for (auto v : xs) all.insert(all.end(), v->begin(), v->end());
+    for (auto v : ys) all.insert(all.end(), v->begin(), v->end());
+    if (!d->tab_dev) { CUDA_TRY(cudaMalloc(&d->tab_dev, all.size() * sizeof(double))); }
+    CUDA_TRY(cudaMemcpyAsync(d->tab_dev, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    const double *b = d->tab_dev + TAB_APRON;
+    AxisTab &tx = d->P.tx, &ty = d->P.ty;
+    tx.h = b; tx.fs = b + mx; tx.rfs = b + 2 * mx; tx.ep = b + 3 * mx; tx.em = b + 4 * mx; tx.d = b + 5 * mx; tx.rd = b + 6 * mx;
+    b += 7 * mx;
+    ty.h = b; ty.fs = b + my; ty.rfs = b + 2 * my; ty.ep = b + 3 * my; ty.em = b + 4 * my; ty.d = b + 5 * my; ty.rd = b + 6 * my;
+    return SPRUCE_OK;
+}
+
+// open-boundary scalars, evolution.cpp:163-167 (host libm pow, exactly as the reference evaluates them)
+void build_ghost_proto(spruce_domain *d)
+{
+    const spruce_config &c = d->cfg;
+    GhostArgs &G = d->ghost_proto;
+    memset(&G, 0, sizeof(G));
+    G.open_strength = c.open_boundary_strength;
+    const int bcs[4] = {c.x_bound_1, c.x_bound_2, c.y_bound_1, c.y_bound_2};
+    for (int side = 0; side < 4; side++) {
+        const std::vector<double> &dd = side < 2 ? d->dxg : d->dyg;
+        const int n = side < 2 ? c.xdim : c.ydim;
+        const bool lower = (side == 0 || side == 2);
+        const int i1 = lower ? 0 : n - 1, i2 = lower ? 1 : n - 2, i3 = lower ? 2 : n - 3;
+        const double delta_last = dd[i3];
+        const double dist23 = 0.5 * (dd[i2] + dd[i3]);
+        const double dist12 = 0.5 * (dd[i1] + dd[i2]);
+        G.scale_2[side] = std::pow(c.open_boundary_decay_base, dist23 / delta_last);
+        G.scale_1[side] = std::pow(c.open_boundary_decay_base, dist12 / delta_last);
+        G.dist23[side] = dist23;
+        G.h2[side] = 0.5 * dd[i2];
+        G.h3[side] = 0.5 * dd[i3];
+        G.rh3[side] = 1.0 / G.h3[side];
+        if (bcs[side] == SPRUCE_BC_OPEN_UCNP) d->any_ucnp = true;
+        if (bcs[side] == SPRUCE_BC_OPEN || bcs[side] == SPRUCE_BC_REFLECT) d->any_primary_ghost = true;
+    }
+}
+
+void fill_sets(const spruce_domain *d, StageArgs &A, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D)
+{
+    for (int v = 0; v < NEV; v++) { A.S[v] = S.p[v]; A.B[v] = B.p[v]; A.D[v] = D.p[v]; A.K1[v] = d->K1set.p[v]; A.K2[v] = d->K2set.p[v]; }
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    for (int s = 0; s < 4; s++) A.r1strip[s] = d->r1strip[s];
+    A.step_ptr = &d->ctl->step;
+    A.done_ptr = &d->ctl->done;
+    A.dtmin_bits = &d->ctl->dtmin_bits;
+}
+
+int pick_chunk_rows(const spruce_domain *d)
+{
+    // enough CTAs for >= ~4 waves of 148 SMs x resident CTAs, but chunks of at least 16 rows (4 warm-up rows each)
+    const int strips = (d->P.ny + TW - 1) / TW;
+    int rows = 64;
+    while (rows > 16 && (long long)strips * ((d->P.nx + rows - 1) / rows) < 148LL * 5 * 4) rows >>= 1;
+    return rows;
+}
+
+int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode)
+{
+    StageArgs A{};
+    fill_sets(d, A, S, B, D);
+    A.coef = coef; A.primary = primary; A.kmode = kmode;
+    A.chunk_rows = pick_chunk_rows(d);
+    if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
+    dim3 grid((d->P.ny + TW - 1) / TW, (d->P.nx + A.chunk_rows - 1) / A.chunk_rows);
+    k_mhd_stage<<<grid, TW, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+int launch_ghosts(spruce_domain *d, const PlaneSet &U, int primary)
+{
+    if (!(d->any_ucnp || (primary && d->any_primary_ghost))) return SPRUCE_OK;
+    GhostArgs G = d->ghost_proto;
+    for (int v = 0; v < NEV; v++) G.U[v] = U.p[v];
+    for (int s = 0; s < 4; s++) G.r1strip[s] = d->r1strip[s];
+    G.primary = primary;
+    const int n = d->P.ny > d->P.nx ? d->P.ny : d->P.nx;
+    dim3 grid((n + 127) / 128, 4);
+    k_mhd_ghosts<<<grid, 128, 0, d->stream>>>(d->P, G);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+int launch_propagate(spruce_domain *d, int from_state)
+{
+    k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl);
+    PropArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    for (int s = 0; s < 4; s++) A.r1strip[s] = d->r1strip[s];
+    A.temp = d->scratch_temp; A.raw_rho = d->raw_rho ? 1 : 0; A.from_state = from_state;
+    A.dtmin_bits = &d->ctl->dtmin_bits;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_mhd_propagate<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    d->raw_rho = false;
+    return launch_ghosts(d, d->Pset, 1);
+}
+
+int ensure_rk4(spruce_domain *d)
+{
+    if (d->rk4_alloc) return SPRUCE_OK;
+    int rc;
+    if ((rc = alloc_set(d, d->M2set))) return rc;
+    if ((rc = alloc_set(d, d->K1set))) return rc;
+    if ((rc = alloc_set(d, d->K2set))) return rc;
+    d->rk4_alloc = true;
+    return SPRUCE_OK;
+}
+
+// one advanceTime (evolution.cpp:59-82) worth of launches
+int enqueue_step(spruce_domain *d, int hist_slot)
+{
+    int rc;
+    k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot);
+    d->launches++;
+    const int ti = d->cfg.time_integrator;
+    if (ti == SPRUCE_TI_EULER) {                                        // evolution.cpp:84-88
+        if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;
+        std::swap(d->Pset, d->Mset);                                    // D never aliases S: ping-pong instead of in place
+        if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
+    } else if (ti == SPRUCE_TI_RK2) {                                   // evolution.cpp:90-101
+        if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE))) return rc;
+        if ((rc = launch_ghosts(d, d->Mset, 0))) return rc;
+        if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_NONE))) return rc;
+        if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
+    } else {                                                            // evolution.cpp:103-124
+        if ((rc = ensure_rk4(d))) return rc;
+        if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_STORE_K1))) return rc;
+        if ((rc = launch_ghosts(d, d->Mset, 0))) return rc;
+        if ((rc = launch_stage(d, d->Mset, d->Pset, d->M2set, 0.5, 0, KM_STORE_K2))) return rc;
+        if ((rc = launch_ghosts(d, d->M2set, 0))) return rc;
+        if ((rc = launch_stage(d, d->M2set, d->Pset, d->Mset, 1.0, 0, KM_ADD_K2))) return rc;
+        if ((rc = launch_ghosts(d, d->Mset, 0))) return rc;
+        if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
+        if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
+    }
+    k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+struct NameMap { const char *name; int var; };
+const NameMap kVarNames[] = {
+    {"rho", V_rho}, {"temp", V_temp}, {"mom_x", V_mom_x}, {"mom_y", V_mom_y}, {"mom_z", V_mom_z}, {"bi_x", V_bi_x}, {"bi_y", V_bi_y},
+    {"bi_z", V_bi_z}, {"grav_x", V_grav_x}, {"grav_y", V_grav_y}, {"n", V_n}, {"press", V_press}, {"thermal_energy", V_thermal_energy},
+    {"v_x", V_v_x}, {"v_y", V_v_y}, {"v_z", V_v_z}, {"kinetic_energy", V_kinetic_energy}, {"b_x", V_b_x}, {"b_y", V_b_y}, {"b_z", V_b_z},
+    {"b_mag", V_b_mag}, {"b_hat_x", V_b_hat_x}, {"b_hat_y", V_b_hat_y}, {"b_hat_z", V_b_hat_z}, {"dt", V_dt}};
+
+int var_index(const char *name)
+{
+    for (const auto &m : kVarNames) if (!strcmp(m.name, name)) return m.var;
+    return -1;
+}
+// evolved plane index for a variable, or -1
+int evolved_slot(int var)
+{
+    switch (var) {
+    case V_rho: return E_N; case V_mom_x: return E_MX; case V_mom_y: return E_MY; case V_mom_z: return E_MZ;
+    case V_thermal_energy: return E_E; case V_bi_x: return E_BX; case V_bi_y: return E_BY; case V_bi_z: return E_BZ;
+    default: return -1;
+    }
+}
+int static_slot(const char *name)
+{
+    if (!strcmp(name, "be_x")) return S_BEX; if (!strcmp(name, "be_y")) return S_BEY; if (!strcmp(name, "be_z")) return S_BEZ;
+    if (!strcmp(name, "grav_x")) return S_GX; if (!strcmp(name, "grav_y")) return S_GY;
+    return -1;
+}
+
+int h2d_plane(spruce_domain *d, double *dev, const double *host)
+{
+    CUDA_TRY(cudaMemcpy2DAsync(dev, d->P.pitch * sizeof(double), host, d->P.ny * sizeof(double), d->P.ny * sizeof(double), d->P.nx,
+                               cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return SPRUCE_OK;
+}
+int d2h_plane(spruce_domain *d, double *host, const double *dev)
+{
+    CUDA_TRY(cudaMemcpy2DAsync(host, d->P.ny * sizeof(double), dev, d->P.pitch * sizeof(double), d->P.ny * sizeof(double), d->P.nx,
+                               cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return SPRUCE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *spruce_last_error(void) { return g_err; }
+int spruce_abi_version(void) { return SPRUCE_ABI_VERSION; }
+
+int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
+{
+    if (!cfg || !out) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (cfg->abi_version != SPRUCE_ABI_VERSION) return fail(SPRUCE_ERR_ARG, "ABI version mismatch: header %d, library %d", cfg->abi_version, SPRUCE_ABI_VERSION);
+    if (cfg->equation_set != SPRUCE_EQS_IDEAL_MHD) return fail(SPRUCE_ERR_UNSUPPORTED, "equation set %d is not built yet (ideal_mhd only)", cfg->equation_set);
+    // "Grid too small for ghost zones", plasmadomain.cpp:140
+    if (cfg->xdim <= 2 * HALO || cfg->ydim <= 2 * HALO) return fail(SPRUCE_ERR_ARG, "Grid too small for ghost zones");
+    const int bcs[4] = {cfg->x_bound_1, cfg->x_bound_2, cfg->y_bound_1, cfg->y_bound_2};
+    for (int b : bcs) {
+        if (b < 0 || b > SPRUCE_BC_OPEN_UCNP) return fail(SPRUCE_ERR_ARG, "Boundary cond'n must be defined");
+        if (b == SPRUCE_BC_OPEN_MOC) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries are outside the built scope (SURVEY.md 8f-2)");
+    }
+    if (cfg->time_integrator < 0 || cfg->time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "invalid time integrator");
+    if (cfg->n_ranks < 1 || cfg->nx_local < 1 || cfg->row0 < 0 || cfg->row0 + cfg->nx_local > cfg->xdim) return fail(SPRUCE_ERR_ARG, "bad slab [%d,%d) of %d", cfg->row0, cfg->row0 + cfg->nx_local, cfg->xdim);
+    if (cfg->n_ranks > 1 && cfg->nx_local < 2 * HALO) return fail(SPRUCE_ERR_ARG, "slab thinner than the halo");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(SPRUCE_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback (%s)", cudaGetErrorString(e));
+    if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
+
+    spruce_domain *d = new spruce_domain();
+    d->cfg = *cfg;
+    DomainParams &P = d->P;
+    P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;
+    P.gnx = cfg->xdim; P.row0 = cfg->row0;
+    iteration_bounds(*cfg, P);
+    P.xper = (cfg->x_bound_1 == SPRUCE_BC_PERIODIC && cfg->x_bound_2 == SPRUCE_BC_PERIODIC);
+    P.yper = (cfg->y_bound_1 == SPRUCE_BC_PERIODIC && cfg->y_bound_2 == SPRUCE_BC_PERIODIC);
+    P.xwrap = (P.xper && cfg->n_ranks == 1);
+    P.bc_x1 = cfg->x_bound_1; P.bc_x2 = cfg->x_bound_2; P.bc_y1 = cfg->y_bound_1; P.bc_y2 = cfg->y_bound_2;
+    P.m_i = cfg->ion_mass; P.rm_i = 1.0 / cfg->ion_mass;
+    P.gamma = cfg->adiabatic_index; P.gm1 = cfg->adiabatic_index - 1.0;
+    P.n_min = cfg->density_min; P.T_min = cfg->temp_min; P.e_min = cfg->thermal_energy_min;
+    P.fourpi = 4.0 * kPI; P.rfourpi = 1.0 / (4.0 * kPI);
+    P.epsilon = cfg->epsilon;
+
+    d->plane_doubles = (size_t)(P.nx + 2 * HALO) * P.pitch;
+    d->row_off = (size_t)HALO * P.pitch;
+    int rc = SPRUCE_OK;
+    if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SPRUCE_ERR_CUDA, "cudaStreamCreate failed"); }
+    if (!rc) rc = alloc_set(d, d->Pset);
+    if (!rc) rc = alloc_set(d, d->Mset);
+    for (int v = 0; v < NSTATIC && !rc; v++) rc = alloc_plane(d, &d->stat[v]);
+    if (!rc) rc = alloc_plane(d, &d->scratch_temp);
+    if (!rc) rc = alloc_plane(d, &d->scratch_out);
+    for (int s = 0; s < 4 && !rc; s++) {
+        const size_t n = (s < 2 ? P.ny : P.nx) + 16;
+        if (cudaMalloc(&d->r1strip[s], n * sizeof(double)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
+        else { cudaMemsetAsync(d->r1strip[s], 0, n * sizeof(double), d->stream); d->allocs.push_back(d->r1strip[s]); }
+    }
+    if (!rc && cudaMalloc(&d->ctl, sizeof(StepCtl)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
+    if (!rc) {
+        StepCtl h{};
+        h.step = 0.0; h.time = cfg->time; h.max_time = -1.0; h.epsilon = cfg->epsilon; h.iter = 0; h.done = 0;
+        h.dtmin_bits = 0x7FEFFFFFFFFFFFFFULL;
+        if (cudaMemcpy(d->ctl, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMemcpy failed");
+    }
+    if (rc) { spruce_domain_destroy(d); return rc; }
+    *out = d;
+    return SPRUCE_OK;
+}
+
+void spruce_domain_destroy(spruce_domain *d)
+{
+    if (!d) return;
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (double *p : d->allocs) cudaFree(p);
+    if (d->tab_dev) cudaFree(d->tab_dev);
+    if (d->ctl) cudaFree(d->ctl);
+    if (d->dt_hist) cudaFree(d->dt_hist);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int spruce_set_cell_sizes(spruce_domain *d, const double *d_x, size_t n_x, const double *d_y, size_t n_y)
+{
+    CHECK_DOM(d);
+    if (!d_x || !d_y || (int)n_x != d->cfg.xdim || (int)n_y != d->cfg.ydim) return fail(SPRUCE_ERR_ARG, "d_x needs xdim=%d and d_y ydim=%d entries", d->cfg.xdim, d->cfg.ydim);
+    for (size_t k = 0; k < n_x; k++) if (!(d_x[k] > 0.0)) return fail(SPRUCE_ERR_ARG, "d_x[%zu] is not positive", k);
+    for (size_t k = 0; k < n_y; k++) if (!(d_y[k] > 0.0)) return fail(SPRUCE_ERR_ARG, "d_y[%zu] is not positive", k);
+    d->dxg.assign(d_x, d_x + n_x);
+    d->dyg.assign(d_y, d_y + n_y);
+    int rc = upload_tables(d);
+    if (rc) return rc;
+    build_ghost_proto(d);
+    d->have_geom = true;
+    return SPRUCE_OK;
+}
+
+int spruce_grid_upload(spruce_domain *d, const char *name, const double *host, size_t count)
+{
+    CHECK_DOM(d);
+    if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane <%s>: expected %zu values, got %zu", name, (size_t)d->P.nx * d->P.ny, count);
+    if (!strcmp(name, "pos_x") || !strcmp(name, "pos_y") || !strcmp(name, "d_x") || !strcmp(name, "d_y")) return SPRUCE_OK; // host-only grids
+    const int s = static_slot(name);
+    if (s >= 0) return h2d_plane(d, d->stat[s], host);
+    const int var = var_index(name);
+    if (var < 0) return fail(SPRUCE_ERR_ARG, "Variable name <%s> not recognized", name);   // equationset.cpp:181
+    if (var == V_temp) return h2d_plane(d, d->scratch_temp, host);
+    const int ev = evolved_slot(var);
+    if (ev < 0) return fail(SPRUCE_ERR_ARG, "<%s> is a derived variable and cannot be uploaded", name);
+    if (ev == E_N) d->raw_rho = true;
+    return h2d_plane(d, d->Pset.p[ev], host);
+}
+
+int spruce_grid_download(spruce_domain *d, const char *name, double *host, size_t count)
+{
+    CHECK_DOM(d);
+    if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane <%s>: expected %zu values, got %zu", name, (size_t)d->P.nx * d->P.ny, count);
+    const int s = static_slot(name);
+    if (s >= 0) return d2h_plane(d, host, d->stat[s]);
+    const int var = var_index(name);
+    if (var < 0) return fail(SPRUCE_ERR_ARG, "Variable name <%s> not recognized", name);
+    if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "download of <%s> before spruce_eqs_setup", name);
+    const int ev = evolved_slot(var);
+    if (ev > 0) return d2h_plane(d, host, d->Pset.p[ev]);
+    DeriveArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.out = d->scratch_out; A.which = var;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_mhd_derive<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return d2h_plane(d, host, d->scratch_out);
+}
+
+int spruce_eqs_setup(spruce_domain *d)
+{
+    CHECK_DOM(d);
+    if (!d->have_geom) return fail(SPRUCE_ERR_STATE, "spruce_set_cell_sizes must precede spruce_eqs_setup");
+    d->raw_rho = true;
+    int rc = launch_propagate(d, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    d->is_setup = true;
+    return SPRUCE_OK;
+}
+
+int spruce_eqs_propagate_changes(spruce_domain *d)
+{
+    CHECK_DOM(d);
+    if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "propagate before setup");
+    int rc = launch_propagate(d, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return SPRUCE_OK;
+}
+
+int spruce_next_step_size(spruce_domain *d, double *step)
+{
+    CHECK_DOM(d);
+    if (!d->is_setup || !step) return fail(SPRUCE_ERR_STATE, "step size before setup");
+    StepCtl h;
+    CUDA_TRY(cudaMemcpyAsync(&h, d->ctl, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    double m; memcpy(&m, &h.dtmin_bits, sizeof(m));
+    *step = d->cfg.epsilon * m;
+    return SPRUCE_OK;
+}
+
+int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_used, int *steps_done)
+{
+    CHECK_DOM(d);
+    if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "advance before setup");
+    if (n_steps < 0) return fail(SPRUCE_ERR_ARG, "negative step count");
+    if ((size_t)n_steps > d->dt_hist_cap) {
+        if (d->dt_hist) cudaFree(d->dt_hist);
+        d->dt_hist_cap = (size_t)n_steps + 64;
+        CUDA_TRY(cudaMalloc(&d->dt_hist, d->dt_hist_cap * sizeof(double)));
+    }
+    StepCtl h0;
+    CUDA_TRY(cudaMemcpyAsync(&h0, d->ctl, sizeof(h0), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    CUDA_TRY(cudaMemcpyAsync(&d->ctl->max_time, &max_time, sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    for (int s = 0; s < n_steps; s++) { int rc = enqueue_step(d, s); if (rc) return rc; }
+    StepCtl h1;
+    CUDA_TRY(cudaMemcpyAsync(&h1, d->ctl, sizeof(h1), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    const int done = (int)(h1.iter - h0.iter);
+    if (steps_done) *steps_done = done;
+    if (dt_used && done > 0) CUDA_TRY(cudaMemcpy(dt_used, d->dt_hist, (size_t)done * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h1.done) { int zero = 0; CUDA_TRY(cudaMemcpy(&d->ctl->done, &zero, sizeof(int), cudaMemcpyHostToDevice)); }
+    return SPRUCE_OK;
+}
+
+int spruce_get_time(spruce_domain *d, double *time, int64_t *iter)
+{
+    CHECK_DOM(d);
+    StepCtl h;
+    CUDA_TRY(cudaMemcpyAsync(&h, d->ctl, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    if (time) *time = h.time;
+    if (iter) *iter = h.iter;
+    return SPRUCE_OK;
+}
+
+int spruce_eqs_time_derivatives(spruce_domain *d, double *k_out, size_t count)
+{
+    CHECK_DOM(d);
+    if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "time derivatives before setup");
+    const size_t np = (size_t)d->P.nx * d->P.ny;
+    if (!k_out || count != NEV * np) return fail(SPRUCE_ERR_ARG, "k_out needs %zu values", NEV * np);
+    int rc = ensure_rk4(d);
+    if (rc) return rc;
+    if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.0, 0, KM_EXPORT))) return rc;
+    for (int v = 0; v < NEV; v++) if ((rc = d2h_plane(d, k_out + v * np, d->K1set.p[v]))) return rc;
+    return SPRUCE_OK;
+}
+
+int spruce_operator(spruce_domain *, const char *, int, const double *, const double *, double *, size_t)
+{
+    return fail(SPRUCE_ERR_UNSUPPORTED, "stand-alone operators are not built yet");
+}
+
+int spruce_module_thermal_conduction(spruce_domain *, int, int, double, double, double) { return fail(SPRUCE_ERR_UNSUPPORTED, "thermal_conduction is not built yet"); }
+int spruce_module_radiative_losses(spruce_domain *, int, double, double, double, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "radiative_losses is not built yet"); }
+int spruce_module_ambient_heating(spruce_domain *, const double *, size_t) { return fail(SPRUCE_ERR_UNSUPPORTED, "ambient_heating is not built yet"); }
+int spruce_module_subcycles(spruce_domain *, const char *, int *) { return fail(SPRUCE_ERR_UNSUPPORTED, "modules are not built yet"); }
+
+int spruce_halo_buffers(spruce_domain *, void **, void **, void **, void **, size_t *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+int spruce_mgpu_pack(spruce_domain *, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+int spruce_mgpu_unpack(spruce_domain *, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+int spruce_mgpu_stage(spruce_domain *, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+int spruce_mgpu_n_stages(spruce_domain *, int *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+int spruce_mgpu_dt_min_ptr(spruce_domain *, void **) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+int spruce_mgpu_begin_step(spruce_domain *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+int spruce_mgpu_end_step(spruce_domain *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+
+int spruce_stream(spruce_domain *d, void **stream) { CHECK_DOM(d); if (!stream) return fail(SPRUCE_ERR_ARG, "null"); *stream = (void *)d->stream; return SPRUCE_OK; }
+int spruce_synchronize(spruce_domain *d) { CHECK_DOM(d); CUDA_TRY(cudaStreamSynchronize(d->stream)); return SPRUCE_OK; }
+int spruce_launch_count(spruce_domain *d, int64_t *count) { CHECK_DOM(d); if (count) *count = d->launches; return SPRUCE_OK; }
+
+int spruce_time_stage_kernel(spruce_domain *d, int reps, float *ms_mean)
+{
+    CHECK_DOM(d);
+    if (!d->is_setup || reps < 1 || !ms_mean) return fail(SPRUCE_ERR_STATE, "stage timing needs a set-up domain");
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+    int rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE);   // warm-up
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(a, d->stream));
+    for (int k = 0; k < reps; k++) if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE))) return rc;
+    CUDA_TRY(cudaEventRecord(b, d->stream));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_mean = ms / reps;
+    return SPRUCE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+"""Python mirror of the reference's PlasmaDomain / EquationSet surface for the per-timestep advance, on top of the
+C ABI (spruce_b200.capi).  Method names follow the reference (source/mhd/plasmadomain.hpp, source/equationsets/
+equationset.hpp): grid(name), propagateChanges(), computeTimeDerivatives(), advanceTime()/run().
+
+All arithmetic happens on the GPU inside libspruce_b200.so; this file only moves planes and parameters.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+_DP = C.POINTER(C.c_double)
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_DP)
+
+
+def rank1_cell_sizes(d_x: np.ndarray, d_y: np.ndarray):
+    """The reference keeps d_x, d_y as planes but requires d_x(i,j) = d_x(i), d_y(i,j) = d_y(j) (README.md:41)."""
+    dx, dy = np.ascontiguousarray(d_x[:, 0]), np.ascontiguousarray(d_y[0, :])
+    if not (np.array_equal(d_x, np.repeat(dx[:, None], d_x.shape[1], 1)) and np.array_equal(d_y, np.repeat(dy[None, :], d_y.shape[0], 0))):
+        raise capi.SpruceError("d_x must vary with i only and d_y with j only (rectilinear grid, reference README.md:41)")
+    return dx, dy
+
+
+class PlasmaDomain:
+    EVOLVED = ["rho", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z"]          # idealmhd.hpp:32-34
+    STATE = ["rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]   # idealmhd.hpp:28-30
+    DOMAIN = ["be_x", "be_y", "be_z"]
+
+    def __init__(self, planes: dict, ion_mass: float, adiabatic_index: float, *, equation_set="ideal_mhd",
+                 xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator="rk2", epsilon=0.2,
+                 density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6, open_strength=1.0, open_decay=0.5,
+                 time=0.0, device=-1, row0=0, nx_local=None, rank=0, n_ranks=1, setup=True):
+        self.lib = capi.load()
+        gx, gy = planes["d_x"].shape if planes["d_x"].ndim == 2 else (planes["d_x"].size, planes["d_y"].size)
+        if planes["d_x"].ndim == 2:
+            dx, dy = rank1_cell_sizes(planes["d_x"], planes["d_y"])
+        else:
+            dx, dy = np.ascontiguousarray(planes["d_x"], dtype=np.float64), np.ascontiguousarray(planes["d_y"], dtype=np.float64)
+        self.xdim, self.ydim = int(gx), int(gy)
+        self.row0 = int(row0)
+        self.nx = int(self.xdim if nx_local is None else nx_local)
+        cfg = capi.Config(abi_version=capi.ABI_VERSION, equation_set=capi.EQS[equation_set], xdim=self.xdim, ydim=self.ydim,
+                          x_bound_1=capi.BC[xb[0]], x_bound_2=capi.BC[xb[1]], y_bound_1=capi.BC[yb[0]], y_bound_2=capi.BC[yb[1]],
+                          time_integrator=capi.TI[integrator], device=device, row0=self.row0, nx_local=self.nx, rank=rank, n_ranks=n_ranks,
+                          ion_mass=ion_mass, adiabatic_index=adiabatic_index, epsilon=epsilon, density_min=density_min,
+                          temp_min=temp_min, thermal_energy_min=thermal_energy_min, open_boundary_strength=open_strength,
+                          open_boundary_decay_base=open_decay, time=time)
+        h = C.c_void_p()
+        capi.check(self.lib.spruce_domain_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        capi.check(self.lib.spruce_set_cell_sizes(self.h, _dp(dx), dx.size, _dp(dy), dy.size))
+        for name in self.DOMAIN + self.STATE:
+            if name in planes:
+                self.upload(name, planes[name])
+        if setup:
+            self.setup()
+
+    # -- plane transfer (EquationSet::grid(name), equationset.cpp:113-121)
+    def _local(self, a: np.ndarray) -> np.ndarray:
+        a = np.asarray(a, dtype=np.float64)
+        if a.shape[0] == self.xdim and self.nx != self.xdim:
+            a = a[self.row0:self.row0 + self.nx]
+        return np.ascontiguousarray(a)
+
+    def upload(self, name: str, a: np.ndarray):
+        a = self._local(a)
+        capi.check(self.lib.spruce_grid_upload(self.h, name.encode(), _dp(a), a.size))
+
+    def grid(self, name: str) -> np.ndarray:
+        out = np.empty((self.nx, self.ydim))
+        capi.check(self.lib.spruce_grid_download(self.h, name.encode(), _dp(out), out.size))
+        return out
+
+    def evolved(self) -> dict:
+        return {k: self.grid(k) for k in self.EVOLVED}
+
+    # -- EquationSet
+    def setup(self):
+        capi.check(self.lib.spruce_eqs_setup(self.h))
+
+    def propagateChanges(self):
+        capi.check(self.lib.spruce_eqs_propagate_changes(self.h))
+
+    def computeTimeDerivatives(self) -> np.ndarray:
+        k = np.empty((8, self.nx, self.ydim))
+        capi.check(self.lib.spruce_eqs_time_derivatives(self.h, _dp(k), k.size))
+        return k
+
+    def next_step_size(self) -> float:
+        s = C.c_double()
+        capi.check(self.lib.spruce_next_step_size(self.h, C.byref(s)))
+        return s.value
+
+    # -- time loop (PlasmaDomain::advanceTime / run, evolution.cpp:8-82)
+    def advance(self, n_steps: int, max_time: float = -1.0) -> np.ndarray:
+        dts = np.zeros(max(n_steps, 1))
+        done = C.c_int()
+        capi.check(self.lib.spruce_advance(self.h, n_steps, max_time, _dp(dts), C.byref(done)))
+        return dts[:done.value]
+
+    def advanceTime(self) -> float:
+        return float(self.advance(1)[0])
+
+    @property
+    def time(self) -> float:
+        t = C.c_double(); it = C.c_int64()
+        capi.check(self.lib.spruce_get_time(self.h, C.byref(t), C.byref(it)))
+        return t.value
+
+    @property
+    def iter(self) -> int:
+        t = C.c_double(); it = C.c_int64()
+        capi.check(self.lib.spruce_get_time(self.h, C.byref(t), C.byref(it)))
+        return it.value
+
+    # -- modules (config block -> device module), call order = execution order (modulehandler.cpp:92-111)
+    def set_thermal_conduction(self, *, flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-4, weakening_factor=1.0):
+        capi.check(self.lib.spruce_module_thermal_conduction(self.h, int(flux_saturation), capi.TI[integrator], epsilon, dt_subcycle_min, weakening_factor))
+
+    def set_radiative_losses(self, *, integrator="euler", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1, prevent_subcycling=False):
+        capi.check(self.lib.spruce_module_radiative_losses(self.h, capi.TI[integrator], cutoff_ramp, cutoff_temp, epsilon, int(prevent_subcycling)))
+
+    def set_ambient_heating_plane(self, heating: np.ndarray):
+        a = self._local(heating)
+        capi.check(self.lib.spruce_module_ambient_heating(self.h, _dp(a), a.size))
+
+    def subcycles(self, which: str) -> int:
+        n = C.c_int()
+        capi.check(self.lib.spruce_module_subcycles(self.h, which.encode(), C.byref(n)))
+        return n.value
+
+    # -- plumbing
+    def synchronize(self):
+        capi.check(self.lib.spruce_synchronize(self.h))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        capi.check(self.lib.spruce_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        capi.check(self.lib.spruce_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def time_stage_kernel(self, reps=10) -> float:
+        ms = C.c_float()
+        capi.check(self.lib.spruce_time_stage_kernel(self.h, reps, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.spruce_domain_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
