@@ -42,7 +42,7 @@ struct spruce_domain {
     PlaneSet Pset, Mset, M2set, K1set, K2set;
     double *stat[NSTATIC] = {nullptr};
     double *scratch_temp = nullptr, *scratch_out = nullptr;
-    double *r1strip[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *strip[4] = {nullptr, nullptr, nullptr, nullptr}; int strip_pitch = 0;
     double *tab_dev = nullptr;     // all 1-D tables in one allocation
     StepCtl *ctl = nullptr;
     double *dt_hist = nullptr; size_t dt_hist_cap = 0;
@@ -161,7 +161,8 @@ void fill_sets(const spruce_domain *d, StageArgs &A, const PlaneSet &S, const Pl
 {
     for (int v = 0; v < NEV; v++) { A.S[v] = S.p[v]; A.B[v] = B.p[v]; A.D[v] = D.p[v]; A.K1[v] = d->K1set.p[v]; A.K2[v] = d->K2set.p[v]; }
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
-    for (int s = 0; s < 4; s++) A.r1strip[s] = d->r1strip[s];
+    for (int s = 0; s < 4; s++) A.strip[s] = d->strip[s];
+    A.strip_pitch = d->strip_pitch;
     A.step_ptr = &d->ctl->step;
     A.done_ptr = &d->ctl->done;
     A.dtmin_bits = &d->ctl->dtmin_bits;
@@ -170,7 +171,7 @@ void fill_sets(const spruce_domain *d, StageArgs &A, const PlaneSet &S, const Pl
 int pick_chunk_rows(const spruce_domain *d)
 {
     // enough CTAs for >= ~4 waves of 148 SMs x resident CTAs, but chunks of at least 16 rows (4 warm-up rows each)
-    const int strips = (d->P.ny + TW - 1) / TW;
+    const int strips = (d->P.ny + CW - 1) / CW;
     int rows = 64;
     while (rows > 16 && (long long)strips * ((d->P.nx + rows - 1) / rows) < 148LL * 5 * 4) rows >>= 1;
     return rows;
@@ -183,8 +184,8 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     A.chunk_rows = pick_chunk_rows(d);
     if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
-    dim3 grid((d->P.ny + TW - 1) / TW, (d->P.nx + A.chunk_rows - 1) / A.chunk_rows);
-    k_mhd_stage<<<grid, TW, 0, d->stream>>>(d->P, A);
+    dim3 grid((d->P.ny + CW - 1) / CW, (d->P.nx + A.chunk_rows - 1) / A.chunk_rows);
+    k_mhd_stage<<<grid, NT, STAGE_SMEM, d->stream>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
@@ -195,7 +196,8 @@ int launch_ghosts(spruce_domain *d, const PlaneSet &U, int primary)
     if (!(d->any_ucnp || (primary && d->any_primary_ghost))) return SPRUCE_OK;
     GhostArgs G = d->ghost_proto;
     for (int v = 0; v < NEV; v++) G.U[v] = U.p[v];
-    for (int s = 0; s < 4; s++) G.r1strip[s] = d->r1strip[s];
+    for (int s = 0; s < 4; s++) G.strip[s] = d->strip[s];
+    G.strip_pitch = d->strip_pitch;
     G.primary = primary;
     const int n = d->P.ny > d->P.nx ? d->P.ny : d->P.nx;
     dim3 grid((n + 127) / 128, 4);
@@ -211,7 +213,8 @@ int launch_propagate(spruce_domain *d, int from_state)
     PropArgs A{};
     for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
-    for (int s = 0; s < 4; s++) A.r1strip[s] = d->r1strip[s];
+    for (int s = 0; s < 4; s++) A.strip[s] = d->strip[s];
+    A.strip_pitch = d->strip_pitch;
     A.temp = d->scratch_temp; A.raw_rho = d->raw_rho ? 1 : 0; A.from_state = from_state;
     A.dtmin_bits = &d->ctl->dtmin_bits;
     dim3 grid((d->P.ny + 255) / 256, d->P.nx);
@@ -337,6 +340,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (e != cudaSuccess || ndev == 0) return fail(SPRUCE_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback (%s)", cudaGetErrorString(e));
     if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
 
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM));
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     DomainParams &P = d->P;
@@ -362,10 +366,11 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     for (int v = 0; v < NSTATIC && !rc; v++) rc = alloc_plane(d, &d->stat[v]);
     if (!rc) rc = alloc_plane(d, &d->scratch_temp);
     if (!rc) rc = alloc_plane(d, &d->scratch_out);
+    d->strip_pitch = (P.ny > P.nx ? P.ny : P.nx) + 16;
     for (int s = 0; s < 4 && !rc; s++) {
-        const size_t n = (s < 2 ? P.ny : P.nx) + 16;
-        if (cudaMalloc(&d->r1strip[s], n * sizeof(double)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
-        else { cudaMemsetAsync(d->r1strip[s], 0, n * sizeof(double), d->stream); d->allocs.push_back(d->r1strip[s]); }
+        const size_t n = 4 * (size_t)d->strip_pitch;
+        if (cudaMalloc(&d->strip[s], n * sizeof(double)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
+        else { cudaMemsetAsync(d->strip[s], 0, n * sizeof(double), d->stream); d->allocs.push_back(d->strip[s]); }
     }
     if (!rc && cudaMalloc(&d->ctl, sizeof(StepCtl)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
     if (!rc) {

@@ -76,15 +76,21 @@ struct StageArgs {
     const double *step_ptr;       // device scalar: step size of this iteration
     const int *done_ptr;          // device flag: run() reached max_time -> every later launch is a no-op
     unsigned long long *dtmin_bits; // device scalar: running min of dt over the interior, as ordered bits
-    double *r1strip[4];           // post-floor rho of the first interior cell next to an `open` side (x1,x2,y1,y2)
+    double *strip[4];             // per side (x1,x2,y1,y2): what that side's ghost pass reads from its first interior cell
+    int strip_pitch;              //   strip[s][c*strip_pitch + idx], c = 0: post-floor rho, 1..3: momentum as that pass sees it
     int chunk_rows;               // rows per CTA
 };
 
-constexpr int TW = 64;                       // columns (= threads) per CTA
-constexpr int SW = TW + 2 * HALO;            // shared row width
-constexpr int RD = 5;                        // ring depth (rows)
+// ---- tiling of the fused stage kernel ("column marching", see the header comment)
+constexpr int STAGE_WARPS = 2;
+constexpr int NT = 32 * STAGE_WARPS;         // threads per CTA
+constexpr int CW = 31 * STAGE_WARPS;         // output columns per CTA: a warp evaluates 32 y-faces = 31 cells (+ the face it hands on)
+constexpr int SW = CW + 2 * HALO;            // shared row width (66 doubles = 528 B, 16-byte multiple)
+constexpr int RD = 5;                        // ring depth: rows r-1..r+2 in use, row r+3 in flight
 enum { Q_RHO = 0, Q_MX, Q_MY, Q_MZ, Q_E, Q_BIX, Q_BIY, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_VX, Q_VY, Q_VZ, NARR };
 constexpr int NTR = 11;                      // transported quantities Q_RHO..Q_BEZ
+constexpr int NLOAD = 11;                    // arrays filled from global memory (Q_RHO holds n until converted)
+constexpr size_t STAGE_SMEM = (size_t)(RD * NARR * SW + 2 * NTR * NT) * sizeof(double);
 
 __device__ __forceinline__ FaceGeom load_face_geom(const AxisTab &t, int f)
 {
@@ -109,18 +115,44 @@ __device__ __forceinline__ int phys_row(const DomainParams &P, int r)
     return r;
 }
 
-// Pointwise part of updateGhostZones that lands inside the dt bounds: `fixed` and `reflect` zero every momentum
-// component in the two ghost cells AND the first interior cell (evolution.cpp:245-263, 272-282).  fixed sweeps the
-// whole side, reflect only the interior range of the other axis (evolution.cpp:129-151).
-__device__ __forceinline__ bool momentum_zeroed(const DomainParams &P, int g, int j)
+// updateGhostZones runs its four sides in the fixed order x1, x2, y1, y2 (evolution.cpp:126-152), each side reading
+// cells the earlier sides may have changed.  The part that lands inside the dt bounds is pointwise: `fixed` and `reflect`
+// zero every momentum component in the two ghost cells AND the first interior cell (evolution.cpp:245-263, 272-282);
+// fixed sweeps the whole side, reflect only the interior range of the other axis (evolution.cpp:129-151).
+// zone bit s is set when side s zeroes the momentum of cell (g, j).
+__device__ __forceinline__ unsigned zero_zones(const DomainParams &P, int g, int j)
 {
     const bool jin = (j >= P.yl && j <= P.yu), iin = (g >= P.xl && g <= P.xu);
-    bool z = false;
-    if (g <= 2)          z |= (P.bc_x1 == BC_FIXED) || (P.bc_x1 == BC_REFLECT && jin);
-    if (g >= P.gnx - 3)  z |= (P.bc_x2 == BC_FIXED) || (P.bc_x2 == BC_REFLECT && jin);
-    if (j <= 2)          z |= (P.bc_y1 == BC_FIXED) || (P.bc_y1 == BC_REFLECT && iin);
-    if (j >= P.ny - 3)   z |= (P.bc_y2 == BC_FIXED) || (P.bc_y2 == BC_REFLECT && iin);
+    unsigned z = 0;
+    if (g <= 2         && ((P.bc_x1 == BC_FIXED) || (P.bc_x1 == BC_REFLECT && jin))) z |= 1u;
+    if (g >= P.gnx - 3 && ((P.bc_x2 == BC_FIXED) || (P.bc_x2 == BC_REFLECT && jin))) z |= 2u;
+    if (j <= 2         && ((P.bc_y1 == BC_FIXED) || (P.bc_y1 == BC_REFLECT && iin))) z |= 4u;
+    if (j >= P.ny - 3  && ((P.bc_y2 == BC_FIXED) || (P.bc_y2 == BC_REFLECT && iin))) z |= 8u;
     return z;
+}
+__device__ __forceinline__ bool reads_interior(int bc) { return bc == BC_OPEN || bc == BC_OPEN_UCNP; }
+
+// The open / open_ucnp pass of side s reads rho and the momenta of its first interior cell at the moment that pass
+// runs: after the floors, after the zeroing of the sides that ran BEFORE it, before the later ones.  The full-plane
+// kernels record exactly that in the strips (rho additionally before its n round trip, idealmhd.cpp:237 vs :246-247).
+__device__ __forceinline__ void record_strips(const DomainParams &P, double *const *strip, int sp, int g, int r, int j, unsigned z,
+                                              double rfl, double mx, double my, double mz)
+{
+    if (reads_interior(P.bc_x1) && g == 2) {
+        double *s = strip[0]; s[j] = rfl; s[sp + j] = mx; s[2 * sp + j] = my; s[3 * sp + j] = mz;
+    }
+    if (reads_interior(P.bc_x2) && g == P.gnx - 3) {
+        const bool zz = z & 1u; double *s = strip[1];
+        s[j] = rfl; s[sp + j] = zz ? 0.0 : mx; s[2 * sp + j] = zz ? 0.0 : my; s[3 * sp + j] = zz ? 0.0 : mz;
+    }
+    if (reads_interior(P.bc_y1) && j == 2) {
+        const bool zz = z & 3u; double *s = strip[2];
+        s[r] = rfl; s[sp + r] = zz ? 0.0 : mx; s[2 * sp + r] = zz ? 0.0 : my; s[3 * sp + r] = zz ? 0.0 : mz;
+    }
+    if (reads_interior(P.bc_y2) && j == P.ny - 3) {
+        const bool zz = z & 7u; double *s = strip[3];
+        s[r] = rfl; s[sp + r] = zz ? 0.0 : mx; s[2 * sp + r] = zz ? 0.0 : my; s[3 * sp + r] = zz ? 0.0 : mz;
+    }
 }
 
 // enforceMinimums + recomputeDerivedVarsFromEvolvedVars for rho (idealmhd.cpp:237,246-247). Returns n; *r1 = post-floor rho.
@@ -175,72 +207,107 @@ __device__ __forceinline__ void block_min_to_global(double v, unsigned long long
 
 // ---------------------------------------------------------------------------------------------------------
 // Fused Runge-Kutta stage: D = B + (coef*step) * f(S), floors, pointwise boundary zeroing, dt minimum.
-// grid = (ceil(ny/TW), ceil(nx/chunk_rows)), block = TW.
+// grid = (ceil(ny/CW), ceil(nx/chunk_rows)), block = NT, dynamic shared memory = STAGE_SMEM.
+//
+//  * rows enter the shared ring through cp.async (LDGSTS) one iteration ahead of their first use; the loader then
+//    converts n -> rho = n*m_i and derives v = mom/rho once per cell;
+//  * the 11 transported quantities run through ONE rolled loop body (small code, fits the instruction cache);
+//    x-face fluxes are carried from row to row (Fx_s), every x face is evaluated once;
+//  * a lane evaluates only the LEFT y-face of its column and receives the right one from lane+1 by shuffle, so every
+//    y face is evaluated once too; lane 31 of a warp only feeds lane 30 (31 output columns per warp);
+//  * a quantity whose whole stencil window is exactly zero across the warp (be_* in most runs, the z components in
+//    2-D problems) is skipped: its face values, fluxes and derivatives are exactly zero in the reference as well.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TW) k_mhd_stage(const DomainParams P, const StageArgs A)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
 {
-    __shared__ double ring[RD][NARR][SW];
-    if (*A.done_ptr) return;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ double shfl_next(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-    const int tid = threadIdx.x;
-    const int j0 = blockIdx.x * TW;
-    const int j = j0 + tid;
-    const int c = tid + HALO;
+__global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const StageArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    if (*A.done_ptr) return;
+    double (*ring)[NARR][SW] = reinterpret_cast<double (*)[NARR][SW]>(smem);
+    double (*Fx_s)[NT] = reinterpret_cast<double (*)[NT]>(smem + RD * NARR * SW);   // x-face flux carried to the next row
+    double (*T_s)[NT] = Fx_s + NTR;                                                  // transportDivergence2D per quantity
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = blockIdx.x * CW;
+    const int ccol = 31 * warp + lane;            // column inside the CTA (lane 31 duplicates the next warp's lane 0)
+    const int j = j0 + ccol;
+    const int c = ccol + HALO;
     const int r0 = blockIdx.y * A.chunk_rows;
     const int r1 = min(r0 + A.chunk_rows, P.nx);
-    const bool col_out = (j < P.ny);
+    const bool col_out = (lane < 31) && (j < P.ny);
 
-    // column this thread loads: its own, or the periodic image when the strip overhangs the domain
-    int jl = j;
-    bool jl_ok = col_out;
-    if (!col_out && P.yper && j - P.ny < P.ny) { jl = j - P.ny; jl_ok = true; }
-    // halo column handled by threads 0..3 : c = 0,1,TW+2,TW+3
-    const bool halo_thread = tid < 2 * HALO;
-    const int hc = (tid < HALO) ? tid : (TW + tid);
-    int jh = j0 - HALO + hc;
-    bool jh_ok = (jh >= 0 && jh < P.ny);
-    if (!jh_ok && P.yper) { jh = (jh + 2 * P.ny) % P.ny; jh_ok = true; }
+    // ---- loader mapping: thread t fills shared column t (and t+NT for t < SW-NT)
+    int jl[2]; bool jl_ok[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int jj = j0 - HALO + tid + k * NT;
+        bool ok = (jj >= 0 && jj < P.ny);
+        if (!ok && P.yper) { jj = (jj + 2 * P.ny) % P.ny; ok = true; }
+        if (tid + k * NT >= SW) ok = false;
+        jl[k] = jj; jl_ok[k] = ok;
+    }
+    const bool second = (tid + NT < SW);
+    auto slot_of = [&](int r) { return (r - r0 + HALO + RD) % RD; };
+    auto issue_row = [&](int r) {               // cp.async the 11 source arrays of row r
+        const int slot = slot_of(r);
+        const bool rok = row_exists(P, r);
+        const size_t rowoff = (size_t)phys_row(P, r) * P.pitch;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (k == 1 && !second) break;
+            const int cc = tid + k * NT;
+            if (rok && jl_ok[k]) {
+                const size_t off = rowoff + jl[k];
+#pragma unroll
+                for (int v = 0; v < NEV; v++) cp_async8(&ring[slot][v][cc], A.S[v] + off);
+                cp_async8(&ring[slot][Q_BEX][cc], A.st[S_BEX] + off);
+                cp_async8(&ring[slot][Q_BEY][cc], A.st[S_BEY] + off);
+                cp_async8(&ring[slot][Q_BEZ][cc], A.st[S_BEZ] + off);
+            } else {
+#pragma unroll
+                for (int v = 0; v < NLOAD; v++) ring[slot][v][cc] = (v == Q_RHO) ? 1.0 : 0.0;
+            }
+        }
+    };
+    auto convert_row = [&](int r) {             // n -> rho, v = mom/rho (idealmhd.cpp:247-250), own loader columns only
+        const int slot = slot_of(r);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (k == 1 && !second) break;
+            const int cc = tid + k * NT;
+            const double rho = ring[slot][Q_RHO][cc] * P.m_i;
+            ring[slot][Q_RHO][cc] = rho;
+            ring[slot][Q_VX][cc] = ring[slot][Q_MX][cc] / rho;
+            ring[slot][Q_VY][cc] = ring[slot][Q_MY][cc] / rho;
+            ring[slot][Q_VZ][cc] = ring[slot][Q_MZ][cc] / rho;
+        }
+    };
 
     const double step = *A.step_ptr;
     const double s = A.coef * step;
 
-    // ---- row loader: global -> ring slot, with rho = n*m_i and v = mom/rho computed once per cell
-    auto load_cell = [&](int slot, int cc, size_t off, bool ok) {
-        double n_ = 1.0, mx = 0.0, my = 0.0, mz = 0.0, e = 0.0, bx = 0.0, by = 0.0, bz = 0.0, ex = 0.0, ey = 0.0, ez = 0.0;
-        if (ok) {
-            n_ = A.S[E_N][off]; mx = A.S[E_MX][off]; my = A.S[E_MY][off]; mz = A.S[E_MZ][off];
-            e = A.S[E_E][off]; bx = A.S[E_BX][off]; by = A.S[E_BY][off]; bz = A.S[E_BZ][off];
-            ex = A.st[S_BEX][off]; ey = A.st[S_BEY][off]; ez = A.st[S_BEZ][off];
-        }
-        const double rho = n_ * P.m_i;
-        ring[slot][Q_RHO][cc] = rho;
-        ring[slot][Q_MX][cc] = mx; ring[slot][Q_MY][cc] = my; ring[slot][Q_MZ][cc] = mz;
-        ring[slot][Q_E][cc] = e;
-        ring[slot][Q_BIX][cc] = bx; ring[slot][Q_BIY][cc] = by; ring[slot][Q_BIZ][cc] = bz;
-        ring[slot][Q_BEX][cc] = ex; ring[slot][Q_BEY][cc] = ey; ring[slot][Q_BEZ][cc] = ez;
-        ring[slot][Q_VX][cc] = mx / rho; ring[slot][Q_VY][cc] = my / rho; ring[slot][Q_VZ][cc] = mz / rho;
-    };
-    auto slot_of = [&](int r) { return (r - r0 + HALO + RD) % RD; };
-    auto load_row = [&](int r) {
-        const int slot = slot_of(r);
-        const bool rok = row_exists(P, r);
-        const size_t rowoff = (size_t)phys_row(P, r) * P.pitch;
-        load_cell(slot, c, rowoff + jl, rok && jl_ok);
-        if (halo_thread) load_cell(slot, hc, rowoff + jh, rok && jh_ok);
-    };
-
-    // ---- per-thread y geometry (faces j and j+1) and cell sizes
-    const FaceGeom gyL = load_face_geom(P.ty, col_out ? j : 0);
-    const FaceGeom gyR = load_face_geom(P.ty, col_out ? j + 1 : 1);
-    const double dy = P.ty.d[col_out ? j : 0], rdy = P.ty.rd[col_out ? j : 0];
+    // ---- per-thread y geometry: left face of column j, and the cell size
+    const int jt = min(j, P.ny + 1);
+    const FaceGeom gy = load_face_geom(P.ty, jt);
+    const double dy = P.ty.d[min(j, P.ny)], rdy = P.ty.rd[min(j, P.ny)];
 
     // ---- prologue: rows r0-2 .. r0+2
-    for (int r = r0 - HALO; r <= r0 + HALO; r++) load_row(r);
+    for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r);
+    cp_async_commit();
+    cp_async_wait_all();
+    for (int r = r0 - HALO; r <= r0 + HALO; r++) convert_row(r);
     __syncthreads();
 
-    // x-face carry (face r0, between rows r0-1 and r0)
-    double Fx[NTR];                   // S*vf per transported quantity
-    double cIx_biy, cIx_biz, cIx_p, cVfx, cIx_vy, cIx_vz;
+    // x-face carries (face r0, between rows r0-1 and r0)
+    double cIx_biy = 0.0, cIx_biz = 0.0, cIx_p, cVfx, cIx_vy, cIx_vz;
     {
         const FaceGeom g = load_face_geom(P.tx, r0);
         const int sm2 = slot_of(r0 - 2), sm1 = slot_of(r0 - 1), s0 = slot_of(r0), sp1 = slot_of(r0 + 1);
@@ -248,11 +315,11 @@ __global__ void __launch_bounds__(TW) k_mhd_stage(const DomainParams P, const St
         cIx_vy = face_interp(ring[sm1][Q_VY][c], ring[s0][Q_VY][c], g.hm1, g.h0, g.fs, g.rfs);
         cIx_vz = face_interp(ring[sm1][Q_VZ][c], ring[s0][Q_VZ][c], g.hm1, g.h0, g.fs, g.rfs);
         cIx_p = face_interp(ring[sm1][Q_E][c] * P.gm1, ring[s0][Q_E][c] * P.gm1, g.hm1, g.h0, g.fs, g.rfs);
-        double d2;
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < NTR; q++) {
+            double d2;
             const double S = upwind_face(ring[sm2][q][c], ring[sm1][q][c], ring[s0][q][c], ring[sp1][q][c], cVfx, g, &d2);
-            Fx[q] = S * cVfx;
+            Fx_s[q][tid] = S * cVfx;
             if (q == Q_BIY) cIx_biy = d2;
             if (q == Q_BIZ) cIx_biz = d2;
         }
@@ -262,41 +329,48 @@ __global__ void __launch_bounds__(TW) k_mhd_stage(const DomainParams P, const St
 
     for (int r = r0; r < r1; r++) {
         // prefetch row r+3 into the free slot (the slot of row r-2)
-        if (r + 3 <= r1 + HALO - 1) load_row(r + 3);
+        const bool pre = (r + 3 <= r1 + HALO - 1);
+        if (pre) issue_row(r + 3);
+        cp_async_commit();
 
         const int sm1 = slot_of(r - 1), s0 = slot_of(r), sp1 = slot_of(r + 1), sp2 = slot_of(r + 2);
         const int g = P.row0 + r;                                   // global row
         const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
         const double dx = P.tx.d[r], rdx = P.tx.rd[r];
 
-        // ---------------- x face r+1 (between rows r and r+1)
+        // ---------------- x face r+1 (between rows r and r+1): velocity, pressure
         const FaceGeom gx = load_face_geom(P.tx, r + 1);
-        const double vfx1 = face_interp(ring[s0][Q_VX][c], ring[sp1][Q_VX][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
-        const double Ix1_vy = face_interp(ring[s0][Q_VY][c], ring[sp1][Q_VY][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
-        const double Ix1_vz = face_interp(ring[s0][Q_VZ][c], ring[sp1][Q_VZ][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
+        const double vxc = ring[s0][Q_VX][c], vyc = ring[s0][Q_VY][c], vzc = ring[s0][Q_VZ][c];
+        const double vfx1 = face_interp(vxc, ring[sp1][Q_VX][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
+        const double Ix1_vy = face_interp(vyc, ring[sp1][Q_VY][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
+        const double Ix1_vz = face_interp(vzc, ring[sp1][Q_VZ][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
         const double pc = ring[s0][Q_E][c] * P.gm1;                 // press = (gamma-1)*thermal_energy  idealmhd.cpp:253
         const double Ix1_p = face_interp(pc, ring[sp1][Q_E][c] * P.gm1, gx.hm1, gx.h0, gx.fs, gx.rfs);
-        // ---------------- y faces j (L) and j+1 (R) of row r
-        const double vyc = ring[s0][Q_VY][c];
-        const double vfyL = face_interp(ring[s0][Q_VY][c - 1], vyc, gyL.hm1, gyL.h0, gyL.fs, gyL.rfs);
-        const double vfyR = face_interp(vyc, ring[s0][Q_VY][c + 1], gyR.hm1, gyR.h0, gyR.fs, gyR.rfs);
+        // ---------------- y face j (left face of this column); the right face comes from lane+1
+        const double vfyL = face_interp(ring[s0][Q_VY][c - 1], vyc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+        const double IyL_vx = face_interp(ring[s0][Q_VX][c - 1], vxc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+        const double IyL_vz = face_interp(ring[s0][Q_VZ][c - 1], vzc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+        const double IyL_p = face_interp(ring[s0][Q_E][c - 1] * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+        const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = shfl_next(IyL_vz), IyR_p = shfl_next(IyL_p);
 
-        // transportDivergence2D of the 11 transported quantities (derivs.cpp:216-220) and the face interpolations
-        // that the central derivatives reuse
-        double T[NTR];
+        // ---------------- transportDivergence2D of the 11 transported quantities (derivs.cpp:122-162,216-220)
         double Ix1_biy = 0.0, Ix1_biz = 0.0, IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < NTR; q++) {
-            double d2x, d2L, d2R;
-            const double qc = ring[s0][q][c];
-            const double Sx = upwind_face(ring[sm1][q][c], qc, ring[sp1][q][c], ring[sp2][q][c], vfx1, gx, &d2x);
-            const double fx1 = Sx * vfx1;
-            const double SL = upwind_face(ring[s0][q][c - 2], ring[s0][q][c - 1], qc, ring[s0][q][c + 1], vfyL, gyL, &d2L);
-            const double SR = upwind_face(ring[s0][q][c - 1], qc, ring[s0][q][c + 1], ring[s0][q][c + 2], vfyR, gyR, &d2R);
-            const double tx_ = ddiv(fx1 - Fx[q], dx, rdx);                      // derivs.cpp:155-156
-            const double ty_ = ddiv(SR * vfyR - SL * vfyL, dy, rdy);
-            T[q] = tx_ + ty_;
-            Fx[q] = fx1;
+            const double xm1 = ring[sm1][q][c], qc = ring[s0][q][c], xp1 = ring[sp1][q][c], xp2 = ring[sp2][q][c];
+            const double ym2 = ring[s0][q][c - 2], ym1 = ring[s0][q][c - 1], yp1 = ring[s0][q][c + 1];
+            const bool allzero = (xm1 == 0.0) & (qc == 0.0) & (xp1 == 0.0) & (xp2 == 0.0) & (ym2 == 0.0) & (ym1 == 0.0) & (yp1 == 0.0)
+                                 & (Fx_s[q][tid] == 0.0);
+            if (__all_sync(0xffffffffu, allzero)) { T_s[q][tid] = 0.0; continue; }   // exact: every term is 0 in the reference too
+            double d2x, d2L;
+            const double Sx = upwind_face(xm1, qc, xp1, xp2, vfx1, gx, &d2x);
+            const double SL = upwind_face(ym2, ym1, qc, yp1, vfyL, gy, &d2L);
+            const double fx1 = Sx * vfx1, fyL = SL * vfyL;
+            const double fyR = shfl_next(fyL), d2R = shfl_next(d2L);
+            const double tx_ = ddiv(fx1 - Fx_s[q][tid], dx, rdx);               // derivs.cpp:155-156
+            const double ty_ = ddiv(fyR - fyL, dy, rdy);
+            T_s[q][tid] = tx_ + ty_;
+            Fx_s[q][tid] = fx1;
             if (q == Q_BIY) Ix1_biy = d2x;
             if (q == Q_BIZ) { Ix1_biz = d2x; IyL_biz = d2L; IyR_biz = d2R; }
             if (q == Q_BIX) { IyL_bix = d2L; IyR_bix = d2R; }
@@ -308,52 +382,46 @@ __global__ void __launch_bounds__(TW) k_mhd_stage(const DomainParams P, const St
         const double dbiz_dy = ddiv(IyR_biz - IyL_biz, dy, rdy);
         const double dbiz_dx = ddiv(Ix1_biz - cIx_biz, dx, rdx);
         const double dp_dx = ddiv(Ix1_p - cIx_p, dx, rdx);
-        const double pL = ring[s0][Q_E][c - 1] * P.gm1, pR = ring[s0][Q_E][c + 1] * P.gm1;
-        const double dp_dy = ddiv(face_interp(pc, pR, gyR.hm1, gyR.h0, gyR.fs, gyR.rfs)
-                                  - face_interp(pL, pc, gyL.hm1, gyL.h0, gyL.fs, gyL.rfs), dy, rdy);
+        const double dp_dy = ddiv(IyR_p - IyL_p, dy, rdy);
         const double dvx_dx = ddiv(vfx1 - cVfx, dx, rdx);
         const double dvy_dy = ddiv(vfyR - vfyL, dy, rdy);
-        const double vxc = ring[s0][Q_VX][c], vzc = ring[s0][Q_VZ][c];
-        const double dvx_dy = ddiv(face_interp(vxc, ring[s0][Q_VX][c + 1], gyR.hm1, gyR.h0, gyR.fs, gyR.rfs)
-                                   - face_interp(ring[s0][Q_VX][c - 1], vxc, gyL.hm1, gyL.h0, gyL.fs, gyL.rfs), dy, rdy);
-        const double dvz_dy = ddiv(face_interp(vzc, ring[s0][Q_VZ][c + 1], gyR.hm1, gyR.h0, gyR.fs, gyR.rfs)
-                                   - face_interp(ring[s0][Q_VZ][c - 1], vzc, gyL.hm1, gyL.h0, gyL.fs, gyL.rfs), dy, rdy);
+        const double dvx_dy = ddiv(IyR_vx - IyL_vx, dy, rdy);
+        const double dvz_dy = ddiv(IyR_vz - IyL_vz, dy, rdy);
         const double dvy_dx = ddiv(Ix1_vy - cIx_vy, dx, rdx);
         const double dvz_dx = ddiv(Ix1_vz - cIx_vz, dx, rdx);
         // roll the x carries
         cIx_biy = Ix1_biy; cIx_biz = Ix1_biz; cIx_p = Ix1_p; cVfx = vfx1; cIx_vy = Ix1_vy; cIx_vz = Ix1_vz;
 
-        // ---------------- own-cell values
-        const size_t off = (size_t)r * P.pitch + j;    // destination / base offset (local, unwrapped)
-        const double rho = ring[s0][Q_RHO][c];
-        const double bix = ring[s0][Q_BIX][c], biy = ring[s0][Q_BIY][c], biz = ring[s0][Q_BIZ][c];
-        const double bex = ring[s0][Q_BEX][c], bey = ring[s0][Q_BEY][c], bez = ring[s0][Q_BEZ][c];
-        double gxv = 0.0, gyv = 0.0;
-        if (col_out) { gxv = A.st[S_GX][off]; gyv = A.st[S_GY][off]; }
-
-        // ---------------- right-hand side, idealmhd.cpp:51-103 (expression order is load-bearing)
-        double k[NEV];
-        k[E_N] = T[Q_RHO] * -1.0;                                                       // :52
-        const double cdb = ddiv(dbiy_dx - dbix_dy, P.fourpi, P.rfourpi);                // :54  curl2D/(4 pi)
-        const double ncdb = cdb * -1.0;
-        const double czx = dbiz_dy, czy = dbiz_dx * -1.0;                               // curlZ, derivs.cpp:465-469
-        const double bzi = ddiv(biz, P.fourpi, P.rfourpi), bze = ddiv(bez, P.fourpi, P.rfourpi);   // :57-58
-        // CrossProduct2DZ(a,bz) = CrossProductZ2D(-1.0*bz, a) = { -(-bz)*a_y , (-bz)*a_x }   grid.cpp:455-468
-        k[E_MX] = ((((((T[Q_MX] * -1.0) - dp_dx) + rho * gxv) + ncdb * bey) + ncdb * biy) + bzi * czy) + bze * czy;      // :62-66
-        k[E_MY] = ((((((T[Q_MY] * -1.0) - dp_dy) + rho * gyv) + cdb * bex) + cdb * bix) + (bzi * -1.0) * czx) + (bze * -1.0) * czx;  // :67-71
-        const double fze = ddiv(czx * bey - czy * bex, P.fourpi, P.rfourpi);            // :59
-        const double fzi = ddiv(czx * biy - czy * bix, P.fourpi, P.rfourpi);            // :60
-        k[E_MZ] = ((T[Q_MZ] * -1.0) + fze) + fzi;                                       // :72-73
-        k[E_E] = (T[Q_E] * -1.0) - pc * (dvx_dx + dvy_dy);                              // :75-76
-        const double bxs = bix + bex, bys = biy + bey;
-        k[E_BX] = (((T[Q_BIX] * -1.0) - T[Q_BEX]) + bxs * dvx_dx) + bys * dvx_dy;       // :78-80
-        k[E_BY] = (((T[Q_BIY] * -1.0) - T[Q_BEY]) + bxs * dvy_dx) + bys * dvy_dy;       // :81-83
-        k[E_BZ] = (((T[Q_BIZ] * -1.0) - T[Q_BEZ]) + bxs * dvz_dx) + bys * dvz_dy;       // :84-86
-        // ghost mask (:99-103): operators return 0 outside [xl..xu]x[yl..yu] and the mask zeroes the rest
-#pragma unroll
-        for (int v = 0; v < NEV; v++) k[v] = interior ? k[v] : 0.0;
-
         if (col_out) {
+            // ---------------- own-cell values
+            const size_t off = (size_t)r * P.pitch + j;    // destination / base offset (local, unwrapped)
+            const double rho = ring[s0][Q_RHO][c];
+            const double bix = ring[s0][Q_BIX][c], biy = ring[s0][Q_BIY][c], biz = ring[s0][Q_BIZ][c];
+            const double bex = ring[s0][Q_BEX][c], bey = ring[s0][Q_BEY][c], bez = ring[s0][Q_BEZ][c];
+            const double gxv = A.st[S_GX][off], gyv = A.st[S_GY][off];
+
+            // ---------------- right-hand side, idealmhd.cpp:51-103 (expression order is load-bearing)
+            double k[NEV];
+            k[E_N] = T_s[Q_RHO][tid] * -1.0;                                                // :52
+            const double cdb = ddiv(dbiy_dx - dbix_dy, P.fourpi, P.rfourpi);                // :54  curl2D/(4 pi)
+            const double ncdb = cdb * -1.0;
+            const double czx = dbiz_dy, czy = dbiz_dx * -1.0;                               // curlZ, derivs.cpp:465-469
+            const double bzi = ddiv(biz, P.fourpi, P.rfourpi), bze = ddiv(bez, P.fourpi, P.rfourpi);   // :57-58
+            // CrossProduct2DZ(a,bz) = CrossProductZ2D(-1.0*bz, a) = { -(-bz)*a_y , (-bz)*a_x }   grid.cpp:455-468
+            k[E_MX] = ((((((T_s[Q_MX][tid] * -1.0) - dp_dx) + rho * gxv) + ncdb * bey) + ncdb * biy) + bzi * czy) + bze * czy;      // :62-66
+            k[E_MY] = ((((((T_s[Q_MY][tid] * -1.0) - dp_dy) + rho * gyv) + cdb * bex) + cdb * bix) + (bzi * -1.0) * czx) + (bze * -1.0) * czx;  // :67-71
+            const double fze = ddiv(czx * bey - czy * bex, P.fourpi, P.rfourpi);            // :59
+            const double fzi = ddiv(czx * biy - czy * bix, P.fourpi, P.rfourpi);            // :60
+            k[E_MZ] = ((T_s[Q_MZ][tid] * -1.0) + fze) + fzi;                                // :72-73
+            k[E_E] = (T_s[Q_E][tid] * -1.0) - pc * (dvx_dx + dvy_dy);                       // :75-76
+            const double bxs = bix + bex, bys = biy + bey;
+            k[E_BX] = (((T_s[Q_BIX][tid] * -1.0) - T_s[Q_BEX][tid]) + bxs * dvx_dx) + bys * dvx_dy;       // :78-80
+            k[E_BY] = (((T_s[Q_BIY][tid] * -1.0) - T_s[Q_BEY][tid]) + bxs * dvy_dx) + bys * dvy_dy;       // :81-83
+            k[E_BZ] = (((T_s[Q_BIZ][tid] * -1.0) - T_s[Q_BEZ][tid]) + bxs * dvz_dx) + bys * dvz_dy;       // :84-86
+            // ghost mask (:99-103): operators return 0 outside [xl..xu]x[yl..yu] and the mask zeroes the rest
+#pragma unroll
+            for (int v = 0; v < NEV; v++) k[v] = interior ? k[v] : 0.0;
+
             // ---------------- RK4 bookkeeping (evolution.cpp:103-124)
             if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) {
 #pragma unroll
@@ -379,11 +447,9 @@ __global__ void __launch_bounds__(TW) k_mhd_stage(const DomainParams P, const St
                 const double nn = density_floor(P, U[E_N], &rfl);
                 const double e1 = smax(U[E_E], P.e_min);
                 if (A.primary) {
-                    if (momentum_zeroed(P, g, j)) { U[E_MX] = 0.0; U[E_MY] = 0.0; U[E_MZ] = 0.0; }
-                    if (P.bc_x1 == BC_OPEN && g == 2 && A.r1strip[0]) A.r1strip[0][j] = rfl;
-                    if (P.bc_x2 == BC_OPEN && g == P.gnx - 3 && A.r1strip[1]) A.r1strip[1][j] = rfl;
-                    if (P.bc_y1 == BC_OPEN && j == 2 && A.r1strip[2]) A.r1strip[2][r] = rfl;
-                    if (P.bc_y2 == BC_OPEN && j == P.ny - 3 && A.r1strip[3]) A.r1strip[3][r] = rfl;
+                    const unsigned z = zero_zones(P, g, j);
+                    record_strips(P, A.strip, A.strip_pitch, g, r, j, z, rfl, U[E_MX], U[E_MY], U[E_MZ]);
+                    if (z) { U[E_MX] = 0.0; U[E_MY] = 0.0; U[E_MZ] = 0.0; }
                 }
                 A.D[E_N][off] = nn;
                 A.D[E_MX][off] = U[E_MX]; A.D[E_MY][off] = U[E_MY]; A.D[E_MZ][off] = U[E_MZ];
@@ -396,6 +462,8 @@ __global__ void __launch_bounds__(TW) k_mhd_stage(const DomainParams P, const St
                 }
             }
         }
+        cp_async_wait_all();
+        if (pre) convert_row(r + 3);
         __syncthreads();
     }
     if (A.primary && A.kmode != KM_EXPORT) block_min_to_global(dtmin_local, A.dtmin_bits);
@@ -412,7 +480,8 @@ struct PropArgs {
     const double *temp;           // only when from_state
     int raw_rho, from_state;
     unsigned long long *dtmin_bits;
-    double *r1strip[4];
+    double *strip[4];
+    int strip_pitch;
 };
 
 __global__ void __launch_bounds__(256) k_mhd_propagate(const DomainParams P, const PropArgs A)
@@ -434,11 +503,9 @@ __global__ void __launch_bounds__(256) k_mhd_propagate(const DomainParams P, con
         const double nn = density_floor(P, rho_u, &rfl);
         const double e1 = smax(e, P.e_min);
         double mx = A.U[E_MX][off], my = A.U[E_MY][off], mz = A.U[E_MZ][off];
-        if (momentum_zeroed(P, g, j)) { mx = 0.0; my = 0.0; mz = 0.0; A.U[E_MX][off] = 0.0; A.U[E_MY][off] = 0.0; A.U[E_MZ][off] = 0.0; }
-        if (P.bc_x1 == BC_OPEN && g == 2) A.r1strip[0][j] = rfl;
-        if (P.bc_x2 == BC_OPEN && g == P.gnx - 3) A.r1strip[1][j] = rfl;
-        if (P.bc_y1 == BC_OPEN && j == 2) A.r1strip[2][r] = rfl;
-        if (P.bc_y2 == BC_OPEN && j == P.ny - 3) A.r1strip[3][r] = rfl;
+        const unsigned z = zero_zones(P, g, j);
+        record_strips(P, A.strip, A.strip_pitch, g, r, j, z, rfl, mx, my, mz);
+        if (z) { mx = 0.0; my = 0.0; mz = 0.0; A.U[E_MX][off] = 0.0; A.U[E_MY][off] = 0.0; A.U[E_MZ][off] = 0.0; }
         A.U[E_N][off] = nn;
         A.U[E_E][off] = e1;
         if (g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu)
@@ -455,7 +522,8 @@ __global__ void __launch_bounds__(256) k_mhd_propagate(const DomainParams P, con
 // ---------------------------------------------------------------------------------------------------------
 struct GhostArgs {
     double *U[NEV];
-    const double *r1strip[4];
+    const double *strip[4];
+    int strip_pitch;
     int primary;                       // reflect/open act on the primary state only
     // open boundary scalars per side (x1,x2,y1,y2), evaluated on the host with libm pow (evolution.cpp:163-167)
     double scale_1[4], scale_2[4], dist23[4], h2[4], h3[4], rh3[4];   // h2 = 0.5*d(i2), h3 = 0.5*d(i3), rh3 = RN(1/h3)
@@ -481,12 +549,24 @@ __device__ __forceinline__ void ghost_one(const DomainParams &P, const GhostArgs
     else { r1_ = r2_ = r3_ = idx; c1_ = P.ny - 1; c2_ = P.ny - 2; c3_ = P.ny - 3; }
     if (xside && (r3_ < 0 || r3_ >= P.nx)) return;     // that side belongs to another rank's slab
     const size_t o1 = (size_t)r1_ * P.pitch + c1_, o2 = (size_t)r2_ * P.pitch + c2_, o3 = (size_t)r3_ * P.pitch + c3_;
+    // A y side that is `fixed` runs AFTER the x sides and sweeps every i, so it zeroes the momenta an x side has just
+    // written into its ghost cells at j <= 2 / j >= ny-3 (evolution.cpp:143,149).  (reflect only sweeps i in [xl,xu].)
+    const bool later_zero = A.primary && xside && ((P.bc_y1 == BC_FIXED && idx <= 2) || (P.bc_y2 == BC_FIXED && idx >= P.ny - 3));
+    const double *sp = A.strip[side];
+    const int spitch = A.strip_pitch;
 
     if (bc == BC_OPEN_UCNP) {
         // copies the nearest interior cell into both ghost cells for densities, thermal energies, fields, momenta
         // (evolution.cpp:321-331); acts on whichever set is being propagated.
+        const int evs[5] = {E_N, E_E, E_BX, E_BY, E_BZ};
 #pragma unroll
-        for (int v = 0; v < NEV; v++) { const double x = A.U[v][o3]; A.U[v][o1] = x; A.U[v][o2] = x; }
+        for (int k = 0; k < 5; k++) { const double x = A.U[evs[k]][o3]; A.U[evs[k]][o1] = x; A.U[evs[k]][o2] = x; }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double m = A.primary ? sp[(k + 1) * spitch + idx] : A.U[E_MX + k][o3];
+            if (later_zero) m = 0.0;
+            A.U[E_MX + k][o1] = m; A.U[E_MX + k][o2] = m;
+        }
         return;
     }
     if (!A.primary) return;
@@ -498,7 +578,7 @@ __device__ __forceinline__ void ghost_one(const DomainParams &P, const GhostArgs
         return;
     }
     // BC_OPEN (evolution.cpp:158-224)
-    const double rho3 = A.r1strip[side][idx];                 // post-floor rho of i3 (before the n round trip)
+    const double rho3 = sp[idx];                               // post-floor rho of i3 (before the n round trip)
     const double e3 = A.U[E_E][o3];
     const double rho_1 = A.scale_1[side] * rho3, rho_2 = A.scale_2[side] * rho3;
     A.U[E_E][o1] = smax(A.scale_1[side] * e3, P.e_min);       // derived step re-applies the energy floor (idealmhd.cpp:252)
@@ -507,7 +587,7 @@ __device__ __forceinline__ void ghost_one(const DomainParams &P, const GhostArgs
     double c_s = 0.0;
     const double c_new = sqrt(P.gamma * press / rho3);
     if (c_new > c_s) c_s = c_new;
-    const double mx3 = A.U[E_MX][o3], my3 = A.U[E_MY][o3];
+    const double mx3 = sp[spitch + idx], my3 = sp[2 * spitch + idx];
     const double vel_x = mx3 / rho3, vel_y = my3 / rho3;
     double boost = A.open_strength * c_s;
     const bool lower = (side == 0 || side == 2);              // i2 > i1 || j2 > j1
@@ -515,7 +595,8 @@ __device__ __forceinline__ void ghost_one(const DomainParams &P, const GhostArgs
     const double vn = xside ? vel_x : vel_y, vt = xside ? vel_y : vel_x;
     const double bv = lower ? smin(0.0, vn + boost) : smax(0.0, vn + boost);
     const double gv = ddiv(A.dist23[side] * bv - A.h2[side] * vn, A.h3[side], A.rh3[side]);
-    const double mn1 = rho_1 * gv, mn2 = rho_2 * gv, mt1 = rho_1 * vt, mt2 = rho_2 * vt;
+    double mn1 = rho_1 * gv, mn2 = rho_2 * gv, mt1 = rho_1 * vt, mt2 = rho_2 * vt;
+    if (later_zero) { mn1 = mn2 = mt1 = mt2 = 0.0; A.U[E_MZ][o1] = 0.0; A.U[E_MZ][o2] = 0.0; }
     if (xside) { A.U[E_MX][o1] = mn1; A.U[E_MX][o2] = mn2; A.U[E_MY][o1] = mt1; A.U[E_MY][o2] = mt2; }
     else       { A.U[E_MY][o1] = mn1; A.U[E_MY][o2] = mn2; A.U[E_MX][o1] = mt1; A.U[E_MX][o2] = mt2; }
     // derived step: n = max(rho/m_i, n_min) (idealmhd.cpp:246)
