@@ -172,7 +172,7 @@ int pick_chunk_rows(const spruce_domain *d)
 {
     // enough CTAs for >= ~4 waves of 148 SMs x resident CTAs, but chunks of at least 16 rows (4 warm-up rows each)
     const int strips = (d->P.ny + CW - 1) / CW;
-    int rows = 64;
+    int rows = MAX_CHUNK;
     while (rows > 16 && (long long)strips * ((d->P.nx + rows - 1) / rows) < 148LL * 5 * 4) rows >>= 1;
     return rows;
 }
@@ -182,6 +182,7 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     StageArgs A{};
     fill_sets(d, A, S, B, D);
     A.coef = coef; A.primary = primary; A.kmode = kmode;
+    A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
     A.chunk_rows = pick_chunk_rows(d);
     if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
     dim3 grid((d->P.ny + CW - 1) / CW, (d->P.nx + A.chunk_rows - 1) / A.chunk_rows);

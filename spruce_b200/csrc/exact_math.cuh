@@ -79,4 +79,49 @@ __device__ __forceinline__ double upwind_face(double qm2, double qm1, double q0,
     return (pos || neg) ? r : d2;
 }
 
+// ---- the same face value with everything that depends only on the face (not on the transported quantity) hoisted:
+// the sign of the face velocity selects the upwind side once per face, not once per quantity.
+struct FaceSel {
+    double hm1, h0, fs, rfs;   // interpolation weights of the face
+    double w, den, rden;       // extrapolation weight / divisor of the upwind side (ep,fsm | em,fsp)
+    bool pos, any;             // vf > 0 ; vf != 0 (strictly: vf > 0 || vf < 0, NaN -> false)
+};
+__device__ __forceinline__ FaceSel select_face(const FaceGeom &g, double vf)
+{
+    FaceSel s;
+    s.hm1 = g.hm1; s.h0 = g.h0; s.fs = g.fs; s.rfs = g.rfs;
+    s.pos = vf > 0.0;
+    s.any = s.pos || (vf < 0.0);
+    s.w = s.pos ? g.ep : g.em;
+    s.den = s.pos ? g.fsm : g.fsp;
+    s.rden = s.pos ? g.rfsm : g.rfsp;
+    return s;
+}
+__device__ __forceinline__ double flip_sign(double x, unsigned long long m) { return __longlong_as_double(__double_as_longlong(x) ^ (long long)m); }
+
+// upwindSurface (derivs.cpp:47-68) for one quantity.  std::max(d3, std::min(d1,d2)) == -std::min(-d3, std::max(-d1,-d2))
+// selection for selection (the comparisons are mirrored exactly, NaNs and equal values included), so only ONE
+// min/max pair is evaluated, on operands whose sign bit is flipped when the max-outer form is the one required.
+__device__ __forceinline__ double upwind_face_sel(double qm2, double qm1, double q0, double qp1, const FaceSel &f, double *d2out)
+{
+    const double d2 = face_interp(qm1, q0, f.hm1, f.h0, f.fs, f.rfs);
+    *d2out = d2;
+    const double a = f.pos ? qm2 : qp1;
+    const double b = f.pos ? qm1 : q0;          // d3, the upwind cell value
+    const double d1 = a + ddiv((b - a) * f.w, f.den, f.rden);
+    const bool min_outer = (f.pos == (q0 <= qm1));
+    const unsigned long long m = min_outer ? 0ULL : 0x8000000000000000ULL;
+    const double fb = flip_sign(b, m), f1 = flip_sign(d1, m), f2 = flip_sign(d2, m);
+    const double r = flip_sign(smin(fb, smax(f1, f2)), m);
+    return f.any ? r : d2;
+}
+
+// exact test "all eight values are +-0" on the integer pipe
+__device__ __forceinline__ bool all_zero8(double a, double b, double c, double d, double e, double f, double g, double h)
+{
+    const unsigned long long o = (unsigned long long)(__double_as_longlong(a) | __double_as_longlong(b) | __double_as_longlong(c) | __double_as_longlong(d)
+                                                       | __double_as_longlong(e) | __double_as_longlong(f) | __double_as_longlong(g) | __double_as_longlong(h));
+    return (o << 1) == 0ULL;
+}
+
 } // namespace spruce

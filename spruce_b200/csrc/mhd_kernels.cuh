@@ -71,6 +71,7 @@ struct StageArgs {
     double *K1[NEV];              // RK4: k1            (KM_STORE_K1 / KM_FINAL) ; KM_EXPORT: raw k output
     double *K2[NEV];              // RK4: k2 then k2+k3 (KM_STORE_K2 / KM_ADD_K2 / KM_FINAL)
     int kmode;
+    int b_is_s;                   // B aliases S (first stage): own-cell base values come from the shared ring
     int primary;                  // D is the primary state: pointwise boundary zeroing, r1 strips, dt minimum
     double coef;                  // 0.5 or 1.0: s = coef*step (evolution.cpp:95,100)
     const double *step_ptr;       // device scalar: step size of this iteration
@@ -90,7 +91,9 @@ constexpr int RD = 5;                        // ring depth: rows r-1..r+2 in use
 enum { Q_RHO = 0, Q_MX, Q_MY, Q_MZ, Q_E, Q_BIX, Q_BIY, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_VX, Q_VY, Q_VZ, NARR };
 constexpr int NTR = 11;                      // transported quantities Q_RHO..Q_BEZ
 constexpr int NLOAD = 11;                    // arrays filled from global memory (Q_RHO holds n until converted)
-constexpr size_t STAGE_SMEM = (size_t)(RD * NARR * SW + 2 * NTR * NT) * sizeof(double);
+constexpr int MAX_CHUNK = 64;                // rows per CTA (upper bound; sizes the x-geometry table in shared memory)
+constexpr int XT = MAX_CHUNK + 8;            // entries per x table: local rows -3 .. chunk+4
+constexpr size_t STAGE_SMEM = (size_t)(RD * NARR * SW + 2 * NTR * NT + 7 * XT) * sizeof(double);
 
 __device__ __forceinline__ FaceGeom load_face_geom(const AxisTab &t, int f)
 {
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
     double (*ring)[NARR][SW] = reinterpret_cast<double (*)[NARR][SW]>(smem);
     double (*Fx_s)[NT] = reinterpret_cast<double (*)[NT]>(smem + RD * NARR * SW);   // x-face flux carried to the next row
     double (*T_s)[NT] = Fx_s + NTR;                                                  // transportDivergence2D per quantity
+    double (*xt)[XT] = reinterpret_cast<double (*)[XT]>(smem + RD * NARR * SW + 2 * NTR * NT);   // x tables of this chunk: h,fs,rfs,ep,em,d,rd
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j0 = blockIdx.x * CW;
@@ -299,6 +303,25 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
     const FaceGeom gy = load_face_geom(P.ty, jt);
     const double dy = P.ty.d[min(j, P.ny)], rdy = P.ty.rd[min(j, P.ny)];
 
+    // ---- x-direction cell-size tables of this chunk (warp-uniform reads from shared memory in the row loop)
+    {
+        const double *src[7] = {P.tx.h, P.tx.fs, P.tx.rfs, P.tx.ep, P.tx.em, P.tx.d, P.tx.rd};
+        const int nent = (r1 - r0) + 8;
+        for (int e = tid; e < 7 * XT; e += NT) {
+            const int t = e / XT, i = e - t * XT;
+            if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
+        }
+    }
+    auto x_geom = [&](int f) {                   // FaceGeom of x face f (local row index), from shared memory
+        const int i = f - r0 + 3;
+        FaceGeom g;
+        g.hm1 = xt[0][i - 1]; g.h0 = xt[0][i];
+        g.fs = xt[1][i];      g.rfs = xt[2][i];
+        g.ep = xt[3][i];      g.fsm = xt[1][i - 1]; g.rfsm = xt[2][i - 1];
+        g.em = xt[4][i];      g.fsp = xt[1][i + 1]; g.rfsp = xt[2][i + 1];
+        return g;
+    };
+
     // ---- prologue: rows r0-2 .. r0+2
     for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r);
     cp_async_commit();
@@ -309,7 +332,7 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
     // x-face carries (face r0, between rows r0-1 and r0)
     double cIx_biy = 0.0, cIx_biz = 0.0, cIx_p, cVfx, cIx_vy, cIx_vz;
     {
-        const FaceGeom g = load_face_geom(P.tx, r0);
+        const FaceGeom g = x_geom(r0);
         const int sm2 = slot_of(r0 - 2), sm1 = slot_of(r0 - 1), s0 = slot_of(r0), sp1 = slot_of(r0 + 1);
         cVfx = face_interp(ring[sm1][Q_VX][c], ring[s0][Q_VX][c], g.hm1, g.h0, g.fs, g.rfs);
         cIx_vy = face_interp(ring[sm1][Q_VY][c], ring[s0][Q_VY][c], g.hm1, g.h0, g.fs, g.rfs);
@@ -336,10 +359,23 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
         const int sm1 = slot_of(r - 1), s0 = slot_of(r), sp1 = slot_of(r + 1), sp2 = slot_of(r + 2);
         const int g = P.row0 + r;                                   // global row
         const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
-        const double dx = P.tx.d[r], rdx = P.tx.rd[r];
+        const double dx = xt[5][r - r0 + 3], rdx = xt[6][r - r0 + 3];
+
+        // own-cell values that come from global memory are requested now and consumed after the transport loop
+        const size_t off = (size_t)r * P.pitch + (col_out ? j : 0);     // destination / base offset (local, unwrapped)
+        double gxv = 0.0, gyv = 0.0, Bv[NEV];
+#pragma unroll
+        for (int v = 0; v < NEV; v++) Bv[v] = 0.0;
+        if (col_out) {
+            gxv = A.st[S_GX][off]; gyv = A.st[S_GY][off];
+            if (!A.b_is_s) {
+#pragma unroll
+                for (int v = 0; v < NEV; v++) Bv[v] = A.B[v][off];
+            }
+        }
 
         // ---------------- x face r+1 (between rows r and r+1): velocity, pressure
-        const FaceGeom gx = load_face_geom(P.tx, r + 1);
+        const FaceGeom gx = x_geom(r + 1);
         const double vxc = ring[s0][Q_VX][c], vyc = ring[s0][Q_VY][c], vzc = ring[s0][Q_VZ][c];
         const double vfx1 = face_interp(vxc, ring[sp1][Q_VX][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
         const double Ix1_vy = face_interp(vyc, ring[sp1][Q_VY][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
@@ -355,19 +391,19 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
 
         // ---------------- transportDivergence2D of the 11 transported quantities (derivs.cpp:122-162,216-220)
         double Ix1_biy = 0.0, Ix1_biz = 0.0, IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
+        const FaceSel fsx = select_face(gx, vfx1), fsy = select_face(gy, vfyL);
 #pragma unroll 1
         for (int q = 0; q < NTR; q++) {
             const double xm1 = ring[sm1][q][c], qc = ring[s0][q][c], xp1 = ring[sp1][q][c], xp2 = ring[sp2][q][c];
             const double ym2 = ring[s0][q][c - 2], ym1 = ring[s0][q][c - 1], yp1 = ring[s0][q][c + 1];
-            const bool allzero = (xm1 == 0.0) & (qc == 0.0) & (xp1 == 0.0) & (xp2 == 0.0) & (ym2 == 0.0) & (ym1 == 0.0) & (yp1 == 0.0)
-                                 & (Fx_s[q][tid] == 0.0);
-            if (__all_sync(0xffffffffu, allzero)) { T_s[q][tid] = 0.0; continue; }   // exact: every term is 0 in the reference too
+            const double fx0 = Fx_s[q][tid];
+            if (__all_sync(0xffffffffu, all_zero8(xm1, qc, xp1, xp2, ym2, ym1, yp1, fx0))) { T_s[q][tid] = 0.0; continue; }   // exact: every term is 0 in the reference too
             double d2x, d2L;
-            const double Sx = upwind_face(xm1, qc, xp1, xp2, vfx1, gx, &d2x);
-            const double SL = upwind_face(ym2, ym1, qc, yp1, vfyL, gy, &d2L);
+            const double Sx = upwind_face_sel(xm1, qc, xp1, xp2, fsx, &d2x);
+            const double SL = upwind_face_sel(ym2, ym1, qc, yp1, fsy, &d2L);
             const double fx1 = Sx * vfx1, fyL = SL * vfyL;
             const double fyR = shfl_next(fyL), d2R = shfl_next(d2L);
-            const double tx_ = ddiv(fx1 - Fx_s[q][tid], dx, rdx);               // derivs.cpp:155-156
+            const double tx_ = ddiv(fx1 - fx0, dx, rdx);                        // derivs.cpp:155-156
             const double ty_ = ddiv(fyR - fyL, dy, rdy);
             T_s[q][tid] = tx_ + ty_;
             Fx_s[q][tid] = fx1;
@@ -394,11 +430,9 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
 
         if (col_out) {
             // ---------------- own-cell values
-            const size_t off = (size_t)r * P.pitch + j;    // destination / base offset (local, unwrapped)
             const double rho = ring[s0][Q_RHO][c];
             const double bix = ring[s0][Q_BIX][c], biy = ring[s0][Q_BIY][c], biz = ring[s0][Q_BIZ][c];
             const double bex = ring[s0][Q_BEX][c], bey = ring[s0][Q_BEY][c], bez = ring[s0][Q_BEZ][c];
-            const double gxv = A.st[S_GX][off], gyv = A.st[S_GY][off];
 
             // ---------------- right-hand side, idealmhd.cpp:51-103 (expression order is load-bearing)
             double k[NEV];
@@ -439,9 +473,16 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
             if (A.kmode != KM_EXPORT) {
                 // ---------------- applyTimeDerivatives: U += step*k  (two roundings)  equationset.cpp:226-228
                 double U[NEV];
-                U[E_N] = (A.B[E_N][off] * P.m_i) + k[E_N] * s;      // rho = n*m_i
+                if (A.b_is_s) {
+                    U[E_N] = rho + k[E_N] * s;                      // rho = n*m_i was formed when the row entered the ring
+                    U[E_MX] = ring[s0][Q_MX][c] + k[E_MX] * s; U[E_MY] = ring[s0][Q_MY][c] + k[E_MY] * s; U[E_MZ] = ring[s0][Q_MZ][c] + k[E_MZ] * s;
+                    U[E_E] = ring[s0][Q_E][c] + k[E_E] * s;
+                    U[E_BX] = bix + k[E_BX] * s; U[E_BY] = biy + k[E_BY] * s; U[E_BZ] = biz + k[E_BZ] * s;
+                } else {
+                    U[E_N] = (Bv[E_N] * P.m_i) + k[E_N] * s;        // rho = n*m_i
 #pragma unroll
-                for (int v = 1; v < NEV; v++) U[v] = A.B[v][off] + k[v] * s;
+                    for (int v = 1; v < NEV; v++) U[v] = Bv[v] + k[v] * s;
+                }
                 // ---------------- propagateChanges, pointwise part (equationset.cpp:212-220)
                 double rfl;
                 const double nn = density_floor(P, U[E_N], &rfl);
