@@ -389,27 +389,35 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
         const double IyL_p = face_interp(ring[s0][Q_E][c - 1] * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
         const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = shfl_next(IyL_vz), IyR_p = shfl_next(IyL_p);
 
-        // ---------------- transportDivergence2D of the 11 transported quantities (derivs.cpp:122-162,216-220)
+        // ---------------- transportDivergence2D of the 11 transported quantities (derivs.cpp:122-162,216-220),
+        // two quantities per iteration: four independent face chains in flight hide the 8-cycle DFMA latency.
+        // Pairs are ordered so that planes which vanish together (z components; external field) share an iteration.
         double Ix1_biy = 0.0, Ix1_biz = 0.0, IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
         const FaceSel fsx = select_face(gx, vfx1), fsy = select_face(gy, vfyL);
 #pragma unroll 1
-        for (int q = 0; q < NTR; q++) {
-            const double xm1 = ring[sm1][q][c], qc = ring[s0][q][c], xp1 = ring[sp1][q][c], xp2 = ring[sp2][q][c];
-            const double ym2 = ring[s0][q][c - 2], ym1 = ring[s0][q][c - 1], yp1 = ring[s0][q][c + 1];
-            const double fx0 = Fx_s[q][tid];
-            if (__all_sync(0xffffffffu, all_zero8(xm1, qc, xp1, xp2, ym2, ym1, yp1, fx0))) { T_s[q][tid] = 0.0; continue; }   // exact: every term is 0 in the reference too
-            double d2x, d2L;
-            const double Sx = upwind_face_sel(xm1, qc, xp1, xp2, fsx, &d2x);
-            const double SL = upwind_face_sel(ym2, ym1, qc, yp1, fsy, &d2L);
-            const double fx1 = Sx * vfx1, fyL = SL * vfyL;
-            const double fyR = shfl_next(fyL), d2R = shfl_next(d2L);
-            const double tx_ = ddiv(fx1 - fx0, dx, rdx);                        // derivs.cpp:155-156
-            const double ty_ = ddiv(fyR - fyL, dy, rdy);
-            T_s[q][tid] = tx_ + ty_;
-            Fx_s[q][tid] = fx1;
-            if (q == Q_BIY) Ix1_biy = d2x;
-            if (q == Q_BIZ) { Ix1_biz = d2x; IyL_biz = d2L; IyR_biz = d2R; }
-            if (q == Q_BIX) { IyL_bix = d2L; IyR_bix = d2R; }
+        for (int p = 0; p < 6; p++) {
+            // (RHO,E) (MX,MY) (BIX,BIY) (MZ,BIZ) (BEX,BEY) (BEZ,BEZ)
+            const int qa = (0x0A83510 >> (4 * p)) & 15, qb = (0x0A97624 >> (4 * p)) & 15;
+            const double axm1 = ring[sm1][qa][c], aqc = ring[s0][qa][c], axp1 = ring[sp1][qa][c], axp2 = ring[sp2][qa][c];
+            const double aym2 = ring[s0][qa][c - 2], aym1 = ring[s0][qa][c - 1], ayp1 = ring[s0][qa][c + 1];
+            const double bxm1 = ring[sm1][qb][c], bqc = ring[s0][qb][c], bxp1 = ring[sp1][qb][c], bxp2 = ring[sp2][qb][c];
+            const double bym2 = ring[s0][qb][c - 2], bym1 = ring[s0][qb][c - 1], byp1 = ring[s0][qb][c + 1];
+            const double afx0 = Fx_s[qa][tid], bfx0 = Fx_s[qb][tid];
+            const bool zero = all_zero8(axm1, aqc, axp1, axp2, aym2, aym1, ayp1, afx0) && all_zero8(bxm1, bqc, bxp1, bxp2, bym2, bym1, byp1, bfx0);
+            if (__all_sync(0xffffffffu, zero)) { T_s[qa][tid] = 0.0; T_s[qb][tid] = 0.0; continue; }   // exact: every term is 0 in the reference too
+            double ad2x, ad2L, bd2x, bd2L;
+            const double aSx = upwind_face_sel(axm1, aqc, axp1, axp2, fsx, &ad2x);
+            const double bSx = upwind_face_sel(bxm1, bqc, bxp1, bxp2, fsx, &bd2x);
+            const double aSL = upwind_face_sel(aym2, aym1, aqc, ayp1, fsy, &ad2L);
+            const double bSL = upwind_face_sel(bym2, bym1, bqc, byp1, fsy, &bd2L);
+            const double afx1 = aSx * vfx1, afyL = aSL * vfyL, bfx1 = bSx * vfx1, bfyL = bSL * vfyL;
+            const double afyR = shfl_next(afyL), bfyR = shfl_next(bfyL), ad2R = shfl_next(ad2L), bd2R = shfl_next(bd2L);
+            const double atx = ddiv(afx1 - afx0, dx, rdx), btx = ddiv(bfx1 - bfx0, dx, rdx);   // derivs.cpp:155-156
+            const double aty = ddiv(afyR - afyL, dy, rdy), bty = ddiv(bfyR - bfyL, dy, rdy);
+            T_s[qa][tid] = atx + aty; T_s[qb][tid] = btx + bty;
+            Fx_s[qa][tid] = afx1; Fx_s[qb][tid] = bfx1;
+            if (p == 2) { IyL_bix = ad2L; IyR_bix = ad2R; Ix1_biy = bd2x; }
+            if (p == 3) { Ix1_biz = bd2x; IyL_biz = bd2L; IyR_biz = bd2R; }
         }
 
         // central derivatives, derivative1D (derivs.cpp:259)
