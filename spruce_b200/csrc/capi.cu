@@ -3,6 +3,7 @@
 // Compiled with -fmad=false (see exact_math.cuh).  No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/spruce_b200.h"
 #include "mhd_kernels.cuh"
+#include "module_kernels.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -51,10 +52,13 @@ struct spruce_domain {
     GhostArgs ghost_proto{};
     int64_t launches = 0;
     bool any_ucnp = false, any_primary_ghost = false;
-    // modules
-    struct Mod { int kind; } ;
+    // physics modules, in config order (ModuleHandler::instantiateModule, modulehandler.cpp:92-111)
+    enum { MOD_TC = 1, MOD_RL = 2, MOD_AH = 3 };
     std::vector<int> module_order;
+    TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
+    RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
+    unsigned long long *red = nullptr;     // 4 reduction scalars for the sub-cycle counts
 };
 
 namespace {
@@ -237,12 +241,157 @@ int ensure_rk4(spruce_domain *d)
     return SPRUCE_OK;
 }
 
+int derive_to(spruce_domain *d, int var, double *out)
+{
+    DeriveArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.out = out; A.which = var;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_mhd_derive<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+int read_reductions(spruce_domain *d, unsigned long long h[4])
+{
+    CUDA_TRY(cudaMemcpyAsync(h, d->red, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return SPRUCE_OK;
+}
+int reset_reductions(spruce_domain *d)
+{
+    const unsigned long long init[4] = {0x7FEFFFFFFFFFFFFFULL, 0ULL, 0x7FEFFFFFFFFFFFFFULL, 0ULL};
+    CUDA_TRY(cudaMemcpyAsync(d->red, init, sizeof(init), cudaMemcpyHostToDevice, d->stream));
+    return SPRUCE_OK;
+}
+double bits_to_double(unsigned long long b) { double v; memcpy(&v, &b, sizeof(v)); return v; }
+
+// ThermalConduction::numberSubcycles (thermalconduction.cpp:135-149); scratch: Mset planes 0..2 (temp, b_hat_x, b_hat_y)
+int tc_count(spruce_domain *d, double dt, int *nsub)
+{
+    int rc;
+    if ((rc = derive_to(d, V_temp, d->Mset.p[0]))) return rc;
+    if ((rc = derive_to(d, V_b_hat_x, d->Mset.p[1]))) return rc;
+    if ((rc = derive_to(d, V_b_hat_y, d->Mset.p[2]))) return rc;
+    if ((rc = reset_reductions(d))) return rc;
+    TcFields F{d->Mset.p[0], d->Pset.p[E_N], d->Mset.p[1], d->Mset.p[2]};
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_tc_count<<<grid, 128, 0, d->stream>>>(d->P, d->tc, F, d->red);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long h[4];
+    if ((rc = read_reductions(d, h))) return rc;
+    if (d->tc.flux_saturation && bits_to_double(h[1]) == 0.0) { *nsub = 0; return SPRUCE_OK; }   // :143
+    const double a = d->tc_epsilon * bits_to_double(h[0]), b = d->tc.dt_subcycle_min;
+    const double md = (a < b) ? b : a;                                                              // std::max :147
+    *nsub = (int)(dt / md) + 1;                                                                     // :148
+    return SPRUCE_OK;
+}
+
+// ThermalConduction::iterateModule (thermalconduction.cpp:47-112); scratch = the 8 planes of Mset (free between RK steps)
+int tc_iterate(spruce_domain *d, double dt)
+{
+    int rc;
+    double *Ta = d->Mset.p[0], *bhx = d->Mset.p[1], *bhy = d->Mset.p[2], *Tb = d->Mset.p[3], *Tc = d->Mset.p[4];
+    double *K1 = d->Mset.p[5], *K2 = d->Mset.p[6], *K3 = d->Mset.p[7];
+    if ((rc = derive_to(d, V_temp, Ta))) return rc;
+    if ((rc = derive_to(d, V_b_hat_x, bhx))) return rc;
+    if ((rc = derive_to(d, V_b_hat_y, bhy))) return rc;
+    const int ns = d->tc_nsub;
+    const double dts = dt / (double)ns;                                                             // :60
+    double *e = d->Pset.p[E_E];
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    auto stage = [&](const double *Tin, double *Tout, int mode, double c, double *Kst) -> int {
+        TcStageArgs A{};
+        A.F = TcFields{Tin, d->Pset.p[E_N], bhx, bhy};
+        A.C = d->tc; A.e_base = e; A.e_out = e; A.T_out = Tout; A.K_store = Kst; A.K1 = K1; A.K2 = K2; A.K3 = K3; A.mode = mode; A.c = c;
+        k_tc_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
+        d->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return SPRUCE_OK;
+    };
+    for (int s = 0; s < ns; s++) {
+        if (d->tc_integrator == SPRUCE_TI_EULER) {
+            if ((rc = stage(Ta, Tb, TC_FINAL, dts, nullptr))) return rc;
+            std::swap(Ta, Tb);
+        } else if (d->tc_integrator == SPRUCE_TI_RK2) {
+            if ((rc = stage(Ta, Tb, TC_INTERMEDIATE, 0.5 * dts, nullptr))) return rc;
+            if ((rc = stage(Tb, Ta, TC_FINAL, dts, nullptr))) return rc;
+        } else {
+            if ((rc = stage(Ta, Tb, TC_INTERMEDIATE, 0.5 * dts, K1))) return rc;
+            if ((rc = stage(Tb, Tc, TC_INTERMEDIATE, 0.5 * dts, K2))) return rc;
+            if ((rc = stage(Tc, Tb, TC_INTERMEDIATE, dts, K3))) return rc;
+            if ((rc = stage(Tb, Ta, TC_RK4_FINAL, dts, nullptr))) return rc;
+        }
+    }
+    return launch_propagate(d, 0);                                                                  // :110-111
+}
+
+int rl_launch(spruce_domain *d, int count_mode, double dt)
+{
+    RlArgs A{};
+    A.R = d->rl;
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.e_out = d->Pset.p[E_E]; A.n_sub = d->rl_nsub; A.dt = dt; A.red = d->red + 2; A.count_mode = count_mode;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_rl<<<grid, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+// RadiativeLosses::numberSubcycles (radiativelosses.cpp:161-166)
+int rl_count(spruce_domain *d, double dt, int *nsub)
+{
+    int rc;
+    if ((rc = reset_reductions(d))) return rc;
+    if ((rc = rl_launch(d, 1, dt))) return rc;
+    unsigned long long h[4];
+    if ((rc = read_reductions(d, h))) return rc;
+    if (bits_to_double(h[3]) == 0.0) { *nsub = 0; return SPRUCE_OK; }
+    const double sdt = d->rl.epsilon * bits_to_double(h[2]);
+    *nsub = (int)(dt / sdt) + 1;
+    return SPRUCE_OK;
+}
+int rl_iterate(spruce_domain *d, double dt)
+{
+    int rc = rl_launch(d, 0, dt);
+    if (rc) return rc;
+    return launch_propagate(d, 0);                                                                  // radiativelosses.cpp:99-100
+}
+int ah_post(spruce_domain *d)
+{
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_ambient_heating<<<grid, 256, 0, d->stream>>>(d->P, d->Pset.p[E_E], d->heating, &d->ctl->step);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return launch_propagate(d, 0);                                                                  // ambientheating.cpp:43-44
+}
+
 // one advanceTime (evolution.cpp:59-82) worth of launches
 int enqueue_step(spruce_domain *d, int hist_slot)
 {
     int rc;
     k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot);
     d->launches++;
+    if (!d->module_order.empty()) {
+        // the module hooks need the step size on the host (sub-cycle counts decide how many kernels are launched)
+        StepCtl h;
+        CUDA_TRY(cudaMemcpyAsync(&h, d->ctl, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
+        CUDA_TRY(cudaStreamSynchronize(d->stream));
+        if (h.done) return SPRUCE_OK;
+        const double step = h.step;
+        for (int m : d->module_order) {                                  // preIterateModules, evolution.cpp:65
+            if (m == spruce_domain::MOD_TC && (rc = tc_count(d, step, &d->tc_nsub))) return rc;
+            if (m == spruce_domain::MOD_RL && (rc = rl_count(d, step, &d->rl_nsub))) return rc;
+        }
+        for (int m : d->module_order) {                                  // iterateModules, evolution.cpp:66
+            if (m == spruce_domain::MOD_TC && (rc = tc_iterate(d, step))) return rc;
+            if (m == spruce_domain::MOD_RL && (rc = rl_iterate(d, step))) return rc;
+        }
+    }
     const int ti = d->cfg.time_integrator;
     if (ti == SPRUCE_TI_EULER) {                                        // evolution.cpp:84-88
         if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;
@@ -264,6 +413,8 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
         if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
     }
+    for (int m : d->module_order)                                        // postIterateModules, evolution.cpp:74
+        if (m == spruce_domain::MOD_AH && (rc = ah_post(d))) return rc;
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -374,6 +525,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
         else { cudaMemsetAsync(d->strip[s], 0, n * sizeof(double), d->stream); d->allocs.push_back(d->strip[s]); }
     }
     if (!rc && cudaMalloc(&d->ctl, sizeof(StepCtl)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
+    if (!rc && cudaMalloc(&d->red, 4 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
     if (!rc) {
         StepCtl h{};
         h.step = 0.0; h.time = cfg->time; h.max_time = -1.0; h.epsilon = cfg->epsilon; h.iter = 0; h.done = 0;
@@ -392,6 +544,7 @@ void spruce_domain_destroy(spruce_domain *d)
     for (double *p : d->allocs) cudaFree(p);
     if (d->tab_dev) cudaFree(d->tab_dev);
     if (d->ctl) cudaFree(d->ctl);
+    if (d->red) cudaFree(d->red);
     if (d->dt_hist) cudaFree(d->dt_hist);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
@@ -540,10 +693,50 @@ int spruce_operator(spruce_domain *, const char *, int, const double *, const do
     return fail(SPRUCE_ERR_UNSUPPORTED, "stand-alone operators are not built yet");
 }
 
-int spruce_module_thermal_conduction(spruce_domain *, int, int, double, double, double) { return fail(SPRUCE_ERR_UNSUPPORTED, "thermal_conduction is not built yet"); }
-int spruce_module_radiative_losses(spruce_domain *, int, double, double, double, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "radiative_losses is not built yet"); }
-int spruce_module_ambient_heating(spruce_domain *, const double *, size_t) { return fail(SPRUCE_ERR_UNSUPPORTED, "ambient_heating is not built yet"); }
-int spruce_module_subcycles(spruce_domain *, const char *, int *) { return fail(SPRUCE_ERR_UNSUPPORTED, "modules are not built yet"); }
+int spruce_module_thermal_conduction(spruce_domain *d, int flux_saturation, int time_integrator, double epsilon, double dt_subcycle_min, double weakening_factor)
+{
+    CHECK_DOM(d);
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
+    if (time_integrator < 0 || time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid time integrator given for Thermal Conduction module");
+    int rc = ensure_rk4(d);   // not needed for memory, keeps scratch planes uniform
+    (void)rc;
+    d->tc.flux_saturation = flux_saturation ? 1 : 0;
+    d->tc.kappa = weakening_factor * kKappa0;
+    d->tc.dt_subcycle_min = dt_subcycle_min;
+    d->tc_integrator = time_integrator; d->tc_epsilon = epsilon;
+    d->module_order.push_back(spruce_domain::MOD_TC);
+    return SPRUCE_OK;
+}
+int spruce_module_radiative_losses(spruce_domain *d, int time_integrator, double cutoff_ramp, double cutoff_temp, double epsilon, int prevent_subcycling)
+{
+    CHECK_DOM(d);
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
+    if (time_integrator < 0 || time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid time integrator given for Radiative Losses module");
+    d->rl.integrator = time_integrator; d->rl.cutoff_ramp = cutoff_ramp; d->rl.cutoff_temp = cutoff_temp; d->rl.epsilon = epsilon;
+    d->rl.prevent_subcycling = prevent_subcycling ? 1 : 0;
+    d->module_order.push_back(spruce_domain::MOD_RL);
+    return SPRUCE_OK;
+}
+int spruce_module_ambient_heating(spruce_domain *d, const double *heating, size_t count)
+{
+    CHECK_DOM(d);
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
+    if (!heating || count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "heating plane needs %zu values", (size_t)d->P.nx * d->P.ny);
+    if (!d->heating) { int rc = alloc_plane(d, &d->heating); if (rc) return rc; }
+    int rc = h2d_plane(d, d->heating, heating);
+    if (rc) return rc;
+    d->module_order.push_back(spruce_domain::MOD_AH);
+    return SPRUCE_OK;
+}
+int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
+{
+    CHECK_DOM(d);
+    if (!which || !count) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (!strcmp(which, "thermal_conduction")) *count = d->tc_nsub;
+    else if (!strcmp(which, "radiative_losses")) *count = d->rl_nsub;
+    else return fail(SPRUCE_ERR_ARG, "no sub-cycling module named <%s>", which);
+    return SPRUCE_OK;
+}
 
 int spruce_halo_buffers(spruce_domain *, void **, void **, void **, void **, size_t *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
 int spruce_mgpu_pack(spruce_domain *, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }

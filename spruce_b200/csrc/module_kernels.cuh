@@ -1,0 +1,341 @@
+// module_kernels.cuh -- device kernels of the operator-split physics modules on the ideal-MHD state.
+//
+//   ThermalConduction   source/modules/solar/thermalconduction.cpp   (field-aligned Spitzer conduction, flux saturation,
+//                                                                       sub-cycled euler / rk2 / rk4)
+//   RadiativeLosses     source/modules/solar/radiativelosses.cpp     (piecewise power-law optically thin losses, sub-cycled)
+//   AmbientHeating      source/modules/solar/ambientheating.cpp      (e += dt * heating)
+//
+// Arithmetic follows the reference operation by operation (same expression order, no FMA contraction); the only
+// deviation is the libm: std::pow / std::log10 come from CUDA's math library here and from glibc in the reference,
+// which differ in the last bit for some arguments.  Module runs are therefore held to the 1e-9 relative tolerance of
+// the north star, not to bit equality; the sub-cycle counts are compared exactly.
+//
+// Every differential operator of the reference returns 0 outside [xl..xu] x [yl..yu] and nested derivatives consume
+// those zeros; D_x / D_y below reproduce that by testing the interior range of the cell they are
+// evaluated at.
+#pragma once
+#include "mhd_kernels.cuh"
+
+namespace spruce {
+
+constexpr double kKappa0 = 1.0e-6;          // KAPPA_0      source/constants.hpp:15
+constexpr double kMElectron = 9.1094e-28;   // M_ELECTRON   source/constants.hpp:9
+
+__device__ __forceinline__ int wrap_i(const DomainParams &P, int r) { return P.xwrap ? (r + P.nx) % P.nx : r; }
+__device__ __forceinline__ int wrap_j(const DomainParams &P, int j) { return P.yper ? (j + P.ny) % P.ny : j; }
+__device__ __forceinline__ bool is_interior(const DomainParams &P, int r, int j)
+{
+    const int g = P.row0 + r;
+    return g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
+}
+// clamped/wrapped read: rows/cols outside a non-periodic domain are never used by an in-range operator
+__device__ __forceinline__ double rd(const DomainParams &P, const double *f, int r, int j)
+{
+    r = wrap_i(P, r); j = wrap_j(P, j);
+    r = max(-HALO, min(P.nx + HALO - 1, r)); j = max(0, min(P.ny - 1, j));
+    return f[(size_t)r * P.pitch + j];
+}
+
+// temp = max((gamma-1)*e / (2 K_B n), T_min)   thermalconduction.cpp:65, radiativelosses.cpp:56
+__device__ __forceinline__ double temp_of(const DomainParams &P, double e, double n) { return smax((e * P.gm1) / (n * (2.0 * kKB)), P.T_min); }
+
+// derivative1D of an arbitrary per-cell functor F(r, j) (derivs.cpp:223-264); zero outside the interior range
+template <class F>
+__device__ __forceinline__ double Dx(const DomainParams &P, F f, int r, int j)
+{
+    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+    if (!is_interior(P, r, j)) return 0.0;
+    const AxisTab &t = P.tx;
+    const double a = f(r - 1, j), b = f(r, j), c = f(r + 1, j);
+    const double hi = face_interp(b, c, t.h[r], t.h[r + 1], t.fs[r + 1], t.rfs[r + 1]);
+    const double lo = face_interp(a, b, t.h[r - 1], t.h[r], t.fs[r], t.rfs[r]);
+    return ddiv(hi - lo, t.d[r], t.rd[r]);
+}
+template <class F>
+__device__ __forceinline__ double Dy(const DomainParams &P, F f, int r, int j)
+{
+    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+    if (!is_interior(P, r, j)) return 0.0;
+    const AxisTab &t = P.ty;
+    const double a = f(r, j - 1), b = f(r, j), c = f(r, j + 1);
+    const double hi = face_interp(b, c, t.h[j], t.h[j + 1], t.fs[j + 1], t.rfs[j + 1]);
+    const double lo = face_interp(a, b, t.h[j - 1], t.h[j], t.fs[j], t.rfs[j]);
+    return ddiv(hi - lo, t.d[j], t.rd[j]);
+}
+// secondDerivative1D (derivs.cpp:417-455): (I(i,i+1) - 2 q + I(i-1,i)) / (0.5 d)^2
+template <class F>
+__device__ __forceinline__ double D2x(const DomainParams &P, F f, int r, int j)
+{
+    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+    if (!is_interior(P, r, j)) return 0.0;
+    const AxisTab &t = P.tx;
+    const double a = f(r - 1, j), b = f(r, j), c = f(r + 1, j);
+    const double hi = face_interp(b, c, t.h[r], t.h[r + 1], t.fs[r + 1], t.rfs[r + 1]);
+    const double lo = face_interp(a, b, t.h[r - 1], t.h[r], t.fs[r], t.rfs[r]);
+    return ((hi - 2.0 * b) + lo) / (t.h[r] * t.h[r]);
+}
+template <class F>
+__device__ __forceinline__ double D2y(const DomainParams &P, F f, int r, int j)
+{
+    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+    if (!is_interior(P, r, j)) return 0.0;
+    const AxisTab &t = P.ty;
+    const double a = f(r, j - 1), b = f(r, j), c = f(r, j + 1);
+    const double hi = face_interp(b, c, t.h[j], t.h[j + 1], t.fs[j + 1], t.rfs[j + 1]);
+    const double lo = face_interp(a, b, t.h[j - 1], t.h[j], t.fs[j], t.rfs[j]);
+    return ((hi - 2.0 * b) + lo) / (t.h[j] * t.h[j]);
+}
+
+struct TcParams {
+    int flux_saturation;
+    double kappa;              // weakening_factor*KAPPA_0
+    double dt_subcycle_min;
+};
+
+struct TcFields { const double *T, *n, *bhx, *bhy; };   // n, b_hat of the primary state at module entry; T evolves
+
+// fieldAlignedConductiveFlux at one cell (thermalconduction.cpp:154-178); zero outside the interior
+__device__ __forceinline__ void tc_raw_flux(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j, double *fx, double *fy)
+{
+    *fx = 0.0; *fy = 0.0;
+    r = wrap_i(P, r); j = wrap_j(P, j);
+    if (!is_interior(P, r, j)) return;
+    auto T = [&](int a, int b) { return rd(P, F.T, a, b); };
+    const double Tc = T(r, j);
+    const double rho = rd(P, F.n, r, j) * P.m_i;
+    const double kmax = (((P.tx.d[r] * P.ty.d[j]) * kKB) * ddiv(rho, P.m_i, P.rm_i)) / C.dt_subcycle_min;     // :155
+    const double kap = smin(pow(Tc, 5.0 / 2.0) * C.kappa, kmax);                                            // :156
+    const double cx = (kap * -1.0) * Dx(P, T, r, j), cy = (kap * -1.0) * Dy(P, T, r, j);
+    const double bx = rd(P, F.bhx, r, j), by = rd(P, F.bhy, r, j);
+    const double fm = cx * bx + cy * by;                                                                    // :173-175
+    *fx = fm * bx; *fy = fm * by;
+}
+// saturateConductiveFlux scale factor at one cell (thermalconduction.cpp:182-188); acts on every cell of the plane
+__device__ __forceinline__ void tc_saturate(const DomainParams &P, const TcFields &F, int r, int j, double *fx, double *fy)
+{
+    const double c1 = (1.0 / 6.0) * (3.0 / 2.0);
+    r = wrap_i(P, r); j = wrap_j(P, j);
+    const double rho = rd(P, F.n, r, j) * P.m_i;
+    const double sat = ((ddiv(rho, P.m_i, P.rm_i) * c1) * pow(rd(P, F.T, r, j) * kKB, 1.5)) / sqrt(kMElectron);
+    const double fm = sqrt((*fx) * (*fx) + (*fy) * (*fy));
+    const double sc = sat / sqrt(sat * sat + fm * fm);
+    *fx *= sc; *fy *= sc;
+}
+// saturation coefficient of saturationTerms at one cell (thermalconduction.cpp:211-224)
+__device__ __forceinline__ double tc_coefficient(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j)
+{
+    double fx, fy;
+    tc_raw_flux(P, C, F, r, j, &fx, &fy);
+    const double fm = sqrt(fx * fx + fy * fy);
+    tc_saturate(P, F, r, j, &fx, &fy);
+    const double sfm = sqrt(fx * fx + fy * fy);
+    return (fm != 0.0) ? sfm / fm : 1.0;
+}
+
+// thermalEnergyDerivative at one cell (thermalconduction.cpp:114-132)
+__device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j)
+{
+    auto T = [&](int a, int b) { return rd(P, F.T, a, b); };
+    auto BX = [&](int a, int b) { return rd(P, F.bhx, a, b); };
+    auto BY = [&](int a, int b) { return rd(P, F.bhy, a, b); };
+    auto TX = [&](int a, int b) { return Dx(P, T, a, b); };
+    auto TY = [&](int a, int b) { return Dy(P, T, a, b); };
+    const double Tx = TX(r, j), Ty = TY(r, j);
+    const double Txx = D2x(P, T, r, j), Tyy = D2y(P, T, r, j);
+    const double Txy = Dy(P, TX, r, j), Tyx = Dx(P, TY, r, j);            // nested: derivative1D(dtemp_dx,1), derivative1D(dtemp_dy,0)
+    const double bxx = Dx(P, BX, r, j), bxy = Dy(P, BX, r, j), byx = Dx(P, BY, r, j), byy = Dy(P, BY, r, j);
+    const double bhx = BX(r, j), bhy = BY(r, j), Tc = T(r, j);
+    const double bg = bhx * Tx + bhy * Ty;
+    const double t1x = bhx * Txx + bhy * Txy, t1y = bhx * Tyx + bhy * Tyy;
+    const double t2x = Tx * bxx + Ty * bxy, t2y = Tx * byx + Ty * byy;
+    const double cu = byx - bxy;
+    const double t3x = ((cu * -1.0) * -1.0) * Ty, t3y = (cu * -1.0) * Tx;
+    const double p15 = pow(Tc, 3.0 / 2.0), p25 = pow(Tc, 5.0 / 2.0);
+    const double ttx = ((p15 * (5.0 / 2.0)) * Tx) * bg + p25 * ((t1x + t2x) + t3x);
+    const double tty = ((p15 * (5.0 / 2.0)) * Ty) * bg + p25 * ((t1y + t2y) + t3y);
+    double out = (((p25 * bg) * (bxx + byy)) + (bhx * ttx + bhy * tty)) * C.kappa;
+    if (C.flux_saturation) {
+        auto CO = [&](int a, int b) { return tc_coefficient(P, C, F, a, b); };
+        const double coef = CO(r, j);
+        double rx, ry;
+        tc_raw_flux(P, C, F, r, j, &rx, &ry);
+        const double mask = is_interior(P, r, j) ? 1.0 : 0.0;
+        const double add = (mask * -1.0) * (Dx(P, CO, r, j) * rx + Dy(P, CO, r, j) * ry);
+        out = coef * out + add;
+    }
+    return out;
+}
+
+enum { TC_FINAL = 0, TC_INTERMEDIATE = 1, TC_RK4_FINAL = 2 };
+struct TcStageArgs {
+    TcFields F;
+    TcParams C;
+    const double *e_base;      // thermal energy at the start of the sub-cycle
+    double *e_out;             // TC_FINAL / TC_RK4_FINAL: new thermal energy (may alias e_base: own cell only)
+    double *T_out;             // temperature of the produced energy
+    double *K_store;           // optional: store dE of this evaluation (rk4 k1..k3)
+    const double *K1, *K2, *K3;
+    int mode;
+    double c;                  // 0.5*dt_sub or dt_sub
+};
+
+__global__ void __launch_bounds__(128) k_tc_stage(const DomainParams P, const TcStageArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const bool in = is_interior(P, r, j);
+    const double mask = in ? 1.0 : 0.0;
+    double dE = in ? tc_energy_derivative(P, A.C, A.F, r, j) : 0.0;   // ghost cells: multiplied by mask = 0
+    if (A.K_store) A.K_store[off] = dE;
+    const double e0 = A.e_base[off];
+    double e1;
+    if (A.mode == TC_RK4_FINAL) {
+        const double ks = ((A.K1[off] + A.K2[off] * 2.0) + A.K3[off] * 2.0) + dE;
+        e1 = smax(e0 + ((mask * A.c) * ks) / 6.0, P.e_min);                       // :96-97
+    } else {
+        e1 = smax(e0 + (mask * A.c) * dE, P.e_min);                               // :63-64, :70-71, :84 ...
+    }
+    if (A.mode != TC_INTERMEDIATE) A.e_out[off] = e1;
+    A.T_out[off] = temp_of(P, e1, A.F.n[off]);
+}
+
+// numberSubcycles reductions (thermalconduction.cpp:135-149): out[0] = min over the interior of dt_subcycle (ordered bits),
+// out[1] = max over the whole plane of |b_hat . grad T| (ordered bits; saturated case only)
+__global__ void __launch_bounds__(128) k_tc_count(const DomainParams P, const TcParams C, const TcFields F, unsigned long long *out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    double v = 1.7976931348623157e308;
+    unsigned long long gmax = 0ULL;
+    if (j < P.ny) {
+        const size_t off = (size_t)r * P.pitch + j;
+        const double rho = F.n[off] * P.m_i;
+        const double nd = ddiv(rho, P.m_i, P.rm_i);
+        const bool in = is_interior(P, r, j);
+        if (!C.flux_saturation) {
+            if (in) v = (((nd * (kKB / C.kappa)) * P.tx.d[r]) * P.ty.d[j]) / pow(F.T[off], 2.5);      // :139
+        } else {
+            auto T = [&](int a, int b) { return rd(P, F.T, a, b); };
+            const double ftg = Dx(P, T, r, j) * F.bhx[off] + Dy(P, T, r, j) * F.bhy[off];            // :141-142
+            gmax = (unsigned long long)__double_as_longlong(fabs(ftg));
+            if (ftg != ftg) gmax = 0ULL;
+            if (in) {
+                double fx, fy;
+                tc_raw_flux(P, C, F, r, j, &fx, &fy);
+                tc_saturate(P, F, r, j, &fx, &fy);
+                const double km = fabs(sqrt(fx * fx + fy * fy) / ftg);                                // :201-202
+                v = (((kKB / km) * nd) * P.tx.d[r]) * P.ty.d[j];                                      // :145
+            }
+        }
+    }
+    block_min_to_global(v, out);
+    // max of |ftg| (non-negative doubles order like their bit patterns)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, gmax, o); gmax = t > gmax ? t : gmax; }
+    if ((threadIdx.x & 31) == 0 && gmax) atomicMax(out + 1, gmax);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Radiative losses: the loss rate depends on the own cell only, so the whole sub-cycling loop runs in registers.
+// ---------------------------------------------------------------------------------------------------------
+struct RlParams { int integrator, prevent_subcycling; double cutoff_ramp, cutoff_temp, epsilon; };
+
+// computeLosses at one interior cell (radiativelosses.cpp:110-158)
+__device__ __forceinline__ double rl_loss(const RlParams &R, double T, double n, double e_primary, double dt_primary, double eps_domain)
+{
+    if (T < R.cutoff_temp) return 0.0;
+    const double lt = log10(T);
+    double chi, alpha;
+    if (lt <= 4.97) { chi = 1.09e-31; alpha = 2.0; }
+    else if (lt <= 5.67) { chi = 8.87e-17; alpha = -1.0; }
+    else if (lt <= 6.18) { chi = 1.90e-22; alpha = 0.0; }
+    else if (lt <= 6.55) { chi = 3.53e-13; alpha = -1.5; }
+    else if (lt <= 6.90) { chi = 3.46e-25; alpha = 1.0 / 3.0; }
+    else if (lt <= 7.63) { chi = 5.49e-16; alpha = -1.0; }
+    else { chi = 1.96e-27; alpha = 0.5; }
+    double r = pow(n, 2.0) * chi * pow(T, alpha);
+    if (T < R.cutoff_temp + R.cutoff_ramp) { const double ramp = (T - R.cutoff_temp) / R.cutoff_ramp; r *= ramp; }
+    if (R.prevent_subcycling) {
+        if (0.1 * R.epsilon * (e_primary / r) < eps_domain * dt_primary) r = 0.1 * R.epsilon * e_primary / (eps_domain * dt_primary);
+    }
+    return r;
+}
+
+struct RlArgs {
+    RlParams R;
+    const double *U[NEV];
+    const double *st[NSTATIC];
+    double *e_out;
+    int n_sub;
+    double dt;                 // step size of this iteration
+    unsigned long long *red;   // count mode: red[0] = min |e/L| over the whole plane, red[1] = max L
+    int count_mode;
+};
+
+__global__ void __launch_bounds__(128) k_rl(const DomainParams P, const RlArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    double vmin = 1.7976931348623157e308;
+    unsigned long long lmax = 0ULL;
+    if (j < P.ny) {
+        const size_t off = (size_t)r * P.pitch + j;
+        const bool in = is_interior(P, r, j);
+        const double n = A.U[E_N][off];
+        const double e0 = A.U[E_E][off];
+        double dtp = 0.0;
+        if (A.R.prevent_subcycling && in)
+            dtp = cell_dt(P, n * P.m_i, A.U[E_MX][off], A.U[E_MY][off], e0, A.st[S_BEX][off] + A.U[E_BX][off], A.st[S_BEY][off] + A.U[E_BY][off],
+                          A.st[S_BEZ][off] + A.U[E_BZ][off], P.tx.d[r], P.tx.rd[r], P.ty.d[j], P.ty.rd[j]);
+        auto L = [&](double T) { return in ? rl_loss(A.R, T, n, e0, dtp, P.epsilon) : 0.0; };
+        double e = e0, T = temp_of(P, e0, n);
+        if (A.count_mode) {
+            const double l = L(T);
+            const double q = fabs(e0 / l);                                        // radiativelosses.cpp:164 (inf where l == 0)
+            vmin = q;
+            lmax = (l == l && l > 0.0) ? (unsigned long long)__double_as_longlong(l) : 0ULL;
+        } else {
+            const double mask = in ? 1.0 : 0.0;
+            const double dts = A.dt / (double)A.n_sub;                            // :51
+            for (int s = 0; s < A.n_sub; s++) {
+                if (A.R.integrator == 0) {                                        // euler :53-57
+                    e = smax(e - (mask * dts) * L(T), P.e_min);
+                } else if (A.R.integrator == 1) {                                 // rk2 :58-69
+                    const double half = smax(e - (mask * (0.5 * dts)) * L(T), P.e_min);
+                    e = smax(e - (mask * dts) * L(temp_of(P, half, n)), P.e_min);
+                } else {                                                          // rk4 :70-91
+                    const double k1 = L(T) * -1.0;
+                    double im = smax(e + (mask * (0.5 * dts)) * k1, P.e_min);
+                    const double k2 = L(temp_of(P, im, n)) * -1.0;
+                    im = smax(e + (mask * (0.5 * dts)) * k2, P.e_min);
+                    const double k3 = L(temp_of(P, im, n)) * -1.0;
+                    im = smax(e + (mask * dts) * k3, P.e_min);
+                    const double k4 = L(temp_of(P, im, n)) * -1.0;
+                    e = smax(e + ((mask * dts) * (((k1 + k2 * 2.0) + k3 * 2.0) + k4)) / 6.0, P.e_min);
+                }
+                T = temp_of(P, e, n);
+            }
+            A.e_out[off] = e;
+        }
+    }
+    if (A.count_mode) {
+        block_min_to_global(vmin, A.red);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, lmax, o); lmax = t > lmax ? t : lmax; }
+        if ((threadIdx.x & 31) == 0 && lmax) atomicMax(A.red + 1, lmax);
+    }
+}
+
+// AmbientHeating::postIterateModule (ambientheating.cpp:43): e += dt*heating  (tmp = heating*dt, then +=)
+__global__ void __launch_bounds__(256) k_ambient_heating(const DomainParams P, double *e, const double *heating, const double *step_ptr)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    e[off] = e[off] + heating[off] * (*step_ptr);
+}
+
+}  // namespace spruce

@@ -12,7 +12,16 @@ from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_b
 
 pytestmark = pytest.mark.gpu
 
-BUILT_MODULES = set()      # module names the device library implements so far (extended as they land)
+BUILT_MODULES = {"thermal_conduction", "radiative_losses", "ambient_heating"}
+# Modules that call std::pow / std::log10: CUDA's libm and glibc differ in the last bit for some arguments, so these runs are
+# held to the north star's tolerance (relative L-infinity <= 1e-9 per plane, same for the step sizes) instead of bit equality.
+LIBM_MODULES = {"thermal_conduction", "radiative_losses"}
+REL_TOL = 1.0e-9
+
+
+def rel_linf(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
 def make_domain(g: Golden):
@@ -41,17 +50,36 @@ def golden_cases():
 def test_golden_reference_outputs(name):
     g = Golden(name)
     d = make_domain(g)
+    exact = not any(m[0] in LIBM_MODULES for m in g.modules)
     done = 0
+    tc, rl = [], []
     for it in sorted(g.frames):
-        dts = d.advance(it - done)
+        dts = []
+        for _ in range(it - done):
+            dts.append(d.advanceTime())
+            if any(m[0] == "thermal_conduction" for m in g.modules):
+                tc.append(d.subcycles("thermal_conduction"))
+            if any(m[0] == "radiative_losses" for m in g.modules):
+                rl.append(d.subcycles("radiative_losses"))
+        dts = np.array(dts)
         ref = g.steps[done:it]
         assert len(dts) == len(ref)
-        assert all(a == b for a, b in zip(dts, ref)), "step history differs at iteration %d: %s vs %s" % (
-            done + int(np.argmax(dts != ref)) + 1, [x.hex() for x in dts[:3]], [float(x).hex() for x in ref[:3]])
+        if exact:
+            assert all(a == b for a, b in zip(dts, ref)), "step history differs at iteration %d: %s vs %s" % (
+                done + int(np.argmax(dts != ref)) + 1, [x.hex() for x in dts[:3]], [float(x).hex() for x in ref[:3]])
+        else:
+            assert np.max(np.abs(dts - ref) / ref) <= REL_TOL
         done = it
         for v in OUT_VARS:
             got = d.grid(v)
-            assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
+            if exact:
+                assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
+            else:
+                assert rel_linf(got, g.frames[it][v]) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (v, it, rel_linf(got, g.frames[it][v]))
+    if tc:
+        assert tc == g.subcycle_counts("Thermal Subcycles")[:len(tc)]
+    if rl:
+        assert rl == g.subcycle_counts("Radiative Subcycles")[:len(rl)]
     d.close()
 
 
@@ -169,3 +197,41 @@ def test_full_size_4096_translation_invariance():
     # mass is transported in flux form: the cell-volume weighted sum is conserved to rounding
     m0 = float(np.sum(P["rho"])) ; m1 = float(np.sum(a.grid("rho")))
     assert abs(m1 - m0) / m0 < 1e-12
+
+
+@pytest.mark.parametrize("mods", [
+    [("thermal_conduction", dict(flux_saturation=False, integrator="euler"))],
+    [("thermal_conduction", dict(flux_saturation=True, integrator="rk2"))],
+    [("thermal_conduction", dict(flux_saturation=True, integrator="rk4"))],
+    [("radiative_losses", dict(integrator="euler"))],
+    [("radiative_losses", dict(integrator="rk4", prevent_subcycling=True))],
+    [("thermal_conduction", dict(flux_saturation=True)), ("radiative_losses", dict(integrator="rk2")), ("ambient_heating", dict(heating_rate=1.0e-4))],
+])
+def test_solar_modules_vs_oracle(mods):
+    """cfg-2 style run (thermal conduction + radiative losses + ambient heating on a gravity-stratified loop) at a size the
+    oracle finishes in seconds: equal sub-cycle counts, planes and step sizes within 1e-9 relative."""
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    s = synthetic.stratified_loop(70, 90, bump=0.5)
+    kw = dict(xb=("periodic", "periodic"), yb=("fixed", "open"), integrator="rk2")
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    for name, mk in mods:
+        if name == "ambient_heating":
+            o.set_ambient_heating(**mk)
+            mask = np.zeros((70, 90)); mask[:, 2:88] = 1.0
+            d.set_ambient_heating_plane(mask * mk["heating_rate"])
+        else:
+            getattr(o, "set_" + name)(**mk)
+            getattr(d, "set_" + name)(**mk)
+    names = [m[0] for m in mods]
+    for it in range(5):
+        a, b = d.advanceTime(), o.step()
+        assert abs(a - b) / b <= REL_TOL, (it, a, b)
+        if "thermal_conduction" in names:
+            assert d.subcycles("thermal_conduction") == o.subcycles("thermal_conduction")
+        if "radiative_losses" in names:
+            assert d.subcycles("radiative_losses") == o.subcycles("radiative_losses")
+    for v in PlasmaDomain.EVOLVED + ["temp", "dt"]:
+        assert rel_linf(d.grid(v), o.get(v)) <= REL_TOL, "%s: rel Linf %.3e" % (v, rel_linf(d.grid(v), o.get(v)))
