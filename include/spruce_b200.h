@@ -143,6 +143,7 @@ int spruce_mgpu_pack(spruce_domain *dom, int which_state);
 int spruce_mgpu_unpack(spruce_domain *dom, int which_state);
 int spruce_mgpu_stage(spruce_domain *dom, int stage);
 int spruce_mgpu_n_stages(spruce_domain *dom, int *n);
+int spruce_mgpu_stage_output(spruce_domain *dom, int stage, int *which_state);   /* set the stage wrote: 0 primary, 1/2 stage copies */
 int spruce_mgpu_dt_min_ptr(spruce_domain *dom, void **device_double);   /* 1 double on the device: all-reduce(min) it in place */
 int spruce_mgpu_begin_step(spruce_domain *dom);   /* fixes `step` from the (all-reduced) dt minimum */
 int spruce_mgpu_end_step(spruce_domain *dom);     /* t += step; iter++ */

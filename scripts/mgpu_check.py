@@ -1,0 +1,50 @@
+"""torchrun --nproc-per-node N scripts/mgpu_check.py [nx ny steps integrator xbound]
+N-GPU slab run vs the 1-GPU run of the same problem (rank 0 computes both): planes and step sizes must be identical
+bit for bit (min/max reductions are exact and every cell sees the same operands)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spruce_b200 import synthetic  # noqa: E402
+from spruce_b200.domain import PlasmaDomain  # noqa: E402
+from spruce_b200.multigpu import SlabRunner  # noqa: E402
+
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+ny = int(sys.argv[2]) if len(sys.argv) > 2 else 210
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+integ = sys.argv[4] if len(sys.argv) > 4 else "rk2"
+xbound = sys.argv[5] if len(sys.argv) > 5 else "periodic"
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if xbound == "periodic":
+    s = synthetic.orszag_tang(nx, ny, zfull=True)
+    kw = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator=integ, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
+else:
+    s = synthetic.stratified_loop(nx, ny)
+    kw = dict(xb=(xbound, "open"), yb=("reflect", "fixed"), integrator=integ)
+run = SlabRunner(s["planes"], s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, **kw)
+run.step(steps)
+run.dom.synchronize()
+got = {v: run.gather(v) for v in PlasmaDomain.EVOLVED + ["dt"]}
+t_slab = run.dom.time
+ok = True
+if rank == 0:
+    one = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], device=local, **kw)
+    dts = one.advance(steps)
+    for v, a in got.items():
+        b = one.grid(v)
+        same = bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+        ok &= same
+        if not same:
+            bad = np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))
+            print("MISMATCH", v, len(bad), bad[:5].tolist())
+    ok &= (t_slab == one.time)
+    print("mgpu_check world=%d %dx%d %s x=%s steps=%d : %s (t=%r vs %r)" % (world, nx, ny, integ, xbound, steps, "IDENTICAL" if ok else "DIFFERENT", t_slab, one.time))
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

@@ -58,6 +58,7 @@ SYMBOLS = {
     "spruce_mgpu_unpack": (C.c_int, [C.c_void_p, C.c_int]),
     "spruce_mgpu_stage": (C.c_int, [C.c_void_p, C.c_int]),
     "spruce_mgpu_n_stages": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "spruce_mgpu_stage_output": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "spruce_mgpu_dt_min_ptr": (C.c_int, [C.c_void_p, _VPP]),
     "spruce_mgpu_begin_step": (C.c_int, [C.c_void_p]),
     "spruce_mgpu_end_step": (C.c_int, [C.c_void_p]),

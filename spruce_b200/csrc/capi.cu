@@ -59,6 +59,8 @@ struct spruce_domain {
     RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
     unsigned long long *red = nullptr;     // 4 reduction scalars for the sub-cycle counts
+    double *halo[4] = {nullptr, nullptr, nullptr, nullptr};   // send_lo, send_hi, recv_lo, recv_hi
+    size_t halo_doubles = 0;
 };
 
 namespace {
@@ -738,14 +740,121 @@ int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
     return SPRUCE_OK;
 }
 
-int spruce_halo_buffers(spruce_domain *, void **, void **, void **, void **, size_t *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
-int spruce_mgpu_pack(spruce_domain *, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
-int spruce_mgpu_unpack(spruce_domain *, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
-int spruce_mgpu_stage(spruce_domain *, int) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
-int spruce_mgpu_n_stages(spruce_domain *, int *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
-int spruce_mgpu_dt_min_ptr(spruce_domain *, void **) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
-int spruce_mgpu_begin_step(spruce_domain *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
-int spruce_mgpu_end_step(spruce_domain *) { return fail(SPRUCE_ERR_UNSUPPORTED, "multi-GPU is not built yet"); }
+// ---------------------------------------------------------------------------------------------------------------
+// multi-GPU: the caller owns the communicator (torch.distributed / NCCL) and moves the staging buffers
+// ---------------------------------------------------------------------------------------------------------------
+static PlaneSet *set_by_id(spruce_domain *d, int which) { return which == 0 ? &d->Pset : which == 1 ? &d->Mset : which == 2 ? &d->M2set : nullptr; }
+
+int spruce_halo_buffers(spruce_domain *d, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, size_t *bytes)
+{
+    CHECK_DOM(d);
+    if (!d->halo[0]) {
+        d->halo_doubles = (size_t)NEV * HALO * d->P.pitch;
+        for (int k = 0; k < 4; k++) {
+            CUDA_TRY(cudaMalloc(&d->halo[k], d->halo_doubles * sizeof(double)));
+            CUDA_TRY(cudaMemsetAsync(d->halo[k], 0, d->halo_doubles * sizeof(double), d->stream));
+            d->allocs.push_back(d->halo[k]);
+        }
+    }
+    if (send_lo) *send_lo = d->halo[0];
+    if (send_hi) *send_hi = d->halo[1];
+    if (recv_lo) *recv_lo = d->halo[2];
+    if (recv_hi) *recv_hi = d->halo[3];
+    if (bytes) *bytes = d->halo_doubles * sizeof(double);
+    return SPRUCE_OK;
+}
+static int halo_copy(spruce_domain *d, int which, int unpack)
+{
+    PlaneSet *s = set_by_id(d, which);
+    if (!s || !s->p[0]) return fail(SPRUCE_ERR_ARG, "state set %d does not exist", which);
+    int rc = spruce_halo_buffers(d, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    HaloArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = s->p[v];
+    A.lo = unpack ? d->halo[2] : d->halo[0];
+    A.hi = unpack ? d->halo[3] : d->halo[1];
+    A.unpack = unpack;
+    dim3 grid((d->P.pitch + 255) / 256, NEV * HALO);
+    k_halo_copy<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+int spruce_mgpu_pack(spruce_domain *d, int which) { CHECK_DOM(d); return halo_copy(d, which, 0); }
+int spruce_mgpu_unpack(spruce_domain *d, int which) { CHECK_DOM(d); return halo_copy(d, which, 1); }
+
+int spruce_mgpu_n_stages(spruce_domain *d, int *n)
+{
+    CHECK_DOM(d);
+    if (!n) return fail(SPRUCE_ERR_ARG, "null argument");
+    *n = d->cfg.time_integrator == SPRUCE_TI_EULER ? 1 : d->cfg.time_integrator == SPRUCE_TI_RK2 ? 2 : 4;
+    return SPRUCE_OK;
+}
+// Runs RK stage `stage` and packs the halo rows of the set it produced; *out_set (returned through the status-free
+// convention: the id is also the return value of spruce_mgpu_stage_output) tells the caller which set to unpack into.
+static int stage_output_set(const spruce_domain *d, int stage)
+{
+    const int ti = d->cfg.time_integrator;
+    if (ti == SPRUCE_TI_EULER) return 0;
+    if (ti == SPRUCE_TI_RK2) return stage == 0 ? 1 : 0;
+    return stage == 0 ? 1 : stage == 1 ? 2 : stage == 2 ? 1 : 0;
+}
+int spruce_mgpu_stage(spruce_domain *d, int stage)
+{
+    CHECK_DOM(d);
+    if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "stage before setup");
+    int rc;
+    const int ti = d->cfg.time_integrator;
+    if (ti == SPRUCE_TI_EULER) {
+        if (stage != 0) return fail(SPRUCE_ERR_ARG, "euler has one stage");
+        if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;
+        std::swap(d->Pset, d->Mset);
+        if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
+    } else if (ti == SPRUCE_TI_RK2) {
+        if (stage == 0) { if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE)) || (rc = launch_ghosts(d, d->Mset, 0))) return rc; }
+        else if (stage == 1) { if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_NONE)) || (rc = launch_ghosts(d, d->Pset, 1))) return rc; }
+        else return fail(SPRUCE_ERR_ARG, "rk2 has two stages");
+    } else {
+        if ((rc = ensure_rk4(d))) return rc;
+        if (stage == 0) { if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_STORE_K1)) || (rc = launch_ghosts(d, d->Mset, 0))) return rc; }
+        else if (stage == 1) { if ((rc = launch_stage(d, d->Mset, d->Pset, d->M2set, 0.5, 0, KM_STORE_K2)) || (rc = launch_ghosts(d, d->M2set, 0))) return rc; }
+        else if (stage == 2) { if ((rc = launch_stage(d, d->M2set, d->Pset, d->Mset, 1.0, 0, KM_ADD_K2)) || (rc = launch_ghosts(d, d->Mset, 0))) return rc; }
+        else if (stage == 3) { if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL)) || (rc = launch_ghosts(d, d->Pset, 1))) return rc; }
+        else return fail(SPRUCE_ERR_ARG, "rk4 has four stages");
+    }
+    return halo_copy(d, stage_output_set(d, stage), 0);
+}
+int spruce_mgpu_stage_output(spruce_domain *d, int stage, int *which)
+{
+    CHECK_DOM(d);
+    if (!which) return fail(SPRUCE_ERR_ARG, "null argument");
+    *which = stage_output_set(d, stage);
+    return SPRUCE_OK;
+}
+int spruce_mgpu_dt_min_ptr(spruce_domain *d, void **device_double)
+{
+    CHECK_DOM(d);
+    if (!device_double) return fail(SPRUCE_ERR_ARG, "null argument");
+    *device_double = (void *)&d->ctl->dtmin_bits;     // bits of a positive double: min over doubles == min over bit patterns
+    return SPRUCE_OK;
+}
+int spruce_mgpu_begin_step(spruce_domain *d)
+{
+    CHECK_DOM(d);
+    if ((size_t)1 > d->dt_hist_cap) { d->dt_hist_cap = 64; CUDA_TRY(cudaMalloc(&d->dt_hist, d->dt_hist_cap * sizeof(double))); }
+    k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, 0);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+int spruce_mgpu_end_step(spruce_domain *d)
+{
+    CHECK_DOM(d);
+    k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
 
 int spruce_stream(spruce_domain *d, void **stream) { CHECK_DOM(d); if (!stream) return fail(SPRUCE_ERR_ARG, "null"); *stream = (void *)d->stream; return SPRUCE_OK; }
 int spruce_synchronize(spruce_domain *d) { CHECK_DOM(d); CUDA_TRY(cudaStreamSynchronize(d->stream)); return SPRUCE_OK; }

@@ -711,6 +711,27 @@ __global__ void __launch_bounds__(256) k_mhd_derive(const DomainParams P, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Slab decomposition: pack the first/last HALO rows of the 8 evolved planes into contiguous staging buffers
+// (send_lo = rows [0,2), send_hi = rows [nx-2,nx)), and unpack the neighbours' rows into the halo rows
+// (recv_lo -> rows [-2,0), recv_hi -> rows [nx,nx+2)).  Buffer layout: [plane][halo row][pitch].
+// ---------------------------------------------------------------------------------------------------------
+struct HaloArgs { double *U[NEV]; double *lo, *hi; int unpack; };
+__global__ void __launch_bounds__(256) k_halo_copy(const DomainParams P, const HaloArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y / HALO, h = blockIdx.y % HALO;
+    if (j >= P.pitch) return;
+    const size_t b = ((size_t)v * HALO + h) * P.pitch + j;
+    if (!A.unpack) {
+        A.lo[b] = A.U[v][(size_t)h * P.pitch + j];
+        A.hi[b] = A.U[v][(size_t)(P.nx - HALO + h) * P.pitch + j];
+    } else {
+        A.U[v][(size_t)(h - HALO) * P.pitch + j] = A.lo[b];          // rows -2,-1 (the allocation starts 2 rows earlier)
+        A.U[v][(size_t)(P.nx + h) * P.pitch + j] = A.hi[b];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Scalar bookkeeping of advanceTime (evolution.cpp:62,80-81), one thread.
 // ctl[0] = step (double), ctl[1] = time, ctl[2] = max_time (<=0: none); ictl[0] = iter, ictl[1] = done flag
 // ---------------------------------------------------------------------------------------------------------

@@ -235,3 +235,19 @@ def test_solar_modules_vs_oracle(mods):
             assert d.subcycles("radiative_losses") == o.subcycles("radiative_losses")
     for v in PlasmaDomain.EVOLVED + ["temp", "dt"]:
         assert rel_linf(d.grid(v), o.get(v)) <= REL_TOL, "%s: rel Linf %.3e" % (v, rel_linf(d.grid(v), o.get(v)))
+
+
+@pytest.mark.parametrize("args", [("300", "210", "6", "rk2", "periodic"), ("131", "96", "5", "rk4", "periodic"), ("120", "80", "6", "rk2", "fixed"), ("90", "70", "4", "euler", "reflect")])
+def test_slab_decomposition_equals_single_gpu(args):
+    """N-GPU == 1-GPU bit for bit.  Needs >= 2 visible GPUs; spawns torchrun with 2 ranks."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(root / "scripts" / "mgpu_check.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "IDENTICAL" in out, out[-3000:]
