@@ -139,7 +139,7 @@ int spruce_halo_buffers(spruce_domain *dom, void **send_lo, void **send_hi, void
  * phase 0: pack halos of the primary state; then per RK stage s: stage_begin(s) computes stage s and packs the halos
  * of its output; the caller exchanges; stage_end(s) unpacks.  The dt minimum is exchanged with
  * spruce_local_dt_min / spruce_set_global_dt_min (ncclAllReduce(min)). */
-int spruce_mgpu_pack(spruce_domain *dom, int which_state);
+int spruce_mgpu_pack(spruce_domain *dom, int which_state);     /* 0 primary, 1/2 stage copies, 3 static planes (be_*, grav_*) */
 int spruce_mgpu_unpack(spruce_domain *dom, int which_state);
 int spruce_mgpu_stage(spruce_domain *dom, int stage);
 int spruce_mgpu_n_stages(spruce_domain *dom, int *n);

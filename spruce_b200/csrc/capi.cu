@@ -765,7 +765,9 @@ int spruce_halo_buffers(spruce_domain *d, void **send_lo, void **send_hi, void *
 }
 static int halo_copy(spruce_domain *d, int which, int unpack)
 {
-    PlaneSet *s = set_by_id(d, which);
+    PlaneSet stat_view;                    // which == 3: the static planes (be_x, be_y, be_z are transported: they need halo rows too)
+    for (int v = 0; v < NEV; v++) stat_view.p[v] = d->stat[v < NSTATIC ? v : 0];
+    PlaneSet *s = which == 3 ? &stat_view : set_by_id(d, which);
     if (!s || !s->p[0]) return fail(SPRUCE_ERR_ARG, "state set %d does not exist", which);
     int rc = spruce_halo_buffers(d, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;

@@ -103,6 +103,9 @@ class SlabRunner:
         # setup = local populateVariablesFromState, then halos of the primary state and the global dt minimum
         self.dom.setup()
         with torch.cuda.stream(self.stream):
+            capi.check(self.lib.spruce_mgpu_pack(self.dom.h, 3))        # static planes: be_* are transported and need halo rows
+            self._exchange()
+            capi.check(self.lib.spruce_mgpu_unpack(self.dom.h, 3))
             capi.check(self.lib.spruce_mgpu_pack(self.dom.h, 0))
             self._exchange()
             capi.check(self.lib.spruce_mgpu_unpack(self.dom.h, 0))
