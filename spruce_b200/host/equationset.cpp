@@ -1,0 +1,129 @@
+// equationset.cpp -- EquationSet / IdealMHD on the B200 path: registry + config parsing on the host, arithmetic on the device.
+#include "equationset.hpp"
+#include "plasmadomain.hpp"
+#include "utils.hpp"
+#include <algorithm>
+#include <iostream>
+
+EquationSet::EquationSet(PlasmaDomain &pd, std::vector<std::string> var_names) : m_pd(pd), m_var_names(std::move(var_names))
+{
+    m_grids.assign(m_var_names.size(), Grid::Zero(1, 1));
+    m_output_flags.assign(m_var_names.size(), false);
+    for (size_t i = 0; i < m_var_names.size(); i++) m_var_indices[m_var_names[i]] = (int)i;
+}
+
+bool EquationSet::isEquationSetName(const std::string &name) { return std::find(m_sets.begin(), m_sets.end(), name) != m_sets.end(); }
+
+std::unique_ptr<EquationSet> EquationSet::instantiateDefault(PlasmaDomain &pd, const std::string &name)
+{
+    if (name == "ideal_mhd") return std::unique_ptr<EquationSet>(new IdealMHD(pd));
+    if (isEquationSetName(name)) spruce_die("Equation set <" + name + "> is not ported to the B200 path yet (ideal_mhd is).");
+    spruce_die("Equation set name <" + name + "> not recognized.");
+}
+
+// equationset.cpp:38-56: an inactive set's block is skipped, an active one is instantiated and configured from its block
+void EquationSet::instantiateWithConfig(std::unique_ptr<EquationSet> &eqs, PlasmaDomain &pd, std::ifstream &in, const std::string &name, bool active)
+{
+    if (active) {
+        eqs = instantiateDefault(pd, name);
+        eqs->configureEquationSet(in);
+        return;
+    }
+    std::string line;
+    std::getline(in, line); clearWhitespace(line);
+    SPRUCE_REQUIRE(!line.empty() && line[0] == '{', "All Equation set activation/deactivation configs must be immediately followed by curly brackets");
+    do { if (!std::getline(in, line)) break; clearWhitespace(line); } while (line.empty() || line[0] != '}');
+}
+
+// equationset.cpp:64-85 (blank and comment lines inside the block are skipped instead of looping forever)
+void EquationSet::configureEquationSet(std::ifstream &in)
+{
+    std::vector<std::string> lhs_all, rhs_all;
+    std::string line, lhs, rhs;
+    std::getline(in, line);
+    SPRUCE_REQUIRE(!line.empty() && line[0] == '{', "All equation set activation configs must be immediately followed by curly brackets (on their own lines)");
+    while (std::getline(in, line)) {
+        if (!line.empty() && line[0] == '}') break;
+        clearWhitespace(line);
+        if (line.empty() || line[0] == '#') continue;
+        splitAssignment(line, lhs, rhs);
+        lhs_all.push_back(lhs); rhs_all.push_back(rhs);
+    }
+    parseEquationSetConfigs(lhs_all, rhs_all);
+}
+
+bool EquationSet::allStateGridsInitialized() const
+{
+    for (int i : state_variables()) if (m_grids[i].size() == 1) return false;
+    return true;
+}
+
+// equationset.cpp:87-104: populateVariablesFromState runs on the device
+void EquationSet::setupEquationSet()
+{
+    SPRUCE_REQUIRE(allStateGridsInitialized(), "All variables specified as state variables for the current EquationSet must be specified in the .state file");
+    m_pd.createDevice();
+    for (int v : state_variables()) PlasmaDomain::check(spruce_grid_upload(m_pd.device(), index2name(v).c_str(), m_grids[v].ptr(), m_grids[v].size()));
+    PlasmaDomain::check(spruce_eqs_setup(m_pd.device()));
+    name2index("dt");
+}
+
+int EquationSet::name2index(const std::string &name) const
+{
+    auto it = m_var_indices.find(name);
+    if (it == m_var_indices.end()) spruce_die("Variable name <" + name + "> not recognized");
+    return it->second;
+}
+int EquationSet::name2evolvedindex(const std::string &name) const
+{
+    const std::vector<int> ev = evolved_variables();
+    for (size_t i = 0; i < ev.size(); i++) if (index2name(ev[i]) == name) return (int)i;
+    spruce_die("<" + name + "> does not correspond to an evolved variable.");
+}
+
+Grid &EquationSet::grid(int index)
+{
+    SPRUCE_REQUIRE(index >= 0 && index < num_variables(), "Grid index must be within range of m_grids");
+    Grid &g = m_grids[index];
+    if (g.rows() != (int)m_pd.xdim() || g.cols() != (int)m_pd.ydim()) g = Grid(m_pd.xdim(), m_pd.ydim());
+    PlasmaDomain::check(spruce_grid_download(m_pd.device(), m_var_names[index].c_str(), g.ptr(), g.size()));
+    return g;
+}
+Grid &EquationSet::grid(const std::string &name) { return grid(name2index(name)); }
+
+void EquationSet::pushGrid(const std::string &name)
+{
+    Grid &g = m_grids[name2index(name)];
+    PlasmaDomain::check(spruce_grid_upload(m_pd.device(), name.c_str(), g.ptr(), g.size()));
+}
+
+std::vector<Grid> EquationSet::computeTimeDerivatives()
+{
+    const size_t np = m_pd.xdim() * m_pd.ydim(), ne = evolved_variables().size();
+    std::vector<double> k(ne * np);
+    PlasmaDomain::check(spruce_eqs_time_derivatives(m_pd.device(), k.data(), k.size()));
+    std::vector<Grid> out;
+    for (size_t v = 0; v < ne; v++) out.emplace_back(m_pd.xdim(), m_pd.ydim(), std::vector<double>(k.begin() + v * np, k.begin() + (v + 1) * np));
+    return out;
+}
+void EquationSet::propagateChanges() { PlasmaDomain::check(spruce_eqs_propagate_changes(m_pd.device())); }
+double EquationSet::nextStepSize()
+{
+    double s = 0.0;
+    PlasmaDomain::check(spruce_next_step_size(m_pd.device(), &s));
+    return s;
+}
+
+IdealMHD::IdealMHD(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
+int IdealMHD::device_id() const { return SPRUCE_EQS_IDEAL_MHD; }
+
+// idealmhd.cpp:12-40: same keys; the MoC limiters belong to the open_moc boundary, which is outside the built scope
+void IdealMHD::parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i];
+        if (k == "global_viscosity" || k == "viscosity_opt" || k == "moc_b_lower_lim" || k == "moc_b_upper_lim" || k == "moc_mom_lower_lim" || k == "moc_mom_upper_lim") continue;
+        if (k == "moc_b_limiting" || k == "moc_mom_limiting") { SPRUCE_REQUIRE(rhs[i] != "true", "MoC limiting needs the open_moc boundary, which this build does not provide"); continue; }
+        spruce_die(k + " is not recognized for this equation set.");
+    }
+}

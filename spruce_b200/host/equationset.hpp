@@ -1,0 +1,97 @@
+// equationset.hpp -- host mirror of the reference's EquationSet plug-in interface (source/equationsets/equationset.hpp:18-171)
+// for the B200 path: the variable registry, name/index maps and output flags stay here; every arithmetic member
+// (computeTimeDerivatives, applyTimeDerivatives, propagateChanges, getDT) is a call into libspruce_b200.so.
+#pragma once
+#include "grid.hpp"
+#include <fstream>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+class PlasmaDomain;
+
+class EquationSet {
+public:
+    static const inline std::vector<std::string> m_sets{"ideal_mhd", "ideal_mhd_cons", "ideal_mhd_2E", "ideal_2F"};   // equationset.hpp:22
+    static bool isEquationSetName(const std::string &name);
+    static std::unique_ptr<EquationSet> instantiateDefault(PlasmaDomain &pd, const std::string &name);
+    static void instantiateWithConfig(std::unique_ptr<EquationSet> &eqs, PlasmaDomain &pd, std::ifstream &in, const std::string &name, bool active);
+
+    EquationSet(PlasmaDomain &pd, std::vector<std::string> var_names);
+    virtual ~EquationSet() {}
+    void configureEquationSet(std::ifstream &in);
+    void setupEquationSet();                       // uploads the state variables, runs populateVariablesFromState on the device
+
+    virtual int device_id() const = 0;            // SPRUCE_EQS_*
+    virtual std::vector<int> state_variables() const = 0;
+    virtual std::vector<int> evolved_variables() const = 0;
+    virtual std::vector<std::string> species() const = 0;
+    virtual std::vector<int> densities() const = 0;
+    virtual std::vector<int> number_densities() const = 0;
+    virtual std::vector<std::vector<int>> momenta() const = 0;
+    virtual std::vector<std::vector<int>> velocities() const = 0;
+    virtual std::vector<int> thermal_energies() const = 0;
+    virtual std::vector<int> pressures() const = 0;
+    virtual std::vector<int> temperatures() const = 0;
+    virtual std::vector<int> fields() const = 0;
+    virtual std::vector<int> timescale() const = 0;
+
+    Grid &grid(int index);                         // refreshed from the device (derived variables are materialised on demand)
+    Grid &grid(const std::string &name);
+    Grid &hostGrid(int index) { return m_grids[index]; }   // host staging copy as read from the .state file
+    void pushGrid(const std::string &name);        // host staging copy -> device (a host-side module edited an evolved plane)
+    void setOutputFlag(int index, bool flag) { m_output_flags[index] = flag; }
+    void setOutputFlag(const std::string &name, bool flag) { m_output_flags[name2index(name)] = flag; }
+    bool getOutputFlag(int index) const { return m_output_flags[index]; }
+
+    std::vector<std::string> allNames() const { return m_var_names; }
+    std::string index2name(int index) const { return m_var_names[index]; }
+    int name2index(const std::string &name) const;
+    int name2evolvedindex(const std::string &name) const;
+    bool is_var(const std::string &name) const { return m_var_indices.count(name) != 0; }
+    int num_variables() const { return (int)m_var_names.size(); }
+    int num_species() const { return (int)species().size(); }
+    bool allStateGridsInitialized() const;
+
+    std::vector<Grid> computeTimeDerivatives();    // one RHS evaluation on the primary state (equationset.cpp:204-210)
+    void propagateChanges();                       // equationset.cpp:212-220 on the device
+    double nextStepSize();                         // epsilon * getDT().min(...)  (evolution.cpp:62)
+
+protected:
+    PlasmaDomain &m_pd;
+    std::vector<Grid> m_grids;
+    const std::vector<std::string> m_var_names;
+    std::unordered_map<std::string, int> m_var_indices;
+    std::vector<bool> m_output_flags;
+    virtual void parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) = 0;
+};
+
+// source/equationsets/idealmhd.hpp:14-67
+class IdealMHD : public EquationSet {
+public:
+    explicit IdealMHD(PlasmaDomain &pd);
+    enum Vars { rho, temp, mom_x, mom_y, mom_z, bi_x, bi_y, bi_z, grav_x, grav_y, n, press, thermal_energy, v_x, v_y, v_z, kinetic_energy,
+                b_x, b_y, b_z, b_mag, b_hat_x, b_hat_y, b_hat_z, dt };
+    static std::vector<std::string> def_var_names()
+    {
+        return {"rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y", "n", "press", "thermal_energy", "v_x", "v_y", "v_z",
+                "kinetic_energy", "b_x", "b_y", "b_z", "b_mag", "b_hat_x", "b_hat_y", "b_hat_z", "dt"};
+    }
+    int device_id() const override;
+    std::vector<int> state_variables() const override { return {rho, temp, mom_x, mom_y, mom_z, bi_x, bi_y, bi_z, grav_x, grav_y}; }
+    std::vector<int> evolved_variables() const override { return {rho, mom_x, mom_y, mom_z, thermal_energy, bi_x, bi_y, bi_z}; }
+    std::vector<std::string> species() const override { return {"i"}; }
+    std::vector<int> densities() const override { return {rho}; }
+    std::vector<int> number_densities() const override { return {n}; }
+    std::vector<std::vector<int>> momenta() const override { return {{mom_x, mom_y, mom_z}}; }
+    std::vector<std::vector<int>> velocities() const override { return {{v_x, v_y, v_z}}; }
+    std::vector<int> thermal_energies() const override { return {thermal_energy}; }
+    std::vector<int> pressures() const override { return {press}; }
+    std::vector<int> temperatures() const override { return {temp}; }
+    std::vector<int> fields() const override { return {bi_x, bi_y, bi_z}; }
+    std::vector<int> timescale() const override { return {dt}; }
+
+private:
+    void parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};

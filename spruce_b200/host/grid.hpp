@@ -1,0 +1,52 @@
+// grid.hpp -- host-side staging type with the reference Grid's shape and text format (source/mhd/grid.hpp:15-165).
+// On the B200 path a Grid never carries arithmetic: the field store is the device arena behind include/spruce_b200.h.
+// What remains on the host is what file I/O and module set-up need: element access in the reference layout
+// (row-major i*cols + j, source/mhd/grid.cpp:516-526) and the character-delimited text form (grid.cpp:412-427).
+#pragma once
+#include <cassert>
+#include <cstdio>
+#include <limits>
+#include <string>
+#include <vector>
+
+class Grid {
+public:
+    Grid() : m_rows(1), m_cols(1), m_data(1, 0.0) {}
+    Grid(size_t rows, size_t cols, double val = 0.0) : m_rows(rows), m_cols(cols), m_data(rows * cols, val) {}
+    Grid(size_t rows, size_t cols, std::vector<double> data) : m_rows(rows), m_cols(cols), m_data(std::move(data)) { assert(m_data.size() == rows * cols); }
+    static Grid Zero(size_t rows, size_t cols) { return Grid(rows, cols, 0.0); }
+    static Grid Ones(size_t rows, size_t cols) { return Grid(rows, cols, 1.0); }
+
+    double &operator()(size_t i, size_t j) { assert(i < m_rows && j < m_cols); return m_data[i * m_cols + j]; }
+    double operator()(size_t i, size_t j) const { assert(i < m_rows && j < m_cols); return m_data[i * m_cols + j]; }
+    int rows() const { return (int)m_rows; }
+    int cols() const { return (int)m_cols; }
+    int size() const { return (int)m_data.size(); }
+    const std::vector<double> &data() const { return m_data; }
+    std::vector<double> &data() { return m_data; }
+    const double *ptr() const { return m_data.data(); }
+    double *ptr() { return m_data.data(); }
+
+    // Same text as the reference's ostringstream << double with `precision` significant digits (default float format ==
+    // printf %.{p}g); precision -1 means digits10 + 1 = 16.  Elements separated by element_delim, rows by row_delim, the
+    // last row delimiter replaced by end_delim.
+    std::string format(char element_delim = ',', char row_delim = '\n', int precision = 4, char end_delim = '\n') const
+    {
+        const int p = precision == -1 ? std::numeric_limits<double>::digits10 + 1 : (precision <= 0 ? 6 : precision);
+        std::string out;
+        out.reserve(m_data.size() * (size_t)(p + 8));
+        char buf[64];
+        for (size_t i = 0; i < m_rows; i++) {
+            for (size_t j = 0; j < m_cols; j++) {
+                const int n = std::snprintf(buf, sizeof(buf), "%.*g", p, m_data[i * m_cols + j]);
+                out.append(buf, (size_t)n);
+                out.push_back(j + 1 < m_cols ? element_delim : (i + 1 < m_rows ? row_delim : end_delim));
+            }
+        }
+        return out;
+    }
+
+private:
+    size_t m_rows, m_cols;
+    std::vector<double> m_data;
+};

@@ -1,0 +1,91 @@
+// module.hpp -- host mirror of the reference's Module plug-in interface and ModuleHandler
+// (source/modules/module.hpp:15-58, modulehandler.hpp:17-39).  A ported module parses its own config block exactly as
+// in the reference and registers itself on the device in setupModule(); its per-step hooks then run inside
+// spruce_advance in config order.  The hook virtuals stay for host-side modules that are not ported.
+#pragma once
+#include "grid.hpp"
+#include <fstream>
+#include <memory>
+#include <string>
+#include <vector>
+
+class PlasmaDomain;
+
+class Module {
+public:
+    explicit Module(PlasmaDomain &pd) : m_pd(pd) {}
+    virtual ~Module() {}
+    void configureModule(std::ifstream &in);
+    virtual void setupModule() {}
+    virtual void iterateModule(double) {}
+    virtual void preIterateModule(double) {}
+    virtual void postIterateModule(double) {}
+    virtual void computeTimeDerivativesModule(const std::vector<Grid> &, std::vector<Grid> &) {}
+    virtual void preRecomputeDerivedModule(std::vector<Grid> &) const {}
+    virtual std::string commandLineMessage() const { return ""; }
+    virtual void fileOutput(std::vector<std::string> &, std::vector<Grid> &) {}
+    virtual std::vector<std::string> config_names() const { return {}; }
+    virtual bool device_resident() const { return false; }   // true: hooks run on the GPU inside spruce_advance
+
+protected:
+    PlasmaDomain &m_pd;
+    virtual void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) = 0;
+};
+
+class ModuleHandler {
+public:
+    explicit ModuleHandler(PlasmaDomain &pd) : m_pd(pd) {}
+    void setupModules();
+    void instantiateModule(const std::string &name, std::ifstream &in, bool active = true);
+    bool isModuleName(const std::string &name) const;
+    std::vector<std::string> getCommandLineMessages() const;
+    void getFileOutputData(std::vector<std::string> &names, std::vector<Grid> &grids) const;
+    bool empty() const { return m_modules.empty(); }
+
+private:
+    PlasmaDomain &m_pd;
+    std::vector<std::unique_ptr<Module>> m_modules;
+    static inline std::vector<std::string> m_module_names = {   // modulehandler.hpp:34-38
+        "radiative_losses", "thermal_conduction", "ambient_heating", "anomalous_resistivity", "momentum_injection", "localized_heating",
+        "field_heating", "tracer_particles", "sg_filtering", "coulomb_explosion", "eic_thermalization", "artificial_viscosity", "global_temperature",
+        "mass_injection", "ambient_heating_sink", "physical_viscosity", "div_cleaning", "boundary_outflow"};
+};
+
+// source/modules/solar/thermalconduction.hpp
+class ThermalConduction : public Module {
+public:
+    explicit ThermalConduction(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override;
+    bool device_resident() const override { return true; }
+private:
+    bool flux_saturation = false, output_to_file = false, inactive_mode = false;
+    double epsilon = 0.0, dt_subcycle_min = 0.0, weakening_factor = 1.0;
+    std::string time_integrator;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+// source/modules/solar/radiativelosses.hpp
+class RadiativeLosses : public Module {
+public:
+    explicit RadiativeLosses(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override;
+    bool device_resident() const override { return true; }
+private:
+    double cutoff_ramp = 0.0, cutoff_temp = 0.0, epsilon = 0.0;
+    bool output_to_file = false, inactive_mode = false, prevent_subcycling = false;
+    std::string time_integrator;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+// source/modules/solar/ambientheating.hpp
+class AmbientHeating : public Module {
+public:
+    explicit AmbientHeating(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override { return exp_mode ? "Ambient Heating On (Exp. Mode)" : "Ambient Heating On"; }
+    bool device_resident() const override { return true; }
+private:
+    double heating_rate = 0.0, exp_base_heating_rate = 0.0, exp_scale_height = 1.0, split_exp_scale_height = 1.0, split_exp_start_height = 0.0;
+    bool exp_mode = false, split_exp_mode = false;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};

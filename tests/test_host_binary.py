@@ -1,0 +1,68 @@
+"""End-to-end drop-in check of the host shell (spruce_b200/bin/run: C++ PlasmaDomain / EquationSet / Module mirror over the
+C ABI) against the UNMODIFIED reference binary (oracle/_ref/run) on the same .state / .config files:
+mhd.out and end.state must be byte-identical for ideal MHD, and numerically within 1e-9 for runs with libm-dependent
+modules.  Both programs end a completed run with SIGABRT (exit status 134), as the reference does on purpose."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import refrun
+from spruce_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+OURS = ROOT / "spruce_b200" / "bin" / "run"
+
+
+def run_ours(state, cfg_text, out_dir):
+    out_dir.mkdir(parents=True, exist_ok=True)
+    (out_dir / "run.config").write_text(cfg_text)
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out_dir), "-s", str(state)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode in (-6, 134), r.stderr.decode()[-2000:]
+    assert "Simulation successfully reached max simulation time or iterations" in r.stderr.decode()
+    return r.stdout.decode()
+
+
+CASES = {
+    "ot_periodic_rk2": (lambda: synthetic.orszag_tang(48, 40, zfull=True), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("periodic", "periodic"), density_min=1.0, temp_min=1.0,
+                        thermal_energy_min=1e-30, max_iterations=12, iter_output_interval=3, write_precision=17), True),
+    "loop_open_reflect_rk4": (lambda: synthetic.stratified_loop(40, 36), dict(integrator="rk4", xb=("reflect", "open"), yb=("fixed", "open"), max_iterations=7, iter_output_interval=2,
+                              output_flags=("rho", "temp", "press", "v_x", "v_y", "v_z", "n", "dt", "b_mag", "b_hat_x", "kinetic_energy", "thermal_energy", "b_x")), True),
+    "loop_time_output_euler": (lambda: synthetic.stratified_loop(36, 30), dict(integrator="euler", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=9, iter_output_interval=-1), True),
+    "loop_solar_modules": (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=5, iter_output_interval=1,
+                           modules=[("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4")]),
+                                    ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
+                                    ("ambient_heating", [("heating_rate", "1.0e-4")])]), False),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_run_binary_matches_reference_files(name, tmp_path):
+    if not OURS.exists():
+        subprocess.run(["make", "-C", str(ROOT / "spruce_b200" / "host")], check=True)
+    assert refrun.have_reference(), "oracle/_ref/run must travel with the repo"
+    gen, ckw, exact = CASES[name]
+    s = gen()
+    state = tmp_path / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"], comments=["# drop-in test " + name])
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, **ckw)
+    if name == "loop_time_output_euler":
+        cfg = cfg.replace("time_output_interval = -1.0", "time_output_interval = 2.0")
+    refrun.run_reference(state, cfg, tmp_path / "ref", threads=4)
+    stdout = run_ours(state, cfg, tmp_path / "ours")
+    for fname in ("mhd.out", "end.state"):
+        a, b = (tmp_path / "ours" / fname).read_bytes(), (tmp_path / "ref" / fname).read_bytes()
+        if exact:
+            assert a == b, "%s differs from the reference's (%d vs %d bytes)" % (fname, len(a), len(b))
+    if not exact:
+        ma, pa = refrun.read_state(tmp_path / "ours" / "end.state")
+        mb, pb = refrun.read_state(tmp_path / "ref" / "end.state")
+        assert ma["t"] == mb["t"] and list(pa) == list(pb)
+        for k in pb:
+            assert np.max(np.abs(pa[k] - pb[k])) <= 1e-9 * max(np.max(np.abs(pb[k])), 1e-300), k
+        _, fa = refrun.read_out(tmp_path / "ours" / "mhd.out")
+        _, fb = refrun.read_out(tmp_path / "ref" / "mhd.out")
+        assert len(fa) == len(fb) and [f["t"] for f in fa] == [f["t"] for f in fb]
+        assert "Thermal Subcycles" in stdout and "Radiative Subcycles" in stdout
