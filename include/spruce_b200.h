@@ -148,6 +148,11 @@ int spruce_mgpu_dt_min_ptr(spruce_domain *dom, void **device_double);   /* 1 dou
 int spruce_mgpu_begin_step(spruce_domain *dom);   /* fixes `step` from the (all-reduced) dt minimum */
 int spruce_mgpu_end_step(spruce_domain *dom);     /* t += step; iter++ */
 
+/* Planes uploaded as identically zero (mom_z, bi_z, be_x, be_y, be_z: bits 0..4) let the stage kernel skip transports that
+ * are exactly zero in the reference as well.  With n_ranks > 1 the knowledge must be global: read the local mask, OR it over
+ * the ranks, set it (set_global_mask < 0: only read). */
+int spruce_plane_activity(spruce_domain *dom, int *local_mask, int set_global_mask);
+
 /* stream on which every kernel of this handle is launched (cudaStream_t as void*), for event timing */
 int spruce_stream(spruce_domain *dom, void **stream);
 int spruce_synchronize(spruce_domain *dom);

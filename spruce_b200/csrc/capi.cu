@@ -4,10 +4,12 @@
 #include "../../include/spruce_b200.h"
 #include "mhd_kernels.cuh"
 #include "module_kernels.cuh"
+#include "mhd_stage_xy.cuh"
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,6 +62,9 @@ struct spruce_domain {
     double *heating = nullptr;
     unsigned long long *red = nullptr;     // 4 reduction scalars for the sub-cycle counts
     double *halo[4] = {nullptr, nullptr, nullptr, nullptr};   // send_lo, send_hi, recv_lo, recv_hi
+    // planes that were uploaded as identically zero: bit 0 mom_z, 1 bi_z, 2 be_x, 3 be_y, 4 be_z (global knowledge; see spruce_plane_activity)
+    unsigned nonzero_mask = 0x1F;
+    int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
 };
 
@@ -183,6 +188,25 @@ int pick_chunk_rows(const spruce_domain *d)
     return rows;
 }
 
+// Transported quantities that can be non-zero.  The z system {mom_z, bi_z} stays identically zero when mom_z, bi_z and be_z
+// are zero planes (idealmhd.cpp:72-73,84-86), and a zero external-field plane is static.
+ActiveList active_quantities(const spruce_domain *d)
+{
+    ActiveList L{};
+    const unsigned m = d->nonzero_mask;
+    const bool zsys = (m & 0x13u) != 0;           // mom_z | bi_z | be_z
+    int n = 0;
+    auto add = [&](int q) { L.q[n++] = (unsigned char)q; };
+    add(Q_RHO); add(Q_E); add(Q_MX); add(Q_MY); add(Q_BIX); add(Q_BIY);
+    if (zsys) { add(Q_MZ); add(Q_BIZ); }
+    if (m & 0x04u) add(Q_BEX);
+    if (m & 0x08u) add(Q_BEY);
+    if (m & 0x10u) add(Q_BEZ);
+    if (n & 1) { L.q[n] = L.q[n - 1]; n++; }      // pad to an even count: the duplicate recomputes the same values
+    L.n = n;
+    return L;
+}
+
 int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode)
 {
     StageArgs A{};
@@ -192,7 +216,8 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.chunk_rows = pick_chunk_rows(d);
     if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
     dim3 grid((d->P.ny + CW - 1) / CW, (d->P.nx + A.chunk_rows - 1) / A.chunk_rows);
-    k_mhd_stage<<<grid, NT, STAGE_SMEM, d->stream>>>(d->P, A);
+    if (d->stage_kernel == 5) k_mhd_stage_xy<<<grid, XY_NT, XY_SMEM, d->stream>>>(d->P, A, active_quantities(d));
+    else k_mhd_stage<<<grid, NT, STAGE_SMEM, d->stream>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
@@ -495,8 +520,10 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
 
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
+    if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     DomainParams &P = d->P;
     P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;
     P.gnx = cfg->xdim; P.row0 = cfg->row0;
@@ -573,6 +600,14 @@ int spruce_grid_upload(spruce_domain *d, const char *name, const double *host, s
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane <%s>: expected %zu values, got %zu", name, (size_t)d->P.nx * d->P.ny, count);
     if (!strcmp(name, "pos_x") || !strcmp(name, "pos_y") || !strcmp(name, "d_x") || !strcmp(name, "d_y")) return SPRUCE_OK; // host-only grids
+    {   // zero-plane bookkeeping for the planes whose transport can be skipped exactly
+        const char *tracked[5] = {"mom_z", "bi_z", "be_x", "be_y", "be_z"};
+        for (int b = 0; b < 5; b++) if (!strcmp(name, tracked[b])) {
+            bool nz = false;
+            for (size_t k = 0; k < count && !nz; k++) nz = (host[k] != 0.0);
+            if (nz) d->nonzero_mask |= (1u << b); else d->nonzero_mask &= ~(1u << b);
+        }
+    }
     const int s = static_slot(name);
     if (s >= 0) return h2d_plane(d, d->stat[s], host);
     const int var = var_index(name);
@@ -855,6 +890,16 @@ int spruce_mgpu_end_step(spruce_domain *d)
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+// Zero-plane knowledge must be GLOBAL with a slab decomposition (a neighbour's halo rows may be non-zero): every rank
+// reports its local mask and sets the OR over all ranks.  bit 0 mom_z, 1 bi_z, 2 be_x, 3 be_y, 4 be_z.
+int spruce_plane_activity(spruce_domain *d, int *local_mask, int set_global_mask)
+{
+    CHECK_DOM(d);
+    if (local_mask) *local_mask = (int)d->nonzero_mask;
+    if (set_global_mask >= 0) d->nonzero_mask = (unsigned)set_global_mask & 0x1Fu;
     return SPRUCE_OK;
 }
 

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
     // ---- x-direction cell-size tables of this chunk (warp-uniform reads from shared memory in the row loop)
     {
         const double *src[7] = {P.tx.h, P.tx.fs, P.tx.rfs, P.tx.ep, P.tx.em, P.tx.d, P.tx.rd};
-        const int nent = (r1 - r0) + 8;
+        const int nent = (r1 - r0) + 6;     // local rows -3 .. chunk+2
         for (int e = tid; e < 7 * XT; e += NT) {
             const int t = e / XT, i = e - t * XT;
             if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
             if (q == Q_BIZ) cIx_biz = d2;
         }
     }
+    __syncthreads();      // row r0-2 was read above; its ring slot is the prefetch target of the first iteration
 
     double dtmin_local = 1.7976931348623157e308;
 
@@ -363,16 +364,16 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
 
         // own-cell values that come from global memory are requested now and consumed after the transport loop
         const size_t off = (size_t)r * P.pitch + (col_out ? j : 0);     // destination / base offset (local, unwrapped)
-        double gxv = 0.0, gyv = 0.0, Bv[NEV];
+        // (no branch on col_out: a divergent branch here would leave the warp split for the whole transport loop)
+        double gxv, gyv, Bv[NEV];
 #pragma unroll
         for (int v = 0; v < NEV; v++) Bv[v] = 0.0;
-        if (col_out) {
-            gxv = A.st[S_GX][off]; gyv = A.st[S_GY][off];
-            if (!A.b_is_s) {
+        gxv = A.st[S_GX][off]; gyv = A.st[S_GY][off];
+        if (!A.b_is_s) {
 #pragma unroll
-                for (int v = 0; v < NEV; v++) Bv[v] = A.B[v][off];
-            }
+            for (int v = 0; v < NEV; v++) Bv[v] = A.B[v][off];
         }
+        __syncwarp();
 
         // ---------------- x face r+1 (between rows r and r+1): velocity, pressure
         const FaceGeom gx = x_geom(r + 1);

@@ -1,0 +1,345 @@
+// mhd_stage_xy.cuh -- the fused Runge-Kutta stage kernel, direction-specialised warps ("v5").
+//
+// Same arithmetic and the same outputs, bit for bit, as k_mhd_stage (mhd_kernels.cuh); different work split.
+// The column-marching kernel is bound by dependency latency at 8 warps/SM: the shared-memory ring (5 rows x 14 arrays)
+// and ~200 registers per thread cap the residency.  Here a CTA still owns 62 columns and marches along x, but FOUR
+// warps share the ring:
+//     warps 0,1 ("X")  evaluate the x-direction faces of the transported quantities (flux carried row to row),
+//                      the x central derivatives, and finish the outputs  n, mom_x, mom_y, mom_z;
+//     warps 2,3 ("Y")  evaluate the y-direction faces (left face per lane, right face by shuffle), the y central
+//                      derivatives, finish  thermal_energy, bi_x, bi_y, bi_z  and the cell's dt.
+// Partial results cross through small shared-memory arrays at one barrier per row (two in the final stage, for dt).
+// Per-thread state halves (<= 128 registers), 16 warps/SM are resident on the same shared-memory budget.
+//
+// Zero planes: the z system {mom_z, bi_z} stays identically zero when mom_z, bi_z and be_z start as zero planes
+// (idealmhd.cpp:72-73,84-86: every term of d(mom_z)/dt and d(bi_z)/dt carries one of them), and a zero external-field
+// plane is static.  The host tracks this (capi.cu: active_quantities) and hands the kernel the list of transported
+// quantities that can be non-zero; the others contribute exact zeros in the reference too and are not evaluated.
+#pragma once
+#include "mhd_kernels.cuh"
+
+namespace spruce {
+
+constexpr int XY_NT = 128;                   // 2 X warps + 2 Y warps
+constexpr int XY_RV = 3;                     // velocity ring depth (rows r, r+1 in use, r+2 being formed)
+constexpr int XY_XT = MAX_CHUNK + 8;
+// shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, T exchange, derivative exchange, dt exchange
+constexpr int XY_OFF_RING = 0;
+constexpr int XY_OFF_VEL = XY_OFF_RING + RD * NTR * SW;
+constexpr int XY_OFF_XT = XY_OFF_VEL + XY_RV * 3 * SW;
+constexpr int XY_OFF_FX = XY_OFF_XT + 7 * XY_XT;
+constexpr int XY_OFF_TQ = XY_OFF_FX + NTR * 64;
+constexpr int XY_OFF_DC = XY_OFF_TQ + NTR * 64;
+constexpr int XY_OFF_DT = XY_OFF_DC + 6 * 64;
+constexpr int XY_DOUBLES = XY_OFF_DT + 3 * 64;
+constexpr size_t XY_SMEM = (size_t)XY_DOUBLES * sizeof(double);
+
+struct ActiveList { int n; unsigned char q[12]; };    // transported quantities that can be non-zero, padded to an even count
+
+__global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList L)
+{
+    extern __shared__ __align__(16) double smem[];
+    if (*A.done_ptr) return;
+    double (*ring)[NTR][SW] = reinterpret_cast<double (*)[NTR][SW]>(smem + XY_OFF_RING);
+    double (*vel)[3][SW] = reinterpret_cast<double (*)[3][SW]>(smem + XY_OFF_VEL);
+    double (*xt)[XY_XT] = reinterpret_cast<double (*)[XY_XT]>(smem + XY_OFF_XT);
+    double (*Fx_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_FX);
+    double (*Tq_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_TQ);
+    double (*Dc_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_DC);
+    double (*Dt_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_DT);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool isX = warp < 2;
+    const int wcol = warp & 1;
+    const int ccol = 31 * wcol + lane;            // column inside the CTA; lane 31 duplicates the next warp's lane 0
+    const int col = 32 * wcol + lane;             // slot in the per-column exchange arrays
+    const int j0 = blockIdx.x * CW;
+    const int j = j0 + ccol;
+    const int c = ccol + HALO;
+    const int r0 = blockIdx.y * A.chunk_rows;
+    const int r1 = min(r0 + A.chunk_rows, P.nx);
+    const bool col_out = (lane < 31) && (j < P.ny);
+
+    // ---- loader: thread t < SW owns shared column t
+    const bool loader = tid < SW;
+    int jl = j0 - HALO + tid;
+    bool jl_ok = loader && (jl >= 0 && jl < P.ny);
+    if (loader && !jl_ok && P.yper) { jl = (jl + 2 * P.ny) % P.ny; jl_ok = true; }
+    auto slot_of = [&](int r) { return (r - r0 + HALO + RD) % RD; };
+    auto vslot_of = [&](int r) { return (r - r0 + HALO + 3 * XY_RV) % XY_RV; };
+    auto issue_row = [&](int r) {
+        if (!loader) return;
+        const int slot = slot_of(r);
+        if (row_exists(P, r) && jl_ok) {
+            const size_t off = (size_t)phys_row(P, r) * P.pitch + jl;
+#pragma unroll
+            for (int v = 0; v < NEV; v++) cp_async8(&ring[slot][v][tid], A.S[v] + off);
+            cp_async8(&ring[slot][Q_BEX][tid], A.st[S_BEX] + off);
+            cp_async8(&ring[slot][Q_BEY][tid], A.st[S_BEY] + off);
+            cp_async8(&ring[slot][Q_BEZ][tid], A.st[S_BEZ] + off);
+        } else {
+#pragma unroll
+            for (int v = 0; v < NTR; v++) ring[slot][v][tid] = (v == Q_RHO) ? 1.0 : 0.0;
+        }
+    };
+    auto convert_rho = [&](int r) { if (loader) { const int s_ = slot_of(r); ring[s_][Q_RHO][tid] = ring[s_][Q_RHO][tid] * P.m_i; } };   // idealmhd.cpp:247
+    auto form_vel = [&](int r) {                                                                                                       // idealmhd.cpp:248-250
+        if (!loader) return;
+        const int s_ = slot_of(r), v_ = vslot_of(r);
+        const double rho = ring[s_][Q_RHO][tid];
+        vel[v_][0][tid] = ring[s_][Q_MX][tid] / rho;
+        vel[v_][1][tid] = ring[s_][Q_MY][tid] / rho;
+        vel[v_][2][tid] = ring[s_][Q_MZ][tid] / rho;
+    };
+
+    const double step = *A.step_ptr;
+    const double s = A.coef * step;
+
+    // ---- x tables of this chunk and zeroed exchange arrays (inactive quantities read as exact zeros)
+    {
+        const double *src[7] = {P.tx.h, P.tx.fs, P.tx.rfs, P.tx.ep, P.tx.em, P.tx.d, P.tx.rd};
+        const int nent = (r1 - r0) + 6;     // local rows -3 .. chunk+2: everything x_geom() touches, nothing past the table apron
+        for (int e = tid; e < 7 * XY_XT; e += XY_NT) {
+            const int t = e / XY_XT, i = e - t * XY_XT;
+            if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
+        }
+        for (int e = tid; e < 2 * NTR * 64; e += XY_NT) (&Fx_s[0][0])[e] = 0.0;      // Fx_s and Tq_s are contiguous
+    }
+    auto x_geom = [&](int f) {
+        const int i = f - r0 + 3;
+        FaceGeom g;
+        g.hm1 = xt[0][i - 1]; g.h0 = xt[0][i];
+        g.fs = xt[1][i];      g.rfs = xt[2][i];
+        g.ep = xt[3][i];      g.fsm = xt[1][i - 1]; g.rfsm = xt[2][i - 1];
+        g.em = xt[4][i];      g.fsp = xt[1][i + 1]; g.rfsp = xt[2][i + 1];
+        return g;
+    };
+
+    // ---- per-thread y geometry (Y warps: left face of column j; both roles: cell size)
+    const int jt = min(j, P.ny + 1);
+    const FaceGeom gy = load_face_geom(P.ty, jt);
+    const double dy = P.ty.d[min(j, P.ny)], rdy = P.ty.rd[min(j, P.ny)];
+
+    // ---- prologue: rows r0-2 .. r0+2 land, rho is formed for all of them, velocity for rows r0-1, r0, r0+1
+    for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r);
+    cp_async_commit();
+    cp_async_wait_all();
+    for (int r = r0 - HALO; r <= r0 + HALO; r++) convert_rho(r);
+    for (int r = r0 - 1; r <= r0 + 1; r++) form_vel(r);
+    __syncthreads();
+
+    // X warps: carries of face r0 (between rows r0-1 and r0)
+    double cIx_biy = 0.0, cIx_biz = 0.0, cIx_p = 0.0, cVfx = 0.0, cIx_vy = 0.0, cIx_vz = 0.0;
+    if (isX) {
+        const FaceGeom g = x_geom(r0);
+        const int sm2 = slot_of(r0 - 2), sm1 = slot_of(r0 - 1), s0 = slot_of(r0), sp1 = slot_of(r0 + 1);
+        const int vm1 = vslot_of(r0 - 1), v0 = vslot_of(r0);
+        cVfx = face_interp(vel[vm1][0][c], vel[v0][0][c], g.hm1, g.h0, g.fs, g.rfs);
+        cIx_vy = face_interp(vel[vm1][1][c], vel[v0][1][c], g.hm1, g.h0, g.fs, g.rfs);
+        cIx_vz = face_interp(vel[vm1][2][c], vel[v0][2][c], g.hm1, g.h0, g.fs, g.rfs);
+        cIx_p = face_interp(ring[sm1][Q_E][c] * P.gm1, ring[s0][Q_E][c] * P.gm1, g.hm1, g.h0, g.fs, g.rfs);
+        const FaceSel fs0 = select_face(g, cVfx);
+#pragma unroll 1
+        for (int k = 0; k < L.n; k++) {
+            const int q = L.q[k];
+            double d2;
+            const double S = upwind_face_sel(ring[sm2][q][c], ring[sm1][q][c], ring[s0][q][c], ring[sp1][q][c], fs0, &d2);
+            Fx_s[q][col] = S * cVfx;
+            if (q == Q_BIY) cIx_biy = d2;
+            if (q == Q_BIZ) cIx_biz = d2;
+        }
+    }
+    __syncthreads();      // row r0-2 was read above; its ring slot is the prefetch target of the first iteration
+
+    double dtmin_local = 1.7976931348623157e308;
+
+    for (int r = r0; r < r1; r++) {
+        const bool pre = (r + 3 <= r1 + HALO - 1);
+        if (pre) issue_row(r + 3);
+        cp_async_commit();
+
+        const int sm1 = slot_of(r - 1), s0 = slot_of(r), sp1 = slot_of(r + 1), sp2 = slot_of(r + 2);
+        const int v0 = vslot_of(r), v1 = vslot_of(r + 1);
+        const int g = P.row0 + r;
+        const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
+        const double dx = xt[5][r - r0 + 3], rdx = xt[6][r - r0 + 3];
+        const size_t off = (size_t)r * P.pitch + (col_out ? j : 0);
+        const double pc = ring[s0][Q_E][c] * P.gm1;                 // press = (gamma-1)*thermal_energy  idealmhd.cpp:253
+
+        // own-cell values from global memory: requested now, consumed after the barrier
+        // (no branch on col_out here: lanes without an output column read column 0 of the row -- a divergent branch at this
+        //  point would leave the warp split, and un-reconverged, for the whole of phase 1)
+        double g0, g1, B0 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;
+        {
+            const double *pa = isX ? A.st[S_GX] : A.B[E_E], *pb = isX ? A.st[S_GY] : A.B[E_BX];
+            g0 = pa[off]; g1 = pb[off];                      // X: gravity ; Y: B[thermal_energy], B[bi_x]
+            if (!A.b_is_s) {                                 // warp-uniform
+                const double *p0 = isX ? A.B[E_N] : A.B[E_BY], *p1 = isX ? A.B[E_MX] : A.B[E_BZ], *p2 = isX ? A.B[E_MY] : A.B[E_BY], *p3 = isX ? A.B[E_MZ] : A.B[E_BZ];
+                B0 = p0[off]; B1 = p1[off]; B2 = p2[off]; B3 = p3[off];
+            }
+        }
+        __syncwarp();
+
+        // ================================================================ phase 1: one direction per warp
+        double T0 = 0.0, T1 = 0.0, T2 = 0.0, T3 = 0.0, T4 = 0.0, T5 = 0.0, T6 = 0.0;   // own-direction parts of the own outputs' transports
+        double d_a = 0.0, d_b = 0.0, d_c = 0.0, d_d = 0.0, d_e = 0.0, d_f = 0.0;       // central derivatives kept by this role
+        if (isX) {
+            // ---- x face r+1 (between rows r and r+1)
+            const FaceGeom gx = x_geom(r + 1);
+            const double vfx1 = face_interp(vel[v0][0][c], vel[v1][0][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
+            const double Ix1_vy = face_interp(vel[v0][1][c], vel[v1][1][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
+            const double Ix1_vz = face_interp(vel[v0][2][c], vel[v1][2][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
+            const double Ix1_p = face_interp(pc, ring[sp1][Q_E][c] * P.gm1, gx.hm1, gx.h0, gx.fs, gx.rfs);
+            const FaceSel fsx = select_face(gx, vfx1);
+            double Ix1_biy = 0.0, Ix1_biz = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < L.n; k += 2) {
+                const int qa = L.q[k], qb = L.q[k + 1];
+                double ad2, bd2;
+                const double aS = upwind_face_sel(ring[sm1][qa][c], ring[s0][qa][c], ring[sp1][qa][c], ring[sp2][qa][c], fsx, &ad2);
+                const double bS = upwind_face_sel(ring[sm1][qb][c], ring[s0][qb][c], ring[sp1][qb][c], ring[sp2][qb][c], fsx, &bd2);
+                const double af1 = aS * vfx1, bf1 = bS * vfx1;
+                const double at = ddiv(af1 - Fx_s[qa][col], dx, rdx), bt = ddiv(bf1 - Fx_s[qb][col], dx, rdx);   // derivs.cpp:155-156
+                Fx_s[qa][col] = af1; Fx_s[qb][col] = bf1;
+                if (qa > Q_MZ) Tq_s[qa][col] = at;                    // x parts of the Y-owned transports cross to the Y warps
+                if (qb > Q_MZ) Tq_s[qb][col] = bt;
+                if (qa == Q_RHO) T0 = at; if (qb == Q_RHO) T0 = bt;
+                if (qa == Q_MX) T1 = at;  if (qb == Q_MX) T1 = bt;
+                if (qa == Q_MY) T2 = at;  if (qb == Q_MY) T2 = bt;
+                if (qa == Q_MZ) T3 = at;  if (qb == Q_MZ) T3 = bt;
+                if (qa == Q_BIY) Ix1_biy = ad2; if (qb == Q_BIY) Ix1_biy = bd2;
+                if (qa == Q_BIZ) Ix1_biz = ad2; if (qb == Q_BIZ) Ix1_biz = bd2;
+            }
+            d_a = ddiv(Ix1_biy - cIx_biy, dx, rdx);                 // d(bi_y)/dx
+            d_b = ddiv(Ix1_biz - cIx_biz, dx, rdx);                 // d(bi_z)/dx
+            d_c = ddiv(Ix1_p - cIx_p, dx, rdx);                     // d(p)/dx
+            Dc_s[0][col] = ddiv(vfx1 - cVfx, dx, rdx);              // d(v_x)/dx  -> Y
+            Dc_s[1][col] = ddiv(Ix1_vy - cIx_vy, dx, rdx);          // d(v_y)/dx  -> Y
+            Dc_s[2][col] = ddiv(Ix1_vz - cIx_vz, dx, rdx);          // d(v_z)/dx  -> Y
+            cIx_biy = Ix1_biy; cIx_biz = Ix1_biz; cIx_p = Ix1_p; cVfx = vfx1; cIx_vy = Ix1_vy; cIx_vz = Ix1_vz;
+        } else {
+            // ---- y face j (left face of this column); the right face comes from lane+1
+            const double vxc = vel[v0][0][c], vyc = vel[v0][1][c], vzc = vel[v0][2][c];
+            const double vfyL = face_interp(vel[v0][1][c - 1], vyc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+            const double IyL_vx = face_interp(vel[v0][0][c - 1], vxc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+            const double IyL_vz = face_interp(vel[v0][2][c - 1], vzc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+            const double IyL_p = face_interp(ring[s0][Q_E][c - 1] * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+            const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = shfl_next(IyL_vz), IyR_p = shfl_next(IyL_p);
+            const FaceSel fsy = select_face(gy, vfyL);
+            double IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < L.n; k += 2) {
+                const int qa = L.q[k], qb = L.q[k + 1];
+                double ad2, bd2;
+                const double aS = upwind_face_sel(ring[s0][qa][c - 2], ring[s0][qa][c - 1], ring[s0][qa][c], ring[s0][qa][c + 1], fsy, &ad2);
+                const double bS = upwind_face_sel(ring[s0][qb][c - 2], ring[s0][qb][c - 1], ring[s0][qb][c], ring[s0][qb][c + 1], fsy, &bd2);
+                const double afL = aS * vfyL, bfL = bS * vfyL;
+                const double afR = shfl_next(afL), bfR = shfl_next(bfL), ad2R = shfl_next(ad2), bd2R = shfl_next(bd2);
+                const double at = ddiv(afR - afL, dy, rdy), bt = ddiv(bfR - bfL, dy, rdy);
+                // Tq_s is split by ownership: X reads Tq_s[RHO,MX,MY,MZ] (the y parts, written here), Y reads Tq_s[E,BI*,BE*] (written by X)
+                if (qa <= Q_MZ) Tq_s[qa][col] = at;
+                if (qb <= Q_MZ) Tq_s[qb][col] = bt;
+                if (qa == Q_E) T0 = at;   if (qb == Q_E) T0 = bt;
+                if (qa == Q_BIX) T1 = at; if (qb == Q_BIX) T1 = bt;
+                if (qa == Q_BIY) T2 = at; if (qb == Q_BIY) T2 = bt;
+                if (qa == Q_BIZ) T3 = at; if (qb == Q_BIZ) T3 = bt;
+                if (qa == Q_BEX) T4 = at; if (qb == Q_BEX) T4 = bt;
+                if (qa == Q_BEY) T5 = at; if (qb == Q_BEY) T5 = bt;
+                if (qa == Q_BEZ) T6 = at; if (qb == Q_BEZ) T6 = bt;
+                if (qa == Q_BIX) { IyL_bix = ad2; IyR_bix = ad2R; } if (qb == Q_BIX) { IyL_bix = bd2; IyR_bix = bd2R; }
+                if (qa == Q_BIZ) { IyL_biz = ad2; IyR_biz = ad2R; } if (qb == Q_BIZ) { IyL_biz = bd2; IyR_biz = bd2R; }
+            }
+            Dc_s[3][col] = ddiv(IyR_bix - IyL_bix, dy, rdy);        // d(bi_x)/dy -> X
+            Dc_s[4][col] = ddiv(IyR_biz - IyL_biz, dy, rdy);        // d(bi_z)/dy -> X
+            Dc_s[5][col] = ddiv(IyR_p - IyL_p, dy, rdy);            // d(p)/dy    -> X
+            d_d = ddiv(vfyR - vfyL, dy, rdy);                       // d(v_y)/dy
+            d_e = ddiv(IyR_vx - IyL_vx, dy, rdy);                   // d(v_x)/dy
+            d_f = ddiv(IyR_vz - IyL_vz, dy, rdy);                   // d(v_z)/dy
+        }
+        __syncthreads();                                            // partial results are visible to the other role
+
+        // ================================================================ phase 2: finish the outputs
+        __syncwarp();
+        double e1 = 0.0, Ubx = 0.0, Uby = 0.0, Ubz = 0.0;           // Y keeps its new values for dt
+        if (col_out) {
+            const double bix = ring[s0][Q_BIX][c], biy = ring[s0][Q_BIY][c], biz = ring[s0][Q_BIZ][c];
+            const double bex = ring[s0][Q_BEX][c], bey = ring[s0][Q_BEY][c], bez = ring[s0][Q_BEZ][c];
+            if (isX) {
+                const double rho = ring[s0][Q_RHO][c];
+                const double dbix_dy = Dc_s[3][col], dbiz_dy = Dc_s[4][col], dp_dy = Dc_s[5][col];
+                const double T_rho = T0 + Tq_s[Q_RHO][col], T_mx = T1 + Tq_s[Q_MX][col], T_my = T2 + Tq_s[Q_MY][col], T_mz = T3 + Tq_s[Q_MZ][col];
+                double k0 = T_rho * -1.0;                                                        // idealmhd.cpp:52
+                const double cdb = ddiv(d_a - dbix_dy, P.fourpi, P.rfourpi);                    // :54
+                const double ncdb = cdb * -1.0;
+                const double czx = dbiz_dy, czy = d_b * -1.0;                                   // curlZ, derivs.cpp:465-469
+                const double bzi = ddiv(biz, P.fourpi, P.rfourpi), bze = ddiv(bez, P.fourpi, P.rfourpi);   // :57-58
+                double k1 = ((((((T_mx * -1.0) - d_c) + rho * g0) + ncdb * bey) + ncdb * biy) + bzi * czy) + bze * czy;                       // :62-66
+                double k2 = ((((((T_my * -1.0) - dp_dy) + rho * g1) + cdb * bex) + cdb * bix) + (bzi * -1.0) * czx) + (bze * -1.0) * czx;   // :67-71
+                const double fze = ddiv(czx * bey - czy * bex, P.fourpi, P.rfourpi);            // :59
+                const double fzi = ddiv(czx * biy - czy * bix, P.fourpi, P.rfourpi);            // :60
+                double k3 = ((T_mz * -1.0) + fze) + fzi;                                        // :72-73
+                if (!interior) { k0 = 0.0; k1 = 0.0; k2 = 0.0; k3 = 0.0; }                      // ghost mask :99-103
+                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_N][off] = k0; A.K1[E_MX][off] = k1; A.K1[E_MY][off] = k2; A.K1[E_MZ][off] = k3; }
+                else if (A.kmode == KM_STORE_K2) { A.K2[E_N][off] = k0; A.K2[E_MX][off] = k1; A.K2[E_MY][off] = k2; A.K2[E_MZ][off] = k3; }
+                else if (A.kmode == KM_ADD_K2) { A.K2[E_N][off] = A.K2[E_N][off] + k0; A.K2[E_MX][off] = A.K2[E_MX][off] + k1; A.K2[E_MY][off] = A.K2[E_MY][off] + k2; A.K2[E_MZ][off] = A.K2[E_MZ][off] + k3; }
+                else if (A.kmode == KM_FINAL) {                                                 // evolution.cpp:121
+                    k0 = (A.K1[E_N][off] + k0) / 6.0 + A.K2[E_N][off] / 3.0;   k1 = (A.K1[E_MX][off] + k1) / 6.0 + A.K2[E_MX][off] / 3.0;
+                    k2 = (A.K1[E_MY][off] + k2) / 6.0 + A.K2[E_MY][off] / 3.0; k3 = (A.K1[E_MZ][off] + k3) / 6.0 + A.K2[E_MZ][off] / 3.0;
+                }
+                if (A.kmode != KM_EXPORT) {
+                    double Un, Umx, Umy, Umz;                                                   // equationset.cpp:226-228
+                    if (A.b_is_s) { Un = rho + k0 * s; Umx = ring[s0][Q_MX][c] + k1 * s; Umy = ring[s0][Q_MY][c] + k2 * s; Umz = ring[s0][Q_MZ][c] + k3 * s; }
+                    else { Un = (B0 * P.m_i) + k0 * s; Umx = B1 + k1 * s; Umy = B2 + k2 * s; Umz = B3 + k3 * s; }
+                    double rfl;
+                    const double nn = density_floor(P, Un, &rfl);
+                    if (A.primary) {
+                        const unsigned z = zero_zones(P, g, j);
+                        record_strips(P, A.strip, A.strip_pitch, g, r, j, z, rfl, Umx, Umy, Umz);
+                        if (z) { Umx = 0.0; Umy = 0.0; Umz = 0.0; }
+                    }
+                    A.D[E_N][off] = nn; A.D[E_MX][off] = Umx; A.D[E_MY][off] = Umy; A.D[E_MZ][off] = Umz;
+                    if (A.primary) { Dt_s[0][col] = nn * P.m_i; Dt_s[1][col] = Umx; Dt_s[2][col] = Umy; }
+                }
+            } else {
+                const double dvx_dx = Dc_s[0][col], dvy_dx = Dc_s[1][col], dvz_dx = Dc_s[2][col];
+                const double T_e = Tq_s[Q_E][col] + T0, T_bix = Tq_s[Q_BIX][col] + T1, T_biy = Tq_s[Q_BIY][col] + T2, T_biz = Tq_s[Q_BIZ][col] + T3;
+                const double T_bex = Tq_s[Q_BEX][col] + T4, T_bey = Tq_s[Q_BEY][col] + T5, T_bez = Tq_s[Q_BEZ][col] + T6;
+                double k4 = (T_e * -1.0) - pc * (dvx_dx + d_d);                                 // :75-76
+                const double bxs = bix + bex, bys = biy + bey;
+                double k5 = (((T_bix * -1.0) - T_bex) + bxs * dvx_dx) + bys * d_e;              // :78-80
+                double k6 = (((T_biy * -1.0) - T_bey) + bxs * dvy_dx) + bys * d_d;              // :81-83
+                double k7 = (((T_biz * -1.0) - T_bez) + bxs * dvz_dx) + bys * d_f;              // :84-86
+                if (!interior) { k4 = 0.0; k5 = 0.0; k6 = 0.0; k7 = 0.0; }
+                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_E][off] = k4; A.K1[E_BX][off] = k5; A.K1[E_BY][off] = k6; A.K1[E_BZ][off] = k7; }
+                else if (A.kmode == KM_STORE_K2) { A.K2[E_E][off] = k4; A.K2[E_BX][off] = k5; A.K2[E_BY][off] = k6; A.K2[E_BZ][off] = k7; }
+                else if (A.kmode == KM_ADD_K2) { A.K2[E_E][off] = A.K2[E_E][off] + k4; A.K2[E_BX][off] = A.K2[E_BX][off] + k5; A.K2[E_BY][off] = A.K2[E_BY][off] + k6; A.K2[E_BZ][off] = A.K2[E_BZ][off] + k7; }
+                else if (A.kmode == KM_FINAL) {
+                    k4 = (A.K1[E_E][off] + k4) / 6.0 + A.K2[E_E][off] / 3.0;   k5 = (A.K1[E_BX][off] + k5) / 6.0 + A.K2[E_BX][off] / 3.0;
+                    k6 = (A.K1[E_BY][off] + k6) / 6.0 + A.K2[E_BY][off] / 3.0; k7 = (A.K1[E_BZ][off] + k7) / 6.0 + A.K2[E_BZ][off] / 3.0;
+                }
+                if (A.kmode != KM_EXPORT) {
+                    double Ue;
+                    if (A.b_is_s) { Ue = ring[s0][Q_E][c] + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = biz + k7 * s; }
+                    else { Ue = g0 + k4 * s; Ubx = g1 + k5 * s; Uby = B0 + k6 * s; Ubz = B1 + k7 * s; }     // Y's base values were prefetched into g0, g1, B0, B1
+                    e1 = smax(Ue, P.e_min);
+                    A.D[E_E][off] = e1; A.D[E_BX][off] = Ubx; A.D[E_BY][off] = Uby; A.D[E_BZ][off] = Ubz;
+                    Ubx = bex + Ubx; Uby = bey + Uby; Ubz = bez + Ubz;                           // total field for dt
+                }
+            }
+        }
+        if (A.primary && A.kmode != KM_EXPORT) {
+            __syncthreads();                                        // rho, mom_x, mom_y of the X warps are visible
+            if (!isX && interior) {
+                const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], e1, Ubx, Uby, Ubz, dx, rdx, dy, rdy);
+                dtmin_local = smin(dtmin_local, dtc);
+            }
+        }
+        cp_async_wait_all();
+        if (pre) convert_rho(r + 3);                                // the row that just landed
+        if (r + 2 <= r1) form_vel(r + 2);                           // into the velocity slot of row r-1 (dead since the last barrier)
+        __syncthreads();
+    }
+    if (A.primary && A.kmode != KM_EXPORT) block_min_to_global(dtmin_local, A.dtmin_bits);
+}
+
+}  // namespace spruce

@@ -101,6 +101,13 @@ class SlabRunner:
             capi.check(self.lib.spruce_mgpu_stage_output(self.dom.h, s, C.byref(w)))
             self.out_set.append(w.value)
         # setup = local populateVariablesFromState, then halos of the primary state and the global dt minimum
+        # zero-plane knowledge must be global (a neighbour's halo rows may be non-zero): OR the per-rank masks
+        lm = C.c_int()
+        capi.check(self.lib.spruce_plane_activity(self.dom.h, C.byref(lm), -1))
+        bits = torch.tensor([(lm.value >> b) & 1 for b in range(5)], dtype=torch.int32, device="cuda")
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX)
+        gm = sum(int(v) << b for b, v in enumerate(bits.tolist()))
+        capi.check(self.lib.spruce_plane_activity(self.dom.h, None, gm))
         self.dom.setup()
         with torch.cuda.stream(self.stream):
             capi.check(self.lib.spruce_mgpu_pack(self.dom.h, 3))        # static planes: be_* are transported and need halo rows
