@@ -183,7 +183,7 @@ int pick_chunk_rows(const spruce_domain *d)
 {
     // enough CTAs for >= ~4 waves of 148 SMs x resident CTAs, but chunks of at least 16 rows (4 warm-up rows each)
     const int strips = (d->P.ny + CW - 1) / CW;
-    int rows = MAX_CHUNK;
+    int rows = d->stage_kernel == 5 ? XY_CHUNK : MAX_CHUNK;
     while (rows > 16 && (long long)strips * ((d->P.nx + rows - 1) / rows) < 148LL * 5 * 4) rows >>= 1;
     return rows;
 }
@@ -195,14 +195,14 @@ ActiveList active_quantities(const spruce_domain *d)
     ActiveList L{};
     const unsigned m = d->nonzero_mask;
     const bool zsys = (m & 0x13u) != 0;           // mom_z | bi_z | be_z
-    int n = 0;
-    auto add = [&](int q) { L.q[n++] = (unsigned char)q; };
+    int n = 0, last = 0;
+    auto add = [&](int q) { L.q |= (unsigned long long)q << (4 * n); n++; last = q; };
     add(Q_RHO); add(Q_E); add(Q_MX); add(Q_MY); add(Q_BIX); add(Q_BIY);
     if (zsys) { add(Q_MZ); add(Q_BIZ); }
     if (m & 0x04u) add(Q_BEX);
     if (m & 0x08u) add(Q_BEY);
     if (m & 0x10u) add(Q_BEZ);
-    if (n & 1) { L.q[n] = L.q[n - 1]; n++; }      // pad to an even count: the duplicate recomputes the same values
+    if (n & 1) add(last);                         // pad to an even count: the duplicate recomputes the same values
     L.n = n;
     return L;
 }

@@ -116,6 +116,24 @@ __device__ __forceinline__ double upwind_face_sel(double qm2, double qm1, double
     return f.any ? r : d2;
 }
 
+// Same face value when the caller has already picked the far cell of the extrapolation (q[f-2] for flow in the + direction,
+// q[f+1] for the - direction): far, qm1 = q[f-1], q0 = q[f].
+__device__ __forceinline__ double upwind_face_far(double far, double qm1, double q0, const FaceSel &f, double *d2out)
+{
+    const double d2 = face_interp(qm1, q0, f.hm1, f.h0, f.fs, f.rfs);
+    *d2out = d2;
+    const double b = f.pos ? qm1 : q0;          // d3, the upwind cell value
+    const double d1 = far + ddiv((b - far) * f.w, f.den, f.rden);
+    const bool min_outer = (f.pos == (q0 <= qm1));
+    const unsigned hm = min_outer ? 0u : 0x80000000u;       // flip the sign bit (high word only) when the max-outer form is required
+    const double fb = __hiloint2double(__double2hiint(b) ^ hm, __double2loint(b));
+    const double f1 = __hiloint2double(__double2hiint(d1) ^ hm, __double2loint(d1));
+    const double f2 = __hiloint2double(__double2hiint(d2) ^ hm, __double2loint(d2));
+    const double m = smin(fb, smax(f1, f2));
+    const double r = __hiloint2double(__double2hiint(m) ^ hm, __double2loint(m));
+    return f.any ? r : d2;
+}
+
 // exact test "all eight values are +-0" on the integer pipe
 __device__ __forceinline__ bool all_zero8(double a, double b, double c, double d, double e, double f, double g, double h)
 {

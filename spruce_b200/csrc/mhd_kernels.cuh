@@ -188,7 +188,7 @@ __device__ __forceinline__ double cell_dt(const DomainParams &P, double rho, dou
 }
 
 // block-wide NaN-ignoring minimum of positive doubles -> atomicMin on the ordered bit pattern
-__device__ __forceinline__ void block_min_to_global(double v, unsigned long long *target)
+__device__ __forceinline__ void block_min_impl(double v, unsigned long long *target, unsigned long long *wmin)
 {
     unsigned long long b = (v == v) ? (unsigned long long)__double_as_longlong(v) : 0x7FF0000000000000ULL;
     if (v < 0.0) b = 0ULL;   // cannot happen for a valid dt; keeps ordering total
@@ -197,7 +197,6 @@ __device__ __forceinline__ void block_min_to_global(double v, unsigned long long
         unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
         b = (t < b) ? t : b;
     }
-    __shared__ unsigned long long wmin[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) wmin[w] = b;
     __syncthreads();
@@ -206,6 +205,11 @@ __device__ __forceinline__ void block_min_to_global(double v, unsigned long long
         for (int k = 1; k < nw; k++) b = (wmin[k] < b) ? wmin[k] : b;
         atomicMin(target, b);
     }
+}
+__device__ __forceinline__ void block_min_to_global(double v, unsigned long long *target)
+{
+    __shared__ unsigned long long wmin[32];
+    block_min_impl(v, target, wmin);
 }
 
 // ---------------------------------------------------------------------------------------------------------

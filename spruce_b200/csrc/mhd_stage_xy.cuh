@@ -22,19 +22,24 @@ namespace spruce {
 
 constexpr int XY_NT = 128;                   // 2 X warps + 2 Y warps
 constexpr int XY_RV = 3;                     // velocity ring depth (rows r, r+1 in use, r+2 being formed)
-constexpr int XY_XT = MAX_CHUNK + 8;
-// shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, T exchange, derivative exchange, dt exchange
+constexpr int XY_CHUNK = 32;                 // rows per CTA (upper bound)
+constexpr int XY_XT = XY_CHUNK + 6;          // x-table entries: local rows -3 .. chunk+2
+constexpr int XW = 64;                       // width of the per-column exchange arrays: one private slot per (warp column, lane)
+// shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, x / y parts of the transports,
+// derivative exchange, dt exchange (read by the Y warps one iteration later, before the X warps overwrite it)
 constexpr int XY_OFF_RING = 0;
 constexpr int XY_OFF_VEL = XY_OFF_RING + RD * NTR * SW;
 constexpr int XY_OFF_XT = XY_OFF_VEL + XY_RV * 3 * SW;
 constexpr int XY_OFF_FX = XY_OFF_XT + 7 * XY_XT;
-constexpr int XY_OFF_TQ = XY_OFF_FX + NTR * 64;
-constexpr int XY_OFF_DC = XY_OFF_TQ + NTR * 64;
-constexpr int XY_OFF_DT = XY_OFF_DC + 6 * 64;
-constexpr int XY_DOUBLES = XY_OFF_DT + 3 * 64;
+constexpr int XY_OFF_TX = XY_OFF_FX + NTR * XW;
+constexpr int XY_OFF_TY = XY_OFF_TX + NTR * XW;
+constexpr int XY_OFF_DC = XY_OFF_TY + NTR * XW;
+constexpr int XY_OFF_DT = XY_OFF_DC + 3 * XW;               // aliases Dc_s[3..5]: a thread reads its Dc/Dt slot before it overwrites it
+constexpr int XY_DOUBLES = XY_OFF_DC + 6 * XW;
 constexpr size_t XY_SMEM = (size_t)XY_DOUBLES * sizeof(double);
+static_assert(XY_SMEM <= 57344, "four CTAs per SM need <= 56 KB each");
 
-struct ActiveList { int n; unsigned char q[12]; };    // transported quantities that can be non-zero, padded to an even count
+struct ActiveList { int n; unsigned long long q; };   // transported quantities that can be non-zero (one nibble each), padded to an even count
 
 __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList L)
 {
@@ -43,16 +48,19 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
     double (*ring)[NTR][SW] = reinterpret_cast<double (*)[NTR][SW]>(smem + XY_OFF_RING);
     double (*vel)[3][SW] = reinterpret_cast<double (*)[3][SW]>(smem + XY_OFF_VEL);
     double (*xt)[XY_XT] = reinterpret_cast<double (*)[XY_XT]>(smem + XY_OFF_XT);
-    double (*Fx_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_FX);
-    double (*Tq_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_TQ);
-    double (*Dc_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_DC);
-    double (*Dt_s)[64] = reinterpret_cast<double (*)[64]>(smem + XY_OFF_DT);
+    double (*Fx_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_FX);
+    double (*TX_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_TX);     // x parts of transportDivergence2D, every quantity
+    double (*TY_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_TY);     // y parts
+    double (*Dc_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_DC);
+    double (*Dt_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_DT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool isX = warp < 2;
     const int wcol = warp & 1;
     const int ccol = 31 * wcol + lane;            // column inside the CTA; lane 31 duplicates the next warp's lane 0
-    const int col = 32 * wcol + lane;             // slot in the per-column exchange arrays
+    const int col = 32 * wcol + lane;             // private slot in the per-column exchange arrays (the X and the Y thread of a
+                                                  //  column share it; lane 31 duplicates a column but owns its own slot)
+    const int fcol = col;
     const int j0 = blockIdx.x * CW;
     const int j = j0 + ccol;
     const int c = ccol + HALO;
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const int t = e / XY_XT, i = e - t * XY_XT;
             if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
         }
-        for (int e = tid; e < 2 * NTR * 64; e += XY_NT) (&Fx_s[0][0])[e] = 0.0;      // Fx_s and Tq_s are contiguous
+        for (int e = tid; e < 3 * NTR * XW + 6 * XW; e += XY_NT) (&Fx_s[0][0])[e] = 0.0;      // Fx_s, TX_s, TY_s, Dc_s are contiguous
     }
     auto x_geom = [&](int f) {
         const int i = f - r0 + 3;
@@ -141,10 +149,10 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         const FaceSel fs0 = select_face(g, cVfx);
 #pragma unroll 1
         for (int k = 0; k < L.n; k++) {
-            const int q = L.q[k];
+            const int q = (int)((L.q >> (4 * k)) & 15ULL);
             double d2;
             const double S = upwind_face_sel(ring[sm2][q][c], ring[sm1][q][c], ring[s0][q][c], ring[sp1][q][c], fs0, &d2);
-            Fx_s[q][col] = S * cVfx;
+            Fx_s[q][fcol] = S * cVfx;
             if (q == Q_BIY) cIx_biy = d2;
             if (q == Q_BIZ) cIx_biz = d2;
         }
@@ -152,6 +160,9 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
     __syncthreads();      // row r0-2 was read above; its ring slot is the prefetch target of the first iteration
 
     double dtmin_local = 1.7976931348623157e308;
+    // Y warps: the cell whose dt is still to be evaluated (its rho / momenta arrive from the X warps one barrier later)
+    bool dt_pending = false;
+    double dt_e = 0.0, dt_bx = 0.0, dt_by = 0.0, dt_bz = 0.0, dt_dx = 1.0, dt_rdx = 1.0;
 
     for (int r = r0; r < r1; r++) {
         const bool pre = (r + 3 <= r1 + HALO - 1);
@@ -181,7 +192,6 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         __syncwarp();
 
         // ================================================================ phase 1: one direction per warp
-        double T0 = 0.0, T1 = 0.0, T2 = 0.0, T3 = 0.0, T4 = 0.0, T5 = 0.0, T6 = 0.0;   // own-direction parts of the own outputs' transports
         double d_a = 0.0, d_b = 0.0, d_c = 0.0, d_d = 0.0, d_e = 0.0, d_f = 0.0;       // central derivatives kept by this role
         if (isX) {
             // ---- x face r+1 (between rows r and r+1)
@@ -191,22 +201,19 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const double Ix1_vz = face_interp(vel[v0][2][c], vel[v1][2][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
             const double Ix1_p = face_interp(pc, ring[sp1][Q_E][c] * P.gm1, gx.hm1, gx.h0, gx.fs, gx.rfs);
             const FaceSel fsx = select_face(gx, vfx1);
+            // the far cell of the extrapolation: row r-1 for flow in +x, row r+2 for flow in -x -- one load from a selected row
+            const double *far_row = &ring[fsx.pos ? sm1 : sp2][0][c];
             double Ix1_biy = 0.0, Ix1_biz = 0.0;
 #pragma unroll 1
             for (int k = 0; k < L.n; k += 2) {
-                const int qa = L.q[k], qb = L.q[k + 1];
+                const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
                 double ad2, bd2;
-                const double aS = upwind_face_sel(ring[sm1][qa][c], ring[s0][qa][c], ring[sp1][qa][c], ring[sp2][qa][c], fsx, &ad2);
-                const double bS = upwind_face_sel(ring[sm1][qb][c], ring[s0][qb][c], ring[sp1][qb][c], ring[sp2][qb][c], fsx, &bd2);
+                const double aS = upwind_face_far(far_row[qa * SW], ring[s0][qa][c], ring[sp1][qa][c], fsx, &ad2);
+                const double bS = upwind_face_far(far_row[qb * SW], ring[s0][qb][c], ring[sp1][qb][c], fsx, &bd2);
                 const double af1 = aS * vfx1, bf1 = bS * vfx1;
-                const double at = ddiv(af1 - Fx_s[qa][col], dx, rdx), bt = ddiv(bf1 - Fx_s[qb][col], dx, rdx);   // derivs.cpp:155-156
-                Fx_s[qa][col] = af1; Fx_s[qb][col] = bf1;
-                if (qa > Q_MZ) Tq_s[qa][col] = at;                    // x parts of the Y-owned transports cross to the Y warps
-                if (qb > Q_MZ) Tq_s[qb][col] = bt;
-                if (qa == Q_RHO) T0 = at; if (qb == Q_RHO) T0 = bt;
-                if (qa == Q_MX) T1 = at;  if (qb == Q_MX) T1 = bt;
-                if (qa == Q_MY) T2 = at;  if (qb == Q_MY) T2 = bt;
-                if (qa == Q_MZ) T3 = at;  if (qb == Q_MZ) T3 = bt;
+                const double at = ddiv(af1 - Fx_s[qa][fcol], dx, rdx), bt = ddiv(bf1 - Fx_s[qb][fcol], dx, rdx);   // derivs.cpp:155-156
+                Fx_s[qa][fcol] = af1; Fx_s[qb][fcol] = bf1;
+                TX_s[qa][col] = at;  TX_s[qb][col] = bt;
                 if (qa == Q_BIY) Ix1_biy = ad2; if (qb == Q_BIY) Ix1_biy = bd2;
                 if (qa == Q_BIZ) Ix1_biz = ad2; if (qb == Q_BIZ) Ix1_biz = bd2;
             }
@@ -218,6 +225,12 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             Dc_s[2][col] = ddiv(Ix1_vz - cIx_vz, dx, rdx);          // d(v_z)/dx  -> Y
             cIx_biy = Ix1_biy; cIx_biz = Ix1_biz; cIx_p = Ix1_p; cVfx = vfx1; cIx_vy = Ix1_vy; cIx_vz = Ix1_vz;
         } else {
+            // ---- dt of the previous row: its rho and momenta were published by the X warps before the last barrier
+            if (dt_pending) {
+                const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
+                dtmin_local = smin(dtmin_local, dtc);
+            }
+            __syncwarp();
             // ---- y face j (left face of this column); the right face comes from lane+1
             const double vxc = vel[v0][0][c], vyc = vel[v0][1][c], vzc = vel[v0][2][c];
             const double vfyL = face_interp(vel[v0][1][c - 1], vyc, gy.hm1, gy.h0, gy.fs, gy.rfs);
@@ -226,26 +239,18 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const double IyL_p = face_interp(ring[s0][Q_E][c - 1] * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
             const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = shfl_next(IyL_vz), IyR_p = shfl_next(IyL_p);
             const FaceSel fsy = select_face(gy, vfyL);
+            const double *far_col = &ring[s0][0][fsy.pos ? c - 2 : c + 1];
             double IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
 #pragma unroll 1
             for (int k = 0; k < L.n; k += 2) {
-                const int qa = L.q[k], qb = L.q[k + 1];
+                const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
                 double ad2, bd2;
-                const double aS = upwind_face_sel(ring[s0][qa][c - 2], ring[s0][qa][c - 1], ring[s0][qa][c], ring[s0][qa][c + 1], fsy, &ad2);
-                const double bS = upwind_face_sel(ring[s0][qb][c - 2], ring[s0][qb][c - 1], ring[s0][qb][c], ring[s0][qb][c + 1], fsy, &bd2);
+                const double aS = upwind_face_far(far_col[qa * SW], ring[s0][qa][c - 1], ring[s0][qa][c], fsy, &ad2);
+                const double bS = upwind_face_far(far_col[qb * SW], ring[s0][qb][c - 1], ring[s0][qb][c], fsy, &bd2);
                 const double afL = aS * vfyL, bfL = bS * vfyL;
                 const double afR = shfl_next(afL), bfR = shfl_next(bfL), ad2R = shfl_next(ad2), bd2R = shfl_next(bd2);
-                const double at = ddiv(afR - afL, dy, rdy), bt = ddiv(bfR - bfL, dy, rdy);
-                // Tq_s is split by ownership: X reads Tq_s[RHO,MX,MY,MZ] (the y parts, written here), Y reads Tq_s[E,BI*,BE*] (written by X)
-                if (qa <= Q_MZ) Tq_s[qa][col] = at;
-                if (qb <= Q_MZ) Tq_s[qb][col] = bt;
-                if (qa == Q_E) T0 = at;   if (qb == Q_E) T0 = bt;
-                if (qa == Q_BIX) T1 = at; if (qb == Q_BIX) T1 = bt;
-                if (qa == Q_BIY) T2 = at; if (qb == Q_BIY) T2 = bt;
-                if (qa == Q_BIZ) T3 = at; if (qb == Q_BIZ) T3 = bt;
-                if (qa == Q_BEX) T4 = at; if (qb == Q_BEX) T4 = bt;
-                if (qa == Q_BEY) T5 = at; if (qb == Q_BEY) T5 = bt;
-                if (qa == Q_BEZ) T6 = at; if (qb == Q_BEZ) T6 = bt;
+                TY_s[qa][col] = ddiv(afR - afL, dy, rdy);
+                TY_s[qb][col] = ddiv(bfR - bfL, dy, rdy);
                 if (qa == Q_BIX) { IyL_bix = ad2; IyR_bix = ad2R; } if (qb == Q_BIX) { IyL_bix = bd2; IyR_bix = bd2R; }
                 if (qa == Q_BIZ) { IyL_biz = ad2; IyR_biz = ad2R; } if (qb == Q_BIZ) { IyL_biz = bd2; IyR_biz = bd2R; }
             }
@@ -260,14 +265,15 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
 
         // ================================================================ phase 2: finish the outputs
         __syncwarp();
-        double e1 = 0.0, Ubx = 0.0, Uby = 0.0, Ubz = 0.0;           // Y keeps its new values for dt
+        dt_pending = false;
         if (col_out) {
             const double bix = ring[s0][Q_BIX][c], biy = ring[s0][Q_BIY][c], biz = ring[s0][Q_BIZ][c];
             const double bex = ring[s0][Q_BEX][c], bey = ring[s0][Q_BEY][c], bez = ring[s0][Q_BEZ][c];
             if (isX) {
                 const double rho = ring[s0][Q_RHO][c];
                 const double dbix_dy = Dc_s[3][col], dbiz_dy = Dc_s[4][col], dp_dy = Dc_s[5][col];
-                const double T_rho = T0 + Tq_s[Q_RHO][col], T_mx = T1 + Tq_s[Q_MX][col], T_my = T2 + Tq_s[Q_MY][col], T_mz = T3 + Tq_s[Q_MZ][col];
+                const double T_rho = TX_s[Q_RHO][col] + TY_s[Q_RHO][col], T_mx = TX_s[Q_MX][col] + TY_s[Q_MX][col];
+                const double T_my = TX_s[Q_MY][col] + TY_s[Q_MY][col], T_mz = TX_s[Q_MZ][col] + TY_s[Q_MZ][col];
                 double k0 = T_rho * -1.0;                                                        // idealmhd.cpp:52
                 const double cdb = ddiv(d_a - dbix_dy, P.fourpi, P.rfourpi);                    // :54
                 const double ncdb = cdb * -1.0;
@@ -302,8 +308,9 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 }
             } else {
                 const double dvx_dx = Dc_s[0][col], dvy_dx = Dc_s[1][col], dvz_dx = Dc_s[2][col];
-                const double T_e = Tq_s[Q_E][col] + T0, T_bix = Tq_s[Q_BIX][col] + T1, T_biy = Tq_s[Q_BIY][col] + T2, T_biz = Tq_s[Q_BIZ][col] + T3;
-                const double T_bex = Tq_s[Q_BEX][col] + T4, T_bey = Tq_s[Q_BEY][col] + T5, T_bez = Tq_s[Q_BEZ][col] + T6;
+                const double T_e = TX_s[Q_E][col] + TY_s[Q_E][col];
+                const double T_bix = TX_s[Q_BIX][col] + TY_s[Q_BIX][col], T_biy = TX_s[Q_BIY][col] + TY_s[Q_BIY][col], T_biz = TX_s[Q_BIZ][col] + TY_s[Q_BIZ][col];
+                const double T_bex = TX_s[Q_BEX][col] + TY_s[Q_BEX][col], T_bey = TX_s[Q_BEY][col] + TY_s[Q_BEY][col], T_bez = TX_s[Q_BEZ][col] + TY_s[Q_BEZ][col];
                 double k4 = (T_e * -1.0) - pc * (dvx_dx + d_d);                                 // :75-76
                 const double bxs = bix + bex, bys = biy + bey;
                 double k5 = (((T_bix * -1.0) - T_bex) + bxs * dvx_dx) + bys * d_e;              // :78-80
@@ -318,20 +325,15 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                     k6 = (A.K1[E_BY][off] + k6) / 6.0 + A.K2[E_BY][off] / 3.0; k7 = (A.K1[E_BZ][off] + k7) / 6.0 + A.K2[E_BZ][off] / 3.0;
                 }
                 if (A.kmode != KM_EXPORT) {
-                    double Ue;
+                    double Ue, Ubx, Uby, Ubz;
                     if (A.b_is_s) { Ue = ring[s0][Q_E][c] + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = biz + k7 * s; }
                     else { Ue = g0 + k4 * s; Ubx = g1 + k5 * s; Uby = B0 + k6 * s; Ubz = B1 + k7 * s; }     // Y's base values were prefetched into g0, g1, B0, B1
-                    e1 = smax(Ue, P.e_min);
+                    const double e1 = smax(Ue, P.e_min);
                     A.D[E_E][off] = e1; A.D[E_BX][off] = Ubx; A.D[E_BY][off] = Uby; A.D[E_BZ][off] = Ubz;
-                    Ubx = bex + Ubx; Uby = bey + Uby; Ubz = bez + Ubz;                           // total field for dt
+                    if (A.primary && interior) {                                                 // dt of this cell: evaluated after the next barrier
+                        dt_pending = true; dt_e = e1; dt_bx = bex + Ubx; dt_by = bey + Uby; dt_bz = bez + Ubz; dt_dx = dx; dt_rdx = rdx;
+                    }
                 }
-            }
-        }
-        if (A.primary && A.kmode != KM_EXPORT) {
-            __syncthreads();                                        // rho, mom_x, mom_y of the X warps are visible
-            if (!isX && interior) {
-                const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], e1, Ubx, Uby, Ubz, dx, rdx, dy, rdy);
-                dtmin_local = smin(dtmin_local, dtc);
             }
         }
         cp_async_wait_all();
@@ -339,7 +341,13 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         if (r + 2 <= r1) form_vel(r + 2);                           // into the velocity slot of row r-1 (dead since the last barrier)
         __syncthreads();
     }
-    if (A.primary && A.kmode != KM_EXPORT) block_min_to_global(dtmin_local, A.dtmin_bits);
+    if (A.primary && A.kmode != KM_EXPORT) {
+        if (!isX && dt_pending) {
+            const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
+            dtmin_local = smin(dtmin_local, dtc);
+        }
+        block_min_impl(dtmin_local, A.dtmin_bits, reinterpret_cast<unsigned long long *>(&TX_s[0][0]));   // TX_s is dead after the last barrier
+    }
 }
 
 }  // namespace spruce
