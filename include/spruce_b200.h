@@ -127,6 +127,14 @@ int spruce_module_radiative_losses(spruce_domain *dom, int time_integrator, doub
 /* AmbientHeating::setupModule (solar/ambientheating.cpp:28-40): heating = nx_local*ydim plane built on the host
  * (the exp() profile is evaluated there with the host libm, as the reference does once at setup). */
 int spruce_module_ambient_heating(spruce_domain *dom, const double *heating, size_t count);
+/* Viscosity (source/modules/viscosity.cpp): module-level options (parseModuleConfigs :6-24), then one call per term of the
+ * comma-separated lists visc_opt / visc_strength / visc_vars_to_diff / visc_vars_to_evol / visc_species (setupModule :37-110).
+ * Terms with strength <= 1 are added to the right-hand side (computeTimeDerivativesModule :112-123), terms with strength > 1
+ * are sub-cycled (iterateModule :125-180).  visc_opt "boundary"/"boundary_global" need the strength profile of
+ * getBoundaryViscosity (:278-325), built on the host (libm exp) like the reference does. */
+int spruce_module_viscosity(spruce_domain *dom, int hv_time_integrator, double hv_epsilon, int gradient_correction);
+int spruce_module_viscosity_term(spruce_domain *dom, const char *visc_opt, double strength, const char *var_to_diff, const char *var_to_evol,
+                                 const char *species, const double *strength_plane, size_t count);
 /* curr_num_subcycles of the last advance: which = "thermal_conduction" | "radiative_losses" */
 int spruce_module_subcycles(spruce_domain *dom, const char *which, int *count);
 

@@ -52,6 +52,8 @@ def lib():
         L.oracle_operator.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3
         L.oracle_set_thermal_conduction.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         L.oracle_set_radiative_losses.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.oracle_set_viscosity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.oracle_set_ambient_heating.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         _lib = L
     return _lib
@@ -132,6 +134,16 @@ class Oracle:
                             split_exp_mode=False, split_exp_scale_height=1.0, split_exp_start_height=0.0):
         lib().oracle_set_ambient_heating(self.h, heating_rate, int(exp_mode), exp_base_heating_rate, exp_scale_height,
                                          int(split_exp_mode), split_exp_scale_height, split_exp_start_height)
+
+    def set_viscosity(self, terms, *, hv_integrator="euler", hv_epsilon=1.0, gradient_correction=False):
+        """terms: list of dict(opt=local|global|boundary|boundary_global, strength=, var_diff=, var_evol=, species='i', strength_grid=None)"""
+        lib().oracle_set_viscosity(self.h, TI[hv_integrator], hv_epsilon, int(gradient_correction))
+        opts = {"local": 0, "global": 1, "boundary": 2, "boundary_global": 3}
+        for tm in terms:
+            sg = tm.get("strength_grid")
+            sgp = _dp(np.ascontiguousarray(sg, dtype=np.float64)) if sg is not None else None
+            lib().oracle_add_viscosity_term(self.h, opts[tm["opt"]], tm["strength"], VARS.index(tm["var_diff"]), VARS.index(tm["var_evol"]),
+                                            ord(tm.get("species", "i")), sgp)
 
     def close(self):
         if self.h:

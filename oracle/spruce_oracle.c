@@ -45,7 +45,14 @@ typedef struct {
     int rl_on, rl_integrator, rl_prevent_subcycling; double rl_cutoff_ramp, rl_cutoff_temp, rl_epsilon; int rl_nsub;
     /* ambient_heating (ambientheating.hpp) */
     int ah_on; double *ah_heating;
-    int order[8]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah */
+    /* artificial_viscosity (source/modules/viscosity.hpp) : up to 8 terms */
+    int av_on, av_nterms, av_hv_integrator, av_gradient_correction; double av_hv_epsilon;
+    int av_opt[8];            /* 0 local, 1 global, 2 boundary, 3 boundary_global */
+    double av_strength[8];
+    int av_diff[8], av_evol[8];   /* variable indices (equation-set numbering) */
+    int av_species[8];        /* 'i' or 'e' */
+    double *av_strength_grid[8];  /* boundary options: profile built by the caller (host libm exp) */
+    int order[8]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah 4=av */
 } modules_t;
 
 typedef struct oracle {
@@ -416,7 +423,8 @@ static void propagate_changes(const oracle *o, double **G, double **P)
 }
 
 /* ------------------------------------------------------------------ modules */
-static void module_rhs_hooks(const oracle *o, double *const *G, double **k) { (void)o; (void)G; (void)k; }
+static void av_rhs(const oracle *o, double *const *G, double **k);
+static void module_rhs_hooks(const oracle *o, double *const *G, double **k) { if (o->mod.av_on) av_rhs(o, G, k); }
 
 /* equationset.cpp:204-210 */
 static void compute_time_derivatives(const oracle *o, double *const *G, double **k)
@@ -442,6 +450,87 @@ static double min_range(const oracle *o, const double *a, int il, int jl, int iu
     int ny = o->ny; double m = 1.7976931348623157e308;
     for (int i = il; i <= iu; i++) for (int j = jl; j <= ju; j++) m = smin(m, a[IDX(i, j)]);
     return m;
+}
+
+/* ---- artificial viscosity (source/modules/viscosity.cpp) */
+static int ev_index(int var) { for (int v = 0; v < NEV; v++) if (EVOLVED[v] == var) return v; return -1; }
+static int is_mom(int v) { return v == V_mom_x || v == V_mom_y || v == V_mom_z; }
+static int is_vel(int v) { return v == V_v_x || v == V_v_y || v == V_v_z; }
+/* constructSingleViscosityGrid :185-267 ; G = the grid set the RHS is evaluated on; dt / dt_min always come from the PRIMARY state (Q13) */
+static void av_single(const oracle *o, double *const *G, int i, double *out)
+{
+    int n = o->n;
+    const modules_t *m = &o->mod;
+    int xl = o->xl, yl = o->yl, xu = o->xu, yu = o->yu;
+    double dt_min = min_range(o, o->g[V_dt], xl, yl, xu, yu);
+    double *coef = pl_new(o), *lap = pl_new(o), *scale = pl_new(o);
+    for (int c = 0; c < n; c++) {
+        double str = (m->av_opt[i] == 0 || m->av_opt[i] == 1) ? m->av_strength[i] : m->av_strength_grid[i][c];
+        double dtg = (m->av_opt[i] == 0 || m->av_opt[i] == 2) ? o->g[V_dt][c] : dt_min;
+        coef[c] = (((str * 1.0) / (1.0 / (o->dx[c] * o->dx[c]) + 1.0 / (o->dy[c] * o->dy[c]))) / 2.) / dtg;       /* :213 */
+        scale[c] = 1.0;
+    }
+    laplacian(o, G[m->av_diff[i]], lap);                                                                          /* :225 */
+    if (is_mom(m->av_evol[i]) && is_vel(m->av_diff[i])) for (int c = 0; c < n; c++) scale[c] = G[V_n][c] * o->m_i;              /* :229-239 */
+    if (m->av_evol[i] == V_thermal_energy && m->av_diff[i] == V_temp) for (int c = 0; c < n; c++) scale[c] = G[V_n][c] * (K_B / (o->gamma - 1));   /* :244-254 */
+    if (m->av_gradient_correction) {                                                                               /* :261-265 */
+        double *cs = pl_new(o), *a = pl_new(o), *b = pl_new(o), *cc = pl_new(o), *d = pl_new(o);
+        for (int c = 0; c < n; c++) cs[c] = coef[c] * scale[c];
+        derivative1D(o, cs, 0, a); derivative1D(o, G[m->av_diff[i]], 0, b); derivative1D(o, cs, 1, cc); derivative1D(o, G[m->av_diff[i]], 1, d);
+        for (int c = 0; c < n; c++) out[c] = ((coef[c] * lap[c]) * scale[c] + a[c] * b[c]) + cc[c] * d[c];
+        free(cs); free(a); free(b); free(cc); free(d);
+    } else for (int c = 0; c < n; c++) out[c] = (coef[c] * lap[c]) * scale[c];
+    free(coef); free(lap); free(scale);
+}
+/* computeTimeDerivativesModule :112-123 */
+static void av_rhs(const oracle *o, double *const *G, double **k)
+{
+    double *dq = pl_new(o);
+    for (int i = 0; i < o->mod.av_nterms; i++) {
+        av_single(o, G, i, dq);                      /* constructViscosityGrids evaluates every term */
+        if (o->mod.av_strength[i] <= 1.0) { double *kk = k[ev_index(o->mod.av_evol[i])]; for (int c = 0; c < o->n; c++) kk[c] += dq[c] * o->mask[c]; }
+    }
+    free(dq);
+}
+/* iterateModule :125-180 : hyper-viscous terms (strength > 1) are sub-cycled on the primary state */
+static void av_iterate(oracle *o, double dt)
+{
+    int n = o->n;
+    double *dq = pl_new(o), *d2 = pl_new(o), *d3 = pl_new(o), *d4 = pl_new(o), *init = pl_new(o);
+    for (int i = 0; i < o->mod.av_nterms; i++) {
+        if (o->mod.av_strength[i] <= 1.0) continue;
+        double *ge = o->g[o->mod.av_evol[i]];
+        int ns = (int)(ceil(o->mod.av_strength[i] / o->mod.av_hv_epsilon) + 0.1);
+        double dts = dt / (double)ns;
+        for (int sc = 0; sc < ns; sc++) {
+            if (o->mod.av_hv_integrator == TI_EULER) {
+                av_single(o, o->g, i, dq);
+                for (int c = 0; c < n; c++) ge[c] = ge[c] + (o->mask[c] * dts) * dq[c];
+                propagate_changes(o, o->g, o->g);
+            } else if (o->mod.av_hv_integrator == TI_RK2) {
+                memcpy(init, ge, sizeof(double) * n);
+                av_single(o, o->g, i, dq);
+                for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * (0.5 * dts)) * dq[c];
+                propagate_changes(o, o->g, o->g);
+                av_single(o, o->g, i, dq);
+                for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * dts) * dq[c];
+                propagate_changes(o, o->g, o->g);
+            } else {
+                memcpy(init, ge, sizeof(double) * n);
+                av_single(o, o->g, i, dq);
+                for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * (0.5 * dts)) * dq[c];
+                propagate_changes(o, o->g, o->g); av_single(o, o->g, i, d2);
+                for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * (0.5 * dts)) * d2[c];
+                propagate_changes(o, o->g, o->g); av_single(o, o->g, i, d3);
+                for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * dts) * d3[c];
+                propagate_changes(o, o->g, o->g); av_single(o, o->g, i, d4);
+                for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * dts) * ((((dq[c] + d2[c] * 2.0) + d3[c] * 2.0) + d4[c]) / 6.0);
+                propagate_changes(o, o->g, o->g);
+            }
+        }
+        propagate_changes(o, o->g, o->g);
+    }
+    free(dq); free(d2); free(d3); free(d4); free(init);
 }
 
 /* ---- thermal conduction (source/modules/solar/thermalconduction.cpp) */
@@ -672,6 +761,7 @@ static double advance_time(oracle *o)
     for (int m = 0; m < o->mod.n_modules; m++) {                                         /* iterate :66 */
         if (o->mod.order[m] == 1) tc_iterate(o, step);
         if (o->mod.order[m] == 2) rl_iterate(o, step);
+        if (o->mod.order[m] == 4) av_iterate(o, step);
     }
     double **k1 = kalloc(o);
     if (o->integrator == TI_EULER) {                                                     /* :84-88 */
@@ -777,6 +867,19 @@ void oracle_set_ambient_heating(oracle *o, double heating_rate, int exp_mode, do
         }
     }
     o->mod.order[o->mod.n_modules++] = 3;
+}
+void oracle_set_viscosity(oracle *o, int hv_integrator, double hv_epsilon, int gradient_correction)
+{
+    o->mod.av_on = 1; o->mod.av_hv_integrator = hv_integrator; o->mod.av_hv_epsilon = hv_epsilon; o->mod.av_gradient_correction = gradient_correction;
+    o->mod.order[o->mod.n_modules++] = 4;
+}
+/* strength_grid: nx*ny profile for the boundary options (copied), NULL otherwise */
+void oracle_add_viscosity_term(oracle *o, int opt, double strength, int var_diff, int var_evol, int species, const double *strength_grid)
+{
+    int i = o->mod.av_nterms++;
+    o->mod.av_opt[i] = opt; o->mod.av_strength[i] = strength; o->mod.av_diff[i] = var_diff; o->mod.av_evol[i] = var_evol; o->mod.av_species[i] = species;
+    o->mod.av_strength_grid[i] = NULL;
+    if (strength_grid) { o->mod.av_strength_grid[i] = pl_dup(o, strength_grid); }
 }
 double oracle_step(oracle *o) { return advance_time(o); }
 void oracle_run(oracle *o, int nsteps, double *dt_out) { for (int s = 0; s < nsteps; s++) { double d = advance_time(o); if (dt_out) dt_out[s] = d; } }

@@ -55,11 +55,17 @@ struct spruce_domain {
     int64_t launches = 0;
     bool any_ucnp = false, any_primary_ghost = false;
     // physics modules, in config order (ModuleHandler::instantiateModule, modulehandler.cpp:92-111)
-    enum { MOD_TC = 1, MOD_RL = 2, MOD_AH = 3 };
+    enum { MOD_TC = 1, MOD_RL = 2, MOD_AH = 3, MOD_AV = 4 };
     std::vector<int> module_order;
     TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
     RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
+    // artificial_viscosity (source/modules/viscosity.cpp): terms in config order
+    struct ViscTerm { int opt; double strength; int var_diff; int var_evol; int species; double *strength_plane; };
+    std::vector<ViscTerm> visc;
+    int visc_hv_integrator = 0, visc_gradient_correction = 0; double visc_hv_epsilon = 1.0;
+    double *vscratch[8] = {nullptr}; double *dt_plane = nullptr;
+    const double *cur_xterm[4] = {nullptr}; int cur_xtarget[4] = {0}; int cur_nx = 0;
     unsigned long long *red = nullptr;     // 4 reduction scalars for the sub-cycle counts
     double *halo[4] = {nullptr, nullptr, nullptr, nullptr};   // send_lo, send_hi, recv_lo, recv_hi
     // planes that were uploaded as identically zero: bit 0 mom_z, 1 bi_z, 2 be_x, 3 be_y, 4 be_z (global knowledge; see spruce_plane_activity)
@@ -207,10 +213,14 @@ ActiveList active_quantities(const spruce_domain *d)
     return L;
 }
 
+int prepare_rhs_modules(spruce_domain *d, const PlaneSet &S);
 int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode)
 {
+    if (!d->visc.empty()) { int rcv = prepare_rhs_modules(d, S); if (rcv) return rcv; }
     StageArgs A{};
     fill_sets(d, A, S, B, D);
+    A.n_xterm = d->visc.empty() ? 0 : d->cur_nx;
+    for (int t = 0; t < A.n_xterm; t++) { A.xterm[t] = d->cur_xterm[t]; A.xtarget[t] = d->cur_xtarget[t]; }
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
     A.chunk_rows = pick_chunk_rows(d);
@@ -268,10 +278,10 @@ int ensure_rk4(spruce_domain *d)
     return SPRUCE_OK;
 }
 
-int derive_to(spruce_domain *d, int var, double *out)
+int derive_to(spruce_domain *d, int var, double *out, const PlaneSet *set = nullptr)
 {
     DeriveArgs A{};
-    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NEV; v++) A.U[v] = (set ? set : &d->Pset)->p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
     A.out = out; A.which = var;
     dim3 grid((d->P.ny + 255) / 256, d->P.nx);
@@ -397,6 +407,112 @@ int ah_post(spruce_domain *d)
     return launch_propagate(d, 0);                                                                  // ambientheating.cpp:43-44
 }
 
+// ---- artificial viscosity (source/modules/viscosity.cpp)
+int evolved_slot(int var);
+const double *materialise_var(spruce_domain *d, const PlaneSet &S, int var, double *scratch, int *rc)
+{
+    *rc = SPRUCE_OK;
+    const int ev = evolved_slot(var);
+    if (ev > 0) return S.p[ev];
+    if (var == V_grav_x) return d->stat[S_GX];
+    if (var == V_grav_y) return d->stat[S_GY];
+    *rc = derive_to(d, var, scratch, &S);
+    return scratch;
+}
+int visc_needs_dt_plane(const spruce_domain *d) { for (auto &t : d->visc) if (t.opt == 0 || t.opt == 2) return 1; return 0; }
+int visc_refresh_dt(spruce_domain *d) { return visc_needs_dt_plane(d) ? derive_to(d, V_dt, d->dt_plane) : SPRUCE_OK; }
+// constructSingleViscosityGrid :185-267 for term i on grid set S -> out
+int visc_term(spruce_domain *d, const PlaneSet &S, int i, double *out, int masked)
+{
+    const auto &t = d->visc[i];
+    int rc;
+    const double *q = materialise_var(d, S, t.var_diff, d->vscratch[7], &rc);
+    if (rc) return rc;
+    ViscArgs A{};
+    A.q = q; A.n = S.p[E_N];
+    A.dt_plane = (t.opt == 0 || t.opt == 2) ? d->dt_plane : nullptr;
+    A.dt_min_bits = &d->ctl->dtmin_bits;
+    A.strength_plane = (t.opt == 2 || t.opt == 3) ? t.strength_plane : nullptr;
+    A.strength = t.strength;
+    const bool evol_mom = (t.var_evol == V_mom_x || t.var_evol == V_mom_y || t.var_evol == V_mom_z);
+    const bool diff_vel = (t.var_diff == V_v_x || t.var_diff == V_v_y || t.var_diff == V_v_z);
+    A.scale_mode = (evol_mom && diff_vel) ? 1 : (t.var_evol == V_thermal_energy && t.var_diff == V_temp) ? 2 : 0;
+    A.gradient_correction = d->visc_gradient_correction; A.masked = masked; A.out = out;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_visc_term<<<grid, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+// Module::computeTimeDerivativesModule for every RHS-form term (strength <= 1), evaluated on grid set S (viscosity.cpp:112-123)
+int prepare_rhs_modules(spruce_domain *d, const PlaneSet &S)
+{
+    d->cur_nx = 0;
+    for (size_t i = 0; i < d->visc.size(); i++) {
+        if (d->visc[i].strength > 1.0) continue;
+        if (d->cur_nx >= 4) return fail(SPRUCE_ERR_UNSUPPORTED, "at most 4 right-hand-side viscosity terms");
+        int rc = visc_term(d, S, (int)i, d->vscratch[d->cur_nx], 1);
+        if (rc) return rc;
+        d->cur_xterm[d->cur_nx] = d->vscratch[d->cur_nx];
+        d->cur_xtarget[d->cur_nx] = evolved_slot(d->visc[i].var_evol);
+        d->cur_nx++;
+    }
+    return SPRUCE_OK;
+}
+int launch_propagate(spruce_domain *d, int from_state);
+// Viscosity::iterateModule :125-180 : sub-cycled hyper-viscous terms on the primary state
+int av_iterate(spruce_domain *d, double dt)
+{
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    const size_t plane_bytes = (size_t)d->P.nx * d->P.pitch * sizeof(double);
+    for (size_t i = 0; i < d->visc.size(); i++) {
+        const auto &t = d->visc[i];
+        if (t.strength <= 1.0) continue;
+        const int ev = evolved_slot(t.var_evol);
+        double *evol = d->Pset.p[ev];
+        const int ns = (int)(std::ceil(t.strength / d->visc_hv_epsilon) + 0.1);              // :130
+        const double dts = dt / (double)ns;
+        double *T[4] = {d->vscratch[0], d->vscratch[1], d->vscratch[2], d->vscratch[3]}, *init = d->vscratch[4];
+        int rc;
+        auto apply = [&](const double *base, double cc, int n_terms) -> int {
+            AxpyArgs A{};
+            A.base = base; A.t1 = T[0]; A.t2 = n_terms == 4 ? T[1] : nullptr; A.t3 = n_terms == 4 ? T[2] : nullptr; A.t4 = n_terms == 4 ? T[3] : nullptr;
+            A.c = cc; A.out = evol; A.base_is_n = (ev == E_N);
+            k_visc_apply<<<grid, 256, 0, d->stream>>>(d->P, A);
+            d->launches++;
+            CUDA_TRY(cudaGetLastError());
+            if (ev == E_N) d->raw_rho = true;
+            return launch_propagate(d, 0);
+        };
+        auto term = [&](double *out) -> int { int r_ = visc_refresh_dt(d); return r_ ? r_ : visc_term(d, d->Pset, (int)i, out, 0); };
+        for (int sc = 0; sc < ns; sc++) {
+            if (d->visc_hv_integrator == SPRUCE_TI_EULER) {
+                if ((rc = term(T[0])) || (rc = apply(evol, dts, 1))) return rc;
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(init, evol, plane_bytes, cudaMemcpyDeviceToDevice, d->stream));
+                if (d->visc_hv_integrator == SPRUCE_TI_RK2) {
+                    if ((rc = term(T[0])) || (rc = apply(init, 0.5 * dts, 1))) return rc;
+                    if ((rc = term(T[0])) || (rc = apply(init, dts, 1))) return rc;
+                } else {
+                    if ((rc = term(T[0])) || (rc = apply(init, 0.5 * dts, 1))) return rc;
+                    std::swap(T[0], T[1]);            // keep dqdt1 in T[1] while T[0] is reused as the working term
+                    if ((rc = term(T[0])) || (rc = apply(init, 0.5 * dts, 1))) return rc;
+                    std::swap(T[0], T[2]);
+                    if ((rc = term(T[0])) || (rc = apply(init, dts, 1))) return rc;
+                    std::swap(T[0], T[3]);
+                    if ((rc = term(T[0]))) return rc;
+                    // now: T[1] = dqdt1, T[2] = dqdt2, T[3] = dqdt3, T[0] = dqdt4  -> (d1 + 2 d2 + 2 d3 + d4)/6
+                    double *d1 = T[1], *d2 = T[2], *d3 = T[3], *d4 = T[0];
+                    T[0] = d1; T[1] = d2; T[2] = d3; T[3] = d4;
+                    if ((rc = apply(init, dts, 4))) return rc;
+                }
+            }
+        }
+        if ((rc = launch_propagate(d, 0))) return rc;                                        // :178
+    }
+    return SPRUCE_OK;
+}
+
 // one advanceTime (evolution.cpp:59-82) worth of launches
 int enqueue_step(spruce_domain *d, int hist_slot)
 {
@@ -417,8 +533,10 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         for (int m : d->module_order) {                                  // iterateModules, evolution.cpp:66
             if (m == spruce_domain::MOD_TC && (rc = tc_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_RL && (rc = rl_iterate(d, step))) return rc;
+            if (m == spruce_domain::MOD_AV && (rc = av_iterate(d, step))) return rc;
         }
     }
+    if (!d->visc.empty() && (rc = visc_refresh_dt(d))) return rc;     // Viscosity reads the PRIMARY state's dt plane
     const int ti = d->cfg.time_integrator;
     if (ti == SPRUCE_TI_EULER) {                                        // evolution.cpp:84-88
         if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;
@@ -725,9 +843,28 @@ int spruce_eqs_time_derivatives(spruce_domain *d, double *k_out, size_t count)
     return SPRUCE_OK;
 }
 
-int spruce_operator(spruce_domain *, const char *, int, const double *, const double *, double *, size_t)
+int spruce_operator(spruce_domain *d, const char *op, int index, const double *q, const double *vel, double *out, size_t count)
 {
-    return fail(SPRUCE_ERR_UNSUPPORTED, "stand-alone operators are not built yet");
+    CHECK_DOM(d);
+    if (!op || !q || !out) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (!d->have_geom) return fail(SPRUCE_ERR_STATE, "operators need the cell sizes");
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "stand-alone operators are single-rank");
+    if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane size mismatch");
+    const int code = !strcmp(op, "derivative1D") ? 0 : !strcmp(op, "secondDerivative1D") ? 1 : !strcmp(op, "laplacian") ? 2 : !strcmp(op, "transportDerivative1D") ? 3 : -1;
+    if (code < 0) return fail(SPRUCE_ERR_ARG, "unknown operator <%s>", op);
+    if (code == 3 && !vel) return fail(SPRUCE_ERR_ARG, "transportDerivative1D needs a velocity plane");
+    if (index != 0 && index != 1) return fail(SPRUCE_ERR_ARG, "This function assumes two dimensions");
+    int rc = ensure_rk4(d);                     // K1 planes double as operand scratch
+    if (rc) return rc;
+    if ((rc = h2d_plane(d, d->K1set.p[0], q))) return rc;
+    if (vel && (rc = h2d_plane(d, d->K1set.p[1], vel))) return rc;
+    OpArgs A{};
+    A.q = d->K1set.p[0]; A.vel = d->K1set.p[1]; A.out = d->K1set.p[2]; A.op = code; A.index = index;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_operator<<<grid, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return d2h_plane(d, out, d->K1set.p[2]);
 }
 
 int spruce_module_thermal_conduction(spruce_domain *d, int flux_saturation, int time_integrator, double epsilon, double dt_subcycle_min, double weakening_factor)
@@ -763,6 +900,41 @@ int spruce_module_ambient_heating(spruce_domain *d, const double *heating, size_
     int rc = h2d_plane(d, d->heating, heating);
     if (rc) return rc;
     d->module_order.push_back(spruce_domain::MOD_AH);
+    return SPRUCE_OK;
+}
+int spruce_module_viscosity(spruce_domain *d, int hv_time_integrator, double hv_epsilon, int gradient_correction)
+{
+    CHECK_DOM(d);
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
+    if (hv_time_integrator < 0 || hv_time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid hyperviscous time integrator given for Viscosity module");
+    d->visc_hv_integrator = hv_time_integrator; d->visc_hv_epsilon = hv_epsilon; d->visc_gradient_correction = gradient_correction ? 1 : 0;
+    for (int k = 0; k < 8; k++) if (!d->vscratch[k]) { int rc = alloc_plane(d, &d->vscratch[k]); if (rc) return rc; }
+    if (!d->dt_plane) { int rc = alloc_plane(d, &d->dt_plane); if (rc) return rc; }
+    d->module_order.push_back(spruce_domain::MOD_AV);
+    return SPRUCE_OK;
+}
+int spruce_module_viscosity_term(spruce_domain *d, const char *visc_opt, double strength, const char *var_to_diff, const char *var_to_evol,
+                                 const char *species, const double *strength_plane, size_t count)
+{
+    CHECK_DOM(d);
+    if (!visc_opt || !var_to_diff || !var_to_evol) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (!d->dt_plane) return fail(SPRUCE_ERR_STATE, "spruce_module_viscosity must precede its terms");
+    spruce_domain::ViscTerm t{};
+    t.opt = !strcmp(visc_opt, "local") ? 0 : !strcmp(visc_opt, "global") ? 1 : !strcmp(visc_opt, "boundary") ? 2 : !strcmp(visc_opt, "boundary_global") ? 3 : -1;
+    if (t.opt < 0) return fail(SPRUCE_ERR_ARG, "Viscosity option must be global, local, or boundary.");
+    t.strength = strength;
+    t.var_diff = var_index(var_to_diff);
+    t.var_evol = var_index(var_to_evol);
+    if (t.var_diff < 0) return fail(SPRUCE_ERR_ARG, "Each variable to differentiate must be a valid variable within the chosen equation set.");
+    if (t.var_evol < 0 || evolved_slot(t.var_evol) < 0) return fail(SPRUCE_ERR_ARG, "Each variable to evolve must be a valid evolved variable within the chosen equation set.");
+    t.species = (species && species[0]) ? species[0] : 'i';
+    if (t.opt >= 2) {
+        if (!strength_plane || count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "boundary viscosity needs its strength profile (%zu values)", (size_t)d->P.nx * d->P.ny);
+        int rc = alloc_plane(d, &t.strength_plane);
+        if (rc) return rc;
+        if ((rc = h2d_plane(d, t.strength_plane, strength_plane))) return rc;
+    }
+    d->visc.push_back(t);
     return SPRUCE_OK;
 }
 int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)

@@ -80,6 +80,9 @@ struct StageArgs {
     double *strip[4];             // per side (x1,x2,y1,y2): what that side's ghost pass reads from its first interior cell
     int strip_pitch;              //   strip[s][c*strip_pitch + idx], c = 0: post-floor rho, 1..3: momentum as that pass sees it
     int chunk_rows;               // rows per CTA
+    // module contributions to the right-hand side (Module::computeTimeDerivativesModule): already masked planes that are
+    // added to k[target] in module order, after the ghost mask (equationset.cpp:208, viscosity.cpp:117-118)
+    const double *xterm[4]; int xtarget[4]; int n_xterm;
 };
 
 // ---- tiling of the fused stage kernel ("column marching", see the header comment)
@@ -468,6 +471,11 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
             // ghost mask (:99-103): operators return 0 outside [xl..xu]x[yl..yu] and the mask zeroes the rest
 #pragma unroll
             for (int v = 0; v < NEV; v++) k[v] = interior ? k[v] : 0.0;
+            for (int t = 0; t < A.n_xterm; t++) {
+                const double x = A.xterm[t][off];
+#pragma unroll
+                for (int v = 0; v < NEV; v++) if (A.xtarget[t] == v) k[v] = k[v] + x;
+            }
 
             // ---------------- RK4 bookkeeping (evolution.cpp:103-124)
             if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) {

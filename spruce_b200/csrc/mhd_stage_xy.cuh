@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 const double fzi = ddiv(czx * biy - czy * bix, P.fourpi, P.rfourpi);            // :60
                 double k3 = ((T_mz * -1.0) + fze) + fzi;                                        // :72-73
                 if (!interior) { k0 = 0.0; k1 = 0.0; k2 = 0.0; k3 = 0.0; }                      // ghost mask :99-103
+                for (int t = 0; t < A.n_xterm; t++) {                                           // module RHS terms, in module order
+                    const int tg = A.xtarget[t];
+                    if (tg <= E_MZ) { const double x = A.xterm[t][off]; if (tg == E_N) k0 = k0 + x; if (tg == E_MX) k1 = k1 + x; if (tg == E_MY) k2 = k2 + x; if (tg == E_MZ) k3 = k3 + x; }
+                }
                 if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_N][off] = k0; A.K1[E_MX][off] = k1; A.K1[E_MY][off] = k2; A.K1[E_MZ][off] = k3; }
                 else if (A.kmode == KM_STORE_K2) { A.K2[E_N][off] = k0; A.K2[E_MX][off] = k1; A.K2[E_MY][off] = k2; A.K2[E_MZ][off] = k3; }
                 else if (A.kmode == KM_ADD_K2) { A.K2[E_N][off] = A.K2[E_N][off] + k0; A.K2[E_MX][off] = A.K2[E_MX][off] + k1; A.K2[E_MY][off] = A.K2[E_MY][off] + k2; A.K2[E_MZ][off] = A.K2[E_MZ][off] + k3; }
@@ -317,6 +321,10 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 double k6 = (((T_biy * -1.0) - T_bey) + bxs * dvy_dx) + bys * d_d;              // :81-83
                 double k7 = (((T_biz * -1.0) - T_bez) + bxs * dvz_dx) + bys * d_f;              // :84-86
                 if (!interior) { k4 = 0.0; k5 = 0.0; k6 = 0.0; k7 = 0.0; }
+                for (int t = 0; t < A.n_xterm; t++) {
+                    const int tg = A.xtarget[t];
+                    if (tg > E_MZ) { const double x = A.xterm[t][off]; if (tg == E_E) k4 = k4 + x; if (tg == E_BX) k5 = k5 + x; if (tg == E_BY) k6 = k6 + x; if (tg == E_BZ) k7 = k7 + x; }
+                }
                 if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_E][off] = k4; A.K1[E_BX][off] = k5; A.K1[E_BY][off] = k6; A.K1[E_BZ][off] = k7; }
                 else if (A.kmode == KM_STORE_K2) { A.K2[E_E][off] = k4; A.K2[E_BX][off] = k5; A.K2[E_BY][off] = k6; A.K2[E_BZ][off] = k7; }
                 else if (A.kmode == KM_ADD_K2) { A.K2[E_E][off] = A.K2[E_E][off] + k4; A.K2[E_BX][off] = A.K2[E_BX][off] + k5; A.K2[E_BY][off] = A.K2[E_BY][off] + k6; A.K2[E_BZ][off] = A.K2[E_BZ][off] + k7; }

@@ -338,4 +338,106 @@ __global__ void __launch_bounds__(256) k_ambient_heating(const DomainParams P, d
     e[off] = e[off] + heating[off] * (*step_ptr);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Artificial viscosity (source/modules/viscosity.cpp:185-267): one term  dq = visc_coeff * laplacian(q) * scale_fac
+// (+ gradient correction), q = the variable to differentiate of the grid set the RHS is evaluated on (materialised by
+// k_mhd_derive when it is a derived variable), timescale from the PRIMARY state's dt plane / its minimum.
+// ---------------------------------------------------------------------------------------------------------
+struct ViscArgs {
+    const double *q;             // variable to differentiate
+    const double *n;             // number density of the same grid set (scale factor)
+    const double *dt_plane;      // primary dt plane (local / boundary) or nullptr
+    const unsigned long long *dt_min_bits;   // primary dt minimum over the dt bounds (global / boundary_global)
+    const double *strength_plane;            // boundary profiles, or nullptr
+    double strength;
+    int scale_mode;              // 0: 1 ; 1: n*m_i (momentum <- velocity) ; 2: n*(K_B/(gamma-1)) (thermal energy <- temperature)
+    int gradient_correction;
+    int masked;                  // multiply by the ghost-zone mask (RHS form, viscosity.cpp:117)
+    double *out;
+};
+
+__global__ void __launch_bounds__(128) k_visc_term(const DomainParams P, const ViscArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const double dtm = __longlong_as_double((long long)*A.dt_min_bits);
+    auto Q = [&](int a, int b) { return rd(P, A.q, a, b); };
+    auto coef = [&](int a, int b) {                                                   // :213
+        a = wrap_i(P, a); b = wrap_j(P, b);
+        const double str = A.strength_plane ? rd(P, A.strength_plane, a, b) : A.strength;
+        const double dtg = A.dt_plane ? rd(P, A.dt_plane, a, b) : dtm;
+        const double dx = P.tx.d[a], dy = P.ty.d[b];
+        return (((str * 1.0) / (1.0 / (dx * dx) + 1.0 / (dy * dy))) / 2.) / dtg;
+    };
+    auto scale = [&](int a, int b) {                                                  // :228-258
+        if (A.scale_mode == 1) return rd(P, A.n, a, b) * P.m_i;
+        if (A.scale_mode == 2) return rd(P, A.n, a, b) * (kKB / (P.gamma - 1));
+        return 1.0;
+    };
+    const double lap = D2x(P, Q, r, j) + D2y(P, Q, r, j);                             // laplacian, derivs.cpp:458-462
+    double out = (coef(r, j) * lap) * scale(r, j);                                    // :266
+    if (A.gradient_correction) {                                                      // :261-265
+        auto CS = [&](int a, int b) { return coef(a, b) * scale(a, b); };
+        out = (out + Dx(P, CS, r, j) * Dx(P, Q, r, j)) + Dy(P, CS, r, j) * Dy(P, Q, r, j);
+    }
+    if (A.masked) out = out * (is_interior(P, r, j) ? 1.0 : 0.0);
+    A.out[off] = out;
+}
+
+// grid_to_evol = base + (mask*c)*term   (viscosity.cpp:135,145,150,...) ; rk4 combination when d2..d4 are given (:173-174)
+struct AxpyArgs { const double *base; const double *t1, *t2, *t3, *t4; double c; double *out; int base_is_n; };
+__global__ void __launch_bounds__(256) k_visc_apply(const DomainParams P, const AxpyArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const double mask = is_interior(P, r, j) ? 1.0 : 0.0;
+    double t = A.t1[off];
+    if (A.t4) t = (((A.t1[off] + A.t2[off] * 2.0) + A.t3[off] * 2.0) + A.t4[off]) / 6.0;
+    const double b = A.base_is_n ? A.base[off] * P.m_i : A.base[off];
+    A.out[off] = b + (mask * A.c) * t;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PlasmaDomain differential operators on a plane (source/mhd/derivs.cpp), for host-side modules that are not ported.
+// op: 0 derivative1D, 1 secondDerivative1D, 2 laplacian, 3 transportDerivative1D (needs vel)
+// ---------------------------------------------------------------------------------------------------------
+struct OpArgs { const double *q, *vel; double *out; int op, index; };
+__global__ void __launch_bounds__(128) k_operator(const DomainParams P, const OpArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    auto Q = [&](int a, int b) { return rd(P, A.q, a, b); };
+    double out = 0.0;
+    if (A.op == 0) out = A.index == 0 ? Dx(P, Q, r, j) : Dy(P, Q, r, j);
+    else if (A.op == 1) out = A.index == 0 ? D2x(P, Q, r, j) : D2y(P, Q, r, j);
+    else if (A.op == 2) out = D2x(P, Q, r, j) + D2y(P, Q, r, j);
+    else if (is_interior(P, r, j)) {
+        // transportDerivative1D (derivs.cpp:122-162): (S[f+1]*vf[f+1] - S[f]*vf[f]) / d
+        auto V = [&](int a, int b) { return rd(P, A.vel, a, b); };
+        const AxisTab &t = A.index == 0 ? P.tx : P.ty;
+        const int i0 = A.index == 0 ? r : j;
+        double flux[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int f = i0 + k;
+            auto at = [&](int i) { return A.index == 0 ? Q(i, j) : Q(r, i); };
+            auto vat = [&](int i) { return A.index == 0 ? V(i, j) : V(r, i); };
+            const FaceGeom g = load_face_geom(t, f);
+            const double vf = face_interp(vat(f - 1), vat(f), g.hm1, g.h0, g.fs, g.rfs);
+            double d2;
+            const double S = upwind_face(at(f - 2), at(f - 1), at(f), at(f + 1), vf, g, &d2);
+            flux[k] = S * vf;
+        }
+        out = ddiv(flux[1] - flux[0], t.d[i0], t.rd[i0]);
+    }
+    A.out[off] = out;
+}
+
 }  // namespace spruce

@@ -130,6 +130,23 @@ class PlasmaDomain:
         a = self._local(heating)
         capi.check(self.lib.spruce_module_ambient_heating(self.h, _dp(a), a.size))
 
+    def set_viscosity(self, terms, *, hv_integrator="euler", hv_epsilon=1.0, gradient_correction=False):
+        """terms: list of dict(opt, strength, var_diff, var_evol, species='i', strength_grid=None) in config order."""
+        capi.check(self.lib.spruce_module_viscosity(self.h, capi.TI[hv_integrator], hv_epsilon, int(gradient_correction)))
+        for tm in terms:
+            sg = tm.get("strength_grid")
+            if sg is not None:
+                sg = self._local(sg)
+            capi.check(self.lib.spruce_module_viscosity_term(self.h, tm["opt"].encode(), tm["strength"], tm["var_diff"].encode(), tm["var_evol"].encode(),
+                                                             tm.get("species", "i").encode(), _dp(sg) if sg is not None else None, sg.size if sg is not None else 0))
+
+    def operator(self, op: str, index: int, q: np.ndarray, vel: np.ndarray = None) -> np.ndarray:
+        q = self._local(q)
+        out = np.empty_like(q)
+        v = self._local(vel) if vel is not None else None
+        capi.check(self.lib.spruce_operator(self.h, op.encode(), index, _dp(q), _dp(v) if v is not None else None, _dp(out), q.size))
+        return out
+
     def subcycles(self, which: str) -> int:
         n = C.c_int()
         capi.check(self.lib.spruce_module_subcycles(self.h, which.encode(), C.byref(n)))

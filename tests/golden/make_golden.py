@@ -35,6 +35,7 @@ SOLAR_FLOORS = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6
 
 TC = lambda **kw: ("thermal_conduction", list(dict(dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4", output_to_file="true"), **kw).items()))
 RL = lambda **kw: ("radiative_losses", list(dict(dict(cutoff_ramp="1.0e3", cutoff_temp="3.0e4", epsilon="0.1", output_to_file="true"), **kw).items()))
+AV = lambda **kw: ("artificial_viscosity", list(kw.items()))
 AH = lambda **kw: ("ambient_heating", list(dict(dict(heating_rate="1.0e-4"), **kw).items()))
 
 CASES = {
@@ -59,6 +60,16 @@ CASES = {
     "loop_ah_exp": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[AH(exp_mode="true", exp_base_heating_rate="3.0e-4", exp_scale_height="6.0e8")], **SOLAR_FLOORS), 3, (1, 3)),
     "loop_solar_all": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"),
                        modules=[TC(flux_saturation="true"), RL(time_integrator="rk2"), AH()], **SOLAR_FLOORS), 6, (1, 6)),
+    # artificial viscosity (source/modules/viscosity.cpp): RHS terms (strength <= 1) and sub-cycled hyper-viscosity (> 1)
+    "loop_visc_rhs": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"),
+                      modules=[AV(visc_opt="local,global,local", visc_strength="0.5,0.3,0.2", visc_vars_to_diff="v_x,v_y,temp", visc_vars_to_evol="mom_x,mom_y,thermal_energy",
+                                  visc_length="0,0,0", visc_species="i,i,i")], **SOLAR_FLOORS), 5, (1, 5)),
+    "loop_visc_boundary_hv": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk4", xb=("reflect", "open"), yb=("fixed", "open"),
+                      modules=[AV(visc_opt="boundary,global,boundary_global", visc_strength="0.8,3.0,0.6", visc_vars_to_diff="v_x,v_y,mom_z", visc_vars_to_evol="mom_x,mom_y,mom_z",
+                                  visc_length="5.0e8,0,8.0e8", visc_species="i,i,i", hv_time_integrator="rk2", hv_epsilon="1.0", gradient_correction="true")], **SOLAR_FLOORS), 4, (1, 4)),
+    "ot_visc_hv_rk4": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
+                      modules=[AV(visc_opt="local,global", visc_strength="2.5,0.4", visc_vars_to_diff="v_x,temp", visc_vars_to_evol="mom_x,thermal_energy",
+                                  visc_length="0,0", visc_species="i,i", hv_time_integrator="rk4", hv_epsilon="1.0")], **INACTIVE_FLOORS), 3, (1, 3)),
     # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
     "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
 }

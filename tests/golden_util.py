@@ -68,7 +68,37 @@ def module_kwargs(name, kv):
                     split_exp_mode=b(kv.get("split_exp_mode", "false")),
                     split_exp_scale_height=float(kv.get("split_exp_scale_height", "1.0")),
                     split_exp_start_height=float(kv.get("split_exp_start_height", "0.0")))
+    if name == "artificial_viscosity":
+        n = len(kv["visc_opt"].split(","))
+        cols = {k: kv[k].split(",") for k in ("visc_opt", "visc_strength", "visc_vars_to_diff", "visc_vars_to_evol", "visc_length", "visc_species")}
+        terms = [dict(opt=cols["visc_opt"][i], strength=float(cols["visc_strength"][i]), var_diff=cols["visc_vars_to_diff"][i],
+                      var_evol=cols["visc_vars_to_evol"][i], length=float(cols["visc_length"][i]), species=cols["visc_species"][i]) for i in range(n)]
+        return dict(terms=terms, hv_integrator=kv.get("hv_time_integrator", "euler"), hv_epsilon=float(kv.get("hv_epsilon", "1.0")),
+                    gradient_correction=b(kv.get("gradient_correction", "false")))
     raise KeyError(name)
+
+
+def boundary_viscosity_profile(pos_x, pos_y, strength, length):
+    """Viscosity::getBoundaryViscosity, gaussian shape (reference source/modules/viscosity.cpp:278-325), with the host libm --
+    a static profile the reference also builds on the host."""
+    import math
+    ex = np.vectorize(math.exp)
+    x_min, x_max, y_min, y_max = pos_x.min(), pos_x.max(), pos_y.min(), pos_y.max()
+    r = np.zeros_like(pos_x)
+    for a in ((pos_x - x_min), (pos_x - x_max), (pos_y - y_max), (pos_y - y_min)):
+        q = a / length
+        r = r + ex((q * q) * -2.3) * strength
+    return np.where(strength < r, strength, r)
+
+
+def viscosity_terms_with_profiles(planes, terms):
+    out = []
+    for tm in terms:
+        tm = dict(tm)
+        if tm["opt"] in ("boundary", "boundary_global"):
+            tm["strength_grid"] = boundary_viscosity_profile(planes["pos_x"], planes["pos_y"], tm["strength"], tm["length"])
+        out.append(tm)
+    return out
 
 
 def same_bits(a, b):

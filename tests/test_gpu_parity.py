@@ -12,7 +12,7 @@ from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_b
 
 pytestmark = pytest.mark.gpu
 
-BUILT_MODULES = {"thermal_conduction", "radiative_losses", "ambient_heating"}
+BUILT_MODULES = {"thermal_conduction", "radiative_losses", "ambient_heating", "artificial_viscosity"}
 # Modules that call std::pow / std::log10: CUDA's libm and glibc differ in the last bit for some arguments, so these runs are
 # held to the north star's tolerance (relative L-infinity <= 1e-9 per plane, same for the step sizes) instead of bit equality.
 LIBM_MODULES = {"thermal_conduction", "radiative_losses"}
@@ -32,6 +32,9 @@ def make_domain(g: Golden):
         if name == "ambient_heating":
             from ambient import heating_plane
             d.set_ambient_heating_plane(heating_plane(g, kw))
+        elif name == "artificial_viscosity":
+            from golden_util import viscosity_terms_with_profiles
+            d.set_viscosity(viscosity_terms_with_profiles(g.planes, kw.pop("terms")), **kw)
         else:
             getattr(d, "set_" + name)(**kw)
     return d
@@ -251,3 +254,22 @@ def test_slab_decomposition_equals_single_gpu(args):
                         "--master-port", "29517", str(root / "scripts" / "mgpu_check.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     out = r.stdout.decode()
     assert r.returncode == 0 and "IDENTICAL" in out, out[-3000:]
+
+
+def test_operators_vs_oracle():
+    """spruce_operator: the PlasmaDomain differential operators on a host plane (source/mhd/derivs.cpp), bit for bit."""
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    for xb, yb, gen in [(("periodic", "periodic"), ("periodic", "periodic"), lambda: synthetic.orszag_tang(70, 51, zfull=True)),
+                        (("fixed", "open"), ("reflect", "fixed"), lambda: synthetic.stratified_loop(45, 66))]:
+        s = gen()
+        kw = dict(xb=xb, yb=yb)
+        o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+        d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+        q, v = o.get("temp"), o.get("v_x") - 0.3 * o.get("v_y")
+        for op in ("derivative1D", "secondDerivative1D", "transportDerivative1D"):
+            for index in (0, 1):
+                a, b = d.operator(op, index, q, v), o.operator(op, index, q, v)
+                assert same_bits(a, b), "%s index %d: %s" % (op, index, mismatch(a, b))
+        assert same_bits(d.operator("laplacian", 0, q), o.operator("laplacian", 0, q))

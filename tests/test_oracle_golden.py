@@ -4,14 +4,18 @@ source/mhd/evolution.cpp:62) and every evolved plane + temp + dt after the recor
 import numpy as np
 import pytest
 
-from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_bits
+from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_bits, viscosity_terms_with_profiles
 from oracle.oracle import Oracle
 
 
 def make_oracle(g: Golden) -> Oracle:
     o = Oracle(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
     for name, kv in g.modules:
-        getattr(o, "set_" + name)(**module_kwargs(name, kv))
+        kw = module_kwargs(name, kv)
+        if name == "artificial_viscosity":
+            o.set_viscosity(viscosity_terms_with_profiles(g.planes, kw.pop("terms")), **kw)
+        else:
+            getattr(o, "set_" + name)(**kw)
     return o
 
 
