@@ -36,10 +36,11 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
         return;
     }
     SPRUCE_REQUIRE(dynamic_cast<IdealMHD *>(m_pd.m_eqs.get()) != nullptr, "Module designed for IdealMHD EquationSet (ensure that equation_set is set before modules in the config)");
-    if (name == "thermal_conduction") m_modules.emplace_back(new ThermalConduction(m_pd));
+    if (name == "artificial_viscosity") m_modules.emplace_back(new Viscosity(m_pd));
+    else if (name == "thermal_conduction") m_modules.emplace_back(new ThermalConduction(m_pd));
     else if (name == "radiative_losses") m_modules.emplace_back(new RadiativeLosses(m_pd));
     else if (name == "ambient_heating") m_modules.emplace_back(new AmbientHeating(m_pd));
-    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating are).");
+    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity are).");
     m_modules.back()->configureModule(in);
 }
 
@@ -157,4 +158,74 @@ void AmbientHeating::setupModule()
         heating(i, j) = h;
     }
     PlasmaDomain::check(spruce_module_ambient_heating(m_pd.device(), heating.ptr(), heating.size()));
+}
+
+// viscosity.cpp:6-24
+void Viscosity::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "visc_output_visc" || k == "visc_output_lap" || k == "visc_output_strength" || k == "visc_output_timescale") m_any_output = m_any_output || (v == "true");
+        else if (k == "hv_time_integrator") m_hv_time_integrator = v;
+        else if (k == "gradient_correction") m_gradient_correction = (v == "true");
+        else if (k == "hv_epsilon") m_hv_epsilon = std::stod(v);
+        else if (k == "visc_opt") m_inp_visc_opt = v;
+        else if (k == "boundary_falloff_shape") m_boundary_falloff_shape = v;
+        else if (k == "visc_strength") m_inp_strength = v;
+        else if (k == "visc_vars_to_diff") m_inp_vars_to_diff = v;
+        else if (k == "visc_vars_to_evol") m_inp_vars_to_evol = v;
+        else if (k == "visc_length") m_inp_length = v;
+        else if (k == "visc_species") m_inp_species = v;
+        else std::cerr << k << " config not recognized.\n";
+    }
+}
+// viscosity.cpp:278-325, gaussian and exp shapes (the elliptical shapes are not ported); host libm, static profile
+Grid Viscosity::getBoundaryViscosity(double strength, double length) const
+{
+    const Grid &x = m_pd.m_grids[PlasmaDomain::pos_x], &y = m_pd.m_grids[PlasmaDomain::pos_y];
+    const size_t nx = m_pd.xdim(), ny = m_pd.ydim();
+    double x_min = x(0, 0), x_max = x(0, 0), y_min = y(0, 0), y_max = y(0, 0);
+    for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
+        x_min = std::min(x_min, x(i, j)); x_max = std::max(x_max, x(i, j)); y_min = std::min(y_min, y(i, j)); y_max = std::max(y_max, y(i, j));
+    }
+    const bool gauss = (m_boundary_falloff_shape == "gaussian");
+    Grid result = Grid::Zero(nx, ny);
+    for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
+        const double xv = x(i, j), yv = y(i, j);
+        double r = 0.0;
+        if (gauss) {
+            const double a[4] = {(xv - x_min) / length, (xv - x_max) / length, (yv - y_max) / length, (yv - y_min) / length};
+            for (double q : a) r = r + std::exp((q * q) * -2.3) * strength;
+        } else {
+            r = r + std::exp(((xv - x_min) * -2.3) / length) * strength;
+            r = r + std::exp(((xv - x_max) * 2.3) / length) * strength;
+            r = r + std::exp(((yv - y_max) * 2.3) / length) * strength;
+            r = r + std::exp(((yv - y_min) * -2.3) / length) * strength;
+        }
+        result(i, j) = (strength < r) ? strength : r;
+    }
+    return result;
+}
+// viscosity.cpp:37-110
+void Viscosity::setupModule()
+{
+    for (std::string *s : {&m_inp_visc_opt, &m_inp_strength, &m_inp_vars_to_diff, &m_inp_vars_to_evol, &m_inp_length, &m_inp_species}) clearWhitespace(*s);
+    const std::vector<std::string> opt = splitString(m_inp_visc_opt, ','), str = splitString(m_inp_strength, ','), diff = splitString(m_inp_vars_to_diff, ','),
+                                   evol = splitString(m_inp_vars_to_evol, ','), len = splitString(m_inp_length, ','), spec = splitString(m_inp_species, ',');
+    const size_t n = opt.size();
+    SPRUCE_REQUIRE(n > 0 && str.size() == n && diff.size() == n && evol.size() == n && len.size() == n && spec.size() == n, "every viscosity list must have one entry per term");
+    if (m_boundary_falloff_shape.empty()) m_boundary_falloff_shape = "gaussian";
+    SPRUCE_REQUIRE(m_boundary_falloff_shape == "gaussian" || m_boundary_falloff_shape == "exp", "Invalid boundary falloff shape given for Viscosity module (gaussian and exp are ported)");
+    no_file_output(m_any_output, "artificial_viscosity");
+    PlasmaDomain::check(spruce_module_viscosity(m_pd.device(), integrator_id(m_hv_time_integrator, "Viscosity"), m_hv_epsilon, m_gradient_correction));
+    for (size_t i = 0; i < n; i++) {
+        SPRUCE_REQUIRE(std::stod(len[i]) >= 0, "Length constants must greater than or equal to zero.");
+        const double strength = std::stod(str[i]);
+        if (opt[i] == "boundary" || opt[i] == "boundary_global") {
+            const Grid prof = getBoundaryViscosity(strength, std::stod(len[i]));
+            PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), prof.ptr(), prof.size()));
+        } else {
+            PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), nullptr, 0));
+        }
+    }
 }

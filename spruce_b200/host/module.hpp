@@ -51,6 +51,20 @@ private:
         "mass_injection", "ambient_heating_sink", "physical_viscosity", "div_cleaning", "boundary_outflow"};
 };
 
+// source/modules/viscosity.hpp ("artificial_viscosity")
+class Viscosity : public Module {
+public:
+    explicit Viscosity(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    bool device_resident() const override { return true; }
+private:
+    std::string m_inp_visc_opt, m_inp_strength, m_inp_vars_to_diff, m_inp_vars_to_evol, m_inp_length, m_inp_species;
+    std::string m_hv_time_integrator, m_boundary_falloff_shape;
+    bool m_gradient_correction = false, m_any_output = false;
+    double m_hv_epsilon = 1.0;
+    Grid getBoundaryViscosity(double strength, double length) const;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
 // source/modules/solar/thermalconduction.hpp
 class ThermalConduction : public Module {
 public:

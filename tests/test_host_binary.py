@@ -31,6 +31,10 @@ CASES = {
     "loop_open_reflect_rk4": (lambda: synthetic.stratified_loop(40, 36), dict(integrator="rk4", xb=("reflect", "open"), yb=("fixed", "open"), max_iterations=7, iter_output_interval=2,
                               output_flags=("rho", "temp", "press", "v_x", "v_y", "v_z", "n", "dt", "b_mag", "b_hat_x", "kinetic_energy", "thermal_energy", "b_x")), True),
     "loop_time_output_euler": (lambda: synthetic.stratified_loop(36, 30), dict(integrator="euler", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=9, iter_output_interval=-1), True),
+    "loop_viscosity": (lambda: synthetic.stratified_loop(40, 36), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "fixed"), max_iterations=5, iter_output_interval=1, write_precision=17,
+                       modules=[("artificial_viscosity", [("visc_opt", "boundary,global,local"), ("visc_strength", "0.8,2.0,0.3"), ("visc_vars_to_diff", "v_x,v_y,temp"),
+                                                          ("visc_vars_to_evol", "mom_x,mom_y,thermal_energy"), ("visc_length", "5.0e8,0,0"), ("visc_species", "i,i,i"),
+                                                          ("hv_time_integrator", "rk2")])]), True),
     "loop_solar_modules": (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=5, iter_output_interval=1,
                            modules=[("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4")]),
                                     ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
