@@ -135,6 +135,12 @@ int spruce_module_ambient_heating(spruce_domain *dom, const double *heating, siz
 int spruce_module_viscosity(spruce_domain *dom, int hv_time_integrator, double hv_epsilon, int gradient_correction);
 int spruce_module_viscosity_term(spruce_domain *dom, const char *visc_opt, double strength, const char *var_to_diff, const char *var_to_evol,
                                  const char *species, const double *strength_plane, size_t count);
+/* Ideal2F::parseEquationSetConfigs (source/equationsets/ideal2F.cpp:5-28): use_sub_cycling (reference default true, which aborts
+ * in computeTimeDerivatives -- only false can run, and spruce_eqs_setup refuses true) and remove_curl_terms. */
+int spruce_eqs_ideal2f_options(spruce_domain *dom, int use_sub_cycling, int remove_curl_terms);
+/* EICThermalization (source/modules/ucnp/eic_thermalization.cpp:27-44): electron-ion collisional energy exchange added to the
+ * right-hand side of e_thermal_energy / i_thermal_energy.  ideal_2F domains only. */
+int spruce_module_eic_thermalization(spruce_domain *dom);
 /* curr_num_subcycles of the last advance: which = "thermal_conduction" | "radiative_losses" */
 int spruce_module_subcycles(spruce_domain *dom, const char *which, int *count);
 

@@ -5,6 +5,7 @@
 #include "mhd_kernels.cuh"
 #include "module_kernels.cuh"
 #include "mhd_stage_xy.cuh"
+#include "ideal2f_kernels.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -23,6 +24,7 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(SPRUCE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define NOT_2F(d, what) do { if ((d)->tf) return fail(SPRUCE_ERR_UNSUPPORTED, "%s is not available with the ideal_2F equation set", what); } while (0)
 #define CHECK_DOM(d) do { if (!(d)) return fail(SPRUCE_ERR_ARG, "null domain handle"); } while (0)
 
 namespace {
@@ -33,10 +35,13 @@ struct HostAxis {          // 1-D tables of one axis on the host, index -TAB_APR
     std::vector<double> h, fs, rfs, ep, em, d, rd;
 };
 
+struct TwoFluid;
+
 }  // namespace
 
 struct spruce_domain {
     spruce_config cfg{};
+    TwoFluid *tf = nullptr;        // ideal_2F state (ideal2f_host.cuh); null for ideal_mhd
     DomainParams P{};
     cudaStream_t stream = nullptr;
     size_t plane_doubles = 0;      // allocation size of one plane incl. halo rows
@@ -609,6 +614,8 @@ int d2h_plane(spruce_domain *d, double *host, const double *dev)
     return SPRUCE_OK;
 }
 
+#include "ideal2f_host.cuh"
+
 }  // namespace
 
 extern "C" {
@@ -620,7 +627,9 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
 {
     if (!cfg || !out) return fail(SPRUCE_ERR_ARG, "null argument");
     if (cfg->abi_version != SPRUCE_ABI_VERSION) return fail(SPRUCE_ERR_ARG, "ABI version mismatch: header %d, library %d", cfg->abi_version, SPRUCE_ABI_VERSION);
-    if (cfg->equation_set != SPRUCE_EQS_IDEAL_MHD) return fail(SPRUCE_ERR_UNSUPPORTED, "equation set %d is not built yet (ideal_mhd only)", cfg->equation_set);
+    const bool two_fluid = (cfg->equation_set == SPRUCE_EQS_IDEAL_2F);
+    if (cfg->equation_set != SPRUCE_EQS_IDEAL_MHD && !two_fluid) return fail(SPRUCE_ERR_UNSUPPORTED, "equation set %d is not built (ideal_mhd and ideal_2F only)", cfg->equation_set);
+    if (two_fluid) { int rc2 = tf_check_boundaries(*cfg); if (rc2) return rc2; }
     // "Grid too small for ghost zones", plasmadomain.cpp:140
     if (cfg->xdim <= 2 * HALO || cfg->ydim <= 2 * HALO) return fail(SPRUCE_ERR_ARG, "Grid too small for ghost zones");
     const int bcs[4] = {cfg->x_bound_1, cfg->x_bound_2, cfg->y_bound_1, cfg->y_bound_2};
@@ -660,8 +669,9 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     d->row_off = (size_t)HALO * P.pitch;
     int rc = SPRUCE_OK;
     if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SPRUCE_ERR_CUDA, "cudaStreamCreate failed"); }
-    if (!rc) rc = alloc_set(d, d->Pset);
-    if (!rc) rc = alloc_set(d, d->Mset);
+    if (!rc && two_fluid) rc = tf_create(d);
+    if (!rc && !two_fluid) rc = alloc_set(d, d->Pset);
+    if (!rc && !two_fluid) rc = alloc_set(d, d->Mset);
     for (int v = 0; v < NSTATIC && !rc; v++) rc = alloc_plane(d, &d->stat[v]);
     if (!rc) rc = alloc_plane(d, &d->scratch_temp);
     if (!rc) rc = alloc_plane(d, &d->scratch_out);
@@ -694,6 +704,7 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->red) cudaFree(d->red);
     if (d->dt_hist) cudaFree(d->dt_hist);
     if (d->stream) cudaStreamDestroy(d->stream);
+    delete d->tf;
     delete d;
 }
 
@@ -718,6 +729,7 @@ int spruce_grid_upload(spruce_domain *d, const char *name, const double *host, s
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane <%s>: expected %zu values, got %zu", name, (size_t)d->P.nx * d->P.ny, count);
     if (!strcmp(name, "pos_x") || !strcmp(name, "pos_y") || !strcmp(name, "d_x") || !strcmp(name, "d_y")) return SPRUCE_OK; // host-only grids
+    if (d->tf) return tf_upload(d, name, host);
     {   // zero-plane bookkeeping for the planes whose transport can be skipped exactly
         const char *tracked[5] = {"mom_z", "bi_z", "be_x", "be_y", "be_z"};
         for (int b = 0; b < 5; b++) if (!strcmp(name, tracked[b])) {
@@ -742,6 +754,7 @@ int spruce_grid_download(spruce_domain *d, const char *name, double *host, size_
     CHECK_DOM(d);
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane <%s>: expected %zu values, got %zu", name, (size_t)d->P.nx * d->P.ny, count);
+    if (d->tf) return tf_download(d, name, host);
     const int s = static_slot(name);
     if (s >= 0) return d2h_plane(d, host, d->stat[s]);
     const int var = var_index(name);
@@ -765,7 +778,10 @@ int spruce_eqs_setup(spruce_domain *d)
     CHECK_DOM(d);
     if (!d->have_geom) return fail(SPRUCE_ERR_STATE, "spruce_set_cell_sizes must precede spruce_eqs_setup");
     d->raw_rho = true;
-    int rc = launch_propagate(d, 1);
+    // Ideal2F defaults to use_sub_cycling = true, whose time derivatives leave six 1x1 grids that abort at the ghost-zone mask
+    // multiply (ideal2F.cpp:73-94, grid.cpp:84): only the non-sub-cycled Maxwell update can run at all
+    if (d->tf && d->tf->use_sub_cycling) return fail(SPRUCE_ERR_UNSUPPORTED, "ideal_2F: use_sub_cycling = true aborts in the reference (size-mismatched grids); set use_sub_cycling = false");
+    int rc = d->tf ? tf_launch_propagate(d, 1) : launch_propagate(d, 1);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     d->is_setup = true;
@@ -776,7 +792,7 @@ int spruce_eqs_propagate_changes(spruce_domain *d)
 {
     CHECK_DOM(d);
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "propagate before setup");
-    int rc = launch_propagate(d, 0);
+    int rc = d->tf ? tf_launch_propagate(d, 0) : launch_propagate(d, 0);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     return SPRUCE_OK;
@@ -808,7 +824,7 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     CUDA_TRY(cudaMemcpyAsync(&h0, d->ctl, sizeof(h0), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     CUDA_TRY(cudaMemcpyAsync(&d->ctl->max_time, &max_time, sizeof(double), cudaMemcpyHostToDevice, d->stream));
-    for (int s = 0; s < n_steps; s++) { int rc = enqueue_step(d, s); if (rc) return rc; }
+    for (int s = 0; s < n_steps; s++) { int rc = d->tf ? tf_enqueue_step(d, s) : enqueue_step(d, s); if (rc) return rc; }
     StepCtl h1;
     CUDA_TRY(cudaMemcpyAsync(&h1, d->ctl, sizeof(h1), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
@@ -834,6 +850,7 @@ int spruce_eqs_time_derivatives(spruce_domain *d, double *k_out, size_t count)
 {
     CHECK_DOM(d);
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "time derivatives before setup");
+    if (d->tf) return tf_time_derivatives(d, k_out, count);
     const size_t np = (size_t)d->P.nx * d->P.ny;
     if (!k_out || count != NEV * np) return fail(SPRUCE_ERR_ARG, "k_out needs %zu values", NEV * np);
     int rc = ensure_rk4(d);
@@ -870,6 +887,7 @@ int spruce_operator(spruce_domain *d, const char *op, int index, const double *q
 int spruce_module_thermal_conduction(spruce_domain *d, int flux_saturation, int time_integrator, double epsilon, double dt_subcycle_min, double weakening_factor)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "thermal_conduction");
     if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
     if (time_integrator < 0 || time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid time integrator given for Thermal Conduction module");
     int rc = ensure_rk4(d);   // not needed for memory, keeps scratch planes uniform
@@ -884,6 +902,7 @@ int spruce_module_thermal_conduction(spruce_domain *d, int flux_saturation, int 
 int spruce_module_radiative_losses(spruce_domain *d, int time_integrator, double cutoff_ramp, double cutoff_temp, double epsilon, int prevent_subcycling)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "radiative_losses");
     if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
     if (time_integrator < 0 || time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid time integrator given for Radiative Losses module");
     d->rl.integrator = time_integrator; d->rl.cutoff_ramp = cutoff_ramp; d->rl.cutoff_temp = cutoff_temp; d->rl.epsilon = epsilon;
@@ -894,6 +913,7 @@ int spruce_module_radiative_losses(spruce_domain *d, int time_integrator, double
 int spruce_module_ambient_heating(spruce_domain *d, const double *heating, size_t count)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "ambient_heating");
     if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
     if (!heating || count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "heating plane needs %zu values", (size_t)d->P.nx * d->P.ny);
     if (!d->heating) { int rc = alloc_plane(d, &d->heating); if (rc) return rc; }
@@ -905,6 +925,7 @@ int spruce_module_ambient_heating(spruce_domain *d, const double *heating, size_
 int spruce_module_viscosity(spruce_domain *d, int hv_time_integrator, double hv_epsilon, int gradient_correction)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "artificial_viscosity");
     if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
     if (hv_time_integrator < 0 || hv_time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid hyperviscous time integrator given for Viscosity module");
     d->visc_hv_integrator = hv_time_integrator; d->visc_hv_epsilon = hv_epsilon; d->visc_gradient_correction = gradient_correction ? 1 : 0;
@@ -917,6 +938,7 @@ int spruce_module_viscosity_term(spruce_domain *d, const char *visc_opt, double 
                                  const char *species, const double *strength_plane, size_t count)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "artificial_viscosity");
     if (!visc_opt || !var_to_diff || !var_to_evol) return fail(SPRUCE_ERR_ARG, "null argument");
     if (!d->dt_plane) return fail(SPRUCE_ERR_STATE, "spruce_module_viscosity must precede its terms");
     spruce_domain::ViscTerm t{};
@@ -937,6 +959,22 @@ int spruce_module_viscosity_term(spruce_domain *d, const char *visc_opt, double 
     d->visc.push_back(t);
     return SPRUCE_OK;
 }
+int spruce_eqs_ideal2f_options(spruce_domain *d, int use_sub_cycling, int remove_curl_terms)
+{
+    CHECK_DOM(d);
+    if (!d->tf) return fail(SPRUCE_ERR_STATE, "ideal_2F options on a domain with another equation set");
+    d->tf->use_sub_cycling = use_sub_cycling ? 1 : 0;
+    d->tf->remove_curl_terms = remove_curl_terms ? 1 : 0;
+    return SPRUCE_OK;
+}
+int spruce_module_eic_thermalization(spruce_domain *d)
+{
+    CHECK_DOM(d);
+    // setupModule looks its grids up by name in the equation set and aborts when one is missing (eic_thermalization.cpp:13-24)
+    if (!d->tf) return fail(SPRUCE_ERR_ARG, "Grid <e_temp> was not found within the EquationSet.");
+    d->tf->eic = 1;
+    return SPRUCE_OK;
+}
 int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
 {
     CHECK_DOM(d);
@@ -955,6 +993,7 @@ static PlaneSet *set_by_id(spruce_domain *d, int which) { return which == 0 ? &d
 int spruce_halo_buffers(spruce_domain *d, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, size_t *bytes)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "slab decomposition");
     if (!d->halo[0]) {
         d->halo_doubles = (size_t)NEV * HALO * d->P.pitch;
         for (int k = 0; k < 4; k++) {
@@ -989,8 +1028,8 @@ static int halo_copy(spruce_domain *d, int which, int unpack)
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }
-int spruce_mgpu_pack(spruce_domain *d, int which) { CHECK_DOM(d); return halo_copy(d, which, 0); }
-int spruce_mgpu_unpack(spruce_domain *d, int which) { CHECK_DOM(d); return halo_copy(d, which, 1); }
+int spruce_mgpu_pack(spruce_domain *d, int which) { CHECK_DOM(d); NOT_2F(d, "slab decomposition"); return halo_copy(d, which, 0); }
+int spruce_mgpu_unpack(spruce_domain *d, int which) { CHECK_DOM(d); NOT_2F(d, "slab decomposition"); return halo_copy(d, which, 1); }
 
 int spruce_mgpu_n_stages(spruce_domain *d, int *n)
 {
@@ -1011,6 +1050,7 @@ static int stage_output_set(const spruce_domain *d, int stage)
 int spruce_mgpu_stage(spruce_domain *d, int stage)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "slab decomposition");
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "stage before setup");
     int rc;
     const int ti = d->cfg.time_integrator;
@@ -1050,6 +1090,7 @@ int spruce_mgpu_dt_min_ptr(spruce_domain *d, void **device_double)
 int spruce_mgpu_begin_step(spruce_domain *d)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "slab decomposition");
     if ((size_t)1 > d->dt_hist_cap) { d->dt_hist_cap = 64; CUDA_TRY(cudaMalloc(&d->dt_hist, d->dt_hist_cap * sizeof(double))); }
     k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, 0);
     d->launches++;
@@ -1059,6 +1100,7 @@ int spruce_mgpu_begin_step(spruce_domain *d)
 int spruce_mgpu_end_step(spruce_domain *d)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "slab decomposition");
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1070,6 +1112,7 @@ int spruce_mgpu_end_step(spruce_domain *d)
 int spruce_plane_activity(spruce_domain *d, int *local_mask, int set_global_mask)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "plane activity");
     if (local_mask) *local_mask = (int)d->nonzero_mask;
     if (set_global_mask >= 0) d->nonzero_mask = (unsigned)set_global_mask & 0x1Fu;
     return SPRUCE_OK;
@@ -1082,6 +1125,7 @@ int spruce_launch_count(spruce_domain *d, int64_t *count) { CHECK_DOM(d); if (co
 int spruce_time_stage_kernel(spruce_domain *d, int reps, float *ms_mean)
 {
     CHECK_DOM(d);
+    NOT_2F(d, "the stage-kernel timer");
     if (!d->is_setup || reps < 1 || !ms_mean) return fail(SPRUCE_ERR_STATE, "stage timing needs a set-up domain");
     cudaEvent_t a, b;
     CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));

@@ -31,12 +31,20 @@ class PlasmaDomain:
     EVOLVED = ["rho", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z"]          # idealmhd.hpp:32-34
     STATE = ["rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]   # idealmhd.hpp:28-30
     DOMAIN = ["be_x", "be_y", "be_z"]
+    # ideal2F.hpp:40-46
+    EVOLVED_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy",
+                  "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"]
+    STATE_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_temp", "e_temp", "bi_x", "bi_y", "bi_z",
+                "E_x", "E_y", "E_z", "grav_x", "grav_y"]
 
-    def __init__(self, planes: dict, ion_mass: float, adiabatic_index: float, *, equation_set="ideal_mhd",
+    def __init__(self, planes: dict, ion_mass: float, adiabatic_index: float, *, equation_set="ideal_mhd", eqs_options=None,
                  xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator="rk2", epsilon=0.2,
                  density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6, open_strength=1.0, open_decay=0.5,
                  time=0.0, device=-1, row0=0, nx_local=None, rank=0, n_ranks=1, setup=True):
         self.lib = capi.load()
+        self.equation_set = equation_set
+        if equation_set == "ideal_2F":
+            self.EVOLVED, self.STATE = self.EVOLVED_2F, self.STATE_2F
         gx, gy = planes["d_x"].shape if planes["d_x"].ndim == 2 else (planes["d_x"].size, planes["d_y"].size)
         if planes["d_x"].ndim == 2:
             dx, dy = rank1_cell_sizes(planes["d_x"], planes["d_y"])
@@ -55,6 +63,10 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_domain_create(C.byref(cfg), C.byref(h)))
         self.h = h
         capi.check(self.lib.spruce_set_cell_sizes(self.h, _dp(dx), dx.size, _dp(dy), dy.size))
+        if equation_set == "ideal_2F":
+            o = dict(use_sub_cycling=True, remove_curl_terms=False)          # Ideal2F defaults, ideal2F.hpp:62-65
+            o.update(eqs_options or {})
+            capi.check(self.lib.spruce_eqs_ideal2f_options(self.h, int(o["use_sub_cycling"]), int(o["remove_curl_terms"])))
         for name in self.DOMAIN + self.STATE:
             if name in planes:
                 self.upload(name, planes[name])
@@ -88,7 +100,7 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_eqs_propagate_changes(self.h))
 
     def computeTimeDerivatives(self) -> np.ndarray:
-        k = np.empty((8, self.nx, self.ydim))
+        k = np.empty((len(self.EVOLVED), self.nx, self.ydim))
         capi.check(self.lib.spruce_eqs_time_derivatives(self.h, _dp(k), k.size))
         return k
 
@@ -129,6 +141,9 @@ class PlasmaDomain:
     def set_ambient_heating_plane(self, heating: np.ndarray):
         a = self._local(heating)
         capi.check(self.lib.spruce_module_ambient_heating(self.h, _dp(a), a.size))
+
+    def set_eic_thermalization(self):
+        capi.check(self.lib.spruce_module_eic_thermalization(self.h))
 
     def set_viscosity(self, terms, *, hv_integrator="euler", hv_epsilon=1.0, gradient_correction=False):
         """terms: list of dict(opt, strength, var_diff, var_evol, species='i', strength_grid=None) in config order."""

@@ -115,3 +115,35 @@ def stratified_loop(nx: int, ny: int, *, length: float = 4.0e9, zfull: bool = Tr
         P["be_z"] = 0.05 * B0 * np.exp(-Y / (2 * H)) * np.cos(k * X)
         P["grav_x"] = 0.02 * g * np.sin(k * X)
     return dict(planes=P, ion_mass=M_I, adiabatic_index=GAMMA)
+
+
+M_SR = 1.455e-22          # strontium ion mass, reference source/constants.hpp:17
+M_E = 9.1094e-28          # electron mass, reference source/constants.hpp:9
+E_CGS = 4.80320425e-10    # reference source/constants.hpp:19
+
+
+def ucnp_cloud(nx: int, ny: int, *, length: float = 1.0, n0: float = 1.0e9, sigma: float = 0.1, Te: float = 20.0, Ti: float = 1.0,
+               drift: float = 0.0, bfield: float = 0.0) -> dict:
+    """Two-fluid ultracold-neutral-plasma expansion probe: Gaussian Sr+ / electron cloud on a non-uniform
+    grid, quasi-neutral, optional initial drift and a weak magnetic field so that every two-fluid term is exercised.
+    Planes = the 7 domain grids + Ideal2F::state_variables() (reference source/equationsets/ideal2F.hpp:40-42)."""
+    dx = stretched_spacing(nx, length, 0.15)
+    dy = stretched_spacing(ny, length, 0.10)
+    px, py = centres(dx) - 0.5 * length, centres(dy) - 0.5 * length
+    X = np.repeat(px[:, None], ny, axis=1)
+    Y = np.repeat(py[None, :], nx, axis=0)
+    n = n0 * np.exp(-(X * X + Y * Y) / (2.0 * sigma * sigma)) + 1.0e-4 * n0
+    z = np.zeros((nx, ny))
+    vx = drift * X / sigma
+    vy = -0.5 * drift * Y / sigma
+    P = {
+        "d_x": np.repeat(dx[:, None], ny, axis=1), "d_y": np.repeat(dy[None, :], nx, axis=0), "pos_x": X, "pos_y": Y,
+        "be_x": z + bfield, "be_y": z - 0.5 * bfield, "be_z": z.copy(),
+        "i_rho": n * M_SR, "e_rho": n * (1.0 + 1.0e-3 * np.sin(6.0 * X / length) * np.cos(5.0 * Y / length)) * M_E,
+        "i_mom_x": n * M_SR * vx, "i_mom_y": n * M_SR * vy, "e_mom_x": n * M_E * vx * 1.1, "e_mom_y": n * M_E * vy * 0.9,
+        "i_temp": z + Ti, "e_temp": z + Te,
+        "bi_x": z + 0.0, "bi_y": z + 0.0, "bi_z": z + 0.3 * bfield * np.cos(3.0 * X / length),
+        "E_x": 1.0e-6 * X / sigma * np.exp(-(X * X + Y * Y) / (2.0 * sigma * sigma)), "E_y": 1.0e-6 * Y / sigma * np.exp(-(X * X + Y * Y) / (2.0 * sigma * sigma)), "E_z": z.copy(),
+        "grav_x": z.copy(), "grav_y": z.copy(),
+    }
+    return dict(planes=P, ion_mass=M_SR, adiabatic_index=GAMMA)

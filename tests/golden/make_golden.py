@@ -28,10 +28,19 @@ from spruce_b200 import synthetic  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
 OUT_VARS = ["rho", "temp", "thermal_energy", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "dt"]
+OUT_VARS_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy", "E_x", "E_y", "E_z",
+               "bi_x", "bi_y", "bi_z", "i_temp", "e_temp", "dt", "dt_i", "j_x", "rho_c", "divE", "divB", "curlE_z", "e_dPdx", "b_hat_x"]
 NX, NY = 32, 28
 
 INACTIVE_FLOORS = dict(density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
 SOLAR_FLOORS = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+
+UCNP_FLOORS = dict(density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+TF = dict(eqs="ideal_2F", eqs_block=[("use_sub_cycling", "false")])
+EIC = ("eic_thermalization", [])
+UC = ("open_ucnp", "open_ucnp")
+PP = ("periodic", "periodic")
+CLOUD = dict(nx=NX, ny=NY, drift=2.0e3, bfield=5.0)
 
 TC = lambda **kw: ("thermal_conduction", list(dict(dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4", output_to_file="true"), **kw).items()))
 RL = lambda **kw: ("radiative_losses", list(dict(dict(cutoff_ramp="1.0e3", cutoff_temp="3.0e4", epsilon="0.1", output_to_file="true"), **kw).items()))
@@ -70,6 +79,14 @@ CASES = {
     "ot_visc_hv_rk4": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
                       modules=[AV(visc_opt="local,global", visc_strength="2.5,0.4", visc_vars_to_diff="v_x,temp", visc_vars_to_evol="mom_x,thermal_energy",
                                   visc_length="0,0", visc_species="i,i", hv_time_integrator="rk4", hv_epsilon="1.0")], **INACTIVE_FLOORS), 3, (1, 3)),
+    # two-fluid equation set (source/equationsets/ideal2F.cpp, non-sub-cycled Maxwell update) + EIC thermalization (BASELINE.json configs[2])
+    "tf_ucnp_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, **TF, **UCNP_FLOORS), 8, (1, 8)),
+    "tf_ucnp_eic_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, modules=[EIC], **TF, **UCNP_FLOORS), 8, (1, 8)),
+    "tf_pp_euler": ("ucnp_cloud", CLOUD, dict(integrator="euler", xb=PP, yb=PP, **TF, **UCNP_FLOORS), 5, (1, 5)),
+    "tf_pu_eic_rk4": ("ucnp_cloud", CLOUD, dict(integrator="rk4", xb=PP, yb=UC, modules=[EIC], **TF, **UCNP_FLOORS), 4, (1, 4)),
+    "tf_fr_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=("fixed", "reflect"), yb=("reflect", "fixed"), **TF, **UCNP_FLOORS), 6, (1, 6)),
+    "tf_floors_nocurl_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=PP, eqs="ideal_2F", eqs_block=[("use_sub_cycling", "false"), ("remove_curl_terms", "true")],
+                             density_min=3.0e6, temp_min=1.0e-3, thermal_energy_min=2.0e-10), 5, (1, 5)),
     # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
     "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
 }
@@ -99,11 +116,12 @@ def make(name):
     tmp = Path(tempfile.mkdtemp(prefix="golden_"))
     try:
         refrun.write_state(tmp / "in.state", s["planes"], s["ion_mass"], s["adiabatic_index"])
-        cfg = refrun.ideal_mhd_config(max_iterations=nsteps, output_flags=OUT_VARS, std_out_interval=1, **ckw)
+        out_vars = OUT_VARS_2F if ckw.get("eqs") == "ideal_2F" else OUT_VARS
+        cfg = refrun.ideal_mhd_config(max_iterations=nsteps, output_flags=out_vars, std_out_interval=1, **ckw)
         _, stdout = refrun.run_reference(tmp / "in.state", cfg, tmp / "out", threads=8)
         _, frames = refrun.read_out(tmp / "out" / "mhd.out")
         assert len(frames) == nsteps + 1, (len(frames), nsteps)
-        nx, ny = s["planes"]["rho"].shape
+        nx, ny = s["planes"]["d_x"].shape
         xl, xu, yl, yu = interior(ckw, nx, ny)
         eps = ckw.get("epsilon", 0.2)
         steps = np.array([eps * np.nanmin(f["dt"][xl:xu + 1, yl:yu + 1]) for f in frames[:-1]])
@@ -114,12 +132,12 @@ def make(name):
         out["steps"] = steps
         out["times_6digits"] = times
         for fi in keep:
-            for v in OUT_VARS:
+            for v in out_vars:
                 out["f%d_%s" % (fi, v)] = frames[fi][v]
             for v in frames[fi]:
-                if v not in OUT_VARS and v != "t":       # module output planes (thermal_conduction, rad, ...)
+                if v not in out_vars and v != "t":       # module output planes (thermal_conduction, rad, ...)
                     out["f%d_mod_%s" % (fi, v)] = frames[fi][v]
-        desc = dict(case=name, generator=gen, gen_kwargs=gkw, n_steps=nsteps, keep=list(keep),
+        desc = dict(case=name, out_vars=out_vars, generator=gen, gen_kwargs=gkw, n_steps=nsteps, keep=list(keep),
                     config={k: v for k, v in ckw.items()}, config_text=cfg,
                     subcycle_log=[ln for ln in stdout.splitlines() if "Subcycles" in ln][:nsteps])
         out["desc"] = np.array(json.dumps(desc))

@@ -12,8 +12,14 @@ OUT_VARS = ["rho", "temp", "thermal_energy", "mom_x", "mom_y", "mom_z", "bi_x", 
 EVOLVED = ["rho", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z"]
 
 
-def cases(prefixes=None):
+EVOLVED_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy",
+              "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"]
+
+
+def cases(prefixes=None, two_fluid=False):
+    """Fixture names; the two-fluid fixtures (tf_*) are pinned against the device path only (no CPU restatement of Ideal2F)."""
     names = sorted(p.stem for p in GOLDEN.glob("*.npz"))
+    names = [n for n in names if n.startswith("tf_") == two_fluid]
     if prefixes:
         names = [n for n in names if any(n.startswith(p) for p in prefixes)]
     return names
@@ -30,7 +36,8 @@ class Golden:
         self.steps = z["steps"]
         self.n_steps = self.desc["n_steps"]
         self.keep = self.desc["keep"]
-        self.frames = {fi: {v: z["f%d_%s" % (fi, v)] for v in OUT_VARS} for fi in self.keep}
+        self.out_vars = self.desc.get("out_vars", OUT_VARS)
+        self.frames = {fi: {v: z["f%d_%s" % (fi, v)] for v in self.out_vars} for fi in self.keep}
         self.module_planes = {fi: {k.split("_mod_", 1)[1]: z[k] for k in z.files if k.startswith("f%d_mod_" % fi)} for fi in self.keep}
         cfg = self.desc["config"]
         self.cfg = cfg
@@ -39,6 +46,8 @@ class Golden:
                        thermal_energy_min=cfg["thermal_energy_min"],
                        open_strength=cfg.get("open_strength", 1.0), open_decay=cfg.get("open_decay", 0.5))
         self.modules = [(m[0], dict(m[1])) for m in cfg.get("modules", [])]
+        self.equation_set = cfg.get("eqs", "ideal_mhd")
+        self.eqs_options = {k: (v == "true") for k, v in cfg.get("eqs_block", [])}
 
     def subcycle_counts(self, label):
         """Per-iteration sub-cycle counts parsed from the reference's stdout lines ('Thermal Subcycles: N')."""

@@ -86,6 +86,53 @@ def test_golden_reference_outputs(name):
     d.close()
 
 
+@pytest.mark.parametrize("name", cases(two_fluid=True))
+def test_two_fluid_golden_reference_outputs(name):
+    """Ideal2F (+ EIC thermalization) against fixtures written by the unmodified reference binary.  Bit-for-bit without the
+    module; eic_thermalization evaluates pow / log (glibc vs CUDA libm), so those runs are held to REL_TOL."""
+    from spruce_b200.domain import PlasmaDomain
+    g = Golden(name)
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, equation_set="ideal_2F", eqs_options=g.eqs_options, **g.kw)
+    exact = True
+    for m, _ in g.modules:
+        assert m == "eic_thermalization"
+        d.set_eic_thermalization()
+        exact = False
+    done = 0
+    for it in sorted(g.frames):
+        dts = d.advance(it - done)
+        ref = g.steps[done:it]
+        assert len(dts) == len(ref)
+        if exact:
+            assert all(a == b for a, b in zip(dts, ref)), "step history differs: %s vs %s" % ([x.hex() for x in dts[:3]], [float(x).hex() for x in ref[:3]])
+        else:
+            assert np.max(np.abs(dts - ref) / ref) <= REL_TOL
+        done = it
+        for v in g.out_vars:
+            got = d.grid(v)
+            if exact:
+                assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
+            else:
+                assert rel_linf(got, g.frames[it][v]) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (v, it, rel_linf(got, g.frames[it][v]))
+    d.close()
+
+
+def test_two_fluid_refusals():
+    """use_sub_cycling = true (the Ideal2F default) cannot run in the reference; eic_thermalization needs Ideal2F grids."""
+    from spruce_b200 import capi, synthetic
+    from spruce_b200.domain import PlasmaDomain
+    s = synthetic.ucnp_cloud(24, 20)
+    with pytest.raises(capi.SpruceError, match="use_sub_cycling"):
+        PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_2F", xb=("open_ucnp",) * 2, yb=("open_ucnp",) * 2)
+    with pytest.raises(capi.SpruceError, match="open"):
+        PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_2F", xb=("open", "open"), eqs_options=dict(use_sub_cycling=False))
+    o = synthetic.orszag_tang(24, 20)
+    d = PlasmaDomain(o["planes"], o["ion_mass"], o["adiabatic_index"])
+    with pytest.raises(capi.SpruceError, match="e_temp"):
+        d.set_eic_thermalization()
+    d.close()
+
+
 @pytest.mark.parametrize("integrator,xb,yb", [
     ("rk2", ("periodic", "periodic"), ("periodic", "periodic")),
     ("rk4", ("periodic", "periodic"), ("periodic", "periodic")),
