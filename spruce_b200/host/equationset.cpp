@@ -17,7 +17,8 @@ bool EquationSet::isEquationSetName(const std::string &name) { return std::find(
 std::unique_ptr<EquationSet> EquationSet::instantiateDefault(PlasmaDomain &pd, const std::string &name)
 {
     if (name == "ideal_mhd") return std::unique_ptr<EquationSet>(new IdealMHD(pd));
-    if (isEquationSetName(name)) spruce_die("Equation set <" + name + "> is not ported to the B200 path yet (ideal_mhd is).");
+    if (name == "ideal_2F") return std::unique_ptr<EquationSet>(new Ideal2F(pd));
+    if (isEquationSetName(name)) spruce_die("Equation set <" + name + "> is not ported to the B200 path yet (ideal_mhd and ideal_2F are).");
     spruce_die("Equation set name <" + name + "> not recognized.");
 }
 
@@ -63,6 +64,7 @@ void EquationSet::setupEquationSet()
 {
     SPRUCE_REQUIRE(allStateGridsInitialized(), "All variables specified as state variables for the current EquationSet must be specified in the .state file");
     m_pd.createDevice();
+    configureDevice();
     for (int v : state_variables()) PlasmaDomain::check(spruce_grid_upload(m_pd.device(), index2name(v).c_str(), m_grids[v].ptr(), m_grids[v].size()));
     PlasmaDomain::check(spruce_eqs_setup(m_pd.device()));
     name2index("dt");
@@ -126,4 +128,25 @@ void IdealMHD::parseEquationSetConfigs(std::vector<std::string> lhs, std::vector
         if (k == "moc_b_limiting" || k == "moc_mom_limiting") { SPRUCE_REQUIRE(rhs[i] != "true", "MoC limiting needs the open_moc boundary, which this build does not provide"); continue; }
         spruce_die(k + " is not recognized for this equation set.");
     }
+}
+
+Ideal2F::Ideal2F(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
+int Ideal2F::device_id() const { return SPRUCE_EQS_IDEAL_2F; }
+
+// ideal2F.cpp:10-28
+void Ideal2F::parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i];
+        if (k == "use_sub_cycling") m_use_sub_cycling = (rhs[i] == "true");
+        else if (k == "epsilon_courant") std::stod(rhs[i]);          // only read by the sub-cycled Maxwell update
+        else if (k == "verbose_2F") { }
+        else if (k == "remove_curl_terms") m_remove_curl_terms = (rhs[i] == "true");
+        else spruce_die(k + " is not recognized for this equation set.");
+    }
+}
+void Ideal2F::configureDevice()
+{
+    if (m_remove_curl_terms) m_use_sub_cycling = false;              // setupEquationSetDerived, ideal2F.cpp:24-28
+    PlasmaDomain::check(spruce_eqs_ideal2f_options(m_pd.device(), m_use_sub_cycling ? 1 : 0, m_remove_curl_terms ? 1 : 0));
 }

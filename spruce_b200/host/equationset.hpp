@@ -24,6 +24,7 @@ public:
     void setupEquationSet();                       // uploads the state variables, runs populateVariablesFromState on the device
 
     virtual int device_id() const = 0;            // SPRUCE_EQS_*
+    virtual void configureDevice() {}             // hand the parsed equation-set block to the device (after createDevice)
     virtual std::vector<int> state_variables() const = 0;
     virtual std::vector<int> evolved_variables() const = 0;
     virtual std::vector<std::string> species() const = 0;
@@ -93,5 +94,38 @@ public:
     std::vector<int> timescale() const override { return {dt}; }
 
 private:
+    void parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+
+// source/equationsets/ideal2F.hpp:16-77 -- ion + electron fluids with Maxwell's equations (the non-sub-cycled update)
+class Ideal2F : public EquationSet {
+public:
+    explicit Ideal2F(PlasmaDomain &pd);
+    enum Vars { i_rho, e_rho, i_mom_x, i_mom_y, e_mom_x, e_mom_y, i_temp, e_temp, bi_x, bi_y, bi_z, E_x, E_y, E_z, grav_x, grav_y,
+                i_n, e_n, i_v_x, i_v_y, e_v_x, e_v_y, j_x, j_y, i_press, e_press, press, i_thermal_energy, e_thermal_energy,
+                rho, rho_c, n, dn, dt, dt_i, b_x, b_y, b_z, b_mag, b_mag_xy, b_hat_x, b_hat_y, curlE_z, divE, divB, i_dPdx, e_dPdx };
+    static std::vector<std::string> def_var_names()
+    {
+        return {"i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_temp", "e_temp", "bi_x", "bi_y", "bi_z", "E_x", "E_y", "E_z", "grav_x", "grav_y",
+                "i_n", "e_n", "i_v_x", "i_v_y", "e_v_x", "e_v_y", "j_x", "j_y", "i_press", "e_press", "press", "i_thermal_energy", "e_thermal_energy",
+                "rho", "rho_c", "n", "dn", "dt", "dt_i", "b_x", "b_y", "b_z", "b_mag", "b_mag_xy", "b_hat_x", "b_hat_y", "curlE_z", "divE", "divB", "i_dPdx", "e_dPdx"};
+    }
+    int device_id() const override;
+    void configureDevice() override;
+    std::vector<int> state_variables() const override { return {i_rho, e_rho, i_mom_x, i_mom_y, e_mom_x, e_mom_y, i_temp, e_temp, bi_x, bi_y, bi_z, E_x, E_y, E_z, grav_x, grav_y}; }
+    std::vector<int> evolved_variables() const override { return {i_rho, e_rho, i_mom_x, i_mom_y, e_mom_x, e_mom_y, i_thermal_energy, e_thermal_energy, E_x, E_y, E_z, bi_x, bi_y, bi_z}; }
+    std::vector<std::string> species() const override { return {"i", "e"}; }
+    std::vector<int> densities() const override { return {i_rho, e_rho}; }
+    std::vector<int> number_densities() const override { return {i_n, e_n}; }
+    std::vector<std::vector<int>> momenta() const override { return {{i_mom_x, i_mom_y}, {e_mom_x, e_mom_y}}; }
+    std::vector<std::vector<int>> velocities() const override { return {{i_v_x, i_v_y}, {e_v_x, e_v_y}}; }
+    std::vector<int> thermal_energies() const override { return {i_thermal_energy, e_thermal_energy}; }
+    std::vector<int> pressures() const override { return {i_press, e_press}; }
+    std::vector<int> temperatures() const override { return {i_temp, e_temp}; }
+    std::vector<int> fields() const override { return {E_x, E_y, E_z}; }
+    std::vector<int> timescale() const override { return {dt_i, dt}; }
+
+private:
+    bool m_use_sub_cycling = true, m_remove_curl_terms = false;       // ideal2F.hpp:62-65
     void parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };

@@ -35,12 +35,17 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
         do { if (!std::getline(in, line)) break; clearWhitespace(line); } while (line.empty() || line[0] != '}');
         return;
     }
+    if (name == "eic_thermalization") {
+        m_modules.emplace_back(new EICThermalization(m_pd));
+        m_modules.back()->configureModule(in);
+        return;
+    }
     SPRUCE_REQUIRE(dynamic_cast<IdealMHD *>(m_pd.m_eqs.get()) != nullptr, "Module designed for IdealMHD EquationSet (ensure that equation_set is set before modules in the config)");
     if (name == "artificial_viscosity") m_modules.emplace_back(new Viscosity(m_pd));
     else if (name == "thermal_conduction") m_modules.emplace_back(new ThermalConduction(m_pd));
     else if (name == "radiative_losses") m_modules.emplace_back(new RadiativeLosses(m_pd));
     else if (name == "ambient_heating") m_modules.emplace_back(new AmbientHeating(m_pd));
-    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity are).");
+    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, eic_thermalization are).");
     m_modules.back()->configureModule(in);
 }
 
@@ -228,4 +233,12 @@ void Viscosity::setupModule()
             PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), nullptr, 0));
         }
     }
+}
+
+// eic_thermalization.cpp:12-25: every grid the module reads must exist in the equation set
+void EICThermalization::setupModule()
+{
+    for (const char *name : {"n", "e_temp", "e_thermal_energy", "i_thermal_energy"})
+        if (!m_pd.m_eqs->is_var(name)) spruce_die(std::string("Grid <") + name + "> was not found within the EquationSet.");
+    PlasmaDomain::check(spruce_module_eic_thermalization(m_pd.device()));
 }

@@ -103,3 +103,12 @@ private:
     bool exp_mode = false, split_exp_mode = false;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
+// source/modules/ucnp/eic_thermalization.hpp -- electron-ion collisional energy exchange (two-fluid equation set only)
+class EICThermalization : public Module {
+public:
+    explicit EICThermalization(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    bool device_resident() const override { return true; }
+private:
+    void parseModuleConfigs(std::vector<std::string>, std::vector<std::string>) override {}   // eic_thermalization.cpp:7-10: no keys
+};

@@ -86,4 +86,5 @@ private:
     TimeIntegrator stringToTimeIntegrator(const std::string &str) const;
     static std::string num2str(double num);
     friend class ModuleHandler;
+    friend class EICThermalization;
 };

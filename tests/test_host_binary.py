@@ -39,6 +39,13 @@ CASES = {
                            modules=[("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4")]),
                                     ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
                                     ("ambient_heating", [("heating_rate", "1.0e-4")])]), False),
+    # BASELINE.json configs[2]: two-fluid UCNP expansion (ideal_2F, open_ucnp on all sides), without and with EIC thermalization
+    "ucnp_two_fluid": (lambda: synthetic.ucnp_cloud(40, 36, drift=2.0e3, bfield=5.0), dict(integrator="rk2", xb=("open_ucnp", "open_ucnp"), yb=("open_ucnp", "open_ucnp"), max_iterations=6,
+                       iter_output_interval=2, write_precision=17, eqs="ideal_2F", eqs_block=[("use_sub_cycling", "false")], density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30,
+                       output_flags=("i_rho", "e_rho", "i_mom_x", "e_mom_y", "i_temp", "e_temp", "E_x", "E_y", "E_z", "bi_z", "j_x", "j_y", "divE", "divB", "dt", "dt_i", "n", "dn", "press")), True),
+    "ucnp_two_fluid_eic": (lambda: synthetic.ucnp_cloud(40, 36, drift=2.0e3, bfield=5.0), dict(integrator="rk4", xb=("open_ucnp", "open_ucnp"), yb=("periodic", "periodic"), max_iterations=4,
+                           iter_output_interval=1, eqs="ideal_2F", eqs_block=[("use_sub_cycling", "false")], density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30,
+                           output_flags=("i_rho", "e_rho", "i_temp", "e_temp", "E_x", "dt"), modules=[("eic_thermalization", [])]), False),
 }
 
 
@@ -69,4 +76,5 @@ def test_run_binary_matches_reference_files(name, tmp_path):
         _, fa = refrun.read_out(tmp_path / "ours" / "mhd.out")
         _, fb = refrun.read_out(tmp_path / "ref" / "mhd.out")
         assert len(fa) == len(fb) and [f["t"] for f in fa] == [f["t"] for f in fb]
-        assert "Thermal Subcycles" in stdout and "Radiative Subcycles" in stdout
+        if name == "loop_solar_modules":
+            assert "Thermal Subcycles" in stdout and "Radiative Subcycles" in stdout
