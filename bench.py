@@ -157,17 +157,21 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.size
-    s = synthetic.orszag_tang(n, n)
+    if world > 1:
+        from spruce_b200.multigpu import partition
+        s = synthetic.orszag_tang(n, n, rows=partition(n, world)[rank])      # every rank builds only its own slab
+    else:
+        s = synthetic.orszag_tang(n, n)
     planes = s["planes"]
-    dx, dy = np.ascontiguousarray(planes["d_x"][:, 0]), np.ascontiguousarray(planes["d_y"][0, :])
+    dx, dy = np.ascontiguousarray(s["dx"]), np.ascontiguousarray(s["dy"])
     names = ["be_x", "be_y", "be_z", "rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
 
     if world > 1:
-        from spruce_b200.multigpu import SlabRunner, partition
+        from spruce_b200.multigpu import SlabRunner
         cells = n * n
         host = {k: planes[k] for k in names}
         host["d_x"], host["d_y"] = dx, dy
-        runner = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, **KW)
+        runner = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=args.transport, xdim=n, **KW)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -180,12 +184,13 @@ def run_ours(args):
         achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
         result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                               "peak_source": peak_src, "kernel": "k_mhd_stage", "alg_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
-                              "note": "per GPU; includes the halo pack / NCCL send-recv / unpack and the dt all-reduce between launches"}
+                              "note": "per GPU; includes the halo exchange (%s) and the dt all-gather between launches" % ("peer stores over NVLink from the pack kernel" if args.transport == "p2p" else "NCCL send/recv")}
+        result["transport"] = args.transport
         runner.close()
         # end to end: slab upload from host memory + setup + first halo exchange + K steps + download of the evolved slabs
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        r2 = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, **KW)
+        r2 = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=args.transport, xdim=n, **KW)
         r2.step(args.steps)
         out = {k: r2.dom.grid(k) for k in PlasmaDomain.EVOLVED}
         torch.cuda.synchronize(); dist.barrier()
@@ -281,7 +286,7 @@ def emit(args, r, world):
             "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "OT-%d: synthetic doubly periodic Orszag-Tang vortex, non-uniform rectilinear %dx%d grid, ideal MHD, RK2, epsilon 0.2 (BASELINE.json configs[3])" % (args.size, args.size, args.size),
-                       "parallelism": "slab%d" % world if world > 1 else "single", "l2": "working set per step (21 planes, %.1f GB) >> 126 MB L2: inputs larger than L2" % (21 * args.size ** 2 * 8 / 1e9),
+                       "parallelism": ("slab%d along x, halo exchange: %s" % (world, r.get("transport", "p2p"))) if world > 1 else "single", "l2": "working set per step (21 planes, %.1f GB) >> 126 MB L2: inputs larger than L2" % (21 * args.size ** 2 * 8 / 1e9),
                        "mode": "exact (bit-identical to the reference CPU build)"},
             "clocks": r["clocks"], "gpu_launches": r["launches"], "e2e": r["e2e"], "roofline": r["roofline"]}
     if r.get("cpu"):
@@ -297,6 +302,7 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: library peer stores over NVLink, or torch.distributed NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -153,6 +153,16 @@ int spruce_halo_buffers(spruce_domain *dom, void **send_lo, void **send_hi, void
  * phase 0: pack halos of the primary state; then per RK stage s: stage_begin(s) computes stage s and packs the halos
  * of its output; the caller exchanges; stage_end(s) unpacks.  The dt minimum is exchanged with
  * spruce_local_dt_min / spruce_set_global_dt_min (ncclAllReduce(min)). */
+/* Peer-store transport (the default): every rank exports one device segment through CUDA IPC (64-byte cudaIpcMemHandle_t),
+ * the caller gathers the handles of all ranks (any host-side channel; 64 bytes per rank, rank order) and hands them to
+ * spruce_mgpu_ipc_connect.  From then on spruce_advance works on a slab exactly as on a whole domain: after every stage the
+ * pack kernel stores the edge rows straight into the ring neighbours' segments over NVLink and publishes a sequence number,
+ * the unpack kernel acquires the neighbours' numbers; the dt minimum is all-gathered the same way.  No host synchronisation
+ * and no collective-library call inside the time loop.  Call order: create, upload, plane_activity, ipc_export / gather /
+ * ipc_connect, eqs_setup, initial_exchange (needs every rank to have connected: barrier before it), advance. */
+int spruce_mgpu_ipc_export(spruce_domain *dom, void *handle64);
+int spruce_mgpu_ipc_connect(spruce_domain *dom, const void *handles, int n_handles);
+int spruce_mgpu_initial_exchange(spruce_domain *dom);
 int spruce_mgpu_pack(spruce_domain *dom, int which_state);     /* 0 primary, 1/2 stage copies, 3 static planes (be_*, grav_*) */
 int spruce_mgpu_unpack(spruce_domain *dom, int which_state);
 int spruce_mgpu_stage(spruce_domain *dom, int stage);

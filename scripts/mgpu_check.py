@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N scripts/mgpu_check.py [nx ny steps integrator xbound]
+"""torchrun --nproc-per-node N scripts/mgpu_check.py [nx ny steps integrator xbound transport]
 N-GPU slab run vs the 1-GPU run of the same problem (rank 0 computes both): planes and step sizes must be identical
 bit for bit (min/max reductions are exact and every cell sees the same operands)."""
 import os
@@ -18,6 +18,7 @@ ny = int(sys.argv[2]) if len(sys.argv) > 2 else 210
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 integ = sys.argv[4] if len(sys.argv) > 4 else "rk2"
 xbound = sys.argv[5] if len(sys.argv) > 5 else "periodic"
+transport = sys.argv[6] if len(sys.argv) > 6 else "p2p"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -27,7 +28,7 @@ if xbound == "periodic":
 else:
     s = synthetic.stratified_loop(nx, ny)
     kw = dict(xb=(xbound, "open"), yb=("reflect", "fixed"), integrator=integ)
-run = SlabRunner(s["planes"], s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, **kw)
+run = SlabRunner(s["planes"], s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=transport, **kw)
 run.step(steps)
 run.dom.synchronize()
 got = {v: run.gather(v) for v in PlasmaDomain.EVOLVED + ["dt"]}
@@ -44,7 +45,7 @@ if rank == 0:
             bad = np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))
             print("MISMATCH", v, len(bad), bad[:5].tolist())
     ok &= (t_slab == one.time)
-    print("mgpu_check world=%d %dx%d %s x=%s steps=%d : %s (t=%r vs %r)" % (world, nx, ny, integ, xbound, steps, "IDENTICAL" if ok else "DIFFERENT", t_slab, one.time))
+    print("mgpu_check world=%d %s %dx%d %s x=%s steps=%d : %s (t=%r vs %r)" % (world, transport, nx, ny, integ, xbound, steps, "IDENTICAL" if ok else "DIFFERENT", t_slab, one.time))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

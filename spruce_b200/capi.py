@@ -58,6 +58,9 @@ SYMBOLS = {
     "spruce_module_eic_thermalization": (C.c_int, [C.c_void_p]),
     "spruce_module_subcycles": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]),
     "spruce_halo_buffers": (C.c_int, [C.c_void_p, _VPP, _VPP, _VPP, _VPP, C.POINTER(C.c_size_t)]),
+    "spruce_mgpu_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "spruce_mgpu_ipc_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "spruce_mgpu_initial_exchange": (C.c_int, [C.c_void_p]),
     "spruce_mgpu_pack": (C.c_int, [C.c_void_p, C.c_int]),
     "spruce_mgpu_unpack": (C.c_int, [C.c_void_p, C.c_int]),
     "spruce_mgpu_stage": (C.c_int, [C.c_void_p, C.c_int]),

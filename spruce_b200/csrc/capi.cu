@@ -77,6 +77,12 @@ struct spruce_domain {
     unsigned nonzero_mask = 0x1F;
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
+    // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
+    void *seg = nullptr; size_t seg_bytes = 0;
+    void *peer_seg[MAX_RANKS] = {nullptr};      // mapped segments of the other ranks (own rank: seg)
+    bool peers_connected = false;
+    unsigned long long halo_seq = 0, dt_seq = 0;
+    unsigned int *push_counter = nullptr;
 };
 
 namespace {
@@ -518,6 +524,76 @@ int av_iterate(spruce_domain *d, double dt)
     return SPRUCE_OK;
 }
 
+
+// ---- peer-store transport -------------------------------------------------------------------------------------------
+size_t seg_flags_bytes() { return (sizeof(PeerFlags) + 255) & ~(size_t)255; }
+PeerFlags *seg_flags(void *seg) { return (PeerFlags *)seg; }
+double *seg_buf(const spruce_domain *d, void *seg, int side, int parity)
+{
+    return (double *)((char *)seg + seg_flags_bytes()) + ((size_t)side * 2 + parity) * d->halo_doubles;
+}
+int ensure_segment(spruce_domain *d)
+{
+    if (d->seg) return SPRUCE_OK;
+    d->halo_doubles = (size_t)NEV * HALO * d->P.pitch;
+    d->seg_bytes = seg_flags_bytes() + 4 * d->halo_doubles * sizeof(double);
+    CUDA_TRY(cudaMalloc(&d->seg, d->seg_bytes));
+    CUDA_TRY(cudaMemset(d->seg, 0, d->seg_bytes));
+    CUDA_TRY(cudaMalloc(&d->push_counter, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(d->push_counter, 0, sizeof(unsigned int)));
+    return SPRUCE_OK;
+}
+void ring_neighbours(const spruce_domain *d, int *lo, int *hi)
+{
+    const int r = d->cfg.rank, w = d->cfg.n_ranks;
+    *lo = r > 0 ? r - 1 : (d->P.xper ? w - 1 : -1);
+    *hi = r < w - 1 ? r + 1 : (d->P.xper ? 0 : -1);
+}
+// push my edge rows of `U` into the neighbours' segments, then wait for theirs and copy them into my halo rows
+int peer_exchange(spruce_domain *d, double *const *U)
+{
+    if (!d->peers_connected) return fail(SPRUCE_ERR_STATE, "peer transport used before spruce_mgpu_ipc_connect");
+    const unsigned long long q = ++d->halo_seq;
+    const int par = (int)(q & 1);
+    int lo, hi;
+    ring_neighbours(d, &lo, &hi);
+    PushArgs S{};
+    for (int v = 0; v < NEV; v++) S.U[v] = U[v];
+    if (lo >= 0) { S.peer_lo_buf = seg_buf(d, d->peer_seg[lo], 1, par); S.peer_lo_flag = &seg_flags(d->peer_seg[lo])->halo_seq[1][0]; }   // I am its UPPER neighbour
+    if (hi >= 0) { S.peer_hi_buf = seg_buf(d, d->peer_seg[hi], 0, par); S.peer_hi_flag = &seg_flags(d->peer_seg[hi])->halo_seq[0][0]; }
+    S.seq = q; S.counter = d->push_counter; S.done_ptr = &d->ctl->done;
+    dim3 grid((d->P.pitch + 255) / 256, NEV * HALO);
+    k_halo_push<<<grid, 256, 0, d->stream>>>(d->P, S);
+    PullArgs R{};
+    for (int v = 0; v < NEV; v++) R.U[v] = U[v];
+    if (lo >= 0) { R.lo_buf = seg_buf(d, d->seg, 0, par); R.lo_flag = &seg_flags(d->seg)->halo_seq[0][0]; }
+    if (hi >= 0) { R.hi_buf = seg_buf(d, d->seg, 1, par); R.hi_flag = &seg_flags(d->seg)->halo_seq[1][0]; }
+    R.seq = q; R.error = &seg_flags(d->seg)->error; R.done_ptr = &d->ctl->done;
+    k_halo_pull<<<grid, 256, 0, d->stream>>>(d->P, R);
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+int peer_dt_allgather(spruce_domain *d)
+{
+    DtGatherArgs A{};
+    A.ctl = d->ctl; A.mine = seg_flags(d->seg); A.rank = d->cfg.rank; A.world = d->cfg.n_ranks; A.seq = ++d->dt_seq;
+    for (int r = 0; r < d->cfg.n_ranks; r++) A.peer[r] = seg_flags(d->peer_seg[r]);
+    k_dt_publish<<<1, MAX_RANKS, 0, d->stream>>>(A);
+    k_dt_collect<<<1, MAX_RANKS, 0, d->stream>>>(A);
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+// ghost zones of the set a stage produced, then (slab decomposition) its halo rows from the ring neighbours
+int finish_stage(spruce_domain *d, const PlaneSet &U, int primary)
+{
+    int rc = launch_ghosts(d, U, primary);
+    if (rc || d->cfg.n_ranks == 1) return rc;
+    return peer_exchange(d, U.p);
+}
+
 // one advanceTime (evolution.cpp:59-82) worth of launches
 int enqueue_step(spruce_domain *d, int hist_slot)
 {
@@ -546,23 +622,24 @@ int enqueue_step(spruce_domain *d, int hist_slot)
     if (ti == SPRUCE_TI_EULER) {                                        // evolution.cpp:84-88
         if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;
         std::swap(d->Pset, d->Mset);                                    // D never aliases S: ping-pong instead of in place
-        if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
+        if ((rc = finish_stage(d, d->Pset, 1))) return rc;
     } else if (ti == SPRUCE_TI_RK2) {                                   // evolution.cpp:90-101
         if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE))) return rc;
-        if ((rc = launch_ghosts(d, d->Mset, 0))) return rc;
+        if ((rc = finish_stage(d, d->Mset, 0))) return rc;
         if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_NONE))) return rc;
-        if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
+        if ((rc = finish_stage(d, d->Pset, 1))) return rc;
     } else {                                                            // evolution.cpp:103-124
         if ((rc = ensure_rk4(d))) return rc;
         if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_STORE_K1))) return rc;
-        if ((rc = launch_ghosts(d, d->Mset, 0))) return rc;
+        if ((rc = finish_stage(d, d->Mset, 0))) return rc;
         if ((rc = launch_stage(d, d->Mset, d->Pset, d->M2set, 0.5, 0, KM_STORE_K2))) return rc;
-        if ((rc = launch_ghosts(d, d->M2set, 0))) return rc;
+        if ((rc = finish_stage(d, d->M2set, 0))) return rc;
         if ((rc = launch_stage(d, d->M2set, d->Pset, d->Mset, 1.0, 0, KM_ADD_K2))) return rc;
-        if ((rc = launch_ghosts(d, d->Mset, 0))) return rc;
+        if ((rc = finish_stage(d, d->Mset, 0))) return rc;
         if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
-        if ((rc = launch_ghosts(d, d->Pset, 1))) return rc;
+        if ((rc = finish_stage(d, d->Pset, 1))) return rc;
     }
+    if (d->cfg.n_ranks > 1 && (rc = peer_dt_allgather(d))) return rc;   // global min(dt) for the next step (evolution.cpp:62)
     for (int m : d->module_order)                                        // postIterateModules, evolution.cpp:74
         if (m == spruce_domain::MOD_AH && (rc = ah_post(d))) return rc;
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
@@ -703,6 +780,9 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->ctl) cudaFree(d->ctl);
     if (d->red) cudaFree(d->red);
     if (d->dt_hist) cudaFree(d->dt_hist);
+    for (int r = 0; r < MAX_RANKS; r++) if (d->peer_seg[r] && d->peer_seg[r] != d->seg) cudaIpcCloseMemHandle(d->peer_seg[r]);
+    if (d->seg) cudaFree(d->seg);
+    if (d->push_counter) cudaFree(d->push_counter);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d->tf;
     delete d;
@@ -815,6 +895,8 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     CHECK_DOM(d);
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "advance before setup");
     if (n_steps < 0) return fail(SPRUCE_ERR_ARG, "negative step count");
+    if (d->cfg.n_ranks > 1 && !d->peers_connected) return fail(SPRUCE_ERR_STATE, "a slab of a decomposed domain advances either through spruce_mgpu_stage (caller-owned exchange) or, after spruce_mgpu_ipc_connect, through spruce_advance");
+    if (d->cfg.n_ranks > 1 && !d->module_order.empty()) return fail(SPRUCE_ERR_UNSUPPORTED, "physics modules run on a single rank in this version");
     if ((size_t)n_steps > d->dt_hist_cap) {
         if (d->dt_hist) cudaFree(d->dt_hist);
         d->dt_hist_cap = (size_t)n_steps + 64;
@@ -1104,6 +1186,52 @@ int spruce_mgpu_end_step(spruce_domain *d)
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+// ---- peer-store transport: export my segment, map the neighbours', exchange the initial halos
+int spruce_mgpu_ipc_export(spruce_domain *d, void *handle64)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "slab decomposition");
+    if (!handle64) return fail(SPRUCE_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    int rc = ensure_segment(d);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, d->seg));
+    memcpy(handle64, &h, sizeof(h));
+    return SPRUCE_OK;
+}
+int spruce_mgpu_ipc_connect(spruce_domain *d, const void *handles, int n_handles)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "slab decomposition");
+    if (!handles || n_handles != d->cfg.n_ranks || n_handles > MAX_RANKS) return fail(SPRUCE_ERR_ARG, "need one 64-byte handle per rank (%d ranks, at most %d)", d->cfg.n_ranks, MAX_RANKS);
+    int rc = ensure_segment(d);
+    if (rc) return rc;
+    for (int r = 0; r < n_handles; r++) {
+        if (r == d->cfg.rank) { d->peer_seg[r] = d->seg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, sizeof(h));
+        CUDA_TRY(cudaIpcOpenMemHandle(&d->peer_seg[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    d->peers_connected = true;
+    return SPRUCE_OK;
+}
+// after spruce_eqs_setup on every rank: halo rows of the static planes and of the primary state, global dt minimum
+int spruce_mgpu_initial_exchange(spruce_domain *d)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "slab decomposition");
+    if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "initial exchange before setup");
+    double *stat_view[NEV];
+    for (int v = 0; v < NEV; v++) stat_view[v] = d->stat[v < NSTATIC ? v : 0];
+    int rc;
+    if ((rc = peer_exchange(d, stat_view))) return rc;
+    if ((rc = peer_exchange(d, d->Pset.p))) return rc;
+    if ((rc = peer_dt_allgather(d))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
     return SPRUCE_OK;
 }
 

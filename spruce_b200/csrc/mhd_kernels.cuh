@@ -745,6 +745,116 @@ __global__ void __launch_bounds__(256) k_halo_copy(const DomainParams P, const H
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Peer-store halo exchange over NVLink (slab decomposition, one process per GPU).  Every rank exports ONE device
+// segment through CUDA IPC (PeerSegment below); its ring neighbours map it and WRITE their edge rows straight into it
+// from the pack kernel (st.global to peer memory travels over NVLink / NVSwitch), then publish a sequence number with a
+// system-scope release.  The receiver's unpack kernel acquires that number before it copies the rows into its halo.
+// No host synchronisation, no collective library call on the data path: a whole spruce_advance(n) is enqueued at once.
+//
+// Buffer reuse: exchange number q uses buffer q & 1.  A rank can be at most one exchange ahead of a neighbour (it
+// needs that neighbour's rows of exchange q+1 before it can produce exchange q+2, and the neighbour only sends those
+// after unpacking exchange q), so two buffers are enough.  The same argument covers the dt slots (one global
+// all-gather per step, which every rank completes before it starts the next step).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MAX_RANKS = 16;
+struct PeerFlags {                                            // one 128-byte line per independently written word
+    unsigned long long halo_seq[2][16];                       // [side][0]: last exchange written by my lower / upper neighbour
+    unsigned long long dt_seq[MAX_RANKS][16];                 // [r][0]: last step whose local dt minimum rank r has stored
+    unsigned long long dt_bits[2][MAX_RANKS];                 // [parity][r]
+    int error; int pad[31];                                   // set when a wait timed out (peer died): every later launch drains
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag >= seq; gives up after ~20 s (a dead peer must not hang the box) and raises the segment's error word
+__device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq, int *error)
+{
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys(flag) < seq) {
+        __nanosleep(64);
+        if ((++spins & 0x3FFu) == 0) {
+            if (*(volatile int *)error) return false;
+            if (global_timer_ns() - t0 > 20000000000ULL) { atomicExch(error, 1); return false; }
+        }
+    }
+    return true;
+}
+
+struct PushArgs {
+    const double *U[NEV];
+    double *peer_lo_buf, *peer_hi_buf;          // lower neighbour's "from above" buffer / upper neighbour's "from below" buffer (null: no neighbour)
+    unsigned long long *peer_lo_flag, *peer_hi_flag;
+    unsigned long long seq;
+    unsigned int *counter;                       // local: blocks that have finished their stores
+    const int *done_ptr;
+};
+__global__ void __launch_bounds__(256) k_halo_push(const DomainParams P, const PushArgs A)
+{
+    if (*A.done_ptr) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y / HALO, h = blockIdx.y % HALO;
+    if (j < P.pitch) {
+        const size_t b = ((size_t)v * HALO + h) * P.pitch + j;
+        if (A.peer_lo_buf) A.peer_lo_buf[b] = A.U[v][(size_t)h * P.pitch + j];
+        if (A.peer_hi_buf) A.peer_hi_buf[b] = A.U[v][(size_t)(P.nx - HALO + h) * P.pitch + j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(A.counter, 1u) == total - 1) {        // last block: every block's rows are visible system-wide
+            *A.counter = 0;
+            __threadfence_system();
+            if (A.peer_lo_flag) st_release_sys(A.peer_lo_flag, A.seq);
+            if (A.peer_hi_flag) st_release_sys(A.peer_hi_flag, A.seq);
+        }
+    }
+}
+
+struct PullArgs {
+    double *U[NEV];
+    const double *lo_buf, *hi_buf;               // my segment: rows from the lower / upper neighbour (null: physical boundary)
+    const unsigned long long *lo_flag, *hi_flag;
+    unsigned long long seq;
+    int *error;
+    const int *done_ptr;
+};
+__global__ void __launch_bounds__(256) k_halo_pull(const DomainParams P, const PullArgs A)
+{
+    if (*A.done_ptr) return;
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        bool good = true;
+        if (A.lo_buf) good = wait_seq(A.lo_flag, A.seq, A.error);
+        if (good && A.hi_buf) good = wait_seq(A.hi_flag, A.seq, A.error);
+        ok = good ? 1 : 0;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y / HALO, h = blockIdx.y % HALO;
+    if (j >= P.pitch) return;
+    const size_t b = ((size_t)v * HALO + h) * P.pitch + j;
+    if (A.lo_buf) A.U[v][(size_t)(h - HALO) * P.pitch + j] = __ldcv(A.lo_buf + b);
+    if (A.hi_buf) A.U[v][(size_t)(P.nx + h) * P.pitch + j] = __ldcv(A.hi_buf + b);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Scalar bookkeeping of advanceTime (evolution.cpp:62,80-81), one thread.
 // ctl[0] = step (double), ctl[1] = time, ctl[2] = max_time (<=0: none); ictl[0] = iter, ictl[1] = done flag
 // ---------------------------------------------------------------------------------------------------------
@@ -760,5 +870,37 @@ __global__ void k_step_begin(StepCtl *c, double *dt_hist, int slot)
 }
 __global__ void k_dtmin_reset(StepCtl *c) { if (!c->done) c->dtmin_bits = 0x7FEFFFFFFFFFFFFFULL; }
 __global__ void k_step_end(StepCtl *c) { if (c->done) return; c->time += c->step; c->iter += 1; }
+
+// dt all-gather over peer memory: thread r stores my local minimum into rank r's slot, then publishes the step number;
+// the collect kernel waits for every rank's number and takes the minimum (min of positive doubles == min of their bit patterns)
+struct DtGatherArgs { StepCtl *ctl; PeerFlags *peer[MAX_RANKS]; PeerFlags *mine; int rank, world; unsigned long long seq; };
+__global__ void k_dt_publish(const DtGatherArgs A)
+{
+    if (A.ctl->done) return;
+    const int r = threadIdx.x;
+    if (r >= A.world) return;
+    const unsigned long long bits = A.ctl->dtmin_bits;
+    PeerFlags *f = A.peer[r];
+    f->dt_bits[A.seq & 1][A.rank] = bits;
+    __threadfence_system();
+    st_release_sys(&f->dt_seq[A.rank][0], A.seq);
+}
+__global__ void k_dt_collect(const DtGatherArgs A)
+{
+    if (A.ctl->done) return;
+    __shared__ unsigned long long m[MAX_RANKS];
+    const int r = threadIdx.x;
+    if (r < A.world) {
+        const bool ok = wait_seq(&A.mine->dt_seq[r][0], A.seq, &A.mine->error);
+        m[r] = ok ? *(volatile unsigned long long *)&A.mine->dt_bits[A.seq & 1][r] : 0x7FEFFFFFFFFFFFFFULL;
+    }
+    __syncthreads();
+    if (r == 0) {
+        unsigned long long best = m[0];
+        for (int k = 1; k < A.world; k++) best = m[k] < best ? m[k] : best;
+        A.ctl->dtmin_bits = best;
+        if (A.mine->error) A.ctl->done = 2;               // a peer stopped answering: drain the remaining launches
+    }
+}
 
 } // namespace spruce

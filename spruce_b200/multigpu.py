@@ -10,6 +10,12 @@ The domain is split along x (i): rows are contiguous `ydim` runs in the referenc
 after the last stage the dt minimum (one double) is all-reduced with MIN.  min/max are exact, so N-GPU runs
 reproduce the 1-GPU run bit for bit (tests/test_gpu_parity.py::test_two_slabs...).
 
+Two transports (SlabRunner(transport=...)):
+  "p2p"  (default) the library's own peer-store exchange: the pack kernel writes the edge rows into the neighbours' memory over
+         NVLink (CUDA IPC mapping) and signals with a sequence number; torch.distributed only carries the 64-byte IPC handles at
+         start-up.  The whole time loop is one spruce_advance call per rank.
+  "nccl" the caller-owned exchange described above (batch_isend_irecv + all_reduce), kept as the reference transport.
+
 The partition / neighbour / exchange logic is backend independent (`exchange_halos`) and is covered on CPU with
 gloo and world_size 2 (tests/test_multigpu_host.py).
 """
@@ -70,14 +76,16 @@ class _DevBuf:
 
 
 class SlabRunner:
-    def __init__(self, planes, ion_mass, adiabatic_index, *, rank, world, device, **kw):
+    def __init__(self, planes, ion_mass, adiabatic_index, *, rank, world, device, transport="p2p", xdim=None, **kw):
         import torch
         import torch.distributed as dist
         from . import capi
         from .domain import PlasmaDomain
         self.torch, self.dist, self.capi = torch, dist, capi
         self.rank, self.world = rank, world
-        xdim = planes["rho"].shape[0]
+        # `planes` holds either global planes or (xdim given) only this rank's rows; d_x is always the global 1-D array then
+        xdim = planes["rho"].shape[0] if xdim is None else xdim
+        self.transport = transport
         self.row0, self.nx = partition(xdim, world)[rank]
         self.periodic_x = kw.get("xb", ("periodic", "periodic")) == ("periodic", "periodic")
         self.dom = PlasmaDomain(planes, ion_mass, adiabatic_index, device=device, row0=self.row0, nx_local=self.nx,
@@ -108,6 +116,18 @@ class SlabRunner:
         dist.all_reduce(bits, op=dist.ReduceOp.MAX)
         gm = sum(int(v) << b for b, v in enumerate(bits.tolist()))
         capi.check(self.lib.spruce_plane_activity(self.dom.h, None, gm))
+        if transport == "p2p":
+            mine = (C.c_char * 64)()
+            capi.check(self.lib.spruce_mgpu_ipc_export(self.dom.h, mine))
+            t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).cuda()
+            allh = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allh, t)
+            blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+            capi.check(self.lib.spruce_mgpu_ipc_connect(self.dom.h, blob, world))
+            self.dom.setup()
+            dist.barrier()                      # every rank has mapped its neighbours and finished its local setup
+            capi.check(self.lib.spruce_mgpu_initial_exchange(self.dom.h))
+            return
         self.dom.setup()
         with torch.cuda.stream(self.stream):
             capi.check(self.lib.spruce_mgpu_pack(self.dom.h, 3))        # static planes: be_* are transported and need halo rows
@@ -125,6 +145,8 @@ class SlabRunner:
     def step(self, n_steps: int = 1):
         """n_steps x advanceTime on the slab; everything is stream ordered (no host synchronisation inside)."""
         capi, lib, h, dist = self.capi, self.lib, self.dom.h, self.dist
+        if self.transport == "p2p":
+            return self.dom.advance(n_steps)
         with self.torch.cuda.stream(self.stream):
             for _ in range(n_steps):
                 capi.check(lib.spruce_mgpu_begin_step(h))

@@ -33,13 +33,18 @@ def centres(d: np.ndarray) -> np.ndarray:
 
 
 def orszag_tang(nx: int, ny: int | None = None, *, length: float = 1.0e9, zfull: bool = False,
-                temp_mod: float = 0.0, stretch: float = 0.2) -> dict:
-    """Returns dict(planes=..., ion_mass=..., adiabatic_index=...) with all planes the reference needs
-    (7 domain grids + IdealMHD state variables)."""
+                temp_mod: float = 0.0, stretch: float = 0.2, rows: tuple | None = None) -> dict:
+    """Returns dict(planes=..., ion_mass=..., adiabatic_index=..., dx=, dy=) with all planes the reference needs
+    (7 domain grids + IdealMHD state variables).  rows=(row0, n): only those x rows of every plane (a slab of a
+    decomposed domain; values identical to the same rows of the full planes); dx, dy are always the global 1-D sizes."""
     ny = nx if ny is None else ny
     dx = stretched_spacing(nx, length, stretch)
     dy = stretched_spacing(ny, length, stretch)
     px, py = centres(dx), centres(dy)
+    dx_g, dy_g = dx, dy
+    if rows is not None:
+        px, dx = px[rows[0]:rows[0] + rows[1]], dx[rows[0]:rows[0] + rows[1]]
+        nx = rows[1]
     X = np.repeat(px[:, None], ny, axis=1)
     Y = np.repeat(py[None, :], nx, axis=0)
     rho0, T0 = 1.0e-15, 1.0e6
@@ -75,7 +80,7 @@ def orszag_tang(nx: int, ny: int | None = None, *, length: float = 1.0e9, zfull:
         g0 = 0.05 * cs * cs / (length / 10.0)
         P["grav_x"] = g0 * np.sin(k * X)
         P["grav_y"] = -g0 * (1.0 + 0.2 * np.cos(k * Y))
-    return dict(planes=P, ion_mass=M_I, adiabatic_index=GAMMA)
+    return dict(planes=P, ion_mass=M_I, adiabatic_index=GAMMA, dx=dx_g, dy=dy_g)
 
 
 def stratified_loop(nx: int, ny: int, *, length: float = 4.0e9, zfull: bool = True, bump: float = 0.0) -> dict:

@@ -287,9 +287,11 @@ def test_solar_modules_vs_oracle(mods):
         assert rel_linf(d.grid(v), o.get(v)) <= REL_TOL, "%s: rel Linf %.3e" % (v, rel_linf(d.grid(v), o.get(v)))
 
 
-@pytest.mark.parametrize("args", [("300", "210", "6", "rk2", "periodic"), ("131", "96", "5", "rk4", "periodic"), ("120", "80", "6", "rk2", "fixed"), ("90", "70", "4", "euler", "reflect")])
+@pytest.mark.parametrize("args", [("300", "210", "6", "rk2", "periodic", "p2p"), ("131", "96", "5", "rk4", "periodic", "p2p"), ("120", "80", "6", "rk2", "fixed", "p2p"),
+                                  ("90", "70", "4", "euler", "reflect", "p2p"), ("300", "210", "6", "rk2", "periodic", "nccl"), ("120", "80", "6", "rk4", "fixed", "nccl")])
 def test_slab_decomposition_equals_single_gpu(args):
-    """N-GPU == 1-GPU bit for bit.  Needs >= 2 visible GPUs; spawns torchrun with 2 ranks."""
+    """N-GPU == 1-GPU bit for bit, for both halo transports (library peer stores over NVLink; NCCL send/recv).
+    Needs >= 2 visible GPUs; spawns torchrun with 2 ranks."""
     import subprocess
     import sys
     import torch
