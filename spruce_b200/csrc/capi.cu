@@ -83,6 +83,9 @@ struct spruce_domain {
     bool peers_connected = false;
     unsigned long long halo_seq = 0, dt_seq = 0;
     unsigned int *push_counter = nullptr;
+    cudaStream_t comm_stream = nullptr;          // high priority: edge chunks + push + pull, concurrent with the interior chunks
+    cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+    bool overlap = true;
 };
 
 namespace {
@@ -225,9 +228,10 @@ ActiveList active_quantities(const spruce_domain *d)
 }
 
 int prepare_rhs_modules(spruce_domain *d, const PlaneSet &S);
-int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode)
+int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int part = 0)
 {
-    if (!d->visc.empty()) { int rcv = prepare_rhs_modules(d, S); if (rcv) return rcv; }
+    // part 0: every row chunk on the main stream; 1: the first and last chunk on the communication stream; 2: the chunks between on the main stream
+    if (part == 0 && !d->visc.empty()) { int rcv = prepare_rhs_modules(d, S); if (rcv) return rcv; }
     StageArgs A{};
     fill_sets(d, A, S, B, D);
     A.n_xterm = d->visc.empty() ? 0 : d->cur_nx;
@@ -235,10 +239,16 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
     A.chunk_rows = pick_chunk_rows(d);
-    if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
-    dim3 grid((d->P.ny + CW - 1) / CW, (d->P.nx + A.chunk_rows - 1) / A.chunk_rows);
-    if (d->stage_kernel == 5) k_mhd_stage_xy<<<grid, XY_NT, XY_SMEM, d->stream>>>(d->P, A, active_quantities(d));
-    else k_mhd_stage<<<grid, NT, STAGE_SMEM, d->stream>>>(d->P, A);
+    if (part == 0 && primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
+    const int nchunks = (d->P.nx + A.chunk_rows - 1) / A.chunk_rows;
+    A.chunk0 = 0; A.chunk_stride = 1;
+    int gy = nchunks;
+    cudaStream_t st = d->stream;
+    if (part == 1) { A.chunk_stride = nchunks - 1; gy = 2; st = d->comm_stream; }
+    if (part == 2) { A.chunk0 = 1; gy = nchunks - 2; }
+    dim3 grid((d->P.ny + CW - 1) / CW, gy);
+    if (d->stage_kernel == 5) k_mhd_stage_xy<<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, active_quantities(d));
+    else k_mhd_stage<<<grid, NT, STAGE_SMEM, st>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
@@ -541,6 +551,12 @@ int ensure_segment(spruce_domain *d)
     CUDA_TRY(cudaMemset(d->seg, 0, d->seg_bytes));
     CUDA_TRY(cudaMalloc(&d->push_counter, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(d->push_counter, 0, sizeof(unsigned int)));
+    int lo_pri = 0, hi_pri = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CUDA_TRY(cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi_pri));
+    CUDA_TRY(cudaEventCreateWithFlags(&d->ev_main, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&d->ev_comm, cudaEventDisableTiming));
+    if (const char *ov = getenv("SPRUCE_HALO_OVERLAP")) d->overlap = atoi(ov) != 0;
     return SPRUCE_OK;
 }
 void ring_neighbours(const spruce_domain *d, int *lo, int *hi)
@@ -550,8 +566,9 @@ void ring_neighbours(const spruce_domain *d, int *lo, int *hi)
     *hi = r < w - 1 ? r + 1 : (d->P.xper ? 0 : -1);
 }
 // push my edge rows of `U` into the neighbours' segments, then wait for theirs and copy them into my halo rows
-int peer_exchange(spruce_domain *d, double *const *U)
+int peer_exchange(spruce_domain *d, double *const *U, cudaStream_t st = nullptr)
 {
+    if (!st) st = d->stream;
     if (!d->peers_connected) return fail(SPRUCE_ERR_STATE, "peer transport used before spruce_mgpu_ipc_connect");
     const unsigned long long q = ++d->halo_seq;
     const int par = (int)(q & 1);
@@ -563,13 +580,13 @@ int peer_exchange(spruce_domain *d, double *const *U)
     if (hi >= 0) { S.peer_hi_buf = seg_buf(d, d->peer_seg[hi], 0, par); S.peer_hi_flag = &seg_flags(d->peer_seg[hi])->halo_seq[0][0]; }
     S.seq = q; S.counter = d->push_counter; S.done_ptr = &d->ctl->done;
     dim3 grid((d->P.pitch + 255) / 256, NEV * HALO);
-    k_halo_push<<<grid, 256, 0, d->stream>>>(d->P, S);
+    k_halo_push<<<grid, 256, 0, st>>>(d->P, S);
     PullArgs R{};
     for (int v = 0; v < NEV; v++) R.U[v] = U[v];
     if (lo >= 0) { R.lo_buf = seg_buf(d, d->seg, 0, par); R.lo_flag = &seg_flags(d->seg)->halo_seq[0][0]; }
     if (hi >= 0) { R.hi_buf = seg_buf(d, d->seg, 1, par); R.hi_flag = &seg_flags(d->seg)->halo_seq[1][0]; }
     R.seq = q; R.error = &seg_flags(d->seg)->error; R.done_ptr = &d->ctl->done;
-    k_halo_pull<<<grid, 256, 0, d->stream>>>(d->P, R);
+    k_halo_pull<<<grid, 256, 0, st>>>(d->P, R);
     d->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
@@ -592,6 +609,30 @@ int finish_stage(spruce_domain *d, const PlaneSet &U, int primary)
     int rc = launch_ghosts(d, U, primary);
     if (rc || d->cfg.n_ranks == 1) return rc;
     return peer_exchange(d, U.p);
+}
+// One RK stage of a slab.  When no ghost-zone pass follows the stage (periodic y and no physical x boundary that writes ghost cells),
+// the first and last row chunk run on the high-priority communication stream, followed there by the push / pull of the halo rows,
+// while the chunks in between run on the main stream: the exchange hides behind the interior compute.
+int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode)
+{
+    int rc;
+    const int crows = pick_chunk_rows(d), nchunks = (d->P.nx + crows - 1) / crows;
+    const bool ghosts = d->any_ucnp || (primary && d->any_primary_ghost);
+    const bool last_chunk_holds_edge = d->P.nx - (nchunks - 1) * crows >= HALO;       // the pushed rows nx-2, nx-1 must both come from the edge launch
+    const bool split = d->cfg.n_ranks > 1 && d->peers_connected && d->overlap && !ghosts && d->visc.empty() && nchunks >= 4 && last_chunk_holds_edge;
+    if (!split) {
+        if ((rc = launch_stage(d, S, B, D, coef, primary, kmode))) return rc;
+        return finish_stage(d, D, primary);
+    }
+    if (primary) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
+    CUDA_TRY(cudaEventRecord(d->ev_main, d->stream));
+    CUDA_TRY(cudaStreamWaitEvent(d->comm_stream, d->ev_main, 0));
+    if ((rc = launch_stage(d, S, B, D, coef, primary, kmode, 1))) return rc;
+    if ((rc = peer_exchange(d, D.p, d->comm_stream))) return rc;
+    CUDA_TRY(cudaEventRecord(d->ev_comm, d->comm_stream));
+    if ((rc = launch_stage(d, S, B, D, coef, primary, kmode, 2))) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(d->stream, d->ev_comm, 0));
+    return SPRUCE_OK;
 }
 
 // one advanceTime (evolution.cpp:59-82) worth of launches
@@ -620,24 +661,17 @@ int enqueue_step(spruce_domain *d, int hist_slot)
     if (!d->visc.empty() && (rc = visc_refresh_dt(d))) return rc;     // Viscosity reads the PRIMARY state's dt plane
     const int ti = d->cfg.time_integrator;
     if (ti == SPRUCE_TI_EULER) {                                        // evolution.cpp:84-88
-        if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;
-        std::swap(d->Pset, d->Mset);                                    // D never aliases S: ping-pong instead of in place
-        if ((rc = finish_stage(d, d->Pset, 1))) return rc;
+        if ((rc = stage_and_exchange(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;   // ghost zones / halos of Mset ...
+        std::swap(d->Pset, d->Mset);                                    // ... which now becomes the primary set (D never aliases S: ping-pong)
     } else if (ti == SPRUCE_TI_RK2) {                                   // evolution.cpp:90-101
-        if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE))) return rc;
-        if ((rc = finish_stage(d, d->Mset, 0))) return rc;
-        if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_NONE))) return rc;
-        if ((rc = finish_stage(d, d->Pset, 1))) return rc;
+        if ((rc = stage_and_exchange(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE))) return rc;
+        if ((rc = stage_and_exchange(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_NONE))) return rc;
     } else {                                                            // evolution.cpp:103-124
         if ((rc = ensure_rk4(d))) return rc;
-        if ((rc = launch_stage(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_STORE_K1))) return rc;
-        if ((rc = finish_stage(d, d->Mset, 0))) return rc;
-        if ((rc = launch_stage(d, d->Mset, d->Pset, d->M2set, 0.5, 0, KM_STORE_K2))) return rc;
-        if ((rc = finish_stage(d, d->M2set, 0))) return rc;
-        if ((rc = launch_stage(d, d->M2set, d->Pset, d->Mset, 1.0, 0, KM_ADD_K2))) return rc;
-        if ((rc = finish_stage(d, d->Mset, 0))) return rc;
-        if ((rc = launch_stage(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
-        if ((rc = finish_stage(d, d->Pset, 1))) return rc;
+        if ((rc = stage_and_exchange(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_STORE_K1))) return rc;
+        if ((rc = stage_and_exchange(d, d->Mset, d->Pset, d->M2set, 0.5, 0, KM_STORE_K2))) return rc;
+        if ((rc = stage_and_exchange(d, d->M2set, d->Pset, d->Mset, 1.0, 0, KM_ADD_K2))) return rc;
+        if ((rc = stage_and_exchange(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
     }
     if (d->cfg.n_ranks > 1 && (rc = peer_dt_allgather(d))) return rc;   // global min(dt) for the next step (evolution.cpp:62)
     for (int m : d->module_order)                                        // postIterateModules, evolution.cpp:74
@@ -783,6 +817,9 @@ void spruce_domain_destroy(spruce_domain *d)
     for (int r = 0; r < MAX_RANKS; r++) if (d->peer_seg[r] && d->peer_seg[r] != d->seg) cudaIpcCloseMemHandle(d->peer_seg[r]);
     if (d->seg) cudaFree(d->seg);
     if (d->push_counter) cudaFree(d->push_counter);
+    if (d->comm_stream) { cudaStreamSynchronize(d->comm_stream); cudaStreamDestroy(d->comm_stream); }
+    if (d->ev_main) cudaEventDestroy(d->ev_main);
+    if (d->ev_comm) cudaEventDestroy(d->ev_comm);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d->tf;
     delete d;

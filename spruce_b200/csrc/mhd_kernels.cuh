@@ -80,6 +80,7 @@ struct StageArgs {
     double *strip[4];             // per side (x1,x2,y1,y2): what that side's ghost pass reads from its first interior cell
     int strip_pitch;              //   strip[s][c*strip_pitch + idx], c = 0: post-floor rho, 1..3: momentum as that pass sees it
     int chunk_rows;               // rows per CTA
+    int chunk0, chunk_stride;     // CTA row blockIdx.y works on chunk chunk0 + blockIdx.y*chunk_stride (edge / interior launches of a slab)
     // module contributions to the right-hand side (Module::computeTimeDerivativesModule): already masked planes that are
     // added to k[target] in module order, after the ghost mask (equationset.cpp:208, viscosity.cpp:117-118)
     const double *xterm[4]; int xtarget[4]; int n_xterm;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const
     const int ccol = 31 * warp + lane;            // column inside the CTA (lane 31 duplicates the next warp's lane 0)
     const int j = j0 + ccol;
     const int c = ccol + HALO;
-    const int r0 = blockIdx.y * A.chunk_rows;
+    const int r0 = (A.chunk0 + (int)blockIdx.y * A.chunk_stride) * A.chunk_rows;
     const int r1 = min(r0 + A.chunk_rows, P.nx);
     const bool col_out = (lane < 31) && (j < P.ny);
 

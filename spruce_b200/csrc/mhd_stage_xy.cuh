@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
     const int j0 = blockIdx.x * CW;
     const int j = j0 + ccol;
     const int c = ccol + HALO;
-    const int r0 = blockIdx.y * A.chunk_rows;
+    const int r0 = (A.chunk0 + (int)blockIdx.y * A.chunk_stride) * A.chunk_rows;
     const int r1 = min(r0 + A.chunk_rows, P.nx);
     const bool col_out = (lane < 31) && (j < P.ny);
 
