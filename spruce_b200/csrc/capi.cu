@@ -75,6 +75,7 @@ struct spruce_domain {
     double *halo[4] = {nullptr, nullptr, nullptr, nullptr};   // send_lo, send_hi, recv_lo, recv_hi
     // planes that were uploaded as identically zero: bit 0 mom_z, 1 bi_z, 2 be_x, 3 be_y, 4 be_z (global knowledge; see spruce_plane_activity)
     unsigned nonzero_mask = 0x1F;
+    bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
@@ -247,7 +248,12 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     if (part == 1) { A.chunk_stride = nchunks - 1; gy = 2; st = d->comm_stream; }
     if (part == 2) { A.chunk0 = 1; gy = nchunks - 2; }
     dim3 grid((d->P.ny + CW - 1) / CW, gy);
-    if (d->stage_kernel == 5) k_mhd_stage_xy<<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, active_quantities(d));
+    if (d->stage_kernel == 5) {
+        const ActiveList L = active_quantities(d);
+        if (d->static_lists && L.n == 6 && L.q == XY_LIST_2D) k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, L);
+        else if (d->static_lists && L.n == 12 && L.q == XY_LIST_FULL) k_mhd_stage_xy<12, XY_LIST_FULL><<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, L);
+        else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, L);
+    }
     else k_mhd_stage<<<grid, NT, STAGE_SMEM, st>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -758,10 +764,13 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
 
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
+    if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     DomainParams &P = d->P;
     P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;
     P.gnx = cfg->xdim; P.row0 = cfg->row0;

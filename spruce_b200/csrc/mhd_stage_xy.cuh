@@ -41,8 +41,25 @@ static_assert(XY_SMEM <= 57344, "four CTAs per SM need <= 56 KB each");
 
 struct ActiveList { int n; unsigned long long q; };   // transported quantities that can be non-zero (one nibble each), padded to an even count
 
-__global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList L)
+// LN > 0: the active list is the compile-time constant (LN, LQ) -- the quantity loops unroll completely, every shared-memory
+// offset and every "is this bi_y?" test folds away.  LN == 0: the list comes from the launch argument (rolled loops).
+constexpr unsigned long long xy_list(int a = -1, int b = -1, int c = -1, int d = -1, int e = -1, int f = -1, int g = -1, int h = -1, int i = -1, int j = -1, int k = -1, int l = -1)
 {
+    const int v[12] = {a, b, c, d, e, f, g, h, i, j, k, l};
+    unsigned long long q = 0;
+    for (int t = 0; t < 12; t++) if (v[t] >= 0) q |= (unsigned long long)v[t] << (4 * t);
+    return q;
+}
+constexpr unsigned long long XY_LIST_2D = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY);                                              // no z system, no external field
+constexpr unsigned long long XY_LIST_FULL = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY, Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_BEZ);   // everything (padded to 12)
+
+template <int LN, unsigned long long LQ>
+__global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
+{
+    constexpr int UNR = LN > 0 ? LN : 1;
+    ActiveList L;
+    L.n = LN > 0 ? LN : Larg.n;
+    L.q = LN > 0 ? LQ : Larg.q;
     extern __shared__ __align__(16) double smem[];
     if (*A.done_ptr) return;
     double (*ring)[NTR][SW] = reinterpret_cast<double (*)[NTR][SW]>(smem + XY_OFF_RING);
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         cIx_vz = face_interp(vel[vm1][2][c], vel[v0][2][c], g.hm1, g.h0, g.fs, g.rfs);
         cIx_p = face_interp(ring[sm1][Q_E][c] * P.gm1, ring[s0][Q_E][c] * P.gm1, g.hm1, g.h0, g.fs, g.rfs);
         const FaceSel fs0 = select_face(g, cVfx);
-#pragma unroll 1
+#pragma unroll UNR
         for (int k = 0; k < L.n; k++) {
             const int q = (int)((L.q >> (4 * k)) & 15ULL);
             double d2;
@@ -204,7 +221,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             // the far cell of the extrapolation: row r-1 for flow in +x, row r+2 for flow in -x -- one load from a selected row
             const double *far_row = &ring[fsx.pos ? sm1 : sp2][0][c];
             double Ix1_biy = 0.0, Ix1_biz = 0.0;
-#pragma unroll 1
+#pragma unroll UNR
             for (int k = 0; k < L.n; k += 2) {
                 const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
                 double ad2, bd2;
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const FaceSel fsy = select_face(gy, vfyL);
             const double *far_col = &ring[s0][0][fsy.pos ? c - 2 : c + 1];
             double IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
-#pragma unroll 1
+#pragma unroll UNR
             for (int k = 0; k < L.n; k += 2) {
                 const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
                 double ad2, bd2;
