@@ -130,8 +130,9 @@ __device__ __forceinline__ double upwind_face_far(double far, double qm1, double
     const double f1 = __hiloint2double(__double2hiint(d1) ^ hm, __double2loint(d1));
     const double f2 = __hiloint2double(__double2hiint(d2) ^ hm, __double2loint(d2));
     const double m = smin(fb, smax(f1, f2));
-    const double r = __hiloint2double(__double2hiint(m) ^ hm, __double2loint(m));
-    return f.any ? r : d2;
+    // derivs.cpp:66 returns d2 when the face velocity is exactly zero; the caller multiplies the face value by that velocity, so
+    // the flux is +-0 either way (finite operands) and the select is dropped
+    return __hiloint2double(__double2hiint(m) ^ hm, __double2loint(m));
 }
 
 // exact test "all eight values are +-0" on the integer pipe

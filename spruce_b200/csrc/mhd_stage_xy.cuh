@@ -92,11 +92,14 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
     if (loader && !jl_ok && P.yper) { jl = (jl + 2 * P.ny) % P.ny; jl_ok = true; }
     auto slot_of = [&](int r) { return (r - r0 + HALO + RD) % RD; };
     auto vslot_of = [&](int r) { return (r - r0 + HALO + 3 * XY_RV) % XY_RV; };
-    auto issue_row = [&](int r) {
+    auto next_slot = [](int s_) { return s_ == RD - 1 ? 0 : s_ + 1; };
+    auto next_vslot = [](int s_) { return s_ == XY_RV - 1 ? 0 : s_ + 1; };
+    auto issue_row = [&](int r, int slot) {
         if (!loader) return;
-        const int slot = slot_of(r);
         if (row_exists(P, r) && jl_ok) {
-            const size_t off = (size_t)phys_row(P, r) * P.pitch + jl;
+            int pr = r;                                        // single-rank periodic x: rows -2..nx+1 wrap with one add (no modulo)
+            if (P.xwrap) pr = r < 0 ? r + P.nx : (r >= P.nx ? r - P.nx : r);
+            const size_t off = (size_t)pr * P.pitch + jl;
 #pragma unroll
             for (int v = 0; v < NEV; v++) cp_async8(&ring[slot][v][tid], A.S[v] + off);
             cp_async8(&ring[slot][Q_BEX][tid], A.st[S_BEX] + off);
@@ -107,14 +110,15 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             for (int v = 0; v < NTR; v++) ring[slot][v][tid] = (v == Q_RHO) ? 1.0 : 0.0;
         }
     };
-    auto convert_rho = [&](int r) { if (loader) { const int s_ = slot_of(r); ring[s_][Q_RHO][tid] = ring[s_][Q_RHO][tid] * P.m_i; } };   // idealmhd.cpp:247
-    auto form_vel = [&](int r) {                                                                                                       // idealmhd.cpp:248-250
+    auto convert_rho = [&](int s_) { if (loader) { ring[s_][Q_RHO][tid] = ring[s_][Q_RHO][tid] * P.m_i; } };   // idealmhd.cpp:247
+    // v = mom / rho (idealmhd.cpp:248-250): one IEEE reciprocal, then the exact-division correction per component (exact_math.cuh)
+    auto form_vel = [&](int s_, int v_) {
         if (!loader) return;
-        const int s_ = slot_of(r), v_ = vslot_of(r);
         const double rho = ring[s_][Q_RHO][tid];
-        vel[v_][0][tid] = ring[s_][Q_MX][tid] / rho;
-        vel[v_][1][tid] = ring[s_][Q_MY][tid] / rho;
-        vel[v_][2][tid] = ring[s_][Q_MZ][tid] / rho;
+        const double rr = 1.0 / rho;
+        vel[v_][0][tid] = ddiv(ring[s_][Q_MX][tid], rho, rr);
+        vel[v_][1][tid] = ddiv(ring[s_][Q_MY][tid], rho, rr);
+        vel[v_][2][tid] = (LN == 6) ? 0.0 : ddiv(ring[s_][Q_MZ][tid], rho, rr);      // the 2-D list is only chosen when mom_z is identically zero
     };
 
     const double step = *A.step_ptr;
@@ -146,11 +150,11 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
     const double dy = P.ty.d[min(j, P.ny)], rdy = P.ty.rd[min(j, P.ny)];
 
     // ---- prologue: rows r0-2 .. r0+2 land, rho is formed for all of them, velocity for rows r0-1, r0, r0+1
-    for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r);
+    for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r, slot_of(r));
     cp_async_commit();
     cp_async_wait_all();
-    for (int r = r0 - HALO; r <= r0 + HALO; r++) convert_rho(r);
-    for (int r = r0 - 1; r <= r0 + 1; r++) form_vel(r);
+    for (int r = r0 - HALO; r <= r0 + HALO; r++) convert_rho(slot_of(r));
+    for (int r = r0 - 1; r <= r0 + 1; r++) form_vel(slot_of(r), vslot_of(r));
     __syncthreads();
 
     // X warps: carries of face r0 (between rows r0-1 and r0)
@@ -181,13 +185,14 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
     bool dt_pending = false;
     double dt_e = 0.0, dt_bx = 0.0, dt_by = 0.0, dt_bz = 0.0, dt_dx = 1.0, dt_rdx = 1.0;
 
+    int s0 = slot_of(r0), v0 = vslot_of(r0);       // ring slots rotate by one per row: no modulo in the loop
     for (int r = r0; r < r1; r++) {
+        const int sm1 = s0 == 0 ? RD - 1 : s0 - 1, sp1 = next_slot(s0), sp2 = next_slot(sp1), sp3 = next_slot(sp2);
+        const int v1 = next_vslot(v0), v2 = next_vslot(v1);
         const bool pre = (r + 3 <= r1 + HALO - 1);
-        if (pre) issue_row(r + 3);
+        if (pre) issue_row(r + 3, sp3);
         cp_async_commit();
 
-        const int sm1 = slot_of(r - 1), s0 = slot_of(r), sp1 = slot_of(r + 1), sp2 = slot_of(r + 2);
-        const int v0 = vslot_of(r), v1 = vslot_of(r + 1);
         const int g = P.row0 + r;
         const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
         const double dx = xt[5][r - r0 + 3], rdx = xt[6][r - r0 + 3];
@@ -362,9 +367,10 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             }
         }
         cp_async_wait_all();
-        if (pre) convert_rho(r + 3);                                // the row that just landed
-        if (r + 2 <= r1) form_vel(r + 2);                           // into the velocity slot of row r-1 (dead since the last barrier)
+        if (pre) convert_rho(sp3);                                  // the row that just landed
+        if (r + 2 <= r1) form_vel(sp2, v2);                         // into the velocity slot of row r-1 (dead since the last barrier)
         __syncthreads();
+        s0 = sp1; v0 = v1;
     }
     if (A.primary && A.kmode != KM_EXPORT) {
         if (!isX && dt_pending) {
