@@ -19,16 +19,35 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 integ = sys.argv[4] if len(sys.argv) > 4 else "rk2"
 xbound = sys.argv[5] if len(sys.argv) > 5 else "periodic"
 transport = sys.argv[6] if len(sys.argv) > 6 else "p2p"
+modules = [m for m in (sys.argv[7].split(",") if len(sys.argv) > 7 else []) if m]
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-if xbound == "periodic":
+def add_modules(dom):
+    for m in modules:                       # same order on every domain = execution order
+        if m == "tc":
+            dom.set_thermal_conduction(flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-4)
+        elif m == "tcsat":
+            dom.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4)
+        elif m == "rl":
+            dom.set_radiative_losses(integrator="rk2", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1)
+        elif m == "ah":
+            dom.set_ambient_heating_plane(np.full((dom.nx, dom.ydim), 1.0e-4))
+        else:
+            raise SystemExit("unknown module " + m)
+
+
+if modules:
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    kw = dict(xb=("periodic", "periodic") if xbound == "periodic" else (xbound, "open"), yb=("fixed", "fixed"), integrator=integ)
+elif xbound == "periodic":
     s = synthetic.orszag_tang(nx, ny, zfull=True)
     kw = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator=integ, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
 else:
     s = synthetic.stratified_loop(nx, ny)
     kw = dict(xb=(xbound, "open"), yb=("reflect", "fixed"), integrator=integ)
 run = SlabRunner(s["planes"], s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=transport, **kw)
+add_modules(run.dom)
 run.step(steps)
 run.dom.synchronize()
 got = {v: run.gather(v) for v in PlasmaDomain.EVOLVED + ["dt"]}
@@ -36,7 +55,13 @@ t_slab = run.dom.time
 ok = True
 if rank == 0:
     one = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], device=local, **kw)
+    add_modules(one)
     dts = one.advance(steps)
+    for m, key in (("tc", "thermal_conduction"), ("tcsat", "thermal_conduction"), ("rl", "radiative_losses")):
+        if m in modules:
+            a, b = run.dom.subcycles(key), one.subcycles(key)
+            print("subcycles", key, a, b)
+            ok &= (a == b)
     for v, a in got.items():
         b = one.grid(v)
         same = bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
@@ -45,7 +70,7 @@ if rank == 0:
             bad = np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))
             print("MISMATCH", v, len(bad), bad[:5].tolist())
     ok &= (t_slab == one.time)
-    print("mgpu_check world=%d %s %dx%d %s x=%s steps=%d : %s (t=%r vs %r)" % (world, transport, nx, ny, integ, xbound, steps, "IDENTICAL" if ok else "DIFFERENT", t_slab, one.time))
+    print("mgpu_check world=%d %s %dx%d %s x=%s modules=%s steps=%d : %s (t=%r vs %r)" % (world, transport, nx, ny, integ, xbound, ",".join(modules) or "-", steps, "IDENTICAL" if ok else "DIFFERENT", t_slab, one.time))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -82,7 +82,7 @@ struct spruce_domain {
     void *seg = nullptr; size_t seg_bytes = 0;
     void *peer_seg[MAX_RANKS] = {nullptr};      // mapped segments of the other ranks (own rank: seg)
     bool peers_connected = false;
-    unsigned long long halo_seq = 0, dt_seq = 0;
+    unsigned long long halo_seq = 0, dt_seq = 0, red_seq = 0;
     unsigned int *push_counter = nullptr;
     cudaStream_t comm_stream = nullptr;          // high priority: edge chunks + push + pull, concurrent with the interior chunks
     cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
@@ -311,15 +311,20 @@ int derive_to(spruce_domain *d, int var, double *out, const PlaneSet *set = null
     for (int v = 0; v < NEV; v++) A.U[v] = (set ? set : &d->Pset)->p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
     A.out = out; A.which = var;
-    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    // a slab also fills its halo rows (the neighbours' cells are resident there), so that stencils on derived planes need no exchange
+    const int halo = d->cfg.n_ranks > 1 ? HALO : 0;
+    A.row_off = -halo;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx + 2 * halo);
     k_mhd_derive<<<grid, 256, 0, d->stream>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }
 
+int peer_red_allgather(spruce_domain *d);
 int read_reductions(spruce_domain *d, unsigned long long h[4])
 {
+    if (d->cfg.n_ranks > 1) { int rc = peer_red_allgather(d); if (rc) return rc; }     // min / max over all slabs (exact: same counts as one GPU)
     CUDA_TRY(cudaMemcpyAsync(h, d->red, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     return SPRUCE_OK;
@@ -331,6 +336,25 @@ int reset_reductions(spruce_domain *d)
     return SPRUCE_OK;
 }
 double bits_to_double(unsigned long long b) { double v; memcpy(&v, &b, sizeof(v)); return v; }
+
+int peer_exchange(spruce_domain *d, double *const *U, cudaStream_t st);
+int peer_dt_allgather(spruce_domain *d);
+// slab decomposition: halo rows of one plane (a module's working plane) from the ring neighbours
+int exchange_plane(spruce_domain *d, double *plane)
+{
+    if (d->cfg.n_ranks == 1) return SPRUCE_OK;
+    double *v[NEV];
+    for (int k = 0; k < NEV; k++) v[k] = plane;
+    return peer_exchange(d, v, nullptr);
+}
+// after a module's closing propagateChanges: halo rows of the primary state and the global dt minimum
+int after_module_propagate(spruce_domain *d)
+{
+    if (d->cfg.n_ranks == 1) return SPRUCE_OK;
+    int rc = peer_exchange(d, d->Pset.p, nullptr);
+    if (rc) return rc;
+    return peer_dt_allgather(d);
+}
 
 // ThermalConduction::numberSubcycles (thermalconduction.cpp:135-149); scratch: Mset planes 0..2 (temp, b_hat_x, b_hat_y)
 int tc_count(spruce_domain *d, double dt, int *nsub)
@@ -374,7 +398,7 @@ int tc_iterate(spruce_domain *d, double dt)
         k_tc_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
         d->launches++;
         CUDA_TRY(cudaGetLastError());
-        return SPRUCE_OK;
+        return exchange_plane(d, Tout);                  // the next stage differentiates this temperature plane across the slab edge
     };
     for (int s = 0; s < ns; s++) {
         if (d->tc_integrator == SPRUCE_TI_EULER) {
@@ -390,7 +414,8 @@ int tc_iterate(spruce_domain *d, double dt)
             if ((rc = stage(Tb, Ta, TC_RK4_FINAL, dts, nullptr))) return rc;
         }
     }
-    return launch_propagate(d, 0);                                                                  // :110-111
+    if ((rc = launch_propagate(d, 0))) return rc;                                                   // :110-111
+    return after_module_propagate(d);
 }
 
 int rl_launch(spruce_domain *d, int count_mode, double dt)
@@ -423,7 +448,8 @@ int rl_iterate(spruce_domain *d, double dt)
 {
     int rc = rl_launch(d, 0, dt);
     if (rc) return rc;
-    return launch_propagate(d, 0);                                                                  // radiativelosses.cpp:99-100
+    if ((rc = launch_propagate(d, 0))) return rc;                                                   // radiativelosses.cpp:99-100
+    return after_module_propagate(d);
 }
 int ah_post(spruce_domain *d)
 {
@@ -431,7 +457,9 @@ int ah_post(spruce_domain *d)
     k_ambient_heating<<<grid, 256, 0, d->stream>>>(d->P, d->Pset.p[E_E], d->heating, &d->ctl->step);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
-    return launch_propagate(d, 0);                                                                  // ambientheating.cpp:43-44
+    int rc = launch_propagate(d, 0);                                                                // ambientheating.cpp:43-44
+    if (rc) return rc;
+    return after_module_propagate(d);
 }
 
 // ---- artificial viscosity (source/modules/viscosity.cpp)
@@ -572,7 +600,7 @@ void ring_neighbours(const spruce_domain *d, int *lo, int *hi)
     *hi = r < w - 1 ? r + 1 : (d->P.xper ? 0 : -1);
 }
 // push my edge rows of `U` into the neighbours' segments, then wait for theirs and copy them into my halo rows
-int peer_exchange(spruce_domain *d, double *const *U, cudaStream_t st = nullptr)
+int peer_exchange(spruce_domain *d, double *const *U, cudaStream_t st)
 {
     if (!st) st = d->stream;
     if (!d->peers_connected) return fail(SPRUCE_ERR_STATE, "peer transport used before spruce_mgpu_ipc_connect");
@@ -597,6 +625,18 @@ int peer_exchange(spruce_domain *d, double *const *U, cudaStream_t st = nullptr)
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }
+int peer_red_allgather(spruce_domain *d)
+{
+    if (!d->peers_connected) return fail(SPRUCE_ERR_STATE, "module reductions on a slab need spruce_mgpu_ipc_connect");
+    RedGatherArgs A{};
+    A.red = d->red; A.mine = seg_flags(d->seg); A.rank = d->cfg.rank; A.world = d->cfg.n_ranks; A.seq = ++d->red_seq;
+    for (int r = 0; r < d->cfg.n_ranks; r++) A.peer[r] = seg_flags(d->peer_seg[r]);
+    k_red_publish<<<1, MAX_RANKS, 0, d->stream>>>(A);
+    k_red_collect<<<1, MAX_RANKS, 0, d->stream>>>(A);
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
 int peer_dt_allgather(spruce_domain *d)
 {
     DtGatherArgs A{};
@@ -614,7 +654,7 @@ int finish_stage(spruce_domain *d, const PlaneSet &U, int primary)
 {
     int rc = launch_ghosts(d, U, primary);
     if (rc || d->cfg.n_ranks == 1) return rc;
-    return peer_exchange(d, U.p);
+    return peer_exchange(d, U.p, nullptr);
 }
 // One RK stage of a slab.  When no ghost-zone pass follows the stage (periodic y and no physical x boundary that writes ghost cells),
 // the first and last row chunk run on the high-priority communication stream, followed there by the push / pull of the halo rows,
@@ -942,7 +982,7 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "advance before setup");
     if (n_steps < 0) return fail(SPRUCE_ERR_ARG, "negative step count");
     if (d->cfg.n_ranks > 1 && !d->peers_connected) return fail(SPRUCE_ERR_STATE, "a slab of a decomposed domain advances either through spruce_mgpu_stage (caller-owned exchange) or, after spruce_mgpu_ipc_connect, through spruce_advance");
-    if (d->cfg.n_ranks > 1 && !d->module_order.empty()) return fail(SPRUCE_ERR_UNSUPPORTED, "physics modules run on a single rank in this version");
+    if (d->cfg.n_ranks > 1 && !d->visc.empty()) return fail(SPRUCE_ERR_UNSUPPORTED, "artificial_viscosity runs on a single rank in this version");
     if ((size_t)n_steps > d->dt_hist_cap) {
         if (d->dt_hist) cudaFree(d->dt_hist);
         d->dt_hist_cap = (size_t)n_steps + 64;
@@ -1016,7 +1056,6 @@ int spruce_module_thermal_conduction(spruce_domain *d, int flux_saturation, int 
 {
     CHECK_DOM(d);
     NOT_2F(d, "thermal_conduction");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
     if (time_integrator < 0 || time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid time integrator given for Thermal Conduction module");
     int rc = ensure_rk4(d);   // not needed for memory, keeps scratch planes uniform
     (void)rc;
@@ -1031,7 +1070,6 @@ int spruce_module_radiative_losses(spruce_domain *d, int time_integrator, double
 {
     CHECK_DOM(d);
     NOT_2F(d, "radiative_losses");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
     if (time_integrator < 0 || time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid time integrator given for Radiative Losses module");
     d->rl.integrator = time_integrator; d->rl.cutoff_ramp = cutoff_ramp; d->rl.cutoff_temp = cutoff_temp; d->rl.epsilon = epsilon;
     d->rl.prevent_subcycling = prevent_subcycling ? 1 : 0;
@@ -1042,7 +1080,6 @@ int spruce_module_ambient_heating(spruce_domain *d, const double *heating, size_
 {
     CHECK_DOM(d);
     NOT_2F(d, "ambient_heating");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
     if (!heating || count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "heating plane needs %zu values", (size_t)d->P.nx * d->P.ny);
     if (!d->heating) { int rc = alloc_plane(d, &d->heating); if (rc) return rc; }
     int rc = h2d_plane(d, d->heating, heating);
@@ -1054,7 +1091,7 @@ int spruce_module_viscosity(spruce_domain *d, int hv_time_integrator, double hv_
 {
     CHECK_DOM(d);
     NOT_2F(d, "artificial_viscosity");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "device modules are single-rank in this build");
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "artificial_viscosity runs on a single rank in this version");
     if (hv_time_integrator < 0 || hv_time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid hyperviscous time integrator given for Viscosity module");
     d->visc_hv_integrator = hv_time_integrator; d->visc_hv_epsilon = hv_epsilon; d->visc_gradient_correction = gradient_correction ? 1 : 0;
     for (int k = 0; k < 8; k++) if (!d->vscratch[k]) { int rc = alloc_plane(d, &d->vscratch[k]); if (rc) return rc; }
@@ -1274,8 +1311,8 @@ int spruce_mgpu_initial_exchange(spruce_domain *d)
     double *stat_view[NEV];
     for (int v = 0; v < NEV; v++) stat_view[v] = d->stat[v < NSTATIC ? v : 0];
     int rc;
-    if ((rc = peer_exchange(d, stat_view))) return rc;
-    if ((rc = peer_exchange(d, d->Pset.p))) return rc;
+    if ((rc = peer_exchange(d, stat_view, nullptr))) return rc;
+    if ((rc = peer_exchange(d, d->Pset.p, nullptr))) return rc;
     if ((rc = peer_dt_allgather(d))) return rc;
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     return SPRUCE_OK;

@@ -175,10 +175,12 @@ __device__ __forceinline__ double density_floor(const DomainParams &P, double rh
 __device__ __forceinline__ double cell_dt(const DomainParams &P, double rho, double mx, double my, double e,
                                           double bx, double by, double bz, double dx, double rdx, double dy, double rdy)
 {
-    const double vx = mx / rho, vy = my / rho;
+    // three quotients share the divisor rho: one IEEE reciprocal + the exact-division correction each (exact_math.cuh)
+    const double rr = 1.0 / rho;
+    const double vx = ddiv(mx, rho, rr), vy = ddiv(my, rho, rr);
     const double p = e * P.gm1;
     const double bm = sqrt((bx * bx + by * by) + bz * bz);
-    const double cs = sqrt((p * P.gamma) / rho);
+    const double cs = sqrt(ddiv(p * P.gamma, rho, rr));
     const double cs2 = cs * cs;
     const double va = bm / sqrt(rho * P.fourpi);
     const double va2 = va * va;
@@ -186,7 +188,10 @@ __device__ __forceinline__ double cell_dt(const DomainParams &P, double rho, dou
     const double delta = sqrt(1.0 - ((cs2 * 4.0) * va2) / (s * s));
     const double vfast = sqrt((s * 0.5) * (1.0 + delta));
     const double vslow = sqrt((s * 0.5) * (1.0 - delta));
-    const double vmx = sqrt(vx * vx), vmy = sqrt(vy * vy);
+    // sqrt(RN(v*v)) == |v| in binary64 round-to-nearest whenever v*v neither underflows nor overflows (Boldo 2015); zero maps to zero
+    const double ax = fabs(vx), ay = fabs(vy);
+    const double vmx = (ax == 0.0 || (ax > 1.0e-140 && ax < 1.0e140)) ? ax : sqrt(vx * vx);
+    const double vmy = (ay == 0.0 || (ay > 1.0e-140 && ay < 1.0e140)) ? ay : sqrt(vy * vy);
     const double M = smax(smax(smax(cs, va), vfast), vslow);
     return 1.0 / (ddiv(vmx + M, dx, rdx) + ddiv(vmy + M, dy, rdy));
 }
@@ -683,14 +688,14 @@ enum { V_rho = 0, V_temp, V_mom_x, V_mom_y, V_mom_z, V_bi_x, V_bi_y, V_bi_z, V_g
        V_n, V_press, V_thermal_energy, V_v_x, V_v_y, V_v_z, V_kinetic_energy,
        V_b_x, V_b_y, V_b_z, V_b_mag, V_b_hat_x, V_b_hat_y, V_b_hat_z, V_dt, V_COUNT };
 
-struct DeriveArgs { const double *U[NEV]; const double *st[NSTATIC]; double *out; int which; };
+struct DeriveArgs { const double *U[NEV]; const double *st[NSTATIC]; double *out; int which; int row_off; };   // row_off = -HALO: also the halo rows of a slab
 
 __global__ void __launch_bounds__(256) k_mhd_derive(const DomainParams P, const DeriveArgs A)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+    const int r = (int)blockIdx.y + A.row_off;
     if (j >= P.ny) return;
-    const size_t off = (size_t)r * P.pitch + j;
+    const long long off = (long long)r * P.pitch + j;
     const double n_ = A.U[E_N][off];
     const double rho = n_ * P.m_i;
     const double e = A.U[E_E][off];
@@ -762,6 +767,8 @@ struct PeerFlags {                                            // one 128-byte li
     unsigned long long halo_seq[2][16];                       // [side][0]: last exchange written by my lower / upper neighbour
     unsigned long long dt_seq[MAX_RANKS][16];                 // [r][0]: last step whose local dt minimum rank r has stored
     unsigned long long dt_bits[2][MAX_RANKS];                 // [parity][r]
+    unsigned long long red_seq[MAX_RANKS][16];                // [r][0]: last module reduction rank r has stored
+    unsigned long long red_bits[2][MAX_RANKS][4];             // [parity][r][min, max, min, max] (bit patterns of non-negative doubles)
     int error; int pad[31];                                   // set when a wait timed out (peer died): every later launch drains
 };
 
@@ -901,6 +908,35 @@ __global__ void k_dt_collect(const DtGatherArgs A)
         for (int k = 1; k < A.world; k++) best = m[k] < best ? m[k] : best;
         A.ctl->dtmin_bits = best;
         if (A.mine->error) A.ctl->done = 2;               // a peer stopped answering: drain the remaining launches
+    }
+}
+
+// all-gather + reduce of the four module reduction words (sub-cycle counts): slots 0, 2 are minima, 1, 3 maxima
+struct RedGatherArgs { unsigned long long *red; PeerFlags *peer[MAX_RANKS]; PeerFlags *mine; int rank, world; unsigned long long seq; };
+__global__ void k_red_publish(const RedGatherArgs A)
+{
+    const int r = threadIdx.x;
+    if (r >= A.world) return;
+    PeerFlags *f = A.peer[r];
+#pragma unroll
+    for (int k = 0; k < 4; k++) f->red_bits[A.seq & 1][A.rank][k] = A.red[k];
+    __threadfence_system();
+    st_release_sys(&f->red_seq[A.rank][0], A.seq);
+}
+__global__ void k_red_collect(const RedGatherArgs A)
+{
+    __shared__ unsigned long long m[MAX_RANKS][4];
+    __shared__ int okf[MAX_RANKS];
+    const int r = threadIdx.x;
+    if (r < A.world) {
+        okf[r] = wait_seq(&A.mine->red_seq[r][0], A.seq, &A.mine->error) ? 1 : 0;
+        for (int k = 0; k < 4; k++) m[r][k] = *(volatile unsigned long long *)&A.mine->red_bits[A.seq & 1][r][k];
+    }
+    __syncthreads();
+    if (r < 4) {
+        unsigned long long best = m[0][r];
+        for (int k = 1; k < A.world; k++) { const unsigned long long v = m[k][r]; best = (r & 1) ? (v > best ? v : best) : (v < best ? v : best); }
+        A.red[r] = best;
     }
 }
 

@@ -26,7 +26,8 @@ __device__ __forceinline__ int wrap_j(const DomainParams &P, int j) { return P.y
 __device__ __forceinline__ bool is_interior(const DomainParams &P, int r, int j)
 {
     const int g = P.row0 + r;
-    return g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
+    // periodic x has no ghost rows (xl = 0, xu = gnx-1); on a slab the halo rows g = -1, gnx, ... are real (wrapped) interior rows
+    return (P.xper || (g >= P.xl && g <= P.xu)) && j >= P.yl && j <= P.yu;
 }
 // clamped/wrapped read: rows/cols outside a non-periodic domain are never used by an in-range operator
 __device__ __forceinline__ double rd(const DomainParams &P, const double *f, int r, int j)

@@ -305,6 +305,24 @@ def test_slab_decomposition_equals_single_gpu(args):
     assert r.returncode == 0 and "IDENTICAL" in out, out[-3000:]
 
 
+@pytest.mark.parametrize("args", [("128", "96", "4", "rk2", "periodic", "p2p", "tc,rl,ah"), ("96", "80", "3", "euler", "reflect", "p2p", "tc,rl"),
+                                  ("200", "64", "3", "rk4", "periodic", "p2p", "ah,tcsat,rl")])
+def test_slab_decomposition_with_modules_equals_single_gpu(args):
+    """Thermal conduction (halo exchange of the temperature plane per sub-cycle stage, sub-cycle counts from min / max all-gathers
+    over peer memory), radiative losses and ambient heating on 2 slabs == 1 GPU, bit for bit, with equal sub-cycle counts."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29518", str(root / "scripts" / "mgpu_check.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "IDENTICAL" in out, out[-3000:]
+
+
 def test_operators_vs_oracle():
     """spruce_operator: the PlasmaDomain differential operators on a host plane (source/mhd/derivs.cpp), bit for bit."""
     from oracle.oracle import Oracle
