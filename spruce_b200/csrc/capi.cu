@@ -75,6 +75,7 @@ struct spruce_domain {
     double *halo[4] = {nullptr, nullptr, nullptr, nullptr};   // send_lo, send_hi, recv_lo, recv_hi
     // planes that were uploaded as identically zero: bit 0 mom_z, 1 bi_z, 2 be_x, 3 be_y, 4 be_z (global knowledge; see spruce_plane_activity)
     unsigned nonzero_mask = 0x1F;
+    bool in_mgpu_stage_api = false;        // inside spruce_mgpu_stage (caller-owned exchange and dt reduction)
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
@@ -198,7 +199,12 @@ void fill_sets(const spruce_domain *d, StageArgs &A, const PlaneSet &S, const Pl
     A.step_ptr = &d->ctl->step;
     A.done_ptr = &d->ctl->done;
     A.dtmin_bits = &d->ctl->dtmin_bits;
+    A.inv_thr_ptr = &d->ctl->inv_thr;
 }
+
+// the dt skip test (dt_can_skip) lives in k_mhd_stage_xy only, and needs k_dt_validate / k_dt_full after the step's last stage:
+// spruce_advance provides that; the caller-driven spruce_mgpu_stage path (NCCL transport) evaluates every cell
+int dt_prune_enabled(const spruce_domain *d) { return (d->stage_kernel == 5 && !d->in_mgpu_stage_api) ? 1 : 0; }
 
 int pick_chunk_rows(const spruce_domain *d)
 {
@@ -240,7 +246,7 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
     A.chunk_rows = pick_chunk_rows(d);
-    if (part == 0 && primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
+    if (part == 0 && primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
     const int nchunks = (d->P.nx + A.chunk_rows - 1) / A.chunk_rows;
     A.chunk0 = 0; A.chunk_stride = 1;
     int gy = nchunks;
@@ -278,7 +284,7 @@ int launch_ghosts(spruce_domain *d, const PlaneSet &U, int primary)
 
 int launch_propagate(spruce_domain *d, int from_state)
 {
-    k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl);
+    k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, 0);
     PropArgs A{};
     for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
@@ -670,7 +676,7 @@ int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, c
         if ((rc = launch_stage(d, S, B, D, coef, primary, kmode))) return rc;
         return finish_stage(d, D, primary);
     }
-    if (primary) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
+    if (primary) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
     CUDA_TRY(cudaEventRecord(d->ev_main, d->stream));
     CUDA_TRY(cudaStreamWaitEvent(d->comm_stream, d->ev_main, 0));
     if ((rc = launch_stage(d, S, B, D, coef, primary, kmode, 1))) return rc;
@@ -678,6 +684,26 @@ int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, c
     CUDA_TRY(cudaEventRecord(d->ev_comm, d->comm_stream));
     if ((rc = launch_stage(d, S, B, D, coef, primary, kmode, 2))) return rc;
     CUDA_TRY(cudaStreamWaitEvent(d->stream, d->ev_comm, 0));
+    return SPRUCE_OK;
+}
+
+// after the step's last stage: all-gather of the slabs' minima, then the check that the skip test's window held (else: every cell)
+int finish_dt(spruce_domain *d)
+{
+    int rc;
+    const bool multi = d->cfg.n_ranks > 1;
+    if (multi && (rc = peer_dt_allgather(d))) return rc;
+    if (!dt_prune_enabled(d)) return SPRUCE_OK;
+    k_dt_validate<<<1, 1, 0, d->stream>>>(d->ctl);
+    DtFullArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.ctl = d->ctl;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_dt_full<<<grid, 256, 0, d->stream>>>(d->P, A);            // returns at once unless the window was missed
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    if (multi && (rc = peer_dt_allgather(d))) return rc;
     return SPRUCE_OK;
 }
 
@@ -719,7 +745,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         if ((rc = stage_and_exchange(d, d->M2set, d->Pset, d->Mset, 1.0, 0, KM_ADD_K2))) return rc;
         if ((rc = stage_and_exchange(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
     }
-    if (d->cfg.n_ranks > 1 && (rc = peer_dt_allgather(d))) return rc;   // global min(dt) for the next step (evolution.cpp:62)
+    if ((rc = finish_dt(d))) return rc;                                 // global min(dt) for the next step (evolution.cpp:62)
     for (int m : d->module_order)                                        // postIterateModules, evolution.cpp:74
         if (m == spruce_domain::MOD_AH && (rc = ah_post(d))) return rc;
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
@@ -847,6 +873,9 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
         StepCtl h{};
         h.step = 0.0; h.time = cfg->time; h.max_time = -1.0; h.epsilon = cfg->epsilon; h.iter = 0; h.done = 0;
         h.dtmin_bits = 0x7FEFFFFFFFFFFFFFULL;
+        h.need_full = 0; h.inv_thr = 0.0; h.thr_bits = 0x7FF0000000000000ULL;
+        h.prune_factor = 1.25;                     // window of the dt skip test: cells certainly above 1.25 x the last minimum are not evaluated
+        if (const char *pf = getenv("SPRUCE_DT_PRUNE")) h.prune_factor = atof(pf);
         if (cudaMemcpy(d->ctl, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMemcpy failed");
     }
     if (rc) { spruce_domain_destroy(d); return rc; }
@@ -1217,6 +1246,7 @@ int spruce_mgpu_stage(spruce_domain *d, int stage)
     CHECK_DOM(d);
     NOT_2F(d, "slab decomposition");
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "stage before setup");
+    d->in_mgpu_stage_api = true;            // the caller reduces dt itself: every cell's dt is evaluated (no skip test)
     int rc;
     const int ti = d->cfg.time_integrator;
     if (ti == SPRUCE_TI_EULER) {

@@ -100,7 +100,7 @@ int tf_launch_stage(spruce_domain *d, const PlaneSet2 &S, const PlaneSet2 &B, co
     tf_base(d, A);
     for (int v = 0; v < NEV2; v++) { A.S[v] = S.p[v]; A.B[v] = B.p[v]; A.D[v] = D.p[v]; }
     A.coef = coef; A.primary = primary; A.kmode = kmode;
-    if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl); d->launches++; }
+    if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, 0); d->launches++; }
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_2f_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
     d->launches++;
@@ -111,7 +111,7 @@ int tf_launch_stage(spruce_domain *d, const PlaneSet2 &S, const PlaneSet2 &B, co
 int tf_launch_propagate(spruce_domain *d, int from_state)
 {
     TwoFluid *t = d->tf;
-    k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl);
+    k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, 0);
     TfPropArgs A{};
     tf_base(d, A.base);
     for (int v = 0; v < NEV2; v++) A.U[v] = t->P.p[v];

@@ -77,6 +77,7 @@ struct StageArgs {
     const double *step_ptr;       // device scalar: step size of this iteration
     const int *done_ptr;          // device flag: run() reached max_time -> every later launch is a no-op
     unsigned long long *dtmin_bits; // device scalar: running min of dt over the interior, as ordered bits
+    const double *inv_thr_ptr;    // device scalar R = 1/(F * previous global min dt), 0 = evaluate every cell (see dt_can_skip)
     double *strip[4];             // per side (x1,x2,y1,y2): what that side's ghost pass reads from its first interior cell
     int strip_pitch;              //   strip[s][c*strip_pitch + idx], c = 0: post-floor rho, 1..3: momentum as that pass sees it
     int chunk_rows;               // rows per CTA
@@ -194,6 +195,22 @@ __device__ __forceinline__ double cell_dt(const DomainParams &P, double rho, dou
     const double vmy = (ay == 0.0 || (ay > 1.0e-140 && ay < 1.0e140)) ? ay : sqrt(vy * vy);
     const double M = smax(smax(smax(cs, va), vfast), vslow);
     return 1.0 / (ddiv(vmx + M, dx, rdx) + ddiv(vmy + M, dy, rdy));
+}
+
+// Only the MINIMUM of dt over the cells is ever used (evolution.cpp:62).  A cell whose dt is certainly above thr = F * (previous
+// global minimum) cannot be the new minimum as long as the new minimum turns out <= thr (k_dt_validate checks that afterwards and
+// k_dt_full re-evaluates every cell when it does not hold).  Certain means: with M <= sqrt(c_s^2 + v_A^2) (v_fast^2 = s/2 (1+delta) <= s)
+//   1/dt <= (|v_x| + sqrt(s))/dx + (|v_y| + sqrt(s))/dy  <  R = 1/thr
+// which, multiplied through by rho and squared, needs neither a division nor a square root:
+//   t = R rho - (|m_x|/dx + |m_y|/dy) > 0   and   (gamma p + b^2/4pi) rho (1/dx + 1/dy)^2 (1 + 1e-3) < t^2 .
+// The 1e-3 margin covers every rounding in this test by twelve orders of magnitude; NaN or underflow makes the test fail (= evaluate).
+__device__ __forceinline__ bool dt_can_skip(const DomainParams &P, double R, double rho, double mx, double my, double e,
+                                            double bx, double by, double bz, double rdx, double rdy)
+{
+    const double t = R * rho - (fabs(mx) * rdx + fabs(my) * rdy);
+    const double S = (e * P.gm1) * P.gamma + ((bx * bx + by * by) + bz * bz) * P.rfourpi;
+    const double g = rdx + rdy;
+    return (t > 0.0) && (((S * rho) * (g * g)) * 1.001 < t * t);
 }
 
 // block-wide NaN-ignoring minimum of positive doubles -> atomicMin on the ordered bit pattern
@@ -866,7 +883,8 @@ __global__ void __launch_bounds__(256) k_halo_pull(const DomainParams P, const P
 // Scalar bookkeeping of advanceTime (evolution.cpp:62,80-81), one thread.
 // ctl[0] = step (double), ctl[1] = time, ctl[2] = max_time (<=0: none); ictl[0] = iter, ictl[1] = done flag
 // ---------------------------------------------------------------------------------------------------------
-struct StepCtl { double step, time, max_time, epsilon; long long iter; int done; int pad; unsigned long long dtmin_bits; };
+struct StepCtl { double step, time, max_time, epsilon; long long iter; int done; int need_full; unsigned long long dtmin_bits;
+                 double inv_thr; unsigned long long thr_bits; double prune_factor; };
 
 // begin: step = epsilon * min(dt) ; reset the running minimum for the propagate at the end of this step
 __global__ void k_step_begin(StepCtl *c, double *dt_hist, int slot)
@@ -876,8 +894,39 @@ __global__ void k_step_begin(StepCtl *c, double *dt_hist, int slot)
     c->step = c->epsilon * __longlong_as_double((long long)c->dtmin_bits);   // evolution.cpp:62
     if (dt_hist) dt_hist[slot] = c->step;
 }
-__global__ void k_dtmin_reset(StepCtl *c) { if (!c->done) c->dtmin_bits = 0x7FEFFFFFFFFFFFFFULL; }
+// reset the running minimum; prune != 0: the stage kernel that follows may skip cells whose dt is certainly above F * (current minimum)
+__global__ void k_dtmin_reset(StepCtl *c, int prune)
+{
+    if (c->done) return;
+    const double prev = __longlong_as_double((long long)c->dtmin_bits);
+    c->need_full = 0;
+    if (prune && c->prune_factor > 0.0 && prev > 0.0 && prev < 1.0e300) {
+        const double thr = c->prune_factor * prev;
+        c->thr_bits = (unsigned long long)__double_as_longlong(thr);
+        c->inv_thr = 1.0 / thr;
+    } else { c->inv_thr = 0.0; c->thr_bits = 0x7FF0000000000000ULL; }
+    c->dtmin_bits = 0x7FEFFFFFFFFFFFFFULL;
+}
+// after the primary stage (and, on slabs, the all-gather): was the new minimum inside the window the skip test assumed?
+__global__ void k_dt_validate(StepCtl *c) { if (!c->done) c->need_full = (c->inv_thr > 0.0 && c->dtmin_bits > c->thr_bits) ? 1 : 0; }
 __global__ void k_step_end(StepCtl *c) { if (c->done) return; c->time += c->step; c->iter += 1; }
+
+// the rare fallback of the skip test: dt of every interior cell of the primary state, exact (recomputeDT, idealmhd.cpp:279-304)
+struct DtFullArgs { const double *U[NEV]; const double *st[NSTATIC]; StepCtl *ctl; };
+__global__ void __launch_bounds__(256) k_dt_full(const DomainParams P, const DtFullArgs A)
+{
+    if (A.ctl->done || !A.ctl->need_full) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    double dtc = 1.7976931348623157e308;
+    const int g = P.row0 + r;
+    if (j < P.ny && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu) {
+        const size_t off = (size_t)r * P.pitch + j;
+        dtc = cell_dt(P, A.U[E_N][off] * P.m_i, A.U[E_MX][off], A.U[E_MY][off], A.U[E_E][off], A.st[S_BEX][off] + A.U[E_BX][off],
+                      A.st[S_BEY][off] + A.U[E_BY][off], A.st[S_BEZ][off] + A.U[E_BZ][off], P.tx.d[r], P.tx.rd[r], P.ty.d[j], P.ty.rd[j]);
+    }
+    block_min_to_global(dtc, &A.ctl->dtmin_bits);
+}
 
 // dt all-gather over peer memory: thread r stores my local minimum into rank r's slot, then publishes the step number;
 // the collect kernel waits for every rank's number and takes the minimum (min of positive doubles == min of their bit patterns)

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
 
     const double step = *A.step_ptr;
     const double s = A.coef * step;
+    const double inv_thr = A.primary ? *A.inv_thr_ptr : 0.0;
 
     // ---- x tables of this chunk and zeroed exchange arrays (inactive quantities read as exact zeros)
     {
@@ -249,8 +250,11 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         } else {
             // ---- dt of the previous row: its rho and momenta were published by the X warps before the last barrier
             if (dt_pending) {
-                const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
-                dtmin_local = smin(dtmin_local, dtc);
+                const double rho_ = Dt_s[0][col], mx_ = Dt_s[1][col], my_ = Dt_s[2][col];
+                if (!dt_can_skip(P, inv_thr, rho_, mx_, my_, dt_e, dt_bx, dt_by, dt_bz, dt_rdx, rdy)) {
+                    const double dtc = cell_dt(P, rho_, mx_, my_, dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
+                    dtmin_local = smin(dtmin_local, dtc);
+                }
             }
             __syncwarp();
             // ---- y face j (left face of this column); the right face comes from lane+1
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         s0 = sp1; v0 = v1;
     }
     if (A.primary && A.kmode != KM_EXPORT) {
-        if (!isX && dt_pending) {
+        if (!isX && dt_pending && !dt_can_skip(P, inv_thr, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_rdx, rdy)) {
             const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
             dtmin_local = smin(dtmin_local, dtc);
         }
