@@ -874,7 +874,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
         h.step = 0.0; h.time = cfg->time; h.max_time = -1.0; h.epsilon = cfg->epsilon; h.iter = 0; h.done = 0;
         h.dtmin_bits = 0x7FEFFFFFFFFFFFFFULL;
         h.need_full = 0; h.inv_thr = 0.0; h.thr_bits = 0x7FF0000000000000ULL;
-        h.prune_factor = 1.25;                     // window of the dt skip test: cells certainly above 1.25 x the last minimum are not evaluated
+        h.prune_factor = 1.05;                     // window of the dt skip test: cells certainly above 1.05 x the last minimum are not evaluated
         if (const char *pf = getenv("SPRUCE_DT_PRUNE")) h.prune_factor = atof(pf);
         if (cudaMemcpy(d->ctl, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMemcpy failed");
     }

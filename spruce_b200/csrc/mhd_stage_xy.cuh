@@ -22,7 +22,7 @@ namespace spruce {
 
 constexpr int XY_NT = 128;                   // 2 X warps + 2 Y warps
 constexpr int XY_RV = 3;                     // velocity ring depth (rows r, r+1 in use, r+2 being formed)
-constexpr int XY_CHUNK = 32;                 // rows per CTA (upper bound)
+constexpr int XY_CHUNK = 48;                 // rows per CTA (upper bound)
 constexpr int XY_XT = XY_CHUNK + 6;          // x-table entries: local rows -3 .. chunk+2
 constexpr int XW = 64;                       // width of the per-column exchange arrays: one private slot per (warp column, lane)
 // shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, x / y parts of the transports,

@@ -84,8 +84,13 @@ class PlasmaDomain:
         a = self._local(a)
         capi.check(self.lib.spruce_grid_upload(self.h, name.encode(), _dp(a), a.size))
 
-    def grid(self, name: str) -> np.ndarray:
-        out = np.empty((self.nx, self.ydim))
+    def grid(self, name: str, out: np.ndarray = None) -> np.ndarray:
+        """Plane `name` of the primary state (derived variables are evaluated on demand).  `out`: a caller-owned C-contiguous
+        float64 (nx, ydim) buffer to fill -- e.g. pinned host memory, which the device copies into at full PCIe speed."""
+        if out is None:
+            out = np.empty((self.nx, self.ydim))
+        elif out.shape != (self.nx, self.ydim) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise capi.SpruceError("out must be a C-contiguous float64 array of shape (%d, %d)" % (self.nx, self.ydim))
         capi.check(self.lib.spruce_grid_download(self.h, name.encode(), _dp(out), out.size))
         return out
 
