@@ -135,6 +135,11 @@ int spruce_module_ambient_heating(spruce_domain *dom, const double *heating, siz
 int spruce_module_viscosity(spruce_domain *dom, int hv_time_integrator, double hv_epsilon, int gradient_correction);
 int spruce_module_viscosity_term(spruce_domain *dom, const char *visc_opt, double strength, const char *var_to_diff, const char *var_to_evol,
                                  const char *species, const double *strength_plane, size_t count);
+/* PhysicalViscosity (source/modules/solar/physicalviscosity.cpp:47-245): Braginskii eta_0 viscous heating and force, sub-cycled
+ * (euler | rk2) inside iterateModule.  coeff_plane = constructCoefficientGrid(coeff, ramp_length, buffer_length) (:247-267), built by
+ * the host exactly as the reference does.  count of sub-cycles: spruce_module_subcycles(dom, "physical_viscosity", &n). */
+int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on,
+                                     int force_on, int gradient_correction, int time_integrator, int inactive_mode);
 /* Ideal2F::parseEquationSetConfigs (source/equationsets/ideal2F.cpp:5-28): use_sub_cycling (reference default true, which aborts
  * in computeTimeDerivatives -- only false can run, and spruce_eqs_setup refuses true) and remove_curl_terms. */
 int spruce_eqs_ideal2f_options(spruce_domain *dom, int use_sub_cycling, int remove_curl_terms);

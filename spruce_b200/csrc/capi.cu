@@ -60,7 +60,10 @@ struct spruce_domain {
     int64_t launches = 0;
     bool any_ucnp = false, any_primary_ghost = false;
     // physics modules, in config order (ModuleHandler::instantiateModule, modulehandler.cpp:92-111)
-    enum { MOD_TC = 1, MOD_RL = 2, MOD_AH = 3, MOD_AV = 4 };
+    enum { MOD_TC = 1, MOD_RL = 2, MOD_AH = 3, MOD_AV = 4, MOD_PV = 5 };
+    // physical_viscosity (source/modules/solar/physicalviscosity.cpp)
+    struct { double coeff = 0.0, epsilon = 1.0; int heating_on = 1, force_on = 1, gc = 0, integrator = 0, inactive = 0, nsub = 1;
+             double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; } pv;
     std::vector<int> module_order;
     TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
     RlParams rl{}; int rl_nsub = 0;
@@ -687,6 +690,59 @@ int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, c
     return SPRUCE_OK;
 }
 
+
+// ---- PhysicalViscosity::iterateModule (physicalviscosity.cpp:150-245)
+int exchange_planes4(spruce_domain *d, double *a, double *b, double *c, double *e)
+{
+    if (d->cfg.n_ranks == 1) return SPRUCE_OK;
+    double *v[NEV] = {a, b, c, e, a, b, c, e};
+    return peer_exchange(d, v, nullptr);
+}
+int pv_iterate(spruce_domain *d, double dt)
+{
+    int rc;
+    auto &pv = d->pv;
+    const int vars_v[3] = {V_v_x, V_v_y, V_v_z}, vars_b[3] = {V_b_hat_x, V_b_hat_y, V_b_hat_z};
+    for (int k = 0; k < 3; k++) { if ((rc = derive_to(d, vars_v[k], pv.v[0][k]))) return rc; if ((rc = derive_to(d, vars_b[k], pv.bh[k]))) return rc; }
+    if ((rc = derive_to(d, V_temp, pv.T[0]))) return rc;
+    PvArgs A{};
+    for (int k = 0; k < 3; k++) { A.bh[k] = pv.bh[k]; A.mom[k] = d->Pset.p[E_MX + k]; }
+    A.n = d->Pset.p[E_N]; A.cg = pv.cg; A.e = d->Pset.p[E_E];
+    A.coeff = pv.coeff; A.heating_on = pv.heating_on; A.force_on = pv.force_on; A.gc = pv.gc; A.red = d->red;
+    // computeViscousSubcycles :66-80 -- evaluated here, in iterate, on the state earlier modules have already changed
+    for (int k = 0; k < 3; k++) A.v[k] = pv.v[0][k];
+    A.T = pv.T[0];
+    if ((rc = reset_reductions(d))) return rc;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_pv_count<<<grid, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long h[4];
+    if ((rc = read_reductions(d, h))) return rc;
+    pv.nsub = (int)(dt / (pv.epsilon * bits_to_double(h[0]))) + 1;
+    const double dts = dt / pv.nsub;
+    int cur = 0;
+    auto stage = [&](int from, int to, double half, int final_stage) -> int {
+        for (int k = 0; k < 3; k++) { A.v[k] = pv.v[from][k]; A.v_out[k] = pv.v[to][k]; }
+        A.T = pv.T[from]; A.T_out = pv.T[to]; A.dt = dts; A.half = half; A.final_stage = final_stage;
+        k_pv_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
+        d->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return exchange_planes4(d, pv.v[to][0], pv.v[to][1], pv.v[to][2], pv.T[to]);
+    };
+    if (!pv.inactive && (pv.heating_on || pv.force_on)) {
+        for (int s = 0; s < pv.nsub; s++) {
+            if (pv.integrator == SPRUCE_TI_EULER) { if ((rc = stage(cur, cur ^ 1, 1.0, 1))) return rc; cur ^= 1; }
+            else {                                                      // rk2: half step into the other set, full step back
+                if ((rc = stage(cur, cur ^ 1, 0.5, 0))) return rc;
+                if ((rc = stage(cur ^ 1, cur, 1.0, 1))) return rc;
+            }
+        }
+    }
+    if ((rc = launch_propagate(d, 0))) return rc;                       // :244
+    return after_module_propagate(d);
+}
+
 // after the step's last stage: all-gather of the slabs' minima, then the check that the skip test's window held (else: every cell)
 int finish_dt(spruce_domain *d)
 {
@@ -728,6 +784,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
             if (m == spruce_domain::MOD_TC && (rc = tc_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_RL && (rc = rl_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_AV && (rc = av_iterate(d, step))) return rc;
+            if (m == spruce_domain::MOD_PV && (rc = pv_iterate(d, step))) return rc;
         }
     }
     if (!d->visc.empty() && (rc = visc_refresh_dt(d))) return rc;     // Viscosity reads the PRIMARY state's dt plane
@@ -1116,6 +1173,26 @@ int spruce_module_ambient_heating(spruce_domain *d, const double *heating, size_
     d->module_order.push_back(spruce_domain::MOD_AH);
     return SPRUCE_OK;
 }
+int spruce_module_physical_viscosity(spruce_domain *d, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on, int force_on,
+                                     int gradient_correction, int time_integrator, int inactive_mode)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "physical_viscosity");
+    if (!coeff_plane || count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "coefficient plane needs %zu values", (size_t)d->P.nx * d->P.ny);
+    if (time_integrator != SPRUCE_TI_EULER && time_integrator != SPRUCE_TI_RK2) return fail(SPRUCE_ERR_ARG, "Invalid time integrator given for Physical Viscosity module");
+    auto &pv = d->pv;
+    int rc;
+    if (!pv.cg) {
+        if ((rc = alloc_plane(d, &pv.cg))) return rc;
+        for (int s = 0; s < 2; s++) { for (int k = 0; k < 3; k++) if ((rc = alloc_plane(d, &pv.v[s][k]))) return rc; if ((rc = alloc_plane(d, &pv.T[s]))) return rc; }
+        for (int k = 0; k < 3; k++) if ((rc = alloc_plane(d, &pv.bh[k]))) return rc;
+    }
+    if ((rc = h2d_plane(d, pv.cg, coeff_plane))) return rc;
+    pv.coeff = coeff; pv.epsilon = epsilon; pv.heating_on = heating_on ? 1 : 0; pv.force_on = force_on ? 1 : 0;
+    pv.gc = gradient_correction ? 1 : 0; pv.integrator = time_integrator; pv.inactive = inactive_mode ? 1 : 0;
+    d->module_order.push_back(spruce_domain::MOD_PV);
+    return SPRUCE_OK;
+}
 int spruce_module_viscosity(spruce_domain *d, int hv_time_integrator, double hv_epsilon, int gradient_correction)
 {
     CHECK_DOM(d);
@@ -1175,6 +1252,7 @@ int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
     if (!which || !count) return fail(SPRUCE_ERR_ARG, "null argument");
     if (!strcmp(which, "thermal_conduction")) *count = d->tc_nsub;
     else if (!strcmp(which, "radiative_losses")) *count = d->rl_nsub;
+    else if (!strcmp(which, "physical_viscosity")) *count = d->pv.nsub;
     else return fail(SPRUCE_ERR_ARG, "no sub-cycling module named <%s>", which);
     return SPRUCE_OK;
 }

@@ -407,6 +407,134 @@ __global__ void __launch_bounds__(256) k_visc_apply(const DomainParams P, const 
 // PlasmaDomain differential operators on a plane (source/mhd/derivs.cpp), for host-side modules that are not ported.
 // op: 0 derivative1D, 1 secondDerivative1D, 2 laplacian, 3 transportDerivative1D (needs vel)
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// PhysicalViscosity (source/modules/solar/physicalviscosity.cpp): Braginskii eta_0 viscous heating and force, sub-cycled.
+// One kernel per sub-cycle stage.  The force is a derivative of products of first derivatives; everything it needs lives on the
+// plus-shaped stencil {(r,j), (r+-1,j), (r,j+-1)}: the six velocity derivatives, T^(5/2) and b_hat are evaluated once at each of
+// those five points (derivatives are zero outside the interior) and shared by the 3 x 2 tensor terms.
+// ---------------------------------------------------------------------------------------------------------
+struct PvArgs {
+    const double *v[3], *T, *bh[3], *n, *cg;       // velocity and temperature of this stage; b_hat, n of the primary state; coefficient plane
+    double *e, *mom[3];                             // primary thermal_energy / momenta (read; written in the final stage)
+    double *v_out[3], *T_out;                       // velocity and temperature after this stage (never alias v, T)
+    double coeff, dt, half;                         // half = 0.5 for the RK2 half step (e, mom stay untouched), 1.0 otherwise
+    int heating_on, force_on, gc, final_stage;
+    unsigned long long *red;                        // count mode: red[0] = min timescale
+};
+struct PvPoint { double dxv[3], dyv[3], t25, b[3], cg; };
+
+__device__ __forceinline__ void pv_point(const DomainParams &P, const PvArgs &A, int a, int b, PvPoint &o)
+{
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        auto V = [&](int x, int y) { return rd(P, A.v[k], x, y); };
+        o.dxv[k] = Dx(P, V, a, b);
+        o.dyv[k] = Dy(P, V, a, b);
+        o.b[k] = rd(P, A.bh[k], a, b);
+    }
+    o.t25 = pow(rd(P, A.T, a, b), 2.5);
+    o.cg = rd(P, A.cg, a, b);
+}
+// same_factor_off_diag (physicalviscosity.cpp:90-93)
+__device__ __forceinline__ double pv_sfo(const PvPoint &p)
+{
+    return ((p.b[0] * (p.b[1] * p.dyv[0]) + p.b[1] * (p.b[0] * p.dxv[1])) + p.b[2] * (p.b[0] * p.dxv[2] + p.b[1] * p.dyv[2])) - (p.dxv[0] + p.dyv[1]) / 3.0;
+}
+// derivative1D of a plane whose values at (lower, centre, upper) along one axis are given (derivs.cpp:223-264)
+__device__ __forceinline__ double pv_d3(const AxisTab &t, int i, double lo, double c, double hi)
+{
+    const double up = face_interp(c, hi, t.h[i], t.h[i + 1], t.fs[i + 1], t.rfs[i + 1]);
+    const double dn = face_interp(lo, c, t.h[i - 1], t.h[i], t.fs[i], t.rfs[i]);
+    return ddiv(up - dn, t.d[i], t.rd[i]);
+}
+
+__global__ void __launch_bounds__(128) k_pv_stage(const DomainParams P, const PvArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const bool in = is_interior(P, r, j);
+    const double mask = in ? 1.0 : 0.0;
+    const double rho = A.n[off] * P.m_i;
+    double heating = 0.0, force[3] = {0.0, 0.0, 0.0};
+    PvPoint c;
+    pv_point(P, A, r, j, c);
+    if (A.heating_on && A.coeff != 0.0) {                                                          // computeHeating :47-64
+        const double X = ((c.b[0] * (c.b[0] * c.dxv[0] + c.b[1] * c.dyv[0]) + c.b[1] * (c.b[0] * c.dxv[1] + c.b[1] * c.dyv[1]))
+                          + c.b[2] * (c.b[0] * c.dxv[2] + c.b[1] * c.dyv[2])) - (c.dxv[0] + c.dyv[1]) / 3.0;
+        heating = mask * (((c.cg * 3.0) * c.t25) * (X * X));
+    }
+    if (A.force_on && in) {                                                                        // computeViscousForce :82-140 (zero outside: mask)
+        PvPoint xm, xp, ym, yp;
+        pv_point(P, A, r - 1, j, xm); pv_point(P, A, r + 1, j, xp);
+        pv_point(P, A, r, j - 1, ym); pv_point(P, A, r, j + 1, yp);
+        const PvPoint *lo[2] = {&xm, &ym}, *hi[2] = {&xp, &yp};
+        const double sfo_c = pv_sfo(c), sfo_lo[2] = {pv_sfo(xm), pv_sfo(ym)}, sfo_hi[2] = {pv_sfo(xp), pv_sfo(yp)};
+        const double sfd = c.b[0] * (c.b[0] * c.dxv[0]) + c.b[1] * (c.b[1] * c.dyv[1]);             // same_factor_diag :94-95
+        auto BX = [&](int x, int y) { return rd(P, A.bh[0], x, y); };
+        auto BY = [&](int x, int y) { return rd(P, A.bh[1], x, y); };
+        auto VX = [&](int x, int y) { return rd(P, A.v[0], x, y); };
+        auto VY = [&](int x, int y) { return rd(P, A.v[1], x, y); };
+        const double dxbx = Dx(P, BX, r, j), dybx = Dy(P, BX, r, j), dxby = Dx(P, BY, r, j), dyby = Dy(P, BY, r, j);
+        // grad_b_terms_diag :96-101; derivative1D(del_y_v_y,0) and derivative1D(del_x_v_x,1) from the neighbours' derivatives
+        const double gbd[2] = {
+            ((((c.b[0] * 2.0) * dxbx) * c.dxv[0] + (c.b[0] * c.b[0]) * D2x(P, VX, r, j)) + ((c.b[1] * 2.0) * dxby) * c.dyv[1]) + (c.b[1] * c.b[1]) * pv_d3(P.tx, r, xm.dyv[1], c.dyv[1], xp.dyv[1]),
+            ((((c.b[0] * 2.0) * dybx) * c.dxv[0] + (c.b[0] * c.b[0]) * pv_d3(P.ty, j, ym.dxv[0], c.dxv[0], yp.dxv[0])) + ((c.b[1] * 2.0) * dyby) * c.dyv[1]) + (c.b[1] * c.b[1]) * D2y(P, VY, r, j)};
+#pragma unroll
+        for (int jj = 0; jj < 3; jj++) {
+            double res = 0.0;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const double delta = (i == jj) ? 1.0 / 3.0 : 0.0;
+                const AxisTab &t = i == 0 ? P.tx : P.ty;
+                const int idx = i == 0 ? r : j;
+                auto G = [&](const PvPoint &p) { return A.gc ? (p.t25 * p.cg) * (delta - p.b[i] * p.b[jj]) : p.t25 * (delta - p.b[i] * p.b[jj]); };
+                const double g_lo = G(*lo[i]), g_c = G(c), g_hi = G(*hi[i]);
+                res = res + pv_d3(t, idx, g_lo * sfo_lo[i], g_c * sfo_c, g_hi * sfo_hi[i]);                               // :110-113 / :121-124
+                res = res + (A.gc ? ((gbd[i] * c.t25) * c.cg) * (delta - c.b[i] * c.b[jj]) : (gbd[i] * c.t25) * (delta - c.b[i] * c.b[jj]));   // :114-115 / :125-126
+                res = res + sfd * pv_d3(t, idx, g_lo, g_c, g_hi);                                                          // :116-118 / :127-129
+            }
+            force[jj] = A.gc ? res * (mask * -3.0) : res * ((c.cg * -3.0) * mask);                                         // :132-136
+        }
+    }
+    const double hs = A.half;
+    double e1 = A.e[off], T1 = A.T[off];
+    if (A.heating_on) {                                                                            // :176-185 / :214-218
+        e1 = smax(e1 + (hs == 1.0 ? heating * A.dt : (heating * 0.5) * A.dt), P.e_min);
+        T1 = smax((e1 * P.gm1) / (A.n[off] * (2.0 * kKB)), P.T_min);
+    }
+    A.T_out[off] = T1;
+    if (A.final_stage && A.heating_on) A.e[off] = e1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double v1 = A.v[k][off];
+        if (A.force_on) {                                                                          // :186-193 / :219-226
+            const double m1 = A.mom[k][off] + (hs == 1.0 ? force[k] * A.dt : (force[k] * 0.5) * A.dt);
+            v1 = m1 / rho;
+            if (A.final_stage) A.mom[k][off] = m1;
+        }
+        A.v_out[k][off] = v1;
+    }
+}
+
+// computeViscousSubcycles (physicalviscosity.cpp:66-80): min over the interior of dx dy rho / (3 f coeff T^2.5), f = 3 cos^2 + 1
+__global__ void __launch_bounds__(128) k_pv_count(const DomainParams P, const PvArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    double ts = 1.7976931348623157e308;
+    if (j < P.ny && is_interior(P, r, j)) {
+        const size_t off = (size_t)r * P.pitch + j;
+        const double vx = A.v[0][off], vy = A.v[1][off];
+        const double vm = sqrt(vx * vx + vy * vy);
+        const double s_ = (A.bh[0][off] * vx) / vm + (A.bh[1][off] * vy) / vm;
+        const double df = (vm == 0.0) ? 4.0 : (s_ * s_) * 3.0 + 1.0;
+        ts = ((P.tx.d[r] * P.ty.d[j]) * (A.n[off] * P.m_i)) / (((df * 3.0) * smax(A.cg[off], 0.000001 * A.coeff)) * pow(A.T[off], 2.5));
+    }
+    block_min_to_global(ts, A.red);
+}
+
 struct OpArgs { const double *q, *vel; double *out; int op, index; };
 __global__ void __launch_bounds__(128) k_operator(const DomainParams P, const OpArgs A)
 {

@@ -147,6 +147,13 @@ class PlasmaDomain:
         a = self._local(heating)
         capi.check(self.lib.spruce_module_ambient_heating(self.h, _dp(a), a.size))
 
+    def set_physical_viscosity(self, coeff_plane: np.ndarray, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False,
+                               integrator="euler", inactive_mode=False):
+        """coeff_plane = PhysicalViscosity::constructCoefficientGrid(coeff, ramp_length, buffer_length) (physicalviscosity.cpp:247-267)."""
+        a = self._local(coeff_plane)
+        capi.check(self.lib.spruce_module_physical_viscosity(self.h, coeff, _dp(a), a.size, epsilon, int(heating_on), int(force_on),
+                                                             int(gradient_correction), capi.TI[integrator], int(inactive_mode)))
+
     def set_eic_thermalization(self):
         capi.check(self.lib.spruce_module_eic_thermalization(self.h))
 

@@ -45,6 +45,7 @@ CLOUD = dict(nx=NX, ny=NY, drift=2.0e3, bfield=5.0)
 TC = lambda **kw: ("thermal_conduction", list(dict(dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4", output_to_file="true"), **kw).items()))
 RL = lambda **kw: ("radiative_losses", list(dict(dict(cutoff_ramp="1.0e3", cutoff_temp="3.0e4", epsilon="0.1", output_to_file="true"), **kw).items()))
 AV = lambda **kw: ("artificial_viscosity", list(kw.items()))
+PV = lambda **kw: ("physical_viscosity", list(dict(dict(coeff="3.0e-15", epsilon="0.1"), **kw).items()))
 AH = lambda **kw: ("ambient_heating", list(dict(dict(heating_rate="1.0e-4"), **kw).items()))
 
 CASES = {
@@ -79,6 +80,14 @@ CASES = {
     "ot_visc_hv_rk4": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
                       modules=[AV(visc_opt="local,global", visc_strength="2.5,0.4", visc_vars_to_diff="v_x,temp", visc_vars_to_evol="mom_x,thermal_energy",
                                   visc_length="0,0", visc_species="i,i", hv_time_integrator="rk4", hv_epsilon="1.0")], **INACTIVE_FLOORS), 3, (1, 3)),
+    # Braginskii physical viscosity (source/modules/solar/physicalviscosity.cpp): heating + force, euler / rk2 sub-cycles, coefficient ramp
+    "loop_pv_euler": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[PV()], **SOLAR_FLOORS), 4, (1, 4)),
+    "loop_pv_rk2_gc": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="euler", xb=("reflect", "open"), yb=("fixed", "open"),
+                       modules=[PV(time_integrator="rk2", gradient_correction="true", ramp_length="6.0e8", coeff="1.0e-14")], **SOLAR_FLOORS), 3, (1, 3)),
+    "ot_pv_heat_only": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
+                        modules=[PV(force_on="false", coeff="4.0e-16", epsilon="0.2")], **INACTIVE_FLOORS), 3, (1, 3)),
+    "ot_pv_force_only_rk2": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="rk4", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
+                        modules=[PV(heating_on="false", time_integrator="rk2", coeff="4.0e-16", epsilon="0.2")], **INACTIVE_FLOORS), 3, (1, 3)),
     # two-fluid equation set (source/equationsets/ideal2F.cpp, non-sub-cycled Maxwell update) + EIC thermalization (BASELINE.json configs[2])
     "tf_ucnp_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, **TF, **UCNP_FLOORS), 8, (1, 8)),
     "tf_ucnp_eic_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, modules=[EIC], **TF, **UCNP_FLOORS), 8, (1, 8)),
@@ -139,7 +148,7 @@ def make(name):
                     out["f%d_mod_%s" % (fi, v)] = frames[fi][v]
         desc = dict(case=name, out_vars=out_vars, generator=gen, gen_kwargs=gkw, n_steps=nsteps, keep=list(keep),
                     config={k: v for k, v in ckw.items()}, config_text=cfg,
-                    subcycle_log=[ln for ln in stdout.splitlines() if "Subcycles" in ln][:nsteps])
+                    subcycle_log=[ln for ln in stdout.splitlines() if "Subcycle" in ln][:nsteps])
         out["desc"] = np.array(json.dumps(desc))
         np.savez_compressed(HERE / (name + ".npz"), **out)
         print("%-20s steps=%d first dt=%s  -> %s.npz" % (name, nsteps, float(steps[0]).hex(), name))

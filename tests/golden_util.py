@@ -16,10 +16,15 @@ EVOLVED_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_t
               "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"]
 
 
-def cases(prefixes=None, two_fluid=False):
+NO_ORACLE = ("physical_viscosity",)      # modules without a CPU restatement in oracle/: the reference's fixtures check the device path directly
+
+
+def cases(prefixes=None, two_fluid=False, oracle_only=False):
     """Fixture names; the two-fluid fixtures (tf_*) are pinned against the device path only (no CPU restatement of Ideal2F)."""
     names = sorted(p.stem for p in GOLDEN.glob("*.npz"))
     names = [n for n in names if n.startswith("tf_") == two_fluid]
+    if oracle_only:
+        names = [n for n in names if "_pv_" not in n]
     if prefixes:
         names = [n for n in names if any(n.startswith(p) for p in prefixes)]
     return names
@@ -49,6 +54,15 @@ class Golden:
         self.equation_set = cfg.get("eqs", "ideal_mhd")
         self.eqs_options = {k: (v == "true") for k, v in cfg.get("eqs_block", [])}
 
+    def viscous_subcycle_counts(self):
+        """'... , N Subcycle(s)' of the physical_viscosity message (physicalviscosity.cpp:283)."""
+        out = []
+        for ln in self.desc["subcycle_log"]:
+            for part in ln.split("|"):
+                if "Subcycle(s)" in part:
+                    out.append(int(part.split("Subcycle(s)")[0].split(",")[-1].split()[-1]))
+        return out
+
     def subcycle_counts(self, label):
         """Per-iteration sub-cycle counts parsed from the reference's stdout lines ('Thermal Subcycles: N')."""
         out = []
@@ -77,6 +91,11 @@ def module_kwargs(name, kv):
                     split_exp_mode=b(kv.get("split_exp_mode", "false")),
                     split_exp_scale_height=float(kv.get("split_exp_scale_height", "1.0")),
                     split_exp_start_height=float(kv.get("split_exp_start_height", "0.0")))
+    if name == "physical_viscosity":
+        return dict(coeff=float(kv.get("coeff", "0.0")), ramp_length=float(kv.get("ramp_length", "0.0")), buffer_length=float(kv.get("buffer_length", "0.0")),
+                    epsilon=float(kv.get("epsilon", "1.0")), heating_on=b(kv.get("heating_on", "true")), force_on=b(kv.get("force_on", "true")),
+                    gradient_correction=b(kv.get("gradient_correction", "false")), integrator=kv.get("time_integrator", "euler") or "euler",
+                    inactive_mode=b(kv.get("inactive_mode", "false")))
     if name == "artificial_viscosity":
         n = len(kv["visc_opt"].split(","))
         cols = {k: kv[k].split(",") for k in ("visc_opt", "visc_strength", "visc_vars_to_diff", "visc_vars_to_evol", "visc_length", "visc_species")}
@@ -128,3 +147,17 @@ def mismatch(a, b):
         rel = np.nanmax(np.abs(a - b)) / max(np.nanmax(np.abs(b)), 1e-300)
     idx = np.argwhere(bad)[:5].tolist()
     return "%d/%d cells differ, rel Linf %.3e, first at %s" % (n, a.size, rel, idx)
+
+
+def physical_viscosity_coefficient(planes, coeff, ramp_length):
+    """PhysicalViscosity::constructCoefficientGrid (reference source/modules/solar/physicalviscosity.cpp:247-267), on the host as the
+    reference builds it (buffer_length is parsed but unused there)."""
+    x, y = planes["pos_x"], planes["pos_y"]
+    if ramp_length == 0.0:
+        return coeff * np.ones_like(x)
+    x_max, y_max, x_min, y_min = x.max(), y.max(), x.min(), y.min()
+    xc, yc = 0.5 * (x_min + x_max), 0.5 * (y_min + y_max)
+    s = (x - xc) ** 2 / (x_max - xc) ** 2.0 + (y - yc) ** 2 / (y_max - yc) ** 2.0
+    s_length = ramp_length / min(x_max - xc, y_max - yc)
+    res = 1.0 / 0.99 * np.maximum(np.exp(-2.3 * (np.maximum(s + 2.0 * s_length - 1.0, 0.0) / s_length) ** 2) - 0.01, 0.0)
+    return coeff * res

@@ -12,10 +12,10 @@ from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_b
 
 pytestmark = pytest.mark.gpu
 
-BUILT_MODULES = {"thermal_conduction", "radiative_losses", "ambient_heating", "artificial_viscosity"}
+BUILT_MODULES = {"thermal_conduction", "radiative_losses", "ambient_heating", "artificial_viscosity", "physical_viscosity"}
 # Modules that call std::pow / std::log10: CUDA's libm and glibc differ in the last bit for some arguments, so these runs are
 # held to the north star's tolerance (relative L-infinity <= 1e-9 per plane, same for the step sizes) instead of bit equality.
-LIBM_MODULES = {"thermal_conduction", "radiative_losses"}
+LIBM_MODULES = {"thermal_conduction", "radiative_losses", "physical_viscosity"}
 REL_TOL = 1.0e-9
 
 
@@ -35,6 +35,10 @@ def make_domain(g: Golden):
         elif name == "artificial_viscosity":
             from golden_util import viscosity_terms_with_profiles
             d.set_viscosity(viscosity_terms_with_profiles(g.planes, kw.pop("terms")), **kw)
+        elif name == "physical_viscosity":
+            from golden_util import physical_viscosity_coefficient
+            ramp = kw.pop("ramp_length"); kw.pop("buffer_length")
+            d.set_physical_viscosity(physical_viscosity_coefficient(g.planes, kw["coeff"], ramp), **kw)
         else:
             getattr(d, "set_" + name)(**kw)
     return d
@@ -55,11 +59,13 @@ def test_golden_reference_outputs(name):
     d = make_domain(g)
     exact = not any(m[0] in LIBM_MODULES for m in g.modules)
     done = 0
-    tc, rl = [], []
+    tc, rl, pv = [], [], []
     for it in sorted(g.frames):
         dts = []
         for _ in range(it - done):
             dts.append(d.advanceTime())
+            if any(m[0] == "physical_viscosity" for m in g.modules):
+                pv.append(d.subcycles("physical_viscosity"))
             if any(m[0] == "thermal_conduction" for m in g.modules):
                 tc.append(d.subcycles("thermal_conduction"))
             if any(m[0] == "radiative_losses" for m in g.modules):
@@ -83,6 +89,8 @@ def test_golden_reference_outputs(name):
         assert tc == g.subcycle_counts("Thermal Subcycles")[:len(tc)]
     if rl:
         assert rl == g.subcycle_counts("Radiative Subcycles")[:len(rl)]
+    if pv:
+        assert pv == g.viscous_subcycle_counts()[:len(pv)]
     d.close()
 
 

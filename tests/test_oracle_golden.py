@@ -19,7 +19,7 @@ def make_oracle(g: Golden) -> Oracle:
     return o
 
 
-@pytest.mark.parametrize("name", cases())
+@pytest.mark.parametrize("name", cases(oracle_only=True))
 def test_oracle_reproduces_reference(name):
     g = Golden(name)
     o = make_oracle(g)
