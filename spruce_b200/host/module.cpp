@@ -45,7 +45,8 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "thermal_conduction") m_modules.emplace_back(new ThermalConduction(m_pd));
     else if (name == "radiative_losses") m_modules.emplace_back(new RadiativeLosses(m_pd));
     else if (name == "ambient_heating") m_modules.emplace_back(new AmbientHeating(m_pd));
-    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, eic_thermalization are).");
+    else if (name == "physical_viscosity") m_modules.emplace_back(new PhysicalViscosity(m_pd));
+    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, eic_thermalization are).");
     m_modules.back()->configureModule(in);
 }
 
@@ -241,4 +242,68 @@ void EICThermalization::setupModule()
     for (const char *name : {"n", "e_temp", "e_thermal_energy", "i_thermal_energy"})
         if (!m_pd.m_eqs->is_var(name)) spruce_die(std::string("Grid <") + name + "> was not found within the EquationSet.");
     PlasmaDomain::check(spruce_module_eic_thermalization(m_pd.device()));
+}
+
+// physicalviscosity.cpp:17-35
+void PhysicalViscosity::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "output_to_file") output_to_file = (v == "true");
+        else if (k == "coeff") coeff = std::stod(v);
+        else if (k == "ramp_length") ramp_length = std::stod(v);
+        else if (k == "buffer_length") buffer_length = std::stod(v);
+        else if (k == "epsilon") epsilon = std::stod(v);
+        else if (k == "heating_on") heating_on = (v == "true");
+        else if (k == "force_on") force_on = (v == "true");
+        else if (k == "inactive_mode") inactive_mode = (v == "true");
+        else if (k == "gradient_correction") gradient_correction = (v == "true");
+        else if (k == "time_integrator") time_integrator = v;
+        else if (k == "ms_electron_heating_fraction") ms_electron_heating_fraction = std::stod(v);
+        else std::cerr << k << " config not recognized.\n";
+    }
+}
+// physicalviscosity.cpp:247-267: elliptical Gaussian ramp of the coefficient towards the domain edge (buffer_length is parsed but unused)
+Grid PhysicalViscosity::constructCoefficientGrid(double strength, double ramp, double) const
+{
+    const size_t nx = m_pd.xdim(), ny = m_pd.ydim();
+    Grid result = Grid::Ones(nx, ny);
+    if (ramp == 0.0) { for (double &q : result.data()) q = strength * q; return result; }
+    const Grid &x = m_pd.m_grids[PlasmaDomain::pos_x], &y = m_pd.m_grids[PlasmaDomain::pos_y];
+    double x_min = x(0, 0), x_max = x(0, 0), y_min = y(0, 0), y_max = y(0, 0);
+    for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
+        x_min = std::min(x_min, x(i, j)); x_max = std::max(x_max, x(i, j)); y_min = std::min(y_min, y(i, j)); y_max = std::max(y_max, y(i, j));
+    }
+    const double xc = 0.5 * (x_min + x_max), yc = 0.5 * (y_min + y_max);
+    const double px = std::pow(x_max - xc, 2.0), py = std::pow(y_max - yc, 2.0);
+    const double s_length = ramp / std::min(x_max - xc, y_max - yc);
+    for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
+        const double ex = x(i, j) - xc, ey = y(i, j) - yc;
+        const double s = (ex * ex) / px + (ey * ey) / py;
+        const double a = std::max((s + 2.0 * s_length) - 1.0, 0.0) / s_length;
+        result(i, j) = strength * ((1.0 / 0.99) * std::max(std::exp((a * a) * -2.3) - 0.01, 0.0));
+    }
+    return result;
+}
+// physicalviscosity.cpp:37-45
+void PhysicalViscosity::setupModule()
+{
+    SPRUCE_REQUIRE(time_integrator.empty() || time_integrator == "euler" || time_integrator == "rk2", "Invalid time integrator given for Physical Viscosity module");
+    SPRUCE_REQUIRE(ms_electron_heating_fraction >= 0.0 && ms_electron_heating_fraction <= 1.0, "Physical Viscosity MS electron heating fraction must be between 0 and 1");
+    no_file_output(output_to_file, "physical_viscosity");
+    const Grid cg = constructCoefficientGrid(coeff, ramp_length, buffer_length);
+    PlasmaDomain::check(spruce_module_physical_viscosity(m_pd.device(), coeff, cg.ptr(), cg.size(), epsilon, heating_on, force_on, gradient_correction,
+                                                         integrator_id(time_integrator, "Physical Viscosity"), inactive_mode));
+}
+// physicalviscosity.cpp:269-287
+std::string PhysicalViscosity::commandLineMessage() const
+{
+    std::string message;
+    if (heating_on) { message += "Viscous Heating"; message += (coeff == 0.0) ? " Zero" : " On"; if (force_on) message += ", "; }
+    if (force_on) { message += "Viscous Force"; message += (coeff == 0.0) ? " Zero" : " On"; }
+    int n = 1;
+    PlasmaDomain::check(spruce_module_subcycles(m_pd.device(), "physical_viscosity", &n));
+    if (force_on || heating_on) message += ", " + std::to_string(n) + " Subcycle(s)";
+    if (inactive_mode) message += " (Not Applied)";
+    return message;
 }

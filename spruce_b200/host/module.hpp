@@ -112,3 +112,17 @@ public:
 private:
     void parseModuleConfigs(std::vector<std::string>, std::vector<std::string>) override {}   // eic_thermalization.cpp:7-10: no keys
 };
+// source/modules/solar/physicalviscosity.hpp ("physical_viscosity")
+class PhysicalViscosity : public Module {
+public:
+    explicit PhysicalViscosity(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override;
+    bool device_resident() const override { return true; }
+private:
+    double coeff = 0.0, ramp_length = 0.0, buffer_length = 0.0, epsilon = 1.0, ms_electron_heating_fraction = 0.0;
+    bool heating_on = true, force_on = true, output_to_file = false, inactive_mode = false, gradient_correction = false;
+    std::string time_integrator;
+    Grid constructCoefficientGrid(double strength, double ramp_length, double buffer_length) const;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};

@@ -87,4 +87,5 @@ private:
     static std::string num2str(double num);
     friend class ModuleHandler;
     friend class EICThermalization;
+    friend class PhysicalViscosity;
 };

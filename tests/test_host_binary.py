@@ -39,6 +39,8 @@ CASES = {
                            modules=[("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4")]),
                                     ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
                                     ("ambient_heating", [("heating_rate", "1.0e-4")])]), False),
+    "loop_physical_viscosity": (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"), max_iterations=4, iter_output_interval=1,
+                                modules=[("physical_viscosity", [("coeff", "1.0e-14"), ("epsilon", "0.1"), ("ramp_length", "6.0e8"), ("time_integrator", "rk2"), ("gradient_correction", "true")])]), False),
     # BASELINE.json configs[2]: two-fluid UCNP expansion (ideal_2F, open_ucnp on all sides), without and with EIC thermalization
     "ucnp_two_fluid": (lambda: synthetic.ucnp_cloud(40, 36, drift=2.0e3, bfield=5.0), dict(integrator="rk2", xb=("open_ucnp", "open_ucnp"), yb=("open_ucnp", "open_ucnp"), max_iterations=6,
                        iter_output_interval=2, write_precision=17, eqs="ideal_2F", eqs_block=[("use_sub_cycling", "false")], density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30,
