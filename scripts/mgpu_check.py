@@ -31,6 +31,8 @@ def add_modules(dom):
             dom.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4)
         elif m == "rl":
             dom.set_radiative_losses(integrator="rk2", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1)
+        elif m == "pv":
+            dom.set_physical_viscosity(np.full((dom.nx, dom.ydim), 3.0e-15), coeff=3.0e-15, epsilon=0.1, integrator="rk2", gradient_correction=True)
         elif m == "ah":
             dom.set_ambient_heating_plane(np.full((dom.nx, dom.ydim), 1.0e-4))
         else:
@@ -57,7 +59,7 @@ if rank == 0:
     one = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], device=local, **kw)
     add_modules(one)
     dts = one.advance(steps)
-    for m, key in (("tc", "thermal_conduction"), ("tcsat", "thermal_conduction"), ("rl", "radiative_losses")):
+    for m, key in (("tc", "thermal_conduction"), ("tcsat", "thermal_conduction"), ("rl", "radiative_losses"), ("pv", "physical_viscosity")):
         if m in modules:
             a, b = run.dom.subcycles(key), one.subcycles(key)
             print("subcycles", key, a, b)
