@@ -183,7 +183,7 @@ def run_ours(args):
         alg_bytes_per_launch = 0.5 * ALG_BYTES_PER_CELL_STEP * cells / world          # per GPU
         achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
         result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                              "peak_source": peak_src, "kernel": "k_mhd_stage", "alg_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
+                              "peak_source": peak_src, "kernel": "k_mhd_stage_xy", "alg_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
                               "note": "per GPU; includes the halo exchange (%s) and the dt all-gather between launches" % ("peer stores over NVLink from the pack kernel" if args.transport == "p2p" else "NCCL send/recv")}
         result["transport"] = args.transport
         runner.close()
@@ -249,9 +249,9 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "k_mhd_stage", "alg_bytes_per_launch": alg_bytes_per_launch,
+                "peak_source": peak_src, "kernel": "k_mhd_stage_xy", "alg_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_launch_ms, "stage1_alone_ms": stage_ms,
-                "note": "FP64-issue co-bound: exact-parity arithmetic needs ~1.1e3 DFMA-pipe instructions per cell per stage (DESIGN.md)"}
+                "note": "instruction-issue co-bound: bit-exact arithmetic needs ~625 FP64-pipe + ~920 other warp-instructions per 32 cells per stage (DESIGN.md 4); avg_launch_ms = timed region / (2 stage launches x steps), the 5 one-thread bookkeeping kernels per step are < 1 percent of it"}
 
     # ---- end to end through the public API with host buffers
     dom.close()
