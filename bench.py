@@ -157,11 +157,20 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.size
+    with_tc = args.workload == "mhd_tc"
+    tmod = 0.1 if with_tc else 0.0           # SURVEY 8d cfg-C: temperature modulated so that conduction is non-trivial
+
+    def add_modules(dom):
+        if with_tc:
+            # kappa weakened by 1e-3 so that the explicit sub-cycles stay few and stable at 4096^2 .. 16384^2 (at full strength the reference's
+            # own dt_subcycle_min clamp runs the scheme at a diffusion number of ~1 on these fine grids and the fields blow up)
+            dom.set_thermal_conduction(flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-7, weakening_factor=1.0e-3)
+
     if world > 1:
         from spruce_b200.multigpu import partition
-        s = synthetic.orszag_tang(n, n, rows=partition(n, world)[rank])      # every rank builds only its own slab
+        s = synthetic.orszag_tang(n, n, rows=partition(n, world)[rank], temp_mod=tmod)      # every rank builds only its own slab
     else:
-        s = synthetic.orszag_tang(n, n)
+        s = synthetic.orszag_tang(n, n, temp_mod=tmod)
     planes = s["planes"]
     dx, dy = np.ascontiguousarray(s["dx"]), np.ascontiguousarray(s["dy"])
     names = ["be_x", "be_y", "be_z", "rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
@@ -172,10 +181,12 @@ def run_ours(args):
         host = {k: planes[k] for k in names}
         host["d_x"], host["d_y"] = dx, dy
         runner = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=args.transport, xdim=n, **KW)
+        add_modules(runner.dom)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         result = runner.bench(args.steps, args.warmup)
+        result["tc_subcycles"] = runner.dom.subcycles("thermal_conduction") if with_tc else None
         result["clocks"] = sampler.stop() if rank == 0 else None
         peak, peak_src = hbm_peak()
         n_stage = 2 * args.steps
@@ -191,6 +202,7 @@ def run_ours(args):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         r2 = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=args.transport, xdim=n, **KW)
+        add_modules(r2.dom)
         r2.step(args.steps)
         out = {k: r2.dom.grid(k) for k in PlasmaDomain.EVOLVED}
         torch.cuda.synchronize(); dist.barrier()
@@ -213,6 +225,7 @@ def run_ours(args):
     host["d_x"], host["d_y"] = dx, dy
     ion_mass, gamma = s["ion_mass"], s["adiabatic_index"]
     dom = PlasmaDomain(host, ion_mass, gamma, device=local, **KW)
+    add_modules(dom)
     del planes, s
     stream = torch.cuda.ExternalStream(dom.stream())
     cells = n * n
@@ -233,6 +246,7 @@ def run_ours(args):
     launches = dom.launch_count() - l0
     assert len(dts) == args.steps and np.all(dts > 0) and np.all(np.isfinite(dts))
     value = cells * args.steps / (ms * 1e-3)
+    tc_sub = dom.subcycles("thermal_conduction") if with_tc else None
 
     # ---- stage kernel alone (roofline numerator is per launch)
     stage_ms = dom.time_stage_kernel(10)
@@ -259,6 +273,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     dom = PlasmaDomain(host, ion_mass, gamma, device=local, **KW)     # uploads 13 planes from pinned memory + setup
+    add_modules(dom)
     dts2 = dom.advance(args.steps)
     out = {k: dom.grid(k, out=outbuf[k]) for k in PlasmaDomain.EVOLVED}  # into caller-owned pinned host buffers
     t1 = time.perf_counter()
@@ -278,7 +293,7 @@ def run_ours(args):
         if r is not None:
             cpu = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": "unmodified reference binary (oracle/_ref/run), OT-512 (same generator), wall(10 it) - wall(2 it), %d OpenMP threads" % threads}
-    result = dict(value=value, ms=ms, launches=launches, clocks=clocks, roofline=roofline, e2e=e2e, cpu=cpu)
+    result = dict(value=value, ms=ms, launches=launches, clocks=clocks, roofline=roofline, e2e=e2e, cpu=cpu, tc_subcycles=tc_sub)
     emit(args, result, 1)
 
 
@@ -292,6 +307,11 @@ def emit(args, r, world):
             "clocks": r["clocks"], "gpu_launches": r["launches"], "e2e": r["e2e"], "roofline": r["roofline"]}
     if r.get("cpu"):
         line["cpu_baseline"] = r["cpu"]
+    if args.workload == "mhd_tc":
+        line["config"]["workload"] = ("OT-%d + thermal conduction: the same grid with temp = T0 (1 + 0.1 sin kx sin ky), ideal MHD RK2 + thermal_conduction "
+                                      "(unsaturated, euler sub-cycles, epsilon 0.1, weakening_factor 1e-3) (BASELINE.json configs[4], SURVEY 8d cfg-C)" % args.size)
+        line["config"]["thermal_conduction_subcycles_last_step"] = r.get("tc_subcycles")
+        line["roofline"]["note"] = "stage-kernel roofline is not meaningful for this workload (the step also runs the conduction sub-cycles); value is whole-step throughput"
     print(json.dumps(line))
 
 
@@ -303,6 +323,7 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mhd", choices=["mhd", "mhd_tc"], help="mhd: BASELINE configs[3] (the bench line); mhd_tc: configs[4], MHD + thermal conduction")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: library peer stores over NVLink, or torch.distributed NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Throughput of the secondary paths on one GPU (device-timed): two-fluid RK2 step, MHD + thermal conduction, MHD + physical viscosity.
+usage: module_perf.py [size]"""
+import json, sys, time
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from spruce_b200 import synthetic
+from spruce_b200.domain import PlasmaDomain
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+out = {}
+
+def timed(dom, steps):
+    dom.advance(3)
+    st = torch.cuda.ExternalStream(dom.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record(st)
+    dom.advance(steps)
+    e1.record(st); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+s = synthetic.ucnp_cloud(n + 1, n + 1, drift=2.0e3, bfield=5.0)
+d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False), xb=("open_ucnp",) * 2, yb=("open_ucnp",) * 2,
+                 integrator="rk2", density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
+d.set_eic_thermalization()
+ms = timed(d, 10)
+out["ideal_2F+eic rk2 %d^2" % (n + 1)] = dict(ms_per_step=ms, cell_updates_per_s=(n + 1) ** 2 / ms * 1e3, hbm_frac=(n + 1) ** 2 * 624 / (ms * 1e-3) / 6551.4e9)
+d.close()
+
+KW = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator="rk2", epsilon=0.2, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
+s = synthetic.orszag_tang(n, n, temp_mod=0.1)
+for name, setup in (("mhd only", lambda d: None),
+                    ("mhd + thermal_conduction (unsaturated, euler)", lambda d: d.set_thermal_conduction(flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-4)),
+                    ("mhd + thermal_conduction (saturated, rk2)", lambda d: d.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4)),
+                    ("mhd + physical_viscosity (euler)", lambda d: d.set_physical_viscosity(np.full((n, n), 4.0e-16), coeff=4.0e-16, epsilon=0.2))):
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **KW)
+    setup(d)
+    ms = timed(d, 10)
+    e = dict(ms_per_step=ms, cell_updates_per_s=n * n / ms * 1e3)
+    for k in ("thermal_conduction", "physical_viscosity"):
+        if k.split("_")[0] in name.replace("thermal", "thermal_conduction").replace("physical", "physical_viscosity") and k in name:
+            e["subcycles_last_step"] = d.subcycles(k)
+    out["%s %d^2" % (name, n)] = e
+    d.close()
+print(json.dumps(out, indent=1))

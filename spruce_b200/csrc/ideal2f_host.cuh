@@ -8,6 +8,7 @@ struct PlaneSet2 { double *p[NEV2] = {nullptr}; };
 struct TwoFluid {
     PlaneSet2 P, M, M2, K1, K2;
     double *i_temp = nullptr, *e_temp = nullptr;     // uploaded state temperatures, consumed by setup
+    double *vel[4] = {nullptr};                        // species velocities of the state a stage evaluates (k_2f_velocity)
     bool rk4_alloc = false;
     int use_sub_cycling = 1;                           // Ideal2F default (ideal2F.hpp:62)
     int remove_curl_terms = 0;
@@ -38,6 +39,7 @@ int tf_create(spruce_domain *d)
     if ((rc = tf_alloc_set(d, t->M))) return rc;
     if ((rc = alloc_plane(d, &t->i_temp))) return rc;
     if ((rc = alloc_plane(d, &t->e_temp))) return rc;
+    for (int k = 0; k < 4; k++) if ((rc = alloc_plane(d, &t->vel[k]))) return rc;
     return SPRUCE_OK;
 }
 int tf_ensure_rk4(spruce_domain *d)
@@ -101,9 +103,15 @@ int tf_launch_stage(spruce_domain *d, const PlaneSet2 &S, const PlaneSet2 &B, co
     for (int v = 0; v < NEV2; v++) { A.S[v] = S.p[v]; A.B[v] = B.p[v]; A.D[v] = D.p[v]; }
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, 0); d->launches++; }
+    TfVelArgs V{};
+    for (int v = 0; v < NEV2; v++) V.U[v] = S.p[v];
+    for (int k = 0; k < 4; k++) { V.vel[k] = d->tf->vel[k]; A.vel[k] = d->tf->vel[k]; }
+    V.done_ptr = &d->ctl->done;
+    dim3 vgrid((d->P.ny + 255) / 256, d->P.nx);
+    k_2f_velocity<<<vgrid, 256, 0, d->stream>>>(d->P, V);
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_2f_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
-    d->launches++;
+    d->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }

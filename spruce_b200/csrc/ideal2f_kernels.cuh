@@ -30,6 +30,7 @@ struct TfArgs {
     const double *step_ptr;
     const int *done_ptr;
     unsigned long long *dtmin_bits;
+    const double *vel[4];       // i_v_x, i_v_y, e_v_x, e_v_y of the state S, every cell (k_2f_velocity), so that no stencil operand needs a division
     double m_e, rm_e;           // electron mass and RN(1/m_e)
     int curl_terms;             // !remove_curl_terms
 };
@@ -98,10 +99,10 @@ __global__ void __launch_bounds__(128) k_2f_stage(const DomainParams P, const Tf
         for (int v = 0; v < NEV2; v++) k[v] = 0.0;
         if (interior) {
             auto F = [&](int v) { return [&, v](int a, int b) { return rd(P, A.S[v], a, b); }; };
-            auto iv_x = [&](int a, int b) { return rd(P, A.S[F_IMX], a, b) / rd(P, A.S[F_IRHO], a, b); };
-            auto iv_y = [&](int a, int b) { return rd(P, A.S[F_IMY], a, b) / rd(P, A.S[F_IRHO], a, b); };
-            auto ev_x = [&](int a, int b) { return rd(P, A.S[F_EMX], a, b) / rd(P, A.S[F_ERHO], a, b); };
-            auto ev_y = [&](int a, int b) { return rd(P, A.S[F_EMY], a, b) / rd(P, A.S[F_ERHO], a, b); };
+            auto iv_x = [&](int a, int b) { return rd(P, A.vel[0], a, b); };       // = i_mom_x / i_rho etc. (ideal2F.cpp:123-126), formed once per cell
+            auto iv_y = [&](int a, int b) { return rd(P, A.vel[1], a, b); };
+            auto ev_x = [&](int a, int b) { return rd(P, A.vel[2], a, b); };
+            auto ev_y = [&](int a, int b) { return rd(P, A.vel[3], a, b); };
             auto i_p = [&](int a, int b) { return rd(P, A.S[F_IE], a, b) * P.gm1; };
             auto e_p = [&](int a, int b) { return rd(P, A.S[F_EE], a, b) * P.gm1; };
             auto b_x = [&](int a, int b) { return rd(P, A.st[S_BEX], a, b) + rd(P, A.S[F_BX], a, b); };
@@ -180,6 +181,20 @@ __global__ void __launch_bounds__(128) k_2f_stage(const DomainParams P, const Tf
         }
     }
     if (A.primary && A.kmode != KM_EXPORT) block_min_to_global(dtc, A.dtmin_bits);
+}
+
+// species velocities of one state, every cell incl. ghost cells (recomputeDerivedVarsFromEvolvedVars, ideal2F.cpp:123-126)
+struct TfVelArgs { const double *U[NEV2]; double *vel[4]; const int *done_ptr; };
+__global__ void __launch_bounds__(256) k_2f_velocity(const DomainParams P, const TfVelArgs A)
+{
+    if (*A.done_ptr) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const double ir = A.U[F_IRHO][off], er = A.U[F_ERHO][off];
+    A.vel[0][off] = A.U[F_IMX][off] / ir; A.vel[1][off] = A.U[F_IMY][off] / ir;
+    A.vel[2][off] = A.U[F_EMX][off] / er; A.vel[3][off] = A.U[F_EMY][off] / er;
 }
 
 // propagateChanges on the primary state (setup, module edits): floors, pointwise zeroing, dt minimum
