@@ -56,6 +56,22 @@ __device__ __forceinline__ double T1(const DomainParams &P, FQ Q, FV V, int inde
     return ddiv(flux[1] - flux[0], t.d[i0], t.rd[i0]);
 }
 
+// Out-of-line forms of the two stencil operators on planes.  The right-hand side uses 16 transport and 20 central derivatives per
+// cell; inlined that is ~12 000 instructions (190 KB) of straight-line code per thread, far beyond the instruction cache.  As real
+// functions the kernel is ~2 000 instructions.  Same arithmetic, operation by operation.
+__device__ __noinline__ double tf_T1(const DomainParams &P, const double *q, const double *v, int index, int r, int j)
+{
+    auto Q = [&](int a, int b) { return rd(P, q, a, b); };
+    auto V = [&](int a, int b) { return rd(P, v, a, b); };
+    return T1(P, Q, V, index, r, j);
+}
+// derivative1D along `index` of the plane expression (a [+ b]) * scale   (scale = 1.0 is exact; b may be null)
+__device__ __noinline__ double tf_D(const DomainParams &P, const double *a, const double *b, double scale, int index, int r, int j)
+{
+    auto F = [&](int x, int y) { return (b ? rd(P, a, x, y) + rd(P, b, x, y) : rd(P, a, x, y)) * scale; };
+    return index == 0 ? Dx(P, F, r, j) : Dy(P, F, r, j);
+}
+
 // Ideal2F::recomputeDT for one cell (ideal2F.cpp:169-198): electron Langmuir group speed, min with the EM Courant limit
 __device__ __forceinline__ double tf_cell_dt(const DomainParams &P, const TfArgs &A, double e_rho, double emx, double emy, double e_e, double dx, double dy)
 {
@@ -84,7 +100,7 @@ __device__ __forceinline__ double tf_cell_dt_ion(const DomainParams &P, double i
 // fixed / reflect zero every momentum of both species in the two ghost cells and the first interior cell (primary state only)
 __device__ __forceinline__ bool tf_zeroed(const DomainParams &P, int g, int j) { return zero_zones(P, g, j) != 0u; }
 
-__global__ void __launch_bounds__(128) k_2f_stage(const DomainParams P, const TfArgs A)
+__global__ void __launch_bounds__(128) k_2f_stage(const __grid_constant__ DomainParams P, const __grid_constant__ TfArgs A)
 {
     if (*A.done_ptr) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,42 +114,36 @@ __global__ void __launch_bounds__(128) k_2f_stage(const DomainParams P, const Tf
 #pragma unroll
         for (int v = 0; v < NEV2; v++) k[v] = 0.0;
         if (interior) {
-            auto F = [&](int v) { return [&, v](int a, int b) { return rd(P, A.S[v], a, b); }; };
-            auto iv_x = [&](int a, int b) { return rd(P, A.vel[0], a, b); };       // = i_mom_x / i_rho etc. (ideal2F.cpp:123-126), formed once per cell
-            auto iv_y = [&](int a, int b) { return rd(P, A.vel[1], a, b); };
-            auto ev_x = [&](int a, int b) { return rd(P, A.vel[2], a, b); };
-            auto ev_y = [&](int a, int b) { return rd(P, A.vel[3], a, b); };
-            auto i_p = [&](int a, int b) { return rd(P, A.S[F_IE], a, b) * P.gm1; };
-            auto e_p = [&](int a, int b) { return rd(P, A.S[F_EE], a, b) * P.gm1; };
-            auto b_x = [&](int a, int b) { return rd(P, A.st[S_BEX], a, b) + rd(P, A.S[F_BX], a, b); };
-            auto b_y = [&](int a, int b) { return rd(P, A.st[S_BEY], a, b) + rd(P, A.S[F_BY], a, b); };
-            auto TDi = [&](int v) { return T1(P, F(v), iv_x, 0, r, j) + T1(P, F(v), iv_y, 1, r, j); };      // transportDivergence2D, derivs.cpp:216-220
-            auto TDe = [&](int v) { return T1(P, F(v), ev_x, 0, r, j) + T1(P, F(v), ev_y, 1, r, j); };
+            const double *ivxp = A.vel[0], *ivyp = A.vel[1], *evxp = A.vel[2], *evyp = A.vel[3];       // = i_mom_x / i_rho etc. (ideal2F.cpp:123-126), formed once per cell
+            auto TDi = [&](int v) { return tf_T1(P, A.S[v], ivxp, 0, r, j) + tf_T1(P, A.S[v], ivyp, 1, r, j); };      // transportDivergence2D, derivs.cpp:216-220
+            auto TDe = [&](int v) { return tf_T1(P, A.S[v], evxp, 0, r, j) + tf_T1(P, A.S[v], evyp, 1, r, j); };
+            auto Dpl = [&](const double *pl, int index) { return tf_D(P, pl, nullptr, 1.0, index, r, j); };
             const double i_rho = A.S[F_IRHO][off], e_rho = A.S[F_ERHO][off];
             const double i_n = ddiv(i_rho, P.m_i, P.rm_i), e_n = ddiv(e_rho, A.m_e, A.rm_e);
-            const double ivx = iv_x(r, j), ivy = iv_y(r, j), evx = ev_x(r, j), evy = ev_y(r, j);
+            const double ivx = ivxp[off], ivy = ivyp[off], evx = evxp[off], evy = evyp[off];
             const double bz = A.S[F_BZ][off], Ex = A.S[F_EX][off], Ey = A.S[F_EY][off];
             const double gx = A.st[S_GX][off], gy = A.st[S_GY][off];
+            const double ip_c = A.S[F_IE][off] * P.gm1, ep_c = A.S[F_EE][off] * P.gm1;
             // Lorentz forces, ideal2F.cpp:42-52
             const double icx = ivy * bz, icy = (ivx * -1.0) * bz, ecx = evy * bz, ecy = (evx * -1.0) * bz;
             const double iFx = (i_n * kE) * (Ex + icx / kC), iFy = (i_n * kE) * (Ey + icy / kC);
             const double eFx = (e_n * -kE) * (Ex + ecx / kC), eFy = (e_n * -kE) * (Ey + ecy / kC);
             k[F_IRHO] = TDi(F_IRHO) * -1.0;                                                                 // :39
             k[F_ERHO] = TDe(F_ERHO) * -1.0;                                                                 // :40
-            k[F_IMX] = (((TDi(F_IMX) * -1.0) - Dx(P, i_p, r, j)) + i_rho * gx) + iFx;                      // :54-56
-            k[F_IMY] = (((TDi(F_IMY) * -1.0) - Dy(P, i_p, r, j)) + i_rho * gy) + iFy;                      // :57-59
-            k[F_EMX] = (((TDe(F_EMX) * -1.0) - Dx(P, e_p, r, j)) + e_rho * gx) + eFx;                      // :60-62
-            k[F_EMY] = (((TDe(F_EMY) * -1.0) - Dy(P, e_p, r, j)) + e_rho * gy) + eFy;                      // :63-65
-            k[F_IE] = (TDi(F_IE) * -1.0) - i_p(r, j) * (Dx(P, iv_x, r, j) + Dy(P, iv_y, r, j));            // :67-68
-            k[F_EE] = (TDe(F_EE) * -1.0) - e_p(r, j) * (Dx(P, ev_x, r, j) + Dy(P, ev_y, r, j));            // :69-70
+            k[F_IMX] = (((TDi(F_IMX) * -1.0) - tf_D(P, A.S[F_IE], nullptr, P.gm1, 0, r, j)) + i_rho * gx) + iFx;   // :54-56
+            k[F_IMY] = (((TDi(F_IMY) * -1.0) - tf_D(P, A.S[F_IE], nullptr, P.gm1, 1, r, j)) + i_rho * gy) + iFy;   // :57-59
+            k[F_EMX] = (((TDe(F_EMX) * -1.0) - tf_D(P, A.S[F_EE], nullptr, P.gm1, 0, r, j)) + e_rho * gx) + eFx;   // :60-62
+            k[F_EMY] = (((TDe(F_EMY) * -1.0) - tf_D(P, A.S[F_EE], nullptr, P.gm1, 1, r, j)) + e_rho * gy) + eFy;   // :63-65
+            k[F_IE] = (TDi(F_IE) * -1.0) - ip_c * (Dpl(ivxp, 0) + Dpl(ivyp, 1));                           // :67-68
+            k[F_EE] = (TDe(F_EE) * -1.0) - ep_c * (Dpl(evxp, 0) + Dpl(evyp, 1));                           // :69-70
             const double jx = (i_n * kE) * ivx - (e_n * kE) * evx, jy = (i_n * kE) * ivy - (e_n * kE) * evy;   // :128-129
             if (A.curl_terms) {                                                                             // :75-80
-                k[F_EX] = Dy(P, F(F_BZ), r, j) * kC - jx * (4. * kPI);
-                k[F_EY] = Dx(P, F(F_BZ), r, j) * -kC - jy * (4. * kPI);
-                k[F_EZ] = (Dx(P, b_y, r, j) - Dy(P, b_x, r, j)) * kC;
-                k[F_BX] = Dy(P, F(F_EZ), r, j) * -kC;
-                k[F_BY] = Dx(P, F(F_EZ), r, j) * kC;
-                k[F_BZ] = (Dy(P, F(F_EX), r, j) - Dx(P, F(F_EY), r, j)) * kC;
+                k[F_EX] = Dpl(A.S[F_BZ], 1) * kC - jx * (4. * kPI);
+                k[F_EY] = Dpl(A.S[F_BZ], 0) * -kC - jy * (4. * kPI);
+                k[F_EZ] = (tf_D(P, A.st[S_BEY], A.S[F_BY], 1.0, 0, r, j) - tf_D(P, A.st[S_BEX], A.S[F_BX], 1.0, 1, r, j)) * kC;
+                k[F_BX] = Dpl(A.S[F_EZ], 1) * -kC;
+                k[F_BY] = Dpl(A.S[F_EZ], 0) * kC;
+                k[F_BZ] = (Dpl(A.S[F_EX], 1) - Dpl(A.S[F_EY], 0)) * kC;
             } else {                                                                                        // :83-88
                 k[F_EX] = (jx * (4. * kPI)) * -1.0;
                 k[F_EY] = (jy * (4. * kPI)) * -1.0;

@@ -21,8 +21,9 @@ namespace spruce {
 constexpr double kKappa0 = 1.0e-6;          // KAPPA_0      source/constants.hpp:15
 constexpr double kMElectron = 9.1094e-28;   // M_ELECTRON   source/constants.hpp:9
 
-__device__ __forceinline__ int wrap_i(const DomainParams &P, int r) { return P.xwrap ? (r + P.nx) % P.nx : r; }
-__device__ __forceinline__ int wrap_j(const DomainParams &P, int j) { return P.yper ? (j + P.ny) % P.ny : j; }
+// periodic wrap of an index that is at most one period out of range (stencil offsets are <= 4): compare-and-add, no integer modulo
+__device__ __forceinline__ int wrap_i(const DomainParams &P, int r) { return P.xwrap ? (r < 0 ? r + P.nx : (r >= P.nx ? r - P.nx : r)) : r; }
+__device__ __forceinline__ int wrap_j(const DomainParams &P, int j) { return P.yper ? (j < 0 ? j + P.ny : (j >= P.ny ? j - P.ny : j)) : j; }
 __device__ __forceinline__ bool is_interior(const DomainParams &P, int r, int j)
 {
     const int g = P.row0 + r;
