@@ -33,7 +33,7 @@ s = synthetic.orszag_tang(n, n, temp_mod=0.1)
 for name, setup in (("mhd only", lambda d: None),
                     ("mhd + thermal_conduction (unsaturated, euler)", lambda d: d.set_thermal_conduction(flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-4)),
                     ("mhd + thermal_conduction (saturated, rk2)", lambda d: d.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4)),
-                    ("mhd + physical_viscosity (euler)", lambda d: d.set_physical_viscosity(np.full((n, n), 4.0e-16), coeff=4.0e-16, epsilon=0.2))):
+                    ("mhd + physical_viscosity (euler)", lambda d: d.set_physical_viscosity(np.full((n, n), 4.0e-18), coeff=4.0e-18, epsilon=0.2))):
     d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **KW)
     setup(d)
     ms = timed(d, 10)

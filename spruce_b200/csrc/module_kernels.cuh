@@ -124,7 +124,8 @@ __device__ __forceinline__ void tc_saturate(const DomainParams &P, const TcField
     *fx *= sc; *fy *= sc;
 }
 // saturation coefficient of saturationTerms at one cell (thermalconduction.cpp:211-224)
-__device__ __forceinline__ double tc_coefficient(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j)
+// (out of line: the saturation terms evaluate it at five points; inlined five times the kernel no longer fits the instruction cache)
+__device__ __noinline__ double tc_coefficient(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j)
 {
     double fx, fy;
     tc_raw_flux(P, C, F, r, j, &fx, &fy);
@@ -181,7 +182,7 @@ struct TcStageArgs {
     double c;                  // 0.5*dt_sub or dt_sub
 };
 
-__global__ void __launch_bounds__(128) k_tc_stage(const DomainParams P, const TcStageArgs A)
+__global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ DomainParams P, const __grid_constant__ TcStageArgs A)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
@@ -424,7 +425,7 @@ struct PvArgs {
 };
 struct PvPoint { double dxv[3], dyv[3], t25, b[3], cg; };
 
-__device__ __forceinline__ void pv_point(const DomainParams &P, const PvArgs &A, int a, int b, PvPoint &o)
+__device__ __noinline__ void pv_point(const DomainParams &P, const PvArgs &A, int a, int b, PvPoint &o)
 {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -449,7 +450,7 @@ __device__ __forceinline__ double pv_d3(const AxisTab &t, int i, double lo, doub
     return ddiv(up - dn, t.d[i], t.rd[i]);
 }
 
-__global__ void __launch_bounds__(128) k_pv_stage(const DomainParams P, const PvArgs A)
+__global__ void __launch_bounds__(128) k_pv_stage(const __grid_constant__ DomainParams P, const __grid_constant__ PvArgs A)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
