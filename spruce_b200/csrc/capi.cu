@@ -47,6 +47,7 @@ struct spruce_domain {
     size_t plane_doubles = 0;      // allocation size of one plane incl. halo rows
     size_t row_off = 0;            // offset (doubles) of local row 0 inside an allocation
     std::vector<double *> allocs;  // every cudaMalloc, for destroy
+    double *pool = nullptr; size_t pool_planes = 0, pool_used = 0;   // pooled planes of the base arena
     PlaneSet Pset, Mset, M2set, K1set, K2set;
     double *stat[NSTATIC] = {nullptr};
     double *scratch_temp = nullptr, *scratch_out = nullptr;
@@ -95,12 +96,19 @@ struct spruce_domain {
 
 namespace {
 
+// planes are carved from one pooled allocation made at create time (one cudaMalloc instead of ~25); later requests beyond the
+// pool (RK4 sets, module work planes) get their own allocation
 int alloc_plane(spruce_domain *d, double **out)
 {
     double *base = nullptr;
-    CUDA_TRY(cudaMalloc(&base, d->plane_doubles * sizeof(double)));
+    if (d->pool && d->pool_used < d->pool_planes) {
+        base = d->pool + d->pool_used * d->plane_doubles;
+        d->pool_used++;
+    } else {
+        CUDA_TRY(cudaMalloc(&base, d->plane_doubles * sizeof(double)));
+        d->allocs.push_back(base);
+    }
     CUDA_TRY(cudaMemsetAsync(base, 0, d->plane_doubles * sizeof(double), d->stream));
-    d->allocs.push_back(base);
     *out = base + d->row_off;
     return SPRUCE_OK;
 }
@@ -912,6 +920,11 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     d->row_off = (size_t)HALO * P.pitch;
     int rc = SPRUCE_OK;
     if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SPRUCE_ERR_CUDA, "cudaStreamCreate failed"); }
+    if (!rc) {                                                        // base arena: evolved sets + static + scratch (+ two-fluid extras)
+        d->pool_planes = two_fluid ? (2 * 14 + 2 + 4 + NSTATIC + 2) : (2 * NEV + NSTATIC + 2);
+        if (cudaMalloc(&d->pool, d->pool_planes * d->plane_doubles * sizeof(double)) != cudaSuccess) { cudaGetLastError(); d->pool = nullptr; d->pool_planes = 0; }
+        else d->allocs.push_back(d->pool);
+    }
     if (!rc && two_fluid) rc = tf_create(d);
     if (!rc && !two_fluid) rc = alloc_set(d, d->Pset);
     if (!rc && !two_fluid) rc = alloc_set(d, d->Mset);
