@@ -195,8 +195,8 @@ def run_ours(args):
         achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
         result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                               "peak_source": peak_src, "kernel": "k_mhd_stage_xy", "alg_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
-                              "note": "per GPU; includes the halo exchange (%s) and the dt all-gather between launches" % ("peer stores over NVLink from the pack kernel" if args.transport == "p2p" else "NCCL send/recv")}
-        result["transport"] = args.transport
+                              "note": "per GPU; includes the halo exchange (%s) and the dt all-gather between launches" % ("peer stores over NVLink from the pack kernel" if runner.transport == "p2p" else "NCCL send/recv")}
+        result["transport"] = runner.transport
         runner.close()
         # end to end: slab upload from host memory + setup + first halo exchange + K steps + download of the evolved slabs
         dist.barrier(); torch.cuda.synchronize()

@@ -118,12 +118,22 @@ class SlabRunner:
         capi.check(self.lib.spruce_plane_activity(self.dom.h, None, gm))
         if transport == "p2p":
             mine = (C.c_char * 64)()
-            capi.check(self.lib.spruce_mgpu_ipc_export(self.dom.h, mine))
+            ok = self.lib.spruce_mgpu_ipc_export(self.dom.h, mine) == 0
             t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).cuda()
             allh = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(allh, t)
             blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
-            capi.check(self.lib.spruce_mgpu_ipc_connect(self.dom.h, blob, world))
+            ok = ok and self.lib.spruce_mgpu_ipc_connect(self.dom.h, blob, world) == 0
+            # every rank must have mapped its peers (CUDA IPC needs peer access between the devices and a shared IPC namespace);
+            # otherwise ALL ranks switch to the NCCL transport together
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if rank == 0:
+                    import sys
+                    print("spruce_b200: CUDA IPC peer mapping unavailable (%s); using the NCCL halo transport" % capi.load().spruce_last_error().decode(), file=sys.stderr)
+                transport = self.transport = "nccl"
+        if transport == "p2p":
             self.dom.setup()
             dist.barrier()                      # every rank has mapped its neighbours and finished its local setup
             capi.check(self.lib.spruce_mgpu_initial_exchange(self.dom.h))
