@@ -65,6 +65,30 @@ __device__ __noinline__ double tf_T1(const DomainParams &P, const double *q, con
     auto V = [&](int a, int b) { return rd(P, v, a, b); };
     return T1(P, Q, V, index, r, j);
 }
+// transportDerivative1D of four planes that share one velocity (a species' density, two momenta and thermal energy): the face
+// velocities and the face geometry are evaluated once for the four (derivs.cpp:122-162 evaluates them once per call as well)
+__device__ __noinline__ void tf_T4(const DomainParams &P, const double *q0, const double *q1, const double *q2, const double *q3, const double *v,
+                                   int index, int r, int j, double *out)
+{
+    const AxisTab &t = index == 0 ? P.tx : P.ty;
+    const int i0 = index == 0 ? r : j;
+    auto vat = [&](int i) { return index == 0 ? rd(P, v, i, j) : rd(P, v, r, i); };
+    const FaceGeom g0 = load_face_geom(t, i0), g1 = load_face_geom(t, i0 + 1);
+    const double vf0 = face_interp(vat(i0 - 1), vat(i0), g0.hm1, g0.h0, g0.fs, g0.rfs);
+    const double vf1 = face_interp(vat(i0), vat(i0 + 1), g1.hm1, g1.h0, g1.fs, g1.rfs);
+    const double *qs[4] = {q0, q1, q2, q3};
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const double *q = qs[k];
+        auto at = [&](int i) { return index == 0 ? rd(P, q, i, j) : rd(P, q, r, i); };
+        const double a = at(i0 - 2), b = at(i0 - 1), c = at(i0), d = at(i0 + 1), e = at(i0 + 2);
+        double d2;
+        const double S0 = upwind_face(a, b, c, d, vf0, g0, &d2);
+        const double S1 = upwind_face(b, c, d, e, vf1, g1, &d2);
+        out[k] = ddiv(S1 * vf1 - S0 * vf0, t.d[i0], t.rd[i0]);
+    }
+}
+
 // derivative1D along `index` of the plane expression (a [+ b]) * scale   (scale = 1.0 is exact; b may be null)
 __device__ __noinline__ double tf_D(const DomainParams &P, const double *a, const double *b, double scale, int index, int r, int j)
 {
@@ -115,8 +139,14 @@ __global__ void __launch_bounds__(128) k_2f_stage(const __grid_constant__ Domain
         for (int v = 0; v < NEV2; v++) k[v] = 0.0;
         if (interior) {
             const double *ivxp = A.vel[0], *ivyp = A.vel[1], *evxp = A.vel[2], *evyp = A.vel[3];       // = i_mom_x / i_rho etc. (ideal2F.cpp:123-126), formed once per cell
-            auto TDi = [&](int v) { return tf_T1(P, A.S[v], ivxp, 0, r, j) + tf_T1(P, A.S[v], ivyp, 1, r, j); };      // transportDivergence2D, derivs.cpp:216-220
-            auto TDe = [&](int v) { return tf_T1(P, A.S[v], evxp, 0, r, j) + tf_T1(P, A.S[v], evyp, 1, r, j); };
+            // transportDivergence2D (derivs.cpp:216-220) of rho, mom_x, mom_y, thermal_energy of each species: x term + y term
+            double tix[4], tiy[4], tex[4], tey[4];
+            tf_T4(P, A.S[F_IRHO], A.S[F_IMX], A.S[F_IMY], A.S[F_IE], ivxp, 0, r, j, tix);
+            tf_T4(P, A.S[F_IRHO], A.S[F_IMX], A.S[F_IMY], A.S[F_IE], ivyp, 1, r, j, tiy);
+            tf_T4(P, A.S[F_ERHO], A.S[F_EMX], A.S[F_EMY], A.S[F_EE], evxp, 0, r, j, tex);
+            tf_T4(P, A.S[F_ERHO], A.S[F_EMX], A.S[F_EMY], A.S[F_EE], evyp, 1, r, j, tey);
+            auto TDi = [&](int v) { const int k_ = v == F_IRHO ? 0 : v == F_IMX ? 1 : v == F_IMY ? 2 : 3; return tix[k_] + tiy[k_]; };
+            auto TDe = [&](int v) { const int k_ = v == F_ERHO ? 0 : v == F_EMX ? 1 : v == F_EMY ? 2 : 3; return tex[k_] + tey[k_]; };
             auto Dpl = [&](const double *pl, int index) { return tf_D(P, pl, nullptr, 1.0, index, r, j); };
             const double i_rho = A.S[F_IRHO][off], e_rho = A.S[F_ERHO][off];
             const double i_n = ddiv(i_rho, P.m_i, P.rm_i), e_n = ddiv(e_rho, A.m_e, A.rm_e);
@@ -150,11 +180,12 @@ __global__ void __launch_bounds__(128) k_2f_stage(const __grid_constant__ Domain
             }
             if (A.eic) {                                                                                    // eic_thermalization.cpp:27-44
                 const double n = i_n, Te = (A.S[F_EE][off] * P.gm1) / (e_n * kKB);                          // n = i_n (ideal2F.cpp:145), e_temp :134
-                const double a = pow((3. / 4. / kPI) / n, 1. / 3.);
+                const double a = cbrt((3. / 4. / kPI) / n);                     // std::pow(x, 1./3.) to ~4e-16 relative (module held to 1e-9)
                 const double w_pe = sqrt(n * (4. * kPI * kE * kE / A.m_e));
                 const double Gam = ((kE * kE / kKB) / Te) / a;
-                const double Lam = (1. / sqrt(3.)) / pow(Gam, 3. / 2.);
-                const double gam_ei = ((pow(Gam, 3. / 2.) * sqrt(2. / 3. / kPI)) * w_pe) * log(Lam);
+                const double g15 = Gam * sqrt(Gam);                              // Gam^(3/2), within 1.5 ulp of std::pow
+                const double Lam = (1. / sqrt(3.)) / g15;
+                const double gam_ei = ((g15 * sqrt(2. / 3. / kPI)) * w_pe) * log(Lam);
                 const double nu_ei = gam_ei * (2. * A.m_e / P.m_i);
                 const double dE = nu_ei * (A.S[F_EE][off] - A.S[F_IE][off]);
                 k[F_EE] = k[F_EE] - dE;                    // mask = 1 here

@@ -38,6 +38,12 @@ __device__ __forceinline__ double rd(const DomainParams &P, const double *f, int
     return f[(size_t)r * P.pitch + j];
 }
 
+// x^(3/2), x^(5/2) for the modules' std::pow(T, 1.5 | 2.5): sqrt is correctly rounded, so x*sqrt(x) and (x*x)*sqrt(x) are within 1.5 ulp of the
+// exact power -- the same distance CUDA's pow keeps from glibc's -- at a tenth of the instructions.  These modules are held to a relative
+// 1e-9 (with equal sub-cycle counts), not to bit equality, precisely because of libm; negative arguments give NaN and 0 gives 0 as pow does.
+__device__ __forceinline__ double pow15(double x) { return x * sqrt(x); }
+__device__ __forceinline__ double pow25(double x) { return (x * x) * sqrt(x); }
+
 // temp = max((gamma-1)*e / (2 K_B n), T_min)   thermalconduction.cpp:65, radiativelosses.cpp:56
 __device__ __forceinline__ double temp_of(const DomainParams &P, double e, double n) { return smax((e * P.gm1) / (n * (2.0 * kKB)), P.T_min); }
 
@@ -106,7 +112,7 @@ __device__ __forceinline__ void tc_raw_flux(const DomainParams &P, const TcParam
     const double Tc = T(r, j);
     const double rho = rd(P, F.n, r, j) * P.m_i;
     const double kmax = (((P.tx.d[r] * P.ty.d[j]) * kKB) * ddiv(rho, P.m_i, P.rm_i)) / C.dt_subcycle_min;     // :155
-    const double kap = smin(pow(Tc, 5.0 / 2.0) * C.kappa, kmax);                                            // :156
+    const double kap = smin(pow25(Tc) * C.kappa, kmax);                                            // :156
     const double cx = (kap * -1.0) * Dx(P, T, r, j), cy = (kap * -1.0) * Dy(P, T, r, j);
     const double bx = rd(P, F.bhx, r, j), by = rd(P, F.bhy, r, j);
     const double fm = cx * bx + cy * by;                                                                    // :173-175
@@ -118,7 +124,7 @@ __device__ __forceinline__ void tc_saturate(const DomainParams &P, const TcField
     const double c1 = (1.0 / 6.0) * (3.0 / 2.0);
     r = wrap_i(P, r); j = wrap_j(P, j);
     const double rho = rd(P, F.n, r, j) * P.m_i;
-    const double sat = ((ddiv(rho, P.m_i, P.rm_i) * c1) * pow(rd(P, F.T, r, j) * kKB, 1.5)) / sqrt(kMElectron);
+    const double sat = ((ddiv(rho, P.m_i, P.rm_i) * c1) * pow15(rd(P, F.T, r, j) * kKB)) / sqrt(kMElectron);
     const double fm = sqrt((*fx) * (*fx) + (*fy) * (*fy));
     const double sc = sat / sqrt(sat * sat + fm * fm);
     *fx *= sc; *fy *= sc;
@@ -153,7 +159,7 @@ __device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C,
     const double t2x = Tx * bxx + Ty * bxy, t2y = Tx * byx + Ty * byy;
     const double cu = byx - bxy;
     const double t3x = ((cu * -1.0) * -1.0) * Ty, t3y = (cu * -1.0) * Tx;
-    const double p15 = pow(Tc, 3.0 / 2.0), p25 = pow(Tc, 5.0 / 2.0);
+    const double p15 = pow15(Tc), p25 = pow25(Tc);
     const double ttx = ((p15 * (5.0 / 2.0)) * Tx) * bg + p25 * ((t1x + t2x) + t3x);
     const double tty = ((p15 * (5.0 / 2.0)) * Ty) * bg + p25 * ((t1y + t2y) + t3y);
     double out = (((p25 * bg) * (bxx + byy)) + (bhx * ttx + bhy * tty)) * C.kappa;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(128) k_tc_count(const DomainParams P, const Tc
         const double nd = ddiv(rho, P.m_i, P.rm_i);
         const bool in = is_interior(P, r, j);
         if (!C.flux_saturation) {
-            if (in) v = (((nd * (kKB / C.kappa)) * P.tx.d[r]) * P.ty.d[j]) / pow(F.T[off], 2.5);      // :139
+            if (in) v = (((nd * (kKB / C.kappa)) * P.tx.d[r]) * P.ty.d[j]) / pow25(F.T[off]);      // :139
         } else {
             auto T = [&](int a, int b) { return rd(P, F.T, a, b); };
             const double ftg = Dx(P, T, r, j) * F.bhx[off] + Dy(P, T, r, j) * F.bhy[off];            // :141-142
@@ -258,7 +264,7 @@ __device__ __forceinline__ double rl_loss(const RlParams &R, double T, double n,
     else if (lt <= 6.90) { chi = 3.46e-25; alpha = 1.0 / 3.0; }
     else if (lt <= 7.63) { chi = 5.49e-16; alpha = -1.0; }
     else { chi = 1.96e-27; alpha = 0.5; }
-    double r = pow(n, 2.0) * chi * pow(T, alpha);
+    double r = (n * n) * chi * pow(T, alpha);      // pow(n, 2.0) is exactly RN(n*n)
     if (T < R.cutoff_temp + R.cutoff_ramp) { const double ramp = (T - R.cutoff_temp) / R.cutoff_ramp; r *= ramp; }
     if (R.prevent_subcycling) {
         if (0.1 * R.epsilon * (e_primary / r) < eps_domain * dt_primary) r = 0.1 * R.epsilon * e_primary / (eps_domain * dt_primary);
@@ -434,7 +440,7 @@ __device__ __noinline__ void pv_point(const DomainParams &P, const PvArgs &A, in
         o.dyv[k] = Dy(P, V, a, b);
         o.b[k] = rd(P, A.bh[k], a, b);
     }
-    o.t25 = pow(rd(P, A.T, a, b), 2.5);
+    o.t25 = pow25(rd(P, A.T, a, b));
     o.cg = rd(P, A.cg, a, b);
 }
 // same_factor_off_diag (physicalviscosity.cpp:90-93)
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(128) k_pv_count(const DomainParams P, const Pv
         const double vm = sqrt(vx * vx + vy * vy);
         const double s_ = (A.bh[0][off] * vx) / vm + (A.bh[1][off] * vy) / vm;
         const double df = (vm == 0.0) ? 4.0 : (s_ * s_) * 3.0 + 1.0;
-        ts = ((P.tx.d[r] * P.ty.d[j]) * (A.n[off] * P.m_i)) / (((df * 3.0) * smax(A.cg[off], 0.000001 * A.coeff)) * pow(A.T[off], 2.5));
+        ts = ((P.tx.d[r] * P.ty.d[j]) * (A.n[off] * P.m_i)) / (((df * 3.0) * smax(A.cg[off], 0.000001 * A.coeff)) * pow25(A.T[off]));
     }
     block_min_to_global(ts, A.red);
 }
