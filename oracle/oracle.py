@@ -54,6 +54,17 @@ def lib():
         L.oracle_set_radiative_losses.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.oracle_set_viscosity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.oracle2f_create.restype = C.c_void_p
+        L.oracle2f_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle2f_destroy.argtypes = [C.c_void_p]
+        L.oracle2f_plane.restype = C.POINTER(C.c_double)
+        L.oracle2f_plane.argtypes = [C.c_void_p, C.c_int]
+        L.oracle2f_setup.argtypes = [C.c_void_p]
+        L.oracle2f_step.restype = C.c_double
+        L.oracle2f_step.argtypes = [C.c_void_p]
+        L.oracle2f_rhs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.oracle2f_time.restype = C.c_double
+        L.oracle2f_time.argtypes = [C.c_void_p]
         L.oracle_set_ambient_heating.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         _lib = L
     return _lib
@@ -148,6 +159,63 @@ class Oracle:
     def close(self):
         if self.h:
             lib().oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+VARS_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_temp", "e_temp", "bi_x", "bi_y", "bi_z", "E_x", "E_y", "E_z", "grav_x", "grav_y",
+           "i_n", "e_n", "i_v_x", "i_v_y", "e_v_x", "e_v_y", "j_x", "j_y", "i_press", "e_press", "press", "i_thermal_energy", "e_thermal_energy",
+           "rho", "rho_c", "n", "dn", "dt", "dt_i", "b_x", "b_y", "b_z", "b_mag", "b_mag_xy", "b_hat_x", "b_hat_y", "curlE_z", "divE", "divB", "i_dPdx", "e_dPdx"]   # ideal2F.hpp:24-31
+EVOLVED_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy", "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"]
+
+
+class Oracle2F:
+    """One two-fluid (Ideal2F, use_sub_cycling = false) domain evolved by the C restatement (oracle/ideal2f_oracle.inc)."""
+
+    def __init__(self, planes, ion_mass, adiabatic_index, *, xb=("open_ucnp", "open_ucnp"), yb=("open_ucnp", "open_ucnp"), integrator="rk2", epsilon=0.2,
+                 density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30, remove_curl_terms=False, eic=False, setup=True, **_unused):
+        L = lib()
+        nx, ny = planes["i_rho"].shape
+        self.nx, self.ny = nx, ny
+        self.base = L.oracle_create(nx, ny, BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]], TI[integrator], ion_mass, adiabatic_index, epsilon,
+                                    density_min, temp_min, thermal_energy_min, 1.0, 0.5)
+        for name, which in DOMAIN.items():
+            if name in planes:
+                np.ctypeslib.as_array(L.oracle_plane(self.base, which), shape=(nx, ny))[...] = planes[name]
+        self.h = L.oracle2f_create(self.base, int(remove_curl_terms), int(eic))
+        for name, a in planes.items():
+            if name in VARS_2F:
+                self.view(name)[...] = a
+        if setup:
+            L.oracle2f_setup(self.h)
+
+    def view(self, name) -> np.ndarray:
+        return np.ctypeslib.as_array(lib().oracle2f_plane(self.h, VARS_2F.index(name)), shape=(self.nx, self.ny))
+
+    def get(self, name) -> np.ndarray:
+        return self.view(name).copy()
+
+    def step(self) -> float:
+        return lib().oracle2f_step(self.h)
+
+    def rhs(self) -> np.ndarray:
+        k = np.zeros((14, self.nx, self.ny))
+        lib().oracle2f_rhs(self.h, _dp(k))
+        return k
+
+    @property
+    def time(self) -> float:
+        return lib().oracle2f_time(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().oracle2f_destroy(self.h)
+            lib().oracle_destroy(self.base)
             self.h = None
 
     def __del__(self):

@@ -11,6 +11,9 @@
  * unmodified reference binary (oracle/_ref/run) committed under tests/golden/ (generator:
  * tests/golden/make_golden.py).  The reference itself ships no tests or golden vectors.
  *
+ * The two-fluid equation set (Ideal2F) and EIC thermalization are restated in ideal2f_oracle.inc (included at the end of
+ * this file) and pinned the same way against the tf_*.npz fixtures.
+ *
  * Reference citations are given per function as file:line relative to the reference tree.
  * Layout: plane[i*ny + j], i = x index, j = y index (source/mhd/grid.cpp:516-526).
  */
@@ -899,3 +902,8 @@ void oracle_operator(oracle *o, int op, int index, const double *q, const double
     else if (op == 2) laplacian(o, q, out);
     else if (op == 3) transport_derivative1D(o, q, vel, index, out);
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Two-fluid equation set (Ideal2F) + EIC thermalization: separate restatement on top of the operators above.
+ * --------------------------------------------------------------------------------------------------------- */
+#include "ideal2f_oracle.inc"

@@ -125,6 +125,41 @@ def test_two_fluid_golden_reference_outputs(name):
     d.close()
 
 
+@pytest.mark.parametrize("nx,ny,integrator,xb,yb,eic,rct", [
+    (151, 133, "rk2", ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), False, False),
+    (97, 121, "rk4", ("periodic", "periodic"), ("periodic", "periodic"), False, False),
+    (66, 131, "euler", ("fixed", "reflect"), ("periodic", "periodic"), False, False),
+    (130, 67, "rk2", ("periodic", "periodic"), ("open_ucnp", "open_ucnp"), False, True),
+    (129, 129, "rk2", ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), True, False),
+])
+def test_two_fluid_vs_oracle(nx, ny, integrator, xb, yb, eic, rct):
+    """Ideal2F at sizes beyond the fixtures (odd, not multiples of the block width) against the pinned CPU restatement
+    (oracle/ideal2f_oracle.inc): right-hand side, step sizes and every evolved + derived plane bit for bit; with EIC thermalization
+    (libm pow / log on both sides, CUDA vs glibc) to REL_TOL."""
+    from oracle.oracle import EVOLVED_2F, Oracle2F
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    s = synthetic.ucnp_cloud(nx, ny, drift=2.0e3, bfield=5.0)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
+    o = Oracle2F(s["planes"], s["ion_mass"], s["adiabatic_index"], remove_curl_terms=rct, eic=eic, **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False, remove_curl_terms=rct), **kw)
+    if eic:
+        d.set_eic_thermalization()
+    same = (lambda a, b: same_bits(a, b)) if not eic else (lambda a, b: rel_linf(a, b) <= REL_TOL)
+    for v in ("i_thermal_energy", "e_thermal_energy", "dt", "dt_i", "e_temp", "j_x", "divE"):
+        assert same_bits(d.grid(v), o.get(v)), "after setup, %s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    k_dev, k_ref = d.computeTimeDerivatives(), o.rhs()
+    for i, nm in enumerate(EVOLVED_2F):
+        assert same(k_dev[i], k_ref[i]), "d(%s)/dt: %s" % (nm, mismatch(k_dev[i], k_ref[i]))
+    nsteps = 4
+    ref = np.array([o.step() for _ in range(nsteps)])
+    dts = d.advance(nsteps)
+    assert (np.array_equal(dts, ref) if not eic else np.max(np.abs(dts - ref) / ref) <= REL_TOL), (dts, ref)
+    for v in EVOLVED_2F + ["dt", "dt_i", "i_temp", "e_temp", "j_y", "rho_c", "divB", "curlE_z", "i_dPdx", "b_hat_y", "press"]:
+        assert same(d.grid(v), o.get(v)), "%s after %d steps: %s" % (v, nsteps, mismatch(d.grid(v), o.get(v)))
+    o.close(); d.close()
+
+
 def test_two_fluid_refusals():
     """use_sub_cycling = true (the Ideal2F default) cannot run in the reference; eic_thermalization needs Ideal2F grids."""
     from spruce_b200 import capi, synthetic

@@ -37,3 +37,20 @@ def test_oracle_reproduces_reference(name):
         assert tc == g.subcycle_counts("Thermal Subcycles")
     if "radiative_losses" in names:
         assert rl == g.subcycle_counts("Radiative Subcycles")
+
+
+@pytest.mark.parametrize("name", cases(two_fluid=True))
+def test_two_fluid_oracle_reproduces_reference(name):
+    """oracle/ideal2f_oracle.inc (Ideal2F + EIC thermalization) against the tf_* fixtures of the unmodified reference binary: bit for bit,
+    EIC included (the restatement and the reference both call glibc's pow / log)."""
+    from oracle.oracle import Oracle2F
+    g = Golden(name)
+    assert all(m[0] == "eic_thermalization" for m in g.modules)
+    o = Oracle2F(g.planes, g.ion_mass, g.adiabatic_index, remove_curl_terms=g.eqs_options.get("remove_curl_terms", False), eic=bool(g.modules), **g.kw)
+    for it in range(1, g.n_steps + 1):
+        step = o.step()
+        assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())
+        if it in g.frames:
+            for v in g.out_vars:
+                assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
+    o.close()
