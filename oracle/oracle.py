@@ -54,6 +54,7 @@ def lib():
         L.oracle_set_radiative_losses.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.oracle_set_viscosity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2f_create.restype = C.c_void_p
         L.oracle2f_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle2f_destroy.argtypes = [C.c_void_p]
@@ -133,7 +134,12 @@ class Oracle:
         return lib().oracle_time(self.h)
 
     def subcycles(self, which) -> int:
-        return lib().oracle_subcycles(self.h, {"thermal_conduction": 1, "radiative_losses": 2}[which])
+        return lib().oracle_subcycles(self.h, {"thermal_conduction": 1, "radiative_losses": 2, "physical_viscosity": 5}[which])
+
+    def set_physical_viscosity(self, coeff_plane, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False, integrator="euler",
+                               inactive_mode=False):
+        a = np.ascontiguousarray(coeff_plane, dtype=np.float64)
+        lib().oracle_set_physical_viscosity(self.h, coeff, _dp(a), epsilon, int(heating_on), int(force_on), int(gradient_correction), TI[integrator], int(inactive_mode))
 
     def set_thermal_conduction(self, *, flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-4, weakening_factor=1.0):
         lib().oracle_set_thermal_conduction(self.h, int(flux_saturation), TI[integrator], epsilon, dt_subcycle_min, weakening_factor)

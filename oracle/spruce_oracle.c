@@ -55,7 +55,9 @@ typedef struct {
     int av_diff[8], av_evol[8];   /* variable indices (equation-set numbering) */
     int av_species[8];        /* 'i' or 'e' */
     double *av_strength_grid[8];  /* boundary options: profile built by the caller (host libm exp) */
-    int order[8]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah 4=av */
+    /* physical_viscosity (source/modules/solar/physicalviscosity.hpp) */
+    int pv_on, pv_heating_on, pv_force_on, pv_gc, pv_integrator, pv_inactive, pv_nsub; double pv_coeff, pv_epsilon; double *pv_cg;
+    int order[8]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah 4=av 5=pv */
 } modules_t;
 
 typedef struct oracle {
@@ -455,6 +457,9 @@ static double min_range(const oracle *o, const double *a, int il, int jl, int iu
     return m;
 }
 
+static void propagate_changes(const oracle *o, double **G, double **P);
+#include "physical_viscosity_oracle.inc"
+
 /* ---- artificial viscosity (source/modules/viscosity.cpp) */
 static int ev_index(int var) { for (int v = 0; v < NEV; v++) if (EVOLVED[v] == var) return v; return -1; }
 static int is_mom(int v) { return v == V_mom_x || v == V_mom_y || v == V_mom_z; }
@@ -765,6 +770,7 @@ static double advance_time(oracle *o)
         if (o->mod.order[m] == 1) tc_iterate(o, step);
         if (o->mod.order[m] == 2) rl_iterate(o, step);
         if (o->mod.order[m] == 4) av_iterate(o, step);
+        if (o->mod.order[m] == 5) pv_iterate(o, step);
     }
     double **k1 = kalloc(o);
     if (o->integrator == TI_EULER) {                                                     /* :84-88 */
@@ -818,6 +824,7 @@ void oracle_destroy(oracle *o)
     for (size_t k = 0; k < sizeof(dom) / sizeof(dom[0]); k++) free(dom[k]);
     for (int v = 0; v < NV; v++) free(o->g[v]);
     free(o->mod.ah_heating);
+    free(o->mod.pv_cg);
     free(o);
 }
 /* which: 0 d_x 1 d_y 2 be_x 3 be_y 4 be_z 5 pos_x 6 pos_y 7 mask(read only) ; 100+v equation-set variable v */
@@ -887,7 +894,14 @@ void oracle_add_viscosity_term(oracle *o, int opt, double strength, int var_diff
 double oracle_step(oracle *o) { return advance_time(o); }
 void oracle_run(oracle *o, int nsteps, double *dt_out) { for (int s = 0; s < nsteps; s++) { double d = advance_time(o); if (dt_out) dt_out[s] = d; } }
 double oracle_time(const oracle *o) { return o->t; }
-int oracle_subcycles(const oracle *o, int which) { return which == 1 ? o->mod.tc_nsub : o->mod.rl_nsub; }
+int oracle_subcycles(const oracle *o, int which) { return which == 1 ? o->mod.tc_nsub : which == 5 ? o->mod.pv_nsub : o->mod.rl_nsub; }
+void oracle_set_physical_viscosity(oracle *o, double coeff, const double *coeff_plane, double epsilon, int heating_on, int force_on, int gradient_correction,
+                                   int integrator, int inactive_mode)
+{
+    o->mod.pv_on = 1; o->mod.pv_coeff = coeff; o->mod.pv_cg = pl_dup(o, coeff_plane); o->mod.pv_epsilon = epsilon; o->mod.pv_heating_on = heating_on;
+    o->mod.pv_force_on = force_on; o->mod.pv_gc = gradient_correction; o->mod.pv_integrator = integrator; o->mod.pv_inactive = inactive_mode; o->mod.pv_nsub = 1;
+    o->mod.order[o->mod.n_modules++] = 5;
+}
 /* one evaluation of the ideal-MHD right-hand side on the primary state; k: 8 planes [NEV][n] contiguous */
 void oracle_rhs(oracle *o, double *k)
 {

@@ -16,9 +16,6 @@ EVOLVED_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_t
               "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"]
 
 
-NO_ORACLE = ("physical_viscosity",)      # modules without a CPU restatement in oracle/: the reference's fixtures check the device path directly
-
-
 def cases(prefixes=None, two_fluid=False, oracle_only=False):
     """Fixture names; the two-fluid fixtures (tf_*) are pinned against the device path only (no CPU restatement of Ideal2F)."""
     names = sorted(p.stem for p in GOLDEN.glob("*.npz"))
@@ -159,5 +156,8 @@ def physical_viscosity_coefficient(planes, coeff, ramp_length):
     xc, yc = 0.5 * (x_min + x_max), 0.5 * (y_min + y_max)
     s = (x - xc) ** 2 / (x_max - xc) ** 2.0 + (y - yc) ** 2 / (y_max - yc) ** 2.0
     s_length = ramp_length / min(x_max - xc, y_max - yc)
-    res = 1.0 / 0.99 * np.maximum(np.exp(-2.3 * (np.maximum(s + 2.0 * s_length - 1.0, 0.0) / s_length) ** 2) - 0.01, 0.0)
+    import math
+    arg = -2.3 * (np.maximum(s + 2.0 * s_length - 1.0, 0.0) / s_length) ** 2
+    ex = np.vectorize(math.exp, otypes=[np.float64])(arg)       # libm's exp, as the reference's Grid::exp (numpy's SIMD exp differs in the last bit)
+    res = 1.0 / 0.99 * np.maximum(ex - 0.01, 0.0)
     return coeff * res

@@ -4,7 +4,7 @@ source/mhd/evolution.cpp:62) and every evolved plane + temp + dt after the recor
 import numpy as np
 import pytest
 
-from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_bits, viscosity_terms_with_profiles
+from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, physical_viscosity_coefficient, same_bits, viscosity_terms_with_profiles
 from oracle.oracle import Oracle
 
 
@@ -14,20 +14,24 @@ def make_oracle(g: Golden) -> Oracle:
         kw = module_kwargs(name, kv)
         if name == "artificial_viscosity":
             o.set_viscosity(viscosity_terms_with_profiles(g.planes, kw.pop("terms")), **kw)
+        elif name == "physical_viscosity":
+            ramp = kw.pop("ramp_length"); kw.pop("buffer_length")
+            o.set_physical_viscosity(physical_viscosity_coefficient(g.planes, kw["coeff"], ramp), **kw)
         else:
             getattr(o, "set_" + name)(**kw)
     return o
 
 
-@pytest.mark.parametrize("name", cases(oracle_only=True))
+@pytest.mark.parametrize("name", cases())
 def test_oracle_reproduces_reference(name):
     g = Golden(name)
     o = make_oracle(g)
-    tc, rl = [], []
+    tc, rl, pv = [], [], []
     for it in range(1, g.n_steps + 1):
         step = o.step()
         tc.append(o.subcycles("thermal_conduction"))
         rl.append(o.subcycles("radiative_losses"))
+        pv.append(o.subcycles("physical_viscosity"))
         assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())
         if it in g.frames:
             for v in OUT_VARS:
@@ -37,6 +41,8 @@ def test_oracle_reproduces_reference(name):
         assert tc == g.subcycle_counts("Thermal Subcycles")
     if "radiative_losses" in names:
         assert rl == g.subcycle_counts("Radiative Subcycles")
+    if "physical_viscosity" in names:
+        assert pv == g.viscous_subcycle_counts()
 
 
 @pytest.mark.parametrize("name", cases(two_fluid=True))
