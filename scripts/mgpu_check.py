@@ -33,13 +33,23 @@ def add_modules(dom):
             dom.set_radiative_losses(integrator="rk2", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1)
         elif m == "pv":
             dom.set_physical_viscosity(np.full((dom.nx, dom.ydim), 3.0e-15), coeff=3.0e-15, epsilon=0.1, integrator="rk2", gradient_correction=True)
+        elif m == "2f":
+            pass
+        elif m == "2feic":
+            dom.set_eic_thermalization()
         elif m == "ah":
             dom.set_ambient_heating_plane(np.full((dom.nx, dom.ydim), 1.0e-4))
         else:
             raise SystemExit("unknown module " + m)
 
 
-if modules:
+two_fluid = any(m.startswith("2f") for m in modules)
+if two_fluid:
+    s = synthetic.ucnp_cloud(nx, ny, drift=2.0e3, bfield=5.0)
+    ub = ("open_ucnp", "open_ucnp")
+    kw = dict(equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False), xb=("periodic", "periodic") if xbound == "periodic" else ub, yb=ub, integrator=integ,
+              density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
+elif modules:
     s = synthetic.stratified_loop(nx, ny, bump=0.5)
     kw = dict(xb=("periodic", "periodic") if xbound == "periodic" else (xbound, "open"), yb=("fixed", "fixed"), integrator=integ)
 elif xbound == "periodic":
@@ -52,7 +62,7 @@ run = SlabRunner(s["planes"], s["ion_mass"], s["adiabatic_index"], rank=rank, wo
 add_modules(run.dom)
 run.step(steps)
 run.dom.synchronize()
-got = {v: run.gather(v) for v in PlasmaDomain.EVOLVED + ["dt"]}
+got = {v: run.gather(v) for v in (run.dom.EVOLVED + ["dt"])}
 t_slab = run.dom.time
 ok = True
 if rank == 0:

@@ -64,7 +64,7 @@ struct spruce_domain {
     enum { MOD_TC = 1, MOD_RL = 2, MOD_AH = 3, MOD_AV = 4, MOD_PV = 5 };
     // physical_viscosity (source/modules/solar/physicalviscosity.cpp)
     struct { double coeff = 0.0, epsilon = 1.0; int heating_on = 1, force_on = 1, gc = 0, integrator = 0, inactive = 0, nsub = 1;
-             double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; } pv;
+             double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; bool cg_halo_done = false; } pv;
     std::vector<int> module_order;
     TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
     RlParams rl{}; int rl_nsub = 0;
@@ -713,6 +713,10 @@ int pv_iterate(spruce_domain *d, double dt)
     const int vars_v[3] = {V_v_x, V_v_y, V_v_z}, vars_b[3] = {V_b_hat_x, V_b_hat_y, V_b_hat_z};
     for (int k = 0; k < 3; k++) { if ((rc = derive_to(d, vars_v[k], pv.v[0][k]))) return rc; if ((rc = derive_to(d, vars_b[k], pv.bh[k]))) return rc; }
     if ((rc = derive_to(d, V_temp, pv.T[0]))) return rc;
+    if (!pv.cg_halo_done) {                          // the coefficient plane is static: its halo rows travel once (gradient correction differentiates it)
+        if ((rc = exchange_plane(d, pv.cg))) return rc;
+        pv.cg_halo_done = true;
+    }
     PvArgs A{};
     for (int k = 0; k < 3; k++) { A.bh[k] = pv.bh[k]; A.mom[k] = d->Pset.p[E_MX + k]; }
     A.n = d->Pset.p[E_N]; A.cg = pv.cg; A.e = d->Pset.p[E_E];
@@ -1402,7 +1406,6 @@ int spruce_mgpu_end_step(spruce_domain *d)
 int spruce_mgpu_ipc_export(spruce_domain *d, void *handle64)
 {
     CHECK_DOM(d);
-    NOT_2F(d, "slab decomposition");
     if (!handle64) return fail(SPRUCE_ERR_ARG, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     int rc = ensure_segment(d);
@@ -1415,7 +1418,6 @@ int spruce_mgpu_ipc_export(spruce_domain *d, void *handle64)
 int spruce_mgpu_ipc_connect(spruce_domain *d, const void *handles, int n_handles)
 {
     CHECK_DOM(d);
-    NOT_2F(d, "slab decomposition");
     if (!handles || n_handles != d->cfg.n_ranks || n_handles > MAX_RANKS) return fail(SPRUCE_ERR_ARG, "need one 64-byte handle per rank (%d ranks, at most %d)", d->cfg.n_ranks, MAX_RANKS);
     int rc = ensure_segment(d);
     if (rc) return rc;
@@ -1432,8 +1434,8 @@ int spruce_mgpu_ipc_connect(spruce_domain *d, const void *handles, int n_handles
 int spruce_mgpu_initial_exchange(spruce_domain *d)
 {
     CHECK_DOM(d);
-    NOT_2F(d, "slab decomposition");
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "initial exchange before setup");
+    if (d->tf) { int rc2 = tf_initial_exchange(d); if (rc2) return rc2; CUDA_TRY(cudaStreamSynchronize(d->stream)); return SPRUCE_OK; }
     double *stat_view[NEV];
     for (int v = 0; v < NEV; v++) stat_view[v] = d->stat[v < NSTATIC ? v : 0];
     int rc;
@@ -1449,7 +1451,6 @@ int spruce_mgpu_initial_exchange(spruce_domain *d)
 int spruce_plane_activity(spruce_domain *d, int *local_mask, int set_global_mask)
 {
     CHECK_DOM(d);
-    NOT_2F(d, "plane activity");
     if (local_mask) *local_mask = (int)d->nonzero_mask;
     if (set_global_mask >= 0) d->nonzero_mask = (unsigned)set_global_mask & 0x1Fu;
     return SPRUCE_OK;

@@ -78,7 +78,6 @@ int tf_check_boundaries(const spruce_config &c)
         wall |= (b[s] == SPRUCE_BC_FIXED || b[s] == SPRUCE_BC_REFLECT);
     }
     if (ucnp && wall) return fail(SPRUCE_ERR_UNSUPPORTED, "ideal_2F: open_ucnp mixed with fixed/reflect sides is not built yet");
-    if (c.n_ranks != 1) return fail(SPRUCE_ERR_UNSUPPORTED, "ideal_2F runs on one rank in this version");
     return SPRUCE_OK;
 }
 
@@ -95,6 +94,22 @@ int tf_launch_ghosts(spruce_domain *d, const PlaneSet2 &U, int primary)
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }
+// slab decomposition: halo rows of the 14 evolved planes from the ring neighbours (two packed exchanges of 8 planes)
+int tf_exchange(spruce_domain *d, const PlaneSet2 &U)
+{
+    if (d->cfg.n_ranks == 1) return SPRUCE_OK;
+    double *a[NEV], *b[NEV];
+    for (int k = 0; k < NEV; k++) { a[k] = U.p[k]; b[k] = U.p[NEV + (k % (NEV2 - NEV))]; }
+    int rc = peer_exchange(d, a, nullptr);
+    if (rc) return rc;
+    return peer_exchange(d, b, nullptr);
+}
+int tf_finish_stage(spruce_domain *d, const PlaneSet2 &U, int primary)
+{
+    int rc = tf_launch_ghosts(d, U, primary);
+    if (rc) return rc;
+    return tf_exchange(d, U);
+}
 
 int tf_launch_stage(spruce_domain *d, const PlaneSet2 &S, const PlaneSet2 &B, const PlaneSet2 &D, double coef, int primary, int kmode)
 {
@@ -107,7 +122,9 @@ int tf_launch_stage(spruce_domain *d, const PlaneSet2 &S, const PlaneSet2 &B, co
     for (int v = 0; v < NEV2; v++) V.U[v] = S.p[v];
     for (int k = 0; k < 4; k++) { V.vel[k] = d->tf->vel[k]; A.vel[k] = d->tf->vel[k]; }
     V.done_ptr = &d->ctl->done;
-    dim3 vgrid((d->P.ny + 255) / 256, d->P.nx);
+    const int halo = d->cfg.n_ranks > 1 ? HALO : 0;                   // the neighbours' cells are resident in the halo rows
+    V.row_off = -halo;
+    dim3 vgrid((d->P.ny + 255) / 256, d->P.nx + 2 * halo);
     k_2f_velocity<<<vgrid, 256, 0, d->stream>>>(d->P, V);
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_2f_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
@@ -131,6 +148,16 @@ int tf_launch_propagate(spruce_domain *d, int from_state)
     CUDA_TRY(cudaGetLastError());
     return tf_launch_ghosts(d, t->P, 1);
 }
+// after spruce_eqs_setup on every rank of a decomposed two-fluid run: halo rows of the static planes and the primary state, global dt minimum
+int tf_initial_exchange(spruce_domain *d)
+{
+    double *stat_view[NEV];
+    for (int v = 0; v < NEV; v++) stat_view[v] = d->stat[v < NSTATIC ? v : 0];
+    int rc;
+    if ((rc = peer_exchange(d, stat_view, nullptr))) return rc;
+    if ((rc = tf_exchange(d, d->tf->P))) return rc;
+    return peer_dt_allgather(d);
+}
 
 int tf_enqueue_step(spruce_domain *d, int hist_slot)
 {
@@ -142,23 +169,24 @@ int tf_enqueue_step(spruce_domain *d, int hist_slot)
     if (ti == SPRUCE_TI_EULER) {
         if ((rc = tf_launch_stage(d, t->P, t->P, t->M, 1.0, 1, KM_NONE))) return rc;
         std::swap(t->P, t->M);
-        if ((rc = tf_launch_ghosts(d, t->P, 1))) return rc;
+        if ((rc = tf_finish_stage(d, t->P, 1))) return rc;
     } else if (ti == SPRUCE_TI_RK2) {
         if ((rc = tf_launch_stage(d, t->P, t->P, t->M, 0.5, 0, KM_NONE))) return rc;
-        if ((rc = tf_launch_ghosts(d, t->M, 0))) return rc;
+        if ((rc = tf_finish_stage(d, t->M, 0))) return rc;
         if ((rc = tf_launch_stage(d, t->M, t->P, t->P, 1.0, 1, KM_NONE))) return rc;
-        if ((rc = tf_launch_ghosts(d, t->P, 1))) return rc;
+        if ((rc = tf_finish_stage(d, t->P, 1))) return rc;
     } else {
         if ((rc = tf_ensure_rk4(d))) return rc;
         if ((rc = tf_launch_stage(d, t->P, t->P, t->M, 0.5, 0, KM_STORE_K1))) return rc;
-        if ((rc = tf_launch_ghosts(d, t->M, 0))) return rc;
+        if ((rc = tf_finish_stage(d, t->M, 0))) return rc;
         if ((rc = tf_launch_stage(d, t->M, t->P, t->M2, 0.5, 0, KM_STORE_K2))) return rc;
-        if ((rc = tf_launch_ghosts(d, t->M2, 0))) return rc;
+        if ((rc = tf_finish_stage(d, t->M2, 0))) return rc;
         if ((rc = tf_launch_stage(d, t->M2, t->P, t->M, 1.0, 0, KM_ADD_K2))) return rc;
-        if ((rc = tf_launch_ghosts(d, t->M, 0))) return rc;
+        if ((rc = tf_finish_stage(d, t->M, 0))) return rc;
         if ((rc = tf_launch_stage(d, t->M, t->P, t->P, 1.0, 1, KM_FINAL))) return rc;
-        if ((rc = tf_launch_ghosts(d, t->P, 1))) return rc;
+        if ((rc = tf_finish_stage(d, t->P, 1))) return rc;
     }
+    if (d->cfg.n_ranks > 1 && (rc = peer_dt_allgather(d))) return rc;
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
     d->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -225,14 +225,14 @@ __global__ void __launch_bounds__(128) k_2f_stage(const __grid_constant__ Domain
 }
 
 // species velocities of one state, every cell incl. ghost cells (recomputeDerivedVarsFromEvolvedVars, ideal2F.cpp:123-126)
-struct TfVelArgs { const double *U[NEV2]; double *vel[4]; const int *done_ptr; };
+struct TfVelArgs { const double *U[NEV2]; double *vel[4]; const int *done_ptr; int row_off; };     // row_off = -HALO: also the halo rows of a slab
 __global__ void __launch_bounds__(256) k_2f_velocity(const DomainParams P, const TfVelArgs A)
 {
     if (*A.done_ptr) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+    const int r = (int)blockIdx.y + A.row_off;
     if (j >= P.ny) return;
-    const size_t off = (size_t)r * P.pitch + j;
+    const long long off = (long long)r * P.pitch + j;
     const double ir = A.U[F_IRHO][off], er = A.U[F_ERHO][off];
     A.vel[0][off] = A.U[F_IMX][off] / ir; A.vel[1][off] = A.U[F_IMY][off] / ir;
     A.vel[2][off] = A.U[F_EMX][off] / er; A.vel[3][off] = A.U[F_EMY][off] / er;
@@ -277,12 +277,13 @@ __global__ void k_2f_ghosts(const DomainParams P, const TfGhostArgs A)
     const int bc = side == 0 ? P.bc_x1 : side == 1 ? P.bc_x2 : side == 2 ? P.bc_y1 : P.bc_y2;
     if (bc != BC_OPEN_UCNP && bc != BC_REFLECT) return;
     const bool xside = side < 2;
-    if (xside) { if (idx < P.yl || idx > P.yu) return; } else { if (idx < P.xl || idx > P.xu) return; }
-    int r1_, r2_, r3_, c1_, c2_, c3_;
-    if (side == 0) { r1_ = 0; r2_ = 1; r3_ = 2; c1_ = c2_ = c3_ = idx; }
-    else if (side == 1) { r1_ = P.nx - 1; r2_ = P.nx - 2; r3_ = P.nx - 3; c1_ = c2_ = c3_ = idx; }
+    if (xside) { if (idx < P.yl || idx > P.yu) return; } else { const int g = P.row0 + idx; if (g < P.xl || g > P.xu) return; }
+    int r1_, r2_, r3_, c1_, c2_, c3_;                                  // local rows; an x side belongs to the first / last slab only
+    if (side == 0) { r1_ = 0 - P.row0; r2_ = 1 - P.row0; r3_ = 2 - P.row0; c1_ = c2_ = c3_ = idx; }
+    else if (side == 1) { r1_ = P.gnx - 1 - P.row0; r2_ = P.gnx - 2 - P.row0; r3_ = P.gnx - 3 - P.row0; c1_ = c2_ = c3_ = idx; }
     else if (side == 2) { r1_ = r2_ = r3_ = idx; c1_ = 0; c2_ = 1; c3_ = 2; }
     else { r1_ = r2_ = r3_ = idx; c1_ = P.ny - 1; c2_ = P.ny - 2; c3_ = P.ny - 3; }
+    if (xside && (r3_ < 0 || r3_ >= P.nx)) return;
     const size_t o1 = (size_t)r1_ * P.pitch + c1_, o2 = (size_t)r2_ * P.pitch + c2_, o3 = (size_t)r3_ * P.pitch + c3_;
     if (bc == BC_OPEN_UCNP) {
         const int vars[11] = {F_IRHO, F_ERHO, F_IE, F_EE, F_EX, F_EY, F_EZ, F_IMX, F_IMY, F_EMX, F_EMY};

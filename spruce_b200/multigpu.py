@@ -84,7 +84,10 @@ class SlabRunner:
         self.torch, self.dist, self.capi = torch, dist, capi
         self.rank, self.world = rank, world
         # `planes` holds either global planes or (xdim given) only this rank's rows; d_x is always the global 1-D array then
-        xdim = planes["rho"].shape[0] if xdim is None else xdim
+        if xdim is None:
+            if planes["d_x"].ndim != 2:
+                raise ValueError("xdim is required when the planes hold only this rank's rows")
+            xdim = planes["d_x"].shape[0]
         self.transport = transport
         self.row0, self.nx = partition(xdim, world)[rank]
         self.periodic_x = kw.get("xb", ("periodic", "periodic")) == ("periodic", "periodic")
@@ -92,22 +95,7 @@ class SlabRunner:
                                 rank=rank, n_ranks=world, setup=False, **kw)
         self.lib = self.dom.lib
         self.stream = torch.cuda.ExternalStream(self.dom.stream())
-        ptrs = [C.c_void_p() for _ in range(4)]
-        nbytes = C.c_size_t()
-        capi.check(self.lib.spruce_halo_buffers(self.dom.h, *[C.byref(p) for p in ptrs], C.byref(nbytes)))
-        n = nbytes.value // 8
-        self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = [torch.as_tensor(_DevBuf(p.value, n), device="cuda") for p in ptrs]
-        p = C.c_void_p()
-        capi.check(self.lib.spruce_mgpu_dt_min_ptr(self.dom.h, C.byref(p)))
-        self.dtmin = torch.as_tensor(_DevBuf(p.value, 1), device="cuda")
-        ns = C.c_int()
-        capi.check(self.lib.spruce_mgpu_n_stages(self.dom.h, C.byref(ns)))
-        self.n_stages = ns.value
-        self.out_set = []
-        for s in range(self.n_stages):
-            w = C.c_int()
-            capi.check(self.lib.spruce_mgpu_stage_output(self.dom.h, s, C.byref(w)))
-            self.out_set.append(w.value)
+        self._nccl_ready = False
         # setup = local populateVariablesFromState, then halos of the primary state and the global dt minimum
         # zero-plane knowledge must be global (a neighbour's halo rows may be non-zero): OR the per-rank masks
         lm = C.c_int()
@@ -138,6 +126,7 @@ class SlabRunner:
             dist.barrier()                      # every rank has mapped its neighbours and finished its local setup
             capi.check(self.lib.spruce_mgpu_initial_exchange(self.dom.h))
             return
+        self._init_nccl_buffers()
         self.dom.setup()
         with torch.cuda.stream(self.stream):
             capi.check(self.lib.spruce_mgpu_pack(self.dom.h, 3))        # static planes: be_* are transported and need halo rows
@@ -148,6 +137,27 @@ class SlabRunner:
             capi.check(self.lib.spruce_mgpu_unpack(self.dom.h, 0))
             dist.all_reduce(self.dtmin, op=dist.ReduceOp.MIN)
         self.dom.synchronize()
+
+    def _init_nccl_buffers(self):
+        """Tensors aliasing the library's packed halo buffers and dt word, for the caller-driven (NCCL) transport."""
+        torch, capi = self.torch, self.capi
+        ptrs = [C.c_void_p() for _ in range(4)]
+        nbytes = C.c_size_t()
+        capi.check(self.lib.spruce_halo_buffers(self.dom.h, *[C.byref(p) for p in ptrs], C.byref(nbytes)))
+        n = nbytes.value // 8
+        self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = [torch.as_tensor(_DevBuf(p.value, n), device="cuda") for p in ptrs]
+        p = C.c_void_p()
+        capi.check(self.lib.spruce_mgpu_dt_min_ptr(self.dom.h, C.byref(p)))
+        self.dtmin = torch.as_tensor(_DevBuf(p.value, 1), device="cuda")
+        ns = C.c_int()
+        capi.check(self.lib.spruce_mgpu_n_stages(self.dom.h, C.byref(ns)))
+        self.n_stages = ns.value
+        self.out_set = []
+        for s in range(self.n_stages):
+            w = C.c_int()
+            capi.check(self.lib.spruce_mgpu_stage_output(self.dom.h, s, C.byref(w)))
+            self.out_set.append(w.value)
+        self._nccl_ready = True
 
     def _exchange(self):
         exchange_halos(self.dist, self.send_lo, self.send_hi, self.recv_lo, self.recv_hi, self.rank, self.world, self.periodic_x)
