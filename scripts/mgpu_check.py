@@ -33,6 +33,11 @@ def add_modules(dom):
             dom.set_radiative_losses(integrator="rk2", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1)
         elif m == "pv":
             dom.set_physical_viscosity(np.full((dom.nx, dom.ydim), 3.0e-15), coeff=3.0e-15, epsilon=0.1, integrator="rk2", gradient_correction=True)
+        elif m == "av":
+            prof = 0.8 * np.exp(-((s["planes"]["pos_y"] - s["planes"]["pos_y"].min()) / 6.0e8) ** 2)     # a boundary-style strength profile (global plane)
+            dom.set_viscosity([dict(opt="local", strength=0.5, var_diff="v_x", var_evol="mom_x"), dict(opt="global", strength=3.0, var_diff="v_y", var_evol="mom_y"),
+                               dict(opt="boundary", strength=0.8, var_diff="temp", var_evol="thermal_energy", strength_grid=prof)],
+                              hv_integrator="rk2", hv_epsilon=1.0, gradient_correction=True)
         elif m == "2f":
             pass
         elif m == "2feic":

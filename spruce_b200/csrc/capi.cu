@@ -70,7 +70,7 @@ struct spruce_domain {
     RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
     // artificial_viscosity (source/modules/viscosity.cpp): terms in config order
-    struct ViscTerm { int opt; double strength; int var_diff; int var_evol; int species; double *strength_plane; };
+    struct ViscTerm { int opt; double strength; int var_diff; int var_evol; int species; double *strength_plane; bool halo_done = false; };
     std::vector<ViscTerm> visc;
     int visc_hv_integrator = 0, visc_gradient_correction = 0; double visc_hv_epsilon = 1.0;
     double *vscratch[8] = {nullptr}; double *dt_plane = nullptr;
@@ -494,10 +494,15 @@ const double *materialise_var(spruce_domain *d, const PlaneSet &S, int var, doub
 int visc_needs_dt_plane(const spruce_domain *d) { for (auto &t : d->visc) if (t.opt == 0 || t.opt == 2) return 1; return 0; }
 int visc_refresh_dt(spruce_domain *d) { return visc_needs_dt_plane(d) ? derive_to(d, V_dt, d->dt_plane) : SPRUCE_OK; }
 // constructSingleViscosityGrid :185-267 for term i on grid set S -> out
+int exchange_plane(spruce_domain *d, double *plane);
 int visc_term(spruce_domain *d, const PlaneSet &S, int i, double *out, int masked)
 {
-    const auto &t = d->visc[i];
+    auto &t = d->visc[i];
     int rc;
+    if (t.strength_plane && !t.halo_done) {          // static boundary profile: its halo rows travel once (gradient correction differentiates it)
+        if ((rc = exchange_plane(d, t.strength_plane))) return rc;
+        t.halo_done = true;
+    }
     const double *q = materialise_var(d, S, t.var_diff, d->vscratch[7], &rc);
     if (rc) return rc;
     ViscArgs A{};
@@ -554,7 +559,8 @@ int av_iterate(spruce_domain *d, double dt)
             d->launches++;
             CUDA_TRY(cudaGetLastError());
             if (ev == E_N) d->raw_rho = true;
-            return launch_propagate(d, 0);
+            int rp = launch_propagate(d, 0);
+            return rp ? rp : after_module_propagate(d);
         };
         auto term = [&](double *out) -> int { int r_ = visc_refresh_dt(d); return r_ ? r_ : visc_term(d, d->Pset, (int)i, out, 0); };
         for (int sc = 0; sc < ns; sc++) {
@@ -580,7 +586,7 @@ int av_iterate(spruce_domain *d, double dt)
                 }
             }
         }
-        if ((rc = launch_propagate(d, 0))) return rc;                                        // :178
+        if ((rc = launch_propagate(d, 0)) || (rc = after_module_propagate(d))) return rc;    // :178
     }
     return SPRUCE_OK;
 }
@@ -1090,7 +1096,6 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "advance before setup");
     if (n_steps < 0) return fail(SPRUCE_ERR_ARG, "negative step count");
     if (d->cfg.n_ranks > 1 && !d->peers_connected) return fail(SPRUCE_ERR_STATE, "a slab of a decomposed domain advances either through spruce_mgpu_stage (caller-owned exchange) or, after spruce_mgpu_ipc_connect, through spruce_advance");
-    if (d->cfg.n_ranks > 1 && !d->visc.empty()) return fail(SPRUCE_ERR_UNSUPPORTED, "artificial_viscosity runs on a single rank in this version");
     if ((size_t)n_steps > d->dt_hist_cap) {
         if (d->dt_hist) cudaFree(d->dt_hist);
         d->dt_hist_cap = (size_t)n_steps + 64;
@@ -1219,7 +1224,6 @@ int spruce_module_viscosity(spruce_domain *d, int hv_time_integrator, double hv_
 {
     CHECK_DOM(d);
     NOT_2F(d, "artificial_viscosity");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "artificial_viscosity runs on a single rank in this version");
     if (hv_time_integrator < 0 || hv_time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid hyperviscous time integrator given for Viscosity module");
     d->visc_hv_integrator = hv_time_integrator; d->visc_hv_epsilon = hv_epsilon; d->visc_gradient_correction = gradient_correction ? 1 : 0;
     for (int k = 0; k < 8; k++) if (!d->vscratch[k]) { int rc = alloc_plane(d, &d->vscratch[k]); if (rc) return rc; }

@@ -350,7 +350,7 @@ def test_slab_decomposition_equals_single_gpu(args):
 
 @pytest.mark.parametrize("args", [("128", "96", "4", "rk2", "periodic", "p2p", "tc,rl,ah"), ("96", "80", "3", "euler", "reflect", "p2p", "tc,rl"),
                                   ("200", "64", "3", "rk4", "periodic", "p2p", "ah,tcsat,rl"), ("128", "96", "3", "rk2", "periodic", "p2p", "pv,tc"),
-                                  ("130", "97", "4", "rk2", "ucnp", "p2p", "2feic"), ("131", "96", "3", "rk4", "periodic", "p2p", "2f")])
+                                  ("120", "90", "3", "rk4", "periodic", "p2p", "av"), ("130", "97", "4", "rk2", "ucnp", "p2p", "2feic"), ("131", "96", "3", "rk4", "periodic", "p2p", "2f")])
 def test_slab_decomposition_with_modules_equals_single_gpu(args):
     """("2f": the two-fluid equation set on slabs.)  Thermal conduction (halo exchange of the temperature plane per sub-cycle stage, sub-cycle counts from min / max all-gathers
     over peer memory), radiative losses and ambient heating on 2 slabs == 1 GPU, bit for bit, with equal sub-cycle counts."""
