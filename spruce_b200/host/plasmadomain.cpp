@@ -116,19 +116,15 @@ void PlasmaDomain::readStateFile(const fs::path &state_file, bool continue_mode)
         if (line.empty()) continue;
         const std::string var_name = line;
         Grid g(m_xdim, m_ydim);
-        std::string row;
+        std::vector<std::string> rows(m_xdim);
+        for (size_t i = 0; i < m_xdim; i++) getCleanedLine(in, rows[i]);
+        std::vector<size_t> counts(m_xdim, 0);
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)m_xdim; i++)                       // rows parse independently (std::from_chars)
+            counts[(size_t)i] = parseDelimitedRow(rows[(size_t)i].data(), rows[(size_t)i].data() + rows[(size_t)i].size(), g.ptr() + (size_t)i * m_ydim, m_ydim);
         for (size_t i = 0; i < m_xdim; i++) {
-            getCleanedLine(in, row);
-            const char *p = row.c_str();
-            size_t j = 0;
-            while (*p) {
-                char *end = nullptr;
-                const double v = std::strtod(p, &end);
-                SPRUCE_REQUIRE(end != p, "Encountered non-numerical row in .state file sooner than expected");
-                SPRUCE_REQUIRE(j < m_ydim, "Row in .state file is too long (greater than ydim)");
-                g(i, j++) = v;
-                p = (*end == ',') ? end + 1 : end;
-            }
+            SPRUCE_REQUIRE(counts[i] != (size_t)-1, "Encountered non-numerical row in .state file sooner than expected");
+            SPRUCE_REQUIRE(counts[i] <= m_ydim, "Row in .state file is too long (greater than ydim)");
         }
         auto it = std::find(m_gridnames.begin(), m_gridnames.end(), var_name);
         if (it != m_gridnames.end()) m_grids[it - m_gridnames.begin()] = g;

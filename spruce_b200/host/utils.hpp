@@ -1,6 +1,7 @@
 // utils.hpp -- string helpers with the reference's semantics (source/mhd/utils.cpp:8-53).
 #pragma once
 #include <algorithm>
+#include <charconv>
 #include <cstdlib>
 #include <iostream>
 #include <sstream>
@@ -53,4 +54,26 @@ inline void splitAssignment(const std::string &line, std::string &lhs, std::stri
     lhs.clear(); rhs.clear();
     std::getline(ss, lhs, '=');
     std::getline(ss, rhs, '#');
+}
+
+// One delimiter-separated row of numbers (already stripped of whitespace) -> out[0..max_n).  Returns the number of values, or
+// (size_t)-1 when a field is not a number.  std::from_chars accepts exactly what the reference's writers emit (no leading '+').
+inline size_t parseDelimitedRow(const char *p, const char *end, double *out, size_t max_n, char delim = ',')
+{
+    size_t n = 0;
+    while (p < end) {
+        double v = 0.0;
+        const auto r = std::from_chars(p, end, v);
+        if (r.ec == std::errc::result_out_of_range) {              // overflow / underflow: strtod's value (inf / denormal / 0), as the reference's stod-free reader gets
+            char *e2 = nullptr;
+            v = std::strtod(std::string(p, r.ptr).c_str(), &e2);
+        } else if (r.ec != std::errc() || r.ptr == p) {
+            return (size_t)-1;
+        }
+        if (n >= max_n) return max_n + 1;                          // row too long
+        out[n++] = v;
+        p = (r.ptr < end && *r.ptr == delim) ? r.ptr + 1 : r.ptr;
+        if (r.ptr < end && *r.ptr != delim) return (size_t)-1;
+    }
+    return n;
 }
