@@ -1253,6 +1253,9 @@ int spruce_module_viscosity_term(spruce_domain *d, const char *visc_opt, double 
         if (rc) return rc;
         if ((rc = h2d_plane(d, t.strength_plane, strength_plane))) return rc;
     }
+    // a viscosity term may feed the z system from any variable: mom_z / bi_z can then leave zero even if they were uploaded as zero planes
+    if (evolved_slot(t.var_evol) == E_MZ) d->nonzero_mask |= 0x01u;
+    if (evolved_slot(t.var_evol) == E_BZ) d->nonzero_mask |= 0x02u;
     d->visc.push_back(t);
     return SPRUCE_OK;
 }

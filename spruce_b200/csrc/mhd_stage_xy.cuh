@@ -100,11 +100,22 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             int pr = r;                                        // single-rank periodic x: rows -2..nx+1 wrap with one add (no modulo)
             if (P.xwrap) pr = r < 0 ? r + P.nx : (r >= P.nx ? r - P.nx : r);
             const size_t off = (size_t)pr * P.pitch + jl;
+            if (LN == 6) {
+                // 2-D list: mom_z, bi_z and the external field are identically zero planes (host-tracked); their ring rows are zeroed
+                // once in the prologue and never loaded
+                cp_async8(&ring[slot][Q_RHO][tid], A.S[E_N] + off); cp_async8(&ring[slot][Q_MX][tid], A.S[E_MX] + off);
+                cp_async8(&ring[slot][Q_MY][tid], A.S[E_MY] + off); cp_async8(&ring[slot][Q_E][tid], A.S[E_E] + off);
+                cp_async8(&ring[slot][Q_BIX][tid], A.S[E_BX] + off); cp_async8(&ring[slot][Q_BIY][tid], A.S[E_BY] + off);
+            } else {
 #pragma unroll
-            for (int v = 0; v < NEV; v++) cp_async8(&ring[slot][v][tid], A.S[v] + off);
-            cp_async8(&ring[slot][Q_BEX][tid], A.st[S_BEX] + off);
-            cp_async8(&ring[slot][Q_BEY][tid], A.st[S_BEY] + off);
-            cp_async8(&ring[slot][Q_BEZ][tid], A.st[S_BEZ] + off);
+                for (int v = 0; v < NEV; v++) cp_async8(&ring[slot][v][tid], A.S[v] + off);
+                cp_async8(&ring[slot][Q_BEX][tid], A.st[S_BEX] + off);
+                cp_async8(&ring[slot][Q_BEY][tid], A.st[S_BEY] + off);
+                cp_async8(&ring[slot][Q_BEZ][tid], A.st[S_BEZ] + off);
+            }
+        } else if (LN == 6) {
+            ring[slot][Q_RHO][tid] = 1.0; ring[slot][Q_MX][tid] = 0.0; ring[slot][Q_MY][tid] = 0.0;
+            ring[slot][Q_E][tid] = 0.0; ring[slot][Q_BIX][tid] = 0.0; ring[slot][Q_BIY][tid] = 0.0;
         } else {
 #pragma unroll
             for (int v = 0; v < NTR; v++) ring[slot][v][tid] = (v == Q_RHO) ? 1.0 : 0.0;
@@ -134,6 +145,13 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
         }
         for (int e = tid; e < 3 * NTR * XW + 6 * XW; e += XY_NT) (&Fx_s[0][0])[e] = 0.0;      // Fx_s, TX_s, TY_s, Dc_s are contiguous
+        if (LN == 6 && loader) {
+            const int zq[5] = {Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ};
+#pragma unroll
+            for (int sl = 0; sl < RD; sl++)
+#pragma unroll
+                for (int k = 0; k < 5; k++) ring[sl][zq[k]][tid] = 0.0;
+        }
     }
     auto x_geom = [&](int f) {
         const int i = f - r0 + 3;
