@@ -57,6 +57,10 @@ template <int LN, unsigned long long LQ>
 __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
 {
     constexpr int UNR = LN > 0 ? LN : 1;
+    // Z: the z system (mom_z, bi_z, v_z) and the external field can be non-zero.  In the 2-D instance (LN == 6) they are exact zeros in the
+    // reference as well, so every term that only adds +-0 is left out (the results can differ in the sign of a zero, nothing else) and
+    // the all-zero planes mom_z / bi_z are neither computed nor stored (their planes are zero-initialised and stay zero).
+    constexpr bool Z = (LN != 6);
     ActiveList L;
     L.n = LN > 0 ? LN : Larg.n;
     L.q = LN > 0 ? LQ : Larg.q;
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         const int vm1 = vslot_of(r0 - 1), v0 = vslot_of(r0);
         cVfx = face_interp(vel[vm1][0][c], vel[v0][0][c], g.hm1, g.h0, g.fs, g.rfs);
         cIx_vy = face_interp(vel[vm1][1][c], vel[v0][1][c], g.hm1, g.h0, g.fs, g.rfs);
-        cIx_vz = face_interp(vel[vm1][2][c], vel[v0][2][c], g.hm1, g.h0, g.fs, g.rfs);
+        if (Z) cIx_vz = face_interp(vel[vm1][2][c], vel[v0][2][c], g.hm1, g.h0, g.fs, g.rfs);
         cIx_p = face_interp(ring[sm1][Q_E][c] * P.gm1, ring[s0][Q_E][c] * P.gm1, g.hm1, g.h0, g.fs, g.rfs);
         const FaceSel fs0 = select_face(g, cVfx);
 #pragma unroll UNR
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const FaceGeom gx = x_geom(r + 1);
             const double vfx1 = face_interp(vel[v0][0][c], vel[v1][0][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
             const double Ix1_vy = face_interp(vel[v0][1][c], vel[v1][1][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
-            const double Ix1_vz = face_interp(vel[v0][2][c], vel[v1][2][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
+            const double Ix1_vz = Z ? face_interp(vel[v0][2][c], vel[v1][2][c], gx.hm1, gx.h0, gx.fs, gx.rfs) : 0.0;
             const double Ix1_p = face_interp(pc, ring[sp1][Q_E][c] * P.gm1, gx.hm1, gx.h0, gx.fs, gx.rfs);
             const FaceSel fsx = select_face(gx, vfx1);
             // the far cell of the extrapolation: row r-1 for flow in +x, row r+2 for flow in -x -- one load from a selected row
@@ -259,11 +263,11 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 if (qa == Q_BIZ) Ix1_biz = ad2; if (qb == Q_BIZ) Ix1_biz = bd2;
             }
             d_a = ddiv(Ix1_biy - cIx_biy, dx, rdx);                 // d(bi_y)/dx
-            d_b = ddiv(Ix1_biz - cIx_biz, dx, rdx);                 // d(bi_z)/dx
+            if (Z) d_b = ddiv(Ix1_biz - cIx_biz, dx, rdx);          // d(bi_z)/dx
             d_c = ddiv(Ix1_p - cIx_p, dx, rdx);                     // d(p)/dx
             Dc_s[0][col] = ddiv(vfx1 - cVfx, dx, rdx);              // d(v_x)/dx  -> Y
             Dc_s[1][col] = ddiv(Ix1_vy - cIx_vy, dx, rdx);          // d(v_y)/dx  -> Y
-            Dc_s[2][col] = ddiv(Ix1_vz - cIx_vz, dx, rdx);          // d(v_z)/dx  -> Y
+            if (Z) Dc_s[2][col] = ddiv(Ix1_vz - cIx_vz, dx, rdx);   // d(v_z)/dx  -> Y
             cIx_biy = Ix1_biy; cIx_biz = Ix1_biz; cIx_p = Ix1_p; cVfx = vfx1; cIx_vy = Ix1_vy; cIx_vz = Ix1_vz;
         } else {
             // ---- dt of the previous row: its rho and momenta were published by the X warps before the last barrier
@@ -279,9 +283,9 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const double vxc = vel[v0][0][c], vyc = vel[v0][1][c], vzc = vel[v0][2][c];
             const double vfyL = face_interp(vel[v0][1][c - 1], vyc, gy.hm1, gy.h0, gy.fs, gy.rfs);
             const double IyL_vx = face_interp(vel[v0][0][c - 1], vxc, gy.hm1, gy.h0, gy.fs, gy.rfs);
-            const double IyL_vz = face_interp(vel[v0][2][c - 1], vzc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+            const double IyL_vz = Z ? face_interp(vel[v0][2][c - 1], vzc, gy.hm1, gy.h0, gy.fs, gy.rfs) : 0.0;
             const double IyL_p = face_interp(ring[s0][Q_E][c - 1] * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
-            const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = shfl_next(IyL_vz), IyR_p = shfl_next(IyL_p);
+            const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = Z ? shfl_next(IyL_vz) : 0.0, IyR_p = shfl_next(IyL_p);
             const FaceSel fsy = select_face(gy, vfyL);
             const double *far_col = &ring[s0][0][fsy.pos ? c - 2 : c + 1];
             double IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
@@ -299,11 +303,11 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 if (qa == Q_BIZ) { IyL_biz = ad2; IyR_biz = ad2R; } if (qb == Q_BIZ) { IyL_biz = bd2; IyR_biz = bd2R; }
             }
             Dc_s[3][col] = ddiv(IyR_bix - IyL_bix, dy, rdy);        // d(bi_x)/dy -> X
-            Dc_s[4][col] = ddiv(IyR_biz - IyL_biz, dy, rdy);        // d(bi_z)/dy -> X
+            if (Z) Dc_s[4][col] = ddiv(IyR_biz - IyL_biz, dy, rdy); // d(bi_z)/dy -> X
             Dc_s[5][col] = ddiv(IyR_p - IyL_p, dy, rdy);            // d(p)/dy    -> X
             d_d = ddiv(vfyR - vfyL, dy, rdy);                       // d(v_y)/dy
             d_e = ddiv(IyR_vx - IyL_vx, dy, rdy);                   // d(v_x)/dy
-            d_f = ddiv(IyR_vz - IyL_vz, dy, rdy);                   // d(v_z)/dy
+            if (Z) d_f = ddiv(IyR_vz - IyL_vz, dy, rdy);            // d(v_z)/dy
         }
         __syncthreads();                                            // partial results are visible to the other role
 
@@ -317,33 +321,39 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 const double rho = ring[s0][Q_RHO][c];
                 const double dbix_dy = Dc_s[3][col], dbiz_dy = Dc_s[4][col], dp_dy = Dc_s[5][col];
                 const double T_rho = TX_s[Q_RHO][col] + TY_s[Q_RHO][col], T_mx = TX_s[Q_MX][col] + TY_s[Q_MX][col];
-                const double T_my = TX_s[Q_MY][col] + TY_s[Q_MY][col], T_mz = TX_s[Q_MZ][col] + TY_s[Q_MZ][col];
+                const double T_my = TX_s[Q_MY][col] + TY_s[Q_MY][col], T_mz = Z ? TX_s[Q_MZ][col] + TY_s[Q_MZ][col] : 0.0;
                 double k0 = T_rho * -1.0;                                                        // idealmhd.cpp:52
                 const double cdb = ddiv(d_a - dbix_dy, P.fourpi, P.rfourpi);                    // :54
                 const double ncdb = cdb * -1.0;
                 const double czx = dbiz_dy, czy = d_b * -1.0;                                   // curlZ, derivs.cpp:465-469
-                const double bzi = ddiv(biz, P.fourpi, P.rfourpi), bze = ddiv(bez, P.fourpi, P.rfourpi);   // :57-58
-                double k1 = ((((((T_mx * -1.0) - d_c) + rho * g0) + ncdb * bey) + ncdb * biy) + bzi * czy) + bze * czy;                       // :62-66
-                double k2 = ((((((T_my * -1.0) - dp_dy) + rho * g1) + cdb * bex) + cdb * bix) + (bzi * -1.0) * czx) + (bze * -1.0) * czx;   // :67-71
-                const double fze = ddiv(czx * bey - czy * bex, P.fourpi, P.rfourpi);            // :59
-                const double fzi = ddiv(czx * biy - czy * bix, P.fourpi, P.rfourpi);            // :60
-                double k3 = ((T_mz * -1.0) + fze) + fzi;                                        // :72-73
+                double k1, k2, k3 = 0.0;
+                if (Z) {
+                    const double bzi = ddiv(biz, P.fourpi, P.rfourpi), bze = ddiv(bez, P.fourpi, P.rfourpi);   // :57-58
+                    k1 = ((((((T_mx * -1.0) - d_c) + rho * g0) + ncdb * bey) + ncdb * biy) + bzi * czy) + bze * czy;                       // :62-66
+                    k2 = ((((((T_my * -1.0) - dp_dy) + rho * g1) + cdb * bex) + cdb * bix) + (bzi * -1.0) * czx) + (bze * -1.0) * czx;   // :67-71
+                    const double fze = ddiv(czx * bey - czy * bex, P.fourpi, P.rfourpi);        // :59
+                    const double fzi = ddiv(czx * biy - czy * bix, P.fourpi, P.rfourpi);        // :60
+                    k3 = ((T_mz * -1.0) + fze) + fzi;                                           // :72-73
+                } else {                               // be_* = bi_z = 0: the omitted products are exact zeros
+                    k1 = (((T_mx * -1.0) - d_c) + rho * g0) + ncdb * biy;
+                    k2 = (((T_my * -1.0) - dp_dy) + rho * g1) + cdb * bix;
+                }
                 if (!interior) { k0 = 0.0; k1 = 0.0; k2 = 0.0; k3 = 0.0; }                      // ghost mask :99-103
                 for (int t = 0; t < A.n_xterm; t++) {                                           // module RHS terms, in module order
                     const int tg = A.xtarget[t];
                     if (tg <= E_MZ) { const double x = A.xterm[t][off]; if (tg == E_N) k0 = k0 + x; if (tg == E_MX) k1 = k1 + x; if (tg == E_MY) k2 = k2 + x; if (tg == E_MZ) k3 = k3 + x; }
                 }
-                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_N][off] = k0; A.K1[E_MX][off] = k1; A.K1[E_MY][off] = k2; A.K1[E_MZ][off] = k3; }
-                else if (A.kmode == KM_STORE_K2) { A.K2[E_N][off] = k0; A.K2[E_MX][off] = k1; A.K2[E_MY][off] = k2; A.K2[E_MZ][off] = k3; }
-                else if (A.kmode == KM_ADD_K2) { A.K2[E_N][off] = A.K2[E_N][off] + k0; A.K2[E_MX][off] = A.K2[E_MX][off] + k1; A.K2[E_MY][off] = A.K2[E_MY][off] + k2; A.K2[E_MZ][off] = A.K2[E_MZ][off] + k3; }
+                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_N][off] = k0; A.K1[E_MX][off] = k1; A.K1[E_MY][off] = k2; if (Z || A.kmode == KM_EXPORT) A.K1[E_MZ][off] = k3; }
+                else if (A.kmode == KM_STORE_K2) { A.K2[E_N][off] = k0; A.K2[E_MX][off] = k1; A.K2[E_MY][off] = k2; if (Z) A.K2[E_MZ][off] = k3; }
+                else if (A.kmode == KM_ADD_K2) { A.K2[E_N][off] = A.K2[E_N][off] + k0; A.K2[E_MX][off] = A.K2[E_MX][off] + k1; A.K2[E_MY][off] = A.K2[E_MY][off] + k2; if (Z) A.K2[E_MZ][off] = A.K2[E_MZ][off] + k3; }
                 else if (A.kmode == KM_FINAL) {                                                 // evolution.cpp:121
                     k0 = (A.K1[E_N][off] + k0) / 6.0 + A.K2[E_N][off] / 3.0;   k1 = (A.K1[E_MX][off] + k1) / 6.0 + A.K2[E_MX][off] / 3.0;
-                    k2 = (A.K1[E_MY][off] + k2) / 6.0 + A.K2[E_MY][off] / 3.0; k3 = (A.K1[E_MZ][off] + k3) / 6.0 + A.K2[E_MZ][off] / 3.0;
+                    k2 = (A.K1[E_MY][off] + k2) / 6.0 + A.K2[E_MY][off] / 3.0; if (Z) k3 = (A.K1[E_MZ][off] + k3) / 6.0 + A.K2[E_MZ][off] / 3.0;
                 }
                 if (A.kmode != KM_EXPORT) {
                     double Un, Umx, Umy, Umz;                                                   // equationset.cpp:226-228
-                    if (A.b_is_s) { Un = rho + k0 * s; Umx = ring[s0][Q_MX][c] + k1 * s; Umy = ring[s0][Q_MY][c] + k2 * s; Umz = ring[s0][Q_MZ][c] + k3 * s; }
-                    else { Un = (B0 * P.m_i) + k0 * s; Umx = B1 + k1 * s; Umy = B2 + k2 * s; Umz = B3 + k3 * s; }
+                    if (A.b_is_s) { Un = rho + k0 * s; Umx = ring[s0][Q_MX][c] + k1 * s; Umy = ring[s0][Q_MY][c] + k2 * s; Umz = Z ? ring[s0][Q_MZ][c] + k3 * s : 0.0; }
+                    else { Un = (B0 * P.m_i) + k0 * s; Umx = B1 + k1 * s; Umy = B2 + k2 * s; Umz = Z ? B3 + k3 * s : 0.0; }
                     double rfl;
                     const double nn = density_floor(P, Un, &rfl);
                     if (A.primary) {
@@ -351,37 +361,44 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                         record_strips(P, A.strip, A.strip_pitch, g, r, j, z, rfl, Umx, Umy, Umz);
                         if (z) { Umx = 0.0; Umy = 0.0; Umz = 0.0; }
                     }
-                    A.D[E_N][off] = nn; A.D[E_MX][off] = Umx; A.D[E_MY][off] = Umy; A.D[E_MZ][off] = Umz;
+                    A.D[E_N][off] = nn; A.D[E_MX][off] = Umx; A.D[E_MY][off] = Umy; if (Z) A.D[E_MZ][off] = Umz;
                     if (A.primary) { Dt_s[0][col] = nn * P.m_i; Dt_s[1][col] = Umx; Dt_s[2][col] = Umy; }
                 }
             } else {
                 const double dvx_dx = Dc_s[0][col], dvy_dx = Dc_s[1][col], dvz_dx = Dc_s[2][col];
                 const double T_e = TX_s[Q_E][col] + TY_s[Q_E][col];
-                const double T_bix = TX_s[Q_BIX][col] + TY_s[Q_BIX][col], T_biy = TX_s[Q_BIY][col] + TY_s[Q_BIY][col], T_biz = TX_s[Q_BIZ][col] + TY_s[Q_BIZ][col];
-                const double T_bex = TX_s[Q_BEX][col] + TY_s[Q_BEX][col], T_bey = TX_s[Q_BEY][col] + TY_s[Q_BEY][col], T_bez = TX_s[Q_BEZ][col] + TY_s[Q_BEZ][col];
+                const double T_bix = TX_s[Q_BIX][col] + TY_s[Q_BIX][col], T_biy = TX_s[Q_BIY][col] + TY_s[Q_BIY][col];
                 double k4 = (T_e * -1.0) - pc * (dvx_dx + d_d);                                 // :75-76
-                const double bxs = bix + bex, bys = biy + bey;
-                double k5 = (((T_bix * -1.0) - T_bex) + bxs * dvx_dx) + bys * d_e;              // :78-80
-                double k6 = (((T_biy * -1.0) - T_bey) + bxs * dvy_dx) + bys * d_d;              // :81-83
-                double k7 = (((T_biz * -1.0) - T_bez) + bxs * dvz_dx) + bys * d_f;              // :84-86
+                double k5, k6, k7 = 0.0;
+                if (Z) {
+                    const double T_biz = TX_s[Q_BIZ][col] + TY_s[Q_BIZ][col];
+                    const double T_bex = TX_s[Q_BEX][col] + TY_s[Q_BEX][col], T_bey = TX_s[Q_BEY][col] + TY_s[Q_BEY][col], T_bez = TX_s[Q_BEZ][col] + TY_s[Q_BEZ][col];
+                    const double bxs = bix + bex, bys = biy + bey;
+                    k5 = (((T_bix * -1.0) - T_bex) + bxs * dvx_dx) + bys * d_e;                 // :78-80
+                    k6 = (((T_biy * -1.0) - T_bey) + bxs * dvy_dx) + bys * d_d;                 // :81-83
+                    k7 = (((T_biz * -1.0) - T_bez) + bxs * dvz_dx) + bys * d_f;                 // :84-86
+                } else {                               // be_* = 0, v_z = 0: T(be_k) and the bi_z equation are exact zeros
+                    k5 = ((T_bix * -1.0) + bix * dvx_dx) + biy * d_e;
+                    k6 = ((T_biy * -1.0) + bix * dvy_dx) + biy * d_d;
+                }
                 if (!interior) { k4 = 0.0; k5 = 0.0; k6 = 0.0; k7 = 0.0; }
                 for (int t = 0; t < A.n_xterm; t++) {
                     const int tg = A.xtarget[t];
                     if (tg > E_MZ) { const double x = A.xterm[t][off]; if (tg == E_E) k4 = k4 + x; if (tg == E_BX) k5 = k5 + x; if (tg == E_BY) k6 = k6 + x; if (tg == E_BZ) k7 = k7 + x; }
                 }
-                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_E][off] = k4; A.K1[E_BX][off] = k5; A.K1[E_BY][off] = k6; A.K1[E_BZ][off] = k7; }
-                else if (A.kmode == KM_STORE_K2) { A.K2[E_E][off] = k4; A.K2[E_BX][off] = k5; A.K2[E_BY][off] = k6; A.K2[E_BZ][off] = k7; }
-                else if (A.kmode == KM_ADD_K2) { A.K2[E_E][off] = A.K2[E_E][off] + k4; A.K2[E_BX][off] = A.K2[E_BX][off] + k5; A.K2[E_BY][off] = A.K2[E_BY][off] + k6; A.K2[E_BZ][off] = A.K2[E_BZ][off] + k7; }
+                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_E][off] = k4; A.K1[E_BX][off] = k5; A.K1[E_BY][off] = k6; if (Z || A.kmode == KM_EXPORT) A.K1[E_BZ][off] = k7; }
+                else if (A.kmode == KM_STORE_K2) { A.K2[E_E][off] = k4; A.K2[E_BX][off] = k5; A.K2[E_BY][off] = k6; if (Z) A.K2[E_BZ][off] = k7; }
+                else if (A.kmode == KM_ADD_K2) { A.K2[E_E][off] = A.K2[E_E][off] + k4; A.K2[E_BX][off] = A.K2[E_BX][off] + k5; A.K2[E_BY][off] = A.K2[E_BY][off] + k6; if (Z) A.K2[E_BZ][off] = A.K2[E_BZ][off] + k7; }
                 else if (A.kmode == KM_FINAL) {
                     k4 = (A.K1[E_E][off] + k4) / 6.0 + A.K2[E_E][off] / 3.0;   k5 = (A.K1[E_BX][off] + k5) / 6.0 + A.K2[E_BX][off] / 3.0;
-                    k6 = (A.K1[E_BY][off] + k6) / 6.0 + A.K2[E_BY][off] / 3.0; k7 = (A.K1[E_BZ][off] + k7) / 6.0 + A.K2[E_BZ][off] / 3.0;
+                    k6 = (A.K1[E_BY][off] + k6) / 6.0 + A.K2[E_BY][off] / 3.0; if (Z) k7 = (A.K1[E_BZ][off] + k7) / 6.0 + A.K2[E_BZ][off] / 3.0;
                 }
                 if (A.kmode != KM_EXPORT) {
                     double Ue, Ubx, Uby, Ubz;
-                    if (A.b_is_s) { Ue = ring[s0][Q_E][c] + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = biz + k7 * s; }
-                    else { Ue = g0 + k4 * s; Ubx = g1 + k5 * s; Uby = B0 + k6 * s; Ubz = B1 + k7 * s; }     // Y's base values were prefetched into g0, g1, B0, B1
+                    if (A.b_is_s) { Ue = ring[s0][Q_E][c] + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = Z ? biz + k7 * s : 0.0; }
+                    else { Ue = g0 + k4 * s; Ubx = g1 + k5 * s; Uby = B0 + k6 * s; Ubz = Z ? B1 + k7 * s : 0.0; }     // Y's base values were prefetched into g0, g1, B0, B1
                     const double e1 = smax(Ue, P.e_min);
-                    A.D[E_E][off] = e1; A.D[E_BX][off] = Ubx; A.D[E_BY][off] = Uby; A.D[E_BZ][off] = Ubz;
+                    A.D[E_E][off] = e1; A.D[E_BX][off] = Ubx; A.D[E_BY][off] = Uby; if (Z) A.D[E_BZ][off] = Ubz;
                     if (A.primary && interior) {                                                 // dt of this cell: evaluated after the next barrier
                         dt_pending = true; dt_e = e1; dt_bx = bex + Ubx; dt_by = bey + Uby; dt_bz = bez + Ubz; dt_dx = dx; dt_rdx = rdx;
                     }
