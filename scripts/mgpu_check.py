@@ -57,8 +57,8 @@ if two_fluid:
 elif modules:
     s = synthetic.stratified_loop(nx, ny, bump=0.5)
     kw = dict(xb=("periodic", "periodic") if xbound == "periodic" else (xbound, "open"), yb=("fixed", "fixed"), integrator=integ)
-elif xbound == "periodic":
-    s = synthetic.orszag_tang(nx, ny, zfull=True)
+elif xbound in ("periodic", "periodic2d"):
+    s = synthetic.orszag_tang(nx, ny, zfull=(xbound == "periodic"))       # periodic2d: zero z system / external field -> the 2-D kernel instance
     kw = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator=integ, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
 else:
     s = synthetic.stratified_loop(nx, ny)
