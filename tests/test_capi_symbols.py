@@ -70,3 +70,40 @@ def test_rank1_cell_size_validation():
     dx[2, 3] *= 1.0001
     with pytest.raises(capi.SpruceError):
         domain.rank1_cell_sizes(dx, dy)
+
+
+def test_create_argument_errors_mirror_the_reference_messages():
+    """spruce_domain_create validates its arguments before it touches a device: the messages are the reference's own
+    (plasmadomain.cpp:140 'Grid too small for ghost zones', evolution.cpp 'Boundary cond'n must be defined') or name the unbuilt feature."""
+    import ctypes as C
+    from spruce_b200 import capi
+    L = capi.load()
+
+    def create(**kw):
+        base = dict(abi_version=capi.ABI_VERSION, equation_set=0, xdim=16, ydim=12, x_bound_1=0, x_bound_2=0, y_bound_1=0, y_bound_2=0, time_integrator=1,
+                    device=-1, row0=0, nx_local=16, rank=0, n_ranks=1, ion_mass=1.6726e-24, adiabatic_index=5.0 / 3.0, epsilon=0.2, density_min=1.0,
+                    temp_min=1.0, thermal_energy_min=1e-30, open_boundary_strength=1.0, open_boundary_decay_base=0.5, time=0.0)
+        base.update(kw)
+        cfg = capi.Config(**base)
+        h = C.c_void_p()
+        rc = L.spruce_domain_create(C.byref(cfg), C.byref(h))
+        return rc, L.spruce_last_error().decode()
+
+    rc, msg = create(abi_version=capi.ABI_VERSION + 7)
+    assert rc != 0 and "ABI version" in msg
+    rc, msg = create(xdim=4, nx_local=4)
+    assert rc != 0 and "Grid too small for ghost zones" in msg
+    rc, msg = create(x_bound_1=9)
+    assert rc != 0 and "Boundary cond'n must be defined" in msg
+    rc, msg = create(y_bound_2=capi.BC["open_moc"])
+    assert rc != 0 and "open_moc" in msg
+    rc, msg = create(equation_set=1)
+    assert rc != 0 and "equation set" in msg
+    rc, msg = create(equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["open"])
+    assert rc != 0 and "open boundaries" in msg
+    rc, msg = create(equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["open_ucnp"], y_bound_1=capi.BC["fixed"])
+    assert rc != 0 and "open_ucnp mixed" in msg
+    rc, msg = create(n_ranks=4, row0=12, nx_local=8)
+    assert rc != 0 and "bad slab" in msg
+    rc, msg = create(time_integrator=7)
+    assert rc != 0 and "time integrator" in msg
