@@ -267,9 +267,9 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     dim3 grid((d->P.ny + CW - 1) / CW, gy);
     if (d->stage_kernel == 5) {
         const ActiveList L = active_quantities(d);
-        if (d->static_lists && L.n == 6 && L.q == XY_LIST_2D) k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, L);
-        else if (d->static_lists && L.n == 12 && L.q == XY_LIST_FULL) k_mhd_stage_xy<12, XY_LIST_FULL><<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, L);
-        else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, XY_SMEM, st>>>(d->P, A, L);
+        if (d->static_lists && L.n == 6 && L.q == XY_LIST_2D) k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, xy_smem_bytes(xy_rows(6)), st>>>(d->P, A, L);
+        else if (d->static_lists && L.n == 12 && L.q == XY_LIST_FULL) k_mhd_stage_xy<12, XY_LIST_FULL><<<grid, XY_NT, xy_smem_bytes(NTR), st>>>(d->P, A, L);
+        else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, xy_smem_bytes(NTR), st>>>(d->P, A, L);
     }
     else k_mhd_stage<<<grid, NT, STAGE_SMEM, st>>>(d->P, A);
     d->launches++;
@@ -905,9 +905,9 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
 
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XY_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(xy_rows(6))));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;

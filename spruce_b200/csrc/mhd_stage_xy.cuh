@@ -26,18 +26,21 @@ constexpr int XY_CHUNK = 48;                 // rows per CTA (upper bound)
 constexpr int XY_XT = XY_CHUNK + 6;          // x-table entries: local rows -3 .. chunk+2
 constexpr int XW = 64;                       // width of the per-column exchange arrays: one private slot per (warp column, lane)
 // shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, x / y parts of the transports,
-// derivative exchange, dt exchange (read by the Y warps one iteration later, before the X warps overwrite it)
-constexpr int XY_OFF_RING = 0;
-constexpr int XY_OFF_VEL = XY_OFF_RING + RD * NTR * SW;
-constexpr int XY_OFF_XT = XY_OFF_VEL + XY_RV * 3 * SW;
-constexpr int XY_OFF_FX = XY_OFF_XT + 7 * XY_XT;
-constexpr int XY_OFF_TX = XY_OFF_FX + NTR * XW;
-constexpr int XY_OFF_TY = XY_OFF_TX + NTR * XW;
-constexpr int XY_OFF_DC = XY_OFF_TY + NTR * XW;
-constexpr int XY_OFF_DT = XY_OFF_DC + 3 * XW;               // aliases Dc_s[3..5]: a thread reads its Dc/Dt slot before it overwrites it
-constexpr int XY_DOUBLES = XY_OFF_DC + 6 * XW;
-constexpr size_t XY_SMEM = (size_t)XY_DOUBLES * sizeof(double);
-static_assert(XY_SMEM <= 57344, "four CTAs per SM need <= 56 KB each");
+// derivative exchange, dt exchange (read by the Y warps one iteration later, before the X warps overwrite it).
+// nq = quantity rows kept in the ring and in the per-quantity exchange arrays: all 11, or only the 6 of the 2-D instance.
+__host__ __device__ constexpr int xy_off_vel(int nq) { return RD * nq * SW; }
+__host__ __device__ constexpr int xy_off_xt(int nq) { return xy_off_vel(nq) + XY_RV * 3 * SW; }
+__host__ __device__ constexpr int xy_off_fx(int nq) { return xy_off_xt(nq) + 7 * XY_XT; }
+__host__ __device__ constexpr int xy_off_tx(int nq) { return xy_off_fx(nq) + nq * XW; }
+__host__ __device__ constexpr int xy_off_ty(int nq) { return xy_off_tx(nq) + nq * XW; }
+__host__ __device__ constexpr int xy_off_dc(int nq) { return xy_off_ty(nq) + nq * XW; }
+__host__ __device__ constexpr int xy_off_dt(int nq) { return xy_off_dc(nq) + 3 * XW; }             // aliases Dc_s[3..5]: a thread reads its Dc/Dt slot before it overwrites it
+__host__ __device__ constexpr int xy_doubles(int nq) { return xy_off_dc(nq) + 6 * XW; }
+__host__ __device__ constexpr size_t xy_smem_bytes(int nq) { return (size_t)xy_doubles(nq) * sizeof(double); }
+__host__ __device__ constexpr int xy_rows(int ln) { return ln == 6 ? 6 : NTR; }
+__host__ __device__ constexpr int xy_ctas_per_sm(int ln) { return ln == 6 ? 5 : 4; }               // the 2-D instance: 36 KB of shared memory and <= 96 registers -> 20 warps / SM
+static_assert(xy_smem_bytes(NTR) <= 57344, "four CTAs per SM need <= 56 KB each");
+static_assert(xy_smem_bytes(6) <= 45000, "five CTAs per SM need <= 45 KB each");
 
 struct ActiveList { int n; unsigned long long q; };   // transported quantities that can be non-zero (one nibble each), padded to an even count
 
@@ -54,7 +57,7 @@ constexpr unsigned long long XY_LIST_2D = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX,
 constexpr unsigned long long XY_LIST_FULL = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY, Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_BEZ);   // everything (padded to 12)
 
 template <int LN, unsigned long long LQ>
-__global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
+__global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
 {
     constexpr int UNR = LN > 0 ? LN : 1;
     // Z: the z system (mom_z, bi_z, v_z) and the external field can be non-zero.  In the 2-D instance (LN == 6) they are exact zeros in the
@@ -66,14 +69,21 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
     L.q = LN > 0 ? LQ : Larg.q;
     extern __shared__ __align__(16) double smem[];
     if (*A.done_ptr) return;
-    double (*ring)[NTR][SW] = reinterpret_cast<double (*)[NTR][SW]>(smem + XY_OFF_RING);
-    double (*vel)[3][SW] = reinterpret_cast<double (*)[3][SW]>(smem + XY_OFF_VEL);
-    double (*xt)[XY_XT] = reinterpret_cast<double (*)[XY_XT]>(smem + XY_OFF_XT);
-    double (*Fx_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_FX);
-    double (*TX_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_TX);     // x parts of transportDivergence2D, every quantity
-    double (*TY_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_TY);     // y parts
-    double (*Dc_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_DC);
-    double (*Dt_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + XY_OFF_DT);
+    constexpr int NQ = xy_rows(LN);
+    // row of quantity q inside a ring slot / an exchange array: identity, or the compact order rho, mom_x, mom_y, e, bi_x, bi_y of the 2-D instance
+    auto QI = [](int q) { return LN == 6 ? (q < Q_MZ ? q : q - 1) : q; };
+    double *ringp = smem;
+    double (*vel)[3][SW] = reinterpret_cast<double (*)[3][SW]>(smem + xy_off_vel(NQ));
+    double (*xt)[XY_XT] = reinterpret_cast<double (*)[XY_XT]>(smem + xy_off_xt(NQ));
+    double *Fx_p = smem + xy_off_fx(NQ);                                          // [quantity row][XW]
+    double *TX_p = smem + xy_off_tx(NQ);                                          // x parts of transportDivergence2D, every quantity
+    double *TY_p = smem + xy_off_ty(NQ);                                          // y parts
+    double (*Dc_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_dc(NQ));
+    double (*Dt_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_dt(NQ));
+#define RG(sl, q, cc) ringp[((sl) * NQ + QI(q)) * SW + (cc)]
+#define FXS(q, cc) Fx_p[QI(q) * XW + (cc)]
+#define TXS(q, cc) TX_p[QI(q) * XW + (cc)]
+#define TYS(q, cc) TY_p[QI(q) * XW + (cc)]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool isX = warp < 2;
@@ -107,33 +117,33 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             if (LN == 6) {
                 // 2-D list: mom_z, bi_z and the external field are identically zero planes (host-tracked); their ring rows are zeroed
                 // once in the prologue and never loaded
-                cp_async8(&ring[slot][Q_RHO][tid], A.S[E_N] + off); cp_async8(&ring[slot][Q_MX][tid], A.S[E_MX] + off);
-                cp_async8(&ring[slot][Q_MY][tid], A.S[E_MY] + off); cp_async8(&ring[slot][Q_E][tid], A.S[E_E] + off);
-                cp_async8(&ring[slot][Q_BIX][tid], A.S[E_BX] + off); cp_async8(&ring[slot][Q_BIY][tid], A.S[E_BY] + off);
+                cp_async8(&RG(slot, Q_RHO, tid), A.S[E_N] + off); cp_async8(&RG(slot, Q_MX, tid), A.S[E_MX] + off);
+                cp_async8(&RG(slot, Q_MY, tid), A.S[E_MY] + off); cp_async8(&RG(slot, Q_E, tid), A.S[E_E] + off);
+                cp_async8(&RG(slot, Q_BIX, tid), A.S[E_BX] + off); cp_async8(&RG(slot, Q_BIY, tid), A.S[E_BY] + off);
             } else {
 #pragma unroll
-                for (int v = 0; v < NEV; v++) cp_async8(&ring[slot][v][tid], A.S[v] + off);
-                cp_async8(&ring[slot][Q_BEX][tid], A.st[S_BEX] + off);
-                cp_async8(&ring[slot][Q_BEY][tid], A.st[S_BEY] + off);
-                cp_async8(&ring[slot][Q_BEZ][tid], A.st[S_BEZ] + off);
+                for (int v = 0; v < NEV; v++) cp_async8(&RG(slot, v, tid), A.S[v] + off);
+                cp_async8(&RG(slot, Q_BEX, tid), A.st[S_BEX] + off);
+                cp_async8(&RG(slot, Q_BEY, tid), A.st[S_BEY] + off);
+                cp_async8(&RG(slot, Q_BEZ, tid), A.st[S_BEZ] + off);
             }
         } else if (LN == 6) {
-            ring[slot][Q_RHO][tid] = 1.0; ring[slot][Q_MX][tid] = 0.0; ring[slot][Q_MY][tid] = 0.0;
-            ring[slot][Q_E][tid] = 0.0; ring[slot][Q_BIX][tid] = 0.0; ring[slot][Q_BIY][tid] = 0.0;
+            RG(slot, Q_RHO, tid) = 1.0; RG(slot, Q_MX, tid) = 0.0; RG(slot, Q_MY, tid) = 0.0;
+            RG(slot, Q_E, tid) = 0.0; RG(slot, Q_BIX, tid) = 0.0; RG(slot, Q_BIY, tid) = 0.0;
         } else {
 #pragma unroll
-            for (int v = 0; v < NTR; v++) ring[slot][v][tid] = (v == Q_RHO) ? 1.0 : 0.0;
+            for (int v = 0; v < NTR; v++) RG(slot, v, tid) = (v == Q_RHO) ? 1.0 : 0.0;
         }
     };
-    auto convert_rho = [&](int s_) { if (loader) { ring[s_][Q_RHO][tid] = ring[s_][Q_RHO][tid] * P.m_i; } };   // idealmhd.cpp:247
+    auto convert_rho = [&](int s_) { if (loader) { RG(s_, Q_RHO, tid) = RG(s_, Q_RHO, tid) * P.m_i; } };   // idealmhd.cpp:247
     // v = mom / rho (idealmhd.cpp:248-250): one IEEE reciprocal, then the exact-division correction per component (exact_math.cuh)
     auto form_vel = [&](int s_, int v_) {
         if (!loader) return;
-        const double rho = ring[s_][Q_RHO][tid];
+        const double rho = RG(s_, Q_RHO, tid);
         const double rr = 1.0 / rho;
-        vel[v_][0][tid] = ddiv(ring[s_][Q_MX][tid], rho, rr);
-        vel[v_][1][tid] = ddiv(ring[s_][Q_MY][tid], rho, rr);
-        vel[v_][2][tid] = (LN == 6) ? 0.0 : ddiv(ring[s_][Q_MZ][tid], rho, rr);      // the 2-D list is only chosen when mom_z is identically zero
+        vel[v_][0][tid] = ddiv(RG(s_, Q_MX, tid), rho, rr);
+        vel[v_][1][tid] = ddiv(RG(s_, Q_MY, tid), rho, rr);
+        vel[v_][2][tid] = (LN == 6) ? 0.0 : ddiv(RG(s_, Q_MZ, tid), rho, rr);      // the 2-D list is only chosen when mom_z is identically zero
     };
 
     const double step = *A.step_ptr;
@@ -148,14 +158,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const int t = e / XY_XT, i = e - t * XY_XT;
             if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
         }
-        for (int e = tid; e < 3 * NTR * XW + 6 * XW; e += XY_NT) (&Fx_s[0][0])[e] = 0.0;      // Fx_s, TX_s, TY_s, Dc_s are contiguous
-        if (LN == 6 && loader) {
-            const int zq[5] = {Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ};
-#pragma unroll
-            for (int sl = 0; sl < RD; sl++)
-#pragma unroll
-                for (int k = 0; k < 5; k++) ring[sl][zq[k]][tid] = 0.0;
-        }
+        for (int e = tid; e < 3 * NQ * XW + 6 * XW; e += XY_NT) Fx_p[e] = 0.0;              // Fx, TX, TY, Dc are contiguous
     }
     auto x_geom = [&](int f) {
         const int i = f - r0 + 3;
@@ -189,14 +192,14 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         cVfx = face_interp(vel[vm1][0][c], vel[v0][0][c], g.hm1, g.h0, g.fs, g.rfs);
         cIx_vy = face_interp(vel[vm1][1][c], vel[v0][1][c], g.hm1, g.h0, g.fs, g.rfs);
         if (Z) cIx_vz = face_interp(vel[vm1][2][c], vel[v0][2][c], g.hm1, g.h0, g.fs, g.rfs);
-        cIx_p = face_interp(ring[sm1][Q_E][c] * P.gm1, ring[s0][Q_E][c] * P.gm1, g.hm1, g.h0, g.fs, g.rfs);
+        cIx_p = face_interp(RG(sm1, Q_E, c) * P.gm1, RG(s0, Q_E, c) * P.gm1, g.hm1, g.h0, g.fs, g.rfs);
         const FaceSel fs0 = select_face(g, cVfx);
 #pragma unroll UNR
         for (int k = 0; k < L.n; k++) {
             const int q = (int)((L.q >> (4 * k)) & 15ULL);
             double d2;
-            const double S = upwind_face_sel(ring[sm2][q][c], ring[sm1][q][c], ring[s0][q][c], ring[sp1][q][c], fs0, &d2);
-            Fx_s[q][fcol] = S * cVfx;
+            const double S = upwind_face_sel(RG(sm2, q, c), RG(sm1, q, c), RG(s0, q, c), RG(sp1, q, c), fs0, &d2);
+            FXS(q, fcol) = S * cVfx;
             if (q == Q_BIY) cIx_biy = d2;
             if (q == Q_BIZ) cIx_biz = d2;
         }
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
         const double dx = xt[5][r - r0 + 3], rdx = xt[6][r - r0 + 3];
         const size_t off = (size_t)r * P.pitch + (col_out ? j : 0);
-        const double pc = ring[s0][Q_E][c] * P.gm1;                 // press = (gamma-1)*thermal_energy  idealmhd.cpp:253
+        const double pc = RG(s0, Q_E, c) * P.gm1;                 // press = (gamma-1)*thermal_energy  idealmhd.cpp:253
 
         // own-cell values from global memory: requested now, consumed after the barrier
         // (no branch on col_out here: lanes without an output column read column 0 of the row -- a divergent branch at this
@@ -244,21 +247,21 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const double vfx1 = face_interp(vel[v0][0][c], vel[v1][0][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
             const double Ix1_vy = face_interp(vel[v0][1][c], vel[v1][1][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
             const double Ix1_vz = Z ? face_interp(vel[v0][2][c], vel[v1][2][c], gx.hm1, gx.h0, gx.fs, gx.rfs) : 0.0;
-            const double Ix1_p = face_interp(pc, ring[sp1][Q_E][c] * P.gm1, gx.hm1, gx.h0, gx.fs, gx.rfs);
+            const double Ix1_p = face_interp(pc, RG(sp1, Q_E, c) * P.gm1, gx.hm1, gx.h0, gx.fs, gx.rfs);
             const FaceSel fsx = select_face(gx, vfx1);
             // the far cell of the extrapolation: row r-1 for flow in +x, row r+2 for flow in -x -- one load from a selected row
-            const double *far_row = &ring[fsx.pos ? sm1 : sp2][0][c];
+            const double *far_row = &RG(fsx.pos ? sm1 : sp2, 0, c);
             double Ix1_biy = 0.0, Ix1_biz = 0.0;
 #pragma unroll UNR
             for (int k = 0; k < L.n; k += 2) {
                 const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
                 double ad2, bd2;
-                const double aS = upwind_face_far(far_row[qa * SW], ring[s0][qa][c], ring[sp1][qa][c], fsx, &ad2);
-                const double bS = upwind_face_far(far_row[qb * SW], ring[s0][qb][c], ring[sp1][qb][c], fsx, &bd2);
+                const double aS = upwind_face_far(far_row[QI(qa) * SW], RG(s0, qa, c), RG(sp1, qa, c), fsx, &ad2);
+                const double bS = upwind_face_far(far_row[QI(qb) * SW], RG(s0, qb, c), RG(sp1, qb, c), fsx, &bd2);
                 const double af1 = aS * vfx1, bf1 = bS * vfx1;
-                const double at = ddiv(af1 - Fx_s[qa][fcol], dx, rdx), bt = ddiv(bf1 - Fx_s[qb][fcol], dx, rdx);   // derivs.cpp:155-156
-                Fx_s[qa][fcol] = af1; Fx_s[qb][fcol] = bf1;
-                TX_s[qa][col] = at;  TX_s[qb][col] = bt;
+                const double at = ddiv(af1 - FXS(qa, fcol), dx, rdx), bt = ddiv(bf1 - FXS(qb, fcol), dx, rdx);   // derivs.cpp:155-156
+                FXS(qa, fcol) = af1; FXS(qb, fcol) = bf1;
+                TXS(qa, col) = at;  TXS(qb, col) = bt;
                 if (qa == Q_BIY) Ix1_biy = ad2; if (qb == Q_BIY) Ix1_biy = bd2;
                 if (qa == Q_BIZ) Ix1_biz = ad2; if (qb == Q_BIZ) Ix1_biz = bd2;
             }
@@ -284,21 +287,21 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const double vfyL = face_interp(vel[v0][1][c - 1], vyc, gy.hm1, gy.h0, gy.fs, gy.rfs);
             const double IyL_vx = face_interp(vel[v0][0][c - 1], vxc, gy.hm1, gy.h0, gy.fs, gy.rfs);
             const double IyL_vz = Z ? face_interp(vel[v0][2][c - 1], vzc, gy.hm1, gy.h0, gy.fs, gy.rfs) : 0.0;
-            const double IyL_p = face_interp(ring[s0][Q_E][c - 1] * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
+            const double IyL_p = face_interp(RG(s0, Q_E, c - 1) * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
             const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = Z ? shfl_next(IyL_vz) : 0.0, IyR_p = shfl_next(IyL_p);
             const FaceSel fsy = select_face(gy, vfyL);
-            const double *far_col = &ring[s0][0][fsy.pos ? c - 2 : c + 1];
+            const double *far_col = &RG(s0, 0, fsy.pos ? c - 2 : c + 1);
             double IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
 #pragma unroll UNR
             for (int k = 0; k < L.n; k += 2) {
                 const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
                 double ad2, bd2;
-                const double aS = upwind_face_far(far_col[qa * SW], ring[s0][qa][c - 1], ring[s0][qa][c], fsy, &ad2);
-                const double bS = upwind_face_far(far_col[qb * SW], ring[s0][qb][c - 1], ring[s0][qb][c], fsy, &bd2);
+                const double aS = upwind_face_far(far_col[QI(qa) * SW], RG(s0, qa, c - 1), RG(s0, qa, c), fsy, &ad2);
+                const double bS = upwind_face_far(far_col[QI(qb) * SW], RG(s0, qb, c - 1), RG(s0, qb, c), fsy, &bd2);
                 const double afL = aS * vfyL, bfL = bS * vfyL;
                 const double afR = shfl_next(afL), bfR = shfl_next(bfL), ad2R = shfl_next(ad2), bd2R = shfl_next(bd2);
-                TY_s[qa][col] = ddiv(afR - afL, dy, rdy);
-                TY_s[qb][col] = ddiv(bfR - bfL, dy, rdy);
+                TYS(qa, col) = ddiv(afR - afL, dy, rdy);
+                TYS(qb, col) = ddiv(bfR - bfL, dy, rdy);
                 if (qa == Q_BIX) { IyL_bix = ad2; IyR_bix = ad2R; } if (qb == Q_BIX) { IyL_bix = bd2; IyR_bix = bd2R; }
                 if (qa == Q_BIZ) { IyL_biz = ad2; IyR_biz = ad2R; } if (qb == Q_BIZ) { IyL_biz = bd2; IyR_biz = bd2R; }
             }
@@ -315,13 +318,13 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
         __syncwarp();
         dt_pending = false;
         if (col_out) {
-            const double bix = ring[s0][Q_BIX][c], biy = ring[s0][Q_BIY][c], biz = ring[s0][Q_BIZ][c];
-            const double bex = ring[s0][Q_BEX][c], bey = ring[s0][Q_BEY][c], bez = ring[s0][Q_BEZ][c];
+            const double bix = RG(s0, Q_BIX, c), biy = RG(s0, Q_BIY, c), biz = Z ? RG(s0, Q_BIZ, c) : 0.0;
+            const double bex = Z ? RG(s0, Q_BEX, c) : 0.0, bey = Z ? RG(s0, Q_BEY, c) : 0.0, bez = Z ? RG(s0, Q_BEZ, c) : 0.0;
             if (isX) {
-                const double rho = ring[s0][Q_RHO][c];
+                const double rho = RG(s0, Q_RHO, c);
                 const double dbix_dy = Dc_s[3][col], dbiz_dy = Dc_s[4][col], dp_dy = Dc_s[5][col];
-                const double T_rho = TX_s[Q_RHO][col] + TY_s[Q_RHO][col], T_mx = TX_s[Q_MX][col] + TY_s[Q_MX][col];
-                const double T_my = TX_s[Q_MY][col] + TY_s[Q_MY][col], T_mz = Z ? TX_s[Q_MZ][col] + TY_s[Q_MZ][col] : 0.0;
+                const double T_rho = TXS(Q_RHO, col) + TYS(Q_RHO, col), T_mx = TXS(Q_MX, col) + TYS(Q_MX, col);
+                const double T_my = TXS(Q_MY, col) + TYS(Q_MY, col), T_mz = Z ? TXS(Q_MZ, col) + TYS(Q_MZ, col) : 0.0;
                 double k0 = T_rho * -1.0;                                                        // idealmhd.cpp:52
                 const double cdb = ddiv(d_a - dbix_dy, P.fourpi, P.rfourpi);                    // :54
                 const double ncdb = cdb * -1.0;
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 }
                 if (A.kmode != KM_EXPORT) {
                     double Un, Umx, Umy, Umz;                                                   // equationset.cpp:226-228
-                    if (A.b_is_s) { Un = rho + k0 * s; Umx = ring[s0][Q_MX][c] + k1 * s; Umy = ring[s0][Q_MY][c] + k2 * s; Umz = Z ? ring[s0][Q_MZ][c] + k3 * s : 0.0; }
+                    if (A.b_is_s) { Un = rho + k0 * s; Umx = RG(s0, Q_MX, c) + k1 * s; Umy = RG(s0, Q_MY, c) + k2 * s; Umz = Z ? RG(s0, Q_MZ, c) + k3 * s : 0.0; }
                     else { Un = (B0 * P.m_i) + k0 * s; Umx = B1 + k1 * s; Umy = B2 + k2 * s; Umz = Z ? B3 + k3 * s : 0.0; }
                     double rfl;
                     const double nn = density_floor(P, Un, &rfl);
@@ -366,13 +369,13 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 }
             } else {
                 const double dvx_dx = Dc_s[0][col], dvy_dx = Dc_s[1][col], dvz_dx = Dc_s[2][col];
-                const double T_e = TX_s[Q_E][col] + TY_s[Q_E][col];
-                const double T_bix = TX_s[Q_BIX][col] + TY_s[Q_BIX][col], T_biy = TX_s[Q_BIY][col] + TY_s[Q_BIY][col];
+                const double T_e = TXS(Q_E, col) + TYS(Q_E, col);
+                const double T_bix = TXS(Q_BIX, col) + TYS(Q_BIX, col), T_biy = TXS(Q_BIY, col) + TYS(Q_BIY, col);
                 double k4 = (T_e * -1.0) - pc * (dvx_dx + d_d);                                 // :75-76
                 double k5, k6, k7 = 0.0;
                 if (Z) {
-                    const double T_biz = TX_s[Q_BIZ][col] + TY_s[Q_BIZ][col];
-                    const double T_bex = TX_s[Q_BEX][col] + TY_s[Q_BEX][col], T_bey = TX_s[Q_BEY][col] + TY_s[Q_BEY][col], T_bez = TX_s[Q_BEZ][col] + TY_s[Q_BEZ][col];
+                    const double T_biz = TXS(Q_BIZ, col) + TYS(Q_BIZ, col);
+                    const double T_bex = TXS(Q_BEX, col) + TYS(Q_BEX, col), T_bey = TXS(Q_BEY, col) + TYS(Q_BEY, col), T_bez = TXS(Q_BEZ, col) + TYS(Q_BEZ, col);
                     const double bxs = bix + bex, bys = biy + bey;
                     k5 = (((T_bix * -1.0) - T_bex) + bxs * dvx_dx) + bys * d_e;                 // :78-80
                     k6 = (((T_biy * -1.0) - T_bey) + bxs * dvy_dx) + bys * d_d;                 // :81-83
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
                 }
                 if (A.kmode != KM_EXPORT) {
                     double Ue, Ubx, Uby, Ubz;
-                    if (A.b_is_s) { Ue = ring[s0][Q_E][c] + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = Z ? biz + k7 * s : 0.0; }
+                    if (A.b_is_s) { Ue = RG(s0, Q_E, c) + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = Z ? biz + k7 * s : 0.0; }
                     else { Ue = g0 + k4 * s; Ubx = g1 + k5 * s; Uby = B0 + k6 * s; Ubz = Z ? B1 + k7 * s : 0.0; }     // Y's base values were prefetched into g0, g1, B0, B1
                     const double e1 = smax(Ue, P.e_min);
                     A.D[E_E][off] = e1; A.D[E_BX][off] = Ubx; A.D[E_BY][off] = Uby; if (Z) A.D[E_BZ][off] = Ubz;
@@ -416,8 +419,12 @@ __global__ void __launch_bounds__(XY_NT, 4) k_mhd_stage_xy(const DomainParams P,
             const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
             dtmin_local = smin(dtmin_local, dtc);
         }
-        block_min_impl(dtmin_local, A.dtmin_bits, reinterpret_cast<unsigned long long *>(&TX_s[0][0]));   // TX_s is dead after the last barrier
+        block_min_impl(dtmin_local, A.dtmin_bits, reinterpret_cast<unsigned long long *>(TX_p));   // the TX array is dead after the last barrier
     }
 }
+#undef RG
+#undef FXS
+#undef TXS
+#undef TYS
 
 }  // namespace spruce
