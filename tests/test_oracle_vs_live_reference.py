@@ -1,0 +1,99 @@
+"""The oracle against LIVE runs of the unmodified reference binary (oracle/_ref/run, built from the reference's own sources by
+oracle/Makefile and shipped with the repo): a seeded sweep over boundary-condition combinations, integrators, floors and
+generators beyond the committed fixtures.  Step-size history and every output plane must agree bit for bit.
+CPU only; a few seconds per case (the reference is run on grids of a few hundred cells)."""
+import itertools
+import shutil
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from golden_util import mismatch, same_bits
+from oracle import refrun
+from oracle.oracle import Oracle, Oracle2F
+from spruce_b200 import synthetic
+
+pytestmark = pytest.mark.skipif(not refrun.have_reference(), reason="oracle/_ref/run is not built")
+
+MHD_OUT = ["rho", "temp", "thermal_energy", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "dt"]
+TF_OUT = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy", "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z", "dt", "dt_i", "j_x", "divE"]
+
+
+def run_reference(state, cfg_kw, out_vars, nsteps):
+    tmp = Path(tempfile.mkdtemp(prefix="live_ref_"))
+    try:
+        refrun.write_state(tmp / "in.state", state["planes"], state["ion_mass"], state["adiabatic_index"])
+        cfg = refrun.ideal_mhd_config(max_iterations=nsteps, output_flags=out_vars, **cfg_kw)
+        refrun.run_reference(tmp / "in.state", cfg, tmp / "out", threads=2)
+        _, frames = refrun.read_out(tmp / "out" / "mhd.out")
+        return frames
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def interior(xb, yb, nx, ny):
+    return (0 if xb[0] == "periodic" else 2, nx - 1 if xb[1] == "periodic" else nx - 3, 0 if yb[0] == "periodic" else 2, ny - 1 if yb[1] == "periodic" else ny - 3)
+
+
+def mhd_cases():
+    rng = np.random.default_rng(20261017)
+    sides = ["periodic", "open", "fixed", "reflect", "open_ucnp"]
+    out = []
+    for k in range(8):
+        xb = ("periodic", "periodic") if rng.random() < 0.3 else tuple(rng.choice(sides[1:], 2))
+        yb = ("periodic", "periodic") if rng.random() < 0.3 else tuple(rng.choice(sides[1:], 2))
+        out.append((k, tuple(map(str, xb)), tuple(map(str, yb)), str(rng.choice(["euler", "rk2", "rk4"])), int(rng.integers(18, 30)), int(rng.integers(17, 27)),
+                    bool(rng.random() < 0.5), float(rng.choice([1.0e7, 3.0e8]))))
+    return out
+
+
+@pytest.mark.parametrize("k,xb,yb,integrator,nx,ny,loop,nmin", mhd_cases())
+def test_ideal_mhd_oracle_equals_live_reference(k, xb, yb, integrator, nx, ny, loop, nmin):
+    s = synthetic.stratified_loop(nx, ny) if loop else synthetic.orszag_tang(nx, ny, zfull=True)
+    floors = dict(density_min=nmin, temp_min=1.0e4, thermal_energy_min=1.0e-6) if loop else dict(density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 3
+    frames = run_reference(s, kw, MHD_OUT, nsteps)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for it in range(1, nsteps + 1):
+        step = o.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "case %d iteration %d: step %s vs %s" % (k, it, step.hex(), float(ref_step).hex())
+    for v in MHD_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "case %d %s: %s" % (k, v, mismatch(o.get(v), frames[nsteps][v]))
+    o.close()
+
+
+def tf_cases():
+    rng = np.random.default_rng(4242)
+    sides = ["periodic", "fixed", "reflect", "open_ucnp"]        # `open` aborts in the reference for a two-fluid set
+    out = []
+    for k in range(6):
+        xb = ("periodic", "periodic") if rng.random() < 0.3 else tuple(rng.choice(sides[1:], 2))
+        yb = ("periodic", "periodic") if rng.random() < 0.3 else tuple(rng.choice(sides[1:], 2))
+        out.append((k, tuple(map(str, xb)), tuple(map(str, yb)), str(rng.choice(["euler", "rk2", "rk4"])), int(rng.integers(17, 28)), int(rng.integers(17, 26)),
+                    bool(rng.random() < 0.5), bool(rng.random() < 0.3)))
+    return out
+
+
+@pytest.mark.parametrize("k,xb,yb,integrator,nx,ny,eic,rct", tf_cases())
+def test_two_fluid_oracle_equals_live_reference(k, xb, yb, integrator, nx, ny, eic, rct):
+    """Includes open_ucnp sides next to fixed / reflect sides (the ghost-pass ordering the device path does not build yet)."""
+    s = synthetic.ucnp_cloud(nx, ny, drift=2.0e3, bfield=5.0)
+    floors = dict(density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    block = [("use_sub_cycling", "false")] + ([("remove_curl_terms", "true")] if rct else [])
+    kw = dict(xb=xb, yb=yb, integrator=integrator, eqs="ideal_2F", eqs_block=block, modules=[("eic_thermalization", [])] if eic else [], **floors)
+    nsteps = 3
+    frames = run_reference(s, kw, TF_OUT, nsteps)
+    o = Oracle2F(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, remove_curl_terms=rct, eic=eic, **floors)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for it in range(1, nsteps + 1):
+        step = o.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "case %d iteration %d: step %s vs %s" % (k, it, step.hex(), float(ref_step).hex())
+    for v in TF_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "case %d %s: %s" % (k, v, mismatch(o.get(v), frames[nsteps][v]))
+    o.close()
