@@ -97,3 +97,45 @@ def test_two_fluid_oracle_equals_live_reference(k, xb, yb, integrator, nx, ny, e
     for v in TF_OUT:
         assert same_bits(o.get(v), frames[nsteps][v]), "case %d %s: %s" % (k, v, mismatch(o.get(v), frames[nsteps][v]))
     o.close()
+
+
+MODULE_SETS = [
+    ("tc_unsat_rk4+rl_rk2", [("thermal_conduction", dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4", time_integrator="rk4")),
+                             ("radiative_losses", dict(cutoff_ramp="1.0e3", cutoff_temp="3.0e4", epsilon="0.1", time_integrator="rk2"))], ("periodic", "periodic"), ("fixed", "open"), "rk2"),
+    ("rl_euler+ah+tc_sat", [("radiative_losses", dict(cutoff_ramp="1.0e3", cutoff_temp="3.0e4", epsilon="0.1")), ("ambient_heating", dict(heating_rate="2.0e-4")),
+                            ("thermal_conduction", dict(flux_saturation="true", epsilon="0.1", dt_subcycle_min="1.0e-4", time_integrator="rk2"))], ("reflect", "open"), ("fixed", "fixed"), "euler"),
+    ("pv_rk2+tc", [("physical_viscosity", dict(coeff="5.0e-15", epsilon="0.1", time_integrator="rk2", ramp_length="5.0e8")),
+                   ("thermal_conduction", dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4"))], ("periodic", "periodic"), ("reflect", "fixed"), "rk4"),
+    ("av_mixed", [("artificial_viscosity", dict(visc_opt="global,local,boundary", visc_strength="0.4,2.2,0.7", visc_vars_to_diff="v_x,v_y,temp", visc_vars_to_evol="mom_x,mom_y,thermal_energy",
+                                                visc_length="0,0,6.0e8", visc_species="i,i,i", hv_time_integrator="rk4", gradient_correction="true"))], ("fixed", "open"), ("reflect", "open"), "rk2"),
+]
+
+
+@pytest.mark.parametrize("name,modules,xb,yb,integrator", MODULE_SETS, ids=[m[0] for m in MODULE_SETS])
+def test_module_oracle_equals_live_reference(name, modules, xb, yb, integrator):
+    """Module restatements (glibc libm on both sides) against live reference runs: bit for bit, module order = config order."""
+    from golden_util import module_kwargs, physical_viscosity_coefficient, viscosity_terms_with_profiles
+    nx, ny = 26, 23
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 3
+    frames = run_reference(s, dict(kw, modules=[(m, list(kv.items())) for m, kv in modules]), MHD_OUT, nsteps)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    for m, kv in modules:
+        a = module_kwargs(m, kv)
+        if m == "artificial_viscosity":
+            o.set_viscosity(viscosity_terms_with_profiles(s["planes"], a.pop("terms")), **a)
+        elif m == "physical_viscosity":
+            ramp = a.pop("ramp_length"); a.pop("buffer_length")
+            o.set_physical_viscosity(physical_viscosity_coefficient(s["planes"], a["coeff"], ramp), **a)
+        else:
+            getattr(o, "set_" + m)(**a)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for it in range(1, nsteps + 1):
+        step = o.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "%s iteration %d: step %s vs %s" % (name, it, step.hex(), float(ref_step).hex())
+    for v in MHD_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
+    o.close()
