@@ -54,6 +54,7 @@ def lib():
         L.oracle_set_radiative_losses.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.oracle_set_viscosity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2f_create.restype = C.c_void_p
         L.oracle2f_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -135,6 +136,9 @@ class Oracle:
 
     def subcycles(self, which) -> int:
         return lib().oracle_subcycles(self.h, {"thermal_conduction": 1, "radiative_losses": 2, "physical_viscosity": 5}[which])
+
+    def set_global_viscosity(self, v: float):
+        lib().oracle_set_global_viscosity(self.h, v)
 
     def set_physical_viscosity(self, coeff_plane, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False, integrator="euler",
                                inactive_mode=False):

@@ -65,6 +65,7 @@ typedef struct oracle {
     int xb1, xb2, yb1, yb2, integrator;
     int xl, xu, yl, yu;
     double m_i, gamma, epsilon, n_min, T_min, e_min, open_strength, open_decay;
+    double global_viscosity;    /* IdealMHD m_global_viscosity (idealmhd.hpp:48): only the open_moc boundary uses it */
     double *dx, *dy, *bex, *bey, *bez, *posx, *posy, *mask;
     double *g[NV];
     double t; int iter;
@@ -210,7 +211,10 @@ static void laplacian(const oracle *o, const double *q, double *out)
 
 /* ------------------------------------------------------------------ IdealMHD (source/equationsets/idealmhd.cpp) */
 
-/* idealmhd.cpp:42-105 (no open_moc side: characteristic terms are +0) */
+static int moc_any(const oracle *o);
+static void moc_add_characteristic_evolution(const oracle *o, double *const *G, double **k);
+
+/* idealmhd.cpp:42-105 (without an open_moc side the characteristic terms are +0) */
 static void ideal_mhd_rhs(const oracle *o, double *const *G, double **k /* NEV planes, allocated */)
 {
     const int n = o->n;
@@ -273,7 +277,12 @@ static void ideal_mhd_rhs(const oracle *o, double *const *G, double **k /* NEV p
             k[5 + a][c] = (((tm[c] * -1.0) - te[c]) + (bi[0][c] + be[0][c]) * t[c]) + (bi[1][c] + be[1][c]) * u[c];
     }
     /* mask multiply and (zero) characteristic add :99-103 */
-    for (int v = 0; v < NEV; v++) for (int c = 0; c < n; c++) { k[v][c] *= o->mask[c]; k[v][c] += 0.0; }
+    if (moc_any(o)) {
+        for (int v = 0; v < NEV; v++) for (int c = 0; c < n; c++) k[v][c] *= o->mask[c];
+        moc_add_characteristic_evolution(o, G, k);
+    } else {
+        for (int v = 0; v < NEV; v++) for (int c = 0; c < n; c++) { k[v][c] *= o->mask[c]; k[v][c] += 0.0; }
+    }
     free(t); free(u); free(dbyx); free(dbxy); free(czx); free(czy); free(cdb); free(pgx); free(pgy); free(tm); free(te); free(dvxx); free(dvyy);
 }
 
@@ -459,6 +468,7 @@ static double min_range(const oracle *o, const double *a, int il, int jl, int iu
 
 static void propagate_changes(const oracle *o, double **G, double **P);
 #include "physical_viscosity_oracle.inc"
+#include "moc_oracle.inc"
 
 /* ---- artificial viscosity (source/modules/viscosity.cpp) */
 static int ev_index(int var) { for (int v = 0; v < NEV; v++) if (EVOLVED[v] == var) return v; return -1; }
@@ -761,7 +771,9 @@ static void ah_post_iterate(oracle *o, double dt)
 /* evolution.cpp:59-82 ; returns the step size used */
 static double advance_time(oracle *o)
 {
-    double step = o->epsilon * min_range(o, o->g[V_dt], o->xl, o->yl, o->xu, o->yu);   /* :62 (dt bounds = interior; no open_moc) */
+    /* :62; dt bounds = interior, widened by the ghost zone on open_moc sides (plasmadomain.cpp:155-159) */
+    double step = o->epsilon * min_range(o, o->g[V_dt], o->xl - (o->xb1 == BC_OPEN_MOC ? N_GHOST : 0), o->yl - (o->yb1 == BC_OPEN_MOC ? N_GHOST : 0),
+                                         o->xu + (o->xb2 == BC_OPEN_MOC ? N_GHOST : 0), o->yu + (o->yb2 == BC_OPEN_MOC ? N_GHOST : 0));
     for (int m = 0; m < o->mod.n_modules; m++) {                                         /* preIterate :65 */
         if (o->mod.order[m] == 1) o->mod.tc_nsub = tc_number_subcycles(o, step);
         if (o->mod.order[m] == 2) o->mod.rl_nsub = rl_number_subcycles(o, step);
@@ -891,6 +903,7 @@ void oracle_add_viscosity_term(oracle *o, int opt, double strength, int var_diff
     o->mod.av_strength_grid[i] = NULL;
     if (strength_grid) { o->mod.av_strength_grid[i] = pl_dup(o, strength_grid); }
 }
+void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
 double oracle_step(oracle *o) { return advance_time(o); }
 void oracle_run(oracle *o, int nsteps, double *dt_out) { for (int s = 0; s < nsteps; s++) { double d = advance_time(o); if (dt_out) dt_out[s] = d; } }
 double oracle_time(const oracle *o) { return o->t; }

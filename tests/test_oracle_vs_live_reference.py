@@ -139,3 +139,34 @@ def test_module_oracle_equals_live_reference(name, modules, xb, yb, integrator):
     for v in MHD_OUT:
         assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
     o.close()
+
+
+MOC_CASES = [
+    ("y2_moc_euler", ("periodic", "periodic"), ("fixed", "open_moc"), "euler", 0.0, 26, 23),
+    ("y1_moc_rk2_visc", ("periodic", "periodic"), ("open_moc", "fixed"), "rk2", 0.3, 24, 25),
+    ("x1_moc_rk4", ("open_moc", "reflect"), ("fixed", "open"), "rk4", 0.0, 27, 22),
+    ("x_moc_y_moc_rk2", ("open_moc", "open_moc"), ("open_moc", "open_moc"), "rk2", 0.1, 25, 24),
+    ("x2_moc_y_open_euler", ("fixed", "open_moc"), ("open", "open_moc"), "euler", 0.0, 23, 26),
+]
+
+
+@pytest.mark.parametrize("name,xb,yb,integrator,gvisc,nx,ny", MOC_CASES, ids=[m[0] for m in MOC_CASES])
+def test_open_moc_oracle_equals_live_reference(name, xb, yb, integrator, gvisc, nx, ny):
+    """The method-of-characteristics open boundary (oracle/moc_oracle.inc; not built on the device yet) against live
+    reference runs: characteristic decomposition, inflow replacement, corner handling, widened dt bounds, global_viscosity."""
+    s = synthetic.stratified_loop(nx, ny)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 3
+    frames = run_reference(s, dict(kw, eqs_block=[("global_viscosity", repr(gvisc))]), MHD_OUT, nsteps)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    o.set_global_viscosity(gvisc)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    xl -= 2 * (xb[0] == "open_moc"); xu += 2 * (xb[1] == "open_moc"); yl -= 2 * (yb[0] == "open_moc"); yu += 2 * (yb[1] == "open_moc")
+    for it in range(1, nsteps + 1):
+        step = o.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "%s iteration %d: step %s vs %s" % (name, it, step.hex(), float(ref_step).hex())
+    for v in MHD_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
+    o.close()
