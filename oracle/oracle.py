@@ -54,6 +54,7 @@ def lib():
         L.oracle_set_radiative_losses.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.oracle_set_viscosity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_add_small_module.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2f_create.restype = C.c_void_p
@@ -136,6 +137,19 @@ class Oracle:
 
     def subcycles(self, which) -> int:
         return lib().oracle_subcycles(self.h, {"thermal_conduction": 1, "radiative_losses": 2, "physical_viscosity": 5}[which])
+
+    SMALL = {"ambient_heating_sink": (6, ["heating_rate", "exp_mode", "exp_base_heating_rate", "exp_scale_height", "center_x", "half_width"]),
+             "localized_heating": (7, ["start_time", "duration", "max_heating_rate", "stddev_x", "stddev_y", "center_x", "center_y", "ramp_time"]),
+             "mass_injection": (8, ["start_time", "duration", "max_injection_rate", "stddev_x", "stddev_y", "center_x", "center_y"]),
+             "momentum_injection": (9, ["start_time", "duration", "max_accel", "stddev_x", "stddev_y", "center_x", "center_y", "dir_x", "dir_y", "template_angle", "oscillatory", "oscillation_period"]),
+             "div_cleaning": (10, ["epsilon", "time_scale"]),
+             "field_heating": (11, ["coeff", "current_pow", "b_pow", "n_pow", "roc_pow", "inactive_mode"])}
+
+    def add_small_module(self, name: str, **kw):
+        """Small solar source-term modules (oracle/solar_small_modules_oracle.inc); keyword names = the reference's config keys."""
+        kind, keys = self.SMALL[name]
+        p = np.array([float(kw.get(k, 0.0)) for k in keys])
+        lib().oracle_add_small_module(self.h, kind, _dp(p), p.size)
 
     def set_global_viscosity(self, v: float):
         lib().oracle_set_global_viscosity(self.h, v)

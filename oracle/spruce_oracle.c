@@ -57,7 +57,8 @@ typedef struct {
     double *av_strength_grid[8];  /* boundary options: profile built by the caller (host libm exp) */
     /* physical_viscosity (source/modules/solar/physicalviscosity.hpp) */
     int pv_on, pv_heating_on, pv_force_on, pv_gc, pv_integrator, pv_inactive, pv_nsub; double pv_coeff, pv_epsilon; double *pv_cg;
-    int order[8]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah 4=av 5=pv */
+    void *small[8]; int n_small;  /* small solar modules (solar_small_modules_oracle.inc); order id = 100 + index */
+    int order[16]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah 4=av 5=pv, 100+k = small module k */
 } modules_t;
 
 typedef struct oracle {
@@ -469,6 +470,7 @@ static double min_range(const oracle *o, const double *a, int il, int jl, int iu
 static void propagate_changes(const oracle *o, double **G, double **P);
 #include "physical_viscosity_oracle.inc"
 #include "moc_oracle.inc"
+#include "solar_small_modules_oracle.inc"
 
 /* ---- artificial viscosity (source/modules/viscosity.cpp) */
 static int ev_index(int var) { for (int v = 0; v < NEV; v++) if (EVOLVED[v] == var) return v; return -1; }
@@ -777,12 +779,14 @@ static double advance_time(oracle *o)
     for (int m = 0; m < o->mod.n_modules; m++) {                                         /* preIterate :65 */
         if (o->mod.order[m] == 1) o->mod.tc_nsub = tc_number_subcycles(o, step);
         if (o->mod.order[m] == 2) o->mod.rl_nsub = rl_number_subcycles(o, step);
+        if (o->mod.order[m] >= 100) small_module_pre(o, (small_module *)o->mod.small[o->mod.order[m] - 100]);
     }
     for (int m = 0; m < o->mod.n_modules; m++) {                                         /* iterate :66 */
         if (o->mod.order[m] == 1) tc_iterate(o, step);
         if (o->mod.order[m] == 2) rl_iterate(o, step);
         if (o->mod.order[m] == 4) av_iterate(o, step);
         if (o->mod.order[m] == 5) pv_iterate(o, step);
+        if (o->mod.order[m] >= 100) small_module_iterate(o, (small_module *)o->mod.small[o->mod.order[m] - 100], step);
     }
     double **k1 = kalloc(o);
     if (o->integrator == TI_EULER) {                                                     /* :84-88 */
@@ -806,7 +810,10 @@ static double advance_time(oracle *o)
         kfree(k2); kfree(k3); kfree(k4);
     }
     kfree(k1);
-    for (int m = 0; m < o->mod.n_modules; m++) if (o->mod.order[m] == 3) ah_post_iterate(o, step);   /* :74 */
+    for (int m = 0; m < o->mod.n_modules; m++) {                                         /* postIterate :74 */
+        if (o->mod.order[m] == 3) ah_post_iterate(o, step);
+        if (o->mod.order[m] >= 100) small_module_post(o, (small_module *)o->mod.small[o->mod.order[m] - 100], step);
+    }
     o->t += step; o->iter++;
     return step;
 }
@@ -902,6 +909,16 @@ void oracle_add_viscosity_term(oracle *o, int opt, double strength, int var_diff
     o->mod.av_opt[i] = opt; o->mod.av_strength[i] = strength; o->mod.av_diff[i] = var_diff; o->mod.av_evol[i] = var_evol; o->mod.av_species[i] = species;
     o->mod.av_strength_grid[i] = NULL;
     if (strength_grid) { o->mod.av_strength_grid[i] = pl_dup(o, strength_grid); }
+}
+/* kind: 6 ambient_heating_sink, 7 localized_heating, 8 mass_injection, 9 momentum_injection, 10 div_cleaning, 11 field_heating; p: see small_module_setup */
+void oracle_add_small_module(oracle *o, int kind, const double *p, int np)
+{
+    small_module *m = (small_module *)calloc(1, sizeof(small_module));
+    m->kind = kind;
+    for (int k = 0; k < np && k < 12; k++) m->p[k] = p[k];
+    small_module_setup(o, m);
+    o->mod.small[o->mod.n_small] = m;
+    o->mod.order[o->mod.n_modules++] = 100 + o->mod.n_small++;
 }
 void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
 double oracle_step(oracle *o) { return advance_time(o); }
