@@ -143,7 +143,9 @@ class Oracle:
              "mass_injection": (8, ["start_time", "duration", "max_injection_rate", "stddev_x", "stddev_y", "center_x", "center_y"]),
              "momentum_injection": (9, ["start_time", "duration", "max_accel", "stddev_x", "stddev_y", "center_x", "center_y", "dir_x", "dir_y", "template_angle", "oscillatory", "oscillation_period"]),
              "div_cleaning": (10, ["epsilon", "time_scale"]),
-             "field_heating": (11, ["coeff", "current_pow", "b_pow", "n_pow", "roc_pow", "inactive_mode"])}
+             "field_heating": (11, ["coeff", "current_pow", "b_pow", "n_pow", "roc_pow", "inactive_mode"]),
+             # boundary: 0 x_bound_1, 1 x_bound_2, 2 y_bound_1, 3 y_bound_2 ; falloff_shape: 0 exp, 1 gaussian, 2 flat
+             "boundary_outflow": (12, ["max_accel", "falloff_length", "boundary", "falloff_shape", "feather_length", "field_aligned_mode", "dynamic_mode", "dynamic_time", "dynamic_target_speed"])}
 
     def add_small_module(self, name: str, **kw):
         """Small solar source-term modules (oracle/solar_small_modules_oracle.inc); keyword names = the reference's config keys."""
