@@ -54,6 +54,9 @@ def lib():
         L.oracle_set_radiative_losses.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.oracle_set_viscosity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_set_anomalous_resistivity.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.oracle_anomalous_subcycles.restype = C.c_int
+        L.oracle_anomalous_subcycles.argtypes = [C.c_void_p]
         L.oracle_add_small_module.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -152,6 +155,20 @@ class Oracle:
         kind, keys = self.SMALL[name]
         p = np.array([float(kw.get(k, 0.0)) for k in keys])
         lib().oracle_add_small_module(self.h, kind, _dp(p), p.size)
+
+    def set_anomalous_resistivity(self, *, time_scale=1.0, frobenius_metric_coeff=1.0e50, smoothing_sigma=3.0, safety_factor=1.0, metric_smoothing=True,
+                                  time_integrator="euler", template_mode="flood_fill", flood_fill_max_radius=-1.0, flood_fill_argmin_radius=5.0e9,
+                                  flood_fill_min_current=-1.0, flood_fill_current_ramp_length=1.0e-5, flood_fill_threshold=1.0, resistivity_model="time_scale",
+                                  gradient_correction=False, resistivity_model_params=(0.0, 0.0, 0.0)):
+        """AnomalousResistivity with the reference's defaults (anomalousresistivity.hpp:16-39); call after setup."""
+        mp = list(resistivity_model_params) + [0.0, 0.0, 0.0]
+        p = np.array([time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, float(metric_smoothing), TI[time_integrator or "euler"],
+                      float(template_mode == "flood_fill"), flood_fill_max_radius, flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length,
+                      flood_fill_threshold, {"time_scale": 0.0, "syntelis_19": 1.0, "ys_94": 2.0}[resistivity_model], float(gradient_correction), mp[0], mp[1], mp[2]])
+        lib().oracle_set_anomalous_resistivity(self.h, _dp(p))
+
+    def anomalous_subcycles(self) -> int:
+        return lib().oracle_anomalous_subcycles(self.h)
 
     def set_global_viscosity(self, v: float):
         lib().oracle_set_global_viscosity(self.h, v)

@@ -57,6 +57,7 @@ typedef struct {
     double *av_strength_grid[8];  /* boundary options: profile built by the caller (host libm exp) */
     /* physical_viscosity (source/modules/solar/physicalviscosity.hpp) */
     int pv_on, pv_heating_on, pv_force_on, pv_gc, pv_integrator, pv_inactive, pv_nsub; double pv_coeff, pv_epsilon; double *pv_cg;
+    void *anom;                   /* anomalous_resistivity (anomalous_resistivity_oracle.inc); order id 13 */
     void *small[8]; int n_small;  /* small solar modules (solar_small_modules_oracle.inc); order id = 100 + index */
     int order[16]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah 4=av 5=pv, 100+k = small module k */
 } modules_t;
@@ -471,6 +472,7 @@ static void propagate_changes(const oracle *o, double **G, double **P);
 #include "physical_viscosity_oracle.inc"
 #include "moc_oracle.inc"
 #include "solar_small_modules_oracle.inc"
+#include "anomalous_resistivity_oracle.inc"
 
 /* ---- artificial viscosity (source/modules/viscosity.cpp) */
 static int ev_index(int var) { for (int v = 0; v < NEV; v++) if (EVOLVED[v] == var) return v; return -1; }
@@ -787,6 +789,7 @@ static double advance_time(oracle *o)
         if (o->mod.order[m] == 4) av_iterate(o, step);
         if (o->mod.order[m] == 5) pv_iterate(o, step);
         if (o->mod.order[m] >= 100) small_module_iterate(o, (small_module *)o->mod.small[o->mod.order[m] - 100], step);
+        if (o->mod.order[m] == 13) ar_iterate(o, (anom_res *)o->mod.anom, step);
     }
     double **k1 = kalloc(o);
     if (o->integrator == TI_EULER) {                                                     /* :84-88 */
@@ -920,6 +923,20 @@ void oracle_add_small_module(oracle *o, int kind, const double *p, int np)
     o->mod.small[o->mod.n_small] = m;
     o->mod.order[o->mod.n_modules++] = 100 + o->mod.n_small++;
 }
+/* p: time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, metric_smoothing, time_integrator, flood_fill (1) / frobenius (0), flood_fill_max_radius,
+ *    flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length, flood_fill_threshold, resistivity_model (0 time_scale, 1 syntelis_19, 2 ys_94),
+ *    gradient_correction, model parameter 0..2.  The module's setupModule needs the populated state: call after oracle_setup. */
+void oracle_set_anomalous_resistivity(oracle *o, const double *p)
+{
+    anom_res *A = (anom_res *)calloc(1, sizeof(anom_res));
+    A->time_scale = p[0]; A->frob_coeff = p[1]; A->sigma = p[2]; A->safety = p[3]; A->smoothing = (int)p[4]; A->integrator = (int)p[5]; A->flood_fill = (int)p[6];
+    A->max_radius = p[7]; A->argmin_radius = p[8]; A->min_current = p[9]; A->ramp_length = p[10]; A->threshold = p[11]; A->model = (int)p[12]; A->gc = (int)p[13];
+    A->params[0] = p[14]; A->params[1] = p[15]; A->params[2] = p[16];
+    o->mod.anom = A;
+    ar_setup(o, A);
+    o->mod.order[o->mod.n_modules++] = 13;
+}
+int oracle_anomalous_subcycles(const oracle *o) { return o->mod.anom ? ((anom_res *)o->mod.anom)->nsub : 0; }
 void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
 double oracle_step(oracle *o) { return advance_time(o); }
 void oracle_run(oracle *o, int nsteps, double *dt_out) { for (int s = 0; s < nsteps; s++) { double d = advance_time(o); if (dt_out) dt_out[s] = d; } }

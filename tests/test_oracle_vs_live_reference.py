@@ -226,3 +226,46 @@ def test_small_solar_modules_oracle_equals_live_reference(name, modules, xb, yb,
     for v in MHD_OUT:
         assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
     o.close()
+
+
+AR_CASES = [
+    ("ar_default_floodfill", dict(time_scale="0.3", safety_factor="0.5", flood_fill_threshold="1.5", smoothing_sigma="1.0"), ("fixed", "open"), ("fixed", "open"), "rk2"),
+    ("ar_frobenius_rk2_gc", dict(time_scale="3.0", template_mode="frobenius", frobenius_metric_coeff="1.0e58", time_integrator="rk2", gradient_correction="true", smoothing_sigma="0.8"),
+     ("reflect", "fixed"), ("fixed", "fixed"), "euler"),
+    ("ar_syntelis_rk4", dict(resistivity_model="syntelis_19", resistivity_model_params="1.0e14,4.0e14,0.5", time_integrator="rk4", flood_fill_threshold="2.5", metric_smoothing="false",
+                             flood_fill_min_current="0.3", flood_fill_current_ramp_length="0.5", safety_factor="0.5"), ("fixed", "fixed"), ("fixed", "open"), "rk2"),
+    ("ar_ys94_radius", dict(resistivity_model="ys_94", resistivity_model_params="0.2,2.0e14,3.0e15", flood_fill_threshold="3.0", flood_fill_max_radius="1.2e9", flood_fill_argmin_radius="6.0e8",
+                            smoothing_sigma="1.2"), ("open", "open"), ("fixed", "open"), "rk4"),
+]
+
+
+@pytest.mark.parametrize("name,kv,xb,yb,integrator", AR_CASES, ids=[m[0] for m in AR_CASES])
+def test_anomalous_resistivity_oracle_equals_live_reference(name, kv, xb, yb, integrator):
+    """anomalous_resistivity (oracle/anomalous_resistivity_oracle.inc; not on the device yet): null-point tracking, flood-fill /
+    Frobenius templates with Gaussian smoothing, three resistivity models, euler / rk2 / rk4 sub-cycles, Joule heating -- bit for bit."""
+    nx, ny = 23, 23
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 3
+    frames = run_reference(s, dict(kw, modules=[("anomalous_resistivity", list(kv.items()))]), MHD_OUT, nsteps)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    a = {}
+    for k, v in kv.items():
+        if k == "resistivity_model_params":
+            a[k] = tuple(float(x) for x in v.split(","))
+        elif v in ("true", "false"):
+            a[k] = v == "true"
+        elif k in ("template_mode", "resistivity_model", "time_integrator"):
+            a[k] = v
+        else:
+            a[k] = float(v)
+    o.set_anomalous_resistivity(**a)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for it in range(1, nsteps + 1):
+        step = o.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "%s iteration %d: step %s vs %s" % (name, it, step.hex(), float(ref_step).hex())
+    for v in MHD_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
+    o.close()
