@@ -81,6 +81,7 @@ struct spruce_domain {
     unsigned nonzero_mask = 0x1F;
     bool in_mgpu_stage_api = false;        // inside spruce_mgpu_stage (caller-owned exchange and dt reduction)
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
+    bool stage_variants = false;           // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=1)
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
@@ -267,9 +268,22 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     dim3 grid((d->P.ny + CW - 1) / CW, gy);
     if (d->stage_kernel == 5) {
         const ActiveList L = active_quantities(d);
-        if (d->static_lists && L.n == 6 && L.q == XY_LIST_2D) k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, xy_smem_bytes(xy_rows(6)), st>>>(d->P, A, L);
-        else if (d->static_lists && L.n == 12 && L.q == XY_LIST_FULL) k_mhd_stage_xy<12, XY_LIST_FULL><<<grid, XY_NT, xy_smem_bytes(NTR), st>>>(d->P, A, L);
-        else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, xy_smem_bytes(NTR), st>>>(d->P, A, L);
+        // compile-time integrator stage (SPRUCE_STAGE_VARIANTS=1, off by default): plain euler / rk2 stages without module terms
+        int var = 0;
+        if (d->stage_variants && kmode == KM_NONE && A.n_xterm == 0) var = A.b_is_s ? (primary ? 3 : 1) : (primary ? 2 : 0);
+        const size_t sm6 = xy_smem_bytes(xy_rows(6)), smf = xy_smem_bytes(NTR);
+        if (d->static_lists && L.n == 6 && L.q == XY_LIST_2D) {
+            if (var == 1) k_mhd_stage_xy<6, XY_LIST_2D, 1><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
+            else if (var == 2) k_mhd_stage_xy<6, XY_LIST_2D, 2><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
+            else if (var == 3) k_mhd_stage_xy<6, XY_LIST_2D, 3><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
+            else k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
+        } else if (d->static_lists && L.n == 12 && L.q == XY_LIST_FULL) {
+            if (var == 1) k_mhd_stage_xy<12, XY_LIST_FULL, 1><<<grid, XY_NT, smf, st>>>(d->P, A, L);
+            else if (var == 2) k_mhd_stage_xy<12, XY_LIST_FULL, 2><<<grid, XY_NT, smf, st>>>(d->P, A, L);
+            else if (var == 3) k_mhd_stage_xy<12, XY_LIST_FULL, 3><<<grid, XY_NT, smf, st>>>(d->P, A, L);
+            else k_mhd_stage_xy<12, XY_LIST_FULL><<<grid, XY_NT, smf, st>>>(d->P, A, L);
+        }
+        else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, smf, st>>>(d->P, A, L);
     }
     else k_mhd_stage<<<grid, NT, STAGE_SMEM, st>>>(d->P, A);
     d->launches++;
@@ -908,10 +922,20 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(xy_rows(6))));
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
+    {   // the compile-time integrator-stage instances (SPRUCE_STAGE_VARIANTS)
+        const int sm6 = (int)xy_smem_bytes(xy_rows(6)), smf = (int)xy_smem_bytes(NTR);
+        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+    }
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
+    if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0;
     DomainParams &P = d->P;
     P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;
     P.gnx = cfg->xdim; P.row0 = cfg->row0;

@@ -56,10 +56,17 @@ constexpr unsigned long long xy_list(int a = -1, int b = -1, int c = -1, int d =
 constexpr unsigned long long XY_LIST_2D = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY);                                              // no z system, no external field
 constexpr unsigned long long XY_LIST_FULL = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY, Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_BEZ);   // everything (padded to 12)
 
-template <int LN, unsigned long long LQ>
+// VAR > 0: the integrator stage is a compile-time constant too (no K planes, no module right-hand-side terms):
+//   1: B == S, secondary (first stage of rk2)   2: B != S, primary (last stage of rk2)   3: B == S, primary (euler).
+// VAR == 0 takes kmode / b_is_s / primary / n_xterm from the launch arguments (every integrator, every module).
+template <int LN, unsigned long long LQ, int VAR = 0>
 __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
 {
     constexpr int UNR = LN > 0 ? LN : 1;
+#define kmode (VAR ? (int)KM_NONE : A.kmode)
+#define b_is_s (VAR ? (VAR != 2 ? 1 : 0) : A.b_is_s)
+#define primary (VAR ? (VAR != 1 ? 1 : 0) : A.primary)
+#define n_xterm (VAR ? 0 : A.n_xterm)
     // Z: the z system (mom_z, bi_z, v_z) and the external field can be non-zero.  In the 2-D instance (LN == 6) they are exact zeros in the
     // reference as well, so every term that only adds +-0 is left out (the results can differ in the sign of a zero, nothing else) and
     // the all-zero planes mom_z / bi_z are neither computed nor stored (their planes are zero-initialised and stay zero).
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
 
     const double step = *A.step_ptr;
     const double s = A.coef * step;
-    const double inv_thr = A.primary ? *A.inv_thr_ptr : 0.0;
+    const double inv_thr = primary ? *A.inv_thr_ptr : 0.0;
 
     // ---- x tables of this chunk and zeroed exchange arrays (inactive quantities read as exact zeros)
     {
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
         {
             const double *pa = isX ? A.st[S_GX] : A.B[E_E], *pb = isX ? A.st[S_GY] : A.B[E_BX];
             g0 = pa[off]; g1 = pb[off];                      // X: gravity ; Y: B[thermal_energy], B[bi_x]
-            if (!A.b_is_s) {                                 // warp-uniform
+            if (!b_is_s) {                                 // warp-uniform
                 const double *p0 = isX ? A.B[E_N] : A.B[E_BY], *p1 = isX ? A.B[E_MX] : A.B[E_BZ], *p2 = isX ? A.B[E_MY] : A.B[E_BY], *p3 = isX ? A.B[E_MZ] : A.B[E_BZ];
                 B0 = p0[off]; B1 = p1[off]; B2 = p2[off]; B3 = p3[off];
             }
@@ -342,30 +349,30 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
                     k2 = (((T_my * -1.0) - dp_dy) + rho * g1) + cdb * bix;
                 }
                 if (!interior) { k0 = 0.0; k1 = 0.0; k2 = 0.0; k3 = 0.0; }                      // ghost mask :99-103
-                for (int t = 0; t < A.n_xterm; t++) {                                           // module RHS terms, in module order
+                for (int t = 0; t < n_xterm; t++) {                                           // module RHS terms, in module order
                     const int tg = A.xtarget[t];
                     if (tg <= E_MZ) { const double x = A.xterm[t][off]; if (tg == E_N) k0 = k0 + x; if (tg == E_MX) k1 = k1 + x; if (tg == E_MY) k2 = k2 + x; if (tg == E_MZ) k3 = k3 + x; }
                 }
-                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_N][off] = k0; A.K1[E_MX][off] = k1; A.K1[E_MY][off] = k2; if (Z || A.kmode == KM_EXPORT) A.K1[E_MZ][off] = k3; }
-                else if (A.kmode == KM_STORE_K2) { A.K2[E_N][off] = k0; A.K2[E_MX][off] = k1; A.K2[E_MY][off] = k2; if (Z) A.K2[E_MZ][off] = k3; }
-                else if (A.kmode == KM_ADD_K2) { A.K2[E_N][off] = A.K2[E_N][off] + k0; A.K2[E_MX][off] = A.K2[E_MX][off] + k1; A.K2[E_MY][off] = A.K2[E_MY][off] + k2; if (Z) A.K2[E_MZ][off] = A.K2[E_MZ][off] + k3; }
-                else if (A.kmode == KM_FINAL) {                                                 // evolution.cpp:121
+                if (kmode == KM_STORE_K1 || kmode == KM_EXPORT) { A.K1[E_N][off] = k0; A.K1[E_MX][off] = k1; A.K1[E_MY][off] = k2; if (Z || kmode == KM_EXPORT) A.K1[E_MZ][off] = k3; }
+                else if (kmode == KM_STORE_K2) { A.K2[E_N][off] = k0; A.K2[E_MX][off] = k1; A.K2[E_MY][off] = k2; if (Z) A.K2[E_MZ][off] = k3; }
+                else if (kmode == KM_ADD_K2) { A.K2[E_N][off] = A.K2[E_N][off] + k0; A.K2[E_MX][off] = A.K2[E_MX][off] + k1; A.K2[E_MY][off] = A.K2[E_MY][off] + k2; if (Z) A.K2[E_MZ][off] = A.K2[E_MZ][off] + k3; }
+                else if (kmode == KM_FINAL) {                                                 // evolution.cpp:121
                     k0 = (A.K1[E_N][off] + k0) / 6.0 + A.K2[E_N][off] / 3.0;   k1 = (A.K1[E_MX][off] + k1) / 6.0 + A.K2[E_MX][off] / 3.0;
                     k2 = (A.K1[E_MY][off] + k2) / 6.0 + A.K2[E_MY][off] / 3.0; if (Z) k3 = (A.K1[E_MZ][off] + k3) / 6.0 + A.K2[E_MZ][off] / 3.0;
                 }
-                if (A.kmode != KM_EXPORT) {
+                if (kmode != KM_EXPORT) {
                     double Un, Umx, Umy, Umz;                                                   // equationset.cpp:226-228
-                    if (A.b_is_s) { Un = rho + k0 * s; Umx = RG(s0, Q_MX, c) + k1 * s; Umy = RG(s0, Q_MY, c) + k2 * s; Umz = Z ? RG(s0, Q_MZ, c) + k3 * s : 0.0; }
+                    if (b_is_s) { Un = rho + k0 * s; Umx = RG(s0, Q_MX, c) + k1 * s; Umy = RG(s0, Q_MY, c) + k2 * s; Umz = Z ? RG(s0, Q_MZ, c) + k3 * s : 0.0; }
                     else { Un = (B0 * P.m_i) + k0 * s; Umx = B1 + k1 * s; Umy = B2 + k2 * s; Umz = Z ? B3 + k3 * s : 0.0; }
                     double rfl;
                     const double nn = density_floor(P, Un, &rfl);
-                    if (A.primary) {
+                    if (primary) {
                         const unsigned z = zero_zones(P, g, j);
                         record_strips(P, A.strip, A.strip_pitch, g, r, j, z, rfl, Umx, Umy, Umz);
                         if (z) { Umx = 0.0; Umy = 0.0; Umz = 0.0; }
                     }
                     A.D[E_N][off] = nn; A.D[E_MX][off] = Umx; A.D[E_MY][off] = Umy; if (Z) A.D[E_MZ][off] = Umz;
-                    if (A.primary) { Dt_s[0][col] = nn * P.m_i; Dt_s[1][col] = Umx; Dt_s[2][col] = Umy; }
+                    if (primary) { Dt_s[0][col] = nn * P.m_i; Dt_s[1][col] = Umx; Dt_s[2][col] = Umy; }
                 }
             } else {
                 const double dvx_dx = Dc_s[0][col], dvy_dx = Dc_s[1][col], dvz_dx = Dc_s[2][col];
@@ -385,24 +392,24 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
                     k6 = ((T_biy * -1.0) + bix * dvy_dx) + biy * d_d;
                 }
                 if (!interior) { k4 = 0.0; k5 = 0.0; k6 = 0.0; k7 = 0.0; }
-                for (int t = 0; t < A.n_xterm; t++) {
+                for (int t = 0; t < n_xterm; t++) {
                     const int tg = A.xtarget[t];
                     if (tg > E_MZ) { const double x = A.xterm[t][off]; if (tg == E_E) k4 = k4 + x; if (tg == E_BX) k5 = k5 + x; if (tg == E_BY) k6 = k6 + x; if (tg == E_BZ) k7 = k7 + x; }
                 }
-                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { A.K1[E_E][off] = k4; A.K1[E_BX][off] = k5; A.K1[E_BY][off] = k6; if (Z || A.kmode == KM_EXPORT) A.K1[E_BZ][off] = k7; }
-                else if (A.kmode == KM_STORE_K2) { A.K2[E_E][off] = k4; A.K2[E_BX][off] = k5; A.K2[E_BY][off] = k6; if (Z) A.K2[E_BZ][off] = k7; }
-                else if (A.kmode == KM_ADD_K2) { A.K2[E_E][off] = A.K2[E_E][off] + k4; A.K2[E_BX][off] = A.K2[E_BX][off] + k5; A.K2[E_BY][off] = A.K2[E_BY][off] + k6; if (Z) A.K2[E_BZ][off] = A.K2[E_BZ][off] + k7; }
-                else if (A.kmode == KM_FINAL) {
+                if (kmode == KM_STORE_K1 || kmode == KM_EXPORT) { A.K1[E_E][off] = k4; A.K1[E_BX][off] = k5; A.K1[E_BY][off] = k6; if (Z || kmode == KM_EXPORT) A.K1[E_BZ][off] = k7; }
+                else if (kmode == KM_STORE_K2) { A.K2[E_E][off] = k4; A.K2[E_BX][off] = k5; A.K2[E_BY][off] = k6; if (Z) A.K2[E_BZ][off] = k7; }
+                else if (kmode == KM_ADD_K2) { A.K2[E_E][off] = A.K2[E_E][off] + k4; A.K2[E_BX][off] = A.K2[E_BX][off] + k5; A.K2[E_BY][off] = A.K2[E_BY][off] + k6; if (Z) A.K2[E_BZ][off] = A.K2[E_BZ][off] + k7; }
+                else if (kmode == KM_FINAL) {
                     k4 = (A.K1[E_E][off] + k4) / 6.0 + A.K2[E_E][off] / 3.0;   k5 = (A.K1[E_BX][off] + k5) / 6.0 + A.K2[E_BX][off] / 3.0;
                     k6 = (A.K1[E_BY][off] + k6) / 6.0 + A.K2[E_BY][off] / 3.0; if (Z) k7 = (A.K1[E_BZ][off] + k7) / 6.0 + A.K2[E_BZ][off] / 3.0;
                 }
-                if (A.kmode != KM_EXPORT) {
+                if (kmode != KM_EXPORT) {
                     double Ue, Ubx, Uby, Ubz;
-                    if (A.b_is_s) { Ue = RG(s0, Q_E, c) + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = Z ? biz + k7 * s : 0.0; }
+                    if (b_is_s) { Ue = RG(s0, Q_E, c) + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = Z ? biz + k7 * s : 0.0; }
                     else { Ue = g0 + k4 * s; Ubx = g1 + k5 * s; Uby = B0 + k6 * s; Ubz = Z ? B1 + k7 * s : 0.0; }     // Y's base values were prefetched into g0, g1, B0, B1
                     const double e1 = smax(Ue, P.e_min);
                     A.D[E_E][off] = e1; A.D[E_BX][off] = Ubx; A.D[E_BY][off] = Uby; if (Z) A.D[E_BZ][off] = Ubz;
-                    if (A.primary && interior) {                                                 // dt of this cell: evaluated after the next barrier
+                    if (primary && interior) {                                                 // dt of this cell: evaluated after the next barrier
                         dt_pending = true; dt_e = e1; dt_bx = bex + Ubx; dt_by = bey + Uby; dt_bz = bez + Ubz; dt_dx = dx; dt_rdx = rdx;
                     }
                 }
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
         __syncthreads();
         s0 = sp1; v0 = v1;
     }
-    if (A.primary && A.kmode != KM_EXPORT) {
+    if (primary && kmode != KM_EXPORT) {
         if (!isX && dt_pending && !dt_can_skip(P, inv_thr, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_rdx, rdy)) {
             const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
             dtmin_local = smin(dtmin_local, dtc);
@@ -422,6 +429,10 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
         block_min_impl(dtmin_local, A.dtmin_bits, reinterpret_cast<unsigned long long *>(TX_p));   // the TX array is dead after the last barrier
     }
 }
+#undef kmode
+#undef b_is_s
+#undef primary
+#undef n_xterm
 #undef RG
 #undef FXS
 #undef TXS
