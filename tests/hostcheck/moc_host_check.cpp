@@ -1,0 +1,26 @@
+// moc_host_check.cpp -- TEST INFRASTRUCTURE.  Compiles the product's per-cell open_moc arithmetic (spruce_b200/csrc/moc_kernels.cuh,
+// namespace spruce::moc -- the very functions the CUDA kernel k_moc_stage calls) with the host compiler, so that
+// tests/test_moc_host_check.py can compare it bit for bit against the CPU oracle without a GPU.  Nothing in the product links this.
+#include "../../spruce_b200/csrc/moc_kernels.cuh"
+
+extern "C" int moc_host_terms(const double *const *planes /* n mx my mz e bix biy biz bex bey bez gx gy */, const double *dx, const double *dy,
+                              int nx, int ny, const int *bc, double m_i, double gamma, double visc, double *k_out /* [8][nx*ny] */, unsigned char *owned)
+{
+    spruce::moc::Field F;
+    F.n = planes[0]; F.mx = planes[1]; F.my = planes[2]; F.mz = planes[3]; F.e = planes[4]; F.bix = planes[5]; F.biy = planes[6]; F.biz = planes[7];
+    F.bex = planes[8]; F.bey = planes[9]; F.bez = planes[10]; F.gx = planes[11]; F.gy = planes[12];
+    F.dx = dx; F.dy = dy; F.nx = nx; F.ny = ny; F.pitch = ny;
+    for (int s = 0; s < 4; s++) F.bc[s] = bc[s];
+    F.m_i = m_i; F.gamma = gamma; F.gm1 = gamma - 1.0; F.visc = visc;
+    const size_t n = (size_t)nx * ny;
+    int count = 0;
+    for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) {
+        double k[8];
+        const bool own = spruce::moc::moc_cell_terms(F, i, j, k);
+        owned[(size_t)i * ny + j] = own ? 1 : 0;
+        if (!own) continue;
+        count++;
+        for (int v = 0; v < 8; v++) k_out[v * n + (size_t)i * ny + j] = k[v];
+    }
+    return count;
+}

@@ -1,0 +1,93 @@
+"""The product's per-cell open_moc arithmetic (spruce_b200/csrc/moc_kernels.cuh, the functions the CUDA kernel k_moc_stage calls),
+compiled for the HOST by tests/hostcheck/moc_host_check.cpp and compared bit for bit with the CPU oracle's right-hand side in the
+evolved ghost cells -- the part of the open_moc device path that can be proven without a GPU.  The oracle itself is pinned against
+live reference runs (tests/test_oracle_vs_live_reference.py).  Not a product path: the library has no CPU fallback."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from golden_util import mismatch, same_bits
+from oracle.oracle import Oracle
+from spruce_b200 import synthetic
+
+ROOT = Path(__file__).resolve().parents[1]
+SRC = ROOT / "tests" / "hostcheck" / "moc_host_check.cpp"
+LIB = ROOT / "tests" / "hostcheck" / "_build" / "libmoc_host_check.so"
+BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3, "open_moc": 4, "open_ucnp": 5}
+EVOLVED = ["rho", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z"]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    LIB.parent.mkdir(exist_ok=True)
+    hdr = ROOT / "spruce_b200" / "csrc" / "moc_kernels.cuh"
+    if not LIB.exists() or LIB.stat().st_mtime < max(SRC.stat().st_mtime, hdr.stat().st_mtime):
+        # x86-64 baseline ISA has no FMA; -ffp-contract=off states it anyway (the CUDA build uses -fmad=false)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(LIB), str(SRC)], check=True)
+    L = C.CDLL(str(LIB))
+    L.moc_host_terms.restype = C.c_int
+    return L
+
+
+def host_terms(L, o, xb, yb, visc, ion_mass, adiabatic_index):
+    names = ["n", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z", "be_x", "be_y", "be_z", "grav_x", "grav_y"]
+    planes = [np.ascontiguousarray(o.get(v), dtype=np.float64) for v in names]
+    nx, ny = planes[0].shape
+    dx = np.ascontiguousarray(o.get("d_x")[:, 0]); dy = np.ascontiguousarray(o.get("d_y")[0, :])
+    arr = (C.c_void_p * 13)(*[p.ctypes.data for p in planes])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    k = np.zeros((8, nx, ny)); owned = np.zeros((nx, ny), dtype=np.uint8)
+    cnt = L.moc_host_terms(arr, dx.ctypes.data_as(C.c_void_p), dy.ctypes.data_as(C.c_void_p), C.c_int(nx), C.c_int(ny), bc,
+                           C.c_double(ion_mass), C.c_double(adiabatic_index), C.c_double(visc), k.ctypes.data_as(C.c_void_p), owned.ctypes.data_as(C.c_void_p))
+    return k, owned.astype(bool), cnt
+
+
+def dt_bounds(xb, yb, nx, ny):
+    lo = lambda b: 0 if b in ("periodic", "open_moc") else 2
+    hi = lambda b, n: n - 1 if b in ("periodic", "open_moc") else n - 3
+    return lo(xb[0]), hi(xb[1], nx), lo(yb[0]), hi(yb[1], ny)
+
+
+CASES = [
+    ("y2_moc", ("periodic", "periodic"), ("fixed", "open_moc"), 0.0, 26, 23),
+    ("y1_moc_visc", ("periodic", "periodic"), ("open_moc", "fixed"), 0.3, 24, 25),
+    ("x1_moc", ("open_moc", "reflect"), ("fixed", "open"), 0.0, 27, 22),
+    ("all_moc_visc", ("open_moc", "open_moc"), ("open_moc", "open_moc"), 0.1, 25, 24),
+    ("x2_moc_y2_moc", ("fixed", "open_moc"), ("open", "open_moc"), 0.0, 23, 26),
+    ("x_moc_y_periodic_visc", ("open_moc", "open_moc"), ("periodic", "periodic"), 0.2, 22, 27),
+    ("x1_moc_only", ("open_moc", "fixed"), ("reflect", "reflect"), 0.0, 31, 19),
+]
+
+
+@pytest.mark.parametrize("name,xb,yb,gvisc,nx,ny", CASES, ids=[c[0] for c in CASES])
+def test_product_moc_cell_terms_equal_oracle_rhs(lib, name, xb, yb, gvisc, nx, ny):
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    kw = dict(xb=xb, yb=yb, integrator="rk2", density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    o.set_global_viscosity(gvisc)
+    n_owned = 0
+    for it in range(4):                                       # the flow develops: inflow / outflow switches change sign along the strips
+        xl, xu, yl, yu = dt_bounds(xb, yb, nx, ny)
+        dxp, dyp, dt = o.get("d_x"), o.get("d_y"), o.get("dt")
+        term = (1.0 / (1.0 / (dxp * dxp) + 1.0 / (dyp * dyp))) / dt
+        visc = gvisc * 0.5 * float(np.min(term[xl:xu + 1, yl:yu + 1]))                    # idealmhd.cpp:90
+        k_ref = o.rhs()
+        k, owned, cnt = host_terms(lib, o, xb, yb, visc, s["ion_mass"], s["adiabatic_index"])
+        assert cnt == int(owned.sum()) and cnt > 0
+        n_owned = cnt
+        mask = np.zeros((nx, ny), dtype=bool)                                               # ghost cells = outside the interior bounds
+        ilo = lambda b: 0 if b == "periodic" else 2
+        ihi = lambda b, n: n - 1 if b == "periodic" else n - 3
+        mask[ilo(xb[0]):ihi(xb[1], nx) + 1, ilo(yb[0]):ihi(yb[1], ny) + 1] = True
+        assert not np.any(owned & mask), "an interior cell was claimed by an open_moc side"
+        for v, nm in enumerate(EVOLVED):
+            ref = np.where(owned, k_ref[v], 0.0)
+            assert same_bits(np.where(owned, k[v], 0.0), ref), "%s it %d d(%s)/dt: %s" % (name, it, nm, mismatch(np.where(owned, k[v], 0.0), ref))
+            ghost_not_owned = (~mask) & (~owned)
+            assert np.all(k_ref[v][ghost_not_owned] == 0.0), "the oracle evolves a ghost cell the product does not claim (%s)" % nm
+        o.step()
+    assert n_owned > 0
+    o.close()
