@@ -140,6 +140,12 @@ int spruce_module_viscosity_term(spruce_domain *dom, const char *visc_opt, doubl
  * the host exactly as the reference does.  count of sub-cycles: spruce_module_subcycles(dom, "physical_viscosity", &n). */
 int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on,
                                      int force_on, int gradient_correction, int time_integrator, int inactive_mode);
+/* IdealMHD::parseEquationSetConfigs (source/equationsets/idealmhd.cpp:12-40): global_viscosity (idealmhd.hpp:48, default 0), read only
+ * by the characteristic open boundary (global_visc_coeff, idealmhd.cpp:90).  open_moc sides themselves (idealmhd.cpp:306-615) are
+ * selected through spruce_config.x_bound_* / y_bound_* = SPRUCE_BC_OPEN_MOC; until that path has been validated on a GPU
+ * spruce_domain_create refuses it unless the environment sets SPRUCE_EXPERIMENTAL_MOC=1.  moc_b_limiting / moc_mom_limiting
+ * (idealmhd.cpp:107-223) are not built. */
+int spruce_eqs_ideal_mhd_options(spruce_domain *dom, double global_viscosity);
 /* Ideal2F::parseEquationSetConfigs (source/equationsets/ideal2F.cpp:5-28): use_sub_cycling (reference default true, which aborts
  * in computeTimeDerivatives -- only false can run, and spruce_eqs_setup refuses true) and remove_curl_terms. */
 int spruce_eqs_ideal2f_options(spruce_domain *dom, int use_sub_cycling, int remove_curl_terms);

@@ -55,6 +55,7 @@ SYMBOLS = {
     "spruce_module_viscosity": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "spruce_module_viscosity_term": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double, C.c_char_p, C.c_char_p, C.c_char_p, _DP, C.c_size_t]),
     "spruce_module_physical_viscosity": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "spruce_eqs_ideal_mhd_options": (C.c_int, [C.c_void_p, C.c_double]),
     "spruce_eqs_ideal2f_options": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "spruce_module_eic_thermalization": (C.c_int, [C.c_void_p]),
     "spruce_module_subcycles": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]),

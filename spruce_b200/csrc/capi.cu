@@ -5,6 +5,7 @@
 #include "mhd_kernels.cuh"
 #include "module_kernels.cuh"
 #include "mhd_stage_xy.cuh"
+#include "moc_stage.cuh"
 #include "ideal2f_kernels.cuh"
 
 #include <cmath>
@@ -81,6 +82,8 @@ struct spruce_domain {
     unsigned nonzero_mask = 0x1F;
     bool in_mgpu_stage_api = false;        // inside spruce_mgpu_stage (caller-owned exchange and dt reduction)
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
+    // open_moc (moc_stage.cuh): evolved ghost cells; SPRUCE_EXPERIMENTAL_MOC=1 until the launch side has been validated on a GPU
+    bool moc_any = false; double global_viscosity = 0.0; unsigned long long *moc_visc_bits = nullptr; double *moc_base = nullptr;
     bool stage_variants = false;           // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=1)
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
@@ -216,7 +219,8 @@ void fill_sets(const spruce_domain *d, StageArgs &A, const PlaneSet &S, const Pl
 
 // the dt skip test (dt_can_skip) lives in k_mhd_stage_xy only, and needs k_dt_validate / k_dt_full after the step's last stage:
 // spruce_advance provides that; the caller-driven spruce_mgpu_stage path (NCCL transport) evaluates every cell
-int dt_prune_enabled(const spruce_domain *d) { return (d->stage_kernel == 5 && !d->in_mgpu_stage_api) ? 1 : 0; }
+// open_moc: the minimum also runs over evolved ghost cells, which k_dt_full does not visit -> every cell is evaluated
+int dt_prune_enabled(const spruce_domain *d) { return (d->stage_kernel == 5 && !d->in_mgpu_stage_api && !d->moc_any) ? 1 : 0; }
 
 int pick_chunk_rows(const spruce_domain *d)
 {
@@ -247,10 +251,13 @@ ActiveList active_quantities(const spruce_domain *d)
 }
 
 int prepare_rhs_modules(spruce_domain *d, const PlaneSet &S);
+int launch_moc(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int dt_only);
+int launch_moc_save(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D);
 int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int part = 0)
 {
     // part 0: every row chunk on the main stream; 1: the first and last chunk on the communication stream; 2: the chunks between on the main stream
     if (part == 0 && !d->visc.empty()) { int rcv = prepare_rhs_modules(d, S); if (rcv) return rcv; }
+    if (d->moc_any && kmode != KM_EXPORT) { int rcm = launch_moc_save(d, S, B, D); if (rcm) return rcm; }
     StageArgs A{};
     fill_sets(d, A, S, B, D);
     A.n_xterm = d->visc.empty() ? 0 : d->cur_nx;
@@ -288,6 +295,49 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     else k_mhd_stage<<<grid, NT, STAGE_SMEM, st>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (d->moc_any) return launch_moc(d, S, B, D, coef, primary, kmode, 0);      // single rank: part == 0, same stream
+    return SPRUCE_OK;
+}
+
+// open_moc sides: the characteristic update of their ghost cells, after the stage kernel of the same stage (moc_stage.cuh);
+// dt_only: after a propagateChanges, the dt of those cells of the primary state
+void fill_moc(spruce_domain *d, MocArgs &A, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int dt_only)
+{
+    for (int v = 0; v < NEV; v++) { A.S[v] = S.p[v]; A.B[v] = B.p[v]; A.D[v] = D.p[v]; A.K1[v] = d->K1set.p[v]; A.K2[v] = d->K2set.p[v]; }
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.kmode = kmode; A.primary = primary; A.dt_only = dt_only; A.coef = coef;
+    A.step_ptr = &d->ctl->step; A.done_ptr = &d->ctl->done; A.dtmin_bits = &d->ctl->dtmin_bits;
+    A.global_viscosity = d->global_viscosity;
+    A.base_buf = d->moc_base;
+}
+// before the stage kernel of a stage: the base state of the evolved ghost cells (see MocArgs::base_buf)
+int launch_moc_save(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D)
+{
+    if (!d->moc_base) CUDA_TRY(cudaMalloc(&d->moc_base, (size_t)NEV * moc_threads(d->P) * sizeof(double)));
+    MocArgs A{};
+    fill_moc(d, A, S, B, D, 0.0, 0, KM_NONE, 0);
+    k_moc_save<<<(moc_threads(d->P) + 127) / 128, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+int launch_moc(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int dt_only)
+{
+    if (!d->moc_any) return SPRUCE_OK;
+    MocArgs A{};
+    fill_moc(d, A, S, B, D, coef, primary, kmode, dt_only);
+    if (!dt_only && d->global_viscosity != 0.0) {             // global_visc_coeff of this right-hand-side evaluation (idealmhd.cpp:90)
+        if (!d->moc_visc_bits) CUDA_TRY(cudaMalloc(&d->moc_visc_bits, sizeof(unsigned long long)));
+        static const unsigned long long kMax = 0x7FEFFFFFFFFFFFFFULL;
+        CUDA_TRY(cudaMemcpyAsync(d->moc_visc_bits, &kMax, sizeof(kMax), cudaMemcpyHostToDevice, d->stream));
+        dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+        k_moc_visc_min<<<grid, 128, 0, d->stream>>>(d->P, A, d->moc_visc_bits);
+        d->launches++;
+        A.visc_min_bits = d->moc_visc_bits;
+    }
+    k_moc_stage<<<(moc_threads(d->P) + 127) / 128, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }
 
@@ -322,7 +372,9 @@ int launch_propagate(spruce_domain *d, int from_state)
     d->launches += 2;
     CUDA_TRY(cudaGetLastError());
     d->raw_rho = false;
-    return launch_ghosts(d, d->Pset, 1);
+    int rc = launch_ghosts(d, d->Pset, 1);
+    if (rc || !d->moc_any) return rc;
+    return launch_moc(d, d->Pset, d->Pset, d->Pset, 0.0, 1, KM_NONE, 1);
 }
 
 int ensure_rk4(spruce_domain *d)
@@ -907,7 +959,16 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     const int bcs[4] = {cfg->x_bound_1, cfg->x_bound_2, cfg->y_bound_1, cfg->y_bound_2};
     for (int b : bcs) {
         if (b < 0 || b > SPRUCE_BC_OPEN_UCNP) return fail(SPRUCE_ERR_ARG, "Boundary cond'n must be defined");
-        if (b == SPRUCE_BC_OPEN_MOC) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries are outside the built scope (SURVEY.md 8f-2)");
+    }
+    bool moc_any = false;
+    for (int b : bcs) if (b == SPRUCE_BC_OPEN_MOC) moc_any = true;
+    if (moc_any) {
+        const char *ex = getenv("SPRUCE_EXPERIMENTAL_MOC");
+        if (!ex || atoi(ex) == 0) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries: the device path is built but has not been validated on a GPU yet; set SPRUCE_EXPERIMENTAL_MOC=1 to use it (SURVEY.md 8f-2)");
+        if (two_fluid) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries exist for ideal_mhd only (idealmhd.cpp:306)");
+        if (cfg->n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries on a slab decomposition are not built");
+        for (int a = 0; a < 2; a++)       // a periodic side opposite an open_moc side is not a configuration the reference can run
+            if ((bcs[2 * a] == SPRUCE_BC_PERIODIC) != (bcs[2 * a + 1] == SPRUCE_BC_PERIODIC)) return fail(SPRUCE_ERR_ARG, "periodic boundaries come in pairs");
     }
     if (cfg->time_integrator < 0 || cfg->time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "invalid time integrator");
     if (cfg->n_ranks < 1 || cfg->nx_local < 1 || cfg->row0 < 0 || cfg->row0 + cfg->nx_local > cfg->xdim) return fail(SPRUCE_ERR_ARG, "bad slab [%d,%d) of %d", cfg->row0, cfg->row0 + cfg->nx_local, cfg->xdim);
@@ -936,6 +997,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0;
+    d->moc_any = moc_any;
     DomainParams &P = d->P;
     P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;
     P.gnx = cfg->xdim; P.row0 = cfg->row0;
@@ -995,6 +1057,8 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->tab_dev) cudaFree(d->tab_dev);
     if (d->ctl) cudaFree(d->ctl);
     if (d->red) cudaFree(d->red);
+    if (d->moc_visc_bits) cudaFree(d->moc_visc_bits);
+    if (d->moc_base) cudaFree(d->moc_base);
     if (d->dt_hist) cudaFree(d->dt_hist);
     for (int r = 0; r < MAX_RANKS; r++) if (d->peer_seg[r] && d->peer_seg[r] != d->seg) cudaIpcCloseMemHandle(d->peer_seg[r]);
     if (d->seg) cudaFree(d->seg);
@@ -1281,6 +1345,13 @@ int spruce_module_viscosity_term(spruce_domain *d, const char *visc_opt, double 
     if (evolved_slot(t.var_evol) == E_MZ) d->nonzero_mask |= 0x01u;
     if (evolved_slot(t.var_evol) == E_BZ) d->nonzero_mask |= 0x02u;
     d->visc.push_back(t);
+    return SPRUCE_OK;
+}
+int spruce_eqs_ideal_mhd_options(spruce_domain *d, double global_viscosity)
+{
+    CHECK_DOM(d);
+    if (d->tf) return fail(SPRUCE_ERR_STATE, "ideal_mhd options on a domain with another equation set");
+    d->global_viscosity = global_viscosity;          // only the open_moc boundary reads it (idealmhd.cpp:90)
     return SPRUCE_OK;
 }
 int spruce_eqs_ideal2f_options(spruce_domain *d, int use_sub_cycling, int remove_curl_terms)

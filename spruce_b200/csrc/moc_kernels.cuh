@@ -15,7 +15,7 @@
 // to the "libm" tolerance class of DESIGN.md section 2 (<= 1e-9), although it is bit-identical in every case tested so far.
 //
 // The per-cell arithmetic (namespace spruce::moc, everything up to moc_cell_terms) is plain C++ with no CUDA dependence so that
-// tests/moc_host_check.cpp can compile THE SAME SOURCE with g++ and compare it, bit for bit, against the CPU oracle without a GPU.
+// tests/hostcheck/moc_host_check.cpp can compile THE SAME SOURCE with g++ and check it, bit for bit, on a machine without a GPU.
 #pragma once
 #include <cmath>
 #include <cstddef>
@@ -372,6 +372,72 @@ MOC_HD bool moc_cell_terms(const Field &F, int i, int j, double *k)
     k[1] = rho * res[1] + vx * r0; k[2] = rho * res[2] + vy * r0; k[3] = rho * res[3] + vz * r0;
     k[4] = res[4]; k[5] = res[5]; k[6] = res[6]; k[7] = res[7];
     return true;
+}
+
+// ---- the update of one evolved ghost cell: equationset.cpp:226-228 (U += k*s), enforceMinimums (idealmhd.cpp:234-239), the
+// pointwise part of updateGhostZones that can reach it (fixed / reflect sides zero the momenta of their ghost cells on the PRIMARY
+// state, evolution.cpp:245-263,272-282), the rho -> n round trip of the derived step (:246-247) and recomputeDT (:279-304).
+enum { MBC_FIXED = 2, MBC_REFLECT = 3 };
+struct Floors { double n_min, e_min; };
+struct Updated { double n, mx, my, mz, e, bx, by, bz; };
+
+MOC_HD bool momentum_zeroed(const Field &F, int i, int j)
+{
+    const int xl = F.bc[0] == MBC_PERIODIC ? 0 : NG, xu = F.bc[1] == MBC_PERIODIC ? F.nx - 1 : F.nx - NG - 1;
+    const int yl = F.bc[2] == MBC_PERIODIC ? 0 : NG, yu = F.bc[3] == MBC_PERIODIC ? F.ny - 1 : F.ny - NG - 1;
+    const bool jin = (j >= yl && j <= yu), iin = (i >= xl && i <= xu);
+    if (i <= 2        && (F.bc[0] == MBC_FIXED || (F.bc[0] == MBC_REFLECT && jin))) return true;
+    if (i >= F.nx - 3 && (F.bc[1] == MBC_FIXED || (F.bc[1] == MBC_REFLECT && jin))) return true;
+    if (j <= 2        && (F.bc[2] == MBC_FIXED || (F.bc[2] == MBC_REFLECT && iin))) return true;
+    if (j >= F.ny - 3 && (F.bc[3] == MBC_FIXED || (F.bc[3] == MBC_REFLECT && iin))) return true;
+    return false;
+}
+// base[0..7] = n, mom_x, mom_y, mom_z, thermal_energy, bi_x, bi_y, bi_z of the state the increment is added to
+MOC_HD Updated advance_cell(const Field &F, const Floors &fl, const double *base, const double *k, double s, bool primary, int i, int j)
+{
+    Updated u;
+    const double rho_u = (base[0] * F.m_i) + k[0] * s;
+    u.mx = base[1] + k[1] * s; u.my = base[2] + k[2] * s; u.mz = base[3] + k[3] * s;
+    const double e_u = base[4] + k[4] * s;
+    u.bx = base[5] + k[5] * s; u.by = base[6] + k[6] * s; u.bz = base[7] + k[7] * s;
+    const double n1 = smax_(rho_u / F.m_i, fl.n_min);            // enforceMinimums :237
+    const double rr = n1 * F.m_i;
+    u.n = smax_(rr / F.m_i, fl.n_min);                           // derived step :246
+    u.e = smax_(e_u, fl.e_min);
+    if (primary && momentum_zeroed(F, i, j)) { u.mx = 0.0; u.my = 0.0; u.mz = 0.0; }
+    return u;
+}
+// recomputeDT (idealmhd.cpp:279-304) for one cell; b = be + bi
+MOC_HD double cell_dt_plain(const Field &F, double n, double mx, double my, double e, double bx, double by, double bz, double dx, double dy)
+{
+    const double rho = n * F.m_i;
+    const double vx = mx / rho, vy = my / rho;
+    const double p = e * F.gm1;
+    const double bm = sqrt((bx * bx + by * by) + bz * bz);
+    const double cs = sqrt(F.gamma * p / rho);
+    const double cs2 = cs * cs;
+    const double va = bm / sqrt(rho * (4.0 * kPi));
+    const double va2 = va * va;
+    const double sm = cs2 + va2;
+    const double delta = sqrt(1.0 - ((cs2 * 4.0) * va2) / (sm * sm));
+    const double vfast = sqrt((sm * 0.5) * (1.0 + delta));
+    const double vslow = sqrt((sm * 0.5) * (1.0 - delta));
+    const double vmx = sqrt(vx * vx), vmy = sqrt(vy * vy);
+    const double M = smax_(smax_(smax_(cs, va), vfast), vslow);
+    return 1.0 / ((vmx + M) / dx + (vmy + M) / dy);
+}
+// is (i, j) inside the bounds of the time-step minimum (the interior widened by the ghost zone on open_moc sides, plasmadomain.cpp:155-159)?
+MOC_HD bool in_dt_bounds(const Field &F, int i, int j)
+{
+    const int xl = (F.bc[0] == MBC_PERIODIC || F.bc[0] == MBC_OPEN_MOC) ? 0 : NG, xu = (F.bc[1] == MBC_PERIODIC || F.bc[1] == MBC_OPEN_MOC) ? F.nx - 1 : F.nx - NG - 1;
+    const int yl = (F.bc[2] == MBC_PERIODIC || F.bc[2] == MBC_OPEN_MOC) ? 0 : NG, yu = (F.bc[3] == MBC_PERIODIC || F.bc[3] == MBC_OPEN_MOC) ? F.ny - 1 : F.ny - NG - 1;
+    return i >= xl && i <= xu && j >= yl && j <= yu;
+}
+MOC_HD bool in_interior(const Field &F, int i, int j)
+{
+    const int xl = F.bc[0] == MBC_PERIODIC ? 0 : NG, xu = F.bc[1] == MBC_PERIODIC ? F.nx - 1 : F.nx - NG - 1;
+    const int yl = F.bc[2] == MBC_PERIODIC ? 0 : NG, yu = F.bc[3] == MBC_PERIODIC ? F.ny - 1 : F.ny - NG - 1;
+    return i >= xl && i <= xu && j >= yl && j <= yu;
 }
 
 // one term of the minimum behind global_visc_coeff (idealmhd.cpp:90) given the cell's dt

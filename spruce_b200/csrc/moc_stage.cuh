@@ -1,0 +1,140 @@
+// moc_stage.cuh -- kernels of the `open_moc` boundary (see moc_kernels.cuh for the arithmetic and the reference lines it replaces).
+//
+// k_moc_stage runs right after the fused stage kernel of the same Runge-Kutta stage.  The stage kernel has treated the ghost cells
+// of an open_moc side like any other ghost cell (right-hand side masked to zero, idealmhd.cpp:99-103); this kernel recomputes those
+// cells with the characteristic right-hand side the reference adds after the mask (char_evolution, idealmhd.cpp:88-103): one thread
+// per evolved ghost cell evaluates k from the stage's input state S, applies the integrator's K-plane rule (evolution.cpp:103-124),
+// writes D = B + k*s with the floors and the pointwise boundary zeroing, and -- in the step's last stage -- folds the cell's new dt into
+// the running minimum, whose bounds include the ghost zone on open_moc sides (plasmadomain.cpp:155-159).
+// k_moc_visc_min evaluates the minimum behind global_visc_coeff (idealmhd.cpp:90) when global_viscosity != 0.
+// STATUS: written after the round-1 GPU budget was spent.  The arithmetic is proven on the host (tests/test_moc_host_check.py);
+// the launch side has not run on a GPU yet (tests/test_zz_gpu_unvalidated.py).
+#pragma once
+#include "mhd_kernels.cuh"
+#include "moc_kernels.cuh"
+
+namespace spruce {
+
+struct MocArgs {
+    const double *S[NEV];         // state the right-hand side is evaluated on
+    const double *B[NEV];         // state the increment is added to
+    double *D[NEV];               // destination
+    const double *st[NSTATIC];
+    double *K1[NEV], *K2[NEV];
+    double *base_buf;             // [NEV][moc_threads]: B of the strip cells, saved BEFORE the stage kernel -- in the last stage D aliases B,
+                                  // and the stage kernel's masked update of a ghost cell (n -> rho -> n round trip) is not the identity
+    int kmode, primary;
+    int dt_only;                  // after a propagateChanges: only the dt of the evolved ghost cells of D (= primary state)
+    double coef;
+    const double *step_ptr;
+    const int *done_ptr;
+    unsigned long long *dtmin_bits;
+    const unsigned long long *visc_min_bits;   // minimum of visc_min_term over the dt bounds (ordered bits), null when global_viscosity == 0
+    double global_viscosity;
+};
+
+__device__ __forceinline__ moc::Field moc_field(const DomainParams &P, const double *const *U, const double *const *st, double visc)
+{
+    moc::Field F;
+    F.n = U[E_N]; F.mx = U[E_MX]; F.my = U[E_MY]; F.mz = U[E_MZ]; F.e = U[E_E]; F.bix = U[E_BX]; F.biy = U[E_BY]; F.biz = U[E_BZ];
+    F.bex = st[S_BEX]; F.bey = st[S_BEY]; F.bez = st[S_BEZ]; F.gx = st[S_GX]; F.gy = st[S_GY];
+    F.dx = P.tx.d; F.dy = P.ty.d;
+    F.nx = P.nx; F.ny = P.ny; F.pitch = P.pitch;
+    F.bc[0] = P.bc_x1; F.bc[1] = P.bc_x2; F.bc[2] = P.bc_y1; F.bc[3] = P.bc_y2;
+    F.m_i = P.m_i; F.gamma = P.gamma; F.gm1 = P.gm1; F.visc = visc;
+    return F;
+}
+
+// thread t -> (side, ghost layer, index along the side) -> cell (i, j); false when t is past the last strip cell
+__device__ __forceinline__ bool moc_thread_cell(const DomainParams &P, int t, int *side, int *i, int *j)
+{
+    const int nxs = HALO * P.ny, nys = HALO * P.nx;
+    if (t < nxs) { *side = 0; *i = t / P.ny; *j = t % P.ny; return true; }
+    t -= nxs;
+    if (t < nxs) { *side = 1; *i = P.nx - HALO + t / P.ny; *j = t % P.ny; return true; }
+    t -= nxs;
+    if (t < nys) { *side = 2; *j = t / P.nx; *i = t % P.nx; return true; }
+    t -= nys;
+    if (t < nys) { *side = 3; *j = P.ny - HALO + t / P.nx; *i = t % P.nx; return true; }
+    return false;
+}
+// a corner cell evolved by two sides is handled by the thread of the first of them
+__device__ __forceinline__ bool moc_thread_owns(const moc::Field &F, int side, int i, int j)
+{
+    if (!moc::side_owns(F, side, i, j)) return false;
+    for (int s = 0; s < side; s++) if (moc::side_owns(F, s, i, j)) return false;
+    return true;
+}
+
+inline int moc_threads(const DomainParams &P) { return 2 * HALO * (P.nx + P.ny); }     // = T in the kernels
+
+// before the stage kernel: keep the base state of the evolved ghost cells
+__global__ void __launch_bounds__(128) k_moc_save(const DomainParams P, const MocArgs A)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int side, i, j;
+    if (*A.done_ptr || !moc_thread_cell(P, t, &side, &i, &j)) return;
+    const moc::Field F = moc_field(P, A.S, A.st, 0.0);
+    if (!moc_thread_owns(F, side, i, j)) return;
+    const size_t q = (size_t)i * P.pitch + j;
+    const int T = 2 * HALO * (P.nx + P.ny);
+    for (int v = 0; v < NEV; v++) A.base_buf[(size_t)v * T + t] = A.B[v][q];
+}
+
+__global__ void __launch_bounds__(128) k_moc_visc_min(const DomainParams P, const MocArgs A, unsigned long long *out_bits)
+{
+    // every cell inside the dt bounds: (1/(1/dx^2 + 1/dy^2)) / dt of the stage's input state
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    double v = 1.7976931348623157e308;
+    if (!*A.done_ptr && j < P.ny) {
+        const moc::Field F = moc_field(P, A.S, A.st, 0.0);
+        if (moc::in_dt_bounds(F, i, j)) {
+            const size_t q = (size_t)i * P.pitch + j;
+            const double dt = moc::cell_dt_plain(F, F.n[q], F.mx[q], F.my[q], F.e[q], F.bex[q] + F.bix[q], F.bey[q] + F.biy[q], F.bez[q] + F.biz[q], F.dx[i], F.dy[j]);
+            v = moc::visc_min_term(F.dx[i], F.dy[j], dt);
+        }
+    }
+    block_min_to_global(v, out_bits);
+}
+
+__global__ void __launch_bounds__(128) k_moc_stage(const DomainParams P, const MocArgs A)
+{
+    double dtc = 1.7976931348623157e308;
+    int side, i, j;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!*A.done_ptr && moc_thread_cell(P, t, &side, &i, &j)) {
+        double visc = 0.0;
+        if (A.visc_min_bits) visc = (A.global_viscosity * 0.5) * __longlong_as_double((long long)*A.visc_min_bits);      // idealmhd.cpp:90
+        const moc::Field F = moc_field(P, A.S, A.st, visc);
+        if (moc_thread_owns(F, side, i, j)) {
+            const size_t q = (size_t)i * P.pitch + j;
+            if (A.dt_only) {
+                if (moc::in_dt_bounds(F, i, j) && !moc::in_interior(F, i, j))
+                    dtc = moc::cell_dt_plain(F, F.n[q], F.mx[q], F.my[q], F.e[q], F.bex[q] + F.bix[q], F.bey[q] + F.biy[q], F.bez[q] + F.biz[q], F.dx[i], F.dy[j]);
+            } else {
+                double k[NEV];
+                moc::moc_cell_terms(F, i, j, k);
+                // integrator K planes (evolution.cpp:103-124); the stage kernel has stored / added the masked zero for this cell already
+                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { for (int v = 0; v < NEV; v++) A.K1[v][q] = k[v]; }
+                else if (A.kmode == KM_STORE_K2) { for (int v = 0; v < NEV; v++) A.K2[v][q] = k[v]; }
+                else if (A.kmode == KM_ADD_K2) { for (int v = 0; v < NEV; v++) A.K2[v][q] = A.K2[v][q] + k[v]; }
+                else if (A.kmode == KM_FINAL) { for (int v = 0; v < NEV; v++) k[v] = (A.K1[v][q] + k[v]) / 6.0 + A.K2[v][q] / 3.0; }
+                if (A.kmode != KM_EXPORT) {
+                    const double s = A.coef * *A.step_ptr;
+                    double base[NEV];
+                    const int T = 2 * HALO * (P.nx + P.ny);
+                    for (int v = 0; v < NEV; v++) base[v] = A.base_buf[(size_t)v * T + t];
+                    const moc::Floors fl{P.n_min, P.e_min};
+                    const moc::Updated u = moc::advance_cell(F, fl, base, k, s, A.primary != 0, i, j);
+                    A.D[E_N][q] = u.n; A.D[E_MX][q] = u.mx; A.D[E_MY][q] = u.my; A.D[E_MZ][q] = u.mz;
+                    A.D[E_E][q] = u.e; A.D[E_BX][q] = u.bx; A.D[E_BY][q] = u.by; A.D[E_BZ][q] = u.bz;
+                    if (A.primary && moc::in_dt_bounds(F, i, j) && !moc::in_interior(F, i, j))
+                        dtc = moc::cell_dt_plain(F, u.n, u.mx, u.my, u.e, F.bex[q] + u.bx, F.bey[q] + u.by, F.bez[q] + u.bz, F.dx[i], F.dy[j]);
+                }
+            }
+        }
+    }
+    if (A.dt_only || (A.primary && A.kmode != KM_EXPORT)) block_min_to_global(dtc, A.dtmin_bits);
+}
+
+}  // namespace spruce

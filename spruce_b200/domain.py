@@ -67,6 +67,8 @@ class PlasmaDomain:
             o = dict(use_sub_cycling=True, remove_curl_terms=False)          # Ideal2F defaults, ideal2F.hpp:62-65
             o.update(eqs_options or {})
             capi.check(self.lib.spruce_eqs_ideal2f_options(self.h, int(o["use_sub_cycling"]), int(o["remove_curl_terms"])))
+        elif eqs_options and "global_viscosity" in eqs_options:               # IdealMHD::parseEquationSetConfigs, idealmhd.cpp:15
+            capi.check(self.lib.spruce_eqs_ideal_mhd_options(self.h, float(eqs_options["global_viscosity"])))
         for name in self.DOMAIN + self.STATE:
             if name in planes:
                 self.upload(name, planes[name])

@@ -119,16 +119,19 @@ double EquationSet::nextStepSize()
 IdealMHD::IdealMHD(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
 int IdealMHD::device_id() const { return SPRUCE_EQS_IDEAL_MHD; }
 
-// idealmhd.cpp:12-40: same keys; the MoC limiters belong to the open_moc boundary, which is outside the built scope
+// idealmhd.cpp:12-40: same keys; the MoC limiters (idealmhd.cpp:107-223) are not built
 void IdealMHD::parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
 {
     for (size_t i = 0; i < lhs.size(); i++) {
         const std::string &k = lhs[i];
-        if (k == "global_viscosity" || k == "viscosity_opt" || k == "moc_b_lower_lim" || k == "moc_b_upper_lim" || k == "moc_mom_lower_lim" || k == "moc_mom_upper_lim") continue;
-        if (k == "moc_b_limiting" || k == "moc_mom_limiting") { SPRUCE_REQUIRE(rhs[i] != "true", "MoC limiting needs the open_moc boundary, which this build does not provide"); continue; }
+        if (k == "global_viscosity") { m_global_viscosity = std::stod(rhs[i]); continue; }
+        if (k == "viscosity_opt" || k == "moc_b_lower_lim" || k == "moc_b_upper_lim" || k == "moc_mom_lower_lim" || k == "moc_mom_upper_lim") continue;
+        if (k == "moc_b_limiting" || k == "moc_mom_limiting") { SPRUCE_REQUIRE(rhs[i] != "true", "MoC limiting (moc_b_limiting / moc_mom_limiting) is not built"); continue; }
         spruce_die(k + " is not recognized for this equation set.");
     }
 }
+
+void IdealMHD::configureDevice() { PlasmaDomain::check(spruce_eqs_ideal_mhd_options(m_pd.device(), m_global_viscosity)); }
 
 Ideal2F::Ideal2F(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
 int Ideal2F::device_id() const { return SPRUCE_EQS_IDEAL_2F; }

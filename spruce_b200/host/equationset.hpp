@@ -93,7 +93,9 @@ public:
     std::vector<int> fields() const override { return {bi_x, bi_y, bi_z}; }
     std::vector<int> timescale() const override { return {dt}; }
 
+    void configureDevice() override;
 private:
+    double m_global_viscosity = 0.0;              // idealmhd.hpp:48; read by the open_moc boundary only (idealmhd.cpp:90)
     void parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
 

@@ -24,3 +24,34 @@ extern "C" int moc_host_terms(const double *const *planes /* n mx my mz e bix bi
     }
     return count;
 }
+
+// one euler step of the evolved ghost cells (D = P + step*k(P), floors, pointwise zeroing) and their new dt
+extern "C" int moc_host_euler(const double *const *planes, const double *dx, const double *dy, int nx, int ny, const int *bc, double m_i, double gamma, double visc,
+                              double n_min, double e_min, double step, double *out /* [8][nx*ny] */, double *dt_out, unsigned char *owned)
+{
+    spruce::moc::Field F;
+    F.n = planes[0]; F.mx = planes[1]; F.my = planes[2]; F.mz = planes[3]; F.e = planes[4]; F.bix = planes[5]; F.biy = planes[6]; F.biz = planes[7];
+    F.bex = planes[8]; F.bey = planes[9]; F.bez = planes[10]; F.gx = planes[11]; F.gy = planes[12];
+    F.dx = dx; F.dy = dy; F.nx = nx; F.ny = ny; F.pitch = ny;
+    for (int s = 0; s < 4; s++) F.bc[s] = bc[s];
+    F.m_i = m_i; F.gamma = gamma; F.gm1 = gamma - 1.0; F.visc = visc;
+    const spruce::moc::Floors fl{n_min, e_min};
+    const size_t n = (size_t)nx * ny;
+    int count = 0;
+    for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) {
+        const size_t q = (size_t)i * ny + j;
+        double k[8];
+        const bool own = spruce::moc::moc_cell_terms(F, i, j, k);
+        owned[q] = own ? 1 : 0;
+        if (!own) continue;
+        count++;
+        double base[8];
+        for (int v = 0; v < 8; v++) base[v] = planes[v][q];
+        const spruce::moc::Updated u = spruce::moc::advance_cell(F, fl, base, k, 1.0 * step, true, i, j);
+        const double vals[8] = {u.n, u.mx, u.my, u.mz, u.e, u.bx, u.by, u.bz};
+        for (int v = 0; v < 8; v++) out[v * n + q] = vals[v];
+        dt_out[q] = spruce::moc::in_dt_bounds(F, i, j) && !spruce::moc::in_interior(F, i, j)
+                        ? spruce::moc::cell_dt_plain(F, u.n, u.mx, u.my, u.e, F.bex[q] + u.bx, F.bey[q] + u.by, F.bez[q] + u.bz, dx[i], dy[j]) : -1.0;
+    }
+    return count;
+}

@@ -91,3 +91,37 @@ def test_product_moc_cell_terms_equal_oracle_rhs(lib, name, xb, yb, gvisc, nx, n
         o.step()
     assert n_owned > 0
     o.close()
+
+
+@pytest.mark.parametrize("name,xb,yb,gvisc,nx,ny", CASES, ids=[c[0] for c in CASES])
+def test_product_moc_euler_update_equals_oracle_step(lib, name, xb, yb, gvisc, nx, ny):
+    """advance_cell + cell_dt_plain (the tail of k_moc_stage): one euler step of the evolved ghost cells -- increment, floors, the
+    momentum zeroing of fixed / reflect sides that sweep into the strip, n round trip -- and their new dt, against the oracle's step."""
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="euler", **floors)
+    o.set_global_viscosity(gvisc)
+    lib.moc_host_euler.restype = C.c_int
+    names = ["n", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z", "be_x", "be_y", "be_z", "grav_x", "grav_y"]
+    for it in range(3):
+        planes = [np.ascontiguousarray(o.get(v), dtype=np.float64) for v in names]
+        dxp, dyp, dt = o.get("d_x"), o.get("d_y"), o.get("dt")
+        xl, xu, yl, yu = dt_bounds(xb, yb, nx, ny)
+        visc = gvisc * 0.5 * float(np.min(((1.0 / (1.0 / (dxp * dxp) + 1.0 / (dyp * dyp))) / dt)[xl:xu + 1, yl:yu + 1]))
+        dx = np.ascontiguousarray(dxp[:, 0]); dy = np.ascontiguousarray(dyp[0, :])
+        arr = (C.c_void_p * 13)(*[p.ctypes.data for p in planes])
+        bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+        out = np.zeros((8, nx, ny)); dt_out = np.zeros((nx, ny)); owned = np.zeros((nx, ny), dtype=np.uint8)
+        step = o.step()
+        cnt = lib.moc_host_euler(arr, dx.ctypes.data_as(C.c_void_p), dy.ctypes.data_as(C.c_void_p), C.c_int(nx), C.c_int(ny), bc, C.c_double(s["ion_mass"]),
+                                 C.c_double(s["adiabatic_index"]), C.c_double(visc), C.c_double(floors["density_min"]), C.c_double(floors["thermal_energy_min"]),
+                                 C.c_double(step), out.ctypes.data_as(C.c_void_p), dt_out.ctypes.data_as(C.c_void_p), owned.ctypes.data_as(C.c_void_p))
+        own = owned.astype(bool)
+        assert cnt == int(own.sum()) and cnt > 0
+        for v, nm in enumerate(names[:8]):
+            ref = np.where(own, o.get(nm), 0.0)
+            assert same_bits(np.where(own, out[v], 0.0), ref), "%s it %d %s: %s" % (name, it, nm, mismatch(np.where(own, out[v], 0.0), ref))
+        have_dt = own & (dt_out >= 0.0)
+        assert np.any(have_dt)
+        assert same_bits(np.where(have_dt, dt_out, 0.0), np.where(have_dt, o.get("dt"), 0.0)), "%s it %d dt: %s" % (name, it, mismatch(np.where(have_dt, dt_out, 0.0), np.where(have_dt, o.get("dt"), 0.0)))
+    o.close()

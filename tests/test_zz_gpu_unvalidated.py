@@ -61,3 +61,46 @@ def test_compile_time_stage_variants_vs_oracle(integ, zfull, nx, ny, xb, yb):
     validated build (scripts/sass_identity.py)."""
     out = run_isolated(STAGE_VARIANT_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, xb=xb, yb=yb), {"SPRUCE_STAGE_VARIANTS": "1"})
     assert "ok" in out
+
+
+MOC_CODE = """
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    xb, yb, integ, gvisc, nx, ny = {xb!r}, {yb!r}, {integ!r}, {gvisc!r}, {nx}, {ny}
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    o.set_global_viscosity(gvisc)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], eqs_options=dict(global_viscosity=gvisc), **kw)
+    assert same_bits(d.grid("dt"), o.get("dt")), "dt after setup: " + mismatch(d.grid("dt"), o.get("dt"))
+    k_dev, k_ref = d.computeTimeDerivatives(), o.rhs()
+    for i, nm in enumerate(PlasmaDomain.EVOLVED):
+        assert same_bits(k_dev[i], k_ref[i]), "d(%s)/dt: %s" % (nm, mismatch(k_dev[i], k_ref[i]))
+    ref = o.run(6)
+    dts = d.advance(6)
+    assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+    for v in PlasmaDomain.EVOLVED + ["dt", "temp", "v_x"]:
+        assert same_bits(d.grid(v), o.get(v)), "%s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("xb,yb,integ,gvisc,nx,ny", [
+    (("periodic", "periodic"), ("fixed", "open_moc"), "euler", 0.0, 126, 93),
+    (("periodic", "periodic"), ("open_moc", "fixed"), "rk2", 0.3, 64, 125),
+    (("open_moc", "reflect"), ("fixed", "open"), "rk4", 0.0, 97, 72),
+    (("open_moc", "open_moc"), ("open_moc", "open_moc"), "rk2", 0.1, 85, 134),
+    (("fixed", "open_moc"), ("open", "open_moc"), "euler", 0.0, 73, 66),
+    (("open_moc", "open_moc"), ("periodic", "periodic"), "rk4", 0.2, 70, 130),
+])
+def test_open_moc_vs_oracle(xb, yb, integ, gvisc, nx, ny):
+    """The method-of-characteristics open boundary on the device (moc_stage.cuh: k_moc_stage, k_moc_visc_min) against the CPU
+    restatement that is pinned to live reference runs: right-hand side incl. the evolved ghost cells, step-size history with the
+    widened bounds, every plane.  The per-cell arithmetic is already proven on the host (tests/test_moc_host_check.py); this is the
+    launch side: thread-to-cell mapping, corner ownership, K planes of rk4, order against the stage kernel and the ghost passes."""
+    out = run_isolated(MOC_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
+    assert "ok" in out
