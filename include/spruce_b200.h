@@ -140,6 +140,22 @@ int spruce_module_viscosity_term(spruce_domain *dom, const char *visc_opt, doubl
  * the host exactly as the reference does.  count of sub-cycles: spruce_module_subcycles(dom, "physical_viscosity", &n). */
 int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on,
                                      int force_on, int gradient_correction, int time_integrator, int inactive_mode);
+/* Pointwise solar source terms applied in postIterateModule (evolution.cpp:74), each followed by propagateChanges.  Gaussian templates
+ * (SolarUtils::GaussianGrid / GaussianGridRotated, source/solar/solarutils.cpp:65-98; centres and widths in grid cells, combined with
+ * their periodic images as the reference does) are built by the library from the reference's config keys:
+ *   AmbientHeatingSink  source/modules/solar/ambientheatingsink.cpp:27-42   reduction = the plane setupModule builds (needs pos_x / pos_y: host)
+ *   LocalizedHeating    source/modules/solar/localizedheating.cpp:31-66     active for start_time <= t <= start_time + duration, linear ramps
+ *   MassInjection       source/modules/solar/massinjection.cpp:27-52
+ *   MomentumInjection   source/modules/solar/momentuminjection.cpp:35-74    incl. the reference's min-combination with the periodic images
+ * Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
+int spruce_module_ambient_heating_sink(spruce_domain *dom, const double *reduction, size_t count);
+int spruce_module_localized_heating(spruce_domain *dom, double start_time, double duration, double max_heating_rate, double stddev_x, double stddev_y,
+                                    double center_x, double center_y, double ramp_time);
+int spruce_module_mass_injection(spruce_domain *dom, double start_time, double duration, double max_injection_rate, double stddev_x, double stddev_y,
+                                 double center_x, double center_y);
+int spruce_module_momentum_injection(spruce_domain *dom, double start_time, double duration, double max_accel, double stddev_x, double stddev_y,
+                                     double center_x, double center_y, double dir_x, double dir_y, double template_angle, int oscillatory,
+                                     double oscillation_period);
 /* IdealMHD::parseEquationSetConfigs (source/equationsets/idealmhd.cpp:12-40): global_viscosity (idealmhd.hpp:48, default 0), read only
  * by the characteristic open boundary (global_visc_coeff, idealmhd.cpp:90).  open_moc sides themselves (idealmhd.cpp:306-615) are
  * selected through spruce_config.x_bound_* / y_bound_* = SPRUCE_BC_OPEN_MOC; until that path has been validated on a GPU

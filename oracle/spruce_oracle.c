@@ -923,6 +923,16 @@ void oracle_add_small_module(oracle *o, int kind, const double *p, int np)
     o->mod.small[o->mod.n_small] = m;
     o->mod.order[o->mod.n_modules++] = 100 + o->mod.n_small++;
 }
+/* test accessor: template / coefficient plane k of small module idx; returns 0 when that plane does not exist (yet: the Gaussian templates
+ * of kinds 7 and 8 are built by the first preIterateModule) */
+int oracle_small_module_plane(oracle *o, int idx, int k, double *out)
+{
+    if (idx < 0 || idx >= o->mod.n_small || k < 0 || k > 1) return 0;
+    const small_module *m = (const small_module *)o->mod.small[idx];
+    if (!m->plane[k]) return 0;
+    memcpy(out, m->plane[k], sizeof(double) * o->n);
+    return 1;
+}
 /* p: time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, metric_smoothing, time_integrator, flood_fill (1) / frobenius (0), flood_fill_max_radius,
  *    flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length, flood_fill_threshold, resistivity_model (0 time_scale, 1 syntelis_19, 2 ys_94),
  *    gradient_correction, model parameter 0..2.  The module's setupModule needs the populated state: call after oracle_setup. */

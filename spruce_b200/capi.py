@@ -55,6 +55,10 @@ SYMBOLS = {
     "spruce_module_viscosity": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "spruce_module_viscosity_term": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double, C.c_char_p, C.c_char_p, C.c_char_p, _DP, C.c_size_t]),
     "spruce_module_physical_viscosity": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "spruce_module_ambient_heating_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "spruce_module_localized_heating": (C.c_int, [C.c_void_p] + [C.c_double] * 8),
+    "spruce_module_mass_injection": (C.c_int, [C.c_void_p] + [C.c_double] * 7),
+    "spruce_module_momentum_injection": (C.c_int, [C.c_void_p] + [C.c_double] * 10 + [C.c_int, C.c_double]),
     "spruce_eqs_ideal_mhd_options": (C.c_int, [C.c_void_p, C.c_double]),
     "spruce_eqs_ideal2f_options": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "spruce_module_eic_thermalization": (C.c_int, [C.c_void_p]),

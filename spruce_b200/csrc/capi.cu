@@ -6,6 +6,7 @@
 #include "module_kernels.cuh"
 #include "mhd_stage_xy.cuh"
 #include "moc_stage.cuh"
+#include "solar_templates.hpp"
 #include "ideal2f_kernels.cuh"
 
 #include <cmath>
@@ -66,7 +67,11 @@ struct spruce_domain {
     // physical_viscosity (source/modules/solar/physicalviscosity.cpp)
     struct { double coeff = 0.0, epsilon = 1.0; int heating_on = 1, force_on = 1, gc = 0, integrator = 0, inactive = 0, nsub = 1;
              double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; bool cg_halo_done = false; } pv;
-    std::vector<int> module_order;
+    std::vector<int> module_order;                 // MOD_* ; MOD_SRC0 + k = sources[k]
+    enum { MOD_SRC0 = 100 };
+    // pointwise solar source terms (module_kernels.cuh: k_source_term), in config order
+    struct SourceTerm { int kind = 0; double start = 0.0, duration = 0.0, ramp_time = 0.0, max_accel = 0.0, period = 1.0; int oscillatory = 0; double *plane[2] = {nullptr, nullptr}; };
+    std::vector<SourceTerm> sources;
     TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
     RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
@@ -534,6 +539,33 @@ int rl_iterate(spruce_domain *d, double dt)
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // radiativelosses.cpp:99-100
     return after_module_propagate(d);
 }
+// postIterateModule of a pointwise source term; time = m_time at the start of the step (evolution.cpp:74 runs before the time update)
+int src_post(spruce_domain *d, const spruce_domain::SourceTerm &m, double time, double step)
+{
+    double f = step;
+    if (m.kind != SRC_SINK && (time < m.start || time > m.start + m.duration)) return SPRUCE_OK;        // localizedheating.cpp:52 etc.: no propagate either
+    if (m.kind == SRC_HEATING) {                                                                         // localizedheating.cpp:53-59
+        const double t = time - m.start;
+        double ramp = 1.0;
+        if (t < m.ramp_time && t <= 0.5 * m.duration) ramp = t / m.ramp_time;
+        else if (t > m.duration - m.ramp_time && t > 0.5 * m.duration) ramp = (m.duration - t) / m.ramp_time;
+        f = step * ramp;
+    } else if (m.kind == SRC_MOMENTUM) {                                                                 // momentuminjection.cpp:70
+        const double osc = m.oscillatory ? std::sin(2.0 * kPI * (time - m.start) / m.period) : 1.0;
+        f = step * (osc * m.max_accel);
+    }
+    SrcArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    A.p0 = m.plane[0]; A.p1 = m.plane[1]; A.kind = m.kind; A.f = f; A.done_ptr = &d->ctl->done;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_source_term<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (m.kind == SRC_MASS) d->raw_rho = true;                     // E_N holds rho until the propagate's floor / n round trip
+    int rc = launch_propagate(d, 0);
+    if (rc) return rc;
+    return after_module_propagate(d);
+}
 int ah_post(spruce_domain *d)
 {
     dim3 grid((d->P.ny + 255) / 256, d->P.nx);
@@ -853,6 +885,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
     int rc;
     k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot);
     d->launches++;
+    double step_time = 0.0, step_size = 0.0;                             // host copies for the post-iterate hooks
     if (!d->module_order.empty()) {
         // the module hooks need the step size on the host (sub-cycle counts decide how many kernels are launched)
         StepCtl h;
@@ -860,6 +893,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         CUDA_TRY(cudaStreamSynchronize(d->stream));
         if (h.done) return SPRUCE_OK;
         const double step = h.step;
+        step_time = h.time; step_size = h.step;
         for (int m : d->module_order) {                                  // preIterateModules, evolution.cpp:65
             if (m == spruce_domain::MOD_TC && (rc = tc_count(d, step, &d->tc_nsub))) return rc;
             if (m == spruce_domain::MOD_RL && (rc = rl_count(d, step, &d->rl_nsub))) return rc;
@@ -887,8 +921,10 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         if ((rc = stage_and_exchange(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
     }
     if ((rc = finish_dt(d))) return rc;                                 // global min(dt) for the next step (evolution.cpp:62)
-    for (int m : d->module_order)                                        // postIterateModules, evolution.cpp:74
+    for (int m : d->module_order) {                                      // postIterateModules, evolution.cpp:74
         if (m == spruce_domain::MOD_AH && (rc = ah_post(d))) return rc;
+        if (m >= spruce_domain::MOD_SRC0 && (rc = src_post(d, d->sources[m - spruce_domain::MOD_SRC0], step_time, step_size))) return rc;
+    }
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1287,6 +1323,73 @@ int spruce_module_ambient_heating(spruce_domain *d, const double *heating, size_
     if (rc) return rc;
     d->module_order.push_back(spruce_domain::MOD_AH);
     return SPRUCE_OK;
+}
+// ---- pointwise solar source terms -------------------------------------------------------------------------------------
+namespace {
+solar::Geom template_geom(const spruce_domain *d)
+{
+    solar::Geom g;
+    g.nx_local = d->P.nx; g.ny = d->P.ny; g.row0 = d->P.row0; g.xdim = d->cfg.xdim; g.ydim = d->cfg.ydim;
+    g.x_periodic = d->cfg.x_bound_1 == SPRUCE_BC_PERIODIC; g.y_periodic = d->cfg.y_bound_1 == SPRUCE_BC_PERIODIC;
+    return g;
+}
+int add_source(spruce_domain *d, spruce_domain::SourceTerm &m, const std::vector<double> *p0, const std::vector<double> *p1)
+{
+    const std::vector<double> *pl[2] = {p0, p1};
+    for (int k = 0; k < 2; k++) {
+        if (!pl[k]) continue;
+        int rc = alloc_plane(d, &m.plane[k]);
+        if (rc) return rc;
+        if ((rc = h2d_plane(d, m.plane[k], pl[k]->data()))) return rc;
+    }
+    d->sources.push_back(m);
+    d->module_order.push_back(spruce_domain::MOD_SRC0 + (int)d->sources.size() - 1);
+    return SPRUCE_OK;
+}
+}  // namespace
+
+int spruce_module_ambient_heating_sink(spruce_domain *d, const double *reduction, size_t count)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "ambient_heating_sink");
+    const size_t np = (size_t)d->P.nx * d->P.ny;
+    if (!reduction || count != np) return fail(SPRUCE_ERR_ARG, "reduction plane needs %zu values", np);
+    spruce_domain::SourceTerm m; m.kind = SRC_SINK;
+    const std::vector<double> p(reduction, reduction + np);
+    return add_source(d, m, &p, nullptr);
+}
+int spruce_module_localized_heating(spruce_domain *d, double start_time, double duration, double max_heating_rate, double stddev_x, double stddev_y,
+                                    double center_x, double center_y, double ramp_time)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "localized_heating");
+    spruce_domain::SourceTerm m; m.kind = SRC_HEATING; m.start = start_time; m.duration = duration; m.ramp_time = ramp_time;
+    std::vector<double> p;
+    solar::positive_template(template_geom(d), max_heating_rate, stddev_x, stddev_y, center_x, center_y, p);
+    return add_source(d, m, &p, nullptr);
+}
+int spruce_module_mass_injection(spruce_domain *d, double start_time, double duration, double max_injection_rate, double stddev_x, double stddev_y,
+                                 double center_x, double center_y)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "mass_injection");
+    spruce_domain::SourceTerm m; m.kind = SRC_MASS; m.start = start_time; m.duration = duration;
+    std::vector<double> p;
+    solar::positive_template(template_geom(d), max_injection_rate, stddev_x, stddev_y, center_x, center_y, p);
+    return add_source(d, m, &p, nullptr);
+}
+int spruce_module_momentum_injection(spruce_domain *d, double start_time, double duration, double max_accel, double stddev_x, double stddev_y, double center_x,
+                                     double center_y, double dir_x, double dir_y, double template_angle, int oscillatory, double oscillation_period)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "momentum_injection");
+    if (dir_x == 0.0 && dir_y == 0.0) return fail(SPRUCE_ERR_ARG, "Momentum Injection module must be given a nonzero acceleration direction");
+    if (!(template_angle > -90.0 && template_angle < 90.0)) return fail(SPRUCE_ERR_ARG, "GaussianGridRotated requires angles between -90 deg and +90 deg");
+    spruce_domain::SourceTerm m; m.kind = SRC_MOMENTUM; m.start = start_time; m.duration = duration; m.max_accel = max_accel;
+    m.oscillatory = oscillatory ? 1 : 0; m.period = oscillation_period;
+    std::vector<double> p[2];
+    solar::momentum_templates(template_geom(d), stddev_x, stddev_y, center_x, center_y, dir_x, dir_y, template_angle, p[0], p[1]);
+    return add_source(d, m, &p[0], &p[1]);
 }
 int spruce_module_physical_viscosity(spruce_domain *d, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on, int force_on,
                                      int gradient_correction, int time_integrator, int inactive_mode)

@@ -349,6 +349,35 @@ __global__ void __launch_bounds__(256) k_ambient_heating(const DomainParams P, d
 
 
 // ---------------------------------------------------------------------------------------------------------
+// Pointwise solar source terms with a static spatial template (postIterateModule hooks, evolution.cpp:74):
+//   SRC_SINK      AmbientHeatingSink  ambientheatingsink.cpp:36   thermal_energy -= dt*reduction          (the mask is part of the plane)
+//   SRC_HEATING   LocalizedHeating    localizedheating.cpp:60     thermal_energy += mask*((dt*ramp)*template)
+//   SRC_MASS      MassInjection       massinjection.cpp:49        rho += mask*((dt*template)*m_i)         (E_N then holds rho: raw_rho propagate)
+//   SRC_MOMENTUM  MomentumInjection   momentuminjection.cpp:71-72 mom_k += mask*(((dt*(osc*max_accel))*template_k)*rho)
+// f = the host-evaluated scalar of this step (dt, dt*ramp, dt, dt*(osc*max_accel)).
+// STATUS: written after the round-1 GPU budget was spent; not yet run on a GPU (tests/test_zz_gpu_unvalidated.py).
+// ---------------------------------------------------------------------------------------------------------
+enum { SRC_SINK = 0, SRC_HEATING = 1, SRC_MASS = 2, SRC_MOMENTUM = 3 };
+struct SrcArgs { double *U[NEV]; const double *p0, *p1; int kind; double f; const int *done_ptr; };
+
+__global__ void __launch_bounds__(256) k_source_term(const DomainParams P, const SrcArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny || *A.done_ptr) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const double mask = is_interior(P, r, j) ? 1.0 : 0.0;
+    if (A.kind == SRC_SINK) A.U[E_E][off] = A.U[E_E][off] - A.f * A.p0[off];
+    else if (A.kind == SRC_HEATING) A.U[E_E][off] = A.U[E_E][off] + mask * (A.f * A.p0[off]);
+    else if (A.kind == SRC_MASS) A.U[E_N][off] = (A.U[E_N][off] * P.m_i) + mask * ((A.f * A.p0[off]) * P.m_i);
+    else {
+        const double rho = A.U[E_N][off] * P.m_i;
+        A.U[E_MX][off] = A.U[E_MX][off] + mask * ((A.f * A.p0[off]) * rho);
+        A.U[E_MY][off] = A.U[E_MY][off] + mask * ((A.f * A.p1[off]) * rho);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Artificial viscosity (source/modules/viscosity.cpp:185-267): one term  dq = visc_coeff * laplacian(q) * scale_fac
 // (+ gradient correction), q = the variable to differentiate of the grid set the RHS is evaluated on (materialised by
 // k_mhd_derive when it is a derived variable), timescale from the PRIMARY state's dt plane / its minimum.

@@ -149,6 +149,23 @@ class PlasmaDomain:
         a = self._local(heating)
         capi.check(self.lib.spruce_module_ambient_heating(self.h, _dp(a), a.size))
 
+    # -- pointwise solar source terms (post-iterate hooks); keyword names are the reference's config keys
+    def set_ambient_heating_sink_plane(self, reduction: np.ndarray):
+        """reduction = the plane AmbientHeatingSink::setupModule builds (ambientheatingsink.cpp:27-33)."""
+        a = self._local(reduction)
+        capi.check(self.lib.spruce_module_ambient_heating_sink(self.h, _dp(a), a.size))
+
+    def set_localized_heating(self, *, start_time, duration, max_heating_rate, stddev_x, stddev_y, center_x, center_y, ramp_time=0.0):
+        capi.check(self.lib.spruce_module_localized_heating(self.h, start_time, duration, max_heating_rate, stddev_x, stddev_y, center_x, center_y, ramp_time))
+
+    def set_mass_injection(self, *, start_time, duration, max_injection_rate, stddev_x, stddev_y, center_x, center_y):
+        capi.check(self.lib.spruce_module_mass_injection(self.h, start_time, duration, max_injection_rate, stddev_x, stddev_y, center_x, center_y))
+
+    def set_momentum_injection(self, *, start_time, duration, max_accel, stddev_x, stddev_y, center_x, center_y, dir_x, dir_y, template_angle=0.0,
+                               oscillatory=False, oscillation_period=1.0):
+        capi.check(self.lib.spruce_module_momentum_injection(self.h, start_time, duration, max_accel, stddev_x, stddev_y, center_x, center_y, dir_x, dir_y,
+                                                             template_angle, int(oscillatory), oscillation_period))
+
     def set_physical_viscosity(self, coeff_plane: np.ndarray, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False,
                                integrator="euler", inactive_mode=False):
         """coeff_plane = PhysicalViscosity::constructCoefficientGrid(coeff, ramp_length, buffer_length) (physicalviscosity.cpp:247-267)."""

@@ -46,7 +46,12 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "radiative_losses") m_modules.emplace_back(new RadiativeLosses(m_pd));
     else if (name == "ambient_heating") m_modules.emplace_back(new AmbientHeating(m_pd));
     else if (name == "physical_viscosity") m_modules.emplace_back(new PhysicalViscosity(m_pd));
-    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, eic_thermalization are).");
+    else if (name == "ambient_heating_sink") m_modules.emplace_back(new AmbientHeatingSink(m_pd));
+    else if (name == "localized_heating") m_modules.emplace_back(new GaussianSource(m_pd, GaussianSource::Heating));
+    else if (name == "mass_injection") m_modules.emplace_back(new GaussianSource(m_pd, GaussianSource::Mass));
+    else if (name == "momentum_injection") m_modules.emplace_back(new GaussianSource(m_pd, GaussianSource::Momentum));
+    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
+                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection are).");
     m_modules.back()->configureModule(in);
 }
 
@@ -164,6 +169,87 @@ void AmbientHeating::setupModule()
         heating(i, j) = h;
     }
     PlasmaDomain::check(spruce_module_ambient_heating(m_pd.device(), heating.ptr(), heating.size()));
+}
+
+// ambientheatingsink.cpp:12-25
+void AmbientHeatingSink::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "heating_rate") heating_rate = std::stod(v);
+        else if (k == "exp_mode") exp_mode = (v == "true");
+        else if (k == "exp_base_heating_rate") exp_base_heating_rate = std::stod(v);
+        else if (k == "exp_scale_height") exp_scale_height = std::stod(v);
+        else if (k == "center_x") center_x = std::stod(v);
+        else if (k == "half_width") half_width = std::stod(v);
+        else if (k == "ms_electron_heating_fraction") ms_electron_heating_fraction = std::stod(v);
+        else std::cerr << k << " config not recognized.\n";
+    }
+}
+// ambientheatingsink.cpp:27-33: the reduction plane (host libm), applied on the device after every step (:35-37)
+void AmbientHeatingSink::setupModule()
+{
+    SPRUCE_REQUIRE(ms_electron_heating_fraction >= 0.0 && ms_electron_heating_fraction <= 1.0, "Ambient Heating Sink MS electron heating fraction must be between 0 and 1");
+    const size_t nx = m_pd.xdim(), ny = m_pd.ydim();
+    const Grid &mask = m_pd.ghostZoneMask(), &pos_x = m_pd.m_grids[PlasmaDomain::pos_x], &pos_y = m_pd.m_grids[PlasmaDomain::pos_y];
+    Grid reduction(nx, ny);
+    for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
+        if (exp_mode) {
+            const double q = (pos_x(i, j) - center_x) / half_width;
+            const double para = 1.0 - q * q;
+            reduction(i, j) = ((mask(i, j) * exp_base_heating_rate) * std::exp((-1.0 * pos_y(i, j)) / exp_scale_height)) * ((para < 0.0) ? 0.0 : para);
+        } else reduction(i, j) = mask(i, j) * heating_rate;
+    }
+    PlasmaDomain::check(spruce_module_ambient_heating_sink(m_pd.device(), reduction.ptr(), reduction.size()));
+}
+
+// localizedheating.cpp:14-29, massinjection.cpp:14-26, momentuminjection.cpp:16-33
+void GaussianSource::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    const char *peak_key = m_kind == Heating ? "max_heating_rate" : m_kind == Mass ? "max_injection_rate" : "max_accel";
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "start_time") start_time = std::stod(v);
+        else if (k == "duration") duration = std::stod(v);
+        else if (k == peak_key) peak = std::stod(v);
+        else if (k == "stddev_x") stddev_x = std::stod(v);
+        else if (k == "stddev_y") stddev_y = std::stod(v);
+        else if (k == "center_x") center_x = std::stod(v);
+        else if (k == "center_y") center_y = std::stod(v);
+        else if (m_kind == Heating && k == "ramp_time") ramp_time = std::stod(v);
+        else if (m_kind == Heating && k == "ms_electron_heating_fraction") ms_electron_heating_fraction = std::stod(v);
+        else if (m_kind == Momentum && k == "dir_x") dir_x = std::stod(v);
+        else if (m_kind == Momentum && k == "dir_y") dir_y = std::stod(v);
+        else if (m_kind == Momentum && k == "template_angle") template_angle = std::stod(v);
+        else if (m_kind == Momentum && k == "oscillatory") oscillatory = (v == "true");
+        else if (m_kind == Momentum && k == "oscillation_period") oscillation_period = std::stod(v);
+        else std::cerr << k << " config not recognized.\n";
+    }
+}
+void GaussianSource::setupModule()
+{
+    spruce_domain *dev = m_pd.device();
+    if (m_kind == Heating) {
+        SPRUCE_REQUIRE(ms_electron_heating_fraction >= 0.0 && ms_electron_heating_fraction <= 1.0, "Localized Heating MS electron heating fraction must be between 0 and 1");
+        PlasmaDomain::check(spruce_module_localized_heating(dev, start_time, duration, peak, stddev_x, stddev_y, center_x, center_y, ramp_time));
+    } else if (m_kind == Mass) {
+        PlasmaDomain::check(spruce_module_mass_injection(dev, start_time, duration, peak, stddev_x, stddev_y, center_x, center_y));
+    } else {
+        SPRUCE_REQUIRE(!(dir_x == 0.0 && dir_y == 0.0), "Momentum Injection module must be given a nonzero acceleration direction");
+        PlasmaDomain::check(spruce_module_momentum_injection(dev, start_time, duration, peak, stddev_x, stddev_y, center_x, center_y, dir_x, dir_y, template_angle,
+                                                             oscillatory ? 1 : 0, oscillation_period));
+    }
+}
+// localizedheating.cpp:69-78, massinjection.cpp:55-64, momentuminjection.cpp:78-87
+std::string GaussianSource::commandLineMessage() const
+{
+    std::ostringstream oss;
+    oss.precision(4);
+    oss << center_x << "," << center_y;
+    std::string result = std::string(m_kind == Heating ? "Heating at " : m_kind == Mass ? "Mass injection at " : "Momentum injection at ") + oss.str();
+    const double t = m_pd.time();
+    result += (t < start_time || t > start_time + duration) ? " Off" : " On";
+    return result;
 }
 
 // viscosity.cpp:6-24

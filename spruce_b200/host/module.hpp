@@ -103,6 +103,34 @@ private:
     bool exp_mode = false, split_exp_mode = false;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
+// ---- pointwise solar source terms (post-iterate hooks); the device library builds the Gaussian templates from these keys
+// source/modules/solar/ambientheatingsink.hpp
+class AmbientHeatingSink : public Module {
+public:
+    explicit AmbientHeatingSink(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override { return exp_mode ? "Ambient Heating On (Exp. Mode)" : "Ambient Heating On"; }   // ambientheatingsink.cpp:44-47
+    bool device_resident() const override { return true; }
+private:
+    double heating_rate = 0.0, exp_base_heating_rate = 0.0, exp_scale_height = 1.0, center_x = 0.0, half_width = 1.0, ms_electron_heating_fraction = 0.5;
+    bool exp_mode = false;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+// source/modules/solar/localizedheating.hpp, massinjection.hpp, momentuminjection.hpp share their window / Gaussian keys
+class GaussianSource : public Module {
+public:
+    enum Kind { Heating, Mass, Momentum };
+    GaussianSource(PlasmaDomain &pd, Kind kind) : Module(pd), m_kind(kind) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override;
+    bool device_resident() const override { return true; }
+private:
+    Kind m_kind;
+    double start_time = 0.0, duration = 0.0, peak = 0.0, stddev_x = 1.0, stddev_y = 1.0, center_x = 0.0, center_y = 0.0, ramp_time = 0.0;
+    double dir_x = 0.0, dir_y = 0.0, template_angle = 0.0, oscillation_period = 1.0, ms_electron_heating_fraction = 0.0;
+    bool oscillatory = false;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
 // source/modules/ucnp/eic_thermalization.hpp -- electron-ion collisional energy exchange (two-fluid equation set only)
 class EICThermalization : public Module {
 public:

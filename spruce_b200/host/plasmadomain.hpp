@@ -36,6 +36,7 @@ public:
     // ---- what the reference exposes to EquationSets / Modules through friend declarations (plasmadomain.hpp:65-91)
     spruce_domain *device() const { return m_dev; }
     size_t xdim() const { return m_xdim; }
+    double time() const { return m_time; }                                                     // m_time, plasmadomain.hpp:75
     size_t ydim() const { return m_ydim; }
     int xl() const { return m_xl; }
     int xu() const { return m_xu; }

@@ -104,3 +104,66 @@ def test_open_moc_vs_oracle(xb, yb, integ, gvisc, nx, ny):
     launch side: thread-to-cell mapping, corner ownership, K planes of rk4, order against the stage kernel and the ghost passes."""
     out = run_isolated(MOC_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
     assert "ok" in out
+
+
+SOURCE_CODE = """
+    import math
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    mods, xb, yb, integ, nx, ny = {mods!r}, {xb!r}, {yb!r}, {integ!r}, {nx}, {ny}
+    s = synthetic.stratified_loop(nx, ny)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    for name, a in mods:
+        o.add_small_module(name, **a)
+        if name == "ambient_heating_sink":            # AmbientHeatingSink::setupModule (ambientheatingsink.cpp:27-33), host libm
+            X, Y = s["planes"]["pos_x"], s["planes"]["pos_y"]
+            mask = np.zeros((nx, ny))
+            il = lambda b: 0 if b == "periodic" else 2
+            ih = lambda b, n: n if b == "periodic" else n - 2
+            mask[il(xb[0]):ih(xb[1], nx), il(yb[0]):ih(yb[1], ny)] = 1.0
+            if a.get("exp_mode"):
+                ex = np.vectorize(math.exp)((-1.0 * Y) / a["exp_scale_height"])
+                q = (X - a["center_x"]) / a["half_width"]
+                red = ((mask * a["exp_base_heating_rate"]) * ex) * np.maximum(1.0 - q * q, 0.0)
+            else:
+                red = mask * a["heating_rate"]
+            d.set_ambient_heating_sink_plane(red)
+        else:
+            b = dict(a)
+            if "oscillatory" in b: b["oscillatory"] = bool(b["oscillatory"])
+            getattr(d, "set_" + name)(**b)
+    ref = o.run(8)
+    dts = d.advance(8)
+    assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+    for v in PlasmaDomain.EVOLVED + ["dt", "temp"]:
+        assert same_bits(d.grid(v), o.get(v)), "%s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("mods,xb,yb,integ,nx,ny", [
+    ([("ambient_heating_sink", dict(heating_rate=1.0e-5)),
+      ("localized_heating", dict(start_time=0.0, duration=5.0, max_heating_rate=1.0e-3, stddev_x=3.0, stddev_y=4.0, center_x=10.0, center_y=8.0, ramp_time=1.0))],
+     ("periodic", "periodic"), ("fixed", "fixed"), "rk2", 96, 70),
+    ([("ambient_heating_sink", dict(exp_mode=1.0, exp_base_heating_rate=2.0e-5, exp_scale_height=8.0e8, center_x=2.0e9, half_width=1.5e9)),
+      ("mass_injection", dict(start_time=0.5, duration=10.0, max_injection_rate=1.0e6, stddev_x=3.0, stddev_y=3.0, center_x=12.0, center_y=10.0))],
+     ("reflect", "open"), ("fixed", "open"), "euler", 75, 88),
+    ([("momentum_injection", dict(start_time=0.0, duration=50.0, max_accel=1.0e3, stddev_x=4.0, stddev_y=3.0, center_x=13.0, center_y=9.0, dir_x=1.0, dir_y=0.5,
+                                  template_angle=20.0, oscillatory=1.0, oscillation_period=3.0))],
+     ("fixed", "open"), ("reflect", "fixed"), "rk2", 81, 64),
+    ([("momentum_injection", dict(start_time=0.0, duration=50.0, max_accel=1.0e3, stddev_x=4.0, stddev_y=3.0, center_x=13.0, center_y=9.0, dir_x=-1.0, dir_y=0.5,
+                                  template_angle=0.0, oscillatory=0.0, oscillation_period=1.0)),
+      ("localized_heating", dict(start_time=0.3, duration=2.0, max_heating_rate=5.0e-4, stddev_x=5.0, stddev_y=2.0, center_x=1.0, center_y=60.0, ramp_time=0.4))],
+     ("periodic", "periodic"), ("periodic", "periodic"), "rk4", 66, 67),
+])
+def test_pointwise_solar_source_terms_vs_oracle(mods, xb, yb, integ, nx, ny):
+    """ambient_heating_sink, localized_heating, mass_injection, momentum_injection on the device (k_source_term + the host-built templates
+    of solar_templates.hpp, which tests/test_solar_templates_host_check.py proves bit-identical on the host) against the pinned oracle."""
+    out = run_isolated(SOURCE_CODE.format(mods=mods, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {})
+    assert "ok" in out
