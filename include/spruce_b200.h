@@ -156,6 +156,12 @@ int spruce_module_mass_injection(spruce_domain *dom, double start_time, double d
 int spruce_module_momentum_injection(spruce_domain *dom, double start_time, double duration, double max_accel, double stddev_x, double stddev_y,
                                      double center_x, double center_y, double dir_x, double dir_y, double template_angle, int oscillatory,
                                      double oscillation_period);
+/* DivCleaning (source/modules/solar/divcleaning.cpp:21-47): post-iterate, sub-cycled diffusion of div(b) out of bi_x / bi_y; sub-cycle count through
+ * spruce_module_subcycles(dom, "div_cleaning", &n).  FieldHeating (source/modules/solar/fieldheating.cpp:30-58): heating from |curl b|, |b|, n and the field
+ * line radius of curvature, evaluated before the modules iterate and applied in iterateModule; inactive_mode computes it without applying it.
+ * Single rank.  Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
+int spruce_module_div_cleaning(spruce_domain *dom, double epsilon, double time_scale);
+int spruce_module_field_heating(spruce_domain *dom, double coeff, double current_pow, double b_pow, double n_pow, double roc_pow, int inactive_mode);
 /* IdealMHD::parseEquationSetConfigs (source/equationsets/idealmhd.cpp:12-40): global_viscosity (idealmhd.hpp:48, default 0), read only
  * by the characteristic open boundary (global_visc_coeff, idealmhd.cpp:90).  open_moc sides themselves (idealmhd.cpp:306-615) are
  * selected through spruce_config.x_bound_* / y_bound_* = SPRUCE_BC_OPEN_MOC; until that path has been validated on a GPU

@@ -59,6 +59,8 @@ SYMBOLS = {
     "spruce_module_localized_heating": (C.c_int, [C.c_void_p] + [C.c_double] * 8),
     "spruce_module_mass_injection": (C.c_int, [C.c_void_p] + [C.c_double] * 7),
     "spruce_module_momentum_injection": (C.c_int, [C.c_void_p] + [C.c_double] * 10 + [C.c_int, C.c_double]),
+    "spruce_module_div_cleaning": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "spruce_module_field_heating": (C.c_int, [C.c_void_p] + [C.c_double] * 5 + [C.c_int]),
     "spruce_eqs_ideal_mhd_options": (C.c_int, [C.c_void_p, C.c_double]),
     "spruce_eqs_ideal2f_options": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "spruce_module_eic_thermalization": (C.c_int, [C.c_void_p]),

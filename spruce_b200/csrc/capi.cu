@@ -68,7 +68,9 @@ struct spruce_domain {
     struct { double coeff = 0.0, epsilon = 1.0; int heating_on = 1, force_on = 1, gc = 0, integrator = 0, inactive = 0, nsub = 1;
              double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; bool cg_halo_done = false; } pv;
     std::vector<int> module_order;                 // MOD_* ; MOD_SRC0 + k = sources[k]
-    enum { MOD_SRC0 = 100 };
+    enum { MOD_SRC0 = 100, MOD_DC = 6, MOD_FH = 7 };
+    struct { double epsilon = 0.1, time_scale = 1.0; int nsub = 0; } dc;                            // div_cleaning (divcleaning.hpp:22-23)
+    struct { double coeff = 0.0, current_pow = 0.0, b_pow = 0.0, n_pow = 0.0, roc_pow = 0.0; int inactive = 0; double *H = nullptr; } fh;   // field_heating
     // pointwise solar source terms (module_kernels.cuh: k_source_term), in config order
     struct SourceTerm { int kind = 0; double start = 0.0, duration = 0.0, ramp_time = 0.0, max_accel = 0.0, period = 1.0; int oscillatory = 0; double *plane[2] = {nullptr, nullptr}; };
     std::vector<SourceTerm> sources;
@@ -566,6 +568,75 @@ int src_post(spruce_domain *d, const spruce_domain::SourceTerm &m, double time, 
     if (rc) return rc;
     return after_module_propagate(d);
 }
+int launch_op(spruce_domain *d, int code, int index, const double *q, double *out)
+{
+    OpArgs A{};
+    A.q = q; A.vel = nullptr; A.out = out; A.op = code; A.index = index;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_operator<<<grid, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+// DivCleaning::postIterateModule (divcleaning.cpp:26-47); scratch: Mset planes 0..4 (b_x, b_y, first derivative, mixed derivative, second derivative)
+int dc_post(spruce_domain *d, double dt)
+{
+    int rc;
+    double *bx = d->Mset.p[0], *by = d->Mset.p[1], *a = d->Mset.p[2], *b = d->Mset.p[3], *s2 = d->Mset.p[4];
+    double *bix = d->Pset.p[E_BX], *biy = d->Pset.p[E_BY];
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    const int ns = (int)(dt / (d->dc.epsilon * d->dc.time_scale)) + 1;                              // :30
+    const double dts = dt / ((double)ns);
+    d->dc.nsub = ns;
+    k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, bx, d->stat[S_BEX], bix);                        // b_x = be_x + bi_x (idealmhd.cpp:262)
+    k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, by, d->stat[S_BEY], biy);
+    d->launches += 2;
+    for (int s = 0; s < ns; s++) {
+        DcArgs A{};
+        A.dts = dts; A.time_scale = d->dc.time_scale;
+        if ((rc = launch_op(d, 0, 1, by, a)) || (rc = launch_op(d, 0, 0, a, b)) || (rc = launch_op(d, 1, 0, bx, s2))) return rc;    // d/dx(d/dy b_y) + d2/dx2 b_x  :36-37
+        A.bi = bix; A.mixed = b; A.second = s2;
+        k_dc_update<<<grid, 256, 0, d->stream>>>(d->P, A);
+        if ((rc = launch_op(d, 0, 0, bx, a)) || (rc = launch_op(d, 0, 1, a, b)) || (rc = launch_op(d, 1, 1, by, s2))) return rc;    // b_x is still the sub-cycle's starting value  :38-40
+        A.bi = biy;
+        k_dc_update<<<grid, 256, 0, d->stream>>>(d->P, A);
+        k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, bx, bix, d->stat[S_BEX]);                    // :41-42
+        k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, by, biy, d->stat[S_BEY]);
+        d->launches += 4;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = launch_propagate(d, 0))) return rc;                                                   // :46
+    return after_module_propagate(d);
+}
+// FieldHeating::preIterateModule (fieldheating.cpp:30-46); scratch: Mset planes 0..4
+int fh_pre(spruce_domain *d)
+{
+    int rc;
+    const int vars[5] = {V_b_x, V_b_y, V_b_hat_x, V_b_hat_y, V_b_mag};
+    for (int k = 0; k < 5; k++) if ((rc = derive_to(d, vars[k], d->Mset.p[k]))) return rc;
+    FhArgs A{};
+    A.bx = d->Mset.p[0]; A.by = d->Mset.p[1]; A.bhx = d->Mset.p[2]; A.bhy = d->Mset.p[3]; A.bmag = d->Mset.p[4]; A.n = d->Pset.p[E_N];
+    A.H = d->fh.H; A.coeff = d->fh.coeff; A.current_pow = d->fh.current_pow; A.b_pow = d->fh.b_pow; A.n_pow = d->fh.n_pow; A.roc_pow = d->fh.roc_pow;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_fh_compute<<<grid, 128, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+// FieldHeating::iterateModule (fieldheating.cpp:48-58)
+int fh_iterate(spruce_domain *d, double dt)
+{
+    FhArgs A{};
+    A.H = d->fh.H; A.e = d->Pset.p[E_E]; A.dt = dt; A.inactive = d->fh.inactive;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_fh_apply<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (d->fh.inactive) return SPRUCE_OK;                                                           // :53
+    int rc = launch_propagate(d, 0);
+    if (rc) return rc;
+    return after_module_propagate(d);
+}
 int ah_post(spruce_domain *d)
 {
     dim3 grid((d->P.ny + 255) / 256, d->P.nx);
@@ -897,12 +968,14 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         for (int m : d->module_order) {                                  // preIterateModules, evolution.cpp:65
             if (m == spruce_domain::MOD_TC && (rc = tc_count(d, step, &d->tc_nsub))) return rc;
             if (m == spruce_domain::MOD_RL && (rc = rl_count(d, step, &d->rl_nsub))) return rc;
+            if (m == spruce_domain::MOD_FH && (rc = fh_pre(d))) return rc;
         }
         for (int m : d->module_order) {                                  // iterateModules, evolution.cpp:66
             if (m == spruce_domain::MOD_TC && (rc = tc_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_RL && (rc = rl_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_AV && (rc = av_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_PV && (rc = pv_iterate(d, step))) return rc;
+            if (m == spruce_domain::MOD_FH && (rc = fh_iterate(d, step))) return rc;
         }
     }
     if (!d->visc.empty() && (rc = visc_refresh_dt(d))) return rc;     // Viscosity reads the PRIMARY state's dt plane
@@ -923,6 +996,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
     if ((rc = finish_dt(d))) return rc;                                 // global min(dt) for the next step (evolution.cpp:62)
     for (int m : d->module_order) {                                      // postIterateModules, evolution.cpp:74
         if (m == spruce_domain::MOD_AH && (rc = ah_post(d))) return rc;
+        if (m == spruce_domain::MOD_DC && (rc = dc_post(d, step_size))) return rc;
         if (m >= spruce_domain::MOD_SRC0 && (rc = src_post(d, d->sources[m - spruce_domain::MOD_SRC0], step_time, step_size))) return rc;
     }
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
@@ -1391,6 +1465,26 @@ int spruce_module_momentum_injection(spruce_domain *d, double start_time, double
     solar::momentum_templates(template_geom(d), stddev_x, stddev_y, center_x, center_y, dir_x, dir_y, template_angle, p[0], p[1]);
     return add_source(d, m, &p[0], &p[1]);
 }
+int spruce_module_div_cleaning(spruce_domain *d, double epsilon, double time_scale)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "div_cleaning");
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "div_cleaning on a slab decomposition is not built");
+    if (!(epsilon > 0.0) || !(time_scale > 0.0)) return fail(SPRUCE_ERR_ARG, "div_cleaning needs epsilon > 0 and time_scale > 0");
+    d->dc.epsilon = epsilon; d->dc.time_scale = time_scale;
+    d->module_order.push_back(spruce_domain::MOD_DC);
+    return SPRUCE_OK;
+}
+int spruce_module_field_heating(spruce_domain *d, double coeff, double current_pow, double b_pow, double n_pow, double roc_pow, int inactive_mode)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "field_heating");
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "field_heating on a slab decomposition is not built");
+    d->fh.coeff = coeff; d->fh.current_pow = current_pow; d->fh.b_pow = b_pow; d->fh.n_pow = n_pow; d->fh.roc_pow = roc_pow; d->fh.inactive = inactive_mode ? 1 : 0;
+    if (!d->fh.H) { int rc = alloc_plane(d, &d->fh.H); if (rc) return rc; }
+    d->module_order.push_back(spruce_domain::MOD_FH);
+    return SPRUCE_OK;
+}
 int spruce_module_physical_viscosity(spruce_domain *d, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on, int force_on,
                                      int gradient_correction, int time_integrator, int inactive_mode)
 {
@@ -1480,6 +1574,7 @@ int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
     if (!strcmp(which, "thermal_conduction")) *count = d->tc_nsub;
     else if (!strcmp(which, "radiative_losses")) *count = d->rl_nsub;
     else if (!strcmp(which, "physical_viscosity")) *count = d->pv.nsub;
+    else if (!strcmp(which, "div_cleaning")) *count = d->dc.nsub;
     else return fail(SPRUCE_ERR_ARG, "no sub-cycling module named <%s>", which);
     return SPRUCE_OK;
 }

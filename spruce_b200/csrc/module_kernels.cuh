@@ -378,6 +378,80 @@ __global__ void __launch_bounds__(256) k_source_term(const DomainParams P, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// DivCleaning (source/modules/solar/divcleaning.cpp:21-47): sub-cycled diffusion of div(b) out of bi_x, bi_y.  The mixed and second
+// derivatives are whole-plane passes of k_operator (derivative1D returns zero outside the interior, as the reference's does, so the
+// composition d/dx(d/dy b_y) sees zeros in the ghost rows exactly like the reference); this kernel is the update of one component:
+//   bi += ((mask*dt_sub) * coeff) * (mixed + second),   coeff = ((1/(1/dx^2 + 1/dy^2))/2)/time_scale      (:24, :36-40)
+// STATUS: not yet run on a GPU (tests/test_zz_gpu_unvalidated.py).
+// ---------------------------------------------------------------------------------------------------------
+struct DcArgs { double *bi; const double *mixed, *second; double dts, time_scale; };
+__global__ void __launch_bounds__(256) k_dc_update(const DomainParams P, const DcArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const double mask = is_interior(P, r, j) ? 1.0 : 0.0;
+    const double dx = P.tx.d[r], dy = P.ty.d[j];
+    const double coeff = ((1.0 / (1.0 / (dx * dx) + 1.0 / (dy * dy))) / 2.0) / A.time_scale;
+    A.bi[off] = A.bi[off] + ((mask * A.dts) * coeff) * (A.mixed[off] + A.second[off]);
+}
+__global__ void __launch_bounds__(256) k_plane_sum(const DomainParams P, double *out, const double *a, const double *b)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    out[off] = a[off] + b[off];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FieldHeating (source/modules/solar/fieldheating.cpp:30-58): heating = coeff * (c/4pi |curl b|)^current_pow * |b|^b_pow * n^n_pow / roc^roc_pow,
+// roc = 1/max(|(b_hat . grad) b_hat|, 1e-16), evaluated in preIterateModule on the state BEFORE any module iterates (:30-46);
+// iterateModule (:48-58) applies thermal_energy += mask*(dt*heating).  pow with run-time exponents: the libm tolerance class.
+// Operands: derived planes b_x, b_y, b_hat_x, b_hat_y, b_mag materialised by k_mhd_derive.  STATUS: not yet run on a GPU.
+// ---------------------------------------------------------------------------------------------------------
+constexpr double kCLight = 29979245800.0;            // C, source/constants.hpp:18
+struct FhArgs { const double *bx, *by, *bhx, *bhy, *bmag, *n; double *H; double *e; double coeff, current_pow, b_pow, n_pow, roc_pow, dt; int inactive; };
+__global__ void __launch_bounds__(128) k_fh_compute(const DomainParams P, const FhArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    double h = A.coeff;
+    if (A.coeff == 0.0) { A.H[off] = 0.0; return; }
+    if (A.current_pow != 0.0) {
+        auto BX = [&](int a, int b) { return rd(P, A.bx, a, b); };
+        auto BY = [&](int a, int b) { return rd(P, A.by, a, b); };
+        const double curl = Dx(P, BY, r, j) - Dy(P, BX, r, j);                                  // curl2D, derivs.cpp:472-474
+        h = h * pow((kCLight / (4.0 * kPI)) * fabs(curl), A.current_pow);
+    }
+    if (A.b_pow != 0.0) h = h * pow(A.bmag[off], A.b_pow);
+    if (A.n_pow != 0.0) h = h * pow(A.n[off], A.n_pow);
+    if (A.roc_pow != 0.0) {
+        auto HX = [&](int a, int b) { return rd(P, A.bhx, a, b); };
+        auto HY = [&](int a, int b) { return rd(P, A.bhy, a, b); };
+        const double hx = A.bhx[off], hy = A.bhy[off];
+        const double cx = hx * Dx(P, HX, r, j) + hy * Dy(P, HX, r, j), cy = hx * Dx(P, HY, r, j) + hy * Dy(P, HY, r, j);
+        const double roc = 1.0 / smax(sqrt(cx * cx + cy * cy), 1.0e-16);
+        h = h / pow(roc, A.roc_pow);
+    }
+    A.H[off] = h;
+}
+__global__ void __launch_bounds__(256) k_fh_apply(const DomainParams P, const FhArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const double mask = is_interior(P, r, j) ? 1.0 : 0.0;
+    const double h = mask * (A.dt * A.H[off]);
+    A.H[off] = h;
+    if (!A.inactive) A.e[off] = A.e[off] + h;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Artificial viscosity (source/modules/viscosity.cpp:185-267): one term  dq = visc_coeff * laplacian(q) * scale_fac
 // (+ gradient correction), q = the variable to differentiate of the grid set the RHS is evaluated on (materialised by
 // k_mhd_derive when it is a derived variable), timescale from the PRIMARY state's dt plane / its minimum.

@@ -166,6 +166,12 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_module_momentum_injection(self.h, start_time, duration, max_accel, stddev_x, stddev_y, center_x, center_y, dir_x, dir_y,
                                                              template_angle, int(oscillatory), oscillation_period))
 
+    def set_div_cleaning(self, *, epsilon=0.1, time_scale=1.0):
+        capi.check(self.lib.spruce_module_div_cleaning(self.h, epsilon, time_scale))
+
+    def set_field_heating(self, *, coeff=0.0, current_pow=0.0, b_pow=0.0, n_pow=0.0, roc_pow=0.0, inactive_mode=False):
+        capi.check(self.lib.spruce_module_field_heating(self.h, coeff, current_pow, b_pow, n_pow, roc_pow, int(inactive_mode)))
+
     def set_physical_viscosity(self, coeff_plane: np.ndarray, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False,
                                integrator="euler", inactive_mode=False):
         """coeff_plane = PhysicalViscosity::constructCoefficientGrid(coeff, ramp_length, buffer_length) (physicalviscosity.cpp:247-267)."""

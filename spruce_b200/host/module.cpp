@@ -50,8 +50,10 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "localized_heating") m_modules.emplace_back(new GaussianSource(m_pd, GaussianSource::Heating));
     else if (name == "mass_injection") m_modules.emplace_back(new GaussianSource(m_pd, GaussianSource::Mass));
     else if (name == "momentum_injection") m_modules.emplace_back(new GaussianSource(m_pd, GaussianSource::Momentum));
+    else if (name == "div_cleaning") m_modules.emplace_back(new DivCleaning(m_pd));
+    else if (name == "field_heating") m_modules.emplace_back(new FieldHeating(m_pd));
     else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
-                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection are).");
+                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating are).");
     m_modules.back()->configureModule(in);
 }
 
@@ -250,6 +252,47 @@ std::string GaussianSource::commandLineMessage() const
     const double t = m_pd.time();
     result += (t < start_time || t > start_time + duration) ? " Off" : " On";
     return result;
+}
+
+// divcleaning.cpp:11-19
+void DivCleaning::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "epsilon") epsilon = std::stod(v);
+        if (k == "time_scale") time_scale = std::stod(v);
+        else std::cerr << k << " config not recognized.\n";            // the reference prints this for "epsilon" too (an if where an else-if was meant)
+    }
+}
+void DivCleaning::setupModule() { PlasmaDomain::check(spruce_module_div_cleaning(m_pd.device(), epsilon, time_scale)); }
+
+// fieldheating.cpp:14-28
+void FieldHeating::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "output_to_file") output_to_file = (v == "true");
+        else if (k == "coeff") coeff = std::stod(v);
+        else if (k == "current_pow") current_pow = std::stod(v);
+        else if (k == "b_pow") b_pow = std::stod(v);
+        else if (k == "n_pow") n_pow = std::stod(v);
+        else if (k == "roc_pow") roc_pow = std::stod(v);
+        else if (k == "inactive_mode") inactive_mode = (v == "true");
+        else std::cerr << k << " config not recognized.\n";
+    }
+}
+void FieldHeating::setupModule()
+{
+    no_file_output(output_to_file, "field_heating");
+    PlasmaDomain::check(spruce_module_field_heating(m_pd.device(), coeff, current_pow, b_pow, n_pow, roc_pow, inactive_mode ? 1 : 0));
+}
+// fieldheating.cpp:64-71
+std::string FieldHeating::commandLineMessage() const
+{
+    std::string message = "Field Heating";
+    message += (coeff == 0.0) ? " Zero" : " On";
+    if (inactive_mode) message += " (Not Applied)";
+    return message;
 }
 
 // viscosity.cpp:6-24

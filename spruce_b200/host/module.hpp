@@ -131,6 +131,29 @@ private:
     bool oscillatory = false;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
+// source/modules/solar/divcleaning.hpp
+class DivCleaning : public Module {
+public:
+    explicit DivCleaning(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override { return "Div. Cleaning On"; }
+    bool device_resident() const override { return true; }
+private:
+    double epsilon = 0.1, time_scale = 1.0;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+// source/modules/solar/fieldheating.hpp
+class FieldHeating : public Module {
+public:
+    explicit FieldHeating(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override;
+    bool device_resident() const override { return true; }
+private:
+    double coeff = 0.0, current_pow = 0.0, b_pow = 0.0, n_pow = 0.0, roc_pow = 0.0;
+    bool inactive_mode = false, output_to_file = false;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
 // source/modules/ucnp/eic_thermalization.hpp -- electron-ion collisional energy exchange (two-fluid equation set only)
 class EICThermalization : public Module {
 public:

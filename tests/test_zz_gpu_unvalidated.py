@@ -167,3 +167,50 @@ def test_pointwise_solar_source_terms_vs_oracle(mods, xb, yb, integ, nx, ny):
     of solar_templates.hpp, which tests/test_solar_templates_host_check.py proves bit-identical on the host) against the pinned oracle."""
     out = run_isolated(SOURCE_CODE.format(mods=mods, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {})
     assert "ok" in out
+
+
+DC_FH_CODE = """
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    mods, xb, yb, integ, nx, ny, exact = {mods!r}, {xb!r}, {yb!r}, {integ!r}, {nx}, {ny}, {exact!r}
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    for name, a in mods:
+        o.add_small_module(name, **a)
+        b = dict(a)
+        if "inactive_mode" in b: b["inactive_mode"] = bool(b["inactive_mode"])
+        getattr(d, "set_" + name)(**b)
+    rel = lambda x, y: float(np.max(np.abs(x - y)) / max(np.max(np.abs(y)), 1e-300))
+    ref = o.run(6)
+    dts = d.advance(6)
+    if exact:
+        assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+    else:
+        assert np.max(np.abs(np.array(dts) - np.array(ref)) / np.array(ref)) <= 1e-9
+    for v in PlasmaDomain.EVOLVED + ["dt", "temp"]:
+        if exact:
+            assert same_bits(d.grid(v), o.get(v)), "%s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+        else:
+            assert rel(d.grid(v), o.get(v)) <= 1e-9, "%s: rel Linf %.3e" % (v, rel(d.grid(v), o.get(v)))
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("mods,xb,yb,integ,nx,ny,exact", [
+    ([("div_cleaning", dict(epsilon=0.1, time_scale=5.0))], ("fixed", "open"), ("reflect", "fixed"), "rk2", 81, 64, True),
+    ([("div_cleaning", dict(epsilon=0.05, time_scale=2.0))], ("periodic", "periodic"), ("fixed", "fixed"), "euler", 70, 93, True),
+    ([("field_heating", dict(coeff=1.0, current_pow=1.0, b_pow=0.5, n_pow=0.25, roc_pow=0.5, inactive_mode=0.0))], ("periodic", "periodic"), ("fixed", "open"), "rk2", 77, 66, False),
+    ([("field_heating", dict(coeff=3.0e-3, current_pow=0.0, b_pow=2.0, n_pow=0.0, roc_pow=0.0, inactive_mode=0.0)), ("div_cleaning", dict(epsilon=0.1, time_scale=5.0))],
+     ("reflect", "reflect"), ("open", "fixed"), "rk4", 65, 72, False),
+])
+def test_div_cleaning_and_field_heating_vs_oracle(mods, xb, yb, integ, nx, ny, exact):
+    """div_cleaning (whole-plane operator passes + k_dc_update; bit for bit) and field_heating (k_fh_compute / k_fh_apply; pow with run-time
+    exponents, CUDA vs glibc: <= 1e-9) against the pinned oracle."""
+    out = run_isolated(DC_FH_CODE.format(mods=mods, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny, exact=exact), {})
+    assert "ok" in out
