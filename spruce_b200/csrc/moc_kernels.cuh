@@ -350,6 +350,29 @@ MOC_HD bool side_owns(const Field &F, int s, int i, int j)
     return a >= S.alo && a <= S.ahi && b >= S.Flo && b <= S.Fhi;
 }
 
+// ---- thread -> cell mapping of the strip kernels (moc_stage.cuh): 2 ghost layers x the full length of each of the four sides
+MOC_HD int n_threads(int nx, int ny) { return 2 * NG * (nx + ny); }
+MOC_HD bool thread_cell(int nx, int ny, int t, int *side, int *i, int *j)
+{
+    const int nxs = NG * ny, nys = NG * nx;
+    if (t < 0) return false;
+    if (t < nxs) { *side = 0; *i = t / ny; *j = t % ny; return true; }
+    t -= nxs;
+    if (t < nxs) { *side = 1; *i = nx - NG + t / ny; *j = t % ny; return true; }
+    t -= nxs;
+    if (t < nys) { *side = 2; *j = t / nx; *i = t % nx; return true; }
+    t -= nys;
+    if (t < nys) { *side = 3; *j = ny - NG + t / nx; *i = t % nx; return true; }
+    return false;
+}
+// a corner cell evolved by two sides is handled by the thread of the first of them
+MOC_HD bool thread_owns(const Field &F, int side, int i, int j)
+{
+    if (!side_owns(F, side, i, j)) return false;
+    for (int s = 0; s < side; s++) if (side_owns(F, s, i, j)) return false;
+    return true;
+}
+
 // computeTimeDerivativesCharacteristicBoundary at cell (i, j) (idealmhd.cpp:306-331 + :88-103): the characteristic part of
 // d/dt of the EVOLVED variables rho, mom_x, mom_y, mom_z, thermal_energy, bi_x, bi_y, bi_z.  Returns false when no open_moc side
 // evolves this cell (k stays untouched).

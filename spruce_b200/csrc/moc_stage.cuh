@@ -45,28 +45,10 @@ __device__ __forceinline__ moc::Field moc_field(const DomainParams &P, const dou
     return F;
 }
 
-// thread t -> (side, ghost layer, index along the side) -> cell (i, j); false when t is past the last strip cell
-__device__ __forceinline__ bool moc_thread_cell(const DomainParams &P, int t, int *side, int *i, int *j)
-{
-    const int nxs = HALO * P.ny, nys = HALO * P.nx;
-    if (t < nxs) { *side = 0; *i = t / P.ny; *j = t % P.ny; return true; }
-    t -= nxs;
-    if (t < nxs) { *side = 1; *i = P.nx - HALO + t / P.ny; *j = t % P.ny; return true; }
-    t -= nxs;
-    if (t < nys) { *side = 2; *j = t / P.nx; *i = t % P.nx; return true; }
-    t -= nys;
-    if (t < nys) { *side = 3; *j = P.ny - HALO + t / P.nx; *i = t % P.nx; return true; }
-    return false;
-}
-// a corner cell evolved by two sides is handled by the thread of the first of them
-__device__ __forceinline__ bool moc_thread_owns(const moc::Field &F, int side, int i, int j)
-{
-    if (!moc::side_owns(F, side, i, j)) return false;
-    for (int s = 0; s < side; s++) if (moc::side_owns(F, s, i, j)) return false;
-    return true;
-}
+__device__ __forceinline__ bool moc_thread_cell(const DomainParams &P, int t, int *side, int *i, int *j) { return moc::thread_cell(P.nx, P.ny, t, side, i, j); }
+__device__ __forceinline__ bool moc_thread_owns(const moc::Field &F, int side, int i, int j) { return moc::thread_owns(F, side, i, j); }
 
-inline int moc_threads(const DomainParams &P) { return 2 * HALO * (P.nx + P.ny); }     // = T in the kernels
+inline int moc_threads(const DomainParams &P) { return moc::n_threads(P.nx, P.ny); }     // = T in the kernels
 
 // before the stage kernel: keep the base state of the evolved ghost cells
 __global__ void __launch_bounds__(128) k_moc_save(const DomainParams P, const MocArgs A)

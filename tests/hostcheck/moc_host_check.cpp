@@ -55,3 +55,20 @@ extern "C" int moc_host_euler(const double *const *planes, const double *dx, con
     }
     return count;
 }
+
+// the strip kernels' thread -> cell mapping: visits[i*ny + j] = number of threads that own cell (i, j); returns the thread count
+extern "C" int moc_host_thread_visits(int nx, int ny, const int *bc, int *visits)
+{
+    spruce::moc::Field F{};
+    F.nx = nx; F.ny = ny; F.pitch = ny;
+    for (int s = 0; s < 4; s++) F.bc[s] = bc[s];
+    const int T = spruce::moc::n_threads(nx, ny);
+    for (int t = 0; t < T + 64; t++) {                  // past-the-end threads of the last block must map to nothing
+        int side, i, j;
+        if (!spruce::moc::thread_cell(nx, ny, t, &side, &i, &j)) continue;
+        if (t >= T) return -1;
+        if (i < 0 || i >= nx || j < 0 || j >= ny) return -2;
+        if (spruce::moc::thread_owns(F, side, i, j)) visits[(size_t)i * ny + j]++;
+    }
+    return T;
+}

@@ -125,3 +125,18 @@ def test_product_moc_euler_update_equals_oracle_step(lib, name, xb, yb, gvisc, n
         assert np.any(have_dt)
         assert same_bits(np.where(have_dt, dt_out, 0.0), np.where(have_dt, o.get("dt"), 0.0)), "%s it %d dt: %s" % (name, it, mismatch(np.where(have_dt, dt_out, 0.0), np.where(have_dt, o.get("dt"), 0.0)))
     o.close()
+
+
+@pytest.mark.parametrize("name,xb,yb,gvisc,nx,ny", CASES, ids=[c[0] for c in CASES])
+def test_strip_kernel_thread_mapping_visits_every_evolved_ghost_cell_once(lib, name, xb, yb, gvisc, nx, ny):
+    """thread_cell / thread_owns (what k_moc_save and k_moc_stage index with): every cell some open_moc side evolves is owned by exactly one
+    thread (corner cells belong to two sides), no other cell by any, and threads past the end map to nothing."""
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="euler", density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    _, owned, _ = host_terms(lib, o, xb, yb, 0.0, s["ion_mass"], s["adiabatic_index"])
+    visits = np.zeros((nx, ny), dtype=np.int32)
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    T = lib.moc_host_thread_visits(C.c_int(nx), C.c_int(ny), bc, visits.ctypes.data_as(C.c_void_p))
+    assert T == 4 * (nx + ny)
+    assert np.array_equal(visits, owned.astype(np.int32))
+    o.close()
