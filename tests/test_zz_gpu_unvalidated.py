@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parents[1]
 UNVALIDATED = pytest.mark.xfail(reason="written after the round-1 GPU budget was spent; never executed on a GPU", strict=False)
 
 
-def run_isolated(code: str, env: dict, timeout: int = 600):
+def run_isolated(code: str, env: dict, timeout: int = 90):
     e = dict(os.environ); e.update(env)
     e["PYTHONPATH"] = os.pathsep.join([str(ROOT), str(ROOT / "tests"), e.get("PYTHONPATH", "")])
     r = subprocess.run([sys.executable, "-c", textwrap.dedent(code)], cwd=str(ROOT), env=e, capture_output=True, text=True, timeout=timeout)
