@@ -60,6 +60,8 @@ def lib():
         L.oracle_add_small_module.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.oracle_small_module_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.oracle_small_module_plane.restype = C.c_int
+        L.oracle_outflow_mean.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_outflow_mean.restype = C.c_double
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2f_create.restype = C.c_void_p
@@ -162,6 +164,10 @@ class Oracle:
         """Template / coefficient plane k of the idx-th small module (None until it exists); for checking the product's host-built templates."""
         out = np.zeros((self.nx, self.ny))
         return out if lib().oracle_small_module_plane(self.h, idx, k, _dp(out)) else None
+
+    def outflow_mean(self, idx: int) -> float:
+        """BoundaryOutflow::computeMeanOutflow of the idx-th small module on the current state."""
+        return lib().oracle_outflow_mean(self.h, idx)
 
     def set_anomalous_resistivity(self, *, time_scale=1.0, frobenius_metric_coeff=1.0e50, smoothing_sigma=3.0, safety_factor=1.0, metric_smoothing=True,
                                   time_integrator="euler", template_mode="flood_fill", flood_fill_max_radius=-1.0, flood_fill_argmin_radius=5.0e9,

@@ -933,6 +933,13 @@ int oracle_small_module_plane(oracle *o, int idx, int k, double *out)
     memcpy(out, m->plane[k], sizeof(double) * o->n);
     return 1;
 }
+/* test accessor: BoundaryOutflow::computeMeanOutflow of small module idx on the current state */
+double oracle_outflow_mean(oracle *o, int idx)
+{
+    if (idx < 0 || idx >= o->mod.n_small) return 0.0;
+    const small_module *m = (const small_module *)o->mod.small[idx];
+    return m->kind == 12 ? outflow_mean(o, m) : 0.0;
+}
 /* p: time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, metric_smoothing, time_integrator, flood_fill (1) / frobenius (0), flood_fill_max_radius,
  *    flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length, flood_fill_threshold, resistivity_model (0 time_scale, 1 syntelis_19, 2 ys_94),
  *    gradient_correction, model parameter 0..2.  The module's setupModule needs the populated state: call after oracle_setup. */

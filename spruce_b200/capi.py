@@ -61,6 +61,9 @@ SYMBOLS = {
     "spruce_module_momentum_injection": (C.c_int, [C.c_void_p] + [C.c_double] * 10 + [C.c_int, C.c_double]),
     "spruce_module_div_cleaning": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "spruce_module_field_heating": (C.c_int, [C.c_void_p] + [C.c_double] * 5 + [C.c_int]),
+    "spruce_module_boundary_outflow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                                 C.c_double, C.c_double]),
+    "spruce_module_boundary_outflow_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "spruce_eqs_ideal_mhd_options": (C.c_int, [C.c_void_p, C.c_double]),
     "spruce_eqs_ideal2f_options": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "spruce_module_eic_thermalization": (C.c_int, [C.c_void_p]),

@@ -9,6 +9,7 @@
 #include "solar_templates.hpp"
 #include "ideal2f_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -68,7 +69,9 @@ struct spruce_domain {
     struct { double coeff = 0.0, epsilon = 1.0; int heating_on = 1, force_on = 1, gc = 0, integrator = 0, inactive = 0, nsub = 1;
              double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; bool cg_halo_done = false; } pv;
     std::vector<int> module_order;                 // MOD_* ; MOD_SRC0 + k = sources[k]
-    enum { MOD_SRC0 = 100, MOD_DC = 6, MOD_FH = 7 };
+    enum { MOD_SRC0 = 100, MOD_DC = 6, MOD_FH = 7, MOD_BO = 8 };
+    struct { double max_accel = 0.0, dynamic_time = 1.0, target = 0.0, mean = 0.0, accel = 0.0; int boundary = 3, field_aligned = 0, dynamic = 0;
+             int win[4] = {0, 0, 0, 0}; double *tmpl = nullptr, *max_dev = nullptr; } bo;                // boundary_outflow
     struct { double epsilon = 0.1, time_scale = 1.0; int nsub = 0; } dc;                            // div_cleaning (divcleaning.hpp:22-23)
     struct { double coeff = 0.0, current_pow = 0.0, b_pow = 0.0, n_pow = 0.0, roc_pow = 0.0; int inactive = 0; double *H = nullptr; } fh;   // field_heating
     // pointwise solar source terms (module_kernels.cuh: k_source_term), in config order
@@ -637,6 +640,36 @@ int fh_iterate(spruce_domain *d, double dt)
     if (rc) return rc;
     return after_module_propagate(d);
 }
+// BoundaryOutflow::postIterateModule (boundaryoutflow.cpp:39-63)
+int bo_post(spruce_domain *d, double dt)
+{
+    auto &bo = d->bo;
+    BoArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.tmpl = bo.tmpl; A.xl = bo.win[0]; A.xu = bo.win[1]; A.yl = bo.win[2]; A.yu = bo.win[3];
+    A.boundary = bo.boundary; A.field_aligned = bo.field_aligned; A.max_out = bo.max_dev;
+    const double init = -1.0 * bo.target;                                                            // :227
+    CUDA_TRY(cudaMemcpyAsync(bo.max_dev, &init, sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    dim3 g1((d->P.ny + 127) / 128, d->P.nx), g2((d->P.ny + 255) / 256, d->P.nx);
+    k_bo_mean<<<g1, 128, 0, d->stream>>>(d->P, A);
+    CUDA_TRY(cudaMemcpyAsync(&bo.mean, bo.max_dev, sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    double accel = bo.max_accel;
+    if (bo.dynamic) {                                                                                // :42-46
+        accel = (bo.target - bo.mean) / bo.dynamic_time;
+        accel = std::min(accel, bo.max_accel);
+        accel = std::max(accel, 0.0);
+    }
+    bo.accel = accel;
+    A.dt = dt; A.accel = accel;
+    k_bo_apply<<<g2, 256, 0, d->stream>>>(d->P, A);
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    int rc = launch_propagate(d, 0);
+    if (rc) return rc;
+    return after_module_propagate(d);
+}
 int ah_post(spruce_domain *d)
 {
     dim3 grid((d->P.ny + 255) / 256, d->P.nx);
@@ -997,6 +1030,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
     for (int m : d->module_order) {                                      // postIterateModules, evolution.cpp:74
         if (m == spruce_domain::MOD_AH && (rc = ah_post(d))) return rc;
         if (m == spruce_domain::MOD_DC && (rc = dc_post(d, step_size))) return rc;
+        if (m == spruce_domain::MOD_BO && (rc = bo_post(d, step_size))) return rc;
         if (m >= spruce_domain::MOD_SRC0 && (rc = src_post(d, d->sources[m - spruce_domain::MOD_SRC0], step_time, step_size))) return rc;
     }
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
@@ -1169,6 +1203,7 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->red) cudaFree(d->red);
     if (d->moc_visc_bits) cudaFree(d->moc_visc_bits);
     if (d->moc_base) cudaFree(d->moc_base);
+    if (d->bo.max_dev) cudaFree(d->bo.max_dev);
     if (d->dt_hist) cudaFree(d->dt_hist);
     for (int r = 0; r < MAX_RANKS; r++) if (d->peer_seg[r] && d->peer_seg[r] != d->seg) cudaIpcCloseMemHandle(d->peer_seg[r]);
     if (d->seg) cudaFree(d->seg);
@@ -1483,6 +1518,39 @@ int spruce_module_field_heating(spruce_domain *d, double coeff, double current_p
     d->fh.coeff = coeff; d->fh.current_pow = current_pow; d->fh.b_pow = b_pow; d->fh.n_pow = n_pow; d->fh.roc_pow = roc_pow; d->fh.inactive = inactive_mode ? 1 : 0;
     if (!d->fh.H) { int rc = alloc_plane(d, &d->fh.H); if (rc) return rc; }
     d->module_order.push_back(spruce_domain::MOD_FH);
+    return SPRUCE_OK;
+}
+int spruce_module_boundary_outflow(spruce_domain *d, const double *pos_x, const double *pos_y, size_t count, double max_accel, double falloff_length, int boundary,
+                                   int falloff_shape, double feather_length, int field_aligned_mode, int dynamic_mode, double dynamic_time, double dynamic_target_speed)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "boundary_outflow");
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "boundary_outflow on a slab decomposition is not built");
+    const size_t np = (size_t)d->P.nx * d->P.ny;
+    if (!pos_x || !pos_y || count != np) return fail(SPRUCE_ERR_ARG, "pos_x / pos_y need %zu values", np);
+    if (boundary < 0 || boundary > 3) return fail(SPRUCE_ERR_ARG, "BoundaryOutflow boundary config must be {x,y}_bound_{1,2}");
+    if (falloff_shape < 0 || falloff_shape > 2) return fail(SPRUCE_ERR_ARG, "BoundaryOutflow shape must be exp or gaussian or flat");
+    auto &bo = d->bo;
+    bo.max_accel = max_accel; bo.boundary = boundary; bo.field_aligned = field_aligned_mode ? 1 : 0; bo.dynamic = dynamic_mode ? 1 : 0;
+    bo.dynamic_time = dynamic_time; bo.target = dynamic_target_speed;
+    const int bcs[4] = {d->cfg.x_bound_1, d->cfg.x_bound_2, d->cfg.y_bound_1, d->cfg.y_bound_2};
+    const solar::Window w = solar::outflow_bounds(d->cfg.xdim, d->cfg.ydim, bcs, boundary, SPRUCE_BC_PERIODIC, SPRUCE_BC_OPEN_MOC, HALO);
+    std::vector<double> t;
+    solar::outflow_template(d->cfg.xdim, d->cfg.ydim, w, pos_x, pos_y, falloff_length, feather_length, boundary, falloff_shape, t);
+    const solar::Window m = solar::outflow_mean_window(d->cfg.ydim, w, pos_x, pos_y, falloff_length, feather_length, boundary);
+    bo.win[0] = m.xl; bo.win[1] = m.xu; bo.win[2] = m.yl; bo.win[3] = m.yu;
+    int rc;
+    if (!bo.tmpl && (rc = alloc_plane(d, &bo.tmpl))) return rc;
+    if ((rc = h2d_plane(d, bo.tmpl, t.data()))) return rc;
+    if (!bo.max_dev) CUDA_TRY(cudaMalloc(&bo.max_dev, sizeof(double)));
+    d->module_order.push_back(spruce_domain::MOD_BO);
+    return SPRUCE_OK;
+}
+int spruce_module_boundary_outflow_state(spruce_domain *d, double *mean_outflow, double *curr_accel)
+{
+    CHECK_DOM(d);
+    if (mean_outflow) *mean_outflow = d->bo.mean;
+    if (curr_accel) *curr_accel = d->bo.accel;
     return SPRUCE_OK;
 }
 int spruce_module_physical_viscosity(spruce_domain *d, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on, int force_on,

@@ -452,6 +452,59 @@ __global__ void __launch_bounds__(256) k_fh_apply(const DomainParams P, const Fh
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// BoundaryOutflow (source/modules/solar/boundaryoutflow.cpp:39-63, 140-236): an acceleration near one boundary, along x / y or along
+// the field, optionally steered (dynamic_mode) towards a target outflow speed by the largest field-aligned outflow found in a
+// window next to that boundary.  k_bo_mean: that maximum (std::max semantics: a NaN candidate is never selected); k_bo_apply:
+//   mom += (dt*(accel*template)) [* b_hat_k] * rho .   b_hat, v are the derived variables of idealmhd.cpp:248-277, formed per cell.
+// STATUS: not yet run on a GPU.
+// ---------------------------------------------------------------------------------------------------------
+struct BoArgs { double *U[NEV]; const double *st[NSTATIC]; const double *tmpl; int xl, xu, yl, yu; int boundary, field_aligned; double dt, accel; double *max_out; };
+__device__ __forceinline__ void bo_bhat(const DomainParams &P, const BoArgs &A, size_t off, double *hx, double *hy)
+{
+    const double bx = A.st[S_BEX][off] + A.U[E_BX][off], by = A.st[S_BEY][off] + A.U[E_BY][off], bz = A.st[S_BEZ][off] + A.U[E_BZ][off];
+    const double bm = sqrt((bx * bx + by * by) + bz * bz);
+    if (bm == 0.0) { *hx = 0.0; *hy = 0.0; } else { *hx = bx / bm; *hy = by / bm; }
+}
+__global__ void __launch_bounds__(128) k_bo_mean(const DomainParams P, const BoArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny || r < A.xl || r > A.xu || j < A.yl || j > A.yu) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    double hx, hy;
+    bo_bhat(P, A, off, &hx, &hy);
+    const double rho = A.U[E_N][off] * P.m_i;
+    double cur = hx * (A.U[E_MX][off] / rho) + hy * (A.U[E_MY][off] / rho);
+    if (A.boundary == 0 && hx > 0.0) cur *= -1.0;
+    else if (A.boundary == 1 && hx < 0.0) cur *= -1.0;
+    else if (A.boundary == 3 && hy < 0.0) cur *= -1.0;
+    else if (A.boundary == 2 && hy > 0.0) cur *= -1.0;
+    unsigned long long *addr = reinterpret_cast<unsigned long long *>(A.max_out);
+    unsigned long long old = *addr;
+    while (__longlong_as_double((long long)old) < cur) {                          // std::max(max, curr): replace only when max < curr
+        const unsigned long long seen = atomicCAS(addr, old, (unsigned long long)__double_as_longlong(cur));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+__global__ void __launch_bounds__(256) k_bo_apply(const DomainParams P, const BoArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const double a = A.dt * (A.accel * A.tmpl[off]);                               // dt*accel, accel = curr_accel*accel_template  (:47, :50-61)
+    const double rho = A.U[E_N][off] * P.m_i;
+    if (A.field_aligned) {
+        double hx, hy;
+        bo_bhat(P, A, off, &hx, &hy);
+        A.U[E_MX][off] = A.U[E_MX][off] + (a * hx) * rho;
+        A.U[E_MY][off] = A.U[E_MY][off] + (a * hy) * rho;
+    } else if (A.boundary < 2) A.U[E_MX][off] = A.U[E_MX][off] + a * rho;
+    else A.U[E_MY][off] = A.U[E_MY][off] + a * rho;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Artificial viscosity (source/modules/viscosity.cpp:185-267): one term  dq = visc_coeff * laplacian(q) * scale_fac
 // (+ gradient correction), q = the variable to differentiate of the grid set the RHS is evaluated on (materialised by
 // k_mhd_derive when it is a derived variable), timescale from the PRIMARY state's dt plane / its minimum.

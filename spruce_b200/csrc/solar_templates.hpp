@@ -5,7 +5,9 @@
 //   MomentumInjection templates                         source/modules/solar/momentuminjection.cpp:35-67
 // Plain C++ (no CUDA): capi.cu includes it, and tests/hostcheck compiles it with g++ to check it without a GPU.
 #pragma once
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace spruce {
@@ -77,6 +79,76 @@ inline void momentum_templates(const Geom &g, double sx, double sy, double cx, d
         }
         for (double &q : *p[k]) q = (a > 0.0) ? ((q < 0.0) ? 0.0 : q) : ((0.0 < q) ? 0.0 : q);
     }
+}
+
+// ---- BoundaryOutflow (source/modules/solar/boundaryoutflow.cpp): single rank, pos_x / pos_y are full planes (ydim doubles per row)
+enum { OB_X1 = 0, OB_X2 = 1, OB_Y1 = 2, OB_Y2 = 3 };            // boundary
+enum { OS_EXP = 0, OS_GAUSSIAN = 1, OS_FLAT = 2 };               // falloff_shape
+struct Window { int xl, xu, yl, yu; };
+
+// interior bounds, extended into the ghost zone on the chosen side when that side is open_moc (m_*_dt, plasmadomain.cpp:138-159)
+inline Window outflow_bounds(int xdim, int ydim, const int bc[4], int boundary, int bc_periodic, int bc_open_moc, int n_ghost)
+{
+    auto lo = [&](int b) { return b == bc_periodic ? 0 : n_ghost; };
+    auto hi = [&](int b, int n) { return b == bc_periodic ? n - 1 : n - n_ghost - 1; };
+    Window w{lo(bc[0]), hi(bc[1], xdim), lo(bc[2]), hi(bc[3], ydim)};
+    if (boundary == OB_X1 && bc[0] == bc_open_moc) w.xl -= n_ghost;
+    else if (boundary == OB_X2 && bc[1] == bc_open_moc) w.xu += n_ghost;
+    else if (boundary == OB_Y2 && bc[3] == bc_open_moc) w.yu += n_ghost;
+    else if (boundary == OB_Y1 && bc[2] == bc_open_moc) w.yl -= n_ghost;
+    return w;
+}
+// constructBoundaryAccel (boundaryoutflow.cpp:76-137)
+inline void outflow_template(int xdim, int ydim, const Window &w, const double *x, const double *y, double length, double feather, int boundary, int shape,
+                             std::vector<double> &out)
+{
+    const size_t n = (size_t)xdim * ydim;
+    double xmin = x[0], xmax = x[0], ymin = y[0], ymax = y[0];
+    for (size_t c = 0; c < n; c++) { xmin = std::min(xmin, x[c]); xmax = std::max(xmax, x[c]); ymin = std::min(ymin, y[c]); ymax = std::max(ymax, y[c]); }
+    std::vector<double> res(n, 0.0);
+    for (size_t c = 0; c < n; c++) {
+        if (shape == OS_EXP)
+            res[c] = boundary == OB_X1 ? std::exp((-2.3 * (x[c] - xmin)) / length) : boundary == OB_X2 ? std::exp((2.3 * (x[c] - xmax)) / length)
+                   : boundary == OB_Y2 ? std::exp((2.3 * (y[c] - ymax)) / length) : std::exp((-2.3 * (y[c] - ymin)) / length);
+        else if (shape == OS_GAUSSIAN) {
+            const double q = boundary == OB_X1 ? (x[c] - xmin) / length : boundary == OB_X2 ? ((-x[c]) + xmax) / length
+                           : boundary == OB_Y2 ? ((-y[c]) + ymax) / length : (y[c] - ymin) / length;
+            res[c] = std::exp(-2.3 * (q * q));
+        }
+    }
+    if (shape == OS_FLAT) {
+        const double ext = boundary == OB_X1 ? xmin : boundary == OB_X2 ? xmax : boundary == OB_Y2 ? ymax : ymin;
+        const double *p = boundary < OB_Y1 ? x : y;
+        for (int i = w.xl; i <= w.xu; i++) for (int j = w.yl; j <= w.yu; j++) if (std::abs(p[(size_t)i * ydim + j] - ext) <= length) res[(size_t)i * ydim + j] = 1.0;
+    }
+    if (feather > 0.0) {
+        const double *p = boundary < OB_Y1 ? y : x;
+        const double pmax = boundary < OB_Y1 ? ymax : xmax, pmin = boundary < OB_Y1 ? ymin : xmin;
+        for (size_t c = 0; c < n; c++) {
+            const double a = std::max(p[c] - (pmax - 2.0 * feather), 0.0) / feather, b = std::min(p[c] - (pmin + 2.0 * feather), 0.0) / feather;
+            res[c] *= std::max(std::exp(-2.3 * (a * a)) * std::exp(-2.3 * (b * b)) - 0.01, 0.0);
+        }
+    }
+    out.assign(n, 0.0);
+    for (int i = w.xl; i <= w.xu; i++) for (int j = w.yl; j <= w.yu; j++) out[(size_t)i * ydim + j] = 1.0 * res[(size_t)i * ydim + j];
+}
+// the index window of computeMeanOutflow (boundaryoutflow.cpp:140-213): the bounds above, narrowed by the feather and falloff lengths
+inline Window outflow_mean_window(int ydim, Window w, const double *x, const double *y, double falloff, double feather, int boundary)
+{
+    auto X = [&](int i) { return x[(size_t)i * ydim]; };           // x(i, 0)
+    auto Y = [&](int j) { return y[j]; };                           // y(0, j)
+    if (boundary < OB_Y1) {
+        for (int j = w.yl; j <= w.yu; j++) if (Y(j) - Y(w.yl) >= feather) { w.yl = j; break; }
+        for (int j = w.yu; j >= w.yl; j--) if (Y(w.yu) - Y(j) >= feather) { w.yu = j; break; }
+        if (boundary == OB_X1) { for (int i = w.xl; i <= w.xu; i++) if (X(i) - X(w.xl) >= falloff) { w.xu = i; break; } }
+        else { for (int i = w.xu; i >= w.xl; i--) if (X(w.xu) - X(i) >= falloff) { w.xl = i; break; } }
+    } else {
+        for (int i = w.xl; i <= w.xu; i++) if (X(i) - X(w.xl) >= feather) { w.xl = i; break; }
+        for (int i = w.xu; i >= w.xl; i--) if (X(w.xu) - X(i) >= feather) { w.xu = i; break; }
+        if (boundary == OB_Y1) { for (int j = w.yl; j <= w.yu; j++) if (Y(j) - Y(w.yl) >= falloff) { w.yu = j; break; } }
+        else { for (int j = w.yu; j >= w.yl; j--) if (Y(w.yu) - Y(j) >= falloff) { w.yl = j; break; } }
+    }
+    return w;
 }
 
 }  // namespace solar

@@ -172,6 +172,19 @@ class PlasmaDomain:
     def set_field_heating(self, *, coeff=0.0, current_pow=0.0, b_pow=0.0, n_pow=0.0, roc_pow=0.0, inactive_mode=False):
         capi.check(self.lib.spruce_module_field_heating(self.h, coeff, current_pow, b_pow, n_pow, roc_pow, int(inactive_mode)))
 
+    def set_boundary_outflow(self, pos_x: np.ndarray, pos_y: np.ndarray, *, max_accel, falloff_length, boundary="y_bound_2", falloff_shape="exp", feather_length=0.0,
+                             field_aligned_mode=False, dynamic_mode=False, dynamic_time=1.0, dynamic_target_speed=0.0):
+        x = np.ascontiguousarray(pos_x, dtype=np.float64); y = np.ascontiguousarray(pos_y, dtype=np.float64)
+        capi.check(self.lib.spruce_module_boundary_outflow(self.h, _dp(x), _dp(y), x.size, max_accel, falloff_length,
+                                                           {"x_bound_1": 0, "x_bound_2": 1, "y_bound_1": 2, "y_bound_2": 3}[boundary],
+                                                           {"exp": 0, "gaussian": 1, "flat": 2}[falloff_shape], feather_length, int(field_aligned_mode), int(dynamic_mode),
+                                                           dynamic_time, dynamic_target_speed))
+
+    def boundary_outflow_state(self):
+        m, a = C.c_double(), C.c_double()
+        capi.check(self.lib.spruce_module_boundary_outflow_state(self.h, C.byref(m), C.byref(a)))
+        return m.value, a.value
+
     def set_physical_viscosity(self, coeff_plane: np.ndarray, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False,
                                integrator="euler", inactive_mode=False):
         """coeff_plane = PhysicalViscosity::constructCoefficientGrid(coeff, ramp_length, buffer_length) (physicalviscosity.cpp:247-267)."""

@@ -52,8 +52,9 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "momentum_injection") m_modules.emplace_back(new GaussianSource(m_pd, GaussianSource::Momentum));
     else if (name == "div_cleaning") m_modules.emplace_back(new DivCleaning(m_pd));
     else if (name == "field_heating") m_modules.emplace_back(new FieldHeating(m_pd));
+    else if (name == "boundary_outflow") m_modules.emplace_back(new BoundaryOutflow(m_pd));
     else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
-                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating are).");
+                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating, boundary_outflow are).");
     m_modules.back()->configureModule(in);
 }
 
@@ -293,6 +294,42 @@ std::string FieldHeating::commandLineMessage() const
     message += (coeff == 0.0) ? " Zero" : " On";
     if (inactive_mode) message += " (Not Applied)";
     return message;
+}
+
+// boundaryoutflow.cpp:16-31
+void BoundaryOutflow::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "max_accel") max_accel = std::stod(v);
+        else if (k == "falloff_length") falloff_length = std::stod(v);
+        else if (k == "boundary") boundary = v;
+        else if (k == "falloff_shape") falloff_shape = v;
+        else if (k == "feather_length") feather_length = std::stod(v);
+        else if (k == "field_aligned_mode") field_aligned_mode = (v == "true");
+        else if (k == "dynamic_mode") dynamic_mode = (v == "true");
+        else if (k == "dynamic_time") dynamic_time = std::stod(v);
+        else if (k == "dynamic_target_speed") dynamic_target_speed = std::stod(v);
+        else std::cerr << k << " config not recognized.\n";
+    }
+}
+// boundaryoutflow.cpp:33-37: the template and the outflow window are built by the device library from pos_x / pos_y
+void BoundaryOutflow::setupModule()
+{
+    SPRUCE_REQUIRE(falloff_shape == "exp" || falloff_shape == "gaussian" || falloff_shape == "flat", "BoundaryOutflow shape must be exp or gaussian or flat");
+    const int b = boundary == "x_bound_1" ? 0 : boundary == "x_bound_2" ? 1 : boundary == "y_bound_1" ? 2 : boundary == "y_bound_2" ? 3 : -1;
+    SPRUCE_REQUIRE(b >= 0, "BoundaryOutflow boundary config must be {x,y}_bound_{1,2}");
+    const int sh = falloff_shape == "exp" ? 0 : falloff_shape == "gaussian" ? 1 : 2;
+    const Grid &x = m_pd.m_grids[PlasmaDomain::pos_x], &y = m_pd.m_grids[PlasmaDomain::pos_y];
+    PlasmaDomain::check(spruce_module_boundary_outflow(m_pd.device(), x.ptr(), y.ptr(), x.size(), max_accel, falloff_length, b, sh, feather_length,
+                                                       field_aligned_mode ? 1 : 0, dynamic_mode ? 1 : 0, dynamic_time, dynamic_target_speed));
+}
+// boundaryoutflow.cpp:65-74
+std::string BoundaryOutflow::commandLineMessage() const
+{
+    double mean = 0.0, accel = 0.0;
+    PlasmaDomain::check(spruce_module_boundary_outflow_state(m_pd.device(), &mean, &accel));
+    return boundary + " boundary outflow enforced (max " + std::to_string(mean) + " cm/s outflow) (accel. " + std::to_string(accel) + " cm/s^2)";
 }
 
 // viscosity.cpp:6-24

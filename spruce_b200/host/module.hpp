@@ -154,6 +154,19 @@ private:
     bool inactive_mode = false, output_to_file = false;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
+// source/modules/solar/boundaryoutflow.hpp
+class BoundaryOutflow : public Module {
+public:
+    explicit BoundaryOutflow(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override;
+    bool device_resident() const override { return true; }
+private:
+    double max_accel = 0.0, falloff_length = 1.0, feather_length = 0.0, dynamic_time = 1.0, dynamic_target_speed = 0.0;
+    std::string boundary = "y_bound_2", falloff_shape = "exp";
+    bool field_aligned_mode = false, dynamic_mode = false;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
 // source/modules/ucnp/eic_thermalization.hpp -- electron-ion collisional energy exchange (two-fluid equation set only)
 class EICThermalization : public Module {
 public:

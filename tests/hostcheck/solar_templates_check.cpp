@@ -24,3 +24,14 @@ extern "C" void tmpl_momentum(int xdim, int ydim, int row0, int nx_local, int xp
     std::memcpy(out_x, px.data(), px.size() * sizeof(double));
     std::memcpy(out_y, py.data(), py.size() * sizeof(double));
 }
+// BoundaryOutflow: accel_template and the window of computeMeanOutflow; bc codes as in include/spruce_b200.h (periodic 0, open_moc 4)
+extern "C" void tmpl_outflow(int xdim, int ydim, const int *bc, const double *x, const double *y, double length, double feather, int boundary, int shape,
+                             double *out, int *win)
+{
+    const spruce::solar::Window w = spruce::solar::outflow_bounds(xdim, ydim, bc, boundary, 0, 4, 2);
+    std::vector<double> t;
+    spruce::solar::outflow_template(xdim, ydim, w, x, y, length, feather, boundary, shape, t);
+    std::memcpy(out, t.data(), t.size() * sizeof(double));
+    const spruce::solar::Window m = spruce::solar::outflow_mean_window(ydim, w, x, y, length, feather, boundary);
+    win[0] = m.xl; win[1] = m.xu; win[2] = m.yl; win[3] = m.yu;
+}

@@ -72,3 +72,43 @@ def test_momentum_templates_equal_oracle(lib, xb, yb, angle, dirs):
     assert same_bits(ox, rx), mismatch(ox, rx)
     assert same_bits(oy, ry), mismatch(oy, ry)
     o.close()
+
+
+BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3, "open_moc": 4, "open_ucnp": 5}
+OUTFLOW = [
+    (("periodic", "periodic"), ("fixed", "open_moc"), "y_bound_2", "exp", 6.0e8, 3.0e8),
+    (("periodic", "periodic"), ("fixed", "open"), "y_bound_2", "gaussian", 5.0e8, 0.0),
+    (("open_moc", "fixed"), ("reflect", "reflect"), "x_bound_1", "flat", 4.0e8, 2.0e8),
+    (("fixed", "open"), ("fixed", "fixed"), "x_bound_2", "exp", 7.0e8, 2.5e8),
+    (("fixed", "fixed"), ("open_moc", "fixed"), "y_bound_1", "gaussian", 3.0e8, 1.0e8),
+]
+
+
+@pytest.mark.parametrize("xb,yb,boundary,shape,length,feather", OUTFLOW)
+def test_boundary_outflow_template_and_window_equal_oracle(lib, xb, yb, boundary, shape, length, feather):
+    nx, ny = 31, 28
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="euler", density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    bnd = {"x_bound_1": 0, "x_bound_2": 1, "y_bound_1": 2, "y_bound_2": 3}[boundary]
+    shp = {"exp": 0, "gaussian": 1, "flat": 2}[shape]
+    target = 2.0e6
+    o.add_small_module("boundary_outflow", max_accel=2.0e3, falloff_length=length, boundary=bnd, falloff_shape=shp, feather_length=feather, field_aligned_mode=1.0,
+                       dynamic_mode=1.0, dynamic_time=10.0, dynamic_target_speed=target)
+    ref = o.small_module_plane(0)
+    assert ref is not None and np.count_nonzero(ref) > 0
+    X = np.ascontiguousarray(s["planes"]["pos_x"], dtype=np.float64); Y = np.ascontiguousarray(s["planes"]["pos_y"], dtype=np.float64)
+    out = np.zeros((nx, ny)); win = (C.c_int * 4)()
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    lib.tmpl_outflow(nx, ny, bc, dp(X), dp(Y), C.c_double(length), C.c_double(feather), bnd, shp, dp(out), win)
+    assert same_bits(out, ref), mismatch(out, ref)
+    # the window, through the quantity it exists for: max over it of the signed field-aligned speed (boundaryoutflow.cpp:215-236), on a developed flow
+    for _ in range(3):
+        o.step()
+    xl, xu, yl, yu = list(win)
+    hx, hy, vx, vy = (o.get(v)[xl:xu + 1, yl:yu + 1] for v in ("b_hat_x", "b_hat_y", "v_x", "v_y"))
+    cur = hx * vx + hy * vy
+    flip = (hx > 0.0) if bnd == 0 else (hx < 0.0) if bnd == 1 else (hy < 0.0) if bnd == 3 else (hy > 0.0)
+    cur = np.where(flip, cur * -1.0, cur)
+    mine = max(-1.0 * target, float(np.max(cur))) if cur.size else -1.0 * target
+    assert mine == o.outflow_mean(0), (mine, o.outflow_mean(0), list(win))
+    o.close()

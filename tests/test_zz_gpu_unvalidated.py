@@ -214,3 +214,44 @@ def test_div_cleaning_and_field_heating_vs_oracle(mods, xb, yb, integ, nx, ny, e
     exponents, CUDA vs glibc: <= 1e-9) against the pinned oracle."""
     out = run_isolated(DC_FH_CODE.format(mods=mods, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny, exact=exact), {})
     assert "ok" in out
+
+
+OUTFLOW_CODE = """
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    a, xb, yb, integ, nx, ny = {a!r}, {xb!r}, {yb!r}, {integ!r}, {nx}, {ny}
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    B = dict(x_bound_1=0, x_bound_2=1, y_bound_1=2, y_bound_2=3); S = dict(exp=0, gaussian=1, flat=2)
+    o.add_small_module("boundary_outflow", max_accel=a["max_accel"], falloff_length=a["falloff_length"], boundary=B[a["boundary"]], falloff_shape=S[a["falloff_shape"]],
+                       feather_length=a["feather_length"], field_aligned_mode=float(a["field_aligned_mode"]), dynamic_mode=float(a["dynamic_mode"]),
+                       dynamic_time=a["dynamic_time"], dynamic_target_speed=a["dynamic_target_speed"])
+    d.set_boundary_outflow(s["planes"]["pos_x"], s["planes"]["pos_y"], **a)
+    ref = o.run(7)
+    dts = d.advance(7)
+    assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+    for v in PlasmaDomain.EVOLVED + ["dt", "temp"]:
+        assert same_bits(d.grid(v), o.get(v)), "%s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("a,xb,yb,integ,nx,ny,moc", [
+    (dict(max_accel=2.0e3, falloff_length=6.0e8, boundary="y_bound_2", falloff_shape="exp", feather_length=3.0e8, field_aligned_mode=True, dynamic_mode=True,
+          dynamic_time=10.0, dynamic_target_speed=2.0e6), ("periodic", "periodic"), ("fixed", "open"), "rk2", 88, 71, False),
+    (dict(max_accel=1.0e3, falloff_length=4.0e8, boundary="x_bound_1", falloff_shape="flat", feather_length=2.0e8, field_aligned_mode=False, dynamic_mode=False,
+          dynamic_time=1.0, dynamic_target_speed=0.0), ("open", "fixed"), ("reflect", "reflect"), "euler", 67, 90, False),
+    (dict(max_accel=2.0e3, falloff_length=5.0e8, boundary="y_bound_2", falloff_shape="gaussian", feather_length=0.0, field_aligned_mode=True, dynamic_mode=True,
+          dynamic_time=5.0, dynamic_target_speed=1.0e6), ("periodic", "periodic"), ("fixed", "open_moc"), "rk2", 72, 69, True),
+])
+def test_boundary_outflow_vs_oracle(a, xb, yb, integ, nx, ny, moc):
+    """boundary_outflow on the device (k_bo_mean, k_bo_apply; template and window built by solar_templates.hpp, host-checked) against the pinned oracle;
+    the last case combines it with an open_moc side, whose ghost zone the template reaches into."""
+    out = run_isolated(OUTFLOW_CODE.format(a=a, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"} if moc else {})
+    assert "ok" in out
