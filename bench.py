@@ -304,7 +304,9 @@ def emit(args, r, world):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "OT-%d: synthetic doubly periodic Orszag-Tang vortex, non-uniform rectilinear %dx%d grid, ideal MHD, RK2, epsilon 0.2 (BASELINE.json configs[3])" % (args.size, args.size, args.size),
                        "parallelism": ("slab%d along x, halo exchange: %s" % (world, r.get("transport", "p2p"))) if world > 1 else "single", "l2": "working set per step (21 planes, %.1f GB) >> 126 MB L2: inputs larger than L2" % (21 * args.size ** 2 * 8 / 1e9),
-                       "mode": "exact (bit-identical to the reference CPU build)"},
+                       "mode": "exact (bit-identical to the reference CPU build)" if args.arith == "exact" else
+                               "relaxed (opt-in: FMA contraction + one-multiplication table divisions in the stage kernel; fields within 1e-9 of the reference, step sizes not bit-identical)",
+                       "stage_variants": bool(args.stage_variants)},
             "clocks": r["clocks"], "gpu_launches": r["launches"], "e2e": r["e2e"], "roofline": r["roofline"]}
     if r.get("cpu"):
         line["cpu_baseline"] = r["cpu"]
@@ -325,10 +327,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="mhd", choices=["mhd", "mhd_tc"], help="mhd: BASELINE configs[3] (the bench line); mhd_tc: configs[4], MHD + thermal conduction")
+    ap.add_argument("--arith", default="exact", choices=["exact", "relaxed"],
+                    help="exact (default, the bench line): every operation individually rounded, bit-identical to the reference; relaxed: the opt-in stage kernel of "
+                         "stage_relaxed.cu (FMA contraction, one-multiplication table divisions; fields within the north star's 1e-9, step sizes not bit-identical)")
+    ap.add_argument("--stage-variants", action="store_true", help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS=1)")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: library peer stores over NVLink, or torch.distributed NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.arith == "relaxed":
+        os.environ["SPRUCE_ARITH"] = "relaxed"              # read by spruce_domain_create
+    if args.stage_variants:
+        os.environ["SPRUCE_STAGE_VARIANTS"] = "1"
     if args.impl == "reference":
         run_reference_arm(args)
     else:

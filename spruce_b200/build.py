@@ -1,8 +1,8 @@
 """Builds the CUDA shared library in-tree: spruce_b200/lib/libspruce_b200.so (sm_100a only).
 
-nvcc cross-compiles without a GPU.  -fmad=false is REQUIRED: the kernels reproduce the reference's individually
+nvcc cross-compiles without a GPU.  -fmad=false is REQUIRED for capi.cu: the kernels reproduce the reference's individually
 rounded FP64 arithmetic, and the only fused operations are the explicit fma() calls of the exact division
-(csrc/exact_math.cuh).
+(csrc/exact_math.cuh).  stage_relaxed.cu is the one unit compiled with contraction: the opt-in relaxed stage kernel.
 """
 from __future__ import annotations
 
@@ -14,12 +14,14 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 SRC = PKG / "csrc"
 LIB = PKG / "lib" / "libspruce_b200.so"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
+COMMON_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+# translation units and their floating-point contraction: everything is exact (-fmad=false) except the opt-in relaxed stage kernel
+UNITS = [("capi.cu", "-fmad=false"), ("stage_relaxed.cu", "-fmad=true")]
+OBJ = PKG / "lib" / "obj"
 
 
 def sources():
-    return [SRC / "capi.cu"]
+    return [SRC / name for name, _ in UNITS]
 
 
 def needs_build() -> bool:
@@ -35,17 +37,36 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), *map(str, sources())]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
     env = dict(os.environ)
     env.pop("CXX", None); env.pop("CC", None)   # let nvcc pick the system host compiler
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
-    if verbose or r.returncode:
-        sys.stderr.write(r.stdout.decode())
-    if r.returncode:
-        raise RuntimeError("nvcc failed (%d)" % r.returncode)
+    OBJ.mkdir(parents=True, exist_ok=True)
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stdout.decode())
+        if r.returncode:
+            raise RuntimeError("nvcc failed (%d)" % r.returncode)
+
+    objs = []
+    procs = []
+    for name, fmad in UNITS:                     # the units compile concurrently
+        obj = OBJ / (Path(name).stem + ".o")
+        cmd = [nvcc, *COMMON_FLAGS, fmad, "-c", "-o", str(obj), str(SRC / name)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)))
+        objs.append(obj)
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        if verbose or pr.returncode:
+            sys.stderr.write(out.decode())
+        if pr.returncode:
+            raise RuntimeError("nvcc failed (%d): %s" % (pr.returncode, " ".join(cmd)))
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB), *map(str, objs)])
     return LIB
 
 

@@ -20,6 +20,9 @@
 
 using namespace spruce;
 
+// stage_relaxed.cu: the stage kernel in relaxed arithmetic (its own translation unit, compiled with FMA contraction)
+extern "C" __attribute__((visibility("hidden"))) int spruce_relaxed_launch_stage(unsigned gx, unsigned gy, void *stream, const void *P, const void *A, const void *L, int list, int var);
+
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, ...)
 {
@@ -94,6 +97,7 @@ struct spruce_domain {
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
     // open_moc (moc_stage.cuh): evolved ghost cells; SPRUCE_EXPERIMENTAL_MOC=1 until the launch side has been validated on a GPU
     bool moc_any = false; double global_viscosity = 0.0; unsigned long long *moc_visc_bits = nullptr; double *moc_base = nullptr;
+    bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
     bool stage_variants = false;           // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=1)
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
@@ -289,6 +293,11 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
         int var = 0;
         if (d->stage_variants && kmode == KM_NONE && A.n_xterm == 0) var = A.b_is_s ? (primary ? 3 : 1) : (primary ? 2 : 0);
         const size_t sm6 = xy_smem_bytes(xy_rows(6)), smf = xy_smem_bytes(NTR);
+        const bool list2d = L.n == 6 && L.q == XY_LIST_2D, listfull = L.n == 12 && L.q == XY_LIST_FULL;
+        if (d->relaxed && d->static_lists && (list2d || listfull)) {          // any other list runs the exact run-time-list kernel below
+            const int e = spruce_relaxed_launch_stage(grid.x, grid.y, (void *)st, &d->P, &A, &L, list2d ? 6 : 12, var);
+            if (e != 0) return fail(SPRUCE_ERR_CUDA, "relaxed stage kernel: %s", cudaGetErrorString((cudaError_t)e));
+        } else
         if (d->static_lists && L.n == 6 && L.q == XY_LIST_2D) {
             if (var == 1) k_mhd_stage_xy<6, XY_LIST_2D, 1><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
             else if (var == 2) k_mhd_stage_xy<6, XY_LIST_2D, 2><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
@@ -1141,6 +1150,10 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0;
+    if (const char *ar = getenv("SPRUCE_ARITH")) {
+        if (!strcmp(ar, "relaxed")) d->relaxed = true;
+        else if (strcmp(ar, "exact")) { delete d; return fail(SPRUCE_ERR_ARG, "SPRUCE_ARITH must be exact or relaxed"); }
+    }
     d->moc_any = moc_any;
     DomainParams &P = d->P;
     P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;

@@ -22,6 +22,10 @@
 
 namespace spruce {
 
+#ifdef SPRUCE_RELAXED
+// relaxed arithmetic (stage_relaxed.cu only): one multiplication by the correctly rounded reciprocal, |error| <= 1.5 ulp
+__device__ __forceinline__ double ddiv(double a, double b, double rb) { (void)b; return a * rb; }
+#else
 __device__ __forceinline__ double ddiv(double a, double b, double rb)
 {
     double q = a * rb;
@@ -30,6 +34,7 @@ __device__ __forceinline__ double ddiv(double a, double b, double rb)
     e = fma(-b, q, a);
     return fma(e, rb, q);
 }
+#endif
 
 // std::min / std::max semantics of the reference's Grid::min/max (source/mhd/grid.cpp:110-163):
 // std::min(a,b) = (b < a) ? b : a ; std::max(a,b) = (a < b) ? b : a  -- NaN handling differs from fmin/fmax.

@@ -255,3 +255,44 @@ def test_boundary_outflow_vs_oracle(a, xb, yb, integ, nx, ny, moc):
     the last case combines it with an open_moc side, whose ghost zone the template reaches into."""
     out = run_isolated(OUTFLOW_CODE.format(a=a, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"} if moc else {})
     assert "ok" in out
+
+
+RELAXED_CODE = """
+    import numpy as np
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    integ, zfull, nx, ny, nsteps = {integ!r}, {zfull!r}, {nx}, {ny}, {nsteps}
+    s = synthetic.orszag_tang(nx, ny, zfull=zfull)
+    kw = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator=integ, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    ref = np.array(o.run(nsteps)); dts = np.array(d.advance(nsteps))
+    assert len(dts) == len(ref)                                           # identical step count
+    TOL = 1.0e-9                                                          # the north star's stated FP64 tolerance after 100 steps
+    assert np.max(np.abs(dts - ref) / ref) <= TOL, float(np.max(np.abs(dts - ref) / ref))
+    worst = 0.0
+    for v in PlasmaDomain.EVOLVED + ["dt", "temp"]:
+        a, b = d.grid(v), o.get(v)
+        r = float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+        assert r <= TOL, "%s: rel Linf %.3e" % (v, r)
+        worst = max(worst, r)
+    assert np.any(dts != ref) or worst > 0.0, "relaxed arithmetic reproduced the reference bit for bit: the relaxed kernel was probably not the one that ran"
+    print("ok worst rel Linf %.3e, dt rel %.3e" % (worst, float(np.max(np.abs(dts - ref) / ref))))
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("integ,zfull,nx,ny,nsteps,variants", [
+    ("rk2", False, 256, 256, 100, "0"),
+    ("rk2", False, 256, 256, 100, "1"),
+    ("rk2", True, 150, 203, 100, "1"),
+    ("rk4", False, 131, 96, 60, "0"),
+    ("euler", True, 96, 131, 60, "1"),
+])
+def test_relaxed_arithmetic_within_north_star_tolerance(integ, zfull, nx, ny, nsteps, variants):
+    """SPRUCE_ARITH=relaxed (stage_relaxed.cu: FMA contraction, one-multiplication table divisions): identical step count, step sizes and every
+    field within 1e-9 relative L-infinity of the oracle after 100 steps -- the north star's stated floating-point bar; the default build stays
+    bit-identical.  Also checks that the result is NOT bit-identical, i.e. that the relaxed kernel really ran."""
+    out = run_isolated(RELAXED_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, nsteps=nsteps), {"SPRUCE_ARITH": "relaxed", "SPRUCE_STAGE_VARIANTS": variants}, timeout=240)
+    assert "ok" in out
