@@ -44,6 +44,14 @@ def add_modules(dom):
             dom.set_eic_thermalization()
         elif m == "ah":
             dom.set_ambient_heating_plane(np.full((dom.nx, dom.ydim), 1.0e-4))
+        elif m in ("moc", "mocv"):
+            pass                                # a boundary condition, selected below
+        elif m == "src":                        # the pointwise solar source terms (templates are built per slab from global cell indices)
+            dom.set_ambient_heating_sink_plane(np.full((dom.xdim, dom.ydim), 1.0e-5))
+            dom.set_localized_heating(start_time=0.0, duration=5.0, max_heating_rate=1.0e-3, stddev_x=9.0, stddev_y=4.0, center_x=0.5 * nx, center_y=8.0, ramp_time=1.0)
+            dom.set_mass_injection(start_time=0.0, duration=10.0, max_injection_rate=1.0e6, stddev_x=7.0, stddev_y=3.0, center_x=0.5 * nx + 3.0, center_y=10.0)
+            dom.set_momentum_injection(start_time=0.0, duration=50.0, max_accel=1.0e3, stddev_x=8.0, stddev_y=3.0, center_x=0.5 * nx - 2.0, center_y=9.0, dir_x=1.0, dir_y=0.5,
+                                       template_angle=20.0, oscillatory=True, oscillation_period=3.0)
         else:
             raise SystemExit("unknown module " + m)
 
@@ -54,6 +62,11 @@ if two_fluid:
     ub = ("open_ucnp", "open_ucnp")
     kw = dict(equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False), xb=("periodic", "periodic") if xbound == "periodic" else ub, yb=ub, integrator=integ,
               density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
+elif "moc" in modules or "mocv" in modules:
+    # open_moc sides (needs SPRUCE_EXPERIMENTAL_MOC=1): x periodic with a y side, or x sides (first / last slab) plus a y side -> corners on the end slabs
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    kw = dict(xb=("periodic", "periodic") if xbound == "periodic" else ("open_moc", "open_moc"), yb=("open_moc", "fixed") if xbound == "periodic" else ("fixed", "open_moc"),
+              integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6, eqs_options=dict(global_viscosity=0.2 if "mocv" in modules else 0.0))
 elif modules:
     s = synthetic.stratified_loop(nx, ny, bump=0.5)
     kw = dict(xb=("periodic", "periodic") if xbound == "periodic" else (xbound, "open"), yb=("fixed", "fixed"), integrator=integ)

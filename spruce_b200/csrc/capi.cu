@@ -96,7 +96,7 @@ struct spruce_domain {
     bool in_mgpu_stage_api = false;        // inside spruce_mgpu_stage (caller-owned exchange and dt reduction)
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
     // open_moc (moc_stage.cuh): evolved ghost cells; SPRUCE_EXPERIMENTAL_MOC=1 until the launch side has been validated on a GPU
-    bool moc_any = false; double global_viscosity = 0.0; unsigned long long *moc_visc_bits = nullptr; double *moc_base = nullptr;
+    bool moc_any = false; double global_viscosity = 0.0; double *moc_base = nullptr;
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
     bool stage_variants = false;           // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=1)
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
@@ -266,6 +266,8 @@ ActiveList active_quantities(const spruce_domain *d)
 
 int prepare_rhs_modules(spruce_domain *d, const PlaneSet &S);
 int launch_moc(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int dt_only);
+int reset_reductions(spruce_domain *d);
+int peer_red_allgather(spruce_domain *d);
 int launch_moc_save(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D);
 int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int part = 0)
 {
@@ -346,13 +348,15 @@ int launch_moc(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const Pla
     MocArgs A{};
     fill_moc(d, A, S, B, D, coef, primary, kmode, dt_only);
     if (!dt_only && d->global_viscosity != 0.0) {             // global_visc_coeff of this right-hand-side evaluation (idealmhd.cpp:90)
-        if (!d->moc_visc_bits) CUDA_TRY(cudaMalloc(&d->moc_visc_bits, sizeof(unsigned long long)));
-        static const unsigned long long kMax = 0x7FEFFFFFFFFFFFFFULL;
-        CUDA_TRY(cudaMemcpyAsync(d->moc_visc_bits, &kMax, sizeof(kMax), cudaMemcpyHostToDevice, d->stream));
+        // the minimum goes through the module reduction scalars (slot 0 = a minimum): on slabs they are all-gathered over the peer segments
+        if (d->cfg.n_ranks > 1 && !d->peers_connected) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc with global_viscosity != 0 on slabs needs the peer transport (spruce_mgpu_ipc_connect)");
+        int rc = reset_reductions(d);
+        if (rc) return rc;
         dim3 grid((d->P.ny + 127) / 128, d->P.nx);
-        k_moc_visc_min<<<grid, 128, 0, d->stream>>>(d->P, A, d->moc_visc_bits);
+        k_moc_visc_min<<<grid, 128, 0, d->stream>>>(d->P, A, d->red);
         d->launches++;
-        A.visc_min_bits = d->moc_visc_bits;
+        if (d->cfg.n_ranks > 1 && (rc = peer_red_allgather(d))) return rc;
+        A.visc_min_bits = d->red;
     }
     k_moc_stage<<<(moc_threads(d->P) + 127) / 128, 128, 0, d->stream>>>(d->P, A);
     d->launches++;
@@ -899,7 +903,8 @@ int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, c
     const int crows = pick_chunk_rows(d), nchunks = (d->P.nx + crows - 1) / crows;
     const bool ghosts = d->any_ucnp || (primary && d->any_primary_ghost);
     const bool last_chunk_holds_edge = d->P.nx - (nchunks - 1) * crows >= HALO;       // the pushed rows nx-2, nx-1 must both come from the edge launch
-    const bool split = d->cfg.n_ranks > 1 && d->peers_connected && d->overlap && !ghosts && d->visc.empty() && nchunks >= 4 && last_chunk_holds_edge;
+    const bool split = d->cfg.n_ranks > 1 && d->peers_connected && d->overlap && !ghosts && d->visc.empty() && nchunks >= 4 && last_chunk_holds_edge
+                       && !d->moc_any;                                                  // the strip kernel follows the whole stage kernel and writes edge rows
     if (!split) {
         if ((rc = launch_stage(d, S, B, D, coef, primary, kmode))) return rc;
         return finish_stage(d, D, primary);
@@ -1119,7 +1124,6 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
         const char *ex = getenv("SPRUCE_EXPERIMENTAL_MOC");
         if (!ex || atoi(ex) == 0) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries: the device path is built but has not been validated on a GPU yet; set SPRUCE_EXPERIMENTAL_MOC=1 to use it (SURVEY.md 8f-2)");
         if (two_fluid) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries exist for ideal_mhd only (idealmhd.cpp:306)");
-        if (cfg->n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries on a slab decomposition are not built");
         for (int a = 0; a < 2; a++)       // a periodic side opposite an open_moc side is not a configuration the reference can run
             if ((bcs[2 * a] == SPRUCE_BC_PERIODIC) != (bcs[2 * a + 1] == SPRUCE_BC_PERIODIC)) return fail(SPRUCE_ERR_ARG, "periodic boundaries come in pairs");
     }
@@ -1214,7 +1218,6 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->tab_dev) cudaFree(d->tab_dev);
     if (d->ctl) cudaFree(d->ctl);
     if (d->red) cudaFree(d->red);
-    if (d->moc_visc_bits) cudaFree(d->moc_visc_bits);
     if (d->moc_base) cudaFree(d->moc_base);
     if (d->bo.max_dev) cudaFree(d->bo.max_dev);
     if (d->dt_hist) cudaFree(d->dt_hist);

@@ -33,13 +33,15 @@ constexpr int NG = 2;                                  // N_GHOST
 constexpr double kPi = 3.14159265358979323846;         // source/constants.hpp:16
 enum { MBC_PERIODIC = 0, MBC_OPEN_MOC = 4 };
 
-// The state the characteristic terms are evaluated on.  Planes are row-major, `pitch` doubles per row, row index = global x index
-// (open_moc is single-rank for now).  Plane `n` holds the number density (rho = n*m_i, idealmhd.cpp:247).
+// The state the characteristic terms are evaluated on.  Planes are row-major, `pitch` doubles per row, and are indexed by the GLOBAL row
+// (x) index: on a slab the caller passes plane pointers shifted back by row0 rows (and dx shifted by row0 entries), so that only rows the
+// slab holds -- its own plus two halo rows on each side -- are ever touched.  Plane `n` holds the number density (rho = n*m_i, idealmhd.cpp:247).
 struct Field {
     const double *n, *mx, *my, *mz, *e, *bix, *biy, *biz;
     const double *bex, *bey, *bez, *gx, *gy;
     const double *dx, *dy;                             // cell sizes: dx[i], dy[j]
-    int nx, ny, pitch;
+    int nx, ny, pitch;                                 // GLOBAL extent
+    int x_halo;                                        // slab of a periodic-x domain: the rows -2,-1 / nx,nx+1 are resident halo rows, x indices are not wrapped
     int bc[4];                                         // x1, x2, y1, y2
     double m_i, gamma, gm1;
     double visc;                                       // global_visc_coeff (idealmhd.cpp:90)
@@ -86,7 +88,7 @@ struct Ctx { const Field *F; Side S; };
 MOC_HD size_t cidx(const Ctx &c, int a, int b) { return c.S.bidx == 0 ? (size_t)a * c.F->pitch + b : (size_t)b * c.F->pitch + a; }
 MOC_HD double dn(const Ctx &c, int a) { return c.S.bidx == 0 ? c.F->dx[a] : c.F->dy[a]; }
 MOC_HD double dp(const Ctx &c, int b) { return c.S.bidx == 0 ? c.F->dy[b] : c.F->dx[b]; }
-MOC_HD int wrapb(const Ctx &c, int b) { return c.S.ppar ? (b + c.S.M) % c.S.M : b; }
+MOC_HD int wrapb(const Ctx &c, int b) { return (c.S.ppar && !(c.S.bidx == 1 && c.F->x_halo)) ? (b + c.S.M) % c.S.M : b; }
 
 enum Role { R_RHO = 0, R_EN, R_PRESS, R_VPERP, R_VPARA, R_VGUIDE, R_BEPERP, R_BEPARA, R_BEGUIDE, R_BIPERP, R_BIPARA, R_BIGUIDE,
             R_BPERP, R_RHOVPARA, R_RHOVGUIDE, R_RHOVPERP };
@@ -350,19 +352,20 @@ MOC_HD bool side_owns(const Field &F, int s, int i, int j)
     return a >= S.alo && a <= S.ahi && b >= S.Flo && b <= S.Fhi;
 }
 
-// ---- thread -> cell mapping of the strip kernels (moc_stage.cuh): 2 ghost layers x the full length of each of the four sides
-MOC_HD int n_threads(int nx, int ny) { return 2 * NG * (nx + ny); }
-MOC_HD bool thread_cell(int nx, int ny, int t, int *side, int *i, int *j)
+// ---- thread -> cell mapping of the strip kernels (moc_stage.cuh): 2 ghost layers x the slab's part of each of the four sides.
+// A slab holds rows [row0, row0 + nx_local) of gnx; the x sides belong to the first / last slab (slabs are at least 2*NG rows thick).
+MOC_HD int n_threads(int nx_local, int ny) { return 2 * NG * (nx_local + ny); }
+MOC_HD bool thread_cell(int nx_local, int ny, int row0, int gnx, int t, int *side, int *i, int *j)
 {
-    const int nxs = NG * ny, nys = NG * nx;
+    const int nxs = NG * ny, nys = NG * nx_local;
     if (t < 0) return false;
-    if (t < nxs) { *side = 0; *i = t / ny; *j = t % ny; return true; }
+    if (t < nxs) { *side = 0; *i = t / ny; *j = t % ny; return row0 == 0; }
     t -= nxs;
-    if (t < nxs) { *side = 1; *i = nx - NG + t / ny; *j = t % ny; return true; }
+    if (t < nxs) { *side = 1; *i = gnx - NG + t / ny; *j = t % ny; return row0 + nx_local == gnx; }
     t -= nxs;
-    if (t < nys) { *side = 2; *j = t / nx; *i = t % nx; return true; }
+    if (t < nys) { *side = 2; *j = t / nx_local; *i = row0 + t % nx_local; return true; }
     t -= nys;
-    if (t < nys) { *side = 3; *j = ny - NG + t / nx; *i = t % nx; return true; }
+    if (t < nys) { *side = 3; *j = ny - NG + t / nx_local; *i = row0 + t % nx_local; return true; }
     return false;
 }
 // a corner cell evolved by two sides is handled by the thread of the first of them

@@ -7,6 +7,8 @@
 // writes D = B + k*s with the floors and the pointwise boundary zeroing, and -- in the step's last stage -- folds the cell's new dt into
 // the running minimum, whose bounds include the ghost zone on open_moc sides (plasmadomain.cpp:155-159).
 // k_moc_visc_min evaluates the minimum behind global_visc_coeff (idealmhd.cpp:90) when global_viscosity != 0.
+// Slabs: cells are addressed by their GLOBAL row; a rank evolves the part of each strip it holds (the x sides belong to the first / last
+// slab), reading its halo rows for the stencils along x; the minimum behind global_visc_coeff is all-gathered over the peer segments.
 // STATUS: written after the round-1 GPU budget was spent.  The arithmetic is proven on the host (tests/test_moc_host_check.py);
 // the launch side has not run on a GPU yet (tests/test_zz_gpu_unvalidated.py).
 #pragma once
@@ -36,16 +38,19 @@ struct MocArgs {
 __device__ __forceinline__ moc::Field moc_field(const DomainParams &P, const double *const *U, const double *const *st, double visc)
 {
     moc::Field F;
-    F.n = U[E_N]; F.mx = U[E_MX]; F.my = U[E_MY]; F.mz = U[E_MZ]; F.e = U[E_E]; F.bix = U[E_BX]; F.biy = U[E_BY]; F.biz = U[E_BZ];
-    F.bex = st[S_BEX]; F.bey = st[S_BEY]; F.bez = st[S_BEZ]; F.gx = st[S_GX]; F.gy = st[S_GY];
-    F.dx = P.tx.d; F.dy = P.ty.d;
-    F.nx = P.nx; F.ny = P.ny; F.pitch = P.pitch;
+    // global row indexing: shift every plane (and the x table) back by the slab's first row
+    const long long sh = (long long)P.row0 * P.pitch;
+    F.n = U[E_N] - sh; F.mx = U[E_MX] - sh; F.my = U[E_MY] - sh; F.mz = U[E_MZ] - sh; F.e = U[E_E] - sh; F.bix = U[E_BX] - sh; F.biy = U[E_BY] - sh; F.biz = U[E_BZ] - sh;
+    F.bex = st[S_BEX] - sh; F.bey = st[S_BEY] - sh; F.bez = st[S_BEZ] - sh; F.gx = st[S_GX] - sh; F.gy = st[S_GY] - sh;
+    F.dx = P.tx.d - P.row0; F.dy = P.ty.d;
+    F.nx = P.gnx; F.ny = P.ny; F.pitch = P.pitch;
+    F.x_halo = (P.xper && !P.xwrap) ? 1 : 0;
     F.bc[0] = P.bc_x1; F.bc[1] = P.bc_x2; F.bc[2] = P.bc_y1; F.bc[3] = P.bc_y2;
     F.m_i = P.m_i; F.gamma = P.gamma; F.gm1 = P.gm1; F.visc = visc;
     return F;
 }
 
-__device__ __forceinline__ bool moc_thread_cell(const DomainParams &P, int t, int *side, int *i, int *j) { return moc::thread_cell(P.nx, P.ny, t, side, i, j); }
+__device__ __forceinline__ bool moc_thread_cell(const DomainParams &P, int t, int *side, int *i, int *j) { return moc::thread_cell(P.nx, P.ny, P.row0, P.gnx, t, side, i, j); }   // (i, j): GLOBAL
 __device__ __forceinline__ bool moc_thread_owns(const moc::Field &F, int side, int i, int j) { return moc::thread_owns(F, side, i, j); }
 
 inline int moc_threads(const DomainParams &P) { return moc::n_threads(P.nx, P.ny); }     // = T in the kernels
@@ -58,7 +63,7 @@ __global__ void __launch_bounds__(128) k_moc_save(const DomainParams P, const Mo
     if (*A.done_ptr || !moc_thread_cell(P, t, &side, &i, &j)) return;
     const moc::Field F = moc_field(P, A.S, A.st, 0.0);
     if (!moc_thread_owns(F, side, i, j)) return;
-    const size_t q = (size_t)i * P.pitch + j;
+    const size_t q = (size_t)(i - P.row0) * P.pitch + j;               // local offset into the (unshifted) planes
     const int T = 2 * HALO * (P.nx + P.ny);
     for (int v = 0; v < NEV; v++) A.base_buf[(size_t)v * T + t] = A.B[v][q];
 }
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(128) k_moc_save(const DomainParams P, const Mo
 __global__ void __launch_bounds__(128) k_moc_visc_min(const DomainParams P, const MocArgs A, unsigned long long *out_bits)
 {
     // every cell inside the dt bounds: (1/(1/dx^2 + 1/dy^2)) / dt of the stage's input state
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = P.row0 + (int)blockIdx.y;       // i: GLOBAL row of this slab's local row blockIdx.y
     double v = 1.7976931348623157e308;
     if (!*A.done_ptr && j < P.ny) {
         const moc::Field F = moc_field(P, A.S, A.st, 0.0);
@@ -89,7 +94,8 @@ __global__ void __launch_bounds__(128) k_moc_stage(const DomainParams P, const M
         if (A.visc_min_bits) visc = (A.global_viscosity * 0.5) * __longlong_as_double((long long)*A.visc_min_bits);      // idealmhd.cpp:90
         const moc::Field F = moc_field(P, A.S, A.st, visc);
         if (moc_thread_owns(F, side, i, j)) {
-            const size_t q = (size_t)i * P.pitch + j;
+            const size_t q = (size_t)i * P.pitch + j;                          // into the row-shifted planes of F (global row index)
+            const size_t ql = (size_t)(i - P.row0) * P.pitch + j;              // into the slab's own planes (K1, K2, D)
             if (A.dt_only) {
                 if (moc::in_dt_bounds(F, i, j) && !moc::in_interior(F, i, j))
                     dtc = moc::cell_dt_plain(F, F.n[q], F.mx[q], F.my[q], F.e[q], F.bex[q] + F.bix[q], F.bey[q] + F.biy[q], F.bez[q] + F.biz[q], F.dx[i], F.dy[j]);
@@ -97,10 +103,10 @@ __global__ void __launch_bounds__(128) k_moc_stage(const DomainParams P, const M
                 double k[NEV];
                 moc::moc_cell_terms(F, i, j, k);
                 // integrator K planes (evolution.cpp:103-124); the stage kernel has stored / added the masked zero for this cell already
-                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { for (int v = 0; v < NEV; v++) A.K1[v][q] = k[v]; }
-                else if (A.kmode == KM_STORE_K2) { for (int v = 0; v < NEV; v++) A.K2[v][q] = k[v]; }
-                else if (A.kmode == KM_ADD_K2) { for (int v = 0; v < NEV; v++) A.K2[v][q] = A.K2[v][q] + k[v]; }
-                else if (A.kmode == KM_FINAL) { for (int v = 0; v < NEV; v++) k[v] = (A.K1[v][q] + k[v]) / 6.0 + A.K2[v][q] / 3.0; }
+                if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) { for (int v = 0; v < NEV; v++) A.K1[v][ql] = k[v]; }
+                else if (A.kmode == KM_STORE_K2) { for (int v = 0; v < NEV; v++) A.K2[v][ql] = k[v]; }
+                else if (A.kmode == KM_ADD_K2) { for (int v = 0; v < NEV; v++) A.K2[v][ql] = A.K2[v][ql] + k[v]; }
+                else if (A.kmode == KM_FINAL) { for (int v = 0; v < NEV; v++) k[v] = (A.K1[v][ql] + k[v]) / 6.0 + A.K2[v][ql] / 3.0; }
                 if (A.kmode != KM_EXPORT) {
                     const double s = A.coef * *A.step_ptr;
                     double base[NEV];
@@ -108,8 +114,8 @@ __global__ void __launch_bounds__(128) k_moc_stage(const DomainParams P, const M
                     for (int v = 0; v < NEV; v++) base[v] = A.base_buf[(size_t)v * T + t];
                     const moc::Floors fl{P.n_min, P.e_min};
                     const moc::Updated u = moc::advance_cell(F, fl, base, k, s, A.primary != 0, i, j);
-                    A.D[E_N][q] = u.n; A.D[E_MX][q] = u.mx; A.D[E_MY][q] = u.my; A.D[E_MZ][q] = u.mz;
-                    A.D[E_E][q] = u.e; A.D[E_BX][q] = u.bx; A.D[E_BY][q] = u.by; A.D[E_BZ][q] = u.bz;
+                    A.D[E_N][ql] = u.n; A.D[E_MX][ql] = u.mx; A.D[E_MY][ql] = u.my; A.D[E_MZ][ql] = u.mz;
+                    A.D[E_E][ql] = u.e; A.D[E_BX][ql] = u.bx; A.D[E_BY][ql] = u.by; A.D[E_BZ][ql] = u.bz;
                     if (A.primary && moc::in_dt_bounds(F, i, j) && !moc::in_interior(F, i, j))
                         dtc = moc::cell_dt_plain(F, u.n, u.mx, u.my, u.e, F.bex[q] + u.bx, F.bey[q] + u.by, F.bez[q] + u.bz, F.dx[i], F.dy[j]);
                 }

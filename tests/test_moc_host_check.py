@@ -140,3 +140,36 @@ def test_strip_kernel_thread_mapping_visits_every_evolved_ghost_cell_once(lib, n
     assert T == 4 * (nx + ny)
     assert np.array_equal(visits, owned.astype(np.int32))
     o.close()
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 5])
+@pytest.mark.parametrize("name,xb,yb,gvisc,nx,ny", CASES, ids=[c[0] for c in CASES])
+def test_slab_decomposed_evaluation_equals_oracle_rhs(lib, name, xb, yb, gvisc, nx, ny, n_ranks):
+    """The slab form of the open_moc path: each rank holds its rows plus two halo rows (NaN beyond a physical x boundary), addresses them by
+    global row through shifted pointers as moc_field() does, and runs the strip kernels' thread loop.  Every evolved ghost cell must be owned
+    by exactly one thread of exactly one rank, written only by the rank that holds it, and carry the oracle's right-hand side bit for bit."""
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o.set_global_viscosity(gvisc)
+    for _ in range(2):
+        o.step()
+    xl, xu, yl, yu = dt_bounds(xb, yb, nx, ny)
+    dxp, dyp, dt = o.get("d_x"), o.get("d_y"), o.get("dt")
+    visc = gvisc * 0.5 * float(np.min(((1.0 / (1.0 / (dxp * dxp) + 1.0 / (dyp * dyp))) / dt)[xl:xu + 1, yl:yu + 1]))
+    k_ref = o.rhs()
+    _, owned, _ = host_terms(lib, o, xb, yb, visc, s["ion_mass"], s["adiabatic_index"])
+    names = ["n", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z", "be_x", "be_y", "be_z", "grav_x", "grav_y"]
+    planes = [np.ascontiguousarray(o.get(v), dtype=np.float64) for v in names]
+    dx = np.ascontiguousarray(dxp[:, 0]); dy = np.ascontiguousarray(dyp[0, :])
+    arr = (C.c_void_p * 13)(*[p.ctypes.data for p in planes])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    k = np.zeros((8, nx, ny)); visits = np.zeros((nx, ny), dtype=np.int32)
+    lib.moc_host_terms_slabs.restype = C.c_int
+    rc = lib.moc_host_terms_slabs(arr, dx.ctypes.data_as(C.c_void_p), dy.ctypes.data_as(C.c_void_p), C.c_int(nx), C.c_int(ny), bc, C.c_double(s["ion_mass"]),
+                                  C.c_double(s["adiabatic_index"]), C.c_double(visc), C.c_int(n_ranks), k.ctypes.data_as(C.c_void_p), visits.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert np.array_equal(visits, owned.astype(np.int32))
+    for v, nm in enumerate(EVOLVED):
+        ref = np.where(owned, k_ref[v], 0.0)
+        assert same_bits(np.where(owned, k[v], 0.0), ref), "%s %d ranks d(%s)/dt: %s" % (name, n_ranks, nm, mismatch(np.where(owned, k[v], 0.0), ref))
+    o.close()

@@ -296,3 +296,19 @@ def test_relaxed_arithmetic_within_north_star_tolerance(integ, zfull, nx, ny, ns
     bit-identical.  Also checks that the result is NOT bit-identical, i.e. that the relaxed kernel really ran."""
     out = run_isolated(RELAXED_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, nsteps=nsteps), {"SPRUCE_ARITH": "relaxed", "SPRUCE_STAGE_VARIANTS": variants}, timeout=240)
     assert "ok" in out
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("args", [("96", "80", "4", "rk2", "periodic", "p2p", "moc"), ("90", "70", "4", "rk4", "open_moc", "p2p", "mocv"),
+                                  ("96", "80", "3", "euler", "open_moc", "nccl", "moc"), ("128", "96", "4", "rk2", "periodic", "p2p", "src")])
+def test_slab_decomposition_of_the_unvalidated_paths_equals_single_gpu(args):
+    """open_moc sides and the pointwise solar source terms on 2 slabs == 1 GPU, bit for bit (the slab form of the open_moc evaluation is proven on the
+    host by tests/test_moc_host_check.py; this is the launch side).  Needs >= 2 visible GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    e = dict(os.environ); e["SPRUCE_EXPERIMENTAL_MOC"] = "1"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", str(ROOT / "scripts" / "mgpu_check.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, env=e)
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "IDENTICAL" in out, out[-3000:]
