@@ -102,8 +102,6 @@ def test_create_argument_errors_mirror_the_reference_messages():
     try:
         rc, msg = create(y_bound_2=capi.BC["open_moc"], y_bound_1=capi.BC["fixed"], equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["fixed"], x_bound_2=capi.BC["fixed"])
         assert rc != 0 and "ideal_mhd only" in msg
-        rc, msg = create(y_bound_2=capi.BC["open_moc"], y_bound_1=capi.BC["fixed"], n_ranks=2, nx_local=8)
-        assert rc != 0 and "slab" in msg
         rc, msg = create(y_bound_2=capi.BC["open_moc"])
         assert rc != 0 and "pairs" in msg
     finally:
