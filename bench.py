@@ -306,7 +306,7 @@ def emit(args, r, world):
                        "parallelism": ("slab%d along x, halo exchange: %s" % (world, r.get("transport", "p2p"))) if world > 1 else "single", "l2": "working set per step (21 planes, %.1f GB) >> 126 MB L2: inputs larger than L2" % (21 * args.size ** 2 * 8 / 1e9),
                        "mode": "exact (bit-identical to the reference CPU build)" if args.arith == "exact" else
                                "relaxed (opt-in: FMA contraction + one-multiplication table divisions in the stage kernel; fields within 1e-9 of the reference, step sizes not bit-identical)",
-                       "stage_variants": bool(args.stage_variants)},
+                       "stage_variants": int(args.stage_variants)},
             "clocks": r["clocks"], "gpu_launches": r["launches"], "e2e": r["e2e"], "roofline": r["roofline"]}
     if r.get("cpu"):
         line["cpu_baseline"] = r["cpu"]
@@ -330,7 +330,8 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "relaxed"],
                     help="exact (default, the bench line): every operation individually rounded, bit-identical to the reference; relaxed: the opt-in stage kernel of "
                          "stage_relaxed.cu (FMA contraction, one-multiplication table divisions; fields within the north star's 1e-9, step sizes not bit-identical)")
-    ap.add_argument("--stage-variants", action="store_true", help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS=1)")
+    ap.add_argument("--stage-variants", type=int, default=0, nargs="?", const=1, choices=[0, 1, 2],
+                    help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS): 1 = on, 2 = also the six-CTAs-per-SM build of the 2-D instance")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: library peer stores over NVLink, or torch.distributed NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -338,7 +339,7 @@ def main():
     if args.arith == "relaxed":
         os.environ["SPRUCE_ARITH"] = "relaxed"              # read by spruce_domain_create
     if args.stage_variants:
-        os.environ["SPRUCE_STAGE_VARIANTS"] = "1"
+        os.environ["SPRUCE_STAGE_VARIANTS"] = str(args.stage_variants)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -56,16 +56,17 @@ constexpr unsigned long long xy_list(int a = -1, int b = -1, int c = -1, int d =
 constexpr unsigned long long XY_LIST_2D = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY);                                              // no z system, no external field
 constexpr unsigned long long XY_LIST_FULL = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY, Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_BEZ);   // everything (padded to 12)
 
-// VAR > 0: the integrator stage is a compile-time constant too (no K planes, no module right-hand-side terms):
+// VAR > 0: the integrator stage is a compile-time constant too (no K planes, no module right-hand-side terms).  VAR & 3 =
 //   1: B == S, secondary (first stage of rk2)   2: B != S, primary (last stage of rk2)   3: B == S, primary (euler).
+// VAR & 4 (2-D instance only): compiled for SIX resident CTAs per SM (80 registers, a few dozen bytes of spill; 6 x 37 KB of shared memory).
 // VAR == 0 takes kmode / b_is_s / primary / n_xterm from the launch arguments (every integrator, every module).
 template <int LN, unsigned long long LQ, int VAR = 0>
-__global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
+__global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
 {
     constexpr int UNR = LN > 0 ? LN : 1;
 #define kmode (VAR ? (int)KM_NONE : A.kmode)
-#define b_is_s (VAR ? (VAR != 2 ? 1 : 0) : A.b_is_s)
-#define primary (VAR ? (VAR != 1 ? 1 : 0) : A.primary)
+#define b_is_s (VAR ? ((VAR & 3) != 2 ? 1 : 0) : A.b_is_s)
+#define primary (VAR ? ((VAR & 3) != 1 ? 1 : 0) : A.primary)
 #define n_xterm (VAR ? 0 : A.n_xterm)
     // Z: the z system (mom_z, bi_z, v_z) and the external field can be non-zero.  In the 2-D instance (LN == 6) they are exact zeros in the
     // reference as well, so every term that only adds +-0 is left out (the results can differ in the sign of a zero, nothing else) and

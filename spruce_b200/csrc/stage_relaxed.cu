@@ -25,6 +25,10 @@ cudaError_t launch_one(dim3 grid, cudaStream_t st, const R::DomainParams &P, con
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(R::k_mhd_stage_xy<LN, LQ, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        if (VAR & 4) {                           // six CTAs per SM need the largest shared-memory carve-out
+            e = cudaFuncSetAttribute(R::k_mhd_stage_xy<LN, LQ, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
         configured = true;
     }
     R::k_mhd_stage_xy<LN, LQ, VAR><<<grid, R::XY_NT, smem, st>>>(P, A, L);
@@ -36,6 +40,11 @@ cudaError_t launch_var(int var, dim3 grid, cudaStream_t st, const R::DomainParam
     if (var == 1) return launch_one<LN, LQ, 1>(grid, st, P, A, L);
     if (var == 2) return launch_one<LN, LQ, 2>(grid, st, P, A, L);
     if (var == 3) return launch_one<LN, LQ, 3>(grid, st, P, A, L);
+    if (LN == 6) {                               // six CTAs per SM: the 2-D instance only
+        if (var == 5) return launch_one<6, R::XY_LIST_2D, 5>(grid, st, P, A, L);
+        if (var == 6) return launch_one<6, R::XY_LIST_2D, 6>(grid, st, P, A, L);
+        if (var == 7) return launch_one<6, R::XY_LIST_2D, 7>(grid, st, P, A, L);
+    } else if (var & 4) return launch_var<LN, LQ>(var & 3, grid, st, P, A, L);
     return launch_one<LN, LQ, 0>(grid, st, P, A, L);
 }
 }  // namespace

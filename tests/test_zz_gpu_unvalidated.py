@@ -47,6 +47,7 @@ STAGE_VARIANT_CODE = """
 
 
 @UNVALIDATED
+@pytest.mark.parametrize("variants", ["1", "2"])            # 2: also the six-CTAs-per-SM build of the 2-D instance
 @pytest.mark.parametrize("integ,zfull,nx,ny,xb,yb", [
     ("rk2", False, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),      # 2-D list: k_mhd_stage_xy<6, ., 1> then <6, ., 2>
     ("rk2", True, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),       # full list: <12, ., 1> / <12, ., 2>
@@ -55,11 +56,11 @@ STAGE_VARIANT_CODE = """
     ("rk2", False, 97, 140, ("open", "fixed"), ("reflect", "open")),                   # primary-stage strips + ghost passes
     ("rk4", False, 99, 77, ("periodic", "periodic"), ("periodic", "periodic")),        # K planes: falls back to the run-time instance
 ])
-def test_compile_time_stage_variants_vs_oracle(integ, zfull, nx, ny, xb, yb):
+def test_compile_time_stage_variants_vs_oracle(integ, zfull, nx, ny, xb, yb, variants):
     """SPRUCE_STAGE_VARIANTS=1 selects instances of k_mhd_stage_xy whose integrator stage (kmode / b_is_s / primary / no module terms)
     is a template constant (mhd_stage_xy.cuh, VAR).  Same source, same arithmetic; the default instances are SASS-identical to the
     validated build (scripts/sass_identity.py)."""
-    out = run_isolated(STAGE_VARIANT_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, xb=xb, yb=yb), {"SPRUCE_STAGE_VARIANTS": "1"})
+    out = run_isolated(STAGE_VARIANT_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, xb=xb, yb=yb), {"SPRUCE_STAGE_VARIANTS": variants})
     assert "ok" in out
 
 
@@ -286,6 +287,7 @@ RELAXED_CODE = """
 @pytest.mark.parametrize("integ,zfull,nx,ny,nsteps,variants", [
     ("rk2", False, 256, 256, 100, "0"),
     ("rk2", False, 256, 256, 100, "1"),
+    ("rk2", False, 256, 256, 100, "2"),
     ("rk2", True, 150, 203, 100, "1"),
     ("rk4", False, 131, 96, 60, "0"),
     ("euler", True, 96, 131, 60, "1"),
