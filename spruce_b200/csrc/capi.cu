@@ -30,6 +30,7 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(SPRUCE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CUDA_TRY_D(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { delete d; return fail(SPRUCE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
 #define NOT_2F(d, what) do { if ((d)->tf) return fail(SPRUCE_ERR_UNSUPPORTED, "%s is not available with the ideal_2F equation set", what); } while (0)
 #define CHECK_DOM(d) do { if (!(d)) return fail(SPRUCE_ERR_ARG, "null domain handle"); } while (0)
 
@@ -1145,21 +1146,6 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(xy_rows(6))));
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
-    {   // the compile-time integrator-stage instances (SPRUCE_STAGE_VARIANTS)
-        const int sm6 = (int)xy_smem_bytes(xy_rows(6)), smf = (int)xy_smem_bytes(NTR);
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // 6 x 37 KB
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
-        CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
-    }
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
@@ -1170,6 +1156,22 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
         else if (strcmp(ar, "exact")) { delete d; return fail(SPRUCE_ERR_ARG, "SPRUCE_ARITH must be exact or relaxed"); }
     }
     d->moc_any = moc_any;
+    if (d->stage_variants) {   // the compile-time integrator-stage instances: configured only when asked for (the default path stays exactly the validated one)
+        const int sm6 = (int)xy_smem_bytes(xy_rows(6)), smf = (int)xy_smem_bytes(NTR);
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // 6 x 37 KB
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+    }
+
     DomainParams &P = d->P;
     P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;
     P.gnx = cfg->xdim; P.row0 = cfg->row0;
