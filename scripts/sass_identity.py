@@ -5,6 +5,7 @@ instance of the new build.
 
     cuobjdump -sass old/libspruce_b200.so > /tmp/old.sass      # or pass the .so files themselves
     python scripts/sass_identity.py /tmp/old.sass spruce_b200/lib/libspruce_b200.so
+    python scripts/sass_identity.py profiles/r1_validated_kernels.sass.gz spruce_b200/lib/libspruce_b200.so     # against the build the round-1 GPU runs validated
 
 A trailing default template argument that the new build added (`..., 0>` mangled as `ELi0EEEv`) is ignored when names are matched.
 Exit status 1 when any function present in both builds differs.  No GPU needed."""
@@ -16,6 +17,9 @@ import sys
 def sass_lines(path):
     if path.endswith(".so"):
         return subprocess.run(["cuobjdump", "-sass", path], check=True, capture_output=True, text=True).stdout.splitlines()
+    if path.endswith(".gz"):
+        import gzip
+        return gzip.open(path, "rt").read().splitlines()
     return open(path).read().splitlines()
 
 
