@@ -96,6 +96,29 @@ CASES = {
     "tf_fr_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=("fixed", "reflect"), yb=("reflect", "fixed"), **TF, **UCNP_FLOORS), 6, (1, 6)),
     "tf_floors_nocurl_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=PP, eqs="ideal_2F", eqs_block=[("use_sub_cycling", "false"), ("remove_curl_terms", "true")],
                              density_min=3.0e6, temp_min=1.0e-3, thermal_energy_min=2.0e-10), 5, (1, 5)),
+    # ---- "next" rows of SURVEY 8f: the method-of-characteristics open boundary and the small solar modules (prefixes moc_ / sm_ / ar_:
+    #      pinned for the oracle by tests/test_oracle_golden.py, and for the not-yet-GPU-validated device paths by tests/test_zz_gpu_unvalidated.py)
+    "moc_y2_euler": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.4), dict(integrator="euler", xb=PP, yb=("fixed", "open_moc"), **SOLAR_FLOORS), 5, (1, 5)),
+    "moc_all_visc_rk2": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.4), dict(integrator="rk2", xb=("open_moc", "open_moc"), yb=("open_moc", "open_moc"),
+                         eqs_block=[("global_viscosity", "0.1")], **SOLAR_FLOORS), 5, (1, 5)),
+    "moc_x1_mixed_rk4": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.4), dict(integrator="rk4", xb=("open_moc", "reflect"), yb=("fixed", "open"), **SOLAR_FLOORS), 4, (1, 4)),
+    "sm_sink_heat_mass_rk2": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=PP, yb=("fixed", "fixed"), modules=[
+        ("ambient_heating_sink", [("exp_mode", "true"), ("exp_base_heating_rate", "2.0e-5"), ("exp_scale_height", "8.0e8"), ("center_x", "2.0e9"), ("half_width", "1.5e9")]),
+        ("localized_heating", [("start_time", "0.0"), ("duration", "5.0"), ("max_heating_rate", "1.0e-3"), ("stddev_x", "3.0"), ("stddev_y", "4.0"), ("center_x", "2.0"), ("center_y", "8.0"), ("ramp_time", "1.0")]),
+        ("mass_injection", [("start_time", "0.5"), ("duration", "10.0"), ("max_injection_rate", "1.0e6"), ("stddev_x", "3.0"), ("stddev_y", "3.0"), ("center_x", "12.0"), ("center_y", "10.0")])],
+        **SOLAR_FLOORS), 6, (1, 6)),
+    "sm_momentum_divclean_rk2": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("fixed", "open"), yb=("reflect", "fixed"), modules=[
+        ("momentum_injection", [("start_time", "0.0"), ("duration", "50.0"), ("max_accel", "1.0e3"), ("stddev_x", "4.0"), ("stddev_y", "3.0"), ("center_x", "13.0"), ("center_y", "9.0"),
+                                ("dir_x", "1.0"), ("dir_y", "0.5"), ("template_angle", "20.0"), ("oscillatory", "true"), ("oscillation_period", "3.0")]),
+        ("div_cleaning", [("epsilon", "0.1"), ("time_scale", "5.0")])], **SOLAR_FLOORS), 5, (1, 5)),
+    "sm_field_heating_euler": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="euler", xb=PP, yb=("fixed", "open"), modules=[
+        ("field_heating", [("coeff", "1.0"), ("current_pow", "1.0"), ("b_pow", "0.5"), ("n_pow", "0.25"), ("roc_pow", "0.5")])], **SOLAR_FLOORS), 4, (1, 4)),
+    "sm_outflow_dynamic_rk2": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.4), dict(integrator="rk2", xb=PP, yb=("fixed", "open"), modules=[
+        ("boundary_outflow", [("max_accel", "2.0e3"), ("falloff_length", "6.0e8"), ("boundary", "y_bound_2"), ("falloff_shape", "exp"), ("feather_length", "3.0e8"),
+                              ("field_aligned_mode", "true"), ("dynamic_mode", "true"), ("dynamic_time", "10.0"), ("dynamic_target_speed", "2.0e6")])], **SOLAR_FLOORS), 5, (1, 5)),
+    # (square grid: circularMask / currentThresholdMask loop j over result.rows(), anomalousresistivity.cpp:285,297 -- the reference aborts when xdim > ydim)
+    "ar_floodfill_rk2": ("stratified_loop", dict(nx=26, ny=26, bump=0.5), dict(integrator="rk2", xb=("fixed", "open"), yb=("fixed", "open"), modules=[
+        ("anomalous_resistivity", [("time_scale", "0.3"), ("safety_factor", "0.5"), ("flood_fill_threshold", "1.5"), ("smoothing_sigma", "1.0")])], **SOLAR_FLOORS), 3, (1, 3)),
     # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
     "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
 }
@@ -112,10 +135,12 @@ def example_state():
 
 
 def interior(cfg, nx, ny):
-    xl = 0 if cfg["xb"][0] == "periodic" else 2
-    xu = nx - 1 if cfg["xb"][1] == "periodic" else nx - 3
-    yl = 0 if cfg["yb"][0] == "periodic" else 2
-    yu = ny - 1 if cfg["yb"][1] == "periodic" else ny - 3
+    """bounds of the time-step minimum: the interior, widened by the ghost zone on open_moc sides (plasmadomain.cpp:138-159)"""
+    wide = ("periodic", "open_moc")
+    xl = 0 if cfg["xb"][0] in wide else 2
+    xu = nx - 1 if cfg["xb"][1] in wide else nx - 3
+    yl = 0 if cfg["yb"][0] in wide else 2
+    yu = ny - 1 if cfg["yb"][1] in wide else ny - 3
     return xl, xu, yl, yu
 
 

@@ -4,7 +4,8 @@ source/mhd/evolution.cpp:62) and every evolved plane + temp + dt after the recor
 import numpy as np
 import pytest
 
-from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, physical_viscosity_coefficient, same_bits, viscosity_terms_with_profiles
+from golden_util import (Golden, OUT_VARS, cases, mismatch, module_kwargs, physical_viscosity_coefficient, same_bits, small_module_kwargs,
+                         viscosity_terms_with_profiles)
 from oracle.oracle import Oracle
 
 
@@ -58,5 +59,29 @@ def test_two_fluid_oracle_reproduces_reference(name):
         assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())
         if it in g.frames:
             for v in g.out_vars:
+                assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
+    o.close()
+
+
+@pytest.mark.parametrize("name", cases(extended=True))
+def test_extended_oracle_reproduces_reference(name):
+    """The restatements of the SURVEY 8f rows -- open_moc boundary (oracle/moc_oracle.inc, with global_viscosity), the small solar modules
+    (solar_small_modules_oracle.inc) and anomalous_resistivity (anomalous_resistivity_oracle.inc) -- against committed fixtures of the unmodified
+    reference binary (tests/golden/make_golden.py): step-size history and every plane, bit for bit.  (tests/test_oracle_vs_live_reference.py
+    sweeps more configurations against live runs where the reference binary is present.)"""
+    g = Golden(name)
+    o = Oracle(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
+    if "global_viscosity" in g.eqs_raw:
+        o.set_global_viscosity(float(g.eqs_raw["global_viscosity"]))
+    for mname, kv in g.modules:
+        if mname == "anomalous_resistivity":
+            o.set_anomalous_resistivity(**{k: float(v) for k, v in kv.items()})
+        else:
+            o.add_small_module(mname, **small_module_kwargs(mname, kv)[0])
+    for it in range(1, g.n_steps + 1):
+        step = o.step()
+        assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())
+        if it in g.frames:
+            for v in OUT_VARS:
                 assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
     o.close()

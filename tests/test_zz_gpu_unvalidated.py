@@ -314,3 +314,49 @@ def test_slab_decomposition_of_the_unvalidated_paths_equals_single_gpu(args):
                         "--master-port", "29519", str(ROOT / "scripts" / "mgpu_check.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, env=e)
     out = r.stdout.decode()
     assert r.returncode == 0 and "IDENTICAL" in out, out[-3000:]
+
+
+GOLDEN_CODE = """
+    import numpy as np
+    from golden_util import Golden, OUT_VARS, same_bits, mismatch, small_module_kwargs, sink_reduction_plane
+    from spruce_b200.domain import PlasmaDomain
+    g = Golden({name!r})
+    exact = {exact!r}
+    opts = dict(global_viscosity=float(g.eqs_raw["global_viscosity"])) if "global_viscosity" in g.eqs_raw else None
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, eqs_options=opts, **g.kw)
+    for mname, kv in g.modules:
+        prod = small_module_kwargs(mname, kv)[1]
+        if mname == "ambient_heating_sink":
+            d.set_ambient_heating_sink_plane(sink_reduction_plane(g.planes, prod, g.kw["xb"], g.kw["yb"]))
+        elif mname == "boundary_outflow":
+            d.set_boundary_outflow(g.planes["pos_x"], g.planes["pos_y"], **prod)
+        else:
+            getattr(d, "set_" + mname)(**prod)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+    done = 0
+    for it in sorted(g.frames):
+        dts = d.advance(it - done)
+        ref = g.steps[done:it]
+        if exact:
+            assert all(a == b for a, b in zip(dts, ref)), ([x.hex() for x in dts], [float(x).hex() for x in ref])
+        else:
+            assert np.max(np.abs(np.array(dts) - ref) / ref) <= 1e-9
+        done = it
+        for v in g.out_vars:
+            got = d.grid(v)
+            if exact:
+                assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
+            else:
+                assert rel(got, g.frames[it][v]) <= 1e-9, "%s after iteration %d: %.3e" % (v, it, rel(got, g.frames[it][v]))
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("name,exact", [("moc_y2_euler", True), ("moc_all_visc_rk2", True), ("moc_x1_mixed_rk4", True), ("sm_sink_heat_mass_rk2", True),
+                                        ("sm_momentum_divclean_rk2", True), ("sm_field_heating_euler", False), ("sm_outflow_dynamic_rk2", True)])
+def test_extended_golden_reference_outputs(name, exact):
+    """The device paths of the SURVEY 8f rows against committed outputs of the UNMODIFIED reference binary (tests/golden/moc_*, sm_*): step-size
+    history and every output plane, bit for bit (field_heating: pow with run-time exponents, <= 1e-9)."""
+    out = run_isolated(GOLDEN_CODE.format(name=name, exact=exact), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
+    assert "ok" in out
