@@ -360,3 +360,58 @@ def test_extended_golden_reference_outputs(name, exact):
     history and every output plane, bit for bit (field_heating: pow with run-time exponents, <= 1e-9)."""
     out = run_isolated(GOLDEN_CODE.format(name=name, exact=exact), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
     assert "ok" in out
+
+
+SOLAR = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+HOST_CASES = {
+    "moc_visc": (dict(nx=40, ny=36, bump=0.4), dict(integrator="rk2", xb=("open_moc", "open_moc"), yb=("fixed", "open_moc"), eqs_block=[("global_viscosity", "0.1")], max_iterations=5,
+                 iter_output_interval=1, write_precision=17, **SOLAR), True),
+    "source_terms": (dict(nx=40, ny=36), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=6, iter_output_interval=2, write_precision=17, modules=[
+        ("ambient_heating_sink", [("exp_mode", "true"), ("exp_base_heating_rate", "2.0e-5"), ("exp_scale_height", "8.0e8"), ("center_x", "2.0e9"), ("half_width", "1.5e9")]),
+        ("localized_heating", [("start_time", "0.0"), ("duration", "5.0"), ("max_heating_rate", "1.0e-3"), ("stddev_x", "3.0"), ("stddev_y", "4.0"), ("center_x", "2.0"), ("center_y", "8.0"), ("ramp_time", "1.0")]),
+        ("mass_injection", [("start_time", "0.5"), ("duration", "10.0"), ("max_injection_rate", "1.0e6"), ("stddev_x", "3.0"), ("stddev_y", "3.0"), ("center_x", "12.0"), ("center_y", "10.0")]),
+        ("momentum_injection", [("start_time", "0.0"), ("duration", "50.0"), ("max_accel", "1.0e3"), ("stddev_x", "4.0"), ("stddev_y", "3.0"), ("center_x", "13.0"), ("center_y", "9.0"),
+                                ("dir_x", "1.0"), ("dir_y", "0.5"), ("template_angle", "20.0"), ("oscillatory", "true"), ("oscillation_period", "3.0")])], **SOLAR), True),
+    "divclean_outflow": (dict(nx=40, ny=36, bump=0.4), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=5, iter_output_interval=1, write_precision=17, modules=[
+        ("div_cleaning", [("epsilon", "0.1"), ("time_scale", "5.0")]),
+        ("boundary_outflow", [("max_accel", "2.0e3"), ("falloff_length", "6.0e8"), ("boundary", "y_bound_2"), ("falloff_shape", "exp"), ("feather_length", "3.0e8"),
+                              ("field_aligned_mode", "true"), ("dynamic_mode", "true"), ("dynamic_time", "10.0"), ("dynamic_target_speed", "2.0e6")])], **SOLAR), True),
+    "field_heating": (dict(nx=40, ny=36, bump=0.5), dict(integrator="euler", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=4, iter_output_interval=1, modules=[
+        ("field_heating", [("coeff", "1.0"), ("current_pow", "1.0"), ("b_pow", "0.5"), ("n_pow", "0.25"), ("roc_pow", "0.5")])], **SOLAR), False),
+}
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("name", list(HOST_CASES))
+def test_host_shell_matches_reference_files_on_the_8f_rows(name, tmp_path):
+    """The C++ host shell (spruce_b200/bin/run) with open_moc sides / the solar modules of SURVEY 8f against the UNMODIFIED reference binary on the same
+    .state / .config: mhd.out and end.state byte-identical (field_heating: within 1e-9)."""
+    import numpy as np
+    from oracle import refrun
+    from spruce_b200 import synthetic
+    ours = ROOT / "spruce_b200" / "bin" / "run"
+    if not ours.exists():
+        subprocess.run(["make", "-C", str(ROOT / "spruce_b200" / "host")], check=True)
+    assert refrun.have_reference(), "oracle/_ref/run must travel with the repo"
+    gkw, ckw, exact = HOST_CASES[name]
+    s = synthetic.stratified_loop(**gkw)
+    state = tmp_path / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"], comments=["# drop-in test " + name])
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, **ckw)
+    refrun.run_reference(state, cfg, tmp_path / "ref", threads=4)
+    out_dir = tmp_path / "ours"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    (out_dir / "run.config").write_text(cfg)
+    e = dict(os.environ); e["SPRUCE_EXPERIMENTAL_MOC"] = "1"
+    r = subprocess.run([str(ours), "-m", "input", "-o", str(out_dir), "-s", str(state)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120, env=e)
+    assert r.returncode in (-6, 134) and "Simulation successfully reached max simulation time or iterations" in r.stderr.decode(), r.stderr.decode()[-2000:]
+    for fname in ("mhd.out", "end.state"):
+        a, b = (out_dir / fname).read_bytes(), (tmp_path / "ref" / fname).read_bytes()
+        if exact:
+            assert a == b, "%s differs from the reference's (%d vs %d bytes)" % (fname, len(a), len(b))
+    if not exact:
+        ma, pa = refrun.read_state(out_dir / "end.state")
+        mb, pb = refrun.read_state(tmp_path / "ref" / "end.state")
+        assert ma["t"] == mb["t"] and list(pa) == list(pb)
+        for k in pb:
+            assert np.max(np.abs(pa[k] - pb[k])) <= 1e-9 * max(np.max(np.abs(pb[k])), 1e-300), k
