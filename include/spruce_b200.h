@@ -159,13 +159,13 @@ int spruce_module_momentum_injection(spruce_domain *dom, double start_time, doub
 /* DivCleaning (source/modules/solar/divcleaning.cpp:21-47): post-iterate, sub-cycled diffusion of div(b) out of bi_x / bi_y; sub-cycle count through
  * spruce_module_subcycles(dom, "div_cleaning", &n).  FieldHeating (source/modules/solar/fieldheating.cpp:30-58): heating from |curl b|, |b|, n and the field
  * line radius of curvature, evaluated before the modules iterate and applied in iterateModule; inactive_mode computes it without applying it.
- * Single rank.  Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
+ * Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
 int spruce_module_div_cleaning(spruce_domain *dom, double epsilon, double time_scale);
 int spruce_module_field_heating(spruce_domain *dom, double coeff, double current_pow, double b_pow, double n_pow, double roc_pow, int inactive_mode);
 /* BoundaryOutflow (source/modules/solar/boundaryoutflow.cpp:33-236): boundary 0..3 = x_bound_1, x_bound_2, y_bound_1, y_bound_2; falloff_shape 0 exp,
- * 1 gaussian, 2 flat.  pos_x / pos_y = the PlasmaDomain position grids (host planes): the library builds accel_template (constructBoundaryAccel, :76-137)
+ * 1 gaussian, 2 flat.  pos_x / pos_y = the PlasmaDomain position grids of the WHOLE domain (xdim*ydim values, also on a slab): the library builds accel_template (constructBoundaryAccel, :76-137)
  * and the window of computeMeanOutflow (:140-213) from them.  spruce_module_boundary_outflow_state returns mean_outflow / curr_accel of the last step for
- * commandLineMessage (:65-74).  Single rank.  Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
+ * commandLineMessage (:65-74).  Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
 int spruce_module_boundary_outflow(spruce_domain *dom, const double *pos_x, const double *pos_y, size_t count, double max_accel, double falloff_length,
                                    int boundary, int falloff_shape, double feather_length, int field_aligned_mode, int dynamic_mode, double dynamic_time,
                                    double dynamic_target_speed);

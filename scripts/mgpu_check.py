@@ -44,6 +44,13 @@ def add_modules(dom):
             dom.set_eic_thermalization()
         elif m == "ah":
             dom.set_ambient_heating_plane(np.full((dom.nx, dom.ydim), 1.0e-4))
+        elif m == "dc":
+            dom.set_div_cleaning(epsilon=0.1, time_scale=5.0)
+        elif m == "fh":
+            dom.set_field_heating(coeff=1.0, current_pow=1.0, b_pow=0.5, n_pow=0.25, roc_pow=0.5)
+        elif m == "bo":
+            dom.set_boundary_outflow(s["planes"]["pos_x"], s["planes"]["pos_y"], max_accel=2.0e3, falloff_length=6.0e8, boundary="x_bound_2", falloff_shape="exp",
+                                     feather_length=3.0e8, field_aligned_mode=True, dynamic_mode=True, dynamic_time=10.0, dynamic_target_speed=2.0e6)
         elif m in ("moc", "mocv"):
             pass                                # a boundary condition, selected below
         elif m == "src":                        # the pointwise solar source terms (templates are built per slab from global cell indices)

@@ -75,7 +75,7 @@ struct spruce_domain {
     std::vector<int> module_order;                 // MOD_* ; MOD_SRC0 + k = sources[k]
     enum { MOD_SRC0 = 100, MOD_DC = 6, MOD_FH = 7, MOD_BO = 8 };
     struct { double max_accel = 0.0, dynamic_time = 1.0, target = 0.0, mean = 0.0, accel = 0.0; int boundary = 3, field_aligned = 0, dynamic = 0;
-             int win[4] = {0, 0, 0, 0}; double *tmpl = nullptr, *max_dev = nullptr; } bo;                // boundary_outflow
+             int win[4] = {0, 0, 0, 0}; double *tmpl = nullptr; } bo;                // boundary_outflow
     struct { double epsilon = 0.1, time_scale = 1.0; int nsub = 0; } dc;                            // div_cleaning (divcleaning.hpp:22-23)
     struct { double coeff = 0.0, current_pow = 0.0, b_pow = 0.0, n_pow = 0.0, roc_pow = 0.0; int inactive = 0; double *H = nullptr; } fh;   // field_heating
     // pointwise solar source terms (module_kernels.cuh: k_source_term), in config order
@@ -613,10 +613,12 @@ int dc_post(spruce_domain *d, double dt)
     k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, bx, d->stat[S_BEX], bix);                        // b_x = be_x + bi_x (idealmhd.cpp:262)
     k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, by, d->stat[S_BEY], biy);
     d->launches += 2;
+    // slabs: a plane that is differentiated along x needs its halo rows (b_x, and the y-derivative of b_y before its x-derivative)
+    if ((rc = exchange_plane(d, bx))) return rc;
     for (int s = 0; s < ns; s++) {
         DcArgs A{};
         A.dts = dts; A.time_scale = d->dc.time_scale;
-        if ((rc = launch_op(d, 0, 1, by, a)) || (rc = launch_op(d, 0, 0, a, b)) || (rc = launch_op(d, 1, 0, bx, s2))) return rc;    // d/dx(d/dy b_y) + d2/dx2 b_x  :36-37
+        if ((rc = launch_op(d, 0, 1, by, a)) || (rc = exchange_plane(d, a)) || (rc = launch_op(d, 0, 0, a, b)) || (rc = launch_op(d, 1, 0, bx, s2))) return rc;    // d/dx(d/dy b_y) + d2/dx2 b_x  :36-37
         A.bi = bix; A.mixed = b; A.second = s2;
         k_dc_update<<<grid, 256, 0, d->stream>>>(d->P, A);
         if ((rc = launch_op(d, 0, 0, bx, a)) || (rc = launch_op(d, 0, 1, a, b)) || (rc = launch_op(d, 1, 1, by, s2))) return rc;    // b_x is still the sub-cycle's starting value  :38-40
@@ -625,6 +627,7 @@ int dc_post(spruce_domain *d, double dt)
         k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, bx, bix, d->stat[S_BEX]);                    // :41-42
         k_plane_sum<<<grid, 256, 0, d->stream>>>(d->P, by, biy, d->stat[S_BEY]);
         d->launches += 4;
+        if ((rc = exchange_plane(d, bx))) return rc;
     }
     CUDA_TRY(cudaGetLastError());
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // :46
@@ -667,13 +670,16 @@ int bo_post(spruce_domain *d, double dt)
     for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
     A.tmpl = bo.tmpl; A.xl = bo.win[0]; A.xu = bo.win[1]; A.yl = bo.win[2]; A.yu = bo.win[3];
-    A.boundary = bo.boundary; A.field_aligned = bo.field_aligned; A.max_out = bo.max_dev;
-    const double init = -1.0 * bo.target;                                                            // :227
-    CUDA_TRY(cudaMemcpyAsync(bo.max_dev, &init, sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    A.boundary = bo.boundary; A.field_aligned = bo.field_aligned; A.max_key = &d->red[1];            // slot 1 of the module reductions: a maximum
+    int rc = reset_reductions(d);
+    if (rc) return rc;
     dim3 g1((d->P.ny + 127) / 128, d->P.nx), g2((d->P.ny + 255) / 256, d->P.nx);
     k_bo_mean<<<g1, 128, 0, d->stream>>>(d->P, A);
-    CUDA_TRY(cudaMemcpyAsync(&bo.mean, bo.max_dev, sizeof(double), cudaMemcpyDeviceToHost, d->stream));
-    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    unsigned long long h[4];
+    if ((rc = read_reductions(d, h))) return rc;                                                     // all-gathered over the slabs
+    const double init = -1.0 * bo.target;                                                            // :227
+    bo.mean = init;
+    if (h[1] != 0ULL) { const double best = bo_unkey(h[1]); if (init < best) bo.mean = best; }
     double accel = bo.max_accel;
     if (bo.dynamic) {                                                                                // :42-46
         accel = (bo.target - bo.mean) / bo.dynamic_time;
@@ -685,8 +691,7 @@ int bo_post(spruce_domain *d, double dt)
     k_bo_apply<<<g2, 256, 0, d->stream>>>(d->P, A);
     d->launches += 2;
     CUDA_TRY(cudaGetLastError());
-    int rc = launch_propagate(d, 0);
-    if (rc) return rc;
+    if ((rc = launch_propagate(d, 0))) return rc;
     return after_module_propagate(d);
 }
 int ah_post(spruce_domain *d)
@@ -1232,7 +1237,6 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->ctl) cudaFree(d->ctl);
     if (d->red) cudaFree(d->red);
     if (d->moc_base) cudaFree(d->moc_base);
-    if (d->bo.max_dev) cudaFree(d->bo.max_dev);
     if (d->dt_hist) cudaFree(d->dt_hist);
     for (int r = 0; r < MAX_RANKS; r++) if (d->peer_seg[r] && d->peer_seg[r] != d->seg) cudaIpcCloseMemHandle(d->peer_seg[r]);
     if (d->seg) cudaFree(d->seg);
@@ -1533,7 +1537,6 @@ int spruce_module_div_cleaning(spruce_domain *d, double epsilon, double time_sca
 {
     CHECK_DOM(d);
     NOT_2F(d, "div_cleaning");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "div_cleaning on a slab decomposition is not built");
     if (!(epsilon > 0.0) || !(time_scale > 0.0)) return fail(SPRUCE_ERR_ARG, "div_cleaning needs epsilon > 0 and time_scale > 0");
     d->dc.epsilon = epsilon; d->dc.time_scale = time_scale;
     d->module_order.push_back(spruce_domain::MOD_DC);
@@ -1543,7 +1546,6 @@ int spruce_module_field_heating(spruce_domain *d, double coeff, double current_p
 {
     CHECK_DOM(d);
     NOT_2F(d, "field_heating");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "field_heating on a slab decomposition is not built");
     d->fh.coeff = coeff; d->fh.current_pow = current_pow; d->fh.b_pow = b_pow; d->fh.n_pow = n_pow; d->fh.roc_pow = roc_pow; d->fh.inactive = inactive_mode ? 1 : 0;
     if (!d->fh.H) { int rc = alloc_plane(d, &d->fh.H); if (rc) return rc; }
     d->module_order.push_back(spruce_domain::MOD_FH);
@@ -1554,9 +1556,8 @@ int spruce_module_boundary_outflow(spruce_domain *d, const double *pos_x, const 
 {
     CHECK_DOM(d);
     NOT_2F(d, "boundary_outflow");
-    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "boundary_outflow on a slab decomposition is not built");
-    const size_t np = (size_t)d->P.nx * d->P.ny;
-    if (!pos_x || !pos_y || count != np) return fail(SPRUCE_ERR_ARG, "pos_x / pos_y need %zu values", np);
+    const size_t np = (size_t)d->cfg.xdim * d->cfg.ydim;                    // the GLOBAL position planes, on every slab (extrema and windows are global)
+    if (!pos_x || !pos_y || count != np) return fail(SPRUCE_ERR_ARG, "pos_x / pos_y need the %zu values of the whole domain", np);
     if (boundary < 0 || boundary > 3) return fail(SPRUCE_ERR_ARG, "BoundaryOutflow boundary config must be {x,y}_bound_{1,2}");
     if (falloff_shape < 0 || falloff_shape > 2) return fail(SPRUCE_ERR_ARG, "BoundaryOutflow shape must be exp or gaussian or flat");
     auto &bo = d->bo;
@@ -1570,8 +1571,7 @@ int spruce_module_boundary_outflow(spruce_domain *d, const double *pos_x, const 
     bo.win[0] = m.xl; bo.win[1] = m.xu; bo.win[2] = m.yl; bo.win[3] = m.yu;
     int rc;
     if (!bo.tmpl && (rc = alloc_plane(d, &bo.tmpl))) return rc;
-    if ((rc = h2d_plane(d, bo.tmpl, t.data()))) return rc;
-    if (!bo.max_dev) CUDA_TRY(cudaMalloc(&bo.max_dev, sizeof(double)));
+    if ((rc = h2d_plane(d, bo.tmpl, t.data() + (size_t)d->P.row0 * d->cfg.ydim))) return rc;        // this slab's rows
     d->module_order.push_back(spruce_domain::MOD_BO);
     return SPRUCE_OK;
 }

@@ -454,11 +454,26 @@ __global__ void __launch_bounds__(256) k_fh_apply(const DomainParams P, const Fh
 // ---------------------------------------------------------------------------------------------------------
 // BoundaryOutflow (source/modules/solar/boundaryoutflow.cpp:39-63, 140-236): an acceleration near one boundary, along x / y or along
 // the field, optionally steered (dynamic_mode) towards a target outflow speed by the largest field-aligned outflow found in a
-// window next to that boundary.  k_bo_mean: that maximum (std::max semantics: a NaN candidate is never selected); k_bo_apply:
+// window next to that boundary.  k_bo_mean: that maximum (std::max semantics: a NaN candidate is never selected), as an order-preserving integer key; k_bo_apply:
 //   mom += (dt*(accel*template)) [* b_hat_k] * rho .   b_hat, v are the derived variables of idealmhd.cpp:248-277, formed per cell.
 // STATUS: not yet run on a GPU.
 // ---------------------------------------------------------------------------------------------------------
-struct BoArgs { double *U[NEV]; const double *st[NSTATIC]; const double *tmpl; int xl, xu, yl, yu; int boundary, field_aligned; double dt, accel; double *max_out; };
+struct BoArgs { double *U[NEV]; const double *st[NSTATIC]; const double *tmpl; int xl, xu, yl, yu; /* GLOBAL index window */ int boundary, field_aligned; double dt, accel;
+                unsigned long long *max_key; /* running maximum as an order-preserving key (bo_key), so that slabs can be combined by an integer max */ };
+// order-preserving map double -> unsigned: a < b  <=>  bo_key(a) < bo_key(b) (no NaN); 0 is below every key
+__host__ __device__ inline unsigned long long bo_key(double x)
+{
+    unsigned long long b;
+    memcpy(&b, &x, sizeof(b));
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__host__ __device__ inline double bo_unkey(unsigned long long k)
+{
+    const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k;
+    double x;
+    memcpy(&x, &b, sizeof(x));
+    return x;
+}
 __device__ __forceinline__ void bo_bhat(const DomainParams &P, const BoArgs &A, size_t off, double *hx, double *hy)
 {
     const double bx = A.st[S_BEX][off] + A.U[E_BX][off], by = A.st[S_BEY][off] + A.U[E_BY][off], bz = A.st[S_BEZ][off] + A.U[E_BZ][off];
@@ -469,7 +484,8 @@ __global__ void __launch_bounds__(128) k_bo_mean(const DomainParams P, const BoA
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
-    if (j >= P.ny || r < A.xl || r > A.xu || j < A.yl || j > A.yu) return;
+    const int g = P.row0 + r;
+    if (j >= P.ny || g < A.xl || g > A.xu || j < A.yl || j > A.yu) return;
     const size_t off = (size_t)r * P.pitch + j;
     double hx, hy;
     bo_bhat(P, A, off, &hx, &hy);
@@ -479,13 +495,7 @@ __global__ void __launch_bounds__(128) k_bo_mean(const DomainParams P, const BoA
     else if (A.boundary == 1 && hx < 0.0) cur *= -1.0;
     else if (A.boundary == 3 && hy < 0.0) cur *= -1.0;
     else if (A.boundary == 2 && hy > 0.0) cur *= -1.0;
-    unsigned long long *addr = reinterpret_cast<unsigned long long *>(A.max_out);
-    unsigned long long old = *addr;
-    while (__longlong_as_double((long long)old) < cur) {                          // std::max(max, curr): replace only when max < curr
-        const unsigned long long seen = atomicCAS(addr, old, (unsigned long long)__double_as_longlong(cur));
-        if (seen == old) break;
-        old = seen;
-    }
+    if (cur == cur) atomicMax(A.max_key, bo_key(cur));                           // std::max(max, curr) never selects a NaN candidate
 }
 __global__ void __launch_bounds__(256) k_bo_apply(const DomainParams P, const BoArgs A)
 {
