@@ -64,6 +64,13 @@ def lib():
         L.oracle_outflow_mean.restype = C.c_double
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
+        L.oracle2e_destroy.argtypes = [C.c_void_p]
+        L.oracle2e_plane.argtypes = [C.c_void_p, C.c_int]; L.oracle2e_plane.restype = C.POINTER(C.c_double)
+        L.oracle2e_setup.argtypes = [C.c_void_p]
+        L.oracle2e_step.argtypes = [C.c_void_p]; L.oracle2e_step.restype = C.c_double
+        L.oracle2e_rhs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.oracle2e_time.argtypes = [C.c_void_p]; L.oracle2e_time.restype = C.c_double
         L.oracle2f_create.restype = C.c_void_p
         L.oracle2f_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle2f_destroy.argtypes = [C.c_void_p]
@@ -271,6 +278,62 @@ class Oracle2F:
     def close(self):
         if getattr(self, "h", None):
             lib().oracle2f_destroy(self.h)
+            lib().oracle_destroy(self.base)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+VARS_2E = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y", "n", "i_press", "e_press", "press", "i_thermal_energy", "e_thermal_energy",
+           "v_x", "v_y", "kinetic_energy", "b_x", "b_y", "b_mag", "b_hat_x", "b_hat_y", "dt"]                 # idealmhd2E.hpp:18-22
+EVOLVED_2E = ["rho", "mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy", "bi_x", "bi_y"]              # idealmhd2E.hpp:31-33
+
+
+class Oracle2E:
+    """One IdealMHD2E domain (one fluid, separate ion / electron thermal energies) evolved by the C restatement (oracle/ideal_mhd2e_oracle.inc)."""
+
+    def __init__(self, planes, ion_mass, adiabatic_index, *, xb=("periodic", "periodic"), yb=("fixed", "fixed"), integrator="rk2", epsilon=0.2,
+                 density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6, open_strength=1.0, open_decay=0.5, setup=True, **_unused):
+        L = lib()
+        nx, ny = planes["rho"].shape
+        self.nx, self.ny = nx, ny
+        self.base = L.oracle_create(nx, ny, BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]], TI[integrator], ion_mass, adiabatic_index, epsilon,
+                                    density_min, temp_min, thermal_energy_min, open_strength, open_decay)
+        for name, which in DOMAIN.items():
+            if name in planes:
+                np.ctypeslib.as_array(L.oracle_plane(self.base, which), shape=(nx, ny))[...] = planes[name]
+        self.h = L.oracle2e_create(self.base)
+        for name, a in planes.items():
+            if name in VARS_2E:
+                self.view(name)[...] = a
+        if setup:
+            L.oracle2e_setup(self.h)
+
+    def view(self, name) -> np.ndarray:
+        return np.ctypeslib.as_array(lib().oracle2e_plane(self.h, VARS_2E.index(name)), shape=(self.nx, self.ny))
+
+    def get(self, name) -> np.ndarray:
+        return self.view(name).copy()
+
+    def step(self) -> float:
+        return lib().oracle2e_step(self.h)
+
+    def rhs(self) -> np.ndarray:
+        k = np.zeros((7, self.nx, self.ny))
+        lib().oracle2e_rhs(self.h, _dp(k))
+        return k
+
+    @property
+    def time(self) -> float:
+        return lib().oracle2e_time(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().oracle2e_destroy(self.h)
             lib().oracle_destroy(self.base)
             self.h = None
 

@@ -985,3 +985,4 @@ void oracle_operator(oracle *o, int op, int index, const double *q, const double
  * Two-fluid equation set (Ideal2F) + EIC thermalization: separate restatement on top of the operators above.
  * --------------------------------------------------------------------------------------------------------- */
 #include "ideal2f_oracle.inc"
+#include "ideal_mhd2e_oracle.inc"

@@ -269,3 +269,55 @@ def test_anomalous_resistivity_oracle_equals_live_reference(name, kv, xb, yb, in
     for v in MHD_OUT:
         assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
     o.close()
+
+
+E2_OUT = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "i_thermal_energy", "e_thermal_energy", "press", "n", "v_x", "kinetic_energy", "b_mag", "b_hat_y", "dt"]
+
+
+def e2_state(nx, ny, loop):
+    """An IdealMHD2E state (idealmhd2E.hpp:27-29) from the ideal-MHD generators: unequal ion / electron temperatures."""
+    s = synthetic.stratified_loop(nx, ny, bump=0.4) if loop else synthetic.orszag_tang(nx, ny, zfull=False)
+    P = s["planes"]
+    pl = {k: P[k] for k in ("d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z")}
+    X, Y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    pl["rho"] = P["rho"]
+    pl["i_temp"] = P["temp"] * (1.0 + 0.2 * np.sin(2 * np.pi * X / nx))
+    pl["e_temp"] = P["temp"] * (0.7 + 0.1 * np.cos(2 * np.pi * Y / ny))
+    for k in ("mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"):
+        pl[k] = P[k]
+    return dict(planes=pl, ion_mass=s["ion_mass"], adiabatic_index=s["adiabatic_index"])
+
+
+def e2_cases():
+    rng = np.random.default_rng(777)
+    sides = ["periodic", "open", "fixed", "reflect", "open_ucnp"]
+    out = []
+    for k in range(8):
+        xb = ("periodic", "periodic") if rng.random() < 0.3 else tuple(rng.choice(sides[1:], 2))
+        yb = ("periodic", "periodic") if rng.random() < 0.3 else tuple(rng.choice(sides[1:], 2))
+        out.append((k, tuple(map(str, xb)), tuple(map(str, yb)), str(rng.choice(["euler", "rk2", "rk4"])), int(rng.integers(18, 30)), int(rng.integers(17, 27)),
+                    bool(rng.random() < 0.6), float(rng.choice([1.0e7, 3.0e8]))))
+    return out
+
+
+@pytest.mark.parametrize("k,xb,yb,integrator,nx,ny,loop,nmin", e2_cases())
+def test_ideal_mhd_2e_oracle_equals_live_reference(k, xb, yb, integrator, nx, ny, loop, nmin):
+    """IdealMHD2E (oracle/ideal_mhd2e_oracle.inc; SURVEY 8f-4, no device path yet) against live reference runs: mixed boundary sets with the
+    two-"species" boundary passes, all integrators, active density floors -- step sizes and every output plane bit for bit."""
+    from oracle.oracle import Oracle2E
+    s = e2_state(nx, ny, loop)
+    floors = dict(density_min=nmin, temp_min=1.0e4, thermal_energy_min=1.0e-6) if loop else dict(density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 3
+    frames = run_reference(s, dict(kw, eqs="ideal_mhd_2E"), E2_OUT, nsteps)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for v in E2_OUT:
+        assert same_bits(o.get(v), frames[0][v]), "case %d after setup %s: %s" % (k, v, mismatch(o.get(v), frames[0][v]))
+    for it in range(1, nsteps + 1):
+        step = o.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "case %d iteration %d: step %s vs %s" % (k, it, step.hex(), float(ref_step).hex())
+    for v in E2_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "case %d %s: %s" % (k, v, mismatch(o.get(v), frames[nsteps][v]))
+    o.close()
