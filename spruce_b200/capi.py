@@ -14,7 +14,7 @@ ABI_VERSION = 1
 
 BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3, "open_moc": 4, "open_ucnp": 5}    # plasmadomain.hpp:22-26
 TI = {"euler": 0, "rk2": 1, "rk4": 2}                                                        # plasmadomain.hpp:29-32
-EQS = {"ideal_mhd": 0, "ideal_2F": 3}                                                        # equationset.hpp:22
+EQS = {"ideal_mhd": 0, "ideal_mhd_2E": 2, "ideal_2F": 3}                                                        # equationset.hpp:22
 
 
 class SpruceError(RuntimeError):

@@ -7,6 +7,8 @@
 #include "mhd_stage_xy.cuh"
 #include "moc_stage.cuh"
 #include "solar_templates.hpp"
+#include "mhd2e_cells.cuh"
+#include "mhd2e_step.hpp"
 #include "ideal2f_kernels.cuh"
 
 #include <algorithm>
@@ -31,7 +33,8 @@ static int fail(int code, const char *fmt, ...)
 }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(SPRUCE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define CUDA_TRY_D(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { delete d; return fail(SPRUCE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
-#define NOT_2F(d, what) do { if ((d)->tf) return fail(SPRUCE_ERR_UNSUPPORTED, "%s is not available with the ideal_2F equation set", what); } while (0)
+#define NOT_2F(d, what) do { if ((d)->tf) return fail(SPRUCE_ERR_UNSUPPORTED, "%s is not available with the ideal_2F equation set", what); \
+                             if ((d)->e2) return fail(SPRUCE_ERR_UNSUPPORTED, "%s is not available with the ideal_mhd_2E equation set", what); } while (0)
 #define CHECK_DOM(d) do { if (!(d)) return fail(SPRUCE_ERR_ARG, "null domain handle"); } while (0)
 
 namespace {
@@ -43,12 +46,14 @@ struct HostAxis {          // 1-D tables of one axis on the host, index -TAB_APR
 };
 
 struct TwoFluid;
+struct OneFluid2E;
 
 }  // namespace
 
 struct spruce_domain {
     spruce_config cfg{};
     TwoFluid *tf = nullptr;        // ideal_2F state (ideal2f_host.cuh); null for ideal_mhd
+    OneFluid2E *e2 = nullptr;      // ideal_mhd_2E state (mhd2e_host.cuh)
     DomainParams P{};
     cudaStream_t stream = nullptr;
     size_t plane_doubles = 0;      // allocation size of one plane incl. halo rows
@@ -1108,6 +1113,8 @@ int d2h_plane(spruce_domain *d, double *host, const double *dev)
 }
 
 #include "ideal2f_host.cuh"
+#include "mhd2e_host.cuh"
+static_assert((int)SPRUCE_TI_EULER == (int)e2::TI2_EULER && (int)SPRUCE_TI_RK2 == (int)e2::TI2_RK2 && (int)SPRUCE_TI_RK4 == (int)e2::TI2_RK4, "integrator codes");
 
 }  // namespace
 
@@ -1120,9 +1127,11 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
 {
     if (!cfg || !out) return fail(SPRUCE_ERR_ARG, "null argument");
     if (cfg->abi_version != SPRUCE_ABI_VERSION) return fail(SPRUCE_ERR_ARG, "ABI version mismatch: header %d, library %d", cfg->abi_version, SPRUCE_ABI_VERSION);
-    const bool two_fluid = (cfg->equation_set == SPRUCE_EQS_IDEAL_2F);
-    if (cfg->equation_set != SPRUCE_EQS_IDEAL_MHD && !two_fluid) return fail(SPRUCE_ERR_UNSUPPORTED, "equation set %d is not built (ideal_mhd and ideal_2F only)", cfg->equation_set);
+    const bool two_fluid = (cfg->equation_set == SPRUCE_EQS_IDEAL_2F), two_energy = (cfg->equation_set == SPRUCE_EQS_IDEAL_MHD_2E);
+    if (cfg->equation_set != SPRUCE_EQS_IDEAL_MHD && !two_fluid && !two_energy)
+        return fail(SPRUCE_ERR_UNSUPPORTED, "equation set %d is not built (ideal_mhd, ideal_mhd_2E and ideal_2F only)", cfg->equation_set);
     if (two_fluid) { int rc2 = tf_check_boundaries(*cfg); if (rc2) return rc2; }
+    if (two_energy) { int rc2 = e2_check(*cfg); if (rc2) return rc2; }
     // "Grid too small for ghost zones", plasmadomain.cpp:140
     if (cfg->xdim <= 2 * HALO || cfg->ydim <= 2 * HALO) return fail(SPRUCE_ERR_ARG, "Grid too small for ghost zones");
     const int bcs[4] = {cfg->x_bound_1, cfg->x_bound_2, cfg->y_bound_1, cfg->y_bound_2};
@@ -1196,13 +1205,14 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     int rc = SPRUCE_OK;
     if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SPRUCE_ERR_CUDA, "cudaStreamCreate failed"); }
     if (!rc) {                                                        // base arena: evolved sets + static + scratch (+ two-fluid extras)
-        d->pool_planes = two_fluid ? (2 * 14 + 2 + 4 + NSTATIC + 2) : (2 * NEV + NSTATIC + 2);
+        d->pool_planes = two_fluid ? (2 * 14 + 2 + 4 + NSTATIC + 2) : two_energy ? (2 * 7 + 2 + NSTATIC + 2) : (2 * NEV + NSTATIC + 2);
         if (cudaMalloc(&d->pool, d->pool_planes * d->plane_doubles * sizeof(double)) != cudaSuccess) { cudaGetLastError(); d->pool = nullptr; d->pool_planes = 0; }
         else d->allocs.push_back(d->pool);
     }
     if (!rc && two_fluid) rc = tf_create(d);
-    if (!rc && !two_fluid) rc = alloc_set(d, d->Pset);
-    if (!rc && !two_fluid) rc = alloc_set(d, d->Mset);
+    if (!rc && two_energy) rc = e2_create(d);
+    if (!rc && !two_fluid && !two_energy) rc = alloc_set(d, d->Pset);
+    if (!rc && !two_fluid && !two_energy) rc = alloc_set(d, d->Mset);
     for (int v = 0; v < NSTATIC && !rc; v++) rc = alloc_plane(d, &d->stat[v]);
     if (!rc) rc = alloc_plane(d, &d->scratch_temp);
     if (!rc) rc = alloc_plane(d, &d->scratch_out);
@@ -1246,6 +1256,7 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->ev_comm) cudaEventDestroy(d->ev_comm);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d->tf;
+    delete d->e2;
     delete d;
 }
 
@@ -1271,6 +1282,7 @@ int spruce_grid_upload(spruce_domain *d, const char *name, const double *host, s
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane <%s>: expected %zu values, got %zu", name, (size_t)d->P.nx * d->P.ny, count);
     if (!strcmp(name, "pos_x") || !strcmp(name, "pos_y") || !strcmp(name, "d_x") || !strcmp(name, "d_y")) return SPRUCE_OK; // host-only grids
     if (d->tf) return tf_upload(d, name, host);
+    if (d->e2) return e2_upload(d, name, host);
     {   // zero-plane bookkeeping for the planes whose transport can be skipped exactly
         const char *tracked[5] = {"mom_z", "bi_z", "be_x", "be_y", "be_z"};
         for (int b = 0; b < 5; b++) if (!strcmp(name, tracked[b])) {
@@ -1301,6 +1313,7 @@ int spruce_grid_download(spruce_domain *d, const char *name, double *host, size_
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane <%s>: expected %zu values, got %zu", name, (size_t)d->P.nx * d->P.ny, count);
     if (d->tf) return tf_download(d, name, host);
+    if (d->e2) return e2_download(d, name, host);
     const int s = static_slot(name);
     if (s >= 0) return d2h_plane(d, host, d->stat[s]);
     const int var = var_index(name);
@@ -1327,7 +1340,7 @@ int spruce_eqs_setup(spruce_domain *d)
     // Ideal2F defaults to use_sub_cycling = true, whose time derivatives leave six 1x1 grids that abort at the ghost-zone mask
     // multiply (ideal2F.cpp:73-94, grid.cpp:84): only the non-sub-cycled Maxwell update can run at all
     if (d->tf && d->tf->use_sub_cycling) return fail(SPRUCE_ERR_UNSUPPORTED, "ideal_2F: use_sub_cycling = true aborts in the reference (size-mismatched grids); set use_sub_cycling = false");
-    int rc = d->tf ? tf_launch_propagate(d, 1) : launch_propagate(d, 1);
+    int rc = d->tf ? tf_launch_propagate(d, 1) : d->e2 ? e2_launch_propagate(d, 1) : launch_propagate(d, 1);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     d->is_setup = true;
@@ -1338,7 +1351,7 @@ int spruce_eqs_propagate_changes(spruce_domain *d)
 {
     CHECK_DOM(d);
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "propagate before setup");
-    int rc = d->tf ? tf_launch_propagate(d, 0) : launch_propagate(d, 0);
+    int rc = d->tf ? tf_launch_propagate(d, 0) : d->e2 ? e2_launch_propagate(d, 0) : launch_propagate(d, 0);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     return SPRUCE_OK;
@@ -1371,7 +1384,7 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     CUDA_TRY(cudaMemcpyAsync(&h0, d->ctl, sizeof(h0), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     CUDA_TRY(cudaMemcpyAsync(&d->ctl->max_time, &max_time, sizeof(double), cudaMemcpyHostToDevice, d->stream));
-    for (int s = 0; s < n_steps; s++) { int rc = d->tf ? tf_enqueue_step(d, s) : enqueue_step(d, s); if (rc) return rc; }
+    for (int s = 0; s < n_steps; s++) { int rc = d->tf ? tf_enqueue_step(d, s) : d->e2 ? e2_enqueue_step(d, s) : enqueue_step(d, s); if (rc) return rc; }
     StepCtl h1;
     CUDA_TRY(cudaMemcpyAsync(&h1, d->ctl, sizeof(h1), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
@@ -1398,6 +1411,7 @@ int spruce_eqs_time_derivatives(spruce_domain *d, double *k_out, size_t count)
     CHECK_DOM(d);
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "time derivatives before setup");
     if (d->tf) return tf_time_derivatives(d, k_out, count);
+    if (d->e2) return e2_time_derivatives(d, k_out, count);
     const size_t np = (size_t)d->P.nx * d->P.ny;
     if (!k_out || count != NEV * np) return fail(SPRUCE_ERR_ARG, "k_out needs %zu values", NEV * np);
     int rc = ensure_rk4(d);
@@ -1644,7 +1658,7 @@ int spruce_module_viscosity_term(spruce_domain *d, const char *visc_opt, double 
 int spruce_eqs_ideal_mhd_options(spruce_domain *d, double global_viscosity)
 {
     CHECK_DOM(d);
-    if (d->tf) return fail(SPRUCE_ERR_STATE, "ideal_mhd options on a domain with another equation set");
+    if (d->tf || d->e2) return fail(SPRUCE_ERR_STATE, "ideal_mhd options on a domain with another equation set");
     d->global_viscosity = global_viscosity;          // only the open_moc boundary reads it (idealmhd.cpp:90)
     return SPRUCE_OK;
 }

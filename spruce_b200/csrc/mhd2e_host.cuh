@@ -1,0 +1,265 @@
+// mhd2e_host.cuh -- kernels and launch sequences of the IdealMHD2E equation set (included by capi.cu inside its anonymous namespace, after
+// the plane helpers).  The arithmetic is mhd2e_cells.cuh, the stage order mhd2e_step.hpp -- both proven on the host against the CPU
+// restatement (tests/test_mhd2e_host_check.py); this file only maps "every cell" / "every boundary index" onto threads.
+// First version: one thread per cell, operands straight from global memory (the pattern the two-fluid kernel started from), single rank.
+// STATUS: written after the round-1 GPU budget was spent; compiled, not yet run on a GPU (tests/test_zz_gpu_unvalidated.py).
+#pragma once
+#include "mhd2e_cells.cuh"
+#include "mhd2e_step.hpp"
+
+struct E2Args {
+    e2::Geo g;
+    e2::CPlanes S, B;
+    e2::Planes D, Pg;             // destination; the set the open / reflect / fixed passes write
+    e2::Statics T;
+    double *K1[e2::NEV2], *K23[e2::NEV2];
+    const double *i_temp, *e_temp;
+    double *out;
+    int kmode, final_stage, side, var, from_state;
+    double coef;
+    const double *step_ptr;
+    const int *done_ptr;
+    unsigned long long *dtmin_bits;
+};
+
+// right-hand side, K rule, increment, floors: one thread per cell
+__global__ void __launch_bounds__(128) k_2e_cells(const E2Args A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= A.g.ny || *A.done_ptr) return;
+    const size_t c = e2::at(A.g, i, j);
+    double k[e2::NEV2], k1[e2::NEV2], k23[e2::NEV2];
+    e2::rhs_cell(A.g, A.S, A.T, i, j, k);
+    const bool need_k = A.kmode != e2::KM2_NONE;
+    if (need_k) {
+        for (int v = 0; v < e2::NEV2; v++) { k1[v] = A.K1[v][c]; k23[v] = (A.kmode == e2::KM2_STORE_K1 || A.kmode == e2::KM2_EXPORT) ? 0.0 : A.K23[v][c]; }
+        e2::k_rule(A.kmode, k, k1, k23, e2::NEV2);
+        if (A.kmode == e2::KM2_STORE_K1 || A.kmode == e2::KM2_EXPORT) { for (int v = 0; v < e2::NEV2; v++) A.K1[v][c] = k1[v]; }
+        else if (A.kmode != e2::KM2_FINAL) { for (int v = 0; v < e2::NEV2; v++) A.K23[v][c] = k23[v]; }
+    }
+    if (A.kmode == e2::KM2_EXPORT) return;
+    double base[e2::NEV2], out[e2::NEV2];
+    for (int v = 0; v < e2::NEV2; v++) base[v] = A.B.u[v][c];
+    e2::apply_cell(A.g, base, k, A.coef * *A.step_ptr, out);
+    for (int v = 0; v < e2::NEV2; v++) A.D.u[v][c] = out[v];
+}
+// one boundary pass (launched four times, side = 0..3 in the reference's order)
+__global__ void __launch_bounds__(128) k_2e_ghost(const E2Args A)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (*A.done_ptr || a >= e2::side_length(A.g, A.side)) return;
+    e2::ghost_cell(A.g, A.D, A.Pg, A.side, a);
+}
+// recomputeDerivedVarsFromEvolvedVars feedback (rho round trip, energy floors) and, in the step's last stage, the dt minimum;
+// from_state: recomputeEvolvedVarsFromStateVars + enforceMinimums first (setup)
+__global__ void __launch_bounds__(128) k_2e_settle(const E2Args A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    double dtc = 1.7976931348623157e308;
+    if (j < A.g.ny && !*A.done_ptr) {
+        const size_t c = e2::at(A.g, i, j);
+        double u[e2::NEV2];
+        for (int v = 0; v < e2::NEV2; v++) u[v] = A.D.u[v][c];
+        e2::settle_cell(A.g, u);
+        for (int v = 0; v < e2::NEV2; v++) A.D.u[v][c] = u[v];
+        if (A.final_stage && e2::interior(A.g, i, j)) dtc = e2::dt_cell(A.g, u, A.T.bex[c], A.T.bey[c], A.g.dx[i], A.g.dy[j]);
+    }
+    if (A.final_stage) block_min_to_global(dtc, A.dtmin_bits);
+}
+__global__ void __launch_bounds__(128) k_2e_from_state(const E2Args A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= A.g.ny) return;
+    const size_t c = e2::at(A.g, i, j);
+    double u[e2::NEV2], zero[e2::NEV2] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, out[e2::NEV2];
+    for (int v = 0; v < e2::NEV2; v++) u[v] = A.D.u[v][c];
+    if (A.from_state) e2::from_state_cell(A.g, u[e2::Q_RHO2], A.i_temp[c], A.e_temp[c], &u[e2::Q_EI2], &u[e2::Q_EE2]);
+    e2::apply_cell(A.g, u, zero, 0.0, out);                                  // enforceMinimums
+    for (int v = 0; v < e2::NEV2; v++) A.D.u[v][c] = out[v];
+}
+__global__ void __launch_bounds__(128) k_2e_derive(const E2Args A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= A.g.ny) return;
+    A.out[e2::at(A.g, i, j)] = e2::derive_cell(A.g, A.S, A.T, A.var, i, j);
+}
+
+struct OneFluid2E {
+    double *set[3][e2::NEV2] = {{nullptr}};          // storage of the three state sets
+    double *K1[e2::NEV2] = {nullptr}, *K23[e2::NEV2] = {nullptr};
+    double *i_temp = nullptr, *e_temp = nullptr;     // uploaded state temperatures, consumed by setup
+    int order[3] = {0, 1, 2};                        // logical set (0 = primary) -> storage
+    bool rk4_alloc = false;
+    e2::Geo g{};
+};
+
+const char *const kE2EvolvedNames[e2::NEV2] = {"rho", "mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy", "bi_x", "bi_y"};
+const char *const kE2VarNames[e2::V2_COUNT] = {"rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y", "n", "i_press", "e_press", "press",
+                                               "i_thermal_energy", "e_thermal_energy", "v_x", "v_y", "kinetic_energy", "b_x", "b_y", "b_mag", "b_hat_x", "b_hat_y", "dt"};
+int e2_var_index(const char *name) { for (int v = 0; v < e2::V2_COUNT; v++) if (!strcmp(kE2VarNames[v], name)) return v; return -1; }
+int e2_evolved_slot(const char *name) { for (int v = 0; v < e2::NEV2; v++) if (!strcmp(kE2EvolvedNames[v], name)) return v; return -1; }
+
+int e2_check(const spruce_config &c)
+{
+    if (c.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "ideal_mhd_2E on a slab decomposition is not built");
+    const int b[4] = {c.x_bound_1, c.x_bound_2, c.y_bound_1, c.y_bound_2};
+    for (int s = 0; s < 4; s++) if (b[s] == SPRUCE_BC_OPEN_MOC) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries exist for ideal_mhd only (idealmhd.cpp:306)");
+    return SPRUCE_OK;
+}
+int e2_create(spruce_domain *d)
+{
+    OneFluid2E *t = new OneFluid2E();
+    d->e2 = t;
+    int rc;
+    for (int s = 0; s < 2; s++) for (int v = 0; v < e2::NEV2; v++) if ((rc = alloc_plane(d, &t->set[s][v]))) return rc;
+    if ((rc = alloc_plane(d, &t->i_temp)) || (rc = alloc_plane(d, &t->e_temp))) return rc;
+    return SPRUCE_OK;
+}
+int e2_ensure_rk4(spruce_domain *d)
+{
+    OneFluid2E *t = d->e2;
+    if (t->rk4_alloc) return SPRUCE_OK;
+    int rc;
+    for (int v = 0; v < e2::NEV2; v++) if ((rc = alloc_plane(d, &t->set[2][v])) || (rc = alloc_plane(d, &t->K1[v])) || (rc = alloc_plane(d, &t->K23[v]))) return rc;
+    t->rk4_alloc = true;
+    return SPRUCE_OK;
+}
+// geometry and parameters of the per-cell functions; the open-boundary decay factors come from the host libm as in the reference
+void e2_geometry(spruce_domain *d)
+{
+    e2::Geo &g = d->e2->g;
+    const spruce_config &c = d->cfg;
+    g.nx = d->P.nx; g.ny = d->P.ny; g.pitch = d->P.pitch;
+    g.bc[0] = c.x_bound_1; g.bc[1] = c.x_bound_2; g.bc[2] = c.y_bound_1; g.bc[3] = c.y_bound_2;
+    g.xl = d->P.xl; g.xu = d->P.xu; g.yl = d->P.yl; g.yu = d->P.yu; g.xper = d->P.xper; g.yper = d->P.yper;
+    g.m_i = c.ion_mass; g.gamma = c.adiabatic_index; g.n_min = c.density_min; g.T_min = c.temp_min; g.e_min = c.thermal_energy_min;
+    g.open_strength = c.open_boundary_strength;
+    g.dx = d->dxg.data(); g.dy = d->dyg.data();          // host copies for open_scales() ...
+    e2::open_scales(g, c.open_boundary_decay_base);
+    g.dx = d->P.tx.d; g.dy = d->P.ty.d;                  // ... device tables for the kernels
+}
+void e2_base(spruce_domain *d, E2Args &A)
+{
+    OneFluid2E *t = d->e2;
+    A.g = t->g;
+    A.T.bex = d->stat[S_BEX]; A.T.bey = d->stat[S_BEY]; A.T.gx = d->stat[S_GX]; A.T.gy = d->stat[S_GY];
+    for (int v = 0; v < e2::NEV2; v++) { A.K1[v] = t->K1[v]; A.K23[v] = t->K23[v]; }
+    A.step_ptr = &d->ctl->step; A.done_ptr = &d->ctl->done; A.dtmin_bits = &d->ctl->dtmin_bits;
+    A.i_temp = t->i_temp; A.e_temp = t->e_temp;
+}
+void e2_set(const OneFluid2E *t, int logical, e2::Planes &p) { for (int v = 0; v < e2::NEV2; v++) p.u[v] = t->set[t->order[logical]][v]; }
+void e2_cset(const OneFluid2E *t, int logical, e2::CPlanes &p) { for (int v = 0; v < e2::NEV2; v++) p.u[v] = t->set[t->order[logical]][v]; }
+
+// the boundary passes (four launches, in order) and the settle / dt pass of set D
+int e2_finish(spruce_domain *d, E2Args &A, int final_stage)
+{
+    const int n = d->P.ny > d->P.nx ? d->P.ny : d->P.nx;
+    for (int side = 0; side < 4; side++) {
+        const int bc = A.g.bc[side];
+        if (bc == SPRUCE_BC_PERIODIC || bc == SPRUCE_BC_OPEN_MOC) continue;
+        A.side = side;
+        k_2e_ghost<<<(n + 127) / 128, 128, 0, d->stream>>>(A);
+        d->launches++;
+    }
+    A.final_stage = final_stage;
+    if (final_stage) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, 0); d->launches++; }
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_2e_settle<<<grid, 128, 0, d->stream>>>(A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
+// the executor mhd2e_step.hpp's advance() drives (the host check drives the same template with loops)
+struct E2DeviceExec {
+    spruce_domain *d;
+    int stage(int S, int B, int D, double coef, int kmode, int ghost_primary, int final_stage)
+    {
+        OneFluid2E *t = d->e2;
+        E2Args A{};
+        e2_base(d, A);
+        e2_cset(t, S, A.S); e2_cset(t, B, A.B); e2_set(t, D, A.D); e2_set(t, ghost_primary, A.Pg);
+        A.coef = coef; A.kmode = kmode;
+        dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+        k_2e_cells<<<grid, 128, 0, d->stream>>>(A);
+        d->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (kmode == e2::KM2_EXPORT) return SPRUCE_OK;
+        return e2_finish(d, A, final_stage);
+    }
+    void swap_sets(int a, int b) { std::swap(d->e2->order[a], d->e2->order[b]); }
+};
+
+// setupEquationSet / propagateChanges on the primary state (equationset.cpp:96-104, 212-220)
+int e2_launch_propagate(spruce_domain *d, int from_state)
+{
+    OneFluid2E *t = d->e2;
+    if (from_state) e2_geometry(d);
+    E2Args A{};
+    e2_base(d, A);
+    e2_set(t, 0, A.D); e2_set(t, 0, A.Pg); e2_cset(t, 0, A.S);
+    A.from_state = from_state;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_2e_from_state<<<grid, 128, 0, d->stream>>>(A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return e2_finish(d, A, 1);
+}
+int e2_enqueue_step(spruce_domain *d, int hist_slot)
+{
+    k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot);
+    d->launches++;
+    int rc;
+    if (d->cfg.time_integrator == SPRUCE_TI_RK4 && (rc = e2_ensure_rk4(d))) return rc;
+    E2DeviceExec x{d};
+    if ((rc = e2::advance(x, d->cfg.time_integrator))) return rc;                  // SPRUCE_TI_* = e2::TI2_* = 0, 1, 2
+    k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+int e2_upload(spruce_domain *d, const char *name, const double *host)
+{
+    OneFluid2E *t = d->e2;
+    if (!strcmp(name, "be_z")) return SPRUCE_OK;                                     // not a variable of this set (2-D field); accepted and ignored
+    const int s = static_slot(name);
+    if (s >= 0) return h2d_plane(d, d->stat[s], host);
+    if (!strcmp(name, "i_temp")) return h2d_plane(d, t->i_temp, host);
+    if (!strcmp(name, "e_temp")) return h2d_plane(d, t->e_temp, host);
+    const int ev = e2_evolved_slot(name);
+    if (ev >= 0) return h2d_plane(d, t->set[t->order[0]][ev], host);
+    if (e2_var_index(name) < 0) return fail(SPRUCE_ERR_ARG, "Variable name <%s> not recognized", name);
+    return fail(SPRUCE_ERR_ARG, "<%s> is a derived variable and cannot be uploaded", name);
+}
+int e2_download(spruce_domain *d, const char *name, double *host)
+{
+    OneFluid2E *t = d->e2;
+    const int s = static_slot(name);
+    if (s >= 0) return d2h_plane(d, host, d->stat[s]);
+    const int var = e2_var_index(name);
+    if (var < 0) return fail(SPRUCE_ERR_ARG, "Variable name <%s> not recognized", name);
+    if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "download of <%s> before spruce_eqs_setup", name);
+    const int ev = e2_evolved_slot(name);
+    if (ev >= 0) return d2h_plane(d, host, t->set[t->order[0]][ev]);
+    E2Args A{};
+    e2_base(d, A);
+    e2_cset(t, 0, A.S);
+    A.out = d->scratch_out; A.var = var;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_2e_derive<<<grid, 128, 0, d->stream>>>(A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return d2h_plane(d, host, d->scratch_out);
+}
+int e2_time_derivatives(spruce_domain *d, double *k_out, size_t count)
+{
+    OneFluid2E *t = d->e2;
+    const size_t np = (size_t)d->P.nx * d->P.ny;
+    if (!k_out || count != e2::NEV2 * np) return fail(SPRUCE_ERR_ARG, "k_out needs %zu values", e2::NEV2 * np);
+    int rc = e2_ensure_rk4(d);
+    if (rc) return rc;
+    E2DeviceExec x{d};
+    if ((rc = x.stage(0, 0, 1, 0.0, e2::KM2_EXPORT, 0, 0))) return rc;
+    for (int v = 0; v < e2::NEV2; v++) if ((rc = d2h_plane(d, k_out + v * np, t->K1[v]))) return rc;
+    return SPRUCE_OK;
+}

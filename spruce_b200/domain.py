@@ -31,6 +31,8 @@ class PlasmaDomain:
     EVOLVED = ["rho", "mom_x", "mom_y", "mom_z", "thermal_energy", "bi_x", "bi_y", "bi_z"]          # idealmhd.hpp:32-34
     STATE = ["rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]   # idealmhd.hpp:28-30
     DOMAIN = ["be_x", "be_y", "be_z"]
+    EVOLVED_2E = ["rho", "mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy", "bi_x", "bi_y"]    # idealmhd2E.hpp:31-33
+    STATE_2E = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"]      # idealmhd2E.hpp:27-29
     # ideal2F.hpp:40-46
     EVOLVED_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy",
                   "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"]
@@ -45,6 +47,8 @@ class PlasmaDomain:
         self.equation_set = equation_set
         if equation_set == "ideal_2F":
             self.EVOLVED, self.STATE = self.EVOLVED_2F, self.STATE_2F
+        elif equation_set == "ideal_mhd_2E":
+            self.EVOLVED, self.STATE = self.EVOLVED_2E, self.STATE_2E
         gx, gy = planes["d_x"].shape if planes["d_x"].ndim == 2 else (planes["d_x"].size, planes["d_y"].size)
         if planes["d_x"].ndim == 2:
             dx, dy = rank1_cell_sizes(planes["d_x"], planes["d_y"])
