@@ -18,7 +18,8 @@ std::unique_ptr<EquationSet> EquationSet::instantiateDefault(PlasmaDomain &pd, c
 {
     if (name == "ideal_mhd") return std::unique_ptr<EquationSet>(new IdealMHD(pd));
     if (name == "ideal_2F") return std::unique_ptr<EquationSet>(new Ideal2F(pd));
-    if (isEquationSetName(name)) spruce_die("Equation set <" + name + "> is not ported to the B200 path yet (ideal_mhd and ideal_2F are).");
+    if (name == "ideal_mhd_2E") return std::unique_ptr<EquationSet>(new IdealMHD2E(pd));
+    if (isEquationSetName(name)) spruce_die("Equation set <" + name + "> is not ported to the B200 path yet (ideal_mhd, ideal_mhd_2E and ideal_2F are).");
     spruce_die("Equation set name <" + name + "> not recognized.");
 }
 
@@ -132,6 +133,18 @@ void IdealMHD::parseEquationSetConfigs(std::vector<std::string> lhs, std::vector
 }
 
 void IdealMHD::configureDevice() { PlasmaDomain::check(spruce_eqs_ideal_mhd_options(m_pd.device(), m_global_viscosity)); }
+
+IdealMHD2E::IdealMHD2E(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
+int IdealMHD2E::device_id() const { return SPRUCE_EQS_IDEAL_MHD_2E; }
+// idealmhd2E.cpp:10-20: both keys are parsed and never read by this equation set
+void IdealMHD2E::parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        if (lhs[i] == "global_viscosity") std::stod(rhs[i]);
+        else if (lhs[i] == "viscosity_opt") { }
+        else spruce_die(lhs[i] + " is not recognized for this equation set.");
+    }
+}
 
 Ideal2F::Ideal2F(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
 int Ideal2F::device_id() const { return SPRUCE_EQS_IDEAL_2F; }

@@ -377,6 +377,9 @@ HOST_CASES = {
         ("div_cleaning", [("epsilon", "0.1"), ("time_scale", "5.0")]),
         ("boundary_outflow", [("max_accel", "2.0e3"), ("falloff_length", "6.0e8"), ("boundary", "y_bound_2"), ("falloff_shape", "exp"), ("feather_length", "3.0e8"),
                               ("field_aligned_mode", "true"), ("dynamic_mode", "true"), ("dynamic_time", "10.0"), ("dynamic_target_speed", "2.0e6")])], **SOLAR), True),
+    "ideal_mhd_2e": (dict(nx=40, ny=36, two_energy=True), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"), eqs="ideal_mhd_2E", max_iterations=6, iter_output_interval=2,
+                     write_precision=17, output_flags=("rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "i_thermal_energy", "e_thermal_energy", "press", "n", "v_x", "b_mag", "dt"),
+                     **SOLAR), True),
     "field_heating": (dict(nx=40, ny=36, bump=0.5), dict(integrator="euler", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=4, iter_output_interval=1, modules=[
         ("field_heating", [("coeff", "1.0"), ("current_pow", "1.0"), ("b_pow", "0.5"), ("n_pow", "0.25"), ("roc_pow", "0.5")])], **SOLAR), False),
 }
@@ -395,7 +398,11 @@ def test_host_shell_matches_reference_files_on_the_8f_rows(name, tmp_path):
         subprocess.run(["make", "-C", str(ROOT / "spruce_b200" / "host")], check=True)
     assert refrun.have_reference(), "oracle/_ref/run must travel with the repo"
     gkw, ckw, exact = HOST_CASES[name]
-    s = synthetic.stratified_loop(**gkw)
+    if gkw.get("two_energy"):
+        from test_oracle_vs_live_reference import e2_state
+        s = e2_state(gkw["nx"], gkw["ny"], True)
+    else:
+        s = synthetic.stratified_loop(**gkw)
     state = tmp_path / "in.state"
     refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"], comments=["# drop-in test " + name])
     cfg = refrun.ideal_mhd_config(std_out_interval=1, **ckw)
