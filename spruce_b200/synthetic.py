@@ -152,3 +152,18 @@ def ucnp_cloud(nx: int, ny: int, *, length: float = 1.0, n0: float = 1.0e9, sigm
         "grav_x": z.copy(), "grav_y": z.copy(),
     }
     return dict(planes=P, ion_mass=M_SR, adiabatic_index=GAMMA)
+
+
+def two_energy(nx: int, ny: int, loop: bool = True, bump: float = 0.4):
+    """An IdealMHD2E state (state variables of idealmhd2E.hpp:27-29) from the ideal-MHD generators: the same density, momenta and field with
+    unequal, spatially varying ion / electron temperatures."""
+    s = stratified_loop(nx, ny, bump=bump) if loop else orszag_tang(nx, ny, zfull=False)
+    P = s["planes"]
+    pl = {k: P[k] for k in ("d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z")}
+    X, Y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    pl["rho"] = P["rho"]
+    pl["i_temp"] = P["temp"] * (1.0 + 0.2 * np.sin(2 * np.pi * X / nx))
+    pl["e_temp"] = P["temp"] * (0.7 + 0.1 * np.cos(2 * np.pi * Y / ny))
+    for k in ("mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"):
+        pl[k] = P[k]
+    return dict(planes=pl, ion_mass=s["ion_mass"], adiabatic_index=s["adiabatic_index"])

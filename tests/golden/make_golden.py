@@ -28,6 +28,7 @@ from spruce_b200 import synthetic  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
 OUT_VARS = ["rho", "temp", "thermal_energy", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "dt"]
+OUT_VARS_2E = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "i_thermal_energy", "e_thermal_energy", "press", "n", "v_x", "kinetic_energy", "b_mag", "b_hat_y", "dt"]
 OUT_VARS_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy", "E_x", "E_y", "E_z",
                "bi_x", "bi_y", "bi_z", "i_temp", "e_temp", "dt", "dt_i", "j_x", "rho_c", "divE", "divB", "curlE_z", "e_dPdx", "b_hat_x"]
 NX, NY = 32, 28
@@ -119,6 +120,9 @@ CASES = {
     # (square grid: circularMask / currentThresholdMask loop j over result.rows(), anomalousresistivity.cpp:285,297 -- the reference aborts when xdim > ydim)
     "ar_floodfill_rk2": ("stratified_loop", dict(nx=26, ny=26, bump=0.5), dict(integrator="rk2", xb=("fixed", "open"), yb=("fixed", "open"), modules=[
         ("anomalous_resistivity", [("time_scale", "0.3"), ("safety_factor", "0.5"), ("flood_fill_threshold", "1.5"), ("smoothing_sigma", "1.0")])], **SOLAR_FLOORS), 3, (1, 3)),
+    # IdealMHD2E (source/equationsets/idealmhd2E.cpp): one fluid, separate ion / electron thermal energies
+    "e2_mixed_rk2": ("two_energy", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"), eqs="ideal_mhd_2E", **SOLAR_FLOORS), 8, (1, 8)),
+    "e2_pp_ucnp_rk4": ("two_energy", dict(nx=NX, ny=NY), dict(integrator="rk4", xb=PP, yb=UC, eqs="ideal_mhd_2E", **SOLAR_FLOORS), 4, (1, 4)),
     # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
     "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
 }
@@ -150,7 +154,7 @@ def make(name):
     tmp = Path(tempfile.mkdtemp(prefix="golden_"))
     try:
         refrun.write_state(tmp / "in.state", s["planes"], s["ion_mass"], s["adiabatic_index"])
-        out_vars = OUT_VARS_2F if ckw.get("eqs") == "ideal_2F" else OUT_VARS
+        out_vars = OUT_VARS_2F if ckw.get("eqs") == "ideal_2F" else OUT_VARS_2E if ckw.get("eqs") == "ideal_mhd_2E" else OUT_VARS
         cfg = refrun.ideal_mhd_config(max_iterations=nsteps, output_flags=out_vars, std_out_interval=1, **ckw)
         _, stdout = refrun.run_reference(tmp / "in.state", cfg, tmp / "out", threads=8)
         _, frames = refrun.read_out(tmp / "out" / "mhd.out")

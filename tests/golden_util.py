@@ -16,7 +16,7 @@ EVOLVED_2F = ["i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_t
               "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"]
 
 
-EXTENDED = ("moc_", "sm_", "ar_")      # open_moc boundary, small solar modules, anomalous resistivity
+EXTENDED = ("moc_", "sm_", "ar_", "e2_")      # open_moc boundary, small solar modules, anomalous resistivity, IdealMHD2E
 
 
 def cases(prefixes=None, two_fluid=False, oracle_only=False, extended=False):

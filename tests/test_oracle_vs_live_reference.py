@@ -275,17 +275,7 @@ E2_OUT = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "i_therma
 
 
 def e2_state(nx, ny, loop):
-    """An IdealMHD2E state (idealmhd2E.hpp:27-29) from the ideal-MHD generators: unequal ion / electron temperatures."""
-    s = synthetic.stratified_loop(nx, ny, bump=0.4) if loop else synthetic.orszag_tang(nx, ny, zfull=False)
-    P = s["planes"]
-    pl = {k: P[k] for k in ("d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z")}
-    X, Y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
-    pl["rho"] = P["rho"]
-    pl["i_temp"] = P["temp"] * (1.0 + 0.2 * np.sin(2 * np.pi * X / nx))
-    pl["e_temp"] = P["temp"] * (0.7 + 0.1 * np.cos(2 * np.pi * Y / ny))
-    for k in ("mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"):
-        pl[k] = P[k]
-    return dict(planes=pl, ion_mass=s["ion_mass"], adiabatic_index=s["adiabatic_index"])
+    return synthetic.two_energy(nx, ny, loop=loop)
 
 
 def e2_cases():

@@ -324,7 +324,7 @@ GOLDEN_CODE = """
     g = Golden({name!r})
     exact = {exact!r}
     opts = dict(global_viscosity=float(g.eqs_raw["global_viscosity"])) if "global_viscosity" in g.eqs_raw else None
-    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, eqs_options=opts, **g.kw)
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, equation_set=g.equation_set, eqs_options=opts, **g.kw)
     for mname, kv in g.modules:
         prod = small_module_kwargs(mname, kv)[1]
         if mname == "ambient_heating_sink":
@@ -355,7 +355,8 @@ GOLDEN_CODE = """
 
 @UNVALIDATED
 @pytest.mark.parametrize("name,exact", [("moc_y2_euler", True), ("moc_all_visc_rk2", True), ("moc_x1_mixed_rk4", True), ("sm_sink_heat_mass_rk2", True),
-                                        ("sm_momentum_divclean_rk2", True), ("sm_field_heating_euler", False), ("sm_outflow_dynamic_rk2", True)])
+                                        ("sm_momentum_divclean_rk2", True), ("sm_field_heating_euler", False), ("sm_outflow_dynamic_rk2", True),
+                                        ("e2_mixed_rk2", True), ("e2_pp_ucnp_rk4", True)])
 def test_extended_golden_reference_outputs(name, exact):
     """The device paths of the SURVEY 8f rows against committed outputs of the UNMODIFIED reference binary (tests/golden/moc_*, sm_*): step-size
     history and every output plane, bit for bit (field_heating: pow with run-time exponents, <= 1e-9)."""
