@@ -32,9 +32,13 @@ enum { BC2_PERIODIC = 0, BC2_OPEN = 1, BC2_FIXED = 2, BC2_REFLECT = 3, BC2_OPEN_
 constexpr double kPi2 = 3.14159265358979323846;          // source/constants.hpp:16
 constexpr double kKB2 = 1.3807e-16;                      // K_B, source/constants.hpp:8
 
+// Cells are addressed by their GLOBAL (i, j).  On a slab (rows [row0, row0 + nxl) of nx, plus two halo rows on each side) the caller passes plane
+// pointers shifted back by row0 rows and dx shifted back by row0 entries, so that only resident rows are ever touched; with a periodic x axis the
+// halo rows hold the ring neighbours' rows and x indices are not wrapped (x_halo).  A single rank has row0 = 0, nxl = nx, x_halo = 0.
 struct Geo {
     const double *dx, *dy;        // cell sizes
-    int nx, ny, pitch;
+    int nx, ny, pitch;            // GLOBAL extent
+    int row0, nxl, x_halo;
     int bc[4];                    // x1, x2, y1, y2
     int xl, xu, yl, yu;           // interior bounds (computeIterationBounds, plasmadomain.cpp:138-161)
     int xper, yper;
@@ -61,7 +65,7 @@ struct Statics { const double *bex, *bey, *gx, *gy; };
 
 E2_HD double smin2(double a, double b) { return (b < a) ? b : a; }      // std::min / std::max
 E2_HD double smax2(double a, double b) { return (a < b) ? b : a; }
-E2_HD int wi(const Geo &g, int i) { return g.xper ? (i + g.nx) % g.nx : i; }
+E2_HD int wi(const Geo &g, int i) { return (g.xper && !g.x_halo) ? (i + g.nx) % g.nx : i; }
 E2_HD int wj(const Geo &g, int j) { return g.yper ? (j + g.ny) % g.ny : j; }
 E2_HD size_t at(const Geo &g, int i, int j) { return (size_t)i * g.pitch + j; }
 E2_HD bool interior(const Geo &g, int i, int j) { return i >= g.xl && i <= g.xu && j >= g.yl && j <= g.yu; }
@@ -202,14 +206,17 @@ E2_HD void from_state_cell(const Geo &g, double rho, double i_temp, double e_tem
 // ---- boundary passes (evolution.cpp:126-333): one call handles boundary index `a` of side `side` (0..3 = x1, x2, y1, y2).
 // open / reflect / fixed write the PRIMARY state P whatever set is being propagated; open_ucnp writes the propagated set G.
 // The four sides must run one after the other in this order (each reads what the earlier ones wrote).
-E2_HD int side_length(const Geo &g, int side) { return side < 2 ? g.ny : g.nx; }
-E2_HD void ghost_cell(const Geo &g, const Planes &G, const Planes &P, int side, int a)
+// A slab runs the y sides for its own rows (index t -> a = row0 + t) and an x side only when it holds that side's three rows (the first / last slab).
+E2_HD int side_length(const Geo &g, int side) { return side < 2 ? g.ny : g.nxl; }
+E2_HD void ghost_cell(const Geo &g, const Planes &G, const Planes &P, int side, int t)
 {
     const int bc = g.bc[side];
     if (bc == BC2_PERIODIC || bc == BC2_OPEN_MOC) return;
     const bool xside = side < 2, lower = (side % 2) == 0;
     const int ncross = xside ? g.nx : g.ny;
     const int e1 = lower ? 0 : ncross - 1, e2 = lower ? 1 : ncross - 2, e3 = lower ? 2 : ncross - 3;
+    if (xside && (lower ? g.row0 != 0 : g.row0 + g.nxl != g.nx)) return;
+    const int a = xside ? t : g.row0 + t;
     const int lo = xside ? g.yl : g.xl, hi = xside ? g.yu : g.xu;
     const size_t c1 = xside ? at(g, e1, a) : at(g, a, e1), c2 = xside ? at(g, e2, a) : at(g, a, e2), c3 = xside ? at(g, e3, a) : at(g, a, e3);
     if (bc == BC2_FIXED) {                                                                           // :268-282, the whole side
