@@ -43,7 +43,7 @@ enum { SPRUCE_TI_EULER = 0, SPRUCE_TI_RK2 = 1, SPRUCE_TI_RK4 = 2 };
 /* EquationSet::m_sets, source/equationsets/equationset.hpp:22 (index in that list) */
 enum { SPRUCE_EQS_IDEAL_MHD = 0, SPRUCE_EQS_IDEAL_MHD_2E = 2, SPRUCE_EQS_IDEAL_2F = 3 };   /* index in EquationSet::m_sets (equationset.hpp:22); ideal_mhd_2E: one fluid with
                                                                                             separate ion / electron thermal energies (idealmhd2E.cpp) -- written after the round-1
-                                                                                            GPU budget was spent, host-checked, not yet run on a GPU; single rank, no modules */
+                                                                                            GPU budget was spent, host-checked, not yet run on a GPU; no modules */
 
 /* Everything PlasmaDomain reads from the .config / .state headers that the device needs
  * (source/mhd/plasmadomain.hpp:93-153, source/mhd/fileio.cpp:297-325). */

@@ -38,7 +38,7 @@ def add_modules(dom):
             dom.set_viscosity([dict(opt="local", strength=0.5, var_diff="v_x", var_evol="mom_x"), dict(opt="global", strength=3.0, var_diff="v_y", var_evol="mom_y"),
                                dict(opt="boundary", strength=0.8, var_diff="temp", var_evol="thermal_energy", strength_grid=prof)],
                               hv_integrator="rk2", hv_epsilon=1.0, gradient_correction=True)
-        elif m == "2f":
+        elif m in ("2f", "2e"):
             pass
         elif m == "2feic":
             dom.set_eic_thermalization()
@@ -69,6 +69,11 @@ if two_fluid:
     ub = ("open_ucnp", "open_ucnp")
     kw = dict(equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False), xb=("periodic", "periodic") if xbound == "periodic" else ub, yb=ub, integrator=integ,
               density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
+elif "2e" in modules:
+    # IdealMHD2E on slabs: wall-type sides exercise the exchange of the primary state the boundary passes write
+    s = synthetic.two_energy(nx, ny, loop=True)
+    kw = dict(equation_set="ideal_mhd_2E", xb=("periodic", "periodic") if xbound == "periodic" else (xbound, "open"), yb=("fixed", "open"), integrator=integ,
+              density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
 elif "moc" in modules or "mocv" in modules:
     # open_moc sides (needs SPRUCE_EXPERIMENTAL_MOC=1): x periodic with a y side, or x sides (first / last slab) plus a y side -> corners on the end slabs
     s = synthetic.stratified_loop(nx, ny, bump=0.4)

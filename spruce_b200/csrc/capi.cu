@@ -1847,6 +1847,7 @@ int spruce_mgpu_initial_exchange(spruce_domain *d)
     CHECK_DOM(d);
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "initial exchange before setup");
     if (d->tf) { int rc2 = tf_initial_exchange(d); if (rc2) return rc2; CUDA_TRY(cudaStreamSynchronize(d->stream)); return SPRUCE_OK; }
+    if (d->e2) { int rc2 = e2_initial_exchange(d); if (rc2) return rc2; CUDA_TRY(cudaStreamSynchronize(d->stream)); return SPRUCE_OK; }
     double *stat_view[NEV];
     for (int v = 0; v < NEV; v++) stat_view[v] = d->stat[v < NSTATIC ? v : 0];
     int rc;

@@ -1,7 +1,9 @@
 // mhd2e_host.cuh -- kernels and launch sequences of the IdealMHD2E equation set (included by capi.cu inside its anonymous namespace, after
 // the plane helpers).  The arithmetic is mhd2e_cells.cuh, the stage order mhd2e_step.hpp -- both proven on the host against the CPU
 // restatement (tests/test_mhd2e_host_check.py); this file only maps "every cell" / "every boundary index" onto threads.
-// First version: one thread per cell, operands straight from global memory (the pattern the two-fluid kernel started from), single rank.
+// First version: one thread per cell, operands straight from global memory (the pattern the two-fluid kernel started from).  Slabs: cells are
+// addressed by global row through row-shifted plane pointers, the halo rows of a stage's result (and of the primary state when a wall-type
+// boundary pass wrote it) travel over the peer transport after the stage.
 // STATUS: written after the round-1 GPU budget was spent; compiled, not yet run on a GPU (tests/test_zz_gpu_unvalidated.py).
 #pragma once
 #include "mhd2e_cells.cuh"
@@ -25,7 +27,7 @@ struct E2Args {
 // right-hand side, K rule, increment, floors: one thread per cell
 __global__ void __launch_bounds__(128) k_2e_cells(const E2Args A)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = A.g.row0 + (int)blockIdx.y;      // GLOBAL row
     if (j >= A.g.ny || *A.done_ptr) return;
     const size_t c = e2::at(A.g, i, j);
     double k[e2::NEV2], k1[e2::NEV2], k23[e2::NEV2];
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(128) k_2e_ghost(const E2Args A)
 // from_state: recomputeEvolvedVarsFromStateVars + enforceMinimums first (setup)
 __global__ void __launch_bounds__(128) k_2e_settle(const E2Args A)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = A.g.row0 + (int)blockIdx.y;
     double dtc = 1.7976931348623157e308;
     if (j < A.g.ny && !*A.done_ptr) {
         const size_t c = e2::at(A.g, i, j);
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(128) k_2e_settle(const E2Args A)
 }
 __global__ void __launch_bounds__(128) k_2e_from_state(const E2Args A)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = A.g.row0 + (int)blockIdx.y;
     if (j >= A.g.ny) return;
     const size_t c = e2::at(A.g, i, j);
     double u[e2::NEV2], zero[e2::NEV2] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, out[e2::NEV2];
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(128) k_2e_from_state(const E2Args A)
 }
 __global__ void __launch_bounds__(128) k_2e_derive(const E2Args A)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = A.g.row0 + (int)blockIdx.y;
     if (j >= A.g.ny) return;
     A.out[e2::at(A.g, i, j)] = e2::derive_cell(A.g, A.S, A.T, A.var, i, j);
 }
@@ -101,7 +103,6 @@ int e2_evolved_slot(const char *name) { for (int v = 0; v < e2::NEV2; v++) if (!
 
 int e2_check(const spruce_config &c)
 {
-    if (c.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "ideal_mhd_2E on a slab decomposition is not built");
     const int b[4] = {c.x_bound_1, c.x_bound_2, c.y_bound_1, c.y_bound_2};
     for (int s = 0; s < 4; s++) if (b[s] == SPRUCE_BC_OPEN_MOC) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries exist for ideal_mhd only (idealmhd.cpp:306)");
     return SPRUCE_OK;
@@ -129,26 +130,44 @@ void e2_geometry(spruce_domain *d)
 {
     e2::Geo &g = d->e2->g;
     const spruce_config &c = d->cfg;
-    g.nx = d->P.nx; g.ny = d->P.ny; g.pitch = d->P.pitch;
+    g.nx = d->P.gnx; g.ny = d->P.ny; g.pitch = d->P.pitch;
+    g.row0 = d->P.row0; g.nxl = d->P.nx; g.x_halo = (d->P.xper && !d->P.xwrap) ? 1 : 0;
     g.bc[0] = c.x_bound_1; g.bc[1] = c.x_bound_2; g.bc[2] = c.y_bound_1; g.bc[3] = c.y_bound_2;
     g.xl = d->P.xl; g.xu = d->P.xu; g.yl = d->P.yl; g.yu = d->P.yu; g.xper = d->P.xper; g.yper = d->P.yper;
     g.m_i = c.ion_mass; g.gamma = c.adiabatic_index; g.n_min = c.density_min; g.T_min = c.temp_min; g.e_min = c.thermal_energy_min;
     g.open_strength = c.open_boundary_strength;
     g.dx = d->dxg.data(); g.dy = d->dyg.data();          // host copies for open_scales() ...
     e2::open_scales(g, c.open_boundary_decay_base);
-    g.dx = d->P.tx.d; g.dy = d->P.ty.d;                  // ... device tables for the kernels
+    g.dx = d->P.tx.d - d->P.row0; g.dy = d->P.ty.d;      // ... device tables for the kernels (x table indexed by global row)
 }
+// every plane pointer handed to the kernels is shifted back by the slab's first row: cells are addressed by GLOBAL row
+template <class T> T *e2_shift(const spruce_domain *d, T *p) { return p ? p - (long long)d->P.row0 * d->P.pitch : p; }
 void e2_base(spruce_domain *d, E2Args &A)
 {
     OneFluid2E *t = d->e2;
     A.g = t->g;
-    A.T.bex = d->stat[S_BEX]; A.T.bey = d->stat[S_BEY]; A.T.gx = d->stat[S_GX]; A.T.gy = d->stat[S_GY];
-    for (int v = 0; v < e2::NEV2; v++) { A.K1[v] = t->K1[v]; A.K23[v] = t->K23[v]; }
+    A.T.bex = e2_shift(d, d->stat[S_BEX]); A.T.bey = e2_shift(d, d->stat[S_BEY]); A.T.gx = e2_shift(d, d->stat[S_GX]); A.T.gy = e2_shift(d, d->stat[S_GY]);
+    for (int v = 0; v < e2::NEV2; v++) { A.K1[v] = e2_shift(d, t->K1[v]); A.K23[v] = e2_shift(d, t->K23[v]); }
     A.step_ptr = &d->ctl->step; A.done_ptr = &d->ctl->done; A.dtmin_bits = &d->ctl->dtmin_bits;
-    A.i_temp = t->i_temp; A.e_temp = t->e_temp;
+    A.i_temp = e2_shift(d, t->i_temp); A.e_temp = e2_shift(d, t->e_temp);
 }
-void e2_set(const OneFluid2E *t, int logical, e2::Planes &p) { for (int v = 0; v < e2::NEV2; v++) p.u[v] = t->set[t->order[logical]][v]; }
-void e2_cset(const OneFluid2E *t, int logical, e2::CPlanes &p) { for (int v = 0; v < e2::NEV2; v++) p.u[v] = t->set[t->order[logical]][v]; }
+void e2_set(const spruce_domain *d, int logical, e2::Planes &p) { const OneFluid2E *t = d->e2; for (int v = 0; v < e2::NEV2; v++) p.u[v] = e2_shift(d, t->set[t->order[logical]][v]); }
+void e2_cset(const spruce_domain *d, int logical, e2::CPlanes &p) { const OneFluid2E *t = d->e2; for (int v = 0; v < e2::NEV2; v++) p.u[v] = e2_shift(d, t->set[t->order[logical]][v]); }
+// slab decomposition: halo rows of the 7 planes of one logical set from the ring neighbours (one packed exchange of 8 plane slots)
+int e2_exchange(spruce_domain *d, int logical)
+{
+    if (d->cfg.n_ranks == 1) return SPRUCE_OK;
+    OneFluid2E *t = d->e2;
+    double *v[NEV];
+    for (int k = 0; k < NEV; k++) v[k] = t->set[t->order[logical]][k < e2::NEV2 ? k : 0];
+    return peer_exchange(d, v, nullptr);
+}
+bool e2_any_wall(const spruce_domain *d)
+{
+    const int b[4] = {d->cfg.x_bound_1, d->cfg.x_bound_2, d->cfg.y_bound_1, d->cfg.y_bound_2};
+    for (int s = 0; s < 4; s++) if (b[s] == SPRUCE_BC_OPEN || b[s] == SPRUCE_BC_REFLECT || b[s] == SPRUCE_BC_FIXED) return true;
+    return false;
+}
 
 // the boundary passes (four launches, in order) and the settle / dt pass of set D
 int e2_finish(spruce_domain *d, E2Args &A, int final_stage)
@@ -178,14 +197,18 @@ struct E2DeviceExec {
         OneFluid2E *t = d->e2;
         E2Args A{};
         e2_base(d, A);
-        e2_cset(t, S, A.S); e2_cset(t, B, A.B); e2_set(t, D, A.D); e2_set(t, ghost_primary, A.Pg);
+        e2_cset(d, S, A.S); e2_cset(d, B, A.B); e2_set(d, D, A.D); e2_set(d, ghost_primary, A.Pg);
         A.coef = coef; A.kmode = kmode;
         dim3 grid((d->P.ny + 127) / 128, d->P.nx);
         k_2e_cells<<<grid, 128, 0, d->stream>>>(A);
         d->launches++;
         CUDA_TRY(cudaGetLastError());
         if (kmode == e2::KM2_EXPORT) return SPRUCE_OK;
-        return e2_finish(d, A, final_stage);
+        int rc = e2_finish(d, A, final_stage);
+        if (rc || d->cfg.n_ranks == 1) return rc;
+        if ((rc = e2_exchange(d, D))) return rc;
+        if (ghost_primary != D && e2_any_wall(d) && (rc = e2_exchange(d, ghost_primary))) return rc;     // the wall-type passes wrote the primary state
+        return final_stage ? peer_dt_allgather(d) : SPRUCE_OK;
     }
     void swap_sets(int a, int b) { std::swap(d->e2->order[a], d->e2->order[b]); }
 };
@@ -197,7 +220,7 @@ int e2_launch_propagate(spruce_domain *d, int from_state)
     if (from_state) e2_geometry(d);
     E2Args A{};
     e2_base(d, A);
-    e2_set(t, 0, A.D); e2_set(t, 0, A.Pg); e2_cset(t, 0, A.S);
+    e2_set(d, 0, A.D); e2_set(d, 0, A.Pg); e2_cset(d, 0, A.S);
     A.from_state = from_state;
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_2e_from_state<<<grid, 128, 0, d->stream>>>(A);
@@ -243,8 +266,8 @@ int e2_download(spruce_domain *d, const char *name, double *host)
     if (ev >= 0) return d2h_plane(d, host, t->set[t->order[0]][ev]);
     E2Args A{};
     e2_base(d, A);
-    e2_cset(t, 0, A.S);
-    A.out = d->scratch_out; A.var = var;
+    e2_cset(d, 0, A.S);
+    A.out = e2_shift(d, d->scratch_out); A.var = var;
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_2e_derive<<<grid, 128, 0, d->stream>>>(A);
     d->launches++;
@@ -262,4 +285,15 @@ int e2_time_derivatives(spruce_domain *d, double *k_out, size_t count)
     if ((rc = x.stage(0, 0, 1, 0.0, e2::KM2_EXPORT, 0, 0))) return rc;
     for (int v = 0; v < e2::NEV2; v++) if ((rc = d2h_plane(d, k_out + v * np, t->K1[v]))) return rc;
     return SPRUCE_OK;
+}
+
+// after spruce_eqs_setup on every rank of a decomposed run: halo rows of the static planes and the primary state, global dt minimum
+int e2_initial_exchange(spruce_domain *d)
+{
+    double *stat_view[NEV];
+    for (int v = 0; v < NEV; v++) stat_view[v] = d->stat[v < NSTATIC ? v : 0];
+    int rc;
+    if ((rc = peer_exchange(d, stat_view, nullptr))) return rc;
+    if ((rc = e2_exchange(d, 0))) return rc;
+    return peer_dt_allgather(d);
 }

@@ -303,7 +303,8 @@ def test_relaxed_arithmetic_within_north_star_tolerance(integ, zfull, nx, ny, ns
 @UNVALIDATED
 @pytest.mark.parametrize("args", [("96", "80", "4", "rk2", "periodic", "p2p", "moc"), ("90", "70", "4", "rk4", "open_moc", "p2p", "mocv"),
                                   ("96", "80", "3", "euler", "open_moc", "nccl", "moc"), ("128", "96", "4", "rk2", "periodic", "p2p", "src"),
-                                  ("120", "90", "3", "rk2", "periodic", "p2p", "dc,fh"), ("96", "80", "4", "rk2", "reflect", "p2p", "bo,dc")])
+                                  ("120", "90", "3", "rk2", "periodic", "p2p", "dc,fh"), ("96", "80", "4", "rk2", "reflect", "p2p", "bo,dc"),
+                                  ("110", "84", "4", "rk4", "periodic", "p2p", "2e"), ("96", "80", "4", "rk2", "reflect", "p2p", "2e")])
 def test_slab_decomposition_of_the_unvalidated_paths_equals_single_gpu(args):
     """open_moc sides and the pointwise solar source terms on 2 slabs == 1 GPU, bit for bit (the slab form of the open_moc evaluation is proven on the
     host by tests/test_moc_host_check.py; this is the launch side).  Needs >= 2 visible GPUs."""
