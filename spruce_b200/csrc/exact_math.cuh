@@ -18,7 +18,9 @@
 // tests/test_exact_division.py checks the sequence exhaustively in reduced precision and on 1e8 random and
 // adversarial binary64 operand pairs against true division.
 #pragma once
+#ifndef SPRUCE_EXACT_MATH_HOST_CHECK      // tests/hostcheck/exact_math_check.cpp compiles this header for the host with stand-ins for the intrinsics
 #include <cuda_runtime.h>
+#endif
 
 namespace spruce {
 
