@@ -334,8 +334,9 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "relaxed"],
                     help="exact (default, the bench line): every operation individually rounded, bit-identical to the reference; relaxed: the opt-in stage kernel of "
                          "stage_relaxed.cu (FMA contraction, one-multiplication table divisions; fields within the north star's 1e-9, step sizes not bit-identical)")
-    ap.add_argument("--stage-variants", type=int, default=0, nargs="?", const=1, choices=[0, 1, 2],
-                    help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS): 1 = on, 2 = also the six-CTAs-per-SM build of the 2-D instance")
+    ap.add_argument("--stage-variants", type=int, default=0, nargs="?", const=1, choices=[0, 1, 2, 3],
+                    help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS): 1 = on, 2 = also the six-CTAs-per-SM build of the 2-D instance, "
+                         "3 = also its pair-wise mid-row barrier")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: library peer stores over NVLink, or torch.distributed NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:

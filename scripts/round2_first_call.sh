@@ -2,13 +2,13 @@
 # First GPU call of the next round: everything that was written after the round-1 GPU budget was spent, in one go.
 #   gpurun --timeout 1500 -- 'bash scripts/round2_first_call.sh'
 # Results land in gpurun_out/: the isolated tests (XPASS = validated -> drop the xfail marker / the switch), then the bench line in the
-# six arithmetic / instance combinations (same workload, same box, back to back).
+# eight arithmetic / instance combinations (same workload, same box, back to back).
 set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r2_build.log 2>&1
 timeout 1200 python -m pytest tests/test_zz_gpu_unvalidated.py -m gpu -q -rxXs -p no:cacheprovider > gpurun_out/r2_unvalidated.log 2>&1
 tail -40 gpurun_out/r2_unvalidated.log
-for mode in "exact:0" "exact:1" "exact:2" "relaxed:0" "relaxed:1" "relaxed:2"; do
+for mode in "exact:0" "exact:1" "exact:2" "exact:3" "relaxed:0" "relaxed:1" "relaxed:2" "relaxed:3"; do
     arith=${mode%%:*}; sv=${mode#*:}
     name="r2_bench_${arith}_variants${sv}"
     timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --arith "$arith" --stage-variants "$sv" > "gpurun_out/${name}.json" 2> "gpurun_out/${name}.err"

@@ -104,7 +104,7 @@ struct spruce_domain {
     // open_moc (moc_stage.cuh): evolved ghost cells; SPRUCE_EXPERIMENTAL_MOC=1 until the launch side has been validated on a GPU
     bool moc_any = false; double global_viscosity = 0.0; double *moc_base = nullptr;
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
-    int stage_variants = 0;                // compile-time integrator-stage instances of k_mhd_stage_xy: SPRUCE_STAGE_VARIANTS=1, =2: also six CTAs per SM (2-D instance)
+    int stage_variants = 0;                // compile-time integrator-stage instances of k_mhd_stage_xy: SPRUCE_STAGE_VARIANTS=1, =2: also six CTAs per SM (2-D instance), =3: also the pair-wise barrier
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
@@ -300,7 +300,8 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
         // compile-time integrator stage (SPRUCE_STAGE_VARIANTS=1, off by default): plain euler / rk2 stages without module terms
         int var = 0;
         if (d->stage_variants && kmode == KM_NONE && A.n_xterm == 0) var = A.b_is_s ? (primary ? 3 : 1) : (primary ? 2 : 0);
-        if (var && d->stage_variants == 2) var |= 4;                          // the six-CTAs-per-SM build of the 2-D instance
+        if (var && d->stage_variants >= 2) var |= 4;                          // the six-CTAs-per-SM build of the 2-D instance
+        if (var && d->stage_variants == 3) var |= 8;                          // ... with the pair-wise mid-row barrier
         const size_t sm6 = xy_smem_bytes(xy_rows(6)), smf = xy_smem_bytes(NTR);
         const bool list2d = L.n == 6 && L.q == XY_LIST_2D, listfull = L.n == 12 && L.q == XY_LIST_FULL;
         if (d->relaxed && d->static_lists && (list2d || listfull)) {          // any other list runs the exact run-time-list kernel below
@@ -314,9 +315,12 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
             else if (var == 5) k_mhd_stage_xy<6, XY_LIST_2D, 5><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
             else if (var == 6) k_mhd_stage_xy<6, XY_LIST_2D, 6><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
             else if (var == 7) k_mhd_stage_xy<6, XY_LIST_2D, 7><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
+            else if (var == 13) k_mhd_stage_xy<6, XY_LIST_2D, 13><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
+            else if (var == 14) k_mhd_stage_xy<6, XY_LIST_2D, 14><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
+            else if (var == 15) k_mhd_stage_xy<6, XY_LIST_2D, 15><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
             else k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
         } else if (d->static_lists && L.n == 12 && L.q == XY_LIST_FULL) {
-            var &= 3;                                                          // the full instance has one residency
+            var &= 3;                                                          // the full instance has one residency and the CTA-wide barrier
             if (var == 1) k_mhd_stage_xy<12, XY_LIST_FULL, 1><<<grid, XY_NT, smf, st>>>(d->P, A, L);
             else if (var == 2) k_mhd_stage_xy<12, XY_LIST_FULL, 2><<<grid, XY_NT, smf, st>>>(d->P, A, L);
             else if (var == 3) k_mhd_stage_xy<12, XY_LIST_FULL, 3><<<grid, XY_NT, smf, st>>>(d->P, A, L);
@@ -1164,7 +1168,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     d->cfg = *cfg;
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
-    if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) == 2 ? 2 : (atoi(sv) != 0 ? 1 : 0);
+    if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) { const int v = atoi(sv); d->stage_variants = (v >= 1 && v <= 3) ? v : 0; }
     if (const char *ar = getenv("SPRUCE_ARITH")) {
         if (!strcmp(ar, "relaxed")) d->relaxed = true;
         else if (strcmp(ar, "exact")) { delete d; return fail(SPRUCE_ERR_ARG, "SPRUCE_ARITH must be exact or relaxed"); }
@@ -1181,6 +1185,9 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
         CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // 6 x 37 KB
         CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 13>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 14>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 15>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
         CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
         CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));

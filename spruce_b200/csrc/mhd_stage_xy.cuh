@@ -59,6 +59,7 @@ constexpr unsigned long long XY_LIST_FULL = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BI
 // VAR > 0: the integrator stage is a compile-time constant too (no K planes, no module right-hand-side terms).  VAR & 3 =
 //   1: B == S, secondary (first stage of rk2)   2: B != S, primary (last stage of rk2)   3: B == S, primary (euler).
 // VAR & 4 (2-D instance only): compiled for SIX resident CTAs per SM (80 registers, a few dozen bytes of spill; 6 x 37 KB of shared memory).
+// VAR & 8 (with VAR & 4): the mid-row barrier is pair-wise (two 64-thread named barriers) instead of CTA-wide.
 // VAR == 0 takes kmode / b_is_s / primary / n_xterm from the launch arguments (every integrator, every module).
 template <int LN, unsigned long long LQ, int VAR = 0>
 __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
@@ -320,7 +321,11 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
             d_e = ddiv(IyR_vx - IyL_vx, dy, rdy);                   // d(v_x)/dy
             if (Z) d_f = ddiv(IyR_vz - IyL_vz, dy, rdy);            // d(v_z)/dy
         }
-        __syncthreads();                                            // partial results are visible to the other role
+        // partial results are visible to the other role.  The exchange slots are private to a (warp column, lane): X warp w only talks to Y warp w + 2,
+        // so the pair-wise form (VAR & 8) waits for the partner warp alone on named barrier 1 + wcol; the ring itself is published by the CTA-wide
+        // barrier at the end of the iteration.
+        if (VAR & 8) asm volatile("bar.sync %0, 64;" ::"r"(1 + wcol) : "memory");
+        else __syncthreads();
 
         // ================================================================ phase 2: finish the outputs
         __syncwarp();

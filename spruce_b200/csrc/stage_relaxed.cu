@@ -44,7 +44,10 @@ cudaError_t launch_var(int var, dim3 grid, cudaStream_t st, const R::DomainParam
         if (var == 5) return launch_one<6, R::XY_LIST_2D, 5>(grid, st, P, A, L);
         if (var == 6) return launch_one<6, R::XY_LIST_2D, 6>(grid, st, P, A, L);
         if (var == 7) return launch_one<6, R::XY_LIST_2D, 7>(grid, st, P, A, L);
-    } else if (var & 4) return launch_var<LN, LQ>(var & 3, grid, st, P, A, L);
+        if (var == 13) return launch_one<6, R::XY_LIST_2D, 13>(grid, st, P, A, L);
+        if (var == 14) return launch_one<6, R::XY_LIST_2D, 14>(grid, st, P, A, L);
+        if (var == 15) return launch_one<6, R::XY_LIST_2D, 15>(grid, st, P, A, L);
+    } else if (var & 12) return launch_var<LN, LQ>(var & 3, grid, st, P, A, L);
     return launch_one<LN, LQ, 0>(grid, st, P, A, L);
 }
 }  // namespace

@@ -47,7 +47,7 @@ STAGE_VARIANT_CODE = """
 
 
 @UNVALIDATED
-@pytest.mark.parametrize("variants", ["1", "2"])            # 2: also the six-CTAs-per-SM build of the 2-D instance
+@pytest.mark.parametrize("variants", ["1", "2", "3"])       # 2: also the six-CTAs-per-SM build of the 2-D instance; 3: with the pair-wise mid-row barrier
 @pytest.mark.parametrize("integ,zfull,nx,ny,xb,yb", [
     ("rk2", False, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),      # 2-D list: k_mhd_stage_xy<6, ., 1> then <6, ., 2>
     ("rk2", True, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),       # full list: <12, ., 1> / <12, ., 2>
@@ -288,6 +288,7 @@ RELAXED_CODE = """
     ("rk2", False, 256, 256, 100, "0"),
     ("rk2", False, 256, 256, 100, "1"),
     ("rk2", False, 256, 256, 100, "2"),
+    ("rk2", False, 256, 256, 100, "3"),
     ("rk2", True, 150, 203, 100, "1"),
     ("rk4", False, 131, 96, 60, "0"),
     ("euler", True, 96, 131, 60, "1"),
