@@ -103,6 +103,7 @@ struct spruce_domain {
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
     // open_moc (moc_stage.cuh): evolved ghost cells; SPRUCE_EXPERIMENTAL_MOC=1 until the launch side has been validated on a GPU
     bool moc_any = false; double global_viscosity = 0.0; double *moc_base = nullptr;
+    int chunk_rows_override = 0;           // SPRUCE_CHUNK_ROWS (16 .. XY_CHUNK, the range the automatic choice already spans): rows per CTA of the stage kernel, for tuning sweeps; 0 = pick_chunk_rows' own choice
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
     int stage_variants = 0;                // compile-time integrator-stage instances of k_mhd_stage_xy: SPRUCE_STAGE_VARIANTS=1, =2: also six CTAs per SM (2-D instance), =3: also the pair-wise barrier
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
@@ -247,6 +248,7 @@ int pick_chunk_rows(const spruce_domain *d)
     // enough CTAs for >= ~4 waves of 148 SMs x resident CTAs, but chunks of at least 16 rows (4 warm-up rows each)
     const int strips = (d->P.ny + CW - 1) / CW;
     int rows = d->stage_kernel == 5 ? XY_CHUNK : MAX_CHUNK;
+    if (d->chunk_rows_override > 0) return d->chunk_rows_override < rows ? d->chunk_rows_override : rows;      // SPRUCE_CHUNK_ROWS: tuning sweeps
     while (rows > 16 && (long long)strips * ((d->P.nx + rows - 1) / rows) < 148LL * 5 * 4) rows >>= 1;
     return rows;
 }
@@ -1169,6 +1171,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) { const int v = atoi(sv); d->stage_variants = (v >= 1 && v <= 3) ? v : 0; }
+    if (const char *cr = getenv("SPRUCE_CHUNK_ROWS")) { const int v = atoi(cr); if (v >= 16) d->chunk_rows_override = v; }
     if (const char *ar = getenv("SPRUCE_ARITH")) {
         if (!strcmp(ar, "relaxed")) d->relaxed = true;
         else if (strcmp(ar, "exact")) { delete d; return fail(SPRUCE_ERR_ARG, "SPRUCE_ARITH must be exact or relaxed"); }
