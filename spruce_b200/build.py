@@ -28,7 +28,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(SRC.glob("*.cu")) + list(SRC.glob("*.cuh")) + [PKG.parent / "include" / "spruce_b200.h"]
+    deps = list(SRC.glob("*.cu")) + list(SRC.glob("*.cuh")) + list(SRC.glob("*.hpp")) + [PKG.parent / "include" / "spruce_b200.h"]
     return any(p.stat().st_mtime > t for p in deps)
 
 
