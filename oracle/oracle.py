@@ -63,6 +63,7 @@ def lib():
         L.oracle_outflow_mean.argtypes = [C.c_void_p, C.c_int]
         L.oracle_outflow_mean.restype = C.c_double
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_set_moc_limiting.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
         L.oracle2e_destroy.argtypes = [C.c_void_p]
@@ -96,7 +97,7 @@ class Oracle:
 
     def __init__(self, planes, ion_mass, adiabatic_index, *, xb=("periodic", "periodic"), yb=("periodic", "periodic"),
                  integrator="rk2", epsilon=0.2, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6,
-                 open_strength=1.0, open_decay=0.5, setup=True):
+                 open_strength=1.0, open_decay=0.5, setup=True, moc_limiting=None):
         L = lib()
         nx, ny = planes["rho"].shape
         self.nx, self.ny = nx, ny
@@ -107,6 +108,8 @@ class Oracle:
             if name in ("mask",):
                 continue
             self.view(name)[...] = a
+        if moc_limiting:                               # equation-set options are parsed before setupEquationSet: its derived pass already applies them
+            self.set_moc_limiting(**moc_limiting)
         if setup:
             L.oracle_setup(self.h)
 
@@ -192,6 +195,10 @@ class Oracle:
 
     def set_global_viscosity(self, v: float):
         lib().oracle_set_global_viscosity(self.h, v)
+
+    def set_moc_limiting(self, *, b_limiting=False, b_lower=0.1, b_upper=10.0, mom_limiting=False, mom_lower=0.1, mom_upper=10.0):
+        """moc_b_limiting / moc_mom_limiting (idealmhd.cpp:107-223); call before the first step (the setup's derived pass has already run without them)."""
+        lib().oracle_set_moc_limiting(self.h, int(b_limiting), b_lower, b_upper, int(mom_limiting), mom_lower, mom_upper)
 
     def set_physical_viscosity(self, coeff_plane, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False, integrator="euler",
                                inactive_mode=False):

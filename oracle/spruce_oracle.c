@@ -68,6 +68,8 @@ typedef struct oracle {
     int xl, xu, yl, yu;
     double m_i, gamma, epsilon, n_min, T_min, e_min, open_strength, open_decay;
     double global_viscosity;    /* IdealMHD m_global_viscosity (idealmhd.hpp:48): only the open_moc boundary uses it */
+    int moc_b_limiting, moc_mom_limiting;                      /* idealmhd.hpp:59-64 */
+    double moc_b_lim[2], moc_mom_lim[2];                       /* lower, upper */
     double *dx, *dy, *bex, *bey, *bez, *posx, *posy, *mask;
     double *g[NV];
     double t; int iter;
@@ -385,9 +387,50 @@ static void update_ghost_zones(const oracle *o, double **G, double **P)
     else if (o->yb2 == BC_OPEN_UCNP) for (int i = o->xl; i <= o->xu; i++) ucnp_bc(o, G, 3, i);
 }
 
+/* applyMomThresholdingMoC / applyBThresholdingMoC (idealmhd.cpp:107-223): on every open_moc side, the two ghost layers and the first interior layer
+ * are clamped between lower*ref and upper*ref, ref = the value in the second interior layer of the same line; sides in the order x1, x2, y1, y2 */
+static double moc_clamp(double v, double ref, double lo, double hi)
+{
+    return (ref >= 0.0) ? smin(smax(v, lo), hi) : smax(smin(v, lo), hi);
+}
+static void moc_thresholding(const oracle *o, double **G)
+{
+    const int nx = o->nx, ny = o->ny;
+    const int bcs[4] = { o->xb1, o->xb2, o->yb1, o->yb2 };
+    if (o->moc_mom_limiting) {
+        const int moms[3] = { V_mom_x, V_mom_y, V_mom_z };
+        for (int q = 0; q < 3; q++) { double *g = G[moms[q]];
+            for (int s = 0; s < 4; s++) { if (bcs[s] != BC_OPEN_MOC) continue;
+                const int xside = s < 2, lower = (s % 2) == 0, nal = xside ? ny : nx, ncr = xside ? nx : ny;
+                for (int a = 0; a < nal; a++) for (int k = 0; k < N_GHOST + 1; k++) {
+                    const int e = lower ? k : ncr - 1 - k, r = lower ? N_GHOST + 1 : ncr - 2 - N_GHOST;
+                    const size_t c = xside ? IDX(e, a) : IDX(a, e), cr = xside ? IDX(r, a) : IDX(a, r);
+                    const double ref = g[cr];
+                    g[c] = moc_clamp(g[c], ref, o->moc_mom_lim[0] * ref, o->moc_mom_lim[1] * ref);
+                } } }
+    }
+    if (o->moc_b_limiting) {
+        const int bis[3] = { V_bi_x, V_bi_y, V_bi_z };
+        const double *bes[3] = { o->bex, o->bey, o->bez };
+        for (int q = 0; q < 3; q++) { double *g = G[bis[q]]; const double *be = bes[q];
+            for (int s = 0; s < 4; s++) { if (bcs[s] != BC_OPEN_MOC) continue;
+                const int xside = s < 2, lower = (s % 2) == 0, nal = xside ? ny : nx, ncr = xside ? nx : ny;
+                for (int a = 0; a < nal; a++) for (int k = 0; k < N_GHOST + 1; k++) {
+                    /* reference typo (idealmhd.cpp:154): the y_bound_2 reference column of the B limiter is m_xdim-2-N_GHOST, not m_ydim-2-N_GHOST
+                     * (it must lie inside the grid: the reference asserts otherwise) */
+                    const int e = lower ? k : ncr - 1 - k, r = lower ? N_GHOST + 1 : (s == 3 ? nx : ncr) - 2 - N_GHOST;
+                    if (s == 3 && (r < 0 || r >= ny)) continue;
+                    const size_t c = xside ? IDX(e, a) : IDX(a, e), cr = xside ? IDX(r, a) : IDX(a, r);
+                    const double ref = be[cr] + g[cr];
+                    g[c] = moc_clamp(g[c], ref, o->moc_b_lim[0] * ref - be[c], o->moc_b_lim[1] * ref - be[c]);
+                } } }
+    }
+}
+
 /* idealmhd.cpp:241-277 */
 static void recompute_derived(const oracle *o, double **G)
 {
+    if (o->moc_mom_limiting || o->moc_b_limiting) moc_thresholding(o, G);
     for (int c = 0; c < o->n; c++) {
         double n = smax(G[V_rho][c] / o->m_i, o->n_min);
         G[V_n][c] = n;
@@ -955,6 +998,12 @@ void oracle_set_anomalous_resistivity(oracle *o, const double *p)
 }
 int oracle_anomalous_subcycles(const oracle *o) { return o->mod.anom ? ((anom_res *)o->mod.anom)->nsub : 0; }
 void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
+/* moc_b_limiting / moc_mom_limiting with their bounds (idealmhd.cpp:17-36; defaults 0.1 and 10.0, idealmhd.hpp:59-64) */
+void oracle_set_moc_limiting(oracle *o, int b_on, double b_lo, double b_hi, int mom_on, double mom_lo, double mom_hi)
+{
+    o->moc_b_limiting = b_on; o->moc_b_lim[0] = b_lo; o->moc_b_lim[1] = b_hi;
+    o->moc_mom_limiting = mom_on; o->moc_mom_lim[0] = mom_lo; o->moc_mom_lim[1] = mom_hi;
+}
 double oracle_step(oracle *o) { return advance_time(o); }
 void oracle_run(oracle *o, int nsteps, double *dt_out) { for (int s = 0; s < nsteps; s++) { double d = advance_time(o); if (dt_out) dt_out[s] = d; } }
 double oracle_time(const oracle *o) { return o->t; }

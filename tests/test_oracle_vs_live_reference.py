@@ -311,3 +311,39 @@ def test_ideal_mhd_2e_oracle_equals_live_reference(k, xb, yb, integrator, nx, ny
     for v in E2_OUT:
         assert same_bits(o.get(v), frames[nsteps][v]), "case %d %s: %s" % (k, v, mismatch(o.get(v), frames[nsteps][v]))
     o.close()
+
+
+MOC_LIMIT_CASES = [
+    ("y2_b_and_mom", ("periodic", "periodic"), ("fixed", "open_moc"), "rk2", 0.0, dict(b_limiting=True, b_lower=0.9, b_upper=1.05, mom_limiting=True, mom_lower=0.5, mom_upper=1.5), 26, 23),
+    ("all_sides_mom_visc", ("open_moc", "open_moc"), ("open_moc", "open_moc"), "euler", 0.1, dict(mom_limiting=True, mom_lower=0.8, mom_upper=1.1), 25, 24),
+    ("x1_b_negative_lower", ("open_moc", "reflect"), ("fixed", "open"), "rk4", 0.0, dict(b_limiting=True, b_lower=-0.5, b_upper=1.02), 27, 22),
+]
+
+
+@pytest.mark.parametrize("name,xb,yb,integrator,gvisc,lim,nx,ny", MOC_LIMIT_CASES, ids=[m[0] for m in MOC_LIMIT_CASES])
+def test_open_moc_limiters_oracle_equals_live_reference(name, xb, yb, integrator, gvisc, lim, nx, ny):
+    """moc_b_limiting / moc_mom_limiting (idealmhd.cpp:107-223): the clamps of the ghost layers and the first interior layer against the second
+    interior layer, applied side after side at the head of every derived-variable pass (tight bounds so that they really act)."""
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
+    block = [("global_viscosity", repr(gvisc))]
+    block += [("moc_b_limiting", "true"), ("moc_b_lower_lim", repr(lim["b_lower"])), ("moc_b_upper_lim", repr(lim["b_upper"]))] if lim.get("b_limiting") else []
+    block += [("moc_mom_limiting", "true"), ("moc_mom_lower_lim", repr(lim["mom_lower"])), ("moc_mom_upper_lim", repr(lim["mom_upper"]))] if lim.get("mom_limiting") else []
+    nsteps = 3
+    frames = run_reference(s, dict(kw, eqs_block=block), MHD_OUT, nsteps)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], moc_limiting=lim, **kw)
+    o.set_global_viscosity(gvisc)
+    plain = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    plain.set_global_viscosity(gvisc)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for v in MHD_OUT:
+        assert same_bits(o.get(v), frames[0][v]), "%s after setup %s: %s" % (name, v, mismatch(o.get(v), frames[0][v]))
+    for it in range(1, nsteps + 1):
+        step = o.step(); plain.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "%s iteration %d: step %s vs %s" % (name, it, step.hex(), float(ref_step).hex())
+    for v in MHD_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
+    assert any(not same_bits(o.get(v), plain.get(v)) for v in ("mom_x", "mom_y", "bi_x", "bi_y")), "the limiters never acted: the case does not test them"
+    o.close(); plain.close()
