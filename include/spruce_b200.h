@@ -175,9 +175,13 @@ int spruce_module_boundary_outflow_state(spruce_domain *dom, double *mean_outflo
 /* IdealMHD::parseEquationSetConfigs (source/equationsets/idealmhd.cpp:12-40): global_viscosity (idealmhd.hpp:48, default 0), read only
  * by the characteristic open boundary (global_visc_coeff, idealmhd.cpp:90).  open_moc sides themselves (idealmhd.cpp:306-615) are
  * selected through spruce_config.x_bound_* / y_bound_* = SPRUCE_BC_OPEN_MOC; until that path has been validated on a GPU
- * spruce_domain_create refuses it unless the environment sets SPRUCE_EXPERIMENTAL_MOC=1.  moc_b_limiting / moc_mom_limiting
- * (idealmhd.cpp:107-223) are not built. */
+ * spruce_domain_create refuses it unless the environment sets SPRUCE_EXPERIMENTAL_MOC=1. */
 int spruce_eqs_ideal_mhd_options(spruce_domain *dom, double global_viscosity);
+/* moc_b_limiting / moc_mom_limiting with moc_{b,mom}_{lower,upper}_lim (idealmhd.cpp:17-36; applyBThresholdingMoC / applyMomThresholdingMoC :107-223): clamps of
+ * the ghost layers and the first interior layer of every open_moc side at the head of each derived-variable pass, the reference's y_bound_2 index quirk
+ * (:154) included.  Call before spruce_eqs_setup (the setup's own derived pass applies them).  Not available through spruce_mgpu_stage. */
+int spruce_eqs_ideal_mhd_moc_limiting(spruce_domain *dom, int b_limiting, double b_lower_lim, double b_upper_lim, int mom_limiting, double mom_lower_lim,
+                                      double mom_upper_lim);
 /* Ideal2F::parseEquationSetConfigs (source/equationsets/ideal2F.cpp:5-28): use_sub_cycling (reference default true, which aborts
  * in computeTimeDerivatives -- only false can run, and spruce_eqs_setup refuses true) and remove_curl_terms. */
 int spruce_eqs_ideal2f_options(spruce_domain *dom, int use_sub_cycling, int remove_curl_terms);

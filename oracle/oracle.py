@@ -63,6 +63,7 @@ def lib():
         L.oracle_outflow_mean.argtypes = [C.c_void_p, C.c_int]
         L.oracle_outflow_mean.restype = C.c_double
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_apply_moc_thresholding.argtypes = [C.c_void_p]
         L.oracle_set_moc_limiting.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
@@ -195,6 +196,10 @@ class Oracle:
 
     def set_global_viscosity(self, v: float):
         lib().oracle_set_global_viscosity(self.h, v)
+
+    def apply_moc_thresholding(self):
+        """The two limiter passes alone, on the planes as they are (for checking the product's limiter on arbitrary input)."""
+        lib().oracle_apply_moc_thresholding(self.h)
 
     def set_moc_limiting(self, *, b_limiting=False, b_lower=0.1, b_upper=10.0, mom_limiting=False, mom_lower=0.1, mom_upper=10.0):
         """moc_b_limiting / moc_mom_limiting (idealmhd.cpp:107-223); call before the first step (the setup's derived pass has already run without them)."""

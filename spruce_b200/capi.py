@@ -65,6 +65,7 @@ SYMBOLS = {
                                                  C.c_double, C.c_double]),
     "spruce_module_boundary_outflow_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "spruce_eqs_ideal_mhd_options": (C.c_int, [C.c_void_p, C.c_double]),
+    "spruce_eqs_ideal_mhd_moc_limiting": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]),
     "spruce_eqs_ideal2f_options": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "spruce_module_eic_thermalization": (C.c_int, [C.c_void_p]),
     "spruce_module_subcycles": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]),

@@ -103,6 +103,7 @@ struct spruce_domain {
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
     // open_moc (moc_stage.cuh): evolved ghost cells; SPRUCE_EXPERIMENTAL_MOC=1 until the launch side has been validated on a GPU
     bool moc_any = false; double global_viscosity = 0.0; double *moc_base = nullptr;
+    moc::Limits moc_lim{0, 0, 0.1, 10.0, 0.1, 10.0};                      // moc_b_limiting / moc_mom_limiting and their bounds (idealmhd.hpp:59-64)
     int chunk_rows_override = 0;           // SPRUCE_CHUNK_ROWS (16 .. XY_CHUNK, the range the automatic choice already spans): rows per CTA of the stage kernel, for tuning sweeps; 0 = pick_chunk_rows' own choice
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
     int stage_variants = 0;                // compile-time integrator-stage instances of k_mhd_stage_xy: SPRUCE_STAGE_VARIANTS=1, =2: also six CTAs per SM (2-D instance), =3: also the pair-wise barrier
@@ -381,6 +382,38 @@ int launch_moc(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const Pla
     return SPRUCE_OK;
 }
 
+// moc_b_limiting / moc_mom_limiting (idealmhd.cpp:107-223): the head of the derived-variable pass, i.e. after the boundary passes of a propagate.
+// The clamps reach the first interior layer, whose dt the stage kernel has already folded into the minimum: in the step's last stage the minimum
+// is rebuilt from every cell of U (interior by k_dt_full, evolved ghost cells by k_moc_stage in dt-only mode).
+int moc_limit(spruce_domain *d, const PlaneSet &U, int primary)
+{
+    if (!d->moc_any || !(d->moc_lim.b_on || d->moc_lim.mom_on)) return SPRUCE_OK;
+    MocLimitArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = U.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.L = d->moc_lim; A.done_ptr = &d->ctl->done;
+    const int bcs[4] = {d->cfg.x_bound_1, d->cfg.x_bound_2, d->cfg.y_bound_1, d->cfg.y_bound_2};
+    for (int s = 0; s < 4; s++) {
+        if (bcs[s] != SPRUCE_BC_OPEN_MOC) continue;
+        A.side = s;
+        const int n = s < 2 ? d->P.ny : d->P.nx;
+        k_moc_limit<<<(n + 127) / 128, 128, 0, d->stream>>>(d->P, A);
+        d->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (!primary) return SPRUCE_OK;
+    k_moc_force_full_dt<<<1, 1, 0, d->stream>>>(d->ctl);
+    DtFullArgs F{};
+    for (int v = 0; v < NEV; v++) F.U[v] = U.p[v];
+    for (int v = 0; v < NSTATIC; v++) F.st[v] = d->stat[v];
+    F.ctl = d->ctl;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_dt_full<<<grid, 256, 0, d->stream>>>(d->P, F);
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return launch_moc(d, U, U, U, 0.0, 1, KM_NONE, 1);
+}
+
 int launch_ghosts(spruce_domain *d, const PlaneSet &U, int primary)
 {
     if (!(d->any_ucnp || (primary && d->any_primary_ghost))) return SPRUCE_OK;
@@ -414,6 +447,7 @@ int launch_propagate(spruce_domain *d, int from_state)
     d->raw_rho = false;
     int rc = launch_ghosts(d, d->Pset, 1);
     if (rc || !d->moc_any) return rc;
+    if (d->moc_lim.b_on || d->moc_lim.mom_on) return moc_limit(d, d->Pset, 1);       // clamps, then the whole dt minimum again
     return launch_moc(d, d->Pset, d->Pset, d->Pset, 0.0, 1, KM_NONE, 1);
 }
 
@@ -913,6 +947,7 @@ int peer_dt_allgather(spruce_domain *d)
 int finish_stage(spruce_domain *d, const PlaneSet &U, int primary)
 {
     int rc = launch_ghosts(d, U, primary);
+    if (!rc) rc = moc_limit(d, U, primary);
     if (rc || d->cfg.n_ranks == 1) return rc;
     return peer_exchange(d, U.p, nullptr);
 }
@@ -1672,6 +1707,18 @@ int spruce_eqs_ideal_mhd_options(spruce_domain *d, double global_viscosity)
     d->global_viscosity = global_viscosity;          // only the open_moc boundary reads it (idealmhd.cpp:90)
     return SPRUCE_OK;
 }
+int spruce_eqs_ideal_mhd_moc_limiting(spruce_domain *d, int b_limiting, double b_lower_lim, double b_upper_lim, int mom_limiting, double mom_lower_lim, double mom_upper_lim)
+{
+    CHECK_DOM(d);
+    if (d->tf || d->e2) return fail(SPRUCE_ERR_STATE, "ideal_mhd options on a domain with another equation set");
+    if (b_limiting && !(b_lower_lim <= 1.0 && b_upper_lim >= 1.0)) return fail(SPRUCE_ERR_ARG, "MoC B field thresholds: lower <= 1.0 <= upper");      // idealmhd.cpp:21,25
+    if (mom_limiting && !(mom_lower_lim <= 1.0 && mom_upper_lim >= 1.0)) return fail(SPRUCE_ERR_ARG, "MoC momentum thresholds: lower <= 1.0 <= upper");   // :29,33
+    if (b_limiting && d->cfg.y_bound_2 == SPRUCE_BC_OPEN_MOC && d->cfg.xdim - 2 - HALO >= d->cfg.ydim)
+        return fail(SPRUCE_ERR_ARG, "moc_b_limiting on y_bound_2 reads column xdim-2-N_GHOST (idealmhd.cpp:154): outside this grid, the reference aborts");
+    d->moc_lim.b_on = b_limiting ? 1 : 0; d->moc_lim.b_lo = b_lower_lim; d->moc_lim.b_hi = b_upper_lim;
+    d->moc_lim.mom_on = mom_limiting ? 1 : 0; d->moc_lim.mom_lo = mom_lower_lim; d->moc_lim.mom_hi = mom_upper_lim;
+    return SPRUCE_OK;
+}
 int spruce_eqs_ideal2f_options(spruce_domain *d, int use_sub_cycling, int remove_curl_terms)
 {
     CHECK_DOM(d);
@@ -1764,6 +1811,7 @@ static int stage_output_set(const spruce_domain *d, int stage)
 }
 int spruce_mgpu_stage(spruce_domain *d, int stage)
 {
+    if (d && (d->moc_lim.b_on || d->moc_lim.mom_on)) return fail(SPRUCE_ERR_UNSUPPORTED, "the open_moc limiters are not available through spruce_mgpu_stage (use the peer transport)");
     CHECK_DOM(d);
     NOT_2F(d, "slab decomposition");
     if (!d->is_setup) return fail(SPRUCE_ERR_STATE, "stage before setup");

@@ -466,6 +466,43 @@ MOC_HD bool in_interior(const Field &F, int i, int j)
     return i >= xl && i <= xu && j >= yl && j <= yu;
 }
 
+// ---- applyMomThresholdingMoC / applyBThresholdingMoC (idealmhd.cpp:107-223), run at the head of every derived-variable pass when
+// moc_mom_limiting / moc_b_limiting are set: on an open_moc side the two ghost layers and the first interior layer of every line are clamped
+// between lower*ref and upper*ref, ref = the value in the second interior layer of that line.  The sides run one after the other (x1, x2, y1, y2):
+// a later side reads cells an earlier one clamped.  Within a side the lines are independent; the cells of a line are taken outermost first because
+// the reference column of the B limiter on y_bound_2 is m_xdim-2-N_GHOST (reference typo, :154) and can be one of the clamped cells itself.
+struct Limits { int b_on, mom_on; double b_lo, b_hi, mom_lo, mom_hi; };
+struct Mutable { double *mx, *my, *mz, *bix, *biy, *biz; };          // row-shifted like the planes of Field
+MOC_HD double clamp_ref(double v, double ref, double lo, double hi) { return (ref >= 0.0) ? smin_(smax_(v, lo), hi) : smax_(smin_(v, lo), hi); }
+MOC_HD void limit_line(const Field &F, const Mutable &U, const Limits &L, int s, int a)
+{
+    if (F.bc[s] != MBC_OPEN_MOC) return;
+    const bool xside = s < 2, lower = (s % 2) == 0;
+    const int ncr = xside ? F.nx : F.ny;
+    const int r = lower ? NG + 1 : ncr - 2 - NG;
+    if (L.mom_on) {
+        double *m[3] = {U.mx, U.my, U.mz};
+        for (int q = 0; q < 3; q++) for (int k = 0; k < NG + 1; k++) {
+            const int e = lower ? k : ncr - 1 - k;
+            const size_t c = xside ? (size_t)e * F.pitch + a : (size_t)a * F.pitch + e, cr = xside ? (size_t)r * F.pitch + a : (size_t)a * F.pitch + r;
+            const double ref = m[q][cr];
+            m[q][c] = clamp_ref(m[q][c], ref, L.mom_lo * ref, L.mom_hi * ref);
+        }
+    }
+    if (L.b_on) {
+        double *b[3] = {U.bix, U.biy, U.biz};
+        const double *be[3] = {F.bex, F.bey, F.bez};
+        const int rb = (s == 3) ? F.nx - 2 - NG : r;                              // the reference's index on y_bound_2
+        if (s == 3 && (rb < 0 || rb >= F.ny)) return;                             // the reference aborts here (Grid bounds assert)
+        for (int q = 0; q < 3; q++) for (int k = 0; k < NG + 1; k++) {
+            const int e = lower ? k : ncr - 1 - k;
+            const size_t c = xside ? (size_t)e * F.pitch + a : (size_t)a * F.pitch + e, cr = xside ? (size_t)rb * F.pitch + a : (size_t)a * F.pitch + rb;
+            const double ref = be[q][cr] + b[q][cr];
+            b[q][c] = clamp_ref(b[q][c], ref, L.b_lo * ref - be[q][c], L.b_hi * ref - be[q][c]);
+        }
+    }
+}
+
 // one term of the minimum behind global_visc_coeff (idealmhd.cpp:90) given the cell's dt
 MOC_HD double visc_min_term(double dx, double dy, double dt) { return (1.0 / (1.0 / (dx * dx) + 1.0 / (dy * dy))) / dt; }
 

@@ -125,4 +125,34 @@ __global__ void __launch_bounds__(128) k_moc_stage(const DomainParams P, const M
     if (A.dt_only || (A.primary && A.kmode != KM_EXPORT)) block_min_to_global(dtc, A.dtmin_bits);
 }
 
+// moc_b_limiting / moc_mom_limiting: one launch per open_moc side, in the reference's order; one thread per line of the side
+struct MocLimitArgs { double *U[NEV]; const double *st[NSTATIC]; moc::Limits L; int side; const int *done_ptr; };
+__global__ void __launch_bounds__(128) k_moc_limit(const DomainParams P, const MocLimitArgs A)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (*A.done_ptr) return;
+    const bool xside = A.side < 2, lower = (A.side % 2) == 0;
+    int a;
+    if (xside) {                                           // lines = columns; only the slab that holds the side's four rows
+        if (t >= P.ny || (lower ? P.row0 != 0 : P.row0 + P.nx != P.gnx)) return;
+        a = t;
+    } else {                                               // lines = this slab's rows
+        if (t >= P.nx) return;
+        a = P.row0 + t;
+    }
+    const double *U[NEV];
+    for (int v = 0; v < NEV; v++) U[v] = A.U[v];
+    const moc::Field F = moc_field(P, U, A.st, 0.0);
+    const long long sh = (long long)P.row0 * P.pitch;
+    const moc::Mutable M{A.U[E_MX] - sh, A.U[E_MY] - sh, A.U[E_MZ] - sh, A.U[E_BX] - sh, A.U[E_BY] - sh, A.U[E_BZ] - sh};
+    moc::limit_line(F, M, A.L, A.side, a);
+}
+// after the limiters changed cells inside the dt bounds: drop the minimum the stage kernel accumulated and make k_dt_full evaluate every cell
+__global__ void k_moc_force_full_dt(StepCtl *c)
+{
+    if (c->done) return;
+    c->need_full = 1;
+    c->dtmin_bits = 0x7FEFFFFFFFFFFFFFULL;
+}
+
 }  // namespace spruce

@@ -71,8 +71,14 @@ class PlasmaDomain:
             o = dict(use_sub_cycling=True, remove_curl_terms=False)          # Ideal2F defaults, ideal2F.hpp:62-65
             o.update(eqs_options or {})
             capi.check(self.lib.spruce_eqs_ideal2f_options(self.h, int(o["use_sub_cycling"]), int(o["remove_curl_terms"])))
-        elif eqs_options and "global_viscosity" in eqs_options:               # IdealMHD::parseEquationSetConfigs, idealmhd.cpp:15
-            capi.check(self.lib.spruce_eqs_ideal_mhd_options(self.h, float(eqs_options["global_viscosity"])))
+        elif equation_set == "ideal_mhd" and eqs_options:                     # IdealMHD::parseEquationSetConfigs, idealmhd.cpp:12-40
+            o = eqs_options
+            if "global_viscosity" in o:
+                capi.check(self.lib.spruce_eqs_ideal_mhd_options(self.h, float(o["global_viscosity"])))
+            if o.get("moc_b_limiting") or o.get("moc_mom_limiting"):
+                capi.check(self.lib.spruce_eqs_ideal_mhd_moc_limiting(self.h, int(bool(o.get("moc_b_limiting"))), float(o.get("moc_b_lower_lim", 0.1)),
+                                                                      float(o.get("moc_b_upper_lim", 10.0)), int(bool(o.get("moc_mom_limiting"))),
+                                                                      float(o.get("moc_mom_lower_lim", 0.1)), float(o.get("moc_mom_upper_lim", 10.0))))
         for name in self.DOMAIN + self.STATE:
             if name in planes:
                 self.upload(name, planes[name])

@@ -120,19 +120,30 @@ double EquationSet::nextStepSize()
 IdealMHD::IdealMHD(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
 int IdealMHD::device_id() const { return SPRUCE_EQS_IDEAL_MHD; }
 
-// idealmhd.cpp:12-40: same keys; the MoC limiters (idealmhd.cpp:107-223) are not built
+// idealmhd.cpp:12-40: same keys, same bounds checks
 void IdealMHD::parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
 {
     for (size_t i = 0; i < lhs.size(); i++) {
         const std::string &k = lhs[i];
         if (k == "global_viscosity") { m_global_viscosity = std::stod(rhs[i]); continue; }
-        if (k == "viscosity_opt" || k == "moc_b_lower_lim" || k == "moc_b_upper_lim" || k == "moc_mom_lower_lim" || k == "moc_mom_upper_lim") continue;
-        if (k == "moc_b_limiting" || k == "moc_mom_limiting") { SPRUCE_REQUIRE(rhs[i] != "true", "MoC limiting (moc_b_limiting / moc_mom_limiting) is not built"); continue; }
+        if (k == "viscosity_opt") continue;
+        if (k == "moc_b_limiting") { m_moc_b_limiting = (rhs[i] == "true"); continue; }
+        if (k == "moc_mom_limiting") { m_moc_mom_limiting = (rhs[i] == "true"); continue; }
+        if (k == "moc_b_lower_lim") { m_moc_b_lim[0] = std::stod(rhs[i]); SPRUCE_REQUIRE(m_moc_b_lim[0] <= 1.0, "MoC B field lower threshold should be <=1.0"); continue; }
+        if (k == "moc_b_upper_lim") { m_moc_b_lim[1] = std::stod(rhs[i]); SPRUCE_REQUIRE(m_moc_b_lim[1] >= 1.0, "MoC B field upper threshold should be >=1.0"); continue; }
+        if (k == "moc_mom_lower_lim") { m_moc_mom_lim[0] = std::stod(rhs[i]); SPRUCE_REQUIRE(m_moc_mom_lim[0] <= 1.0, "MoC momentum threshold should be <=1.0"); continue; }
+        if (k == "moc_mom_upper_lim") { m_moc_mom_lim[1] = std::stod(rhs[i]); SPRUCE_REQUIRE(m_moc_mom_lim[1] >= 1.0, "MoC momentum threshold should be >=1.0"); continue; }
         spruce_die(k + " is not recognized for this equation set.");
     }
 }
 
-void IdealMHD::configureDevice() { PlasmaDomain::check(spruce_eqs_ideal_mhd_options(m_pd.device(), m_global_viscosity)); }
+void IdealMHD::configureDevice()
+{
+    PlasmaDomain::check(spruce_eqs_ideal_mhd_options(m_pd.device(), m_global_viscosity));
+    if (m_moc_b_limiting || m_moc_mom_limiting)
+        PlasmaDomain::check(spruce_eqs_ideal_mhd_moc_limiting(m_pd.device(), m_moc_b_limiting ? 1 : 0, m_moc_b_lim[0], m_moc_b_lim[1], m_moc_mom_limiting ? 1 : 0,
+                                                              m_moc_mom_lim[0], m_moc_mom_lim[1]));
+}
 
 IdealMHD2E::IdealMHD2E(PlasmaDomain &pd) : EquationSet(pd, def_var_names()) {}
 int IdealMHD2E::device_id() const { return SPRUCE_EQS_IDEAL_MHD_2E; }

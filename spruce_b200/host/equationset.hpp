@@ -96,6 +96,8 @@ public:
     void configureDevice() override;
 private:
     double m_global_viscosity = 0.0;              // idealmhd.hpp:48; read by the open_moc boundary only (idealmhd.cpp:90)
+    bool m_moc_b_limiting = false, m_moc_mom_limiting = false;          // idealmhd.hpp:59-64
+    double m_moc_b_lim[2] = {0.1, 10.0}, m_moc_mom_lim[2] = {0.1, 10.0};
     void parseEquationSetConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
 

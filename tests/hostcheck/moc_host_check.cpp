@@ -119,3 +119,15 @@ extern "C" int moc_host_terms_slabs(const double *const *planes, const double *d
     }
     return 0;
 }
+
+// the limiter passes on arbitrary planes: mutable[6] = mom_x, mom_y, mom_z, bi_x, bi_y, bi_z (in place); be[3]
+extern "C" void moc_host_limit(double *const *mut, const double *const *be, int nx, int ny, const int *bc, int b_on, double b_lo, double b_hi, int mom_on, double mom_lo, double mom_hi)
+{
+    spruce::moc::Field F{};
+    F.nx = nx; F.ny = ny; F.pitch = ny; F.x_halo = 0;
+    for (int s = 0; s < 4; s++) F.bc[s] = bc[s];
+    F.bex = be[0]; F.bey = be[1]; F.bez = be[2];
+    const spruce::moc::Mutable U{mut[0], mut[1], mut[2], mut[3], mut[4], mut[5]};
+    const spruce::moc::Limits L{b_on, mom_on, b_lo, b_hi, mom_lo, mom_hi};
+    for (int s = 0; s < 4; s++) for (int a = 0; a < (s < 2 ? ny : nx); a++) spruce::moc::limit_line(F, U, L, s, a);    // sides in order, lines in any order
+}

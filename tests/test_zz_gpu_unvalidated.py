@@ -467,3 +467,41 @@ def test_ideal_mhd_2e_vs_oracle(xb, yb, integ, nx, ny, loop, nmin):
     and several derived planes bit for bit.  The arithmetic and the stage order are already proven on the host (tests/test_mhd2e_host_check.py)."""
     out = run_isolated(E2_CODE.format(xb=xb, yb=yb, integ=integ, nx=nx, ny=ny, loop=loop, nmin=nmin), {})
     assert "ok" in out
+
+
+MOC_LIMIT_CODE = """
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    xb, yb, integ, gvisc, lim, nx, ny = {xb!r}, {yb!r}, {integ!r}, {gvisc!r}, {lim!r}, {nx}, {ny}
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], moc_limiting=lim, **kw)
+    o.set_global_viscosity(gvisc)
+    opts = dict(global_viscosity=gvisc, moc_b_limiting=lim.get("b_limiting", False), moc_b_lower_lim=lim.get("b_lower", 0.1), moc_b_upper_lim=lim.get("b_upper", 10.0),
+                moc_mom_limiting=lim.get("mom_limiting", False), moc_mom_lower_lim=lim.get("mom_lower", 0.1), moc_mom_upper_lim=lim.get("mom_upper", 10.0))
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], eqs_options=opts, **kw)
+    for v in PlasmaDomain.EVOLVED + ["dt"]:
+        assert same_bits(d.grid(v), o.get(v)), "after setup, %s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    ref = o.run(6)
+    dts = d.advance(6)
+    assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+    for v in PlasmaDomain.EVOLVED + ["dt", "temp", "v_x"]:
+        assert same_bits(d.grid(v), o.get(v)), "%s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("xb,yb,integ,gvisc,lim,nx,ny", [
+    (("periodic", "periodic"), ("fixed", "open_moc"), "rk2", 0.0, dict(b_limiting=True, b_lower=0.9, b_upper=1.05, mom_limiting=True, mom_lower=0.5, mom_upper=1.5), 86, 93),
+    (("open_moc", "open_moc"), ("open_moc", "open_moc"), "euler", 0.1, dict(mom_limiting=True, mom_lower=0.8, mom_upper=1.1), 85, 134),
+    (("open_moc", "reflect"), ("fixed", "open"), "rk4", 0.0, dict(b_limiting=True, b_lower=-0.5, b_upper=1.02), 97, 72),
+])
+def test_open_moc_limiters_vs_oracle(xb, yb, integ, gvisc, lim, nx, ny):
+    """moc_b_limiting / moc_mom_limiting on the device (k_moc_limit after the boundary passes of every propagate, the dt minimum rebuilt in the last stage)
+    against the pinned oracle; limit_line itself is proven on the host (tests/test_moc_host_check.py)."""
+    out = run_isolated(MOC_LIMIT_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, lim=lim, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
+    assert "ok" in out
