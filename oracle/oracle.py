@@ -73,6 +73,7 @@ def lib():
         L.oracle2e_step.argtypes = [C.c_void_p]; L.oracle2e_step.restype = C.c_double
         L.oracle2e_rhs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.oracle2e_time.argtypes = [C.c_void_p]; L.oracle2e_time.restype = C.c_double
+        L.oracle2f_apply_ghosts.argtypes = [C.c_void_p]
         L.oracle2f_create.restype = C.c_void_p
         L.oracle2f_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle2f_destroy.argtypes = [C.c_void_p]
@@ -277,6 +278,10 @@ class Oracle2F:
 
     def step(self) -> float:
         return lib().oracle2f_step(self.h)
+
+    def apply_ghosts(self):
+        """updateGhostZones alone, on the planes as they are (for checking the product's ordered boundary passes on arbitrary input)."""
+        lib().oracle2f_apply_ghosts(self.h)
 
     def rhs(self) -> np.ndarray:
         k = np.zeros((14, self.nx, self.ny))

@@ -8,6 +8,7 @@
 #include "moc_stage.cuh"
 #include "solar_templates.hpp"
 #include "mhd2e_cells.cuh"
+#include "ideal2f_sides.cuh"
 #include "mhd2e_step.hpp"
 #include "ideal2f_kernels.cuh"
 

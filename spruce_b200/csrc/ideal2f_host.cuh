@@ -2,6 +2,47 @@
 // after the plane helpers).  Same step structure as the ideal-MHD path: PlasmaDomain::advanceTime, evolution.cpp:59-124.
 #pragma once
 #include "ideal2f_kernels.cuh"
+#include "ideal2f_sides.cuh"
+
+// ---- ordered boundary passes (ideal2f_sides.cuh): boundary sets in which an open_ucnp side meets a fixed / reflect side.
+// STATUS: written after the round-1 GPU budget was spent; the passes are proven on the host (tests/test_ideal2f_sides_host_check.py), the launch side
+// has not run on a GPU yet (tests/test_zz_gpu_unvalidated.py).  The default path (every other boundary set) is untouched.
+struct TfSideArgs { tf2::Geo g; tf2::Planes G, P; int side; const int *done_ptr; };
+__global__ void __launch_bounds__(128) k_2f_side(const TfSideArgs A)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (*A.done_ptr || t >= tf2::side_length(A.g, A.side)) return;
+    tf2::side_line(A.g, A.G, A.P, A.side, t);
+}
+// k_2f_propagate without the pointwise zeroing and without dt: recomputeEvolvedVarsFromStateVars (setup) and enforceMinimums only
+__global__ void __launch_bounds__(256) k_2f_floors(const DomainParams P, const TfPropArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    double i_rho = A.U[F_IRHO][off], e_rho = A.U[F_ERHO][off], i_e = A.U[F_IE][off], e_e = A.U[F_EE][off];
+    if (A.from_state) {                                                                                 // ideal2F.cpp:107-117
+        const double i_n = ddiv(i_rho, P.m_i, P.rm_i), e_n = ddiv(e_rho, A.base.m_e, A.base.rm_e);
+        i_e = ((i_n * kKB) * A.i_temp[off]) / P.gm1;
+        e_e = ((e_n * kKB) * A.e_temp[off]) / P.gm1;
+    }
+    A.U[F_IRHO][off] = smax(ddiv(i_rho, P.m_i, P.rm_i), P.n_min) * P.m_i;                               // :98-105
+    A.U[F_ERHO][off] = smax(ddiv(e_rho, A.base.m_e, A.base.rm_e), P.n_min) * A.base.m_e;
+    A.U[F_IE][off] = smax(i_e, P.e_min); A.U[F_EE][off] = smax(e_e, P.e_min);
+}
+// recomputeDT over the interior of a finished state (ideal2F.cpp:169-198) -> running minimum
+__global__ void __launch_bounds__(256) k_2f_dt_full(const DomainParams P, const TfPropArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    double dtc = 1.7976931348623157e308;
+    if (!*A.base.done_ptr && j < P.ny && is_interior(P, r, j)) {
+        const size_t off = (size_t)r * P.pitch + j;
+        dtc = tf_cell_dt(P, A.base, A.U[F_ERHO][off], A.U[F_EMX][off], A.U[F_EMY][off], A.U[F_EE][off], P.tx.d[r], P.ty.d[j]);
+    }
+    block_min_to_global(dtc, A.dtmin_bits);
+}
 
 struct PlaneSet2 { double *p[NEV2] = {nullptr}; };
 
@@ -13,6 +54,7 @@ struct TwoFluid {
     int use_sub_cycling = 1;                           // Ideal2F default (ideal2F.hpp:62)
     int remove_curl_terms = 0;
     int eic = 0;                                       // eic_thermalization module configured
+    bool ordered_sides = false;                        // an open_ucnp side meets a fixed / reflect side: literal, ordered boundary passes (ideal2f_sides.cuh)
 };
 
 const char *const kTfEvolvedNames[NEV2] = {"i_rho", "e_rho", "i_mom_x", "i_mom_y", "e_mom_x", "e_mom_y", "i_thermal_energy", "e_thermal_energy",
@@ -34,6 +76,12 @@ int tf_create(spruce_domain *d)
 {
     TwoFluid *t = new TwoFluid();
     d->tf = t;
+    {
+        const int b[4] = {d->cfg.x_bound_1, d->cfg.x_bound_2, d->cfg.y_bound_1, d->cfg.y_bound_2};
+        bool ucnp = false, wall = false;
+        for (int s = 0; s < 4; s++) { ucnp |= (b[s] == SPRUCE_BC_OPEN_UCNP); wall |= (b[s] == SPRUCE_BC_FIXED || b[s] == SPRUCE_BC_REFLECT); }
+        t->ordered_sides = ucnp && wall;
+    }
     int rc;
     if ((rc = tf_alloc_set(d, t->P))) return rc;
     if ((rc = tf_alloc_set(d, t->M))) return rc;
@@ -71,13 +119,10 @@ void tf_base(const spruce_domain *d, TfArgs &A)
 int tf_check_boundaries(const spruce_config &c)
 {
     const int b[4] = {c.x_bound_1, c.x_bound_2, c.y_bound_1, c.y_bound_2};
-    bool ucnp = false, wall = false;
     for (int s = 0; s < 4; s++) {
         if (b[s] == SPRUCE_BC_OPEN) return fail(SPRUCE_ERR_UNSUPPORTED, "open boundaries need a single-fluid equation set (name2index(\"rho\") aborts in the reference)");
-        ucnp |= (b[s] == SPRUCE_BC_OPEN_UCNP);
-        wall |= (b[s] == SPRUCE_BC_FIXED || b[s] == SPRUCE_BC_REFLECT);
+        if (b[s] == SPRUCE_BC_OPEN_MOC) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries exist for ideal_mhd only (idealmhd.cpp:306)");
     }
-    if (ucnp && wall) return fail(SPRUCE_ERR_UNSUPPORTED, "ideal_2F: open_ucnp mixed with fixed/reflect sides is not built yet");
     return SPRUCE_OK;
 }
 
@@ -104,9 +149,40 @@ int tf_exchange(spruce_domain *d, const PlaneSet2 &U)
     if (rc) return rc;
     return peer_exchange(d, b, nullptr);
 }
+// the four boundary passes of the primary state in the reference's order, then the dt minimum over the finished state
+int tf_ordered_sides_and_dt(spruce_domain *d, const PlaneSet2 &U)
+{
+    TfSideArgs A{};
+    A.g.nx = d->P.gnx; A.g.ny = d->P.ny; A.g.pitch = d->P.pitch; A.g.row0 = d->P.row0; A.g.nxl = d->P.nx;
+    A.g.bc[0] = d->cfg.x_bound_1; A.g.bc[1] = d->cfg.x_bound_2; A.g.bc[2] = d->cfg.y_bound_1; A.g.bc[3] = d->cfg.y_bound_2;
+    A.g.xl = d->P.xl; A.g.xu = d->P.xu; A.g.yl = d->P.yl; A.g.yu = d->P.yu;
+    const long long sh = (long long)d->P.row0 * d->P.pitch;
+    for (int v = 0; v < NEV2; v++) { A.G.u[v] = U.p[v] - sh; A.P.u[v] = U.p[v] - sh; }
+    A.done_ptr = &d->ctl->done;
+    const int n = d->P.ny > d->P.nx ? d->P.ny : d->P.nx;
+    for (int side = 0; side < 4; side++) {
+        const int bc = A.g.bc[side];
+        if (bc != SPRUCE_BC_FIXED && bc != SPRUCE_BC_REFLECT && bc != SPRUCE_BC_OPEN_UCNP) continue;
+        A.side = side;
+        k_2f_side<<<(n + 127) / 128, 128, 0, d->stream>>>(A);
+        d->launches++;
+    }
+    k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, 0);
+    TfPropArgs Q{};
+    tf_base(d, Q.base);
+    for (int v = 0; v < NEV2; v++) Q.U[v] = U.p[v];
+    Q.dtmin_bits = &d->ctl->dtmin_bits;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_2f_dt_full<<<grid, 256, 0, d->stream>>>(d->P, Q);
+    d->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
 int tf_finish_stage(spruce_domain *d, const PlaneSet2 &U, int primary)
 {
-    int rc = tf_launch_ghosts(d, U, primary);
+    // ordered mode: an intermediate set only needs the open_ucnp copies (fixed / reflect act on the primary state, where they change nothing
+    // between two of its own propagates), and those never overlap -> the concurrent kernel; the primary state gets the literal ordered passes
+    int rc = (d->tf->ordered_sides && primary) ? tf_ordered_sides_and_dt(d, U) : tf_launch_ghosts(d, U, primary);
     if (rc) return rc;
     return tf_exchange(d, U);
 }
@@ -117,6 +193,7 @@ int tf_launch_stage(spruce_domain *d, const PlaneSet2 &S, const PlaneSet2 &B, co
     tf_base(d, A);
     for (int v = 0; v < NEV2; v++) { A.S[v] = S.p[v]; A.B[v] = B.p[v]; A.D[v] = D.p[v]; }
     A.coef = coef; A.primary = primary; A.kmode = kmode;
+    if (d->tf->ordered_sides) A.primary = 0;          // no pointwise zeroing, no dt in the kernel: tf_ordered_sides_and_dt follows for the primary state
     if (primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, 0); d->launches++; }
     TfVelArgs V{};
     for (int v = 0; v < NEV2; v++) V.U[v] = S.p[v];
@@ -143,6 +220,12 @@ int tf_launch_propagate(spruce_domain *d, int from_state)
     A.i_temp = t->i_temp; A.e_temp = t->e_temp; A.from_state = from_state;
     A.dtmin_bits = &d->ctl->dtmin_bits;
     dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    if (t->ordered_sides) {
+        k_2f_floors<<<grid, 256, 0, d->stream>>>(d->P, A);
+        d->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return tf_ordered_sides_and_dt(d, t->P);
+    }
     k_2f_propagate<<<grid, 256, 0, d->stream>>>(d->P, A);
     d->launches += 2;
     CUDA_TRY(cudaGetLastError());

@@ -110,8 +110,6 @@ def test_create_argument_errors_mirror_the_reference_messages():
     assert rc != 0 and "equation set" in msg
     rc, msg = create(equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["open"])
     assert rc != 0 and "open boundaries" in msg
-    rc, msg = create(equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["open_ucnp"], y_bound_1=capi.BC["fixed"])
-    assert rc != 0 and "open_ucnp mixed" in msg
     rc, msg = create(n_ranks=4, row0=12, nx_local=8)
     assert rc != 0 and "bad slab" in msg
     rc, msg = create(time_integrator=7)

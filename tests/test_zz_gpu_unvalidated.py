@@ -505,3 +505,39 @@ def test_open_moc_limiters_vs_oracle(xb, yb, integ, gvisc, lim, nx, ny):
     against the pinned oracle; limit_line itself is proven on the host (tests/test_moc_host_check.py)."""
     out = run_isolated(MOC_LIMIT_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, lim=lim, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
     assert "ok" in out
+
+
+TF_MIXED_CODE = """
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import EVOLVED_2F, Oracle2F
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    xb, yb, integ, nx, ny = {xb!r}, {yb!r}, {integ!r}, {nx}, {ny}
+    s = synthetic.ucnp_cloud(nx, ny, drift=2.0e3, bfield=5.0)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
+    o = Oracle2F(s["planes"], s["ion_mass"], s["adiabatic_index"], remove_curl_terms=False, eic=False, **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False), **kw)
+    for v in ("i_thermal_energy", "e_thermal_energy", "dt", "i_mom_x", "e_mom_y"):
+        assert same_bits(d.grid(v), o.get(v)), "after setup, %s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    ref = [o.step() for _ in range(6)]
+    dts = d.advance(6)
+    assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+    for v in EVOLVED_2F + ["dt", "dt_i", "e_temp"]:
+        assert same_bits(d.grid(v), o.get(v)), "%s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("xb,yb,integ,nx,ny", [
+    (("open_ucnp", "open_ucnp"), ("reflect", "reflect"), "rk2", 97, 81),      # the case the pointwise form gets wrong: a ucnp pass before a reflect side
+    (("reflect", "open_ucnp"), ("fixed", "open_ucnp"), "rk4", 66, 91),
+    (("open_ucnp", "fixed"), ("open_ucnp", "reflect"), "euler", 80, 75),
+    (("periodic", "periodic"), ("open_ucnp", "reflect"), "rk2", 70, 88),
+])
+def test_two_fluid_ucnp_next_to_wall_sides_vs_oracle(xb, yb, integ, nx, ny):
+    """Ideal2F with an open_ucnp side next to fixed / reflect sides (refused until now): the literal, ordered boundary passes of ideal2f_sides.cuh for the
+    primary state -- proven on the host (tests/test_ideal2f_sides_host_check.py) -- against the two-fluid restatement, bit for bit."""
+    out = run_isolated(TF_MIXED_CODE.format(xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {})
+    assert "ok" in out
