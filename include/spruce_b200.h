@@ -142,6 +142,12 @@ int spruce_module_viscosity_term(spruce_domain *dom, const char *visc_opt, doubl
  * the host exactly as the reference does.  count of sub-cycles: spruce_module_subcycles(dom, "physical_viscosity", &n). */
 int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const double *coeff_plane, size_t count, double epsilon, int heating_on,
                                      int force_on, int gradient_correction, int time_integrator, int inactive_mode);
+/* output_to_file = true of ThermalConduction / RadiativeLosses (thermalconduction.cpp:226-237, radiativelosses.cpp:172-179): the planes Module::fileOutput
+ * appends to mhd.out -- "thermal_conduction" and "rad" = the module's (e_after - e_before)/dt of the last step, "flux_saturation" = the saturation coefficient
+ * of that step's first temperature field (zero planes before the first step, as in the reference).  Enable per module, then download by plane name.
+ * Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
+int spruce_module_output_to_file(spruce_domain *dom, const char *module, int on);
+int spruce_module_output(spruce_domain *dom, const char *plane_name, double *host, size_t count);
 /* Pointwise solar source terms applied in postIterateModule (evolution.cpp:74), each followed by propagateChanges.  Gaussian templates
  * (SolarUtils::GaussianGrid / GaussianGridRotated, source/solar/solarutils.cpp:65-98; centres and widths in grid cells, combined with
  * their periodic images as the reference does) are built by the library from the reference's config keys:

@@ -90,6 +90,9 @@ struct spruce_domain {
     TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
     RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
+    // diagnostic planes of output_to_file = true (thermalconduction.cpp:226-237, radiativelosses.cpp:172-179)
+    bool tc_output = false, rl_output = false;
+    double *tc_avg = nullptr, *tc_sat = nullptr, *rl_avg = nullptr, *old_e = nullptr;
     // artificial_viscosity (source/modules/viscosity.cpp): terms in config order
     struct ViscTerm { int opt; double strength; int var_diff; int var_evol; int species; double *strength_plane; bool halo_done = false; };
     std::vector<ViscTerm> visc;
@@ -549,6 +552,15 @@ int tc_iterate(spruce_domain *d, double dt)
     const double dts = dt / (double)ns;                                                             // :60
     double *e = d->Pset.p[E_E];
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    const dim3 grid256((d->P.ny + 255) / 256, d->P.nx);
+    if (d->tc_output) {                                                                             // :53-59
+        k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, e);
+        d->launches++;
+        if (d->tc.flux_saturation) {
+            k_tc_saturation_plane<<<grid, 128, 0, d->stream>>>(d->P, d->tc, TcFields{Ta, d->Pset.p[E_N], bhx, bhy}, d->tc_sat);
+            d->launches++;
+        }
+    }
     auto stage = [&](const double *Tin, double *Tout, int mode, double c, double *Kst) -> int {
         TcStageArgs A{};
         A.F = TcFields{Tin, d->Pset.p[E_N], bhx, bhy};
@@ -571,6 +583,10 @@ int tc_iterate(spruce_domain *d, double dt)
             if ((rc = stage(Tc, Tb, TC_INTERMEDIATE, dts, K3))) return rc;
             if ((rc = stage(Tb, Ta, TC_RK4_FINAL, dts, nullptr))) return rc;
         }
+    }
+    if (d->tc_output) {                                                                             // :101-104
+        k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->tc_avg, e, d->old_e, dt);
+        d->launches++;
     }
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // :110-111
     return after_module_propagate(d);
@@ -604,8 +620,11 @@ int rl_count(spruce_domain *d, double dt, int *nsub)
 }
 int rl_iterate(spruce_domain *d, double dt)
 {
+    const dim3 grid256((d->P.ny + 255) / 256, d->P.nx);
+    if (d->rl_output) { k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, d->Pset.p[E_E]); d->launches++; }     // radiativelosses.cpp:50
     int rc = rl_launch(d, 0, dt);
     if (rc) return rc;
+    if (d->rl_output) { k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->rl_avg, d->Pset.p[E_E], d->old_e, dt); d->launches++; }   // :93
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // radiativelosses.cpp:99-100
     return after_module_propagate(d);
 }
@@ -1735,6 +1754,31 @@ int spruce_module_eic_thermalization(spruce_domain *d)
     if (!d->tf) return fail(SPRUCE_ERR_ARG, "Grid <e_temp> was not found within the EquationSet.");
     d->tf->eic = 1;
     return SPRUCE_OK;
+}
+int spruce_module_output_to_file(spruce_domain *d, const char *module, int on)
+{
+    CHECK_DOM(d);
+    if (!module) return fail(SPRUCE_ERR_ARG, "null argument");
+    NOT_2F(d, "module diagnostic planes");
+    int rc;
+    if (on && !d->old_e && (rc = alloc_plane(d, &d->old_e))) return rc;
+    if (!strcmp(module, "thermal_conduction")) {
+        d->tc_output = on != 0;
+        if (on && !d->tc_avg && ((rc = alloc_plane(d, &d->tc_avg)) || (rc = alloc_plane(d, &d->tc_sat)))) return rc;
+    } else if (!strcmp(module, "radiative_losses")) {
+        d->rl_output = on != 0;
+        if (on && !d->rl_avg && (rc = alloc_plane(d, &d->rl_avg))) return rc;
+    } else return fail(SPRUCE_ERR_ARG, "no diagnostic planes for module <%s>", module);
+    return SPRUCE_OK;
+}
+int spruce_module_output(spruce_domain *d, const char *name, double *host, size_t count)
+{
+    CHECK_DOM(d);
+    if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane size mismatch");
+    const double *src = !strcmp(name, "thermal_conduction") ? d->tc_avg : !strcmp(name, "flux_saturation") ? d->tc_sat : !strcmp(name, "rad") ? d->rl_avg : nullptr;
+    if (!src) return fail(SPRUCE_ERR_STATE, "diagnostic plane <%s> is not enabled (spruce_module_output_to_file)", name);
+    return d2h_plane(d, host, src);
 }
 int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
 {

@@ -349,6 +349,36 @@ __global__ void __launch_bounds__(256) k_ambient_heating(const DomainParams P, d
 
 
 // ---------------------------------------------------------------------------------------------------------
+// Diagnostic planes of output_to_file = true (ThermalConduction::fileOutput thermalconduction.cpp:226-237, RadiativeLosses::fileOutput
+// radiativelosses.cpp:172-179): the module's average rate of change of the thermal energy over the step, (e_after - e_before)/dt, taken before the
+// closing propagateChanges (:101-103, :93), and the saturation coefficient of the step's first temperature field (:53-58, :103).
+// STATUS: written after the round-1 GPU budget was spent; not yet run on a GPU.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_plane_copy(const DomainParams P, double *dst, const double *src)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    dst[off] = src[off];
+}
+__global__ void __launch_bounds__(256) k_avg_change(const DomainParams P, double *out, const double *e, const double *old, double dt)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    out[off] = (e[off] - old[off]) / dt;
+}
+__global__ void __launch_bounds__(128) k_tc_saturation_plane(const DomainParams P, const TcParams C, const TcFields F, double *out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    out[(size_t)r * P.pitch + j] = tc_coefficient(P, C, F, r, j);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Pointwise solar source terms with a static spatial template (postIterateModule hooks, evolution.cpp:74):
 //   SRC_SINK      AmbientHeatingSink  ambientheatingsink.cpp:36   thermal_energy -= dt*reduction          (the mask is part of the plane)
 //   SRC_HEATING   LocalizedHeating    localizedheating.cpp:60     thermal_energy += mask*((dt*ramp)*template)

@@ -195,6 +195,16 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_module_boundary_outflow_state(self.h, C.byref(m), C.byref(a)))
         return m.value, a.value
 
+    def set_module_output_to_file(self, module: str, on: bool = True):
+        """output_to_file = true of thermal_conduction / radiative_losses: keep the module's diagnostic planes (Module::fileOutput)."""
+        capi.check(self.lib.spruce_module_output_to_file(self.h, module.encode(), int(on)))
+
+    def module_output(self, name: str) -> np.ndarray:
+        """'thermal_conduction', 'flux_saturation' or 'rad' of the last step."""
+        out = np.empty((self.nx, self.ydim))
+        capi.check(self.lib.spruce_module_output(self.h, name.encode(), _dp(out), out.size))
+        return out
+
     def set_physical_viscosity(self, coeff_plane: np.ndarray, *, coeff, epsilon=1.0, heating_on=True, force_on=True, gradient_correction=False,
                                integrator="euler", inactive_mode=False):
         """coeff_plane = PhysicalViscosity::constructCoefficientGrid(coeff, ramp_length, buffer_length) (physicalviscosity.cpp:247-267)."""

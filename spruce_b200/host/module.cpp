@@ -98,8 +98,22 @@ void ThermalConduction::parseModuleConfigs(std::vector<std::string> lhs, std::ve
 void ThermalConduction::setupModule()
 {
     SPRUCE_REQUIRE(!inactive_mode, "thermal_conduction inactive_mode is a diagnostic of the CPU build");
-    no_file_output(output_to_file, "thermal_conduction");
     PlasmaDomain::check(spruce_module_thermal_conduction(m_pd.device(), flux_saturation, integrator_id(time_integrator, "Thermal Conduction"), epsilon, dt_subcycle_min, weakening_factor));
+    if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "thermal_conduction", 1));
+}
+// the device keeps the two diagnostic planes of the last step; zero planes before the first one, like the reference's
+static void append_device_plane(PlasmaDomain &pd, const char *name, std::vector<std::string> &names, std::vector<Grid> &grids)
+{
+    Grid g(pd.xdim(), pd.ydim());
+    PlasmaDomain::check(spruce_module_output(pd.device(), name, g.ptr(), g.size()));
+    names.push_back(name);
+    grids.push_back(g);
+}
+void ThermalConduction::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
+{
+    if (!output_to_file) return;
+    append_device_plane(m_pd, "thermal_conduction", names, grids);
+    append_device_plane(m_pd, "flux_saturation", names, grids);
 }
 std::string ThermalConduction::commandLineMessage() const
 {
@@ -127,8 +141,12 @@ void RadiativeLosses::parseModuleConfigs(std::vector<std::string> lhs, std::vect
 void RadiativeLosses::setupModule()
 {
     SPRUCE_REQUIRE(!inactive_mode, "radiative_losses inactive_mode is a diagnostic of the CPU build");
-    no_file_output(output_to_file, "radiative_losses");
     PlasmaDomain::check(spruce_module_radiative_losses(m_pd.device(), integrator_id(time_integrator, "Radiative Losses"), cutoff_ramp, cutoff_temp, epsilon, prevent_subcycling));
+    if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "radiative_losses", 1));
+}
+void RadiativeLosses::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
+{
+    if (output_to_file) append_device_plane(m_pd, "rad", names, grids);
 }
 std::string RadiativeLosses::commandLineMessage() const
 {

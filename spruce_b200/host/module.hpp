@@ -71,6 +71,7 @@ public:
     explicit ThermalConduction(PlasmaDomain &pd) : Module(pd) {}
     void setupModule() override;
     std::string commandLineMessage() const override;
+    void fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids) override;      // thermalconduction.cpp:226-237
     bool device_resident() const override { return true; }
 private:
     bool flux_saturation = false, output_to_file = false, inactive_mode = false;
@@ -84,6 +85,7 @@ public:
     explicit RadiativeLosses(PlasmaDomain &pd) : Module(pd) {}
     void setupModule() override;
     std::string commandLineMessage() const override;
+    void fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids) override;      // radiativelosses.cpp:172-179
     bool device_resident() const override { return true; }
 private:
     double cutoff_ramp = 0.0, cutoff_temp = 0.0, epsilon = 0.0;

@@ -541,3 +541,41 @@ def test_two_fluid_ucnp_next_to_wall_sides_vs_oracle(xb, yb, integ, nx, ny):
     primary state -- proven on the host (tests/test_ideal2f_sides_host_check.py) -- against the two-fluid restatement, bit for bit."""
     out = run_isolated(TF_MIXED_CODE.format(xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {})
     assert "ok" in out
+
+
+MODULE_PLANES_CODE = """
+    import numpy as np
+    from golden_util import Golden, module_kwargs
+    from ambient import heating_plane
+    from spruce_b200.domain import PlasmaDomain
+    g = Golden({name!r})
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
+    for mname, kv in g.modules:
+        kw = module_kwargs(mname, kv)
+        if mname == "ambient_heating":
+            d.set_ambient_heating_plane(heating_plane(g, kw))
+        else:
+            getattr(d, "set_" + mname)(**kw)
+        if kv.get("output_to_file") == "true":
+            d.set_module_output_to_file(mname)
+    done = 0
+    for it in sorted(g.frames):
+        d.advance(it - done); done = it
+        for pname, ref in g.module_planes[it].items():
+            got = d.module_output(pname)
+            scale = max(float(np.max(np.abs(ref))), 1e-300)
+            err = float(np.max(np.abs(got - ref))) / scale
+            # a rate of change formed from the difference of two nearly equal energies: the module's 1e-9 agreement on e is amplified by e/|de|
+            assert err <= 1.0e-6, "%s after iteration %d: rel Linf %.3e" % (pname, it, err)
+            assert np.count_nonzero(ref) == 0 or np.count_nonzero(got) > 0
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("name", ["loop_rl_euler", "loop_rl_rk4", "loop_tc_euler", "loop_tc_sat_rk2", "loop_tc_sat_rk4", "loop_solar_all"])
+def test_module_diagnostic_planes_vs_reference_fixtures(name):
+    """output_to_file = true of thermal_conduction / radiative_losses: the planes the reference appends to mhd.out ("thermal_conduction", "flux_saturation",
+    "rad"), from the device against the committed fixtures of the unmodified reference binary."""
+    out = run_isolated(MODULE_PLANES_CODE.format(name=name), {})
+    assert "ok" in out
