@@ -16,10 +16,19 @@ ROOT = Path(__file__).resolve().parents[1]
 UNVALIDATED = pytest.mark.xfail(reason="written after the round-1 GPU budget was spent; never executed on a GPU", strict=False)
 
 
+TIMEOUTS = []          # circuit breaker: a hung kernel costs `timeout` seconds of box time per test; after three, the rest of this file is skipped
+
+
 def run_isolated(code: str, env: dict, timeout: int = 90):
+    if len(TIMEOUTS) >= 3:
+        pytest.skip("three isolated runs timed out (%s); the remaining unvalidated tests are skipped to bound the box time" % ", ".join(TIMEOUTS))
     e = dict(os.environ); e.update(env)
     e["PYTHONPATH"] = os.pathsep.join([str(ROOT), str(ROOT / "tests"), e.get("PYTHONPATH", "")])
-    r = subprocess.run([sys.executable, "-c", textwrap.dedent(code)], cwd=str(ROOT), env=e, capture_output=True, text=True, timeout=timeout)
+    try:
+        r = subprocess.run([sys.executable, "-c", textwrap.dedent(code)], cwd=str(ROOT), env=e, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        TIMEOUTS.append(os.environ.get("PYTEST_CURRENT_TEST", "?").split("::")[-1].split(" ")[0])
+        raise
     assert r.returncode == 0, "exit %d\n%s\n%s" % (r.returncode, r.stdout[-3000:], r.stderr[-3000:])
     return r.stdout
 
