@@ -178,6 +178,20 @@ int spruce_module_boundary_outflow(spruce_domain *dom, const double *pos_x, cons
                                    int boundary, int falloff_shape, double feather_length, int field_aligned_mode, int dynamic_mode, double dynamic_time,
                                    double dynamic_target_speed);
 int spruce_module_boundary_outflow_state(spruce_domain *dom, double *mean_outflow, double *curr_accel);
+/* AnomalousResistivity (source/modules/solar/anomalousresistivity.cpp:18-309): localized magnetic diffusion with Joule heating around the tracked null
+ * point, sub-cycled euler / rk2 / rk4 inside iterateModule.  pos_x / pos_y = the PlasmaDomain position grids (xdim*ydim values).  params[SPRUCE_AR_N_PARAMS], the
+ * config keys of parseModuleConfigs (:46-68) with the defaults of anomalousresistivity.hpp:16-39:
+ *   [0] time_scale  [1] frobenius_metric_coeff  [2] smoothing_sigma  [3] safety_factor  [4] metric_smoothing (0/1)  [5] time_integrator (SPRUCE_TI_*)
+ *   [6] template_mode (1 flood_fill, 0 frobenius)  [7] flood_fill_max_radius  [8] flood_fill_argmin_radius  [9] flood_fill_min_current
+ *   [10] flood_fill_current_ramp_length  [11] flood_fill_threshold  [12] resistivity_model (0 time_scale, 1 syntelis_19, 2 ys_94)  [13] gradient_correction (0/1)
+ *   [14..16] resistivity_model_params
+ * setupModule (:18-44: null point = arg-min of the in-plane field over the interior, Gaussian kernel, first template) runs on the state before the first step.
+ * The reference's typos are kept (computeDiffusion(bi_x, bi_x, bi_z) :118, curl2D(bi_x, bi_x) :91, the row-count loop bound of the masks :285/:297).
+ * One rank only: refused on a slab.  spruce_module_anomalous_resistivity_state returns the tracked null point and the last sub-cycle count.
+ * Written after the round-1 GPU budget was spent: the passes are proven on the host (tests/test_anomres_host_check.py), the launches have not run on a GPU. */
+#define SPRUCE_AR_N_PARAMS 17
+int spruce_module_anomalous_resistivity(spruce_domain *dom, const double *pos_x, const double *pos_y, size_t count, const double *params, int n_params);
+int spruce_module_anomalous_resistivity_state(spruce_domain *dom, int *null_i, int *null_j, int *num_subcycles);
 /* IdealMHD::parseEquationSetConfigs (source/equationsets/idealmhd.cpp:12-40): global_viscosity (idealmhd.hpp:48, default 0), read only
  * by the characteristic open boundary (global_visc_coeff, idealmhd.cpp:90).  open_moc sides themselves (idealmhd.cpp:306-615) are
  * selected through spruce_config.x_bound_* / y_bound_* = SPRUCE_BC_OPEN_MOC; until that path has been validated on a GPU

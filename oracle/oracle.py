@@ -56,6 +56,8 @@ def lib():
         L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.oracle_set_anomalous_resistivity.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_anomalous_subcycles.restype = C.c_int
+        L.oracle_anomalous_core.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_int]
+        L.oracle_anomalous_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_anomalous_subcycles.argtypes = [C.c_void_p]
         L.oracle_add_small_module.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.oracle_small_module_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -92,6 +94,17 @@ def lib():
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def anomalous_params(*, time_scale=1.0, frobenius_metric_coeff=1.0e50, smoothing_sigma=3.0, safety_factor=1.0, metric_smoothing=True,
+                     time_integrator="euler", template_mode="flood_fill", flood_fill_max_radius=-1.0, flood_fill_argmin_radius=5.0e9,
+                     flood_fill_min_current=-1.0, flood_fill_current_ramp_length=1.0e-5, flood_fill_threshold=1.0, resistivity_model="time_scale",
+                     gradient_correction=False, resistivity_model_params=(0.0, 0.0, 0.0)):
+    """the 17 numbers oracle_set_anomalous_resistivity takes, with the reference's defaults (anomalousresistivity.hpp:16-39)"""
+    mp = list(resistivity_model_params) + [0.0, 0.0, 0.0]
+    return np.array([time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, float(metric_smoothing), TI[time_integrator or "euler"],
+                     float(template_mode == "flood_fill"), flood_fill_max_radius, flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length,
+                     flood_fill_threshold, {"time_scale": 0.0, "syntelis_19": 1.0, "ys_94": 2.0}[resistivity_model], float(gradient_correction), mp[0], mp[1], mp[2]])
 
 
 class Oracle:
@@ -186,11 +199,20 @@ class Oracle:
                                   flood_fill_min_current=-1.0, flood_fill_current_ramp_length=1.0e-5, flood_fill_threshold=1.0, resistivity_model="time_scale",
                                   gradient_correction=False, resistivity_model_params=(0.0, 0.0, 0.0)):
         """AnomalousResistivity with the reference's defaults (anomalousresistivity.hpp:16-39); call after setup."""
-        mp = list(resistivity_model_params) + [0.0, 0.0, 0.0]
-        p = np.array([time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, float(metric_smoothing), TI[time_integrator or "euler"],
-                      float(template_mode == "flood_fill"), flood_fill_max_radius, flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length,
-                      flood_fill_threshold, {"time_scale": 0.0, "syntelis_19": 1.0, "ys_94": 2.0}[resistivity_model], float(gradient_correction), mp[0], mp[1], mp[2]])
+        p = anomalous_params(**{k: v for k, v in locals().items() if k != "self"})
         lib().oracle_set_anomalous_resistivity(self.h, _dp(p))
+
+    def anomalous_core(self, dt: float, raw_commit: bool = False):
+        """test accessor: one iterateModule(dt) of anomalous_resistivity without write-back / propagateChanges -> (bi_x, bi_y, bi_z, thermal_energy)"""
+        out = np.zeros((4, self.nx, self.ny))
+        lib().oracle_anomalous_core(self.h, C.c_double(dt), _dp(out), C.c_int(int(raw_commit)))
+        return out
+
+    def anomalous_state(self):
+        ij = (C.c_int * 2)()
+        t = np.zeros((self.nx, self.ny))
+        lib().oracle_anomalous_state(self.h, ij, _dp(t))
+        return (ij[0], ij[1]), t
 
     def anomalous_subcycles(self) -> int:
         return lib().oracle_anomalous_subcycles(self.h)

@@ -996,6 +996,26 @@ void oracle_set_anomalous_resistivity(oracle *o, const double *p)
     ar_setup(o, A);
     o->mod.order[o->mod.n_modules++] = 13;
 }
+/* test accessors: one iterateModule(dt) of anomalous_resistivity on the current planes WITHOUT the write-back + propagateChanges; out = bi_x, bi_y, bi_z,
+ * thermal_energy (4 planes).  raw_commit: store the result into the planes as it is (no floors, no boundary pass), so that a second call continues from it. */
+void oracle_anomalous_core(oracle *o, double dt, double *out, int raw_commit)
+{
+    anom_res *A = (anom_res *)o->mod.anom;
+    ar_capture = out;
+    ar_iterate(o, A, dt);
+    ar_capture = NULL;
+    if (raw_commit) {
+        const size_t n = o->n;
+        memcpy(o->g[V_bi_x], out, sizeof(double) * n); memcpy(o->g[V_bi_y], out + n, sizeof(double) * n); memcpy(o->g[V_bi_z], out + 2 * n, sizeof(double) * n);
+        memcpy(o->g[V_thermal_energy], out + 3 * n, sizeof(double) * n);
+    }
+}
+void oracle_anomalous_state(const oracle *o, int *null_ij, double *tmpl)
+{
+    const anom_res *A = (const anom_res *)o->mod.anom;
+    null_ij[0] = A->null_i; null_ij[1] = A->null_j;
+    if (tmpl) memcpy(tmpl, A->tmpl, sizeof(double) * o->n);
+}
 int oracle_anomalous_subcycles(const oracle *o) { return o->mod.anom ? ((anom_res *)o->mod.anom)->nsub : 0; }
 void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
 /* test accessor: applyMomThresholdingMoC + applyBThresholdingMoC on the current planes, nothing else */

@@ -64,6 +64,8 @@ SYMBOLS = {
     "spruce_module_boundary_outflow": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                                  C.c_double, C.c_double]),
     "spruce_module_boundary_outflow_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "spruce_module_anomalous_resistivity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]),
+    "spruce_module_anomalous_resistivity_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "spruce_module_output_to_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "spruce_module_output": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
     "spruce_eqs_ideal_mhd_options": (C.c_int, [C.c_void_p, C.c_double]),

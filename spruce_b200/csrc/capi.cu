@@ -10,6 +10,7 @@
 #include "mhd2e_cells.cuh"
 #include "ideal2f_sides.cuh"
 #include "mhd2e_step.hpp"
+#include "anomres_cells.hpp"
 #include "ideal2f_kernels.cuh"
 
 #include <algorithm>
@@ -79,11 +80,14 @@ struct spruce_domain {
     struct { double coeff = 0.0, epsilon = 1.0; int heating_on = 1, force_on = 1, gc = 0, integrator = 0, inactive = 0, nsub = 1;
              double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; bool cg_halo_done = false; } pv;
     std::vector<int> module_order;                 // MOD_* ; MOD_SRC0 + k = sources[k]
-    enum { MOD_SRC0 = 100, MOD_DC = 6, MOD_FH = 7, MOD_BO = 8 };
+    enum { MOD_SRC0 = 100, MOD_DC = 6, MOD_FH = 7, MOD_BO = 8, MOD_AR = 9 };
     struct { double max_accel = 0.0, dynamic_time = 1.0, target = 0.0, mean = 0.0, accel = 0.0; int boundary = 3, field_aligned = 0, dynamic = 0;
              int win[4] = {0, 0, 0, 0}; double *tmpl = nullptr; } bo;                // boundary_outflow
     struct { double epsilon = 0.1, time_scale = 1.0; int nsub = 0; } dc;                            // div_cleaning (divcleaning.hpp:22-23)
     struct { double coeff = 0.0, current_pow = 0.0, b_pow = 0.0, n_pow = 0.0, roc_pow = 0.0; int inactive = 0; double *H = nullptr; } fh;   // field_heating
+    // anomalous_resistivity (anomres_cells.hpp / anomres_host.cuh)
+    struct { ar::State s{}; bool on = false, ready = false, output = false; double *planes[ar::P_COUNT] = {nullptr}; double *px = nullptr, *py = nullptr, *dtp = nullptr, *kernel = nullptr, *avg = nullptr, *prod = nullptr;
+             std::vector<double> hpx, hpy; } ar;
     // pointwise solar source terms (module_kernels.cuh: k_source_term), in config order
     struct SourceTerm { int kind = 0; double start = 0.0, duration = 0.0, ramp_time = 0.0, max_accel = 0.0, period = 1.0; int oscillatory = 0; double *plane[2] = {nullptr, nullptr}; };
     std::vector<SourceTerm> sources;
@@ -1074,6 +1078,8 @@ int finish_dt(spruce_domain *d)
     return SPRUCE_OK;
 }
 
+#include "anomres_host.cuh"
+
 // one advanceTime (evolution.cpp:59-82) worth of launches
 int enqueue_step(spruce_domain *d, int hist_slot)
 {
@@ -1089,6 +1095,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         if (h.done) return SPRUCE_OK;
         const double step = h.step;
         step_time = h.time; step_size = h.step;
+        if (d->ar.on && !d->ar.ready && (rc = ar_setup_run(d))) return rc;   // setupModule works on the state before the first step
         for (int m : d->module_order) {                                  // preIterateModules, evolution.cpp:65
             if (m == spruce_domain::MOD_TC && (rc = tc_count(d, step, &d->tc_nsub))) return rc;
             if (m == spruce_domain::MOD_RL && (rc = rl_count(d, step, &d->rl_nsub))) return rc;
@@ -1100,6 +1107,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
             if (m == spruce_domain::MOD_AV && (rc = av_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_PV && (rc = pv_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_FH && (rc = fh_iterate(d, step))) return rc;
+            if (m == spruce_domain::MOD_AR && (rc = ar_iterate(d, step))) return rc;
         }
     }
     if (!d->visc.empty() && (rc = visc_refresh_dt(d))) return rc;     // Viscosity reads the PRIMARY state's dt plane
@@ -1630,6 +1638,51 @@ int spruce_module_field_heating(spruce_domain *d, double coeff, double current_p
     d->module_order.push_back(spruce_domain::MOD_FH);
     return SPRUCE_OK;
 }
+int spruce_module_anomalous_resistivity(spruce_domain *d, const double *pos_x, const double *pos_y, size_t count, const double *p, int n_params)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "anomalous_resistivity");
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "anomalous_resistivity runs on a whole domain only (its flood fill and null-point search are global)");
+    const size_t np = (size_t)d->cfg.xdim * d->cfg.ydim;
+    if (!pos_x || !pos_y || count != np) return fail(SPRUCE_ERR_ARG, "pos_x / pos_y need the %zu values of the whole domain", np);
+    if (!p || n_params != SPRUCE_AR_N_PARAMS) return fail(SPRUCE_ERR_ARG, "anomalous_resistivity takes %d parameters", SPRUCE_AR_N_PARAMS);
+    if (d->ar.on) return fail(SPRUCE_ERR_ARG, "anomalous_resistivity is already configured");
+    auto &A = d->ar;
+    ar::Params &q = A.s.p;
+    q.time_scale = p[0]; q.frob_coeff = p[1]; q.sigma = p[2]; q.safety = p[3]; q.smoothing = p[4] != 0.0; q.integrator = (int)p[5]; q.flood_fill = p[6] != 0.0;
+    q.max_radius = p[7]; q.argmin_radius = p[8]; q.min_current = p[9]; q.ramp_length = p[10]; q.threshold = p[11]; q.model = (int)p[12]; q.gradient_correction = p[13] != 0.0;
+    q.model_params[0] = p[14]; q.model_params[1] = p[15]; q.model_params[2] = p[16];
+    if (q.integrator < 0 || q.integrator > 2) return fail(SPRUCE_ERR_ARG, "Invalid time integrator for anomalous resistivity module");
+    if (q.model < 0 || q.model > 2) return fail(SPRUCE_ERR_ARG, "anomalous_resistivity: resistivity_model must be time_scale, syntelis_19 or ys_94");
+    if (q.smoothing && !(q.sigma > 0.0)) return fail(SPRUCE_ERR_ARG, "anomalous_resistivity: smoothing_sigma must be positive");
+    A.s.time_scale = q.time_scale;
+    int rc;
+    for (int k = 0; k < ar::P_COUNT; k++) if ((rc = alloc_plane(d, &A.planes[k]))) return rc;
+    if ((rc = alloc_plane(d, &A.px)) || (rc = alloc_plane(d, &A.py)) || (rc = alloc_plane(d, &A.dtp))) return rc;
+    if ((rc = h2d_plane(d, A.px, pos_x)) || (rc = h2d_plane(d, A.py, pos_y))) return rc;
+    A.hpx.assign(pos_x, pos_x + np); A.hpy.assign(pos_y, pos_y + np);
+    if (q.smoothing) {
+        A.s.kr = ar::smoothing_radius(q.sigma);
+        std::vector<double> w((size_t)(2 * A.s.kr + 1) * (2 * A.s.kr + 1));
+        ar::smoothing_kernel(q.sigma, A.s.kr, w.data());
+        CUDA_TRY(cudaMalloc(&A.kernel, w.size() * sizeof(double)));
+        d->allocs.push_back(A.kernel);
+        CUDA_TRY(cudaMemcpy(A.kernel, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+        A.s.kernel = A.kernel;
+    }
+    A.on = true; A.ready = false;
+    d->module_order.push_back(spruce_domain::MOD_AR);
+    return SPRUCE_OK;
+}
+int spruce_module_anomalous_resistivity_state(spruce_domain *d, int *null_i, int *null_j, int *num_subcycles)
+{
+    CHECK_DOM(d);
+    if (!d->ar.on) return fail(SPRUCE_ERR_ARG, "anomalous_resistivity is not configured");
+    if (null_i) *null_i = d->ar.s.null_i;
+    if (null_j) *null_j = d->ar.s.null_j;
+    if (num_subcycles) *num_subcycles = d->ar.s.nsub;
+    return SPRUCE_OK;
+}
 int spruce_module_boundary_outflow(spruce_domain *d, const double *pos_x, const double *pos_y, size_t count, double max_accel, double falloff_length, int boundary,
                                    int falloff_shape, double feather_length, int field_aligned_mode, int dynamic_mode, double dynamic_time, double dynamic_target_speed)
 {
@@ -1768,6 +1821,9 @@ int spruce_module_output_to_file(spruce_domain *d, const char *module, int on)
     } else if (!strcmp(module, "radiative_losses")) {
         d->rl_output = on != 0;
         if (on && !d->rl_avg && (rc = alloc_plane(d, &d->rl_avg))) return rc;
+    } else if (!strcmp(module, "anomalous_resistivity")) {                                          // anomalousresistivity.cpp:320-329
+        d->ar.output = on != 0;
+        if (on && !d->ar.avg && ((rc = alloc_plane(d, &d->ar.avg)) || (rc = alloc_plane(d, &d->ar.prod)))) return rc;
     } else return fail(SPRUCE_ERR_ARG, "no diagnostic planes for module <%s>", module);
     return SPRUCE_OK;
 }
@@ -1777,6 +1833,17 @@ int spruce_module_output(spruce_domain *d, const char *name, double *host, size_
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane size mismatch");
     const double *src = !strcmp(name, "thermal_conduction") ? d->tc_avg : !strcmp(name, "flux_saturation") ? d->tc_sat : !strcmp(name, "rad") ? d->rl_avg : nullptr;
+    if (d->ar.on && d->ar.output) {
+        if (!strcmp(name, "anomalous_template")) src = d->ar.planes[ar::P_TMPL];
+        else if (!strcmp(name, "joule_heating")) src = d->ar.avg;
+        else if (!strcmp(name, "anomalous_diffusivity")) {                                            // anomalous_template*diffusivity as they stand after the last evaluation
+            const dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+            k_plane_product<<<grid, 256, 0, d->stream>>>(d->P, d->ar.prod, d->ar.planes[ar::P_TMPL], d->ar.planes[ar::P_DIFF]);
+            d->launches++;
+            CUDA_TRY(cudaGetLastError());
+            src = d->ar.prod;
+        }
+    }
     if (!src) return fail(SPRUCE_ERR_STATE, "diagnostic plane <%s> is not enabled (spruce_module_output_to_file)", name);
     return d2h_plane(d, host, src);
 }
@@ -1788,6 +1855,7 @@ int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
     else if (!strcmp(which, "radiative_losses")) *count = d->rl_nsub;
     else if (!strcmp(which, "physical_viscosity")) *count = d->pv.nsub;
     else if (!strcmp(which, "div_cleaning")) *count = d->dc.nsub;
+    else if (!strcmp(which, "anomalous_resistivity")) *count = d->ar.s.nsub;
     else return fail(SPRUCE_ERR_ARG, "no sub-cycling module named <%s>", which);
     return SPRUCE_OK;
 }

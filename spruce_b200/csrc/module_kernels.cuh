@@ -362,6 +362,14 @@ __global__ void __launch_bounds__(256) k_plane_copy(const DomainParams P, double
     const size_t off = (size_t)r * P.pitch + j;
     dst[off] = src[off];
 }
+__global__ void __launch_bounds__(256) k_plane_product(const DomainParams P, double *out, const double *a, const double *b)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    out[off] = a[off] * b[off];
+}
 __global__ void __launch_bounds__(256) k_avg_change(const DomainParams P, double *out, const double *e, const double *old, double dt)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;

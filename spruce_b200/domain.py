@@ -195,6 +195,24 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_module_boundary_outflow_state(self.h, C.byref(m), C.byref(a)))
         return m.value, a.value
 
+    def set_anomalous_resistivity(self, pos_x: np.ndarray, pos_y: np.ndarray, *, time_scale=1.0, frobenius_metric_coeff=1.0e50, smoothing_sigma=3.0, safety_factor=1.0,
+                                  metric_smoothing=True, time_integrator="euler", template_mode="flood_fill", flood_fill_max_radius=-1.0, flood_fill_argmin_radius=5.0e9,
+                                  flood_fill_min_current=-1.0, flood_fill_current_ramp_length=1.0e-5, flood_fill_threshold=1.0, resistivity_model="time_scale",
+                                  gradient_correction=False, resistivity_model_params=(0.0, 0.0, 0.0)):
+        """AnomalousResistivity with the reference's config keys and defaults (anomalousresistivity.hpp:16-39)."""
+        x = np.ascontiguousarray(pos_x, dtype=np.float64); y = np.ascontiguousarray(pos_y, dtype=np.float64)
+        mp = list(resistivity_model_params) + [0.0, 0.0, 0.0]
+        p = np.array([time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, float(metric_smoothing), {"euler": 0, "rk2": 1, "rk4": 2}[time_integrator or "euler"],
+                      float(template_mode == "flood_fill"), flood_fill_max_radius, flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length,
+                      flood_fill_threshold, {"time_scale": 0.0, "syntelis_19": 1.0, "ys_94": 2.0}[resistivity_model], float(gradient_correction), mp[0], mp[1], mp[2]], dtype=np.float64)
+        capi.check(self.lib.spruce_module_anomalous_resistivity(self.h, _dp(x), _dp(y), x.size, _dp(p), p.size))
+
+    def anomalous_resistivity_state(self):
+        """(null_i, null_j), sub-cycles of the last step"""
+        i, j, n = C.c_int(), C.c_int(), C.c_int()
+        capi.check(self.lib.spruce_module_anomalous_resistivity_state(self.h, C.byref(i), C.byref(j), C.byref(n)))
+        return (i.value, j.value), n.value
+
     def set_module_output_to_file(self, module: str, on: bool = True):
         """output_to_file = true of thermal_conduction / radiative_losses: keep the module's diagnostic planes (Module::fileOutput)."""
         capi.check(self.lib.spruce_module_output_to_file(self.h, module.encode(), int(on)))

@@ -53,8 +53,9 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "div_cleaning") m_modules.emplace_back(new DivCleaning(m_pd));
     else if (name == "field_heating") m_modules.emplace_back(new FieldHeating(m_pd));
     else if (name == "boundary_outflow") m_modules.emplace_back(new BoundaryOutflow(m_pd));
+    else if (name == "anomalous_resistivity") m_modules.emplace_back(new AnomalousResistivity(m_pd));
     else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
-                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating, boundary_outflow are).");
+                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating, boundary_outflow, anomalous_resistivity are).");
     m_modules.back()->configureModule(in);
 }
 
@@ -348,6 +349,65 @@ std::string BoundaryOutflow::commandLineMessage() const
     double mean = 0.0, accel = 0.0;
     PlasmaDomain::check(spruce_module_boundary_outflow_state(m_pd.device(), &mean, &accel));
     return boundary + " boundary outflow enforced (max " + std::to_string(mean) + " cm/s outflow) (accel. " + std::to_string(accel) + " cm/s^2)";
+}
+
+// anomalousresistivity.cpp:46-68
+void AnomalousResistivity::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        const std::string &k = lhs[i], &v = rhs[i];
+        if (k == "time_scale") time_scale = std::stod(v);
+        else if (k == "output_to_file") output_to_file = (v == "true");
+        else if (k == "frobenius_metric_coeff") frobenius_metric_coeff = std::stod(v);
+        else if (k == "smoothing_sigma") smoothing_sigma = std::stod(v);
+        else if (k == "safety_factor") safety_factor = std::stod(v);
+        else if (k == "metric_smoothing") metric_smoothing = (v == "true");
+        else if (k == "time_integrator") time_integrator = v;
+        else if (k == "template_mode") template_mode = v;
+        else if (k == "flood_fill_max_radius") flood_fill_max_radius = std::stod(v);
+        else if (k == "flood_fill_argmin_radius") flood_fill_argmin_radius = std::stod(v);
+        else if (k == "flood_fill_min_current") flood_fill_min_current = std::stod(v);
+        else if (k == "flood_fill_current_ramp_length") flood_fill_current_ramp_length = std::stod(v);
+        else if (k == "resistivity_model") resistivity_model = v;
+        else if (k == "gradient_correction") gradient_correction = (v == "true");
+        else if (k == "resistivity_model_params") { resistivity_model_params.clear(); for (const std::string &el : splitString(v, ',')) resistivity_model_params.push_back(std::stod(el)); }
+        else if (k == "flood_fill_threshold") flood_fill_threshold = std::stod(v);
+        else std::cerr << k << " config not recognized.\n";
+    }
+}
+// anomalousresistivity.cpp:18-44: the null point search, the smoothing kernel and the first template are the device library's
+void AnomalousResistivity::setupModule()
+{
+    SPRUCE_REQUIRE(resistivity_model != "time_scale" || time_scale > 0.0, "Anomalous Resistivity time_scale must be specified, and positive, if run in time_scale mode");
+    SPRUCE_REQUIRE(!metric_smoothing || smoothing_sigma > 0.0, "smoothing_sigma must be a positive number");
+    SPRUCE_REQUIRE(time_integrator.empty() || time_integrator == "euler" || time_integrator == "rk2" || time_integrator == "rk4", "Invalid time integrator for anomalous resistivity module");
+    SPRUCE_REQUIRE(template_mode == "flood_fill" || template_mode == "frobenius", "Invalid template_mode for anomalous resistivity module");
+    const int model = resistivity_model == "time_scale" ? 0 : resistivity_model == "syntelis_19" ? 1 : resistivity_model == "ys_94" ? 2 : -1;
+    SPRUCE_REQUIRE(model >= 0, "Invalid resistivity_model for anomalous resistivity module");
+    SPRUCE_REQUIRE(model == 0 || resistivity_model_params.size() == 3, "resistivity_model_params must hold three values for this resistivity_model");
+    double p[SPRUCE_AR_N_PARAMS] = {time_scale, frobenius_metric_coeff, smoothing_sigma, safety_factor, metric_smoothing ? 1.0 : 0.0,
+                                    time_integrator == "rk2" ? 1.0 : time_integrator == "rk4" ? 2.0 : 0.0, template_mode == "flood_fill" ? 1.0 : 0.0, flood_fill_max_radius,
+                                    flood_fill_argmin_radius, flood_fill_min_current, flood_fill_current_ramp_length, flood_fill_threshold, (double)model,
+                                    gradient_correction ? 1.0 : 0.0, 0.0, 0.0, 0.0};
+    for (size_t k = 0; k < resistivity_model_params.size() && k < 3; k++) p[14 + k] = resistivity_model_params[k];
+    const Grid &x = m_pd.m_grids[PlasmaDomain::pos_x], &y = m_pd.m_grids[PlasmaDomain::pos_y];
+    PlasmaDomain::check(spruce_module_anomalous_resistivity(m_pd.device(), x.ptr(), y.ptr(), x.size(), p, SPRUCE_AR_N_PARAMS));
+    if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "anomalous_resistivity", 1));
+}
+// anomalousresistivity.cpp:315-318
+std::string AnomalousResistivity::commandLineMessage() const
+{
+    int n = 0;
+    spruce_module_subcycles(m_pd.device(), "anomalous_resistivity", &n);
+    return "Anomalous Resistivity Subcycles: " + std::to_string(n);
+}
+// anomalousresistivity.cpp:320-329
+void AnomalousResistivity::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
+{
+    if (!output_to_file) return;
+    append_device_plane(m_pd, "anomalous_diffusivity", names, grids);
+    append_device_plane(m_pd, "anomalous_template", names, grids);
+    append_device_plane(m_pd, "joule_heating", names, grids);
 }
 
 // viscosity.cpp:6-24

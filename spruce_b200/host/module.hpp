@@ -169,6 +169,23 @@ private:
     bool field_aligned_mode = false, dynamic_mode = false;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
+// source/modules/solar/anomalousresistivity.hpp ("anomalous_resistivity")
+class AnomalousResistivity : public Module {
+public:
+    explicit AnomalousResistivity(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;
+    std::string commandLineMessage() const override;
+    void fileOutput(std::vector<std::string> &var_names, std::vector<Grid> &var_grids) override;
+    bool device_resident() const override { return true; }
+private:
+    // defaults: anomalousresistivity.hpp:16-39
+    double time_scale = 1.0, frobenius_metric_coeff = 1.0e50, smoothing_sigma = 3.0, safety_factor = 1.0, flood_fill_max_radius = -1.0, flood_fill_argmin_radius = 5.0e9,
+           flood_fill_min_current = -1.0, flood_fill_current_ramp_length = 1.0e-5, flood_fill_threshold = 1.0;
+    bool metric_smoothing = true, gradient_correction = false, output_to_file = false;
+    std::string time_integrator = "", template_mode = "flood_fill", resistivity_model = "time_scale";
+    std::vector<double> resistivity_model_params;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
 // source/modules/ucnp/eic_thermalization.hpp -- electron-ion collisional energy exchange (two-fluid equation set only)
 class EICThermalization : public Module {
 public:

@@ -239,17 +239,8 @@ AR_CASES = [
 ]
 
 
-@pytest.mark.parametrize("name,kv,xb,yb,integrator", AR_CASES, ids=[m[0] for m in AR_CASES])
-def test_anomalous_resistivity_oracle_equals_live_reference(name, kv, xb, yb, integrator):
-    """anomalous_resistivity (oracle/anomalous_resistivity_oracle.inc; not on the device yet): null-point tracking, flood-fill /
-    Frobenius templates with Gaussian smoothing, three resistivity models, euler / rk2 / rk4 sub-cycles, Joule heating -- bit for bit."""
-    nx, ny = 23, 23
-    s = synthetic.stratified_loop(nx, ny, bump=0.5)
-    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
-    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
-    nsteps = 3
-    frames = run_reference(s, dict(kw, modules=[("anomalous_resistivity", list(kv.items()))]), MHD_OUT, nsteps)
-    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+def ar_kwargs(kv):
+    """config strings of an anomalous_resistivity block -> keyword arguments (oracle and product wrappers share the names)"""
     a = {}
     for k, v in kv.items():
         if k == "resistivity_model_params":
@@ -260,7 +251,21 @@ def test_anomalous_resistivity_oracle_equals_live_reference(name, kv, xb, yb, in
             a[k] = v
         else:
             a[k] = float(v)
-    o.set_anomalous_resistivity(**a)
+    return a
+
+
+@pytest.mark.parametrize("name,kv,xb,yb,integrator", AR_CASES, ids=[m[0] for m in AR_CASES])
+def test_anomalous_resistivity_oracle_equals_live_reference(name, kv, xb, yb, integrator):
+    """anomalous_resistivity (oracle/anomalous_resistivity_oracle.inc): null-point tracking, flood-fill /
+    Frobenius templates with Gaussian smoothing, three resistivity models, euler / rk2 / rk4 sub-cycles, Joule heating -- bit for bit."""
+    nx, ny = 23, 23
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 3
+    frames = run_reference(s, dict(kw, modules=[("anomalous_resistivity", list(kv.items()))]), MHD_OUT, nsteps)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    o.set_anomalous_resistivity(**ar_kwargs(kv))
     xl, xu, yl, yu = interior(xb, yb, nx, ny)
     for it in range(1, nsteps + 1):
         step = o.step()

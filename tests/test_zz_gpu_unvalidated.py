@@ -588,3 +588,82 @@ def test_module_diagnostic_planes_vs_reference_fixtures(name):
     "rad"), from the device against the committed fixtures of the unmodified reference binary."""
     out = run_isolated(MODULE_PLANES_CODE.format(name=name), {})
     assert "ok" in out
+
+
+ANOMRES_CODE = """
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    from test_oracle_vs_live_reference import AR_CASES, ar_kwargs
+    from test_anomres_host_check import EXTRA
+    name, kv, xb, yb, integ = [c for c in AR_CASES + EXTRA if c[0] == {name!r}][0]
+    exact = "frobenius" not in name                    # the Frobenius template ends in pow(., 1.5): the libm tolerance class
+    s = synthetic.stratified_loop(23, 23, bump=0.5)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    a = ar_kwargs(kv)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    o.set_anomalous_resistivity(**a)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d.set_anomalous_resistivity(s["planes"]["pos_x"], s["planes"]["pos_y"], **a)
+    d.set_module_output_to_file("anomalous_resistivity")
+    ref = o.run(4)
+    dts = d.advance(4)
+    (ri, rj), rt = o.anomalous_state()
+    (di, dj), nsub = d.anomalous_resistivity_state()
+    assert (di, dj) == (ri, rj), ((di, dj), (ri, rj))
+    assert nsub == o.anomalous_subcycles(), (nsub, o.anomalous_subcycles())
+    tm = d.module_output("anomalous_template")
+    if exact:
+        assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+        assert same_bits(tm, rt), "template: " + mismatch(tm, rt)
+        for v in PlasmaDomain.EVOLVED + ["dt", "temp"]:
+            assert same_bits(d.grid(v), o.get(v)), "%s: %s" % (v, mismatch(d.grid(v), o.get(v)))
+    else:
+        assert np.allclose(dts, ref, rtol=1e-9, atol=0.0), (dts, ref)
+        assert np.max(np.abs(tm - rt)) <= 1e-9 * max(np.max(np.abs(rt)), 1e-300)
+        for v in PlasmaDomain.EVOLVED + ["dt", "temp"]:
+            r = o.get(v); g = d.grid(v)
+            assert np.max(np.abs(g - r)) <= 1e-9 * max(np.max(np.abs(r)), 1e-300), v
+    assert np.count_nonzero(d.module_output("joule_heating")) > 0
+    assert d.module_output("anomalous_diffusivity").shape == tm.shape
+    print("ok")
+"""
+
+
+@UNVALIDATED
+@pytest.mark.parametrize("name", ["ar_default_floodfill", "ar_frobenius_rk2_gc", "ar_syntelis_rk4", "ar_ys94_radius", "ar_periodic_x_euler", "ar_moc_bounds_rk4", "ar_frobenius_plain"])
+def test_anomalous_resistivity_vs_oracle(name):
+    """anomalous_resistivity on the device (anomres_cells.hpp functors as kernels, anomres_host.cuh): whole steps with the module against the CPU
+    restatement -- step sizes, every plane, the tracked null point, the template and the sub-cycle count.  The same functors in the same sequence are
+    proven bit for bit on the host by tests/test_anomres_host_check.py; this is the launch side."""
+    env = {"SPRUCE_EXPERIMENTAL_MOC": "1"} if "moc" in name else {}
+    out = run_isolated(ANOMRES_CODE.format(name=name), env)
+    assert "ok" in out
+
+
+ANOMRES_GOLDEN_CODE = """
+    import numpy as np
+    from golden_util import Golden, same_bits, mismatch, OUT_VARS
+    from spruce_b200.domain import PlasmaDomain
+    g = Golden("ar_floodfill_rk2")
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
+    for mname, kv in g.modules:
+        d.set_anomalous_resistivity(g.planes["pos_x"], g.planes["pos_y"], **{k: float(v) for k, v in kv.items()})
+    done = 0
+    hist = []
+    for it in sorted(g.frames):
+        hist += list(d.advance(it - done)); done = it
+        for v in OUT_VARS:
+            assert same_bits(d.grid(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(d.grid(v), g.frames[it][v]))
+    assert [float(x).hex() for x in hist] == [float(x).hex() for x in g.steps[:done]]
+    print("ok")
+"""
+
+
+@UNVALIDATED
+def test_anomalous_resistivity_vs_reference_fixture():
+    """the committed fixture of the unmodified reference binary with anomalous_resistivity (tests/golden/ar_floodfill_rk2.npz), bit for bit"""
+    out = run_isolated(ANOMRES_GOLDEN_CODE, {})
+    assert "ok" in out
