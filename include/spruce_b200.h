@@ -145,6 +145,8 @@ int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const dou
 /* output_to_file = true of ThermalConduction / RadiativeLosses (thermalconduction.cpp:226-237, radiativelosses.cpp:172-179): the planes Module::fileOutput
  * appends to mhd.out -- "thermal_conduction" and "rad" = the module's (e_after - e_before)/dt of the last step, "flux_saturation" = the saturation coefficient
  * of that step's first temperature field (zero planes before the first step, as in the reference).  Enable per module, then download by plane name.
+ * Also: module "anomalous_resistivity" -> planes "anomalous_diffusivity", "anomalous_template", "joule_heating" (anomalousresistivity.cpp:320-329), and the
+ * plane "field_heating" (fieldheating.cpp:73-80: mask*(dt*heating) of the last step), which needs no enabling.
  * Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
 int spruce_module_output_to_file(spruce_domain *dom, const char *module, int on);
 int spruce_module_output(spruce_domain *dom, const char *plane_name, double *host, size_t count);

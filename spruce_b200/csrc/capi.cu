@@ -1833,6 +1833,7 @@ int spruce_module_output(spruce_domain *d, const char *name, double *host, size_
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane size mismatch");
     const double *src = !strcmp(name, "thermal_conduction") ? d->tc_avg : !strcmp(name, "flux_saturation") ? d->tc_sat : !strcmp(name, "rad") ? d->rl_avg : nullptr;
+    if (!strcmp(name, "field_heating") && d->fh.H) src = d->fh.H;                                  // fieldheating.cpp:73-80: mask*(dt*heating) of the last step, zero before the first
     if (d->ar.on && d->ar.output) {
         if (!strcmp(name, "anomalous_template")) src = d->ar.planes[ar::P_TMPL];
         else if (!strcmp(name, "joule_heating")) src = d->ar.avg;

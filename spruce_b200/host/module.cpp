@@ -303,8 +303,12 @@ void FieldHeating::parseModuleConfigs(std::vector<std::string> lhs, std::vector<
 }
 void FieldHeating::setupModule()
 {
-    no_file_output(output_to_file, "field_heating");
     PlasmaDomain::check(spruce_module_field_heating(m_pd.device(), coeff, current_pow, b_pow, n_pow, roc_pow, inactive_mode ? 1 : 0));
+}
+// fieldheating.cpp:73-80
+void FieldHeating::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
+{
+    if (output_to_file) append_device_plane(m_pd, "field_heating", names, grids);
 }
 // fieldheating.cpp:64-71
 std::string FieldHeating::commandLineMessage() const

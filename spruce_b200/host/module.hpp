@@ -150,6 +150,7 @@ public:
     explicit FieldHeating(PlasmaDomain &pd) : Module(pd) {}
     void setupModule() override;
     std::string commandLineMessage() const override;
+    void fileOutput(std::vector<std::string> &var_names, std::vector<Grid> &var_grids) override;
     bool device_resident() const override { return true; }
 private:
     double coeff = 0.0, current_pow = 0.0, b_pow = 0.0, n_pow = 0.0, roc_pow = 0.0;
