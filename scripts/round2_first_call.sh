@@ -22,3 +22,7 @@ except Exception as e:
     print(n, "FAILED", e)
 PY
 done
+# host text I/O on the box's host cores: thread scaling of the row-parallel formatter / parser
+g++ -O2 -fopenmp -std=c++17 -I spruce_b200/host scripts/text_io_bench.cpp -o /tmp/text_io_bench 2> gpurun_out/r2_text_io.err && for t in 1 8 32; do
+    OMP_NUM_THREADS=$t /tmp/text_io_bench 4096 4 | sed "s/^/threads $t: /" | tee -a gpurun_out/r2_text_io.jsonl
+done
