@@ -1672,6 +1672,9 @@ int spruce_module_anomalous_resistivity(spruce_domain *d, const double *pos_x, c
     }
     A.on = true; A.ready = false;
     d->module_order.push_back(spruce_domain::MOD_AR);
+    // setupModule (:18-44) works on the set-up state: the template of iteration 0's output frame is this one.  A caller that configures modules
+    // before spruce_eqs_setup gets it at the start of the first step instead.
+    if (d->is_setup && (rc = ar_setup_run(d))) return rc;
     return SPRUCE_OK;
 }
 int spruce_module_anomalous_resistivity_state(spruce_domain *d, int *null_i, int *null_j, int *num_subcycles)

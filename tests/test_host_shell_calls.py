@@ -1,0 +1,151 @@
+"""The host shell (spruce_b200/bin/run: the C++ PlasmaDomain / EquationSet / ModuleHandler / Module mirror) run WITHOUT a GPU over a recording
+stand-in for the device library (tests/hostcheck/capi_stub.c, preloaded): a .config with every solar module must become the C-ABI calls the
+reference's classes imply -- ModuleHandler order, parameter meaning, the reference's defaults, enum codes, diagnostic planes appended to mhd.out --
+and the run loop must honour max_iterations / iter_output_interval.  The device side of each call is covered by the GPU parity tests."""
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import refrun
+from spruce_b200 import synthetic
+
+ROOT = Path(__file__).resolve().parents[1]
+OURS = ROOT / "spruce_b200" / "bin" / "run"
+STUB_SRC = ROOT / "tests" / "hostcheck" / "capi_stub.c"
+STUB = ROOT / "tests" / "hostcheck" / "_build" / "libcapi_stub.so"
+
+
+@pytest.fixture(scope="module")
+def stub():
+    STUB.parent.mkdir(exist_ok=True)
+    hdr = ROOT / "include" / "spruce_b200.h"
+    if not STUB.exists() or STUB.stat().st_mtime < max(STUB_SRC.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.run(["gcc", "-std=gnu11", "-O1", "-Wall", "-Werror", "-shared", "-fPIC", "-I", str(ROOT / "include"), str(STUB_SRC), "-o", str(STUB)], check=True)
+    subprocess.run(["make", "-C", str(ROOT / "spruce_b200" / "host")], check=True, stdout=subprocess.DEVNULL)
+    return STUB
+
+
+def run_shell(stub, tmp_path, s, cfg):
+    state = tmp_path / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+    out = tmp_path / "out"
+    out.mkdir()
+    (out / "run.config").write_text(cfg)
+    log = tmp_path / "calls.log"
+    env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(log))
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode in (-6, 134), r.stderr.decode()[-2000:]
+    assert "Simulation successfully reached max simulation time or iterations" in r.stderr.decode(), r.stderr.decode()[-2000:]      # not a spruce_die
+    return log.read_text().splitlines(), r.stdout.decode(), out
+
+
+def args_of(line):
+    return dict(re.findall(r"(\w+)=(\S+)", line))
+
+
+def test_every_solar_module_reaches_the_c_abi_in_config_order(stub, tmp_path):
+    nx, ny = 20, 18
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    modules = [
+        ("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4"), ("time_integrator", "rk4"), ("output_to_file", "true")]),
+        ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1"), ("output_to_file", "true")]),
+        ("ambient_heating", [("heating_rate", "1.0e-4")]),
+        ("ambient_heating_sink", [("heating_rate", "2.0e-4")]),
+        ("localized_heating", [("start_time", "1.0"), ("duration", "10.0"), ("max_heating_rate", "0.5"), ("stddev_x", "3.0"), ("stddev_y", "2.0"), ("center_x", "8.0"), ("center_y", "7.0")]),
+        ("mass_injection", [("start_time", "2.0"), ("duration", "5.0"), ("max_injection_rate", "1.0e6"), ("stddev_x", "2.0"), ("stddev_y", "2.5"), ("center_x", "9.0"), ("center_y", "6.0")]),
+        ("momentum_injection", [("start_time", "0.0"), ("duration", "50.0"), ("max_accel", "1.0e4"), ("stddev_x", "2.0"), ("stddev_y", "2.0"), ("center_x", "10.0"), ("center_y", "9.0"),
+                                ("dir_x", "0.0"), ("dir_y", "1.0"), ("oscillatory", "true"), ("oscillation_period", "7.0")]),
+        ("div_cleaning", [("epsilon", "0.05"), ("time_scale", "4.0")]),
+        ("field_heating", [("coeff", "1.0e-7"), ("current_pow", "0.5"), ("b_pow", "1.0"), ("n_pow", "0.2"), ("roc_pow", "0.3"), ("output_to_file", "true")]),
+        ("boundary_outflow", [("max_accel", "3.0e4"), ("falloff_length", "5.0e8"), ("boundary", "x_bound_2"), ("falloff_shape", "gaussian"), ("feather_length", "1.0e8"),
+                              ("dynamic_mode", "true"), ("dynamic_time", "20.0"), ("dynamic_target_speed", "1.0e6")]),
+        ("anomalous_resistivity", [("time_scale", "0.3"), ("output_to_file", "true"), ("resistivity_model", "ys_94"), ("resistivity_model_params", "0.2,2.0e14,3.0e15"),
+                                   ("time_integrator", "rk4"), ("gradient_correction", "true"), ("flood_fill_threshold", "2.5"), ("metric_smoothing", "false")]),
+        ("physical_viscosity", [("coeff", "1.0e-14"), ("epsilon", "0.1"), ("time_integrator", "rk2"), ("gradient_correction", "true")]),
+    ]
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk4", xb=("fixed", "open"), yb=("reflect", "open"), max_iterations=3, iter_output_interval=2, modules=modules)
+    log, stdout, out = run_shell(stub, tmp_path, s, cfg)
+    calls = [ln.split()[0] for ln in log if ln.startswith("spruce_")]
+
+    create = args_of(log[0])
+    assert log[0].startswith("spruce_domain_create") and create["xdim"] == "20" and create["ydim"] == "18" and create["eqs"] == "0"
+    assert create["bc"] == "2,1,3,1" and create["ti"] == "2"                       # fixed, open, reflect, open; rk4
+    assert float(create["epsilon"]) == 0.2 and create["n_ranks"] == "1"
+
+    # state variables are uploaded before the set-up, modules are configured after it, in config order (modulehandler.cpp:27-65)
+    uploads = [ln.split()[1] for ln in log if ln.startswith("spruce_grid_upload")]
+    assert uploads[:3] == ["be_x", "be_y", "be_z"] and set(uploads[3:]) == {"rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"}
+    i_setup = calls.index("spruce_eqs_setup")
+    assert all(c != "spruce_grid_upload" for c in calls[i_setup:])
+    module_calls = [c for c in calls if c.startswith("spruce_module_") and c not in ("spruce_module_output", "spruce_module_output_to_file", "spruce_module_viscosity_term")]
+    assert module_calls == ["spruce_module_thermal_conduction", "spruce_module_radiative_losses", "spruce_module_ambient_heating", "spruce_module_ambient_heating_sink",
+                            "spruce_module_localized_heating", "spruce_module_mass_injection", "spruce_module_momentum_injection", "spruce_module_div_cleaning",
+                            "spruce_module_field_heating", "spruce_module_boundary_outflow", "spruce_module_anomalous_resistivity", "spruce_module_physical_viscosity"]
+    assert calls.index("spruce_module_thermal_conduction") > i_setup
+
+    line = {c: args_of(next(ln for ln in log if ln.startswith(c + " "))) for c in module_calls if c not in ("spruce_module_ambient_heating", "spruce_module_ambient_heating_sink")}
+    tc = line["spruce_module_thermal_conduction"]
+    assert tc["flux_saturation"] == "1" and tc["ti"] == "2" and float(tc["epsilon"]) == 0.1 and float(tc["dt_subcycle_min"]) == 1.0e-4
+    rl = line["spruce_module_radiative_losses"]
+    assert float(rl["cutoff_ramp"]) == 1.0e3 and float(rl["cutoff_temp"]) == 3.0e4 and float(rl["epsilon"]) == 0.1
+    lh = line["spruce_module_localized_heating"]
+    assert float(lh["start"]) == 1.0 and float(lh["duration"]) == 10.0 and float(lh["max"]) == 0.5 and lh["stddev"] == "3,2" and lh["center"] == "8,7"
+    mi = line["spruce_module_mass_injection"]
+    assert float(mi["start"]) == 2.0 and float(mi["max"]) == 1.0e6 and mi["center"] == "9,6"
+    mo = line["spruce_module_momentum_injection"]
+    assert float(mo["max_accel"]) == 1.0e4 and mo["dir"] == "0,1" and mo["oscillatory"] == "1" and float(mo["period"]) == 7.0
+    dc = line["spruce_module_div_cleaning"]
+    assert float(dc["epsilon"]) == 0.05 and float(dc["time_scale"]) == 4.0
+    fh = line["spruce_module_field_heating"]
+    assert [float(fh[k]) for k in ("coeff", "current_pow", "b_pow", "n_pow", "roc_pow")] == [1.0e-7, 0.5, 1.0, 0.2, 0.3] and fh["inactive"] == "0"
+    bo = line["spruce_module_boundary_outflow"]
+    assert float(bo["max_accel"]) == 3.0e4 and bo["boundary"] == "1" and bo["shape"] == "1" and float(bo["feather"]) == 1.0e8 and bo["dynamic"] == "1" and bo["field_aligned"] == "0"
+    assert float(bo["dynamic_time"]) == 20.0 and float(bo["target"]) == 1.0e6
+    pv = line["spruce_module_physical_viscosity"]
+    assert float(pv["coeff"]) == 1.0e-14 and pv["ti"] == "1" and pv["gradient_correction"] == "1" and pv["heating_on"] == "1" and pv["force_on"] == "1"
+
+    # anomalous_resistivity: the 17 numbers in the header's order, the reference's defaults where the config is silent (anomalousresistivity.hpp:16-39)
+    i_ar = next(i for i, ln in enumerate(log) if ln.startswith("spruce_module_anomalous_resistivity "))
+    p = [float(log[i_ar + 1 + k].split("=")[1]) for k in range(17)]
+    assert p == [0.3, 1.0e50, 3.0, 1.0, 0.0, 2.0, 1.0, -1.0, 5.0e9, -1.0, 1.0e-5, 2.5, 2.0, 1.0, 0.2, 2.0e14, 3.0e15]
+    pos = args_of(log[i_ar + 18])
+    assert pos["count"] == str(nx * ny) and float(pos["sum"]) == pytest.approx(float(np.sum(s["planes"]["pos_x"])), rel=1e-12)
+
+    # planes handed over with a module: the sink's reduction carries the ghost-zone mask, the plain heating plane does not have to
+    i_sink = next(i for i, ln in enumerate(log) if ln.startswith("spruce_module_ambient_heating_sink"))
+    assert args_of(log[i_sink + 1])["count"] == str(nx * ny)
+
+    # output_to_file: enabled per module, every frame (iterations 0, 2 and the final one) appends the diagnostic planes in module order
+    enabled = [ln.split()[1] for ln in log if ln.startswith("spruce_module_output_to_file")]
+    assert enabled == ["thermal_conduction", "radiative_losses", "anomalous_resistivity"]
+    outs = [ln.split()[1] for ln in log if ln.startswith("spruce_module_output ")]
+    frame = ["thermal_conduction", "flux_saturation", "rad", "field_heating", "anomalous_diffusivity", "anomalous_template", "joule_heating"]
+    assert outs[:len(frame)] == frame and len(outs) % len(frame) == 0 and len(outs) // len(frame) >= 2
+    _, frames = refrun.read_out(out / "mhd.out")
+    for f in frames:
+        for name in frame:
+            assert name in f and np.all(f[name] == 7.0), name
+
+    # run loop: three iterations, advance() batched up to the next output / message point
+    assert sum(int(args_of(ln)["done"]) for ln in log if ln.startswith("spruce_advance")) == 3
+    for msg in ("Thermal Subcycles: 9", "Radiative Subcycles: 9", "Anomalous Resistivity Subcycles: 9", "Field Heating On", "x_bound_2 boundary outflow enforced"):
+        assert msg in stdout, msg
+    assert (out / "end.state").exists() and (out / "init.state").exists()
+
+
+def test_moc_options_and_unknown_module(stub, tmp_path):
+    s = synthetic.stratified_loop(16, 14)
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("open_moc", "fixed"), yb=("fixed", "open_moc"), max_iterations=2, iter_output_interval=1,
+                                  eqs_block=[("global_viscosity", "0.25"), ("moc_b_limiting", "true"), ("moc_b_lower_lim", "0.2"), ("moc_mom_limiting", "true"), ("moc_mom_upper_lim", "5.0")])
+    log, _, _ = run_shell(stub, tmp_path, s, cfg)
+    assert args_of(log[0])["bc"] == "4,2,2,4" and args_of(log[0])["ti"] == "0"
+    gv = args_of(next(ln for ln in log if ln.startswith("spruce_eqs_ideal_mhd_options")))
+    assert float(gv["global_viscosity"]) == 0.25
+    lim = next(ln for ln in log if ln.startswith("spruce_eqs_ideal_mhd_moc_limiting")).split()
+    assert lim[1:] == ["b=1", "0.20000000000000001", "10", "mom=1", "0.10000000000000001", "5"]              # silent bounds keep idealmhd.hpp:59-64's defaults
+    calls = [ln.split()[0] for ln in log if ln.startswith("spruce_")]
+    assert calls.index("spruce_eqs_ideal_mhd_moc_limiting") < calls.index("spruce_eqs_setup")
