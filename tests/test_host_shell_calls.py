@@ -149,3 +149,51 @@ def test_moc_options_and_unknown_module(stub, tmp_path):
     assert lim[1:] == ["b=1", "0.20000000000000001", "10", "mom=1", "0.10000000000000001", "5"]              # silent bounds keep idealmhd.hpp:59-64's defaults
     calls = [ln.split()[0] for ln in log if ln.startswith("spruce_")]
     assert calls.index("spruce_eqs_ideal_mhd_moc_limiting") < calls.index("spruce_eqs_setup")
+
+
+def test_continue_mode_resumes_from_end_state_with_its_time(stub, tmp_path):
+    """mhdSolve(prev_run_directory, ...) (mhd.cpp:6-19): end.state + the stored config, m_time taken from the file (fileio.cpp:50-51), run for -d more seconds."""
+    s = synthetic.stratified_loop(16, 14)
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk2", xb=("fixed", "open"), yb=("fixed", "open"), max_iterations=-1, iter_output_interval=2, duration=1.75)
+    log1, _, out = run_shell(stub, tmp_path, s, cfg)
+    adv = [args_of(ln) for ln in log1 if ln.startswith("spruce_advance")]
+    assert sum(int(a["done"]) for a in adv) == 4 and all(float(a["max_time"]) == 1.75 for a in adv)        # 0.5, 0.5, 0.5, then the 0.25 that reaches the duration
+    meta, _ = refrun.read_state(out / "end.state")
+    assert float(meta["t"]) == 1.75
+    log2 = tmp_path / "calls2.log"
+    env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(log2))
+    r = subprocess.run([str(OURS), "-m", "continue", "-o", str(out), "-d", "1.0"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode in (-6, 134) and "Simulation successfully reached" in r.stderr.decode(), r.stderr.decode()[-2000:]
+    lines = log2.read_text().splitlines()
+    assert float(args_of(lines[0])["time"]) == 1.75
+    adv = [args_of(ln) for ln in lines if ln.startswith("spruce_advance")]
+    assert all(float(a["max_time"]) == 2.75 for a in adv) and sum(int(a["done"]) for a in adv) == 2
+    meta, _ = refrun.read_state(out / "end.state")
+    assert float(meta["t"]) == 2.75
+
+
+def test_two_fluid_and_two_energy_sets_select_their_equation_set(stub, tmp_path):
+    s = synthetic.ucnp_cloud(16, 14, drift=2.0e3, bfield=5.0)
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk4", xb=("open_ucnp", "open_ucnp"), yb=("periodic", "periodic"), max_iterations=2, iter_output_interval=1, eqs="ideal_2F",
+                                  eqs_block=[("use_sub_cycling", "false")], density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30, output_flags=("i_rho", "e_rho", "E_x", "dt"),
+                                  modules=[("eic_thermalization", [])])
+    (tmp_path / "a").mkdir()
+    log, _, _ = run_shell(stub, tmp_path / "a", s, cfg)
+    c = args_of(log[0])
+    assert c["eqs"] == "3" and c["bc"] == "5,5,0,0" and c["ti"] == "2"          # index in EquationSet::m_sets (equationset.hpp:22)
+    opt = args_of(next(ln for ln in log if ln.startswith("spruce_eqs_ideal2f_options")))
+    assert opt["use_sub_cycling"] == "0" and opt["remove_curl_terms"] == "0"
+    calls = [ln.split()[0] for ln in log if ln.startswith("spruce_")]
+    assert "spruce_module_eic_thermalization" in calls and calls.index("spruce_module_eic_thermalization") > calls.index("spruce_eqs_setup")
+    uploads = {ln.split()[1] for ln in log if ln.startswith("spruce_grid_upload")}
+    assert {"i_rho", "e_rho", "i_mom_x", "e_mom_x", "i_temp", "e_temp", "E_x", "E_y", "E_z", "bi_x", "bi_y", "bi_z"} <= uploads
+
+    s = synthetic.two_energy(16, 14)
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("reflect", "open"), yb=("fixed", "open"), max_iterations=2, iter_output_interval=1, eqs="ideal_mhd_2E",
+                                  output_flags=("rho", "i_temp", "e_temp", "dt"))
+    (tmp_path / "b").mkdir()
+    log, _, _ = run_shell(stub, tmp_path / "b", s, cfg)
+    c = args_of(log[0])
+    assert c["eqs"] == "2" and c["bc"] == "3,1,2,1" and c["ti"] == "0"
+    uploads = {ln.split()[1] for ln in log if ln.startswith("spruce_grid_upload")}
+    assert {"rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"} <= uploads
