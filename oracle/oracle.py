@@ -56,6 +56,8 @@ def lib():
         L.oracle_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.oracle_set_anomalous_resistivity.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_anomalous_subcycles.restype = C.c_int
+        L.oracle_small_module_hooks.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.oracle_set_time.argtypes = [C.c_void_p, C.c_double]
         L.oracle_anomalous_core.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_int]
         L.oracle_anomalous_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_anomalous_subcycles.argtypes = [C.c_void_p]
@@ -201,6 +203,13 @@ class Oracle:
         """AnomalousResistivity with the reference's defaults (anomalousresistivity.hpp:16-39); call after setup."""
         p = anomalous_params(**{k: v for k, v in locals().items() if k != "self"})
         lib().oracle_set_anomalous_resistivity(self.h, _dp(p))
+
+    def small_module_hooks(self, phase: int, step: float):
+        """test accessor: the small solar modules' hooks of one phase only (0 preIterate, 1 iterate, 2 postIterate) on the current planes"""
+        lib().oracle_small_module_hooks(self.h, C.c_int(phase), C.c_double(step))
+
+    def set_time(self, t: float):
+        lib().oracle_set_time(self.h, C.c_double(t))
 
     def anomalous_core(self, dt: float, raw_commit: bool = False):
         """test accessor: one iterateModule(dt) of anomalous_resistivity without write-back / propagateChanges -> (bi_x, bi_y, bi_z, thermal_energy)"""

@@ -1026,6 +1026,18 @@ void oracle_set_moc_limiting(oracle *o, int b_on, double b_lo, double b_hi, int 
     o->moc_b_limiting = b_on; o->moc_b_lim[0] = b_lo; o->moc_b_lim[1] = b_hi;
     o->moc_mom_limiting = mom_on; o->moc_mom_lim[0] = mom_lo; o->moc_mom_lim[1] = mom_hi;
 }
+/* test accessor: only the small solar modules' hooks of one phase on the current planes (0 preIterate, 1 iterate, 2 postIterate); time is not advanced */
+void oracle_small_module_hooks(oracle *o, int phase, double step)
+{
+    for (int m = 0; m < o->mod.n_modules; m++) {
+        if (o->mod.order[m] < 100) continue;
+        small_module *sm = (small_module *)o->mod.small[o->mod.order[m] - 100];
+        if (phase == 0) small_module_pre(o, sm);
+        else if (phase == 1) small_module_iterate(o, sm, step);
+        else small_module_post(o, sm, step);
+    }
+}
+void oracle_set_time(oracle *o, double t) { o->t = t; }
 double oracle_step(oracle *o) { return advance_time(o); }
 void oracle_run(oracle *o, int nsteps, double *dt_out) { for (int s = 0; s < nsteps; s++) { double d = advance_time(o); if (dt_out) dt_out[s] = d; } }
 double oracle_time(const oracle *o) { return o->t; }
