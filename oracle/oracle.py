@@ -58,6 +58,7 @@ def lib():
         L.oracle_anomalous_subcycles.restype = C.c_int
         L.oracle_small_module_hooks.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.oracle_set_time.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_anomalous_diffusivity.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_anomalous_core.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_int]
         L.oracle_anomalous_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_anomalous_subcycles.argtypes = [C.c_void_p]
@@ -222,6 +223,11 @@ class Oracle:
         t = np.zeros((self.nx, self.ny))
         lib().oracle_anomalous_state(self.h, ij, _dp(t))
         return (ij[0], ij[1]), t
+
+    def anomalous_diffusivity(self):
+        out = np.zeros((self.nx, self.ny))
+        lib().oracle_anomalous_diffusivity(self.h, _dp(out))
+        return out
 
     def anomalous_subcycles(self) -> int:
         return lib().oracle_anomalous_subcycles(self.h)

@@ -1016,6 +1016,7 @@ void oracle_anomalous_state(const oracle *o, int *null_ij, double *tmpl)
     null_ij[0] = A->null_i; null_ij[1] = A->null_j;
     if (tmpl) memcpy(tmpl, A->tmpl, sizeof(double) * o->n);
 }
+void oracle_anomalous_diffusivity(const oracle *o, double *out) { memcpy(out, ((const anom_res *)o->mod.anom)->diffusivity, sizeof(double) * o->n); }
 int oracle_anomalous_subcycles(const oracle *o) { return o->mod.anom ? ((anom_res *)o->mod.anom)->nsub : 0; }
 void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
 /* test accessor: applyMomThresholdingMoC + applyBThresholdingMoC on the current planes, nothing else */

@@ -120,6 +120,10 @@ CASES = {
     # (square grid: circularMask / currentThresholdMask loop j over result.rows(), anomalousresistivity.cpp:285,297 -- the reference aborts when xdim > ydim)
     "ar_floodfill_rk2": ("stratified_loop", dict(nx=26, ny=26, bump=0.5), dict(integrator="rk2", xb=("fixed", "open"), yb=("fixed", "open"), modules=[
         ("anomalous_resistivity", [("time_scale", "0.3"), ("safety_factor", "0.5"), ("flood_fill_threshold", "1.5"), ("smoothing_sigma", "1.0")])], **SOLAR_FLOORS), 3, (1, 3)),
+    # output_to_file planes of anomalous_resistivity (anomalous_diffusivity, anomalous_template, joule_heating) and field_heating
+    "ar_diag_planes": ("stratified_loop", dict(nx=26, ny=26, bump=0.5), dict(integrator="euler", xb=("fixed", "open"), yb=("fixed", "open"), modules=[
+        ("anomalous_resistivity", [("time_scale", "0.3"), ("safety_factor", "0.5"), ("flood_fill_threshold", "1.5"), ("smoothing_sigma", "1.0"), ("output_to_file", "true")]),
+        ("field_heating", [("coeff", "1.0e-7"), ("current_pow", "0.5"), ("b_pow", "1.0"), ("output_to_file", "true")])], **SOLAR_FLOORS), 3, (0, 1, 3)),
     # IdealMHD2E (source/equationsets/idealmhd2E.cpp): one fluid, separate ion / electron thermal energies
     "e2_mixed_rk2": ("two_energy", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"), eqs="ideal_mhd_2E", **SOLAR_FLOORS), 8, (1, 8)),
     "e2_pp_ucnp_rk4": ("two_energy", dict(nx=NX, ny=NY), dict(integrator="rk4", xb=PP, yb=UC, eqs="ideal_mhd_2E", **SOLAR_FLOORS), 4, (1, 4)),

@@ -29,9 +29,9 @@ struct HostExec {
 };
 
 // in: bi_x, bi_y, bi_z, thermal_energy, be_x, be_y, be_z, n, dt, pos_x, pos_y (11 planes); p[17] laid out like oracle_set_anomalous_resistivity
-// out: 4 planes after `iters` iterateModule(dt) calls (each continuing from the raw result of the one before), template plane, null point, nsub
+// out: 4 planes after `iters` iterateModule(dt) calls (each continuing from the raw result of the one before), template and diffusivity planes, null point, nsub
 extern "C" int anomres_host_run(const double *const *in, const double *dx, const double *dy, int nx, int ny, const int *bounds, const int *per, const int *moc_ext,
-                                const double *p, double epsilon, double dt, int iters, int reverse, double *out, double *tmpl, int *null_ij, int *nsub)
+                                const double *p, double epsilon, double dt, int iters, int reverse, double *out, double *tmpl, double *diff, int *null_ij, int *nsub)
 {
     HostExec x;
     x.reverse = reverse;
@@ -52,6 +52,7 @@ extern "C" int anomres_host_run(const double *const *in, const double *dx, const
         if ((rc = iterate(x, x.g, s, in[4], in[5], in[6], in[7], in[8], moc_ext, epsilon, dt))) return rc;
     for (int q = 0; q < 4; q++) std::copy(x.plane(P_BIX + q), x.plane(P_BIX + q) + n, out + q * n);
     std::copy(x.plane(P_TMPL), x.plane(P_TMPL) + n, tmpl);
+    std::copy(x.plane(P_DIFF), x.plane(P_DIFF) + n, diff);
     null_ij[0] = s.null_i; null_ij[1] = s.null_j; *nsub = s.nsub;
     return 0;
 }

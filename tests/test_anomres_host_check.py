@@ -60,15 +60,16 @@ def test_product_anomalous_resistivity_equals_oracle(lib, name, kv, xb, yb, inte
     bounds = (C.c_int * 4)(xl, xu, yl, yu)
     per = (C.c_int * 2)(int(xb[0] == "periodic"), int(yb[0] == "periodic"))
     moc = (C.c_int * 4)(*[int(b == "open_moc") for b in (xb[0], xb[1], yb[0], yb[1])])
-    out = np.zeros((4, nx, ny)); tmpl = np.zeros((nx, ny)); ij = (C.c_int * 2)(); nsub = C.c_int()
+    out = np.zeros((4, nx, ny)); tmpl = np.zeros((nx, ny)); diff = np.zeros((nx, ny)); ij = (C.c_int * 2)(); nsub = C.c_int()
     vp = lambda q: q.ctypes.data_as(C.c_void_p)
     rc = lib.anomres_host_run(arr, vp(dx), vp(dy), C.c_int(nx), C.c_int(ny), bounds, per, moc, vp(p), C.c_double(0.2), C.c_double(dt), C.c_int(iters), C.c_int(reverse),
-                              vp(out), vp(tmpl), ij, C.byref(nsub))
+                              vp(out), vp(tmpl), vp(diff), ij, C.byref(nsub))
     assert rc == 0
     assert (ij[0], ij[1]) == (ri, rj)
     assert nsub.value == o.anomalous_subcycles()
     assert same_bits(tmpl, rt), "%s template: %s" % (name, mismatch(tmpl, rt))
     assert np.count_nonzero(rt) > 0, "the case does not exercise the template"
+    assert same_bits(diff, o.anomalous_diffusivity()), "%s diffusivity: %s" % (name, mismatch(diff, o.anomalous_diffusivity()))       # the other factor of the anomalous_diffusivity output plane
     for q, nm in enumerate(["bi_x", "bi_y", "bi_z", "thermal_energy"]):
         assert same_bits(out[q], ref[q]), "%s %s: %s" % (name, nm, mismatch(out[q], ref[q]))
     assert not same_bits(out[3], planes[3]), "the case does not heat anything"

@@ -86,7 +86,7 @@ def test_extended_oracle_reproduces_reference(name):
         o.set_global_viscosity(float(g.eqs_raw["global_viscosity"]))
     for mname, kv in g.modules:
         if mname == "anomalous_resistivity":
-            o.set_anomalous_resistivity(**{k: float(v) for k, v in kv.items()})
+            o.set_anomalous_resistivity(**{k: float(v) for k, v in kv.items() if k != "output_to_file"})
         else:
             o.add_small_module(mname, **small_module_kwargs(mname, kv)[0])
     for it in range(1, g.n_steps + 1):
@@ -95,4 +95,14 @@ def test_extended_oracle_reproduces_reference(name):
         if it in g.frames:
             for v in OUT_VARS:
                 assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
+            # output_to_file planes the restatement can form (anomalousresistivity.cpp:320-329, fieldheating.cpp:73-80)
+            mp = g.module_planes.get(it, {})
+            if "anomalous_template" in mp:
+                _, tm = o.anomalous_state()
+                assert same_bits(tm, mp["anomalous_template"]), "anomalous_template after iteration %d: %s" % (it, mismatch(tm, mp["anomalous_template"]))
+                prod = tm * o.anomalous_diffusivity()
+                assert same_bits(prod, mp["anomalous_diffusivity"]), "anomalous_diffusivity after iteration %d: %s" % (it, mismatch(prod, mp["anomalous_diffusivity"]))
+            if "field_heating" in mp:
+                k = [m for m, _ in g.modules if m != "anomalous_resistivity"].index("field_heating")
+                assert same_bits(o.small_module_plane(k, 0), mp["field_heating"]), "field_heating after iteration %d" % it
     o.close()

@@ -667,3 +667,41 @@ def test_anomalous_resistivity_vs_reference_fixture():
     """the committed fixture of the unmodified reference binary with anomalous_resistivity (tests/golden/ar_floodfill_rk2.npz), bit for bit"""
     out = run_isolated(ANOMRES_GOLDEN_CODE, {})
     assert "ok" in out
+
+
+ANOMRES_DIAG_CODE = """
+    import numpy as np
+    from golden_util import Golden, same_bits, mismatch, OUT_VARS
+    from spruce_b200.domain import PlasmaDomain
+    g = Golden("ar_diag_planes")
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
+    for mname, kv in g.modules:
+        kw = {k: float(v) for k, v in kv.items() if k != "output_to_file"}
+        if mname == "anomalous_resistivity":
+            d.set_anomalous_resistivity(g.planes["pos_x"], g.planes["pos_y"], **kw)
+            d.set_module_output_to_file("anomalous_resistivity")
+        else:
+            d.set_field_heating(**kw)
+    done = 0
+    for it in sorted(g.frames):
+        if it > done:
+            d.advance(it - done); done = it
+        for v in (OUT_VARS if it else []):
+            r = g.frames[it][v]
+            assert np.max(np.abs(d.grid(v) - r)) <= 1e-9 * max(np.max(np.abs(r)), 1e-300), "%s after iteration %d" % (v, it)      # field_heating calls pow
+        mp = g.module_planes[it]
+        assert same_bits(d.module_output("anomalous_template"), mp["anomalous_template"]) or it > 0, "set-up template (frame 0)"
+        for name in ("anomalous_template", "anomalous_diffusivity", "joule_heating", "field_heating"):
+            got, ref = d.module_output(name), mp[name]
+            assert np.max(np.abs(got - ref)) <= 1e-6 * max(np.max(np.abs(ref)), 1e-300), "%s after iteration %d: %s" % (name, it, mismatch(got, ref))
+            assert np.count_nonzero(got) == np.count_nonzero(ref) or name == "joule_heating", name
+    print("ok")
+"""
+
+
+@UNVALIDATED
+def test_anomalous_resistivity_and_field_heating_diagnostic_planes_vs_reference_fixture():
+    """output_to_file planes of anomalous_resistivity and field_heating against the fixture of the unmodified reference (tests/golden/ar_diag_planes.npz):
+    frame 0 carries the set-up template and zero planes, later frames the last evaluation's template, template*diffusivity, (e_after - e_before)/dt and mask*(dt*heating)."""
+    out = run_isolated(ANOMRES_DIAG_CODE, {})
+    assert "ok" in out
