@@ -59,6 +59,7 @@ def lib():
         L.oracle_small_module_hooks.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.oracle_set_time.argtypes = [C.c_void_p, C.c_double]
         L.oracle_anomalous_diffusivity.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.oracle_module_output.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.oracle_anomalous_core.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_int]
         L.oracle_anomalous_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_anomalous_subcycles.argtypes = [C.c_void_p]
@@ -223,6 +224,12 @@ class Oracle:
         t = np.zeros((self.nx, self.ny))
         lib().oracle_anomalous_state(self.h, ij, _dp(t))
         return (ij[0], ij[1]), t
+
+    def module_output(self, name: str):
+        """output_to_file plane of thermal_conduction / radiative_losses after the last step ("thermal_conduction", "flux_saturation", "rad"); None before the module ran"""
+        out = np.zeros((self.nx, self.ny))
+        ok = lib().oracle_module_output(self.h, {"thermal_conduction": 0, "flux_saturation": 1, "rad": 2}[name], _dp(out))
+        return out if ok else None
 
     def anomalous_diffusivity(self):
         out = np.zeros((self.nx, self.ny))

@@ -44,6 +44,7 @@ static const int EVOLVED[8] = { V_rho, V_mom_x, V_mom_y, V_mom_z, V_thermal_ener
 typedef struct {
     /* thermal_conduction (thermalconduction.hpp) */
     int tc_on, tc_flux_saturation, tc_integrator; double tc_epsilon, tc_dt_subcycle_min, tc_weakening; int tc_nsub;
+    double *tc_avg, *tc_sat, *rl_avg;   /* output_to_file planes (thermalconduction.cpp:101-104, radiativelosses.cpp:93), kept for the tests */
     /* radiative_losses (radiativelosses.hpp) */
     int rl_on, rl_integrator, rl_prevent_subcycling; double rl_cutoff_ramp, rl_cutoff_temp, rl_epsilon; int rl_nsub;
     /* ambient_heating (ambientheating.hpp) */
@@ -706,6 +707,8 @@ static void tc_iterate(oracle *o, double dt)
     double *bhx = pl_dup(o, o->g[V_b_hat_x]), *bhy = pl_dup(o, o->g[V_b_hat_y]);
     double *k1 = pl_new(o), *k2 = pl_new(o), *k3 = pl_new(o), *k4 = pl_new(o), *im = pl_new(o), *imT = pl_new(o);
     double dts = dt / (double)ns;
+    if (!o->mod.tc_avg) { o->mod.tc_avg = pl_new(o); o->mod.tc_sat = pl_new(o); }
+    if (o->mod.tc_flux_saturation) { double *add = pl_new(o); tc_saturation_terms(o, T, o->mod.tc_sat, add); free(add); }      /* :53-59: sat_terms of the entry temperature */
     for (int s = 0; s < ns; s++) {
         if (o->mod.tc_integrator == TI_EULER) {
             tc_energy_derivative(o, T, bhx, bhy, k1);
@@ -730,6 +733,7 @@ static void tc_iterate(oracle *o, double dt)
             temp_from_energy(o, e, nn, T);
         }
     }
+    for (int c = 0; c < n; c++) o->mod.tc_avg[c] = (e[c] - o->g[V_thermal_energy][c]) / dt;                                  /* :102 */
     memcpy(o->g[V_thermal_energy], e, sizeof(double) * n);
     propagate_changes(o, o->g, o->g);
     free(e); free(T); free(nn); free(bhx); free(bhy); free(k1); free(k2); free(k3); free(k4); free(im); free(imT);
@@ -802,6 +806,8 @@ static void rl_iterate(oracle *o, double dt)
             temp_from_energy(o, e, nn, T);
         }
     }
+    if (!o->mod.rl_avg) o->mod.rl_avg = pl_new(o);
+    for (int c = 0; c < n; c++) o->mod.rl_avg[c] = (e[c] - o->g[V_thermal_energy][c]) / dt;                                  /* radiativelosses.cpp:93 */
     memcpy(o->g[V_thermal_energy], e, sizeof(double) * n);
     propagate_changes(o, o->g, o->g);
     free(e); free(T); free(nn); free(k1); free(k2); free(k3); free(k4); free(im); free(imT);
@@ -1017,6 +1023,14 @@ void oracle_anomalous_state(const oracle *o, int *null_ij, double *tmpl)
     if (tmpl) memcpy(tmpl, A->tmpl, sizeof(double) * o->n);
 }
 void oracle_anomalous_diffusivity(const oracle *o, double *out) { memcpy(out, ((const anom_res *)o->mod.anom)->diffusivity, sizeof(double) * o->n); }
+/* test accessor: output_to_file plane of thermal_conduction / radiative_losses after the last step: 0 thermal_conduction, 1 flux_saturation, 2 rad */
+int oracle_module_output(const oracle *o, int which, double *out)
+{
+    const double *p = which == 0 ? o->mod.tc_avg : which == 1 ? o->mod.tc_sat : o->mod.rl_avg;
+    if (!p) return 0;
+    memcpy(out, p, sizeof(double) * o->n);
+    return 1;
+}
 int oracle_anomalous_subcycles(const oracle *o) { return o->mod.anom ? ((anom_res *)o->mod.anom)->nsub : 0; }
 void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
 /* test accessor: applyMomThresholdingMoC + applyBThresholdingMoC on the current planes, nothing else */

@@ -37,6 +37,9 @@ def test_oracle_reproduces_reference(name):
         if it in g.frames:
             for v in OUT_VARS:
                 assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
+            for pname, ref in g.module_planes.get(it, {}).items():          # output_to_file planes: "thermal_conduction", "flux_saturation", "rad"
+                got = o.module_output(pname)
+                assert got is not None and same_bits(got, ref), "module plane %s after iteration %d: %s" % (pname, it, mismatch(got, ref))
     names = [m[0] for m in g.modules]
     if "thermal_conduction" in names:
         assert tc == g.subcycle_counts("Thermal Subcycles")
