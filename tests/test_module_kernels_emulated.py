@@ -18,7 +18,7 @@ ROOT = Path(__file__).resolve().parents[1]
 CSRC = ROOT / "spruce_b200" / "csrc"
 BUILD = ROOT / "tests" / "hostcheck" / "_build"
 LIB = BUILD / "libkernel_emu.so"
-BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3}
+BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3, "open_moc": 4}
 
 PRELUDE = r'''
 #include <algorithm>
@@ -72,6 +72,7 @@ def assemble():
     mk = (CSRC / "mhd_kernels.cuh").read_text()
     mo = (CSRC / "module_kernels.cuh").read_text()
     ca = (CSRC / "capi.cu").read_text()
+    ms = (CSRC / "moc_stage.cuh").read_text()
     parts = [PRELUDE, "#include <vector>\nnamespace spruce {\n",
              cut(mk, "constexpr int HALO", "enum { KM_NONE", include_end=True),
              cut(mk, "__device__ __forceinline__ FaceGeom load_face_geom", "// is global row g / column j inside"),
@@ -80,6 +81,9 @@ def assemble():
              cut(mk, "struct PropArgs {", "// Ghost cells of the non-periodic sides"), "\n",
              cut(mo, "constexpr double kKappa0", "// Artificial viscosity (source/modules/viscosity.cpp"), "\n",
              cut(mo, "struct OpArgs", "}  // namespace spruce"),
+             cut(mk, "struct StepCtl {", "// begin: step = epsilon"),
+             "}  // namespace spruce\n#include \"moc_kernels.cuh\"\nnamespace spruce {\n",
+             cut(ms, "struct MocArgs {", "}  // namespace spruce"),
              cut(ca, "struct HostAxis {", "struct TwoFluid;"),
              cut(ca, "void build_axis(", "int upload_tables("),
              "}  // namespace spruce\n",
@@ -256,4 +260,37 @@ def test_radiative_losses_with_diagnostic_plane_equals_oracle(emu, integ):
     ref = o.module_output("rad")
     assert ns >= 1 and np.count_nonzero(ref) > 0
     assert np.max(np.abs(avg - ref)) <= 1e-9 * np.max(np.abs(ref)), np.max(np.abs(avg - ref)) / np.max(np.abs(ref))
+    emu.emu_destroy(h); o.close()
+
+
+@pytest.mark.parametrize("gvisc", [0.0, 0.3])
+@pytest.mark.parametrize("xb,yb", [(("open_moc", "open_moc"), ("open_moc", "open_moc")), (("periodic", "periodic"), ("open_moc", "open_moc")), (("open_moc", "open_moc"), ("periodic", "periodic"))])
+def test_open_moc_stage_kernels_equal_oracle(emu, xb, yb, gvisc):
+    """k_moc_save / k_moc_visc_min / k_moc_stage (moc_stage.cuh) as launch_moc runs them: the exported right-hand side of the evolved ghost cells equals the oracle's,
+    an euler stage leaves the oracle's new ghost-cell state, and the dt the kernel folds in is the minimum over those cells."""
+    nx, ny = 22, 19
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="euler", **floors)
+    o.set_global_viscosity(gvisc)
+    o.run(2)
+    ev = [np.ascontiguousarray(o.get(v)).copy() for v in EV]
+    st = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in ST]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    h = C.c_void_p(emu.emu_create(C.c_int(nx), C.c_int(ny), bc, C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(floors["density_min"]), C.c_double(floors["temp_min"]),
+                                  C.c_double(floors["thermal_energy_min"]), C.c_double(0.2), vp(dx), vp(dy), (C.c_void_p * 8)(*[a.ctypes.data for a in ev]), (C.c_void_p * 5)(*[a.ctypes.data for a in st])))
+    ghost = np.ones((nx, ny), dtype=bool)
+    ghost[(0 if xb[0] == "periodic" else 2):(nx if xb[0] == "periodic" else nx - 2), (0 if yb[0] == "periodic" else 2):(ny if yb[0] == "periodic" else ny - 2)] = False
+    D = np.zeros((8, nx, ny)); K1 = np.zeros((8, nx, ny)); dtm = C.c_double()
+    k_ref = o.rhs()
+    emu.emu_moc_stage(h, C.c_int(5), C.c_double(1.0), C.c_double(0.0), C.c_int(0), C.c_double(gvisc), vp(D), vp(K1), C.byref(dtm))            # KM_EXPORT
+    for v in range(8):
+        assert np.array_equal(~np.isnan(K1[v]), ghost), "cells written by the export: %d of %d" % (np.count_nonzero(~np.isnan(K1[v])), np.count_nonzero(ghost))
+        assert same_bits(K1[v][ghost], k_ref[v][ghost]), "d(%s)/dt on the evolved ghost cells: %s" % (EV[v], mismatch(K1[v][ghost], k_ref[v][ghost]))
+    step = o.step()
+    emu.emu_moc_stage(h, C.c_int(0), C.c_double(1.0), C.c_double(step), C.c_int(1), C.c_double(gvisc), vp(D), vp(K1), C.byref(dtm))         # KM_NONE, primary
+    for v, name in enumerate(EV):
+        assert same_bits(D[v][ghost], o.get(name)[ghost]), "%s on the evolved ghost cells after an euler stage: %s" % (name, mismatch(D[v][ghost], o.get(name)[ghost]))
+    assert dtm.value.hex() == float(np.min(o.get("dt")[ghost])).hex()
     emu.emu_destroy(h); o.close()
