@@ -1,0 +1,102 @@
+"""IdealMHD2E on the host through the PRODUCT'S OWN launch code: mhd2e_host.cuh's kernels and its orchestration (E2DeviceExec::stage, e2_finish,
+e2_launch_propagate, e2_enqueue_step, e2_geometry ...) are cut from the source, `k<<<grid, block, 0, stream>>>(args)` is rewritten textually to a loop
+over blocks and threads, and the result is compiled with g++ over a minimal stand-in for spruce_domain.  Whole time steps must equal the CPU restatement
+(pinned to the reference) bit for bit: step sizes, the seven evolved planes, the dt plane.  tests/test_mhd2e_host_check.py proves the per-cell functions
+and the stage order; this adds the kernels' thread mapping, argument plumbing, set rotation and the launch sequence itself."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from golden_util import mismatch, same_bits
+from oracle.oracle import EVOLVED_2E, Oracle2E
+from test_module_kernels_emulated import BLOCK_MIN, PRELUDE, cut
+from test_oracle_vs_live_reference import e2_cases, e2_state
+
+ROOT = Path(__file__).resolve().parents[1]
+CSRC = ROOT / "spruce_b200" / "csrc"
+BUILD = ROOT / "tests" / "hostcheck" / "_build"
+LIB = BUILD / "libkernel_emu_2e.so"
+BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3, "open_moc": 4, "open_ucnp": 5}
+TI = {"euler": 0, "rk2": 1, "rk4": 2}
+
+DOMAIN = r'''
+#include "spruce_b200.h"
+#include <cstdlib>
+#include <utility>
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+template <class K, class... A>
+static void launch3(K k, dim3 g, unsigned bx, A... a)
+{
+    gridDim = {g.x, g.y, 1}; blockDim = {bx, 1, 1};
+    for (unsigned y = 0; y < g.y; y++) for (unsigned x = 0; x < g.x; x++) for (unsigned t = 0; t < bx; t++) { blockIdx = {x, y, 0}; threadIdx = {t, 0, 0}; k(a...); }
+}
+#define CUDA_TRY(x) do { (void)(x); } while (0)
+static inline int cudaGetLastError() { return 0; }
+using namespace spruce;
+struct OneFluid2E;
+// the members of capi.cu's spruce_domain that the IdealMHD2E code touches
+struct spruce_domain {
+    spruce_config cfg; DomainParams P; double *stat[NSTATIC] = {nullptr}; StepCtl *ctl = nullptr; double *dt_hist = nullptr; int stream = 0; long long launches = 0;
+    OneFluid2E *e2 = nullptr; std::vector<double> dxg, dyg;
+};
+static int fail(int code, const char *, ...) { return code; }
+static int alloc_plane(spruce_domain *d, double **out) { *out = (double *)std::calloc((size_t)d->P.nx * d->P.pitch, sizeof(double)); return *out ? SPRUCE_OK : SPRUCE_ERR_CUDA; }
+static int peer_exchange(spruce_domain *, double *const *, void *) { return SPRUCE_OK; }
+static int peer_dt_allgather(spruce_domain *) { return SPRUCE_OK; }
+'''
+
+
+def assemble():
+    mk = (CSRC / "mhd_kernels.cuh").read_text()
+    ca = (CSRC / "capi.cu").read_text()
+    e2 = (CSRC / "mhd2e_host.cuh").read_text()
+    body = cut(e2, "struct E2Args {", "int e2_upload(")
+    body, n = re.subn(r"(\w+)<<<(.+?), (\w+), 0, d->stream>>>\(", r"launch3(\1, \2, \3, ", body)
+    assert n >= 6 and "<<<" not in body
+    return "".join([PRELUDE, '#include "mhd2e_cells.cuh"\n#include "mhd2e_step.hpp"\nnamespace spruce {\n',
+                    cut(mk, "constexpr int HALO", "enum { KM_NONE", include_end=True), BLOCK_MIN,
+                    cut(mk, "struct StepCtl {", "// the rare fallback of the skip test"),
+                    cut(ca, "struct HostAxis {", "struct TwoFluid;"), cut(ca, "void build_axis(", "int upload_tables("),
+                    "}  // namespace spruce\n", DOMAIN, body, (ROOT / "tests" / "hostcheck" / "kernel_emu_2e.inc").read_text()])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    BUILD.mkdir(exist_ok=True)
+    src = BUILD / "kernel_emu_2e.cpp"
+    text = assemble()
+    if not LIB.exists() or not src.exists() or src.read_text() != text:
+        src.write_text(text)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
+    L = C.CDLL(str(LIB))
+    L.emu2e_run.restype = C.c_int
+    return L
+
+
+@pytest.mark.parametrize("k,xb,yb,integrator,nx,ny,loop,nmin", e2_cases())
+def test_product_mhd2e_launch_code_runs_whole_steps_equal_to_oracle(emu, k, xb, yb, integrator, nx, ny, loop, nmin):
+    s = e2_state(nx, ny, loop)
+    floors = dict(density_min=nmin, temp_min=1.0e4, thermal_energy_min=1.0e-6) if loop else dict(density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 5
+    ref_steps = [o.step() for _ in range(nsteps)]
+    names = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "be_x", "be_y", "grav_x", "grav_y"]
+    planes = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in names]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    arr = (C.c_void_p * 11)(*[p.ctypes.data for p in planes])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    out = np.zeros((7, nx, ny)); dt = np.zeros((nx, ny)); steps = np.zeros(nsteps)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emu.emu2e_run(arr, vp(dx), vp(dy), C.c_int(nx), C.c_int(ny), bc, C.c_int(TI[integrator]), C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(0.2),
+                       C.c_double(floors["density_min"]), C.c_double(floors["temp_min"]), C.c_double(floors["thermal_energy_min"]), C.c_double(1.0), C.c_double(0.5), C.c_int(nsteps),
+                       vp(out), vp(dt), vp(steps))
+    assert rc == 0
+    assert [float(x).hex() for x in steps] == [x.hex() for x in ref_steps]
+    for v, nm in enumerate(EVOLVED_2E):
+        assert same_bits(out[v], o.get(nm)), "case %d %s: %s" % (k, nm, mismatch(out[v], o.get(nm)))
+    assert same_bits(dt, o.get("dt")), "case %d dt: %s" % (k, mismatch(dt, o.get("dt")))
+    o.close()
