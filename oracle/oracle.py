@@ -60,6 +60,7 @@ def lib():
         L.oracle_set_time.argtypes = [C.c_void_p, C.c_double]
         L.oracle_anomalous_diffusivity.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_module_output.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_anomalous_iterate.argtypes = [C.c_void_p, C.c_double]
         L.oracle_anomalous_core.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_int]
         L.oracle_anomalous_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_anomalous_subcycles.argtypes = [C.c_void_p]
@@ -218,6 +219,10 @@ class Oracle:
         out = np.zeros((4, self.nx, self.ny))
         lib().oracle_anomalous_core(self.h, C.c_double(dt), _dp(out), C.c_int(int(raw_commit)))
         return out
+
+    def anomalous_iterate(self, dt: float):
+        """test accessor: one complete iterateModule(dt) of anomalous_resistivity (write-back and propagateChanges included), nothing else"""
+        lib().oracle_anomalous_iterate(self.h, C.c_double(dt))
 
     def anomalous_state(self):
         ij = (C.c_int * 2)()

@@ -1016,6 +1016,7 @@ void oracle_anomalous_core(oracle *o, double dt, double *out, int raw_commit)
         memcpy(o->g[V_thermal_energy], out + 3 * n, sizeof(double) * n);
     }
 }
+void oracle_anomalous_iterate(oracle *o, double dt) { ar_iterate(o, (anom_res *)o->mod.anom, dt); }
 void oracle_anomalous_state(const oracle *o, int *null_ij, double *tmpl)
 {
     const anom_res *A = (const anom_res *)o->mod.anom;

@@ -1,0 +1,261 @@
+"""Module hooks through capi.cu's OWN functions on the host: the real `struct spruce_domain`, launch_propagate / launch_ghosts / derive_to, dc_post, fh_pre + fh_iterate
+and anomres_host.cuh (ArExec, ar_setup_run, ar_iterate) are cut from the product source, kernel launches rewritten to block / thread loops, the few CUDA runtime
+calls replaced by memcpy-style stand-ins.  One module iteration INCLUDING its propagateChanges (floors, boundary passes of open / reflect sides, dt) must equal the
+oracle's hook bit for bit.  tests/test_module_kernels_emulated.py runs the same kernels from a transcription of the launch order; here the order is the product's."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from golden_util import mismatch, same_bits
+from oracle.oracle import Oracle, anomalous_params
+from spruce_b200 import synthetic
+from test_module_kernels_emulated import BLOCK_MIN, EV, FLOORS, PRELUDE, ST, cut
+from test_oracle_vs_live_reference import AR_CASES, ar_kwargs
+
+ROOT = Path(__file__).resolve().parents[1]
+CSRC = ROOT / "spruce_b200" / "csrc"
+BUILD = ROOT / "tests" / "hostcheck" / "_build"
+LIB = BUILD / "libkernel_emu_capi.so"
+BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3}
+
+RUNTIME = r'''
+#include "spruce_b200.h"
+#include <cstdarg>
+#include <cstdint>
+#include <cstdlib>
+#include <utility>
+#include "moc_kernels.cuh"
+#include "anomres_cells.hpp"
+#include "solar_templates.hpp"
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+template <class K, class... A>
+static void launch3(K k, dim3 g, unsigned bx, A... a)
+{
+    gridDim = {g.x, g.y, 1}; blockDim = {bx, 1, 1};
+    for (unsigned y = 0; y < g.y; y++) for (unsigned x = 0; x < g.x; x++) for (unsigned t = 0; t < bx; t++) { blockIdx = {x, y, 0}; threadIdx = {t, 0, 0}; k(a...); }
+}
+// the CUDA runtime calls the cut functions make
+typedef void *cudaStream_t; typedef void *cudaEvent_t; typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline int cudaGetLastError() { return 0; }
+static inline const char *cudaGetErrorString(int) { return ""; }
+static inline int cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline int cudaMemcpyAsync(void *dst, const void *src, size_t n, int, cudaStream_t) { std::memcpy(dst, src, n); return 0; }
+static inline int cudaMemsetAsync(void *dst, int v, size_t n, cudaStream_t) { std::memset(dst, v, n); return 0; }
+template <class T> static inline int cudaMalloc(T **p, size_t n) { *p = (T *)std::calloc(n, 1); return *p ? 0 : 2; }
+static int fail(int code, const char *, ...) { return code; }
+#define CUDA_TRY(x) do { if ((x) != cudaSuccess) return fail(SPRUCE_ERR_CUDA, "cuda"); } while (0)
+using namespace spruce;
+'''
+STUBS = r'''
+static int peer_red_allgather(spruce_domain *) { return SPRUCE_OK; }
+static int peer_exchange(spruce_domain *, double *const *, cudaStream_t) { return SPRUCE_OK; }
+static int peer_dt_allgather(spruce_domain *) { return SPRUCE_OK; }
+static int moc_limit(spruce_domain *, const PlaneSet &, int) { return SPRUCE_OK; }
+static int launch_moc(spruce_domain *, const PlaneSet &, const PlaneSet &, const PlaneSet &, double, int, int, int) { return SPRUCE_OK; }
+int launch_propagate(spruce_domain *d, int from_state);
+'''
+
+
+def cut_fn(text, signature):
+    """one top-level function of capi.cu: from its signature to the closing brace in column 0"""
+    m = re.search(r"^" + re.escape(signature.split("\n")[0]) + r"[^;{]*\n\{", text, re.M)             # the definition, not a forward declaration
+    assert m, signature
+    return text[m.start():text.index("\n}\n", m.start()) + 3]
+
+
+def rewrite_launches(body):
+    body, n = re.subn(r"(\w+(?:<\w+>)?)<<<(.+?), (\w+), 0, d->stream>>>\(", r"launch3(\1, \2, \3, ", body)
+    assert "<<<" not in body, body[body.index("<<<") - 80:body.index("<<<") + 80]
+    return body
+
+
+def assemble():
+    mk = (CSRC / "mhd_kernels.cuh").read_text()
+    mo = (CSRC / "module_kernels.cuh").read_text()
+    ca = (CSRC / "capi.cu").read_text()
+    ah = (CSRC / "anomres_host.cuh").read_text()
+    fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
+           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post("]
+    one_liners = {"double bits_to_double("}
+    code = []
+    for f in fns:
+        if f in one_liners:
+            i = ca.index("\n" + f) + 1
+            code.append(ca[i:ca.index("\n", i) + 1])
+        elif f == "int exchange_plane(":
+            code.append("static int exchange_plane(spruce_domain *, double *) { return SPRUCE_OK; }\n")      # single rank: the real one returns at once as well
+        else:
+            code.append(cut_fn(ca, f))
+    body = rewrite_launches("".join(code) + ah[ah.index("#pragma once") + len("#pragma once"):])
+    domain = cut(ca, "struct spruce_domain {", "\n};\n") + "\n};\n"
+    return "".join([PRELUDE, RUNTIME, "namespace spruce {\n",
+                    cut(mk, "constexpr int HALO", "enum { KM_NONE", include_end=True),
+                    cut(mk, "__device__ __forceinline__ FaceGeom load_face_geom", "// is global row g / column j inside"),
+                    BLOCK_MIN,
+                    cut(mk, "// is global row g / column j inside", "// block-wide NaN-ignoring minimum"),
+                    cut(mk, "struct PropArgs {", "// Slab decomposition: pack the first/last HALO rows"), "\n",
+                    "constexpr int MAX_RANKS = 16;\n",
+                    cut(mk, "struct StepCtl {", "// the rare fallback of the skip test"),
+                    cut(mo, "constexpr double kKappa0", "// Artificial viscosity (source/modules/viscosity.cpp"), "\n",
+                    cut(mo, "struct OpArgs", "}  // namespace spruce"),
+                    "}  // namespace spruce\n",
+                    "struct PlaneSet { double *p[NEV] = {nullptr}; };\n", cut(ca, "struct HostAxis {", "struct TwoFluid;"), "struct TwoFluid;\nstruct OneFluid2E;\n",
+                    domain, STUBS, body, (ROOT / "tests" / "hostcheck" / "kernel_emu_capi.inc").read_text()])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    BUILD.mkdir(exist_ok=True)
+    src = BUILD / "kernel_emu_capi.cpp"
+    text = assemble()
+    if not LIB.exists() or not src.exists() or src.read_text() != text:
+        src.write_text(text)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
+    L = C.CDLL(str(LIB))
+    L.cemu_create.restype = C.c_void_p
+    L.cemu_dtmin.restype = C.c_double
+    return L
+
+
+def vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_pair(emu, xb, yb, nx, ny, integrator="rk2", warm=2):
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, **FLOORS)
+    o.run(warm)
+    ev = [np.ascontiguousarray(o.get(v)).copy() for v in EV]
+    st = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in ST]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    h = emu.cemu_create(C.c_int(nx), C.c_int(ny), bc, C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(FLOORS["density_min"]), C.c_double(FLOORS["temp_min"]),
+                        C.c_double(FLOORS["thermal_energy_min"]), C.c_double(0.2), vp(dx), vp(dy), (C.c_void_p * 8)(*[a.ctypes.data for a in ev]), (C.c_void_p * 5)(*[a.ctypes.data for a in st]))
+    xl, xu = (0, nx - 1) if xb[0] == "periodic" else (2, nx - 3)
+    yl, yu = (0, ny - 1) if yb[0] == "periodic" else (2, ny - 3)
+    step = 0.2 * float(np.min(o.get("dt")[xl:xu + 1, yl:yu + 1]))
+    return s, o, C.c_void_p(h), step, (xl, xu, yl, yu)
+
+
+def compare(emu, h, o, nx, ny, what, bounds):
+    for k, v in enumerate(EV):
+        got = np.zeros((nx, ny))
+        emu.cemu_get(h, C.c_int(k), vp(got))
+        assert same_bits(got, o.get(v)), "%s: %s differs: %s" % (what, v, mismatch(got, o.get(v)))
+    xl, xu, yl, yu = bounds
+    assert float(emu.cemu_dtmin(h)).hex() == float(np.min(o.get("dt")[xl:xu + 1, yl:yu + 1])).hex(), "dt minimum after the module's propagate"
+
+
+BOUNDS = [(("fixed", "open"), ("reflect", "open")), (("reflect", "reflect"), ("open", "fixed")), (("periodic", "periodic"), ("fixed", "open")), (("open", "open"), ("periodic", "periodic"))]
+
+
+@pytest.mark.parametrize("xb,yb", BOUNDS)
+def test_propagate_with_boundary_passes_equals_oracle_propagate(emu, xb, yb):
+    """launch_propagate (floors, pointwise zeroing, the open / reflect passes in the reference's order, dt) on an oracle state against the oracle's propagateChanges.
+    (Not idempotent by construction: an open pass re-reads first-interior momenta that a later reflect side has zeroed meanwhile -- in the reference as well.)"""
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    assert emu.cemu_propagate(h) == 0
+    o.propagate()
+    compare(emu, h, o, nx, ny, "propagate", b)
+    o.close()
+
+
+@pytest.mark.parametrize("xb,yb", BOUNDS)
+def test_div_cleaning_through_dc_post(emu, xb, yb):
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    ts = 0.37 * step
+    o.add_small_module("div_cleaning", epsilon=0.3, time_scale=ts)
+    ns = emu.cemu_div_cleaning(h, C.c_double(0.3), C.c_double(ts), C.c_double(step))
+    assert ns == int(step / (0.3 * ts)) + 1
+    o.small_module_hooks(2, step)
+    compare(emu, h, o, nx, ny, "div_cleaning", b)
+    o.close()
+
+
+@pytest.mark.parametrize("xb,yb", BOUNDS)
+def test_field_heating_through_fh_pre_and_fh_iterate(emu, xb, yb):
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    kw = dict(coeff=1.0e-7, current_pow=0.5, b_pow=1.0, n_pow=0.2, roc_pow=0.3)
+    o.add_small_module("field_heating", **kw)
+    H = np.zeros((nx, ny))
+    assert emu.cemu_field_heating(h, *[C.c_double(kw[k]) for k in ("coeff", "current_pow", "b_pow", "n_pow", "roc_pow")], C.c_int(0), C.c_double(step), vp(H)) == 0
+    o.small_module_hooks(0, step)
+    o.small_module_hooks(1, step)
+    assert same_bits(H, o.small_module_plane(0, 0)), "heating plane (derived planes through k_mhd_derive): " + mismatch(H, o.small_module_plane(0, 0))
+    compare(emu, h, o, nx, ny, "field_heating", b)
+    o.close()
+
+
+@pytest.mark.parametrize("name,kv,xb,yb,integrator", [c for c in AR_CASES if "frobenius" not in c[0] or True], ids=[c[0] for c in AR_CASES])
+def test_anomalous_resistivity_through_ar_iterate(emu, name, kv, xb, yb, integrator):
+    """ArExec (cells / reduce_min through the reduction slot), ar_setup_run and ar_iterate incl. the dt plane from derive_to, the write-back and the propagate"""
+    nx, ny = 23, 23
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny, integrator=integrator)
+    a = ar_kwargs(kv)
+    o.set_anomalous_resistivity(**a)
+    p = anomalous_params(**a)
+    px = np.ascontiguousarray(s["planes"]["pos_x"], dtype=np.float64); py = np.ascontiguousarray(s["planes"]["pos_y"], dtype=np.float64)
+    ij = (C.c_int * 2)(); nsub = C.c_int(); tmpl = np.zeros((nx, ny))
+    iters = 2
+    assert emu.cemu_anomalous_resistivity(h, vp(px), vp(py), vp(p), C.c_double(step), C.c_int(iters), ij, C.byref(nsub), vp(tmpl)) == 0
+    for _ in range(iters):
+        o.anomalous_iterate(step)
+    (ri, rj), rt = o.anomalous_state()
+    assert (ij[0], ij[1]) == (ri, rj) and nsub.value == o.anomalous_subcycles()
+    assert same_bits(tmpl, rt), "template: " + mismatch(tmpl, rt)
+    compare(emu, h, o, nx, ny, name, b)
+    o.close()
+
+
+@pytest.mark.parametrize("xb,yb", BOUNDS)
+def test_source_terms_through_src_post(emu, xb, yb):
+    """the four pointwise source terms through src_post itself: its time windows, the ramp of localized_heating, the oscillation factor of momentum_injection"""
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    for t in (3.0, 9.5, 30.0):                            # inside every window (rising ramp) / falling ramp, mass injection over / only momentum injection still active
+        o.set_time(t)
+        if t == 3.0:
+            o.add_small_module("ambient_heating_sink", heating_rate=2.0e-4)
+            o.add_small_module("localized_heating", start_time=1.0, duration=10.0, max_heating_rate=0.5, stddev_x=3.0, stddev_y=2.0, center_x=8.0, center_y=7.0, ramp_time=4.0)
+            o.add_small_module("mass_injection", start_time=2.0, duration=5.0, max_injection_rate=1.0e6, stddev_x=2.0, stddev_y=2.5, center_x=9.0, center_y=6.0)
+            o.add_small_module("momentum_injection", start_time=0.0, duration=50.0, max_accel=1.0e4, stddev_x=2.0, stddev_y=2.0, center_x=10.0, center_y=9.0, dir_x=0.6, dir_y=-0.8,
+                               template_angle=20.0, oscillatory=1.0, oscillation_period=7.0)
+            o.small_module_hooks(0, step)
+            planes = [[o.small_module_plane(m, w) for w in (0, 1)] for m in range(4)]
+        par = [(0, 0.0, 0.0, 0.0, 0.0, 0, 1.0), (1, 1.0, 10.0, 4.0, 0.0, 0, 1.0), (2, 2.0, 5.0, 0.0, 0.0, 0, 1.0), (3, 0.0, 50.0, 0.0, 1.0e4, 1, 7.0)]
+        for m, (kind, start, dur, ramp, acc, osc, per) in enumerate(par):
+            p0 = np.ascontiguousarray(planes[m][0]); p1 = np.ascontiguousarray(planes[m][1]) if planes[m][1] is not None else None
+            rc = emu.cemu_source_term(h, C.c_int(kind), C.c_double(start), C.c_double(dur), C.c_double(ramp), C.c_double(acc), C.c_int(osc), C.c_double(per), vp(p0),
+                                      vp(p1) if p1 is not None else None, C.c_double(t), C.c_double(step))
+            assert rc == 0
+        o.small_module_hooks(2, step)
+        compare(emu, h, o, nx, ny, "source terms at t = %g" % t, b)
+    o.close()
+
+
+@pytest.mark.parametrize("boundary,shape,fa,dyn", [("y_bound_2", "exp", False, False), ("x_bound_1", "gaussian", True, True), ("y_bound_1", "flat", True, False), ("x_bound_2", "exp", False, True)])
+@pytest.mark.parametrize("xb,yb", BOUNDS[:2])
+def test_boundary_outflow_through_bo_post(emu, xb, yb, boundary, shape, fa, dyn):
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    codes = {"x_bound_1": 0, "x_bound_2": 1, "y_bound_1": 2, "y_bound_2": 3, "exp": 0, "gaussian": 1, "flat": 2}
+    o.add_small_module("boundary_outflow", max_accel=3.0e4, falloff_length=6.0e8, boundary=float(codes[boundary]), falloff_shape=float(codes[shape]), feather_length=2.0e8,
+                       field_aligned_mode=float(fa), dynamic_mode=float(dyn), dynamic_time=20.0, dynamic_target_speed=1.0e5)
+    ref_mean = o.outflow_mean(0)
+    px = np.ascontiguousarray(s["planes"]["pos_x"], dtype=np.float64); py = np.ascontiguousarray(s["planes"]["pos_y"], dtype=np.float64)
+    mean, accel = C.c_double(), C.c_double()
+    rc = emu.cemu_boundary_outflow(h, vp(px), vp(py), C.c_double(3.0e4), C.c_double(6.0e8), C.c_int(codes[boundary]), C.c_int(codes[shape]), C.c_double(2.0e8), C.c_int(int(fa)),
+                                   C.c_int(int(dyn)), C.c_double(20.0), C.c_double(1.0e5), C.c_double(step), C.byref(mean), C.byref(accel))
+    assert rc == 0
+    assert mean.value.hex() == float(ref_mean).hex(), (mean.value, ref_mean)
+    o.small_module_hooks(2, step)
+    compare(emu, h, o, nx, ny, "boundary_outflow", b)
+    o.close()
