@@ -20,7 +20,7 @@ ROOT = Path(__file__).resolve().parents[1]
 CSRC = ROOT / "spruce_b200" / "csrc"
 BUILD = ROOT / "tests" / "hostcheck" / "_build"
 LIB = BUILD / "libkernel_emu_capi.so"
-BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3}
+BC = {"periodic": 0, "open": 1, "fixed": 2, "reflect": 3, "open_moc": 4}
 
 RUNTIME = r'''
 #include "spruce_b200.h"
@@ -55,9 +55,9 @@ STUBS = r'''
 static int peer_red_allgather(spruce_domain *) { return SPRUCE_OK; }
 static int peer_exchange(spruce_domain *, double *const *, cudaStream_t) { return SPRUCE_OK; }
 static int peer_dt_allgather(spruce_domain *) { return SPRUCE_OK; }
-static int moc_limit(spruce_domain *, const PlaneSet &, int) { return SPRUCE_OK; }
-static int launch_moc(spruce_domain *, const PlaneSet &, const PlaneSet &, const PlaneSet &, double, int, int, int) { return SPRUCE_OK; }
+int launch_moc(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int dt_only);
 int launch_propagate(spruce_domain *d, int from_state);
+int reset_reductions(spruce_domain *d);
 '''
 
 
@@ -79,7 +79,8 @@ def assemble():
     mo = (CSRC / "module_kernels.cuh").read_text()
     ca = (CSRC / "capi.cu").read_text()
     ah = (CSRC / "anomres_host.cuh").read_text()
-    fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
+    ms = (CSRC / "moc_stage.cuh").read_text()
+    fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "void fill_moc(", "int launch_moc_save(", "int launch_moc(", "int moc_limit(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
            "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post("]
     one_liners = {"double bits_to_double("}
     code = []
@@ -100,7 +101,8 @@ def assemble():
                     cut(mk, "// is global row g / column j inside", "// block-wide NaN-ignoring minimum"),
                     cut(mk, "struct PropArgs {", "// Slab decomposition: pack the first/last HALO rows"), "\n",
                     "constexpr int MAX_RANKS = 16;\n",
-                    cut(mk, "struct StepCtl {", "// the rare fallback of the skip test"),
+                    cut(mk, "struct StepCtl {", "// dt all-gather over peer memory"),
+                    cut(ms, "struct MocArgs {", "}  // namespace spruce"),
                     cut(mo, "constexpr double kKappa0", "// Artificial viscosity (source/modules/viscosity.cpp"), "\n",
                     cut(mo, "struct OpArgs", "}  // namespace spruce"),
                     "}  // namespace spruce\n",
@@ -258,4 +260,39 @@ def test_boundary_outflow_through_bo_post(emu, xb, yb, boundary, shape, fa, dyn)
     assert mean.value.hex() == float(ref_mean).hex(), (mean.value, ref_mean)
     o.small_module_hooks(2, step)
     compare(emu, h, o, nx, ny, "boundary_outflow", b)
+    o.close()
+
+
+@pytest.mark.parametrize("limit", [False, True])
+@pytest.mark.parametrize("xb,yb", [(("open_moc", "open_moc"), ("fixed", "open_moc")), (("periodic", "periodic"), ("open_moc", "open_moc")), (("open_moc", "reflect"), ("open_moc", "open"))])
+def test_propagate_on_open_moc_sides_through_launch_moc_and_moc_limit(emu, xb, yb, limit):
+    """launch_propagate with open_moc sides: the dt-only pass of launch_moc over the evolved ghost cells, and with moc_b_limiting / moc_mom_limiting the clamps of
+    moc_limit followed by the rebuilt dt minimum -- against the oracle's propagateChanges on a state whose ghost-zone fields were pushed out of the limits"""
+    nx, ny = 25, 22
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    floors = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", moc_limiting=dict(b_limiting=True, b_lower=0.5, b_upper=1.5, mom_limiting=True, mom_lower=0.5, mom_upper=1.5) if limit else None, **floors)
+    o.run(2)
+    rng = np.random.default_rng(5)
+    for v in ("bi_x", "bi_y", "mom_x", "mom_y"):                       # push boundary values around so that the clamps act
+        a = o.view(v)                                                  # the oracle's own plane, modified in place
+        a[:2, :] *= rng.uniform(0.2, 3.0, size=a[:2, :].shape); a[-2:, :] *= rng.uniform(0.2, 3.0, size=a[-2:, :].shape)
+        a[:, :2] *= rng.uniform(0.2, 3.0, size=a[:, :2].shape); a[:, -2:] *= rng.uniform(0.2, 3.0, size=a[:, -2:].shape)
+    ev = [np.ascontiguousarray(o.get(v)).copy() for v in EV]
+    st = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in ST]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    h = C.c_void_p(emu.cemu_create(C.c_int(nx), C.c_int(ny), bc, C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(floors["density_min"]), C.c_double(floors["temp_min"]),
+                                   C.c_double(floors["thermal_energy_min"]), C.c_double(0.2), vp(dx), vp(dy), (C.c_void_p * 8)(*[a.ctypes.data for a in ev]), (C.c_void_p * 5)(*[a.ctypes.data for a in st])))
+    emu.cemu_set_moc(h, C.c_int(int(limit)), C.c_double(0.5), C.c_double(1.5), C.c_int(int(limit)), C.c_double(0.5), C.c_double(1.5))
+    assert emu.cemu_propagate(h) == 0
+    o.propagate()
+    for k, v in enumerate(EV):
+        got = np.zeros((nx, ny))
+        emu.cemu_get(h, C.c_int(k), vp(got))
+        assert same_bits(got, o.get(v)), "%s differs: %s" % (v, mismatch(got, o.get(v)))
+    lo = lambda bnd: 0 if bnd in ("periodic", "open_moc") else 2
+    hi = lambda bnd, n: n - 1 if bnd in ("periodic", "open_moc") else n - 3
+    ref = float(np.min(o.get("dt")[lo(xb[0]):hi(xb[1], nx) + 1, lo(yb[0]):hi(yb[1], ny) + 1]))
+    assert float(emu.cemu_dtmin(h)).hex() == ref.hex(), "dt minimum over the bounds widened by the open_moc ghost zones"
     o.close()
