@@ -52,9 +52,55 @@ static int fail(int code, const char *, ...) { return code; }
 using namespace spruce;
 '''
 STUBS = r'''
-static int peer_red_allgather(spruce_domain *) { return SPRUCE_OK; }
-static int peer_exchange(spruce_domain *, double *const *, cudaStream_t) { return SPRUCE_OK; }
-static int peer_dt_allgather(spruce_domain *) { return SPRUCE_OK; }
+// the peer transport between slabs, for ranks that are host threads of this process: edge rows through a staging area, reductions through shared slots
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+struct Barrier {
+    std::mutex m; std::condition_variable cv; int n = 1, count = 0, gen = 0;
+    void wait() { std::unique_lock<std::mutex> l(m); const int g = gen; if (++count == n) { gen++; count = 0; cv.notify_all(); } else cv.wait(l, [&] { return g != gen; }); }
+};
+static Barrier g_bar;
+static int g_world = 1;
+static std::vector<double> g_edge[8][2];
+static unsigned long long g_red[8][4], g_dt[8];
+static int peer_exchange(spruce_domain *d, double *const *U, cudaStream_t)
+{
+    if (g_world == 1) return SPRUCE_OK;
+    const int r = d->cfg.rank, W = g_world;
+    const size_t rows = (size_t)HALO * d->P.pitch;
+    g_edge[r][0].resize(NEV * rows); g_edge[r][1].resize(NEV * rows);
+    for (int v = 0; v < NEV; v++) {
+        std::memcpy(&g_edge[r][0][v * rows], U[v], rows * sizeof(double));
+        std::memcpy(&g_edge[r][1][v * rows], U[v] + (size_t)(d->P.nx - HALO) * d->P.pitch, rows * sizeof(double));
+    }
+    g_bar.wait();
+    const int lo = r > 0 ? r - 1 : (d->P.xper ? W - 1 : -1), hi = r < W - 1 ? r + 1 : (d->P.xper ? 0 : -1);
+    for (int v = 0; v < NEV; v++) {
+        if (lo >= 0) std::memcpy(U[v] - rows, &g_edge[lo][1][v * rows], rows * sizeof(double));
+        if (hi >= 0) std::memcpy(U[v] + (size_t)d->P.nx * d->P.pitch, &g_edge[hi][0][v * rows], rows * sizeof(double));
+    }
+    g_bar.wait();
+    return SPRUCE_OK;
+}
+static int peer_red_allgather(spruce_domain *d)
+{
+    if (g_world == 1) return SPRUCE_OK;
+    for (int k = 0; k < 4; k++) g_red[d->cfg.rank][k] = d->red[k];
+    g_bar.wait();
+    for (int r = 0; r < g_world; r++) for (int k = 0; k < 4; k++) d->red[k] = (k & 1) ? std::max(d->red[k], g_red[r][k]) : std::min(d->red[k], g_red[r][k]);
+    g_bar.wait();
+    return SPRUCE_OK;
+}
+static int peer_dt_allgather(spruce_domain *d)
+{
+    if (g_world == 1) return SPRUCE_OK;
+    g_dt[d->cfg.rank] = d->ctl->dtmin_bits;
+    g_bar.wait();
+    for (int r = 0; r < g_world; r++) d->ctl->dtmin_bits = std::min(d->ctl->dtmin_bits, g_dt[r]);
+    g_bar.wait();
+    return SPRUCE_OK;
+}
 int launch_moc(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode, int dt_only);
 int launch_propagate(spruce_domain *d, int from_state);
 int reset_reductions(spruce_domain *d);
@@ -88,8 +134,6 @@ def assemble():
         if f in one_liners:
             i = ca.index("\n" + f) + 1
             code.append(ca[i:ca.index("\n", i) + 1])
-        elif f == "int exchange_plane(":
-            code.append("static int exchange_plane(spruce_domain *, double *) { return SPRUCE_OK; }\n")      # single rank: the real one returns at once as well
         else:
             code.append(cut_fn(ca, f))
     body = rewrite_launches("".join(code) + ah[ah.index("#pragma once") + len("#pragma once"):])
@@ -117,9 +161,10 @@ def emu():
     text = assemble()
     if not LIB.exists() or not src.exists() or src.read_text() != text:
         src.write_text(text)
-        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
     L = C.CDLL(str(LIB))
     L.cemu_create.restype = C.c_void_p
+    L.cemu_create_slab.restype = C.c_void_p
     L.cemu_dtmin.restype = C.c_double
     return L
 
@@ -295,4 +340,55 @@ def test_propagate_on_open_moc_sides_through_launch_moc_and_moc_limit(emu, xb, y
     hi = lambda bnd, n: n - 1 if bnd in ("periodic", "open_moc") else n - 3
     ref = float(np.min(o.get("dt")[lo(xb[0]):hi(xb[1], nx) + 1, lo(yb[0]):hi(yb[1], ny) + 1]))
     assert float(emu.cemu_dtmin(h)).hex() == ref.hex(), "dt minimum over the bounds widened by the open_moc ghost zones"
+    o.close()
+
+
+@pytest.mark.parametrize("which", ["propagate", "div_cleaning", "field_heating"])
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("xb,yb", [(("periodic", "periodic"), ("fixed", "open")), (("fixed", "open"), ("reflect", "open")), (("reflect", "reflect"), ("periodic", "periodic"))])
+def test_module_hooks_on_slabs_equal_the_whole_domain(emu, xb, yb, world, which):
+    """the slab form of the hooks: every rank is a host thread running capi.cu's own functions on its rows (+ halo rows); the peer transport is a staging copy between
+    the threads.  exchange_plane / derive_to's halo rows / after_module_propagate / the dt all-gather must give the oracle's whole-domain result, bit for bit."""
+    nx, ny = 26, 19
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", **FLOORS)
+    o.run(2)
+    ev = [np.ascontiguousarray(o.get(v)).copy() for v in EV]
+    st = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in ST]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    cuts = [round(k * nx / world) for k in range(world + 1)]
+    hs = []
+    for r in range(world):
+        hs.append(emu.cemu_create_slab(C.c_int(r), C.c_int(world), C.c_int(cuts[r]), C.c_int(cuts[r + 1] - cuts[r]), C.c_int(nx), C.c_int(ny), bc, C.c_double(s["ion_mass"]),
+                                       C.c_double(s["adiabatic_index"]), C.c_double(FLOORS["density_min"]), C.c_double(FLOORS["temp_min"]), C.c_double(FLOORS["thermal_energy_min"]),
+                                       C.c_double(0.2), vp(dx), vp(dy), (C.c_void_p * 8)(*[a.ctypes.data for a in ev]), (C.c_void_p * 5)(*[a.ctypes.data for a in st])))
+    xl, xu = (0, nx - 1) if xb[0] == "periodic" else (2, nx - 3)
+    yl, yu = (0, ny - 1) if yb[0] == "periodic" else (2, ny - 3)
+    step = 0.2 * float(np.min(o.get("dt")[xl:xu + 1, yl:yu + 1]))
+    if which == "propagate":
+        p = np.zeros(1); code = 0
+        o.propagate()
+    elif which == "div_cleaning":
+        ts = 0.37 * step
+        p = np.array([0.3, ts, step]); code = 1
+        o.add_small_module("div_cleaning", epsilon=0.3, time_scale=ts)
+        o.small_module_hooks(2, step)
+    else:
+        kw = dict(coeff=1.0e-7, current_pow=0.5, b_pow=1.0, n_pow=0.2, roc_pow=0.3)
+        p = np.array([kw["coeff"], kw["current_pow"], kw["b_pow"], kw["n_pow"], kw["roc_pow"], step]); code = 2
+        o.add_small_module("field_heating", **kw)
+        o.small_module_hooks(0, step); o.small_module_hooks(1, step)
+    assert emu.cemu_run_slabs((C.c_void_p * world)(*hs), C.c_int(world), C.c_int(code), vp(p)) == 0
+    for k, v in enumerate(EV):
+        parts = []
+        for r in range(world):
+            a = np.zeros((cuts[r + 1] - cuts[r], ny))
+            emu.cemu_get_slab(C.c_void_p(hs[r]), C.c_int(k), vp(a))
+            parts.append(a)
+        got = np.concatenate(parts, axis=0)
+        assert same_bits(got, o.get(v)), "%s on %d slabs: %s differs: %s" % (which, world, v, mismatch(got, o.get(v)))
+    ref = float(np.min(o.get("dt")[xl:xu + 1, yl:yu + 1])).hex()
+    for r in range(world):
+        assert float(emu.cemu_dtmin(C.c_void_p(hs[r]))).hex() == ref, "rank %d holds the global dt minimum" % r
     o.close()

@@ -40,7 +40,7 @@ static inline int __double2hiint(double x) { return (int)(__double_as_longlong(x
 static inline int __double2loint(double x) { return (int)(__double_as_longlong(x) & 0xffffffffLL); }
 static inline double __hiloint2double(int hi, int lo) { return __longlong_as_double((long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo)); }
 struct dim3e { unsigned x, y, z; };
-static dim3e threadIdx, blockIdx, blockDim, gridDim;
+static thread_local dim3e threadIdx, blockIdx, blockDim, gridDim;      // thread_local: the slab tests run one host thread per rank
 static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
 // the warp reductions of the sub-cycle count kernels are compiled, never run here
