@@ -392,3 +392,83 @@ def test_module_hooks_on_slabs_equal_the_whole_domain(emu, xb, yb, world, which)
     for r in range(world):
         assert float(emu.cemu_dtmin(C.c_void_p(hs[r]))).hex() == ref, "rank %d holds the global dt minimum" % r
     o.close()
+
+
+def make_slabs(emu, s, o, xb, yb, nx, ny, world):
+    ev = [np.ascontiguousarray(o.get(v)).copy() for v in EV]
+    st = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in ST]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    cuts = [round(k * nx / world) for k in range(world + 1)]
+    hs = [emu.cemu_create_slab(C.c_int(r), C.c_int(world), C.c_int(cuts[r]), C.c_int(cuts[r + 1] - cuts[r]), C.c_int(nx), C.c_int(ny), bc, C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]),
+                               C.c_double(FLOORS["density_min"]), C.c_double(FLOORS["temp_min"]), C.c_double(FLOORS["thermal_energy_min"]), C.c_double(0.2), vp(dx), vp(dy),
+                               (C.c_void_p * 8)(*[a.ctypes.data for a in ev]), (C.c_void_p * 5)(*[a.ctypes.data for a in st])) for r in range(world)]
+    return hs, cuts, (ev, st, dx, dy)       # the arrays must outlive the calls
+
+
+def gather(emu, hs, cuts, ny, k):
+    parts = []
+    for r, h in enumerate(hs):
+        a = np.zeros((cuts[r + 1] - cuts[r], ny))
+        emu.cemu_get_slab(C.c_void_p(h), C.c_int(k), vp(a))
+        parts.append(a)
+    return np.concatenate(parts, axis=0)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("boundary,shape,fa,dyn", [("y_bound_2", "exp", False, True), ("x_bound_1", "gaussian", True, True), ("x_bound_2", "flat", True, False)])
+def test_boundary_outflow_on_slabs(emu, boundary, shape, fa, dyn, world):
+    """the keyed maximum of k_bo_mean travels through the all-gathered module reductions: every rank must find the whole domain's mean outflow"""
+    nx, ny = 26, 19
+    xb, yb = ("fixed", "open"), ("reflect", "open")
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", **FLOORS)
+    o.run(2)
+    hs, cuts, keep = make_slabs(emu, s, o, xb, yb, nx, ny, world)
+    step = 0.2 * float(np.min(o.get("dt")[2:-2, 2:-2]))
+    codes = {"x_bound_1": 0, "x_bound_2": 1, "y_bound_1": 2, "y_bound_2": 3, "exp": 0, "gaussian": 1, "flat": 2}
+    o.add_small_module("boundary_outflow", max_accel=3.0e4, falloff_length=6.0e8, boundary=float(codes[boundary]), falloff_shape=float(codes[shape]), feather_length=2.0e8,
+                       field_aligned_mode=float(fa), dynamic_mode=float(dyn), dynamic_time=20.0, dynamic_target_speed=1.0e5)
+    ref_mean = o.outflow_mean(0)
+    px = np.ascontiguousarray(s["planes"]["pos_x"], dtype=np.float64); py = np.ascontiguousarray(s["planes"]["pos_y"], dtype=np.float64)
+    means = np.zeros(world)
+    rc = emu.cemu_run_slabs_outflow((C.c_void_p * world)(*hs), C.c_int(world), vp(px), vp(py), C.c_double(3.0e4), C.c_double(6.0e8), C.c_int(codes[boundary]), C.c_int(codes[shape]),
+                                    C.c_double(2.0e8), C.c_int(int(fa)), C.c_int(int(dyn)), C.c_double(20.0), C.c_double(1.0e5), C.c_double(step), vp(means))
+    assert rc == 0
+    assert [float(m).hex() for m in means] == [float(ref_mean).hex()] * world
+    o.small_module_hooks(2, step)
+    for k, v in enumerate(EV):
+        got = gather(emu, hs, cuts, ny, k)
+        assert same_bits(got, o.get(v)), "%s differs: %s" % (v, mismatch(got, o.get(v)))
+    o.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("limit", [False, True])
+@pytest.mark.parametrize("xb,yb", [(("open_moc", "open_moc"), ("fixed", "open_moc")), (("periodic", "periodic"), ("open_moc", "open_moc"))])
+def test_open_moc_propagate_on_slabs(emu, xb, yb, limit, world):
+    """launch_moc's dt-only pass and moc_limit on slabs: strip cells addressed by global row, the x sides owned by the first / last slab"""
+    nx, ny = 26, 19
+    s = synthetic.stratified_loop(nx, ny, bump=0.4)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2",
+               moc_limiting=dict(b_limiting=True, b_lower=0.5, b_upper=1.5, mom_limiting=True, mom_lower=0.5, mom_upper=1.5) if limit else None, **FLOORS)
+    o.run(2)
+    rng = np.random.default_rng(5)
+    for v in ("bi_x", "bi_y", "mom_x", "mom_y"):
+        a = o.view(v)
+        a[:2, :] *= rng.uniform(0.2, 3.0, size=a[:2, :].shape); a[-2:, :] *= rng.uniform(0.2, 3.0, size=a[-2:, :].shape)
+        a[:, :2] *= rng.uniform(0.2, 3.0, size=a[:, :2].shape); a[:, -2:] *= rng.uniform(0.2, 3.0, size=a[:, -2:].shape)
+    hs, cuts, keep = make_slabs(emu, s, o, xb, yb, nx, ny, world)
+    for h in hs:
+        emu.cemu_set_moc(C.c_void_p(h), C.c_int(int(limit)), C.c_double(0.5), C.c_double(1.5), C.c_int(int(limit)), C.c_double(0.5), C.c_double(1.5))
+    assert emu.cemu_run_slabs((C.c_void_p * world)(*hs), C.c_int(world), C.c_int(0), vp(np.zeros(1))) == 0
+    o.propagate()
+    for k, v in enumerate(EV):
+        got = gather(emu, hs, cuts, ny, k)
+        assert same_bits(got, o.get(v)), "%s differs: %s" % (v, mismatch(got, o.get(v)))
+    lo = lambda bnd: 0 if bnd in ("periodic", "open_moc") else 2
+    hi = lambda bnd, n: n - 1 if bnd in ("periodic", "open_moc") else n - 3
+    ref = float(np.min(o.get("dt")[lo(xb[0]):hi(xb[1], nx) + 1, lo(yb[0]):hi(yb[1], ny) + 1])).hex()
+    for h in hs:
+        assert float(emu.cemu_dtmin(C.c_void_p(h))).hex() == ref
+    o.close()
