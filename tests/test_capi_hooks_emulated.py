@@ -127,7 +127,7 @@ def assemble():
     ah = (CSRC / "anomres_host.cuh").read_text()
     ms = (CSRC / "moc_stage.cuh").read_text()
     fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "void fill_moc(", "int launch_moc_save(", "int launch_moc(", "int moc_limit(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
-           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post("]
+           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate("]
     one_liners = {"double bits_to_double("}
     code = []
     for f in fns:
@@ -471,4 +471,39 @@ def test_open_moc_propagate_on_slabs(emu, xb, yb, limit, world):
     ref = float(np.min(o.get("dt")[lo(xb[0]):hi(xb[1], nx) + 1, lo(yb[0]):hi(yb[1], ny) + 1])).hex()
     for h in hs:
         assert float(emu.cemu_dtmin(C.c_void_p(h))).hex() == ref
+    o.close()
+
+
+@pytest.mark.parametrize("integ,sat", [("euler", True), ("rk2", True), ("rk4", False), ("rk4", True)])
+@pytest.mark.parametrize("xb,yb", BOUNDS[:2])
+def test_thermal_conduction_through_tc_iterate_with_output_planes(emu, xb, yb, integ, sat):
+    """tc_iterate itself, diagnostic hooks on; 1e-9: T^2.5 is (T*T)*sqrt(T) in the kernel and pow in the reference"""
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    o.set_thermal_conduction(flux_saturation=sat, integrator=integ, epsilon=0.1, dt_subcycle_min=1.0e-4, weakening_factor=1.0)
+    o.step()
+    ns = o.subcycles("thermal_conduction")
+    avg = np.zeros((nx, ny)); satp = np.zeros((nx, ny))
+    assert emu.cemu_thermal_conduction(h, C.c_int(int(sat)), C.c_double(1.0), C.c_double(1.0e-4), C.c_int({"euler": 0, "rk2": 1, "rk4": 2}[integ]), C.c_int(ns), C.c_double(step), vp(avg), vp(satp)) == 0
+    ref_avg, ref_sat = o.module_output("thermal_conduction"), o.module_output("flux_saturation")
+    assert ns >= 1 and np.count_nonzero(ref_avg) > 0
+    assert np.max(np.abs(avg - ref_avg)) <= 1e-9 * np.max(np.abs(ref_avg))
+    if sat:
+        assert np.max(np.abs(satp - ref_sat)) <= 1e-9 * np.max(np.abs(ref_sat))
+    o.close()
+
+
+@pytest.mark.parametrize("integ", ["euler", "rk2", "rk4"])
+@pytest.mark.parametrize("xb,yb", BOUNDS[:2])
+def test_radiative_losses_through_rl_iterate_with_output_plane(emu, xb, yb, integ):
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    o.set_radiative_losses(integrator=integ, cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1, prevent_subcycling=False)
+    o.step()
+    ns = o.subcycles("radiative_losses")
+    avg = np.zeros((nx, ny))
+    assert emu.cemu_radiative_losses(h, C.c_int({"euler": 0, "rk2": 1, "rk4": 2}[integ]), C.c_double(1.0e3), C.c_double(3.0e4), C.c_double(0.1), C.c_int(0), C.c_int(ns), C.c_double(step), vp(avg)) == 0
+    ref = o.module_output("rad")
+    assert ns >= 1 and np.count_nonzero(ref) > 0
+    assert np.max(np.abs(avg - ref)) <= 1e-9 * np.max(np.abs(ref))
     o.close()
