@@ -56,7 +56,7 @@ def assemble():
                     "}  // namespace spruce\n",
                     tk[tk.index('#include "module_kernels.cuh"') + len('#include "module_kernels.cuh"'):],
                     "namespace spruce {\n", cut(ca, "struct HostAxis {", "struct TwoFluid;"), cut(ca, "void build_axis(", "int upload_tables("), "}  // namespace spruce\n",
-                    domain, EXTRA_DOMAIN, body, cut(e2inc, "static void emu_axis(", "// in: rho, i_temp"),
+                    domain, EXTRA_DOMAIN, body, cut(e2inc, "static void emu_axis(", "// in: GLOBAL planes"),
                     (ROOT / "tests" / "hostcheck" / "kernel_emu_2f.inc").read_text()])
 
 

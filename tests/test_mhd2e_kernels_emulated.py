@@ -44,9 +44,53 @@ struct spruce_domain {
     OneFluid2E *e2 = nullptr; std::vector<double> dxg, dyg;
 };
 static int fail(int code, const char *, ...) { return code; }
-static int alloc_plane(spruce_domain *d, double **out) { *out = (double *)std::calloc((size_t)d->P.nx * d->P.pitch, sizeof(double)); return *out ? SPRUCE_OK : SPRUCE_ERR_CUDA; }
-static int peer_exchange(spruce_domain *, double *const *, void *) { return SPRUCE_OK; }
-static int peer_dt_allgather(spruce_domain *) { return SPRUCE_OK; }
+static int alloc_plane(spruce_domain *d, double **out)
+{
+    const int halo = d->cfg.n_ranks > 1 ? HALO : 0;                  // slabs carry two halo rows on each side
+    double *b = (double *)std::calloc((size_t)(d->P.nx + 2 * halo) * d->P.pitch, sizeof(double));
+    *out = b ? b + (size_t)halo * d->P.pitch : nullptr;
+    return b ? SPRUCE_OK : SPRUCE_ERR_CUDA;
+}
+// the peer transport between slabs, for ranks that are host threads of this process (as in tests/test_capi_hooks_emulated.py)
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+struct Barrier {
+    std::mutex m; std::condition_variable cv; int n = 1, count = 0, gen = 0;
+    void wait() { std::unique_lock<std::mutex> l(m); const int g = gen; if (++count == n) { gen++; count = 0; cv.notify_all(); } else cv.wait(l, [&] { return g != gen; }); }
+};
+static Barrier g_bar;
+static int g_world = 1;
+static std::vector<double> g_edge[8][2];
+static unsigned long long g_dt[8];
+static int peer_exchange(spruce_domain *d, double *const *U, void *)
+{
+    if (g_world == 1) return SPRUCE_OK;
+    const int r = d->cfg.rank, W = g_world;
+    const size_t rows = (size_t)HALO * d->P.pitch;
+    g_edge[r][0].resize(NEV * rows); g_edge[r][1].resize(NEV * rows);
+    for (int v = 0; v < NEV; v++) {
+        std::memcpy(&g_edge[r][0][v * rows], U[v], rows * sizeof(double));
+        std::memcpy(&g_edge[r][1][v * rows], U[v] + (size_t)(d->P.nx - HALO) * d->P.pitch, rows * sizeof(double));
+    }
+    g_bar.wait();
+    const int lo = r > 0 ? r - 1 : (d->P.xper ? W - 1 : -1), hi = r < W - 1 ? r + 1 : (d->P.xper ? 0 : -1);
+    for (int v = 0; v < NEV; v++) {
+        if (lo >= 0) std::memcpy(U[v] - rows, &g_edge[lo][1][v * rows], rows * sizeof(double));
+        if (hi >= 0) std::memcpy(U[v] + (size_t)d->P.nx * d->P.pitch, &g_edge[hi][0][v * rows], rows * sizeof(double));
+    }
+    g_bar.wait();
+    return SPRUCE_OK;
+}
+static int peer_dt_allgather(spruce_domain *d)
+{
+    if (g_world == 1) return SPRUCE_OK;
+    g_dt[d->cfg.rank] = d->ctl->dtmin_bits;
+    g_bar.wait();
+    for (int r = 0; r < g_world; r++) d->ctl->dtmin_bits = std::min(d->ctl->dtmin_bits, g_dt[r]);
+    g_bar.wait();
+    return SPRUCE_OK;
+}
 '''
 
 
@@ -54,7 +98,7 @@ def assemble():
     mk = (CSRC / "mhd_kernels.cuh").read_text()
     ca = (CSRC / "capi.cu").read_text()
     e2 = (CSRC / "mhd2e_host.cuh").read_text()
-    body = cut(e2, "struct E2Args {", "int e2_upload(")
+    body = cut(e2, "struct E2Args {", "int e2_upload(") + cut(e2, "// after spruce_eqs_setup on every rank of a decomposed run", "\n}\n") + "\n}\n"
     body, n = re.subn(r"(\w+)<<<(.+?), (\w+), 0, d->stream>>>\(", r"launch3(\1, \2, \3, ", body)
     assert n >= 6 and "<<<" not in body
     return "".join([PRELUDE, '#include "mhd2e_cells.cuh"\n#include "mhd2e_step.hpp"\nnamespace spruce {\n',
@@ -71,14 +115,15 @@ def emu():
     text = assemble()
     if not LIB.exists() or not src.exists() or src.read_text() != text:
         src.write_text(text)
-        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
     L = C.CDLL(str(LIB))
     L.emu2e_run.restype = C.c_int
     return L
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])                          # 2, 3: slabs as host threads, the peer transport a staging copy between them
 @pytest.mark.parametrize("k,xb,yb,integrator,nx,ny,loop,nmin", e2_cases())
-def test_product_mhd2e_launch_code_runs_whole_steps_equal_to_oracle(emu, k, xb, yb, integrator, nx, ny, loop, nmin):
+def test_product_mhd2e_launch_code_runs_whole_steps_equal_to_oracle(emu, k, xb, yb, integrator, nx, ny, loop, nmin, world):
     s = e2_state(nx, ny, loop)
     floors = dict(density_min=nmin, temp_min=1.0e4, thermal_energy_min=1.0e-6) if loop else dict(density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
     o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, **floors)
@@ -91,7 +136,7 @@ def test_product_mhd2e_launch_code_runs_whole_steps_equal_to_oracle(emu, k, xb, 
     bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
     out = np.zeros((7, nx, ny)); dt = np.zeros((nx, ny)); steps = np.zeros(nsteps)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = emu.emu2e_run(arr, vp(dx), vp(dy), C.c_int(nx), C.c_int(ny), bc, C.c_int(TI[integrator]), C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(0.2),
+    rc = emu.emu2e_run(C.c_int(world), arr, vp(dx), vp(dy), C.c_int(nx), C.c_int(ny), bc, C.c_int(TI[integrator]), C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(0.2),
                        C.c_double(floors["density_min"]), C.c_double(floors["temp_min"]), C.c_double(floors["thermal_energy_min"]), C.c_double(1.0), C.c_double(0.5), C.c_int(nsteps),
                        vp(out), vp(dt), vp(steps))
     assert rc == 0
