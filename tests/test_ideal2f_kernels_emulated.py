@@ -28,7 +28,7 @@ static int static_slot(const char *name)
     if (!strcmp(name, "grav_x")) return S_GX; if (!strcmp(name, "grav_y")) return S_GY;
     return -1;
 }
-static int h2d_plane(spruce_domain *d, double *dev, const double *host) { std::memcpy(dev, host, sizeof(double) * (size_t)d->P.nx * d->P.ny); return SPRUCE_OK; }
+static int h2d_plane(spruce_domain *d, double *dev, const double *host) { std::memcpy(dev, host, sizeof(double) * (size_t)d->P.nx * d->P.ny); return SPRUCE_OK; }      // local rows only
 static int d2h_plane(spruce_domain *d, double *host, const double *dev) { std::memcpy(host, dev, sizeof(double) * (size_t)d->P.nx * d->P.ny); return SPRUCE_OK; }
 static int exchange_plane(spruce_domain *, double *) { return SPRUCE_OK; }
 '''
@@ -41,7 +41,7 @@ def assemble():
     tk = (CSRC / "ideal2f_kernels.cuh").read_text()
     th = (CSRC / "ideal2f_host.cuh").read_text()
     e2inc = (ROOT / "tests" / "hostcheck" / "kernel_emu_2e.inc").read_text()
-    body = cut(th, "struct TfSideArgs {", "int tf_time_derivatives(")
+    body = cut(th, "struct TfSideArgs {", "int tf_time_derivatives(")      # includes tf_initial_exchange, tf_upload, tf_download
     body, n = re.subn(r"(\w+)<<<(.+?), (\w+), 0, d->stream>>>\(", r"launch3(\1, \2, \3, ", body)
     assert n >= 8 and "<<<" not in body
     domain = DOMAIN.replace("struct OneFluid2E;", "struct OneFluid2E;\nstruct TwoFluid;").replace(
@@ -67,7 +67,7 @@ def emu():
     text = assemble()
     if not LIB.exists() or not src.exists() or src.read_text() != text:
         src.write_text(text)
-        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
     L = C.CDLL(str(LIB))
     L.emu2f_run.restype = C.c_int
     return L
@@ -88,7 +88,8 @@ CASES = [
 
 @pytest.mark.parametrize("xb,yb,integ,nx,ny,ordered", CASES)
 @pytest.mark.parametrize("eic", [False, True])
-def test_two_fluid_launch_code_runs_whole_steps_equal_to_oracle(emu, xb, yb, integ, nx, ny, ordered, eic):
+@pytest.mark.parametrize("world", [1, 2, 3])                          # 2, 3: slabs as host threads, the peer transport a staging copy between them
+def test_two_fluid_launch_code_runs_whole_steps_equal_to_oracle(emu, xb, yb, integ, nx, ny, ordered, eic, world):
     s = synthetic.ucnp_cloud(nx, ny, drift=2.0e3, bfield=5.0)
     kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
     o = Oracle2F(s["planes"], s["ion_mass"], s["adiabatic_index"], remove_curl_terms=False, eic=eic, **kw)
@@ -100,7 +101,7 @@ def test_two_fluid_launch_code_runs_whole_steps_equal_to_oracle(emu, xb, yb, int
     outs = EVOLVED_2F + ["dt", "dt_i", "e_temp"]
     out = np.zeros((len(outs), nx, ny)); steps = np.zeros(nsteps); flag = C.c_int()
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = emu.emu2f_run((C.c_char_p * len(up))(*[k.encode() for k in up]), (C.c_void_p * len(up))(*[p.ctypes.data for p in planes]), C.c_int(len(up)), vp(dx), vp(dy), C.c_int(nx), C.c_int(ny),
+    rc = emu.emu2f_run(C.c_int(world), (C.c_char_p * len(up))(*[k.encode() for k in up]), (C.c_void_p * len(up))(*[p.ctypes.data for p in planes]), C.c_int(len(up)), vp(dx), vp(dy), C.c_int(nx), C.c_int(ny),
                        (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]]), C.c_int(TI[integ]), C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(0.2),
                        C.c_double(1.0), C.c_double(1.0e-3), C.c_double(1e-30), C.c_int(0), C.c_int(int(eic)), C.c_int(nsteps),
                        (C.c_char_p * len(outs))(*[k.encode() for k in outs]), C.c_int(len(outs)), vp(out), vp(steps), C.byref(flag))
