@@ -253,8 +253,21 @@ def test_anomalous_resistivity_through_ar_iterate(emu, name, kv, xb, yb, integra
     ij = (C.c_int * 2)(); nsub = C.c_int(); tmpl = np.zeros((nx, ny))
     iters = 2
     assert emu.cemu_anomalous_resistivity(h, vp(px), vp(py), vp(p), C.c_double(step), C.c_int(iters), ij, C.byref(nsub), vp(tmpl)) == 0
-    for _ in range(iters):
+    for k in range(iters):
+        if k == iters - 1:                                   # the last iteration's raw result, for the joule_heating plane (anomalousresistivity.cpp:167)
+            e_before = o.get("thermal_energy")
+            e_after = o.anomalous_core(step)[3]
+            o.close()                                        # anomalous_core advanced the tracked null point: rebuild the oracle up to this iteration
+            o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, **FLOORS)
+            o.run(2)
+            o.set_anomalous_resistivity(**a)
+            for _ in range(iters - 1):
+                o.anomalous_iterate(step)
         o.anomalous_iterate(step)
+    joule = np.zeros((nx, ny)); prod = np.zeros((nx, ny))
+    assert emu.cemu_anomalous_outputs(h, vp(joule), vp(prod)) == 0
+    assert same_bits(joule, (e_after - e_before) / step), "joule_heating plane: " + mismatch(joule, (e_after - e_before) / step)
+    assert same_bits(prod, o.anomalous_state()[1] * o.anomalous_diffusivity()), "anomalous_diffusivity plane"
     (ri, rj), rt = o.anomalous_state()
     assert (ij[0], ij[1]) == (ri, rj) and nsub.value == o.anomalous_subcycles()
     assert same_bits(tmpl, rt), "template: " + mismatch(tmpl, rt)
