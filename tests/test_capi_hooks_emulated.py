@@ -520,3 +520,32 @@ def test_radiative_losses_through_rl_iterate_with_output_plane(emu, xb, yb, inte
     assert ns >= 1 and np.count_nonzero(ref) > 0
     assert np.max(np.abs(avg - ref)) <= 1e-9 * np.max(np.abs(ref))
     o.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("xb,yb", [(("periodic", "periodic"), ("fixed", "open")), (("fixed", "open"), ("reflect", "open"))])
+def test_source_terms_on_slabs(emu, xb, yb, world):
+    nx, ny = 26, 19
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", **FLOORS)
+    o.run(2)
+    hs, cuts, keep = make_slabs(emu, s, o, xb, yb, nx, ny, world)
+    xl, xu = (0, nx - 1) if xb[0] == "periodic" else (2, nx - 3)
+    step = 0.2 * float(np.min(o.get("dt")[xl:xu + 1, 2:-2]))
+    t = 3.0
+    o.set_time(t)
+    o.add_small_module("mass_injection", start_time=2.0, duration=5.0, max_injection_rate=1.0e6, stddev_x=2.0, stddev_y=2.5, center_x=9.0, center_y=6.0)
+    o.add_small_module("momentum_injection", start_time=0.0, duration=50.0, max_accel=1.0e4, stddev_x=2.0, stddev_y=2.0, center_x=10.0, center_y=9.0, dir_x=0.6, dir_y=-0.8, template_angle=20.0,
+                       oscillatory=1.0, oscillation_period=7.0)
+    o.small_module_hooks(0, step)
+    planes = [[o.small_module_plane(m, w) for w in (0, 1)] for m in range(2)]
+    for m, (kind, start, dur, acc, osc, per) in enumerate([(2, 2.0, 5.0, 0.0, 0, 1.0), (3, 0.0, 50.0, 1.0e4, 1, 7.0)]):
+        p0 = np.ascontiguousarray(planes[m][0]); p1 = np.ascontiguousarray(planes[m][1]) if planes[m][1] is not None else None
+        rc = emu.cemu_run_slabs_source((C.c_void_p * world)(*hs), C.c_int(world), C.c_int(kind), C.c_double(start), C.c_double(dur), C.c_double(0.0), C.c_double(acc), C.c_int(osc), C.c_double(per),
+                                       vp(p0), vp(p1) if p1 is not None else None, C.c_double(t), C.c_double(step))
+        assert rc == 0
+    o.small_module_hooks(2, step)
+    for k, v in enumerate(EV):
+        got = gather(emu, hs, cuts, ny, k)
+        assert same_bits(got, o.get(v)), "%s differs: %s" % (v, mismatch(got, o.get(v)))
+    o.close()
