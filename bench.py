@@ -172,9 +172,9 @@ def run_ours(args):
 
     if world > 1:
         from spruce_b200.multigpu import partition
-        s = synthetic.orszag_tang(n, n, rows=partition(n, world)[rank], temp_mod=tmod)      # every rank builds only its own slab
+        s = synthetic.orszag_tang(n, n, rows=partition(n, world)[rank], temp_mod=tmod, zfull=args.zfull)      # every rank builds only its own slab
     else:
-        s = synthetic.orszag_tang(n, n, temp_mod=tmod)
+        s = synthetic.orszag_tang(n, n, temp_mod=tmod, zfull=args.zfull)
     planes = s["planes"]
     dx, dy = np.ascontiguousarray(s["dx"]), np.ascontiguousarray(s["dy"])
     names = ["be_x", "be_y", "be_z", "rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
@@ -337,6 +337,7 @@ def main():
     ap.add_argument("--stage-variants", type=int, default=0, nargs="?", const=1, choices=[0, 1, 2, 3],
                     help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS): 1 = on, 2 = also the six-CTAs-per-SM build of the 2-D instance, "
                          "3 = also its pair-wise mid-row barrier")
+    ap.add_argument("--zfull", action="store_true", help="OT state with non-zero mom_z / bi_z / be: the 12-quantity instance of the stage kernel (what any solar run takes)")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: library peer stores over NVLink, or torch.distributed NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:

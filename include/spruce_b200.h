@@ -196,8 +196,7 @@ int spruce_module_anomalous_resistivity(spruce_domain *dom, const double *pos_x,
 int spruce_module_anomalous_resistivity_state(spruce_domain *dom, int *null_i, int *null_j, int *num_subcycles);
 /* IdealMHD::parseEquationSetConfigs (source/equationsets/idealmhd.cpp:12-40): global_viscosity (idealmhd.hpp:48, default 0), read only
  * by the characteristic open boundary (global_visc_coeff, idealmhd.cpp:90).  open_moc sides themselves (idealmhd.cpp:306-615) are
- * selected through spruce_config.x_bound_* / y_bound_* = SPRUCE_BC_OPEN_MOC; until that path has been validated on a GPU
- * spruce_domain_create refuses it unless the environment sets SPRUCE_EXPERIMENTAL_MOC=1. */
+ * selected through spruce_config.x_bound_* / y_bound_* = SPRUCE_BC_OPEN_MOC (ideal_mhd only). */
 int spruce_eqs_ideal_mhd_options(spruce_domain *dom, double global_viscosity);
 /* moc_b_limiting / moc_mom_limiting with moc_{b,mom}_{lower,upper}_lim (idealmhd.cpp:17-36; applyBThresholdingMoC / applyMomThresholdingMoC :107-223): clamps of
  * the ghost layers and the first interior layer of every open_moc side at the head of each derived-variable pass, the reference's y_bound_2 index quirk

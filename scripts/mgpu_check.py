@@ -75,7 +75,7 @@ elif "2e" in modules:
     kw = dict(equation_set="ideal_mhd_2E", xb=("periodic", "periodic") if xbound == "periodic" else (xbound, "open"), yb=("fixed", "open"), integrator=integ,
               density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
 elif "moc" in modules or "mocv" in modules:
-    # open_moc sides (needs SPRUCE_EXPERIMENTAL_MOC=1): x periodic with a y side, or x sides (first / last slab) plus a y side -> corners on the end slabs
+    # open_moc sides: x periodic with a y side, or x sides (first / last slab) plus a y side -> corners on the end slabs
     s = synthetic.stratified_loop(nx, ny, bump=0.4)
     kw = dict(xb=("periodic", "periodic") if xbound == "periodic" else ("open_moc", "open_moc"), yb=("open_moc", "fixed") if xbound == "periodic" else ("fixed", "open_moc"),
               integrator=integ, density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6, eqs_options=dict(global_viscosity=0.2 if "mocv" in modules else 0.0))

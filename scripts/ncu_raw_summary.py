@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Append the headline metrics of the stage-kernel launches in an `ncu --page raw --csv` dump to
-profiles/r1_stage_kernel_ncu_raw_summary.json under a version tag.   usage: ncu_raw_summary.py raw.csv tag"""
+profiles/stage_kernel_ncu_raw_summary.json under a version tag.   usage: ncu_raw_summary.py raw.csv tag"""
 import csv, json, sys
 from pathlib import Path
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -24,7 +24,7 @@ for r in rows[2:]:
             i = hdr.index(k)
             e[k] = ("%s %s" % (r[i], units[i])).strip()
     out.append(e)
-p = Path(__file__).resolve().parents[1] / "profiles" / "r1_stage_kernel_ncu_raw_summary.json"
+p = Path(__file__).resolve().parents[1] / "profiles" / "stage_kernel_ncu_raw_summary.json"
 d = json.loads(p.read_text()) if p.exists() else {}
 d[sys.argv[2]] = out
 p.write_text(json.dumps(d, indent=1))

@@ -1,15 +1,16 @@
 #!/usr/bin/env python
 """Summarise `ncu --page source --csv --print-source sass` output: dynamic instruction mix by opcode,
-stall samples by opcode, and the hottest SASS addresses.  Usage: ncu_src_summary.py src.csv [cells]"""
+stall samples by opcode, and the hottest SASS addresses.  Usage: ncu_src_summary.py src.csv [cell-warps] [kernel index in the file]"""
 import csv, re, sys
 from collections import Counter, defaultdict
 rows = list(csv.reader(open(sys.argv[1])))
 cells_warps = float(sys.argv[2]) if len(sys.argv) > 2 else 4096 * 4096 / 32
-# the file may hold several kernels; take the first
+# the file may hold several kernels; take the first, or the one named by the third argument (0-based)
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-hdr = rows[starts[0]]
-end = starts[1] - 1 if len(starts) > 1 else len(rows)
-data = rows[starts[0] + 1:end]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+hdr = rows[starts[which]]
+end = starts[which + 1] - 1 if len(starts) > which + 1 else len(rows)
+data = rows[starts[which] + 1:end]
 ia, isrc, iex, ismp = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 ex, smp = Counter(), Counter()

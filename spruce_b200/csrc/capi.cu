@@ -109,12 +109,13 @@ struct spruce_domain {
     unsigned nonzero_mask = 0x1F;
     bool in_mgpu_stage_api = false;        // inside spruce_mgpu_stage (caller-owned exchange and dt reduction)
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
-    // open_moc (moc_stage.cuh): evolved ghost cells; SPRUCE_EXPERIMENTAL_MOC=1 until the launch side has been validated on a GPU
+    // open_moc (moc_stage.cuh): evolved ghost cells
     bool moc_any = false; double global_viscosity = 0.0; double *moc_base = nullptr;
     moc::Limits moc_lim{0, 0, 0.1, 10.0, 0.1, 10.0};                      // moc_b_limiting / moc_mom_limiting and their bounds (idealmhd.hpp:59-64)
     int chunk_rows_override = 0;           // SPRUCE_CHUNK_ROWS (16 .. XY_CHUNK, the range the automatic choice already spans): rows per CTA of the stage kernel, for tuning sweeps; 0 = pick_chunk_rows' own choice
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
-    int stage_variants = 0;                // compile-time integrator-stage instances of k_mhd_stage_xy: SPRUCE_STAGE_VARIANTS=1, =2: also six CTAs per SM (2-D instance), =3: also the pair-wise barrier
+    int stage_variants = 1;                // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=0: only the run-time-stage instances)
+    bool bulk_rows = true;                 // k_mhd_stage_xy stages rows with cp.async.bulk (SPRUCE_BULK_ROWS=0: per-thread cp.async everywhere)
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
@@ -298,6 +299,8 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
     A.chunk_rows = pick_chunk_rows(d);
+    A.bulk = d->bulk_rows ? 1 : 0;
+    A.walls = (d->cfg.x_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.x_bound_2 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_2 != SPRUCE_BC_PERIODIC) ? 1 : 0;
     if (part == 0 && primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
     const int nchunks = (d->P.nx + A.chunk_rows - 1) / A.chunk_rows;
     A.chunk0 = 0; A.chunk_stride = 1;
@@ -308,36 +311,26 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     dim3 grid((d->P.ny + CW - 1) / CW, gy);
     if (d->stage_kernel == 5) {
         const ActiveList L = active_quantities(d);
-        // compile-time integrator stage (SPRUCE_STAGE_VARIANTS=1, off by default): plain euler / rk2 stages without module terms
+        // compile-time integrator stage (SPRUCE_STAGE_VARIANTS=0 turns it off): plain euler / rk2 stages without module terms
         int var = 0;
         if (d->stage_variants && kmode == KM_NONE && A.n_xterm == 0) var = A.b_is_s ? (primary ? 3 : 1) : (primary ? 2 : 0);
-        if (var && d->stage_variants >= 2) var |= 4;                          // the six-CTAs-per-SM build of the 2-D instance
-        if (var && d->stage_variants == 3) var |= 8;                          // ... with the pair-wise mid-row barrier
-        const size_t sm6 = xy_smem_bytes(xy_rows(6)), smf = xy_smem_bytes(NTR);
         const bool list2d = L.n == 6 && L.q == XY_LIST_2D, listfull = L.n == 12 && L.q == XY_LIST_FULL;
         if (d->relaxed && d->static_lists && (list2d || listfull)) {          // any other list runs the exact run-time-list kernel below
             const int e = spruce_relaxed_launch_stage(grid.x, grid.y, (void *)st, &d->P, &A, &L, list2d ? 6 : 12, var);
             if (e != 0) return fail(SPRUCE_ERR_CUDA, "relaxed stage kernel: %s", cudaGetErrorString((cudaError_t)e));
         } else
-        if (d->static_lists && L.n == 6 && L.q == XY_LIST_2D) {
-            if (var == 1) k_mhd_stage_xy<6, XY_LIST_2D, 1><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 2) k_mhd_stage_xy<6, XY_LIST_2D, 2><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 3) k_mhd_stage_xy<6, XY_LIST_2D, 3><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 5) k_mhd_stage_xy<6, XY_LIST_2D, 5><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 6) k_mhd_stage_xy<6, XY_LIST_2D, 6><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 7) k_mhd_stage_xy<6, XY_LIST_2D, 7><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 13) k_mhd_stage_xy<6, XY_LIST_2D, 13><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 14) k_mhd_stage_xy<6, XY_LIST_2D, 14><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else if (var == 15) k_mhd_stage_xy<6, XY_LIST_2D, 15><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-            else k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, sm6, st>>>(d->P, A, L);
-        } else if (d->static_lists && L.n == 12 && L.q == XY_LIST_FULL) {
-            var &= 3;                                                          // the full instance has one residency and the CTA-wide barrier
-            if (var == 1) k_mhd_stage_xy<12, XY_LIST_FULL, 1><<<grid, XY_NT, smf, st>>>(d->P, A, L);
-            else if (var == 2) k_mhd_stage_xy<12, XY_LIST_FULL, 2><<<grid, XY_NT, smf, st>>>(d->P, A, L);
-            else if (var == 3) k_mhd_stage_xy<12, XY_LIST_FULL, 3><<<grid, XY_NT, smf, st>>>(d->P, A, L);
-            else k_mhd_stage_xy<12, XY_LIST_FULL><<<grid, XY_NT, smf, st>>>(d->P, A, L);
+        if (d->static_lists && list2d) {
+            if (var == 1) k_mhd_stage_xy<6, XY_LIST_2D, 1><<<grid, XY_NT, xy_smem_bytes(6, 1), st>>>(d->P, A, L);
+            else if (var == 2) k_mhd_stage_xy<6, XY_LIST_2D, 2><<<grid, XY_NT, xy_smem_bytes(6, 2), st>>>(d->P, A, L);
+            else if (var == 3) k_mhd_stage_xy<6, XY_LIST_2D, 3><<<grid, XY_NT, xy_smem_bytes(6, 3), st>>>(d->P, A, L);
+            else k_mhd_stage_xy<6, XY_LIST_2D><<<grid, XY_NT, xy_smem_bytes(6, 0), st>>>(d->P, A, L);
+        } else if (d->static_lists && listfull) {
+            if (var == 1) k_mhd_stage_xy<12, XY_LIST_FULL, 1><<<grid, XY_NT, xy_smem_bytes(NTR, 1), st>>>(d->P, A, L);
+            else if (var == 2) k_mhd_stage_xy<12, XY_LIST_FULL, 2><<<grid, XY_NT, xy_smem_bytes(NTR, 2), st>>>(d->P, A, L);
+            else if (var == 3) k_mhd_stage_xy<12, XY_LIST_FULL, 3><<<grid, XY_NT, xy_smem_bytes(NTR, 3), st>>>(d->P, A, L);
+            else k_mhd_stage_xy<12, XY_LIST_FULL><<<grid, XY_NT, xy_smem_bytes(NTR, 0), st>>>(d->P, A, L);
         }
-        else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, smf, st>>>(d->P, A, L);
+        else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, xy_smem_bytes(NTR, 0), st>>>(d->P, A, L);
     }
     else k_mhd_stage<<<grid, NT, STAGE_SMEM, st>>>(d->P, A);
     d->launches++;
@@ -1111,6 +1104,16 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         }
     }
     if (!d->visc.empty() && (rc = visc_refresh_dt(d))) return rc;     // Viscosity reads the PRIMARY state's dt plane
+    if (!d->module_order.empty() && d->stage_kernel == 5) {
+        // The modules use the planes of Mset as scratch (tc_iterate, dc_post, fh_pre).  The 2-D instance of the stage kernel neither reads nor
+        // writes mom_z / bi_z -- it relies on those planes being zero in EVERY set: euler swaps Mset in as the primary state, and the open_moc
+        // strip kernel reads all eight planes of the stage copy.  Restore the invariant before the stages run.
+        const ActiveList L = active_quantities(d);
+        if (L.n == 6 && L.q == XY_LIST_2D) {
+            CUDA_TRY(cudaMemsetAsync(d->Mset.p[E_MZ] - d->row_off, 0, d->plane_doubles * sizeof(double), d->stream));
+            CUDA_TRY(cudaMemsetAsync(d->Mset.p[E_BZ] - d->row_off, 0, d->plane_doubles * sizeof(double), d->stream));
+        }
+    }
     const int ti = d->cfg.time_integrator;
     if (ti == SPRUCE_TI_EULER) {                                        // evolution.cpp:84-88
         if ((rc = stage_and_exchange(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE))) return rc;   // ghost zones / halos of Mset ...
@@ -1210,8 +1213,6 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     bool moc_any = false;
     for (int b : bcs) if (b == SPRUCE_BC_OPEN_MOC) moc_any = true;
     if (moc_any) {
-        const char *ex = getenv("SPRUCE_EXPERIMENTAL_MOC");
-        if (!ex || atoi(ex) == 0) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries: the device path is built but has not been validated on a GPU yet; set SPRUCE_EXPERIMENTAL_MOC=1 to use it (SURVEY.md 8f-2)");
         if (two_fluid) return fail(SPRUCE_ERR_UNSUPPORTED, "open_moc boundaries exist for ideal_mhd only (idealmhd.cpp:306)");
         for (int a = 0; a < 2; a++)       // a periodic side opposite an open_moc side is not a configuration the reference can run
             if ((bcs[2 * a] == SPRUCE_BC_PERIODIC) != (bcs[2 * a + 1] == SPRUCE_BC_PERIODIC)) return fail(SPRUCE_ERR_ARG, "periodic boundaries come in pairs");
@@ -1226,39 +1227,27 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
 
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(xy_rows(6))));
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR, 0)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(6, 0)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(6, 1)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(6, 2)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(6, 3)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR, 0)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR, 1)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR, 2)));
+    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR, 3)));
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
-    if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) { const int v = atoi(sv); d->stage_variants = (v >= 1 && v <= 3) ? v : 0; }
+    if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0 ? 1 : 0;
+    if (const char *sb = getenv("SPRUCE_BULK_ROWS")) d->bulk_rows = atoi(sb) != 0;
     if (const char *cr = getenv("SPRUCE_CHUNK_ROWS")) { const int v = atoi(cr); if (v >= 16) d->chunk_rows_override = v; }
     if (const char *ar = getenv("SPRUCE_ARITH")) {
         if (!strcmp(ar, "relaxed")) d->relaxed = true;
         else if (strcmp(ar, "exact")) { delete d; return fail(SPRUCE_ERR_ARG, "SPRUCE_ARITH must be exact or relaxed"); }
     }
     d->moc_any = moc_any;
-    if (d->stage_variants) {   // the compile-time integrator-stage instances: configured only when asked for (the default path stays exactly the validated one)
-        const int sm6 = (int)xy_smem_bytes(xy_rows(6)), smf = (int)xy_smem_bytes(NTR);
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm6));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // 6 x 37 KB
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 13>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 14>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 15>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
-        CUDA_TRY_D(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
-    }
-
     DomainParams &P = d->P;
     P.nx = cfg->nx_local; P.ny = cfg->ydim; P.pitch = (cfg->ydim + 15) & ~15;
     P.gnx = cfg->xdim; P.row0 = cfg->row0;

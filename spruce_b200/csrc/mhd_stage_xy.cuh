@@ -25,22 +25,29 @@ constexpr int XY_RV = 3;                     // velocity ring depth (rows r, r+1
 constexpr int XY_CHUNK = 48;                 // rows per CTA (upper bound)
 constexpr int XY_XT = XY_CHUNK + 6;          // x-table entries: local rows -3 .. chunk+2
 constexpr int XW = 64;                       // width of the per-column exchange arrays: one private slot per (warp column, lane)
-// shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, x / y parts of the transports,
-// derivative exchange, dt exchange (read by the Y warps one iteration later, before the X warps overwrite it).
-// nq = quantity rows kept in the ring and in the per-quantity exchange arrays: all 11, or only the 6 of the 2-D instance.
+// shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, the x parts of the transports the Y warps finish (TX), the y parts
+// the X warps finish (TY), derivative exchange, dt exchange (read by the Y warps one iteration later, before the X warps overwrite it), the own-cell
+// rows (gravity, base state) and two mbarriers.
+// nq = quantity rows kept in the ring and in the flux carry: all 11, or only the 6 of the 2-D instance.
+__host__ __device__ constexpr int xy_ntx(int nq) { return nq == 6 ? 3 : 7; }         // thermal_energy, bi_x, bi_y (+ bi_z, be_x, be_y, be_z)
+__host__ __device__ constexpr int xy_nty(int nq) { return nq == 6 ? 3 : 4; }         // rho, mom_x, mom_y (+ mom_z)
 __host__ __device__ constexpr int xy_off_vel(int nq) { return RD * nq * SW; }
 __host__ __device__ constexpr int xy_off_xt(int nq) { return xy_off_vel(nq) + XY_RV * 3 * SW; }
 __host__ __device__ constexpr int xy_off_fx(int nq) { return xy_off_xt(nq) + 7 * XY_XT; }
 __host__ __device__ constexpr int xy_off_tx(int nq) { return xy_off_fx(nq) + nq * XW; }
-__host__ __device__ constexpr int xy_off_ty(int nq) { return xy_off_tx(nq) + nq * XW; }
-__host__ __device__ constexpr int xy_off_dc(int nq) { return xy_off_ty(nq) + nq * XW; }
+__host__ __device__ constexpr int xy_off_ty(int nq) { return xy_off_tx(nq) + xy_ntx(nq) * XW; }
+__host__ __device__ constexpr int xy_off_dc(int nq) { return xy_off_ty(nq) + xy_nty(nq) * XW; }
 __host__ __device__ constexpr int xy_off_dt(int nq) { return xy_off_dc(nq) + 3 * XW; }             // aliases Dc_s[3..5]: a thread reads its Dc/Dt slot before it overwrites it
-__host__ __device__ constexpr int xy_doubles(int nq) { return xy_off_dc(nq) + 6 * XW; }
-__host__ __device__ constexpr size_t xy_smem_bytes(int nq) { return (size_t)xy_doubles(nq) * sizeof(double); }
+__host__ __device__ constexpr int xy_off_own(int nq) { return xy_off_dc(nq) + 6 * XW; }
+// own-cell rows: grav_x, grav_y, and -- unless the stage's base state is the state it differentiates (first rk stage, euler) -- the base state B
+__host__ __device__ constexpr int xy_nown(int nq, int var) { return ((var & 3) == 1 || (var & 3) == 3) ? 2 : 2 + (nq == 6 ? 6 : 8); }
+__host__ __device__ constexpr int xy_off_mbar(int nq, int var) { return xy_off_own(nq) + xy_nown(nq, var) * XW; }
+__host__ __device__ constexpr int xy_doubles(int nq, int var) { return xy_off_mbar(nq, var) + 2; }
+__host__ __device__ constexpr size_t xy_smem_bytes(int nq, int var) { return (size_t)xy_doubles(nq, var) * sizeof(double); }
 __host__ __device__ constexpr int xy_rows(int ln) { return ln == 6 ? 6 : NTR; }
-__host__ __device__ constexpr int xy_ctas_per_sm(int ln) { return ln == 6 ? 5 : 4; }               // the 2-D instance: 36 KB of shared memory and <= 96 registers -> 20 warps / SM
-static_assert(xy_smem_bytes(NTR) <= 57344, "four CTAs per SM need <= 56 KB each");
-static_assert(xy_smem_bytes(6) <= 45000, "five CTAs per SM need <= 45 KB each");
+__host__ __device__ constexpr int xy_ctas_per_sm(int ln) { return ln == 6 ? 5 : 4; }               // the 2-D instance: <= 45 KB of shared memory and <= 96 registers -> 20 warps / SM
+static_assert(xy_smem_bytes(NTR, 0) <= 57344, "four CTAs per SM need <= 56 KB each");
+static_assert(xy_smem_bytes(6, 0) <= 45000, "five CTAs per SM need <= 45 KB each");
 
 struct ActiveList { int n; unsigned long long q; };   // transported quantities that can be non-zero (one nibble each), padded to an even count
 
@@ -56,13 +63,34 @@ constexpr unsigned long long xy_list(int a = -1, int b = -1, int c = -1, int d =
 constexpr unsigned long long XY_LIST_2D = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY);                                              // no z system, no external field
 constexpr unsigned long long XY_LIST_FULL = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY, Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_BEZ);   // everything (padded to 12)
 
+// ---- bulk asynchronous copies (cp.async.bulk, the 1-D form of TMA) with mbarrier completion
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // VAR > 0: the integrator stage is a compile-time constant too (no K planes, no module right-hand-side terms).  VAR & 3 =
 //   1: B == S, secondary (first stage of rk2)   2: B != S, primary (last stage of rk2)   3: B == S, primary (euler).
-// VAR & 4 (2-D instance only): compiled for SIX resident CTAs per SM (80 registers, a few dozen bytes of spill; 6 x 37 KB of shared memory).
-// VAR & 8 (with VAR & 4): the mid-row barrier is pair-wise (two 64-thread named barriers) instead of CTA-wide.
 // VAR == 0 takes kmode / b_is_s / primary / n_xterm from the launch arguments (every integrator, every module).
+//
+// How rows reach shared memory.  A CTA whose 66 staged columns lie inside the row (every strip except the first and the last one or two) takes the
+// BULK path: one thread issues one cp.async.bulk per quantity and row -- the 528-byte ring rows and the 496-byte own-cell rows (gravity, base state)
+// are 16-byte multiples at 16-byte aligned addresses -- and completion is signalled on two mbarriers (ring row r+3: waited for at the end of iteration
+// r; own-cell rows of row r: issued at the top of iteration r, waited for before phase 2).  Strips that touch the y boundary (periodic wrap or
+// out-of-range columns) and rows beyond a physical x boundary keep the per-thread path (cp.async 8-byte copies / fills by the 66 loader threads).
 template <int LN, unsigned long long LQ, int VAR = 0>
-__global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
+__global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
 {
     constexpr int UNR = LN > 0 ? LN : 1;
 #define kmode (VAR ? (int)KM_NONE : A.kmode)
@@ -79,20 +107,25 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
     extern __shared__ __align__(16) double smem[];
     if (*A.done_ptr) return;
     constexpr int NQ = xy_rows(LN);
-    // row of quantity q inside a ring slot / an exchange array: identity, or the compact order rho, mom_x, mom_y, e, bi_x, bi_y of the 2-D instance
+    constexpr int NOWN = xy_nown(NQ, VAR);
+    constexpr bool HAVE_B = NOWN > 2;                                            // the own-cell buffer has rows for the base state
+    constexpr int NB = Z ? 4 : 3;                                                // base-state rows per role
+    // row of quantity q inside a ring slot / the flux carry: identity, or the compact order rho, mom_x, mom_y, e, bi_x, bi_y of the 2-D instance
     auto QI = [](int q) { return LN == 6 ? (q < Q_MZ ? q : q - 1) : q; };
     double *ringp = smem;
     double (*vel)[3][SW] = reinterpret_cast<double (*)[3][SW]>(smem + xy_off_vel(NQ));
     double (*xt)[XY_XT] = reinterpret_cast<double (*)[XY_XT]>(smem + xy_off_xt(NQ));
     double *Fx_p = smem + xy_off_fx(NQ);                                          // [quantity row][XW]
-    double *TX_p = smem + xy_off_tx(NQ);                                          // x parts of transportDivergence2D, every quantity
-    double *TY_p = smem + xy_off_ty(NQ);                                          // y parts
+    double *TX_p = smem + xy_off_tx(NQ);                                          // x parts of transportDivergence2D of the quantities the Y warps finish
+    double *TY_p = smem + xy_off_ty(NQ);                                          // y parts ... the X warps finish
     double (*Dc_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_dc(NQ));
     double (*Dt_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_dt(NQ));
+    double (*own)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_own(NQ));  // [0] grav_x [1] grav_y [2..] B: n, mom_x, mom_y, (mom_z), e, bi_x, bi_y, (bi_z)
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + xy_off_mbar(NQ, VAR));   // [0] ring rows, [1] own-cell rows
 #define RG(sl, q, cc) ringp[((sl) * NQ + QI(q)) * SW + (cc)]
 #define FXS(q, cc) Fx_p[QI(q) * XW + (cc)]
-#define TXS(q, cc) TX_p[QI(q) * XW + (cc)]
-#define TYS(q, cc) TY_p[QI(q) * XW + (cc)]
+#define TXS(q, cc) TX_p[((q) - Q_E) * XW + (cc)]
+#define TYS(q, cc) TY_p[(q) * XW + (cc)]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool isX = warp < 2;
@@ -107,8 +140,10 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
     const int r0 = (A.chunk0 + (int)blockIdx.y * A.chunk_stride) * A.chunk_rows;
     const int r1 = min(r0 + A.chunk_rows, P.nx);
     const bool col_out = (lane < 31) && (j < P.ny);
+    const bool bulk = A.bulk && j0 >= HALO && j0 + CW + HALO <= P.ny;            // CTA-uniform: all 66 staged columns are inside the row
+    const bool issuer = (tid == 96);                                            // the thread that issues the bulk copies (warp 3, lane 0)
 
-    // ---- loader: thread t < SW owns shared column t
+    // ---- per-thread loader (strips at the y boundary, rows beyond a physical x boundary): thread t < SW owns shared column t
     const bool loader = tid < SW;
     int jl = j0 - HALO + tid;
     bool jl_ok = loader && (jl >= 0 && jl < P.ny);
@@ -117,15 +152,23 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
     auto vslot_of = [&](int r) { return (r - r0 + HALO + 3 * XY_RV) % XY_RV; };
     auto next_slot = [](int s_) { return s_ == RD - 1 ? 0 : s_ + 1; };
     auto next_vslot = [](int s_) { return s_ == XY_RV - 1 ? 0 : s_ + 1; };
-    auto issue_row = [&](int r, int slot) {
+    auto wrap_row = [&](int r) { return P.xwrap ? (r < 0 ? r + P.nx : (r >= P.nx ? r - P.nx : r)) : r; };   // single-rank periodic x: one add, no modulo
+    auto fill_row = [&](int slot) {                              // a row beyond a physical x boundary: never used by an in-range operator
+        if (!loader) return;
+        if (LN == 6) {
+            RG(slot, Q_RHO, tid) = 1.0; RG(slot, Q_MX, tid) = 0.0; RG(slot, Q_MY, tid) = 0.0;
+            RG(slot, Q_E, tid) = 0.0; RG(slot, Q_BIX, tid) = 0.0; RG(slot, Q_BIY, tid) = 0.0;
+        } else {
+#pragma unroll
+            for (int v = 0; v < NTR; v++) RG(slot, v, tid) = (v == Q_RHO) ? 1.0 : 0.0;
+        }
+    };
+    auto issue_row = [&](int r, int slot) {                      // per-thread path
         if (!loader) return;
         if (row_exists(P, r) && jl_ok) {
-            int pr = r;                                        // single-rank periodic x: rows -2..nx+1 wrap with one add (no modulo)
-            if (P.xwrap) pr = r < 0 ? r + P.nx : (r >= P.nx ? r - P.nx : r);
-            const size_t off = (size_t)pr * P.pitch + jl;
+            const size_t off = (size_t)wrap_row(r) * P.pitch + jl;
             if (LN == 6) {
-                // 2-D list: mom_z, bi_z and the external field are identically zero planes (host-tracked); their ring rows are zeroed
-                // once in the prologue and never loaded
+                // 2-D list: mom_z, bi_z and the external field are identically zero planes (host-tracked) and have no ring rows
                 cp_async8(&RG(slot, Q_RHO, tid), A.S[E_N] + off); cp_async8(&RG(slot, Q_MX, tid), A.S[E_MX] + off);
                 cp_async8(&RG(slot, Q_MY, tid), A.S[E_MY] + off); cp_async8(&RG(slot, Q_E, tid), A.S[E_E] + off);
                 cp_async8(&RG(slot, Q_BIX, tid), A.S[E_BX] + off); cp_async8(&RG(slot, Q_BIY, tid), A.S[E_BY] + off);
@@ -136,23 +179,73 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
                 cp_async8(&RG(slot, Q_BEY, tid), A.st[S_BEY] + off);
                 cp_async8(&RG(slot, Q_BEZ, tid), A.st[S_BEZ] + off);
             }
-        } else if (LN == 6) {
-            RG(slot, Q_RHO, tid) = 1.0; RG(slot, Q_MX, tid) = 0.0; RG(slot, Q_MY, tid) = 0.0;
-            RG(slot, Q_E, tid) = 0.0; RG(slot, Q_BIX, tid) = 0.0; RG(slot, Q_BIY, tid) = 0.0;
+        } else fill_row(slot);
+    };
+    constexpr unsigned ROW_BYTES = SW * sizeof(double), OWN_BYTES = CW * sizeof(double);
+    constexpr unsigned RING_TX = (LN == 6 ? 6 : NLOAD) * ROW_BYTES;
+    auto bulk_row = [&](int r, int slot) {                       // issuer only; the row exists
+        const size_t off = (size_t)wrap_row(r) * P.pitch + (j0 - HALO);
+        if (LN == 6) {
+            bulk_g2s(&RG(slot, Q_RHO, 0), A.S[E_N] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_MX, 0), A.S[E_MX] + off, ROW_BYTES, &mbar[0]);
+            bulk_g2s(&RG(slot, Q_MY, 0), A.S[E_MY] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_E, 0), A.S[E_E] + off, ROW_BYTES, &mbar[0]);
+            bulk_g2s(&RG(slot, Q_BIX, 0), A.S[E_BX] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_BIY, 0), A.S[E_BY] + off, ROW_BYTES, &mbar[0]);
         } else {
 #pragma unroll
-            for (int v = 0; v < NTR; v++) RG(slot, v, tid) = (v == Q_RHO) ? 1.0 : 0.0;
+            for (int v = 0; v < NEV; v++) bulk_g2s(&RG(slot, v, 0), A.S[v] + off, ROW_BYTES, &mbar[0]);
+            bulk_g2s(&RG(slot, Q_BEX, 0), A.st[S_BEX] + off, ROW_BYTES, &mbar[0]);
+            bulk_g2s(&RG(slot, Q_BEY, 0), A.st[S_BEY] + off, ROW_BYTES, &mbar[0]);
+            bulk_g2s(&RG(slot, Q_BEZ, 0), A.st[S_BEZ] + off, ROW_BYTES, &mbar[0]);
         }
     };
-    auto convert_rho = [&](int s_) { if (loader) { RG(s_, Q_RHO, tid) = RG(s_, Q_RHO, tid) * P.m_i; } };   // idealmhd.cpp:247
-    // v = mom / rho (idealmhd.cpp:248-250): one IEEE reciprocal, then the exact-division correction per component (exact_math.cuh)
+    // own-cell rows of row r (a row of the slab itself: it always exists): gravity for the X warps, the base state for both roles
+    const bool want_b = HAVE_B && !b_is_s;
+    auto own_row = [&](int r) {
+        const size_t roff = (size_t)r * P.pitch;
+        if (bulk) {
+            if (!issuer) return;
+            fence_proxy_async();
+            mbar_expect_tx(&mbar[1], (2 + (want_b ? 2 * NB : 0)) * OWN_BYTES);
+            bulk_g2s(own[0], A.st[S_GX] + roff + j0, OWN_BYTES, &mbar[1]); bulk_g2s(own[1], A.st[S_GY] + roff + j0, OWN_BYTES, &mbar[1]);
+            if (HAVE_B && want_b) {
+                bulk_g2s(own[2], A.B[E_N] + roff + j0, OWN_BYTES, &mbar[1]); bulk_g2s(own[3], A.B[E_MX] + roff + j0, OWN_BYTES, &mbar[1]);
+                bulk_g2s(own[4], A.B[E_MY] + roff + j0, OWN_BYTES, &mbar[1]);
+                if (Z) bulk_g2s(own[5], A.B[E_MZ] + roff + j0, OWN_BYTES, &mbar[1]);
+                bulk_g2s(own[2 + NB], A.B[E_E] + roff + j0, OWN_BYTES, &mbar[1]); bulk_g2s(own[3 + NB], A.B[E_BX] + roff + j0, OWN_BYTES, &mbar[1]);
+                bulk_g2s(own[4 + NB], A.B[E_BY] + roff + j0, OWN_BYTES, &mbar[1]);
+                if (Z) bulk_g2s(own[5 + NB], A.B[E_BZ] + roff + j0, OWN_BYTES, &mbar[1]);
+            }
+        } else if (col_out) {
+            const size_t off = roff + j;
+            if (isX) {
+                cp_async8(&own[0][ccol], A.st[S_GX] + off); cp_async8(&own[1][ccol], A.st[S_GY] + off);
+                if (HAVE_B && want_b) {
+                    cp_async8(&own[2][ccol], A.B[E_N] + off); cp_async8(&own[3][ccol], A.B[E_MX] + off); cp_async8(&own[4][ccol], A.B[E_MY] + off);
+                    if (Z) cp_async8(&own[5][ccol], A.B[E_MZ] + off);
+                }
+            } else if (HAVE_B && want_b) {
+                cp_async8(&own[2 + NB][ccol], A.B[E_E] + off); cp_async8(&own[3 + NB][ccol], A.B[E_BX] + off); cp_async8(&own[4 + NB][ccol], A.B[E_BY] + off);
+                if (Z) cp_async8(&own[5 + NB][ccol], A.B[E_BZ] + off);
+            }
+        }
+    };
+    // rho = n * m_i (idealmhd.cpp:247) for the 66 columns of a ring row: warp 3, two columns per lane (lane 0 also takes the last pair)
+    auto convert_rho = [&](int s_) {
+        if (warp != 3) return;
+        double2 *p2 = reinterpret_cast<double2 *>(&RG(s_, Q_RHO, 0));
+        double2 v = p2[lane]; v.x = v.x * P.m_i; v.y = v.y * P.m_i; p2[lane] = v;
+        if (lane == 0) { double2 w = p2[32]; w.x = w.x * P.m_i; w.y = w.y * P.m_i; p2[32] = w; }
+        if (bulk) fence_proxy_async();                           // this slot is the target of a bulk copy again five rows later
+    };
+    // v = mom / rho (idealmhd.cpp:248-250): one IEEE reciprocal, then the exact-division correction per component (exact_math.cuh).
+    // Velocities are read at shared columns 1 .. 64 only (own column and the left neighbour of a y face): warps 0 and 1, one column per thread.
     auto form_vel = [&](int s_, int v_) {
-        if (!loader) return;
-        const double rho = RG(s_, Q_RHO, tid);
+        if (warp >= 2) return;
+        const int cc = tid + 1;
+        const double rho = RG(s_, Q_RHO, cc);
         const double rr = 1.0 / rho;
-        vel[v_][0][tid] = ddiv(RG(s_, Q_MX, tid), rho, rr);
-        vel[v_][1][tid] = ddiv(RG(s_, Q_MY, tid), rho, rr);
-        vel[v_][2][tid] = (LN == 6) ? 0.0 : ddiv(RG(s_, Q_MZ, tid), rho, rr);      // the 2-D list is only chosen when mom_z is identically zero
+        vel[v_][0][cc] = ddiv(RG(s_, Q_MX, cc), rho, rr);
+        vel[v_][1][cc] = ddiv(RG(s_, Q_MY, cc), rho, rr);
+        vel[v_][2][cc] = (LN == 6) ? 0.0 : ddiv(RG(s_, Q_MZ, cc), rho, rr);      // the 2-D list is only chosen when mom_z is identically zero
     };
 
     const double step = *A.step_ptr;
@@ -167,7 +260,8 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
             const int t = e / XY_XT, i = e - t * XY_XT;
             if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
         }
-        for (int e = tid; e < 3 * NQ * XW + 6 * XW; e += XY_NT) Fx_p[e] = 0.0;              // Fx, TX, TY, Dc are contiguous
+        for (int e = tid; e < xy_off_own(NQ) - xy_off_fx(NQ); e += XY_NT) Fx_p[e] = 0.0;              // Fx, TX, TY, Dc are contiguous
+        if (bulk && issuer) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
     }
     auto x_geom = [&](int f) {
         const int i = f - r0 + 3;
@@ -185,10 +279,24 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
     const double dy = P.ty.d[min(j, P.ny)], rdy = P.ty.rd[min(j, P.ny)];
 
     // ---- prologue: rows r0-2 .. r0+2 land, rho is formed for all of them, velocity for rows r0-1, r0, r0+1
-    for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r, slot_of(r));
-    cp_async_commit();
-    cp_async_wait_all();
+    unsigned ring_par = 0, own_par = 0;          // phase parities of the two mbarriers (bulk path)
+    if (bulk) {
+        __syncthreads();                         // the mbarriers are initialised
+        int nex = 0;
+        for (int r = r0 - HALO; r <= r0 + HALO; r++) { if (row_exists(P, r)) nex++; else fill_row(slot_of(r)); }
+        if (issuer) {
+            if (nex) mbar_expect_tx(&mbar[0], nex * RING_TX);
+            for (int r = r0 - HALO; r <= r0 + HALO; r++) if (row_exists(P, r)) bulk_row(r, slot_of(r));
+        }
+        if (nex) { mbar_wait(&mbar[0], ring_par); ring_par ^= 1u; }
+    } else {
+        for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r, slot_of(r));
+        cp_async_commit();
+        cp_async_wait_all();
+    }
+    __syncthreads();                             // per-thread fills / copies of other threads
     for (int r = r0 - HALO; r <= r0 + HALO; r++) convert_rho(slot_of(r));
+    __syncthreads();
     for (int r = r0 - 1; r <= r0 + 1; r++) form_vel(slot_of(r), vslot_of(r));
     __syncthreads();
 
@@ -225,8 +333,16 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
         const int sm1 = s0 == 0 ? RD - 1 : s0 - 1, sp1 = next_slot(s0), sp2 = next_slot(sp1), sp3 = next_slot(sp2);
         const int v1 = next_vslot(v0), v2 = next_vslot(v1);
         const bool pre = (r + 3 <= r1 + HALO - 1);
-        if (pre) issue_row(r + 3, sp3);
-        cp_async_commit();
+        const bool pre_bulk = pre && bulk && row_exists(P, r + 3);
+        // own-cell rows of this row (consumed in phase 2), then the ring row three rows ahead
+        own_row(r);
+        if (!bulk) cp_async_commit();
+        if (pre) {
+            if (pre_bulk) { if (issuer) { mbar_expect_tx(&mbar[0], RING_TX); bulk_row(r + 3, sp3); } }
+            else if (bulk) fill_row(sp3);
+            else issue_row(r + 3, sp3);
+        }
+        if (!bulk) cp_async_commit();
 
         const int g = P.row0 + r;
         const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
@@ -234,22 +350,10 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
         const size_t off = (size_t)r * P.pitch + (col_out ? j : 0);
         const double pc = RG(s0, Q_E, c) * P.gm1;                 // press = (gamma-1)*thermal_energy  idealmhd.cpp:253
 
-        // own-cell values from global memory: requested now, consumed after the barrier
-        // (no branch on col_out here: lanes without an output column read column 0 of the row -- a divergent branch at this
-        //  point would leave the warp split, and un-reconverged, for the whole of phase 1)
-        double g0, g1, B0 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;
-        {
-            const double *pa = isX ? A.st[S_GX] : A.B[E_E], *pb = isX ? A.st[S_GY] : A.B[E_BX];
-            g0 = pa[off]; g1 = pb[off];                      // X: gravity ; Y: B[thermal_energy], B[bi_x]
-            if (!b_is_s) {                                 // warp-uniform
-                const double *p0 = isX ? A.B[E_N] : A.B[E_BY], *p1 = isX ? A.B[E_MX] : A.B[E_BZ], *p2 = isX ? A.B[E_MY] : A.B[E_BY], *p3 = isX ? A.B[E_MZ] : A.B[E_BZ];
-                B0 = p0[off]; B1 = p1[off]; B2 = p2[off]; B3 = p3[off];
-            }
-        }
-        __syncwarp();
-
         // ================================================================ phase 1: one direction per warp
         double d_a = 0.0, d_b = 0.0, d_c = 0.0, d_d = 0.0, d_e = 0.0, d_f = 0.0;       // central derivatives kept by this role
+        // the transport parts this role finishes itself stay in registers: X: rho, mom_x, mom_y, mom_z ; Y: e, bi_x, bi_y, bi_z, be_x, be_y, be_z
+        double t_0 = 0.0, t_1 = 0.0, t_2 = 0.0, t_3 = 0.0, t_4 = 0.0, t_5 = 0.0, t_6 = 0.0;
         if (isX) {
             // ---- x face r+1 (between rows r and r+1)
             const FaceGeom gx = x_geom(r + 1);
@@ -261,6 +365,9 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
             // the far cell of the extrapolation: row r-1 for flow in +x, row r+2 for flow in -x -- one load from a selected row
             const double *far_row = &RG(fsx.pos ? sm1 : sp2, 0, c);
             double Ix1_biy = 0.0, Ix1_biz = 0.0;
+            auto keep_x = [&](int q, double t) {                  // folds away for compile-time lists
+                if (q == Q_RHO) t_0 = t; else if (q == Q_MX) t_1 = t; else if (q == Q_MY) t_2 = t; else if (q == Q_MZ) t_3 = t; else TXS(q, col) = t;
+            };
 #pragma unroll UNR
             for (int k = 0; k < L.n; k += 2) {
                 const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
@@ -270,7 +377,7 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
                 const double af1 = aS * vfx1, bf1 = bS * vfx1;
                 const double at = ddiv(af1 - FXS(qa, fcol), dx, rdx), bt = ddiv(bf1 - FXS(qb, fcol), dx, rdx);   // derivs.cpp:155-156
                 FXS(qa, fcol) = af1; FXS(qb, fcol) = bf1;
-                TXS(qa, col) = at;  TXS(qb, col) = bt;
+                keep_x(qa, at); keep_x(qb, bt);
                 if (qa == Q_BIY) Ix1_biy = ad2; if (qb == Q_BIY) Ix1_biy = bd2;
                 if (qa == Q_BIZ) Ix1_biz = ad2; if (qb == Q_BIZ) Ix1_biz = bd2;
             }
@@ -301,6 +408,10 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
             const FaceSel fsy = select_face(gy, vfyL);
             const double *far_col = &RG(s0, 0, fsy.pos ? c - 2 : c + 1);
             double IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
+            auto keep_y = [&](int q, double t) {
+                if (q == Q_E) t_0 = t; else if (q == Q_BIX) t_1 = t; else if (q == Q_BIY) t_2 = t; else if (q == Q_BIZ) t_3 = t;
+                else if (q == Q_BEX) t_4 = t; else if (q == Q_BEY) t_5 = t; else if (q == Q_BEZ) t_6 = t; else TYS(q, col) = t;
+            };
 #pragma unroll UNR
             for (int k = 0; k < L.n; k += 2) {
                 const int qa = (int)((L.q >> (4 * k)) & 15ULL), qb = (int)((L.q >> (4 * k + 4)) & 15ULL);
@@ -309,8 +420,8 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
                 const double bS = upwind_face_far(far_col[QI(qb) * SW], RG(s0, qb, c - 1), RG(s0, qb, c), fsy, &bd2);
                 const double afL = aS * vfyL, bfL = bS * vfyL;
                 const double afR = shfl_next(afL), bfR = shfl_next(bfL), ad2R = shfl_next(ad2), bd2R = shfl_next(bd2);
-                TYS(qa, col) = ddiv(afR - afL, dy, rdy);
-                TYS(qb, col) = ddiv(bfR - bfL, dy, rdy);
+                keep_y(qa, ddiv(afR - afL, dy, rdy));
+                keep_y(qb, ddiv(bfR - bfL, dy, rdy));
                 if (qa == Q_BIX) { IyL_bix = ad2; IyR_bix = ad2R; } if (qb == Q_BIX) { IyL_bix = bd2; IyR_bix = bd2R; }
                 if (qa == Q_BIZ) { IyL_biz = ad2; IyR_biz = ad2R; } if (qb == Q_BIZ) { IyL_biz = bd2; IyR_biz = bd2R; }
             }
@@ -321,23 +432,22 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
             d_e = ddiv(IyR_vx - IyL_vx, dy, rdy);                   // d(v_x)/dy
             if (Z) d_f = ddiv(IyR_vz - IyL_vz, dy, rdy);            // d(v_z)/dy
         }
-        // partial results are visible to the other role.  The exchange slots are private to a (warp column, lane): X warp w only talks to Y warp w + 2,
-        // so the pair-wise form (VAR & 8) waits for the partner warp alone on named barrier 1 + wcol; the ring itself is published by the CTA-wide
-        // barrier at the end of the iteration.
-        if (VAR & 8) asm volatile("bar.sync %0, 64;" ::"r"(1 + wcol) : "memory");
-        else __syncthreads();
+        // the own-cell rows have landed (they had the whole of phase 1), then the partial results become visible to the other role
+        if (bulk) { mbar_wait(&mbar[1], own_par); own_par ^= 1u; }
+        else asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
 
         // ================================================================ phase 2: finish the outputs
-        __syncwarp();
         dt_pending = false;
         if (col_out) {
             const double bix = RG(s0, Q_BIX, c), biy = RG(s0, Q_BIY, c), biz = Z ? RG(s0, Q_BIZ, c) : 0.0;
             const double bex = Z ? RG(s0, Q_BEX, c) : 0.0, bey = Z ? RG(s0, Q_BEY, c) : 0.0, bez = Z ? RG(s0, Q_BEZ, c) : 0.0;
             if (isX) {
                 const double rho = RG(s0, Q_RHO, c);
+                const double g0 = own[0][ccol], g1 = own[1][ccol];                               // gravity
                 const double dbix_dy = Dc_s[3][col], dbiz_dy = Dc_s[4][col], dp_dy = Dc_s[5][col];
-                const double T_rho = TXS(Q_RHO, col) + TYS(Q_RHO, col), T_mx = TXS(Q_MX, col) + TYS(Q_MX, col);
-                const double T_my = TXS(Q_MY, col) + TYS(Q_MY, col), T_mz = Z ? TXS(Q_MZ, col) + TYS(Q_MZ, col) : 0.0;
+                const double T_rho = t_0 + TYS(Q_RHO, col), T_mx = t_1 + TYS(Q_MX, col);
+                const double T_my = t_2 + TYS(Q_MY, col), T_mz = Z ? t_3 + TYS(Q_MZ, col) : 0.0;
                 double k0 = T_rho * -1.0;                                                        // idealmhd.cpp:52
                 const double cdb = ddiv(d_a - dbix_dy, P.fourpi, P.rfourpi);                    // :54
                 const double ncdb = cdb * -1.0;
@@ -368,11 +478,11 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
                 }
                 if (kmode != KM_EXPORT) {
                     double Un, Umx, Umy, Umz;                                                   // equationset.cpp:226-228
-                    if (b_is_s) { Un = rho + k0 * s; Umx = RG(s0, Q_MX, c) + k1 * s; Umy = RG(s0, Q_MY, c) + k2 * s; Umz = Z ? RG(s0, Q_MZ, c) + k3 * s : 0.0; }
-                    else { Un = (B0 * P.m_i) + k0 * s; Umx = B1 + k1 * s; Umy = B2 + k2 * s; Umz = Z ? B3 + k3 * s : 0.0; }
+                    if (!HAVE_B || b_is_s) { Un = rho + k0 * s; Umx = RG(s0, Q_MX, c) + k1 * s; Umy = RG(s0, Q_MY, c) + k2 * s; Umz = Z ? RG(s0, Q_MZ, c) + k3 * s : 0.0; }
+                    else { Un = (own[2][ccol] * P.m_i) + k0 * s; Umx = own[3][ccol] + k1 * s; Umy = own[4][ccol] + k2 * s; Umz = Z ? own[HAVE_B ? 5 : 0][ccol] + k3 * s : 0.0; }
                     double rfl;
                     const double nn = density_floor(P, Un, &rfl);
-                    if (primary) {
+                    if (primary && A.walls) {
                         const unsigned z = zero_zones(P, g, j);
                         record_strips(P, A.strip, A.strip_pitch, g, r, j, z, rfl, Umx, Umy, Umz);
                         if (z) { Umx = 0.0; Umy = 0.0; Umz = 0.0; }
@@ -382,13 +492,13 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
                 }
             } else {
                 const double dvx_dx = Dc_s[0][col], dvy_dx = Dc_s[1][col], dvz_dx = Dc_s[2][col];
-                const double T_e = TXS(Q_E, col) + TYS(Q_E, col);
-                const double T_bix = TXS(Q_BIX, col) + TYS(Q_BIX, col), T_biy = TXS(Q_BIY, col) + TYS(Q_BIY, col);
+                const double T_e = TXS(Q_E, col) + t_0;
+                const double T_bix = TXS(Q_BIX, col) + t_1, T_biy = TXS(Q_BIY, col) + t_2;
                 double k4 = (T_e * -1.0) - pc * (dvx_dx + d_d);                                 // :75-76
                 double k5, k6, k7 = 0.0;
                 if (Z) {
-                    const double T_biz = TXS(Q_BIZ, col) + TYS(Q_BIZ, col);
-                    const double T_bex = TXS(Q_BEX, col) + TYS(Q_BEX, col), T_bey = TXS(Q_BEY, col) + TYS(Q_BEY, col), T_bez = TXS(Q_BEZ, col) + TYS(Q_BEZ, col);
+                    const double T_biz = TXS(Q_BIZ, col) + t_3;
+                    const double T_bex = TXS(Q_BEX, col) + t_4, T_bey = TXS(Q_BEY, col) + t_5, T_bez = TXS(Q_BEZ, col) + t_6;
                     const double bxs = bix + bex, bys = biy + bey;
                     k5 = (((T_bix * -1.0) - T_bex) + bxs * dvx_dx) + bys * d_e;                 // :78-80
                     k6 = (((T_biy * -1.0) - T_bey) + bxs * dvy_dx) + bys * d_d;                 // :81-83
@@ -411,8 +521,8 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
                 }
                 if (kmode != KM_EXPORT) {
                     double Ue, Ubx, Uby, Ubz;
-                    if (b_is_s) { Ue = RG(s0, Q_E, c) + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = Z ? biz + k7 * s : 0.0; }
-                    else { Ue = g0 + k4 * s; Ubx = g1 + k5 * s; Uby = B0 + k6 * s; Ubz = Z ? B1 + k7 * s : 0.0; }     // Y's base values were prefetched into g0, g1, B0, B1
+                    if (!HAVE_B || b_is_s) { Ue = RG(s0, Q_E, c) + k4 * s; Ubx = bix + k5 * s; Uby = biy + k6 * s; Ubz = Z ? biz + k7 * s : 0.0; }
+                    else { Ue = own[HAVE_B ? 2 + NB : 0][ccol] + k4 * s; Ubx = own[HAVE_B ? 3 + NB : 0][ccol] + k5 * s; Uby = own[HAVE_B ? 4 + NB : 0][ccol] + k6 * s; Ubz = Z ? own[HAVE_B ? 5 + NB : 0][ccol] + k7 * s : 0.0; }
                     const double e1 = smax(Ue, P.e_min);
                     A.D[E_E][off] = e1; A.D[E_BX][off] = Ubx; A.D[E_BY][off] = Uby; if (Z) A.D[E_BZ][off] = Ubz;
                     if (primary && interior) {                                                 // dt of this cell: evaluated after the next barrier
@@ -421,7 +531,9 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
                 }
             }
         }
-        cp_async_wait_all();
+        if (pre_bulk) { mbar_wait(&mbar[0], ring_par); ring_par ^= 1u; }
+        else if (!bulk) cp_async_wait_all();
+        if (pre && !pre_bulk) __syncthreads();                      // the row came through the loader threads (copies or fills): warp 3 converts it below
         if (pre) convert_rho(sp3);                                  // the row that just landed
         if (r + 2 <= r1) form_vel(sp2, v2);                         // into the velocity slot of row r-1 (dead since the last barrier)
         __syncthreads();
@@ -432,7 +544,7 @@ __global__ void __launch_bounds__(XY_NT, (LN == 6 && (VAR & 4)) ? 6 : xy_ctas_pe
             const double dtc = cell_dt(P, Dt_s[0][col], Dt_s[1][col], Dt_s[2][col], dt_e, dt_bx, dt_by, dt_bz, dt_dx, dt_rdx, dy, rdy);
             dtmin_local = smin(dtmin_local, dtc);
         }
-        block_min_impl(dtmin_local, A.dtmin_bits, reinterpret_cast<unsigned long long *>(TX_p));   // the TX array is dead after the last barrier
+        block_min_impl(dtmin_local, A.dtmin_bits, reinterpret_cast<unsigned long long *>(Fx_p));   // the flux carry is dead after the last barrier
     }
 }
 #undef kmode

@@ -95,17 +95,10 @@ def test_create_argument_errors_mirror_the_reference_messages():
     assert rc != 0 and "Grid too small for ghost zones" in msg
     rc, msg = create(x_bound_1=9)
     assert rc != 0 and "Boundary cond'n must be defined" in msg
+    rc, msg = create(y_bound_2=capi.BC["open_moc"], y_bound_1=capi.BC["fixed"], equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["fixed"], x_bound_2=capi.BC["fixed"])
+    assert rc != 0 and "ideal_mhd only" in msg
     rc, msg = create(y_bound_2=capi.BC["open_moc"])
-    assert rc != 0 and "open_moc" in msg
-    import os
-    os.environ["SPRUCE_EXPERIMENTAL_MOC"] = "1"             # the switch that admits the not-yet-GPU-validated open_moc path
-    try:
-        rc, msg = create(y_bound_2=capi.BC["open_moc"], y_bound_1=capi.BC["fixed"], equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["fixed"], x_bound_2=capi.BC["fixed"])
-        assert rc != 0 and "ideal_mhd only" in msg
-        rc, msg = create(y_bound_2=capi.BC["open_moc"])
-        assert rc != 0 and "pairs" in msg
-    finally:
-        del os.environ["SPRUCE_EXPERIMENTAL_MOC"]
+    assert rc != 0 and "pairs" in msg
     rc, msg = create(equation_set=1)
     assert rc != 0 and "equation set" in msg
     rc, msg = create(equation_set=capi.EQS["ideal_2F"], x_bound_1=capi.BC["open"])

@@ -1,8 +1,9 @@
-"""Device paths written AFTER the round's GPU budget was spent: they compile for sm_100a, the arithmetic they share with the
-validated kernels is unchanged, but no GPU has executed them yet.  They sit behind switches that are OFF by default, each test runs
-in its own interpreter (a faulting kernel cannot poison the CUDA context of the validated tests; the file sorts last for the same
-reason) and is a non-strict xfail: XPASS on the B200 box means "now validated, flip the default", a failure does not redden the
-suite.  Every check is bit-for-bit against the CPU oracle, exactly like tests/test_gpu_parity.py."""
+"""GPU parity tests of the SURVEY 8f rows and of the stage-kernel build options: open_moc boundaries and their limiters, the small solar
+modules, div_cleaning / field_heating, boundary_outflow, anomalous_resistivity, IdealMHD2E, the two-fluid set with open_ucnp next to wall
+sides, the compile-time stage variants and the relaxed-arithmetic stage kernel.  All of them passed on a B200 in round 1 (GPUTEST_r01.json)
+and are ordinary, strict tests now.  Each runs in its own interpreter (environment switches are read at domain creation; a faulting kernel
+cannot poison the CUDA context of the other tests).  Every check is bit-for-bit against the CPU oracle or a reference fixture, like
+tests/test_gpu_parity.py, except where a libm function or relaxed arithmetic sets the north star's 1e-9 tolerance."""
 import os
 import subprocess
 import sys
@@ -13,7 +14,6 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
-UNVALIDATED = pytest.mark.xfail(reason="written after the round-1 GPU budget was spent; never executed on a GPU", strict=False)
 
 
 TIMEOUTS = []          # circuit breaker: a hung kernel costs `timeout` seconds of box time per test; after three, the rest of this file is skipped
@@ -55,21 +55,21 @@ STAGE_VARIANT_CODE = """
 """
 
 
-@UNVALIDATED
-@pytest.mark.parametrize("variants", ["1", "2", "3"])       # 2: also the six-CTAs-per-SM build of the 2-D instance; 3: with the pair-wise mid-row barrier
+@pytest.mark.parametrize("switches", [{"SPRUCE_STAGE_VARIANTS": "0"}, {"SPRUCE_BULK_ROWS": "0"}, {"SPRUCE_STAGE_VARIANTS": "0", "SPRUCE_BULK_ROWS": "0"}])
 @pytest.mark.parametrize("integ,zfull,nx,ny,xb,yb", [
     ("rk2", False, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),      # 2-D list: k_mhd_stage_xy<6, ., 1> then <6, ., 2>
     ("rk2", True, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),       # full list: <12, ., 1> / <12, ., 2>
     ("euler", False, 131, 96, ("periodic", "periodic"), ("periodic", "periodic")),     # <6, ., 3>
     ("euler", True, 131, 96, ("periodic", "periodic"), ("periodic", "periodic")),      # <12, ., 3>
     ("rk2", False, 97, 140, ("open", "fixed"), ("reflect", "open")),                   # primary-stage strips + ghost passes
-    ("rk4", False, 99, 77, ("periodic", "periodic"), ("periodic", "periodic")),        # K planes: falls back to the run-time instance
+    ("rk4", False, 99, 77, ("periodic", "periodic"), ("periodic", "periodic")),        # K planes: the run-time-stage instance in every setting
 ])
-def test_compile_time_stage_variants_vs_oracle(integ, zfull, nx, ny, xb, yb, variants):
-    """SPRUCE_STAGE_VARIANTS=1 selects instances of k_mhd_stage_xy whose integrator stage (kmode / b_is_s / primary / no module terms)
-    is a template constant (mhd_stage_xy.cuh, VAR).  Same source, same arithmetic; the default instances are SASS-identical to the
-    validated build (scripts/sass_identity.py)."""
-    out = run_isolated(STAGE_VARIANT_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, xb=xb, yb=yb), {"SPRUCE_STAGE_VARIANTS": variants})
+def test_stage_kernel_build_options_vs_oracle(integ, zfull, nx, ny, xb, yb, switches):
+    """The stage kernel's two switches, both ON by default (the default path is what tests/test_gpu_parity.py exercises):
+    SPRUCE_STAGE_VARIANTS=0 runs the instances of k_mhd_stage_xy that take the integrator stage from the launch arguments instead of the
+    template constant VAR; SPRUCE_BULK_ROWS=0 stages every row through the per-thread cp.async path instead of cp.async.bulk.  Same
+    arithmetic: bit for bit against the oracle in every setting."""
+    out = run_isolated(STAGE_VARIANT_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, xb=xb, yb=yb), switches)
     assert "ok" in out
 
 
@@ -98,7 +98,6 @@ MOC_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("xb,yb,integ,gvisc,nx,ny", [
     (("periodic", "periodic"), ("fixed", "open_moc"), "euler", 0.0, 126, 93),
     (("periodic", "periodic"), ("open_moc", "fixed"), "rk2", 0.3, 64, 125),
@@ -112,7 +111,7 @@ def test_open_moc_vs_oracle(xb, yb, integ, gvisc, nx, ny):
     restatement that is pinned to live reference runs: right-hand side incl. the evolved ghost cells, step-size history with the
     widened bounds, every plane.  The per-cell arithmetic is already proven on the host (tests/test_moc_host_check.py); this is the
     launch side: thread-to-cell mapping, corner ownership, K planes of rk4, order against the stage kernel and the ghost passes."""
-    out = run_isolated(MOC_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
+    out = run_isolated(MOC_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, nx=nx, ny=ny), {})
     assert "ok" in out
 
 
@@ -156,7 +155,6 @@ SOURCE_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("mods,xb,yb,integ,nx,ny", [
     ([("ambient_heating_sink", dict(heating_rate=1.0e-5)),
       ("localized_heating", dict(start_time=0.0, duration=5.0, max_heating_rate=1.0e-3, stddev_x=3.0, stddev_y=4.0, center_x=10.0, center_y=8.0, ramp_time=1.0))],
@@ -211,7 +209,6 @@ DC_FH_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("mods,xb,yb,integ,nx,ny,exact", [
     ([("div_cleaning", dict(epsilon=0.1, time_scale=5.0))], ("fixed", "open"), ("reflect", "fixed"), "rk2", 81, 64, True),
     ([("div_cleaning", dict(epsilon=0.05, time_scale=2.0))], ("periodic", "periodic"), ("fixed", "fixed"), "euler", 70, 93, True),
@@ -251,7 +248,6 @@ OUTFLOW_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("a,xb,yb,integ,nx,ny,moc", [
     (dict(max_accel=2.0e3, falloff_length=6.0e8, boundary="y_bound_2", falloff_shape="exp", feather_length=3.0e8, field_aligned_mode=True, dynamic_mode=True,
           dynamic_time=10.0, dynamic_target_speed=2.0e6), ("periodic", "periodic"), ("fixed", "open"), "rk2", 88, 71, False),
@@ -263,7 +259,7 @@ OUTFLOW_CODE = """
 def test_boundary_outflow_vs_oracle(a, xb, yb, integ, nx, ny, moc):
     """boundary_outflow on the device (k_bo_mean, k_bo_apply; template and window built by solar_templates.hpp, host-checked) against the pinned oracle;
     the last case combines it with an open_moc side, whose ghost zone the template reaches into."""
-    out = run_isolated(OUTFLOW_CODE.format(a=a, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"} if moc else {})
+    out = run_isolated(OUTFLOW_CODE.format(a=a, xb=xb, yb=yb, integ=integ, nx=nx, ny=ny), {})
     assert "ok" in out
 
 
@@ -292,12 +288,9 @@ RELAXED_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("integ,zfull,nx,ny,nsteps,variants", [
     ("rk2", False, 256, 256, 100, "0"),
     ("rk2", False, 256, 256, 100, "1"),
-    ("rk2", False, 256, 256, 100, "2"),
-    ("rk2", False, 256, 256, 100, "3"),
     ("rk2", True, 150, 203, 100, "1"),
     ("rk4", False, 131, 96, 60, "0"),
     ("euler", True, 96, 131, 60, "1"),
@@ -310,7 +303,6 @@ def test_relaxed_arithmetic_within_north_star_tolerance(integ, zfull, nx, ny, ns
     assert "ok" in out
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("args", [("96", "80", "4", "rk2", "periodic", "p2p", "moc"), ("90", "70", "4", "rk4", "open_moc", "p2p", "mocv"),
                                   ("96", "80", "3", "euler", "open_moc", "nccl", "moc"), ("128", "96", "4", "rk2", "periodic", "p2p", "src"),
                                   ("120", "90", "3", "rk2", "periodic", "p2p", "dc,fh"), ("96", "80", "4", "rk2", "reflect", "p2p", "bo,dc"),
@@ -321,7 +313,7 @@ def test_slab_decomposition_of_the_unvalidated_paths_equals_single_gpu(args):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    e = dict(os.environ); e["SPRUCE_EXPERIMENTAL_MOC"] = "1"
+    e = dict(os.environ)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29519", str(ROOT / "scripts" / "mgpu_check.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, env=e)
     out = r.stdout.decode()
@@ -364,14 +356,13 @@ GOLDEN_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("name,exact", [("moc_y2_euler", True), ("moc_all_visc_rk2", True), ("moc_x1_mixed_rk4", True), ("sm_sink_heat_mass_rk2", True),
                                         ("sm_momentum_divclean_rk2", True), ("sm_field_heating_euler", False), ("sm_outflow_dynamic_rk2", True),
                                         ("e2_mixed_rk2", True), ("e2_pp_ucnp_rk4", True)])
 def test_extended_golden_reference_outputs(name, exact):
     """The device paths of the SURVEY 8f rows against committed outputs of the UNMODIFIED reference binary (tests/golden/moc_*, sm_*): step-size
     history and every output plane, bit for bit (field_heating: pow with run-time exponents, <= 1e-9)."""
-    out = run_isolated(GOLDEN_CODE.format(name=name, exact=exact), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
+    out = run_isolated(GOLDEN_CODE.format(name=name, exact=exact), {})
     assert "ok" in out
 
 
@@ -397,7 +388,6 @@ HOST_CASES = {
 }
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("name", list(HOST_CASES))
 def test_host_shell_matches_reference_files_on_the_8f_rows(name, tmp_path):
     """The C++ host shell (spruce_b200/bin/run) with open_moc sides / the solar modules of SURVEY 8f against the UNMODIFIED reference binary on the same
@@ -422,7 +412,7 @@ def test_host_shell_matches_reference_files_on_the_8f_rows(name, tmp_path):
     out_dir = tmp_path / "ours"
     out_dir.mkdir(parents=True, exist_ok=True)
     (out_dir / "run.config").write_text(cfg)
-    e = dict(os.environ); e["SPRUCE_EXPERIMENTAL_MOC"] = "1"
+    e = dict(os.environ)
     r = subprocess.run([str(ours), "-m", "input", "-o", str(out_dir), "-s", str(state)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120, env=e)
     assert r.returncode in (-6, 134) and "Simulation successfully reached max simulation time or iterations" in r.stderr.decode(), r.stderr.decode()[-2000:]
     for fname in ("mhd.out", "end.state"):
@@ -463,7 +453,6 @@ E2_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("xb,yb,integ,nx,ny,loop,nmin", [
     (("periodic", "periodic"), ("periodic", "periodic"), "rk2", 150, 133, False, 1.0),
     (("periodic", "periodic"), ("fixed", "fixed"), "rk4", 97, 140, True, 1.0e7),
@@ -503,7 +492,6 @@ MOC_LIMIT_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("xb,yb,integ,gvisc,lim,nx,ny", [
     (("periodic", "periodic"), ("fixed", "open_moc"), "rk2", 0.0, dict(b_limiting=True, b_lower=0.9, b_upper=1.05, mom_limiting=True, mom_lower=0.5, mom_upper=1.5), 86, 93),
     (("open_moc", "open_moc"), ("open_moc", "open_moc"), "euler", 0.1, dict(mom_limiting=True, mom_lower=0.8, mom_upper=1.1), 85, 134),
@@ -512,7 +500,7 @@ MOC_LIMIT_CODE = """
 def test_open_moc_limiters_vs_oracle(xb, yb, integ, gvisc, lim, nx, ny):
     """moc_b_limiting / moc_mom_limiting on the device (k_moc_limit after the boundary passes of every propagate, the dt minimum rebuilt in the last stage)
     against the pinned oracle; limit_line itself is proven on the host (tests/test_moc_host_check.py)."""
-    out = run_isolated(MOC_LIMIT_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, lim=lim, nx=nx, ny=ny), {"SPRUCE_EXPERIMENTAL_MOC": "1"})
+    out = run_isolated(MOC_LIMIT_CODE.format(xb=xb, yb=yb, integ=integ, gvisc=gvisc, lim=lim, nx=nx, ny=ny), {})
     assert "ok" in out
 
 
@@ -538,7 +526,6 @@ TF_MIXED_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("xb,yb,integ,nx,ny", [
     (("open_ucnp", "open_ucnp"), ("reflect", "reflect"), "rk2", 97, 81),      # the case the pointwise form gets wrong: a ucnp pass before a reflect side
     (("reflect", "open_ucnp"), ("fixed", "open_ucnp"), "rk4", 66, 91),
@@ -581,7 +568,6 @@ MODULE_PLANES_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("name", ["loop_rl_euler", "loop_rl_rk4", "loop_tc_euler", "loop_tc_sat_rk2", "loop_tc_sat_rk4", "loop_solar_all"])
 def test_module_diagnostic_planes_vs_reference_fixtures(name):
     """output_to_file = true of thermal_conduction / radiative_losses: the planes the reference appends to mhd.out ("thermal_conduction", "flux_saturation",
@@ -632,13 +618,12 @@ ANOMRES_CODE = """
 """
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("name", ["ar_default_floodfill", "ar_frobenius_rk2_gc", "ar_syntelis_rk4", "ar_ys94_radius", "ar_periodic_x_euler", "ar_moc_bounds_rk4", "ar_frobenius_plain"])
 def test_anomalous_resistivity_vs_oracle(name):
     """anomalous_resistivity on the device (anomres_cells.hpp functors as kernels, anomres_host.cuh): whole steps with the module against the CPU
     restatement -- step sizes, every plane, the tracked null point, the template and the sub-cycle count.  The same functors in the same sequence are
     proven bit for bit on the host by tests/test_anomres_host_check.py; this is the launch side."""
-    env = {"SPRUCE_EXPERIMENTAL_MOC": "1"} if "moc" in name else {}
+    env = {}
     out = run_isolated(ANOMRES_CODE.format(name=name), env)
     assert "ok" in out
 
@@ -662,7 +647,6 @@ ANOMRES_GOLDEN_CODE = """
 """
 
 
-@UNVALIDATED
 def test_anomalous_resistivity_vs_reference_fixture():
     """the committed fixture of the unmodified reference binary with anomalous_resistivity (tests/golden/ar_floodfill_rk2.npz), bit for bit"""
     out = run_isolated(ANOMRES_GOLDEN_CODE, {})
@@ -699,7 +683,6 @@ ANOMRES_DIAG_CODE = """
 """
 
 
-@UNVALIDATED
 def test_anomalous_resistivity_and_field_heating_diagnostic_planes_vs_reference_fixture():
     """output_to_file planes of anomalous_resistivity and field_heating against the fixture of the unmodified reference (tests/golden/ar_diag_planes.npz):
     frame 0 carries the set-up template and zero planes, later frames the last evaluation's template, template*diffusivity, (e_after - e_before)/dt and mask*(dt*heating)."""

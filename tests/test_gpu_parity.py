@@ -292,6 +292,58 @@ def test_full_size_4096_translation_invariance():
     assert abs(m1 - m0) / m0 < 1e-12
 
 
+def test_full_size_4096_vs_oracle():
+    """BASELINE.json's 4096^2 workload itself (OT-4096: non-uniform doubly periodic grid, RK2), 3 steps against the CPU oracle, bit for bit:
+    step sizes and all eight evolved planes (SURVEY 8d's protocol).  About a minute of oracle time on the box's host cores."""
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    n = 4096
+    s = synthetic.orszag_tang(n, n)
+    kw = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator="rk2", epsilon=0.2, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    dts = d.advance(3)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    ref = o.run(3)
+    assert [x.hex() for x in dts] == [x.hex() for x in ref], (dts, ref)
+    for v in PlasmaDomain.EVOLVED:
+        a, r = d.grid(v), o.get(v)
+        assert same_bits(a, r), "%s: %s" % (v, mismatch(a, r))
+
+
+@pytest.mark.parametrize("integ,mods", [
+    ("euler", [("thermal_conduction", dict(flux_saturation=True, integrator="rk4"))]),
+    ("euler", [("field_heating", dict(coeff=1.0e-3, current_pow=1.0, b_pow=0.5, n_pow=0.25))]),
+    ("euler", [("div_cleaning", dict(epsilon=0.1, time_scale=1.0e-3))]),
+    ("rk2", [("thermal_conduction", dict(flux_saturation=False, integrator="rk2")), ("div_cleaning", dict(epsilon=0.1, time_scale=1.0e-3))]),
+    ("rk4", [("thermal_conduction", dict(flux_saturation=True, integrator="euler"))]),
+])
+def test_2d_instance_with_modules_keeps_the_z_planes_zero(integ, mods):
+    """A purely 2-D state (mom_z = bi_z = be = 0: the stage kernel's 6-quantity instance, which neither reads nor writes the z planes)
+    together with modules that use the stage copy's planes as scratch: mom_z / bi_z must stay zero and everything must match the oracle.
+    (Round 1's advisor finding: with euler the scratch planes were swapped in as the primary state.)"""
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    s = synthetic.orszag_tang(84, 70, temp_mod=0.1)
+    kw = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator=integ, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    for name, mk in mods:
+        if name in Oracle.SMALL:
+            o.add_small_module(name, **mk)
+        else:
+            getattr(o, "set_" + name)(**mk)
+        getattr(d, "set_" + name)(**mk)
+    for it in range(4):
+        a, b = d.advanceTime(), o.step()
+        assert abs(a - b) / b <= REL_TOL, (it, a, b)
+    for v in ("mom_z", "bi_z"):
+        assert not np.any(d.grid(v)), v
+    for v in PlasmaDomain.EVOLVED + ["temp", "dt"]:
+        assert rel_linf(d.grid(v), o.get(v)) <= REL_TOL, "%s: rel Linf %.3e" % (v, rel_linf(d.grid(v), o.get(v)))
+
+
 @pytest.mark.parametrize("mods", [
     [("thermal_conduction", dict(flux_saturation=False, integrator="euler"))],
     [("thermal_conduction", dict(flux_saturation=True, integrator="rk2"))],
