@@ -105,8 +105,9 @@ struct spruce_domain {
     const double *cur_xterm[4] = {nullptr}; int cur_xtarget[4] = {0}; int cur_nx = 0;
     unsigned long long *red = nullptr;     // 4 reduction scalars for the sub-cycle counts
     double *halo[4] = {nullptr, nullptr, nullptr, nullptr};   // send_lo, send_hi, recv_lo, recv_hi
-    // planes that were uploaded as identically zero: bit 0 mom_z, 1 bi_z, 2 be_x, 3 be_y, 4 be_z (global knowledge; see spruce_plane_activity)
-    unsigned nonzero_mask = 0x1F;
+    // planes that were uploaded as identically zero: bit 0 mom_z, 1 bi_z, 2 be_x, 3 be_y, 4 be_z (global knowledge; see spruce_plane_activity);
+    // bits 5, 6: grav_x, grav_y (own-cell values only: local knowledge is enough)
+    unsigned nonzero_mask = 0x7F;
     bool in_mgpu_stage_api = false;        // inside spruce_mgpu_stage (caller-owned exchange and dt reduction)
     bool static_lists = true;              // use the fully unrolled instances of k_mhd_stage_xy when the active list matches one
     // open_moc (moc_stage.cuh): evolved ghost cells
@@ -300,6 +301,7 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
     A.chunk_rows = pick_chunk_rows(d);
     A.bulk = d->bulk_rows ? 1 : 0;
+    A.grav = (d->nonzero_mask & 0x60u) ? 1 : 0;
     A.walls = (d->cfg.x_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.x_bound_2 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_2 != SPRUCE_BC_PERIODIC) ? 1 : 0;
     if (part == 0 && primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
     const int nchunks = (d->P.nx + A.chunk_rows - 1) / A.chunk_rows;
@@ -1346,8 +1348,8 @@ int spruce_grid_upload(spruce_domain *d, const char *name, const double *host, s
     if (d->tf) return tf_upload(d, name, host);
     if (d->e2) return e2_upload(d, name, host);
     {   // zero-plane bookkeeping for the planes whose transport can be skipped exactly
-        const char *tracked[5] = {"mom_z", "bi_z", "be_x", "be_y", "be_z"};
-        for (int b = 0; b < 5; b++) if (!strcmp(name, tracked[b])) {
+        const char *tracked[7] = {"mom_z", "bi_z", "be_x", "be_y", "be_z", "grav_x", "grav_y"};
+        for (int b = 0; b < 7; b++) if (!strcmp(name, tracked[b])) {
             bool nz = false;                         // +-0 only?  OR of the bit patterns in blocks (vectorisable), early exit per block
             for (size_t k0 = 0; k0 < count && !nz; k0 += 4096) {
                 const size_t k1 = k0 + 4096 < count ? k0 + 4096 : count;
@@ -2027,8 +2029,8 @@ int spruce_mgpu_initial_exchange(spruce_domain *d)
 int spruce_plane_activity(spruce_domain *d, int *local_mask, int set_global_mask)
 {
     CHECK_DOM(d);
-    if (local_mask) *local_mask = (int)d->nonzero_mask;
-    if (set_global_mask >= 0) d->nonzero_mask = (unsigned)set_global_mask & 0x1Fu;
+    if (local_mask) *local_mask = (int)(d->nonzero_mask & 0x1Fu);
+    if (set_global_mask >= 0) d->nonzero_mask = ((unsigned)set_global_mask & 0x1Fu) | (d->nonzero_mask & 0x60u);
     return SPRUCE_OK;
 }
 

@@ -62,6 +62,7 @@ struct StageArgs {
     const double *xterm[4]; int xtarget[4]; int n_xterm;
     int bulk;                     // k_mhd_stage_xy: rows may enter shared memory by cp.async.bulk (every plane 16-byte aligned, even pitch)
     int walls;                    // some side is not periodic: the primary stage evaluates zero_zones / record_strips
+    int grav;                     // a gravity plane of this slab is non-zero (otherwise k_mhd_stage_xy adds rho * 0.0 without reading the planes)
 };
 
 // ---- tiling of the fused stage kernel ("column marching", see the header comment)

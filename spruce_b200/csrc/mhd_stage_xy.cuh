@@ -41,7 +41,10 @@ __host__ __device__ constexpr int xy_off_dt(int nq) { return xy_off_dc(nq) + 3 *
 __host__ __device__ constexpr int xy_off_own(int nq) { return xy_off_dc(nq) + 6 * XW; }
 // own-cell rows: grav_x, grav_y, and -- unless the stage's base state is the state it differentiates (first rk stage, euler) -- the base state B
 __host__ __device__ constexpr int xy_nown(int nq, int var) { return ((var & 3) == 1 || (var & 3) == 3) ? 2 : 2 + (nq == 6 ? 6 : 8); }
-__host__ __device__ constexpr int xy_off_mbar(int nq, int var) { return xy_off_own(nq) + xy_nown(nq, var) * XW; }
+// y geometry: the 2-D instance (96 registers) keeps the seven y tables of its 66 columns in shared memory instead of ten doubles per thread in registers
+__host__ __device__ constexpr int xy_nyt(int nq) { return nq == 6 ? 7 * SW : 0; }
+__host__ __device__ constexpr int xy_off_yt(int nq, int var) { return xy_off_own(nq) + xy_nown(nq, var) * XW; }
+__host__ __device__ constexpr int xy_off_mbar(int nq, int var) { return xy_off_yt(nq, var) + xy_nyt(nq); }
 __host__ __device__ constexpr int xy_doubles(int nq, int var) { return xy_off_mbar(nq, var) + 2; }
 __host__ __device__ constexpr size_t xy_smem_bytes(int nq, int var) { return (size_t)xy_doubles(nq, var) * sizeof(double); }
 __host__ __device__ constexpr int xy_rows(int ln) { return ln == 6 ? 6 : NTR; }
@@ -85,10 +88,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // VAR == 0 takes kmode / b_is_s / primary / n_xterm from the launch arguments (every integrator, every module).
 //
 // How rows reach shared memory.  A CTA whose 66 staged columns lie inside the row (every strip except the first and the last one or two) takes the
-// BULK path: one thread issues one cp.async.bulk per quantity and row -- the 528-byte ring rows and the 496-byte own-cell rows (gravity, base state)
-// are 16-byte multiples at 16-byte aligned addresses -- and completion is signalled on two mbarriers (ring row r+3: waited for at the end of iteration
-// r; own-cell rows of row r: issued at the top of iteration r, waited for before phase 2).  Strips that touch the y boundary (periodic wrap or
-// out-of-range columns) and rows beyond a physical x boundary keep the per-thread path (cp.async 8-byte copies / fills by the 66 loader threads).
+// BULK path: lane 0 of each Y warp issues one cp.async.bulk per quantity for its half of ring row r+3 (528-byte rows, 16-byte aligned) and completion
+// is signalled on an mbarrier that every thread waits for at the end of iteration r.  Strips that touch the y boundary (periodic wrap or out-of-range
+// columns) and rows beyond a physical x boundary keep the per-thread path (cp.async 8-byte copies / fills by the 66 loader threads).  The own-cell
+// values of row r (gravity, base state) are per-thread cp.async copies into private shared-memory slots, issued at the top of iteration r and waited
+// for before phase 2: they occupy no register during phase 1.
 template <int LN, unsigned long long LQ, int VAR = 0>
 __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
 {
@@ -121,7 +125,9 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
     double (*Dc_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_dc(NQ));
     double (*Dt_s)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_dt(NQ));
     double (*own)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_own(NQ));  // [0] grav_x [1] grav_y [2..] B: n, mom_x, mom_y, (mom_z), e, bi_x, bi_y, (bi_z)
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + xy_off_mbar(NQ, VAR));   // [0] ring rows, [1] own-cell rows
+    constexpr bool YTAB = xy_nyt(NQ) > 0;
+    double (*yt)[SW] = reinterpret_cast<double (*)[SW]>(smem + xy_off_yt(NQ, VAR));   // [h, fs, rfs, ep, em, d, rd][shared column]  (YTAB)
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + xy_off_mbar(NQ, VAR));   // [0] ring rows
 #define RG(sl, q, cc) ringp[((sl) * NQ + QI(q)) * SW + (cc)]
 #define FXS(q, cc) Fx_p[QI(q) * XW + (cc)]
 #define TXS(q, cc) TX_p[((q) - Q_E) * XW + (cc)]
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
     const int r1 = min(r0 + A.chunk_rows, P.nx);
     const bool col_out = (lane < 31) && (j < P.ny);
     const bool bulk = A.bulk && j0 >= HALO && j0 + CW + HALO <= P.ny;            // CTA-uniform: all 66 staged columns are inside the row
-    const bool issuer = (tid == 96);                                            // the thread that issues the bulk copies (warp 3, lane 0)
+    const int issuer = (tid == 64) ? 1 : (tid == 96) ? 2 : 0;                   // lane 0 of the two Y warps: each issues half of the bulk copies of a ring row
 
     // ---- per-thread loader (strips at the y boundary, rows beyond a physical x boundary): thread t < SW owns shared column t
     const bool loader = tid < SW;
@@ -181,59 +187,56 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             }
         } else fill_row(slot);
     };
-    constexpr unsigned ROW_BYTES = SW * sizeof(double), OWN_BYTES = CW * sizeof(double);
-    constexpr unsigned RING_TX = (LN == 6 ? 6 : NLOAD) * ROW_BYTES;
-    auto bulk_row = [&](int r, int slot) {                       // issuer only; the row exists
+    constexpr unsigned ROW_BYTES = SW * sizeof(double);
+    constexpr int NLD = (LN == 6 ? 6 : NLOAD), NLD_A = NLD / 2;                  // planes per ring row; the first NLD_A go through issuer 1
+    auto bulk_row_copies = [&](int r, int slot) {                // issuers only; the row exists; the issuer has announced the bytes (expect_tx)
         const size_t off = (size_t)wrap_row(r) * P.pitch + (j0 - HALO);
-        if (LN == 6) {
-            bulk_g2s(&RG(slot, Q_RHO, 0), A.S[E_N] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_MX, 0), A.S[E_MX] + off, ROW_BYTES, &mbar[0]);
-            bulk_g2s(&RG(slot, Q_MY, 0), A.S[E_MY] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_E, 0), A.S[E_E] + off, ROW_BYTES, &mbar[0]);
-            bulk_g2s(&RG(slot, Q_BIX, 0), A.S[E_BX] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_BIY, 0), A.S[E_BY] + off, ROW_BYTES, &mbar[0]);
-        } else {
+        if (issuer == 1) {
+            if (LN == 6) {
+                bulk_g2s(&RG(slot, Q_RHO, 0), A.S[E_N] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_MX, 0), A.S[E_MX] + off, ROW_BYTES, &mbar[0]);
+                bulk_g2s(&RG(slot, Q_MY, 0), A.S[E_MY] + off, ROW_BYTES, &mbar[0]);
+            } else {
 #pragma unroll
-            for (int v = 0; v < NEV; v++) bulk_g2s(&RG(slot, v, 0), A.S[v] + off, ROW_BYTES, &mbar[0]);
-            bulk_g2s(&RG(slot, Q_BEX, 0), A.st[S_BEX] + off, ROW_BYTES, &mbar[0]);
-            bulk_g2s(&RG(slot, Q_BEY, 0), A.st[S_BEY] + off, ROW_BYTES, &mbar[0]);
-            bulk_g2s(&RG(slot, Q_BEZ, 0), A.st[S_BEZ] + off, ROW_BYTES, &mbar[0]);
+                for (int v = 0; v < NLD_A; v++) bulk_g2s(&RG(slot, v, 0), A.S[v] + off, ROW_BYTES, &mbar[0]);
+            }
+        } else {
+            if (LN == 6) {
+                bulk_g2s(&RG(slot, Q_E, 0), A.S[E_E] + off, ROW_BYTES, &mbar[0]);
+                bulk_g2s(&RG(slot, Q_BIX, 0), A.S[E_BX] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_BIY, 0), A.S[E_BY] + off, ROW_BYTES, &mbar[0]);
+            } else {
+#pragma unroll
+                for (int v = NLD_A; v < NEV; v++) bulk_g2s(&RG(slot, v, 0), A.S[v] + off, ROW_BYTES, &mbar[0]);
+                bulk_g2s(&RG(slot, Q_BEX, 0), A.st[S_BEX] + off, ROW_BYTES, &mbar[0]);
+                bulk_g2s(&RG(slot, Q_BEY, 0), A.st[S_BEY] + off, ROW_BYTES, &mbar[0]);
+                bulk_g2s(&RG(slot, Q_BEZ, 0), A.st[S_BEZ] + off, ROW_BYTES, &mbar[0]);
+            }
         }
     };
-    // own-cell rows of row r (a row of the slab itself: it always exists): gravity for the X warps, the base state for both roles
+    // own-cell values of row r (a row of the slab itself: it always exists): gravity for the X warps, the base state for both roles.  Every thread
+    // copies its own (cp.async into its private slots): no register is held across phase 1 and nothing has to be visible to another thread.
     const bool want_b = HAVE_B && !b_is_s;
+    const bool grav = A.grav != 0;                               // a gravity plane is non-zero (host-tracked); otherwise rho * 0.0 is added as the reference does
     auto own_row = [&](int r) {
-        const size_t roff = (size_t)r * P.pitch;
-        if (bulk) {
-            if (!issuer) return;
-            fence_proxy_async();
-            mbar_expect_tx(&mbar[1], (2 + (want_b ? 2 * NB : 0)) * OWN_BYTES);
-            bulk_g2s(own[0], A.st[S_GX] + roff + j0, OWN_BYTES, &mbar[1]); bulk_g2s(own[1], A.st[S_GY] + roff + j0, OWN_BYTES, &mbar[1]);
+        if (!col_out) return;
+        const size_t off = (size_t)r * P.pitch + j;
+        if (isX) {
+            if (grav) { cp_async8(&own[0][ccol], A.st[S_GX] + off); cp_async8(&own[1][ccol], A.st[S_GY] + off); }
             if (HAVE_B && want_b) {
-                bulk_g2s(own[2], A.B[E_N] + roff + j0, OWN_BYTES, &mbar[1]); bulk_g2s(own[3], A.B[E_MX] + roff + j0, OWN_BYTES, &mbar[1]);
-                bulk_g2s(own[4], A.B[E_MY] + roff + j0, OWN_BYTES, &mbar[1]);
-                if (Z) bulk_g2s(own[5], A.B[E_MZ] + roff + j0, OWN_BYTES, &mbar[1]);
-                bulk_g2s(own[2 + NB], A.B[E_E] + roff + j0, OWN_BYTES, &mbar[1]); bulk_g2s(own[3 + NB], A.B[E_BX] + roff + j0, OWN_BYTES, &mbar[1]);
-                bulk_g2s(own[4 + NB], A.B[E_BY] + roff + j0, OWN_BYTES, &mbar[1]);
-                if (Z) bulk_g2s(own[5 + NB], A.B[E_BZ] + roff + j0, OWN_BYTES, &mbar[1]);
+                cp_async8(&own[2][ccol], A.B[E_N] + off); cp_async8(&own[3][ccol], A.B[E_MX] + off); cp_async8(&own[4][ccol], A.B[E_MY] + off);
+                if (Z) cp_async8(&own[HAVE_B ? 5 : 0][ccol], A.B[E_MZ] + off);
             }
-        } else if (col_out) {
-            const size_t off = roff + j;
-            if (isX) {
-                cp_async8(&own[0][ccol], A.st[S_GX] + off); cp_async8(&own[1][ccol], A.st[S_GY] + off);
-                if (HAVE_B && want_b) {
-                    cp_async8(&own[2][ccol], A.B[E_N] + off); cp_async8(&own[3][ccol], A.B[E_MX] + off); cp_async8(&own[4][ccol], A.B[E_MY] + off);
-                    if (Z) cp_async8(&own[5][ccol], A.B[E_MZ] + off);
-                }
-            } else if (HAVE_B && want_b) {
-                cp_async8(&own[2 + NB][ccol], A.B[E_E] + off); cp_async8(&own[3 + NB][ccol], A.B[E_BX] + off); cp_async8(&own[4 + NB][ccol], A.B[E_BY] + off);
-                if (Z) cp_async8(&own[5 + NB][ccol], A.B[E_BZ] + off);
-            }
+        } else if (HAVE_B && want_b) {
+            cp_async8(&own[HAVE_B ? 2 + NB : 0][ccol], A.B[E_E] + off); cp_async8(&own[HAVE_B ? 3 + NB : 0][ccol], A.B[E_BX] + off);
+            cp_async8(&own[HAVE_B ? 4 + NB : 0][ccol], A.B[E_BY] + off);
+            if (Z) cp_async8(&own[HAVE_B ? 5 + NB : 0][ccol], A.B[E_BZ] + off);
         }
     };
-    // rho = n * m_i (idealmhd.cpp:247) for the 66 columns of a ring row: warp 3, two columns per lane (lane 0 also takes the last pair)
+    // rho = n * m_i (idealmhd.cpp:247) for the 66 columns of a ring row: warp 3, two columns per lane (lane 1 also takes the last pair)
     auto convert_rho = [&](int s_) {
         if (warp != 3) return;
         double2 *p2 = reinterpret_cast<double2 *>(&RG(s_, Q_RHO, 0));
         double2 v = p2[lane]; v.x = v.x * P.m_i; v.y = v.y * P.m_i; p2[lane] = v;
-        if (lane == 0) { double2 w = p2[32]; w.x = w.x * P.m_i; w.y = w.y * P.m_i; p2[32] = w; }
+        if (lane == 1) { double2 w = p2[32]; w.x = w.x * P.m_i; w.y = w.y * P.m_i; p2[32] = w; }
         if (bulk) fence_proxy_async();                           // this slot is the target of a bulk copy again five rows later
     };
     // v = mom / rho (idealmhd.cpp:248-250): one IEEE reciprocal, then the exact-division correction per component (exact_math.cuh).
@@ -261,7 +264,14 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
         }
         for (int e = tid; e < xy_off_own(NQ) - xy_off_fx(NQ); e += XY_NT) Fx_p[e] = 0.0;              // Fx, TX, TY, Dc are contiguous
-        if (bulk && issuer) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+        if (YTAB) {
+            const double *srcy[7] = {P.ty.h, P.ty.fs, P.ty.rfs, P.ty.ep, P.ty.em, P.ty.d, P.ty.rd};
+            for (int e = tid; e < 7 * SW; e += XY_NT) {
+                const int t = e / SW, i = e - t * SW;
+                yt[t][i] = srcy[t][min(j0 - HALO + i, P.ny + 2)];          // shared column i = global column j0 - 2 + i; the tables reach ny + 2
+            }
+        }
+        if (bulk && issuer == 1) { mbar_init(&mbar[0], 2); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
     }
     auto x_geom = [&](int f) {
         const int i = f - r0 + 3;
@@ -275,20 +285,33 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
 
     // ---- per-thread y geometry (Y warps: left face of column j; both roles: cell size)
     const int jt = min(j, P.ny + 1);
-    const FaceGeom gy = load_face_geom(P.ty, jt);
-    const double dy = P.ty.d[min(j, P.ny)], rdy = P.ty.rd[min(j, P.ny)];
+    FaceGeom gy_reg{};
+    double dy_reg = 1.0, rdy_reg = 1.0;
+    if (!YTAB) { gy_reg = load_face_geom(P.ty, jt); dy_reg = P.ty.d[min(j, P.ny)]; rdy_reg = P.ty.rd[min(j, P.ny)]; }
+    auto y_geom = [&]() {
+        if (!YTAB) return gy_reg;
+        FaceGeom g;
+        g.hm1 = yt[0][c - 1]; g.h0 = yt[0][c];
+        g.fs = yt[1][c];      g.rfs = yt[2][c];
+        g.ep = yt[3][c];      g.fsm = yt[1][c - 1]; g.rfsm = yt[2][c - 1];
+        g.em = yt[4][c];      g.fsp = yt[1][c + 1]; g.rfsp = yt[2][c + 1];
+        return g;
+    };
+#define dy (YTAB ? yt[5][c] : dy_reg)
+#define rdy (YTAB ? yt[6][c] : rdy_reg)
 
     // ---- prologue: rows r0-2 .. r0+2 land, rho is formed for all of them, velocity for rows r0-1, r0, r0+1
-    unsigned ring_par = 0, own_par = 0;          // phase parities of the two mbarriers (bulk path)
+    unsigned ring_par = 0;                       // phase parity of the ring mbarrier (bulk path)
     if (bulk) {
-        __syncthreads();                         // the mbarriers are initialised
+        __syncthreads();                         // the mbarrier is initialised
         int nex = 0;
         for (int r = r0 - HALO; r <= r0 + HALO; r++) { if (row_exists(P, r)) nex++; else fill_row(slot_of(r)); }
         if (issuer) {
-            if (nex) mbar_expect_tx(&mbar[0], nex * RING_TX);
-            for (int r = r0 - HALO; r <= r0 + HALO; r++) if (row_exists(P, r)) bulk_row(r, slot_of(r));
+            // one phase for all five rows: each issuer arrives once, with the bytes of its half of every existing row
+            mbar_expect_tx(&mbar[0], nex * (issuer == 1 ? NLD_A : NLD - NLD_A) * ROW_BYTES);
+            for (int r = r0 - HALO; r <= r0 + HALO; r++) if (row_exists(P, r)) bulk_row_copies(r, slot_of(r));
         }
-        if (nex) { mbar_wait(&mbar[0], ring_par); ring_par ^= 1u; }
+        mbar_wait(&mbar[0], ring_par); ring_par ^= 1u;
     } else {
         for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r, slot_of(r));
         cp_async_commit();
@@ -336,9 +359,15 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
         const bool pre_bulk = pre && bulk && row_exists(P, r + 3);
         // own-cell rows of this row (consumed in phase 2), then the ring row three rows ahead
         own_row(r);
-        if (!bulk) cp_async_commit();
+        cp_async_commit();
         if (pre) {
-            if (pre_bulk) { if (issuer) { mbar_expect_tx(&mbar[0], RING_TX); bulk_row(r + 3, sp3); } }
+            if (pre_bulk) {
+                if (issuer) {                                    // one arrival per issuer, with the bytes of its half of the row
+                    fence_proxy_async();
+                    mbar_expect_tx(&mbar[0], (issuer == 1 ? NLD_A : NLD - NLD_A) * ROW_BYTES);
+                    bulk_row_copies(r + 3, sp3);
+                }
+            }
             else if (bulk) fill_row(sp3);
             else issue_row(r + 3, sp3);
         }
@@ -399,6 +428,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             }
             __syncwarp();
             // ---- y face j (left face of this column); the right face comes from lane+1
+            const FaceGeom gy = y_geom();
             const double vxc = vel[v0][0][c], vyc = vel[v0][1][c], vzc = vel[v0][2][c];
             const double vfyL = face_interp(vel[v0][1][c - 1], vyc, gy.hm1, gy.h0, gy.fs, gy.rfs);
             const double IyL_vx = face_interp(vel[v0][0][c - 1], vxc, gy.hm1, gy.h0, gy.fs, gy.rfs);
@@ -433,8 +463,8 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             if (Z) d_f = ddiv(IyR_vz - IyL_vz, dy, rdy);            // d(v_z)/dy
         }
         // the own-cell rows have landed (they had the whole of phase 1), then the partial results become visible to the other role
-        if (bulk) { mbar_wait(&mbar[1], own_par); own_par ^= 1u; }
-        else asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        if (bulk) cp_async_wait_all();                              // bulk path: the only cp.async group in flight holds this thread's own-cell values
+        else asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // per-thread path: the younger group is ring row r+3
         __syncthreads();
 
         // ================================================================ phase 2: finish the outputs
@@ -444,7 +474,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             const double bex = Z ? RG(s0, Q_BEX, c) : 0.0, bey = Z ? RG(s0, Q_BEY, c) : 0.0, bez = Z ? RG(s0, Q_BEZ, c) : 0.0;
             if (isX) {
                 const double rho = RG(s0, Q_RHO, c);
-                const double g0 = own[0][ccol], g1 = own[1][ccol];                               // gravity
+                const double g0 = grav ? own[0][ccol] : 0.0, g1 = grav ? own[1][ccol] : 0.0;     // gravity
                 const double dbix_dy = Dc_s[3][col], dbiz_dy = Dc_s[4][col], dp_dy = Dc_s[5][col];
                 const double T_rho = t_0 + TYS(Q_RHO, col), T_mx = t_1 + TYS(Q_MX, col);
                 const double T_my = t_2 + TYS(Q_MY, col), T_mz = Z ? t_3 + TYS(Q_MZ, col) : 0.0;
@@ -547,6 +577,8 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
         block_min_impl(dtmin_local, A.dtmin_bits, reinterpret_cast<unsigned long long *>(Fx_p));   // the flux carry is dead after the last barrier
     }
 }
+#undef dy
+#undef rdy
 #undef kmode
 #undef b_is_s
 #undef primary
