@@ -18,7 +18,7 @@ except Exception as e:
 PY
 }
 run r2c3_exact
-SPRUCE_BULK_ROWS=0 run r2c3_exact_nobulk
+SPRUCE_VEC_ROWS=0 run r2c3_exact_nobulk
 run r2c3_relaxed --arith relaxed
 run r2c3_zfull_exact --zfull
 run r2c3_zfull_relaxed --zfull --arith relaxed

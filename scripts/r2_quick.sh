@@ -19,7 +19,7 @@ except Exception as e:
 PY
 }
 run ${tag}_exact
-SPRUCE_BULK_ROWS=0 run ${tag}_exact_nobulk
+SPRUCE_VEC_ROWS=0 run ${tag}_exact_novec
 run ${tag}_relaxed --arith relaxed
 run ${tag}_zfull_exact --zfull
 run ${tag}_zfull_relaxed --zfull --arith relaxed

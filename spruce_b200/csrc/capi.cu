@@ -116,7 +116,7 @@ struct spruce_domain {
     int chunk_rows_override = 0;           // SPRUCE_CHUNK_ROWS (16 .. XY_CHUNK, the range the automatic choice already spans): rows per CTA of the stage kernel, for tuning sweeps; 0 = pick_chunk_rows' own choice
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
     int stage_variants = 1;                // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=0: only the run-time-stage instances)
-    bool bulk_rows = true;                 // k_mhd_stage_xy stages rows with cp.async.bulk (SPRUCE_BULK_ROWS=0: per-thread cp.async everywhere)
+    bool vec_rows = true;                 // k_mhd_stage_xy copies ring rows in 16-byte chunks where a strip allows it (SPRUCE_VEC_ROWS=0: 8-byte per-column copies everywhere)
     int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
@@ -300,7 +300,7 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
     A.chunk_rows = pick_chunk_rows(d);
-    A.bulk = d->bulk_rows ? 1 : 0;
+    A.vec16 = d->vec_rows ? 1 : 0;
     A.grav = (d->nonzero_mask & 0x60u) ? 1 : 0;
     A.walls = (d->cfg.x_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.x_bound_2 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_2 != SPRUCE_BC_PERIODIC) ? 1 : 0;
     if (part == 0 && primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
@@ -1243,7 +1243,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0 ? 1 : 0;
-    if (const char *sb = getenv("SPRUCE_BULK_ROWS")) d->bulk_rows = atoi(sb) != 0;
+    if (const char *sb = getenv("SPRUCE_VEC_ROWS")) d->vec_rows = atoi(sb) != 0;
     if (const char *cr = getenv("SPRUCE_CHUNK_ROWS")) { const int v = atoi(cr); if (v >= 16) d->chunk_rows_override = v; }
     if (const char *ar = getenv("SPRUCE_ARITH")) {
         if (!strcmp(ar, "relaxed")) d->relaxed = true;

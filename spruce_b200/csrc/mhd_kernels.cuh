@@ -60,7 +60,7 @@ struct StageArgs {
     // module contributions to the right-hand side (Module::computeTimeDerivativesModule): already masked planes that are
     // added to k[target] in module order, after the ghost mask (equationset.cpp:208, viscosity.cpp:117-118)
     const double *xterm[4]; int xtarget[4]; int n_xterm;
-    int bulk;                     // k_mhd_stage_xy: rows may enter shared memory by cp.async.bulk (every plane 16-byte aligned, even pitch)
+    int vec16;                    // k_mhd_stage_xy: ring rows may be copied in 16-byte chunks (every plane 16-byte aligned, even pitch)
     int walls;                    // some side is not periodic: the primary stage evaluates zero_zones / record_strips
     int grav;                     // a gravity plane of this slab is non-zero (otherwise k_mhd_stage_xy adds rho * 0.0 without reading the planes)
 };

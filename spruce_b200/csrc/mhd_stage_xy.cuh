@@ -27,7 +27,7 @@ constexpr int XY_XT = XY_CHUNK + 6;          // x-table entries: local rows -3 .
 constexpr int XW = 64;                       // width of the per-column exchange arrays: one private slot per (warp column, lane)
 // shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, the x parts of the transports the Y warps finish (TX), the y parts
 // the X warps finish (TY), derivative exchange, dt exchange (read by the Y warps one iteration later, before the X warps overwrite it), the own-cell
-// rows (gravity, base state) and two mbarriers.
+// values (gravity, base state) and, for the 2-D instance, the y geometry tables.
 // nq = quantity rows kept in the ring and in the flux carry: all 11, or only the 6 of the 2-D instance.
 __host__ __device__ constexpr int xy_ntx(int nq) { return nq == 6 ? 3 : 7; }         // thermal_energy, bi_x, bi_y (+ bi_z, be_x, be_y, be_z)
 __host__ __device__ constexpr int xy_nty(int nq) { return nq == 6 ? 3 : 4; }         // rho, mom_x, mom_y (+ mom_z)
@@ -44,8 +44,7 @@ __host__ __device__ constexpr int xy_nown(int nq, int var) { return ((var & 3) =
 // y geometry: the 2-D instance (96 registers) keeps the seven y tables of its 66 columns in shared memory instead of ten doubles per thread in registers
 __host__ __device__ constexpr int xy_nyt(int nq) { return nq == 6 ? 7 * SW : 0; }
 __host__ __device__ constexpr int xy_off_yt(int nq, int var) { return xy_off_own(nq) + xy_nown(nq, var) * XW; }
-__host__ __device__ constexpr int xy_off_mbar(int nq, int var) { return xy_off_yt(nq, var) + xy_nyt(nq); }
-__host__ __device__ constexpr int xy_doubles(int nq, int var) { return xy_off_mbar(nq, var) + 2; }
+__host__ __device__ constexpr int xy_doubles(int nq, int var) { return xy_off_yt(nq, var) + xy_nyt(nq); }
 __host__ __device__ constexpr size_t xy_smem_bytes(int nq, int var) { return (size_t)xy_doubles(nq, var) * sizeof(double); }
 __host__ __device__ constexpr int xy_rows(int ln) { return ln == 6 ? 6 : NTR; }
 __host__ __device__ constexpr int xy_ctas_per_sm(int ln) { return ln == 6 ? 5 : 4; }               // the 2-D instance: <= 45 KB of shared memory and <= 96 registers -> 20 warps / SM
@@ -66,33 +65,24 @@ constexpr unsigned long long xy_list(int a = -1, int b = -1, int c = -1, int d =
 constexpr unsigned long long XY_LIST_2D = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY);                                              // no z system, no external field
 constexpr unsigned long long XY_LIST_FULL = xy_list(Q_RHO, Q_E, Q_MX, Q_MY, Q_BIX, Q_BIY, Q_MZ, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_BEZ);   // everything (padded to 12)
 
-// ---- bulk asynchronous copies (cp.async.bulk, the 1-D form of TMA) with mbarrier completion
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gsrc, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // VAR > 0: the integrator stage is a compile-time constant too (no K planes, no module right-hand-side terms).  VAR & 3 =
 //   1: B == S, secondary (first stage of rk2)   2: B != S, primary (last stage of rk2)   3: B == S, primary (euler).
 // VAR == 0 takes kmode / b_is_s / primary / n_xterm from the launch arguments (every integrator, every module).
 //
 // How rows reach shared memory.  A CTA whose 66 staged columns lie inside the row (every strip except the first and the last one or two) takes the
-// BULK path: lane 0 of each Y warp issues one cp.async.bulk per quantity for its half of ring row r+3 (528-byte rows, 16-byte aligned) and completion
-// is signalled on an mbarrier that every thread waits for at the end of iteration r.  Strips that touch the y boundary (periodic wrap or out-of-range
-// columns) and rows beyond a physical x boundary keep the per-thread path (cp.async 8-byte copies / fills by the 66 loader threads).  The own-cell
-// values of row r (gravity, base state) are per-thread cp.async copies into private shared-memory slots, issued at the top of iteration r and waited
-// for before phase 2: they occupy no register during phase 1.
+// VECTOR path: the two Y warps copy ring row r+3 with 16-byte cp.async (a 528-byte row is 33 chunks: one per lane, lane 0 takes the last one too;
+// warp 2 the first half of the quantities, warp 3 the second half), 512 contiguous bytes per instruction.  Strips that touch the y boundary (periodic
+// wrap or out-of-range columns, where a chunk could straddle the seam) keep the per-column path (8-byte cp.async by the 66 loader threads).  The
+// own-cell values of row r (gravity, base state) are per-thread cp.async copies into private shared-memory slots, issued at the top of iteration r
+// and waited for before phase 2: they occupy no register during phase 1.
+// (Measured and not kept: cp.async.bulk + mbarrier for the same rows -- every bulk copy costs ~13 uniform-datapath instructions around the
+//  UBLKCP, issued by single lanes; 4096^2 exact: 2.104 ms/step against 2.072 with the per-column path)
 template <int LN, unsigned long long LQ, int VAR = 0>
 __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(const DomainParams P, const StageArgs A, const ActiveList Larg)
 {
@@ -127,7 +117,6 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
     double (*own)[XW] = reinterpret_cast<double (*)[XW]>(smem + xy_off_own(NQ));  // [0] grav_x [1] grav_y [2..] B: n, mom_x, mom_y, (mom_z), e, bi_x, bi_y, (bi_z)
     constexpr bool YTAB = xy_nyt(NQ) > 0;
     double (*yt)[SW] = reinterpret_cast<double (*)[SW]>(smem + xy_off_yt(NQ, VAR));   // [h, fs, rfs, ep, em, d, rd][shared column]  (YTAB)
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + xy_off_mbar(NQ, VAR));   // [0] ring rows
 #define RG(sl, q, cc) ringp[((sl) * NQ + QI(q)) * SW + (cc)]
 #define FXS(q, cc) Fx_p[QI(q) * XW + (cc)]
 #define TXS(q, cc) TX_p[((q) - Q_E) * XW + (cc)]
@@ -146,8 +135,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
     const int r0 = (A.chunk0 + (int)blockIdx.y * A.chunk_stride) * A.chunk_rows;
     const int r1 = min(r0 + A.chunk_rows, P.nx);
     const bool col_out = (lane < 31) && (j < P.ny);
-    const bool bulk = A.bulk && j0 >= HALO && j0 + CW + HALO <= P.ny;            // CTA-uniform: all 66 staged columns are inside the row
-    const int issuer = (tid == 64) ? 1 : (tid == 96) ? 2 : 0;                   // lane 0 of the two Y warps: each issues half of the bulk copies of a ring row
+    const bool vec = A.vec16 && j0 >= HALO && j0 + CW + HALO <= P.ny;             // CTA-uniform: all 66 staged columns are inside the row -> 16-byte copies
 
     // ---- per-thread loader (strips at the y boundary, rows beyond a physical x boundary): thread t < SW owns shared column t
     const bool loader = tid < SW;
@@ -187,29 +175,30 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             }
         } else fill_row(slot);
     };
-    constexpr unsigned ROW_BYTES = SW * sizeof(double);
-    constexpr int NLD = (LN == 6 ? 6 : NLOAD), NLD_A = NLD / 2;                  // planes per ring row; the first NLD_A go through issuer 1
-    auto bulk_row_copies = [&](int r, int slot) {                // issuers only; the row exists; the issuer has announced the bytes (expect_tx)
-        const size_t off = (size_t)wrap_row(r) * P.pitch + (j0 - HALO);
-        if (issuer == 1) {
-            if (LN == 6) {
-                bulk_g2s(&RG(slot, Q_RHO, 0), A.S[E_N] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_MX, 0), A.S[E_MX] + off, ROW_BYTES, &mbar[0]);
-                bulk_g2s(&RG(slot, Q_MY, 0), A.S[E_MY] + off, ROW_BYTES, &mbar[0]);
-            } else {
-#pragma unroll
-                for (int v = 0; v < NLD_A; v++) bulk_g2s(&RG(slot, v, 0), A.S[v] + off, ROW_BYTES, &mbar[0]);
+    constexpr int NLD = (LN == 6 ? 6 : NLOAD), NLD_A = NLD / 2;                  // planes per ring row; warp 2 copies the first NLD_A, warp 3 the others
+    auto vec_row = [&](int r, int slot) {                        // vector path, warps 2 and 3: lane l owns columns 2l, 2l+1 (lane 0 also 64, 65)
+        if (warp < 2) return;
+        const bool ex = row_exists(P, r);
+        const size_t off = (size_t)wrap_row(r) * P.pitch + (j0 - HALO) + 2 * lane;
+        auto one = [&](int q, const double *plane) {
+            double *dst = &RG(slot, q, 2 * lane);
+            if (ex) { cp_async16(dst, plane + off); if (lane == 0) cp_async16(dst + 64, plane + off + 64); }
+            else {                                               // a row beyond a physical x boundary
+                const double f = (q == Q_RHO) ? 1.0 : 0.0;
+                *reinterpret_cast<double2 *>(dst) = make_double2(f, f);
+                if (lane == 0) *reinterpret_cast<double2 *>(dst + 64) = make_double2(f, f);
             }
+        };
+        if (LN == 6) {
+            if (warp == 2) { one(Q_RHO, A.S[E_N]); one(Q_MX, A.S[E_MX]); one(Q_MY, A.S[E_MY]); }
+            else { one(Q_E, A.S[E_E]); one(Q_BIX, A.S[E_BX]); one(Q_BIY, A.S[E_BY]); }
+        } else if (warp == 2) {
+#pragma unroll
+            for (int v = 0; v < NLD_A; v++) one(v, A.S[v]);
         } else {
-            if (LN == 6) {
-                bulk_g2s(&RG(slot, Q_E, 0), A.S[E_E] + off, ROW_BYTES, &mbar[0]);
-                bulk_g2s(&RG(slot, Q_BIX, 0), A.S[E_BX] + off, ROW_BYTES, &mbar[0]); bulk_g2s(&RG(slot, Q_BIY, 0), A.S[E_BY] + off, ROW_BYTES, &mbar[0]);
-            } else {
 #pragma unroll
-                for (int v = NLD_A; v < NEV; v++) bulk_g2s(&RG(slot, v, 0), A.S[v] + off, ROW_BYTES, &mbar[0]);
-                bulk_g2s(&RG(slot, Q_BEX, 0), A.st[S_BEX] + off, ROW_BYTES, &mbar[0]);
-                bulk_g2s(&RG(slot, Q_BEY, 0), A.st[S_BEY] + off, ROW_BYTES, &mbar[0]);
-                bulk_g2s(&RG(slot, Q_BEZ, 0), A.st[S_BEZ] + off, ROW_BYTES, &mbar[0]);
-            }
+            for (int v = NLD_A; v < NEV; v++) one(v, A.S[v]);
+            one(Q_BEX, A.st[S_BEX]); one(Q_BEY, A.st[S_BEY]); one(Q_BEZ, A.st[S_BEZ]);
         }
     };
     // own-cell values of row r (a row of the slab itself: it always exists): gravity for the X warps, the base state for both roles.  Every thread
@@ -231,13 +220,12 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             if (Z) cp_async8(&own[HAVE_B ? 5 + NB : 0][ccol], A.B[E_BZ] + off);
         }
     };
-    // rho = n * m_i (idealmhd.cpp:247) for the 66 columns of a ring row: warp 3, two columns per lane (lane 1 also takes the last pair)
+    // rho = n * m_i (idealmhd.cpp:247) for the 66 columns of a ring row: warp 2, the columns each lane copied itself on the vector path
     auto convert_rho = [&](int s_) {
-        if (warp != 3) return;
+        if (warp != 2) return;
         double2 *p2 = reinterpret_cast<double2 *>(&RG(s_, Q_RHO, 0));
         double2 v = p2[lane]; v.x = v.x * P.m_i; v.y = v.y * P.m_i; p2[lane] = v;
-        if (lane == 1) { double2 w = p2[32]; w.x = w.x * P.m_i; w.y = w.y * P.m_i; p2[32] = w; }
-        if (bulk) fence_proxy_async();                           // this slot is the target of a bulk copy again five rows later
+        if (lane == 0) { double2 w = p2[32]; w.x = w.x * P.m_i; w.y = w.y * P.m_i; p2[32] = w; }
     };
     // v = mom / rho (idealmhd.cpp:248-250): one IEEE reciprocal, then the exact-division correction per component (exact_math.cuh).
     // Velocities are read at shared columns 1 .. 64 only (own column and the left neighbour of a y face): warps 0 and 1, one column per thread.
@@ -271,7 +259,6 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
                 yt[t][i] = srcy[t][min(j0 - HALO + i, P.ny + 2)];          // shared column i = global column j0 - 2 + i; the tables reach ny + 2
             }
         }
-        if (bulk && issuer == 1) { mbar_init(&mbar[0], 2); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
     }
     auto x_geom = [&](int f) {
         const int i = f - r0 + 3;
@@ -301,22 +288,10 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
 #define rdy (YTAB ? yt[6][c] : rdy_reg)
 
     // ---- prologue: rows r0-2 .. r0+2 land, rho is formed for all of them, velocity for rows r0-1, r0, r0+1
-    unsigned ring_par = 0;                       // phase parity of the ring mbarrier (bulk path)
-    if (bulk) {
-        __syncthreads();                         // the mbarrier is initialised
-        int nex = 0;
-        for (int r = r0 - HALO; r <= r0 + HALO; r++) { if (row_exists(P, r)) nex++; else fill_row(slot_of(r)); }
-        if (issuer) {
-            // one phase for all five rows: each issuer arrives once, with the bytes of its half of every existing row
-            mbar_expect_tx(&mbar[0], nex * (issuer == 1 ? NLD_A : NLD - NLD_A) * ROW_BYTES);
-            for (int r = r0 - HALO; r <= r0 + HALO; r++) if (row_exists(P, r)) bulk_row_copies(r, slot_of(r));
-        }
-        mbar_wait(&mbar[0], ring_par); ring_par ^= 1u;
-    } else {
-        for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r, slot_of(r));
-        cp_async_commit();
-        cp_async_wait_all();
-    }
+    if (vec) for (int r = r0 - HALO; r <= r0 + HALO; r++) vec_row(r, slot_of(r));
+    else for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r, slot_of(r));
+    cp_async_commit();
+    cp_async_wait_all();
     __syncthreads();                             // per-thread fills / copies of other threads
     for (int r = r0 - HALO; r <= r0 + HALO; r++) convert_rho(slot_of(r));
     __syncthreads();
@@ -356,22 +331,11 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
         const int sm1 = s0 == 0 ? RD - 1 : s0 - 1, sp1 = next_slot(s0), sp2 = next_slot(sp1), sp3 = next_slot(sp2);
         const int v1 = next_vslot(v0), v2 = next_vslot(v1);
         const bool pre = (r + 3 <= r1 + HALO - 1);
-        const bool pre_bulk = pre && bulk && row_exists(P, r + 3);
-        // own-cell rows of this row (consumed in phase 2), then the ring row three rows ahead
+        // own-cell values of this row (consumed in phase 2), then the ring row three rows ahead: two cp.async groups
         own_row(r);
         cp_async_commit();
-        if (pre) {
-            if (pre_bulk) {
-                if (issuer) {                                    // one arrival per issuer, with the bytes of its half of the row
-                    fence_proxy_async();
-                    mbar_expect_tx(&mbar[0], (issuer == 1 ? NLD_A : NLD - NLD_A) * ROW_BYTES);
-                    bulk_row_copies(r + 3, sp3);
-                }
-            }
-            else if (bulk) fill_row(sp3);
-            else issue_row(r + 3, sp3);
-        }
-        if (!bulk) cp_async_commit();
+        if (pre) { if (vec) vec_row(r + 3, sp3); else issue_row(r + 3, sp3); }
+        cp_async_commit();
 
         const int g = P.row0 + r;
         const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
@@ -463,8 +427,7 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
             if (Z) d_f = ddiv(IyR_vz - IyL_vz, dy, rdy);            // d(v_z)/dy
         }
         // the own-cell rows have landed (they had the whole of phase 1), then the partial results become visible to the other role
-        if (bulk) cp_async_wait_all();                              // bulk path: the only cp.async group in flight holds this thread's own-cell values
-        else asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // per-thread path: the younger group is ring row r+3
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");     // the own-cell values have landed (the younger group is ring row r+3)
         __syncthreads();
 
         // ================================================================ phase 2: finish the outputs
@@ -561,9 +524,8 @@ __global__ void __launch_bounds__(XY_NT, xy_ctas_per_sm(LN)) k_mhd_stage_xy(cons
                 }
             }
         }
-        if (pre_bulk) { mbar_wait(&mbar[0], ring_par); ring_par ^= 1u; }
-        else if (!bulk) cp_async_wait_all();
-        if (pre && !pre_bulk) __syncthreads();                      // the row came through the loader threads (copies or fills): warp 3 converts it below
+        cp_async_wait_all();
+        if (pre && !vec) __syncthreads();                           // per-column path: the row came through the 66 loader threads, warp 2 converts it below
         if (pre) convert_rho(sp3);                                  // the row that just landed
         if (r + 2 <= r1) form_vel(sp2, v2);                         // into the velocity slot of row r-1 (dead since the last barrier)
         __syncthreads();

@@ -55,7 +55,7 @@ STAGE_VARIANT_CODE = """
 """
 
 
-@pytest.mark.parametrize("switches", [{"SPRUCE_STAGE_VARIANTS": "0"}, {"SPRUCE_BULK_ROWS": "0"}, {"SPRUCE_STAGE_VARIANTS": "0", "SPRUCE_BULK_ROWS": "0"}])
+@pytest.mark.parametrize("switches", [{"SPRUCE_STAGE_VARIANTS": "0"}, {"SPRUCE_VEC_ROWS": "0"}, {"SPRUCE_STAGE_VARIANTS": "0", "SPRUCE_VEC_ROWS": "0"}])
 @pytest.mark.parametrize("integ,zfull,nx,ny,xb,yb", [
     ("rk2", False, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),      # 2-D list: k_mhd_stage_xy<6, ., 1> then <6, ., 2>
     ("rk2", True, 150, 203, ("periodic", "periodic"), ("periodic", "periodic")),       # full list: <12, ., 1> / <12, ., 2>
@@ -67,7 +67,7 @@ STAGE_VARIANT_CODE = """
 def test_stage_kernel_build_options_vs_oracle(integ, zfull, nx, ny, xb, yb, switches):
     """The stage kernel's two switches, both ON by default (the default path is what tests/test_gpu_parity.py exercises):
     SPRUCE_STAGE_VARIANTS=0 runs the instances of k_mhd_stage_xy that take the integrator stage from the launch arguments instead of the
-    template constant VAR; SPRUCE_BULK_ROWS=0 stages every row through the per-thread cp.async path instead of cp.async.bulk.  Same
+    template constant VAR; SPRUCE_VEC_ROWS=0 copies every ring row through the 8-byte per-column path instead of 16-byte chunks.  Same
     arithmetic: bit for bit against the oracle in every setting."""
     out = run_isolated(STAGE_VARIANT_CODE.format(integ=integ, zfull=zfull, nx=nx, ny=ny, xb=xb, yb=yb), switches)
     assert "ok" in out
