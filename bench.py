@@ -134,7 +134,7 @@ def run_reference_arm(args):
         return
     sample = "unmodified reference binary (oracle/_ref/run, g++ -O3 -fopenmp), OT-%d (same generator as the 4096^2 workload), wall(%d it) - wall(%d it), %d OpenMP threads; %s" % (size, w + k, w, threads, r["how"])
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w,
-            "ms_per_step": 1e3 * r["seconds_per_step"] * (args.size / size) ** 2, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * r["seconds_per_step"] * (args.size / size) ** 2, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "OT-%d ideal MHD RK2 doubly periodic non-uniform grid" % args.size, "sample_grid": size,
                        "note": "CPU rate is grid-size independent to about 20 percent (BASELINE.md 2); ms_per_step is scaled to the %d^2 grid" % args.size},
@@ -144,6 +144,58 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def row_digests(plane: np.ndarray) -> bytes:
+    """8-byte digest of every row of a plane (rows = x index): independent of how the rows are split over ranks."""
+    import hashlib
+    a = np.ascontiguousarray(plane)
+    a = a + 0.0                                   # -0.0 -> +0.0: the sign of a zero is the one thing exact mode does not promise (DESIGN.md 2)
+    return b"".join(hashlib.blake2b(a[i].tobytes(), digest_size=8).digest() for i in range(a.shape[0]))
+
+
+def state_hash(digests_by_plane) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for d in digests_by_plane:
+        h.update(d)
+    return h.hexdigest()[:16]
+
+
+def dt_hash(dts) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(np.asarray(dts, dtype=np.float64)).tobytes()).hexdigest()[:16]
+
+
+def slab_parity_check(rank, world, local, transport):
+    """Outside the timed region: the same small problem on rank 0 alone and on `world` slabs; step sizes and every evolved plane must be equal
+    bit for bit (min/max reductions are exact and every cell sees the same operands)."""
+    import torch.distributed as dist
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    from spruce_b200.multigpu import SlabRunner
+    nx, ny, steps = 64 * world + 24, 300, 6
+    ok = True
+    for zfull in (False, True):                   # the 6-quantity and the 12-quantity instance of the stage kernel
+        s = synthetic.orszag_tang(nx, ny, zfull=zfull)
+        runner = SlabRunner(s["planes"], s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=transport, **KW)
+        dts = runner.step(steps)
+        got = {v: runner.gather(v) for v in PlasmaDomain.EVOLVED}
+        runner.close()
+        if rank == 0:
+            one = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], device=local, **KW)
+            ref = np.asarray(one.advance(steps))
+            if dts is not None:
+                ok = ok and [x.hex() for x in np.asarray(dts)] == [x.hex() for x in ref]
+            for v in PlasmaDomain.EVOLVED:
+                a, b = got[v], one.grid(v)
+                ok = ok and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+            one.close()
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    if not flag[0]:
+        raise SystemExit("bench.py: the %d-slab run of the %dx%d parity problem differs from the 1-GPU run" % (world, nx, ny))
+    return {"grid": [nx, ny], "steps": steps, "equal": True}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -184,6 +236,7 @@ def run_ours(args):
         cells = n * n
         host = {k: torch.from_numpy(np.ascontiguousarray(planes[k])).pin_memory().numpy() for k in names}     # this rank's rows, pinned
         host["d_x"], host["d_y"] = dx, dy
+        parity = slab_parity_check(rank, world, local, args.transport)
         runner = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=args.transport, xdim=n, **KW)
         add_modules(runner.dom)
         sampler = ClockSampler(local)
@@ -208,10 +261,18 @@ def run_ours(args):
         t0 = time.perf_counter()
         r2 = SlabRunner(host, s["ion_mass"], s["adiabatic_index"], rank=rank, world=world, device=local, transport=args.transport, xdim=n, **KW)
         add_modules(r2.dom)
-        r2.step(args.steps)
+        dts2 = r2.step(args.steps)
         out = {k: r2.dom.grid(k, out=outbuf[k]) for k in PlasmaDomain.EVOLVED}
         torch.cuda.synchronize(); dist.barrier()
         t1 = time.perf_counter()
+        # hashes of this job (K steps from the initial state): identical on 1, 2, 4, 8 GPUs in exact mode -> the driver's lines can be compared
+        mine = [row_digests(out[k]) for k in PlasmaDomain.EVOLVED]
+        alld = [None] * world
+        dist.all_gather_object(alld, mine)
+        result["parity_vs_1gpu"] = True
+        result["parity_check"] = parity
+        result["dt_hash"] = dt_hash(dts2) if dts2 is not None else None
+        result["state_hash"] = state_hash([b"".join(alld[r][i] for r in range(world)) for i in range(len(PlasmaDomain.EVOLVED))])
         tt = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         result["e2e"] = {"value": cells * args.steps / tt.item(), "unit": UNIT, "h2d_bytes_per_step": len(names) * cells * 8 / args.steps,
@@ -289,6 +350,40 @@ def run_ours(args):
            "seconds": t1 - t0, "definition": "one job = upload 13 input planes from pinned host memory + setup + K steps + download 8 evolved planes (into pinned host buffers) and the K step sizes (the reference's state-in / K steps / state-out pattern)"}
     assert np.isfinite(out["rho"]).all()
     dom.close()
+    hashes = {"dt_hash": dt_hash(dts2), "state_hash": state_hash([row_digests(out[k]) for k in PlasmaDomain.EVOLVED])}
+
+    # ---- the same workload in relaxed arithmetic (opt-in mode, within the north star's 1e-9; the bench line itself stays exact), and the
+    #      12-quantity instance of the stage kernel (what any run with an external field or a z system takes) in exact arithmetic
+    extra = {}
+    if not args.no_extra and args.arith == "exact" and not with_tc:
+        def timed(nsteps, **env):
+            old = {k: os.environ.get(k) for k in env}
+            os.environ.update(env)
+            try:
+                dd = PlasmaDomain(host, ion_mass, gamma, device=local, **KW)
+            finally:
+                for k, v in old.items():
+                    if v is None: os.environ.pop(k, None)
+                    else: os.environ[k] = v
+            st = torch.cuda.ExternalStream(dd.stream())
+            dd.advance(args.warmup)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record(st)
+            dd.advance(nsteps)
+            b.record(st); torch.cuda.synchronize()
+            dd.close()
+            return a.elapsed_time(b) / nsteps
+        ms_r = timed(args.steps, SPRUCE_ARITH="relaxed")
+        ach = ALG_BYTES_PER_CELL_STEP * cells / (ms_r * 1e-3) / 1e9
+        extra["roofline_relaxed"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "ms_per_step": ms_r, "value": cells / (ms_r * 1e-3),
+                                     "mode": "relaxed (SPRUCE_ARITH=relaxed: FMA contraction + one-multiplication table divisions; fields and step sizes within 1e-9 of the reference, tests/test_gpu_extended.py)"}
+        sz = synthetic.orszag_tang(n, n, zfull=True)
+        for k in names:
+            host[k][...] = sz["planes"][k]
+        del sz
+        ms_f = timed(min(args.steps, 20))
+        extra["value_full_instance"] = {"value": cells / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f, "frac": ALG_BYTES_PER_CELL_STEP * cells / (ms_f * 1e-3) / 1e9 / peak,
+                                        "workload": "the same grid with non-zero mom_z, bi_z and external field: the 12-quantity instance of k_mhd_stage_xy (exact arithmetic)"}
 
     # ---- CPU baseline on the host cores (bounded sample)
     cpu = None
@@ -298,13 +393,13 @@ def run_ours(args):
         if r is not None:
             cpu = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": "unmodified reference binary (oracle/_ref/run), OT-512 (same generator), wall(10 it) - wall(2 it), %d OpenMP threads" % threads}
-    result = dict(value=value, ms=ms, launches=launches, clocks=clocks, roofline=roofline, e2e=e2e, cpu=cpu, tc_subcycles=tc_sub)
+    result = dict(value=value, ms=ms, launches=launches, clocks=clocks, roofline=roofline, e2e=e2e, cpu=cpu, tc_subcycles=tc_sub, **hashes, **extra)
     emit(args, result, 1)
 
 
 def emit(args, r, world):
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "OT-%d: synthetic doubly periodic Orszag-Tang vortex, non-uniform rectilinear %dx%d grid, ideal MHD, RK2, epsilon 0.2 (BASELINE.json configs[3])" % (args.size, args.size, args.size),
                        "parallelism": ("slab%d along x, halo exchange: %s" % (world, r.get("transport", "p2p"))) if world > 1 else "single", "l2": "working set per step (21 planes, %.1f GB) >> 126 MB L2: inputs larger than L2" % (21 * args.size ** 2 * 8 / 1e9),
@@ -312,6 +407,9 @@ def emit(args, r, world):
                                "relaxed (opt-in: FMA contraction + one-multiplication table divisions in the stage kernel; fields within 1e-9 of the reference, step sizes not bit-identical)",
                        "stage_variants": int(args.stage_variants)},
             "clocks": r["clocks"], "gpu_launches": r["launches"], "e2e": r["e2e"], "roofline": r["roofline"]}
+    for k in ("roofline_relaxed", "value_full_instance", "parity_vs_1gpu", "parity_check", "dt_hash", "state_hash"):
+        if r.get(k) is not None:
+            line[k] = r[k]
     if r.get("cpu"):
         line["cpu_baseline"] = r["cpu"]
     if args.workload == "mhd_tc":
@@ -330,13 +428,13 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the relaxed-arithmetic and full-instance measurements of the N=1 line")
     ap.add_argument("--workload", default="mhd", choices=["mhd", "mhd_tc"], help="mhd: BASELINE configs[3] (the bench line); mhd_tc: configs[4], MHD + thermal conduction")
     ap.add_argument("--arith", default="exact", choices=["exact", "relaxed"],
                     help="exact (default, the bench line): every operation individually rounded, bit-identical to the reference; relaxed: the opt-in stage kernel of "
                          "stage_relaxed.cu (FMA contraction, one-multiplication table divisions; fields within the north star's 1e-9, step sizes not bit-identical)")
-    ap.add_argument("--stage-variants", type=int, default=0, nargs="?", const=1, choices=[0, 1, 2, 3],
-                    help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS): 1 = on, 2 = also the six-CTAs-per-SM build of the 2-D instance, "
-                         "3 = also its pair-wise mid-row barrier")
+    ap.add_argument("--stage-variants", type=int, default=1, choices=[0, 1],
+                    help="compile-time integrator-stage instances of the stage kernel (SPRUCE_STAGE_VARIANTS; on by default, 0 = the run-time-stage instances)")
     ap.add_argument("--zfull", action="store_true", help="OT state with non-zero mom_z / bi_z / be: the 12-quantity instance of the stage kernel (what any solar run takes)")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 halo exchange: library peer stores over NVLink, or torch.distributed NCCL send/recv")
     args = ap.parse_args()
@@ -344,8 +442,8 @@ def main():
         args.warmup = 3
     if args.arith == "relaxed":
         os.environ["SPRUCE_ARITH"] = "relaxed"              # read by spruce_domain_create
-    if args.stage_variants:
-        os.environ["SPRUCE_STAGE_VARIANTS"] = str(args.stage_variants)
+    if not args.stage_variants:
+        os.environ["SPRUCE_STAGE_VARIANTS"] = "0"
     if args.impl == "reference":
         run_reference_arm(args)
     else:

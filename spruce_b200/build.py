@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for name, fmad in UNITS:                     # the units compile concurrently
         obj = OBJ / (Path(name).stem + ".o")
-        cmd = [nvcc, *COMMON_FLAGS, fmad, "-c", "-o", str(obj), str(SRC / name)]
+        cmd = [nvcc, *COMMON_FLAGS, *os.environ.get("SPRUCE_NVCC_FLAGS", "").split(), fmad, "-c", "-o", str(obj), str(SRC / name)]   # SPRUCE_NVCC_FLAGS: experiments (-D...)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

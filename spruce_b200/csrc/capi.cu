@@ -113,11 +113,12 @@ struct spruce_domain {
     // open_moc (moc_stage.cuh): evolved ghost cells
     bool moc_any = false; double global_viscosity = 0.0; double *moc_base = nullptr;
     moc::Limits moc_lim{0, 0, 0.1, 10.0, 0.1, 10.0};                      // moc_b_limiting / moc_mom_limiting and their bounds (idealmhd.hpp:59-64)
-    int chunk_rows_override = 0;           // SPRUCE_CHUNK_ROWS (16 .. XY_CHUNK, the range the automatic choice already spans): rows per CTA of the stage kernel, for tuning sweeps; 0 = pick_chunk_rows' own choice
+    int chunk_rows_override = 0;           // SPRUCE_CHUNK_ROWS (8 .. XY_CHUNK): rows per CTA of the stage kernel, for tuning sweeps; 0 = plan_chunks' own choice
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
     int stage_variants = 1;                // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=0: only the run-time-stage instances)
     bool vec_rows = true;                 // k_mhd_stage_xy copies ring rows in 16-byte chunks where a strip allows it (SPRUCE_VEC_ROWS=0: 8-byte per-column copies everywhere)
-    int stage_kernel = 5;                  // 5: direction-specialised warps (k_mhd_stage_xy); 4: column marching (k_mhd_stage)
+    bool fused_ctl = false;                // inside a plain step (no modules, no open_moc): the step control runs in k_step_open / k_step_mid / k_step_close
+    bool fuse_ctl_enabled = true;          // SPRUCE_FUSED_CTL=0: always the separate one-thread control kernels
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
     void *seg = nullptr; size_t seg_bytes = 0;
@@ -252,16 +253,42 @@ void fill_sets(const spruce_domain *d, StageArgs &A, const PlaneSet &S, const Pl
 // the dt skip test (dt_can_skip) lives in k_mhd_stage_xy only, and needs k_dt_validate / k_dt_full after the step's last stage:
 // spruce_advance provides that; the caller-driven spruce_mgpu_stage path (NCCL transport) evaluates every cell
 // open_moc: the minimum also runs over evolved ghost cells, which k_dt_full does not visit -> every cell is evaluated
-int dt_prune_enabled(const spruce_domain *d) { return (d->stage_kernel == 5 && !d->in_mgpu_stage_api && !d->moc_any) ? 1 : 0; }
+int dt_prune_enabled(const spruce_domain *d) { return (!d->in_mgpu_stage_api && !d->moc_any) ? 1 : 0; }
 
-int pick_chunk_rows(const spruce_domain *d)
+ActiveList active_quantities(const spruce_domain *d);
+
+// Row chunks of one stage launch.  A CTA marches over `rows` rows (plus 4 warm-up rows and a prologue), so few, long chunks are cheap, but the grid
+// should fill whole waves of resident CTAs (148 SMs x 5 for the 2-D instance, x 4 otherwise).  The plan takes the smallest number of waves the upper
+// bound XY_CHUNK allows and spreads the rows evenly over the CTA rows that fit in them.  On a slab whose halo exchange overlaps the interior
+// (split), the first and the last `edge` rows form their own short launch on the communication stream: it finishes early, its rows travel while
+// the long interior chunks still run.
+struct ChunkPlan { int rows; int edge; int n_interior; };
+ChunkPlan plan_chunks(const spruce_domain *d, bool split)
 {
-    // enough CTAs for >= ~4 waves of 148 SMs x resident CTAs, but chunks of at least 16 rows (4 warm-up rows each)
-    const int strips = (d->P.ny + CW - 1) / CW;
-    int rows = d->stage_kernel == 5 ? XY_CHUNK : MAX_CHUNK;
-    if (d->chunk_rows_override > 0) return d->chunk_rows_override < rows ? d->chunk_rows_override : rows;      // SPRUCE_CHUNK_ROWS: tuning sweeps
-    while (rows > 16 && (long long)strips * ((d->P.nx + rows - 1) / rows) < 148LL * 5 * 4) rows >>= 1;
-    return rows;
+    const int strips = (d->P.ny + CW - 1) / CW, nx = d->P.nx;
+    const ActiveList L = active_quantities(d);
+    const int cap = 148 * ((L.n == 6 && L.q == XY_LIST_2D && d->static_lists) ? xy_ctas_per_sm(6) : xy_ctas_per_sm(0));
+    ChunkPlan p{};
+    p.edge = split ? XY_EDGE_ROWS : 0;
+    const int body = nx - 2 * p.edge, extra = split ? 2 : 0;
+    if (d->chunk_rows_override > 0) p.rows = d->chunk_rows_override < XY_CHUNK ? d->chunk_rows_override : XY_CHUNK;      // SPRUCE_CHUNK_ROWS: tuning sweeps
+    else {
+        const long long min_ctas = (long long)strips * ((body + XY_CHUNK - 1) / XY_CHUNK + extra);
+        const long long waves = (min_ctas + cap - 1) / cap;
+        long long cta_rows = waves * cap / strips - extra;                    // CTA rows that fit in those waves
+        if (cta_rows < 1) cta_rows = 1;
+        p.rows = (int)((body + cta_rows - 1) / cta_rows);
+        if (p.rows > XY_CHUNK) p.rows = XY_CHUNK;
+        if (p.rows < 8) p.rows = 8 < body ? 8 : body;
+    }
+    p.n_interior = (body + p.rows - 1) / p.rows;
+    return p;
+}
+bool can_split(const spruce_domain *d, int primary)
+{
+    const bool ghosts = d->any_ucnp || (primary && d->any_primary_ghost);
+    return d->cfg.n_ranks > 1 && d->peers_connected && d->overlap && !ghosts && d->visc.empty() && !d->moc_any      // the strip kernel follows the whole stage kernel and writes edge rows
+           && d->P.nx >= 2 * XY_EDGE_ROWS + 8;
 }
 
 // Transported quantities that can be non-zero.  The z system {mom_z, bi_z} stays identically zero when mom_z, bi_z and be_z
@@ -299,19 +326,17 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     for (int t = 0; t < A.n_xterm; t++) { A.xterm[t] = d->cur_xterm[t]; A.xtarget[t] = d->cur_xtarget[t]; }
     A.coef = coef; A.primary = primary; A.kmode = kmode;
     A.b_is_s = (S.p[0] == B.p[0]) ? 1 : 0;
-    A.chunk_rows = pick_chunk_rows(d);
     A.vec16 = d->vec_rows ? 1 : 0;
     A.grav = (d->nonzero_mask & 0x60u) ? 1 : 0;
     A.walls = (d->cfg.x_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.x_bound_2 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_2 != SPRUCE_BC_PERIODIC) ? 1 : 0;
-    if (part == 0 && primary && kmode != KM_EXPORT) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
-    const int nchunks = (d->P.nx + A.chunk_rows - 1) / A.chunk_rows;
-    A.chunk0 = 0; A.chunk_stride = 1;
-    int gy = nchunks;
+    if (part == 0 && primary && kmode != KM_EXPORT && !d->fused_ctl) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
+    const ChunkPlan cp = plan_chunks(d, part != 0);
+    A.chunk_rows = cp.rows; A.row_begin = cp.edge; A.row_end = d->P.nx - cp.edge; A.edge2_begin = -1; A.edge2_end = -1;
+    int gy = cp.n_interior;
     cudaStream_t st = d->stream;
-    if (part == 1) { A.chunk_stride = nchunks - 1; gy = 2; st = d->comm_stream; }
-    if (part == 2) { A.chunk0 = 1; gy = nchunks - 2; }
+    if (part == 1) { A.chunk_rows = cp.edge; A.row_begin = 0; A.row_end = cp.edge; A.edge2_begin = d->P.nx - cp.edge; A.edge2_end = d->P.nx; gy = 2; st = d->comm_stream; }
     dim3 grid((d->P.ny + CW - 1) / CW, gy);
-    if (d->stage_kernel == 5) {
+    {
         const ActiveList L = active_quantities(d);
         // compile-time integrator stage (SPRUCE_STAGE_VARIANTS=0 turns it off): plain euler / rk2 stages without module terms
         int var = 0;
@@ -334,7 +359,6 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
         }
         else k_mhd_stage_xy<0, 0ULL><<<grid, XY_NT, xy_smem_bytes(NTR, 0), st>>>(d->P, A, L);
     }
-    else k_mhd_stage<<<grid, NT, STAGE_SMEM, st>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     if (d->moc_any) return launch_moc(d, S, B, D, coef, primary, kmode, 0);      // single rank: part == 0, same stream
@@ -976,16 +1000,12 @@ int finish_stage(spruce_domain *d, const PlaneSet &U, int primary)
 int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode)
 {
     int rc;
-    const int crows = pick_chunk_rows(d), nchunks = (d->P.nx + crows - 1) / crows;
-    const bool ghosts = d->any_ucnp || (primary && d->any_primary_ghost);
-    const bool last_chunk_holds_edge = d->P.nx - (nchunks - 1) * crows >= HALO;       // the pushed rows nx-2, nx-1 must both come from the edge launch
-    const bool split = d->cfg.n_ranks > 1 && d->peers_connected && d->overlap && !ghosts && d->visc.empty() && nchunks >= 4 && last_chunk_holds_edge
-                       && !d->moc_any;                                                  // the strip kernel follows the whole stage kernel and writes edge rows
+    const bool split = can_split(d, primary);
     if (!split) {
         if ((rc = launch_stage(d, S, B, D, coef, primary, kmode))) return rc;
         return finish_stage(d, D, primary);
     }
-    if (primary) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
+    if (primary && !d->fused_ctl) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
     CUDA_TRY(cudaEventRecord(d->ev_main, d->stream));
     CUDA_TRY(cudaStreamWaitEvent(d->comm_stream, d->ev_main, 0));
     if ((rc = launch_stage(d, S, B, D, coef, primary, kmode, 1))) return rc;
@@ -1065,7 +1085,7 @@ int finish_dt(spruce_domain *d)
     for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
     A.ctl = d->ctl;
-    dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx < 64 ? d->P.nx : 64);
     k_dt_full<<<grid, 256, 0, d->stream>>>(d->P, A);            // returns at once unless the window was missed
     d->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -1073,9 +1093,57 @@ int finish_dt(spruce_domain *d)
     return SPRUCE_OK;
 }
 
+// the fused step control of plain runs (mhd_kernels.cuh: k_step_open / k_step_mid / k_step_close)
+void fill_gather(spruce_domain *d, DtGatherArgs &A, unsigned long long seq)
+{
+    A.ctl = d->ctl; A.rank = d->cfg.rank; A.world = d->cfg.n_ranks; A.seq = seq;
+    A.mine = d->cfg.n_ranks > 1 ? seg_flags(d->seg) : nullptr;
+    for (int r = 0; r < d->cfg.n_ranks && d->cfg.n_ranks > 1; r++) A.peer[r] = seg_flags(d->peer_seg[r]);
+}
+int finish_dt_fused(spruce_domain *d, int next_slot)
+{
+    DtGatherArgs G{};
+    fill_gather(d, G, ++d->dt_seq);          // the same sequence as peer_dt_allgather (set-up, module runs): consecutive gathers alternate the buffer parity
+    k_step_mid<<<1, MAX_RANKS, 0, d->stream>>>(G);
+    DtFullArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.ctl = d->ctl;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx < 64 ? d->P.nx : 64);
+    k_dt_full<<<grid, 256, 0, d->stream>>>(d->P, A);            // returns at once unless the window was missed
+    k_step_close<<<1, MAX_RANKS, 0, d->stream>>>(G, d->dt_hist, next_slot, dt_prune_enabled(d));
+    d->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+
 #include "anomres_host.cuh"
 
 // one advanceTime (evolution.cpp:59-82) worth of launches
+// plain run: no module hook, no viscosity term, no open_moc strip kernel, dt skip test in use -> the step control is fused (and the step size of
+// the next step is fixed by this step's closing kernel)
+bool plain_run(const spruce_domain *d)
+{
+    return d->fuse_ctl_enabled && d->module_order.empty() && d->visc.empty() && !d->moc_any && dt_prune_enabled(d) && d->cfg.time_integrator != SPRUCE_TI_RK4
+           && !(d->moc_lim.b_on || d->moc_lim.mom_on);
+}
+int enqueue_step_plain(spruce_domain *d, int hist_slot, bool first, bool last)
+{
+    int rc;
+    if (first) { k_step_open<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot, dt_prune_enabled(d)); d->launches++; }
+    d->fused_ctl = true;
+    if (d->cfg.time_integrator == SPRUCE_TI_EULER) {
+        rc = stage_and_exchange(d, d->Pset, d->Pset, d->Mset, 1.0, 1, KM_NONE);
+        if (!rc) std::swap(d->Pset, d->Mset);
+    } else {
+        rc = stage_and_exchange(d, d->Pset, d->Pset, d->Mset, 0.5, 0, KM_NONE);
+        if (!rc) rc = stage_and_exchange(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_NONE);
+    }
+    d->fused_ctl = false;
+    if (rc) return rc;
+    return finish_dt_fused(d, last ? -1 : hist_slot + 1);
+}
+
 int enqueue_step(spruce_domain *d, int hist_slot)
 {
     int rc;
@@ -1106,7 +1174,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         }
     }
     if (!d->visc.empty() && (rc = visc_refresh_dt(d))) return rc;     // Viscosity reads the PRIMARY state's dt plane
-    if (!d->module_order.empty() && d->stage_kernel == 5) {
+    if (!d->module_order.empty()) {
         // The modules use the planes of Mset as scratch (tc_iterate, dc_post, fh_pre).  The 2-D instance of the stage kernel neither reads nor
         // writes mom_z / bi_z -- it relies on those planes being zero in EVERY set: euler swaps Mset in as the primary state, and the open_moc
         // strip kernel reads all eight planes of the stage copy.  Restore the invariant before the stages run.
@@ -1228,7 +1296,6 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (e != cudaSuccess || ndev == 0) return fail(SPRUCE_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback (%s)", cudaGetErrorString(e));
     if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
 
-    CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<0, 0ULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR, 0)));
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(6, 0)));
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<6, XY_LIST_2D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(6, 1)));
@@ -1240,11 +1307,11 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     CUDA_TRY(cudaFuncSetAttribute(k_mhd_stage_xy<12, XY_LIST_FULL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes(NTR, 3)));
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
-    if (const char *sk = getenv("SPRUCE_STAGE_KERNEL")) d->stage_kernel = atoi(sk) == 4 ? 4 : 5;
+    if (const char *fc = getenv("SPRUCE_FUSED_CTL")) d->fuse_ctl_enabled = atoi(fc) != 0;
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0 ? 1 : 0;
     if (const char *sb = getenv("SPRUCE_VEC_ROWS")) d->vec_rows = atoi(sb) != 0;
-    if (const char *cr = getenv("SPRUCE_CHUNK_ROWS")) { const int v = atoi(cr); if (v >= 16) d->chunk_rows_override = v; }
+    if (const char *cr = getenv("SPRUCE_CHUNK_ROWS")) { const int v = atoi(cr); if (v >= 8) d->chunk_rows_override = v; }
     if (const char *ar = getenv("SPRUCE_ARITH")) {
         if (!strcmp(ar, "relaxed")) d->relaxed = true;
         else if (strcmp(ar, "exact")) { delete d; return fail(SPRUCE_ERR_ARG, "SPRUCE_ARITH must be exact or relaxed"); }
@@ -1448,7 +1515,11 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     CUDA_TRY(cudaMemcpyAsync(&h0, d->ctl, sizeof(h0), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     CUDA_TRY(cudaMemcpyAsync(&d->ctl->max_time, &max_time, sizeof(double), cudaMemcpyHostToDevice, d->stream));
-    for (int s = 0; s < n_steps; s++) { int rc = d->tf ? tf_enqueue_step(d, s) : d->e2 ? e2_enqueue_step(d, s) : enqueue_step(d, s); if (rc) return rc; }
+    const bool plain = !d->tf && !d->e2 && plain_run(d);
+    for (int s = 0; s < n_steps; s++) {
+        int rc = d->tf ? tf_enqueue_step(d, s) : d->e2 ? e2_enqueue_step(d, s) : plain ? enqueue_step_plain(d, s, s == 0, s == n_steps - 1) : enqueue_step(d, s);
+        if (rc) return rc;
+    }
     StepCtl h1;
     CUDA_TRY(cudaMemcpyAsync(&h1, d->ctl, sizeof(h1), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));

@@ -55,8 +55,9 @@ struct StageArgs {
     const double *inv_thr_ptr;    // device scalar R = 1/(F * previous global min dt), 0 = evaluate every cell (see dt_can_skip)
     double *strip[4];             // per side (x1,x2,y1,y2): what that side's ghost pass reads from its first interior cell
     int strip_pitch;              //   strip[s][c*strip_pitch + idx], c = 0: post-floor rho, 1..3: momentum as that pass sees it
-    int chunk_rows;               // rows per CTA
-    int chunk0, chunk_stride;     // CTA row blockIdx.y works on chunk chunk0 + blockIdx.y*chunk_stride (edge / interior launches of a slab)
+    // rows of a launch: CTA row b covers [row_begin + b*chunk_rows, min(.. + chunk_rows, row_end)); in the edge launch of a slab (edge2_begin >= 0)
+    // CTA row 0 covers [row_begin, row_end) and CTA row 1 covers [edge2_begin, edge2_end): the first and the last rows of the slab
+    int chunk_rows, row_begin, row_end, edge2_begin, edge2_end;
     // module contributions to the right-hand side (Module::computeTimeDerivativesModule): already masked planes that are
     // added to k[target] in module order, after the ghost mask (equationset.cpp:208, viscosity.cpp:117-118)
     const double *xterm[4]; int xtarget[4]; int n_xterm;
@@ -74,9 +75,6 @@ constexpr int RD = 5;                        // ring depth: rows r-1..r+2 in use
 enum { Q_RHO = 0, Q_MX, Q_MY, Q_MZ, Q_E, Q_BIX, Q_BIY, Q_BIZ, Q_BEX, Q_BEY, Q_BEZ, Q_VX, Q_VY, Q_VZ, NARR };
 constexpr int NTR = 11;                      // transported quantities Q_RHO..Q_BEZ
 constexpr int NLOAD = 11;                    // arrays filled from global memory (Q_RHO holds n until converted)
-constexpr int MAX_CHUNK = 64;                // rows per CTA (upper bound; sizes the x-geometry table in shared memory)
-constexpr int XT = MAX_CHUNK + 8;            // entries per x table: local rows -3 .. chunk+4
-constexpr size_t STAGE_SMEM = (size_t)(RD * NARR * SW + 2 * NTR * NT + 7 * XT) * sizeof(double);
 
 __device__ __forceinline__ FaceGeom load_face_geom(const AxisTab &t, int f)
 {
@@ -167,17 +165,8 @@ __device__ __forceinline__ void block_min_to_global(double v, unsigned long long
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fused Runge-Kutta stage: D = B + (coef*step) * f(S), floors, pointwise boundary zeroing, dt minimum.
-// grid = (ceil(ny/CW), ceil(nx/chunk_rows)), block = NT, dynamic shared memory = STAGE_SMEM.
-//
-//  * rows enter the shared ring through cp.async (LDGSTS) one iteration ahead of their first use; the loader then
-//    converts n -> rho = n*m_i and derives v = mom/rho once per cell;
-//  * the 11 transported quantities run through ONE rolled loop body (small code, fits the instruction cache);
-//    x-face fluxes are carried from row to row (Fx_s), every x face is evaluated once;
-//  * a lane evaluates only the LEFT y-face of its column and receives the right one from lane+1 by shuffle, so every
-//    y face is evaluated once too; lane 31 of a warp only feeds lane 30 (31 output columns per warp);
-//  * a quantity whose whole stencil window is exactly zero across the warp (be_* in most runs, the z components in
-//    2-D problems) is skipped: its face values, fluxes and derivatives are exactly zero in the reference as well.
+// Helpers of the fused Runge-Kutta stage kernel k_mhd_stage_xy (mhd_stage_xy.cuh): D = B + (coef*step) * f(S), floors, pointwise boundary
+// zeroing, dt minimum.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
 {
@@ -187,300 +176,6 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ double shfl_next(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-
-__global__ void __launch_bounds__(NT, 4) k_mhd_stage(const DomainParams P, const StageArgs A)
-{
-    extern __shared__ __align__(16) double smem[];
-    if (*A.done_ptr) return;
-    double (*ring)[NARR][SW] = reinterpret_cast<double (*)[NARR][SW]>(smem);
-    double (*Fx_s)[NT] = reinterpret_cast<double (*)[NT]>(smem + RD * NARR * SW);   // x-face flux carried to the next row
-    double (*T_s)[NT] = Fx_s + NTR;                                                  // transportDivergence2D per quantity
-    double (*xt)[XT] = reinterpret_cast<double (*)[XT]>(smem + RD * NARR * SW + 2 * NTR * NT);   // x tables of this chunk: h,fs,rfs,ep,em,d,rd
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int j0 = blockIdx.x * CW;
-    const int ccol = 31 * warp + lane;            // column inside the CTA (lane 31 duplicates the next warp's lane 0)
-    const int j = j0 + ccol;
-    const int c = ccol + HALO;
-    const int r0 = (A.chunk0 + (int)blockIdx.y * A.chunk_stride) * A.chunk_rows;
-    const int r1 = min(r0 + A.chunk_rows, P.nx);
-    const bool col_out = (lane < 31) && (j < P.ny);
-
-    // ---- loader mapping: thread t fills shared column t (and t+NT for t < SW-NT)
-    int jl[2]; bool jl_ok[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        int jj = j0 - HALO + tid + k * NT;
-        bool ok = (jj >= 0 && jj < P.ny);
-        if (!ok && P.yper) { jj = (jj + 2 * P.ny) % P.ny; ok = true; }
-        if (tid + k * NT >= SW) ok = false;
-        jl[k] = jj; jl_ok[k] = ok;
-    }
-    const bool second = (tid + NT < SW);
-    auto slot_of = [&](int r) { return (r - r0 + HALO + RD) % RD; };
-    auto issue_row = [&](int r) {               // cp.async the 11 source arrays of row r
-        const int slot = slot_of(r);
-        const bool rok = row_exists(P, r);
-        const size_t rowoff = (size_t)phys_row(P, r) * P.pitch;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (k == 1 && !second) break;
-            const int cc = tid + k * NT;
-            if (rok && jl_ok[k]) {
-                const size_t off = rowoff + jl[k];
-#pragma unroll
-                for (int v = 0; v < NEV; v++) cp_async8(&ring[slot][v][cc], A.S[v] + off);
-                cp_async8(&ring[slot][Q_BEX][cc], A.st[S_BEX] + off);
-                cp_async8(&ring[slot][Q_BEY][cc], A.st[S_BEY] + off);
-                cp_async8(&ring[slot][Q_BEZ][cc], A.st[S_BEZ] + off);
-            } else {
-#pragma unroll
-                for (int v = 0; v < NLOAD; v++) ring[slot][v][cc] = (v == Q_RHO) ? 1.0 : 0.0;
-            }
-        }
-    };
-    auto convert_row = [&](int r) {             // n -> rho, v = mom/rho (idealmhd.cpp:247-250), own loader columns only
-        const int slot = slot_of(r);
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (k == 1 && !second) break;
-            const int cc = tid + k * NT;
-            const double rho = ring[slot][Q_RHO][cc] * P.m_i;
-            ring[slot][Q_RHO][cc] = rho;
-            ring[slot][Q_VX][cc] = ring[slot][Q_MX][cc] / rho;
-            ring[slot][Q_VY][cc] = ring[slot][Q_MY][cc] / rho;
-            ring[slot][Q_VZ][cc] = ring[slot][Q_MZ][cc] / rho;
-        }
-    };
-
-    const double step = *A.step_ptr;
-    const double s = A.coef * step;
-
-    // ---- per-thread y geometry: left face of column j, and the cell size
-    const int jt = min(j, P.ny + 1);
-    const FaceGeom gy = load_face_geom(P.ty, jt);
-    const double dy = P.ty.d[min(j, P.ny)], rdy = P.ty.rd[min(j, P.ny)];
-
-    // ---- x-direction cell-size tables of this chunk (warp-uniform reads from shared memory in the row loop)
-    {
-        const double *src[7] = {P.tx.h, P.tx.fs, P.tx.rfs, P.tx.ep, P.tx.em, P.tx.d, P.tx.rd};
-        const int nent = (r1 - r0) + 6;     // local rows -3 .. chunk+2
-        for (int e = tid; e < 7 * XT; e += NT) {
-            const int t = e / XT, i = e - t * XT;
-            if (i < nent) xt[t][i] = src[t][r0 - 3 + i];
-        }
-    }
-    auto x_geom = [&](int f) {                   // FaceGeom of x face f (local row index), from shared memory
-        const int i = f - r0 + 3;
-        FaceGeom g;
-        g.hm1 = xt[0][i - 1]; g.h0 = xt[0][i];
-        g.fs = xt[1][i];      g.rfs = xt[2][i];
-        g.ep = xt[3][i];      g.fsm = xt[1][i - 1]; g.rfsm = xt[2][i - 1];
-        g.em = xt[4][i];      g.fsp = xt[1][i + 1]; g.rfsp = xt[2][i + 1];
-        return g;
-    };
-
-    // ---- prologue: rows r0-2 .. r0+2
-    for (int r = r0 - HALO; r <= r0 + HALO; r++) issue_row(r);
-    cp_async_commit();
-    cp_async_wait_all();
-    for (int r = r0 - HALO; r <= r0 + HALO; r++) convert_row(r);
-    __syncthreads();
-
-    // x-face carries (face r0, between rows r0-1 and r0)
-    double cIx_biy = 0.0, cIx_biz = 0.0, cIx_p, cVfx, cIx_vy, cIx_vz;
-    {
-        const FaceGeom g = x_geom(r0);
-        const int sm2 = slot_of(r0 - 2), sm1 = slot_of(r0 - 1), s0 = slot_of(r0), sp1 = slot_of(r0 + 1);
-        cVfx = face_interp(ring[sm1][Q_VX][c], ring[s0][Q_VX][c], g.hm1, g.h0, g.fs, g.rfs);
-        cIx_vy = face_interp(ring[sm1][Q_VY][c], ring[s0][Q_VY][c], g.hm1, g.h0, g.fs, g.rfs);
-        cIx_vz = face_interp(ring[sm1][Q_VZ][c], ring[s0][Q_VZ][c], g.hm1, g.h0, g.fs, g.rfs);
-        cIx_p = face_interp(ring[sm1][Q_E][c] * P.gm1, ring[s0][Q_E][c] * P.gm1, g.hm1, g.h0, g.fs, g.rfs);
-#pragma unroll 1
-        for (int q = 0; q < NTR; q++) {
-            double d2;
-            const double S = upwind_face(ring[sm2][q][c], ring[sm1][q][c], ring[s0][q][c], ring[sp1][q][c], cVfx, g, &d2);
-            Fx_s[q][tid] = S * cVfx;
-            if (q == Q_BIY) cIx_biy = d2;
-            if (q == Q_BIZ) cIx_biz = d2;
-        }
-    }
-    __syncthreads();      // row r0-2 was read above; its ring slot is the prefetch target of the first iteration
-
-    double dtmin_local = 1.7976931348623157e308;
-
-    for (int r = r0; r < r1; r++) {
-        // prefetch row r+3 into the free slot (the slot of row r-2)
-        const bool pre = (r + 3 <= r1 + HALO - 1);
-        if (pre) issue_row(r + 3);
-        cp_async_commit();
-
-        const int sm1 = slot_of(r - 1), s0 = slot_of(r), sp1 = slot_of(r + 1), sp2 = slot_of(r + 2);
-        const int g = P.row0 + r;                                   // global row
-        const bool interior = col_out && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu;
-        const double dx = xt[5][r - r0 + 3], rdx = xt[6][r - r0 + 3];
-
-        // own-cell values that come from global memory are requested now and consumed after the transport loop
-        const size_t off = (size_t)r * P.pitch + (col_out ? j : 0);     // destination / base offset (local, unwrapped)
-        // (no branch on col_out: a divergent branch here would leave the warp split for the whole transport loop)
-        double gxv, gyv, Bv[NEV];
-#pragma unroll
-        for (int v = 0; v < NEV; v++) Bv[v] = 0.0;
-        gxv = A.st[S_GX][off]; gyv = A.st[S_GY][off];
-        if (!A.b_is_s) {
-#pragma unroll
-            for (int v = 0; v < NEV; v++) Bv[v] = A.B[v][off];
-        }
-        __syncwarp();
-
-        // ---------------- x face r+1 (between rows r and r+1): velocity, pressure
-        const FaceGeom gx = x_geom(r + 1);
-        const double vxc = ring[s0][Q_VX][c], vyc = ring[s0][Q_VY][c], vzc = ring[s0][Q_VZ][c];
-        const double vfx1 = face_interp(vxc, ring[sp1][Q_VX][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
-        const double Ix1_vy = face_interp(vyc, ring[sp1][Q_VY][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
-        const double Ix1_vz = face_interp(vzc, ring[sp1][Q_VZ][c], gx.hm1, gx.h0, gx.fs, gx.rfs);
-        const double pc = ring[s0][Q_E][c] * P.gm1;                 // press = (gamma-1)*thermal_energy  idealmhd.cpp:253
-        const double Ix1_p = face_interp(pc, ring[sp1][Q_E][c] * P.gm1, gx.hm1, gx.h0, gx.fs, gx.rfs);
-        // ---------------- y face j (left face of this column); the right face comes from lane+1
-        const double vfyL = face_interp(ring[s0][Q_VY][c - 1], vyc, gy.hm1, gy.h0, gy.fs, gy.rfs);
-        const double IyL_vx = face_interp(ring[s0][Q_VX][c - 1], vxc, gy.hm1, gy.h0, gy.fs, gy.rfs);
-        const double IyL_vz = face_interp(ring[s0][Q_VZ][c - 1], vzc, gy.hm1, gy.h0, gy.fs, gy.rfs);
-        const double IyL_p = face_interp(ring[s0][Q_E][c - 1] * P.gm1, pc, gy.hm1, gy.h0, gy.fs, gy.rfs);
-        const double vfyR = shfl_next(vfyL), IyR_vx = shfl_next(IyL_vx), IyR_vz = shfl_next(IyL_vz), IyR_p = shfl_next(IyL_p);
-
-        // ---------------- transportDivergence2D of the 11 transported quantities (derivs.cpp:122-162,216-220),
-        // two quantities per iteration: four independent face chains in flight hide the 8-cycle DFMA latency.
-        // Pairs are ordered so that planes which vanish together (z components; external field) share an iteration.
-        double Ix1_biy = 0.0, Ix1_biz = 0.0, IyL_bix = 0.0, IyR_bix = 0.0, IyL_biz = 0.0, IyR_biz = 0.0;
-        const FaceSel fsx = select_face(gx, vfx1), fsy = select_face(gy, vfyL);
-#pragma unroll 1
-        for (int p = 0; p < 6; p++) {
-            // (RHO,E) (MX,MY) (BIX,BIY) (MZ,BIZ) (BEX,BEY) (BEZ,BEZ)
-            const int qa = (0x0A83510 >> (4 * p)) & 15, qb = (0x0A97624 >> (4 * p)) & 15;
-            const double axm1 = ring[sm1][qa][c], aqc = ring[s0][qa][c], axp1 = ring[sp1][qa][c], axp2 = ring[sp2][qa][c];
-            const double aym2 = ring[s0][qa][c - 2], aym1 = ring[s0][qa][c - 1], ayp1 = ring[s0][qa][c + 1];
-            const double bxm1 = ring[sm1][qb][c], bqc = ring[s0][qb][c], bxp1 = ring[sp1][qb][c], bxp2 = ring[sp2][qb][c];
-            const double bym2 = ring[s0][qb][c - 2], bym1 = ring[s0][qb][c - 1], byp1 = ring[s0][qb][c + 1];
-            const double afx0 = Fx_s[qa][tid], bfx0 = Fx_s[qb][tid];
-            const bool zero = all_zero8(axm1, aqc, axp1, axp2, aym2, aym1, ayp1, afx0) && all_zero8(bxm1, bqc, bxp1, bxp2, bym2, bym1, byp1, bfx0);
-            if (__all_sync(0xffffffffu, zero)) { T_s[qa][tid] = 0.0; T_s[qb][tid] = 0.0; continue; }   // exact: every term is 0 in the reference too
-            double ad2x, ad2L, bd2x, bd2L;
-            const double aSx = upwind_face_sel(axm1, aqc, axp1, axp2, fsx, &ad2x);
-            const double bSx = upwind_face_sel(bxm1, bqc, bxp1, bxp2, fsx, &bd2x);
-            const double aSL = upwind_face_sel(aym2, aym1, aqc, ayp1, fsy, &ad2L);
-            const double bSL = upwind_face_sel(bym2, bym1, bqc, byp1, fsy, &bd2L);
-            const double afx1 = aSx * vfx1, afyL = aSL * vfyL, bfx1 = bSx * vfx1, bfyL = bSL * vfyL;
-            const double afyR = shfl_next(afyL), bfyR = shfl_next(bfyL), ad2R = shfl_next(ad2L), bd2R = shfl_next(bd2L);
-            const double atx = ddiv(afx1 - afx0, dx, rdx), btx = ddiv(bfx1 - bfx0, dx, rdx);   // derivs.cpp:155-156
-            const double aty = ddiv(afyR - afyL, dy, rdy), bty = ddiv(bfyR - bfyL, dy, rdy);
-            T_s[qa][tid] = atx + aty; T_s[qb][tid] = btx + bty;
-            Fx_s[qa][tid] = afx1; Fx_s[qb][tid] = bfx1;
-            if (p == 2) { IyL_bix = ad2L; IyR_bix = ad2R; Ix1_biy = bd2x; }
-            if (p == 3) { Ix1_biz = bd2x; IyL_biz = bd2L; IyR_biz = bd2R; }
-        }
-
-        // central derivatives, derivative1D (derivs.cpp:259)
-        const double dbiy_dx = ddiv(Ix1_biy - cIx_biy, dx, rdx);
-        const double dbix_dy = ddiv(IyR_bix - IyL_bix, dy, rdy);
-        const double dbiz_dy = ddiv(IyR_biz - IyL_biz, dy, rdy);
-        const double dbiz_dx = ddiv(Ix1_biz - cIx_biz, dx, rdx);
-        const double dp_dx = ddiv(Ix1_p - cIx_p, dx, rdx);
-        const double dp_dy = ddiv(IyR_p - IyL_p, dy, rdy);
-        const double dvx_dx = ddiv(vfx1 - cVfx, dx, rdx);
-        const double dvy_dy = ddiv(vfyR - vfyL, dy, rdy);
-        const double dvx_dy = ddiv(IyR_vx - IyL_vx, dy, rdy);
-        const double dvz_dy = ddiv(IyR_vz - IyL_vz, dy, rdy);
-        const double dvy_dx = ddiv(Ix1_vy - cIx_vy, dx, rdx);
-        const double dvz_dx = ddiv(Ix1_vz - cIx_vz, dx, rdx);
-        // roll the x carries
-        cIx_biy = Ix1_biy; cIx_biz = Ix1_biz; cIx_p = Ix1_p; cVfx = vfx1; cIx_vy = Ix1_vy; cIx_vz = Ix1_vz;
-
-        if (col_out) {
-            // ---------------- own-cell values
-            const double rho = ring[s0][Q_RHO][c];
-            const double bix = ring[s0][Q_BIX][c], biy = ring[s0][Q_BIY][c], biz = ring[s0][Q_BIZ][c];
-            const double bex = ring[s0][Q_BEX][c], bey = ring[s0][Q_BEY][c], bez = ring[s0][Q_BEZ][c];
-
-            // ---------------- right-hand side, idealmhd.cpp:51-103 (expression order is load-bearing)
-            double k[NEV];
-            k[E_N] = T_s[Q_RHO][tid] * -1.0;                                                // :52
-            const double cdb = ddiv(dbiy_dx - dbix_dy, P.fourpi, P.rfourpi);                // :54  curl2D/(4 pi)
-            const double ncdb = cdb * -1.0;
-            const double czx = dbiz_dy, czy = dbiz_dx * -1.0;                               // curlZ, derivs.cpp:465-469
-            const double bzi = ddiv(biz, P.fourpi, P.rfourpi), bze = ddiv(bez, P.fourpi, P.rfourpi);   // :57-58
-            // CrossProduct2DZ(a,bz) = CrossProductZ2D(-1.0*bz, a) = { -(-bz)*a_y , (-bz)*a_x }   grid.cpp:455-468
-            k[E_MX] = ((((((T_s[Q_MX][tid] * -1.0) - dp_dx) + rho * gxv) + ncdb * bey) + ncdb * biy) + bzi * czy) + bze * czy;      // :62-66
-            k[E_MY] = ((((((T_s[Q_MY][tid] * -1.0) - dp_dy) + rho * gyv) + cdb * bex) + cdb * bix) + (bzi * -1.0) * czx) + (bze * -1.0) * czx;  // :67-71
-            const double fze = ddiv(czx * bey - czy * bex, P.fourpi, P.rfourpi);            // :59
-            const double fzi = ddiv(czx * biy - czy * bix, P.fourpi, P.rfourpi);            // :60
-            k[E_MZ] = ((T_s[Q_MZ][tid] * -1.0) + fze) + fzi;                                // :72-73
-            k[E_E] = (T_s[Q_E][tid] * -1.0) - pc * (dvx_dx + dvy_dy);                       // :75-76
-            const double bxs = bix + bex, bys = biy + bey;
-            k[E_BX] = (((T_s[Q_BIX][tid] * -1.0) - T_s[Q_BEX][tid]) + bxs * dvx_dx) + bys * dvx_dy;       // :78-80
-            k[E_BY] = (((T_s[Q_BIY][tid] * -1.0) - T_s[Q_BEY][tid]) + bxs * dvy_dx) + bys * dvy_dy;       // :81-83
-            k[E_BZ] = (((T_s[Q_BIZ][tid] * -1.0) - T_s[Q_BEZ][tid]) + bxs * dvz_dx) + bys * dvz_dy;       // :84-86
-            // ghost mask (:99-103): operators return 0 outside [xl..xu]x[yl..yu] and the mask zeroes the rest
-#pragma unroll
-            for (int v = 0; v < NEV; v++) k[v] = interior ? k[v] : 0.0;
-            for (int t = 0; t < A.n_xterm; t++) {
-                const double x = A.xterm[t][off];
-#pragma unroll
-                for (int v = 0; v < NEV; v++) if (A.xtarget[t] == v) k[v] = k[v] + x;
-            }
-
-            // ---------------- RK4 bookkeeping (evolution.cpp:103-124)
-            if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) {
-#pragma unroll
-                for (int v = 0; v < NEV; v++) A.K1[v][off] = k[v];
-            } else if (A.kmode == KM_STORE_K2) {
-#pragma unroll
-                for (int v = 0; v < NEV; v++) A.K2[v][off] = k[v];
-            } else if (A.kmode == KM_ADD_K2) {
-#pragma unroll
-                for (int v = 0; v < NEV; v++) A.K2[v][off] = A.K2[v][off] + k[v];
-            } else if (A.kmode == KM_FINAL) {
-#pragma unroll
-                for (int v = 0; v < NEV; v++) k[v] = (A.K1[v][off] + k[v]) / 6.0 + A.K2[v][off] / 3.0;   // :121
-            }
-            if (A.kmode != KM_EXPORT) {
-                // ---------------- applyTimeDerivatives: U += step*k  (two roundings)  equationset.cpp:226-228
-                double U[NEV];
-                if (A.b_is_s) {
-                    U[E_N] = rho + k[E_N] * s;                      // rho = n*m_i was formed when the row entered the ring
-                    U[E_MX] = ring[s0][Q_MX][c] + k[E_MX] * s; U[E_MY] = ring[s0][Q_MY][c] + k[E_MY] * s; U[E_MZ] = ring[s0][Q_MZ][c] + k[E_MZ] * s;
-                    U[E_E] = ring[s0][Q_E][c] + k[E_E] * s;
-                    U[E_BX] = bix + k[E_BX] * s; U[E_BY] = biy + k[E_BY] * s; U[E_BZ] = biz + k[E_BZ] * s;
-                } else {
-                    U[E_N] = (Bv[E_N] * P.m_i) + k[E_N] * s;        // rho = n*m_i
-#pragma unroll
-                    for (int v = 1; v < NEV; v++) U[v] = Bv[v] + k[v] * s;
-                }
-                // ---------------- propagateChanges, pointwise part (equationset.cpp:212-220)
-                double rfl;
-                const double nn = density_floor(P, U[E_N], &rfl);
-                const double e1 = smax(U[E_E], P.e_min);
-                if (A.primary) {
-                    const unsigned z = zero_zones(P, g, j);
-                    record_strips(P, A.strip, A.strip_pitch, g, r, j, z, rfl, U[E_MX], U[E_MY], U[E_MZ]);
-                    if (z) { U[E_MX] = 0.0; U[E_MY] = 0.0; U[E_MZ] = 0.0; }
-                }
-                A.D[E_N][off] = nn;
-                A.D[E_MX][off] = U[E_MX]; A.D[E_MY][off] = U[E_MY]; A.D[E_MZ][off] = U[E_MZ];
-                A.D[E_E][off] = e1;
-                A.D[E_BX][off] = U[E_BX]; A.D[E_BY][off] = U[E_BY]; A.D[E_BZ][off] = U[E_BZ];
-                if (A.primary && interior) {
-                    const double dtc = cell_dt(P, nn * P.m_i, U[E_MX], U[E_MY], e1, bex + U[E_BX], bey + U[E_BY], bez + U[E_BZ],
-                                               dx, rdx, dy, rdy);
-                    dtmin_local = smin(dtmin_local, dtc);
-                }
-            }
-        }
-        cp_async_wait_all();
-        if (pre) convert_row(r + 3);
-        __syncthreads();
-    }
-    if (A.primary && A.kmode != KM_EXPORT) block_min_to_global(dtmin_local, A.dtmin_bits);
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // Pointwise propagateChanges on the primary state (module hooks, setup): floors, boundary zeroing, dt minimum.
@@ -714,6 +409,8 @@ struct PeerFlags {                                            // one 128-byte li
     unsigned long long dt_bits[2][MAX_RANKS];                 // [parity][r]
     unsigned long long red_seq[MAX_RANKS][16];                // [r][0]: last module reduction rank r has stored
     unsigned long long red_bits[2][MAX_RANKS][4];             // [parity][r][min, max, min, max] (bit patterns of non-negative doubles)
+    unsigned long long full_seq[MAX_RANKS][16];               // [r][0]: last re-evaluated dt minimum (skip window missed) rank r has stored
+    unsigned long long full_bits[2][MAX_RANKS];               // [parity][r]
     int error; int pad[31];                                   // set when a wait timed out (peer died): every later launch drains
 };
 
@@ -812,7 +509,7 @@ __global__ void __launch_bounds__(256) k_halo_pull(const DomainParams P, const P
 // ctl[0] = step (double), ctl[1] = time, ctl[2] = max_time (<=0: none); ictl[0] = iter, ictl[1] = done flag
 // ---------------------------------------------------------------------------------------------------------
 struct StepCtl { double step, time, max_time, epsilon; long long iter; int done; int need_full; unsigned long long dtmin_bits;
-                 double inv_thr; unsigned long long thr_bits; double prune_factor; };
+                 double inv_thr; unsigned long long thr_bits; double prune_factor; unsigned long long full_seq; };
 
 // begin: step = epsilon * min(dt) ; reset the running minimum for the propagate at the end of this step
 __global__ void k_step_begin(StepCtl *c, double *dt_hist, int slot)
@@ -845,13 +542,15 @@ __global__ void __launch_bounds__(256) k_dt_full(const DomainParams P, const DtF
 {
     if (A.ctl->done || !A.ctl->need_full) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
     double dtc = 1.7976931348623157e308;
-    const int g = P.row0 + r;
-    if (j < P.ny && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu) {
-        const size_t off = (size_t)r * P.pitch + j;
-        dtc = cell_dt(P, A.U[E_N][off] * P.m_i, A.U[E_MX][off], A.U[E_MY][off], A.U[E_E][off], A.st[S_BEX][off] + A.U[E_BX][off],
-                      A.st[S_BEY][off] + A.U[E_BY][off], A.st[S_BEZ][off] + A.U[E_BZ][off], P.tx.d[r], P.tx.rd[r], P.ty.d[j], P.ty.rd[j]);
+    for (int r = blockIdx.y; r < P.nx; r += gridDim.y) {       // a few row-strided CTAs: the launch that returns at once stays cheap
+        const int g = P.row0 + r;
+        if (j < P.ny && g >= P.xl && g <= P.xu && j >= P.yl && j <= P.yu) {
+            const size_t off = (size_t)r * P.pitch + j;
+            const double c = cell_dt(P, A.U[E_N][off] * P.m_i, A.U[E_MX][off], A.U[E_MY][off], A.U[E_E][off], A.st[S_BEX][off] + A.U[E_BX][off],
+                                     A.st[S_BEY][off] + A.U[E_BY][off], A.st[S_BEZ][off] + A.U[E_BZ][off], P.tx.d[r], P.tx.rd[r], P.ty.d[j], P.ty.rd[j]);
+            dtc = smin(dtc, c);
+        }
     }
     block_min_to_global(dtc, &A.ctl->dtmin_bits);
 }
@@ -885,6 +584,74 @@ __global__ void k_dt_collect(const DtGatherArgs A)
         for (int k = 1; k < A.world; k++) best = m[k] < best ? m[k] : best;
         A.ctl->dtmin_bits = best;
         if (A.mine->error) A.ctl->done = 2;               // a peer stopped answering: drain the remaining launches
+    }
+}
+
+// ---- the fused step control of plain runs (no modules, no open_moc): three one-block kernels per step instead of eight.
+//   k_step_open   (first step of an advance call)   begin + reset
+//   k_step_mid    after the primary stage           [slabs: all-gather of the dt minimum] + window check
+//   k_dt_full     (returns at once unless the window was missed)
+//   k_step_close                                    [slabs, window missed: all-gather again] + end of this step + begin / reset of the next one
+// One regular all-gather per step with sequence number = step count (buffer parity alternates per step: when a rank publishes gather k+1
+// every rank has finished reading gather k-1, see the halo argument above); the rare second gather has its own words and a device-side counter.
+__device__ __forceinline__ void step_begin_reset(StepCtl *c, double *dt_hist, int slot, int prune)
+{
+    if (c->max_time > 0.0 && !(c->time < c->max_time)) c->done = 1;
+    if (c->done) return;
+    const double prev = __longlong_as_double((long long)c->dtmin_bits);
+    c->step = c->epsilon * prev;                                             // evolution.cpp:62
+    if (dt_hist) dt_hist[slot] = c->step;
+    c->need_full = 0;
+    if (prune && c->prune_factor > 0.0 && prev > 0.0 && prev < 1.0e300) {
+        const double thr = c->prune_factor * prev;
+        c->thr_bits = (unsigned long long)__double_as_longlong(thr);
+        c->inv_thr = 1.0 / thr;
+    } else { c->inv_thr = 0.0; c->thr_bits = 0x7FF0000000000000ULL; }
+    c->dtmin_bits = 0x7FEFFFFFFFFFFFFFULL;
+}
+__global__ void k_step_open(StepCtl *c, double *dt_hist, int slot, int prune) { step_begin_reset(c, dt_hist, slot, prune); }
+
+// all MAX_RANKS threads of the block: exchange `mine_bits` with every rank through the given words, return the minimum in thread 0
+__device__ __forceinline__ unsigned long long block_allgather_min(const DtGatherArgs &A, unsigned long long mine_bits, unsigned long long seq, int full, unsigned long long *m)
+{
+    const int r = threadIdx.x;
+    if (r < A.world) {
+        PeerFlags *f = A.peer[r];
+        if (full) f->full_bits[seq & 1][A.rank] = mine_bits; else f->dt_bits[seq & 1][A.rank] = mine_bits;
+        __threadfence_system();
+        st_release_sys(full ? &f->full_seq[A.rank][0] : &f->dt_seq[A.rank][0], seq);
+        const bool ok = wait_seq(full ? &A.mine->full_seq[r][0] : &A.mine->dt_seq[r][0], seq, &A.mine->error);
+        m[r] = ok ? *(volatile unsigned long long *)(full ? &A.mine->full_bits[seq & 1][r] : &A.mine->dt_bits[seq & 1][r]) : 0x7FEFFFFFFFFFFFFFULL;
+    }
+    __syncthreads();
+    unsigned long long best = m[0];
+    if (r == 0) for (int k = 1; k < A.world; k++) best = m[k] < best ? m[k] : best;
+    return best;
+}
+__global__ void k_step_mid(const DtGatherArgs A)
+{
+    __shared__ unsigned long long m[MAX_RANKS];
+    StepCtl *c = A.ctl;
+    if (c->done) return;
+    if (A.world > 1) {
+        const unsigned long long best = block_allgather_min(A, c->dtmin_bits, A.seq, 0, m);
+        if (threadIdx.x == 0) { c->dtmin_bits = best; if (A.mine->error) c->done = 2; }
+    }
+    if (threadIdx.x == 0) c->need_full = (c->inv_thr > 0.0 && c->dtmin_bits > c->thr_bits) ? 1 : 0;
+}
+__global__ void k_step_close(const DtGatherArgs A, double *dt_hist, int next_slot, int prune)
+{
+    __shared__ unsigned long long m[MAX_RANKS];
+    StepCtl *c = A.ctl;
+    if (c->done) return;
+    if (A.world > 1 && c->need_full) {                                       // block-uniform: every thread reads the same words
+        const unsigned long long fs = c->full_seq + 1;
+        const unsigned long long best = block_allgather_min(A, c->dtmin_bits, fs, 1, m);
+        if (threadIdx.x == 0) { c->dtmin_bits = best; c->full_seq = fs; if (A.mine->error) c->done = 2; }
+    }
+    if (threadIdx.x == 0 && !c->done) {
+        c->time += c->step; c->iter += 1;                                    // evolution.cpp:80-81
+        if (next_slot >= 0) step_begin_reset(c, dt_hist, next_slot, prune);
     }
 }
 
