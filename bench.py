@@ -172,7 +172,7 @@ def slab_parity_check(rank, world, local, transport):
     from spruce_b200 import synthetic
     from spruce_b200.domain import PlasmaDomain
     from spruce_b200.multigpu import SlabRunner
-    nx, ny, steps = 64 * world + 24, 300, 6
+    nx, ny, steps = 180 * world + 8, 200, 6       # >= 168 rows per slab: the overlapped (edge / interior) form of the stage launch, as in the timed run
     ok = True
     for zfull in (False, True):                   # the 6-quantity and the 12-quantity instance of the stage kernel
         s = synthetic.orszag_tang(nx, ny, zfull=zfull)

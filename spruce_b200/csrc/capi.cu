@@ -117,6 +117,10 @@ struct spruce_domain {
     bool relaxed = false;                  // SPRUCE_ARITH=relaxed: stage kernel from stage_relaxed.cu (FMA contraction, one-multiplication table divisions)
     int stage_variants = 1;                // compile-time integrator-stage instances of k_mhd_stage_xy (SPRUCE_STAGE_VARIANTS=0: only the run-time-stage instances)
     bool vec_rows = true;                 // k_mhd_stage_xy copies ring rows in 16-byte chunks where a strip allows it (SPRUCE_VEC_ROWS=0: 8-byte per-column copies everywhere)
+    // SPRUCE_TIMELINE=n: CUDA events around the launches of the first n plain steps of an advance call, printed (ms since the first one) when the
+    // call returns -- the per-step timeline of a slab rank without a system profiler
+    struct Mark { const char *label; cudaEvent_t ev; };
+    std::vector<Mark> marks; int timeline_steps = 0; bool timeline_on = false;
     bool fused_ctl = false;                // inside a plain step (no modules, no open_moc): the step control runs in k_step_open / k_step_mid / k_step_close
     bool fuse_ctl_enabled = true;          // SPRUCE_FUSED_CTL=0: always the separate one-thread control kernels
     size_t halo_doubles = 0;
@@ -132,6 +136,27 @@ struct spruce_domain {
 };
 
 namespace {
+
+void mark(spruce_domain *d, const char *label, cudaStream_t st)
+{
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    d->marks.push_back({label, e});
+}
+void dump_marks(spruce_domain *d)
+{
+    if (d->marks.empty()) return;
+    cudaDeviceSynchronize();
+    for (size_t k = 0; k < d->marks.size(); k++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, d->marks[0].ev, d->marks[k].ev);
+        fprintf(stderr, "[spruce timeline rank %d] %9.4f ms  %s\n", d->cfg.rank, ms, d->marks[k].label);
+    }
+    for (auto &m : d->marks) cudaEventDestroy(m.ev);
+    d->marks.clear();
+}
+#define MARK(d, label, st) do { if ((d)->timeline_on) mark((d), (label), (st)); } while (0)
 
 // planes are carved from one pooled allocation made at create time (one cudaMalloc instead of ~25); later requests beyond the
 // pool (RK4 sets, module work planes) get their own allocation
@@ -269,18 +294,21 @@ ChunkPlan plan_chunks(const spruce_domain *d, bool split)
     const ActiveList L = active_quantities(d);
     const int cap = 148 * ((L.n == 6 && L.q == XY_LIST_2D && d->static_lists) ? xy_ctas_per_sm(6) : xy_ctas_per_sm(0));
     ChunkPlan p{};
-    p.edge = split ? XY_EDGE_ROWS : 0;
-    const int body = nx - 2 * p.edge, extra = split ? 2 : 0;
+    // split: the two edge CTA rows are XY_EDGE_DELTA rows shorter than the interior ones -- they start first (priority stream) and finish
+    // about one halo exchange earlier; `virt` = the rows a uniform split of all CTA rows would have to cover
+    const int delta = split ? XY_EDGE_DELTA : 0, virt = nx + 2 * delta;
     if (d->chunk_rows_override > 0) p.rows = d->chunk_rows_override < XY_CHUNK ? d->chunk_rows_override : XY_CHUNK;      // SPRUCE_CHUNK_ROWS: tuning sweeps
     else {
-        const long long min_ctas = (long long)strips * ((body + XY_CHUNK - 1) / XY_CHUNK + extra);
+        const long long min_ctas = (long long)strips * ((virt + XY_CHUNK - 1) / XY_CHUNK);
         const long long waves = (min_ctas + cap - 1) / cap;
-        long long cta_rows = waves * cap / strips - extra;                    // CTA rows that fit in those waves
+        long long cta_rows = waves * cap / strips;                            // CTA rows that fit in those waves
         if (cta_rows < 1) cta_rows = 1;
-        p.rows = (int)((body + cta_rows - 1) / cta_rows);
+        p.rows = (int)((virt + cta_rows - 1) / cta_rows);
         if (p.rows > XY_CHUNK) p.rows = XY_CHUNK;
-        if (p.rows < 8) p.rows = 8 < body ? 8 : body;
+        if (p.rows < 2 * XY_EDGE_DELTA) p.rows = 2 * XY_EDGE_DELTA;
     }
+    p.edge = split ? p.rows - delta : 0;
+    const int body = nx - 2 * p.edge;
     p.n_interior = (body + p.rows - 1) / p.rows;
     return p;
 }
@@ -288,7 +316,7 @@ bool can_split(const spruce_domain *d, int primary)
 {
     const bool ghosts = d->any_ucnp || (primary && d->any_primary_ghost);
     return d->cfg.n_ranks > 1 && d->peers_connected && d->overlap && !ghosts && d->visc.empty() && !d->moc_any      // the strip kernel follows the whole stage kernel and writes edge rows
-           && d->P.nx >= 2 * XY_EDGE_ROWS + 8;
+           && d->P.nx >= 3 * XY_CHUNK;
 }
 
 // Transported quantities that can be non-zero.  The z system {mom_z, bi_z} stays identically zero when mom_z, bi_z and be_z
@@ -1008,11 +1036,16 @@ int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, c
     if (primary && !d->fused_ctl) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
     CUDA_TRY(cudaEventRecord(d->ev_main, d->stream));
     CUDA_TRY(cudaStreamWaitEvent(d->comm_stream, d->ev_main, 0));
+    MARK(d, "  comm: start", d->comm_stream);
     if ((rc = launch_stage(d, S, B, D, coef, primary, kmode, 1))) return rc;
+    MARK(d, "  comm: edge rows done", d->comm_stream);
     if ((rc = peer_exchange(d, D.p, d->comm_stream))) return rc;
+    MARK(d, "  comm: push + pull done", d->comm_stream);
     CUDA_TRY(cudaEventRecord(d->ev_comm, d->comm_stream));
     if ((rc = launch_stage(d, S, B, D, coef, primary, kmode, 2))) return rc;
+    MARK(d, "  main: interior rows done", d->stream);
     CUDA_TRY(cudaStreamWaitEvent(d->stream, d->ev_comm, 0));
+    MARK(d, "  main: joined", d->stream);
     return SPRUCE_OK;
 }
 
@@ -1130,6 +1163,8 @@ bool plain_run(const spruce_domain *d)
 int enqueue_step_plain(spruce_domain *d, int hist_slot, bool first, bool last)
 {
     int rc;
+    d->timeline_on = hist_slot < d->timeline_steps;
+    MARK(d, "step begin", d->stream);
     if (first) { k_step_open<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot, dt_prune_enabled(d)); d->launches++; }
     d->fused_ctl = true;
     if (d->cfg.time_integrator == SPRUCE_TI_EULER) {
@@ -1141,7 +1176,11 @@ int enqueue_step_plain(spruce_domain *d, int hist_slot, bool first, bool last)
     }
     d->fused_ctl = false;
     if (rc) return rc;
-    return finish_dt_fused(d, last ? -1 : hist_slot + 1);
+    MARK(d, "stages done (main)", d->stream);
+    rc = finish_dt_fused(d, last ? -1 : hist_slot + 1);
+    MARK(d, "step control done", d->stream);
+    d->timeline_on = false;
+    return rc;
 }
 
 int enqueue_step(spruce_domain *d, int hist_slot)
@@ -1308,6 +1347,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     if (const char *fc = getenv("SPRUCE_FUSED_CTL")) d->fuse_ctl_enabled = atoi(fc) != 0;
+    if (const char *tl = getenv("SPRUCE_TIMELINE")) d->timeline_steps = atoi(tl);
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0 ? 1 : 0;
     if (const char *sb = getenv("SPRUCE_VEC_ROWS")) d->vec_rows = atoi(sb) != 0;
@@ -1523,6 +1563,7 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     StepCtl h1;
     CUDA_TRY(cudaMemcpyAsync(&h1, d->ctl, sizeof(h1), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
+    dump_marks(d);
     const int done = (int)(h1.iter - h0.iter);
     if (steps_done) *steps_done = done;
     if (dt_used && done > 0) CUDA_TRY(cudaMemcpy(dt_used, d->dt_hist, (size_t)done * sizeof(double), cudaMemcpyDeviceToHost));

@@ -22,7 +22,7 @@ namespace spruce {
 constexpr int XY_NT = 128;                   // 2 X warps + 2 Y warps
 constexpr int XY_RV = 3;                     // velocity ring depth (rows r, r+1 in use, r+2 being formed)
 constexpr int XY_CHUNK = 56;                 // rows per CTA (upper bound: sizes the x tables in shared memory)
-constexpr int XY_EDGE_ROWS = 16;             // a slab's first / last rows run as their own short launch when the halo exchange overlaps the interior
+constexpr int XY_EDGE_DELTA = 8;             // a slab's first / last CTA rows are this much shorter than the interior ones when the halo exchange overlaps the interior
 constexpr int XY_XT = XY_CHUNK + 6;          // x-table entries: local rows -3 .. chunk+2
 constexpr int XW = 64;                       // width of the per-column exchange arrays: one private slot per (warp column, lane)
 // shared memory (doubles): transported ring, velocity ring, x tables, x-flux carry, the x parts of the transports the Y warps finish (TX), the y parts

@@ -383,6 +383,7 @@ def test_solar_modules_vs_oracle(mods):
 
 
 @pytest.mark.parametrize("args", [("300", "210", "6", "rk2", "periodic", "p2p"), ("131", "96", "5", "rk4", "periodic", "p2p"), ("120", "80", "6", "rk2", "fixed", "p2p"),
+                                  ("400", "130", "5", "rk2", "periodic", "p2p"), ("380", "70", "4", "euler", "periodic", "p2p"),      # >= 168 rows per slab: edge / interior launches overlap the exchange
                                   ("90", "70", "4", "euler", "reflect", "p2p"), ("300", "210", "6", "rk2", "periodic", "nccl"), ("120", "80", "6", "rk4", "fixed", "nccl")])
 def test_slab_decomposition_equals_single_gpu(args):
     """N-GPU == 1-GPU bit for bit, for both halo transports (library peer stores over NVLink; NCCL send/recv).
