@@ -118,6 +118,10 @@ int spruce_eqs_time_derivatives(spruce_domain *dom, double *k_out, size_t count)
  * that are not ported keep working: op = "derivative1D" (:223), "secondDerivative1D" (:417), "laplacian" (:458),
  * "transportDerivative1D" (:122; vel required).  index: 0 = x, 1 = y. Single-rank only. */
 int spruce_operator(spruce_domain *dom, const char *op, int index, const double *q, const double *vel, double *out, size_t count);
+/* The two-operand operators (source/mhd/plasmadomain.hpp:201-242): op = "divergence2D" (a = a_x, b = a_y; derivs.cpp:407-409),
+ * "curl2D" (a = x, b = y; derivs.cpp:472-474: d(y)/dx - d(x)/dy), "transportDivergence2D" (a = quantity, b = vel_x, c = vel_y;
+ * derivs.cpp:216-220).  c may be null for the first two.  Each is two passes of spruce_operator combined per cell on the host. */
+int spruce_operator2(spruce_domain *dom, const char *op, const double *a, const double *b, const double *c, double *out, size_t count);
 
 /* ---- physics modules on the device (source/modules/...) ; call order = execution order (modulehandler.cpp:27-65) */
 /* ThermalConduction::parseModuleConfigs (solar/thermalconduction.cpp:16-30) */

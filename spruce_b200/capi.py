@@ -85,6 +85,7 @@ SYMBOLS = {
     "spruce_mgpu_dt_min_ptr": (C.c_int, [C.c_void_p, _VPP]),
     "spruce_mgpu_begin_step": (C.c_int, [C.c_void_p]),
     "spruce_mgpu_end_step": (C.c_int, [C.c_void_p]),
+    "spruce_operator2": (C.c_int, [C.c_void_p, C.c_char_p, _DP, _DP, _DP, _DP, C.c_size_t]),
     "spruce_plane_activity": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]),
     "spruce_stream": (C.c_int, [C.c_void_p, _VPP]),
     "spruce_synchronize": (C.c_int, [C.c_void_p]),

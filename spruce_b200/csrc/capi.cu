@@ -22,7 +22,22 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 using namespace spruce;
+
+// NVTX ranges around what the host enqueues: the advance call, every step, every Runge-Kutta stage with its exchange, every
+// module hook.  Header-only NVTX v3: without a profiler attached the calls return at once.  SPRUCE_NVTX=0 leaves them out altogether.
+namespace {
+const bool g_nvtx_on = [] { const char *e = getenv("SPRUCE_NVTX"); return !(e && atoi(e) == 0); }();
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char *name) : on(g_nvtx_on) { if (on) nvtxRangePushA(name); }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+}  // namespace
 
 // stage_relaxed.cu: the stage kernel in relaxed arithmetic (its own translation unit, compiled with FMA contraction)
 extern "C" __attribute__((visibility("hidden"))) int spruce_relaxed_launch_stage(unsigned gx, unsigned gy, void *stream, const void *P, const void *A, const void *L, int list, int var);
@@ -1027,6 +1042,7 @@ int finish_stage(spruce_domain *d, const PlaneSet &U, int primary)
 // while the chunks in between run on the main stream: the exchange hides behind the interior compute.
 int stage_and_exchange(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const PlaneSet &D, double coef, int primary, int kmode)
 {
+    NvtxRange range_stage(primary ? "rk stage (primary) + exchange" : "rk stage + exchange");
     int rc;
     const bool split = can_split(d, primary);
     if (!split) {
@@ -1162,6 +1178,7 @@ bool plain_run(const spruce_domain *d)
 }
 int enqueue_step_plain(spruce_domain *d, int hist_slot, bool first, bool last)
 {
+    NvtxRange range_step("spruce step (plain)");
     int rc;
     d->timeline_on = hist_slot < d->timeline_steps;
     MARK(d, "step begin", d->stream);
@@ -1185,6 +1202,7 @@ int enqueue_step_plain(spruce_domain *d, int hist_slot, bool first, bool last)
 
 int enqueue_step(spruce_domain *d, int hist_slot)
 {
+    NvtxRange range_step("spruce step");
     int rc;
     k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot);
     d->launches++;
@@ -1198,11 +1216,15 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         const double step = h.step;
         step_time = h.time; step_size = h.step;
         if (d->ar.on && !d->ar.ready && (rc = ar_setup_run(d))) return rc;   // setupModule works on the state before the first step
-        for (int m : d->module_order) {                                  // preIterateModules, evolution.cpp:65
-            if (m == spruce_domain::MOD_TC && (rc = tc_count(d, step, &d->tc_nsub))) return rc;
-            if (m == spruce_domain::MOD_RL && (rc = rl_count(d, step, &d->rl_nsub))) return rc;
-            if (m == spruce_domain::MOD_FH && (rc = fh_pre(d))) return rc;
+        {
+            NvtxRange range_pre("modules: preIterate");
+            for (int m : d->module_order) {                              // preIterateModules, evolution.cpp:65
+                if (m == spruce_domain::MOD_TC && (rc = tc_count(d, step, &d->tc_nsub))) return rc;
+                if (m == spruce_domain::MOD_RL && (rc = rl_count(d, step, &d->rl_nsub))) return rc;
+                if (m == spruce_domain::MOD_FH && (rc = fh_pre(d))) return rc;
+            }
         }
+        NvtxRange range_it("modules: iterate");
         for (int m : d->module_order) {                                  // iterateModules, evolution.cpp:66
             if (m == spruce_domain::MOD_TC && (rc = tc_iterate(d, step))) return rc;
             if (m == spruce_domain::MOD_RL && (rc = rl_iterate(d, step))) return rc;
@@ -1238,6 +1260,7 @@ int enqueue_step(spruce_domain *d, int hist_slot)
         if ((rc = stage_and_exchange(d, d->Mset, d->Pset, d->Pset, 1.0, 1, KM_FINAL))) return rc;
     }
     if ((rc = finish_dt(d))) return rc;                                 // global min(dt) for the next step (evolution.cpp:62)
+    NvtxRange range_post("modules: postIterate");
     for (int m : d->module_order) {                                      // postIterateModules, evolution.cpp:74
         if (m == spruce_domain::MOD_AH && (rc = ah_post(d))) return rc;
         if (m == spruce_domain::MOD_DC && (rc = dc_post(d, step_size))) return rc;
@@ -1555,6 +1578,7 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     CUDA_TRY(cudaMemcpyAsync(&h0, d->ctl, sizeof(h0), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     CUDA_TRY(cudaMemcpyAsync(&d->ctl->max_time, &max_time, sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    NvtxRange range_adv("spruce_advance");
     const bool plain = !d->tf && !d->e2 && plain_run(d);
     for (int s = 0; s < n_steps; s++) {
         int rc = d->tf ? tf_enqueue_step(d, s) : d->e2 ? e2_enqueue_step(d, s) : plain ? enqueue_step_plain(d, s, s == 0, s == n_steps - 1) : enqueue_step(d, s);
@@ -1619,6 +1643,34 @@ int spruce_operator(spruce_domain *d, const char *op, int index, const double *q
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     return d2h_plane(d, out, d->K1set.p[2]);
+}
+
+// The two-operand operators of PlasmaDomain (derivs.cpp:216-220, 407-414, 471-474): each is the sum / difference of two single-direction passes of
+// the operators above, formed on the host with the same IEEE addition the reference's Grid::operator+ / operator- performs per cell.
+int spruce_operator2(spruce_domain *d, const char *op, const double *a, const double *b, const double *c, double *out, size_t count)
+{
+    CHECK_DOM(d);
+    if (!op || !a || !b || !out) return fail(SPRUCE_ERR_ARG, "null argument");
+    const int code = !strcmp(op, "divergence2D") ? 0 : !strcmp(op, "curl2D") ? 1 : !strcmp(op, "transportDivergence2D") ? 2 : -1;
+    if (code < 0) return fail(SPRUCE_ERR_ARG, "unknown operator <%s>", op);
+    if (code == 2 && !c) return fail(SPRUCE_ERR_ARG, "transportDivergence2D needs both velocity planes");
+    if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane size mismatch");
+    std::vector<double> first(count);
+    int rc;
+    if (code == 0) {          // derivative1D(a_x, 0) + derivative1D(a_y, 1)
+        if ((rc = spruce_operator(d, "derivative1D", 0, a, nullptr, first.data(), count))) return rc;
+        if ((rc = spruce_operator(d, "derivative1D", 1, b, nullptr, out, count))) return rc;
+        for (size_t k = 0; k < count; k++) out[k] = first[k] + out[k];
+    } else if (code == 1) {   // derivative1D(y, 0) - derivative1D(x, 1)
+        if ((rc = spruce_operator(d, "derivative1D", 0, b, nullptr, first.data(), count))) return rc;
+        if ((rc = spruce_operator(d, "derivative1D", 1, a, nullptr, out, count))) return rc;
+        for (size_t k = 0; k < count; k++) out[k] = first[k] - out[k];
+    } else {                  // transportDerivative1D(q, vel[0], 0) + transportDerivative1D(q, vel[1], 1)
+        if ((rc = spruce_operator(d, "transportDerivative1D", 0, a, b, first.data(), count))) return rc;
+        if ((rc = spruce_operator(d, "transportDerivative1D", 1, a, c, out, count))) return rc;
+        for (size_t k = 0; k < count; k++) out[k] = first[k] + out[k];
+    }
+    return SPRUCE_OK;
 }
 
 int spruce_module_thermal_conduction(spruce_domain *d, int flux_saturation, int time_integrator, double epsilon, double dt_subcycle_min, double weakening_factor)

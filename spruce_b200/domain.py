@@ -250,6 +250,14 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_operator(self.h, op.encode(), index, _dp(q), _dp(v) if v is not None else None, _dp(out), q.size))
         return out
 
+    def operator2(self, op: str, a: np.ndarray, b: np.ndarray, c: np.ndarray = None) -> np.ndarray:
+        """divergence2D(a_x, a_y), curl2D(x, y), transportDivergence2D(quantity, vel_x, vel_y) of PlasmaDomain (plasmadomain.hpp:201-242)."""
+        a, b = self._local(a), self._local(b)
+        cc = self._local(c) if c is not None else None
+        out = np.empty_like(a)
+        capi.check(self.lib.spruce_operator2(self.h, op.encode(), _dp(a), _dp(b), _dp(cc) if cc is not None else None, _dp(out), a.size))
+        return out
+
     def subcycles(self, which: str) -> int:
         n = C.c_int()
         capi.check(self.lib.spruce_module_subcycles(self.h, which.encode(), C.byref(n)))

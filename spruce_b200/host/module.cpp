@@ -442,7 +442,10 @@ Grid Viscosity::getBoundaryViscosity(double strength, double length) const
     for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
         x_min = std::min(x_min, x(i, j)); x_max = std::max(x_max, x(i, j)); y_min = std::min(y_min, y(i, j)); y_max = std::max(y_max, y(i, j));
     }
-    const bool gauss = (m_boundary_falloff_shape == "gaussian");
+    // viscosity.cpp:90-93 defaults to gaussian; the *_elliptical shapes (viscosity.cpp:305-319) are not ported: refused, not approximated
+    SPRUCE_REQUIRE(m_boundary_falloff_shape.empty() || m_boundary_falloff_shape == "gaussian" || m_boundary_falloff_shape == "exp",
+                   "boundary_falloff_shape <" + m_boundary_falloff_shape + "> of artificial_viscosity is not ported to the B200 path (gaussian and exp are)");
+    const bool gauss = (m_boundary_falloff_shape.empty() || m_boundary_falloff_shape == "gaussian");
     Grid result = Grid::Zero(nx, ny);
     for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
         const double xv = x(i, j), yv = y(i, j);

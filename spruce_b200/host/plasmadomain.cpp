@@ -186,7 +186,14 @@ void PlasmaDomain::handleSingleConfig(int i, const std::string &rhs)
     else if (k == "time_integrator") m_time_integrator = stringToTimeIntegrator(rhs);
     else if (k == "duration") m_duration = std::stod(rhs);
     else if (k == "write_precision") m_write_precision = std::stoi(rhs);
-    else if (k == "multispecies_mode") m_multispecies_mode = (rhs == "true");
+    else if (k == "multispecies_mode") {
+        // the reference adds the cumulative_electron / ion / joule_heating planes to mhd.out and its modules split their heating with
+        // ms_electron_heating_fraction (fileio.cpp:164-, plasmadomain.hpp): not ported -- refused rather than silently writing a different mhd.out
+        m_multispecies_mode = (rhs == "true");
+        if (m_multispecies_mode) spruce_die("multispecies_mode = true is not ported to the B200 path (cumulative heating planes, ms_electron_heating_fraction)");
+    }
+    else if (k == "sg_opt") m_sg_opt = rhs;                 // read by the sg_filtering module only (plasmadomain.cpp:51), which is not ported and refuses itself
+    else if (k == "x_origin" || k == "y_origin") {}         // accepted and unused, as in the reference (fileio.cpp: parsed, never read on the run path)
 }
 
 PlasmaDomain::BoundaryCondition PlasmaDomain::stringToBoundaryCondition(const std::string &str) const

@@ -46,6 +46,22 @@ public:
     EquationSet *eqs() const { return m_eqs.get(); }
     double ionMass() const { return m_ion_mass; }
     double adiabaticIndex() const { return m_adiabatic_index; }
+    // ---- differential operators for host-side modules that are not ported (plasmadomain.hpp:194-242): a host Grid in, a host Grid out, the
+    //      evaluation on the device through spruce_operator / spruce_operator2 (bit-identical to derivs.cpp over the iteration bounds)
+    Grid derivative1D(const Grid &quantity, int index) const { return deviceOperator("derivative1D", index, quantity, nullptr); }                 // derivs.cpp:223
+    Grid secondDerivative1D(const Grid &quantity, int index) const { return deviceOperator("secondDerivative1D", index, quantity, nullptr); }     // derivs.cpp:417
+    Grid laplacian(const Grid &quantity) const { return deviceOperator("laplacian", 0, quantity, nullptr); }                                      // derivs.cpp:458
+    Grid transportDerivative1D(const Grid &quantity, const Grid &vel, int index) const { return deviceOperator("transportDerivative1D", index, quantity, &vel); }   // derivs.cpp:122
+    Grid divergence2D(const Grid &a_x, const Grid &a_y) const { return deviceOperator2("divergence2D", a_x, a_y, nullptr); }                       // derivs.cpp:407
+    Grid divergence2D(const std::vector<Grid> &a) const { return divergence2D(a.at(0), a.at(1)); }
+    Grid curl2D(const Grid &x, const Grid &y) const { return deviceOperator2("curl2D", x, y, nullptr); }                                          // derivs.cpp:472
+    Grid transportDivergence2D(const Grid &quantity, const std::vector<Grid> &vel) const { return deviceOperator2("transportDivergence2D", quantity, vel.at(0), &vel.at(1)); }   // derivs.cpp:216
+    std::vector<Grid> curlZ(const Grid &z) const                                                                                               // derivs.cpp:465
+    {
+        Grid ry = derivative1D(z, 0);
+        for (double &v : ry.data()) v = -v;
+        return {derivative1D(z, 1), ry};
+    }
     void createDevice();                 // called by EquationSet::setupEquationSet once config + state are known
     static void check(int rc);           // non-zero status -> message on stderr + abort (the reference's assert style)
 
@@ -69,12 +85,25 @@ private:
     double open_boundary_strength{0.0}, open_boundary_decay_base{1.0};
     size_t m_xdim{0}, m_ydim{0};
     bool m_multispecies_mode{false};
+    std::string m_sg_opt;
     double m_ion_mass{0.0}, m_adiabatic_index{0.0};
     double epsilon{0.0}, density_min{0.0}, temp_min{0.0}, thermal_energy_min{0.0};
     ModuleHandler m_module_handler;
     std::unique_ptr<EquationSet> m_eqs;
     spruce_domain *m_dev{nullptr};
 
+    Grid deviceOperator(const char *op, int index, const Grid &q, const Grid *vel) const
+    {
+        Grid out(q.rows(), q.cols());
+        check(spruce_operator(m_dev, op, index, q.ptr(), vel ? vel->ptr() : nullptr, out.ptr(), (size_t)q.size()));
+        return out;
+    }
+    Grid deviceOperator2(const char *op, const Grid &a, const Grid &b, const Grid *c) const
+    {
+        Grid out(a.rows(), a.cols());
+        check(spruce_operator2(m_dev, op, a.ptr(), b.ptr(), c ? c->ptr() : nullptr, out.ptr(), (size_t)a.size()));
+        return out;
+    }
     void computeIterationBounds();
     void outputPreamble();
     void storeGrids();

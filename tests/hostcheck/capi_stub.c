@@ -64,6 +64,8 @@ int spruce_advance(spruce_domain *d, int n, double max_time, double *dt_used, in
     return SPRUCE_OK;
 }
 int spruce_get_time(spruce_domain *d, double *t, int64_t *it) { if (t) *t = d->time; if (it) *it = d->iter; return SPRUCE_OK; }
+int spruce_operator(spruce_domain *d, const char *op, int index, const double *q, const double *vel, double *out, size_t count) { (void)d; (void)q; (void)vel; LOG("spruce_operator %s %d", op, index); memset(out, 0, count * sizeof(double)); return SPRUCE_OK; }
+int spruce_operator2(spruce_domain *d, const char *op, const double *a, const double *b, const double *c, double *out, size_t count) { (void)d; (void)a; (void)b; (void)c; LOG("spruce_operator2 %s", op); memset(out, 0, count * sizeof(double)); return SPRUCE_OK; }
 int spruce_eqs_time_derivatives(spruce_domain *d, double *k, size_t count) { (void)d; memset(k, 0, count * sizeof(double)); LOG("spruce_eqs_time_derivatives"); return SPRUCE_OK; }
 int spruce_module_thermal_conduction(spruce_domain *d, int fs, int ti, double eps, double dtmin, double weak)
 { (void)d; LOG("spruce_module_thermal_conduction flux_saturation=%d ti=%d epsilon=%.17g dt_subcycle_min=%.17g weakening_factor=%.17g", fs, ti, eps, dtmin, weak); return SPRUCE_OK; }
