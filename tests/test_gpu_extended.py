@@ -688,3 +688,34 @@ def test_anomalous_resistivity_and_field_heating_diagnostic_planes_vs_reference_
     frame 0 carries the set-up template and zero planes, later frames the last evaluation's template, template*diffusivity, (e_after - e_before)/dt and mask*(dt*heating)."""
     out = run_isolated(ANOMRES_DIAG_CODE, {})
     assert "ok" in out
+
+
+OPERATOR2_CODE = """
+    import numpy as np
+    from golden_util import same_bits, mismatch
+    from oracle.oracle import Oracle
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    for xb, yb, gen in [(("periodic", "periodic"), ("periodic", "periodic"), lambda: synthetic.orszag_tang(70, 51, zfull=True)),
+                        (("fixed", "open"), ("reflect", "fixed"), lambda: synthetic.stratified_loop(45, 66))]:
+        s = gen()
+        kw = dict(xb=xb, yb=yb)
+        o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+        d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+        q, ax, ay = o.get("temp"), o.get("v_x") - 0.3 * o.get("v_y"), o.get("b_y") + 2.0 * o.get("v_y")
+        # derivs.cpp:407-409, 472-474, 216-220: the oracle's single-direction operators combined with the reference's Grid + / -
+        ref = {"divergence2D": o.operator("derivative1D", 0, ax) + o.operator("derivative1D", 1, ay),
+               "curl2D": o.operator("derivative1D", 0, ay) - o.operator("derivative1D", 1, ax),
+               "transportDivergence2D": o.operator("transportDerivative1D", 0, q, ax) + o.operator("transportDerivative1D", 1, q, ay)}
+        assert same_bits(d.operator2("divergence2D", ax, ay), ref["divergence2D"])
+        assert same_bits(d.operator2("curl2D", ax, ay), ref["curl2D"])
+        assert same_bits(d.operator2("transportDivergence2D", q, ax, ay), ref["transportDivergence2D"])
+    print("ok")
+"""
+
+
+@pytest.mark.xfail(reason="written after round 2's GPU budget was spent (two validated spruce_operator passes combined on the host); first executed by the round-end run", strict=False)
+def test_two_operand_operators_vs_oracle():
+    """spruce_operator2: divergence2D, curl2D, transportDivergence2D of PlasmaDomain (plasmadomain.hpp:201-242), bit for bit."""
+    out = run_isolated(OPERATOR2_CODE, {})
+    assert "ok" in out
