@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 sel=${1:-slab}
 timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -p no:cacheprovider -k "$sel" > gpurun_out/mg2_parity.log 2>&1; echo "slab parity rc=$?"; tail -6 gpurun_out/mg2_parity.log
 if [ "${2:-}" = "ext" ]; then timeout 900 python -m pytest tests/test_gpu_extended.py -x -q -m gpu -p no:cacheprovider -k "slab" > gpurun_out/mg2_ext.log 2>&1; echo "slab ext rc=$?"; tail -6 gpurun_out/mg2_ext.log; fi
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/mg2_bench2.json 2> gpurun_out/mg2_bench2.err; echo "bench2 rc=$?"; grep -v Warning gpurun_out/mg2_bench2.err | tail -5
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/mg2_bench2.json 2> gpurun_out/mg2_bench2.err; echo "bench2 rc=$?"; grep -v Warning gpurun_out/mg2_bench2.err | tail -5
 python - <<'PY'
 import json
 try:

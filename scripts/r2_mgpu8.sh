@@ -1,10 +1,11 @@
 #!/bin/bash
 # 8-GPU call: bench lines at N = 8, 4, 2 (and the hashes to compare with N = 1)
+# LESSON of round 2: a multi-GPU call is charged N x its wall time -- keep every command under a SHORT timeout (a hung 8-GPU bench with timeout 600 x 3 cost 108 GPU-minutes)
 set -u
 mkdir -p gpurun_out
 tag=${1:-mg8}
 for n in ${2:-8 4}; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n bench.py --gpus $n --steps 100 --warmup 5 > gpurun_out/${tag}_bench$n.json 2> gpurun_out/${tag}_bench$n.err; echo "bench$n rc=$?"
+  timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n bench.py --gpus $n --steps 100 --warmup 5 > gpurun_out/${tag}_bench$n.json 2> gpurun_out/${tag}_bench$n.err; echo "bench$n rc=$?"
   python - $n $tag <<'PY'
 import json, sys
 n, tag = sys.argv[1], sys.argv[2]

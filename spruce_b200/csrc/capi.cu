@@ -23,6 +23,7 @@
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
+#include "chunk_plan.hpp"
 
 using namespace spruce;
 
@@ -302,30 +303,12 @@ ActiveList active_quantities(const spruce_domain *d);
 // bound XY_CHUNK allows and spreads the rows evenly over the CTA rows that fit in them.  On a slab whose halo exchange overlaps the interior
 // (split), the first and the last `edge` rows form their own short launch on the communication stream: it finishes early, its rows travel while
 // the long interior chunks still run.
-struct ChunkPlan { int rows; int edge; int n_interior; };
 ChunkPlan plan_chunks(const spruce_domain *d, bool split)
 {
-    const int strips = (d->P.ny + CW - 1) / CW, nx = d->P.nx;
+    const int strips = (d->P.ny + CW - 1) / CW;
     const ActiveList L = active_quantities(d);
     const int cap = 148 * ((L.n == 6 && L.q == XY_LIST_2D && d->static_lists) ? xy_ctas_per_sm(6) : xy_ctas_per_sm(0));
-    ChunkPlan p{};
-    // split: the two edge CTA rows are XY_EDGE_DELTA rows shorter than the interior ones -- they start first (priority stream) and finish
-    // about one halo exchange earlier; `virt` = the rows a uniform split of all CTA rows would have to cover
-    const int delta = split ? XY_EDGE_DELTA : 0, virt = nx + 2 * delta;
-    if (d->chunk_rows_override > 0) p.rows = d->chunk_rows_override < XY_CHUNK ? d->chunk_rows_override : XY_CHUNK;      // SPRUCE_CHUNK_ROWS: tuning sweeps
-    else {
-        const long long min_ctas = (long long)strips * ((virt + XY_CHUNK - 1) / XY_CHUNK);
-        const long long waves = (min_ctas + cap - 1) / cap;
-        long long cta_rows = waves * cap / strips;                            // CTA rows that fit in those waves
-        if (cta_rows < 1) cta_rows = 1;
-        p.rows = (int)((virt + cta_rows - 1) / cta_rows);
-        if (p.rows > XY_CHUNK) p.rows = XY_CHUNK;
-        if (p.rows < 2 * XY_EDGE_DELTA) p.rows = 2 * XY_EDGE_DELTA;
-    }
-    p.edge = split ? p.rows - delta : 0;
-    const int body = nx - 2 * p.edge;
-    p.n_interior = (body + p.rows - 1) / p.rows;
-    return p;
+    return plan_chunk_rows(d->P.nx, strips, cap, split, d->chunk_rows_override);      // chunk_plan.hpp
 }
 bool can_split(const spruce_domain *d, int primary)
 {
@@ -374,10 +357,10 @@ int launch_stage(spruce_domain *d, const PlaneSet &S, const PlaneSet &B, const P
     A.walls = (d->cfg.x_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.x_bound_2 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_1 != SPRUCE_BC_PERIODIC || d->cfg.y_bound_2 != SPRUCE_BC_PERIODIC) ? 1 : 0;
     if (part == 0 && primary && kmode != KM_EXPORT && !d->fused_ctl) { k_dtmin_reset<<<1, 1, 0, d->stream>>>(d->ctl, dt_prune_enabled(d)); d->launches++; }
     const ChunkPlan cp = plan_chunks(d, part != 0);
-    A.chunk_rows = cp.rows; A.row_begin = cp.edge; A.row_end = d->P.nx - cp.edge; A.edge2_begin = -1; A.edge2_end = -1;
-    int gy = cp.n_interior;
-    cudaStream_t st = d->stream;
-    if (part == 1) { A.chunk_rows = cp.edge; A.row_begin = 0; A.row_end = cp.edge; A.edge2_begin = d->P.nx - cp.edge; A.edge2_end = d->P.nx; gy = 2; st = d->comm_stream; }
+    const StageRows sr = stage_rows(cp, d->P.nx, part);
+    A.chunk_rows = sr.chunk_rows; A.row_begin = sr.row_begin; A.row_end = sr.row_end; A.edge2_begin = sr.edge2_begin; A.edge2_end = sr.edge2_end;
+    const int gy = sr.grid_y;
+    cudaStream_t st = part == 1 ? d->comm_stream : d->stream;
     dim3 grid((d->P.ny + CW - 1) / CW, gy);
     {
         const ActiveList L = active_quantities(d);

@@ -16,6 +16,7 @@
 // quantities that can be non-zero; the others contribute exact zeros in the reference too and are not evaluated.
 #pragma once
 #include "mhd_kernels.cuh"
+#include "chunk_plan.hpp"
 
 namespace spruce {
 
@@ -48,6 +49,7 @@ __host__ __device__ constexpr int xy_doubles(int nq, int var) { return xy_off_yt
 __host__ __device__ constexpr size_t xy_smem_bytes(int nq, int var) { return (size_t)xy_doubles(nq, var) * sizeof(double); }
 __host__ __device__ constexpr int xy_rows(int ln) { return ln == 6 ? 6 : NTR; }
 __host__ __device__ constexpr int xy_ctas_per_sm(int ln) { return ln == 6 ? 5 : 4; }               // the 2-D instance: <= 45 KB of shared memory and <= 96 registers -> 20 warps / SM
+static_assert(XY_CHUNK == PLAN_MAX_ROWS && XY_EDGE_DELTA == PLAN_EDGE_DELTA && HALO == PLAN_HALO, "chunk_plan.hpp mirrors these constants");
 static_assert(xy_smem_bytes(NTR, 0) <= 57344, "four CTAs per SM need <= 56 KB each");
 static_assert(xy_smem_bytes(6, 0) <= 45000, "five CTAs per SM need <= 45 KB each");
 
