@@ -71,6 +71,7 @@ def lib():
         L.oracle_outflow_mean.restype = C.c_double
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
         L.oracle_apply_moc_thresholding.argtypes = [C.c_void_p]
+        L.oracle_sg_filter.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_set_moc_limiting.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
@@ -182,6 +183,7 @@ class Oracle:
              "div_cleaning": (10, ["epsilon", "time_scale"]),
              "field_heating": (11, ["coeff", "current_pow", "b_pow", "n_pow", "roc_pow", "inactive_mode"]),
              # boundary: 0 x_bound_1, 1 x_bound_2, 2 y_bound_1, 3 y_bound_2 ; falloff_shape: 0 exp, 1 gaussian, 2 flat
+             "sg_filtering": (13, ["filter_interval"]),
              "boundary_outflow": (12, ["max_accel", "falloff_length", "boundary", "falloff_shape", "feather_length", "field_aligned_mode", "dynamic_mode", "dynamic_time", "dynamic_target_speed"])}
 
     def add_small_module(self, name: str, **kw):
@@ -250,6 +252,12 @@ class Oracle:
     def apply_moc_thresholding(self):
         """The two limiter passes alone, on the planes as they are (for checking the product's limiter on arbitrary input)."""
         lib().oracle_apply_moc_thresholding(self.h)
+
+    def sg_filter(self, plane):
+        """SGFilter::singleVarSavitzkyGolay (sgfilter.cpp:46-82) on an arbitrary plane; returns the filtered copy."""
+        a = np.array(plane, dtype=np.float64, order="C", copy=True)
+        lib().oracle_sg_filter(self.h, _dp(a))
+        return a
 
     def set_moc_limiting(self, *, b_limiting=False, b_lower=0.1, b_upper=10.0, mom_limiting=False, mom_lower=0.1, mom_upper=10.0):
         """moc_b_limiting / moc_mom_limiting (idealmhd.cpp:107-223); call before the first step (the setup's derived pass has already run without them)."""

@@ -1036,6 +1036,8 @@ int oracle_anomalous_subcycles(const oracle *o) { return o->mod.anom ? ((anom_re
 void oracle_set_global_viscosity(oracle *o, double v) { o->global_viscosity = v; }
 /* test accessor: applyMomThresholdingMoC + applyBThresholdingMoC on the current planes, nothing else */
 void oracle_apply_moc_thresholding(oracle *o) { moc_thresholding(o, o->g); }
+/* test accessor: SGFilter::singleVarSavitzkyGolay on an arbitrary plane (for checking the product's host-resident filter) */
+void oracle_sg_filter(oracle *o, double *plane) { sg_filter_plane(o, plane); }
 /* moc_b_limiting / moc_mom_limiting with their bounds (idealmhd.cpp:17-36; defaults 0.1 and 10.0, idealmhd.hpp:59-64) */
 void oracle_set_moc_limiting(oracle *o, int b_on, double b_lo, double b_hi, int mom_on, double mom_lo, double mom_hi)
 {

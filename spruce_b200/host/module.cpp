@@ -2,6 +2,7 @@
 // Config-block parsing follows module.cpp:11-35 / modulehandler.cpp:77-112 of the reference; the parsed values are
 // handed to libspruce_b200.so in setupModule(), in config order (= execution order).
 #include "module.hpp"
+#include "sgfilter.hpp"
 #include "plasmadomain.hpp"
 #include "utils.hpp"
 #include <cmath>
@@ -54,8 +55,10 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "field_heating") m_modules.emplace_back(new FieldHeating(m_pd));
     else if (name == "boundary_outflow") m_modules.emplace_back(new BoundaryOutflow(m_pd));
     else if (name == "anomalous_resistivity") m_modules.emplace_back(new AnomalousResistivity(m_pd));
+    else if (name == "sg_filtering") m_modules.emplace_back(new SGFilter(m_pd));
     else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
-                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating, boundary_outflow, anomalous_resistivity are).");
+                    "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating, boundary_outflow, anomalous_resistivity are; "
+                    "sg_filtering runs on the host).");
     m_modules.back()->configureModule(in);
 }
 
@@ -65,6 +68,10 @@ std::vector<std::string> ModuleHandler::getCommandLineMessages() const
     for (auto &m : m_modules) { const std::string s = m->commandLineMessage(); if (!s.empty()) out.push_back(s); }
     return out;
 }
+bool ModuleHandler::hasHostModules() const { for (auto &m : m_modules) if (!m->device_resident()) return true; return false; }
+void ModuleHandler::preIterateModules(double dt) { for (auto &m : m_modules) if (!m->device_resident()) m->preIterateModule(dt); }
+void ModuleHandler::iterateModules(double dt) { for (auto &m : m_modules) if (!m->device_resident()) m->iterateModule(dt); }
+void ModuleHandler::postIterateModules(double dt) { for (auto &m : m_modules) if (!m->device_resident()) m->postIterateModule(dt); }
 void ModuleHandler::getFileOutputData(std::vector<std::string> &names, std::vector<Grid> &grids) const { for (auto &m : m_modules) m->fileOutput(names, grids); }
 
 static int integrator_id(std::string s, const char *who)
@@ -557,4 +564,35 @@ std::string PhysicalViscosity::commandLineMessage() const
     if (force_on || heating_on) message += ", " + std::to_string(n) + " Subcycle(s)";
     if (inactive_mode) message += " (Not Applied)";
     return message;
+}
+
+// ---- sg_filtering (source/modules/sgfilter.cpp), host-resident
+void SGFilter::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        if (lhs[i] == "filter_interval") filter_interval = (int)std::stod(rhs[i]);       // sgfilter.cpp:14: stod into an int member
+        else std::cerr << lhs[i] << " config not recognized.\n";
+    }
+}
+void SGFilter::postIterateModule(double)
+{
+    // m_iter is the index of the step that has just been integrated: advanceTime increments it after the post-iterate hooks (evolution.cpp:74-81)
+    if (filter_interval > 0 && m_pd.iter() != 0 && m_pd.iter() % filter_interval == 0) applyFilter();
+}
+void SGFilter::applyFilter()
+{
+    const bool xp = m_pd.xPeriodic(), yp = m_pd.yPeriodic();
+    for (const char *name : {"rho", "thermal_energy"}) {                                  // sgfilter.cpp:38
+        Grid &g = m_pd.eqs()->grid(name);                                                 // staged from the device
+        singleVarSavitzkyGolay(g, m_pd.xl(), m_pd.xu(), m_pd.yl(), m_pd.yu(), xp, yp);
+        m_pd.eqs()->pushGrid(name);
+    }
+    m_pd.eqs()->propagateChanges();                                                       // sgfilter.cpp:42
+}
+void SGFilter::singleVarSavitzkyGolay(Grid &grid, int xl, int xu, int yl, int yu, bool x_periodic, bool y_periodic)
+{
+    (void)x_periodic;                                         // the reference wraps the row indices (sgfilter.cpp:62-67) and then never reads them
+    // every tap reads grid(j, j) with j a COLUMN index: the reference's accessor asserts (aborts) as soon as a column index is not a valid row index
+    SPRUCE_REQUIRE(grid.cols() <= grid.rows(), "sg_filtering: the reference reads grid(j, j) for column indices j (sgfilter.cpp:75) and aborts when ydim > xdim");
+    sgFilterPlane(grid, xl, xu, yl, yu, y_periodic);          // sgfilter.hpp
 }

@@ -41,6 +41,12 @@ public:
     std::vector<std::string> getCommandLineMessages() const;
     void getFileOutputData(std::vector<std::string> &names, std::vector<Grid> &grids) const;
     bool empty() const { return m_modules.empty(); }
+    // host-resident modules (device_resident() == false) keep their hooks on the host: PlasmaDomain::run then advances one step per
+    // spruce_advance call and calls them around it, in config order (modulehandler.cpp:42-61)
+    bool hasHostModules() const;
+    void preIterateModules(double dt);
+    void iterateModules(double dt);
+    void postIterateModules(double dt);
 
 private:
     PlasmaDomain &m_pd;
@@ -208,5 +214,19 @@ private:
     bool heating_on = true, force_on = true, output_to_file = false, inactive_mode = false, gradient_correction = false;
     std::string time_integrator;
     Grid constructCoefficientGrid(double strength, double ramp_length, double buffer_length) const;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+// source/modules/sgfilter.hpp ("sg_filtering"): a HOST-resident module -- its post-iterate hook works on host Grids staged through the C ABI
+// (download rho / thermal_energy, filter, upload, propagateChanges), the pattern every un-ported module can use
+class SGFilter : public Module {
+public:
+    explicit SGFilter(PlasmaDomain &pd) : Module(pd) {}
+    void postIterateModule(double dt) override;                                        // sgfilter.cpp:19-23
+    std::string commandLineMessage() const override { return "SG Filtering On"; }      // sgfilter.cpp:25-28
+    // singleVarSavitzkyGolay (sgfilter.cpp:46-82), the reference's index quirk included: the 5 x 5 window reads grid(j[v], j[v])
+    static void singleVarSavitzkyGolay(Grid &grid, int xl, int xu, int yl, int yu, bool x_periodic, bool y_periodic);
+private:
+    int filter_interval = 0;
+    void applyFilter();
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };

@@ -286,16 +286,21 @@ void PlasmaDomain::run(double time_duration, double cluster_time)
     else { SPRUCE_REQUIRE(m_duration >= 0.0, "Duration must be specified on command line, or in state file"); m_max_time = m_duration; }
     std::cout << "Begining simulation...\n";
     const bool per_step_messages = m_std_out_interval > 0 && !m_module_handler.getCommandLineMessages().empty();
+    // host-resident modules (sg_filtering): one step per device call, their hooks around it (evolution.cpp:64-66, 74).  Exact for post-iterate hooks;
+    // a host pre / iterate hook that edits the state makes the device recompute the step size, where the reference keeps the one it took before.
+    const bool host_hooks = m_module_handler.hasHostModules();
     std::vector<double> dts;
     while (m_time < m_max_time && (max_iterations < 0 || m_iter < max_iterations)) {
         int n = max_iterations > 0 ? max_iterations - m_iter : 1024;
         if (m_iter_output_interval > 0) n = std::min(n, m_iter_output_interval - (m_iter % m_iter_output_interval));
-        if (m_time_output_interval > 0.0 || per_step_messages) n = 1;
+        if (m_time_output_interval > 0.0 || per_step_messages || host_hooks) n = 1;
         if (cluster_time > 0) n = std::min(n, 16);
         dts.assign(n, 0.0);
         int done = 0;
+        if (host_hooks) { const double dt = m_eqs->nextStepSize(); m_module_handler.preIterateModules(dt); m_module_handler.iterateModules(dt); }
         check(spruce_advance(m_dev, n, m_max_time, dts.data(), &done));
         SPRUCE_REQUIRE(done > 0, "the device made no progress");
+        if (host_hooks) m_module_handler.postIterateModules(dts[0]);                    // m_iter still names the step just integrated (evolution.cpp:74 before :81)
         bool store_time = false;
         for (int s = 0; s < done; s++) {
             const int old_time_iter = (int)(m_time / m_time_output_interval);

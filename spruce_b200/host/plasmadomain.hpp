@@ -37,6 +37,9 @@ public:
     spruce_domain *device() const { return m_dev; }
     size_t xdim() const { return m_xdim; }
     double time() const { return m_time; }                                                     // m_time, plasmadomain.hpp:75
+    int iter() const { return m_iter; }                                                        // m_iter
+    bool xPeriodic() const { return x_bound_1 == BoundaryCondition::Periodic && x_bound_2 == BoundaryCondition::Periodic; }
+    bool yPeriodic() const { return y_bound_1 == BoundaryCondition::Periodic && y_bound_2 == BoundaryCondition::Periodic; }
     size_t ydim() const { return m_ydim; }
     int xl() const { return m_xl; }
     int xu() const { return m_xu; }

@@ -197,3 +197,50 @@ def test_two_fluid_and_two_energy_sets_select_their_equation_set(stub, tmp_path)
     assert c["eqs"] == "2" and c["bc"] == "3,1,2,1" and c["ti"] == "0"
     uploads = {ln.split()[1] for ln in log if ln.startswith("spruce_grid_upload")}
     assert {"rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"} <= uploads
+
+
+def test_host_resident_module_hooks_run_between_single_device_steps(stub, tmp_path):
+    """sg_filtering stays on the host (host/module.cpp: SGFilter): the run loop advances ONE step per device call and the post-iterate hook stages
+    rho and thermal_energy through the C ABI (download, filter, upload) and propagates -- after the steps whose index is a non-zero multiple of
+    filter_interval (the hook sees m_iter before its increment, evolution.cpp:74-81), next to a device-resident module in the same config."""
+    s = synthetic.stratified_loop(20, 18)
+    modules = [("ambient_heating", [("heating_rate", "1.0e-4")]), ("sg_filtering", [("filter_interval", "2")])]
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=5, iter_output_interval=5, modules=modules)
+    log, stdout, _ = run_shell(stub, tmp_path, s, cfg)
+    assert "SG Filtering On" in stdout                                        # commandLineMessage, sgfilter.cpp:25-28
+    calls = [ln.split()[0] + (" " + ln.split()[1] if ln.startswith("spruce_grid_upload") else "") for ln in log if ln.startswith("spruce_")]
+    run = calls[calls.index("spruce_advance"):]
+    advances = [ln for ln in log if ln.startswith("spruce_advance")]
+    assert len(advances) == 5 and all(args_of(ln)["n"] == "1" for ln in advances)
+    hook = ["spruce_grid_upload rho", "spruce_grid_upload thermal_energy", "spruce_eqs_propagate_changes"]
+    expected = []
+    for it in range(5):                                                       # m_iter of the step just integrated
+        expected.append("spruce_advance")
+        if it != 0 and it % 2 == 0:
+            expected += hook
+    assert [c for c in run if c == "spruce_advance" or c in hook] == expected
+
+
+def test_unported_names_are_refused(stub, tmp_path):
+    s = synthetic.stratified_loop(16, 14)
+    for block, msg in (([("tracer_particles", [])], "tracer_particles"), ([("artificial_viscosity", [("visc_opt", "boundary"), ("visc_strength", "0.5"), ("visc_vars_to_diff", "v_x"), ("visc_vars_to_evol", "mom_x"),
+                                                                                                  ("visc_length", "1.0e8"), ("visc_species", "i"), ("boundary_falloff_shape", "exp_elliptical")])], "falloff shape")):
+        cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), max_iterations=1, iter_output_interval=1, modules=block)
+        state = tmp_path / ("in_%s.state" % msg.replace(" ", "_"))
+        refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+        out = tmp_path / ("out_" + msg.replace(" ", "_"))
+        out.mkdir()
+        (out / "run.config").write_text(cfg)
+        env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / "calls.log"))
+        r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+        err = r.stderr.decode()
+        assert r.returncode in (-6, 134) and msg in err and "successfully reached" not in err, err[-1500:]
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), max_iterations=1, iter_output_interval=1).replace("epsilon", "multispecies_mode = true\nepsilon", 1)
+    state = tmp_path / "in_ms.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+    out = tmp_path / "out_ms"
+    out.mkdir()
+    (out / "run.config").write_text(cfg)
+    env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / "calls.log"))
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode in (-6, 134) and "multispecies_mode" in r.stderr.decode()

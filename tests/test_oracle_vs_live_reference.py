@@ -194,6 +194,10 @@ SMALL_MODULE_CASES = [
     ("outflow_x1_flat+gauss_y1", [("boundary_outflow", dict(max_accel="1.0e3", falloff_length="5.0e8", boundary="x_bound_1", falloff_shape="flat")),
                                   ("boundary_outflow", dict(max_accel="5.0e2", falloff_length="4.0e8", boundary="y_bound_1", falloff_shape="gaussian", feather_length="2.0e8", field_aligned_mode="true"))],
      ("open", "fixed"), ("open", "fixed"), "euler"),
+    # sg_filtering: a HOST-resident module of the product (host/module.cpp: SGFilter); the reference's index quirk (every tap reads grid(j, j)) restated as written
+    ("sg_filter_walls_every_step", [("sg_filtering", dict(filter_interval="1"))], ("fixed", "open"), ("reflect", "fixed"), "rk2"),
+    ("sg_filter_periodic_every_2nd", [("sg_filtering", dict(filter_interval="2"))], ("periodic", "periodic"), ("periodic", "periodic"), "euler"),
+    ("sg_filter+sink", [("ambient_heating_sink", dict(heating_rate="1.0e-5")), ("sg_filtering", dict(filter_interval="3"))], ("periodic", "periodic"), ("fixed", "open"), "rk4"),
     ("field_heating+tc", [("field_heating", dict(coeff="1.0e-7", current_pow="0.5", b_pow="1.0", n_pow="0.2", roc_pow="0.3")),
                           ("thermal_conduction", dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4"))],
      ("fixed", "fixed"), ("fixed", "open"), "rk4"),
