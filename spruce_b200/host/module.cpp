@@ -3,6 +3,7 @@
 // handed to libspruce_b200.so in setupModule(), in config order (= execution order).
 #include "module.hpp"
 #include "sgfilter.hpp"
+#include "tracer.hpp"
 #include "plasmadomain.hpp"
 #include "utils.hpp"
 #include <cmath>
@@ -56,9 +57,10 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "boundary_outflow") m_modules.emplace_back(new BoundaryOutflow(m_pd));
     else if (name == "anomalous_resistivity") m_modules.emplace_back(new AnomalousResistivity(m_pd));
     else if (name == "sg_filtering") m_modules.emplace_back(new SGFilter(m_pd));
+    else if (name == "tracer_particles") m_modules.emplace_back(new TracerParticles(m_pd));
     else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
                     "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating, boundary_outflow, anomalous_resistivity are; "
-                    "sg_filtering runs on the host).");
+                    "sg_filtering and tracer_particles run on the host).");
     m_modules.back()->configureModule(in);
 }
 
@@ -595,4 +597,89 @@ void SGFilter::singleVarSavitzkyGolay(Grid &grid, int xl, int xu, int yl, int yu
     // every tap reads grid(j, j) with j a COLUMN index: the reference's accessor asserts (aborts) as soon as a column index is not a valid row index
     SPRUCE_REQUIRE(grid.cols() <= grid.rows(), "sg_filtering: the reference reads grid(j, j) for column indices j (sgfilter.cpp:75) and aborts when ydim > xdim");
     sgFilterPlane(grid, xl, xu, yl, yu, y_periodic);          // sgfilter.hpp
+}
+
+// ---- tracer_particles (source/modules/solar/tracerparticles.cpp), host-resident
+void TracerParticles::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        if (lhs[i] == "init_file") m_init_filename = fs::path(rhs[i]);
+        else std::cerr << lhs[i] << " config not recognized.\n";
+    }
+}
+void TracerParticles::setupModule()
+{
+    const Grid &px = m_pd.m_grids[PlasmaDomain::pos_x], &py = m_pd.m_grids[PlasmaDomain::pos_y];
+    for (size_t i = 0; i < m_pd.xdim(); i++) x_vec.push_back(px(i, 0));
+    for (size_t j = 0; j < m_pd.ydim(); j++) y_vec.push_back(py(0, j));
+    if (m_pd.m_continue_mode) {                                  // :20-23
+        m_init_filename = m_pd.m_out_directory / fs::path("end.tpstate");
+        SPRUCE_REQUIRE(fs::is_regular_file(m_init_filename), "Continue directory must contain end.tpstate file for tracer particles");
+    } else {                                                     // :24-35: the particle file travels with the run, an old output is discarded
+        const fs::path new_init_path = m_pd.m_out_directory / "init.tpstate";
+        SPRUCE_REQUIRE(fs::is_regular_file(m_init_filename), "Tracer particle initialization file was not found");
+        if (!fs::exists(new_init_path) || !fs::equivalent(m_init_filename, new_init_path)) {
+            if (fs::exists(new_init_path)) fs::remove(new_init_path);
+            fs::copy(m_init_filename, new_init_path, fs::copy_options::overwrite_existing);
+        }
+        const fs::path old_out_path = m_pd.m_out_directory / "particles.tpout";
+        if (fs::exists(old_out_path)) fs::remove(old_out_path);
+    }
+    readTPStateFile(m_init_filename);                            // (the reference's particle-count assertion runs before the file is read, i.e. never fires: :17)
+    if (!m_pd.m_continue_mode) writeToTPOutFile(0.0);
+}
+void TracerParticles::iterateModule(double dt)
+{
+    const Grid v_x = m_pd.eqs()->grid("v_x"), v_y = m_pd.eqs()->grid("v_y");          // staged from the device
+    const bool xper = m_pd.x_bound_1 == PlasmaDomain::BoundaryCondition::Periodic, yper = m_pd.y_bound_1 == PlasmaDomain::BoundaryCondition::Periodic;
+    for (int i = (int)m_particles.size() - 1; i >= 0; i--) {
+        std::vector<double> &p = m_particles[i];
+        const double v_x_p = bilinearInterpolate(p, v_x, x_vec, y_vec), v_y_p = bilinearInterpolate(p, v_y, x_vec, y_vec);
+        const std::vector<double> half = {p[0] + 0.5 * dt * v_x_p, p[1] + 0.5 * dt * v_y_p};
+        const double v_x_h = bilinearInterpolate(half, v_x, x_vec, y_vec), v_y_h = bilinearInterpolate(half, v_y, x_vec, y_vec);
+        p[0] += dt * v_x_h; p[1] += dt * v_y_h;
+        if (p[0] < x_vec[0] || p[0] > x_vec.back()) {
+            if (xper) { const double width = x_vec.back() - x_vec[0]; p[0] = std::fmod((p[0] - x_vec[0] + width), width) + x_vec[0]; }
+            else {
+                m_particles.erase(m_particles.begin() + i); m_labels.erase(m_labels.begin() + i);
+                continue;                                        // the reference goes on to test p[1] through its reference to the erased element (:76): not reproduced
+            }
+        }
+        if (p[1] < y_vec[0] || p[1] > y_vec.back()) {
+            if (yper) { const double height = y_vec.back() - y_vec[0]; p[1] = std::fmod((p[1] - y_vec[0] + height), height) + y_vec[0]; }
+            else { m_particles.erase(m_particles.begin() + i); m_labels.erase(m_labels.begin() + i); }
+        }
+    }
+    const int old_time_iter = (int)(m_pd.m_time / m_pd.m_time_output_interval), new_time_iter = (int)((m_pd.m_time + dt) / m_pd.m_time_output_interval);
+    const bool store_1 = m_pd.m_iter_output_interval > 0 && (m_pd.m_iter + 1) % m_pd.m_iter_output_interval == 0;
+    const bool store_2 = m_pd.m_time_output_interval > 0.0 && new_time_iter > old_time_iter;
+    if (store_1 || store_2) writeToTPOutFile(dt);
+    writeTPStateFile();
+}
+void TracerParticles::readTPStateFile(const fs::path &init_path)
+{
+    SPRUCE_REQUIRE(fs::is_regular_file(init_path), "Tracer particle initialization file must exist");
+    std::ifstream in(init_path.string());
+    std::string line;
+    while (std::getline(in, line)) {
+        clearWhitespace(line);
+        if (line.empty() || line[0] == '#') continue;
+        const std::vector<std::string> parts = splitString(line, '#');
+        m_labels.push_back(parts.size() == 1 ? "" : parts[1]);
+        const std::vector<std::string> xy = splitString(parts[0], ',');
+        m_particles.push_back({std::stod(xy[0]), std::stod(xy[1])});
+    }
+}
+void TracerParticles::writeTPStateFile()
+{
+    std::ofstream out((m_pd.m_out_directory / m_end_filename).string());
+    out.precision(std::numeric_limits<double>::digits10 + 1);
+    for (size_t i = 0; i < m_particles.size(); i++) out << m_particles[i][0] << "," << m_particles[i][1] << "#" << m_labels[i] << std::endl;
+}
+void TracerParticles::writeToTPOutFile(double dt)
+{
+    std::ofstream out((m_pd.m_out_directory / m_out_filename).string(), std::ofstream::app);
+    out.precision(std::numeric_limits<double>::digits10 + 1);
+    out << "t=" << m_pd.m_time + dt << std::endl;
+    for (size_t i = 0; i < m_particles.size(); i++) out << m_particles[i][0] << "," << m_particles[i][1] << "#" << m_labels[i] << std::endl;
 }

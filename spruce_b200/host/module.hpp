@@ -4,7 +4,9 @@
 // spruce_advance in config order.  The hook virtuals stay for host-side modules that are not ported.
 #pragma once
 #include "grid.hpp"
+#include <filesystem>
 #include <fstream>
+namespace fs = std::filesystem;
 #include <memory>
 #include <string>
 #include <vector>
@@ -229,4 +231,22 @@ private:
     int filter_interval = 0;
     void applyFilter();
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+// source/modules/solar/tracerparticles.hpp ("tracer_particles"): HOST-resident -- Lagrangian point particles advected with the flow by a midpoint step
+// per iteration; reads v_x / v_y staged from the device, never edits the state; init.tpstate in, particles.tpout / end.tpstate out
+class TracerParticles : public Module {
+public:
+    explicit TracerParticles(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;                                                        // tracerparticles.cpp:16-41
+    void iterateModule(double dt) override;                                             // tracerparticles.cpp:54-96
+    std::string commandLineMessage() const override { return "Tracer Particles On"; }
+private:
+    fs::path m_out_filename{"particles.tpout"}, m_init_filename{"init.tpstate"}, m_end_filename{"end.tpstate"};
+    std::vector<double> x_vec, y_vec;
+    std::vector<std::vector<double>> m_particles;
+    std::vector<std::string> m_labels;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+    void readTPStateFile(const fs::path &init_path);
+    void writeTPStateFile();
+    void writeToTPOutFile(double dt);
 };

@@ -121,4 +121,5 @@ private:
     friend class ModuleHandler;
     friend class EICThermalization;
     friend class PhysicalViscosity;
+    friend class TracerParticles;
 };

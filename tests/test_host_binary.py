@@ -56,7 +56,10 @@ CASES = {
 # live reference runs), the call sequence over the recording stub (tests/test_host_shell_calls.py); the run on a device is first executed by the round-end suite.
 CASES["loop_sg_filtering"] = (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=7, iter_output_interval=1,
                               write_precision=17, modules=[("ambient_heating", [("heating_rate", "1.0e-4")]), ("sg_filtering", [("filter_interval", "2")])]), True)
-FIRST_RUN_AT_ROUND_END = {"loop_sg_filtering"}
+# tracer_particles: the second host-resident module (host/module.cpp: TracerParticles) -- reads v_x / v_y staged from the device, writes particles.tpout / end.tpstate
+CASES["loop_tracer_particles"] = (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=8, iter_output_interval=2,
+                                  write_precision=17, modules=[("tracer_particles", [("init_file", "__TP_INIT__")])]), True)
+FIRST_RUN_AT_ROUND_END = {"loop_sg_filtering", "loop_tracer_particles"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))
@@ -70,11 +73,17 @@ def test_run_binary_matches_reference_files(name, tmp_path):
     state = tmp_path / "in.state"
     refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"], comments=["# drop-in test " + name])
     cfg = refrun.ideal_mhd_config(std_out_interval=1, **ckw)
+    if name == "loop_tracer_particles":
+        X, Y = s["planes"]["pos_x"][:, 0], s["planes"]["pos_y"][0, :]
+        rng = np.random.default_rng(4)
+        pts = np.column_stack([rng.uniform(X[0], X[-1], 12), rng.uniform(Y[2], Y[-3], 12)])
+        (tmp_path / "init.tpstate").write_text("# tracer particles\n" + "".join("%.17g,%.17g#p%d\n" % (a, b, k) for k, (a, b) in enumerate(pts)))
+        cfg = cfg.replace("__TP_INIT__", str(tmp_path / "init.tpstate"))
     if name == "loop_time_output_euler":
         cfg = cfg.replace("time_output_interval = -1.0", "time_output_interval = 2.0")
     refrun.run_reference(state, cfg, tmp_path / "ref", threads=4)
     stdout = run_ours(state, cfg, tmp_path / "ours")
-    for fname in ("mhd.out", "end.state"):
+    for fname in ("mhd.out", "end.state") + (("particles.tpout", "end.tpstate") if name == "loop_tracer_particles" else ()):
         a, b = (tmp_path / "ours" / fname).read_bytes(), (tmp_path / "ref" / fname).read_bytes()
         if exact:
             assert a == b, "%s differs from the reference's (%d vs %d bytes)" % (fname, len(a), len(b))

@@ -223,7 +223,7 @@ def test_host_resident_module_hooks_run_between_single_device_steps(stub, tmp_pa
 
 def test_unported_names_are_refused(stub, tmp_path):
     s = synthetic.stratified_loop(16, 14)
-    for block, msg in (([("tracer_particles", [])], "tracer_particles"), ([("artificial_viscosity", [("visc_opt", "boundary"), ("visc_strength", "0.5"), ("visc_vars_to_diff", "v_x"), ("visc_vars_to_evol", "mom_x"),
+    for block, msg in (([("no_such_module", [])], "no_such_module"), ([("artificial_viscosity", [("visc_opt", "boundary"), ("visc_strength", "0.5"), ("visc_vars_to_diff", "v_x"), ("visc_vars_to_evol", "mom_x"),
                                                                                                   ("visc_length", "1.0e8"), ("visc_species", "i"), ("boundary_falloff_shape", "exp_elliptical")])], "falloff shape")):
         cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), max_iterations=1, iter_output_interval=1, modules=block)
         state = tmp_path / ("in_%s.state" % msg.replace(" ", "_"))
