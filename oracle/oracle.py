@@ -69,6 +69,8 @@ def lib():
         L.oracle_small_module_plane.restype = C.c_int
         L.oracle_outflow_mean.argtypes = [C.c_void_p, C.c_int]
         L.oracle_outflow_mean.restype = C.c_double
+        L.oracle_coulomb_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_coulomb_plane.restype = C.c_int
         L.oracle_set_global_viscosity.argtypes = [C.c_void_p, C.c_double]
         L.oracle_apply_moc_thresholding.argtypes = [C.c_void_p]
         L.oracle_sg_filter.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -184,6 +186,8 @@ class Oracle:
              "field_heating": (11, ["coeff", "current_pow", "b_pow", "n_pow", "roc_pow", "inactive_mode"]),
              # boundary: 0 x_bound_1, 1 x_bound_2, 2 y_bound_1, 3 y_bound_2 ; falloff_shape: 0 exp, 1 gaussian, 2 flat
              "sg_filtering": (13, ["filter_interval"]),
+             "coulomb_explosion": (14, ["timescale", "lengthscale", "strength"]),
+             "global_temperature": (15, ["gt_strength", "gt_use_diffusion"]),
              "boundary_outflow": (12, ["max_accel", "falloff_length", "boundary", "falloff_shape", "feather_length", "field_aligned_mode", "dynamic_mode", "dynamic_time", "dynamic_target_speed"])}
 
     def add_small_module(self, name: str, **kw):
@@ -196,6 +200,15 @@ class Oracle:
         """Template / coefficient plane k of the idx-th small module (None until it exists); for checking the product's host-built templates."""
         out = np.zeros((self.nx, self.ny))
         return out if lib().oracle_small_module_plane(self.h, idx, k, _dp(out)) else None
+
+    def coulomb_plane(self, idx: int, name: str):
+        """output_to_file plane F_x / F_y / dP_x / dP_y of the coulomb_explosion module at position idx among the small modules; raises if the reference
+        would have aborted (an empty radial bin, a radius outside the bin centres)"""
+        out = np.zeros((self.nx, self.ny))
+        rc = lib().oracle_coulomb_plane(self.h, idx, ["F_x", "F_y", "dP_x", "dP_y"].index(name), _dp(out))
+        if rc != 1:
+            raise RuntimeError("coulomb_explosion: rc %d (2: the reference aborts on this grid)" % rc)
+        return out
 
     def outflow_mean(self, idx: int) -> float:
         """BoundaryOutflow::computeMeanOutflow of the idx-th small module on the current state."""

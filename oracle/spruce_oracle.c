@@ -18,6 +18,7 @@
  * Layout: plane[i*ny + j], i = x index, j = y index (source/mhd/grid.cpp:516-526).
  */
 #include <math.h>
+#include <float.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
@@ -515,6 +516,7 @@ static double min_range(const oracle *o, const double *a, int il, int jl, int iu
 static void propagate_changes(const oracle *o, double **G, double **P);
 #include "physical_viscosity_oracle.inc"
 #include "moc_oracle.inc"
+#include "ucnp_modules_oracle.inc"
 #include "solar_small_modules_oracle.inc"
 #include "anomalous_resistivity_oracle.inc"
 
@@ -981,6 +983,15 @@ int oracle_small_module_plane(oracle *o, int idx, int k, double *out)
     if (!m->plane[k]) return 0;
     memcpy(out, m->plane[k], sizeof(double) * o->n);
     return 1;
+}
+/* test accessor: output_to_file plane k (F_x, F_y, dP_x, dP_y) of the coulomb_explosion module idx; returns -1 for another kind, else 1 + (the reference would have aborted) */
+int oracle_coulomb_plane(oracle *o, int idx, int k, double *out)
+{
+    if (idx < 0 || idx >= o->mod.n_small || k < 0 || k > 3) return -1;
+    const small_module *m = (const small_module *)o->mod.small[idx];
+    if (m->kind != 14) return -1;
+    memcpy(out, ((const coulomb_explosion_t *)m->ext)->var[k], sizeof(double) * o->n);
+    return 1 + m->flag[0];
 }
 /* test accessor: BoundaryOutflow::computeMeanOutflow of small module idx on the current state */
 double oracle_outflow_mean(oracle *o, int idx)

@@ -4,6 +4,7 @@
 #include "module.hpp"
 #include "sgfilter.hpp"
 #include "tracer.hpp"
+#include "ucnp_modules.hpp"
 #include "plasmadomain.hpp"
 #include "utils.hpp"
 #include <cmath>
@@ -42,6 +43,12 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
         m_modules.back()->configureModule(in);
         return;
     }
+    if (name == "coulomb_explosion" || name == "global_temperature") {                  // the UCNP modules take any equation set that has the grids they name
+        if (name == "coulomb_explosion") m_modules.emplace_back(new CoulombExplosion(m_pd));
+        else m_modules.emplace_back(new GlobalTemperature(m_pd));
+        m_modules.back()->configureModule(in);
+        return;
+    }
     SPRUCE_REQUIRE(dynamic_cast<IdealMHD *>(m_pd.m_eqs.get()) != nullptr, "Module designed for IdealMHD EquationSet (ensure that equation_set is set before modules in the config)");
     if (name == "artificial_viscosity") m_modules.emplace_back(new Viscosity(m_pd));
     else if (name == "thermal_conduction") m_modules.emplace_back(new ThermalConduction(m_pd));
@@ -58,9 +65,9 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
     else if (name == "anomalous_resistivity") m_modules.emplace_back(new AnomalousResistivity(m_pd));
     else if (name == "sg_filtering") m_modules.emplace_back(new SGFilter(m_pd));
     else if (name == "tracer_particles") m_modules.emplace_back(new TracerParticles(m_pd));
-    else spruce_die("Module <" + name + "> is not ported to the B200 path yet (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
+    else spruce_die("Module <" + name + "> is not a module of the B200 path (thermal_conduction, radiative_losses, ambient_heating, artificial_viscosity, physical_viscosity, "
                     "eic_thermalization, ambient_heating_sink, localized_heating, mass_injection, momentum_injection, div_cleaning, field_heating, boundary_outflow, anomalous_resistivity are; "
-                    "sg_filtering and tracer_particles run on the host).");
+                    "sg_filtering, tracer_particles, coulomb_explosion and global_temperature run on the host).");
     m_modules.back()->configureModule(in);
 }
 
@@ -682,4 +689,92 @@ void TracerParticles::writeToTPOutFile(double dt)
     out.precision(std::numeric_limits<double>::digits10 + 1);
     out << "t=" << m_pd.m_time + dt << std::endl;
     for (size_t i = 0; i < m_particles.size(); i++) out << m_particles[i][0] << "," << m_particles[i][1] << "#" << m_labels[i] << std::endl;
+}
+
+// ---- coulomb_explosion (source/modules/ucnp/coulomb_explosion.cpp), host-resident
+void CoulombExplosion::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        if (lhs[i] == "timescale") m_timescale = std::stod(rhs[i]);
+        else if (lhs[i] == "lengthscale") m_lengthscale = std::stod(rhs[i]);
+        else if (lhs[i] == "strength") m_strength = std::stod(rhs[i]);
+        else if (lhs[i] == "output_to_file") output_to_file = (rhs[i] == "true");
+        else std::cerr << lhs[i] << " config not recognized.\n";
+    }
+}
+void CoulombExplosion::setupModule()
+{
+    m_vars.assign(num_vars, Grid::Zero(m_pd.xdim(), m_pd.ydim()));
+    for (const char *name : {"press", "n", "mom_x", "mom_y"})
+        if (!m_pd.eqs()->is_var(name)) spruce_die(std::string("Grid <") + name + "> was not found within the EquationSet.");
+}
+void CoulombExplosion::postIterateModule(double dt)
+{
+    if (!(m_pd.time() < 3 * m_timescale)) return;                                         // m_time still names the start of the step (evolution.cpp:74 before :80)
+    const Grid n = m_pd.eqs()->grid("n");                                                 // staged from the device
+    if (output_to_file) {                                                                 // the reference differentiates the pressure every step (:65-66); only fileOutput reads it
+        const Grid press = m_pd.eqs()->grid("press");
+        m_vars[dP_x] = m_pd.derivative1D(press, 0);
+        m_vars[dP_y] = m_pd.derivative1D(press, 1);
+    }
+    const std::string why = ucnp::coulombExplosionForce(m_pd.m_grids[PlasmaDomain::pos_x], m_pd.m_grids[PlasmaDomain::pos_y], n, m_pd.time(), m_timescale, m_lengthscale, m_strength,
+                                                        m_vars[F_x], m_vars[F_y]);
+    if (!why.empty()) spruce_die(why);
+    const Vars force[2] = {F_x, F_y};
+    const char *mom[2] = {"mom_x", "mom_y"};
+    for (int k = 0; k < 2; k++) {                                                         // :83-84
+        Grid &m = m_pd.eqs()->grid(mom[k]);
+        const double *f = m_vars[force[k]].ptr();
+        for (size_t c = 0; c < (size_t)m.size(); c++) m.ptr()[c] += f[c] * dt;
+        m_pd.eqs()->pushGrid(mom[k]);
+    }
+    m_pd.eqs()->propagateChanges();
+}
+void CoulombExplosion::fileOutput(std::vector<std::string> &var_names, std::vector<Grid> &var_grids)
+{
+    if (!output_to_file) return;
+    for (int i = 0; i < num_vars; i++) { var_names.push_back(m_var_names[i]); var_grids.push_back(m_vars[i]); }
+}
+
+// ---- global_temperature (source/modules/ucnp/global_temperature.cpp), host-resident
+void GlobalTemperature::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
+{
+    for (size_t i = 0; i < lhs.size(); i++) {
+        if (lhs[i] == "gt_species") m_species = splitString(rhs[i], ',');
+        else if (lhs[i] == "gt_strength") m_strength = std::stod(rhs[i]);
+        else if (lhs[i] == "gt_use_diffusion") m_use_diffusion = rhs[i] == "true";
+        else if (lhs[i] == "gt_use_global_temp") m_use_global_temp = rhs[i] == "true";
+        else std::cerr << lhs[i] << " config not recognized.\n";
+    }
+}
+void GlobalTemperature::setupModule()
+{
+    SPRUCE_REQUIRE(!m_use_global_temp, "global_temperature: gt_use_global_temp = true is not provided by the B200 path (a domain integral inside every propagateChanges, "
+                                       "global_temperature.cpp:45-64; the device fuses propagateChanges into its stage kernels); gt_use_diffusion is");
+    const std::vector<std::string> species = m_pd.eqs()->species();
+    m_species_ind.assign(m_species.size(), -1);
+    for (size_t i = 0; i < m_species.size(); i++) {
+        for (size_t j = 0; j < species.size(); j++) if (m_species[i] == species[j]) m_species_ind[i] = (int)j;
+        if (m_species_ind[i] < 0) {
+            std::cerr << "Species <" << m_species[i] << "> does not correspond to a species within the active equation set." << std::endl;
+            spruce_die("<gt_species> was specified incorrectly in the .config file.");
+        }
+        SPRUCE_REQUIRE(m_species[i] == "e" || m_species[i] == "i", "Species name must be <e> or <i>.");
+    }
+    m_dr = ucnp::diffusionLengthSquared(m_pd.m_grids[PlasmaDomain::d_x], m_pd.m_grids[PlasmaDomain::d_y], m_pd.ghostZoneMask());
+}
+void GlobalTemperature::postIterateModule(double dt)
+{
+    if (!m_use_diffusion) return;
+    EquationSet *eqs = m_pd.eqs();
+    for (size_t i = 0; i < m_species.size(); i++) {
+        Grid temp = eqs->grid(eqs->temperatures()[m_species_ind[i]]);                     // staged from the device
+        const Grid n = eqs->grid(eqs->number_densities()[m_species_ind[i]]);
+        ucnp::diffuseTemperature(temp, m_dr, dt, m_pd.epsilon, m_strength, [&](const Grid &q) { return m_pd.laplacian(q); });
+        const int e_index = eqs->thermal_energies()[m_species_ind[i]];
+        Grid &e = eqs->grid(e_index);
+        for (size_t c = 0; c < (size_t)e.size(); c++) e.ptr()[c] = n.ptr()[c] * ucnp::kBoltzmann * temp.ptr()[c] / (m_pd.adiabaticIndex() - 1.);      // :90
+        eqs->pushGrid(eqs->index2name(e_index));
+        eqs->propagateChanges();
+    }
 }

@@ -250,3 +250,38 @@ private:
     void writeTPStateFile();
     void writeToTPOutFile(double dt);
 };
+// source/modules/ucnp/coulomb_explosion.hpp ("coulomb_explosion"): HOST-resident -- once per step, a radial histogram of n, the enclosed charge of a
+// decaying non-neutrality and the resulting force on mom_x / mom_y (host/ucnp_modules.hpp); planes staged through the C ABI, then propagateChanges
+class CoulombExplosion : public Module {
+public:
+    explicit CoulombExplosion(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;                                                        // coulomb_explosion.cpp:18-32
+    void postIterateModule(double dt) override;                                         // coulomb_explosion.cpp:49-87
+    std::string commandLineMessage() const override { return "Coulomb Explosion On"; }
+    void fileOutput(std::vector<std::string> &var_names, std::vector<Grid> &var_grids) override;
+    std::vector<std::string> config_names() const override { return {"timescale", "lengthscale", "strength"}; }
+private:
+    double m_timescale = 0.0, m_lengthscale = 0.0, m_strength = 0.0;
+    bool output_to_file = false;
+    enum Vars { F_x, F_y, dP_x, dP_y, num_vars };
+    std::vector<std::string> m_var_names{"F_x", "F_y", "dP_x", "dP_y"};
+    std::vector<Grid> m_vars;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};
+// source/modules/ucnp/global_temperature.hpp ("global_temperature"): HOST-resident -- gt_use_diffusion: sub-cycled midpoint diffusion of each listed species'
+// temperature after the step (laplacian through the device operator), thermal energy rebuilt from it.  gt_use_global_temp (a domain integral inside EVERY
+// propagateChanges, global_temperature.cpp:45-64) is refused: the device fuses propagateChanges into its stage kernels.
+class GlobalTemperature : public Module {
+public:
+    explicit GlobalTemperature(PlasmaDomain &pd) : Module(pd) {}
+    void setupModule() override;                                                        // global_temperature.cpp:17-43
+    void postIterateModule(double dt) override;                                         // global_temperature.cpp:66-94
+    std::vector<std::string> config_names() const override { return {"gt_species", "gt_strength", "gt_use_diffusion", "gt_use_global_temp"}; }
+private:
+    bool m_use_diffusion = false, m_use_global_temp = false;
+    std::vector<std::string> m_species;
+    std::vector<int> m_species_ind;
+    double m_strength = 0.0;
+    Grid m_dr;
+    void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
+};

@@ -122,4 +122,6 @@ private:
     friend class EICThermalization;
     friend class PhysicalViscosity;
     friend class TracerParticles;
+    friend class CoulombExplosion;
+    friend class GlobalTemperature;
 };

@@ -167,3 +167,23 @@ def two_energy(nx: int, ny: int, loop: bool = True, bump: float = 0.4):
     for k in ("mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"):
         pl[k] = P[k]
     return dict(planes=pl, ion_mass=s["ion_mass"], adiabatic_index=s["adiabatic_index"])
+
+
+def ucnp_cloud_mhd(nx: int, ny: int, *, length: float = 1.0, n0: float = 1.0e9, sigma: float = 0.1, T: float = 20.0, drift: float = 0.0) -> dict:
+    """One-fluid (ideal_mhd) ultracold-plasma cloud centred on the origin, for the UCNP modules (coulomb_explosion reads the radius sqrt(x^2 + y^2),
+    global_temperature diffuses temp): Gaussian Sr+ density on a non-uniform grid, smooth temperature variation, optional radial drift."""
+    dx = stretched_spacing(nx, length, 0.15)
+    dy = stretched_spacing(ny, length, 0.10)
+    px, py = centres(dx) - 0.5 * length, centres(dy) - 0.5 * length
+    X = np.repeat(px[:, None], ny, axis=1)
+    Y = np.repeat(py[None, :], nx, axis=0)
+    n = n0 * np.exp(-(X * X + Y * Y) / (2.0 * sigma * sigma)) + 1.0e-3 * n0
+    z = np.zeros((nx, ny))
+    P = {
+        "d_x": np.repeat(dx[:, None], ny, axis=1), "d_y": np.repeat(dy[None, :], nx, axis=0), "pos_x": X, "pos_y": Y,
+        "be_x": z.copy(), "be_y": z.copy(), "be_z": z.copy(),
+        "rho": n * M_SR, "temp": T * (1.0 + 0.3 * np.cos(5.0 * X / length) * np.sin(4.0 * Y / length + 0.3)),
+        "mom_x": n * M_SR * drift * X / sigma, "mom_y": -0.5 * n * M_SR * drift * Y / sigma, "mom_z": z.copy(),
+        "bi_x": z.copy(), "bi_y": z.copy(), "bi_z": z.copy(), "grav_x": z.copy(), "grav_y": z.copy(),
+    }
+    return dict(planes=P, ion_mass=M_SR, adiabatic_index=GAMMA)

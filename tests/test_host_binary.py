@@ -59,7 +59,14 @@ CASES["loop_sg_filtering"] = (lambda: synthetic.stratified_loop(40, 36, bump=0.5
 # tracer_particles: the second host-resident module (host/module.cpp: TracerParticles) -- reads v_x / v_y staged from the device, writes particles.tpout / end.tpstate
 CASES["loop_tracer_particles"] = (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=8, iter_output_interval=2,
                                   write_precision=17, modules=[("tracer_particles", [("init_file", "__TP_INIT__")])]), True)
-FIRST_RUN_AT_ROUND_END = {"loop_sg_filtering", "loop_tracer_particles"}
+# coulomb_explosion / global_temperature: host-resident UCNP modules (host/ucnp_modules.hpp).  The reference runs with ONE OpenMP thread here: its radial binning
+# sums into shared bins from an unsynchronised parallel loop (grid.cpp:306-315)
+UCNP_KW = dict(xb=("open_ucnp", "open_ucnp"), yb=("open_ucnp", "open_ucnp"), density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30, write_precision=17)
+CASES["ucnp_coulomb_explosion"] = (lambda: synthetic.ucnp_cloud_mhd(83, 79, drift=50.0), dict(integrator="rk2", max_iterations=6, iter_output_interval=2, **UCNP_KW,
+                                   modules=[("coulomb_explosion", [("timescale", "1.0e-6"), ("lengthscale", "0.2"), ("strength", "1.0e-3"), ("output_to_file", "true")])]), True)
+CASES["ucnp_global_temperature"] = (lambda: synthetic.ucnp_cloud_mhd(45, 41, drift=20.0), dict(integrator="rk4", max_iterations=6, iter_output_interval=3, **UCNP_KW,
+                                    modules=[("global_temperature", [("gt_species", "i"), ("gt_strength", "3.7"), ("gt_use_diffusion", "true")])]), True)
+FIRST_RUN_AT_ROUND_END = {"loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))
@@ -81,7 +88,7 @@ def test_run_binary_matches_reference_files(name, tmp_path):
         cfg = cfg.replace("__TP_INIT__", str(tmp_path / "init.tpstate"))
     if name == "loop_time_output_euler":
         cfg = cfg.replace("time_output_interval = -1.0", "time_output_interval = 2.0")
-    refrun.run_reference(state, cfg, tmp_path / "ref", threads=4)
+    refrun.run_reference(state, cfg, tmp_path / "ref", threads=1 if name == "ucnp_coulomb_explosion" else 4)
     stdout = run_ours(state, cfg, tmp_path / "ours")
     for fname in ("mhd.out", "end.state") + (("particles.tpout", "end.tpstate") if name == "loop_tracer_particles" else ()):
         a, b = (tmp_path / "ours" / fname).read_bytes(), (tmp_path / "ref" / fname).read_bytes()

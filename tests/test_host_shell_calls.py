@@ -221,6 +221,36 @@ def test_host_resident_module_hooks_run_between_single_device_steps(stub, tmp_pa
     assert [c for c in run if c == "spruce_advance" or c in hook] == expected
 
 
+def test_ucnp_host_modules_stage_their_planes_after_every_step(stub, tmp_path):
+    """coulomb_explosion and global_temperature stay on the host (host/module.cpp, host/ucnp_modules.hpp): after every single device step, in config order,
+    global_temperature runs int(gt_strength) midpoint sub-steps (two laplacian operator passes each), uploads thermal_energy and propagates;
+    coulomb_explosion differentiates the pressure for its output planes, uploads mom_x / mom_y and propagates -- until 3 * timescale has passed."""
+    s = synthetic.ucnp_cloud_mhd(83, 81)
+    modules = [("global_temperature", [("gt_species", "i"), ("gt_strength", "2.5"), ("gt_use_diffusion", "true")]),
+               ("coulomb_explosion", [("timescale", "0.4"), ("lengthscale", "0.2"), ("strength", "1.0e-3"), ("output_to_file", "true")])]
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("open_ucnp", "open_ucnp"), yb=("open_ucnp", "open_ucnp"), max_iterations=4, iter_output_interval=4, modules=modules,
+                                  density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    log, stdout, out = run_shell(stub, tmp_path, s, cfg)
+    assert "Coulomb Explosion On" in stdout
+    calls = []
+    for ln in log:
+        w = ln.split()
+        if w[0] in ("spruce_grid_upload", "spruce_operator"):
+            calls.append(" ".join(w[:3] if w[0] == "spruce_operator" else w[:2]))
+        elif w[0] in ("spruce_advance", "spruce_eqs_propagate_changes"):
+            calls.append(w[0])
+    run = calls[calls.index("spruce_advance"):]
+    gt = ["spruce_operator laplacian 0"] * 4 + ["spruce_grid_upload thermal_energy", "spruce_eqs_propagate_changes"]
+    ce = ["spruce_operator derivative1D 0", "spruce_operator derivative1D 1", "spruce_grid_upload mom_x", "spruce_grid_upload mom_y", "spruce_eqs_propagate_changes"]
+    # the stand-in's steps are 0.5 each: the hook sees t = 0, 0.5, 1.0, 1.5 and 3 * timescale = 1.2
+    expected = []
+    for it in range(4):
+        expected += ["spruce_advance"] + gt + (ce if 0.5 * it < 1.2 else [])
+    assert run == expected
+    frames = (out / "mhd.out").read_text()
+    assert all(("\n%s\n" % v) in frames for v in ("F_x", "F_y", "dP_x", "dP_y"))            # fileOutput, coulomb_explosion.cpp:89-97
+
+
 def test_unported_names_are_refused(stub, tmp_path):
     s = synthetic.stratified_loop(16, 14)
     for block, msg in (([("no_such_module", [])], "no_such_module"), ([("artificial_viscosity", [("visc_opt", "boundary"), ("visc_strength", "0.5"), ("visc_vars_to_diff", "v_x"), ("visc_vars_to_evol", "mom_x"),
@@ -244,3 +274,8 @@ def test_unported_names_are_refused(stub, tmp_path):
     env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / "calls.log"))
     r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert r.returncode in (-6, 134) and "multispecies_mode" in r.stderr.decode()
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), max_iterations=1, iter_output_interval=1,
+                                  modules=[("global_temperature", [("gt_species", "i"), ("gt_strength", "2.0"), ("gt_use_global_temp", "true")])])
+    (out / "run.config").write_text(cfg)
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode in (-6, 134) and "gt_use_global_temp" in r.stderr.decode() and "successfully reached" not in r.stderr.decode()

@@ -356,3 +356,48 @@ def test_open_moc_limiters_oracle_equals_live_reference(name, xb, yb, integrator
         assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
     assert any(not same_bits(o.get(v), plain.get(v)) for v in ("mom_x", "mom_y", "bi_x", "bi_y")), "the limiters never acted: the case does not test them"
     o.close(); plain.close()
+
+
+UCNP_MODULE_CASES = [
+    # coulomb_explosion / global_temperature: HOST-resident modules of the product (host/ucnp_modules.hpp).  One OpenMP thread for the reference:
+    # its radial binning sums into shared bins from an unsynchronised parallel loop (grid.cpp:306-315)
+    ("coulomb_rk2_ucnp_sides", [("coulomb_explosion", dict(timescale="1.0e-6", lengthscale="0.2", strength="1.0e-3", output_to_file="true"))], ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 83, 79, 50.0),
+    ("coulomb_euler_walls_expired", [("coulomb_explosion", dict(timescale="1.0e-7", lengthscale="0.05", strength="5.0e-2", output_to_file="true"))], ("fixed", "reflect"), ("open_ucnp", "fixed"), "euler", 81, 85, 0.0),
+    ("gt_diffusion_rk2", [("global_temperature", dict(gt_species="i", gt_strength="3.7", gt_use_diffusion="true"))], ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 29, 24, 20.0),
+    ("gt_diffusion_periodic+coulomb", [("global_temperature", dict(gt_species="i", gt_strength="2.0", gt_use_diffusion="true")),
+                                       ("coulomb_explosion", dict(timescale="1.0e-6", lengthscale="0.3", strength="1.0e-3"))], ("periodic", "periodic"), ("fixed", "fixed"), "rk4", 81, 80, 10.0),
+    ("gt_diffusion_off", [("global_temperature", dict(gt_species="i", gt_strength="2.0"))], ("periodic", "periodic"), ("periodic", "periodic"), "euler", 21, 22, 0.0),
+]
+
+
+@pytest.mark.parametrize("name,modules,xb,yb,integrator,nx,ny,drift", UCNP_MODULE_CASES, ids=[m[0] for m in UCNP_MODULE_CASES])
+def test_ucnp_modules_oracle_equals_live_reference(name, modules, xb, yb, integrator, nx, ny, drift):
+    s = synthetic.ucnp_cloud_mhd(nx, ny, drift=drift)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    nsteps = 4
+    tmp = Path(tempfile.mkdtemp(prefix="live_ucnp_"))
+    try:
+        refrun.write_state(tmp / "in.state", s["planes"], s["ion_mass"], s["adiabatic_index"])
+        cfg = refrun.ideal_mhd_config(max_iterations=nsteps, output_flags=MHD_OUT, modules=[(m, list(kv.items())) for m, kv in modules], **kw)
+        refrun.run_reference(tmp / "in.state", cfg, tmp / "out", threads=1)
+        _, frames = refrun.read_out(tmp / "out" / "mhd.out")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    assert len(frames) == nsteps + 1, "the reference aborted on this grid (an empty radial bin?)"
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    for m, kv in modules:
+        o.add_small_module(m, **{k: ({"true": 1.0, "false": 0.0}[v] if v in ("true", "false") else float(v)) for k, v in kv.items() if k not in ("gt_species", "output_to_file")})
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for it in range(1, nsteps + 1):
+        step = o.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "%s iteration %d: step %s vs %s" % (name, it, step.hex(), float(ref_step).hex())
+    for v in MHD_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
+    for k, (m, kv) in enumerate(modules):
+        if kv.get("output_to_file") == "true":
+            for v in ("F_x", "F_y", "dP_x", "dP_y"):
+                assert same_bits(o.coulomb_plane(k, v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.coulomb_plane(k, v), frames[nsteps][v]))
+    if "coulomb" in name and "expired" not in name:
+        assert np.abs(o.coulomb_plane([m for m, _ in modules].index("coulomb_explosion"), "F_x")).max() > 0.0
+    o.close()
