@@ -66,9 +66,31 @@ void EquationSet::setupEquationSet()
     SPRUCE_REQUIRE(allStateGridsInitialized(), "All variables specified as state variables for the current EquationSet must be specified in the .state file");
     m_pd.createDevice();
     configureDevice();
-    for (int v : state_variables()) PlasmaDomain::check(spruce_grid_upload(m_pd.device(), index2name(v).c_str(), m_grids[v].ptr(), m_grids[v].size()));
+    for (int v : state_variables()) PlasmaDomain::check(spruce_grid_upload(m_pd.device(), index2name(v).c_str(), m_pd.slab(m_grids[v]), m_pd.slabCount()));
+    if (m_pd.nRanks() > 1) connectSlabs();
     PlasmaDomain::check(spruce_eqs_setup(m_pd.device()));
+    if (m_pd.nRanks() > 1) {
+        SlabComm::instance().barrier();                     // every rank has mapped its neighbours and finished its local setup
+        PlasmaDomain::check(spruce_mgpu_initial_exchange(m_pd.device()));
+    }
     name2index("dt");
+}
+
+// The host side of the peer-store halo transport (spruce_b200.h "multi-GPU"; spruce_b200/multigpu.py does the same over torch.distributed): the zero-plane
+// masks are OR-ed over the ranks, every rank exports one 64-byte CUDA IPC handle and maps all of them.  From then on spruce_advance exchanges halos and the
+// dt minimum between the GPUs itself.
+void EquationSet::connectSlabs()
+{
+    SlabComm &comm = SlabComm::instance();
+    int local_mask = 0;
+    PlasmaDomain::check(spruce_plane_activity(m_pd.device(), &local_mask, -1));
+    PlasmaDomain::check(spruce_plane_activity(m_pd.device(), nullptr, comm.allOr(local_mask)));
+    unsigned char mine[64] = {0}, all[SlabShared::kMaxRanks * 64];
+    int ok = spruce_mgpu_ipc_export(m_pd.device(), mine) == SPRUCE_OK;
+    comm.allGather64(mine, all);
+    ok = ok && spruce_mgpu_ipc_connect(m_pd.device(), all, comm.nRanks()) == SPRUCE_OK;
+    const std::string why = ok ? "" : spruce_last_error();
+    if (!comm.allMin(ok)) spruce_die("run -g: the GPUs of this node cannot map each other's memory (CUDA IPC / peer access)" + (why.empty() ? std::string(" -- on another rank") : ": " + why));
 }
 
 int EquationSet::name2index(const std::string &name) const
@@ -89,7 +111,8 @@ Grid &EquationSet::grid(int index)
     SPRUCE_REQUIRE(index >= 0 && index < num_variables(), "Grid index must be within range of m_grids");
     Grid &g = m_grids[index];
     if (g.rows() != (int)m_pd.xdim() || g.cols() != (int)m_pd.ydim()) g = Grid(m_pd.xdim(), m_pd.ydim());
-    PlasmaDomain::check(spruce_grid_download(m_pd.device(), m_var_names[index].c_str(), g.ptr(), g.size()));
+    PlasmaDomain::check(spruce_grid_download(m_pd.device(), m_var_names[index].c_str(), m_pd.slab(g), m_pd.slabCount()));
+    m_pd.gatherRows(g);                                     // slabs: a collective call -- every rank ends up with the whole plane
     return g;
 }
 Grid &EquationSet::grid(const std::string &name) { return grid(name2index(name)); }
@@ -97,11 +120,12 @@ Grid &EquationSet::grid(const std::string &name) { return grid(name2index(name))
 void EquationSet::pushGrid(const std::string &name)
 {
     Grid &g = m_grids[name2index(name)];
-    PlasmaDomain::check(spruce_grid_upload(m_pd.device(), name.c_str(), g.ptr(), g.size()));
+    PlasmaDomain::check(spruce_grid_upload(m_pd.device(), name.c_str(), m_pd.slab(g), m_pd.slabCount()));
 }
 
 std::vector<Grid> EquationSet::computeTimeDerivatives()
 {
+    SPRUCE_REQUIRE(m_pd.nRanks() == 1, "computeTimeDerivatives() returns whole planes: one rank only");
     const size_t np = m_pd.xdim() * m_pd.ydim(), ne = evolved_variables().size();
     std::vector<double> k(ne * np);
     PlasmaDomain::check(spruce_eqs_time_derivatives(m_pd.device(), k.data(), k.size()));

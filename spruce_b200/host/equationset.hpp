@@ -58,6 +58,7 @@ public:
     std::vector<Grid> computeTimeDerivatives();    // one RHS evaluation on the primary state (equationset.cpp:204-210)
     void propagateChanges();                       // equationset.cpp:212-220 on the device
     double nextStepSize();                         // epsilon * getDT().min(...)  (evolution.cpp:62)
+    void connectSlabs();                           // run -g N: zero-plane masks, CUDA IPC handles (slabcomm.hpp)
 
 protected:
     PlasmaDomain &m_pd;

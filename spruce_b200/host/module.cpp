@@ -122,7 +122,8 @@ void ThermalConduction::setupModule()
 static void append_device_plane(PlasmaDomain &pd, const char *name, std::vector<std::string> &names, std::vector<Grid> &grids)
 {
     Grid g(pd.xdim(), pd.ydim());
-    PlasmaDomain::check(spruce_module_output(pd.device(), name, g.ptr(), g.size()));
+    PlasmaDomain::check(spruce_module_output(pd.device(), name, pd.slab(g), pd.slabCount()));
+    pd.gatherRows(g);
     names.push_back(name);
     grids.push_back(g);
 }
@@ -206,7 +207,7 @@ void AmbientHeating::setupModule()
         }
         heating(i, j) = h;
     }
-    PlasmaDomain::check(spruce_module_ambient_heating(m_pd.device(), heating.ptr(), heating.size()));
+    PlasmaDomain::check(spruce_module_ambient_heating(m_pd.device(), m_pd.slab(heating), m_pd.slabCount()));
 }
 
 // ambientheatingsink.cpp:12-25
@@ -238,7 +239,7 @@ void AmbientHeatingSink::setupModule()
             reduction(i, j) = ((mask(i, j) * exp_base_heating_rate) * std::exp((-1.0 * pos_y(i, j)) / exp_scale_height)) * ((para < 0.0) ? 0.0 : para);
         } else reduction(i, j) = mask(i, j) * heating_rate;
     }
-    PlasmaDomain::check(spruce_module_ambient_heating_sink(m_pd.device(), reduction.ptr(), reduction.size()));
+    PlasmaDomain::check(spruce_module_ambient_heating_sink(m_pd.device(), m_pd.slab(reduction), m_pd.slabCount()));
 }
 
 // localizedheating.cpp:14-29, massinjection.cpp:14-26, momentuminjection.cpp:16-33
@@ -360,7 +361,7 @@ void BoundaryOutflow::setupModule()
     SPRUCE_REQUIRE(b >= 0, "BoundaryOutflow boundary config must be {x,y}_bound_{1,2}");
     const int sh = falloff_shape == "exp" ? 0 : falloff_shape == "gaussian" ? 1 : 2;
     const Grid &x = m_pd.m_grids[PlasmaDomain::pos_x], &y = m_pd.m_grids[PlasmaDomain::pos_y];
-    PlasmaDomain::check(spruce_module_boundary_outflow(m_pd.device(), x.ptr(), y.ptr(), x.size(), max_accel, falloff_length, b, sh, feather_length,
+    PlasmaDomain::check(spruce_module_boundary_outflow(m_pd.device(), m_pd.slab(x), m_pd.slab(y), m_pd.slabCount(), max_accel, falloff_length, b, sh, feather_length,
                                                        field_aligned_mode ? 1 : 0, dynamic_mode ? 1 : 0, dynamic_time, dynamic_target_speed));
 }
 // boundaryoutflow.cpp:65-74
@@ -496,7 +497,7 @@ void Viscosity::setupModule()
         const double strength = std::stod(str[i]);
         if (opt[i] == "boundary" || opt[i] == "boundary_global") {
             const Grid prof = getBoundaryViscosity(strength, std::stod(len[i]));
-            PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), prof.ptr(), prof.size()));
+            PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), m_pd.slab(prof), m_pd.slabCount()));
         } else {
             PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), nullptr, 0));
         }
@@ -559,7 +560,7 @@ void PhysicalViscosity::setupModule()
     SPRUCE_REQUIRE(ms_electron_heating_fraction >= 0.0 && ms_electron_heating_fraction <= 1.0, "Physical Viscosity MS electron heating fraction must be between 0 and 1");
     no_file_output(output_to_file, "physical_viscosity");
     const Grid cg = constructCoefficientGrid(coeff, ramp_length, buffer_length);
-    PlasmaDomain::check(spruce_module_physical_viscosity(m_pd.device(), coeff, cg.ptr(), cg.size(), epsilon, heating_on, force_on, gradient_correction,
+    PlasmaDomain::check(spruce_module_physical_viscosity(m_pd.device(), coeff, m_pd.slab(cg), m_pd.slabCount(), epsilon, heating_on, force_on, gradient_correction,
                                                          integrator_id(time_integrator, "Physical Viscosity"), inactive_mode));
 }
 // physicalviscosity.cpp:269-287

@@ -20,7 +20,9 @@ PlasmaDomain::PlasmaDomain(const fs::path &out_path, const fs::path &config_path
     for (auto &g : m_grids) g = Grid::Zero(1, 1);
     // the .config travels with the run: copy it into the output directory unless it already lives there
     const fs::path new_config_path = m_out_directory / config_path.filename();
-    if (!fs::exists(new_config_path) || !fs::equivalent(config_path, new_config_path)) {
+    if (rank() != 0) {
+        // files are rank 0's business
+    } else if (!fs::exists(new_config_path) || !fs::equivalent(config_path, new_config_path)) {
         std::cout << "Copying " << config_path.string() << " into " << m_out_directory.string() << "...\n";
         if (fs::exists(new_config_path)) fs::remove(new_config_path);
         fs::copy(config_path, new_config_path, fs::copy_options::overwrite_existing);
@@ -35,6 +37,9 @@ PlasmaDomain::PlasmaDomain(const fs::path &out_path, const fs::path &config_path
     std::cout << "Validating input data...\n";
     for (const Grid &g : m_grids) SPRUCE_REQUIRE(g.size() != 1, "All internal grid quantities for PlasmaDomain must be initialized");
     computeIterationBounds();
+    SlabComm::partition((int)m_xdim, nRanks(), rank(), m_row0, m_nx_local);
+    SPRUCE_REQUIRE(m_nx_local >= 4, "every slab needs at least 4 rows: fewer ranks for this grid");
+    SPRUCE_REQUIRE(nRanks() == 1 || !m_module_handler.hasHostModules(), "host-resident modules (sg_filtering, tracer_particles, coulomb_explosion, global_temperature) work on whole planes: one rank only");
     m_eqs->setupEquationSet();
     m_module_handler.setupModules();
     if (!continue_mode && m_overwrite_init) {
@@ -75,7 +80,8 @@ void PlasmaDomain::createDevice()
     c.xdim = (int)m_xdim; c.ydim = (int)m_ydim;
     c.x_bound_1 = (int)x_bound_1; c.x_bound_2 = (int)x_bound_2; c.y_bound_1 = (int)y_bound_1; c.y_bound_2 = (int)y_bound_2;   // same enum order as SPRUCE_BC_*
     c.time_integrator = (int)m_time_integrator;
-    c.device = -1; c.row0 = 0; c.nx_local = (int)m_xdim; c.rank = 0; c.n_ranks = 1;
+    c.device = nRanks() > 1 ? rank() : -1;                            // one rank per GPU, in device order
+    c.row0 = m_row0; c.nx_local = m_nx_local; c.rank = rank(); c.n_ranks = nRanks();
     c.ion_mass = m_ion_mass; c.adiabatic_index = m_adiabatic_index; c.epsilon = epsilon;
     c.density_min = density_min; c.temp_min = temp_min; c.thermal_energy_min = thermal_energy_min;
     c.open_boundary_strength = open_boundary_strength; c.open_boundary_decay_base = open_boundary_decay_base; c.time = m_time;
@@ -87,7 +93,7 @@ void PlasmaDomain::createDevice()
     for (size_t i = 0; i < m_xdim; i++) for (size_t j = 0; j < m_ydim; j++)
         SPRUCE_REQUIRE(m_grids[d_x](i, j) == dx[i] && m_grids[d_y](i, j) == dy[j], "d_x must vary with i only and d_y with j only (rectilinear grid)");
     check(spruce_set_cell_sizes(m_dev, dx.data(), dx.size(), dy.data(), dy.size()));
-    for (int g : {be_x, be_y, be_z}) check(spruce_grid_upload(m_dev, m_gridnames[g].c_str(), m_grids[g].ptr(), m_grids[g].size()));
+    for (int g : {be_x, be_y, be_z}) check(spruce_grid_upload(m_dev, m_gridnames[g].c_str(), slab(m_grids[g]), slabCount()));
 }
 
 // fileio.cpp:14-80
@@ -220,6 +226,7 @@ std::string PlasmaDomain::num2str(double num)
 // fileio.cpp:125-139
 void PlasmaDomain::outputPreamble()
 {
+    if (rank() != 0) return;
     std::ofstream out(m_out_directory / m_out_filename);
     for (const std::string &c : m_comment_lines) out << c << std::endl;
     out << "xdim,ydim" << std::endl << m_xdim << "," << m_ydim << std::endl;
@@ -229,21 +236,27 @@ void PlasmaDomain::outputPreamble()
 // fileio.cpp:144-200
 void PlasmaDomain::storeGrids()
 {
-    m_data_to_write.push_back("t=" + num2str(m_time) + '\n');
+    // on slabs every rank takes part in the gathers (grid(i), the modules' planes); only rank 0 formats and keeps the text
+    const bool writer = rank() == 0;
+    if (writer) m_data_to_write.push_back("t=" + num2str(m_time) + '\n');
     for (int i = 0; i < m_eqs->num_variables(); i++) {
         if (!m_eqs->getOutputFlag(i)) continue;
+        const Grid &g = m_eqs->grid(i);
+        if (!writer) continue;
         m_data_to_write.push_back(m_eqs->index2name(i) + '\n');
-        m_data_to_write.push_back(m_eqs->grid(i).format(',', '\n', m_write_precision));
+        m_data_to_write.push_back(g.format(',', '\n', m_write_precision));
     }
     std::vector<std::string> names; std::vector<Grid> grids;
     m_module_handler.getFileOutputData(names, grids);
-    for (size_t i = 0; i < names.size(); i++) { m_data_to_write.push_back(names[i] + '\n'); m_data_to_write.push_back(grids[i].format(',', '\n', m_write_precision)); }
+    for (size_t i = 0; writer && i < names.size(); i++) { m_data_to_write.push_back(names[i] + '\n'); m_data_to_write.push_back(grids[i].format(',', '\n', m_write_precision)); }
     m_store_counter++;
 }
 
 // fileio.cpp:205-215
 void PlasmaDomain::writeToOutFile()
 {
+    m_store_counter = 0;
+    if (rank() != 0) return;
     std::ofstream out(m_out_directory / m_out_filename, std::ofstream::app);
     for (const std::string &s : m_data_to_write) out << s;
     m_data_to_write.clear();
@@ -253,6 +266,11 @@ void PlasmaDomain::writeToOutFile()
 // fileio.cpp:221-255
 void PlasmaDomain::writeStateFile(const std::string &stem, int precision)
 {
+    if (nRanks() > 1) {                                               // gather first (collective), then rank 0 writes from its staging copies
+        for (int i : m_eqs->state_variables()) m_eqs->grid(i);
+        if (rank() != 0) return;
+    }
+    const bool gathered = nRanks() > 1;
     const fs::path filename = stem == "mhd" ? "mhd" + std::to_string(m_state_identifier) + ".state" : stem + ".state";
     std::ofstream f(m_out_directory / filename);
     for (const std::string &c : m_comment_lines) f << c << std::endl;
@@ -261,7 +279,7 @@ void PlasmaDomain::writeStateFile(const std::string &stem, int precision)
     f << "adiabatic_index\n" << m_adiabatic_index << std::endl;
     f << "t=" << m_time << std::endl;
     for (size_t i = 0; i < m_gridnames.size(); i++) f << m_gridnames[i] << std::endl << m_grids[i].format(',', '\n', precision);
-    for (int i : m_eqs->state_variables()) f << m_eqs->index2name(i) << std::endl << m_eqs->grid(i).format(',', '\n', precision);
+    for (int i : m_eqs->state_variables()) f << m_eqs->index2name(i) << std::endl << (gathered ? m_eqs->hostGrid(i) : m_eqs->grid(i)).format(',', '\n', precision);
 }
 
 void PlasmaDomain::updateStateIdentifier() { m_state_identifier = m_state_identifier == 1 ? 2 : 1; }
@@ -316,10 +334,15 @@ void PlasmaDomain::run(double time_duration, double cluster_time)
             updateStateIdentifier();
             writeStateFile("end");
         }
-        if (cluster_time > 0 && elapsed() > cluster_time) break;
+        if (cluster_time > 0 && SlabComm::instance().broadcast0(elapsed() > cluster_time ? 1 : 0)) break;      // rank 0's clock decides for every rank
     }
     writeToOutFile();
     writeStateFile("end");
+    if (nRanks() > 1) {
+        SlabComm::instance().barrier();
+        SlabComm::instance().markFinished();
+        if (rank() != 0) { spruce_domain_destroy(m_dev); m_dev = nullptr; std::_Exit(0); }       // rank 0 alone reports the end of the run
+    }
     if (m_time >= m_max_time || (max_iterations > 0 && m_iter >= max_iterations)) {
         // the reference ends a completed run with assert(false) so that wrapper scripts stop (evolution.cpp:54-56): same exit status 134
         spruce_die("Simulation successfully reached max simulation time or iterations. Printing this error to end recursive scripts.");

@@ -10,6 +10,8 @@ namespace fs = std::filesystem;
 #include "equationset.hpp"
 #include "grid.hpp"
 #include "module.hpp"
+#include "slabcomm.hpp"
+#include "utils.hpp"
 #include <string>
 #include <vector>
 
@@ -65,6 +67,15 @@ public:
         for (double &v : ry.data()) v = -v;
         return {derivative1D(z, 1), ry};
     }
+    // ---- slab decomposition (`run -g N`, slabcomm.hpp): this rank owns rows [row0, row0 + nxLocal) of every plane; host Grids stay global
+    int rank() const { return SlabComm::instance().rank(); }
+    int nRanks() const { return SlabComm::instance().nRanks(); }
+    int row0() const { return m_row0; }
+    int nxLocal() const { return m_nx_local; }
+    size_t slabCount() const { return (size_t)m_nx_local * m_ydim; }
+    const double *slab(const Grid &g) const { return g.ptr() + (size_t)m_row0 * m_ydim; }
+    double *slab(Grid &g) const { return g.ptr() + (size_t)m_row0 * m_ydim; }
+    void gatherRows(Grid &g) const { SlabComm::instance().allGatherRows(g.ptr(), m_ydim, m_row0, m_nx_local, (size_t)g.size()); }   // every rank ends up with the whole plane
     void createDevice();                 // called by EquationSet::setupEquationSet once config + state are known
     static void check(int rc);           // non-zero status -> message on stderr + abort (the reference's assert style)
 
@@ -87,6 +98,7 @@ private:
     BoundaryCondition x_bound_1{BoundaryCondition::Periodic}, x_bound_2{BoundaryCondition::Periodic}, y_bound_1{BoundaryCondition::Periodic}, y_bound_2{BoundaryCondition::Periodic};
     double open_boundary_strength{0.0}, open_boundary_decay_base{1.0};
     size_t m_xdim{0}, m_ydim{0};
+    int m_row0{0}, m_nx_local{0};
     bool m_multispecies_mode{false};
     std::string m_sg_opt;
     double m_ion_mass{0.0}, m_adiabatic_index{0.0};
@@ -97,12 +109,14 @@ private:
 
     Grid deviceOperator(const char *op, int index, const Grid &q, const Grid *vel) const
     {
+        SPRUCE_REQUIRE(nRanks() == 1, "the operator members work on whole planes: one rank only (spruce_b200.h)");
         Grid out(q.rows(), q.cols());
         check(spruce_operator(m_dev, op, index, q.ptr(), vel ? vel->ptr() : nullptr, out.ptr(), (size_t)q.size()));
         return out;
     }
     Grid deviceOperator2(const char *op, const Grid &a, const Grid &b, const Grid *c) const
     {
+        SPRUCE_REQUIRE(nRanks() == 1, "the operator members work on whole planes: one rank only (spruce_b200.h)");
         Grid out(a.rows(), a.cols());
         check(spruce_operator2(m_dev, op, a.ptr(), b.ptr(), c ? c->ptr() : nullptr, out.ptr(), (size_t)a.size()));
         return out;

@@ -9,9 +9,12 @@
 #include <vector>
 
 // the reference aborts through assert(); keep the message + SIGABRT behaviour without depending on NDEBUG
+// (on N GPUs a dying rank first tells its peers, so that they leave their barriers: slabcomm.hpp)
+inline void (*&spruce_die_hook())() { static void (*hook)() = nullptr; return hook; }
 [[noreturn]] inline void spruce_die(const std::string &msg)
 {
     std::cerr << msg << std::endl;
+    if (spruce_die_hook()) spruce_die_hook()();
     std::abort();
 }
 #define SPRUCE_REQUIRE(cond, msg) do { if (!(cond)) spruce_die(std::string("Assertion `") + #cond + "' failed: " + (msg)); } while (0)

@@ -10,10 +10,16 @@
 
 #define MAXP 64
 struct spruce_domain { spruce_config cfg; char *names[MAXP]; double *planes[MAXP]; size_t counts[MAXP]; int n; double time; long long iter; };
+static int g_rank = 0, g_n_ranks = 1;   /* set by spruce_domain_create before the first line is logged: one log per rank (`run -g N` forks before any call) */
 static FILE *lg(void)
 {
     static FILE *f = NULL;
-    if (!f) { const char *p = getenv("SPRUCE_STUB_LOG"); f = p ? fopen(p, "a") : stderr; }
+    if (!f) {
+        const char *p = getenv("SPRUCE_STUB_LOG");
+        char path[4096];
+        if (p && g_n_ranks > 1) { snprintf(path, sizeof(path), "%s.r%d", p, g_rank); p = path; }
+        f = p ? fopen(p, "a") : stderr;
+    }
     return f;
 }
 #define LOG(...) do { fprintf(lg(), __VA_ARGS__); fputc('\n', lg()); fflush(lg()); } while (0)
@@ -29,6 +35,7 @@ int spruce_domain_create(const spruce_config *c, spruce_domain **out)
 {
     spruce_domain *d = (spruce_domain *)calloc(1, sizeof(*d));
     d->cfg = *c; d->time = c->time;
+    g_rank = c->rank; g_n_ranks = c->n_ranks;
     LOG("spruce_domain_create eqs=%d xdim=%d ydim=%d bc=%d,%d,%d,%d ti=%d row0=%d nx_local=%d n_ranks=%d ion_mass=%.17g gamma=%.17g epsilon=%.17g floors=%.17g,%.17g,%.17g open=%.17g,%.17g time=%.17g",
         c->equation_set, c->xdim, c->ydim, c->x_bound_1, c->x_bound_2, c->y_bound_1, c->y_bound_2, c->time_integrator, c->row0, c->nx_local, c->n_ranks, c->ion_mass, c->adiabatic_index,
         c->epsilon, c->density_min, c->temp_min, c->thermal_energy_min, c->open_boundary_strength, c->open_boundary_decay_base, c->time);
@@ -49,9 +56,25 @@ int spruce_grid_upload(spruce_domain *d, const char *name, const double *h, size
 int spruce_grid_download(spruce_domain *d, const char *name, double *h, size_t count)
 {
     for (int k = 0; k < d->n; k++) if (!strcmp(d->names[k], name) && d->counts[k] == count) { memcpy(h, d->planes[k], count * sizeof(double)); return SPRUCE_OK; }
-    for (size_t i = 0; i < count; i++) h[i] = 1.0;                  /* derived variables: a recognisable constant */
+    for (size_t i = 0; i < count; i++) h[i] = 1.0 + d->cfg.rank;    /* derived variables: a recognisable constant, per rank */
     return SPRUCE_OK;
 }
+int spruce_plane_activity(spruce_domain *d, int *local_mask, int set_global_mask)
+{
+    if (local_mask) *local_mask = 1 << d->cfg.rank;                  /* the OR over the ranks must come back */
+    LOG("spruce_plane_activity set=%d", set_global_mask);
+    return SPRUCE_OK;
+}
+int spruce_mgpu_ipc_export(spruce_domain *d, void *handle64) { memset(handle64, 0xA0 + d->cfg.rank, 64); LOG("spruce_mgpu_ipc_export"); return SPRUCE_OK; }
+int spruce_mgpu_ipc_connect(spruce_domain *d, const void *handles, int n)
+{
+    const unsigned char *h = (const unsigned char *)handles;
+    int ok = n == d->cfg.n_ranks;
+    for (int r = 0; r < n && ok; r++) for (int b = 0; b < 64; b++) if (h[r * 64 + b] != (unsigned char)(0xA0 + r)) ok = 0;
+    LOG("spruce_mgpu_ipc_connect n=%d handles_in_rank_order=%d", n, ok);
+    return SPRUCE_OK;
+}
+int spruce_mgpu_initial_exchange(spruce_domain *d) { (void)d; LOG("spruce_mgpu_initial_exchange"); return SPRUCE_OK; }
 int spruce_eqs_setup(spruce_domain *d) { (void)d; LOG("spruce_eqs_setup"); return SPRUCE_OK; }
 int spruce_eqs_propagate_changes(spruce_domain *d) { (void)d; LOG("spruce_eqs_propagate_changes"); return SPRUCE_OK; }
 int spruce_next_step_size(spruce_domain *d, double *step) { (void)d; *step = 0.5; return SPRUCE_OK; }

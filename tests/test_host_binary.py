@@ -105,3 +105,36 @@ def test_run_binary_matches_reference_files(name, tmp_path):
         assert len(fa) == len(fb) and [f["t"] for f in fa] == [f["t"] for f in fb]
         if name == "loop_solar_modules":
             assert "Thermal Subcycles" in stdout and "Radiative Subcycles" in stdout
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("name,n", [("ot_periodic_rk2", 2), ("loop_open_reflect_rk4", 2), ("loop_solar_modules", 2), ("ot_periodic_rk2", 4)])
+def test_run_binary_on_n_gpus_writes_the_single_gpu_files(name, n, tmp_path):
+    """`run -g N` (host/slabcomm.hpp: one forked rank per GPU, slabs along x, files gathered on rank 0): mhd.out and end.state byte-identical to the one-GPU
+    run of the same binary -- min / max reductions are exact and every cell sees the same operands -- and, for the exact cases, to the reference binary's."""
+    if _n_gpus() < n:
+        pytest.skip("needs %d GPUs" % n)
+    gen, ckw, exact = CASES[name]
+    s = gen()
+    state = tmp_path / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, **ckw)
+    run_ours(state, cfg, tmp_path / "one")
+    out = tmp_path / "many"
+    out.mkdir()
+    (out / "run.config").write_text(cfg)
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state), "-g", str(n)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode in (-6, 134), r.stderr.decode()[-2000:]
+    for fname in ("mhd.out", "end.state"):
+        assert (out / fname).read_bytes() == (tmp_path / "one" / fname).read_bytes(), fname
+    if exact:
+        refrun.run_reference(state, cfg, tmp_path / "ref", threads=4)
+        for fname in ("mhd.out", "end.state"):
+            assert (out / fname).read_bytes() == (tmp_path / "ref" / fname).read_bytes(), fname
