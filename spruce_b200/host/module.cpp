@@ -361,7 +361,8 @@ void BoundaryOutflow::setupModule()
     SPRUCE_REQUIRE(b >= 0, "BoundaryOutflow boundary config must be {x,y}_bound_{1,2}");
     const int sh = falloff_shape == "exp" ? 0 : falloff_shape == "gaussian" ? 1 : 2;
     const Grid &x = m_pd.m_grids[PlasmaDomain::pos_x], &y = m_pd.m_grids[PlasmaDomain::pos_y];
-    PlasmaDomain::check(spruce_module_boundary_outflow(m_pd.device(), m_pd.slab(x), m_pd.slab(y), m_pd.slabCount(), max_accel, falloff_length, b, sh, feather_length,
+    PlasmaDomain::check(spruce_module_boundary_outflow(m_pd.device(), x.ptr(), y.ptr(), x.size(),   // the whole domain on every rank: the template is built from global positions
+                                                       max_accel, falloff_length, b, sh, feather_length,
                                                        field_aligned_mode ? 1 : 0, dynamic_mode ? 1 : 0, dynamic_time, dynamic_target_speed));
 }
 // boundaryoutflow.cpp:65-74
