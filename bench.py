@@ -19,6 +19,7 @@ import argparse
 import json
 import os
 import shutil
+import signal
 import subprocess
 import sys
 import tempfile
@@ -196,6 +197,23 @@ def slab_parity_check(rank, world, local, transport):
     return {"grid": [nx, ny], "steps": steps, "equal": True}
 
 
+def extras_subprocess(mode, gpus, limit_s):
+    """scripts/bench_extras.py in its own process with a time limit: whatever happens there -- a failing kernel, a hang -- the bench line stands."""
+    cmd = [sys.executable, str(ROOT / "scripts" / "bench_extras.py"), "--mode", mode, "--gpus", str(gpus)]
+    try:
+        p = subprocess.Popen(cmd, cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, start_new_session=True)
+        try:
+            out, err = p.communicate(timeout=limit_s)
+        except subprocess.TimeoutExpired:
+            os.killpg(p.pid, signal.SIGKILL)
+            p.communicate()
+            return {"error": "bench_extras.py --mode %s did not finish within %d s" % (mode, limit_s)}
+        lines = [ln for ln in out.decode(errors="replace").splitlines() if ln.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"error": "no output (rc %s): %s" % (p.returncode, err.decode(errors="replace")[-300:])}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def extra_measurements(args, host, names, ion_mass, gamma, local, n, peak):
     """N=1 only, after the bench line's own measurements: the same workload in relaxed arithmetic (opt-in mode, within the north star's 1e-9;
     the bench line itself stays exact), and the 12-quantity instance of the stage kernel (what any run with an external field or a z system
@@ -326,8 +344,22 @@ def run_ours(args):
                          "definition": "one job = every rank uploads its slab of the 13 input planes from pinned host memory + peer mapping + setup + halo exchange + K steps + downloads its slab of the 8 evolved planes into pinned buffers (max over ranks)"}
         assert np.isfinite(out["rho"]).all()
         r2.close()
+        # the drop-in BINARY on the same N GPUs (run -g N) against itself on one GPU, in a subprocess of rank 0; the other ranks wait on a marker file, idle
+        marker = Path(tempfile.gettempdir()) / ("spruce_bench_extras_%s.done" % os.environ.get("MASTER_PORT", "0"))
+        if not args.no_extra and args.workload == "mhd":
+            if rank == 0:
+                marker.unlink(missing_ok=True)
+            dist.barrier(); torch.cuda.synchronize()
+            if rank == 0:
+                result["extras"] = extras_subprocess("ranks", world, 180)
+                marker.write_text("done")
+            else:
+                t_wait = time.perf_counter()
+                while not marker.exists() and time.perf_counter() - t_wait < 240:
+                    time.sleep(0.2)
         if rank == 0:
             emit(args, result, world)
+            marker.unlink(missing_ok=True)
         dist.destroy_process_group()
         return
 
@@ -406,6 +438,8 @@ def run_ours(args):
             extra = extra_measurements(args, host, names, ion_mass, gamma, local, n, peak)
         except Exception as e:                    # the additional measurements must never cost the bench line itself
             extra = {"extra_error": repr(e)[:300]}
+        torch.cuda.synchronize()
+        extra["extras"] = extras_subprocess("single", 1, 300)
 
     # ---- CPU baseline on the host cores (bounded sample)
     cpu = None
@@ -429,7 +463,7 @@ def emit(args, r, world):
                                "relaxed (opt-in: FMA contraction + one-multiplication table divisions in the stage kernel; fields within 1e-9 of the reference, step sizes not bit-identical)",
                        "stage_variants": int(args.stage_variants)},
             "clocks": r["clocks"], "gpu_launches": r["launches"], "e2e": r["e2e"], "roofline": r["roofline"]}
-    for k in ("roofline_relaxed", "value_full_instance", "extra_error", "parity_vs_1gpu", "parity_check", "dt_hash", "state_hash"):
+    for k in ("roofline_relaxed", "value_full_instance", "extra_error", "extras", "parity_vs_1gpu", "parity_check", "dt_hash", "state_hash"):
         if r.get(k) is not None:
             line[k] = r[k]
     if r.get("cpu"):

@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Additional measurements bench.py attaches to its line as "extras" -- run by rank 0 in a SUBPROCESS with a timeout after the line's own numbers are taken, so that
+nothing here can cost the bench line (a failure or a timeout becomes {"error": ...}).  Prints one JSON object.
+
+  --mode single      (N = 1)  the drop-in binary end to end (spruce_b200/bin/run on OT-1024: text .state in, K steps, text end.state out -- SURVEY 8f-1's point:
+                              through the reference's own surface the decimal text dominates), and the per-step cost of the secondary device paths
+                              (scripts/module_perf.py: two-fluid, thermal conduction, physical viscosity)
+  --mode ranks N     (N > 1)  `run -g N` (host/slabcomm.hpp: the drop-in binary on N GPUs) against the same binary on one GPU: mhd.out and end.state must be
+                              byte-identical
+No reference code and nothing under oracle/ is used here."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+RUN = ROOT / "spruce_b200" / "bin" / "run"
+DOMAIN_GRIDS = ["d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z"]
+STATE_VARS = ["rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
+
+
+def write_state(path, s):
+    """The reference's .state text (fileio.cpp:14-80): header, then name / rows of comma-separated values; 17 significant digits are lossless."""
+    P = s["planes"]
+    nx, ny = P["rho"].shape
+    with open(path, "w") as f:
+        f.write("xdim,ydim\n%d,%d\nion_mass\n%.17g\nadiabatic_index\n%.17g\nt=0\n" % (nx, ny, s["ion_mass"], s["adiabatic_index"]))
+        for name in DOMAIN_GRIDS + STATE_VARS:
+            f.write(name + "\n")
+            f.write("\n".join(",".join(map(repr, row)) for row in np.asarray(P[name], dtype=np.float64).tolist()) + "\n")
+
+
+def config(steps, out_every=-1):
+    return ("ideal_mhd = true\n{\n}\ntime_integrator = rk2\nmax_iterations = %d\niter_output_interval = %d\ntime_output_interval = -1.0\nstd_out_interval = -1\nwrite_interval = 1\n"
+            "write_precision = 17\nduration = 1.0e30\nx_bound_1 = periodic\nx_bound_2 = periodic\ny_bound_1 = periodic\ny_bound_2 = periodic\nopen_boundary_strength = 1.0\n"
+            "open_boundary_decay_base = 0.5\nepsilon = 0.2\ndensity_min = 1.0\ntemp_min = 1.0\nthermal_energy_min = 1.0e-30\noutput_flags = rho, temp, mom_x, mom_y, bi_x, bi_y, dt\n") % (steps, out_every)
+
+
+def run_binary(state, out, steps, gpus=1, out_every=-1, timeout=120):
+    out.mkdir(parents=True, exist_ok=True)
+    (out / "run.config").write_text(config(steps, out_every))
+    t0 = time.perf_counter()
+    r = subprocess.run([str(RUN), "-m", "input", "-o", str(out), "-s", str(state)] + (["-g", str(gpus)] if gpus > 1 else []),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    wall = time.perf_counter() - t0
+    if r.returncode not in (-6, 134) or b"successfully reached" not in r.stderr:          # a completed run ends with abort(), like the reference (evolution.cpp:54-56)
+        raise RuntimeError("run rc=%s: %s" % (r.returncode, r.stderr.decode(errors="replace")[-400:]))
+    return wall
+
+
+def mode_single(tmp):
+    from spruce_b200 import synthetic
+    out = {}
+    n, steps = 1024, 100
+    s = synthetic.orszag_tang(n, n)
+    state = tmp / "ot.state"
+    write_state(state, s)
+    w1 = run_binary(state, tmp / "a", 1)
+    wk = run_binary(state, tmp / "b", 1 + steps)
+    out["dropin_binary_e2e"] = {
+        "workload": "OT-%d through spruce_b200/bin/run: parse %.0f MB of .state text, set up, %d RK2 steps, write end.state + mhd.out" % (n, state.stat().st_size / 1e6, 1 + steps),
+        "wall_s": wk, "wall_s_one_step_job": w1, "value": n * n * (1 + steps) / wk, "unit": "cell-updates/s",
+        "stepping_only_value": n * n * steps / max(wk - w1, 1e-9), "note": "stepping_only = wall(%d steps) - wall(1 step): what remains of the job is text I/O and set-up" % (1 + steps)}
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=150)
+        out["secondary_paths_2048"] = json.loads(r.stdout.decode()) if r.returncode == 0 else {"error": r.stderr.decode(errors="replace")[-300:]}
+    except Exception as e:
+        out["secondary_paths_2048"] = {"error": repr(e)[:300]}
+    return out
+
+
+def mode_ranks(tmp, n_gpus):
+    from spruce_b200 import synthetic
+    nx, ny, steps = 96 * n_gpus + 5, 130, 12                       # uneven slabs
+    res = {}
+    for tag, zfull in (("2d", False), ("zfull", True)):
+        s = synthetic.orszag_tang(nx, ny, zfull=zfull)
+        state = tmp / ("in_%s.state" % tag)
+        write_state(state, s)
+        w1 = run_binary(state, tmp / ("one_" + tag), steps, 1, out_every=4)
+        wn = run_binary(state, tmp / ("many_" + tag), steps, n_gpus, out_every=4)
+        same = all((tmp / ("one_" + tag) / f).read_bytes() == (tmp / ("many_" + tag) / f).read_bytes() for f in ("mhd.out", "end.state"))
+        res[tag] = {"files_equal": bool(same), "wall_s_1": w1, "wall_s_n": wn}
+    return {"dropin_binary_ranks": {"grid": [nx, ny], "steps": steps, "n_gpus": n_gpus, "files_equal_to_one_gpu": all(v["files_equal"] for v in res.values()), "cases": res,
+                                    "what": "spruce_b200/bin/run -g N (one forked rank per GPU, slabs along x, peer-store halo exchange, output gathered on rank 0) vs the same binary on one GPU"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", required=True, choices=["single", "ranks"])
+    ap.add_argument("--gpus", type=int, default=2)
+    a = ap.parse_args()
+    with tempfile.TemporaryDirectory(prefix="spruce_extras_") as d:
+        try:
+            out = mode_single(Path(d)) if a.mode == "single" else mode_ranks(Path(d), a.gpus)
+        except Exception as e:
+            out = {"error": repr(e)[:400]}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
