@@ -139,6 +139,7 @@ struct spruce_domain {
     std::vector<Mark> marks; int timeline_steps = 0; bool timeline_on = false;
     bool fused_ctl = false;                // inside a plain step (no modules, no open_moc): the step control runs in k_step_open / k_step_mid / k_step_close
     bool fuse_ctl_enabled = true;          // SPRUCE_FUSED_CTL=0: always the separate one-thread control kernels
+    bool fast_interior = true;             // SPRUCE_FAST_INTERIOR=0: the module stencil kernels use their general (wrapping, range-testing) instance for every cell
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
     void *seg = nullptr; size_t seg_bytes = 0;
@@ -614,6 +615,7 @@ int tc_iterate(spruce_domain *d, double dt)
         TcStageArgs A{};
         A.F = TcFields{Tin, d->Pset.p[E_N], bhx, bhy};
         A.C = d->tc; A.e_base = e; A.e_out = e; A.T_out = Tout; A.K_store = Kst; A.K1 = K1; A.K2 = K2; A.K3 = K3; A.mode = mode; A.c = c;
+        A.fast = d->fast_interior ? 1 : 0;
         k_tc_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
         d->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1353,6 +1355,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     spruce_domain *d = new spruce_domain();
     d->cfg = *cfg;
     if (const char *fc = getenv("SPRUCE_FUSED_CTL")) d->fuse_ctl_enabled = atoi(fc) != 0;
+    if (const char *fi = getenv("SPRUCE_FAST_INTERIOR")) d->fast_interior = atoi(fi) != 0;
     if (const char *tl = getenv("SPRUCE_TIMELINE")) d->timeline_steps = atoi(tl);
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0 ? 1 : 0;

@@ -37,6 +37,24 @@ __device__ __forceinline__ double rd(const DomainParams &P, const double *f, int
     r = max(-HALO, min(P.nx + HALO - 1, r)); j = max(0, min(P.ny - 1, j));
     return f[(size_t)r * P.pitch + j];
 }
+// FAST instances of the stencil helpers below serve cells whose whole stencil (the diamond |di| + |dj| <= 2) lies inside the array AND inside the
+// operators' range, so that neither an index wraps or clamps nor an operator returns its out-of-range zero: the same loads and the same rounded
+// expressions without the index arithmetic and the range tests, which are two thirds of the instructions of the general instances.
+// deep_interior() is the test; the general instances stay for the cells near an edge.
+__device__ __forceinline__ bool deep_interior(const DomainParams &P, int r, int j)
+{
+    const int g = P.row0 + r;
+    const bool x_ok = P.xper ? (!P.xwrap || (r >= HALO && r <= P.nx - 1 - HALO))            // periodic x on a slab: the halo rows hold the neighbours' cells
+                             : (g >= P.xl + HALO && g <= P.xu - HALO);
+    const bool y_ok = P.yper ? (j >= HALO && j <= P.ny - 1 - HALO) : (j >= P.yl + HALO && j <= P.yu - HALO);
+    return x_ok && y_ok;
+}
+template <bool FAST>
+__device__ __forceinline__ double rdT(const DomainParams &P, const double *f, int r, int j)
+{
+    if (FAST) return f[(ptrdiff_t)r * (ptrdiff_t)P.pitch + j];
+    return rd(P, f, r, j);
+}
 
 // x^(3/2), x^(5/2) for the modules' std::pow(T, 1.5 | 2.5): sqrt is correctly rounded, so x*sqrt(x) and (x*x)*sqrt(x) are within 1.5 ulp of the
 // exact power -- the same distance CUDA's pow keeps from glibc's -- at a tenth of the instructions.  These modules are held to a relative
@@ -48,22 +66,26 @@ __device__ __forceinline__ double pow25(double x) { return (x * x) * sqrt(x); }
 __device__ __forceinline__ double temp_of(const DomainParams &P, double e, double n) { return smax((e * P.gm1) / (n * (2.0 * kKB)), P.T_min); }
 
 // derivative1D of an arbitrary per-cell functor F(r, j) (derivs.cpp:223-264); zero outside the interior range
-template <class F>
+template <bool FAST = false, class F>
 __device__ __forceinline__ double Dx(const DomainParams &P, F f, int r, int j)
 {
-    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
-    if (!is_interior(P, r, j)) return 0.0;
+    if (!FAST) {
+        r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+        if (!is_interior(P, r, j)) return 0.0;
+    }
     const AxisTab &t = P.tx;
     const double a = f(r - 1, j), b = f(r, j), c = f(r + 1, j);
     const double hi = face_interp(b, c, t.h[r], t.h[r + 1], t.fs[r + 1], t.rfs[r + 1]);
     const double lo = face_interp(a, b, t.h[r - 1], t.h[r], t.fs[r], t.rfs[r]);
     return ddiv(hi - lo, t.d[r], t.rd[r]);
 }
-template <class F>
+template <bool FAST = false, class F>
 __device__ __forceinline__ double Dy(const DomainParams &P, F f, int r, int j)
 {
-    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
-    if (!is_interior(P, r, j)) return 0.0;
+    if (!FAST) {
+        r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+        if (!is_interior(P, r, j)) return 0.0;
+    }
     const AxisTab &t = P.ty;
     const double a = f(r, j - 1), b = f(r, j), c = f(r, j + 1);
     const double hi = face_interp(b, c, t.h[j], t.h[j + 1], t.fs[j + 1], t.rfs[j + 1]);
@@ -71,22 +93,26 @@ __device__ __forceinline__ double Dy(const DomainParams &P, F f, int r, int j)
     return ddiv(hi - lo, t.d[j], t.rd[j]);
 }
 // secondDerivative1D (derivs.cpp:417-455): (I(i,i+1) - 2 q + I(i-1,i)) / (0.5 d)^2
-template <class F>
+template <bool FAST = false, class F>
 __device__ __forceinline__ double D2x(const DomainParams &P, F f, int r, int j)
 {
-    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
-    if (!is_interior(P, r, j)) return 0.0;
+    if (!FAST) {
+        r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+        if (!is_interior(P, r, j)) return 0.0;
+    }
     const AxisTab &t = P.tx;
     const double a = f(r - 1, j), b = f(r, j), c = f(r + 1, j);
     const double hi = face_interp(b, c, t.h[r], t.h[r + 1], t.fs[r + 1], t.rfs[r + 1]);
     const double lo = face_interp(a, b, t.h[r - 1], t.h[r], t.fs[r], t.rfs[r]);
     return ((hi - 2.0 * b) + lo) / (t.h[r] * t.h[r]);
 }
-template <class F>
+template <bool FAST = false, class F>
 __device__ __forceinline__ double D2y(const DomainParams &P, F f, int r, int j)
 {
-    r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
-    if (!is_interior(P, r, j)) return 0.0;
+    if (!FAST) {
+        r = wrap_i(P, r); j = wrap_j(P, j);      // periodic axes: the neighbour of the first cell is the last one (derivs.cpp:243-256)
+        if (!is_interior(P, r, j)) return 0.0;
+    }
     const AxisTab &t = P.ty;
     const double a = f(r, j - 1), b = f(r, j), c = f(r, j + 1);
     const double hi = face_interp(b, c, t.h[j], t.h[j + 1], t.fs[j + 1], t.rfs[j + 1]);
@@ -103,56 +129,62 @@ struct TcParams {
 struct TcFields { const double *T, *n, *bhx, *bhy; };   // n, b_hat of the primary state at module entry; T evolves
 
 // fieldAlignedConductiveFlux at one cell (thermalconduction.cpp:154-178); zero outside the interior
+template <bool FAST = false>
 __device__ __forceinline__ void tc_raw_flux(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j, double *fx, double *fy)
 {
     *fx = 0.0; *fy = 0.0;
-    r = wrap_i(P, r); j = wrap_j(P, j);
-    if (!is_interior(P, r, j)) return;
-    auto T = [&](int a, int b) { return rd(P, F.T, a, b); };
+    if (!FAST) {
+        r = wrap_i(P, r); j = wrap_j(P, j);
+        if (!is_interior(P, r, j)) return;
+    }
+    auto T = [&](int a, int b) { return rdT<FAST>(P, F.T, a, b); };
     const double Tc = T(r, j);
-    const double rho = rd(P, F.n, r, j) * P.m_i;
+    const double rho = rdT<FAST>(P, F.n, r, j) * P.m_i;
     const double kmax = (((P.tx.d[r] * P.ty.d[j]) * kKB) * ddiv(rho, P.m_i, P.rm_i)) / C.dt_subcycle_min;     // :155
     const double kap = smin(pow25(Tc) * C.kappa, kmax);                                            // :156
-    const double cx = (kap * -1.0) * Dx(P, T, r, j), cy = (kap * -1.0) * Dy(P, T, r, j);
-    const double bx = rd(P, F.bhx, r, j), by = rd(P, F.bhy, r, j);
+    const double cx = (kap * -1.0) * Dx<FAST>(P, T, r, j), cy = (kap * -1.0) * Dy<FAST>(P, T, r, j);
+    const double bx = rdT<FAST>(P, F.bhx, r, j), by = rdT<FAST>(P, F.bhy, r, j);
     const double fm = cx * bx + cy * by;                                                                    // :173-175
     *fx = fm * bx; *fy = fm * by;
 }
 // saturateConductiveFlux scale factor at one cell (thermalconduction.cpp:182-188); acts on every cell of the plane
+template <bool FAST = false>
 __device__ __forceinline__ void tc_saturate(const DomainParams &P, const TcFields &F, int r, int j, double *fx, double *fy)
 {
     const double c1 = (1.0 / 6.0) * (3.0 / 2.0);
-    r = wrap_i(P, r); j = wrap_j(P, j);
-    const double rho = rd(P, F.n, r, j) * P.m_i;
-    const double sat = ((ddiv(rho, P.m_i, P.rm_i) * c1) * pow15(rd(P, F.T, r, j) * kKB)) / sqrt(kMElectron);
+    if (!FAST) { r = wrap_i(P, r); j = wrap_j(P, j); }
+    const double rho = rdT<FAST>(P, F.n, r, j) * P.m_i;
+    const double sat = ((ddiv(rho, P.m_i, P.rm_i) * c1) * pow15(rdT<FAST>(P, F.T, r, j) * kKB)) / sqrt(kMElectron);
     const double fm = sqrt((*fx) * (*fx) + (*fy) * (*fy));
     const double sc = sat / sqrt(sat * sat + fm * fm);
     *fx *= sc; *fy *= sc;
 }
 // saturation coefficient of saturationTerms at one cell (thermalconduction.cpp:211-224)
 // (out of line: the saturation terms evaluate it at five points; inlined five times the kernel no longer fits the instruction cache)
+template <bool FAST = false>
 __device__ __noinline__ double tc_coefficient(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j)
 {
     double fx, fy;
-    tc_raw_flux(P, C, F, r, j, &fx, &fy);
+    tc_raw_flux<FAST>(P, C, F, r, j, &fx, &fy);
     const double fm = sqrt(fx * fx + fy * fy);
-    tc_saturate(P, F, r, j, &fx, &fy);
+    tc_saturate<FAST>(P, F, r, j, &fx, &fy);
     const double sfm = sqrt(fx * fx + fy * fy);
     return (fm != 0.0) ? sfm / fm : 1.0;
 }
 
 // thermalEnergyDerivative at one cell (thermalconduction.cpp:114-132)
+template <bool FAST = false>
 __device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j)
 {
-    auto T = [&](int a, int b) { return rd(P, F.T, a, b); };
-    auto BX = [&](int a, int b) { return rd(P, F.bhx, a, b); };
-    auto BY = [&](int a, int b) { return rd(P, F.bhy, a, b); };
-    auto TX = [&](int a, int b) { return Dx(P, T, a, b); };
-    auto TY = [&](int a, int b) { return Dy(P, T, a, b); };
+    auto T = [&](int a, int b) { return rdT<FAST>(P, F.T, a, b); };
+    auto BX = [&](int a, int b) { return rdT<FAST>(P, F.bhx, a, b); };
+    auto BY = [&](int a, int b) { return rdT<FAST>(P, F.bhy, a, b); };
+    auto TX = [&](int a, int b) { return Dx<FAST>(P, T, a, b); };
+    auto TY = [&](int a, int b) { return Dy<FAST>(P, T, a, b); };
     const double Tx = TX(r, j), Ty = TY(r, j);
-    const double Txx = D2x(P, T, r, j), Tyy = D2y(P, T, r, j);
-    const double Txy = Dy(P, TX, r, j), Tyx = Dx(P, TY, r, j);            // nested: derivative1D(dtemp_dx,1), derivative1D(dtemp_dy,0)
-    const double bxx = Dx(P, BX, r, j), bxy = Dy(P, BX, r, j), byx = Dx(P, BY, r, j), byy = Dy(P, BY, r, j);
+    const double Txx = D2x<FAST>(P, T, r, j), Tyy = D2y<FAST>(P, T, r, j);
+    const double Txy = Dy<FAST>(P, TX, r, j), Tyx = Dx<FAST>(P, TY, r, j);            // nested: derivative1D(dtemp_dx,1), derivative1D(dtemp_dy,0)
+    const double bxx = Dx<FAST>(P, BX, r, j), bxy = Dy<FAST>(P, BX, r, j), byx = Dx<FAST>(P, BY, r, j), byy = Dy<FAST>(P, BY, r, j);
     const double bhx = BX(r, j), bhy = BY(r, j), Tc = T(r, j);
     const double bg = bhx * Tx + bhy * Ty;
     const double t1x = bhx * Txx + bhy * Txy, t1y = bhx * Tyx + bhy * Tyy;
@@ -164,12 +196,12 @@ __device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C,
     const double tty = ((p15 * (5.0 / 2.0)) * Ty) * bg + p25 * ((t1y + t2y) + t3y);
     double out = (((p25 * bg) * (bxx + byy)) + (bhx * ttx + bhy * tty)) * C.kappa;
     if (C.flux_saturation) {
-        auto CO = [&](int a, int b) { return tc_coefficient(P, C, F, a, b); };
+        auto CO = [&](int a, int b) { return tc_coefficient<FAST>(P, C, F, a, b); };
         const double coef = CO(r, j);
         double rx, ry;
-        tc_raw_flux(P, C, F, r, j, &rx, &ry);
-        const double mask = is_interior(P, r, j) ? 1.0 : 0.0;
-        const double add = (mask * -1.0) * (Dx(P, CO, r, j) * rx + Dy(P, CO, r, j) * ry);
+        tc_raw_flux<FAST>(P, C, F, r, j, &rx, &ry);
+        const double mask = (FAST || is_interior(P, r, j)) ? 1.0 : 0.0;
+        const double add = (mask * -1.0) * (Dx<FAST>(P, CO, r, j) * rx + Dy<FAST>(P, CO, r, j) * ry);
         out = coef * out + add;
     }
     return out;
@@ -186,6 +218,7 @@ struct TcStageArgs {
     const double *K1, *K2, *K3;
     int mode;
     double c;                  // 0.5*dt_sub or dt_sub
+    int fast;                  // deep-interior cells take the FAST instance (SPRUCE_FAST_INTERIOR, default on; same results bit for bit)
 };
 
 __global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ DomainParams P, const __grid_constant__ TcStageArgs A)
@@ -196,7 +229,8 @@ __global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ Domain
     const size_t off = (size_t)r * P.pitch + j;
     const bool in = is_interior(P, r, j);
     const double mask = in ? 1.0 : 0.0;
-    double dE = in ? tc_energy_derivative(P, A.C, A.F, r, j) : 0.0;   // ghost cells: multiplied by mask = 0
+    double dE = 0.0;                                                    // ghost cells: multiplied by mask = 0
+    if (in) dE = (A.fast && deep_interior(P, r, j)) ? tc_energy_derivative<true>(P, A.C, A.F, r, j) : tc_energy_derivative<false>(P, A.C, A.F, r, j);
     if (A.K_store) A.K_store[off] = dE;
     const double e0 = A.e_base[off];
     double e1;

@@ -506,6 +506,27 @@ def test_thermal_conduction_through_tc_iterate_with_output_planes(emu, xb, yb, i
     o.close()
 
 
+@pytest.mark.parametrize("integ,sat", [("euler", False), ("rk2", True), ("rk4", True)])
+@pytest.mark.parametrize("xb,yb", BOUNDS)
+def test_thermal_conduction_fast_interior_instance_equals_the_general_one(emu, xb, yb, integ, sat):
+    """k_tc_stage serves deep-interior cells with the FAST instances of the stencil helpers (no index wrap / clamp, no range tests: module_kernels.cuh
+    deep_interior): the thermal energy after tc_iterate and both diagnostic planes must equal the all-general run bit for bit, for every boundary set."""
+    nx, ny = 27, 24
+    res = []
+    for fast in (1, 0):
+        s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+        o.close()
+        emu.cemu_set_fast_interior(h, C.c_int(fast))
+        avg = np.zeros((nx, ny)); satp = np.zeros((nx, ny))
+        assert emu.cemu_thermal_conduction(h, C.c_int(int(sat)), C.c_double(1.0), C.c_double(1.0e-4), C.c_int({"euler": 0, "rk2": 1, "rk4": 2}[integ]), C.c_int(3), C.c_double(step), vp(avg), vp(satp)) == 0
+        e = np.zeros((nx, ny))
+        emu.cemu_get(h, C.c_int(4), vp(e))
+        res.append((e, avg, satp))
+    for a, b2 in zip(res[0], res[1]):
+        assert same_bits(a, b2)
+    assert np.count_nonzero(res[0][1]) > 0
+
+
 @pytest.mark.parametrize("integ", ["euler", "rk2", "rk4"])
 @pytest.mark.parametrize("xb,yb", BOUNDS[:2])
 def test_radiative_losses_through_rl_iterate_with_output_plane(emu, xb, yb, integ):
