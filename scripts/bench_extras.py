@@ -68,11 +68,13 @@ def mode_single(tmp):
         "workload": "OT-%d through spruce_b200/bin/run: parse %.0f MB of .state text, set up, %d RK2 steps, write end.state + mhd.out" % (n, state.stat().st_size / 1e6, 1 + steps),
         "wall_s": wk, "wall_s_one_step_job": w1, "value": n * n * (1 + steps) / wk, "unit": "cell-updates/s",
         "stepping_only_value": n * n * steps / max(wk - w1, 1e-9), "note": "stepping_only = wall(%d steps) - wall(1 step): what remains of the job is text I/O and set-up" % (1 + steps)}
-    try:
-        r = subprocess.run([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=150)
-        out["secondary_paths_2048"] = json.loads(r.stdout.decode()) if r.returncode == 0 else {"error": r.stderr.decode(errors="replace")[-300:]}
-    except Exception as e:
-        out["secondary_paths_2048"] = {"error": repr(e)[:300]}
+    # the secondary device paths, as shipped and with the general (wrapping, range-testing) stencil instances for every cell: what the FAST instances buy
+    for key, env in (("secondary_paths_2048", {}), ("secondary_paths_2048_general_instances", {"SPRUCE_FAST_INTERIOR": "0"})):
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], cwd=str(ROOT), env=dict(os.environ, **env), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+            out[key] = json.loads(r.stdout.decode()) if r.returncode == 0 else {"error": r.stderr.decode(errors="replace")[-300:]}
+        except Exception as e:
+            out[key] = {"error": repr(e)[:300]}
     return out
 
 

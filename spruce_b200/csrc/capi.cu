@@ -1072,7 +1072,7 @@ int pv_iterate(spruce_domain *d, double dt)
     PvArgs A{};
     for (int k = 0; k < 3; k++) { A.bh[k] = pv.bh[k]; A.mom[k] = d->Pset.p[E_MX + k]; }
     A.n = d->Pset.p[E_N]; A.cg = pv.cg; A.e = d->Pset.p[E_E];
-    A.coeff = pv.coeff; A.heating_on = pv.heating_on; A.force_on = pv.force_on; A.gc = pv.gc; A.red = d->red;
+    A.coeff = pv.coeff; A.heating_on = pv.heating_on; A.force_on = pv.force_on; A.gc = pv.gc; A.red = d->red; A.fast = d->fast_interior ? 1 : 0;
     // computeViscousSubcycles :66-80 -- evaluated here, in iterate, on the state earlier modules have already changed
     for (int k = 0; k < 3; k++) A.v[k] = pv.v[0][k];
     A.T = pv.T[0];

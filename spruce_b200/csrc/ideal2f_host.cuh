@@ -110,6 +110,7 @@ void tf_base(const spruce_domain *d, TfArgs &A)
     A.step_ptr = &d->ctl->step; A.done_ptr = &d->ctl->done; A.dtmin_bits = &d->ctl->dtmin_bits;
     A.m_e = kMElectron; A.rm_e = 1.0 / kMElectron;
     A.curl_terms = t->remove_curl_terms ? 0 : 1;
+    A.fast = d->fast_interior ? 1 : 0;
     A.eic = t->eic;
 }
 

@@ -33,7 +33,15 @@ struct TfArgs {
     const double *vel[4];       // i_v_x, i_v_y, e_v_x, e_v_y of the state S, every cell (k_2f_velocity), so that no stencil operand needs a division
     double m_e, rm_e;           // electron mass and RN(1/m_e)
     int curl_terms;             // !remove_curl_terms
+    int fast;                   // cells whose stencil needs no index wrap take the FAST instances of the operators (SPRUCE_FAST_INTERIOR, default on; same results bit for bit)
 };
+
+// The right-hand side is evaluated at interior cells only, whose stencils (transport: +-2, central: +-1 along one axis) never leave the array on a wall side;
+// only a single-rank periodic axis makes an index wrap.  Away from such an edge the operators below run as FAST instances: plain addressing, no wrap, no clamp.
+__device__ __forceinline__ bool tf_no_wrap(const DomainParams &P, int r, int j)
+{
+    return (!P.xwrap || (r >= HALO && r <= P.nx - 1 - HALO)) && (!P.yper || (j >= HALO && j <= P.ny - 1 - HALO));
+}
 
 // transportDerivative1D of functor Q with velocity functor V along `index` at cell (r,j)  (derivs.cpp:122-162)
 template <class FQ, class FV>
@@ -67,12 +75,13 @@ __device__ __noinline__ double tf_T1(const DomainParams &P, const double *q, con
 }
 // transportDerivative1D of four planes that share one velocity (a species' density, two momenta and thermal energy): the face
 // velocities and the face geometry are evaluated once for the four (derivs.cpp:122-162 evaluates them once per call as well)
+template <bool FAST = false>
 __device__ __noinline__ void tf_T4(const DomainParams &P, const double *q0, const double *q1, const double *q2, const double *q3, const double *v,
                                    int index, int r, int j, double *out)
 {
     const AxisTab &t = index == 0 ? P.tx : P.ty;
     const int i0 = index == 0 ? r : j;
-    auto vat = [&](int i) { return index == 0 ? rd(P, v, i, j) : rd(P, v, r, i); };
+    auto vat = [&](int i) { return index == 0 ? rdT<FAST>(P, v, i, j) : rdT<FAST>(P, v, r, i); };
     const FaceGeom g0 = load_face_geom(t, i0), g1 = load_face_geom(t, i0 + 1);
     const double vf0 = face_interp(vat(i0 - 1), vat(i0), g0.hm1, g0.h0, g0.fs, g0.rfs);
     const double vf1 = face_interp(vat(i0), vat(i0 + 1), g1.hm1, g1.h0, g1.fs, g1.rfs);
@@ -80,7 +89,7 @@ __device__ __noinline__ void tf_T4(const DomainParams &P, const double *q0, cons
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
         const double *q = qs[k];
-        auto at = [&](int i) { return index == 0 ? rd(P, q, i, j) : rd(P, q, r, i); };
+        auto at = [&](int i) { return index == 0 ? rdT<FAST>(P, q, i, j) : rdT<FAST>(P, q, r, i); };
         const double a = at(i0 - 2), b = at(i0 - 1), c = at(i0), d = at(i0 + 1), e = at(i0 + 2);
         double d2;
         const double S0 = upwind_face(a, b, c, d, vf0, g0, &d2);
@@ -90,10 +99,11 @@ __device__ __noinline__ void tf_T4(const DomainParams &P, const double *q0, cons
 }
 
 // derivative1D along `index` of the plane expression (a [+ b]) * scale   (scale = 1.0 is exact; b may be null)
+template <bool FAST = false>
 __device__ __noinline__ double tf_D(const DomainParams &P, const double *a, const double *b, double scale, int index, int r, int j)
 {
-    auto F = [&](int x, int y) { return (b ? rd(P, a, x, y) + rd(P, b, x, y) : rd(P, a, x, y)) * scale; };
-    return index == 0 ? Dx(P, F, r, j) : Dy(P, F, r, j);
+    auto F = [&](int x, int y) { return (b ? rdT<FAST>(P, a, x, y) + rdT<FAST>(P, b, x, y) : rdT<FAST>(P, a, x, y)) * scale; };
+    return index == 0 ? Dx<FAST>(P, F, r, j) : Dy<FAST>(P, F, r, j);            // FAST: the cell itself is interior (the caller's condition)
 }
 
 // Ideal2F::recomputeDT for one cell (ideal2F.cpp:169-198): electron Langmuir group speed, min with the EM Courant limit
@@ -124,6 +134,66 @@ __device__ __forceinline__ double tf_cell_dt_ion(const DomainParams &P, double i
 // fixed / reflect zero every momentum of both species in the two ghost cells and the first interior cell (primary state only)
 __device__ __forceinline__ bool tf_zeroed(const DomainParams &P, int g, int j) { return zero_zones(P, g, j) != 0u; }
 
+// computeTimeDerivativesDerived at one interior cell (ideal2F.cpp:30-96) [+ EICThermalization]: k[0..13]
+template <bool FAST>
+__device__ __forceinline__ void tf_rhs(const DomainParams &P, const TfArgs &A, int r, int j, size_t off, double *k)
+{
+    const double *ivxp = A.vel[0], *ivyp = A.vel[1], *evxp = A.vel[2], *evyp = A.vel[3];       // = i_mom_x / i_rho etc. (ideal2F.cpp:123-126), formed once per cell
+    // transportDivergence2D (derivs.cpp:216-220) of rho, mom_x, mom_y, thermal_energy of each species: x term + y term
+    double tix[4], tiy[4], tex[4], tey[4];
+    tf_T4<FAST>(P, A.S[F_IRHO], A.S[F_IMX], A.S[F_IMY], A.S[F_IE], ivxp, 0, r, j, tix);
+    tf_T4<FAST>(P, A.S[F_IRHO], A.S[F_IMX], A.S[F_IMY], A.S[F_IE], ivyp, 1, r, j, tiy);
+    tf_T4<FAST>(P, A.S[F_ERHO], A.S[F_EMX], A.S[F_EMY], A.S[F_EE], evxp, 0, r, j, tex);
+    tf_T4<FAST>(P, A.S[F_ERHO], A.S[F_EMX], A.S[F_EMY], A.S[F_EE], evyp, 1, r, j, tey);
+    auto TDi = [&](int v) { const int k_ = v == F_IRHO ? 0 : v == F_IMX ? 1 : v == F_IMY ? 2 : 3; return tix[k_] + tiy[k_]; };
+    auto TDe = [&](int v) { const int k_ = v == F_ERHO ? 0 : v == F_EMX ? 1 : v == F_EMY ? 2 : 3; return tex[k_] + tey[k_]; };
+    auto Dpl = [&](const double *pl, int index) { return tf_D<FAST>(P, pl, nullptr, 1.0, index, r, j); };
+    const double i_rho = A.S[F_IRHO][off], e_rho = A.S[F_ERHO][off];
+    const double i_n = ddiv(i_rho, P.m_i, P.rm_i), e_n = ddiv(e_rho, A.m_e, A.rm_e);
+    const double ivx = ivxp[off], ivy = ivyp[off], evx = evxp[off], evy = evyp[off];
+    const double bz = A.S[F_BZ][off], Ex = A.S[F_EX][off], Ey = A.S[F_EY][off];
+    const double gx = A.st[S_GX][off], gy = A.st[S_GY][off];
+    const double ip_c = A.S[F_IE][off] * P.gm1, ep_c = A.S[F_EE][off] * P.gm1;
+    // Lorentz forces, ideal2F.cpp:42-52
+    const double icx = ivy * bz, icy = (ivx * -1.0) * bz, ecx = evy * bz, ecy = (evx * -1.0) * bz;
+    const double iFx = (i_n * kE) * (Ex + icx / kC), iFy = (i_n * kE) * (Ey + icy / kC);
+    const double eFx = (e_n * -kE) * (Ex + ecx / kC), eFy = (e_n * -kE) * (Ey + ecy / kC);
+    k[F_IRHO] = TDi(F_IRHO) * -1.0;                                                                 // :39
+    k[F_ERHO] = TDe(F_ERHO) * -1.0;                                                                 // :40
+    k[F_IMX] = (((TDi(F_IMX) * -1.0) - tf_D<FAST>(P, A.S[F_IE], nullptr, P.gm1, 0, r, j)) + i_rho * gx) + iFx;   // :54-56
+    k[F_IMY] = (((TDi(F_IMY) * -1.0) - tf_D<FAST>(P, A.S[F_IE], nullptr, P.gm1, 1, r, j)) + i_rho * gy) + iFy;   // :57-59
+    k[F_EMX] = (((TDe(F_EMX) * -1.0) - tf_D<FAST>(P, A.S[F_EE], nullptr, P.gm1, 0, r, j)) + e_rho * gx) + eFx;   // :60-62
+    k[F_EMY] = (((TDe(F_EMY) * -1.0) - tf_D<FAST>(P, A.S[F_EE], nullptr, P.gm1, 1, r, j)) + e_rho * gy) + eFy;   // :63-65
+    k[F_IE] = (TDi(F_IE) * -1.0) - ip_c * (Dpl(ivxp, 0) + Dpl(ivyp, 1));                           // :67-68
+    k[F_EE] = (TDe(F_EE) * -1.0) - ep_c * (Dpl(evxp, 0) + Dpl(evyp, 1));                           // :69-70
+    const double jx = (i_n * kE) * ivx - (e_n * kE) * evx, jy = (i_n * kE) * ivy - (e_n * kE) * evy;   // :128-129
+    if (A.curl_terms) {                                                                             // :75-80
+        k[F_EX] = Dpl(A.S[F_BZ], 1) * kC - jx * (4. * kPI);
+        k[F_EY] = Dpl(A.S[F_BZ], 0) * -kC - jy * (4. * kPI);
+        k[F_EZ] = (tf_D<FAST>(P, A.st[S_BEY], A.S[F_BY], 1.0, 0, r, j) - tf_D<FAST>(P, A.st[S_BEX], A.S[F_BX], 1.0, 1, r, j)) * kC;
+        k[F_BX] = Dpl(A.S[F_EZ], 1) * -kC;
+        k[F_BY] = Dpl(A.S[F_EZ], 0) * kC;
+        k[F_BZ] = (Dpl(A.S[F_EX], 1) - Dpl(A.S[F_EY], 0)) * kC;
+    } else {                                                                                        // :83-88
+        k[F_EX] = (jx * (4. * kPI)) * -1.0;
+        k[F_EY] = (jy * (4. * kPI)) * -1.0;
+    }
+    if (A.eic) {                                                                                    // eic_thermalization.cpp:27-44
+        const double n = i_n, Te = (A.S[F_EE][off] * P.gm1) / (e_n * kKB);                          // n = i_n (ideal2F.cpp:145), e_temp :134
+        const double a = cbrt((3. / 4. / kPI) / n);                     // std::pow(x, 1./3.) to ~4e-16 relative (module held to 1e-9)
+        const double w_pe = sqrt(n * (4. * kPI * kE * kE / A.m_e));
+        const double Gam = ((kE * kE / kKB) / Te) / a;
+        const double g15 = Gam * sqrt(Gam);                              // Gam^(3/2), within 1.5 ulp of std::pow
+        const double Lam = (1. / sqrt(3.)) / g15;
+        const double gam_ei = ((g15 * sqrt(2. / 3. / kPI)) * w_pe) * log(Lam);
+        const double nu_ei = gam_ei * (2. * A.m_e / P.m_i);
+        const double dE = nu_ei * (A.S[F_EE][off] - A.S[F_IE][off]);
+        k[F_EE] = k[F_EE] - dE;                    // mask = 1 here
+        k[F_IE] = k[F_IE] + dE;
+    }
+
+}
+
 __global__ void __launch_bounds__(128) k_2f_stage(const __grid_constant__ DomainParams P, const __grid_constant__ TfArgs A)
 {
     if (*A.done_ptr) return;
@@ -138,59 +208,8 @@ __global__ void __launch_bounds__(128) k_2f_stage(const __grid_constant__ Domain
 #pragma unroll
         for (int v = 0; v < NEV2; v++) k[v] = 0.0;
         if (interior) {
-            const double *ivxp = A.vel[0], *ivyp = A.vel[1], *evxp = A.vel[2], *evyp = A.vel[3];       // = i_mom_x / i_rho etc. (ideal2F.cpp:123-126), formed once per cell
-            // transportDivergence2D (derivs.cpp:216-220) of rho, mom_x, mom_y, thermal_energy of each species: x term + y term
-            double tix[4], tiy[4], tex[4], tey[4];
-            tf_T4(P, A.S[F_IRHO], A.S[F_IMX], A.S[F_IMY], A.S[F_IE], ivxp, 0, r, j, tix);
-            tf_T4(P, A.S[F_IRHO], A.S[F_IMX], A.S[F_IMY], A.S[F_IE], ivyp, 1, r, j, tiy);
-            tf_T4(P, A.S[F_ERHO], A.S[F_EMX], A.S[F_EMY], A.S[F_EE], evxp, 0, r, j, tex);
-            tf_T4(P, A.S[F_ERHO], A.S[F_EMX], A.S[F_EMY], A.S[F_EE], evyp, 1, r, j, tey);
-            auto TDi = [&](int v) { const int k_ = v == F_IRHO ? 0 : v == F_IMX ? 1 : v == F_IMY ? 2 : 3; return tix[k_] + tiy[k_]; };
-            auto TDe = [&](int v) { const int k_ = v == F_ERHO ? 0 : v == F_EMX ? 1 : v == F_EMY ? 2 : 3; return tex[k_] + tey[k_]; };
-            auto Dpl = [&](const double *pl, int index) { return tf_D(P, pl, nullptr, 1.0, index, r, j); };
-            const double i_rho = A.S[F_IRHO][off], e_rho = A.S[F_ERHO][off];
-            const double i_n = ddiv(i_rho, P.m_i, P.rm_i), e_n = ddiv(e_rho, A.m_e, A.rm_e);
-            const double ivx = ivxp[off], ivy = ivyp[off], evx = evxp[off], evy = evyp[off];
-            const double bz = A.S[F_BZ][off], Ex = A.S[F_EX][off], Ey = A.S[F_EY][off];
-            const double gx = A.st[S_GX][off], gy = A.st[S_GY][off];
-            const double ip_c = A.S[F_IE][off] * P.gm1, ep_c = A.S[F_EE][off] * P.gm1;
-            // Lorentz forces, ideal2F.cpp:42-52
-            const double icx = ivy * bz, icy = (ivx * -1.0) * bz, ecx = evy * bz, ecy = (evx * -1.0) * bz;
-            const double iFx = (i_n * kE) * (Ex + icx / kC), iFy = (i_n * kE) * (Ey + icy / kC);
-            const double eFx = (e_n * -kE) * (Ex + ecx / kC), eFy = (e_n * -kE) * (Ey + ecy / kC);
-            k[F_IRHO] = TDi(F_IRHO) * -1.0;                                                                 // :39
-            k[F_ERHO] = TDe(F_ERHO) * -1.0;                                                                 // :40
-            k[F_IMX] = (((TDi(F_IMX) * -1.0) - tf_D(P, A.S[F_IE], nullptr, P.gm1, 0, r, j)) + i_rho * gx) + iFx;   // :54-56
-            k[F_IMY] = (((TDi(F_IMY) * -1.0) - tf_D(P, A.S[F_IE], nullptr, P.gm1, 1, r, j)) + i_rho * gy) + iFy;   // :57-59
-            k[F_EMX] = (((TDe(F_EMX) * -1.0) - tf_D(P, A.S[F_EE], nullptr, P.gm1, 0, r, j)) + e_rho * gx) + eFx;   // :60-62
-            k[F_EMY] = (((TDe(F_EMY) * -1.0) - tf_D(P, A.S[F_EE], nullptr, P.gm1, 1, r, j)) + e_rho * gy) + eFy;   // :63-65
-            k[F_IE] = (TDi(F_IE) * -1.0) - ip_c * (Dpl(ivxp, 0) + Dpl(ivyp, 1));                           // :67-68
-            k[F_EE] = (TDe(F_EE) * -1.0) - ep_c * (Dpl(evxp, 0) + Dpl(evyp, 1));                           // :69-70
-            const double jx = (i_n * kE) * ivx - (e_n * kE) * evx, jy = (i_n * kE) * ivy - (e_n * kE) * evy;   // :128-129
-            if (A.curl_terms) {                                                                             // :75-80
-                k[F_EX] = Dpl(A.S[F_BZ], 1) * kC - jx * (4. * kPI);
-                k[F_EY] = Dpl(A.S[F_BZ], 0) * -kC - jy * (4. * kPI);
-                k[F_EZ] = (tf_D(P, A.st[S_BEY], A.S[F_BY], 1.0, 0, r, j) - tf_D(P, A.st[S_BEX], A.S[F_BX], 1.0, 1, r, j)) * kC;
-                k[F_BX] = Dpl(A.S[F_EZ], 1) * -kC;
-                k[F_BY] = Dpl(A.S[F_EZ], 0) * kC;
-                k[F_BZ] = (Dpl(A.S[F_EX], 1) - Dpl(A.S[F_EY], 0)) * kC;
-            } else {                                                                                        // :83-88
-                k[F_EX] = (jx * (4. * kPI)) * -1.0;
-                k[F_EY] = (jy * (4. * kPI)) * -1.0;
-            }
-            if (A.eic) {                                                                                    // eic_thermalization.cpp:27-44
-                const double n = i_n, Te = (A.S[F_EE][off] * P.gm1) / (e_n * kKB);                          // n = i_n (ideal2F.cpp:145), e_temp :134
-                const double a = cbrt((3. / 4. / kPI) / n);                     // std::pow(x, 1./3.) to ~4e-16 relative (module held to 1e-9)
-                const double w_pe = sqrt(n * (4. * kPI * kE * kE / A.m_e));
-                const double Gam = ((kE * kE / kKB) / Te) / a;
-                const double g15 = Gam * sqrt(Gam);                              // Gam^(3/2), within 1.5 ulp of std::pow
-                const double Lam = (1. / sqrt(3.)) / g15;
-                const double gam_ei = ((g15 * sqrt(2. / 3. / kPI)) * w_pe) * log(Lam);
-                const double nu_ei = gam_ei * (2. * A.m_e / P.m_i);
-                const double dE = nu_ei * (A.S[F_EE][off] - A.S[F_IE][off]);
-                k[F_EE] = k[F_EE] - dE;                    // mask = 1 here
-                k[F_IE] = k[F_IE] + dE;
-            }
+            if (A.fast && tf_no_wrap(P, r, j)) tf_rhs<true>(P, A, r, j, off, k);
+            else tf_rhs<false>(P, A, r, j, off, k);
         }
         if (A.kmode == KM_STORE_K1 || A.kmode == KM_EXPORT) {
 #pragma unroll

@@ -666,20 +666,22 @@ struct PvArgs {
     double coeff, dt, half;                         // half = 0.5 for the RK2 half step (e, mom stay untouched), 1.0 otherwise
     int heating_on, force_on, gc, final_stage;
     unsigned long long *red;                        // count mode: red[0] = min timescale
+    int fast;                                       // deep-interior cells take the FAST instances (SPRUCE_FAST_INTERIOR, default on; same results bit for bit)
 };
 struct PvPoint { double dxv[3], dyv[3], t25, b[3], cg; };
 
+template <bool FAST = false>
 __device__ __noinline__ void pv_point(const DomainParams &P, const PvArgs &A, int a, int b, PvPoint &o)
 {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        auto V = [&](int x, int y) { return rd(P, A.v[k], x, y); };
-        o.dxv[k] = Dx(P, V, a, b);
-        o.dyv[k] = Dy(P, V, a, b);
-        o.b[k] = rd(P, A.bh[k], a, b);
+        auto V = [&](int x, int y) { return rdT<FAST>(P, A.v[k], x, y); };
+        o.dxv[k] = Dx<FAST>(P, V, a, b);
+        o.dyv[k] = Dy<FAST>(P, V, a, b);
+        o.b[k] = rdT<FAST>(P, A.bh[k], a, b);
     }
-    o.t25 = pow25(rd(P, A.T, a, b));
-    o.cg = rd(P, A.cg, a, b);
+    o.t25 = pow25(rdT<FAST>(P, A.T, a, b));
+    o.cg = rdT<FAST>(P, A.cg, a, b);
 }
 // same_factor_off_diag (physicalviscosity.cpp:90-93)
 __device__ __forceinline__ double pv_sfo(const PvPoint &p)
@@ -694,18 +696,12 @@ __device__ __forceinline__ double pv_d3(const AxisTab &t, int i, double lo, doub
     return ddiv(up - dn, t.d[i], t.rd[i]);
 }
 
-__global__ void __launch_bounds__(128) k_pv_stage(const __grid_constant__ DomainParams P, const __grid_constant__ PvArgs A)
+// heating rate and viscous force at one cell (computeHeating :47-64, computeViscousForce :82-140)
+template <bool FAST>
+__device__ __forceinline__ void pv_cell(const DomainParams &P, const PvArgs &A, int r, int j, bool in, double mask, double &heating, double *force)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (j >= P.ny) return;
-    const size_t off = (size_t)r * P.pitch + j;
-    const bool in = is_interior(P, r, j);
-    const double mask = in ? 1.0 : 0.0;
-    const double rho = A.n[off] * P.m_i;
-    double heating = 0.0, force[3] = {0.0, 0.0, 0.0};
     PvPoint c;
-    pv_point(P, A, r, j, c);
+    pv_point<FAST>(P, A, r, j, c);
     if (A.heating_on && A.coeff != 0.0) {                                                          // computeHeating :47-64
         const double X = ((c.b[0] * (c.b[0] * c.dxv[0] + c.b[1] * c.dyv[0]) + c.b[1] * (c.b[0] * c.dxv[1] + c.b[1] * c.dyv[1]))
                           + c.b[2] * (c.b[0] * c.dxv[2] + c.b[1] * c.dyv[2])) - (c.dxv[0] + c.dyv[1]) / 3.0;
@@ -713,20 +709,20 @@ __global__ void __launch_bounds__(128) k_pv_stage(const __grid_constant__ Domain
     }
     if (A.force_on && in) {                                                                        // computeViscousForce :82-140 (zero outside: mask)
         PvPoint xm, xp, ym, yp;
-        pv_point(P, A, r - 1, j, xm); pv_point(P, A, r + 1, j, xp);
-        pv_point(P, A, r, j - 1, ym); pv_point(P, A, r, j + 1, yp);
+        pv_point<FAST>(P, A, r - 1, j, xm); pv_point<FAST>(P, A, r + 1, j, xp);
+        pv_point<FAST>(P, A, r, j - 1, ym); pv_point<FAST>(P, A, r, j + 1, yp);
         const PvPoint *lo[2] = {&xm, &ym}, *hi[2] = {&xp, &yp};
         const double sfo_c = pv_sfo(c), sfo_lo[2] = {pv_sfo(xm), pv_sfo(ym)}, sfo_hi[2] = {pv_sfo(xp), pv_sfo(yp)};
         const double sfd = c.b[0] * (c.b[0] * c.dxv[0]) + c.b[1] * (c.b[1] * c.dyv[1]);             // same_factor_diag :94-95
-        auto BX = [&](int x, int y) { return rd(P, A.bh[0], x, y); };
-        auto BY = [&](int x, int y) { return rd(P, A.bh[1], x, y); };
-        auto VX = [&](int x, int y) { return rd(P, A.v[0], x, y); };
-        auto VY = [&](int x, int y) { return rd(P, A.v[1], x, y); };
-        const double dxbx = Dx(P, BX, r, j), dybx = Dy(P, BX, r, j), dxby = Dx(P, BY, r, j), dyby = Dy(P, BY, r, j);
+        auto BX = [&](int x, int y) { return rdT<FAST>(P, A.bh[0], x, y); };
+        auto BY = [&](int x, int y) { return rdT<FAST>(P, A.bh[1], x, y); };
+        auto VX = [&](int x, int y) { return rdT<FAST>(P, A.v[0], x, y); };
+        auto VY = [&](int x, int y) { return rdT<FAST>(P, A.v[1], x, y); };
+        const double dxbx = Dx<FAST>(P, BX, r, j), dybx = Dy<FAST>(P, BX, r, j), dxby = Dx<FAST>(P, BY, r, j), dyby = Dy<FAST>(P, BY, r, j);
         // grad_b_terms_diag :96-101; derivative1D(del_y_v_y,0) and derivative1D(del_x_v_x,1) from the neighbours' derivatives
         const double gbd[2] = {
-            ((((c.b[0] * 2.0) * dxbx) * c.dxv[0] + (c.b[0] * c.b[0]) * D2x(P, VX, r, j)) + ((c.b[1] * 2.0) * dxby) * c.dyv[1]) + (c.b[1] * c.b[1]) * pv_d3(P.tx, r, xm.dyv[1], c.dyv[1], xp.dyv[1]),
-            ((((c.b[0] * 2.0) * dybx) * c.dxv[0] + (c.b[0] * c.b[0]) * pv_d3(P.ty, j, ym.dxv[0], c.dxv[0], yp.dxv[0])) + ((c.b[1] * 2.0) * dyby) * c.dyv[1]) + (c.b[1] * c.b[1]) * D2y(P, VY, r, j)};
+            ((((c.b[0] * 2.0) * dxbx) * c.dxv[0] + (c.b[0] * c.b[0]) * D2x<FAST>(P, VX, r, j)) + ((c.b[1] * 2.0) * dxby) * c.dyv[1]) + (c.b[1] * c.b[1]) * pv_d3(P.tx, r, xm.dyv[1], c.dyv[1], xp.dyv[1]),
+            ((((c.b[0] * 2.0) * dybx) * c.dxv[0] + (c.b[0] * c.b[0]) * pv_d3(P.ty, j, ym.dxv[0], c.dxv[0], yp.dxv[0])) + ((c.b[1] * 2.0) * dyby) * c.dyv[1]) + (c.b[1] * c.b[1]) * D2y<FAST>(P, VY, r, j)};
 #pragma unroll
         for (int jj = 0; jj < 3; jj++) {
             double res = 0.0;
@@ -744,6 +740,20 @@ __global__ void __launch_bounds__(128) k_pv_stage(const __grid_constant__ Domain
             force[jj] = A.gc ? res * (mask * -3.0) : res * ((c.cg * -3.0) * mask);                                         // :132-136
         }
     }
+}
+
+__global__ void __launch_bounds__(128, 4) k_pv_stage(const __grid_constant__ DomainParams P, const __grid_constant__ PvArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    const bool in = is_interior(P, r, j);
+    const double mask = in ? 1.0 : 0.0;
+    const double rho = A.n[off] * P.m_i;
+    double heating = 0.0, force[3] = {0.0, 0.0, 0.0};
+    if (A.fast && deep_interior(P, r, j)) pv_cell<true>(P, A, r, j, in, mask, heating, force);
+    else pv_cell<false>(P, A, r, j, in, mask, heating, force);
     const double hs = A.half;
     double e1 = A.e[off], T1 = A.T[off];
     if (A.heating_on) {                                                                            // :176-185 / :214-218

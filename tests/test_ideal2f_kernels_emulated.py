@@ -45,7 +45,7 @@ def assemble():
     body, n = re.subn(r"(\w+)<<<(.+?), (\w+), 0, d->stream>>>\(", r"launch3(\1, \2, \3, ", body)
     assert n >= 8 and "<<<" not in body
     domain = DOMAIN.replace("struct OneFluid2E;", "struct OneFluid2E;\nstruct TwoFluid;").replace(
-        "OneFluid2E *e2 = nullptr;", "OneFluid2E *e2 = nullptr; TwoFluid *tf = nullptr; double *scratch_out = nullptr; bool is_setup = false, any_ucnp = false, any_primary_ghost = false;")
+        "OneFluid2E *e2 = nullptr;", "OneFluid2E *e2 = nullptr; TwoFluid *tf = nullptr; double *scratch_out = nullptr; bool is_setup = false, any_ucnp = false, any_primary_ghost = false, fast_interior = true;")
     return "".join([PRELUDE, '#include "ideal2f_sides.cuh"\nnamespace spruce {\n',
                     cut(mk, "constexpr int HALO", "enum { KM_NONE", include_end=True),
                     cut(mk, "__device__ __forceinline__ FaceGeom load_face_geom", "// is global row g / column j inside"),
