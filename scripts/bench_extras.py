@@ -59,15 +59,18 @@ def mode_single(tmp):
     from spruce_b200 import synthetic
     out = {}
     n, steps = 1024, 100
-    s = synthetic.orszag_tang(n, n)
-    state = tmp / "ot.state"
-    write_state(state, s)
-    w1 = run_binary(state, tmp / "a", 1)
-    wk = run_binary(state, tmp / "b", 1 + steps)
-    out["dropin_binary_e2e"] = {
-        "workload": "OT-%d through spruce_b200/bin/run: parse %.0f MB of .state text, set up, %d RK2 steps, write end.state + mhd.out" % (n, state.stat().st_size / 1e6, 1 + steps),
-        "wall_s": wk, "wall_s_one_step_job": w1, "value": n * n * (1 + steps) / wk, "unit": "cell-updates/s",
-        "stepping_only_value": n * n * steps / max(wk - w1, 1e-9), "note": "stepping_only = wall(%d steps) - wall(1 step): what remains of the job is text I/O and set-up" % (1 + steps)}
+    try:
+        s = synthetic.orszag_tang(n, n)
+        state = tmp / "ot.state"
+        write_state(state, s)
+        w1 = run_binary(state, tmp / "a", 1)
+        wk = run_binary(state, tmp / "b", 1 + steps)
+        out["dropin_binary_e2e"] = {
+            "workload": "OT-%d through spruce_b200/bin/run: parse %.0f MB of .state text, set up, %d RK2 steps, write end.state + mhd.out" % (n, state.stat().st_size / 1e6, 1 + steps),
+            "wall_s": wk, "wall_s_one_step_job": w1, "value": n * n * (1 + steps) / wk, "unit": "cell-updates/s",
+            "stepping_only_value": n * n * steps / max(wk - w1, 1e-9), "note": "stepping_only = wall(%d steps) - wall(1 step): what remains of the job is text I/O and set-up" % (1 + steps)}
+    except Exception as e:
+        out["dropin_binary_e2e"] = {"error": repr(e)[:300]}
     # the secondary device paths, as shipped and with the general (wrapping, range-testing) stencil instances for every cell: what the FAST instances buy
     for key, env in (("secondary_paths_2048", {}), ("secondary_paths_2048_general_instances", {"SPRUCE_FAST_INTERIOR": "0"})):
         try:
