@@ -351,11 +351,11 @@ def run_ours(args):
                 marker.unlink(missing_ok=True)
             dist.barrier(); torch.cuda.synchronize()
             if rank == 0:
-                result["extras"] = extras_subprocess("ranks", world, 180)
+                result["extras"] = extras_subprocess("ranks", world, 330)
                 marker.write_text("done")
             else:
                 t_wait = time.perf_counter()
-                while not marker.exists() and time.perf_counter() - t_wait < 240:
+                while not marker.exists() and time.perf_counter() - t_wait < 400:
                     time.sleep(0.2)
         if rank == 0:
             emit(args, result, world)
@@ -439,7 +439,7 @@ def run_ours(args):
         except Exception as e:                    # the additional measurements must never cost the bench line itself
             extra = {"extra_error": repr(e)[:300]}
         torch.cuda.synchronize()
-        extra["extras"] = extras_subprocess("single", 1, 300)
+        extra["extras"] = extras_subprocess("single", 1, 420)
 
     # ---- CPU baseline on the host cores (bounded sample)
     cpu = None

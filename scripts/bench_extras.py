@@ -55,6 +55,32 @@ def run_binary(state, out, steps, gpus=1, out_every=-1, timeout=120):
     return wall
 
 
+def clean_env():
+    """the environment without the variables of an enclosing torchrun (this script runs below a rank of one)"""
+    drop = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT",
+            "OMP_NUM_THREADS")
+    return {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC_") and not k.startswith("TORCH_NCCL_")}
+
+
+def conduction_workload(n_gpus, size, steps, limit_s):
+    """BASELINE.json configs[4] / SURVEY 8d cfg-C (MHD + thermal conduction) through bench.py's own --workload mhd_tc leg, as a bounded side measurement"""
+    cmd = [sys.executable]
+    if n_gpus > 1:
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n_gpus), "--master-addr", "127.0.0.1", "--master-port", "29873"]
+    cmd += [str(ROOT / "bench.py"), "--gpus", str(n_gpus), "--steps", str(steps), "--warmup", "3", "--workload", "mhd_tc", "--size", str(size), "--no-extra", "--no-cpu-baseline"]
+    try:
+        r = subprocess.run(cmd, cwd=str(ROOT), env=clean_env(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=limit_s)
+        lines = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"error": "rc %s: %s" % (r.returncode, r.stderr.decode(errors="replace")[-300:])}
+        l = json.loads(lines[-1])
+        return {"workload": l["config"]["workload"], "n_gpus": l["n_gpus"], "size": size, "steps": steps, "value": l["value"], "unit": l["unit"], "ms_per_step": l["ms_per_step"],
+                "thermal_conduction_subcycles_last_step": l["config"].get("thermal_conduction_subcycles_last_step"), "e2e_value": (l.get("e2e") or {}).get("value"),
+                "parity_vs_1gpu": l.get("parity_vs_1gpu")}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def mode_single(tmp):
     from spruce_b200 import synthetic
     out = {}
@@ -71,13 +97,13 @@ def mode_single(tmp):
             "stepping_only_value": n * n * steps / max(wk - w1, 1e-9), "note": "stepping_only = wall(%d steps) - wall(1 step): what remains of the job is text I/O and set-up" % (1 + steps)}
     except Exception as e:
         out["dropin_binary_e2e"] = {"error": repr(e)[:300]}
+    out["conduction_workload_4096"] = conduction_workload(1, 4096, 10, 150)
     # the secondary device paths, as shipped and with the general (wrapping, range-testing) stencil instances for every cell: what the FAST instances buy
-    for key, env in (("secondary_paths_2048", {}), ("secondary_paths_2048_general_instances", {"SPRUCE_FAST_INTERIOR": "0"})):
-        try:
-            r = subprocess.run([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], cwd=str(ROOT), env=dict(os.environ, **env), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
-            out[key] = json.loads(r.stdout.decode()) if r.returncode == 0 else {"error": r.stderr.decode(errors="replace")[-300:]}
-        except Exception as e:
-            out[key] = {"error": repr(e)[:300]}
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=150)
+        out["secondary_paths_2048"] = json.loads(r.stdout.decode()) if r.returncode == 0 else {"error": r.stderr.decode(errors="replace")[-300:]}
+    except Exception as e:
+        out["secondary_paths_2048"] = {"error": repr(e)[:300]}
     return out
 
 
@@ -97,6 +123,17 @@ def mode_ranks(tmp, n_gpus):
                                     "what": "spruce_b200/bin/run -g N (one forked rank per GPU, slabs along x, peer-store halo exchange, output gathered on rank 0) vs the same binary on one GPU"}}
 
 
+def mode_ranks_all(tmp, n_gpus):
+    out = {}
+    try:
+        out.update(mode_ranks(tmp, n_gpus))
+    except Exception as e:
+        out["dropin_binary_ranks"] = {"error": repr(e)[:300]}
+    # cfg-C: 16384^2 needs the memory of >= 4 GPUs' slabs to stay small next to the enclosing run's; 8192^2 below that
+    out["conduction_workload"] = conduction_workload(n_gpus, 16384 if n_gpus >= 4 else 8192, 5, 170)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", required=True, choices=["single", "ranks"])
@@ -104,7 +141,7 @@ def main():
     a = ap.parse_args()
     with tempfile.TemporaryDirectory(prefix="spruce_extras_") as d:
         try:
-            out = mode_single(Path(d)) if a.mode == "single" else mode_ranks(Path(d), a.gpus)
+            out = mode_single(Path(d)) if a.mode == "single" else mode_ranks_all(Path(d), a.gpus)
         except Exception as e:
             out = {"error": repr(e)[:400]}
     print(json.dumps(out))

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Throughput of the secondary paths on one GPU (device-timed): two-fluid RK2 step, MHD + thermal conduction, MHD + physical viscosity.
+"""Throughput of the secondary paths on one GPU (device-timed): two-fluid RK2 step, MHD + thermal conduction, MHD + physical viscosity -- each as shipped
+and (key suffix " [general instances]") with SPRUCE_FAST_INTERIOR=0, i.e. the wrapping, range-testing stencil instances for every cell.
 usage: module_perf.py [size]"""
-import json, sys, time
+import json, os, sys, time
 import numpy as np
 import torch
 sys.path.insert(0, ".")
@@ -21,12 +22,14 @@ def timed(dom, steps):
     return e0.elapsed_time(e1) / steps
 
 s = synthetic.ucnp_cloud(n + 1, n + 1, drift=2.0e3, bfield=5.0)
-d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False), xb=("open_ucnp",) * 2, yb=("open_ucnp",) * 2,
-                 integrator="rk2", density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
-d.set_eic_thermalization()
-ms = timed(d, 10)
-out["ideal_2F+eic rk2 %d^2" % (n + 1)] = dict(ms_per_step=ms, cell_updates_per_s=(n + 1) ** 2 / ms * 1e3, hbm_frac=(n + 1) ** 2 * 624 / (ms * 1e-3) / 6551.4e9)
-d.close()
+for fast in ("1", "0"):
+    os.environ["SPRUCE_FAST_INTERIOR"] = fast                      # read by spruce_domain_create
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_2F", eqs_options=dict(use_sub_cycling=False), xb=("open_ucnp",) * 2, yb=("open_ucnp",) * 2,
+                     integrator="rk2", density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1e-30)
+    d.set_eic_thermalization()
+    ms = timed(d, 10)
+    out["ideal_2F+eic rk2 %d^2%s" % (n + 1, "" if fast == "1" else " [general instances]")] = dict(ms_per_step=ms, cell_updates_per_s=(n + 1) ** 2 / ms * 1e3, hbm_frac=(n + 1) ** 2 * 624 / (ms * 1e-3) / 6551.4e9)
+    d.close()
 
 KW = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator="rk2", epsilon=0.2, density_min=1.0, temp_min=1.0, thermal_energy_min=1e-30)
 s = synthetic.orszag_tang(n, n, temp_mod=0.1)
@@ -34,13 +37,17 @@ for name, setup in (("mhd only", lambda d: None),
                     ("mhd + thermal_conduction (unsaturated, euler)", lambda d: d.set_thermal_conduction(flux_saturation=False, integrator="euler", epsilon=0.1, dt_subcycle_min=1.0e-4)),
                     ("mhd + thermal_conduction (saturated, rk2)", lambda d: d.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4)),
                     ("mhd + physical_viscosity (euler)", lambda d: d.set_physical_viscosity(np.full((n, n), 4.0e-18), coeff=4.0e-18, epsilon=0.2))):
-    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **KW)
-    setup(d)
-    ms = timed(d, 10)
-    e = dict(ms_per_step=ms, cell_updates_per_s=n * n / ms * 1e3)
-    for k in ("thermal_conduction", "physical_viscosity"):
-        if k.split("_")[0] in name.replace("thermal", "thermal_conduction").replace("physical", "physical_viscosity") and k in name:
-            e["subcycles_last_step"] = d.subcycles(k)
-    out["%s %d^2" % (name, n)] = e
-    d.close()
+    for fast in ("1", "0"):
+        if fast == "0" and name == "mhd only":
+            continue
+        os.environ["SPRUCE_FAST_INTERIOR"] = fast
+        d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **KW)
+        setup(d)
+        ms = timed(d, 10)
+        e = dict(ms_per_step=ms, cell_updates_per_s=n * n / ms * 1e3)
+        for k in ("thermal_conduction", "physical_viscosity"):
+            if k.split("_")[0] in name.replace("thermal", "thermal_conduction").replace("physical", "physical_viscosity") and k in name:
+                e["subcycles_last_step"] = d.subcycles(k)
+        out["%s %d^2%s" % (name, n, "" if fast == "1" else " [general instances]")] = e
+        d.close()
 print(json.dumps(out, indent=1))
