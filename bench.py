@@ -351,7 +351,7 @@ def run_ours(args):
                 marker.unlink(missing_ok=True)
             dist.barrier(); torch.cuda.synchronize()
             if rank == 0:
-                result["extras"] = extras_subprocess("ranks", world, 330)
+                result["extras"] = extras_subprocess("ranks", world, 360)
                 marker.write_text("done")
             else:
                 t_wait = time.perf_counter()
@@ -439,7 +439,7 @@ def run_ours(args):
         except Exception as e:                    # the additional measurements must never cost the bench line itself
             extra = {"extra_error": repr(e)[:300]}
         torch.cuda.synchronize()
-        extra["extras"] = extras_subprocess("single", 1, 420)
+        extra["extras"] = extras_subprocess("single", 1, 450)
 
     # ---- CPU baseline on the host cores (bounded sample)
     cpu = None

@@ -11,6 +11,7 @@ No reference code and nothing under oracle/ is used here."""
 import argparse
 import json
 import os
+import signal
 import subprocess
 import sys
 import tempfile
@@ -24,6 +25,18 @@ sys.path.insert(0, str(ROOT))
 RUN = ROOT / "spruce_b200" / "bin" / "run"
 DOMAIN_GRIDS = ["d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z"]
 STATE_VARS = ["rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
+
+
+def run_bounded(cmd, limit_s, env=None):
+    """subprocess in its own process group; on a timeout the whole group goes (a torchrun launcher would otherwise leave its workers on the GPUs)"""
+    p = subprocess.Popen(cmd, cwd=str(ROOT), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=limit_s)
+    except subprocess.TimeoutExpired:
+        os.killpg(p.pid, signal.SIGKILL)
+        p.communicate()
+        raise RuntimeError("%s ... did not finish within %d s" % (" ".join(cmd[:4]), limit_s))
+    return p.returncode, out, err
 
 
 def write_state(path, s):
@@ -43,15 +56,14 @@ def config(steps, out_every=-1):
             "open_boundary_decay_base = 0.5\nepsilon = 0.2\ndensity_min = 1.0\ntemp_min = 1.0\nthermal_energy_min = 1.0e-30\noutput_flags = rho, temp, mom_x, mom_y, bi_x, bi_y, dt\n") % (steps, out_every)
 
 
-def run_binary(state, out, steps, gpus=1, out_every=-1, timeout=120):
+def run_binary(state, out, steps, gpus=1, out_every=-1, timeout=40):
     out.mkdir(parents=True, exist_ok=True)
     (out / "run.config").write_text(config(steps, out_every))
     t0 = time.perf_counter()
-    r = subprocess.run([str(RUN), "-m", "input", "-o", str(out), "-s", str(state)] + (["-g", str(gpus)] if gpus > 1 else []),
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    rc, _, err = run_bounded([str(RUN), "-m", "input", "-o", str(out), "-s", str(state)] + (["-g", str(gpus)] if gpus > 1 else []), timeout)
     wall = time.perf_counter() - t0
-    if r.returncode not in (-6, 134) or b"successfully reached" not in r.stderr:          # a completed run ends with abort(), like the reference (evolution.cpp:54-56)
-        raise RuntimeError("run rc=%s: %s" % (r.returncode, r.stderr.decode(errors="replace")[-400:]))
+    if rc not in (-6, 134) or b"successfully reached" not in err:          # a completed run ends with abort(), like the reference (evolution.cpp:54-56)
+        raise RuntimeError("run rc=%s: %s" % (rc, err.decode(errors="replace")[-400:]))
     return wall
 
 
@@ -69,10 +81,10 @@ def conduction_workload(n_gpus, size, steps, limit_s):
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n_gpus), "--master-addr", "127.0.0.1", "--master-port", "29873"]
     cmd += [str(ROOT / "bench.py"), "--gpus", str(n_gpus), "--steps", str(steps), "--warmup", "3", "--workload", "mhd_tc", "--size", str(size), "--no-extra", "--no-cpu-baseline"]
     try:
-        r = subprocess.run(cmd, cwd=str(ROOT), env=clean_env(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=limit_s)
-        lines = [ln for ln in r.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
+        rc, so, se = run_bounded(cmd, limit_s, env=clean_env())
+        lines = [ln for ln in so.decode(errors="replace").splitlines() if ln.startswith("{")]
         if not lines:
-            return {"error": "rc %s: %s" % (r.returncode, r.stderr.decode(errors="replace")[-300:])}
+            return {"error": "rc %s: %s" % (rc, se.decode(errors="replace")[-300:])}
         l = json.loads(lines[-1])
         return {"workload": l["config"]["workload"], "n_gpus": l["n_gpus"], "size": size, "steps": steps, "value": l["value"], "unit": l["unit"], "ms_per_step": l["ms_per_step"],
                 "thermal_conduction_subcycles_last_step": l["config"].get("thermal_conduction_subcycles_last_step"), "e2e_value": (l.get("e2e") or {}).get("value"),
@@ -89,8 +101,8 @@ def mode_single(tmp):
         s = synthetic.orszag_tang(n, n)
         state = tmp / "ot.state"
         write_state(state, s)
-        w1 = run_binary(state, tmp / "a", 1)
-        wk = run_binary(state, tmp / "b", 1 + steps)
+        w1 = run_binary(state, tmp / "a", 1, timeout=60)
+        wk = run_binary(state, tmp / "b", 1 + steps, timeout=60)
         out["dropin_binary_e2e"] = {
             "workload": "OT-%d through spruce_b200/bin/run: parse %.0f MB of .state text, set up, %d RK2 steps, write end.state + mhd.out" % (n, state.stat().st_size / 1e6, 1 + steps),
             "wall_s": wk, "wall_s_one_step_job": w1, "value": n * n * (1 + steps) / wk, "unit": "cell-updates/s",
@@ -100,8 +112,8 @@ def mode_single(tmp):
     out["conduction_workload_4096"] = conduction_workload(1, 4096, 10, 150)
     # the secondary device paths, as shipped and with the general (wrapping, range-testing) stencil instances for every cell: what the FAST instances buy
     try:
-        r = subprocess.run([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=150)
-        out["secondary_paths_2048"] = json.loads(r.stdout.decode()) if r.returncode == 0 else {"error": r.stderr.decode(errors="replace")[-300:]}
+        rc, so, se = run_bounded([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], 150)
+        out["secondary_paths_2048"] = json.loads(so.decode()) if rc == 0 else {"error": se.decode(errors="replace")[-300:]}
     except Exception as e:
         out["secondary_paths_2048"] = {"error": repr(e)[:300]}
     return out
