@@ -109,3 +109,24 @@ def test_host_resident_modules_and_too_many_ranks_are_refused(stub, tmp_path):
         p = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state), "-g", str(n)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
         err = p.stderr.decode()
         assert p.returncode == 1 and msg in err and "successfully reached" not in err and "stopping the other ranks" in err, err[-1500:]
+
+
+def test_continue_mode_on_two_ranks_appends_like_one_rank(stub, tmp_path):
+    """-m continue -g 2: every rank reads end.state (the time included), rank 0 appends to mhd.out; same files and the same exit status (SIGABRT on success) as one rank"""
+    s = synthetic.stratified_loop(22, 18)
+    state = tmp_path / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, max_iterations=3, integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "open"), duration=100.0)
+    outs = {}
+    for tag, g in (("one", []), ("two", ["-g", "2"])):
+        out = tmp_path / ("out_" + tag)
+        out.mkdir()
+        (out / "run.config").write_text(cfg)
+        env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / ("log_" + tag)))
+        for args in (["-m", "input", "-o", str(out), "-s", str(state)], ["-m", "continue", "-o", str(out), "-d", "1.0"]):
+            r = subprocess.run([str(OURS)] + args + g, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+            assert r.returncode in (-6, 134) and "successfully reached" in r.stderr.decode(), r.stderr.decode()[-1500:]
+        outs[tag] = out
+    assert (outs["one"] / "end.state").read_bytes() == (outs["two"] / "end.state").read_bytes()
+    a, b = (outs["one"] / "mhd.out").read_text(), (outs["two"] / "mhd.out").read_text()
+    assert a.count("\nt=") == b.count("\nt=") == 6 and [ln for ln in a.splitlines() if ln.startswith("t=")] == [ln for ln in b.splitlines() if ln.startswith("t=")]
