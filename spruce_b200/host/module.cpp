@@ -5,6 +5,7 @@
 #include "sgfilter.hpp"
 #include "tracer.hpp"
 #include "ucnp_modules.hpp"
+#include "viscosity_profile.hpp"
 #include "plasmadomain.hpp"
 #include "utils.hpp"
 #include <cmath>
@@ -454,31 +455,10 @@ void Viscosity::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std
 // viscosity.cpp:278-325, gaussian and exp shapes (the elliptical shapes are not ported); host libm, static profile
 Grid Viscosity::getBoundaryViscosity(double strength, double length) const
 {
-    const Grid &x = m_pd.m_grids[PlasmaDomain::pos_x], &y = m_pd.m_grids[PlasmaDomain::pos_y];
-    const size_t nx = m_pd.xdim(), ny = m_pd.ydim();
-    double x_min = x(0, 0), x_max = x(0, 0), y_min = y(0, 0), y_max = y(0, 0);
-    for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
-        x_min = std::min(x_min, x(i, j)); x_max = std::max(x_max, x(i, j)); y_min = std::min(y_min, y(i, j)); y_max = std::max(y_max, y(i, j));
-    }
-    // viscosity.cpp:90-93 defaults to gaussian; the *_elliptical shapes (viscosity.cpp:305-319) are not ported: refused, not approximated
-    SPRUCE_REQUIRE(m_boundary_falloff_shape.empty() || m_boundary_falloff_shape == "gaussian" || m_boundary_falloff_shape == "exp",
-                   "boundary_falloff_shape <" + m_boundary_falloff_shape + "> of artificial_viscosity is not ported to the B200 path (gaussian and exp are)");
-    const bool gauss = (m_boundary_falloff_shape.empty() || m_boundary_falloff_shape == "gaussian");
-    Grid result = Grid::Zero(nx, ny);
-    for (size_t i = 0; i < nx; i++) for (size_t j = 0; j < ny; j++) {
-        const double xv = x(i, j), yv = y(i, j);
-        double r = 0.0;
-        if (gauss) {
-            const double a[4] = {(xv - x_min) / length, (xv - x_max) / length, (yv - y_max) / length, (yv - y_min) / length};
-            for (double q : a) r = r + std::exp((q * q) * -2.3) * strength;
-        } else {
-            r = r + std::exp(((xv - x_min) * -2.3) / length) * strength;
-            r = r + std::exp(((xv - x_max) * 2.3) / length) * strength;
-            r = r + std::exp(((yv - y_max) * 2.3) / length) * strength;
-            r = r + std::exp(((yv - y_min) * -2.3) / length) * strength;
-        }
-        result(i, j) = (strength < r) ? strength : r;
-    }
+    Grid result;
+    const std::string shape = m_boundary_falloff_shape.empty() ? "gaussian" : m_boundary_falloff_shape;          // viscosity.cpp:90-93 defaults to gaussian
+    if (!boundaryViscosityProfile(m_pd.m_grids[PlasmaDomain::pos_x], m_pd.m_grids[PlasmaDomain::pos_y], strength, length, shape, result))      // viscosity_profile.hpp
+        spruce_die("boundary_falloff_shape <" + shape + "> in Viscosity module not recognized");
     return result;
 }
 // viscosity.cpp:37-110
@@ -490,7 +470,8 @@ void Viscosity::setupModule()
     const size_t n = opt.size();
     SPRUCE_REQUIRE(n > 0 && str.size() == n && diff.size() == n && evol.size() == n && len.size() == n && spec.size() == n, "every viscosity list must have one entry per term");
     if (m_boundary_falloff_shape.empty()) m_boundary_falloff_shape = "gaussian";
-    SPRUCE_REQUIRE(m_boundary_falloff_shape == "gaussian" || m_boundary_falloff_shape == "exp", "Invalid boundary falloff shape given for Viscosity module (gaussian and exp are ported)");
+    SPRUCE_REQUIRE(m_boundary_falloff_shape == "gaussian" || m_boundary_falloff_shape == "exp" || m_boundary_falloff_shape == "exp_elliptical" || m_boundary_falloff_shape == "gaussian_elliptical",
+                   "Invalid boundary falloff shape given for Viscosity module");
     no_file_output(m_any_output, "artificial_viscosity");
     PlasmaDomain::check(spruce_module_viscosity(m_pd.device(), integrator_id(m_hv_time_integrator, "Viscosity"), m_hv_epsilon, m_gradient_correction));
     for (size_t i = 0; i < n; i++) {

@@ -109,25 +109,41 @@ def module_kwargs(name, kv):
     raise KeyError(name)
 
 
-def boundary_viscosity_profile(pos_x, pos_y, strength, length):
-    """Viscosity::getBoundaryViscosity, gaussian shape (reference source/modules/viscosity.cpp:278-325), with the host libm --
-    a static profile the reference also builds on the host."""
+def boundary_viscosity_profile(pos_x, pos_y, strength, length, shape="gaussian"):
+    """Viscosity::getBoundaryViscosity (reference source/modules/viscosity.cpp:278-325) for its four shapes -- gaussian, exp, exp_elliptical,
+    gaussian_elliptical --, with the host libm: a static profile the reference also builds on the host."""
     import math
     ex = np.vectorize(math.exp)
     x_min, x_max, y_min, y_max = pos_x.min(), pos_x.max(), pos_y.min(), pos_y.max()
     r = np.zeros_like(pos_x)
-    for a in ((pos_x - x_min), (pos_x - x_max), (pos_y - y_max), (pos_y - y_min)):
-        q = a / length
-        r = r + ex((q * q) * -2.3) * strength
+    if shape == "gaussian":
+        for a in ((pos_x - x_min), (pos_x - x_max), (pos_y - y_max), (pos_y - y_min)):
+            q = a / length
+            r = r + ex((q * q) * -2.3) * strength
+    elif shape == "exp":
+        for a, c in (((pos_x - x_min), -2.3), ((pos_x - x_max), 2.3), ((pos_y - y_max), 2.3), ((pos_y - y_min), -2.3)):
+            r = r + ex((a * c) / length) * strength
+    else:
+        kind, ell = shape.split("_")
+        assert ell == "elliptical" and kind in ("exp", "gaussian")
+        xc, yc = 0.5 * (x_min + x_max), 0.5 * (y_min + y_max)
+        s = ((pos_x - xc) * (pos_x - xc)) / math.pow(x_max - xc, 2.0) + ((pos_y - yc) * (pos_y - yc)) / math.pow(y_max - yc, 2.0)      # :309-310
+        s_length = length / min(x_max - xc, y_max - yc)
+        m = np.minimum(s - 1.0, 0.0)
+        if kind == "exp":
+            r = ex((m * 2.3) / s_length) * strength
+        else:
+            q = m / s_length
+            r = ex((q * q) * -2.3) * strength
     return np.where(strength < r, strength, r)
 
 
-def viscosity_terms_with_profiles(planes, terms):
+def viscosity_terms_with_profiles(planes, terms, shape="gaussian"):
     out = []
     for tm in terms:
         tm = dict(tm)
         if tm["opt"] in ("boundary", "boundary_global"):
-            tm["strength_grid"] = boundary_viscosity_profile(planes["pos_x"], planes["pos_y"], tm["strength"], tm["length"])
+            tm["strength_grid"] = boundary_viscosity_profile(planes["pos_x"], planes["pos_y"], tm["strength"], tm["length"], shape)
         out.append(tm)
     return out
 

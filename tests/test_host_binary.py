@@ -66,7 +66,12 @@ CASES["ucnp_coulomb_explosion"] = (lambda: synthetic.ucnp_cloud_mhd(83, 79, drif
                                    modules=[("coulomb_explosion", [("timescale", "1.0e-6"), ("lengthscale", "0.2"), ("strength", "1.0e-3"), ("output_to_file", "true")])]), True)
 CASES["ucnp_global_temperature"] = (lambda: synthetic.ucnp_cloud_mhd(45, 41, drift=20.0), dict(integrator="rk4", max_iterations=6, iter_output_interval=3, **UCNP_KW,
                                     modules=[("global_temperature", [("gt_species", "i"), ("gt_strength", "3.7"), ("gt_use_diffusion", "true")])]), True)
-FIRST_RUN_AT_ROUND_END = {"loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature"}
+# the elliptical boundary profiles of artificial_viscosity (viscosity.cpp:306-319), built by the shell (host/viscosity_profile.hpp) and handed to the device as a plane
+CASES["loop_viscosity_elliptical"] = (lambda: synthetic.stratified_loop(40, 36), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "fixed"), max_iterations=5, iter_output_interval=1, write_precision=17,
+                                      modules=[("artificial_viscosity", [("visc_opt", "boundary,boundary"), ("visc_strength", "0.8,2.0"), ("visc_vars_to_diff", "v_x,temp"),
+                                                                         ("visc_vars_to_evol", "mom_x,thermal_energy"), ("visc_length", "9.0e8,1.2e9"), ("visc_species", "i,i"),
+                                                                         ("hv_time_integrator", "rk2"), ("boundary_falloff_shape", "exp_elliptical")])]), True)
+FIRST_RUN_AT_ROUND_END = {"loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))

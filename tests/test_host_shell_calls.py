@@ -254,7 +254,7 @@ def test_ucnp_host_modules_stage_their_planes_after_every_step(stub, tmp_path):
 def test_unported_names_are_refused(stub, tmp_path):
     s = synthetic.stratified_loop(16, 14)
     for block, msg in (([("no_such_module", [])], "no_such_module"), ([("artificial_viscosity", [("visc_opt", "boundary"), ("visc_strength", "0.5"), ("visc_vars_to_diff", "v_x"), ("visc_vars_to_evol", "mom_x"),
-                                                                                                  ("visc_length", "1.0e8"), ("visc_species", "i"), ("boundary_falloff_shape", "exp_elliptical")])], "falloff shape")):
+                                                                                                  ("visc_length", "1.0e8"), ("visc_species", "i"), ("boundary_falloff_shape", "hexagonal")])], "falloff shape")):
         cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), max_iterations=1, iter_output_interval=1, modules=block)
         state = tmp_path / ("in_%s.state" % msg.replace(" ", "_"))
         refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])

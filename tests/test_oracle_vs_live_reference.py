@@ -111,6 +111,14 @@ MODULE_SETS = [
                    ("thermal_conduction", dict(flux_saturation="false", epsilon="0.1", dt_subcycle_min="1.0e-4"))], ("periodic", "periodic"), ("reflect", "fixed"), "rk4"),
     ("av_mixed", [("artificial_viscosity", dict(visc_opt="global,local,boundary", visc_strength="0.4,2.2,0.7", visc_vars_to_diff="v_x,v_y,temp", visc_vars_to_evol="mom_x,mom_y,thermal_energy",
                                                 visc_length="0,0,6.0e8", visc_species="i,i,i", hv_time_integrator="rk4", gradient_correction="true"))], ("fixed", "open"), ("reflect", "open"), "rk2"),
+    # the other three shapes of Viscosity::getBoundaryViscosity (viscosity.cpp:296-319): the profile restatement of tests/golden_util.py, which the host shell's is held to
+    ("av_boundary_exp", [("artificial_viscosity", dict(visc_opt="boundary,boundary_global", visc_strength="0.9,1.6", visc_vars_to_diff="v_x,temp", visc_vars_to_evol="mom_x,thermal_energy",
+                                                       visc_length="5.0e8,7.0e8", visc_species="i,i", boundary_falloff_shape="exp"))], ("fixed", "fixed"), ("fixed", "open"), "euler"),
+    ("av_boundary_exp_elliptical", [("artificial_viscosity", dict(visc_opt="boundary,local", visc_strength="0.8,0.3", visc_vars_to_diff="v_y,v_x", visc_vars_to_evol="mom_y,mom_x",
+                                                                  visc_length="9.0e8,0", visc_species="i,i", boundary_falloff_shape="exp_elliptical"))], ("reflect", "open"), ("fixed", "fixed"), "rk2"),
+    ("av_boundary_gaussian_elliptical", [("artificial_viscosity", dict(visc_opt="boundary", visc_strength="2.5", visc_vars_to_diff="temp", visc_vars_to_evol="thermal_energy",
+                                                                       visc_length="1.2e9", visc_species="i", boundary_falloff_shape="gaussian_elliptical", hv_time_integrator="rk2"))],
+     ("periodic", "periodic"), ("fixed", "open"), "rk4"),
 ]
 
 
@@ -128,7 +136,7 @@ def test_module_oracle_equals_live_reference(name, modules, xb, yb, integrator):
     for m, kv in modules:
         a = module_kwargs(m, kv)
         if m == "artificial_viscosity":
-            o.set_viscosity(viscosity_terms_with_profiles(s["planes"], a.pop("terms")), **a)
+            o.set_viscosity(viscosity_terms_with_profiles(s["planes"], a.pop("terms"), kv.get("boundary_falloff_shape", "gaussian")), **a)
         elif m == "physical_viscosity":
             ramp = a.pop("ramp_length"); a.pop("buffer_length")
             o.set_physical_viscosity(physical_viscosity_coefficient(s["planes"], a["coeff"], ramp), **a)
