@@ -1,7 +1,7 @@
 // viscosity_profile.hpp -- Viscosity::getBoundaryViscosity of the reference (source/modules/viscosity.cpp:278-325) on host Grids: the static strength profile of a
 // `boundary` / `boundary_global` term of artificial_viscosity, for its four shapes.  Built on the host with the host libm, as the reference builds it, and handed to the
 // device as a plane (spruce_module_viscosity_term).  Same expression order as the reference's Grid arithmetic; tests/test_host_viscosity_profile.py holds it bit for bit
-// to the restatement that tests/test_oracle_vs_live_reference.py pins to live reference runs (all four shapes).
+// to the restatement of the test infrastructure, which is pinned to live runs of the reference binary for all four shapes.
 #pragma once
 #include "grid.hpp"
 #include <algorithm>
