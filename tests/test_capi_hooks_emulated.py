@@ -407,6 +407,38 @@ def test_module_hooks_on_slabs_equal_the_whole_domain(emu, xb, yb, world, which)
     o.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("integ,sat", [("euler", True), ("rk4", False)])
+@pytest.mark.parametrize("xb,yb", [(("periodic", "periodic"), ("fixed", "open")), (("fixed", "open"), ("reflect", "open")), (("reflect", "reflect"), ("periodic", "periodic"))])
+def test_thermal_conduction_on_slabs_equals_the_whole_domain_with_and_without_fast_instances(emu, xb, yb, integ, sat, world):
+    """tc_iterate on 2 and 3 slabs (host threads, halo rows of the temperature plane exchanged after every sub-cycle stage): the thermal energy equals the single-rank
+    run's bit for bit, with the FAST stencil instances on (on a slab every row of a periodic x axis qualifies: the halo rows hold the neighbours' cells) and off."""
+    nx, ny = 27, 22
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", **FLOORS)
+    o.run(2)
+    xl, xu = (0, nx - 1) if xb[0] == "periodic" else (2, nx - 3)
+    yl, yu = (0, ny - 1) if yb[0] == "periodic" else (2, ny - 3)
+    step = 0.2 * float(np.min(o.get("dt")[xl:xu + 1, yl:yu + 1]))
+    code = {"euler": 0, "rk2": 1, "rk4": 2}[integ]
+    # single rank, general instances: the reference point (itself held to the oracle by the tests above)
+    s1, o1, h1, _, _ = make_pair(emu, xb, yb, nx, ny)
+    o1.close()
+    emu.cemu_set_fast_interior(h1, C.c_int(0))
+    dummy = np.zeros((nx, ny))
+    assert emu.cemu_thermal_conduction(h1, C.c_int(int(sat)), C.c_double(1.0), C.c_double(1.0e-4), C.c_int(code), C.c_int(2), C.c_double(step), vp(dummy), vp(dummy.copy())) == 0
+    whole = np.zeros((nx, ny))
+    emu.cemu_get(h1, C.c_int(4), vp(whole))
+    for fast in (1.0, 0.0):
+        hs, cuts, keep = make_slabs(emu, s, o, xb, yb, nx, ny, world)
+        p = np.array([float(sat), 1.0, 1.0e-4, float(code), 2.0, step, fast])
+        assert emu.cemu_run_slabs((C.c_void_p * world)(*hs), C.c_int(world), C.c_int(3), vp(p)) == 0
+        got = gather(emu, hs, cuts, ny, 4)
+        assert same_bits(got, whole), "thermal energy on %d slabs (fast %d): %s" % (world, int(fast), mismatch(got, whole))
+    assert not np.array_equal(whole, o.get("thermal_energy"))
+    o.close()
+
+
 def make_slabs(emu, s, o, xb, yb, nx, ny, world):
     ev = [np.ascontiguousarray(o.get(v)).copy() for v in EV]
     st = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in ST]
