@@ -357,9 +357,11 @@ def run_ours(args):
                 t_wait = time.perf_counter()
                 while not marker.exists() and time.perf_counter() - t_wait < 400:
                     time.sleep(0.2)
+            dist.barrier()                      # every rank has seen the marker: only now may it go
+            if rank == 0:
+                marker.unlink(missing_ok=True)
         if rank == 0:
             emit(args, result, world)
-            marker.unlink(missing_ok=True)
         dist.destroy_process_group()
         return
 
