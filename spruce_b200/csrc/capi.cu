@@ -24,6 +24,7 @@
 
 #include <nvtx3/nvToolsExt.h>
 #include "chunk_plan.hpp"
+#include "host_scan.hpp"
 
 using namespace spruce;
 
@@ -1286,12 +1287,21 @@ int static_slot(const char *name)
     return -1;
 }
 
-int h2d_plane(spruce_domain *d, double *dev, const double *host)
+int h2d_plane_begin(spruce_domain *d, double *dev, const double *host)
 {
     CUDA_TRY(cudaMemcpy2DAsync(dev, d->P.pitch * sizeof(double), host, d->P.ny * sizeof(double), d->P.ny * sizeof(double), d->P.nx,
                                cudaMemcpyHostToDevice, d->stream));
-    CUDA_TRY(cudaStreamSynchronize(d->stream));
     return SPRUCE_OK;
+}
+int h2d_plane_end(spruce_domain *d)
+{
+    CUDA_TRY(cudaStreamSynchronize(d->stream));          // the caller's buffer may be reused once the call returns
+    return SPRUCE_OK;
+}
+int h2d_plane(spruce_domain *d, double *dev, const double *host)
+{
+    const int rc = h2d_plane_begin(d, dev, host);
+    return rc ? rc : h2d_plane_end(d);
 }
 int d2h_plane(spruce_domain *d, double *host, const double *dev)
 {
@@ -1463,28 +1473,32 @@ int spruce_grid_upload(spruce_domain *d, const char *name, const double *host, s
     if (!strcmp(name, "pos_x") || !strcmp(name, "pos_y") || !strcmp(name, "d_x") || !strcmp(name, "d_y")) return SPRUCE_OK; // host-only grids
     if (d->tf) return tf_upload(d, name, host);
     if (d->e2) return e2_upload(d, name, host);
-    {   // zero-plane bookkeeping for the planes whose transport can be skipped exactly
-        const char *tracked[7] = {"mom_z", "bi_z", "be_x", "be_y", "be_z", "grav_x", "grav_y"};
-        for (int b = 0; b < 7; b++) if (!strcmp(name, tracked[b])) {
-            bool nz = false;                         // +-0 only?  OR of the bit patterns in blocks (vectorisable), early exit per block
-            for (size_t k0 = 0; k0 < count && !nz; k0 += 4096) {
-                const size_t k1 = k0 + 4096 < count ? k0 + 4096 : count;
-                unsigned long long acc = 0ULL;
-                for (size_t k = k0; k < k1; k++) { unsigned long long b; memcpy(&b, host + k, sizeof(b)); acc |= b; }
-                nz = (acc << 1) != 0ULL;
-            }
-            if (nz) d->nonzero_mask |= (1u << b); else d->nonzero_mask &= ~(1u << b);
+    // destination first (every name check before any copy is started) ...
+    double *dst = nullptr;
+    const int s = static_slot(name);
+    if (s >= 0) dst = d->stat[s];
+    else {
+        const int var = var_index(name);
+        if (var < 0) return fail(SPRUCE_ERR_ARG, "Variable name <%s> not recognized", name);   // equationset.cpp:181
+        if (var == V_temp) dst = d->scratch_temp;
+        else {
+            const int ev = evolved_slot(var);
+            if (ev < 0) return fail(SPRUCE_ERR_ARG, "<%s> is a derived variable and cannot be uploaded", name);
+            if (ev == E_N) d->raw_rho = true;
+            dst = d->Pset.p[ev];
         }
     }
-    const int s = static_slot(name);
-    if (s >= 0) return h2d_plane(d, d->stat[s], host);
-    const int var = var_index(name);
-    if (var < 0) return fail(SPRUCE_ERR_ARG, "Variable name <%s> not recognized", name);   // equationset.cpp:181
-    if (var == V_temp) return h2d_plane(d, d->scratch_temp, host);
-    const int ev = evolved_slot(var);
-    if (ev < 0) return fail(SPRUCE_ERR_ARG, "<%s> is a derived variable and cannot be uploaded", name);
-    if (ev == E_N) d->raw_rho = true;
-    return h2d_plane(d, d->Pset.p[ev], host);
+    // ... then the copy is started, and while it is in flight the zero-plane bookkeeping scans the host plane (host_scan.hpp): planes whose transport can be
+    // skipped exactly
+    int rc = h2d_plane_begin(d, dst, host);
+    if (rc) return rc;
+    {
+        const char *tracked[7] = {"mom_z", "bi_z", "be_x", "be_y", "be_z", "grav_x", "grav_y"};
+        for (int b = 0; b < 7; b++) if (!strcmp(name, tracked[b])) {
+            if (host_plane_nonzero(host, count)) d->nonzero_mask |= (1u << b); else d->nonzero_mask &= ~(1u << b);
+        }
+    }
+    return h2d_plane_end(d);
 }
 
 int spruce_grid_download(spruce_domain *d, const char *name, double *host, size_t count)
