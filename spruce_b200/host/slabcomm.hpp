@@ -135,8 +135,8 @@ public:
                 std::_Exit(0);
             }
         }
-        int status0 = 0, left = m_n;
-        bool died = false;
+        int status0 = 0, left = m_n, status[SlabShared::kMaxRanks] = {0};
+        bool died = false, unclean[SlabShared::kMaxRanks] = {false};
         while (left > 0) {
             int st = 0;
             const pid_t p = wait(&st);
@@ -145,13 +145,16 @@ public:
             while (r < m_n && pids[r] != p) r++;
             if (r == m_n) continue;
             left--;
+            status[r] = st;
             if (r == 0) status0 = st;
-            const bool clean = finished(r) || (WIFEXITED(st) && WEXITSTATUS(st) == 0);
-            if (!clean && !died) {                                                               // a rank died mid-run: release the others from their barriers
-                died = true;
-                m_sh->failed.store(1);
-                std::fprintf(stderr, "run: rank %d ended early (status 0x%x); stopping the other ranks\n", r, st);
-            }
+            unclean[r] = !(finished(r) || (WIFEXITED(st) && WEXITSTATUS(st) == 0));
+            if (unclean[r] && !died) { died = true; m_sh->failed.store(1); }                     // a rank died mid-run: release the others from their barriers
+        }
+        if (died) {                                                                              // name the rank that failed, not the ones that followed it out (they leave with status 1)
+            int culprit = -1;
+            for (int r = 0; r < m_n && culprit < 0; r++) if (unclean[r] && WIFSIGNALED(status[r])) culprit = r;
+            for (int r = 0; r < m_n && culprit < 0; r++) if (unclean[r]) culprit = r;
+            std::fprintf(stderr, "run: rank %d ended early (status 0x%x); the other ranks were stopped\n", culprit, status[culprit]);
         }
         if (died) return 1;
         if (WIFSIGNALED(status0)) { std::fflush(stderr); signal(WTERMSIG(status0), SIG_DFL); raise(WTERMSIG(status0)); }      // abort-on-success, like the reference

@@ -80,6 +80,8 @@ int spruce_eqs_propagate_changes(spruce_domain *d) { (void)d; LOG("spruce_eqs_pr
 int spruce_next_step_size(spruce_domain *d, double *step) { (void)d; *step = 0.5; return SPRUCE_OK; }
 int spruce_advance(spruce_domain *d, int n, double max_time, double *dt_used, int *done)
 {
+    const char *fr = getenv("SPRUCE_STUB_FAIL_RANK");                /* a rank whose device call fails mid-run (tests/test_host_slab_ranks.py) */
+    if (fr && atoi(fr) == d->cfg.rank && d->iter >= 2) { LOG("spruce_advance FAILS on rank %d", d->cfg.rank); return SPRUCE_ERR_CUDA; }
     int k = 0;
     for (; k < n && d->time < max_time; k++) { double s = 0.5; if (d->time + s > max_time) s = max_time - d->time; d->time += s; d->iter++; if (dt_used) dt_used[k] = s; }
     if (done) *done = k;

@@ -108,7 +108,7 @@ def test_host_resident_modules_and_too_many_ranks_are_refused(stub, tmp_path):
         env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / ("calls_%s.log" % tag)))
         p = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state), "-g", str(n)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
         err = p.stderr.decode()
-        assert p.returncode == 1 and msg in err and "successfully reached" not in err and "stopping the other ranks" in err, err[-1500:]
+        assert p.returncode == 1 and msg in err and "successfully reached" not in err and "the other ranks were stopped" in err, err[-1500:]
 
 
 def test_continue_mode_on_two_ranks_appends_like_one_rank(stub, tmp_path):
@@ -130,3 +130,22 @@ def test_continue_mode_on_two_ranks_appends_like_one_rank(stub, tmp_path):
     assert (outs["one"] / "end.state").read_bytes() == (outs["two"] / "end.state").read_bytes()
     a, b = (outs["one"] / "mhd.out").read_text(), (outs["two"] / "mhd.out").read_text()
     assert a.count("\nt=") == b.count("\nt=") == 6 and [ln for ln in a.splitlines() if ln.startswith("t=")] == [ln for ln in b.splitlines() if ln.startswith("t=")]
+
+
+def test_a_rank_that_dies_mid_run_takes_the_others_down(stub, tmp_path):
+    """rank 1's device call fails after two steps: it aborts with the library's message, the parent releases the other ranks from their barrier (slabcomm.hpp: failure
+    flag) and reports status 1 -- promptly, nobody is left waiting"""
+    import time
+    s = synthetic.stratified_loop(24, 18)
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, max_iterations=6, iter_output_interval=1, integrator="euler", xb=("periodic", "periodic"), yb=("fixed", "open"))
+    state = tmp_path / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+    out = tmp_path / "out"
+    out.mkdir()
+    (out / "run.config").write_text(cfg)
+    env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / "log"), SPRUCE_STUB_FAIL_RANK="1")
+    t0 = time.perf_counter()
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state), "-g", "3"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert time.perf_counter() - t0 < 20.0
+    err = r.stderr.decode()
+    assert r.returncode == 1 and "rank 1 ended early" in err and "successfully reached" not in err, err[-1500:]
