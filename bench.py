@@ -36,6 +36,8 @@ METRIC = "cell-updates/sec at 4096^2 ideal MHD (RK2, FP64)"
 UNIT = "cell-updates/s"
 ALG_BYTES_PER_CELL_STEP = 400.0      # RK2: stage 1 reads 13 planes, writes 8; stage 2 reads 21, writes 8
 FALLBACK_HBM_GBS = 6650.0            # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+T_START = time.perf_counter()
+RUN_BUDGET_S = float(os.environ.get("SPRUCE_BENCH_BUDGET_S", "420"))      # whole bench.py run: the side measurements ("extras") get what the line's own numbers leave of it
 KW = dict(xb=("periodic", "periodic"), yb=("periodic", "periodic"), integrator="rk2", epsilon=0.2,
           density_min=1.0, temp_min=1.0, thermal_energy_min=1.0e-30)
 
@@ -197,9 +199,14 @@ def slab_parity_check(rank, world, local, transport):
     return {"grid": [nx, ny], "steps": steps, "equal": True}
 
 
-def extras_subprocess(mode, gpus, limit_s):
-    """scripts/bench_extras.py in its own process with a time limit: whatever happens there -- a failing kernel, a hang -- the bench line stands."""
-    cmd = [sys.executable, str(ROOT / "scripts" / "bench_extras.py"), "--mode", mode, "--gpus", str(gpus)]
+def extras_subprocess(mode, gpus, limit_s, reserve_s=0.0):
+    """scripts/bench_extras.py in its own process with a time limit: whatever happens there -- a failing kernel, a hang -- the bench line stands.
+    The limit is also cut to what is left of RUN_BUDGET_S (less `reserve_s` for what still follows), so that the whole run stays within minutes; the
+    script gets the same figure and skips the parts that no longer fit."""
+    limit_s = int(min(limit_s, RUN_BUDGET_S - (time.perf_counter() - T_START) - reserve_s))
+    if limit_s < 45:
+        return {"skipped": "no time left in this run's budget of %d s (SPRUCE_BENCH_BUDGET_S)" % RUN_BUDGET_S}
+    cmd = [sys.executable, str(ROOT / "scripts" / "bench_extras.py"), "--mode", mode, "--gpus", str(gpus), "--budget", str(limit_s - 10)]
     try:
         p = subprocess.Popen(cmd, cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, start_new_session=True)
         try:
@@ -351,7 +358,7 @@ def run_ours(args):
                 marker.unlink(missing_ok=True)
             dist.barrier(); torch.cuda.synchronize()
             if rank == 0:
-                result["extras"] = extras_subprocess("ranks", world, 360)
+                result["extras"] = extras_subprocess("ranks", world, 300)
                 marker.write_text("done")
             else:
                 t_wait = time.perf_counter()
@@ -441,7 +448,7 @@ def run_ours(args):
         except Exception as e:                    # the additional measurements must never cost the bench line itself
             extra = {"extra_error": repr(e)[:300]}
         torch.cuda.synchronize()
-        extra["extras"] = extras_subprocess("single", 1, 450)
+        extra["extras"] = extras_subprocess("single", 1, 330, reserve_s=25.0)      # the CPU baseline follows
 
     # ---- CPU baseline on the host cores (bounded sample)
     cpu = None

@@ -27,8 +27,24 @@ DOMAIN_GRIDS = ["d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z"]
 STATE_VARS = ["rho", "temp", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
 
 
+DEADLINE = [float("inf")]               # time.perf_counter() by which this script must have printed its line (--budget)
+
+
+class NoTimeLeft(RuntimeError):
+    pass
+
+
+def remaining(limit_s, least_s=15):
+    """the part's own limit, cut to what is left of the script's budget; a part that would get less than `least_s` is skipped"""
+    left = DEADLINE[0] - time.perf_counter()
+    if left < least_s:
+        raise NoTimeLeft("skipped: %.0f s left of the budget bench.py gave" % max(left, 0.0))
+    return min(limit_s, left)
+
+
 def run_bounded(cmd, limit_s, env=None):
     """subprocess in its own process group; on a timeout the whole group goes (a torchrun launcher would otherwise leave its workers on the GPUs)"""
+    limit_s = remaining(limit_s)
     p = subprocess.Popen(cmd, cwd=str(ROOT), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, start_new_session=True)
     try:
         out, err = p.communicate(timeout=limit_s)
@@ -81,6 +97,7 @@ def conduction_workload(n_gpus, size, steps, limit_s):
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n_gpus), "--master-addr", "127.0.0.1", "--master-port", "29873"]
     cmd += [str(ROOT / "bench.py"), "--gpus", str(n_gpus), "--steps", str(steps), "--warmup", "3", "--workload", "mhd_tc", "--size", str(size), "--no-extra", "--no-cpu-baseline"]
     try:
+        remaining(limit_s, least_s=45)                  # a whole bench.py process: not worth starting with less
         rc, so, se = run_bounded(cmd, limit_s, env=clean_env())
         lines = [ln for ln in so.decode(errors="replace").splitlines() if ln.startswith("{")]
         if not lines:
@@ -109,9 +126,10 @@ def mode_single(tmp):
             "stepping_only_value": n * n * steps / max(wk - w1, 1e-9), "note": "stepping_only = wall(%d steps) - wall(1 step): what remains of the job is text I/O and set-up" % (1 + steps)}
     except Exception as e:
         out["dropin_binary_e2e"] = {"error": repr(e)[:300]}
-    out["conduction_workload_4096"] = conduction_workload(1, 4096, 10, 150)
+    out["conduction_workload_4096"] = conduction_workload(1, 4096, 10, 120)
     # the secondary device paths, as shipped and with the general (wrapping, range-testing) stencil instances for every cell: what the FAST instances buy
     try:
+        remaining(150, least_s=45)
         rc, so, se = run_bounded([sys.executable, str(ROOT / "scripts" / "module_perf.py"), "2048"], 150)
         out["secondary_paths_2048"] = json.loads(so.decode()) if rc == 0 else {"error": se.decode(errors="replace")[-300:]}
     except Exception as e:
@@ -142,7 +160,7 @@ def mode_ranks_all(tmp, n_gpus):
     except Exception as e:
         out["dropin_binary_ranks"] = {"error": repr(e)[:300]}
     # cfg-C: 16384^2 needs the memory of >= 4 GPUs' slabs to stay small next to the enclosing run's; 8192^2 below that
-    out["conduction_workload"] = conduction_workload(n_gpus, 16384 if n_gpus >= 4 else 8192, 5, 170)
+    out["conduction_workload"] = conduction_workload(n_gpus, 16384 if n_gpus >= 4 else 8192, 5, 160)
     return out
 
 
@@ -150,7 +168,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", required=True, choices=["single", "ranks"])
     ap.add_argument("--gpus", type=int, default=2)
+    ap.add_argument("--budget", type=float, default=0.0, help="seconds this script may take in all (0: no limit beyond the parts' own)")
     a = ap.parse_args()
+    if a.budget > 0:
+        DEADLINE[0] = time.perf_counter() + a.budget
     with tempfile.TemporaryDirectory(prefix="spruce_extras_") as d:
         try:
             out = mode_single(Path(d)) if a.mode == "single" else mode_ranks_all(Path(d), a.gpus)

@@ -102,3 +102,25 @@ def test_hashes_do_not_depend_on_the_partition_or_on_the_sign_of_zero():
     b[3, 4] = 1e-300
     assert bench.row_digests(b) != whole
     assert bench.dt_hash([0.1, 0.2]) != bench.dt_hash([0.1, 0.2000000000000001])
+
+
+def test_extras_get_only_what_is_left_of_the_run_budget(monkeypatch):
+    """the side measurements must not stretch the run: with the budget spent they are skipped, otherwise the script is told how long it may take"""
+    import bench
+    monkeypatch.setattr(bench, "RUN_BUDGET_S", 30.0)
+    assert "skipped" in bench.extras_subprocess("single", 1, 330)
+    seen = {}
+
+    class P:
+        pid, returncode = 0, 0
+        def __init__(self, cmd, **kw): seen["cmd"] = cmd
+        def communicate(self, timeout=None):
+            seen["timeout"] = timeout
+            return b'{"ok": 1}\n', b""
+    monkeypatch.setattr(bench, "RUN_BUDGET_S", 1.0e4)
+    monkeypatch.setattr(bench.subprocess, "Popen", P)
+    assert bench.extras_subprocess("single", 1, 330, reserve_s=25.0) == {"ok": 1}
+    assert seen["timeout"] == 330 and seen["cmd"][-2:] == ["--budget", "320"]
+    monkeypatch.setattr(bench, "RUN_BUDGET_S", (bench.time.perf_counter() - bench.T_START) + 125.0)
+    bench.extras_subprocess("single", 1, 330, reserve_s=25.0)
+    assert 95 <= seen["timeout"] <= 100
