@@ -211,7 +211,8 @@ int spruce_eqs_ideal_mhd_moc_limiting(spruce_domain *dom, int b_limiting, double
  * in computeTimeDerivatives -- only false can run, and spruce_eqs_setup refuses true) and remove_curl_terms. */
 int spruce_eqs_ideal2f_options(spruce_domain *dom, int use_sub_cycling, int remove_curl_terms);
 /* EICThermalization (source/modules/ucnp/eic_thermalization.cpp:27-44): electron-ion collisional energy exchange added to the
- * right-hand side of e_thermal_energy / i_thermal_energy.  ideal_2F domains only. */
+ * right-hand side of e_thermal_energy / i_thermal_energy.  ideal_2F and ideal_mhd_2E domains (the equation sets that hold the four grids the module
+ * looks up by name, :12-25: n, e_temp, e_thermal_energy, i_thermal_energy); on ideal_mhd it fails with the reference's message. */
 int spruce_module_eic_thermalization(spruce_domain *dom);
 /* curr_num_subcycles of the last advance: which = "thermal_conduction" | "radiative_losses" */
 int spruce_module_subcycles(spruce_domain *dom, const char *which, int *count);

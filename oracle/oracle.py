@@ -78,6 +78,7 @@ def lib():
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
         L.oracle2e_destroy.argtypes = [C.c_void_p]
+        L.oracle2e_set_eic.argtypes = [C.c_void_p, C.c_int]
         L.oracle2e_plane.argtypes = [C.c_void_p, C.c_int]; L.oracle2e_plane.restype = C.POINTER(C.c_double)
         L.oracle2e_setup.argtypes = [C.c_void_p]
         L.oracle2e_step.argtypes = [C.c_void_p]; L.oracle2e_step.restype = C.c_double
@@ -384,7 +385,7 @@ class Oracle2E:
     """One IdealMHD2E domain (one fluid, separate ion / electron thermal energies) evolved by the C restatement (oracle/ideal_mhd2e_oracle.inc)."""
 
     def __init__(self, planes, ion_mass, adiabatic_index, *, xb=("periodic", "periodic"), yb=("fixed", "fixed"), integrator="rk2", epsilon=0.2,
-                 density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6, open_strength=1.0, open_decay=0.5, setup=True, **_unused):
+                 density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6, open_strength=1.0, open_decay=0.5, setup=True, eic=False, **_unused):
         L = lib()
         nx, ny = planes["rho"].shape
         self.nx, self.ny = nx, ny
@@ -394,6 +395,7 @@ class Oracle2E:
             if name in planes:
                 np.ctypeslib.as_array(L.oracle_plane(self.base, which), shape=(nx, ny))[...] = planes[name]
         self.h = L.oracle2e_create(self.base)
+        L.oracle2e_set_eic(self.h, int(eic))             # eic_thermalization on this equation set (the UCNP configuration: ideal_mhd_2E + eic_thermalization)
         for name, a in planes.items():
             if name in VARS_2E:
                 self.view(name)[...] = a

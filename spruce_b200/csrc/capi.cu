@@ -1962,6 +1962,8 @@ int spruce_module_eic_thermalization(spruce_domain *d)
 {
     CHECK_DOM(d);
     // setupModule looks its grids up by name in the equation set and aborts when one is missing (eic_thermalization.cpp:13-24)
+    // -- ideal_2F and ideal_mhd_2E have all four (n, e_temp, e_thermal_energy, i_thermal_energy), ideal_mhd has no e_temp
+    if (d->e2) { d->e2->g.eic = 1; return SPRUCE_OK; }
     if (!d->tf) return fail(SPRUCE_ERR_ARG, "Grid <e_temp> was not found within the EquationSet.");
     d->tf->eic = 1;
     return SPRUCE_OK;

@@ -31,6 +31,8 @@ enum { Q_RHO2 = 0, Q_MX2, Q_MY2, Q_EI2, Q_EE2, Q_BX2, Q_BY2 };
 enum { BC2_PERIODIC = 0, BC2_OPEN = 1, BC2_FIXED = 2, BC2_REFLECT = 3, BC2_OPEN_MOC = 4, BC2_OPEN_UCNP = 5 };
 constexpr double kPi2 = 3.14159265358979323846;          // source/constants.hpp:16
 constexpr double kKB2 = 1.3807e-16;                      // K_B, source/constants.hpp:8
+constexpr double kE2 = 4.80320425e-10;                   // E (not E_CHARGE), source/constants.hpp:19
+constexpr double kMe2 = 9.1094e-28;                      // M_ELECTRON, source/constants.hpp:9
 
 // Cells are addressed by their GLOBAL (i, j).  On a slab (rows [row0, row0 + nxl) of nx, plus two halo rows on each side) the caller passes plane
 // pointers shifted back by row0 rows and dx shifted back by row0 entries, so that only resident rows are ever touched; with a periodic x axis the
@@ -43,6 +45,7 @@ struct Geo {
     int xl, xu, yl, yu;           // interior bounds (computeIterationBounds, plasmadomain.cpp:138-161)
     int xper, yper;
     double m_i, gamma, n_min, T_min, e_min, open_strength;
+    int eic;                      // eic_thermalization configured (source/modules/ucnp/eic_thermalization.cpp): its term joins the right-hand side
     double scale_1[4], scale_2[4];   // open boundary decay factors per side, pow(open_boundary_decay_base, dist / delta_last) evaluated on the HOST with libm
                                      // exactly as the reference evaluates them (evolution.cpp:163-167); see open_scales()
 };
@@ -159,6 +162,24 @@ E2_HD void rhs_cell(const Geo &g, const CPlanes &S, const Statics &T, int i, int
     k[5] = d1(g, S, T, F_ZE, 1, i, j) + d1(g, S, T, F_ZI, 1, i, j);                                  // curlZ(...)[0] = d/dy   :50-52
     k[6] = (-d1(g, S, T, F_ZE, 0, i, j)) + (-d1(g, S, T, F_ZI, 0, i, j));                            // curlZ(...)[1] = -d/dx  :53
     for (int v = 0; v < NEV2; v++) k[v] = k[v] * 1.0;                                                // the final mask multiply (:56-57) is by 1 in the interior
+    if (g.eic) {
+        // EICThermalization::computeTimeDerivativesModule (eic_thermalization.cpp:27-44), called by EquationSet::computeTimeDerivatives after the set's own
+        // right-hand side (equationset.cpp:204-210): reads n, e_temp and the two thermal energies of the grids being differentiated.  n and e_temp are what
+        // recomputeDerivedVarsFromEvolvedVars left for these (settled) planes, formed as derive_cell forms them.  pow(x, 1./3.) -> cbrt, pow(G, 1.5) -> G sqrt(G)
+        // as in the two-fluid kernel: the module is held to 1e-9, not to the bit.
+        const double n = smax2(rho / g.m_i, g.n_min);
+        const double Te = smax2((gm1 * S.u[Q_EE2][c]) / (kKB2 * n), g.T_min);
+        const double a = cbrt((3. / 4. / kPi2) / n);
+        const double w_pe = sqrt((4. * kPi2 * kE2 * kE2 / kMe2) * n);
+        const double Gam = ((kE2 * kE2 / kKB2) / Te) / a;
+        const double g15 = Gam * sqrt(Gam);
+        const double Lam = (1. / sqrt(3.)) / g15;
+        const double gam_ei = ((sqrt(2. / 3. / kPi2) * g15) * w_pe) * log(Lam);
+        const double nu_ei = (2. * kMe2 / g.m_i) * gam_ei;
+        const double dE = nu_ei * (S.u[Q_EE2][c] - S.u[Q_EI2][c]);
+        k[Q_EE2] = k[Q_EE2] - dE * 1.0;                                                              // -= dEdt * mask, += dEdt * mask (:42-43)
+        k[Q_EI2] = k[Q_EI2] + dE * 1.0;
+    }
 }
 
 // applyTimeDerivatives + enforceMinimums at one cell (equationset.cpp:226-228, idealmhd2E.cpp:60-66): out = floor(base + step*k)

@@ -128,7 +128,7 @@ int e2_ensure_rk4(spruce_domain *d)
 // geometry and parameters of the per-cell functions; the open-boundary decay factors come from the host libm as in the reference
 void e2_geometry(spruce_domain *d)
 {
-    e2::Geo &g = d->e2->g;
+    e2::Geo &g = d->e2->g;                                // (g.eic stays as spruce_module_eic_thermalization left it)
     const spruce_config &c = d->cfg;
     g.nx = d->P.gnx; g.ny = d->P.ny; g.pitch = d->P.pitch;
     g.row0 = d->P.row0; g.nxl = d->P.nx; g.x_halo = (d->P.xper && !d->P.xwrap) ? 1 : 0;

@@ -187,3 +187,23 @@ def ucnp_cloud_mhd(nx: int, ny: int, *, length: float = 1.0, n0: float = 1.0e9, 
         "bi_x": z.copy(), "bi_y": z.copy(), "bi_z": z.copy(), "grav_x": z.copy(), "grav_y": z.copy(),
     }
     return dict(planes=P, ion_mass=M_SR, adiabatic_index=GAMMA)
+
+
+def ucnp_cloud_2e(nx: int, ny: int, *, length: float = 1.0, n0: float = 1.0e9, sigma: float = 0.1, Te: float = 20.0, Ti: float = 1.0, drift: float = 0.0,
+                  bfield: float = 0.0) -> dict:
+    """The UCNP configuration of the one-fluid set with two temperatures (`ideal_mhd_2E` + `eic_thermalization`): the Gaussian Sr+ cloud of
+    ucnp_cloud_mhd with hot electrons and cold ions, both temperatures smoothly varying so that the collisional exchange differs from cell to cell.
+    Planes = the 7 domain grids + IdealMHD2E::state_variables() (reference source/equationsets/idealmhd2E.hpp:27-29)."""
+    s = ucnp_cloud_mhd(nx, ny, length=length, n0=n0, sigma=sigma, drift=drift)
+    P = s["planes"]
+    X, Y = P["pos_x"], P["pos_y"]
+    pl = {k: P[k] for k in ("d_x", "d_y", "pos_x", "pos_y")}
+    z = np.zeros((nx, ny))
+    pl["be_x"], pl["be_y"], pl["be_z"] = z + bfield, z - 0.5 * bfield, z.copy()
+    pl["rho"] = P["rho"]
+    pl["i_temp"] = Ti * (1.0 + 0.2 * np.sin(4.0 * X / length + 0.1) * np.cos(3.0 * Y / length))
+    pl["e_temp"] = Te * (1.0 + 0.3 * np.cos(5.0 * X / length) * np.sin(4.0 * Y / length + 0.3))
+    pl["mom_x"], pl["mom_y"] = P["mom_x"], P["mom_y"]
+    pl["bi_x"], pl["bi_y"] = z + 0.0, 0.2 * bfield * np.cos(3.0 * X / length)
+    pl["grav_x"], pl["grav_y"] = z.copy(), z.copy()
+    return dict(planes=pl, ion_mass=M_SR, adiabatic_index=GAMMA)

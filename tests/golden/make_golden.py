@@ -127,6 +127,8 @@ CASES = {
     # IdealMHD2E (source/equationsets/idealmhd2E.cpp): one fluid, separate ion / electron thermal energies
     "e2_mixed_rk2": ("two_energy", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"), eqs="ideal_mhd_2E", **SOLAR_FLOORS), 8, (1, 8)),
     "e2_pp_ucnp_rk4": ("two_energy", dict(nx=NX, ny=NY), dict(integrator="rk4", xb=PP, yb=UC, eqs="ideal_mhd_2E", **SOLAR_FLOORS), 4, (1, 4)),
+    # the UCNP configuration of that set: ideal_mhd_2E + eic_thermalization on the Sr+ cloud (eic_thermalization.cpp:27-44)
+    "e2_ucnp_eic_rk2": ("ucnp_cloud_2e", dict(nx=NX - 1, ny=NY + 1, drift=20.0, bfield=0.01), dict(integrator="rk2", xb=UC, yb=("open_ucnp", "fixed"), eqs="ideal_mhd_2E", modules=[EIC], **UCNP_FLOORS), 6, (1, 6)),
     # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
     "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
 }

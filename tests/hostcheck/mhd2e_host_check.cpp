@@ -10,6 +10,9 @@
 
 using namespace spruce::e2;
 
+static int g_eic = 0;                                      // eic_thermalization configured for the runs that follow
+extern "C" void mhd2e_host_set_eic(int on) { g_eic = on; }
+
 struct HostExec {
     Geo g;
     Statics T;
@@ -61,6 +64,8 @@ extern "C" int mhd2e_host_run(const double *const *planes_in, const double *dx, 
 {
     HostExec x;
     Geo &g = x.g;
+    g = Geo{};
+    g.eic = g_eic;
     g.dx = dx; g.dy = dy; g.nx = nx; g.ny = ny; g.pitch = ny; g.row0 = 0; g.nxl = nx; g.x_halo = 0;
     for (int s = 0; s < 4; s++) g.bc[s] = bc[s];
     g.xl = bc[0] == BC2_PERIODIC ? 0 : NG; g.xu = bc[1] == BC2_PERIODIC ? nx - 1 : nx - NG - 1;
@@ -196,7 +201,8 @@ extern "C" int mhd2e_host_run_slabs(const double *const *planes_in, const double
     for (int s = 0; s < 4; s++) if (bc[s] == BC2_OPEN || bc[s] == BC2_REFLECT || bc[s] == BC2_FIXED) x.any_wall = true;
     x.g.resize(n_ranks); x.dxl.resize(n_ranks);
     const int H = SlabExec::H, APR = 3;
-    Geo g0;
+    Geo g0{};
+    g0.eic = g_eic;
     g0.dx = dx; g0.dy = dy; g0.nx = nx; g0.ny = ny; g0.pitch = ny; g0.row0 = 0; g0.nxl = nx; g0.x_halo = 0;
     for (int s = 0; s < 4; s++) g0.bc[s] = bc[s];
     g0.xl = bc[0] == BC2_PERIODIC ? 0 : NG; g0.xu = bc[1] == BC2_PERIODIC ? nx - 1 : nx - NG - 1;

@@ -467,6 +467,55 @@ def test_ideal_mhd_2e_vs_oracle(xb, yb, integ, nx, ny, loop, nmin):
     assert "ok" in out
 
 
+E2_EIC_CODE = """
+    import numpy as np
+    from oracle.oracle import EVOLVED_2E, Oracle2E
+    from spruce_b200 import synthetic
+    from spruce_b200.domain import PlasmaDomain
+    xb, yb, integ, nx, ny, drift, bfield = {xb!r}, {yb!r}, {integ!r}, {nx}, {ny}, {drift!r}, {bfield!r}
+    s = synthetic.ucnp_cloud_2e(nx, ny, drift=drift, bfield=bfield)
+    kw = dict(xb=xb, yb=yb, integrator=integ, density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], eic=True, **kw)
+    plain = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], equation_set="ideal_mhd_2E", **kw)
+    d.set_eic_thermalization()
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+    k_dev, k_ref = d.computeTimeDerivatives(), o.rhs()
+    for i, nm in enumerate(EVOLVED_2E):
+        assert rel(k_dev[i], k_ref[i]) <= 1e-9, "d(%s)/dt: %.3e" % (nm, rel(k_dev[i], k_ref[i]))
+    ref = np.array([o.step() for _ in range(6)])
+    for _ in range(6):
+        plain.step()
+    dts = np.array(d.advance(6))
+    assert np.max(np.abs(dts - ref) / ref) <= 1e-9, (dts, ref)
+    for v in EVOLVED_2E + ["dt", "e_temp", "i_temp", "n"]:
+        assert rel(d.grid(v), o.get(v)) <= 1e-9, "%s: %.3e" % (v, rel(d.grid(v), o.get(v)))
+    for v in ("i_thermal_energy", "e_thermal_energy"):
+        assert rel(d.grid(v), plain.get(v)) > 100 * max(rel(d.grid(v), o.get(v)), 1e-15), "the exchange term is not visible in " + v
+    print("ok")
+"""
+
+
+@pytest.mark.xfail(reason="written after round 2's GPU budget was spent (CPU-checked: tests/test_mhd2e_host_check.py, test_mhd2e_kernels_emulated.py); first executed by the round-end run", strict=False)
+@pytest.mark.parametrize("xb,yb,integ,nx,ny,drift,bfield", [
+    (("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 131, 97, 20.0, 0.01),
+    (("fixed", "reflect"), ("open_ucnp", "fixed"), "rk4", 90, 133, 10.0, 0.02),
+    (("periodic", "periodic"), ("periodic", "periodic"), "euler", 140, 66, 0.0, 0.01),
+])
+def test_ideal_mhd_2e_with_eic_thermalization_vs_oracle(xb, yb, integ, nx, ny, drift, bfield):
+    """ideal_mhd_2E + eic_thermalization on the device (the UCNP configuration; Geo::eic in mhd2e_cells.cuh) against the restatement that live reference runs pin bit for
+    bit: right-hand side, step sizes, evolved and derived planes within the module's 1e-9 (cbrt / x sqrt(x) / CUDA log against glibc pow / log), the term visibly acting."""
+    out = run_isolated(E2_EIC_CODE.format(xb=xb, yb=yb, integ=integ, nx=nx, ny=ny, drift=drift, bfield=bfield), {})
+    assert "ok" in out
+
+
+@pytest.mark.xfail(reason="written after round 2's GPU budget was spent; first executed by the round-end run", strict=False)
+def test_ideal_mhd_2e_with_eic_golden_reference_outputs():
+    """the same configuration against a committed fixture of the UNMODIFIED reference binary (tests/golden/e2_ucnp_eic_rk2.npz), <= 1e-9"""
+    out = run_isolated(GOLDEN_CODE.format(name="e2_ucnp_eic_rk2", exact=False), {})
+    assert "ok" in out
+
+
 MOC_LIMIT_CODE = """
     import numpy as np
     from golden_util import same_bits, mismatch

@@ -71,7 +71,10 @@ CASES["loop_viscosity_elliptical"] = (lambda: synthetic.stratified_loop(40, 36),
                                       modules=[("artificial_viscosity", [("visc_opt", "boundary,boundary"), ("visc_strength", "0.8,2.0"), ("visc_vars_to_diff", "v_x,temp"),
                                                                          ("visc_vars_to_evol", "mom_x,thermal_energy"), ("visc_length", "9.0e8,1.2e9"), ("visc_species", "i,i"),
                                                                          ("hv_time_integrator", "rk2"), ("boundary_falloff_shape", "exp_elliptical")])]), True)
-FIRST_RUN_AT_ROUND_END = {"loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
+# the UCNP configuration of the one-fluid, two-temperature set: ideal_mhd_2E + eic_thermalization (eic_thermalization.cpp:27-44 finds all four of its grids in IdealMHD2E)
+CASES["ucnp_mhd2e_eic"] = (lambda: synthetic.ucnp_cloud_2e(41, 37, drift=20.0, bfield=0.01), dict(integrator="rk2", max_iterations=6, iter_output_interval=2, eqs="ideal_mhd_2E", **UCNP_KW,
+                           output_flags=("rho", "i_temp", "e_temp", "i_thermal_energy", "e_thermal_energy", "press", "n", "dt"), modules=[("eic_thermalization", [])]), False)
+FIRST_RUN_AT_ROUND_END = {"ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))

@@ -190,11 +190,13 @@ def test_two_fluid_and_two_energy_sets_select_their_equation_set(stub, tmp_path)
 
     s = synthetic.two_energy(16, 14)
     cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("reflect", "open"), yb=("fixed", "open"), max_iterations=2, iter_output_interval=1, eqs="ideal_mhd_2E",
-                                  output_flags=("rho", "i_temp", "e_temp", "dt"))
+                                  output_flags=("rho", "i_temp", "e_temp", "dt"), modules=[("eic_thermalization", [])])
     (tmp_path / "b").mkdir()
     log, _, _ = run_shell(stub, tmp_path / "b", s, cfg)
     c = args_of(log[0])
     assert c["eqs"] == "2" and c["bc"] == "3,1,2,1" and c["ti"] == "0"
+    calls = [ln.split()[0] for ln in log if ln.startswith("spruce_")]          # the UCNP configuration: ideal_mhd_2E has every grid eic_thermalization looks up
+    assert "spruce_module_eic_thermalization" in calls and calls.index("spruce_module_eic_thermalization") > calls.index("spruce_eqs_setup")
     uploads = {ln.split()[1] for ln in log if ln.startswith("spruce_grid_upload")}
     assert {"rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "grav_x", "grav_y"} <= uploads
 

@@ -27,6 +27,7 @@ def lib():
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(LIB), str(SRC)], check=True)
     L = C.CDLL(str(LIB))
     L.mhd2e_host_run.restype = C.c_int
+    L.mhd2e_host_set_eic(0)
     return L
 
 
@@ -85,3 +86,58 @@ def test_product_mhd2e_slab_steps_equal_oracle(lib, k, xb, yb, integrator, nx, n
     for v, nm in enumerate(EVOLVED_2E):
         assert same_bits(out[v], o.get(nm)), "case %d %d ranks %s: %s" % (k, n_ranks, nm, mismatch(out[v], o.get(nm)))
     o.close()
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+@pytest.mark.parametrize("n_ranks", [1, 2, 3])
+@pytest.mark.parametrize("name,xb,yb,integrator,nx,ny,drift,bfield", [
+    ("ucnp_sides_rk2", ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 27, 25, 20.0, 0.01),
+    ("mixed_walls_rk4", ("fixed", "reflect"), ("open_ucnp", "fixed"), "rk4", 24, 29, 10.0, 0.02),
+    ("periodic_euler", ("periodic", "periodic"), ("periodic", "periodic"), "euler", 22, 21, 0.0, 0.01)])
+def test_product_mhd2e_with_eic_equals_oracle(lib, name, xb, yb, integrator, nx, ny, drift, bfield, n_ranks):
+    """ideal_mhd_2E + eic_thermalization (the UCNP configuration): the product's rhs_cell with Geo::eic set, whole steps on one rank and on slabs, against the
+    restatement that live reference runs pin bit for bit (test_ideal_mhd_2e_with_eic_oracle_equals_live_reference).  The product forms x^(1/3) with cbrt and
+    x^(3/2) with x sqrt(x): held to the module's 1e-9, and the term must have acted (the run without it is further away than that)."""
+    from spruce_b200 import synthetic
+    s = synthetic.ucnp_cloud_2e(nx, ny, drift=drift, bfield=bfield)
+    floors = dict(density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, eic=True, **floors)
+    plain = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 5
+    ref_steps = np.array([o.step() for _ in range(nsteps)])
+    for _ in range(nsteps):
+        plain.step()
+    names = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "be_x", "be_y", "grav_x", "grav_y"]
+    planes = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in names]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    arr = (C.c_void_p * 11)(*[p.ctypes.data for p in planes])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    out = np.zeros((7, nx, ny)); dt = np.zeros((nx, ny)); steps = np.zeros(nsteps); rhs = np.zeros((7, nx, ny))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    common = (arr, vp(dx), vp(dy), C.c_int(nx), C.c_int(ny), bc, C.c_int(TI[integrator]), C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]),
+              C.c_double(0.2), C.c_double(floors["density_min"]), C.c_double(floors["temp_min"]), C.c_double(floors["thermal_energy_min"]),
+              C.c_double(1.0), C.c_double(0.5), C.c_int(nsteps))
+    lib.mhd2e_host_set_eic(1)
+    try:
+        if n_ranks == 1:
+            rc = lib.mhd2e_host_run(*common, vp(out), vp(dt), vp(steps), vp(rhs))
+        else:
+            lib.mhd2e_host_run_slabs.restype = C.c_int
+            rc = lib.mhd2e_host_run_slabs(*common, C.c_int(n_ranks), vp(out), vp(steps))
+    finally:
+        lib.mhd2e_host_set_eic(0)
+    assert rc == 0
+    assert np.max(np.abs(steps - ref_steps) / ref_steps) <= 1e-9
+    for v, nm in enumerate(EVOLVED_2E):
+        assert rel(out[v], o.get(nm)) <= 1e-9, "%s %s: %.3e" % (name, nm, rel(out[v], o.get(nm)))
+    for nm in ("i_thermal_energy", "e_thermal_energy"):
+        v = EVOLVED_2E.index(nm)
+        assert rel(out[v], plain.get(nm)) > 100 * max(rel(out[v], o.get(nm)), 1e-15), "%s: the exchange term is not visible in %s" % (name, nm)
+    if n_ranks == 1:
+        k_ref = o.rhs()
+        for v, nm in enumerate(EVOLVED_2E):
+            assert rel(rhs[v], k_ref[v]) <= 1e-9, "%s d(%s)/dt: %.3e" % (name, nm, rel(rhs[v], k_ref[v]))
+    o.close(); plain.close()

@@ -118,6 +118,7 @@ def emu():
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
     L = C.CDLL(str(LIB))
     L.emu2e_run.restype = C.c_int
+    L.emu2e_set_eic(0)
     return L
 
 
@@ -145,3 +146,46 @@ def test_product_mhd2e_launch_code_runs_whole_steps_equal_to_oracle(emu, k, xb, 
         assert same_bits(out[v], o.get(nm)), "case %d %s: %s" % (k, nm, mismatch(out[v], o.get(nm)))
     assert same_bits(dt, o.get("dt")), "case %d dt: %s" % (k, mismatch(dt, o.get("dt")))
     o.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("name,xb,yb,integrator,nx,ny,drift,bfield", [
+    ("ucnp_sides_rk2", ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 27, 25, 20.0, 0.01),
+    ("mixed_walls_rk4", ("fixed", "reflect"), ("open_ucnp", "fixed"), "rk4", 24, 29, 10.0, 0.02),
+    ("periodic_euler", ("periodic", "periodic"), ("periodic", "periodic"), "euler", 22, 21, 0.0, 0.01)])
+def test_product_mhd2e_launch_code_with_eic_thermalization(emu, name, xb, yb, integrator, nx, ny, drift, bfield, world):
+    """ideal_mhd_2E + eic_thermalization through the product's kernels and launch code (Geo::eic as spruce_module_eic_thermalization sets it), one rank and slabs:
+    within the module's 1e-9 of the restatement that live reference runs pin, and visibly different from the run without the module."""
+    from spruce_b200 import synthetic
+    s = synthetic.ucnp_cloud_2e(nx, ny, drift=drift, bfield=bfield)
+    floors = dict(density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, eic=True, **floors)
+    plain = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, **floors)
+    nsteps = 5
+    ref_steps = np.array([o.step() for _ in range(nsteps)])
+    for _ in range(nsteps):
+        plain.step()
+    names = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "be_x", "be_y", "grav_x", "grav_y"]
+    planes = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in names]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    arr = (C.c_void_p * 11)(*[p.ctypes.data for p in planes])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    out = np.zeros((7, nx, ny)); dt = np.zeros((nx, ny)); steps = np.zeros(nsteps)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.emu2e_set_eic(1)
+    try:
+        rc = emu.emu2e_run(C.c_int(world), arr, vp(dx), vp(dy), C.c_int(nx), C.c_int(ny), bc, C.c_int(TI[integrator]), C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(0.2),
+                           C.c_double(floors["density_min"]), C.c_double(floors["temp_min"]), C.c_double(floors["thermal_energy_min"]), C.c_double(1.0), C.c_double(0.5), C.c_int(nsteps),
+                           vp(out), vp(dt), vp(steps))
+    finally:
+        emu.emu2e_set_eic(0)
+    assert rc == 0
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+    assert np.max(np.abs(steps - ref_steps) / ref_steps) <= 1e-9
+    for v, nm in enumerate(EVOLVED_2E):
+        assert rel(out[v], o.get(nm)) <= 1e-9, "%s %s: %.3e" % (name, nm, rel(out[v], o.get(nm)))
+    assert rel(dt, o.get("dt")) <= 1e-9
+    for nm in ("i_thermal_energy", "e_thermal_energy"):
+        v = EVOLVED_2E.index(nm)
+        assert rel(out[v], plain.get(nm)) > 100 * max(rel(out[v], o.get(nm)), 1e-15), "%s: the exchange term is not visible in %s" % (name, nm)
+    o.close(); plain.close()

@@ -75,7 +75,7 @@ def test_extended_oracle_reproduces_reference(name):
     g = Golden(name)
     if g.equation_set == "ideal_mhd_2E":
         from oracle.oracle import Oracle2E
-        o = Oracle2E(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
+        o = Oracle2E(g.planes, g.ion_mass, g.adiabatic_index, eic=any(m == "eic_thermalization" for m, _ in g.modules), **g.kw)
         for it in range(1, g.n_steps + 1):
             step = o.step()
             assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())

@@ -330,6 +330,37 @@ def test_ideal_mhd_2e_oracle_equals_live_reference(k, xb, yb, integrator, nx, ny
     o.close()
 
 
+E2_EIC_CASES = [
+    # (name, xb, yb, integrator, nx, ny, drift, bfield): the UCNP configuration -- ideal_mhd_2E + eic_thermalization (eic_thermalization.cpp:27-44 looks its four grids up by
+    # name; IdealMHD2E has them all)
+    ("ucnp_sides_rk2", ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 27, 25, 20.0, 0.0),
+    ("mixed_walls_rk4_field", ("fixed", "reflect"), ("open_ucnp", "fixed"), "rk4", 24, 29, 10.0, 2.0),
+    ("periodic_euler", ("periodic", "periodic"), ("periodic", "periodic"), "euler", 22, 21, 0.0, 1.0),
+]
+
+
+@pytest.mark.parametrize("name,xb,yb,integrator,nx,ny,drift,bfield", E2_EIC_CASES, ids=[c[0] for c in E2_EIC_CASES])
+def test_ideal_mhd_2e_with_eic_oracle_equals_live_reference(name, xb, yb, integrator, nx, ny, drift, bfield):
+    """ideal_mhd_2E + eic_thermalization (oracle2e_set_eic): step sizes and every output plane bit for bit (glibc pow / log on both sides); the module must
+    have acted (the run without it differs)."""
+    from oracle.oracle import Oracle2E
+    s = synthetic.ucnp_cloud_2e(nx, ny, drift=drift, bfield=bfield)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    nsteps = 4
+    frames = run_reference(s, dict(kw, eqs="ideal_mhd_2E", modules=[("eic_thermalization", [])]), E2_OUT, nsteps)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], eic=True, **kw)
+    plain = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], **kw)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for it in range(1, nsteps + 1):
+        step = o.step(); plain.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "%s iteration %d: step %s vs %s" % (name, it, step.hex(), float(ref_step).hex())
+    for v in E2_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
+    assert not same_bits(o.get("e_thermal_energy"), plain.get("e_thermal_energy")) and not same_bits(o.get("i_thermal_energy"), plain.get("i_thermal_energy"))
+    o.close(); plain.close()
+
+
 MOC_LIMIT_CASES = [
     ("y2_b_and_mom", ("periodic", "periodic"), ("fixed", "open_moc"), "rk2", 0.0, dict(b_limiting=True, b_lower=0.9, b_upper=1.05, mom_limiting=True, mom_lower=0.5, mom_upper=1.5), 26, 23),
     ("all_sides_mom_visc", ("open_moc", "open_moc"), ("open_moc", "open_moc"), "euler", 0.1, dict(mom_limiting=True, mom_lower=0.8, mom_upper=1.1), 25, 24),
