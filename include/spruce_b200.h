@@ -150,8 +150,8 @@ int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const dou
  * appends to mhd.out -- "thermal_conduction" and "rad" = the module's (e_after - e_before)/dt of the last step, "flux_saturation" = the saturation coefficient
  * of that step's first temperature field (zero planes before the first step, as in the reference).  Enable per module, then download by plane name.
  * Also: module "anomalous_resistivity" -> planes "anomalous_diffusivity", "anomalous_template", "joule_heating" (anomalousresistivity.cpp:320-329), and the
- * plane "field_heating" (fieldheating.cpp:73-80: mask*(dt*heating) of the last step), which needs no enabling.
- * Written after the round-1 GPU budget was spent: compiled, not yet run on a GPU. */
+ * plane "field_heating" (fieldheating.cpp:73-80: mask*(dt*heating) of the last step), which needs no enabling; module "physical_viscosity" -> planes
+ * "viscous_heating", "viscous_force_x" / "_y" / "_z" (physicalviscosity.cpp:292-308: the averages over the last step's sub-cycles, also in inactive_mode). */
 int spruce_module_output_to_file(spruce_domain *dom, const char *module, int on);
 int spruce_module_output(spruce_domain *dom, const char *plane_name, double *host, size_t count);
 /* Pointwise solar source terms applied in postIterateModule (evolution.cpp:74), each followed by propagateChanges.  Gaussian templates

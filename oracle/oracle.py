@@ -76,6 +76,7 @@ def lib():
         L.oracle_sg_filter.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_set_moc_limiting.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_physical_viscosity_iterate.argtypes = [C.c_void_p, C.c_double]
         L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
         L.oracle2e_destroy.argtypes = [C.c_void_p]
         L.oracle2e_set_eic.argtypes = [C.c_void_p, C.c_int]
@@ -236,6 +237,10 @@ class Oracle:
         lib().oracle_anomalous_core(self.h, C.c_double(dt), _dp(out), C.c_int(int(raw_commit)))
         return out
 
+    def physical_viscosity_iterate(self, dt: float):
+        """PhysicalViscosity::iterateModule alone, on the current state"""
+        lib().oracle_physical_viscosity_iterate(self.h, C.c_double(dt))
+
     def anomalous_iterate(self, dt: float):
         """test accessor: one complete iterateModule(dt) of anomalous_resistivity (write-back and propagateChanges included), nothing else"""
         lib().oracle_anomalous_iterate(self.h, C.c_double(dt))
@@ -247,9 +252,11 @@ class Oracle:
         return (ij[0], ij[1]), t
 
     def module_output(self, name: str):
-        """output_to_file plane of thermal_conduction / radiative_losses after the last step ("thermal_conduction", "flux_saturation", "rad"); None before the module ran"""
+        """output_to_file plane of thermal_conduction / radiative_losses / physical_viscosity after the last step ("thermal_conduction", "flux_saturation", "rad",
+        "viscous_heating", "viscous_force_x" / "_y" / "_z"); None before the module ran"""
         out = np.zeros((self.nx, self.ny))
-        ok = lib().oracle_module_output(self.h, {"thermal_conduction": 0, "flux_saturation": 1, "rad": 2}[name], _dp(out))
+        which = {"thermal_conduction": 0, "flux_saturation": 1, "rad": 2, "viscous_heating": 3, "viscous_force_x": 4, "viscous_force_y": 5, "viscous_force_z": 6}[name]
+        ok = lib().oracle_module_output(self.h, which, _dp(out))
         return out if ok else None
 
     def anomalous_diffusivity(self):

@@ -59,6 +59,7 @@ typedef struct {
     double *av_strength_grid[8];  /* boundary options: profile built by the caller (host libm exp) */
     /* physical_viscosity (source/modules/solar/physicalviscosity.hpp) */
     int pv_on, pv_heating_on, pv_force_on, pv_gc, pv_integrator, pv_inactive, pv_nsub; double pv_coeff, pv_epsilon; double *pv_cg;
+    double *pv_avg[4];                  /* output_to_file planes: viscous_heating, viscous_force_x/y/z (physicalviscosity.cpp:151-152,166,170,218,222,292-308) */
     void *anom;                   /* anomalous_resistivity (anomalous_resistivity_oracle.inc); order id 13 */
     void *small[8]; int n_small;  /* small solar modules (solar_small_modules_oracle.inc); order id = 100 + index */
     int order[16]; int n_modules; /* module ids in config order: 1=tc 2=rl 3=ah 4=av 5=pv, 100+k = small module k */
@@ -898,6 +899,7 @@ void oracle_destroy(oracle *o)
     for (int v = 0; v < NV; v++) free(o->g[v]);
     free(o->mod.ah_heating);
     free(o->mod.pv_cg);
+    for (int k = 0; k < 4; k++) free(o->mod.pv_avg[k]);
     free(o);
 }
 /* which: 0 d_x 1 d_y 2 be_x 3 be_y 4 be_z 5 pos_x 6 pos_y 7 mask(read only) ; 100+v equation-set variable v */
@@ -1027,6 +1029,8 @@ void oracle_anomalous_core(oracle *o, double dt, double *out, int raw_commit)
         memcpy(o->g[V_thermal_energy], out + 3 * n, sizeof(double) * n);
     }
 }
+/* test accessor: PhysicalViscosity::iterateModule alone (sub-cycle count, sub-cycles, closing propagateChanges) */
+void oracle_physical_viscosity_iterate(oracle *o, double dt) { pv_iterate(o, dt); }
 void oracle_anomalous_iterate(oracle *o, double dt) { ar_iterate(o, (anom_res *)o->mod.anom, dt); }
 void oracle_anomalous_state(const oracle *o, int *null_ij, double *tmpl)
 {
@@ -1035,10 +1039,11 @@ void oracle_anomalous_state(const oracle *o, int *null_ij, double *tmpl)
     if (tmpl) memcpy(tmpl, A->tmpl, sizeof(double) * o->n);
 }
 void oracle_anomalous_diffusivity(const oracle *o, double *out) { memcpy(out, ((const anom_res *)o->mod.anom)->diffusivity, sizeof(double) * o->n); }
-/* test accessor: output_to_file plane of thermal_conduction / radiative_losses after the last step: 0 thermal_conduction, 1 flux_saturation, 2 rad */
+/* test accessor: output_to_file plane of thermal_conduction / radiative_losses / physical_viscosity after the last step: 0 thermal_conduction, 1 flux_saturation, 2 rad,
+ * 3 viscous_heating, 4-6 viscous_force_x/y/z */
 int oracle_module_output(const oracle *o, int which, double *out)
 {
-    const double *p = which == 0 ? o->mod.tc_avg : which == 1 ? o->mod.tc_sat : o->mod.rl_avg;
+    const double *p = which == 0 ? o->mod.tc_avg : which == 1 ? o->mod.tc_sat : which == 2 ? o->mod.rl_avg : (which >= 3 && which <= 6) ? o->mod.pv_avg[which - 3] : NULL;
     if (!p) return 0;
     memcpy(out, p, sizeof(double) * o->n);
     return 1;

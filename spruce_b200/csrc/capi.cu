@@ -95,7 +95,8 @@ struct spruce_domain {
     enum { MOD_TC = 1, MOD_RL = 2, MOD_AH = 3, MOD_AV = 4, MOD_PV = 5 };
     // physical_viscosity (source/modules/solar/physicalviscosity.cpp)
     struct { double coeff = 0.0, epsilon = 1.0; int heating_on = 1, force_on = 1, gc = 0, integrator = 0, inactive = 0, nsub = 1;
-             double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; bool cg_halo_done = false; } pv;
+             double *cg = nullptr, *v[2][3] = {{nullptr}}, *T[2] = {nullptr}, *bh[3] = {nullptr}; bool cg_halo_done = false;
+             double *avg[4] = {nullptr}; bool output = false; } pv;   // avg: output_to_file planes viscous_heating, viscous_force_x/y/z
     std::vector<int> module_order;                 // MOD_* ; MOD_SRC0 + k = sources[k]
     enum { MOD_SRC0 = 100, MOD_DC = 6, MOD_FH = 7, MOD_BO = 8, MOD_AR = 9 };
     struct { double max_accel = 0.0, dynamic_time = 1.0, target = 0.0, mean = 0.0, accel = 0.0; int boundary = 3, field_aligned = 0, dynamic = 0;
@@ -1059,6 +1060,54 @@ int exchange_planes4(spruce_domain *d, double *a, double *b, double *c, double *
     double *v[NEV] = {a, b, c, e, a, b, c, e};
     return peer_exchange(d, v, nullptr);
 }
+PvArgs pv_args(spruce_domain *d)
+{
+    auto &pv = d->pv;
+    PvArgs A{};
+    for (int k = 0; k < 3; k++) { A.bh[k] = pv.bh[k]; A.mom[k] = d->Pset.p[E_MX + k]; A.v[k] = pv.v[0][k]; }
+    A.T = pv.T[0];
+    A.n = d->Pset.p[E_N]; A.cg = pv.cg; A.e = d->Pset.p[E_E];
+    A.coeff = pv.coeff; A.heating_on = pv.heating_on; A.force_on = pv.force_on; A.gc = pv.gc; A.red = d->red; A.fast = d->fast_interior ? 1 : 0;
+    return A;
+}
+// the sub-cycles of iterateModule (physicalviscosity.cpp:148-245) for pv.nsub sub-cycles, from the velocity / temperature / b_hat planes pv_iterate derived
+int pv_substeps(spruce_domain *d, double dt)
+{
+    int rc;
+    auto &pv = d->pv;
+    PvArgs A = pv_args(d);
+    const dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    const double dts = dt / pv.nsub;
+    if (pv.output) {                                                    // avg_heating / avg_force start every iterate at zero (:151-152)
+        for (int k = 0; k < 4; k++) { A.avg[k] = pv.avg[k]; CUDA_TRY(cudaMemsetAsync(pv.avg[k] - d->row_off, 0, d->plane_doubles * sizeof(double), d->stream)); }
+        A.nsub = (double)pv.nsub;
+    }
+    int cur = 0;
+    auto stage = [&](int from, int to, double half, int final_stage) -> int {
+        for (int k = 0; k < 3; k++) { A.v[k] = pv.v[from][k]; A.v_out[k] = pv.v[to][k]; }
+        A.T = pv.T[from]; A.T_out = pv.T[to]; A.dt = dts; A.half = half; A.final_stage = final_stage;
+        k_pv_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
+        d->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return A.diag_only ? SPRUCE_OK : exchange_planes4(d, pv.v[to][0], pv.v[to][1], pv.v[to][2], pv.T[to]);
+    };
+    if (!pv.inactive && (pv.heating_on || pv.force_on)) {
+        for (int s = 0; s < pv.nsub; s++) {
+            if (pv.integrator == SPRUCE_TI_EULER) { if ((rc = stage(cur, cur ^ 1, 1.0, 1))) return rc; cur ^= 1; }
+            else {                                                      // rk2: half step into the other set, full step back
+                if ((rc = stage(cur, cur ^ 1, 0.5, 0))) return rc;
+                if ((rc = stage(cur ^ 1, cur, 1.0, 1))) return rc;
+            }
+        }
+    } else if (pv.inactive && pv.output && (pv.heating_on || pv.force_on)) {
+        // inactive_mode: the reference still evaluates heating and force in every sub-cycle, for the output planes only (:163-171, :199-223); the state does not
+        // change in between, so one evaluation is added nsub times
+        A.diag_only = 1; A.repeat = pv.nsub;
+        if ((rc = stage(0, 1, 1.0, 1))) return rc;
+    }
+    if ((rc = launch_propagate(d, 0))) return rc;                       // :244
+    return after_module_propagate(d);
+}
 int pv_iterate(spruce_domain *d, double dt)
 {
     int rc;
@@ -1070,42 +1119,17 @@ int pv_iterate(spruce_domain *d, double dt)
         if ((rc = exchange_plane(d, pv.cg))) return rc;
         pv.cg_halo_done = true;
     }
-    PvArgs A{};
-    for (int k = 0; k < 3; k++) { A.bh[k] = pv.bh[k]; A.mom[k] = d->Pset.p[E_MX + k]; }
-    A.n = d->Pset.p[E_N]; A.cg = pv.cg; A.e = d->Pset.p[E_E];
-    A.coeff = pv.coeff; A.heating_on = pv.heating_on; A.force_on = pv.force_on; A.gc = pv.gc; A.red = d->red; A.fast = d->fast_interior ? 1 : 0;
     // computeViscousSubcycles :66-80 -- evaluated here, in iterate, on the state earlier modules have already changed
-    for (int k = 0; k < 3; k++) A.v[k] = pv.v[0][k];
-    A.T = pv.T[0];
+    const PvArgs A = pv_args(d);
     if ((rc = reset_reductions(d))) return rc;
-    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    const dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_pv_count<<<grid, 128, 0, d->stream>>>(d->P, A);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     unsigned long long h[4];
     if ((rc = read_reductions(d, h))) return rc;
     pv.nsub = (int)(dt / (pv.epsilon * bits_to_double(h[0]))) + 1;
-    const double dts = dt / pv.nsub;
-    int cur = 0;
-    auto stage = [&](int from, int to, double half, int final_stage) -> int {
-        for (int k = 0; k < 3; k++) { A.v[k] = pv.v[from][k]; A.v_out[k] = pv.v[to][k]; }
-        A.T = pv.T[from]; A.T_out = pv.T[to]; A.dt = dts; A.half = half; A.final_stage = final_stage;
-        k_pv_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
-        d->launches++;
-        CUDA_TRY(cudaGetLastError());
-        return exchange_planes4(d, pv.v[to][0], pv.v[to][1], pv.v[to][2], pv.T[to]);
-    };
-    if (!pv.inactive && (pv.heating_on || pv.force_on)) {
-        for (int s = 0; s < pv.nsub; s++) {
-            if (pv.integrator == SPRUCE_TI_EULER) { if ((rc = stage(cur, cur ^ 1, 1.0, 1))) return rc; cur ^= 1; }
-            else {                                                      // rk2: half step into the other set, full step back
-                if ((rc = stage(cur, cur ^ 1, 0.5, 0))) return rc;
-                if ((rc = stage(cur ^ 1, cur, 1.0, 1))) return rc;
-            }
-        }
-    }
-    if ((rc = launch_propagate(d, 0))) return rc;                       // :244
-    return after_module_propagate(d);
+    return pv_substeps(d, dt);
 }
 
 // after the step's last stage: all-gather of the slabs' minima, then the check that the skip test's window held (else: every cell)
@@ -1984,6 +2008,9 @@ int spruce_module_output_to_file(spruce_domain *d, const char *module, int on)
     } else if (!strcmp(module, "anomalous_resistivity")) {                                          // anomalousresistivity.cpp:320-329
         d->ar.output = on != 0;
         if (on && !d->ar.avg && ((rc = alloc_plane(d, &d->ar.avg)) || (rc = alloc_plane(d, &d->ar.prod)))) return rc;
+    } else if (!strcmp(module, "physical_viscosity")) {                                             // physicalviscosity.cpp:292-308
+        d->pv.output = on != 0;
+        if (on && !d->pv.avg[0]) for (int k = 0; k < 4; k++) if ((rc = alloc_plane(d, &d->pv.avg[k]))) return rc;
     } else return fail(SPRUCE_ERR_ARG, "no diagnostic planes for module <%s>", module);
     return SPRUCE_OK;
 }
@@ -1993,6 +2020,10 @@ int spruce_module_output(spruce_domain *d, const char *name, double *host, size_
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane size mismatch");
     const double *src = !strcmp(name, "thermal_conduction") ? d->tc_avg : !strcmp(name, "flux_saturation") ? d->tc_sat : !strcmp(name, "rad") ? d->rl_avg : nullptr;
+    if (d->pv.output && d->pv.avg[0]) {                                                             // zero planes before the first step, like the reference's (:38-39, :295)
+        const char *pvn[4] = {"viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"};
+        for (int k = 0; k < 4; k++) if (!strcmp(name, pvn[k])) src = d->pv.avg[k];
+    }
     if (!strcmp(name, "field_heating") && d->fh.H) src = d->fh.H;                                  // fieldheating.cpp:73-80: mask*(dt*heating) of the last step, zero before the first
     if (d->ar.on && d->ar.output) {
         if (!strcmp(name, "anomalous_template")) src = d->ar.planes[ar::P_TMPL];

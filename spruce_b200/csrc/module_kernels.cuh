@@ -667,6 +667,12 @@ struct PvArgs {
     int heating_on, force_on, gc, final_stage;
     unsigned long long *red;                        // count mode: red[0] = min timescale
     int fast;                                       // deep-interior cells take the FAST instances (SPRUCE_FAST_INTERIOR, default on; same results bit for bit)
+    // output_to_file (physicalviscosity.cpp:151-152, 166, 170, 218, 222, 292-308): avg[0] = viscous_heating, avg[1..3] = viscous_force_x/y/z -- zeroed by the host before the
+    // sub-cycles, every FULL-step stage adds its heating / force divided by the sub-cycle count.  diag_only (inactive_mode): nothing else is written, and the same
+    // stage value is added `repeat` times (the state never changes between the reference's sub-cycles then).
+    double *avg[4];
+    double nsub;
+    int diag_only, repeat;
 };
 struct PvPoint { double dxv[3], dyv[3], t25, b[3], cg; };
 
@@ -754,6 +760,25 @@ __global__ void __launch_bounds__(128, 4) k_pv_stage(const __grid_constant__ Dom
     double heating = 0.0, force[3] = {0.0, 0.0, 0.0};
     if (A.fast && deep_interior(P, r, j)) pv_cell<true>(P, A, r, j, in, mask, heating, force);
     else pv_cell<false>(P, A, r, j, in, mask, heating, force);
+    if (A.avg[0] && A.final_stage) {
+        const int reps = A.diag_only ? A.repeat : 1;
+        if (A.heating_on) {
+            double a = A.avg[0][off];
+            const double q = heating / A.nsub;
+            for (int s = 0; s < reps; s++) a = a + q;
+            A.avg[0][off] = a;
+        }
+        if (A.force_on) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double a = A.avg[1 + k][off];
+                const double q = force[k] / A.nsub;
+                for (int s = 0; s < reps; s++) a = a + q;
+                A.avg[1 + k][off] = a;
+            }
+        }
+    }
+    if (A.diag_only) return;
     const double hs = A.half;
     double e1 = A.e[off], T1 = A.T[off];
     if (A.heating_on) {                                                                            // :176-185 / :214-218

@@ -540,10 +540,17 @@ void PhysicalViscosity::setupModule()
 {
     SPRUCE_REQUIRE(time_integrator.empty() || time_integrator == "euler" || time_integrator == "rk2", "Invalid time integrator given for Physical Viscosity module");
     SPRUCE_REQUIRE(ms_electron_heating_fraction >= 0.0 && ms_electron_heating_fraction <= 1.0, "Physical Viscosity MS electron heating fraction must be between 0 and 1");
-    no_file_output(output_to_file, "physical_viscosity");
     const Grid cg = constructCoefficientGrid(coeff, ramp_length, buffer_length);
     PlasmaDomain::check(spruce_module_physical_viscosity(m_pd.device(), coeff, m_pd.slab(cg), m_pd.slabCount(), epsilon, heating_on, force_on, gradient_correction,
                                                          integrator_id(time_integrator, "Physical Viscosity"), inactive_mode));
+    if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "physical_viscosity", 1));
+}
+// physicalviscosity.cpp:292-308: the sub-cycle averages of the last step, kept on the device (zero planes before the first step)
+void PhysicalViscosity::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
+{
+    if (!output_to_file) return;
+    if (heating_on) append_device_plane(m_pd, "viscous_heating", names, grids);
+    if (force_on) for (const char *nm : {"viscous_force_x", "viscous_force_y", "viscous_force_z"}) append_device_plane(m_pd, nm, names, grids);
 }
 // physicalviscosity.cpp:269-287
 std::string PhysicalViscosity::commandLineMessage() const

@@ -210,6 +210,7 @@ public:
     explicit PhysicalViscosity(PlasmaDomain &pd) : Module(pd) {}
     void setupModule() override;
     std::string commandLineMessage() const override;
+    void fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids) override;
     bool device_resident() const override { return true; }
 private:
     double coeff = 0.0, ramp_length = 0.0, buffer_length = 0.0, epsilon = 1.0, ms_electron_heating_fraction = 0.0;

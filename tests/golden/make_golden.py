@@ -89,6 +89,11 @@ CASES = {
                         modules=[PV(force_on="false", coeff="4.0e-16", epsilon="0.2")], **INACTIVE_FLOORS), 3, (1, 3)),
     "ot_pv_force_only_rk2": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="rk4", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
                         modules=[PV(heating_on="false", time_integrator="rk2", coeff="4.0e-16", epsilon="0.2")], **INACTIVE_FLOORS), 3, (1, 3)),
+    # ... and its output_to_file planes (viscous_heating, viscous_force_x/y/z: the sub-cycle averages of physicalviscosity.cpp:151-170,218-222), also in inactive mode
+    "loop_pv_diag_rk2": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"),
+                         modules=[PV(time_integrator="rk2", gradient_correction="true", ramp_length="6.0e8", coeff="1.0e-14", output_to_file="true")], **SOLAR_FLOORS), 3, (1, 3)),
+    "ot_pv_diag_inactive": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
+                            modules=[PV(coeff="4.0e-16", epsilon="0.2", inactive_mode="true", output_to_file="true")], **INACTIVE_FLOORS), 3, (1, 3)),
     # two-fluid equation set (source/equationsets/ideal2F.cpp, non-sub-cycled Maxwell update) + EIC thermalization (BASELINE.json configs[2])
     "tf_ucnp_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, **TF, **UCNP_FLOORS), 8, (1, 8)),
     "tf_ucnp_eic_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, modules=[EIC], **TF, **UCNP_FLOORS), 8, (1, 8)),

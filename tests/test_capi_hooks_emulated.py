@@ -127,7 +127,8 @@ def assemble():
     ah = (CSRC / "anomres_host.cuh").read_text()
     ms = (CSRC / "moc_stage.cuh").read_text()
     fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "void fill_moc(", "int launch_moc_save(", "int launch_moc(", "int moc_limit(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
-           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate("]
+           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(",
+           "int exchange_planes4(", "PvArgs pv_args(", "int pv_substeps("]
     one_liners = {"double bits_to_double("}
     code = []
     for f in fns:
@@ -148,6 +149,7 @@ def assemble():
                     cut(mk, "struct StepCtl {", "// dt all-gather over peer memory"),
                     cut(ms, "struct MocArgs {", "}  // namespace spruce"),
                     cut(mo, "constexpr double kKappa0", "// Artificial viscosity (source/modules/viscosity.cpp"), "\n",
+                    cut(mo, "struct PvArgs {", "struct OpArgs"),
                     cut(mo, "struct OpArgs", "}  // namespace spruce"),
                     "}  // namespace spruce\n",
                     "struct PlaneSet { double *p[NEV] = {nullptr}; };\n", cut(ca, "struct HostAxis {", "struct TwoFluid;"), "struct TwoFluid;\nstruct OneFluid2E;\n",
@@ -602,3 +604,53 @@ def test_source_terms_on_slabs(emu, xb, yb, world):
         got = gather(emu, hs, cuts, ny, k)
         assert same_bits(got, o.get(v)), "%s differs: %s" % (v, mismatch(got, o.get(v)))
     o.close()
+
+
+PV_CASES = [("euler_both", "euler", True, True, False, False), ("rk2_gc_both", "rk2", True, True, True, False), ("rk2_force_only", "rk2", False, True, False, False),
+            ("euler_heat_only", "euler", True, False, False, False), ("euler_inactive", "euler", True, True, False, True), ("rk2_inactive", "rk2", True, True, True, True)]
+
+
+@pytest.mark.parametrize("fast", [1, 0])
+@pytest.mark.parametrize("name,integ,heating,force,gc,inactive", PV_CASES, ids=[c[0] for c in PV_CASES])
+@pytest.mark.parametrize("xb,yb", BOUNDS[:3])
+def test_physical_viscosity_through_pv_substeps_with_output_planes(emu, xb, yb, name, integ, heating, force, gc, inactive, fast):
+    """pv_substeps itself (capi.cu: the sub-cycles of PhysicalViscosity::iterateModule, k_pv_stage from its own source), output_to_file planes on: the evolved planes,
+    the dt minimum and viscous_heating / viscous_force_x/y/z -- the averages over the sub-cycles (physicalviscosity.cpp:151-170, 218-222), also in inactive_mode --
+    within 1e-9 of the oracle, whose planes two reference fixtures pin bit for bit (loop_pv_diag_rk2, ot_pv_diag_inactive).  T^2.5 is (T*T)*sqrt(T) in the kernel."""
+    from golden_util import physical_viscosity_coefficient
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    emu.cemu_set_fast_interior(h, C.c_int(fast))
+    coeff = 1.0e-14
+    cg = np.ascontiguousarray(physical_viscosity_coefficient(s["planes"], coeff, 6.0e8))
+    o.set_physical_viscosity(cg, coeff=coeff, epsilon=0.1, heating_on=heating, force_on=force, gradient_correction=gc, integrator=integ, inactive_mode=inactive)
+    before = o.get("thermal_energy").copy()
+    o.step()
+    ns = o.subcycles("physical_viscosity")
+    assert ns >= 2
+    out = np.zeros((4, nx, ny))
+    assert emu.cemu_physical_viscosity(h, vp(cg), C.c_double(coeff), C.c_int(int(heating)), C.c_int(int(force)), C.c_int(int(gc)), C.c_int({"euler": 0, "rk2": 1}[integ]),
+                                       C.c_int(int(inactive)), C.c_int(ns), C.c_double(step), vp(out)) == 0
+    names = (["viscous_heating"] if heating else []) + (["viscous_force_x", "viscous_force_y", "viscous_force_z"] if force else [])
+    for k, nm in enumerate(["viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"]):
+        ref = o.module_output(nm)
+        if nm in names:
+            assert np.count_nonzero(ref) > 0
+            assert np.max(np.abs(out[k] - ref)) <= 1e-9 * np.max(np.abs(ref)), "%s %s: %.3e" % (name, nm, np.max(np.abs(out[k] - ref)) / np.max(np.abs(ref)))
+        else:
+            assert not out[k].any() and not ref.any()
+    # the state after the hook's closing propagate: the oracle ran a whole step (hook, then the MHD stages), so compare with a second oracle that runs the hook alone
+    o2 = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", **FLOORS)
+    o2.run(2)
+    o2.set_physical_viscosity(cg, coeff=coeff, epsilon=0.1, heating_on=heating, force_on=force, gradient_correction=gc, integrator=integ, inactive_mode=inactive)
+    o2.physical_viscosity_iterate(step)
+    for k, v in enumerate(EV):
+        got = np.zeros((nx, ny))
+        emu.cemu_get(h, C.c_int(k), vp(got))
+        ref = o2.get(v)
+        assert np.max(np.abs(got - ref)) <= 1e-9 * max(np.max(np.abs(ref)), 1e-300), "%s %s" % (name, v)
+        if inactive:
+            assert same_bits(got, ref)
+    if not inactive and heating:
+        assert not same_bits(o2.get("thermal_energy"), before)
+    o.close(); o2.close()

@@ -53,10 +53,19 @@ def golden_cases():
     return out
 
 
-@pytest.mark.parametrize("name", golden_cases())
+# fixtures added after round 2's GPU budget was spent (they carry the output_to_file planes of physical_viscosity): first executed by the round-end run
+FIRST_RUN_FIXTURES = {"loop_pv_diag_rk2", "ot_pv_diag_inactive"}
+PV_PLANES = ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z")
+
+
+@pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="fixture written after round 2's GPU budget was spent; first device run", strict=False))
+                                  if n in FIRST_RUN_FIXTURES else n for n in golden_cases()])
 def test_golden_reference_outputs(name):
     g = Golden(name)
     d = make_domain(g)
+    pv_out = any(m[0] == "physical_viscosity" and m[1].get("output_to_file") == "true" for m in g.modules)
+    if pv_out:
+        d.set_module_output_to_file("physical_viscosity")
     exact = not any(m[0] in LIBM_MODULES for m in g.modules)
     done = 0
     tc, rl, pv = [], [], []
@@ -85,6 +94,10 @@ def test_golden_reference_outputs(name):
                 assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
             else:
                 assert rel_linf(got, g.frames[it][v]) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (v, it, rel_linf(got, g.frames[it][v]))
+        if pv_out:                                                   # physicalviscosity.cpp:292-308: the averages over the last step's sub-cycles
+            for pname in PV_PLANES:
+                ref = g.module_planes[it][pname]
+                assert np.count_nonzero(ref) > 0 and rel_linf(d.module_output(pname), ref) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (pname, it, rel_linf(d.module_output(pname), ref))
     if tc:
         assert tc == g.subcycle_counts("Thermal Subcycles")[:len(tc)]
     if rl:

@@ -74,7 +74,11 @@ CASES["loop_viscosity_elliptical"] = (lambda: synthetic.stratified_loop(40, 36),
 # the UCNP configuration of the one-fluid, two-temperature set: ideal_mhd_2E + eic_thermalization (eic_thermalization.cpp:27-44 finds all four of its grids in IdealMHD2E)
 CASES["ucnp_mhd2e_eic"] = (lambda: synthetic.ucnp_cloud_2e(41, 37, drift=20.0, bfield=0.01), dict(integrator="rk2", max_iterations=6, iter_output_interval=2, eqs="ideal_mhd_2E", **UCNP_KW,
                            output_flags=("rho", "i_temp", "e_temp", "i_thermal_energy", "e_thermal_energy", "press", "n", "dt"), modules=[("eic_thermalization", [])]), False)
-FIRST_RUN_AT_ROUND_END = {"ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
+# the output_to_file planes of physical_viscosity (physicalviscosity.cpp:292-308) appended to mhd.out by the shell's fileOutput
+CASES["loop_physical_viscosity_output"] = (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"), max_iterations=4, iter_output_interval=2,
+                                           write_precision=17, modules=[("physical_viscosity", [("coeff", "1.0e-14"), ("epsilon", "0.1"), ("ramp_length", "6.0e8"), ("time_integrator", "rk2"),
+                                                                                                ("output_to_file", "true")])]), False)
+FIRST_RUN_AT_ROUND_END = {"loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))
@@ -111,6 +115,14 @@ def test_run_binary_matches_reference_files(name, tmp_path):
         _, fa = refrun.read_out(tmp_path / "ours" / "mhd.out")
         _, fb = refrun.read_out(tmp_path / "ref" / "mhd.out")
         assert len(fa) == len(fb) and [f["t"] for f in fa] == [f["t"] for f in fb]
+        if name in ("loop_physical_viscosity_output", "ucnp_mhd2e_eic"):          # lossless mhd.out (write_precision 17): every plane of every frame, module planes included
+            for f1, f2 in zip(fa, fb):
+                assert list(f1) == list(f2)
+                for k in f2:
+                    if k != "t":
+                        assert np.max(np.abs(f1[k] - f2[k])) <= 1e-9 * max(np.max(np.abs(f2[k])), 1e-300), k
+            if name == "loop_physical_viscosity_output":
+                assert all(k in fb[-1] and np.count_nonzero(fb[-1][k]) for k in ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"))
         if name == "loop_solar_modules":
             assert "Thermal Subcycles" in stdout and "Radiative Subcycles" in stdout
 

@@ -65,7 +65,7 @@ def test_every_solar_module_reaches_the_c_abi_in_config_order(stub, tmp_path):
                               ("dynamic_mode", "true"), ("dynamic_time", "20.0"), ("dynamic_target_speed", "1.0e6")]),
         ("anomalous_resistivity", [("time_scale", "0.3"), ("output_to_file", "true"), ("resistivity_model", "ys_94"), ("resistivity_model_params", "0.2,2.0e14,3.0e15"),
                                    ("time_integrator", "rk4"), ("gradient_correction", "true"), ("flood_fill_threshold", "2.5"), ("metric_smoothing", "false")]),
-        ("physical_viscosity", [("coeff", "1.0e-14"), ("epsilon", "0.1"), ("time_integrator", "rk2"), ("gradient_correction", "true")]),
+        ("physical_viscosity", [("coeff", "1.0e-14"), ("epsilon", "0.1"), ("time_integrator", "rk2"), ("gradient_correction", "true"), ("output_to_file", "true")]),
     ]
     cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk4", xb=("fixed", "open"), yb=("reflect", "open"), max_iterations=3, iter_output_interval=2, modules=modules)
     log, stdout, out = run_shell(stub, tmp_path, s, cfg)
@@ -121,9 +121,10 @@ def test_every_solar_module_reaches_the_c_abi_in_config_order(stub, tmp_path):
 
     # output_to_file: enabled per module, every frame (iterations 0, 2 and the final one) appends the diagnostic planes in module order
     enabled = [ln.split()[1] for ln in log if ln.startswith("spruce_module_output_to_file")]
-    assert enabled == ["thermal_conduction", "radiative_losses", "anomalous_resistivity"]
+    assert enabled == ["thermal_conduction", "radiative_losses", "anomalous_resistivity", "physical_viscosity"]
     outs = [ln.split()[1] for ln in log if ln.startswith("spruce_module_output ")]
-    frame = ["thermal_conduction", "flux_saturation", "rad", "field_heating", "anomalous_diffusivity", "anomalous_template", "joule_heating"]
+    frame = ["thermal_conduction", "flux_saturation", "rad", "field_heating", "anomalous_diffusivity", "anomalous_template", "joule_heating",
+             "viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"]                                         # physicalviscosity.cpp:292-308
     assert outs[:len(frame)] == frame and len(outs) % len(frame) == 0 and len(outs) // len(frame) >= 2
     _, frames = refrun.read_out(out / "mhd.out")
     for f in frames:
