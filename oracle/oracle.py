@@ -310,6 +310,12 @@ class Oracle:
             lib().oracle_add_viscosity_term(self.h, opts[tm["opt"]], tm["strength"], VARS.index(tm["var_diff"]), VARS.index(tm["var_evol"]),
                                             ord(tm.get("species", "i")), sgp)
 
+    def viscosity_output(self, which: str, term: int):
+        """the plane Viscosity::fileOutput appends for term `term`: "dqdt", "lap", "str" or "dt" (viscosity.cpp:351-376), as the last evaluation left it"""
+        out = np.zeros((self.nx, self.ny))
+        ok = lib().oracle_viscosity_output(self.h, {"dqdt": 0, "lap": 1, "str": 2, "dt": 3}[which], term, _dp(out))
+        return out if ok else None
+
     def close(self):
         if self.h:
             lib().oracle_destroy(self.h)

@@ -57,6 +57,8 @@ typedef struct {
     int av_diff[8], av_evol[8];   /* variable indices (equation-set numbering) */
     int av_species[8];        /* 'i' or 'e' */
     double *av_strength_grid[8];  /* boundary options: profile built by the caller (host libm exp) */
+    double *av_out[4][8];         /* the planes fileOutput appends per term (viscosity.cpp:351-376): [0] m_grids_dqdt, [1] m_grids_lap, [2] m_grids_strength, [3] m_grids_dt --
+                                   * whatever the LAST evaluation of the term left there (zero planes before the first one, :99-102) */
     /* physical_viscosity (source/modules/solar/physicalviscosity.hpp) */
     int pv_on, pv_heating_on, pv_force_on, pv_gc, pv_integrator, pv_inactive, pv_nsub; double pv_coeff, pv_epsilon; double *pv_cg;
     double *pv_avg[4];                  /* output_to_file planes: viscous_heating, viscous_force_x/y/z (physicalviscosity.cpp:151-152,166,170,218,222,292-308) */
@@ -540,6 +542,13 @@ static void av_single(const oracle *o, double *const *G, int i, double *out)
         scale[c] = 1.0;
     }
     laplacian(o, G[m->av_diff[i]], lap);                                                                          /* :225 */
+    if (m->av_out[1][i]) {                                                                                        /* m_grids_lap :225, m_grids_strength :195-196, m_grids_dt :209-210 */
+        memcpy(m->av_out[1][i], lap, sizeof(double) * n);
+        for (int c = 0; c < n; c++) {
+            m->av_out[2][i][c] = (m->av_opt[i] == 0 || m->av_opt[i] == 1) ? m->av_strength[i] : m->av_strength_grid[i][c];
+            m->av_out[3][i][c] = (m->av_opt[i] == 0 || m->av_opt[i] == 2) ? o->g[V_dt][c] : dt_min;
+        }
+    }
     if (is_mom(m->av_evol[i]) && is_vel(m->av_diff[i])) for (int c = 0; c < n; c++) scale[c] = G[V_n][c] * o->m_i;              /* :229-239 */
     if (m->av_evol[i] == V_thermal_energy && m->av_diff[i] == V_temp) for (int c = 0; c < n; c++) scale[c] = G[V_n][c] * (K_B / (o->gamma - 1));   /* :244-254 */
     if (m->av_gradient_correction) {                                                                               /* :261-265 */
@@ -557,7 +566,10 @@ static void av_rhs(const oracle *o, double *const *G, double **k)
     double *dq = pl_new(o);
     for (int i = 0; i < o->mod.av_nterms; i++) {
         av_single(o, G, i, dq);                      /* constructViscosityGrids evaluates every term */
-        if (o->mod.av_strength[i] <= 1.0) { double *kk = k[ev_index(o->mod.av_evol[i])]; for (int c = 0; c < o->n; c++) kk[c] += dq[c] * o->mask[c]; }
+        if (o->mod.av_strength[i] <= 1.0) {
+            double *kk = k[ev_index(o->mod.av_evol[i])], *keep = o->mod.av_out[0][i];
+            for (int c = 0; c < o->n; c++) { const double t = dq[c] * o->mask[c]; if (keep) keep[c] = t; kk[c] += t; }       /* m_grids_dqdt[i] = dqdt * mask, :116-118 */
+        }
     }
     free(dq);
 }
@@ -582,6 +594,7 @@ static void av_iterate(oracle *o, double dt)
                 for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * (0.5 * dts)) * dq[c];
                 propagate_changes(o, o->g, o->g);
                 av_single(o, o->g, i, dq);
+                if (o->mod.av_out[0][i]) memcpy(o->mod.av_out[0][i], dq, sizeof(double) * n);                     /* m_grids_dqdt[i] = dqdt (unmasked), :148 */
                 for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * dts) * dq[c];
                 propagate_changes(o, o->g, o->g);
             } else {
@@ -593,6 +606,7 @@ static void av_iterate(oracle *o, double dt)
                 propagate_changes(o, o->g, o->g); av_single(o, o->g, i, d3);
                 for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * dts) * d3[c];
                 propagate_changes(o, o->g, o->g); av_single(o, o->g, i, d4);
+                if (o->mod.av_out[0][i]) for (int c = 0; c < n; c++) o->mod.av_out[0][i][c] = (((dq[c] + d2[c] * 2.0) + d3[c] * 2.0) + d4[c]) / 6.0;   /* :172 */
                 for (int c = 0; c < n; c++) ge[c] = init[c] + (o->mask[c] * dts) * ((((dq[c] + d2[c] * 2.0) + d3[c] * 2.0) + d4[c]) / 6.0);
                 propagate_changes(o, o->g, o->g);
             }
@@ -900,6 +914,7 @@ void oracle_destroy(oracle *o)
     free(o->mod.ah_heating);
     free(o->mod.pv_cg);
     for (int k = 0; k < 4; k++) free(o->mod.pv_avg[k]);
+    for (int w = 0; w < 4; w++) for (int i = 0; i < 8; i++) free(o->mod.av_out[w][i]);
     free(o);
 }
 /* which: 0 d_x 1 d_y 2 be_x 3 be_y 4 be_z 5 pos_x 6 pos_y 7 mask(read only) ; 100+v equation-set variable v */
@@ -965,6 +980,14 @@ void oracle_add_viscosity_term(oracle *o, int opt, double strength, int var_diff
     o->mod.av_opt[i] = opt; o->mod.av_strength[i] = strength; o->mod.av_diff[i] = var_diff; o->mod.av_evol[i] = var_evol; o->mod.av_species[i] = species;
     o->mod.av_strength_grid[i] = NULL;
     if (strength_grid) { o->mod.av_strength_grid[i] = pl_dup(o, strength_grid); }
+    for (int w = 0; w < 4; w++) o->mod.av_out[w][i] = pl_new(o);
+}
+/* test accessor: plane `which` (0 dqdt, 1 lap, 2 str, 3 dt) of viscosity term i as fileOutput would write it now */
+int oracle_viscosity_output(const oracle *o, int which, int i, double *out)
+{
+    if (which < 0 || which > 3 || i < 0 || i >= o->mod.av_nterms) return 0;
+    memcpy(out, o->mod.av_out[which][i], sizeof(double) * o->n);
+    return 1;
 }
 /* kind: 6 ambient_heating_sink, 7 localized_heating, 8 mass_injection, 9 momentum_injection, 10 div_cleaning, 11 field_heating; p: see small_module_setup */
 void oracle_add_small_module(oracle *o, int kind, const double *p, int np)

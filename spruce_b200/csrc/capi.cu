@@ -116,8 +116,10 @@ struct spruce_domain {
     bool tc_output = false, rl_output = false;
     double *tc_avg = nullptr, *tc_sat = nullptr, *rl_avg = nullptr, *old_e = nullptr;
     // artificial_viscosity (source/modules/viscosity.cpp): terms in config order
-    struct ViscTerm { int opt; double strength; int var_diff; int var_evol; int species; double *strength_plane; bool halo_done = false; };
+    struct ViscTerm { int opt; double strength; int var_diff; int var_evol; int species; double *strength_plane; bool halo_done = false;
+                      double *o_dqdt = nullptr, *o_lap = nullptr, *o_dt = nullptr; };      // output planes (spruce_module_output_to_file "artificial_viscosity")
     std::vector<ViscTerm> visc;
+    bool visc_output = false; bool visc_evaluated = false;   // visc_evaluated: some term has been evaluated (the reference's strength planes are zero until then)
     int visc_hv_integrator = 0, visc_gradient_correction = 0; double visc_hv_epsilon = 1.0;
     double *vscratch[8] = {nullptr}; double *dt_plane = nullptr;
     const double *cur_xterm[4] = {nullptr}; int cur_xtarget[4] = {0}; int cur_nx = 0;
@@ -839,7 +841,8 @@ int visc_needs_dt_plane(const spruce_domain *d) { for (auto &t : d->visc) if (t.
 int visc_refresh_dt(spruce_domain *d) { return visc_needs_dt_plane(d) ? derive_to(d, V_dt, d->dt_plane) : SPRUCE_OK; }
 // constructSingleViscosityGrid :185-267 for term i on grid set S -> out
 int exchange_plane(spruce_domain *d, double *plane);
-int visc_term(spruce_domain *d, const PlaneSet &S, int i, double *out, int masked)
+// keep_dq: this evaluation is one the reference stores in m_grids_dqdt[i] (the masked RHS form :116, the second evaluation of an rk2 sub-cycle :148)
+int visc_term(spruce_domain *d, const PlaneSet &S, int i, double *out, int masked, int keep_dq = 0)
 {
     auto &t = d->visc[i];
     int rc;
@@ -859,6 +862,7 @@ int visc_term(spruce_domain *d, const PlaneSet &S, int i, double *out, int maske
     const bool diff_vel = (t.var_diff == V_v_x || t.var_diff == V_v_y || t.var_diff == V_v_z);
     A.scale_mode = (evol_mom && diff_vel) ? 1 : (t.var_evol == V_thermal_energy && t.var_diff == V_temp) ? 2 : 0;
     A.gradient_correction = d->visc_gradient_correction; A.masked = masked; A.out = out;
+    if (d->visc_output) { A.lap_out = t.o_lap; A.dtg_out = t.o_dt; A.dq_out = keep_dq ? t.o_dqdt : nullptr; d->visc_evaluated = true; }
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_visc_term<<<grid, 128, 0, d->stream>>>(d->P, A);
     d->launches++;
@@ -870,9 +874,14 @@ int prepare_rhs_modules(spruce_domain *d, const PlaneSet &S)
 {
     d->cur_nx = 0;
     for (size_t i = 0; i < d->visc.size(); i++) {
-        if (d->visc[i].strength > 1.0) continue;
+        if (d->visc[i].strength > 1.0) {
+            // constructViscosityGrids evaluates EVERY term on this grid set (:269-276); a hyper-viscous term's result is dropped, but its laplacian / timescale planes
+            // are now those of this evaluation -- only the output planes can tell
+            if (d->visc_output) { int rc = visc_term(d, S, (int)i, nullptr, 0); if (rc) return rc; }
+            continue;
+        }
         if (d->cur_nx >= 4) return fail(SPRUCE_ERR_UNSUPPORTED, "at most 4 right-hand-side viscosity terms");
-        int rc = visc_term(d, S, (int)i, d->vscratch[d->cur_nx], 1);
+        int rc = visc_term(d, S, (int)i, d->vscratch[d->cur_nx], 1, 1);
         if (rc) return rc;
         d->cur_xterm[d->cur_nx] = d->vscratch[d->cur_nx];
         d->cur_xtarget[d->cur_nx] = evolved_slot(d->visc[i].var_evol);
@@ -898,7 +907,7 @@ int av_iterate(spruce_domain *d, double dt)
         auto apply = [&](const double *base, double cc, int n_terms) -> int {
             AxpyArgs A{};
             A.base = base; A.t1 = T[0]; A.t2 = n_terms == 4 ? T[1] : nullptr; A.t3 = n_terms == 4 ? T[2] : nullptr; A.t4 = n_terms == 4 ? T[3] : nullptr;
-            A.c = cc; A.out = evol; A.base_is_n = (ev == E_N);
+            A.c = cc; A.out = evol; A.base_is_n = (ev == E_N); A.comb_out = d->visc_output ? t.o_dqdt : nullptr;
             k_visc_apply<<<grid, 256, 0, d->stream>>>(d->P, A);
             d->launches++;
             CUDA_TRY(cudaGetLastError());
@@ -906,7 +915,7 @@ int av_iterate(spruce_domain *d, double dt)
             int rp = launch_propagate(d, 0);
             return rp ? rp : after_module_propagate(d);
         };
-        auto term = [&](double *out) -> int { int r_ = visc_refresh_dt(d); return r_ ? r_ : visc_term(d, d->Pset, (int)i, out, 0); };
+        auto term = [&](double *out, int keep_dq = 0) -> int { int r_ = visc_refresh_dt(d); return r_ ? r_ : visc_term(d, d->Pset, (int)i, out, 0, keep_dq); };
         for (int sc = 0; sc < ns; sc++) {
             if (d->visc_hv_integrator == SPRUCE_TI_EULER) {
                 if ((rc = term(T[0])) || (rc = apply(evol, dts, 1))) return rc;
@@ -914,7 +923,7 @@ int av_iterate(spruce_domain *d, double dt)
                 CUDA_TRY(cudaMemcpyAsync(init, evol, plane_bytes, cudaMemcpyDeviceToDevice, d->stream));
                 if (d->visc_hv_integrator == SPRUCE_TI_RK2) {
                     if ((rc = term(T[0])) || (rc = apply(init, 0.5 * dts, 1))) return rc;
-                    if ((rc = term(T[0])) || (rc = apply(init, dts, 1))) return rc;
+                    if ((rc = term(T[0], 1)) || (rc = apply(init, dts, 1))) return rc;
                 } else {
                     if ((rc = term(T[0])) || (rc = apply(init, 0.5 * dts, 1))) return rc;
                     std::swap(T[0], T[1]);            // keep dqdt1 in T[1] while T[0] is reused as the working term
@@ -2008,6 +2017,9 @@ int spruce_module_output_to_file(spruce_domain *d, const char *module, int on)
     } else if (!strcmp(module, "anomalous_resistivity")) {                                          // anomalousresistivity.cpp:320-329
         d->ar.output = on != 0;
         if (on && !d->ar.avg && ((rc = alloc_plane(d, &d->ar.avg)) || (rc = alloc_plane(d, &d->ar.prod)))) return rc;
+    } else if (!strcmp(module, "artificial_viscosity")) {                                           // viscosity.cpp:351-376; call after the terms are configured
+        d->visc_output = on != 0;
+        if (on) for (auto &t : d->visc) if (!t.o_lap && ((rc = alloc_plane(d, &t.o_dqdt)) || (rc = alloc_plane(d, &t.o_lap)) || (rc = alloc_plane(d, &t.o_dt)))) return rc;
     } else if (!strcmp(module, "physical_viscosity")) {                                             // physicalviscosity.cpp:292-308
         d->pv.output = on != 0;
         if (on && !d->pv.avg[0]) for (int k = 0; k < 4; k++) if ((rc = alloc_plane(d, &d->pv.avg[k]))) return rc;
@@ -2023,6 +2035,23 @@ int spruce_module_output(spruce_domain *d, const char *name, double *host, size_
     if (d->pv.output && d->pv.avg[0]) {                                                             // zero planes before the first step, like the reference's (:38-39, :295)
         const char *pvn[4] = {"viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"};
         for (int k = 0; k < 4; k++) if (!strcmp(name, pvn[k])) src = d->pv.avg[k];
+    }
+    if (d->visc_output) {                                                                            // "visc_dqdt:<i>", "visc_lap:<i>", "visc_dt:<i>" of term i (config order)
+        const char *pre[3] = {"visc_dqdt:", "visc_lap:", "visc_dt:"};
+        for (int w = 0; w < 3; w++) if (!strncmp(name, pre[w], strlen(pre[w]))) {
+            const int i = atoi(name + strlen(pre[w]));
+            if (i < 0 || i >= (int)d->visc.size() || !d->visc[i].o_lap) return fail(SPRUCE_ERR_ARG, "no viscosity term <%s>", name);
+            src = w == 0 ? d->visc[i].o_dqdt : w == 1 ? d->visc[i].o_lap : d->visc[i].o_dt;
+        }
+        if (!strncmp(name, "visc_str:", 9)) {                                                         // m_grids_strength[i] (:195-196): zero until the first evaluation of any term
+            const int i = atoi(name + 9);
+            if (i < 0 || i >= (int)d->visc.size()) return fail(SPRUCE_ERR_ARG, "no viscosity term <%s>", name);
+            const auto &t = d->visc[i];
+            if (d->visc_evaluated && (t.opt == 2 || t.opt == 3)) return d2h_plane(d, host, t.strength_plane);
+            const double v = d->visc_evaluated ? t.strength : 0.0;
+            for (size_t k = 0; k < count; k++) host[k] = v;
+            return SPRUCE_OK;
+        }
     }
     if (!strcmp(name, "field_heating") && d->fh.H) src = d->fh.H;                                  // fieldheating.cpp:73-80: mask*(dt*heating) of the last step, zero before the first
     if (d->ar.on && d->ar.output) {

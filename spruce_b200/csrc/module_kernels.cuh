@@ -601,7 +601,11 @@ struct ViscArgs {
     int scale_mode;              // 0: 1 ; 1: n*m_i (momentum <- velocity) ; 2: n*(K_B/(gamma-1)) (thermal energy <- temperature)
     int gradient_correction;
     int masked;                  // multiply by the ghost-zone mask (RHS form, viscosity.cpp:117)
-    double *out;
+    double *out;                 // may be null (an evaluation made only for the planes below)
+    // the planes Viscosity::fileOutput appends (viscosity.cpp:351-376), each the leftover of the term's last evaluation; null = not kept
+    double *lap_out;             // m_grids_lap[i]  (:225)
+    double *dtg_out;             // m_grids_dt[i]   (:209-210: the primary dt plane, or its minimum everywhere)
+    double *dq_out;              // m_grids_dqdt[i] (:116 masked RHS term; :148 second rk2 evaluation)
 };
 
 __global__ void __launch_bounds__(128) k_visc_term(const DomainParams P, const ViscArgs A)
@@ -631,11 +635,14 @@ __global__ void __launch_bounds__(128) k_visc_term(const DomainParams P, const V
         out = (out + Dx(P, CS, r, j) * Dx(P, Q, r, j)) + Dy(P, CS, r, j) * Dy(P, Q, r, j);
     }
     if (A.masked) out = out * (is_interior(P, r, j) ? 1.0 : 0.0);
-    A.out[off] = out;
+    if (A.out) A.out[off] = out;
+    if (A.lap_out) A.lap_out[off] = lap;
+    if (A.dtg_out) A.dtg_out[off] = A.dt_plane ? A.dt_plane[off] : dtm;
+    if (A.dq_out) A.dq_out[off] = out;
 }
 
 // grid_to_evol = base + (mask*c)*term   (viscosity.cpp:135,145,150,...) ; rk4 combination when d2..d4 are given (:173-174)
-struct AxpyArgs { const double *base; const double *t1, *t2, *t3, *t4; double c; double *out; int base_is_n; };
+struct AxpyArgs { const double *base; const double *t1, *t2, *t3, *t4; double c; double *out; int base_is_n; double *comb_out; /* rk4: m_grids_dqdt[i] (:172), or null */ };
 __global__ void __launch_bounds__(256) k_visc_apply(const DomainParams P, const AxpyArgs A)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -645,6 +652,7 @@ __global__ void __launch_bounds__(256) k_visc_apply(const DomainParams P, const 
     const double mask = is_interior(P, r, j) ? 1.0 : 0.0;
     double t = A.t1[off];
     if (A.t4) t = (((A.t1[off] + A.t2[off] * 2.0) + A.t3[off] * 2.0) + A.t4[off]) / 6.0;
+    if (A.t4 && A.comb_out) A.comb_out[off] = t;
     const double b = A.base_is_n ? A.base[off] * P.m_i : A.base[off];
     A.out[off] = b + (mask * A.c) * t;
 }

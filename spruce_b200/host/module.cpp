@@ -92,10 +92,6 @@ static int integrator_id(std::string s, const char *who)
     if (s == "rk4") return SPRUCE_TI_RK4;
     spruce_die(std::string("Invalid time integrator given for ") + who + " module");
 }
-static void no_file_output(bool flag, const char *who)
-{
-    if (flag) std::cerr << who << ": output_to_file is not provided by the B200 path yet; the run proceeds without the module's diagnostic planes.\n";
-}
 
 // thermalconduction.cpp:16-30
 void ThermalConduction::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
@@ -438,7 +434,10 @@ void Viscosity::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std
 {
     for (size_t i = 0; i < lhs.size(); i++) {
         const std::string &k = lhs[i], &v = rhs[i];
-        if (k == "visc_output_visc" || k == "visc_output_lap" || k == "visc_output_strength" || k == "visc_output_timescale") m_any_output = m_any_output || (v == "true");
+        if (k == "visc_output_visc") m_output_visc = (v == "true");                 // (the reference leaves these four uninitialised when the config is silent,
+        else if (k == "visc_output_lap") m_output_lap = (v == "true");              //  viscosity.hpp:60-63: here they default to false)
+        else if (k == "visc_output_strength") m_output_strength = (v == "true");
+        else if (k == "visc_output_timescale") m_output_timescale = (v == "true");
         else if (k == "hv_time_integrator") m_hv_time_integrator = v;
         else if (k == "gradient_correction") m_gradient_correction = (v == "true");
         else if (k == "hv_epsilon") m_hv_epsilon = std::stod(v);
@@ -472,7 +471,6 @@ void Viscosity::setupModule()
     if (m_boundary_falloff_shape.empty()) m_boundary_falloff_shape = "gaussian";
     SPRUCE_REQUIRE(m_boundary_falloff_shape == "gaussian" || m_boundary_falloff_shape == "exp" || m_boundary_falloff_shape == "exp_elliptical" || m_boundary_falloff_shape == "gaussian_elliptical",
                    "Invalid boundary falloff shape given for Viscosity module");
-    no_file_output(m_any_output, "artificial_viscosity");
     PlasmaDomain::check(spruce_module_viscosity(m_pd.device(), integrator_id(m_hv_time_integrator, "Viscosity"), m_hv_epsilon, m_gradient_correction));
     for (size_t i = 0; i < n; i++) {
         SPRUCE_REQUIRE(std::stod(len[i]) >= 0, "Length constants must greater than or equal to zero.");
@@ -482,6 +480,22 @@ void Viscosity::setupModule()
             PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), m_pd.slab(prof), m_pd.slabCount()));
         } else {
             PlasmaDomain::check(spruce_module_viscosity_term(m_pd.device(), opt[i].c_str(), strength, diff[i].c_str(), evol[i].c_str(), spec[i].c_str(), nullptr, 0));
+        }
+    }
+    m_vars_to_evol = evol;
+    if (m_output_visc || m_output_lap || m_output_strength || m_output_timescale) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "artificial_viscosity", 1));
+}
+// viscosity.cpp:351-376: per flag, one plane per term in config order -- <evolved>_dqdt, _lap, _str, _dt (:103-107) --, each what the term's last evaluation on the
+// device left (zero planes before the first one)
+void Viscosity::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
+{
+    const struct { bool on; const char *plane, *suffix; } kinds[4] = {{m_output_visc, "visc_dqdt:", "_dqdt"}, {m_output_lap, "visc_lap:", "_lap"},
+                                                                      {m_output_strength, "visc_str:", "_str"}, {m_output_timescale, "visc_dt:", "_dt"}};
+    for (const auto &k : kinds) {
+        if (!k.on) continue;
+        for (size_t i = 0; i < m_vars_to_evol.size(); i++) {
+            append_device_plane(m_pd, (k.plane + std::to_string(i)).c_str(), names, grids);
+            names.back() = m_vars_to_evol[i] + k.suffix;
         }
     }
 }

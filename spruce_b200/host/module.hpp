@@ -64,11 +64,13 @@ class Viscosity : public Module {
 public:
     explicit Viscosity(PlasmaDomain &pd) : Module(pd) {}
     void setupModule() override;
+    void fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids) override;      // viscosity.cpp:351-376
     bool device_resident() const override { return true; }
 private:
     std::string m_inp_visc_opt, m_inp_strength, m_inp_vars_to_diff, m_inp_vars_to_evol, m_inp_length, m_inp_species;
     std::string m_hv_time_integrator, m_boundary_falloff_shape;
-    bool m_gradient_correction = false, m_any_output = false;
+    std::vector<std::string> m_vars_to_evol;
+    bool m_gradient_correction = false, m_output_visc = false, m_output_lap = false, m_output_strength = false, m_output_timescale = false;
     double m_hv_epsilon = 1.0;
     Grid getBoundaryViscosity(double strength, double length) const;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;

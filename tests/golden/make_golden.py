@@ -81,6 +81,21 @@ CASES = {
     "ot_visc_hv_rk4": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
                       modules=[AV(visc_opt="local,global", visc_strength="2.5,0.4", visc_vars_to_diff="v_x,temp", visc_vars_to_evol="mom_x,thermal_energy",
                                   visc_length="0,0", visc_species="i,i", hv_time_integrator="rk4", hv_epsilon="1.0")], **INACTIVE_FLOORS), 3, (1, 3)),
+    # ... and the planes Viscosity::fileOutput appends per term (viscosity.cpp:351-376: <evolved>_dqdt, _lap, _str, _dt -- whatever the term's LAST evaluation left), all four
+    # flags set explicitly (the reference leaves them uninitialised otherwise, viscosity.hpp:60-63)
+    "loop_visc_diag_hv_rk2": ("stratified_loop", dict(nx=NX, ny=NY), dict(integrator="rk2", xb=("reflect", "open"), yb=("fixed", "open"),
+                      modules=[AV(visc_opt="boundary,global,boundary_global,local", visc_strength="0.8,3.0,0.6,0.5", visc_vars_to_diff="v_x,v_y,mom_z,temp",
+                                  visc_vars_to_evol="mom_x,mom_y,mom_z,thermal_energy", visc_length="5.0e8,0,8.0e8,0", visc_species="i,i,i,i", hv_time_integrator="rk2", hv_epsilon="1.0",
+                                  gradient_correction="true", visc_output_visc="true", visc_output_lap="true", visc_output_strength="true", visc_output_timescale="true")],
+                      **SOLAR_FLOORS), 3, (0, 1, 3)),
+    "ot_visc_diag_hv_rk4": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
+                      modules=[AV(visc_opt="local,global", visc_strength="2.5,0.4", visc_vars_to_diff="v_x,temp", visc_vars_to_evol="mom_x,thermal_energy", visc_length="0,0", visc_species="i,i",
+                                  hv_time_integrator="rk4", hv_epsilon="1.0", visc_output_visc="true", visc_output_lap="true", visc_output_strength="false", visc_output_timescale="true")],
+                      **INACTIVE_FLOORS), 3, (1, 3)),
+    "ot_visc_diag_hv_euler": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="rk4", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
+                      modules=[AV(visc_opt="global,local", visc_strength="2.5,0.4", visc_vars_to_diff="v_y,temp", visc_vars_to_evol="mom_y,thermal_energy", visc_length="0,0", visc_species="i,i",
+                                  hv_time_integrator="euler", hv_epsilon="1.0", visc_output_visc="true", visc_output_lap="true", visc_output_strength="true", visc_output_timescale="false")],
+                      **INACTIVE_FLOORS), 2, (1, 2)),
     # Braginskii physical viscosity (source/modules/solar/physicalviscosity.cpp): heating + force, euler / rk2 sub-cycles, coefficient ramp
     "loop_pv_euler": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[PV()], **SOLAR_FLOORS), 4, (1, 4)),
     "loop_pv_rk2_gc": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="euler", xb=("reflect", "open"), yb=("fixed", "open"),

@@ -109,6 +109,18 @@ def module_kwargs(name, kv):
     raise KeyError(name)
 
 
+def viscosity_plane_request(modules, pname):
+    """'<evolved>_dqdt' / '_lap' / '_str' / '_dt' of Viscosity::fileOutput (viscosity.cpp:103-107, 351-376) -> (which, term index), or None for other names"""
+    for suffix in ("dqdt", "lap", "str", "dt"):
+        if pname.endswith("_" + suffix):
+            for name, kv in modules:
+                if name == "artificial_viscosity":
+                    evol = kv["visc_vars_to_evol"].split(",")
+                    if pname[:-len(suffix) - 1] in evol:
+                        return suffix, evol.index(pname[:-len(suffix) - 1])
+    return None
+
+
 def boundary_viscosity_profile(pos_x, pos_y, strength, length, shape="gaussian"):
     """Viscosity::getBoundaryViscosity (reference source/modules/viscosity.cpp:278-325) for its four shapes -- gaussian, exp, exp_elliptical,
     gaussian_elliptical --, with the host libm: a static profile the reference also builds on the host."""

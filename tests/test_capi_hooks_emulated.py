@@ -128,8 +128,9 @@ def assemble():
     ms = (CSRC / "moc_stage.cuh").read_text()
     fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "void fill_moc(", "int launch_moc_save(", "int launch_moc(", "int moc_limit(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
            "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(",
-           "int exchange_planes4(", "PvArgs pv_args(", "int pv_substeps("]
-    one_liners = {"double bits_to_double("}
+           "int exchange_planes4(", "PvArgs pv_args(", "int pv_substeps(",
+           "int evolved_slot(int var)\n{", "const double *materialise_var(", "int visc_needs_dt_plane(", "int visc_refresh_dt(", "int visc_term(", "int prepare_rhs_modules(", "int av_iterate("]
+    one_liners = {"double bits_to_double(", "int visc_needs_dt_plane(", "int visc_refresh_dt("}
     code = []
     for f in fns:
         if f in one_liners:
@@ -149,6 +150,7 @@ def assemble():
                     cut(mk, "struct StepCtl {", "// dt all-gather over peer memory"),
                     cut(ms, "struct MocArgs {", "}  // namespace spruce"),
                     cut(mo, "constexpr double kKappa0", "// Artificial viscosity (source/modules/viscosity.cpp"), "\n",
+                    cut(mo, "struct ViscArgs {", "// PlasmaDomain differential operators on a plane"),
                     cut(mo, "struct PvArgs {", "struct OpArgs"),
                     cut(mo, "struct OpArgs", "}  // namespace spruce"),
                     "}  // namespace spruce\n",
@@ -654,3 +656,46 @@ def test_physical_viscosity_through_pv_substeps_with_output_planes(emu, xb, yb, 
     if not inactive and heating:
         assert not same_bits(o2.get("thermal_energy"), before)
     o.close(); o2.close()
+
+
+AV_CASES = [
+    ("rhs_and_hv_rk2_gc", [("boundary", 0.8, "v_x", "mom_x", 5.0e8), ("global", 3.0, "v_y", "mom_y", 0.0), ("boundary_global", 0.6, "mom_z", "mom_z", 8.0e8), ("local", 0.5, "temp", "thermal_energy", 0.0)], "rk2", True),
+    ("hv_rk4", [("local", 2.5, "v_x", "mom_x", 0.0), ("global", 0.4, "temp", "thermal_energy", 0.0)], "rk4", False),
+    ("hv_euler", [("global", 2.5, "v_y", "mom_y", 0.0), ("local", 0.4, "temp", "thermal_energy", 0.0)], "euler", False),
+]
+
+
+@pytest.mark.parametrize("name,terms,hv_integ,gc", AV_CASES, ids=[c[0] for c in AV_CASES])
+@pytest.mark.parametrize("xb,yb", BOUNDS[:3])
+def test_artificial_viscosity_output_planes_through_av_iterate_and_the_rhs_evaluation(emu, xb, yb, name, terms, hv_integ, gc):
+    """The planes Viscosity::fileOutput appends per term (viscosity.cpp:351-376: dqdt, lap, str, dt -- each the leftover of the term's LAST evaluation), kept by
+    k_visc_term / k_visc_apply when spruce_module_output_to_file("artificial_viscosity") is on.  One euler step of the reference is: the hyper-viscous sub-cycles
+    (av_iterate), then ONE right-hand-side evaluation on the primary state in which every term is evaluated again (prepare_rhs_modules).  The product's own functions run
+    that sequence on the host; every plane of every term, bit for bit against the oracle, whose planes three reference fixtures pin (*_visc_diag_*)."""
+    from golden_util import boundary_viscosity_profile
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny, integrator="euler")
+    full = []
+    for opt, strength, vd, ve, length in terms:
+        sg = np.ascontiguousarray(boundary_viscosity_profile(s["planes"]["pos_x"], s["planes"]["pos_y"], strength, length)) if opt.startswith("boundary") else None
+        full.append(dict(opt=opt, strength=strength, var_diff=vd, var_evol=ve, species="i", strength_grid=sg))
+    o.set_viscosity(full, hv_integrator=hv_integ, hv_epsilon=1.0, gradient_correction=gc)
+    emu.cemu_viscosity_begin(h, C.c_int({"euler": 0, "rk2": 1, "rk4": 2}[hv_integ]), C.c_double(1.0), C.c_int(int(gc)))
+    from oracle.oracle import VARS
+    for t in full:
+        sgp = vp(t["strength_grid"]) if t["strength_grid"] is not None else None
+        assert emu.cemu_viscosity_term(h, C.c_int({"local": 0, "global": 1, "boundary": 2, "boundary_global": 3}[t["opt"]]), C.c_double(t["strength"]), C.c_int(VARS.index(t["var_diff"])),
+                                       C.c_int(VARS.index(t["var_evol"])), sgp) == 0
+    out = np.zeros((len(full), 4, nx, ny))
+    before = np.zeros((len(full), 4, nx, ny))
+    xl, xu, yl, yu = b
+    dtmin_now = float(np.min(o.get("dt")[xl:xu + 1, yl:yu + 1]))
+    assert emu.cemu_viscosity_run(h, C.c_double(step), C.c_double(dtmin_now), vp(before), vp(out)) == 0
+    assert not before.any()                                       # zero planes before the first evaluation (:99-102)
+    o.step()
+    for i in range(len(full)):
+        for w, which in enumerate(("dqdt", "lap", "str", "dt")):
+            ref = o.viscosity_output(which, i)
+            assert same_bits(out[i, w], ref), "%s term %d %s: %s" % (name, i, which, mismatch(out[i, w], ref))
+        assert np.count_nonzero(out[i, 1]) > 0
+    o.close()

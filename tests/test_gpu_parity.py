@@ -8,7 +8,7 @@ as doubles."""
 import numpy as np
 import pytest
 
-from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_bits
+from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_bits, viscosity_plane_request
 
 pytestmark = pytest.mark.gpu
 
@@ -53,8 +53,8 @@ def golden_cases():
     return out
 
 
-# fixtures added after round 2's GPU budget was spent (they carry the output_to_file planes of physical_viscosity): first executed by the round-end run
-FIRST_RUN_FIXTURES = {"loop_pv_diag_rk2", "ot_pv_diag_inactive"}
+# fixtures added after round 2's GPU budget was spent (they carry the output planes of physical_viscosity / artificial_viscosity): first executed by the round-end run
+FIRST_RUN_FIXTURES = {"loop_pv_diag_rk2", "ot_pv_diag_inactive", "loop_visc_diag_hv_rk2", "ot_visc_diag_hv_rk4", "ot_visc_diag_hv_euler"}
 PV_PLANES = ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z")
 
 
@@ -66,6 +66,12 @@ def test_golden_reference_outputs(name):
     pv_out = any(m[0] == "physical_viscosity" and m[1].get("output_to_file") == "true" for m in g.modules)
     if pv_out:
         d.set_module_output_to_file("physical_viscosity")
+    av_out = any(m[0] == "artificial_viscosity" and any(v == "true" for k, v in m[1].items() if k.startswith("visc_output_")) for m in g.modules)
+    if av_out:
+        d.set_module_output_to_file("artificial_viscosity")
+        for pname, ref in g.module_planes.get(0, {}).items():          # before the first step: zero planes (viscosity.cpp:99-102)
+            which, term = viscosity_plane_request(g.modules, pname)
+            assert not ref.any() and not d.module_output("visc_%s:%d" % (which, term)).any(), pname
     exact = not any(m[0] in LIBM_MODULES for m in g.modules)
     done = 0
     tc, rl, pv = [], [], []
@@ -94,6 +100,11 @@ def test_golden_reference_outputs(name):
                 assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
             else:
                 assert rel_linf(got, g.frames[it][v]) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (v, it, rel_linf(got, g.frames[it][v]))
+        if av_out and it > 0:                                        # viscosity.cpp:351-376: what each term's last evaluation left, bit for bit
+            for pname, ref in g.module_planes[it].items():
+                which, term = viscosity_plane_request(g.modules, pname)
+                got = d.module_output("visc_%s:%d" % (which, term))
+                assert same_bits(got, ref), "%s after iteration %d: %s" % (pname, it, mismatch(got, ref))
         if pv_out:                                                   # physicalviscosity.cpp:292-308: the averages over the last step's sub-cycles
             for pname in PV_PLANES:
                 ref = g.module_planes[it][pname]

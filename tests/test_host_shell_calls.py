@@ -282,3 +282,25 @@ def test_unported_names_are_refused(stub, tmp_path):
     (out / "run.config").write_text(cfg)
     r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert r.returncode in (-6, 134) and "gt_use_global_temp" in r.stderr.decode() and "successfully reached" not in r.stderr.decode()
+
+
+def test_artificial_viscosity_output_planes_are_requested_per_term_and_named_like_the_reference(stub, tmp_path):
+    """visc_output_visc / _lap / _strength / _timescale (viscosity.cpp:9-12, 351-376): enabled after the terms are configured; every frame appends, per flag, one plane per
+    term in config order under the reference's names <evolved>_dqdt / _lap / _str / _dt"""
+    s = synthetic.stratified_loop(20, 18, bump=0.5)
+    modules = [("artificial_viscosity", [("visc_opt", "boundary,global"), ("visc_strength", "0.8,3.0"), ("visc_vars_to_diff", "v_x,temp"), ("visc_vars_to_evol", "mom_x,thermal_energy"),
+                                         ("visc_length", "5.0e8,0"), ("visc_species", "i,i"), ("hv_time_integrator", "rk2"), ("visc_output_visc", "true"), ("visc_output_lap", "false"),
+                                         ("visc_output_strength", "true"), ("visc_output_timescale", "true")])]
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk2", xb=("fixed", "open"), yb=("reflect", "open"), max_iterations=2, iter_output_interval=1, modules=modules)
+    log, stdout, out = run_shell(stub, tmp_path, s, cfg)
+    calls = [ln.split()[0] for ln in log if ln.startswith("spruce_")]
+    i_en = next(i for i, ln in enumerate(log) if ln.startswith("spruce_module_output_to_file artificial_viscosity 1"))
+    assert all(i < i_en for i, ln in enumerate(log) if ln.startswith("spruce_module_viscosity_term"))
+    assert calls.count("spruce_module_viscosity_term") == 2
+    outs = [ln.split()[1] for ln in log if ln.startswith("spruce_module_output ")]
+    frame = ["visc_dqdt:0", "visc_dqdt:1", "visc_str:0", "visc_str:1", "visc_dt:0", "visc_dt:1"]
+    assert outs[:len(frame)] == frame and len(outs) == 3 * len(frame)
+    names, frames = refrun.read_out(out / "mhd.out")
+    for f in frames:
+        got = [k for k in f if k.endswith(("_dqdt", "_lap", "_str", "_dt")) and k != "dt"]
+        assert got == ["mom_x_dqdt", "thermal_energy_dqdt", "mom_x_str", "thermal_energy_str", "mom_x_dt", "thermal_energy_dt"], got

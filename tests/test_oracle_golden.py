@@ -4,7 +4,7 @@ source/mhd/evolution.cpp:62) and every evolved plane + temp + dt after the recor
 import numpy as np
 import pytest
 
-from golden_util import (Golden, OUT_VARS, cases, mismatch, module_kwargs, physical_viscosity_coefficient, same_bits, small_module_kwargs,
+from golden_util import (Golden, OUT_VARS, cases, mismatch, module_kwargs, physical_viscosity_coefficient, same_bits, small_module_kwargs, viscosity_plane_request,
                          viscosity_terms_with_profiles)
 from oracle.oracle import Oracle
 
@@ -38,7 +38,8 @@ def test_oracle_reproduces_reference(name):
             for v in OUT_VARS:
                 assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
             for pname, ref in g.module_planes.get(it, {}).items():          # output_to_file planes: "thermal_conduction", "flux_saturation", "rad"
-                got = o.module_output(pname)
+                vq = viscosity_plane_request(g.modules, pname)
+                got = o.viscosity_output(*vq) if vq else o.module_output(pname)
                 assert got is not None and same_bits(got, ref), "module plane %s after iteration %d: %s" % (pname, it, mismatch(got, ref))
     names = [m[0] for m in g.modules]
     if "thermal_conduction" in names:
