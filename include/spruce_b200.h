@@ -151,7 +151,9 @@ int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const dou
  * of that step's first temperature field (zero planes before the first step, as in the reference).  Enable per module, then download by plane name.
  * Also: module "anomalous_resistivity" -> planes "anomalous_diffusivity", "anomalous_template", "joule_heating" (anomalousresistivity.cpp:320-329), and the
  * plane "field_heating" (fieldheating.cpp:73-80: mask*(dt*heating) of the last step), which needs no enabling; module "physical_viscosity" -> planes
- * "viscous_heating", "viscous_force_x" / "_y" / "_z" (physicalviscosity.cpp:292-308: the averages over the last step's sub-cycles, also in inactive_mode). */
+ * "viscous_heating", "viscous_force_x" / "_y" / "_z" (physicalviscosity.cpp:292-308: the averages over the last step's sub-cycles, also in inactive_mode); module
+ * "artificial_viscosity" (enable AFTER its terms are configured) -> planes "visc_dqdt:<i>", "visc_lap:<i>", "visc_str:<i>", "visc_dt:<i>" of term i in config order
+ * (viscosity.cpp:351-376: m_grids_dqdt / _lap / _strength / _dt, each what the term's last evaluation left; zero planes before the first one). */
 int spruce_module_output_to_file(spruce_domain *dom, const char *module, int on);
 int spruce_module_output(spruce_domain *dom, const char *plane_name, double *host, size_t count);
 /* Pointwise solar source terms applied in postIterateModule (evolution.cpp:74), each followed by propagateChanges.  Gaussian templates
