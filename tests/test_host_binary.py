@@ -164,3 +164,28 @@ def test_run_binary_on_n_gpus_writes_the_single_gpu_files(name, n, tmp_path):
         refrun.run_reference(state, cfg, tmp_path / "ref", threads=4)
         for fname in ("mhd.out", "end.state"):
             assert (out / fname).read_bytes() == (tmp_path / "ref" / fname).read_bytes(), fname
+
+
+@pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked (tests/test_host_gengrids.py, test_host_shell_calls.py), first device run", strict=False)
+def test_a_generated_ucnp_set_runs_like_the_reference(tmp_path):
+    """The whole UCNP workflow on this side of the path: spruce_b200/bin/gengrids writes a set (its files equal the reference generator's byte for byte,
+    tests/test_host_gengrids.py), spruce_b200/bin/run evolves it; the reference binary evolves the same files: mhd.out and end.state byte-identical (ideal_mhd_2E, no libm module)."""
+    from test_host_gengrids import BASE, CASES, CONFIG
+    subprocess.run(["make", "-C", str(ROOT / "spruce_b200" / "host")], check=True)
+    assert refrun.have_reference()
+    settings, config, _ = CASES["sweep_2e_nonuniform_runs"]
+    (tmp_path / "sweep.settings").write_text(BASE.format(**dict(settings, nx=41, ny=37, n="1e9", n_dist="gaussian", te=20,
+                                                                extra="max_iterations = cgs = 6\niter_output_interval = cgs = 2\nwrite_precision = cgs = 17\nstd_out_interval = cgs = 1\n")))
+    (tmp_path / "template.config").write_text(CONFIG.format(**config).replace("eic_thermalization = true\n{\n}\n", ""))
+    r = subprocess.run([str(ROOT / "spruce_b200" / "bin" / "gengrids"), "-p", str(tmp_path / "sets"), "-s", str(tmp_path / "sweep.settings"), "-c", str(tmp_path / "template.config")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    set_dir = tmp_path / "sets" / "set_0"
+    cfg = (set_dir / "ucnp.config").read_text()                  # as generated: six steps of ~1e-12 s end long before the sweep's duration of 0.3 tau
+    refrun.run_reference(set_dir / "init.state", cfg, tmp_path / "ref", threads=4)
+    run_ours(set_dir / "init.state", cfg, tmp_path / "ours")
+    for fname in ("mhd.out", "end.state"):
+        a, b = (tmp_path / "ours" / fname).read_bytes(), (tmp_path / "ref" / fname).read_bytes()
+        assert a == b, "%s differs from the reference's (%d vs %d bytes)" % (fname, len(a), len(b))
+    _, frames = refrun.read_out(tmp_path / "ref" / "mhd.out")
+    assert len(frames) == 4

@@ -304,3 +304,32 @@ def test_artificial_viscosity_output_planes_are_requested_per_term_and_named_lik
     for f in frames:
         got = [k for k in f if k.endswith(("_dqdt", "_lap", "_str", "_dt")) and k != "dt"]
         assert got == ["mom_x_dqdt", "thermal_energy_dqdt", "mom_x_str", "thermal_energy_str", "mom_x_dt", "thermal_energy_dt"], got
+
+
+def test_a_set_written_by_the_problem_generator_runs_through_the_shell(stub, tmp_path):
+    """spruce_b200/bin/gengrids (the reference's execs/gengrids.cpp; tests/test_host_gengrids.py holds its files to the reference generator's byte for byte) -> `run`: the
+    generated ucnp.config / init.state of a set are the inputs of the drop-in binary as they stand -- ideal_mhd_2E with eic_thermalization on the generator's odd, non-uniform
+    grid, the step count taken from a settings row named like a config key"""
+    from test_host_gengrids import BASE, CASES, CONFIG
+    settings, config, _ = CASES["sweep_2e_nonuniform_runs"]
+    (tmp_path / "sweep.settings").write_text(BASE.format(**dict(settings, n="1e9", n_dist="gaussian", extra="max_iterations = cgs = 2\nstd_out_interval = cgs = 1\n")))
+    (tmp_path / "template.config").write_text(CONFIG.format(**config))
+    gen = ROOT / "spruce_b200" / "bin" / "gengrids"
+    r = subprocess.run([str(gen), "-p", str(tmp_path / "sets"), "-s", str(tmp_path / "sweep.settings"), "-c", str(tmp_path / "template.config")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    set_dir = tmp_path / "sets" / "set_0"
+    out = tmp_path / "out"
+    out.mkdir()
+    (out / "run.config").write_text((set_dir / "ucnp.config").read_text())
+    log = tmp_path / "calls.log"
+    env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(log))
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(set_dir / "init.state")], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode in (-6, 134) and "Simulation successfully reached max simulation time or iterations" in r.stderr.decode(), r.stderr.decode()[-2000:]
+    lines = log.read_text().splitlines()
+    c = args_of(lines[0])
+    assert c["eqs"] == "2" and c["xdim"] == "21" and c["ydim"] == "17" and c["bc"] == "5,5,5,5" and float(c["epsilon"]) == 0.15      # epsilon: the sweep's row replaced the template's line
+    calls = [ln.split()[0] for ln in lines if ln.startswith("spruce_")]
+    assert "spruce_module_eic_thermalization" in calls
+    assert 1 <= sum(int(args_of(ln)["done"]) for ln in lines if ln.startswith("spruce_advance")) <= 2       # max_iterations = 2 from the sweep, or its duration (0.3 tau) first
+    uploads = {ln.split()[1] for ln in lines if ln.startswith("spruce_grid_upload")}
+    assert {"be_x", "be_y", "rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y"} <= uploads
