@@ -155,6 +155,14 @@ int spruce_module_physical_viscosity(spruce_domain *dom, double coeff, const dou
  * "artificial_viscosity" (enable AFTER its terms are configured) -> planes "visc_dqdt:<i>", "visc_lap:<i>", "visc_str:<i>", "visc_dt:<i>" of term i in config order
  * (viscosity.cpp:351-376: m_grids_dqdt / _lap / _strength / _dt, each what the term's last evaluation left; zero planes before the first one). */
 int spruce_module_output_to_file(spruce_domain *dom, const char *module, int on);
+/* multispecies_mode = true of PlasmaDomain (source/mhd/plasmadomain.hpp:134-135, fileio.cpp:164-183, 322): three cumulative planes -- "cumulative_electron_heating",
+ * "cumulative_ion_heating", "cumulative_joule_heating", downloaded by name with spruce_module_output -- to which thermal_conduction, radiative_losses, ambient_heating,
+ * ambient_heating_sink, localized_heating and physical_viscosity add their energy input, split by the module's ms_electron_heating_fraction (defaults as in the
+ * reference: 1, 1, 0.5, 0.5, 0, 0), and anomalous_resistivity its joule heating.  The host resets them after every stored frame (evolution.cpp:36-41).
+ * ideal_mhd domains only. */
+int spruce_multispecies_mode(spruce_domain *dom, int on);
+int spruce_multispecies_reset(spruce_domain *dom);
+int spruce_module_ms_fraction(spruce_domain *dom, const char *module, double ms_electron_heating_fraction);
 int spruce_module_output(spruce_domain *dom, const char *plane_name, double *host, size_t count);
 /* Pointwise solar source terms applied in postIterateModule (evolution.cpp:74), each followed by propagateChanges.  Gaussian templates
  * (SolarUtils::GaussianGrid / GaussianGridRotated, source/solar/solarutils.cpp:65-98; centres and widths in grid cells, combined with

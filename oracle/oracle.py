@@ -77,6 +77,11 @@ def lib():
         L.oracle_set_moc_limiting.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle_physical_viscosity_iterate.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_set_multispecies.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_ms_fraction.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.oracle_ms_plane.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.oracle_ms_plane.restype = C.c_int
+        L.oracle_ms_reset.argtypes = [C.c_void_p]
         L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
         L.oracle2e_destroy.argtypes = [C.c_void_p]
         L.oracle2e_set_eic.argtypes = [C.c_void_p, C.c_int]
@@ -236,6 +241,23 @@ class Oracle:
         out = np.zeros((4, self.nx, self.ny))
         lib().oracle_anomalous_core(self.h, C.c_double(dt), _dp(out), C.c_int(int(raw_commit)))
         return out
+
+    def set_multispecies(self, on: bool = True, **fractions):
+        """multispecies_mode = true; fractions: ms_electron_heating_fraction per module (thermal_conduction=, radiative_losses=, ambient_heating=, physical_viscosity=,
+        ambient_heating_sink=, localized_heating=), the reference's defaults otherwise"""
+        lib().oracle_set_multispecies(self.h, int(on))
+        ids = {"thermal_conduction": 1, "radiative_losses": 2, "ambient_heating": 3, "physical_viscosity": 5, "ambient_heating_sink": 6, "localized_heating": 7}
+        for k, v in fractions.items():
+            lib().oracle_set_ms_fraction(self.h, ids[k], float(v))
+
+    def ms_plane(self, name: str):
+        """cumulative_electron_heating / cumulative_ion_heating / cumulative_joule_heating since the last ms_reset()"""
+        out = np.zeros((self.nx, self.ny))
+        ok = lib().oracle_ms_plane(self.h, {"cumulative_electron_heating": 0, "cumulative_ion_heating": 1, "cumulative_joule_heating": 2}[name], _dp(out))
+        return out if ok else None
+
+    def ms_reset(self):
+        lib().oracle_ms_reset(self.h)
 
     def physical_viscosity_iterate(self, dt: float):
         """PhysicalViscosity::iterateModule alone, on the current state"""

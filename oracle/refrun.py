@@ -117,7 +117,7 @@ def ideal_mhd_config(*, integrator="rk2", max_iterations=10, xb=("periodic", "pe
                      output_flags=("rho", "temp", "thermal_energy", "mom_x", "mom_y", "mom_z", "bi_x", "bi_y", "bi_z", "dt"),
                      iter_output_interval=1, write_precision=17, open_strength=1.0, open_decay=0.5,
                      eqs="ideal_mhd", eqs_block=(), modules=(), std_out_interval=-1, duration=1.0e30,
-                     write_interval=1):
+                     write_interval=1, multispecies=False):
     """Config text accepted by the current reference code: equation-set block FIRST,
     braces in column 0, no blank lines inside it.  modules: iterable of (name, [(key, value), ...])."""
     L = ["%s = true" % eqs, "{"]
@@ -143,6 +143,8 @@ def ideal_mhd_config(*, integrator="rk2", max_iterations=10, xb=("periodic", "pe
     ]
     if output_flags:
         L.append("output_flags = " + ", ".join(output_flags))
+    if multispecies:
+        L.append("multispecies_mode = true")
     for name, kvs in modules:
         L += ["%s = true" % name, "{"]
         L += ["%s = %s" % kv for kv in kvs]

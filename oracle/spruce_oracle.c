@@ -61,6 +61,9 @@ typedef struct {
                                    * whatever the LAST evaluation of the term left there (zero planes before the first one, :99-102) */
     /* physical_viscosity (source/modules/solar/physicalviscosity.hpp) */
     int pv_on, pv_heating_on, pv_force_on, pv_gc, pv_integrator, pv_inactive, pv_nsub; double pv_coeff, pv_epsilon; double *pv_cg;
+    /* multispecies_mode (plasmadomain.hpp:134-135): cumulative electron / ion / joule heating between outputs, fed by the modules with their
+     * ms_electron_heating_fraction; ms_frac is indexed by module: 1 tc, 2 rl, 3 ah, 5 pv, 6 ambient_heating_sink, 7 localized_heating */
+    int ms_on; double ms_frac[8]; double *ms_cum[3];
     double *pv_avg[4];                  /* output_to_file planes: viscous_heating, viscous_force_x/y/z (physicalviscosity.cpp:151-152,166,170,218,222,292-308) */
     void *anom;                   /* anomalous_resistivity (anomalous_resistivity_oracle.inc); order id 13 */
     void *small[8]; int n_small;  /* small solar modules (solar_small_modules_oracle.inc); order id = 100 + index */
@@ -517,6 +520,11 @@ static double min_range(const oracle *o, const double *a, int il, int jl, int iu
 }
 
 static void propagate_changes(const oracle *o, double **G, double **P);
+/* multispecies_mode: a module's energy input w goes to the cumulative planes as  ion += (1 - f) * w  (if f < 1),  electron += f * w  (if f > 0), f = the module's
+ * ms_electron_heating_fraction (e.g. thermalconduction.cpp:105-108).  W(fr) is the per-cell expression with the fraction factor `fr` placed where the reference places it. */
+#define MS_FEED(o, module, OP, W) do { if ((o)->mod.ms_on) { const double f_ = (o)->mod.ms_frac[module]; \
+        if (f_ < 1.0) { const double fr = 1.0 - f_; for (int c = 0; c < (o)->n; c++) (o)->mod.ms_cum[1][c] OP (W); } \
+        if (f_ > 0.0) { const double fr = f_; for (int c = 0; c < (o)->n; c++) (o)->mod.ms_cum[0][c] OP (W); } } } while (0)
 #include "physical_viscosity_oracle.inc"
 #include "moc_oracle.inc"
 #include "ucnp_modules_oracle.inc"
@@ -751,6 +759,7 @@ static void tc_iterate(oracle *o, double dt)
         }
     }
     for (int c = 0; c < n; c++) o->mod.tc_avg[c] = (e[c] - o->g[V_thermal_energy][c]) / dt;                                  /* :102 */
+    MS_FEED(o, 1, +=, (e[c] - o->g[V_thermal_energy][c]) * fr);                                                              /* :105-108 */
     memcpy(o->g[V_thermal_energy], e, sizeof(double) * n);
     propagate_changes(o, o->g, o->g);
     free(e); free(T); free(nn); free(bhx); free(bhy); free(k1); free(k2); free(k3); free(k4); free(im); free(imT);
@@ -825,6 +834,7 @@ static void rl_iterate(oracle *o, double dt)
     }
     if (!o->mod.rl_avg) o->mod.rl_avg = pl_new(o);
     for (int c = 0; c < n; c++) o->mod.rl_avg[c] = (e[c] - o->g[V_thermal_energy][c]) / dt;                                  /* radiativelosses.cpp:93 */
+    MS_FEED(o, 2, +=, (e[c] - o->g[V_thermal_energy][c]) * fr);                                                              /* :94-97 */
     memcpy(o->g[V_thermal_energy], e, sizeof(double) * n);
     propagate_changes(o, o->g, o->g);
     free(e); free(T); free(nn); free(k1); free(k2); free(k3); free(k4); free(im); free(imT);
@@ -835,6 +845,7 @@ static void ah_post_iterate(oracle *o, double dt)
 {
     for (int c = 0; c < o->n; c++) o->g[V_thermal_energy][c] += o->mod.ah_heating[c] * dt;
     propagate_changes(o, o->g, o->g);
+    MS_FEED(o, 3, +=, ((o->mask[c] * fr) * o->mod.ah_heating[c]) * dt);                                                      /* :45-48 */
 }
 
 /* ------------------------------------------------------------------ time loop (source/mhd/evolution.cpp) */
@@ -893,6 +904,9 @@ oracle *oracle_create(int nx, int ny, int xb1, int xb2, int yb1, int yb2, int in
                       double open_strength, double open_decay)
 {
     oracle *o = (oracle *)calloc(1, sizeof(oracle));
+    /* ms_electron_heating_fraction defaults: thermalconduction.hpp:34, radiativelosses.hpp:31 (1.0); ambientheating.hpp:28, ambientheatingsink.hpp:28 (0.5);
+     * physicalviscosity.hpp:33, localizedheating.hpp:28 (0.0) */
+    o->mod.ms_frac[1] = 1.0; o->mod.ms_frac[2] = 1.0; o->mod.ms_frac[3] = 0.5; o->mod.ms_frac[6] = 0.5;
     o->nx = nx; o->ny = ny; o->n = nx * ny;
     o->xb1 = xb1; o->xb2 = xb2; o->yb1 = yb1; o->yb2 = yb2; o->integrator = integrator;
     o->m_i = m_i; o->gamma = gamma; o->epsilon = epsilon; o->n_min = n_min; o->T_min = T_min; o->e_min = e_min;
@@ -915,6 +929,7 @@ void oracle_destroy(oracle *o)
     free(o->mod.pv_cg);
     for (int k = 0; k < 4; k++) free(o->mod.pv_avg[k]);
     for (int w = 0; w < 4; w++) for (int i = 0; i < 8; i++) free(o->mod.av_out[w][i]);
+    for (int k = 0; k < 3; k++) free(o->mod.ms_cum[k]);
     free(o);
 }
 /* which: 0 d_x 1 d_y 2 be_x 3 be_y 4 be_z 5 pos_x 6 pos_y 7 mask(read only) ; 100+v equation-set variable v */
@@ -1052,6 +1067,22 @@ void oracle_anomalous_core(oracle *o, double dt, double *out, int raw_commit)
         memcpy(o->g[V_thermal_energy], out + 3 * n, sizeof(double) * n);
     }
 }
+/* multispecies_mode = true (fileio.cpp:322; planes zeroed at construction, plasmadomain.cpp:55-59) and the modules' ms_electron_heating_fraction */
+void oracle_set_multispecies(oracle *o, int on)
+{
+    o->mod.ms_on = on;
+    for (int k = 0; k < 3; k++) { if (!o->mod.ms_cum[k]) o->mod.ms_cum[k] = pl_new(o); memset(o->mod.ms_cum[k], 0, sizeof(double) * o->n); }
+}
+void oracle_set_ms_fraction(oracle *o, int module, double f) { if (module >= 0 && module < 8) o->mod.ms_frac[module] = f; }
+/* which: 0 cumulative_electron_heating, 1 cumulative_ion_heating, 2 cumulative_joule_heating */
+int oracle_ms_plane(const oracle *o, int which, double *out)
+{
+    if (!o->mod.ms_on || which < 0 || which > 2) return 0;
+    memcpy(out, o->mod.ms_cum[which], sizeof(double) * o->n);
+    return 1;
+}
+/* the reset after every stored frame (evolution.cpp:36-41) */
+void oracle_ms_reset(oracle *o) { if (o->mod.ms_on) for (int k = 0; k < 3; k++) memset(o->mod.ms_cum[k], 0, sizeof(double) * o->n); }
 /* test accessor: PhysicalViscosity::iterateModule alone (sub-cycle count, sub-cycles, closing propagateChanges) */
 void oracle_physical_viscosity_iterate(oracle *o, double dt) { pv_iterate(o, dt); }
 void oracle_anomalous_iterate(oracle *o, double dt) { ar_iterate(o, (anom_res *)o->mod.anom, dt); }

@@ -81,6 +81,7 @@ int ar_iterate(spruce_domain *d, double dt)
         k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->ar.avg, x.plane(ar::P_E), d->Pset.p[E_E], dt);
         d->launches++;
     }
+    if ((rc = ms_feed(d, MS_JOULE, x.plane(ar::P_E), d->Pset.p[E_E], 0.0))) return rc;                                  // m_cumulative_joule_heating, :168-170
     for (int q = 0; q < 4; q++) x.cells(ar::Copy{g, d->Pset.p[src[q]], x.plane(ar::P_BIX + q)});                       // :175-176
     if (x.err) return x.err;
     if ((rc = launch_propagate(d, 0))) return rc;                                                                        // :177

@@ -107,7 +107,11 @@ struct spruce_domain {
     struct { ar::State s{}; bool on = false, ready = false, output = false; double *planes[ar::P_COUNT] = {nullptr}; double *px = nullptr, *py = nullptr, *dtp = nullptr, *kernel = nullptr, *avg = nullptr, *prod = nullptr;
              std::vector<double> hpx, hpy; } ar;
     // pointwise solar source terms (module_kernels.cuh: k_source_term), in config order
-    struct SourceTerm { int kind = 0; double start = 0.0, duration = 0.0, ramp_time = 0.0, max_accel = 0.0, period = 1.0; int oscillatory = 0; double *plane[2] = {nullptr, nullptr}; };
+    struct SourceTerm { int kind = 0; double start = 0.0, duration = 0.0, ramp_time = 0.0, max_accel = 0.0, period = 1.0; int oscillatory = 0; double *plane[2] = {nullptr, nullptr};
+                        double ms_fraction = 0.0; };      // ms_electron_heating_fraction: 0.5 for the sink, 0.0 for localized_heating (ambientheatingsink.hpp:28, localizedheating.hpp:28)
+    // multispecies_mode (plasmadomain.hpp:134-135): cumulative electron / ion / joule heating between outputs; the modules' electron fractions with the reference's defaults
+    bool ms_on = false; double *ms_cum[3] = {nullptr, nullptr, nullptr};
+    double ms_frac_tc = 1.0, ms_frac_rl = 1.0, ms_frac_ah = 0.5, ms_frac_pv = 0.0;
     std::vector<SourceTerm> sources;
     TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
     RlParams rl{}; int rl_nsub = 0;
@@ -572,6 +576,19 @@ int after_module_propagate(spruce_domain *d)
 }
 
 // ThermalConduction::numberSubcycles (thermalconduction.cpp:135-149); scratch: Mset planes 0..2 (temp, b_hat_x, b_hat_y)
+// one feed of the cumulative planes of multispecies_mode (k_ms_feed); dt comes from the device step control when the form needs it
+int ms_feed(spruce_domain *d, int mode, const double *a, const double *b, double f, double sign = 1.0)
+{
+    if (!d->ms_on) return SPRUCE_OK;
+    MsArgs A{};
+    A.cum_i = mode == MS_JOULE ? d->ms_cum[2] : d->ms_cum[1]; A.cum_e = d->ms_cum[0];
+    A.a = a; A.b = b; A.f = f; A.sign = sign; A.mode = mode; A.dt_ptr = &d->ctl->step; A.done_ptr = &d->ctl->done;
+    const dim3 grid((d->P.ny + 255) / 256, d->P.nx);
+    k_ms_feed<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
 int tc_count(spruce_domain *d, double dt, int *nsub)
 {
     int rc;
@@ -607,9 +624,11 @@ int tc_iterate(spruce_domain *d, double dt)
     double *e = d->Pset.p[E_E];
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     const dim3 grid256((d->P.ny + 255) / 256, d->P.nx);
-    if (d->tc_output) {                                                                             // :53-59
+    if (d->tc_output || d->ms_on) {                                                                 // :53-59
         k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, e);
         d->launches++;
+    }
+    if (d->tc_output) {
         if (d->tc.flux_saturation) {
             k_tc_saturation_plane<<<grid, 128, 0, d->stream>>>(d->P, d->tc, TcFields{Ta, d->Pset.p[E_N], bhx, bhy}, d->tc_sat);
             d->launches++;
@@ -643,6 +662,7 @@ int tc_iterate(spruce_domain *d, double dt)
         k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->tc_avg, e, d->old_e, dt);
         d->launches++;
     }
+    if ((rc = ms_feed(d, MS_DIFF, e, d->old_e, d->ms_frac_tc))) return rc;                          // :105-108
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // :110-111
     return after_module_propagate(d);
 }
@@ -676,10 +696,11 @@ int rl_count(spruce_domain *d, double dt, int *nsub)
 int rl_iterate(spruce_domain *d, double dt)
 {
     const dim3 grid256((d->P.ny + 255) / 256, d->P.nx);
-    if (d->rl_output) { k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, d->Pset.p[E_E]); d->launches++; }     // radiativelosses.cpp:50
+    if (d->rl_output || d->ms_on) { k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, d->Pset.p[E_E]); d->launches++; }     // radiativelosses.cpp:50
     int rc = rl_launch(d, 0, dt);
     if (rc) return rc;
     if (d->rl_output) { k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->rl_avg, d->Pset.p[E_E], d->old_e, dt); d->launches++; }   // :93
+    if ((rc = ms_feed(d, MS_DIFF, d->Pset.p[E_E], d->old_e, d->ms_frac_rl))) return rc;             // :94-97
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // radiativelosses.cpp:99-100
     return after_module_propagate(d);
 }
@@ -708,7 +729,10 @@ int src_post(spruce_domain *d, const spruce_domain::SourceTerm &m, double time, 
     if (m.kind == SRC_MASS) d->raw_rho = true;                     // E_N holds rho until the propagate's floor / n round trip
     int rc = launch_propagate(d, 0);
     if (rc) return rc;
-    return after_module_propagate(d);
+    if ((rc = after_module_propagate(d))) return rc;
+    if (m.kind == SRC_SINK) return ms_feed(d, MS_RATE, m.plane[0], nullptr, m.ms_fraction, -1.0);        // ambientheatingsink.cpp:38-41
+    if (m.kind == SRC_HEATING) return ms_feed(d, MS_PULSE, m.plane[0], nullptr, m.ms_fraction);           // localizedheating.cpp:63-66
+    return SPRUCE_OK;
 }
 int launch_op(spruce_domain *d, int code, int index, const double *q, double *out)
 {
@@ -822,7 +846,8 @@ int ah_post(spruce_domain *d)
     CUDA_TRY(cudaGetLastError());
     int rc = launch_propagate(d, 0);                                                                // ambientheating.cpp:43-44
     if (rc) return rc;
-    return after_module_propagate(d);
+    if ((rc = after_module_propagate(d))) return rc;
+    return ms_feed(d, MS_RATE, d->heating, nullptr, d->ms_frac_ah);                                 // :45-48
 }
 
 // ---- artificial viscosity (source/modules/viscosity.cpp)
@@ -1091,6 +1116,7 @@ int pv_substeps(spruce_domain *d, double dt)
         for (int k = 0; k < 4; k++) { A.avg[k] = pv.avg[k]; CUDA_TRY(cudaMemsetAsync(pv.avg[k] - d->row_off, 0, d->plane_doubles * sizeof(double), d->stream)); }
         A.nsub = (double)pv.nsub;
     }
+    if (d->ms_on) { A.ms_i = d->ms_cum[1]; A.ms_e = d->ms_cum[0]; A.ms_f = d->ms_frac_pv; }
     int cur = 0;
     auto stage = [&](int from, int to, double half, int final_stage) -> int {
         for (int k = 0; k < 3; k++) { A.v[k] = pv.v[from][k]; A.v_out[k] = pv.v[to][k]; }
@@ -1771,7 +1797,7 @@ int spruce_module_ambient_heating_sink(spruce_domain *d, const double *reduction
     NOT_2F(d, "ambient_heating_sink");
     const size_t np = (size_t)d->P.nx * d->P.ny;
     if (!reduction || count != np) return fail(SPRUCE_ERR_ARG, "reduction plane needs %zu values", np);
-    spruce_domain::SourceTerm m; m.kind = SRC_SINK;
+    spruce_domain::SourceTerm m; m.kind = SRC_SINK; m.ms_fraction = 0.5;
     const std::vector<double> p(reduction, reduction + np);
     return add_source(d, m, &p, nullptr);
 }
@@ -2001,6 +2027,45 @@ int spruce_module_eic_thermalization(spruce_domain *d)
     d->tf->eic = 1;
     return SPRUCE_OK;
 }
+// multispecies_mode = true (fileio.cpp:322): the three cumulative planes exist from now on, zero (plasmadomain.cpp:55-59)
+int spruce_multispecies_mode(spruce_domain *d, int on)
+{
+    CHECK_DOM(d);
+    NOT_2F(d, "multispecies_mode");
+    int rc;
+    if (on) {
+        for (int k = 0; k < 3; k++) if (!d->ms_cum[k] && (rc = alloc_plane(d, &d->ms_cum[k]))) return rc;
+        if (!d->old_e && (rc = alloc_plane(d, &d->old_e))) return rc;
+    }
+    d->ms_on = on != 0;
+    return SPRUCE_OK;
+}
+// the reset after every stored frame (evolution.cpp:36-41)
+int spruce_multispecies_reset(spruce_domain *d)
+{
+    CHECK_DOM(d);
+    if (!d->ms_on) return SPRUCE_OK;
+    for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(d->ms_cum[k] - d->row_off, 0, d->plane_doubles * sizeof(double), d->stream));
+    return SPRUCE_OK;
+}
+// ms_electron_heating_fraction of a module (thermalconduction.cpp:27,40 and the like): 0 <= f <= 1; call after the module is configured
+int spruce_module_ms_fraction(spruce_domain *d, const char *module, double f)
+{
+    CHECK_DOM(d);
+    if (!module) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (!(f >= 0.0 && f <= 1.0)) return fail(SPRUCE_ERR_ARG, "%s MS electron heating fraction must be between 0 and 1", module);
+    if (!strcmp(module, "thermal_conduction")) d->ms_frac_tc = f;
+    else if (!strcmp(module, "radiative_losses")) d->ms_frac_rl = f;
+    else if (!strcmp(module, "ambient_heating")) d->ms_frac_ah = f;
+    else if (!strcmp(module, "physical_viscosity")) d->ms_frac_pv = f;
+    else if (!strcmp(module, "ambient_heating_sink") || !strcmp(module, "localized_heating")) {
+        const int kind = !strcmp(module, "localized_heating") ? SRC_HEATING : SRC_SINK;
+        bool any = false;
+        for (auto &m : d->sources) if (m.kind == kind) { m.ms_fraction = f; any = true; }
+        if (!any) return fail(SPRUCE_ERR_STATE, "ms_electron_heating_fraction of <%s> before the module is configured", module);
+    } else return fail(SPRUCE_ERR_ARG, "module <%s> has no ms_electron_heating_fraction", module);
+    return SPRUCE_OK;
+}
 int spruce_module_output_to_file(spruce_domain *d, const char *module, int on)
 {
     CHECK_DOM(d);
@@ -2032,6 +2097,10 @@ int spruce_module_output(spruce_domain *d, const char *name, double *host, size_
     if (!name || !host) return fail(SPRUCE_ERR_ARG, "null argument");
     if (count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "plane size mismatch");
     const double *src = !strcmp(name, "thermal_conduction") ? d->tc_avg : !strcmp(name, "flux_saturation") ? d->tc_sat : !strcmp(name, "rad") ? d->rl_avg : nullptr;
+    if (d->ms_on) {                                                                                  // multispecies_mode: what has accumulated since the last reset
+        const char *msn[3] = {"cumulative_electron_heating", "cumulative_ion_heating", "cumulative_joule_heating"};
+        for (int k = 0; k < 3; k++) if (!strcmp(name, msn[k])) src = d->ms_cum[k];
+    }
     if (d->pv.output && d->pv.avg[0]) {                                                             // zero planes before the first step, like the reference's (:38-39, :295)
         const char *pvn[4] = {"viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"};
         for (int k = 0; k < 4; k++) if (!strcmp(name, pvn[k])) src = d->pv.avg[k];

@@ -412,6 +412,30 @@ __global__ void __launch_bounds__(256) k_avg_change(const DomainParams P, double
     const size_t off = (size_t)r * P.pitch + j;
     out[off] = (e[off] - old[off]) / dt;
 }
+// multispecies_mode (plasmadomain.hpp:134-135): a module's energy input w joins the cumulative planes as  ion (+/-)= (1 - f) w  when f < 1,  electron (+/-)= f w  when f > 0,
+// f = the module's ms_electron_heating_fraction.  w per cell, the fraction factor fr placed where the reference places it:
+//   MS_DIFF   (a - b) fr              thermalconduction.cpp:105-108, radiativelosses.cpp:94-97        (a = sub-cycled energy, b = energy before)
+//   MS_RATE   ((mask fr) a) dt        ambientheating.cpp:45-48, ambientheatingsink.cpp:38-41 (sign -1)
+//   MS_PULSE  (mask fr) (a dt)        localizedheating.cpp:63-66 (without the ramp factor, as there)
+//   MS_JOULE  joule += a - b          anomalousresistivity.cpp:168-170  (cum_i = the joule plane, no fraction)
+enum { MS_DIFF = 0, MS_RATE = 1, MS_PULSE = 2, MS_JOULE = 3 };
+struct MsArgs { double *cum_i, *cum_e; const double *a, *b; double f, sign; int mode; const double *dt_ptr; const int *done_ptr; };
+__global__ void __launch_bounds__(256) k_ms_feed(const DomainParams P, const MsArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny || (A.done_ptr && *A.done_ptr)) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    if (A.mode == MS_JOULE) { A.cum_i[off] = A.cum_i[off] + (A.a[off] - A.b[off]); return; }
+    const double mask = is_interior(P, r, j) ? 1.0 : 0.0, dt = A.dt_ptr ? *A.dt_ptr : 0.0;
+    auto w = [&](double fr) {
+        if (A.mode == MS_DIFF) return (A.a[off] - A.b[off]) * fr;
+        if (A.mode == MS_RATE) return ((mask * fr) * A.a[off]) * dt;
+        return (mask * fr) * (A.a[off] * dt);
+    };
+    if (A.f < 1.0) A.cum_i[off] = A.sign < 0.0 ? A.cum_i[off] - w(1.0 - A.f) : A.cum_i[off] + w(1.0 - A.f);
+    if (A.f > 0.0) A.cum_e[off] = A.sign < 0.0 ? A.cum_e[off] - w(A.f) : A.cum_e[off] + w(A.f);
+}
 __global__ void __launch_bounds__(128) k_tc_saturation_plane(const DomainParams P, const TcParams C, const TcFields F, double *out)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -681,6 +705,7 @@ struct PvArgs {
     double *avg[4];
     double nsub;
     int diag_only, repeat;
+    double *ms_i, *ms_e; double ms_f;               // multispecies_mode: cumulative ion / electron heating planes and the module's electron fraction (:174-177, :226-229); null = off
 };
 struct PvPoint { double dxv[3], dyv[3], t25, b[3], cg; };
 
@@ -787,6 +812,10 @@ __global__ void __launch_bounds__(128, 4) k_pv_stage(const __grid_constant__ Dom
         }
     }
     if (A.diag_only) return;
+    if (A.ms_i && A.final_stage && A.heating_on) {                                                  // heating applied in this sub-cycle: (1 - f) heating dt_sub to the ions, f ... to the electrons
+        if (A.ms_f < 1.0) A.ms_i[off] = A.ms_i[off] + (heating * (1.0 - A.ms_f)) * A.dt;
+        if (A.ms_f > 0.0) A.ms_e[off] = A.ms_e[off] + (heating * A.ms_f) * A.dt;
+    }
     const double hs = A.half;
     double e1 = A.e[off], T1 = A.T[off];
     if (A.heating_on) {                                                                            // :176-185 / :214-218

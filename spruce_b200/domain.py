@@ -230,6 +230,16 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_module_physical_viscosity(self.h, coeff, _dp(a), a.size, epsilon, int(heating_on), int(force_on),
                                                              int(gradient_correction), capi.TI[integrator], int(inactive_mode)))
 
+    def set_multispecies(self, on: bool = True, **fractions):
+        """multispecies_mode = true (plasmadomain.hpp:134-135); fractions: ms_electron_heating_fraction per module name (set after the module is configured)"""
+        capi.check(self.lib.spruce_multispecies_mode(self.h, int(on)))
+        for module, f in fractions.items():
+            capi.check(self.lib.spruce_module_ms_fraction(self.h, module.encode(), float(f)))
+
+    def multispecies_reset(self):
+        """the reset the run loop makes after every stored frame (evolution.cpp:36-41)"""
+        capi.check(self.lib.spruce_multispecies_reset(self.h))
+
     def set_eic_thermalization(self):
         capi.check(self.lib.spruce_module_eic_thermalization(self.h))
 

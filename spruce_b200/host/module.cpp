@@ -93,6 +93,13 @@ static int integrator_id(std::string s, const char *who)
     spruce_die(std::string("Invalid time integrator given for ") + who + " module");
 }
 
+// ms_electron_heating_fraction (multispecies_mode): checked like the reference's asserts (e.g. thermalconduction.cpp:40), handed over when the config sets it
+// (the library holds the reference's defaults)
+static void send_ms_fraction(PlasmaDomain &pd, const char *module, const char *label, double f, bool given)
+{
+    if (!(f >= 0.0 && f <= 1.0)) spruce_die(std::string(label) + " MS electron heating fraction must be between 0 and 1");
+    if (given) PlasmaDomain::check(spruce_module_ms_fraction(pd.device(), module, f));
+}
 // thermalconduction.cpp:16-30
 void ThermalConduction::parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs)
 {
@@ -105,7 +112,7 @@ void ThermalConduction::parseModuleConfigs(std::vector<std::string> lhs, std::ve
         else if (k == "time_integrator") time_integrator = v;
         else if (k == "inactive_mode") inactive_mode = (v == "true");
         else if (k == "weakening_factor") weakening_factor = std::stod(v);
-        else if (k == "ms_electron_heating_fraction") { }
+        else if (k == "ms_electron_heating_fraction") { ms_electron_heating_fraction = std::stod(v); ms_given = true; }
         else std::cerr << k << " config not recognized for Thermal Conduction Module.\n";
     }
 }
@@ -114,6 +121,7 @@ void ThermalConduction::setupModule()
     SPRUCE_REQUIRE(!inactive_mode, "thermal_conduction inactive_mode is a diagnostic of the CPU build");
     PlasmaDomain::check(spruce_module_thermal_conduction(m_pd.device(), flux_saturation, integrator_id(time_integrator, "Thermal Conduction"), epsilon, dt_subcycle_min, weakening_factor));
     if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "thermal_conduction", 1));
+    send_ms_fraction(m_pd, "thermal_conduction", "Thermal Conduction", ms_electron_heating_fraction, ms_given);
 }
 // the device keeps the two diagnostic planes of the last step; zero planes before the first one, like the reference's
 static void append_device_plane(PlasmaDomain &pd, const char *name, std::vector<std::string> &names, std::vector<Grid> &grids)
@@ -149,7 +157,7 @@ void RadiativeLosses::parseModuleConfigs(std::vector<std::string> lhs, std::vect
         else if (k == "time_integrator") time_integrator = v;
         else if (k == "inactive_mode") inactive_mode = (v == "true");
         else if (k == "prevent_subcycling") prevent_subcycling = (v == "true");
-        else if (k == "ms_electron_heating_fraction") { }
+        else if (k == "ms_electron_heating_fraction") { ms_electron_heating_fraction = std::stod(v); ms_given = true; }
         else std::cerr << k << " config not recognized.\n";
     }
 }
@@ -158,6 +166,7 @@ void RadiativeLosses::setupModule()
     SPRUCE_REQUIRE(!inactive_mode, "radiative_losses inactive_mode is a diagnostic of the CPU build");
     PlasmaDomain::check(spruce_module_radiative_losses(m_pd.device(), integrator_id(time_integrator, "Radiative Losses"), cutoff_ramp, cutoff_temp, epsilon, prevent_subcycling));
     if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "radiative_losses", 1));
+    send_ms_fraction(m_pd, "radiative_losses", "Rad. Losses", ms_electron_heating_fraction, ms_given);
 }
 void RadiativeLosses::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
 {
@@ -182,7 +191,7 @@ void AmbientHeating::parseModuleConfigs(std::vector<std::string> lhs, std::vecto
         else if (k == "split_exp_mode") split_exp_mode = (v == "true");
         else if (k == "split_exp_scale_height") split_exp_scale_height = std::stod(v);
         else if (k == "split_exp_start_height") split_exp_start_height = std::stod(v);
-        else if (k == "ms_electron_heating_fraction") { }
+        else if (k == "ms_electron_heating_fraction") { ms_electron_heating_fraction = std::stod(v); ms_given = true; }
         else std::cerr << k << " config not recognized.\n";
     }
 }
@@ -205,6 +214,7 @@ void AmbientHeating::setupModule()
         heating(i, j) = h;
     }
     PlasmaDomain::check(spruce_module_ambient_heating(m_pd.device(), m_pd.slab(heating), m_pd.slabCount()));
+    send_ms_fraction(m_pd, "ambient_heating", "Ambient Heating", ms_electron_heating_fraction, ms_given);
 }
 
 // ambientheatingsink.cpp:12-25
@@ -218,7 +228,7 @@ void AmbientHeatingSink::parseModuleConfigs(std::vector<std::string> lhs, std::v
         else if (k == "exp_scale_height") exp_scale_height = std::stod(v);
         else if (k == "center_x") center_x = std::stod(v);
         else if (k == "half_width") half_width = std::stod(v);
-        else if (k == "ms_electron_heating_fraction") ms_electron_heating_fraction = std::stod(v);
+        else if (k == "ms_electron_heating_fraction") { ms_electron_heating_fraction = std::stod(v); ms_given = true; }
         else std::cerr << k << " config not recognized.\n";
     }
 }
@@ -237,6 +247,7 @@ void AmbientHeatingSink::setupModule()
         } else reduction(i, j) = mask(i, j) * heating_rate;
     }
     PlasmaDomain::check(spruce_module_ambient_heating_sink(m_pd.device(), m_pd.slab(reduction), m_pd.slabCount()));
+    send_ms_fraction(m_pd, "ambient_heating_sink", "Ambient Heating Sink", ms_electron_heating_fraction, ms_given);
 }
 
 // localizedheating.cpp:14-29, massinjection.cpp:14-26, momentuminjection.cpp:16-33
@@ -253,7 +264,7 @@ void GaussianSource::parseModuleConfigs(std::vector<std::string> lhs, std::vecto
         else if (k == "center_x") center_x = std::stod(v);
         else if (k == "center_y") center_y = std::stod(v);
         else if (m_kind == Heating && k == "ramp_time") ramp_time = std::stod(v);
-        else if (m_kind == Heating && k == "ms_electron_heating_fraction") ms_electron_heating_fraction = std::stod(v);
+        else if (m_kind == Heating && k == "ms_electron_heating_fraction") { ms_electron_heating_fraction = std::stod(v); ms_given = true; }
         else if (m_kind == Momentum && k == "dir_x") dir_x = std::stod(v);
         else if (m_kind == Momentum && k == "dir_y") dir_y = std::stod(v);
         else if (m_kind == Momentum && k == "template_angle") template_angle = std::stod(v);
@@ -268,6 +279,7 @@ void GaussianSource::setupModule()
     if (m_kind == Heating) {
         SPRUCE_REQUIRE(ms_electron_heating_fraction >= 0.0 && ms_electron_heating_fraction <= 1.0, "Localized Heating MS electron heating fraction must be between 0 and 1");
         PlasmaDomain::check(spruce_module_localized_heating(dev, start_time, duration, peak, stddev_x, stddev_y, center_x, center_y, ramp_time));
+        send_ms_fraction(m_pd, "localized_heating", "Localized Heating", ms_electron_heating_fraction, ms_given);
     } else if (m_kind == Mass) {
         PlasmaDomain::check(spruce_module_mass_injection(dev, start_time, duration, peak, stddev_x, stddev_y, center_x, center_y));
     } else {
@@ -523,7 +535,7 @@ void PhysicalViscosity::parseModuleConfigs(std::vector<std::string> lhs, std::ve
         else if (k == "inactive_mode") inactive_mode = (v == "true");
         else if (k == "gradient_correction") gradient_correction = (v == "true");
         else if (k == "time_integrator") time_integrator = v;
-        else if (k == "ms_electron_heating_fraction") ms_electron_heating_fraction = std::stod(v);
+        else if (k == "ms_electron_heating_fraction") { ms_electron_heating_fraction = std::stod(v); ms_given = true; }
         else std::cerr << k << " config not recognized.\n";
     }
 }
@@ -558,6 +570,7 @@ void PhysicalViscosity::setupModule()
     PlasmaDomain::check(spruce_module_physical_viscosity(m_pd.device(), coeff, m_pd.slab(cg), m_pd.slabCount(), epsilon, heating_on, force_on, gradient_correction,
                                                          integrator_id(time_integrator, "Physical Viscosity"), inactive_mode));
     if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "physical_viscosity", 1));
+    send_ms_fraction(m_pd, "physical_viscosity", "Physical Viscosity", ms_electron_heating_fraction, ms_given);
 }
 // physicalviscosity.cpp:292-308: the sub-cycle averages of the last step, kept on the device (zero planes before the first step)
 void PhysicalViscosity::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)

@@ -27,6 +27,7 @@ public:
     virtual std::string commandLineMessage() const { return ""; }
     virtual void fileOutput(std::vector<std::string> &, std::vector<Grid> &) {}
     virtual std::vector<std::string> config_names() const { return {}; }
+    bool ms_given = false;               // the config block sets ms_electron_heating_fraction (multispecies_mode)
     virtual bool device_resident() const { return false; }   // true: hooks run on the GPU inside spruce_advance
 
 protected:
@@ -85,7 +86,7 @@ public:
     bool device_resident() const override { return true; }
 private:
     bool flux_saturation = false, output_to_file = false, inactive_mode = false;
-    double epsilon = 0.0, dt_subcycle_min = 0.0, weakening_factor = 1.0;
+    double epsilon = 0.0, dt_subcycle_min = 0.0, weakening_factor = 1.0, ms_electron_heating_fraction = 1.0;      // thermalconduction.hpp:34
     std::string time_integrator;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };
@@ -98,7 +99,7 @@ public:
     void fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids) override;      // radiativelosses.cpp:172-179
     bool device_resident() const override { return true; }
 private:
-    double cutoff_ramp = 0.0, cutoff_temp = 0.0, epsilon = 0.0;
+    double cutoff_ramp = 0.0, cutoff_temp = 0.0, epsilon = 0.0, ms_electron_heating_fraction = 1.0;      // radiativelosses.hpp:31
     bool output_to_file = false, inactive_mode = false, prevent_subcycling = false;
     std::string time_integrator;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
@@ -112,6 +113,7 @@ public:
     bool device_resident() const override { return true; }
 private:
     double heating_rate = 0.0, exp_base_heating_rate = 0.0, exp_scale_height = 1.0, split_exp_scale_height = 1.0, split_exp_start_height = 0.0;
+    double ms_electron_heating_fraction = 0.5;      // ambientheating.hpp:28
     bool exp_mode = false, split_exp_mode = false;
     void parseModuleConfigs(std::vector<std::string> lhs, std::vector<std::string> rhs) override;
 };

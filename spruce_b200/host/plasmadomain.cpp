@@ -41,6 +41,7 @@ PlasmaDomain::PlasmaDomain(const fs::path &out_path, const fs::path &config_path
     SPRUCE_REQUIRE(m_nx_local >= 4, "every slab needs at least 4 rows: fewer ranks for this grid");
     SPRUCE_REQUIRE(nRanks() == 1 || !m_module_handler.hasHostModules(), "host-resident modules (sg_filtering, tracer_particles, coulomb_explosion, global_temperature) work on whole planes: one rank only");
     m_eqs->setupEquationSet();
+    if (m_multispecies_mode) check(spruce_multispecies_mode(m_dev, 1));       // before the modules: they hand their ms_electron_heating_fraction over in setupModule
     m_module_handler.setupModules();
     if (!continue_mode && m_overwrite_init) {
         std::cout << "Writing out init.state...\n";
@@ -192,12 +193,7 @@ void PlasmaDomain::handleSingleConfig(int i, const std::string &rhs)
     else if (k == "time_integrator") m_time_integrator = stringToTimeIntegrator(rhs);
     else if (k == "duration") m_duration = std::stod(rhs);
     else if (k == "write_precision") m_write_precision = std::stoi(rhs);
-    else if (k == "multispecies_mode") {
-        // the reference adds the cumulative_electron / ion / joule_heating planes to mhd.out and its modules split their heating with
-        // ms_electron_heating_fraction (fileio.cpp:164-, plasmadomain.hpp): not ported -- refused rather than silently writing a different mhd.out
-        m_multispecies_mode = (rhs == "true");
-        if (m_multispecies_mode) spruce_die("multispecies_mode = true is not ported to the B200 path (cumulative heating planes, ms_electron_heating_fraction)");
-    }
+    else if (k == "multispecies_mode") m_multispecies_mode = (rhs == "true");      // cumulative_electron / ion / joule_heating planes in mhd.out (fileio.cpp:164-183), kept on the device
     else if (k == "sg_opt") m_sg_opt = rhs;                 // read by the sg_filtering module only (plasmadomain.cpp:51), which is not ported and refuses itself
     else if (k == "x_origin" || k == "y_origin") {}         // accepted and unused, as in the reference (fileio.cpp: parsed, never read on the run path)
 }
@@ -245,6 +241,14 @@ void PlasmaDomain::storeGrids()
         if (!writer) continue;
         m_data_to_write.push_back(m_eqs->index2name(i) + '\n');
         m_data_to_write.push_back(g.format(',', '\n', m_write_precision));
+    }
+    if (m_multispecies_mode) {                                                  // fileio.cpp:164-183: between the equation set's variables and the modules' planes
+        for (const char *name : {"cumulative_electron_heating", "cumulative_ion_heating", "cumulative_joule_heating"}) {
+            Grid g(m_xdim, m_ydim);
+            check(spruce_module_output(m_dev, name, slab(g), slabCount()));
+            gatherRows(g);
+            if (writer) { m_data_to_write.push_back(std::string(name) + '\n'); m_data_to_write.push_back(g.format(',', '\n', m_write_precision)); }
+        }
     }
     std::vector<std::string> names; std::vector<Grid> grids;
     m_module_handler.getFileOutputData(names, grids);
@@ -328,7 +332,10 @@ void PlasmaDomain::run(double time_duration, double cluster_time)
             store_time = m_time_output_interval > 0.0 && (int)(m_time / m_time_output_interval) > old_time_iter;
         }
         const bool store_iter = m_iter_output_interval > 0 && m_iter % m_iter_output_interval == 0;
-        if (store_iter || store_time) storeGrids();
+        if (store_iter || store_time) {
+            storeGrids();
+            if (m_multispecies_mode) check(spruce_multispecies_reset(m_dev));          // cumulative quantities restart between outputs (evolution.cpp:36-41)
+        }
         if (m_write_interval > 0 && m_store_counter > 0 && m_store_counter % m_write_interval == 0) {
             writeToOutFile();
             updateStateIdentifier();

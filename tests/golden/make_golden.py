@@ -109,6 +109,16 @@ CASES = {
                          modules=[PV(time_integrator="rk2", gradient_correction="true", ramp_length="6.0e8", coeff="1.0e-14", output_to_file="true")], **SOLAR_FLOORS), 3, (1, 3)),
     "ot_pv_diag_inactive": ("orszag_tang", dict(nx=NX, ny=NY, zfull=True), dict(integrator="euler", xb=("periodic", "periodic"), yb=("periodic", "periodic"),
                             modules=[PV(coeff="4.0e-16", epsilon="0.2", inactive_mode="true", output_to_file="true")], **INACTIVE_FLOORS), 3, (1, 3)),
+    # multispecies_mode (plasmadomain.hpp:134-135, evolution.cpp:36-41, fileio.cpp:164-183): cumulative electron / ion / joule heating between outputs, fed by the modules
+    # with their ms_electron_heating_fraction
+    "loop_ms_solar_rk2": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), multispecies=True, modules=[
+        TC(flux_saturation="true", ms_electron_heating_fraction="0.7"), RL(), AH(ms_electron_heating_fraction="0.3"),
+        PV(coeff="1.0e-14", time_integrator="rk2", ms_electron_heating_fraction="0.4")], **SOLAR_FLOORS), 3, (0, 1, 3)),
+    "ar_ms_joule_sources_rk2": ("stratified_loop", dict(nx=26, ny=26, bump=0.5), dict(integrator="rk2", xb=("fixed", "open"), yb=("fixed", "open"), multispecies=True, modules=[
+        ("anomalous_resistivity", [("time_scale", "0.3"), ("safety_factor", "0.5"), ("flood_fill_threshold", "1.5"), ("smoothing_sigma", "1.0")]),
+        ("ambient_heating_sink", [("heating_rate", "2.0e-5")]),
+        ("localized_heating", [("start_time", "0.0"), ("duration", "5.0"), ("max_heating_rate", "1.0e-3"), ("stddev_x", "3.0"), ("stddev_y", "4.0"), ("center_x", "2.0"), ("center_y", "8.0"),
+                               ("ramp_time", "1.0"), ("ms_electron_heating_fraction", "0.2")])], **SOLAR_FLOORS), 3, (1, 3)),
     # two-fluid equation set (source/equationsets/ideal2F.cpp, non-sub-cycled Maxwell update) + EIC thermalization (BASELINE.json configs[2])
     "tf_ucnp_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, **TF, **UCNP_FLOORS), 8, (1, 8)),
     "tf_ucnp_eic_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, modules=[EIC], **TF, **UCNP_FLOORS), 8, (1, 8)),

@@ -109,6 +109,14 @@ def module_kwargs(name, kv):
     raise KeyError(name)
 
 
+MS_PLANES = ("cumulative_electron_heating", "cumulative_ion_heating", "cumulative_joule_heating")
+
+
+def multispecies_fractions(modules):
+    """ms_electron_heating_fraction of every module block that sets it (the others keep the reference's defaults)"""
+    return {name: float(kv["ms_electron_heating_fraction"]) for name, kv in modules if "ms_electron_heating_fraction" in kv}
+
+
 def viscosity_plane_request(modules, pname):
     """'<evolved>_dqdt' / '_lap' / '_str' / '_dt' of Viscosity::fileOutput (viscosity.cpp:103-107, 351-376) -> (which, term index), or None for other names"""
     for suffix in ("dqdt", "lap", "str", "dt"):
@@ -206,6 +214,7 @@ def small_module_kwargs(name, kv):
         ora = {k: (B[v] if k == "boundary" else S[v] if k == "falloff_shape" else val(v)) for k, v in kv.items()}
         prod = {k: (v if k in ("boundary", "falloff_shape") else (v == "true") if v in ("true", "false") else float(v)) for k, v in kv.items()}
         return ora, prod
+    kv = {k: v for k, v in kv.items() if k != "ms_electron_heating_fraction"}       # multispecies_mode: handed over separately (multispecies_fractions)
     ora = {k: val(v) for k, v in kv.items()}
     prod = {k: ((v == "true") if v in ("true", "false") else float(v)) for k, v in kv.items()}
     return ora, prod

@@ -127,7 +127,7 @@ def assemble():
     ah = (CSRC / "anomres_host.cuh").read_text()
     ms = (CSRC / "moc_stage.cuh").read_text()
     fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "void fill_moc(", "int launch_moc_save(", "int launch_moc(", "int moc_limit(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
-           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(",
+           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int ms_feed(", "int ah_post(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(",
            "int exchange_planes4(", "PvArgs pv_args(", "int pv_substeps(",
            "int evolved_slot(int var)\n{", "const double *materialise_var(", "int visc_needs_dt_plane(", "int visc_refresh_dt(", "int visc_term(", "int prepare_rhs_modules(", "int av_iterate("]
     one_liners = {"double bits_to_double(", "int visc_needs_dt_plane(", "int visc_refresh_dt("}
@@ -698,4 +698,91 @@ def test_artificial_viscosity_output_planes_through_av_iterate_and_the_rhs_evalu
             ref = o.viscosity_output(which, i)
             assert same_bits(out[i, w], ref), "%s term %d %s: %s" % (name, i, which, mismatch(out[i, w], ref))
         assert np.count_nonzero(out[i, 1]) > 0
+    o.close()
+
+
+def ms_planes(emu, h, nx, ny):
+    out = np.zeros((3, nx, ny))
+    emu.cemu_ms_planes(h, vp(out))
+    return dict(zip(("cumulative_electron_heating", "cumulative_ion_heating", "cumulative_joule_heating"), out))
+
+
+@pytest.mark.parametrize("xb,yb", BOUNDS[:3])
+def test_multispecies_cumulative_planes_of_the_pointwise_modules_bit_for_bit(emu, xb, yb):
+    """multispecies_mode (plasmadomain.hpp:134-135): ambient_heating_sink (default fraction 0.5, subtracting), localized_heating (0.2, inside its window, without the ramp
+    factor as in the reference), ambient_heating (0.3) and anomalous_resistivity (joule plane) through src_post / ah_post / ar_iterate and k_ms_feed: the three cumulative
+    planes bit-equal to the oracle's, which two reference fixtures pin (loop_ms_solar_rk2, ar_ms_joule_sources_rk2)"""
+    nx, ny = 23, 23
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    o.set_multispecies(True, localized_heating=0.2, ambient_heating=0.3)
+    assert emu.cemu_multispecies(h, C.c_double(1.0), C.c_double(1.0), C.c_double(0.3), C.c_double(0.0)) == 0
+    emu.cemu_set_source_ms_fractions(C.c_double(0.5), C.c_double(0.2))
+    o.set_time(3.0)
+    o.add_small_module("ambient_heating_sink", heating_rate=2.0e-4)
+    o.add_small_module("localized_heating", start_time=1.0, duration=10.0, max_heating_rate=0.5, stddev_x=3.0, stddev_y=2.0, center_x=8.0, center_y=7.0, ramp_time=4.0)
+    o.small_module_hooks(0, step)
+    planes = [o.small_module_plane(m, 0) for m in range(2)]
+    for m, (kind, start, dur, ramp) in enumerate([(0, 0.0, 0.0, 0.0), (1, 1.0, 10.0, 4.0)]):
+        p0 = np.ascontiguousarray(planes[m])
+        assert emu.cemu_source_term(h, C.c_int(kind), C.c_double(start), C.c_double(dur), C.c_double(ramp), C.c_double(0.0), C.c_int(0), C.c_double(1.0), vp(p0), None, C.c_double(3.0), C.c_double(step)) == 0
+    o.small_module_hooks(2, step)
+    compare(emu, h, o, nx, ny, "sink + localized heating", b)
+    a = ar_kwargs(AR_CASES[0][1])
+    o.set_anomalous_resistivity(**a)
+    px = np.ascontiguousarray(s["planes"]["pos_x"], dtype=np.float64); py = np.ascontiguousarray(s["planes"]["pos_y"], dtype=np.float64)
+    ij = (C.c_int * 2)(); nsub = C.c_int(); tmpl = np.zeros((nx, ny))
+    assert emu.cemu_anomalous_resistivity(h, vp(px), vp(py), vp(anomalous_params(**a)), C.c_double(step), C.c_int(1), ij, C.byref(nsub), vp(tmpl)) == 0
+    o.anomalous_iterate(step)
+    got = ms_planes(emu, h, nx, ny)
+    for name in got:
+        ref = o.ms_plane(name)
+        assert np.count_nonzero(ref) > 0 and same_bits(got[name], ref), "%s: %s" % (name, mismatch(got[name], ref))
+    # ambient_heating is a post-iterate hook of a whole step in the oracle; its feed ((mask fr) heating) dt does not depend on the state: compare the increment
+    heating = np.ascontiguousarray(1.0e-4 * (1.0 + 0.1 * np.cos(np.arange(nx * ny).reshape(nx, ny))))
+    before = ms_planes(emu, h, nx, ny)
+    assert emu.cemu_ambient_heating(h, vp(heating), C.c_double(step)) == 0
+    after = ms_planes(emu, h, nx, ny)
+    xl, xu, yl, yu = b
+    mask = np.zeros((nx, ny)); mask[xl:xu + 1, yl:yu + 1] = 1.0
+    assert same_bits(after["cumulative_ion_heating"], before["cumulative_ion_heating"] + ((mask * (1.0 - 0.3)) * heating) * step)
+    assert same_bits(after["cumulative_electron_heating"], before["cumulative_electron_heating"] + ((mask * 0.3) * heating) * step)
+    assert same_bits(after["cumulative_joule_heating"], before["cumulative_joule_heating"])
+    o.close()
+
+
+@pytest.mark.parametrize("xb,yb", BOUNDS[:2])
+def test_multispecies_cumulative_planes_of_the_subcycled_modules(emu, xb, yb):
+    """thermal_conduction (fraction 0.7), radiative_losses (0.4) and physical_viscosity (0.6, rk2 sub-cycles) with multispecies_mode on: the electron / ion planes after
+    tc_iterate + rl_iterate, then after pv_substeps, within the modules' 1e-9 of the oracle's (libm powers); the joule plane stays zero"""
+    from golden_util import physical_viscosity_coefficient
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    o.set_multispecies(True, thermal_conduction=0.7, radiative_losses=0.4, physical_viscosity=0.6)
+    assert emu.cemu_multispecies(h, C.c_double(0.7), C.c_double(0.4), C.c_double(0.5), C.c_double(0.6)) == 0
+    o.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4, weakening_factor=1.0)
+    o.set_radiative_losses(integrator="rk2", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1, prevent_subcycling=False)
+    o.step()
+    avg = np.zeros((nx, ny)); satp = np.zeros((nx, ny))
+    assert emu.cemu_thermal_conduction(h, C.c_int(1), C.c_double(1.0), C.c_double(1.0e-4), C.c_int(1), C.c_int(o.subcycles("thermal_conduction")), C.c_double(step), vp(avg), vp(satp)) == 0
+    assert emu.cemu_radiative_losses(h, C.c_int(1), C.c_double(1.0e3), C.c_double(3.0e4), C.c_double(0.1), C.c_int(0), C.c_int(o.subcycles("radiative_losses")), C.c_double(step), vp(avg)) == 0
+    got = ms_planes(emu, h, nx, ny)
+    for name in ("cumulative_electron_heating", "cumulative_ion_heating"):
+        ref = o.ms_plane(name)
+        assert np.count_nonzero(ref) > 0 and np.max(np.abs(got[name] - ref)) <= 1e-9 * np.max(np.abs(ref)), name
+    assert not got["cumulative_joule_heating"].any()
+    o.close()
+    # physical viscosity on a fresh pair (the oracle above has gone through a whole step)
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    o.set_multispecies(True, physical_viscosity=0.6)
+    assert emu.cemu_multispecies(h, C.c_double(1.0), C.c_double(1.0), C.c_double(0.5), C.c_double(0.6)) == 0
+    coeff = 1.0e-14
+    cg = np.ascontiguousarray(physical_viscosity_coefficient(s["planes"], coeff, 6.0e8))
+    o.set_physical_viscosity(cg, coeff=coeff, epsilon=0.1, heating_on=True, force_on=True, gradient_correction=False, integrator="rk2", inactive_mode=False)
+    o.physical_viscosity_iterate(step)
+    out = np.zeros((4, nx, ny))
+    assert emu.cemu_physical_viscosity(h, vp(cg), C.c_double(coeff), C.c_int(1), C.c_int(1), C.c_int(0), C.c_int(1), C.c_int(0), C.c_int(o.subcycles("physical_viscosity")), C.c_double(step), vp(out)) == 0
+    got = ms_planes(emu, h, nx, ny)
+    for name in ("cumulative_electron_heating", "cumulative_ion_heating"):
+        ref = o.ms_plane(name)
+        assert np.count_nonzero(ref) > 0 and np.max(np.abs(got[name] - ref)) <= 1e-9 * np.max(np.abs(ref)), name
     o.close()

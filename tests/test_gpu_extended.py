@@ -739,6 +739,43 @@ def test_anomalous_resistivity_and_field_heating_diagnostic_planes_vs_reference_
     assert "ok" in out
 
 
+MULTISPECIES_AR_CODE = """
+    import numpy as np
+    from golden_util import Golden, MS_PLANES, OUT_VARS, same_bits, mismatch, multispecies_fractions, small_module_kwargs, sink_reduction_plane
+    from spruce_b200.domain import PlasmaDomain
+    g = Golden("ar_ms_joule_sources_rk2")
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, **g.kw)
+    for mname, kv in g.modules:
+        if mname == "anomalous_resistivity":
+            d.set_anomalous_resistivity(g.planes["pos_x"], g.planes["pos_y"], **{k: float(v) for k, v in kv.items()})
+        elif mname == "ambient_heating_sink":
+            d.set_ambient_heating_sink_plane(sink_reduction_plane(g.planes, small_module_kwargs(mname, kv)[1], g.kw["xb"], g.kw["yb"]))
+        else:
+            getattr(d, "set_" + mname)(**small_module_kwargs(mname, kv)[1])
+    d.set_multispecies(True, **multispecies_fractions(g.modules))
+    hist = []
+    for it in range(1, g.n_steps + 1):
+        hist += list(d.advance(1))
+        if it in g.frames:
+            for v in OUT_VARS:
+                assert same_bits(d.grid(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(d.grid(v), g.frames[it][v]))
+            for name in MS_PLANES:
+                got, ref = d.module_output(name), g.module_planes[it][name]
+                assert np.count_nonzero(ref) > 0 and same_bits(got, ref), "%s after iteration %d: %s" % (name, it, mismatch(got, ref))
+        d.multispecies_reset()                  # the fixture stores every iteration (evolution.cpp:36-41)
+    assert [float(x).hex() for x in hist] == [float(x).hex() for x in g.steps[:g.n_steps]]
+    print("ok")
+"""
+
+
+@pytest.mark.xfail(reason="written after round 2's GPU budget was spent (CPU-checked: tests/test_capi_hooks_emulated.py); first executed by the round-end run", strict=False)
+def test_multispecies_joule_and_source_planes_vs_reference_fixture():
+    """multispecies_mode on the device: the joule heating of anomalous_resistivity and the electron / ion shares of ambient_heating_sink and localized_heating against the fixture
+    of the unmodified reference (tests/golden/ar_ms_joule_sources_rk2.npz), bit for bit"""
+    out = run_isolated(MULTISPECIES_AR_CODE, {})
+    assert "ok" in out
+
+
 OPERATOR2_CODE = """
     import numpy as np
     from golden_util import same_bits, mismatch

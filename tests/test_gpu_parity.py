@@ -8,7 +8,7 @@ as doubles."""
 import numpy as np
 import pytest
 
-from golden_util import Golden, OUT_VARS, cases, mismatch, module_kwargs, same_bits, viscosity_plane_request
+from golden_util import Golden, MS_PLANES, OUT_VARS, cases, mismatch, module_kwargs, multispecies_fractions, same_bits, viscosity_plane_request
 
 pytestmark = pytest.mark.gpu
 
@@ -54,7 +54,7 @@ def golden_cases():
 
 
 # fixtures added after round 2's GPU budget was spent (they carry the output planes of physical_viscosity / artificial_viscosity): first executed by the round-end run
-FIRST_RUN_FIXTURES = {"loop_pv_diag_rk2", "ot_pv_diag_inactive", "loop_visc_diag_hv_rk2", "ot_visc_diag_hv_rk4", "ot_visc_diag_hv_euler"}
+FIRST_RUN_FIXTURES = {"loop_ms_solar_rk2", "loop_pv_diag_rk2", "ot_pv_diag_inactive", "loop_visc_diag_hv_rk2", "ot_visc_diag_hv_rk4", "ot_visc_diag_hv_euler"}
 PV_PLANES = ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z")
 
 
@@ -63,6 +63,9 @@ PV_PLANES = ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_f
 def test_golden_reference_outputs(name):
     g = Golden(name)
     d = make_domain(g)
+    ms_on = bool(g.cfg.get("multispecies"))
+    if ms_on:                                                         # multispecies_mode = true: cumulative electron / ion / joule heating (plasmadomain.hpp:134-135)
+        d.set_multispecies(True, **multispecies_fractions(g.modules))
     pv_out = any(m[0] == "physical_viscosity" and m[1].get("output_to_file") == "true" for m in g.modules)
     if pv_out:
         d.set_module_output_to_file("physical_viscosity")
@@ -78,6 +81,8 @@ def test_golden_reference_outputs(name):
     for it in sorted(g.frames):
         dts = []
         for _ in range(it - done):
+            if ms_on and done + len(dts) > 0:
+                d.multispecies_reset()                               # the fixtures store every iteration: the planes restart after each (evolution.cpp:36-41)
             dts.append(d.advanceTime())
             if any(m[0] == "physical_viscosity" for m in g.modules):
                 pv.append(d.subcycles("physical_viscosity"))
@@ -100,6 +105,10 @@ def test_golden_reference_outputs(name):
                 assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
             else:
                 assert rel_linf(got, g.frames[it][v]) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (v, it, rel_linf(got, g.frames[it][v]))
+        if ms_on:
+            for pname in MS_PLANES:
+                ref = g.module_planes[it][pname]
+                assert rel_linf(d.module_output(pname), ref) <= REL_TOL or not ref.any() and not d.module_output(pname).any(), "%s after iteration %d" % (pname, it)
         if av_out and it > 0:                                        # viscosity.cpp:351-376: what each term's last evaluation left, bit for bit
             for pname, ref in g.module_planes[it].items():
                 which, term = viscosity_plane_request(g.modules, pname)

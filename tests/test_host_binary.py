@@ -84,7 +84,15 @@ CASES["loop_viscosity_output"] = (lambda: synthetic.stratified_loop(40, 36), dic
                                                                      ("visc_vars_to_evol", "mom_x,mom_y,thermal_energy"), ("visc_length", "5.0e8,0,0"), ("visc_species", "i,i,i"),
                                                                      ("hv_time_integrator", "rk2"), ("gradient_correction", "true"), ("visc_output_visc", "true"), ("visc_output_lap", "true"),
                                                                      ("visc_output_strength", "true"), ("visc_output_timescale", "true")])]), True)
-FIRST_RUN_AT_ROUND_END = {"loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
+# multispecies_mode = true (plasmadomain.hpp:134-135): the cumulative electron / ion / joule heating planes in mhd.out, accumulated over the two steps between outputs
+CASES["loop_multispecies"] = (lambda: synthetic.stratified_loop(40, 36, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=6, iter_output_interval=2,
+                              write_precision=17, multispecies=True,
+                              modules=[("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4"), ("ms_electron_heating_fraction", "0.7")]),
+                                       ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
+                                       ("ambient_heating", [("heating_rate", "1.0e-4"), ("ms_electron_heating_fraction", "0.3")]),
+                                       ("localized_heating", [("start_time", "0.0"), ("duration", "50.0"), ("max_heating_rate", "1.0e-3"), ("stddev_x", "3.0"), ("stddev_y", "4.0"),
+                                                              ("center_x", "2.0"), ("center_y", "8.0"), ("ramp_time", "1.0"), ("ms_electron_heating_fraction", "0.2")])]), False)
+FIRST_RUN_AT_ROUND_END = {"loop_multispecies", "loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))
@@ -121,12 +129,14 @@ def test_run_binary_matches_reference_files(name, tmp_path):
         _, fa = refrun.read_out(tmp_path / "ours" / "mhd.out")
         _, fb = refrun.read_out(tmp_path / "ref" / "mhd.out")
         assert len(fa) == len(fb) and [f["t"] for f in fa] == [f["t"] for f in fb]
-        if name in ("loop_physical_viscosity_output", "ucnp_mhd2e_eic"):          # lossless mhd.out (write_precision 17): every plane of every frame, module planes included
+        if name in ("loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_multispecies"):          # lossless mhd.out (write_precision 17): every plane of every frame, module planes included
             for f1, f2 in zip(fa, fb):
                 assert list(f1) == list(f2)
                 for k in f2:
                     if k != "t":
                         assert np.max(np.abs(f1[k] - f2[k])) <= 1e-9 * max(np.max(np.abs(f2[k])), 1e-300), k
+            if name == "loop_multispecies":
+                assert all(np.count_nonzero(fb[-1][k]) for k in ("cumulative_electron_heating", "cumulative_ion_heating")) and "cumulative_joule_heating" in fb[-1]
             if name == "loop_physical_viscosity_output":
                 assert all(k in fb[-1] and np.count_nonzero(fb[-1][k]) for k in ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"))
         if name == "loop_solar_modules":

@@ -268,15 +268,11 @@ def test_unported_names_are_refused(stub, tmp_path):
         r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
         err = r.stderr.decode()
         assert r.returncode in (-6, 134) and msg in err and "successfully reached" not in err, err[-1500:]
-    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), max_iterations=1, iter_output_interval=1).replace("epsilon", "multispecies_mode = true\nepsilon", 1)
     state = tmp_path / "in_ms.state"
     refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
     out = tmp_path / "out_ms"
     out.mkdir()
-    (out / "run.config").write_text(cfg)
     env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / "calls.log"))
-    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
-    assert r.returncode in (-6, 134) and "multispecies_mode" in r.stderr.decode()
     cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="euler", xb=("fixed", "fixed"), yb=("fixed", "fixed"), max_iterations=1, iter_output_interval=1,
                                   modules=[("global_temperature", [("gt_species", "i"), ("gt_strength", "2.0"), ("gt_use_global_temp", "true")])])
     (out / "run.config").write_text(cfg)
@@ -333,3 +329,39 @@ def test_a_set_written_by_the_problem_generator_runs_through_the_shell(stub, tmp
     assert 1 <= sum(int(args_of(ln)["done"]) for ln in lines if ln.startswith("spruce_advance")) <= 2       # max_iterations = 2 from the sweep, or its duration (0.3 tau) first
     uploads = {ln.split()[1] for ln in lines if ln.startswith("spruce_grid_upload")}
     assert {"be_x", "be_y", "rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y"} <= uploads
+
+
+def test_multispecies_mode_enables_stores_and_resets_the_cumulative_planes(stub, tmp_path):
+    """multispecies_mode = true (plasmadomain.hpp:134-135): enabled on the device before the modules are set up, each module's ms_electron_heating_fraction handed over when its
+    block sets one (and range-checked like the reference's asserts), the three cumulative planes appended to every stored frame between the equation set's variables and the
+    modules' planes (fileio.cpp:164-183), reset after every store inside the time loop (evolution.cpp:36-41) -- not after the frame the constructor writes"""
+    s = synthetic.stratified_loop(20, 18, bump=0.5)
+    modules = [("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4"), ("ms_electron_heating_fraction", "0.7"), ("output_to_file", "true")]),
+               ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
+               ("ambient_heating", [("heating_rate", "1.0e-4"), ("ms_electron_heating_fraction", "0.3")]),
+               ("localized_heating", [("start_time", "0.0"), ("duration", "10.0"), ("max_heating_rate", "0.5"), ("stddev_x", "3.0"), ("stddev_y", "2.0"), ("center_x", "8.0"), ("center_y", "7.0"),
+                                      ("ms_electron_heating_fraction", "0.2")])]
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=4, iter_output_interval=2, modules=modules, multispecies=True)
+    log, stdout, out = run_shell(stub, tmp_path, s, cfg)
+    calls = [ln.split()[0] for ln in log if ln.startswith("spruce_")]
+    assert calls.index("spruce_eqs_setup") < calls.index("spruce_multispecies_mode") < calls.index("spruce_module_thermal_conduction")
+    fr = {ln.split()[1]: float(args_of(ln)["fraction"]) for ln in log if ln.startswith("spruce_module_ms_fraction")}
+    assert fr == {"thermal_conduction": 0.7, "ambient_heating": 0.3, "localized_heating": 0.2}                # radiative_losses keeps the library's default
+    assert calls.count("spruce_multispecies_reset") == 2                                                         # iterations 2 and 4
+    first_store = calls.index("spruce_module_output")
+    assert first_store < calls.index("spruce_multispecies_reset") and "spruce_advance" not in calls[:first_store]
+    _, frames = refrun.read_out(out / "mhd.out")
+    assert len(frames) == 3
+    for f in frames:
+        keys = list(f)
+        assert keys.index("cumulative_electron_heating") + 1 == keys.index("cumulative_ion_heating") and keys.index("cumulative_ion_heating") + 1 == keys.index("cumulative_joule_heating")
+        assert keys.index("cumulative_joule_heating") < keys.index("thermal_conduction")
+    bad = cfg.replace("ms_electron_heating_fraction = 0.3", "ms_electron_heating_fraction = 1.5")
+    (tmp_path / "b").mkdir()
+    state = tmp_path / "b" / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+    (tmp_path / "b" / "out").mkdir()
+    (tmp_path / "b" / "out" / "run.config").write_text(bad)
+    env = dict(os.environ, LD_PRELOAD=str(stub), SPRUCE_STUB_LOG=str(tmp_path / "b" / "calls.log"))
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(tmp_path / "b" / "out"), "-s", str(state)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode in (-6, 134) and "Ambient Heating MS electron heating fraction must be between 0 and 1" in r.stderr.decode()

@@ -4,7 +4,7 @@ source/mhd/evolution.cpp:62) and every evolved plane + temp + dt after the recor
 import numpy as np
 import pytest
 
-from golden_util import (Golden, OUT_VARS, cases, mismatch, module_kwargs, physical_viscosity_coefficient, same_bits, small_module_kwargs, viscosity_plane_request,
+from golden_util import (Golden, MS_PLANES, OUT_VARS, cases, mismatch, module_kwargs, multispecies_fractions, physical_viscosity_coefficient, same_bits, small_module_kwargs, viscosity_plane_request,
                          viscosity_terms_with_profiles)
 from oracle.oracle import Oracle
 
@@ -20,6 +20,8 @@ def make_oracle(g: Golden) -> Oracle:
             o.set_physical_viscosity(physical_viscosity_coefficient(g.planes, kw["coeff"], ramp), **kw)
         else:
             getattr(o, "set_" + name)(**kw)
+    if g.cfg.get("multispecies"):
+        o.set_multispecies(True, **multispecies_fractions(g.modules))
     return o
 
 
@@ -39,8 +41,9 @@ def test_oracle_reproduces_reference(name):
                 assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
             for pname, ref in g.module_planes.get(it, {}).items():          # output_to_file planes: "thermal_conduction", "flux_saturation", "rad"
                 vq = viscosity_plane_request(g.modules, pname)
-                got = o.viscosity_output(*vq) if vq else o.module_output(pname)
+                got = o.ms_plane(pname) if pname in MS_PLANES else o.viscosity_output(*vq) if vq else o.module_output(pname)
                 assert got is not None and same_bits(got, ref), "module plane %s after iteration %d: %s" % (pname, it, mismatch(got, ref))
+        o.ms_reset()                                                        # the fixtures store every iteration: the cumulative planes restart after each (evolution.cpp:36-41)
     names = [m[0] for m in g.modules]
     if "thermal_conduction" in names:
         assert tc == g.subcycle_counts("Thermal Subcycles")
@@ -93,12 +96,17 @@ def test_extended_oracle_reproduces_reference(name):
             o.set_anomalous_resistivity(**{k: float(v) for k, v in kv.items() if k != "output_to_file"})
         else:
             o.add_small_module(mname, **small_module_kwargs(mname, kv)[0])
+    if g.cfg.get("multispecies"):
+        o.set_multispecies(True, **multispecies_fractions(g.modules))
     for it in range(1, g.n_steps + 1):
         step = o.step()
         assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())
         if it in g.frames:
             for v in OUT_VARS:
                 assert same_bits(o.get(v), g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(o.get(v), g.frames[it][v]))
+            for pname in MS_PLANES:                                         # multispecies_mode: ion / electron shares of the sources, joule heating of anomalous_resistivity
+                if pname in g.module_planes.get(it, {}):
+                    assert same_bits(o.ms_plane(pname), g.module_planes[it][pname]), "%s after iteration %d: %s" % (pname, it, mismatch(o.ms_plane(pname), g.module_planes[it][pname]))
             # output_to_file planes the restatement can form (anomalousresistivity.cpp:320-329, fieldheating.cpp:73-80)
             mp = g.module_planes.get(it, {})
             if "anomalous_template" in mp:
@@ -109,4 +117,5 @@ def test_extended_oracle_reproduces_reference(name):
             if "field_heating" in mp:
                 k = [m for m, _ in g.modules if m != "anomalous_resistivity"].index("field_heating")
                 assert same_bits(o.small_module_plane(k, 0), mp["field_heating"]), "field_heating after iteration %d" % it
+        o.ms_reset()
     o.close()
