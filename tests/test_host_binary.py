@@ -92,7 +92,13 @@ CASES["loop_multispecies"] = (lambda: synthetic.stratified_loop(40, 36, bump=0.5
                                        ("ambient_heating", [("heating_rate", "1.0e-4"), ("ms_electron_heating_fraction", "0.3")]),
                                        ("localized_heating", [("start_time", "0.0"), ("duration", "50.0"), ("max_heating_rate", "1.0e-3"), ("stddev_x", "3.0"), ("stddev_y", "4.0"),
                                                               ("center_x", "2.0"), ("center_y", "8.0"), ("ramp_time", "1.0"), ("ms_electron_heating_fraction", "0.2")])]), False)
-FIRST_RUN_AT_ROUND_END = {"loop_multispecies", "loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
+# the UCNP module set on the two-temperature set: eic_thermalization (device) + coulomb_explosion + global_temperature (host-resident, generic over the equation set's
+# species / temperature / thermal-energy lists); one OpenMP thread for the reference (its radial binning, grid.cpp:306-315)
+CASES["ucnp_mhd2e_module_set"] = (lambda: synthetic.ucnp_cloud_2e(83, 79, drift=20.0, bfield=0.01), dict(integrator="rk2", max_iterations=4, iter_output_interval=2, eqs="ideal_mhd_2E", **UCNP_KW,
+                                  output_flags=("rho", "i_temp", "e_temp", "mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy", "press", "n", "dt"),
+                                  modules=[("eic_thermalization", []), ("coulomb_explosion", [("timescale", "1.0e-6"), ("lengthscale", "0.2"), ("strength", "1.0e-3")]),
+                                           ("global_temperature", [("gt_species", "i"), ("gt_strength", "3.7"), ("gt_use_diffusion", "true")])]), False)
+FIRST_RUN_AT_ROUND_END = {"ucnp_mhd2e_module_set", "loop_multispecies", "loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))
@@ -114,7 +120,7 @@ def test_run_binary_matches_reference_files(name, tmp_path):
         cfg = cfg.replace("__TP_INIT__", str(tmp_path / "init.tpstate"))
     if name == "loop_time_output_euler":
         cfg = cfg.replace("time_output_interval = -1.0", "time_output_interval = 2.0")
-    refrun.run_reference(state, cfg, tmp_path / "ref", threads=1 if name == "ucnp_coulomb_explosion" else 4)
+    refrun.run_reference(state, cfg, tmp_path / "ref", threads=1 if name in ("ucnp_coulomb_explosion", "ucnp_mhd2e_module_set") else 4)
     stdout = run_ours(state, cfg, tmp_path / "ours")
     for fname in ("mhd.out", "end.state") + (("particles.tpout", "end.tpstate") if name == "loop_tracer_particles" else ()):
         a, b = (tmp_path / "ours" / fname).read_bytes(), (tmp_path / "ref" / fname).read_bytes()
