@@ -85,6 +85,8 @@ def lib():
         L.oracle2e_create.argtypes = [C.c_void_p]; L.oracle2e_create.restype = C.c_void_p
         L.oracle2e_destroy.argtypes = [C.c_void_p]
         L.oracle2e_set_eic.argtypes = [C.c_void_p, C.c_int]
+        L.oracle2e_set_viscosity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.oracle2e_add_viscosity_term.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.oracle2e_plane.argtypes = [C.c_void_p, C.c_int]; L.oracle2e_plane.restype = C.POINTER(C.c_double)
         L.oracle2e_setup.argtypes = [C.c_void_p]
         L.oracle2e_step.argtypes = [C.c_void_p]; L.oracle2e_step.restype = C.c_double
@@ -442,6 +444,17 @@ class Oracle2E:
 
     def get(self, name) -> np.ndarray:
         return self.view(name).copy()
+
+    def set_viscosity(self, terms, *, hv_integrator="euler", hv_epsilon=1.0, gradient_correction=False):
+        """artificial_viscosity on this set (configured after eic_thermalization); terms: list of dict(opt=local|global|boundary|boundary_global, strength=, var_diff=,
+        var_evol=, species='i', strength_grid=None), variable names of idealmhd2E.hpp:18-22"""
+        L = lib()
+        L.oracle2e_set_viscosity(self.h, TI[hv_integrator], hv_epsilon, int(gradient_correction))
+        opts = {"local": 0, "global": 1, "boundary": 2, "boundary_global": 3}
+        for tm in terms:
+            sg = tm.get("strength_grid")
+            sgp = _dp(np.ascontiguousarray(sg, dtype=np.float64)) if sg is not None else None
+            L.oracle2e_add_viscosity_term(self.h, opts[tm["opt"]], tm["strength"], VARS_2E.index(tm["var_diff"]), VARS_2E.index(tm["var_evol"]), ord(tm.get("species", "i")), sgp)
 
     def step(self) -> float:
         return lib().oracle2e_step(self.h)

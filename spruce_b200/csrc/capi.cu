@@ -1954,8 +1954,9 @@ int spruce_module_physical_viscosity(spruce_domain *d, double coeff, const doubl
 int spruce_module_viscosity(spruce_domain *d, int hv_time_integrator, double hv_epsilon, int gradient_correction)
 {
     CHECK_DOM(d);
-    NOT_2F(d, "artificial_viscosity");
+    if (d->tf) return fail(SPRUCE_ERR_UNSUPPORTED, "artificial_viscosity is not available with the ideal_2F equation set");
     if (hv_time_integrator < 0 || hv_time_integrator > SPRUCE_TI_RK4) return fail(SPRUCE_ERR_ARG, "Invalid hyperviscous time integrator given for Viscosity module");
+    if (d->e2) return e2_visc_config(d, hv_time_integrator, hv_epsilon, gradient_correction);       // ideal_mhd_2E: mhd2e_host.cuh
     d->visc_hv_integrator = hv_time_integrator; d->visc_hv_epsilon = hv_epsilon; d->visc_gradient_correction = gradient_correction ? 1 : 0;
     for (int k = 0; k < 8; k++) if (!d->vscratch[k]) { int rc = alloc_plane(d, &d->vscratch[k]); if (rc) return rc; }
     if (!d->dt_plane) { int rc = alloc_plane(d, &d->dt_plane); if (rc) return rc; }
@@ -1966,8 +1967,9 @@ int spruce_module_viscosity_term(spruce_domain *d, const char *visc_opt, double 
                                  const char *species, const double *strength_plane, size_t count)
 {
     CHECK_DOM(d);
-    NOT_2F(d, "artificial_viscosity");
+    if (d->tf) return fail(SPRUCE_ERR_UNSUPPORTED, "artificial_viscosity is not available with the ideal_2F equation set");
     if (!visc_opt || !var_to_diff || !var_to_evol) return fail(SPRUCE_ERR_ARG, "null argument");
+    if (d->e2) return e2_visc_add_term(d, visc_opt, strength, var_to_diff, var_to_evol, species, strength_plane, count);
     if (!d->dt_plane) return fail(SPRUCE_ERR_STATE, "spruce_module_viscosity must precede its terms");
     spruce_domain::ViscTerm t{};
     t.opt = !strcmp(visc_opt, "local") ? 0 : !strcmp(visc_opt, "global") ? 1 : !strcmp(visc_opt, "boundary") ? 2 : !strcmp(visc_opt, "boundary_global") ? 3 : -1;

@@ -322,5 +322,53 @@ E2_HD double derive_cell(const Geo &g, const CPlanes &U, const Statics &T, int v
     }
 }
 
+
+// ---- artificial_viscosity on this set (source/modules/viscosity.cpp:185-267; the fourth module of the UCNP set).  One term: dq = visc_coeff * laplacian(q) * scale_fac
+// (+ gradient correction), q = a variable of the grid set the right-hand side is evaluated on.  timescale() = {dt, dt} (idealmhd2E.hpp:45): the timescale is the PRIMARY
+// state's dt plane or its minimum, whichever species the term names.  scale_mode 1: momentum <- velocity, n m_i (the set has no i_n, :233-234);
+// 2: thermal energy <- temperature, n K_B / (gamma - 1) for both species (:246-251); 0 otherwise.
+struct ViscTerm2 { int opt; int var_diff; int scale_mode; double strength; const double *strength_plane; };     // opt: 0 local, 1 global, 2 boundary, 3 boundary_global
+struct ViscEnv2 { const double *dt_plane; double dt_min; int gc; };
+// derivative1D / secondDerivative1D (derivs.cpp:223-264, 417-456) of a per-cell functor f(i, j); zero outside the interior
+template <class F> E2_HD double d1_of(const Geo &g, F f, int dir, int i, int j)
+{
+    if (!interior(g, i, j)) return 0.0;
+    const int im = dir == 0 ? wi(g, i - 1) : i, ip = dir == 0 ? wi(g, i + 1) : i, jm = dir == 1 ? wj(g, j - 1) : j, jp = dir == 1 ? wj(g, j + 1) : j;
+    const double q0 = f(im, jm), q1 = f(i, j), q2 = f(ip, jp);
+    const double h0 = ha(g, dir, i, j, -1), h1 = ha(g, dir, i, j, 0), h2 = ha(g, dir, i, j, 1);
+    return (interp(q1, q2, h1, h2) - interp(q0, q1, h0, h1)) / (dir == 0 ? g.dx[i] : g.dy[j]);
+}
+template <class F> E2_HD double d2_of(const Geo &g, F f, int dir, int i, int j)
+{
+    if (!interior(g, i, j)) return 0.0;
+    const int im = dir == 0 ? wi(g, i - 1) : i, ip = dir == 0 ? wi(g, i + 1) : i, jm = dir == 1 ? wj(g, j - 1) : j, jp = dir == 1 ? wj(g, j + 1) : j;
+    const double q0 = f(im, jm), q1 = f(i, j), q2 = f(ip, jp);
+    const double h0 = ha(g, dir, i, j, -1), h1 = ha(g, dir, i, j, 0), h2 = ha(g, dir, i, j, 1);
+    return ((interp(q1, q2, h1, h2) - 2.0 * q1) + interp(q0, q1, h0, h1)) / (h1 * h1);          // denominator (0.5 d)^2, derivs.cpp:423
+}
+E2_HD double visc_cell(const Geo &g, const CPlanes &S, const Statics &T, const ViscTerm2 &t, const ViscEnv2 &e, int i, int j)
+{
+    auto q = [&](int a, int b) { return derive_cell(g, S, T, t.var_diff, a, b); };
+    auto coef = [&](int a, int b) {                                                                  // :213
+        const size_t c = at(g, a, b);
+        const double str = t.strength_plane ? t.strength_plane[c] : t.strength;
+        const double dtg = (t.opt == 0 || t.opt == 2) ? e.dt_plane[c] : e.dt_min;
+        const double dx = g.dx[a], dy = g.dy[b];
+        return (((str * 1.0) / (1.0 / (dx * dx) + 1.0 / (dy * dy))) / 2.) / dtg;
+    };
+    auto scale = [&](int a, int b) {
+        if (t.scale_mode == 1) return derive_cell(g, S, T, V2_n, a, b) * g.m_i;
+        if (t.scale_mode == 2) return derive_cell(g, S, T, V2_n, a, b) * (kKB2 / (g.gamma - 1));
+        return 1.0;
+    };
+    const double lap = d2_of(g, q, 0, i, j) + d2_of(g, q, 1, i, j);                                 // laplacian, derivs.cpp:458-462
+    double out = (coef(i, j) * lap) * scale(i, j);                                                   // :266
+    if (e.gc) {                                                                                      // :261-265
+        auto cs = [&](int a, int b) { return coef(a, b) * scale(a, b); };
+        out = (out + d1_of(g, cs, 0, i, j) * d1_of(g, q, 0, i, j)) + d1_of(g, cs, 1, i, j) * d1_of(g, q, 1, i, j);
+    }
+    return out;
+}
+
 }  // namespace e2
 }  // namespace spruce

@@ -22,6 +22,11 @@ struct E2Args {
     const double *step_ptr;
     const int *done_ptr;
     unsigned long long *dtmin_bits;
+    // artificial_viscosity (mhd2e_cells.cuh: visc_cell): right-hand-side terms of this stage as planes (k_2e_visc_term wrote them from set S), and one term's description
+    const double *xterm[4]; int xtarget[4]; int n_xterm;
+    e2::ViscTerm2 vt; const double *dt_plane; int visc_gc;
+    // hyper-viscous sub-step (k_2e_visc_apply): out = base + (mask * (frac * step / n_sub)) * term, or the rk4 combination of four terms
+    const double *base, *t1, *t2, *t3, *t4; double frac; int n_sub;
 };
 
 // right-hand side, K rule, increment, floors: one thread per cell
@@ -32,6 +37,10 @@ __global__ void __launch_bounds__(128) k_2e_cells(const E2Args A)
     const size_t c = e2::at(A.g, i, j);
     double k[e2::NEV2], k1[e2::NEV2], k23[e2::NEV2];
     e2::rhs_cell(A.g, A.S, A.T, i, j, k);
+    if (A.n_xterm) {                                                                        // Viscosity::computeTimeDerivativesModule: grids_dt[evol] += dqdt * mask (viscosity.cpp:116-118)
+        const double mask = e2::interior(A.g, i, j) ? 1.0 : 0.0;
+        for (int x = 0; x < A.n_xterm; x++) k[A.xtarget[x]] = k[A.xtarget[x]] + A.xterm[x][c] * mask;
+    }
     const bool need_k = A.kmode != e2::KM2_NONE;
     if (need_k) {
         for (int v = 0; v < e2::NEV2; v++) { k1[v] = A.K1[v][c]; k23[v] = (A.kmode == e2::KM2_STORE_K1 || A.kmode == e2::KM2_EXPORT) ? 0.0 : A.K23[v][c]; }
@@ -86,6 +95,30 @@ __global__ void __launch_bounds__(128) k_2e_derive(const E2Args A)
     A.out[e2::at(A.g, i, j)] = e2::derive_cell(A.g, A.S, A.T, A.var, i, j);
 }
 
+// one viscosity term on grid set S -> out (constructSingleViscosityGrid, viscosity.cpp:185-267); the timescale comes from the PRIMARY state's dt plane / minimum
+__global__ void __launch_bounds__(128) k_2e_visc_term(const E2Args A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = A.g.row0 + (int)blockIdx.y;
+    if (j >= A.g.ny || *A.done_ptr) return;
+    e2::ViscEnv2 env;
+    env.dt_plane = A.dt_plane; env.gc = A.visc_gc;
+    env.dt_min = __longlong_as_double((long long)*A.dtmin_bits);
+    A.out[e2::at(A.g, i, j)] = e2::visc_cell(A.g, A.S, A.T, A.vt, env, i, j);
+}
+// grid_to_evol = base + (mask * c) * term, c = frac * (step / n_sub) (viscosity.cpp:135, 145, 150, ...); the rk4 combination when t2..t4 are given (:172-174)
+__global__ void __launch_bounds__(128) k_2e_visc_apply(const E2Args A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = A.g.row0 + (int)blockIdx.y;
+    if (j >= A.g.ny || *A.done_ptr) return;
+    const size_t c = e2::at(A.g, i, j);
+    const double mask = e2::interior(A.g, i, j) ? 1.0 : 0.0;
+    const double dts = *A.step_ptr / (double)A.n_sub;
+    const double cc = A.frac == 1.0 ? dts : A.frac * dts;
+    double t = A.t1[c];
+    if (A.t4) t = (((A.t1[c] + A.t2[c] * 2.0) + A.t3[c] * 2.0) + A.t4[c]) / 6.0;
+    A.out[c] = A.base[c] + (mask * cc) * t;
+}
+
 struct OneFluid2E {
     double *set[3][e2::NEV2] = {{nullptr}};          // storage of the three state sets
     double *K1[e2::NEV2] = {nullptr}, *K23[e2::NEV2] = {nullptr};
@@ -93,6 +126,11 @@ struct OneFluid2E {
     int order[3] = {0, 1, 2};                        // logical set (0 = primary) -> storage
     bool rk4_alloc = false;
     e2::Geo g{};
+    // artificial_viscosity (source/modules/viscosity.cpp), terms in config order
+    struct VTerm { int opt; int var_diff; int evol; int scale_mode; double strength; double *strength_plane; };
+    std::vector<VTerm> visc;
+    int visc_hv_integrator = 0, visc_gc = 0; double visc_hv_epsilon = 1.0;
+    double *dt_plane = nullptr, *vplane[6] = {nullptr};     // primary dt plane; vplane[0..3]: right-hand-side terms / the four rk4 evaluations, [4]: the sub-step's initial plane, [5]: spare
 };
 
 const char *const kE2EvolvedNames[e2::NEV2] = {"rho", "mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy", "bi_x", "bi_y"};
@@ -189,6 +227,52 @@ int e2_finish(spruce_domain *d, E2Args &A, int final_stage)
     return SPRUCE_OK;
 }
 
+// ---- artificial_viscosity on this set: the primary dt plane, one term as a plane, the right-hand-side terms of a stage
+int e2_visc_refresh_dt(spruce_domain *d)                 // Viscosity reads the PRIMARY state's dt plane: materialised at the step's start and after every hyper-viscous sub-step
+{
+    OneFluid2E *t = d->e2;
+    E2Args A{};
+    e2_base(d, A);
+    e2_cset(d, 0, A.S);
+    A.out = e2_shift(d, t->dt_plane); A.var = e2::V2_dt;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_2e_derive<<<grid, 128, 0, d->stream>>>(A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+int e2_visc_term(spruce_domain *d, int S, int i, double *out)
+{
+    OneFluid2E *t = d->e2;
+    const OneFluid2E::VTerm &v = t->visc[i];
+    E2Args A{};
+    e2_base(d, A);
+    e2_cset(d, S, A.S);
+    A.vt.opt = v.opt; A.vt.var_diff = v.var_diff; A.vt.scale_mode = v.scale_mode; A.vt.strength = v.strength;
+    A.vt.strength_plane = (v.opt == 2 || v.opt == 3) ? e2_shift(d, v.strength_plane) : nullptr;
+    A.dt_plane = e2_shift(d, t->dt_plane); A.visc_gc = t->visc_gc; A.out = e2_shift(d, out);
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    k_2e_visc_term<<<grid, 128, 0, d->stream>>>(A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+// Viscosity::computeTimeDerivativesModule (viscosity.cpp:112-123): every right-hand-side-form term (strength <= 1) evaluated on set S, handed to k_2e_cells as planes
+int e2_visc_rhs_terms(spruce_domain *d, int S, E2Args &A)
+{
+    OneFluid2E *t = d->e2;
+    A.n_xterm = 0;
+    for (size_t i = 0; i < t->visc.size(); i++) {
+        if (t->visc[i].strength > 1.0) continue;
+        if (A.n_xterm >= 4) return fail(SPRUCE_ERR_UNSUPPORTED, "at most 4 right-hand-side viscosity terms");
+        int rc = e2_visc_term(d, S, (int)i, t->vplane[A.n_xterm]);
+        if (rc) return rc;
+        A.xterm[A.n_xterm] = e2_shift(d, t->vplane[A.n_xterm]); A.xtarget[A.n_xterm] = t->visc[i].evol;
+        A.n_xterm++;
+    }
+    return SPRUCE_OK;
+}
+
 // the executor mhd2e_step.hpp's advance() drives (the host check drives the same template with loops)
 struct E2DeviceExec {
     spruce_domain *d;
@@ -199,6 +283,7 @@ struct E2DeviceExec {
         e2_base(d, A);
         e2_cset(d, S, A.S); e2_cset(d, B, A.B); e2_set(d, D, A.D); e2_set(d, ghost_primary, A.Pg);
         A.coef = coef; A.kmode = kmode;
+        if (!t->visc.empty()) { int rv = e2_visc_rhs_terms(d, S, A); if (rv) return rv; }
         dim3 grid((d->P.ny + 127) / 128, d->P.nx);
         k_2e_cells<<<grid, 128, 0, d->stream>>>(A);
         d->launches++;
@@ -228,17 +313,108 @@ int e2_launch_propagate(spruce_domain *d, int from_state)
     CUDA_TRY(cudaGetLastError());
     return e2_finish(d, A, 1);
 }
+// Viscosity::iterateModule (viscosity.cpp:125-180): the hyper-viscous terms (strength > 1) sub-cycled on the primary state, a propagate after every sub-step
+int e2_av_iterate(spruce_domain *d)
+{
+    OneFluid2E *t = d->e2;
+    int rc;
+    dim3 grid((d->P.ny + 127) / 128, d->P.nx);
+    for (size_t i = 0; i < t->visc.size(); i++) {
+        const OneFluid2E::VTerm &v = t->visc[i];
+        if (v.strength <= 1.0) continue;
+        const int ns = (int)(std::ceil(v.strength / t->visc_hv_epsilon) + 0.1);                // :130
+        double *T[4] = {t->vplane[0], t->vplane[1], t->vplane[2], t->vplane[3]}, *init = t->vplane[4];
+        auto evol = [&]() { return t->set[t->order[0]][v.evol]; };                              // (the primary set's storage does not move inside a module hook)
+        auto apply = [&](const double *base, double frac, int n_terms) -> int {
+            E2Args A{};
+            e2_base(d, A);
+            A.base = e2_shift(d, base); A.t1 = e2_shift(d, T[0]); A.t2 = n_terms == 4 ? e2_shift(d, T[1]) : nullptr; A.t3 = n_terms == 4 ? e2_shift(d, T[2]) : nullptr;
+            A.t4 = n_terms == 4 ? e2_shift(d, T[3]) : nullptr; A.frac = frac; A.n_sub = ns; A.out = e2_shift(d, evol());
+            k_2e_visc_apply<<<grid, 128, 0, d->stream>>>(A);
+            d->launches++;
+            CUDA_TRY(cudaGetLastError());
+            int rp = e2_launch_propagate(d, 0);
+            return rp ? rp : e2_visc_refresh_dt(d);
+        };
+        auto term = [&](double *out) -> int { return e2_visc_term(d, 0, (int)i, out); };
+        const size_t plane_bytes = (size_t)d->P.nx * d->P.pitch * sizeof(double);
+        for (int sc = 0; sc < ns; sc++) {
+            if (t->visc_hv_integrator == SPRUCE_TI_EULER) {
+                if ((rc = term(T[0])) || (rc = apply(evol(), 1.0, 1))) return rc;
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(init, evol(), plane_bytes, cudaMemcpyDeviceToDevice, d->stream));
+                if (t->visc_hv_integrator == SPRUCE_TI_RK2) {
+                    if ((rc = term(T[0])) || (rc = apply(init, 0.5, 1))) return rc;
+                    if ((rc = term(T[0])) || (rc = apply(init, 1.0, 1))) return rc;
+                } else {
+                    if ((rc = term(T[0])) || (rc = apply(init, 0.5, 1))) return rc;
+                    std::swap(T[0], T[1]);                                                      // dqdt1 waits in T[1] while T[0] is the working term
+                    if ((rc = term(T[0])) || (rc = apply(init, 0.5, 1))) return rc;
+                    std::swap(T[0], T[2]);
+                    if ((rc = term(T[0])) || (rc = apply(init, 1.0, 1))) return rc;
+                    std::swap(T[0], T[3]);
+                    if ((rc = term(T[0]))) return rc;
+                    double *d1 = T[1], *d2 = T[2], *d3 = T[3], *d4 = T[0];                     // -> (d1 + 2 d2 + 2 d3 + d4) / 6
+                    T[0] = d1; T[1] = d2; T[2] = d3; T[3] = d4;
+                    if ((rc = apply(init, 1.0, 4))) return rc;
+                }
+            }
+        }
+        if ((rc = e2_launch_propagate(d, 0)) || (rc = e2_visc_refresh_dt(d))) return rc;        // :178
+    }
+    return SPRUCE_OK;
+}
 int e2_enqueue_step(spruce_domain *d, int hist_slot)
 {
     k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot);
     d->launches++;
     int rc;
+    if (!d->e2->visc.empty()) {                                                                 // iterateModules (evolution.cpp:66), then the stages read the primary dt plane
+        if ((rc = e2_visc_refresh_dt(d)) || (rc = e2_av_iterate(d))) return rc;
+    }
     if (d->cfg.time_integrator == SPRUCE_TI_RK4 && (rc = e2_ensure_rk4(d))) return rc;
     E2DeviceExec x{d};
     if ((rc = e2::advance(x, d->cfg.time_integrator))) return rc;                  // SPRUCE_TI_* = e2::TI2_* = 0, 1, 2
     k_step_end<<<1, 1, 0, d->stream>>>(d->ctl);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+// spruce_module_viscosity / spruce_module_viscosity_term on this set (Viscosity::setupModule, viscosity.cpp:37-110)
+int e2_visc_config(spruce_domain *d, int hv_time_integrator, double hv_epsilon, int gradient_correction)
+{
+    OneFluid2E *t = d->e2;
+    if (d->cfg.n_ranks > 1) return fail(SPRUCE_ERR_UNSUPPORTED, "artificial_viscosity on ideal_mhd_2E is single-rank (its terms differentiate planes that have no halo exchange yet)");
+    t->visc_hv_integrator = hv_time_integrator; t->visc_hv_epsilon = hv_epsilon; t->visc_gc = gradient_correction ? 1 : 0;
+    int rc;
+    if (!t->dt_plane && (rc = alloc_plane(d, &t->dt_plane))) return rc;
+    for (int k = 0; k < 6; k++) if (!t->vplane[k] && (rc = alloc_plane(d, &t->vplane[k]))) return rc;
+    return SPRUCE_OK;
+}
+int e2_visc_add_term(spruce_domain *d, const char *visc_opt, double strength, const char *var_to_diff, const char *var_to_evol, const char *species, const double *strength_plane, size_t count)
+{
+    OneFluid2E *t = d->e2;
+    if (!t->dt_plane) return fail(SPRUCE_ERR_STATE, "spruce_module_viscosity must precede its terms");
+    OneFluid2E::VTerm v{};
+    v.opt = !strcmp(visc_opt, "local") ? 0 : !strcmp(visc_opt, "global") ? 1 : !strcmp(visc_opt, "boundary") ? 2 : !strcmp(visc_opt, "boundary_global") ? 3 : -1;
+    if (v.opt < 0) return fail(SPRUCE_ERR_ARG, "Viscosity option must be global, local, or boundary.");
+    v.strength = strength;
+    v.var_diff = e2_var_index(var_to_diff);
+    v.evol = e2_evolved_slot(var_to_evol);
+    if (v.var_diff < 0) return fail(SPRUCE_ERR_ARG, "Each variable to differentiate must be a valid variable within the chosen equation set.");
+    if (v.evol < 0) return fail(SPRUCE_ERR_ARG, "Each variable to evolve must be a valid evolved variable within the chosen equation set.");
+    const char sp = (species && species[0]) ? species[0] : 'i';
+    const bool evol_mom = v.evol == e2::Q_MX2 || v.evol == e2::Q_MY2, diff_vel = v.var_diff == e2::V2_v_x || v.var_diff == e2::V2_v_y;
+    const bool evol_e = v.evol == e2::Q_EI2 || v.evol == e2::Q_EE2, diff_T = v.var_diff == e2::V2_i_temp || v.var_diff == e2::V2_e_temp;
+    if (evol_mom && diff_vel && sp != 'i') return fail(SPRUCE_ERR_ARG, "Grid <e_n> was not found within the EquationSet.");      // viscosity.cpp:236: the set has no e_n
+    v.scale_mode = (evol_mom && diff_vel) ? 1 : (evol_e && diff_T) ? 2 : 0;
+    if (v.opt >= 2) {
+        if (!strength_plane || count != (size_t)d->P.nx * d->P.ny) return fail(SPRUCE_ERR_ARG, "boundary viscosity needs its strength profile (%zu values)", (size_t)d->P.nx * d->P.ny);
+        int rc = alloc_plane(d, &v.strength_plane);
+        if (rc) return rc;
+        if ((rc = h2d_plane(d, v.strength_plane, strength_plane))) return rc;
+    }
+    t->visc.push_back(v);
     return SPRUCE_OK;
 }
 int e2_upload(spruce_domain *d, const char *name, const double *host)

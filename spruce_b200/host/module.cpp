@@ -50,9 +50,13 @@ void ModuleHandler::instantiateModule(const std::string &name, std::ifstream &in
         m_modules.back()->configureModule(in);
         return;
     }
+    if (name == "artificial_viscosity") {                                               // generic over the equation set in the reference (viscosity.cpp:26-35); the device library
+        m_modules.emplace_back(new Viscosity(m_pd));                                    // takes it on ideal_mhd and ideal_mhd_2E and refuses ideal_2F with a message
+        m_modules.back()->configureModule(in);
+        return;
+    }
     SPRUCE_REQUIRE(dynamic_cast<IdealMHD *>(m_pd.m_eqs.get()) != nullptr, "Module designed for IdealMHD EquationSet (ensure that equation_set is set before modules in the config)");
-    if (name == "artificial_viscosity") m_modules.emplace_back(new Viscosity(m_pd));
-    else if (name == "thermal_conduction") m_modules.emplace_back(new ThermalConduction(m_pd));
+    if (name == "thermal_conduction") m_modules.emplace_back(new ThermalConduction(m_pd));
     else if (name == "radiative_losses") m_modules.emplace_back(new RadiativeLosses(m_pd));
     else if (name == "ambient_heating") m_modules.emplace_back(new AmbientHeating(m_pd));
     else if (name == "physical_viscosity") m_modules.emplace_back(new PhysicalViscosity(m_pd));

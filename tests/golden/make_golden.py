@@ -159,6 +159,11 @@ CASES = {
     "e2_pp_ucnp_rk4": ("two_energy", dict(nx=NX, ny=NY), dict(integrator="rk4", xb=PP, yb=UC, eqs="ideal_mhd_2E", **SOLAR_FLOORS), 4, (1, 4)),
     # the UCNP configuration of that set: ideal_mhd_2E + eic_thermalization on the Sr+ cloud (eic_thermalization.cpp:27-44)
     "e2_ucnp_eic_rk2": ("ucnp_cloud_2e", dict(nx=NX - 1, ny=NY + 1, drift=20.0, bfield=0.01), dict(integrator="rk2", xb=UC, yb=("open_ucnp", "fixed"), eqs="ideal_mhd_2E", modules=[EIC], **UCNP_FLOORS), 6, (1, 6)),
+    # ... with artificial_viscosity as well (the fourth module of the UCNP set): right-hand-side terms on a momentum and the electron energy, a hyper-viscous rk2 term
+    "e2_ucnp_visc_rk2": ("ucnp_cloud_2e", dict(nx=NX - 1, ny=NY + 1, drift=20.0, bfield=0.01), dict(integrator="rk2", xb=UC, yb=("open_ucnp", "fixed"), eqs="ideal_mhd_2E", modules=[
+        AV(visc_opt="local,global,global", visc_strength="0.5,3.0,0.3", visc_vars_to_diff="v_x,v_y,e_temp", visc_vars_to_evol="mom_x,mom_y,e_thermal_energy", visc_length="0,0,0",
+           visc_species="i,i,e", hv_time_integrator="rk2", hv_epsilon="1.0", gradient_correction="true", visc_output_visc="false", visc_output_lap="false",
+           visc_output_strength="false", visc_output_timescale="false")], **UCNP_FLOORS), 4, (1, 4)),
     # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
     "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
 }

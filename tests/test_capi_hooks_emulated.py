@@ -164,6 +164,7 @@ def emu():
     src = BUILD / "kernel_emu_capi.cpp"
     text = assemble()
     if not LIB.exists() or not src.exists() or src.read_text() != text:
+        LIB.unlink(missing_ok=True)                # a failed compile must not leave the previous library behind
         src.write_text(text)
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
     L = C.CDLL(str(LIB))

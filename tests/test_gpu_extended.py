@@ -516,6 +516,36 @@ def test_ideal_mhd_2e_with_eic_golden_reference_outputs():
     assert "ok" in out
 
 
+E2_VISC_CODE = """
+    import numpy as np
+    from golden_util import Golden, same_bits, mismatch, module_kwargs, viscosity_terms_with_profiles
+    from spruce_b200.domain import PlasmaDomain
+    g = Golden("e2_ucnp_visc_rk2")
+    d = PlasmaDomain(g.planes, g.ion_mass, g.adiabatic_index, equation_set=g.equation_set, **g.kw)
+    for mname, kv in g.modules:
+        kw = module_kwargs(mname, kv)
+        d.set_viscosity(viscosity_terms_with_profiles(g.planes, kw.pop("terms")), **kw)
+    done = 0
+    for it in sorted(g.frames):
+        dts = d.advance(it - done)
+        ref = g.steps[done:it]
+        assert all(a == b for a, b in zip(dts, ref)), ([x.hex() for x in dts], [float(x).hex() for x in ref])
+        done = it
+        for v in g.out_vars:
+            got = d.grid(v)
+            assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
+    print("ok")
+"""
+
+
+@pytest.mark.xfail(reason="written after round 2's GPU budget was spent (CPU-checked: tests/test_mhd2e_kernels_emulated.py); first executed by the round-end run", strict=False)
+def test_ideal_mhd_2e_with_artificial_viscosity_golden_reference_outputs():
+    """artificial_viscosity on ideal_mhd_2E on the device (visc_cell in mhd2e_cells.cuh; right-hand-side terms and hyper-viscous rk2 sub-cycles, gradient correction) against a
+    committed fixture of the UNMODIFIED reference binary (tests/golden/e2_ucnp_visc_rk2.npz): step sizes and every output plane bit for bit"""
+    out = run_isolated(E2_VISC_CODE, {})
+    assert "ok" in out
+
+
 MOC_LIMIT_CODE = """
     import numpy as np
     from golden_util import same_bits, mismatch

@@ -98,7 +98,14 @@ CASES["ucnp_mhd2e_module_set"] = (lambda: synthetic.ucnp_cloud_2e(83, 79, drift=
                                   output_flags=("rho", "i_temp", "e_temp", "mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy", "press", "n", "dt"),
                                   modules=[("eic_thermalization", []), ("coulomb_explosion", [("timescale", "1.0e-6"), ("lengthscale", "0.2"), ("strength", "1.0e-3")]),
                                            ("global_temperature", [("gt_species", "i"), ("gt_strength", "3.7"), ("gt_use_diffusion", "true")])]), False)
-FIRST_RUN_AT_ROUND_END = {"ucnp_mhd2e_module_set", "loop_multispecies", "loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
+# ... and the fourth one, artificial_viscosity, on that set (device-resident: mhd2e_cells.cuh visc_cell); no libm module: byte-identical files
+CASES["ucnp_mhd2e_viscosity"] = (lambda: synthetic.ucnp_cloud_2e(41, 37, drift=20.0, bfield=0.01), dict(integrator="rk2", max_iterations=5, iter_output_interval=1, eqs="ideal_mhd_2E", **UCNP_KW,
+                                 output_flags=("rho", "i_temp", "e_temp", "mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy", "dt"),
+                                 modules=[("artificial_viscosity", [("visc_opt", "local,global,boundary"), ("visc_strength", "0.5,3.0,0.6"), ("visc_vars_to_diff", "v_x,v_y,i_temp"),
+                                                                    ("visc_vars_to_evol", "mom_x,mom_y,i_thermal_energy"), ("visc_length", "0,0,0.3"), ("visc_species", "i,i,i"),
+                                                                    ("hv_time_integrator", "rk4"), ("visc_output_visc", "false"), ("visc_output_lap", "false"),
+                                                                    ("visc_output_strength", "false"), ("visc_output_timescale", "false")])]), True)
+FIRST_RUN_AT_ROUND_END = {"ucnp_mhd2e_viscosity", "ucnp_mhd2e_module_set", "loop_multispecies", "loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))

@@ -94,6 +94,14 @@ static int peer_dt_allgather(spruce_domain *d)
 '''
 
 
+# stand-ins only this set's launch code needs (the viscosity terms upload a profile and copy a plane); tests/test_ideal2f_kernels_emulated.py has its own
+E2_RUNTIME = r'''
+static int h2d_plane(spruce_domain *d, double *dev, const double *host) { std::memcpy(dev, host, (size_t)d->P.nx * d->P.pitch * sizeof(double)); return SPRUCE_OK; }      // pitch == ny here
+enum { cudaMemcpyDeviceToDevice = 3 };
+static inline int cudaMemcpyAsync(void *dst, const void *src, size_t n, int, int) { std::memcpy(dst, src, n); return 0; }
+'''
+
+
 def assemble():
     mk = (CSRC / "mhd_kernels.cuh").read_text()
     ca = (CSRC / "capi.cu").read_text()
@@ -105,7 +113,7 @@ def assemble():
                     cut(mk, "constexpr int HALO", "enum { KM_NONE", include_end=True), BLOCK_MIN,
                     cut(mk, "struct StepCtl {", "// the rare fallback of the skip test"),
                     cut(ca, "struct HostAxis {", "struct TwoFluid;"), cut(ca, "void build_axis(", "int upload_tables("),
-                    "}  // namespace spruce\n", DOMAIN, body, (ROOT / "tests" / "hostcheck" / "kernel_emu_2e.inc").read_text()])
+                    "}  // namespace spruce\n", DOMAIN, E2_RUNTIME, body, (ROOT / "tests" / "hostcheck" / "kernel_emu_2e.inc").read_text()])
 
 
 @pytest.fixture(scope="module")
@@ -114,6 +122,7 @@ def emu():
     src = BUILD / "kernel_emu_2e.cpp"
     text = assemble()
     if not LIB.exists() or not src.exists() or src.read_text() != text:
+        LIB.unlink(missing_ok=True)                # a failed compile must not leave the previous library behind
         src.write_text(text)
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I", str(CSRC), "-I", str(ROOT / "include"), "-o", str(LIB), str(src)], check=True)
     L = C.CDLL(str(LIB))
@@ -188,4 +197,71 @@ def test_product_mhd2e_launch_code_with_eic_thermalization(emu, name, xb, yb, in
     for nm in ("i_thermal_energy", "e_thermal_energy"):
         v = EVOLVED_2E.index(nm)
         assert rel(out[v], plain.get(nm)) > 100 * max(rel(out[v], o.get(nm)), 1e-15), "%s: the exchange term is not visible in %s" % (name, nm)
+    o.close(); plain.close()
+
+
+E2_VISC_EMU_CASES = [
+    ("rhs_terms_rk2_eic", ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 27, 25, True,
+     [("local", 0.5, "v_x", "mom_x", 0.0, "i"), ("global", 0.3, "v_y", "mom_y", 0.0, "i"), ("local", 0.4, "i_temp", "i_thermal_energy", 0.0, "i"), ("global", 0.2, "e_temp", "e_thermal_energy", 0.0, "e")], "euler", False),
+    ("boundary_gc_hv_rk2", ("fixed", "reflect"), ("open_ucnp", "fixed"), "rk4", 24, 29, False,
+     [("boundary", 0.8, "v_x", "mom_x", 0.3, "i"), ("global", 3.0, "v_y", "mom_y", 0.0, "i"), ("boundary_global", 0.6, "e_temp", "e_thermal_energy", 0.2, "e")], "rk2", True),
+    ("hv_rk4_periodic", ("periodic", "periodic"), ("periodic", "periodic"), "euler", 22, 21, False,
+     [("local", 2.5, "i_temp", "i_thermal_energy", 0.0, "i"), ("local", 0.4, "rho", "rho", 0.0, "i")], "rk4", False),
+    ("hv_euler_walls", ("reflect", "open"), ("fixed", "open"), "rk2", 26, 23, False,
+     [("global", 2.0, "v_x", "mom_x", 0.0, "i"), ("local", 0.7, "e_temp", "e_thermal_energy", 0.0, "e")], "euler", True),
+]
+
+
+@pytest.mark.parametrize("name,xb,yb,integrator,nx,ny,eic,terms,hv_integ,gc", E2_VISC_EMU_CASES, ids=[c[0] for c in E2_VISC_EMU_CASES])
+def test_product_mhd2e_launch_code_with_artificial_viscosity(emu, name, xb, yb, integrator, nx, ny, eic, terms, hv_integ, gc):
+    """artificial_viscosity on ideal_mhd_2E (the fourth module of the UCNP set) through the product's kernels and launch code -- visc_cell / k_2e_visc_term, the right-hand-side
+    terms added by k_2e_cells, the hyper-viscous sub-steps of e2_av_iterate with a propagate and a refreshed primary dt plane after each -- whole steps bit-equal to the
+    restatement that live reference runs pin (test_ideal_mhd_2e_with_artificial_viscosity_oracle_equals_live_reference); 1e-9 with eic_thermalization in the mix"""
+    from spruce_b200 import synthetic
+    from golden_util import boundary_viscosity_profile
+    s = synthetic.ucnp_cloud_2e(nx, ny, drift=20.0, bfield=0.01)
+    floors = dict(density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, eic=eic, **floors)
+    full = [dict(opt=t[0], strength=t[1], var_diff=t[2], var_evol=t[3], species=t[5],
+                 strength_grid=boundary_viscosity_profile(s["planes"]["pos_x"], s["planes"]["pos_y"], t[1], t[4]) if t[0].startswith("boundary") else None) for t in terms]
+    o.set_viscosity(full, hv_integrator=hv_integ, hv_epsilon=1.0, gradient_correction=gc)
+    plain = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator=integrator, eic=eic, **floors)
+    nsteps = 4
+    ref_steps = np.array([o.step() for _ in range(nsteps)])
+    for _ in range(nsteps):
+        plain.step()
+    names = ["rho", "i_temp", "e_temp", "mom_x", "mom_y", "bi_x", "bi_y", "be_x", "be_y", "grav_x", "grav_y"]
+    planes = [np.ascontiguousarray(s["planes"][v], dtype=np.float64) for v in names]
+    dx = np.ascontiguousarray(s["planes"]["d_x"][:, 0]); dy = np.ascontiguousarray(s["planes"]["d_y"][0, :])
+    arr = (C.c_void_p * 11)(*[p.ctypes.data for p in planes])
+    bc = (C.c_int * 4)(BC[xb[0]], BC[xb[1]], BC[yb[0]], BC[yb[1]])
+    out = np.zeros((7, nx, ny)); dt = np.zeros((nx, ny)); steps = np.zeros(nsteps)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.emu2e_set_eic(int(eic))
+    emu.emu2e_viscosity_begin(C.c_int(TI[hv_integ]), C.c_int(int(gc)))
+    keep = []
+    for t in full:
+        prof = np.ascontiguousarray(t["strength_grid"], dtype=np.float64) if t["strength_grid"] is not None else None
+        keep.append(prof)
+        emu.emu2e_viscosity_term(t["opt"].encode(), C.c_double(t["strength"]), t["var_diff"].encode(), t["var_evol"].encode(), t["species"].encode(),
+                                 vp(prof) if prof is not None else None, C.c_int(nx * ny))
+    try:
+        rc = emu.emu2e_run(C.c_int(1), arr, vp(dx), vp(dy), C.c_int(nx), C.c_int(ny), bc, C.c_int(TI[integrator]), C.c_double(s["ion_mass"]), C.c_double(s["adiabatic_index"]), C.c_double(0.2),
+                           C.c_double(floors["density_min"]), C.c_double(floors["temp_min"]), C.c_double(floors["thermal_energy_min"]), C.c_double(1.0), C.c_double(0.5), C.c_int(nsteps),
+                           vp(out), vp(dt), vp(steps))
+    finally:
+        emu.emu2e_set_eic(0)
+        emu.emu2e_viscosity_begin(C.c_int(0), C.c_int(0))
+    assert rc == 0
+    if eic:
+        rel = lambda a, b: float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+        assert np.max(np.abs(steps - ref_steps) / ref_steps) <= 1e-9
+        for v, nm in enumerate(EVOLVED_2E):
+            assert rel(out[v], o.get(nm)) <= 1e-9, "%s %s: %.3e" % (name, nm, rel(out[v], o.get(nm)))
+    else:
+        assert [float(x).hex() for x in steps] == [float(x).hex() for x in ref_steps]
+        for v, nm in enumerate(EVOLVED_2E):
+            assert same_bits(out[v], o.get(nm)), "%s %s: %s" % (name, nm, mismatch(out[v], o.get(nm)))
+        assert same_bits(dt, o.get("dt"))
+    assert any(not same_bits(out[v], plain.get(nm)) for v, nm in enumerate(EVOLVED_2E)), "the viscosity never acted"
     o.close(); plain.close()

@@ -80,6 +80,10 @@ def test_extended_oracle_reproduces_reference(name):
     if g.equation_set == "ideal_mhd_2E":
         from oracle.oracle import Oracle2E
         o = Oracle2E(g.planes, g.ion_mass, g.adiabatic_index, eic=any(m == "eic_thermalization" for m, _ in g.modules), **g.kw)
+        for mname, kv in g.modules:
+            if mname == "artificial_viscosity":
+                kw = module_kwargs(mname, kv)
+                o.set_viscosity(viscosity_terms_with_profiles(g.planes, kw.pop("terms")), **kw)
         for it in range(1, g.n_steps + 1):
             step = o.step()
             assert step == g.steps[it - 1], "iteration %d: step %s != reference %s" % (it, step.hex(), float(g.steps[it - 1]).hex())

@@ -361,6 +361,52 @@ def test_ideal_mhd_2e_with_eic_oracle_equals_live_reference(name, xb, yb, integr
     o.close(); plain.close()
 
 
+E2_VISC_CASES = [
+    # (name, xb, yb, integrator, nx, ny, eic, terms [(opt, strength, var_diff, var_evol, length, species)], hv_integrator, gradient_correction): artificial_viscosity on
+    # ideal_mhd_2E (the fourth module of the UCNP set, ConfigHandler.hpp:32): right-hand-side terms on momenta and both thermal energies, hyper-viscous sub-cycles
+    ("rhs_terms_rk2_eic", ("open_ucnp", "open_ucnp"), ("open_ucnp", "open_ucnp"), "rk2", 27, 25, True,
+     [("local", 0.5, "v_x", "mom_x", 0.0, "i"), ("global", 0.3, "v_y", "mom_y", 0.0, "i"), ("local", 0.4, "i_temp", "i_thermal_energy", 0.0, "i"), ("global", 0.2, "e_temp", "e_thermal_energy", 0.0, "e")], "euler", False),
+    ("boundary_gc_hv_rk2", ("fixed", "reflect"), ("open_ucnp", "fixed"), "rk4", 24, 29, False,
+     [("boundary", 0.8, "v_x", "mom_x", 0.3, "i"), ("global", 3.0, "v_y", "mom_y", 0.0, "i"), ("boundary_global", 0.6, "e_temp", "e_thermal_energy", 0.2, "e")], "rk2", True),
+    ("hv_rk4_periodic", ("periodic", "periodic"), ("periodic", "periodic"), "euler", 22, 21, True,
+     [("local", 2.5, "i_temp", "i_thermal_energy", 0.0, "i"), ("local", 0.4, "rho", "rho", 0.0, "i")], "rk4", False),
+]
+
+
+def e2_visc_setup(name, nx, ny, terms, hv_integrator, gc):
+    from golden_util import boundary_viscosity_profile
+    s = synthetic.ucnp_cloud_2e(nx, ny, drift=20.0, bfield=0.01)
+    block = [("visc_opt", ",".join(t[0] for t in terms)), ("visc_strength", ",".join(repr(t[1]) for t in terms)), ("visc_vars_to_diff", ",".join(t[2] for t in terms)),
+             ("visc_vars_to_evol", ",".join(t[3] for t in terms)), ("visc_length", ",".join(repr(t[4]) for t in terms)), ("visc_species", ",".join(t[5] for t in terms)),
+             ("hv_time_integrator", hv_integrator), ("hv_epsilon", "1.0"), ("gradient_correction", "true" if gc else "false"),
+             ("visc_output_visc", "false"), ("visc_output_lap", "false"), ("visc_output_strength", "false"), ("visc_output_timescale", "false")]
+    full = [dict(opt=t[0], strength=t[1], var_diff=t[2], var_evol=t[3], species=t[5],
+                 strength_grid=boundary_viscosity_profile(s["planes"]["pos_x"], s["planes"]["pos_y"], t[1], t[4]) if t[0].startswith("boundary") else None) for t in terms]
+    return s, block, full
+
+
+@pytest.mark.parametrize("name,xb,yb,integrator,nx,ny,eic,terms,hv_integrator,gc", E2_VISC_CASES, ids=[c[0] for c in E2_VISC_CASES])
+def test_ideal_mhd_2e_with_artificial_viscosity_oracle_equals_live_reference(name, xb, yb, integrator, nx, ny, eic, terms, hv_integrator, gc):
+    from oracle.oracle import Oracle2E
+    s, block, full = e2_visc_setup(name, nx, ny, terms, hv_integrator, gc)
+    kw = dict(xb=xb, yb=yb, integrator=integrator, density_min=1.0, temp_min=1.0e-3, thermal_energy_min=1.0e-30)
+    nsteps = 3
+    modules = ([("eic_thermalization", [])] if eic else []) + [("artificial_viscosity", block)]
+    frames = run_reference(s, dict(kw, eqs="ideal_mhd_2E", modules=modules), E2_OUT, nsteps)
+    o = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], eic=eic, **kw)
+    o.set_viscosity(full, hv_integrator=hv_integrator, hv_epsilon=1.0, gradient_correction=gc)
+    plain = Oracle2E(s["planes"], s["ion_mass"], s["adiabatic_index"], eic=eic, **kw)
+    xl, xu, yl, yu = interior(xb, yb, nx, ny)
+    for it in range(1, nsteps + 1):
+        step = o.step(); plain.step()
+        ref_step = 0.2 * np.nanmin(frames[it - 1]["dt"][xl:xu + 1, yl:yu + 1])
+        assert step == ref_step, "%s iteration %d: step %s vs %s" % (name, it, step.hex(), float(ref_step).hex())
+    for v in E2_OUT:
+        assert same_bits(o.get(v), frames[nsteps][v]), "%s %s: %s" % (name, v, mismatch(o.get(v), frames[nsteps][v]))
+    assert any(not same_bits(o.get(v), plain.get(v)) for v in ("mom_x", "mom_y", "i_thermal_energy", "e_thermal_energy")), "the viscosity never acted"
+    o.close(); plain.close()
+
+
 MOC_LIMIT_CASES = [
     ("y2_b_and_mom", ("periodic", "periodic"), ("fixed", "open_moc"), "rk2", 0.0, dict(b_limiting=True, b_lower=0.9, b_upper=1.05, mom_limiting=True, mom_lower=0.5, mom_upper=1.5), 26, 23),
     ("all_sides_mom_visc", ("open_moc", "open_moc"), ("open_moc", "open_moc"), "euler", 0.1, dict(mom_limiting=True, mom_lower=0.8, mom_upper=1.1), 25, 24),

@@ -38,6 +38,7 @@ def emu():
     BUILD.mkdir(exist_ok=True)
     src = BUILD / "stencil_fast.cpp"
     if not LIB.exists() or not src.exists() or src.read_text() != text:
+        LIB.unlink(missing_ok=True)                # a failed compile must not leave the previous library behind
         src.write_text(text)
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(CSRC), "-o", str(LIB), str(src)], check=True)
     L = C.CDLL(str(LIB))
