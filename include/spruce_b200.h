@@ -137,7 +137,8 @@ int spruce_module_ambient_heating(spruce_domain *dom, const double *heating, siz
  * comma-separated lists visc_opt / visc_strength / visc_vars_to_diff / visc_vars_to_evol / visc_species (setupModule :37-110).
  * Terms with strength <= 1 are added to the right-hand side (computeTimeDerivativesModule :112-123), terms with strength > 1
  * are sub-cycled (iterateModule :125-180).  visc_opt "boundary"/"boundary_global" need the strength profile of
- * getBoundaryViscosity (:278-325), built on the host (libm exp) like the reference does. */
+ * getBoundaryViscosity (:278-325), built on the host (libm exp) like the reference does.  ideal_mhd domains, and ideal_mhd_2E domains on one rank (variable names
+ * of idealmhd2E.hpp:18-22; the timescale is the primary dt plane for either species, :45); ideal_2F domains are refused. */
 int spruce_module_viscosity(spruce_domain *dom, int hv_time_integrator, double hv_epsilon, int gradient_correction);
 int spruce_module_viscosity_term(spruce_domain *dom, const char *visc_opt, double strength, const char *var_to_diff, const char *var_to_evol,
                                  const char *species, const double *strength_plane, size_t count);
