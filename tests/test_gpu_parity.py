@@ -96,7 +96,7 @@ def test_golden_reference_outputs(name):
         if exact:
             assert all(a == b for a, b in zip(dts, ref)), "step history differs at iteration %d: %s vs %s" % (
                 done + int(np.argmax(dts != ref)) + 1, [x.hex() for x in dts[:3]], [float(x).hex() for x in ref[:3]])
-        else:
+        elif len(ref):                                               # (a fixture may keep frame 0: nothing stepped yet)
             assert np.max(np.abs(dts - ref) / ref) <= REL_TOL
         done = it
         for v in OUT_VARS:
