@@ -149,3 +149,35 @@ def test_a_rank_that_dies_mid_run_takes_the_others_down(stub, tmp_path):
     assert time.perf_counter() - t0 < 20.0
     err = r.stderr.decode()
     assert r.returncode == 1 and "rank 1 ended early" in err and "successfully reached" not in err, err[-1500:]
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_cumulative_and_viscosity_output_planes_are_gathered_like_every_other_plane(stub, tmp_path, n):
+    """multispecies_mode and the output planes of artificial_viscosity / physical_viscosity on N ranks: every rank enables them, hands its ms_electron_heating_fraction over,
+    resets the cumulative planes after every store; the planes reach mhd.out through the same row gather (the stand-in fills module planes with 7.0 on every rank)"""
+    nx, ny = 23, 18
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    modules = [("ambient_heating", [("heating_rate", "1.0e-4"), ("ms_electron_heating_fraction", "0.3")]),
+               ("artificial_viscosity", [("visc_opt", "global,local"), ("visc_strength", "3.0,0.5"), ("visc_vars_to_diff", "v_x,temp"), ("visc_vars_to_evol", "mom_x,thermal_energy"),
+                                         ("visc_length", "0,0"), ("visc_species", "i,i"), ("hv_time_integrator", "rk2"), ("visc_output_visc", "true"), ("visc_output_lap", "true"),
+                                         ("visc_output_strength", "false"), ("visc_output_timescale", "true")]),
+               ("physical_viscosity", [("coeff", "1.0e-14"), ("epsilon", "0.1"), ("output_to_file", "true")])]
+    cfg = refrun.ideal_mhd_config(std_out_interval=1, integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "open"), max_iterations=4, iter_output_interval=2, modules=modules,
+                                  output_flags=("rho", "mom_x"), multispecies=True)
+    r1, out1, (log1,) = run(stub, tmp_path, s, cfg, 1, "one")
+    rn, outn, logs = run(stub, tmp_path, s, cfg, n, "n%d" % n)
+    for r in (r1, rn):
+        assert r.returncode in (-6, 134), r.stderr.decode()[-2000:]
+    assert (outn / "mhd.out").read_bytes() == (out1 / "mhd.out").read_bytes()
+    _, frames = refrun.read_out(outn / "mhd.out")
+    expected = ["cumulative_electron_heating", "cumulative_ion_heating", "cumulative_joule_heating", "mom_x_dqdt", "thermal_energy_dqdt", "mom_x_lap", "thermal_energy_lap",
+                "mom_x_dt", "thermal_energy_dt", "viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"]
+    for f in frames:
+        assert [k for k in f if k not in ("t", "rho", "mom_x")] == expected
+        assert all(np.all(f[k] == 7.0) for k in expected)
+    for log in logs:
+        names = [ln.split()[0] for ln in log if ln.startswith("spruce_")]
+        assert names.count("spruce_multispecies_mode") == 1 and names.count("spruce_multispecies_reset") == 2
+        assert "spruce_module_ms_fraction ambient_heating fraction=0.29999999999999999" in log
+        assert [ln.split()[1] for ln in log if ln.startswith("spruce_module_output_to_file")] == ["artificial_viscosity", "physical_viscosity"]
+        assert [ln for ln in log if ln.startswith("spruce_module_output ")] == [ln for ln in log1 if ln.startswith("spruce_module_output ")]
