@@ -787,3 +787,45 @@ def test_multispecies_cumulative_planes_of_the_subcycled_modules(emu, xb, yb):
         ref = o.ms_plane(name)
         assert np.count_nonzero(ref) > 0 and np.max(np.abs(got[name] - ref)) <= 1e-9 * np.max(np.abs(ref)), name
     o.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("integ,gc", [("euler", False), ("rk2", True)])
+@pytest.mark.parametrize("xb,yb", [(("periodic", "periodic"), ("fixed", "open")), (("fixed", "open"), ("reflect", "open"))])
+def test_physical_viscosity_on_slabs_equals_the_whole_domain_with_and_without_fast_instances(emu, xb, yb, integ, gc, world):
+    """pv_substeps on 2 and 3 slabs (host threads; velocity and temperature halo rows exchanged after every sub-cycle stage, the coefficient plane's once): momenta, thermal
+    energy and the four output planes equal the single-rank run's bit for bit, FAST stencil instances on and off (the combination no device test has seen yet)"""
+    from golden_util import physical_viscosity_coefficient
+    nx, ny = 27, 22
+    s = synthetic.stratified_loop(nx, ny, bump=0.5)
+    o = Oracle(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", **FLOORS)
+    o.run(2)
+    xl, xu = (0, nx - 1) if xb[0] == "periodic" else (2, nx - 3)
+    yl, yu = (0, ny - 1) if yb[0] == "periodic" else (2, ny - 3)
+    step = 0.2 * float(np.min(o.get("dt")[xl:xu + 1, yl:yu + 1]))
+    coeff, ns, code = 1.0e-14, 3, {"euler": 0, "rk2": 1}[integ]
+    cg = np.ascontiguousarray(physical_viscosity_coefficient(s["planes"], coeff, 6.0e8))
+    s1, o1, h1, _, _ = make_pair(emu, xb, yb, nx, ny)
+    o1.close()
+    emu.cemu_set_fast_interior(h1, C.c_int(0))
+    whole_avg = np.zeros((4, nx, ny))
+    assert emu.cemu_physical_viscosity(h1, vp(cg), C.c_double(coeff), C.c_int(1), C.c_int(1), C.c_int(int(gc)), C.c_int(code), C.c_int(0), C.c_int(ns), C.c_double(step), vp(whole_avg)) == 0
+    whole = [np.zeros((nx, ny)) for _ in EV]
+    for k in range(len(EV)):
+        emu.cemu_get(h1, C.c_int(k), vp(whole[k]))
+    for fast in (1.0, 0.0):
+        hs, cuts, keep = make_slabs(emu, s, o, xb, yb, nx, ny, world)
+        p = np.array([coeff, 1.0, 1.0, float(gc), float(code), 0.0, float(ns), step, fast])
+        avg = np.zeros(4 * nx * ny)
+        assert emu.cemu_run_slabs_pv((C.c_void_p * world)(*hs), C.c_int(world), vp(cg), vp(p), vp(avg)) == 0
+        for k, v in enumerate(EV):
+            got = gather(emu, hs, cuts, ny, k)
+            assert same_bits(got, whole[k]), "%s on %d slabs (fast %d): %s" % (v, world, int(fast), mismatch(got, whole[k]))
+        off = 0
+        for r in range(world):
+            rows = cuts[r + 1] - cuts[r]
+            blk = avg[off:off + 4 * rows * ny].reshape(4, rows, ny); off += 4 * rows * ny
+            for q in range(4):
+                assert same_bits(blk[q], whole_avg[q][cuts[r]:cuts[r + 1]]), "output plane %d of rank %d (fast %d)" % (q, r, int(fast))
+    assert np.count_nonzero(whole_avg[0]) > 0 and not np.array_equal(whole[4], o.get("thermal_energy"))
+    o.close()
