@@ -162,6 +162,9 @@ int spruce_module_output_to_file(spruce_domain *dom, const char *module, int on)
  * reference: 1, 1, 0.5, 0.5, 0, 0), and anomalous_resistivity its joule heating.  The host resets them after every stored frame (evolution.cpp:36-41).
  * ideal_mhd domains only. */
 int spruce_multispecies_mode(spruce_domain *dom, int on);
+/* inactive_mode = true of "thermal_conduction" / "radiative_losses" (thermalconduction.cpp:25,109, radiativelosses.cpp:26,98): the module is evaluated every step -- sub-cycle
+ * count, output_to_file planes, cumulative planes -- and nothing is applied to the state. */
+int spruce_module_inactive_mode(spruce_domain *dom, const char *module, int on);
 int spruce_multispecies_reset(spruce_domain *dom);
 int spruce_module_ms_fraction(spruce_domain *dom, const char *module, double ms_electron_heating_fraction);
 int spruce_module_output(spruce_domain *dom, const char *plane_name, double *host, size_t count);

@@ -77,6 +77,7 @@ def lib():
         L.oracle_set_moc_limiting.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
         L.oracle_set_physical_viscosity.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle_physical_viscosity_iterate.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_set_module_inactive.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_set_multispecies.argtypes = [C.c_void_p, C.c_int]
         L.oracle_set_ms_fraction.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.oracle_ms_plane.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -243,6 +244,10 @@ class Oracle:
         out = np.zeros((4, self.nx, self.ny))
         lib().oracle_anomalous_core(self.h, C.c_double(dt), _dp(out), C.c_int(int(raw_commit)))
         return out
+
+    def set_module_inactive(self, module: str, on: bool = True):
+        """inactive_mode of thermal_conduction / radiative_losses (thermalconduction.cpp:109, radiativelosses.cpp:98): evaluated for the output and cumulative planes, not applied"""
+        lib().oracle_set_module_inactive(self.h, {"thermal_conduction": 1, "radiative_losses": 2}[module], int(on))
 
     def set_multispecies(self, on: bool = True, **fractions):
         """multispecies_mode = true; fractions: ms_electron_heating_fraction per module (thermal_conduction=, radiative_losses=, ambient_heating=, physical_viscosity=,

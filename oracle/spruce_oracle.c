@@ -64,6 +64,7 @@ typedef struct {
     /* multispecies_mode (plasmadomain.hpp:134-135): cumulative electron / ion / joule heating between outputs, fed by the modules with their
      * ms_electron_heating_fraction; ms_frac is indexed by module: 1 tc, 2 rl, 3 ah, 5 pv, 6 ambient_heating_sink, 7 localized_heating */
     int ms_on; double ms_frac[8]; double *ms_cum[3];
+    int tc_inactive, rl_inactive;       /* inactive_mode of thermal_conduction / radiative_losses: everything is evaluated (output planes, cumulative planes), nothing applied */
     double *pv_avg[4];                  /* output_to_file planes: viscous_heating, viscous_force_x/y/z (physicalviscosity.cpp:151-152,166,170,218,222,292-308) */
     void *anom;                   /* anomalous_resistivity (anomalous_resistivity_oracle.inc); order id 13 */
     void *small[8]; int n_small;  /* small solar modules (solar_small_modules_oracle.inc); order id = 100 + index */
@@ -760,8 +761,10 @@ static void tc_iterate(oracle *o, double dt)
     }
     for (int c = 0; c < n; c++) o->mod.tc_avg[c] = (e[c] - o->g[V_thermal_energy][c]) / dt;                                  /* :102 */
     MS_FEED(o, 1, +=, (e[c] - o->g[V_thermal_energy][c]) * fr);                                                              /* :105-108 */
+    if (!o->mod.tc_inactive) {                                                                                               /* :109 */
     memcpy(o->g[V_thermal_energy], e, sizeof(double) * n);
     propagate_changes(o, o->g, o->g);
+    }
     free(e); free(T); free(nn); free(bhx); free(bhy); free(k1); free(k2); free(k3); free(k4); free(im); free(imT);
 }
 
@@ -835,8 +838,10 @@ static void rl_iterate(oracle *o, double dt)
     if (!o->mod.rl_avg) o->mod.rl_avg = pl_new(o);
     for (int c = 0; c < n; c++) o->mod.rl_avg[c] = (e[c] - o->g[V_thermal_energy][c]) / dt;                                  /* radiativelosses.cpp:93 */
     MS_FEED(o, 2, +=, (e[c] - o->g[V_thermal_energy][c]) * fr);                                                              /* :94-97 */
+    if (!o->mod.rl_inactive) {                                                                                               /* :98 */
     memcpy(o->g[V_thermal_energy], e, sizeof(double) * n);
     propagate_changes(o, o->g, o->g);
+    }
     free(e); free(T); free(nn); free(k1); free(k2); free(k3); free(k4); free(im); free(imT);
 }
 
@@ -1073,6 +1078,8 @@ void oracle_set_multispecies(oracle *o, int on)
     o->mod.ms_on = on;
     for (int k = 0; k < 3; k++) { if (!o->mod.ms_cum[k]) o->mod.ms_cum[k] = pl_new(o); memset(o->mod.ms_cum[k], 0, sizeof(double) * o->n); }
 }
+/* inactive_mode of a module: 1 thermal_conduction, 2 radiative_losses */
+void oracle_set_module_inactive(oracle *o, int module, int on) { if (module == 1) o->mod.tc_inactive = on; else if (module == 2) o->mod.rl_inactive = on; }
 void oracle_set_ms_fraction(oracle *o, int module, double f) { if (module >= 0 && module < 8) o->mod.ms_frac[module] = f; }
 /* which: 0 cumulative_electron_heating, 1 cumulative_ion_heating, 2 cumulative_joule_heating */
 int oracle_ms_plane(const oracle *o, int which, double *out)

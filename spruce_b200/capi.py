@@ -69,6 +69,7 @@ SYMBOLS = {
     "spruce_module_output_to_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "spruce_module_output": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
     "spruce_multispecies_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "spruce_module_inactive_mode": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "spruce_multispecies_reset": (C.c_int, [C.c_void_p]),
     "spruce_module_ms_fraction": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "spruce_eqs_ideal_mhd_options": (C.c_int, [C.c_void_p, C.c_double]),

@@ -118,6 +118,7 @@ struct spruce_domain {
     double *heating = nullptr;
     // diagnostic planes of output_to_file = true (thermalconduction.cpp:226-237, radiativelosses.cpp:172-179)
     bool tc_output = false, rl_output = false;
+    bool tc_inactive = false, rl_inactive = false;      // inactive_mode (thermalconduction.cpp:109, radiativelosses.cpp:98): evaluated for the output / cumulative planes, not applied
     double *tc_avg = nullptr, *tc_sat = nullptr, *rl_avg = nullptr, *old_e = nullptr;
     // artificial_viscosity (source/modules/viscosity.cpp): terms in config order
     struct ViscTerm { int opt; double strength; int var_diff; int var_evol; int species; double *strength_plane; bool halo_done = false;
@@ -621,11 +622,16 @@ int tc_iterate(spruce_domain *d, double dt)
     if ((rc = derive_to(d, V_b_hat_y, bhy))) return rc;
     const int ns = d->tc_nsub;
     const double dts = dt / (double)ns;                                                             // :60
-    double *e = d->Pset.p[E_E];
+    // inactive_mode: the sub-cycles run on a copy of the thermal energy (old_e) and only the output / cumulative planes keep their result (:101-109)
+    const bool inactive = d->tc_inactive;
+    if (inactive && !d->tc_output && !d->ms_on) return SPRUCE_OK;                                   // nothing would be kept
+    double *const e_primary = d->Pset.p[E_E];
+    double *e = inactive ? d->old_e : e_primary;
+    const double *e_before = inactive ? e_primary : d->old_e;
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     const dim3 grid256((d->P.ny + 255) / 256, d->P.nx);
     if (d->tc_output || d->ms_on) {                                                                 // :53-59
-        k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, e);
+        k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, e_primary);
         d->launches++;
     }
     if (d->tc_output) {
@@ -659,21 +665,22 @@ int tc_iterate(spruce_domain *d, double dt)
         }
     }
     if (d->tc_output) {                                                                             // :101-104
-        k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->tc_avg, e, d->old_e, dt);
+        k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->tc_avg, e, e_before, dt);
         d->launches++;
     }
-    if ((rc = ms_feed(d, MS_DIFF, e, d->old_e, d->ms_frac_tc))) return rc;                          // :105-108
+    if ((rc = ms_feed(d, MS_DIFF, e, e_before, d->ms_frac_tc))) return rc;                          // :105-108
+    if (inactive) return SPRUCE_OK;                                                                 // :109
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // :110-111
     return after_module_propagate(d);
 }
 
-int rl_launch(spruce_domain *d, int count_mode, double dt)
+int rl_launch(spruce_domain *d, int count_mode, double dt, double *e_out = nullptr)
 {
     RlArgs A{};
     A.R = d->rl;
     for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
-    A.e_out = d->Pset.p[E_E]; A.n_sub = d->rl_nsub; A.dt = dt; A.red = d->red + 2; A.count_mode = count_mode;
+    A.e_out = e_out ? e_out : d->Pset.p[E_E]; A.n_sub = d->rl_nsub; A.dt = dt; A.red = d->red + 2; A.count_mode = count_mode;
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_rl<<<grid, 128, 0, d->stream>>>(d->P, A);
     d->launches++;
@@ -696,11 +703,17 @@ int rl_count(spruce_domain *d, double dt, int *nsub)
 int rl_iterate(spruce_domain *d, double dt)
 {
     const dim3 grid256((d->P.ny + 255) / 256, d->P.nx);
+    // inactive_mode: the kernel writes its result into the copy (old_e) instead of the primary plane; only the output / cumulative planes keep it (:93-98)
+    const bool inactive = d->rl_inactive;
+    if (inactive && !d->rl_output && !d->ms_on) return SPRUCE_OK;
     if (d->rl_output || d->ms_on) { k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, d->Pset.p[E_E]); d->launches++; }     // radiativelosses.cpp:50
-    int rc = rl_launch(d, 0, dt);
+    double *const e_after = inactive ? d->old_e : d->Pset.p[E_E];
+    const double *const e_before = inactive ? d->Pset.p[E_E] : d->old_e;
+    int rc = rl_launch(d, 0, dt, inactive ? d->old_e : nullptr);
     if (rc) return rc;
-    if (d->rl_output) { k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->rl_avg, d->Pset.p[E_E], d->old_e, dt); d->launches++; }   // :93
-    if ((rc = ms_feed(d, MS_DIFF, d->Pset.p[E_E], d->old_e, d->ms_frac_rl))) return rc;             // :94-97
+    if (d->rl_output) { k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->rl_avg, e_after, e_before, dt); d->launches++; }   // :93
+    if ((rc = ms_feed(d, MS_DIFF, e_after, e_before, d->ms_frac_rl))) return rc;                    // :94-97
+    if (inactive) return SPRUCE_OK;                                                                 // :98
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // radiativelosses.cpp:99-100
     return after_module_propagate(d);
 }
@@ -2027,6 +2040,20 @@ int spruce_module_eic_thermalization(spruce_domain *d)
     if (d->e2) { d->e2->g.eic = 1; return SPRUCE_OK; }
     if (!d->tf) return fail(SPRUCE_ERR_ARG, "Grid <e_temp> was not found within the EquationSet.");
     d->tf->eic = 1;
+    return SPRUCE_OK;
+}
+// inactive_mode = true of thermal_conduction / radiative_losses: the module is evaluated (sub-cycle count, output_to_file planes, cumulative planes of multispecies_mode)
+// and nothing is applied to the state (thermalconduction.cpp:109, radiativelosses.cpp:98)
+int spruce_module_inactive_mode(spruce_domain *d, const char *module, int on)
+{
+    CHECK_DOM(d);
+    if (!module) return fail(SPRUCE_ERR_ARG, "null argument");
+    NOT_2F(d, "inactive_mode");
+    int rc;
+    if (on && !d->old_e && (rc = alloc_plane(d, &d->old_e))) return rc;
+    if (!strcmp(module, "thermal_conduction")) d->tc_inactive = on != 0;
+    else if (!strcmp(module, "radiative_losses")) d->rl_inactive = on != 0;
+    else return fail(SPRUCE_ERR_ARG, "module <%s> has no inactive_mode here", module);
     return SPRUCE_OK;
 }
 // multispecies_mode = true (fileio.cpp:322): the three cumulative planes exist from now on, zero (plasmadomain.cpp:55-59)

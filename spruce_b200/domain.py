@@ -230,6 +230,10 @@ class PlasmaDomain:
         capi.check(self.lib.spruce_module_physical_viscosity(self.h, coeff, _dp(a), a.size, epsilon, int(heating_on), int(force_on),
                                                              int(gradient_correction), capi.TI[integrator], int(inactive_mode)))
 
+    def set_module_inactive(self, module: str, on: bool = True):
+        """inactive_mode of thermal_conduction / radiative_losses: evaluated for the output and cumulative planes, not applied"""
+        capi.check(self.lib.spruce_module_inactive_mode(self.h, module.encode(), int(on)))
+
     def set_multispecies(self, on: bool = True, **fractions):
         """multispecies_mode = true (plasmadomain.hpp:134-135); fractions: ms_electron_heating_fraction per module name (set after the module is configured)"""
         capi.check(self.lib.spruce_multispecies_mode(self.h, int(on)))

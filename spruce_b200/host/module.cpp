@@ -122,9 +122,9 @@ void ThermalConduction::parseModuleConfigs(std::vector<std::string> lhs, std::ve
 }
 void ThermalConduction::setupModule()
 {
-    SPRUCE_REQUIRE(!inactive_mode, "thermal_conduction inactive_mode is a diagnostic of the CPU build");
     PlasmaDomain::check(spruce_module_thermal_conduction(m_pd.device(), flux_saturation, integrator_id(time_integrator, "Thermal Conduction"), epsilon, dt_subcycle_min, weakening_factor));
     if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "thermal_conduction", 1));
+    if (inactive_mode) PlasmaDomain::check(spruce_module_inactive_mode(m_pd.device(), "thermal_conduction", 1));       // evaluated, not applied (:109)
     send_ms_fraction(m_pd, "thermal_conduction", "Thermal Conduction", ms_electron_heating_fraction, ms_given);
 }
 // the device keeps the two diagnostic planes of the last step; zero planes before the first one, like the reference's
@@ -146,7 +146,7 @@ std::string ThermalConduction::commandLineMessage() const
 {
     int n = 0;
     spruce_module_subcycles(m_pd.device(), "thermal_conduction", &n);
-    return "Thermal Subcycles: " + std::to_string(n);
+    return "Thermal Subcycles: " + std::to_string(n) + (inactive_mode ? " (Not Applied)" : "");      // thermalconduction.cpp:244
 }
 
 // radiativelosses.cpp:17-31
@@ -167,9 +167,9 @@ void RadiativeLosses::parseModuleConfigs(std::vector<std::string> lhs, std::vect
 }
 void RadiativeLosses::setupModule()
 {
-    SPRUCE_REQUIRE(!inactive_mode, "radiative_losses inactive_mode is a diagnostic of the CPU build");
     PlasmaDomain::check(spruce_module_radiative_losses(m_pd.device(), integrator_id(time_integrator, "Radiative Losses"), cutoff_ramp, cutoff_temp, epsilon, prevent_subcycling));
     if (output_to_file) PlasmaDomain::check(spruce_module_output_to_file(m_pd.device(), "radiative_losses", 1));
+    if (inactive_mode) PlasmaDomain::check(spruce_module_inactive_mode(m_pd.device(), "radiative_losses", 1));         // evaluated, not applied (:98)
     send_ms_fraction(m_pd, "radiative_losses", "Rad. Losses", ms_electron_heating_fraction, ms_given);
 }
 void RadiativeLosses::fileOutput(std::vector<std::string> &names, std::vector<Grid> &grids)
@@ -180,7 +180,7 @@ std::string RadiativeLosses::commandLineMessage() const
 {
     int n = 0;
     spruce_module_subcycles(m_pd.device(), "radiative_losses", &n);
-    return "Radiative Subcycles: " + std::to_string(n);
+    return "Radiative Subcycles: " + std::to_string(n) + (inactive_mode ? " (Not Applied)" : "");    // radiativelosses.cpp:171
 }
 
 // ambientheating.cpp:11-40: the static heating plane is built on the host with the host libm, once, as in the reference

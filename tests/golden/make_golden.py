@@ -119,6 +119,9 @@ CASES = {
         ("ambient_heating_sink", [("heating_rate", "2.0e-5")]),
         ("localized_heating", [("start_time", "0.0"), ("duration", "5.0"), ("max_heating_rate", "1.0e-3"), ("stddev_x", "3.0"), ("stddev_y", "4.0"), ("center_x", "2.0"), ("center_y", "8.0"),
                                ("ramp_time", "1.0"), ("ms_electron_heating_fraction", "0.2")])], **SOLAR_FLOORS), 3, (1, 3)),
+    # inactive_mode of thermal_conduction / radiative_losses (thermalconduction.cpp:109, radiativelosses.cpp:98): output and cumulative planes are formed, the state is not touched
+    "loop_inactive_tc_rl_rk2": ("stratified_loop", dict(nx=NX, ny=NY, bump=0.5), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), multispecies=True, modules=[
+        TC(flux_saturation="true", inactive_mode="true", ms_electron_heating_fraction="0.7"), RL(inactive_mode="true", time_integrator="rk2"), AH()], **SOLAR_FLOORS), 3, (1, 3)),
     # two-fluid equation set (source/equationsets/ideal2F.cpp, non-sub-cycled Maxwell update) + EIC thermalization (BASELINE.json configs[2])
     "tf_ucnp_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, **TF, **UCNP_FLOORS), 8, (1, 8)),
     "tf_ucnp_eic_rk2": ("ucnp_cloud", CLOUD, dict(integrator="rk2", xb=UC, yb=UC, modules=[EIC], **TF, **UCNP_FLOORS), 8, (1, 8)),

@@ -103,6 +103,7 @@ int spruce_module_viscosity_term(spruce_domain *d, const char *opt, double stren
 int spruce_module_physical_viscosity(spruce_domain *d, double coeff, const double *plane, size_t count, double eps, int heat, int force, int gc, int ti, int inactive)
 { (void)d; LOG("spruce_module_physical_viscosity coeff=%.17g epsilon=%.17g heating_on=%d force_on=%d gradient_correction=%d ti=%d inactive=%d", coeff, eps, heat, force, gc, ti, inactive); log_vec("coeff_plane", plane, count); return SPRUCE_OK; }
 int spruce_module_output_to_file(spruce_domain *d, const char *m, int on) { (void)d; LOG("spruce_module_output_to_file %s %d", m, on); return SPRUCE_OK; }
+int spruce_module_inactive_mode(spruce_domain *d, const char *m, int on) { (void)d; LOG("spruce_module_inactive_mode %s %d", m, on); return SPRUCE_OK; }
 int spruce_multispecies_mode(spruce_domain *d, int on) { (void)d; LOG("spruce_multispecies_mode %d", on); return SPRUCE_OK; }
 int spruce_multispecies_reset(spruce_domain *d) { (void)d; LOG("spruce_multispecies_reset"); return SPRUCE_OK; }
 int spruce_module_ms_fraction(spruce_domain *d, const char *m, double f) { (void)d; LOG("spruce_module_ms_fraction %s fraction=%.17g", m, f); return SPRUCE_OK; }

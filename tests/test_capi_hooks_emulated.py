@@ -829,3 +829,34 @@ def test_physical_viscosity_on_slabs_equals_the_whole_domain_with_and_without_fa
                 assert same_bits(blk[q], whole_avg[q][cuts[r]:cuts[r + 1]]), "output plane %d of rank %d (fast %d)" % (q, r, int(fast))
     assert np.count_nonzero(whole_avg[0]) > 0 and not np.array_equal(whole[4], o.get("thermal_energy"))
     o.close()
+
+
+@pytest.mark.parametrize("xb,yb", BOUNDS[:2])
+def test_inactive_mode_of_conduction_and_losses_forms_the_planes_and_leaves_the_state(emu, xb, yb):
+    """inactive_mode = true (thermalconduction.cpp:109, radiativelosses.cpp:98) through tc_iterate / rl_iterate: the sub-cycles run on a copy, the output_to_file and cumulative
+    planes equal the active run's within 1e-9 of the oracle's (pinned by the fixture loop_inactive_tc_rl_rk2), every evolved plane keeps its bits"""
+    nx, ny = 25, 22
+    s, o, h, step, b = make_pair(emu, xb, yb, nx, ny)
+    o.set_multispecies(True, thermal_conduction=0.7)
+    o.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4, weakening_factor=1.0)
+    o.set_radiative_losses(integrator="euler", cutoff_ramp=1.0e3, cutoff_temp=3.0e4, epsilon=0.1, prevent_subcycling=False)
+    o.set_module_inactive("thermal_conduction"); o.set_module_inactive("radiative_losses")
+    before = [np.zeros((nx, ny)) for _ in EV]
+    for k in range(len(EV)):
+        emu.cemu_get(h, C.c_int(k), vp(before[k]))
+    assert emu.cemu_multispecies(h, C.c_double(0.7), C.c_double(1.0), C.c_double(0.5), C.c_double(0.0)) == 0
+    emu.cemu_set_inactive(h, C.c_int(1), C.c_int(1))
+    o.step()
+    avg = np.zeros((nx, ny)); satp = np.zeros((nx, ny)); rad = np.zeros((nx, ny))
+    assert emu.cemu_thermal_conduction(h, C.c_int(1), C.c_double(1.0), C.c_double(1.0e-4), C.c_int(1), C.c_int(o.subcycles("thermal_conduction")), C.c_double(step), vp(avg), vp(satp)) == 0
+    assert emu.cemu_radiative_losses(h, C.c_int(0), C.c_double(1.0e3), C.c_double(3.0e4), C.c_double(0.1), C.c_int(0), C.c_int(o.subcycles("radiative_losses")), C.c_double(step), vp(rad)) == 0
+    for k in range(len(EV)):
+        now = np.zeros((nx, ny))
+        emu.cemu_get(h, C.c_int(k), vp(now))
+        assert same_bits(now, before[k]), EV[k]
+    close = lambda a, r: np.count_nonzero(r) > 0 and np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
+    assert close(avg, o.module_output("thermal_conduction")) and close(satp, o.module_output("flux_saturation")) and close(rad, o.module_output("rad"))
+    got = ms_planes(emu, h, nx, ny)
+    for name in ("cumulative_electron_heating", "cumulative_ion_heating"):
+        assert close(got[name], o.ms_plane(name)), name
+    o.close()

@@ -54,7 +54,7 @@ def golden_cases():
 
 
 # fixtures added after round 2's GPU budget was spent (they carry the output planes of physical_viscosity / artificial_viscosity): first executed by the round-end run
-FIRST_RUN_FIXTURES = {"loop_ms_solar_rk2", "loop_pv_diag_rk2", "ot_pv_diag_inactive", "loop_visc_diag_hv_rk2", "ot_visc_diag_hv_rk4", "ot_visc_diag_hv_euler"}
+FIRST_RUN_FIXTURES = {"loop_inactive_tc_rl_rk2", "loop_ms_solar_rk2", "loop_pv_diag_rk2", "ot_pv_diag_inactive", "loop_visc_diag_hv_rk2", "ot_visc_diag_hv_rk4", "ot_visc_diag_hv_euler"}
 PV_PLANES = ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z")
 
 
@@ -63,6 +63,15 @@ PV_PLANES = ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_f
 def test_golden_reference_outputs(name):
     g = Golden(name)
     d = make_domain(g)
+    tcrl_out = []
+    if name in FIRST_RUN_FIXTURES:                                    # inactive_mode / output_to_file of thermal_conduction and radiative_losses (only the newer fixtures look at them here)
+        for mname, kv in g.modules:
+            if mname in ("thermal_conduction", "radiative_losses"):
+                if kv.get("inactive_mode") == "true":
+                    d.set_module_inactive(mname)
+                if kv.get("output_to_file") == "true":
+                    d.set_module_output_to_file(mname)
+                    tcrl_out += ["thermal_conduction", "flux_saturation"] if mname == "thermal_conduction" else ["rad"]
     ms_on = bool(g.cfg.get("multispecies"))
     if ms_on:                                                         # multispecies_mode = true: cumulative electron / ion / joule heating (plasmadomain.hpp:134-135)
         d.set_multispecies(True, **multispecies_fractions(g.modules))
@@ -105,6 +114,9 @@ def test_golden_reference_outputs(name):
                 assert same_bits(got, g.frames[it][v]), "%s after iteration %d: %s" % (v, it, mismatch(got, g.frames[it][v]))
             else:
                 assert rel_linf(got, g.frames[it][v]) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (v, it, rel_linf(got, g.frames[it][v]))
+        for pname in (tcrl_out if it > 0 else []):
+            ref = g.module_planes[it][pname]
+            assert rel_linf(d.module_output(pname), ref) <= REL_TOL, "%s after iteration %d: rel Linf %.3e" % (pname, it, rel_linf(d.module_output(pname), ref))
         if ms_on:
             for pname in MS_PLANES:
                 ref = g.module_planes[it][pname]

@@ -337,7 +337,7 @@ def test_multispecies_mode_enables_stores_and_resets_the_cumulative_planes(stub,
     modules' planes (fileio.cpp:164-183), reset after every store inside the time loop (evolution.cpp:36-41) -- not after the frame the constructor writes"""
     s = synthetic.stratified_loop(20, 18, bump=0.5)
     modules = [("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4"), ("ms_electron_heating_fraction", "0.7"), ("output_to_file", "true")]),
-               ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
+               ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1"), ("inactive_mode", "true")]),
                ("ambient_heating", [("heating_rate", "1.0e-4"), ("ms_electron_heating_fraction", "0.3")]),
                ("localized_heating", [("start_time", "0.0"), ("duration", "10.0"), ("max_heating_rate", "0.5"), ("stddev_x", "3.0"), ("stddev_y", "2.0"), ("center_x", "8.0"), ("center_y", "7.0"),
                                       ("ms_electron_heating_fraction", "0.2")])]
@@ -348,6 +348,7 @@ def test_multispecies_mode_enables_stores_and_resets_the_cumulative_planes(stub,
     fr = {ln.split()[1]: float(args_of(ln)["fraction"]) for ln in log if ln.startswith("spruce_module_ms_fraction")}
     assert fr == {"thermal_conduction": 0.7, "ambient_heating": 0.3, "localized_heating": 0.2}                # radiative_losses keeps the library's default
     assert calls.count("spruce_multispecies_reset") == 2                                                         # iterations 2 and 4
+    assert "spruce_module_inactive_mode radiative_losses 1" in log and "Radiative Subcycles: 9 (Not Applied)" in stdout and "Thermal Subcycles: 9|" in stdout + "|"
     first_store = calls.index("spruce_module_output")
     assert first_store < calls.index("spruce_multispecies_reset") and "spruce_advance" not in calls[:first_store]
     _, frames = refrun.read_out(out / "mhd.out")

@@ -20,6 +20,8 @@ def make_oracle(g: Golden) -> Oracle:
             o.set_physical_viscosity(physical_viscosity_coefficient(g.planes, kw["coeff"], ramp), **kw)
         else:
             getattr(o, "set_" + name)(**kw)
+        if name in ("thermal_conduction", "radiative_losses") and kv.get("inactive_mode") == "true":
+            o.set_module_inactive(name)
     if g.cfg.get("multispecies"):
         o.set_multispecies(True, **multispecies_fractions(g.modules))
     return o
