@@ -169,11 +169,27 @@ CASES = {
            visc_output_strength="false", visc_output_timescale="false")], **UCNP_FLOORS), 4, (1, 4)),
     # configs[0] of BASELINE.json: the reference's own example.state (fixed up: + be_z, mom_z, bi_z zero planes)
     "example_state_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), **SOLAR_FLOORS), 20, (1, 20)),
+    # configs[1] of BASELINE.json: the reference's own shipped inputs with the solar module set of default.config:57-76 -- thermal conduction with flux
+    # saturation, radiative losses, ambient heating -- on the gravity-stratified bipolar loop (example.state, fixed up) and on examples/solar/solar_gaussian.state
+    "example_state_solar_modules_rk2": ("example_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[
+        TC(flux_saturation="true", output_to_file="false"), RL(output_to_file="false"), AH()], **SOLAR_FLOORS), 6, (1, 6)),
+    "solar_gaussian_state_modules_rk2": ("solar_gaussian_state", dict(), dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), modules=[
+        TC(flux_saturation="true", output_to_file="false"), RL(output_to_file="false"), AH()], **SOLAR_FLOORS), 6, (1, 6)),
 }
 
 
 def example_state():
     meta, planes = refrun.read_state("/root/reference/example.state")
+    z = np.zeros_like(planes["rho"])
+    for k in ("be_z", "mom_z", "bi_z"):
+        planes.setdefault(k, z.copy())
+    order = ["d_x", "d_y", "pos_x", "pos_y", "be_x", "be_y", "be_z", "rho", "temp", "mom_x", "mom_y", "mom_z",
+             "bi_x", "bi_y", "bi_z", "grav_x", "grav_y"]
+    return dict(planes={k: planes[k] for k in order}, ion_mass=meta["ion_mass"], adiabatic_index=meta["adiabatic_index"])
+
+
+def solar_gaussian_state():
+    meta, planes = refrun.read_state("/root/reference/examples/solar/solar_gaussian.state")
     z = np.zeros_like(planes["rho"])
     for k in ("be_z", "mom_z", "bi_z"):
         planes.setdefault(k, z.copy())
@@ -194,7 +210,7 @@ def interior(cfg, nx, ny):
 
 def make(name):
     gen, gkw, ckw, nsteps, keep = CASES[name]
-    s = example_state() if gen == "example_state" else getattr(synthetic, gen)(**gkw)
+    s = example_state() if gen == "example_state" else solar_gaussian_state() if gen == "solar_gaussian_state" else getattr(synthetic, gen)(**gkw)
     tmp = Path(tempfile.mkdtemp(prefix="golden_"))
     try:
         refrun.write_state(tmp / "in.state", s["planes"], s["ion_mass"], s["adiabatic_index"])

@@ -54,7 +54,7 @@ def golden_cases():
 
 
 # fixtures added after round 2's GPU budget was spent (they carry the output planes of physical_viscosity / artificial_viscosity): first executed by the round-end run
-FIRST_RUN_FIXTURES = {"loop_inactive_tc_rl_rk2", "loop_ms_solar_rk2", "loop_pv_diag_rk2", "ot_pv_diag_inactive", "loop_visc_diag_hv_rk2", "ot_visc_diag_hv_rk4", "ot_visc_diag_hv_euler"}
+FIRST_RUN_FIXTURES = {"example_state_solar_modules_rk2", "solar_gaussian_state_modules_rk2", "loop_inactive_tc_rl_rk2", "loop_ms_solar_rk2", "loop_pv_diag_rk2", "ot_pv_diag_inactive", "loop_visc_diag_hv_rk2", "ot_visc_diag_hv_rk4", "ot_visc_diag_hv_euler"}
 PV_PLANES = ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z")
 
 
