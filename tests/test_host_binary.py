@@ -105,7 +105,18 @@ CASES["ucnp_mhd2e_viscosity"] = (lambda: synthetic.ucnp_cloud_2e(41, 37, drift=2
                                                                     ("visc_vars_to_evol", "mom_x,mom_y,i_thermal_energy"), ("visc_length", "0,0,0.3"), ("visc_species", "i,i,i"),
                                                                     ("hv_time_integrator", "rk4"), ("visc_output_visc", "false"), ("visc_output_lap", "false"),
                                                                     ("visc_output_strength", "false"), ("visc_output_timescale", "false")])]), True)
-FIRST_RUN_AT_ROUND_END = {"ucnp_mhd2e_viscosity", "ucnp_mhd2e_module_set", "loop_multispecies", "loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
+# BASELINE.json configs[1]: the reference's own example.state (its planes travel inside the fixture) with the solar module set of default.config:57-76
+def _example_state():
+    from golden_util import Golden
+    g = Golden("example_state_solar_modules_rk2")
+    return dict(planes=g.planes, ion_mass=g.ion_mass, adiabatic_index=g.adiabatic_index)
+
+
+CASES["example_state_solar_modules"] = (_example_state, dict(integrator="rk2", xb=("periodic", "periodic"), yb=("fixed", "fixed"), max_iterations=6, iter_output_interval=3,
+                                        modules=[("thermal_conduction", [("flux_saturation", "true"), ("epsilon", "0.1"), ("dt_subcycle_min", "1.0e-4")]),
+                                                 ("radiative_losses", [("cutoff_ramp", "1.0e3"), ("cutoff_temp", "3.0e4"), ("epsilon", "0.1")]),
+                                                 ("ambient_heating", [("heating_rate", "1.0e-4")])]), False)
+FIRST_RUN_AT_ROUND_END = {"example_state_solar_modules", "ucnp_mhd2e_viscosity", "ucnp_mhd2e_module_set", "loop_multispecies", "loop_viscosity_output", "loop_physical_viscosity_output", "ucnp_mhd2e_eic", "loop_sg_filtering", "loop_tracer_particles", "ucnp_coulomb_explosion", "ucnp_global_temperature", "loop_viscosity_elliptical"}
 
 
 @pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked, first device run", strict=False))
