@@ -33,8 +33,23 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the library if a source is newer than it.  Several processes may call this at once (the ranks of a torchrun launch): a file lock lets one of them
+    compile while the others wait and then find the library up to date."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    with open(LIB.parent / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another process built it while this one waited
+                return LIB
+            return _compile(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _compile(verbose: bool) -> Path:
     LIB.parent.mkdir(parents=True, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
     env = dict(os.environ)
