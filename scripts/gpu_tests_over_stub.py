@@ -1,4 +1,4 @@
-"""The Python of the GPU tests without a GPU: every `-m gpu` test body of tests/test_gpu_parity.py, test_gpu_extended.py and test_gpu_fast_instances.py runs in
+"""The Python of the GPU tests without a GPU: every `-m gpu` test body of tests/test_gpu_parity.py, test_gpu_extended.py, test_gpu_fast_instances.py and test_gpu_device_plan.py runs in
 this process over the recording stand-in for the device library (tests/hostcheck/capi_stub.c, built by tests/test_host_shell_calls.py) with `assert` statements
 stripped:
 
@@ -23,7 +23,7 @@ _dom.PlasmaDomain.advance = lambda self, k, max_time=None: np.full(int(k), 0.5)
 _dom.PlasmaDomain.subcycles = lambda self, name: 1
 _dom.PlasmaDomain.launch_count = lambda self: 0
 import pytest
-import test_gpu_extended as ge, test_gpu_parity as gp, test_gpu_fast_instances as gf
+import test_gpu_extended as ge, test_gpu_parity as gp, test_gpu_fast_instances as gf, test_gpu_device_plan as gd
 def run_inproc(code, env, timeout=90):
     old = {k: os.environ.get(k) for k in env}; os.environ.update(env)
     try:
@@ -52,7 +52,7 @@ def params_of(fn):
         out = [dict(a, **b) for a in out for b in vals]
     return out
 skip = ("4096", "slab", "sanitizer", "n_gpus")
-for mod in (gp, ge, gf):
+for mod in (gp, ge, gf, gd):
     for name, fn in inspect.getmembers(mod, inspect.isfunction):
         if not name.startswith("test_") or any(s in name for s in skip): continue
         for kw in params_of(fn):

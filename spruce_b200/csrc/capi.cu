@@ -148,6 +148,9 @@ struct spruce_domain {
     std::vector<Mark> marks; int timeline_steps = 0; bool timeline_on = false;
     bool fused_ctl = false;                // inside a plain step (no modules, no open_moc): the step control runs in k_step_open / k_step_mid / k_step_close
     bool fuse_ctl_enabled = true;          // SPRUCE_FUSED_CTL=0: always the separate one-thread control kernels
+    // SPRUCE_DEVICE_SUBCYCLES=1: the sub-cycle counts of thermal_conduction / radiative_losses stay on the device (module_kernels.cuh: SubPlan); the host enqueues
+    // tc_budget conduction sub-cycles per step (SPRUCE_TC_BUDGET; adapted after every advance) and no step waits for the host
+    bool dev_sub = false; int tc_budget = 8; SubPlan *plan = nullptr; int replans = 0;
     bool fast_interior = true;             // SPRUCE_FAST_INTERIOR=0: the module stencil kernels use their general (wrapping, range-testing) instance for every cell
     size_t halo_doubles = 0;
     // peer-store transport (CUDA IPC segment: PeerFlags + 2 sides x 2 parities of packed halo rows; mhd_kernels.cuh)
@@ -590,18 +593,24 @@ int ms_feed(spruce_domain *d, int mode, const double *a, const double *b, double
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }
-int tc_count(spruce_domain *d, double dt, int *nsub)
+int tc_count_launch(spruce_domain *d)
 {
     int rc;
     if ((rc = derive_to(d, V_temp, d->Mset.p[0]))) return rc;
     if ((rc = derive_to(d, V_b_hat_x, d->Mset.p[1]))) return rc;
     if ((rc = derive_to(d, V_b_hat_y, d->Mset.p[2]))) return rc;
-    if ((rc = reset_reductions(d))) return rc;
     TcFields F{d->Mset.p[0], d->Pset.p[E_N], d->Mset.p[1], d->Mset.p[2]};
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_tc_count<<<grid, 128, 0, d->stream>>>(d->P, d->tc, F, d->red);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+int tc_count(spruce_domain *d, double dt, int *nsub)
+{
+    int rc;
+    if ((rc = reset_reductions(d))) return rc;
+    if ((rc = tc_count_launch(d))) return rc;
     unsigned long long h[4];
     if ((rc = read_reductions(d, h))) return rc;
     if (d->tc.flux_saturation && bits_to_double(h[1]) == 0.0) { *nsub = 0; return SPRUCE_OK; }   // :143
@@ -612,7 +621,8 @@ int tc_count(spruce_domain *d, double dt, int *nsub)
 }
 
 // ThermalConduction::iterateModule (thermalconduction.cpp:47-112); scratch = the 8 planes of Mset (free between RK steps)
-int tc_iterate(spruce_domain *d, double dt)
+// dev: the device-resident plan decides (SubPlan): tc_budget sub-cycles are enqueued, the stage kernels take count and sub-cycle step from the plan, dt is not used
+int tc_iterate(spruce_domain *d, double dt, bool dev = false)
 {
     int rc;
     double *Ta = d->Mset.p[0], *bhx = d->Mset.p[1], *bhy = d->Mset.p[2], *Tb = d->Mset.p[3], *Tc = d->Mset.p[4];
@@ -620,8 +630,8 @@ int tc_iterate(spruce_domain *d, double dt)
     if ((rc = derive_to(d, V_temp, Ta))) return rc;
     if ((rc = derive_to(d, V_b_hat_x, bhx))) return rc;
     if ((rc = derive_to(d, V_b_hat_y, bhy))) return rc;
-    const int ns = d->tc_nsub;
-    const double dts = dt / (double)ns;                                                             // :60
+    const int ns = dev ? d->tc_budget : d->tc_nsub;
+    const double dts = dev ? 0.0 : dt / (double)ns;                                                 // :60
     // inactive_mode: the sub-cycles run on a copy of the thermal energy (old_e) and only the output / cumulative planes keep their result (:101-109)
     const bool inactive = d->tc_inactive;
     if (inactive && !d->tc_output && !d->ms_on) return SPRUCE_OK;                                   // nothing would be kept
@@ -636,36 +646,39 @@ int tc_iterate(spruce_domain *d, double dt)
     }
     if (d->tc_output) {
         if (d->tc.flux_saturation) {
-            k_tc_saturation_plane<<<grid, 128, 0, d->stream>>>(d->P, d->tc, TcFields{Ta, d->Pset.p[E_N], bhx, bhy}, d->tc_sat);
+            k_tc_saturation_plane<<<grid, 128, 0, d->stream>>>(d->P, d->tc, TcFields{Ta, d->Pset.p[E_N], bhx, bhy}, d->tc_sat, dev ? &d->ctl->done : nullptr);
             d->launches++;
         }
     }
-    auto stage = [&](const double *Tin, double *Tout, int mode, double c, double *Kst) -> int {
+    int sub = 0;
+    auto stage = [&](const double *Tin, double *Tout, int mode, int half, double *Kst) -> int {
         TcStageArgs A{};
         A.F = TcFields{Tin, d->Pset.p[E_N], bhx, bhy};
-        A.C = d->tc; A.e_base = e; A.e_out = e; A.T_out = Tout; A.K_store = Kst; A.K1 = K1; A.K2 = K2; A.K3 = K3; A.mode = mode; A.c = c;
+        A.C = d->tc; A.e_base = e; A.e_out = e; A.T_out = Tout; A.K_store = Kst; A.K1 = K1; A.K2 = K2; A.K3 = K3; A.mode = mode; A.c = half ? 0.5 * dts : dts;
         A.fast = d->fast_interior ? 1 : 0;
+        if (dev) { A.plan = d->plan; A.sub = sub; A.half = half; }
         k_tc_stage<<<grid, 128, 0, d->stream>>>(d->P, A);
         d->launches++;
         CUDA_TRY(cudaGetLastError());
         return exchange_plane(d, Tout);                  // the next stage differentiates this temperature plane across the slab edge
     };
-    for (int s = 0; s < ns; s++) {
+    for (sub = 0; sub < ns; sub++) {
         if (d->tc_integrator == SPRUCE_TI_EULER) {
-            if ((rc = stage(Ta, Tb, TC_FINAL, dts, nullptr))) return rc;
+            if ((rc = stage(Ta, Tb, TC_FINAL, 0, nullptr))) return rc;
             std::swap(Ta, Tb);
         } else if (d->tc_integrator == SPRUCE_TI_RK2) {
-            if ((rc = stage(Ta, Tb, TC_INTERMEDIATE, 0.5 * dts, nullptr))) return rc;
-            if ((rc = stage(Tb, Ta, TC_FINAL, dts, nullptr))) return rc;
+            if ((rc = stage(Ta, Tb, TC_INTERMEDIATE, 1, nullptr))) return rc;
+            if ((rc = stage(Tb, Ta, TC_FINAL, 0, nullptr))) return rc;
         } else {
-            if ((rc = stage(Ta, Tb, TC_INTERMEDIATE, 0.5 * dts, K1))) return rc;
-            if ((rc = stage(Tb, Tc, TC_INTERMEDIATE, 0.5 * dts, K2))) return rc;
-            if ((rc = stage(Tc, Tb, TC_INTERMEDIATE, dts, K3))) return rc;
-            if ((rc = stage(Tb, Ta, TC_RK4_FINAL, dts, nullptr))) return rc;
+            if ((rc = stage(Ta, Tb, TC_INTERMEDIATE, 1, K1))) return rc;
+            if ((rc = stage(Tb, Tc, TC_INTERMEDIATE, 1, K2))) return rc;
+            if ((rc = stage(Tc, Tb, TC_INTERMEDIATE, 0, K3))) return rc;
+            if ((rc = stage(Tb, Ta, TC_RK4_FINAL, 0, nullptr))) return rc;
         }
     }
     if (d->tc_output) {                                                                             // :101-104
-        k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->tc_avg, e, e_before, dt);
+        if (dev) k_avg_change_dev<<<grid256, 256, 0, d->stream>>>(d->P, d->tc_avg, e, e_before, &d->ctl->step, &d->ctl->done);
+        else k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->tc_avg, e, e_before, dt);
         d->launches++;
     }
     if ((rc = ms_feed(d, MS_DIFF, e, e_before, d->ms_frac_tc))) return rc;                          // :105-108
@@ -674,13 +687,14 @@ int tc_iterate(spruce_domain *d, double dt)
     return after_module_propagate(d);
 }
 
-int rl_launch(spruce_domain *d, int count_mode, double dt, double *e_out = nullptr)
+int rl_launch(spruce_domain *d, int count_mode, double dt, double *e_out = nullptr, bool dev = false)
 {
     RlArgs A{};
     A.R = d->rl;
     for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
     for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
     A.e_out = e_out ? e_out : d->Pset.p[E_E]; A.n_sub = d->rl_nsub; A.dt = dt; A.red = d->red + 2; A.count_mode = count_mode;
+    if (dev) { A.plan = d->plan; A.dt_ptr = &d->ctl->step; A.done_ptr = &d->ctl->done; }
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_rl<<<grid, 128, 0, d->stream>>>(d->P, A);
     d->launches++;
@@ -700,7 +714,7 @@ int rl_count(spruce_domain *d, double dt, int *nsub)
     *nsub = (int)(dt / sdt) + 1;
     return SPRUCE_OK;
 }
-int rl_iterate(spruce_domain *d, double dt)
+int rl_iterate(spruce_domain *d, double dt, bool dev = false)
 {
     const dim3 grid256((d->P.ny + 255) / 256, d->P.nx);
     // inactive_mode: the kernel writes its result into the copy (old_e) instead of the primary plane; only the output / cumulative planes keep it (:93-98)
@@ -709,13 +723,45 @@ int rl_iterate(spruce_domain *d, double dt)
     if (d->rl_output || d->ms_on) { k_plane_copy<<<grid256, 256, 0, d->stream>>>(d->P, d->old_e, d->Pset.p[E_E]); d->launches++; }     // radiativelosses.cpp:50
     double *const e_after = inactive ? d->old_e : d->Pset.p[E_E];
     const double *const e_before = inactive ? d->Pset.p[E_E] : d->old_e;
-    int rc = rl_launch(d, 0, dt, inactive ? d->old_e : nullptr);
+    int rc = rl_launch(d, 0, dt, inactive ? d->old_e : nullptr, dev);
     if (rc) return rc;
-    if (d->rl_output) { k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->rl_avg, e_after, e_before, dt); d->launches++; }   // :93
+    if (d->rl_output) {                                                                             // :93
+        if (dev) k_avg_change_dev<<<grid256, 256, 0, d->stream>>>(d->P, d->rl_avg, e_after, e_before, &d->ctl->step, &d->ctl->done);
+        else k_avg_change<<<grid256, 256, 0, d->stream>>>(d->P, d->rl_avg, e_after, e_before, dt);
+        d->launches++;
+    }
     if ((rc = ms_feed(d, MS_DIFF, e_after, e_before, d->ms_frac_rl))) return rc;                    // :94-97
     if (inactive) return SPRUCE_OK;                                                                 // :98
     if ((rc = launch_propagate(d, 0))) return rc;                                                   // radiativelosses.cpp:99-100
     return after_module_propagate(d);
+}
+// ---- device-resident sub-cycle plan (SPRUCE_DEVICE_SUBCYCLES=1; module_kernels.cuh: SubPlan / k_sub_plan)
+// which module sets can run without the host knowing the step size: thermal_conduction, radiative_losses, ambient_heating (the set of the reference's solar runs);
+// every other hook computes launch counts or time windows on the host and keeps the per-step readback
+bool dev_subcycles(const spruce_domain *d)
+{
+    if (!d->dev_sub || !d->plan || d->module_order.empty() || d->ar.on || !d->visc.empty()) return false;
+    for (int m : d->module_order) if (m != spruce_domain::MOD_TC && m != spruce_domain::MOD_RL && m != spruce_domain::MOD_AH) return false;
+    return true;
+}
+// preIterateModules (evolution.cpp:65) of the two sub-cycling modules: both count kernels on the unchanged state, one all-gather over the slabs, one planning thread
+int plan_subcycles(spruce_domain *d)
+{
+    int rc;
+    bool tc_on = false, rl_on = false;
+    for (int m : d->module_order) { tc_on = tc_on || m == spruce_domain::MOD_TC; rl_on = rl_on || m == spruce_domain::MOD_RL; }
+    if ((rc = reset_reductions(d))) return rc;
+    if (tc_on && (rc = tc_count_launch(d))) return rc;
+    if (rl_on && (rc = rl_launch(d, 1, 0.0))) return rc;                 // count mode does not read the step size
+    if (d->cfg.n_ranks > 1 && (rc = peer_red_allgather(d))) return rc;
+    SubPlanArgs A{};
+    A.ctl = d->ctl; A.red = d->red; A.plan = d->plan;
+    A.tc_on = tc_on ? 1 : 0; A.tc_sat = d->tc.flux_saturation; A.tc_eps = d->tc_epsilon; A.tc_dtmin = d->tc.dt_subcycle_min;
+    A.rl_on = rl_on ? 1 : 0; A.rl_eps = d->rl.epsilon; A.tc_budget = d->tc_budget;
+    k_sub_plan<<<1, 1, 0, d->stream>>>(A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
 }
 // postIterateModule of a pointwise source term; time = m_time at the start of the step (evolution.cpp:74 runs before the time update)
 int src_post(spruce_domain *d, const spruce_domain::SourceTerm &m, double time, double step)
@@ -854,7 +900,7 @@ int bo_post(spruce_domain *d, double dt)
 int ah_post(spruce_domain *d)
 {
     dim3 grid((d->P.ny + 255) / 256, d->P.nx);
-    k_ambient_heating<<<grid, 256, 0, d->stream>>>(d->P, d->Pset.p[E_E], d->heating, &d->ctl->step);
+    k_ambient_heating<<<grid, 256, 0, d->stream>>>(d->P, d->Pset.p[E_E], d->heating, &d->ctl->step, &d->ctl->done);
     d->launches++;
     CUDA_TRY(cudaGetLastError());
     int rc = launch_propagate(d, 0);                                                                // ambientheating.cpp:43-44
@@ -1265,7 +1311,15 @@ int enqueue_step(spruce_domain *d, int hist_slot)
     k_step_begin<<<1, 1, 0, d->stream>>>(d->ctl, d->dt_hist, hist_slot);
     d->launches++;
     double step_time = 0.0, step_size = 0.0;                             // host copies for the post-iterate hooks
-    if (!d->module_order.empty()) {
+    if (dev_subcycles(d)) {
+        // counts, sub-cycle step and step size stay on the device: nothing here waits for the host
+        NvtxRange range_dev("modules: preIterate + iterate (device-resident plan)");
+        if ((rc = plan_subcycles(d))) return rc;
+        for (int m : d->module_order) {                                  // iterateModules, evolution.cpp:66
+            if (m == spruce_domain::MOD_TC && (rc = tc_iterate(d, 0.0, true))) return rc;
+            if (m == spruce_domain::MOD_RL && (rc = rl_iterate(d, 0.0, true))) return rc;
+        }
+    } else if (!d->module_order.empty()) {
         // the module hooks need the step size on the host (sub-cycle counts decide how many kernels are launched)
         StepCtl h;
         CUDA_TRY(cudaMemcpyAsync(&h, d->ctl, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
@@ -1438,6 +1492,8 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     d->cfg = *cfg;
     if (const char *fc = getenv("SPRUCE_FUSED_CTL")) d->fuse_ctl_enabled = atoi(fc) != 0;
     if (const char *fi = getenv("SPRUCE_FAST_INTERIOR")) d->fast_interior = atoi(fi) != 0;
+    if (const char *ds = getenv("SPRUCE_DEVICE_SUBCYCLES")) d->dev_sub = atoi(ds) != 0;
+    if (const char *tb = getenv("SPRUCE_TC_BUDGET")) { const int v = atoi(tb); if (v >= 1) d->tc_budget = v; }      // the first advance's budget
     if (const char *tl = getenv("SPRUCE_TIMELINE")) d->timeline_steps = atoi(tl);
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;
     if (const char *sv = getenv("SPRUCE_STAGE_VARIANTS")) d->stage_variants = atoi(sv) != 0 ? 1 : 0;
@@ -1486,6 +1542,10 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     }
     if (!rc && cudaMalloc(&d->ctl, sizeof(StepCtl)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
     if (!rc && cudaMalloc(&d->red, 4 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
+    if (!rc && d->dev_sub) {
+        SubPlan sp{}; sp.tc_last = -1; sp.rl_last = -1;
+        if (cudaMalloc(&d->plan, sizeof(SubPlan)) != cudaSuccess || cudaMemcpy(d->plan, &sp, sizeof(sp), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SPRUCE_ERR_CUDA, "cudaMalloc failed");
+    }
     if (!rc) {
         StepCtl h{};
         h.step = 0.0; h.time = cfg->time; h.max_time = -1.0; h.epsilon = cfg->epsilon; h.iter = 0; h.done = 0;
@@ -1508,6 +1568,7 @@ void spruce_domain_destroy(spruce_domain *d)
     if (d->tab_dev) cudaFree(d->tab_dev);
     if (d->ctl) cudaFree(d->ctl);
     if (d->red) cudaFree(d->red);
+    if (d->plan) cudaFree(d->plan);
     if (d->moc_base) cudaFree(d->moc_base);
     if (d->dt_hist) cudaFree(d->dt_hist);
     for (int r = 0; r < MAX_RANKS; r++) if (d->peer_seg[r] && d->peer_seg[r] != d->seg) cudaIpcCloseMemHandle(d->peer_seg[r]);
@@ -1635,6 +1696,20 @@ int spruce_next_step_size(spruce_domain *d, double *step)
     return SPRUCE_OK;
 }
 
+// which storage currently plays the primary state (an euler step exchanges the roles of two sets on the host)
+static const void *primary_id(const spruce_domain *d)
+{
+    if (d->tf) return d->tf->P.p[0];
+    if (d->e2) return &d->e2->order[0] + d->e2->order[0];
+    return d->Pset.p[0];
+}
+static void undo_euler_swap(spruce_domain *d)
+{
+    if (d->tf) std::swap(d->tf->P, d->tf->M);
+    else if (d->e2) std::swap(d->e2->order[0], d->e2->order[1]);
+    else std::swap(d->Pset, d->Mset);
+}
+
 int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_used, int *steps_done)
 {
     CHECK_DOM(d);
@@ -1652,13 +1727,39 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
     CUDA_TRY(cudaMemcpyAsync(&d->ctl->max_time, &max_time, sizeof(double), cudaMemcpyHostToDevice, d->stream));
     NvtxRange range_adv("spruce_advance");
     const bool plain = !d->tf && !d->e2 && plain_run(d);
-    for (int s = 0; s < n_steps; s++) {
-        int rc = d->tf ? tf_enqueue_step(d, s) : d->e2 ? e2_enqueue_step(d, s) : plain ? enqueue_step_plain(d, s, s == 0, s == n_steps - 1) : enqueue_step(d, s);
-        if (rc) return rc;
-    }
     StepCtl h1;
-    CUDA_TRY(cudaMemcpyAsync(&h1, d->ctl, sizeof(h1), cudaMemcpyDeviceToHost, d->stream));
-    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    for (int first = 0;;) {
+        int swaps = 0;
+        for (int s = first; s < n_steps; s++) {
+            const void *before = primary_id(d);
+            int rc = d->tf ? tf_enqueue_step(d, s) : d->e2 ? e2_enqueue_step(d, s) : plain ? enqueue_step_plain(d, s, s == 0, s == n_steps - 1) : enqueue_step(d, s);
+            if (rc) return rc;
+            if (primary_id(d) != before) swaps++;
+        }
+        CUDA_TRY(cudaMemcpyAsync(&h1, d->ctl, sizeof(h1), cudaMemcpyDeviceToHost, d->stream));
+        CUDA_TRY(cudaStreamSynchronize(d->stream));
+        // steps enqueued after the run had stopped (max_time, sub-cycle budget) were no-ops on the device, but an euler step also exchanges the roles of the
+        // two sets on the host: an odd number of such exchanges would leave the host naming the stale set as the primary state
+        if ((swaps - ((int)(h1.iter - h0.iter) - first)) & 1) undo_euler_swap(d);
+        if (!dev_subcycles(d)) break;
+        // device-resident sub-cycle plan: the counts of the last planned step, the budget of the next advance; a step that needed more conduction sub-cycles than
+        // were enqueued stopped the run before it changed anything (done = 3): raise the budget and enqueue the remaining steps again
+        SubPlan sp;
+        CUDA_TRY(cudaMemcpy(&sp, d->plan, sizeof(sp), cudaMemcpyDeviceToHost));
+        if (h1.done != DONE_SUBCYCLE_BUDGET) {
+            if (sp.tc_last >= 0) { d->tc_nsub = sp.tc_last; d->rl_nsub = sp.rl_last; }
+            d->tc_budget = std::max(4, sp.tc_max + std::max(2, sp.tc_max / 4));
+            sp.tc_max = 0;
+            CUDA_TRY(cudaMemcpy(d->plan, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+            break;
+        }
+        if (sp.tc_need > (1 << 24)) return fail(SPRUCE_ERR_STATE, "thermal_conduction asks for %d sub-cycles in one step", sp.tc_need);
+        d->tc_budget = sp.tc_need + std::max(2, sp.tc_need / 4);
+        d->replans++;
+        first = (int)(h1.iter - h0.iter);
+        const int zero = 0;
+        CUDA_TRY(cudaMemcpy(&d->ctl->done, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    }
     dump_marks(d);
     const int done = (int)(h1.iter - h0.iter);
     if (steps_done) *steps_done = done;
@@ -2175,6 +2276,11 @@ int spruce_module_subcycles(spruce_domain *d, const char *which, int *count)
     else if (!strcmp(which, "physical_viscosity")) *count = d->pv.nsub;
     else if (!strcmp(which, "div_cleaning")) *count = d->dc.nsub;
     else if (!strcmp(which, "anomalous_resistivity")) *count = d->ar.s.nsub;
+    // the device-resident sub-cycle plan (SPRUCE_DEVICE_SUBCYCLES=1): is it in use for the configured module set, the conduction sub-cycles the next advance enqueues per
+    // step, and how often an advance had to raise that number and enqueue again
+    else if (!strcmp(which, "device_plan")) *count = dev_subcycles(d) ? 1 : 0;
+    else if (!strcmp(which, "device_plan_budget")) *count = d->tc_budget;
+    else if (!strcmp(which, "device_plan_replans")) *count = d->replans;
     else return fail(SPRUCE_ERR_ARG, "no sub-cycling module named <%s>", which);
     return SPRUCE_OK;
 }

@@ -207,6 +207,39 @@ __device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C,
     return out;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident sub-cycle plan (opt-in, SPRUCE_DEVICE_SUBCYCLES=1): the sub-cycle counts of thermal conduction and radiative losses
+// (numberSubcycles, thermalconduction.cpp:135-149, radiativelosses.cpp:161-166) are taken from the count kernels' reductions by ONE device thread
+// instead of the host, so that a step with these modules is enqueued without a host round trip.  The host enqueues a BUDGET of conduction
+// sub-cycles; launches beyond the planned count return at once.  A count above the budget stops the run before the step has changed anything
+// (StepCtl::done = 3): spruce_advance raises the budget and re-enqueues from that step.
+// STATUS: written after the round-2 GPU budget was spent; executed on the host from this source (tests/test_capi_hooks_emulated.py), first device run at the round's end.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DONE_SUBCYCLE_BUDGET = 3;     // StepCtl::done: 1 = max_time reached, 2 = a peer stopped answering, 3 = more conduction sub-cycles needed than were enqueued
+struct SubPlan { int tc_nsub, rl_nsub; double tc_dts; int tc_need, tc_max; int tc_last, rl_last; };     // tc_last / rl_last: counts of the last step that was planned (curr_num_subcycles)
+struct SubPlanArgs { StepCtl *ctl; const unsigned long long *red; SubPlan *plan; int tc_on, tc_sat; double tc_eps, tc_dtmin; int rl_on; double rl_eps; int tc_budget; };
+__global__ void k_sub_plan(const SubPlanArgs A)
+{
+    SubPlan *p = A.plan;
+    p->tc_nsub = 0; p->rl_nsub = 0; p->tc_dts = 0.0;
+    if (A.ctl->done) return;
+    const double dt = A.ctl->step;
+    int tc = 0, rl = 0;
+    if (A.tc_on && !(A.tc_sat && __longlong_as_double((long long)A.red[1]) == 0.0)) {              // thermalconduction.cpp:143
+        const double a = A.tc_eps * __longlong_as_double((long long)A.red[0]), b = A.tc_dtmin;
+        const double md = (a < b) ? b : a;                                                          // std::max :147
+        tc = (int)(dt / md) + 1;                                                                    // :148
+    }
+    if (A.rl_on && !(__longlong_as_double((long long)A.red[3]) == 0.0)) {                           // radiativelosses.cpp:162
+        const double sdt = A.rl_eps * __longlong_as_double((long long)A.red[2]);
+        rl = (int)(dt / sdt) + 1;                                                                   // :165
+    }
+    if (tc > p->tc_max) p->tc_max = tc;
+    if (tc > A.tc_budget) { p->tc_need = tc; A.ctl->done = DONE_SUBCYCLE_BUDGET; return; }          // nothing of this step has been applied yet
+    p->tc_nsub = tc; p->rl_nsub = rl; p->tc_last = tc; p->rl_last = rl;
+    p->tc_dts = dt / (double)tc;                                                                    // thermalconduction.cpp:60
+}
+
 enum { TC_FINAL = 0, TC_INTERMEDIATE = 1, TC_RK4_FINAL = 2 };
 struct TcStageArgs {
     TcFields F;
@@ -219,6 +252,8 @@ struct TcStageArgs {
     int mode;
     double c;                  // 0.5*dt_sub or dt_sub
     int fast;                  // deep-interior cells take the FAST instance (SPRUCE_FAST_INTERIOR, default on; same results bit for bit)
+    const SubPlan *plan;       // device-resident plan (or null): sub-cycle `sub` runs only below plan->tc_nsub, c = plan->tc_dts (times 0.5 when `half`)
+    int sub, half;
 };
 
 __global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ DomainParams P, const __grid_constant__ TcStageArgs A)
@@ -226,6 +261,11 @@ __global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ Domain
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (j >= P.ny) return;
+    double cstep = A.c;
+    if (A.plan) {
+        if (A.sub >= A.plan->tc_nsub) return;
+        cstep = A.half ? 0.5 * A.plan->tc_dts : A.plan->tc_dts;
+    }
     const size_t off = (size_t)r * P.pitch + j;
     const bool in = is_interior(P, r, j);
     const double mask = in ? 1.0 : 0.0;
@@ -236,9 +276,9 @@ __global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ Domain
     double e1;
     if (A.mode == TC_RK4_FINAL) {
         const double ks = ((A.K1[off] + A.K2[off] * 2.0) + A.K3[off] * 2.0) + dE;
-        e1 = smax(e0 + ((mask * A.c) * ks) / 6.0, P.e_min);                       // :96-97
+        e1 = smax(e0 + ((mask * cstep) * ks) / 6.0, P.e_min);                     // :96-97
     } else {
-        e1 = smax(e0 + (mask * A.c) * dE, P.e_min);                               // :63-64, :70-71, :84 ...
+        e1 = smax(e0 + (mask * cstep) * dE, P.e_min);                             // :63-64, :70-71, :84 ...
     }
     if (A.mode != TC_INTERMEDIATE) A.e_out[off] = e1;
     A.T_out[off] = temp_of(P, e1, A.F.n[off]);
@@ -315,6 +355,8 @@ struct RlArgs {
     double dt;                 // step size of this iteration
     unsigned long long *red;   // count mode: red[0] = min |e/L| over the whole plane, red[1] = max L
     int count_mode;
+    const SubPlan *plan;       // device-resident plan (or null): n_sub = plan->rl_nsub, dt = *dt_ptr, nothing is written once *done_ptr is set
+    const double *dt_ptr; const int *done_ptr;
 };
 
 __global__ void __launch_bounds__(128) k_rl(const DomainParams P, const RlArgs A)
@@ -341,8 +383,10 @@ __global__ void __launch_bounds__(128) k_rl(const DomainParams P, const RlArgs A
             lmax = (l == l && l > 0.0) ? (unsigned long long)__double_as_longlong(l) : 0ULL;
         } else {
             const double mask = in ? 1.0 : 0.0;
-            const double dts = A.dt / (double)A.n_sub;                            // :51
-            for (int s = 0; s < A.n_sub; s++) {
+            if (A.plan && *A.done_ptr) return;                                    // apply mode has no block-wide reduction below
+            const int n_sub = A.plan ? A.plan->rl_nsub : A.n_sub;
+            const double dts = (A.plan ? *A.dt_ptr : A.dt) / (double)n_sub;       // :51
+            for (int s = 0; s < n_sub; s++) {
                 if (A.R.integrator == 0) {                                        // euler :53-57
                     e = smax(e - (mask * dts) * L(T), P.e_min);
                 } else if (A.R.integrator == 1) {                                 // rk2 :58-69
@@ -372,11 +416,11 @@ __global__ void __launch_bounds__(128) k_rl(const DomainParams P, const RlArgs A
 }
 
 // AmbientHeating::postIterateModule (ambientheating.cpp:43): e += dt*heating  (tmp = heating*dt, then +=)
-__global__ void __launch_bounds__(256) k_ambient_heating(const DomainParams P, double *e, const double *heating, const double *step_ptr)
+__global__ void __launch_bounds__(256) k_ambient_heating(const DomainParams P, double *e, const double *heating, const double *step_ptr, const int *done_ptr)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
-    if (j >= P.ny) return;
+    if (j >= P.ny || (done_ptr && *done_ptr)) return;
     const size_t off = (size_t)r * P.pitch + j;
     e[off] = e[off] + heating[off] * (*step_ptr);
 }
@@ -412,6 +456,15 @@ __global__ void __launch_bounds__(256) k_avg_change(const DomainParams P, double
     const size_t off = (size_t)r * P.pitch + j;
     out[off] = (e[off] - old[off]) / dt;
 }
+// the same with the step size read from the device step control; keeps the previous step's plane once the run has stopped
+__global__ void __launch_bounds__(256) k_avg_change_dev(const DomainParams P, double *out, const double *e, const double *old, const double *dt_ptr, const int *done_ptr)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (j >= P.ny || *done_ptr) return;
+    const size_t off = (size_t)r * P.pitch + j;
+    out[off] = (e[off] - old[off]) / (*dt_ptr);
+}
 // multispecies_mode (plasmadomain.hpp:134-135): a module's energy input w joins the cumulative planes as  ion (+/-)= (1 - f) w  when f < 1,  electron (+/-)= f w  when f > 0,
 // f = the module's ms_electron_heating_fraction.  w per cell, the fraction factor fr placed where the reference places it:
 //   MS_DIFF   (a - b) fr              thermalconduction.cpp:105-108, radiativelosses.cpp:94-97        (a = sub-cycled energy, b = energy before)
@@ -436,11 +489,11 @@ __global__ void __launch_bounds__(256) k_ms_feed(const DomainParams P, const MsA
     if (A.f < 1.0) A.cum_i[off] = A.sign < 0.0 ? A.cum_i[off] - w(1.0 - A.f) : A.cum_i[off] + w(1.0 - A.f);
     if (A.f > 0.0) A.cum_e[off] = A.sign < 0.0 ? A.cum_e[off] - w(A.f) : A.cum_e[off] + w(A.f);
 }
-__global__ void __launch_bounds__(128) k_tc_saturation_plane(const DomainParams P, const TcParams C, const TcFields F, double *out)
+__global__ void __launch_bounds__(128) k_tc_saturation_plane(const DomainParams P, const TcParams C, const TcFields F, double *out, const int *done_ptr)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
-    if (j >= P.ny) return;
+    if (j >= P.ny || (done_ptr && *done_ptr)) return;                   // a stopped run keeps the plane of its last step
     out[(size_t)r * P.pitch + j] = tc_coefficient(P, C, F, r, j);
 }
 

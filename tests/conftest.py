@@ -13,7 +13,7 @@ def pytest_configure(config):
 # Order of the GPU suite (`-m gpu -x`): the parity tests proper first -- core ideal MHD / two-fluid / modules, then the extended rows, then the drop-in binary --,
 # the non-strict first-run tests (written after a round's GPU budget was spent) and the sanitizer runs last, so that whatever happens in a newer test, the record
 # of the validated ones is already written.  Tests without the gpu marker keep pytest's own order.
-_GPU_FILE_ORDER = ["test_gpu_parity.py", "test_gpu_extended.py", "test_host_binary.py", "test_gpu_fast_instances.py", "test_gpu_sanitizer.py"]
+_GPU_FILE_ORDER = ["test_gpu_parity.py", "test_gpu_extended.py", "test_host_binary.py", "test_gpu_fast_instances.py", "test_gpu_device_plan.py", "test_gpu_sanitizer.py"]
 
 
 def pytest_collection_modifyitems(config, items):

@@ -127,7 +127,7 @@ def assemble():
     ah = (CSRC / "anomres_host.cuh").read_text()
     ms = (CSRC / "moc_stage.cuh").read_text()
     fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "void fill_moc(", "int launch_moc_save(", "int launch_moc(", "int moc_limit(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
-           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int ms_feed(", "int ah_post(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(",
+           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int ms_feed(", "int ah_post(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(", "bool dev_subcycles(",
            "int exchange_planes4(", "PvArgs pv_args(", "int pv_substeps(",
            "int evolved_slot(int var)\n{", "const double *materialise_var(", "int visc_needs_dt_plane(", "int visc_refresh_dt(", "int visc_term(", "int prepare_rhs_modules(", "int av_iterate("]
     one_liners = {"double bits_to_double(", "int visc_needs_dt_plane(", "int visc_refresh_dt("}
@@ -860,3 +860,90 @@ def test_inactive_mode_of_conduction_and_losses_forms_the_planes_and_leaves_the_
     for name in ("cumulative_electron_heating", "cumulative_ion_heating"):
         assert close(got[name], o.ms_plane(name)), name
     o.close()
+
+
+# ---- the device-resident sub-cycle plan (SPRUCE_DEVICE_SUBCYCLES=1): k_sub_plan + the plan-driven tc_iterate / rl_iterate against the host-driven form of the same step
+def _bits(x):
+    return int(np.array([x], dtype=np.float64).view(np.uint64)[0])
+
+
+def _run_planned(emu, xb, yb, tc, rl, red, step, budget=None, stopped=0, nx=22, ny=19):
+    """(host-driven run, plan-driven run) of one module step on twin domains: evolved planes, output planes, counts"""
+    out = []
+    for planned in (False, True):
+        s, o, h, _, bounds = make_pair(emu, xb, yb, nx, ny)
+        n = nx * ny
+        avg, sat, rad = np.zeros(n), np.zeros(n), np.zeros(n)
+        redv = (C.c_ulonglong * 4)(*red)
+        common = [C.c_int(int(tc is not None)), C.c_int(int(bool(tc and tc["sat"]))), C.c_double(1.0e-4), C.c_int(tc["integ"] if tc else 0), C.c_double(tc["eps"] if tc else 0.1),
+                  C.c_int(int(rl is not None)), C.c_int(rl["integ"] if rl else 0), C.c_double(rl["eps"] if rl else 0.1), redv, C.c_double(step)]
+        if planned:
+            info = (C.c_int * 7)()
+            assert emu.cemu_planned_modules(h, *common, C.c_int(budget), C.c_int(stopped), vp(avg), vp(sat), vp(rad), info) == 0
+        else:
+            info = (C.c_int * 2)()
+            assert emu.cemu_host_modules(h, *common, vp(avg), vp(sat), vp(rad), info) == 0
+        planes = []
+        for k in range(len(EV)):
+            got = np.zeros((nx, ny))
+            emu.cemu_get(h, C.c_int(k), vp(got))
+            planes.append(got)
+        out.append(dict(planes=planes, avg=avg, sat=sat, rad=rad, info=list(info), before=[np.ascontiguousarray(o.get(v)).copy() for v in EV], dtmin=emu.cemu_dtmin(h)))
+    return out
+
+
+@pytest.mark.parametrize("integ", [0, 1, 2])
+@pytest.mark.parametrize("sat", [False, True])
+@pytest.mark.parametrize("xb,yb", [(("periodic", "periodic"), ("periodic", "periodic")), (("periodic", "periodic"), ("fixed", "open")), (("reflect", "open"), ("fixed", "fixed"))])
+def test_planned_subcycles_equal_the_host_driven_step(emu, xb, yb, integ, sat):
+    """thermal_conduction + radiative_losses: counts planned by k_sub_plan equal the host's numberSubcycles; with more sub-cycles enqueued than planned, the evolved planes,
+    the dt minimum and the three output planes equal the host-driven step bit for bit"""
+    _, _, _, step, _ = make_pair(emu, xb, yb, 22, 19)
+    # reduction words that make thermal_conduction plan 3 and radiative_losses 2 sub-cycles (epsilon = 0.1); word 1 / 3: non-zero maxima
+    red = [_bits(step / 2.5 / 0.1), _bits(1.0), _bits(step / 1.5 / 0.1), _bits(1.0)]
+    host, dev = _run_planned(emu, xb, yb, dict(sat=sat, integ=integ, eps=0.1), dict(integ=integ, eps=0.1), red, step, budget=7)
+    assert host["info"] == [3, 2]
+    assert dev["info"] == [3, 2, 0, 3, 3, 2, 0]
+    for k, v in enumerate(EV):
+        assert same_bits(dev["planes"][k], host["planes"][k]), "%s: %s" % (v, mismatch(dev["planes"][k], host["planes"][k]))
+    assert not same_bits(dev["planes"][EV.index("thermal_energy")], dev["before"][EV.index("thermal_energy")])
+    assert dev["dtmin"] == host["dtmin"]
+    for name in ("avg", "sat", "rad"):
+        assert same_bits(dev[name], host[name]), name
+
+
+def test_planned_subcycles_zero_counts_and_single_modules(emu):
+    """saturated conduction with a vanishing field-aligned gradient plans no sub-cycle (thermalconduction.cpp:143), a vanishing loss maximum none for radiative_losses
+    (radiativelosses.cpp:162); each module alone"""
+    xb, yb = ("periodic", "periodic"), ("fixed", "open")
+    _, _, _, step, _ = make_pair(emu, xb, yb, 22, 19)
+    red = [_bits(step / 2.5 / 0.1), 0, _bits(step / 1.5 / 0.1), 0]
+    host, dev = _run_planned(emu, xb, yb, dict(sat=True, integ=1, eps=0.1), dict(integ=1, eps=0.1), red, step, budget=4)
+    assert host["info"] == [0, 0] and dev["info"][:2] == [0, 0] and dev["info"][4:] == [0, 0, 0]
+    for k in range(len(EV)):
+        assert same_bits(dev["planes"][k], host["planes"][k])
+    red = [_bits(step / 1.5 / 0.1), _bits(1.0), _bits(step / 3.5 / 0.1), _bits(1.0)]
+    for tc, rl, want in ((dict(sat=False, integ=0, eps=0.1), None, [2, 0]), (None, dict(integ=2, eps=0.1), [0, 4])):
+        host, dev = _run_planned(emu, xb, yb, tc, rl, red, step, budget=4)
+        assert host["info"] == want and dev["info"][:2] == want
+        for k in range(len(EV)):
+            assert same_bits(dev["planes"][k], host["planes"][k])
+        assert same_bits(dev["avg"], host["avg"]) and same_bits(dev["rad"], host["rad"])
+
+
+@pytest.mark.parametrize("stopped", [0, 1])
+def test_planned_subcycles_stop_before_anything_changes(emu, stopped):
+    """a count above the enqueued budget stops the run (StepCtl::done = 3) and reports what it needs; a run that had already stopped (max_time) stays stopped: in both cases
+    no evolved plane, no output plane and not the dt minimum may change"""
+    xb, yb = ("periodic", "periodic"), ("fixed", "open")
+    _, _, _, step, _ = make_pair(emu, xb, yb, 22, 19)
+    red = [_bits(step / 4.5 / 0.1), _bits(1.0), _bits(step / 1.5 / 0.1), _bits(1.0)]          # 5 conduction sub-cycles wanted
+    host, dev = _run_planned(emu, xb, yb, dict(sat=True, integ=1, eps=0.1), dict(integ=0, eps=0.1), red, step, budget=4, stopped=stopped)
+    assert host["info"] == [5, 2]
+    if stopped:
+        assert dev["info"] == [0, 0, 0, 0, -1, -1, 1]
+    else:
+        assert dev["info"] == [0, 0, 5, 5, -1, -1, 3]
+    for k, v in enumerate(EV):
+        assert same_bits(dev["planes"][k], dev["before"][k]), v
+    assert not dev["avg"].any() and not dev["sat"].any() and not dev["rad"].any()

@@ -79,9 +79,9 @@ def assemble():
              BLOCK_MIN,
              cut(mk, "// is global row g / column j inside", "// block-wide NaN-ignoring minimum"),
              cut(mk, "struct PropArgs {", "// Ghost cells of the non-periodic sides"), "\n",
+             cut(mk, "struct StepCtl {", "// begin: step = epsilon"),
              cut(mo, "constexpr double kKappa0", "// Artificial viscosity (source/modules/viscosity.cpp"), "\n",
              cut(mo, "struct OpArgs", "}  // namespace spruce"),
-             cut(mk, "struct StepCtl {", "// begin: step = epsilon"),
              "}  // namespace spruce\n#include \"moc_kernels.cuh\"\nnamespace spruce {\n",
              cut(ms, "struct MocArgs {", "}  // namespace spruce"),
              cut(ca, "struct HostAxis {", "struct TwoFluid;"),

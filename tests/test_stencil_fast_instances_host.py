@@ -29,6 +29,7 @@ def emu():
                     BLOCK_MIN,
                     cut(mk, "// is global row g / column j inside", "// block-wide NaN-ignoring minimum"),
                     cut(mk, "struct PropArgs {", "// Ghost cells of the non-periodic sides"), "\n",
+                    cut(mk, "struct StepCtl {", "// begin: step = epsilon"),
                     cut(mo, "constexpr double kKappa0", "}  // namespace spruce"),
                     cut(ca, "struct HostAxis {", "struct TwoFluid;"),
                     cut(ca, "void build_axis(", "int upload_tables("),
