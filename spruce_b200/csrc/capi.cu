@@ -1740,7 +1740,7 @@ int spruce_advance(spruce_domain *d, int n_steps, double max_time, double *dt_us
         CUDA_TRY(cudaStreamSynchronize(d->stream));
         // steps enqueued after the run had stopped (max_time, sub-cycle budget) were no-ops on the device, but an euler step also exchanges the roles of the
         // two sets on the host: an odd number of such exchanges would leave the host naming the stale set as the primary state
-        if ((swaps - ((int)(h1.iter - h0.iter) - first)) & 1) undo_euler_swap(d);
+        if (d->cfg.time_integrator == SPRUCE_TI_EULER && ((swaps - ((int)(h1.iter - h0.iter) - first)) & 1)) undo_euler_swap(d);
         if (!dev_subcycles(d)) break;
         // device-resident sub-cycle plan: the counts of the last planned step, the budget of the next advance; a step that needed more conduction sub-cycles than
         // were enqueued stopped the run before it changed anything (done = 3): raise the budget and enqueue the remaining steps again
