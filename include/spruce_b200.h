@@ -228,7 +228,11 @@ int spruce_eqs_ideal2f_options(spruce_domain *dom, int use_sub_cycling, int remo
  * right-hand side of e_thermal_energy / i_thermal_energy.  ideal_2F and ideal_mhd_2E domains (the equation sets that hold the four grids the module
  * looks up by name, :12-25: n, e_temp, e_thermal_energy, i_thermal_energy); on ideal_mhd it fails with the reference's message. */
 int spruce_module_eic_thermalization(spruce_domain *dom);
-/* curr_num_subcycles of the last advance: which = "thermal_conduction" | "radiative_losses" */
+/* curr_num_subcycles of the last advance: which = "thermal_conduction" | "radiative_losses" | "physical_viscosity" | "div_cleaning" | "anomalous_resistivity".
+ * With SPRUCE_DEVICE_SUBCYCLES=1 in the environment of spruce_domain_create, steps whose modules are thermal_conduction / radiative_losses / ambient_heating are planned on
+ * the device (numberSubcycles, thermalconduction.cpp:135-149, radiativelosses.cpp:161-166, evaluated by one device thread) and spruce_advance(n) waits for the host once,
+ * not per step; which = "device_plan" (1 when the configured module set runs that way), "device_plan_budget" (conduction sub-cycles the next advance enqueues per step),
+ * "device_plan_replans" (how often an advance had to raise that number and enqueue again). */
 int spruce_module_subcycles(spruce_domain *dom, const char *which, int *count);
 
 /* ---- multi-GPU (slab decomposition along x, one process per GPU; DESIGN.md "multi-GPU") */
