@@ -134,6 +134,13 @@ def mode_single(tmp):
         out["secondary_paths_2048"] = json.loads(so.decode()) if rc == 0 else {"error": se.decode(errors="replace")[-300:]}
     except Exception as e:
         out["secondary_paths_2048"] = {"error": repr(e)[:300]}
+    # the solar module set with the device-resident sub-cycle plan off and on (SPRUCE_DEVICE_SUBCYCLES): what the host round trips cost, and the same bits either way
+    try:
+        remaining(60, least_s=30)
+        rc, so, se = run_bounded([sys.executable, str(ROOT / "scripts" / "device_plan_perf.py"), "256", "1024"], 60)
+        out["device_plan_solar_modules"] = json.loads(so.decode()) if rc == 0 else {"error": se.decode(errors="replace")[-300:]}
+    except Exception as e:
+        out["device_plan_solar_modules"] = {"error": repr(e)[:300]}
     return out
 
 
