@@ -113,7 +113,7 @@ struct spruce_domain {
     bool ms_on = false; double *ms_cum[3] = {nullptr, nullptr, nullptr};
     double ms_frac_tc = 1.0, ms_frac_rl = 1.0, ms_frac_ah = 0.5, ms_frac_pv = 0.0;
     std::vector<SourceTerm> sources;
-    TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0;
+    TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0; bool tc_planes_valid = false;
     RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
     // diagnostic planes of output_to_file = true (thermalconduction.cpp:226-237, radiativelosses.cpp:172-179)
@@ -593,12 +593,34 @@ int ms_feed(spruce_domain *d, int mode, const double *a, const double *b, double
     CUDA_TRY(cudaGetLastError());
     return SPRUCE_OK;
 }
+// temp, b_hat_x, b_hat_y of the primary state into Mset planes 0..2, one pass (k_tc_derive)
+int tc_derive(spruce_domain *d)
+{
+    TcDeriveArgs A{};
+    for (int v = 0; v < NEV; v++) A.U[v] = d->Pset.p[v];
+    for (int v = 0; v < NSTATIC; v++) A.st[v] = d->stat[v];
+    A.T = d->Mset.p[0]; A.bhx = d->Mset.p[1]; A.bhy = d->Mset.p[2];
+    const int halo = d->cfg.n_ranks > 1 ? HALO : 0;                     // as derive_to: a slab also fills its halo rows
+    A.row_off = -halo;
+    dim3 grid((d->P.ny + 255) / 256, d->P.nx + 2 * halo);
+    k_tc_derive<<<grid, 256, 0, d->stream>>>(d->P, A);
+    d->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPRUCE_OK;
+}
+// the planes tc_derive left are still those of the state tc_iterate starts from: thermal_conduction is the first module of the run (its iterate hook runs first) and no
+// field_heating pre-iterate hook has used the same scratch planes in between (the other pre-iterate hooks only reduce)
+bool tc_planes_reusable(const spruce_domain *d)
+{
+    if (d->module_order.empty() || d->module_order.front() != spruce_domain::MOD_TC) return false;
+    for (int m : d->module_order) if (m == spruce_domain::MOD_FH) return false;
+    return true;
+}
 int tc_count_launch(spruce_domain *d)
 {
     int rc;
-    if ((rc = derive_to(d, V_temp, d->Mset.p[0]))) return rc;
-    if ((rc = derive_to(d, V_b_hat_x, d->Mset.p[1]))) return rc;
-    if ((rc = derive_to(d, V_b_hat_y, d->Mset.p[2]))) return rc;
+    if ((rc = tc_derive(d))) return rc;
+    d->tc_planes_valid = tc_planes_reusable(d);
     TcFields F{d->Mset.p[0], d->Pset.p[E_N], d->Mset.p[1], d->Mset.p[2]};
     dim3 grid((d->P.ny + 127) / 128, d->P.nx);
     k_tc_count<<<grid, 128, 0, d->stream>>>(d->P, d->tc, F, d->red);
@@ -627,9 +649,8 @@ int tc_iterate(spruce_domain *d, double dt, bool dev = false)
     int rc;
     double *Ta = d->Mset.p[0], *bhx = d->Mset.p[1], *bhy = d->Mset.p[2], *Tb = d->Mset.p[3], *Tc = d->Mset.p[4];
     double *K1 = d->Mset.p[5], *K2 = d->Mset.p[6], *K3 = d->Mset.p[7];
-    if ((rc = derive_to(d, V_temp, Ta))) return rc;
-    if ((rc = derive_to(d, V_b_hat_x, bhx))) return rc;
-    if ((rc = derive_to(d, V_b_hat_y, bhy))) return rc;
+    if (!d->tc_planes_valid && (rc = tc_derive(d))) return rc;          // Ta, bhx, bhy (unless the count kernel's planes still stand)
+    d->tc_planes_valid = false;
     const int ns = dev ? d->tc_budget : d->tc_nsub;
     const double dts = dev ? 0.0 : dt / (double)ns;                                                 // :60
     // inactive_mode: the sub-cycles run on a copy of the thermal energy (old_e) and only the output / cumulative planes keep their result (:101-109)

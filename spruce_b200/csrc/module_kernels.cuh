@@ -128,6 +128,24 @@ struct TcParams {
 
 struct TcFields { const double *T, *n, *bhx, *bhy; };   // n, b_hat of the primary state at module entry; T evolves
 
+// temp, b_hat_x, b_hat_y of the primary state in one pass (the three planes both numberSubcycles and iterateModule start from, thermalconduction.cpp:49-51, :136-138):
+// the expressions of k_mhd_derive's V_temp / V_b_hat_x / V_b_hat_y cases (idealmhd.cpp:254, :262-277), 8 plane reads and 3 writes instead of 18 and 3
+struct TcDeriveArgs { const double *U[NEV]; const double *st[NSTATIC]; double *T, *bhx, *bhy; int row_off; };   // row_off = -HALO: also the halo rows of a slab
+__global__ void __launch_bounds__(256) k_tc_derive(const DomainParams P, const TcDeriveArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)blockIdx.y + A.row_off;
+    if (j >= P.ny) return;
+    const long long off = (long long)r * P.pitch + j;
+    const double n_ = A.U[E_N][off];
+    const double p = A.U[E_E][off] * P.gm1;
+    A.T[off] = smax(p / (n_ * (2 * kKB)), P.T_min);
+    const double bx = A.st[S_BEX][off] + A.U[E_BX][off], by = A.st[S_BEY][off] + A.U[E_BY][off], bz = A.st[S_BEZ][off] + A.U[E_BZ][off];
+    const double bm = sqrt((bx * bx + by * by) + bz * bz);
+    A.bhx[off] = (bm == 0.0) ? 0.0 : bx / bm;                           // catchNullFieldDirection
+    A.bhy[off] = (bm == 0.0) ? 0.0 : by / bm;
+}
+
 // fieldAlignedConductiveFlux at one cell (thermalconduction.cpp:154-178); zero outside the interior
 template <bool FAST = false>
 __device__ __forceinline__ void tc_raw_flux(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j, double *fx, double *fy)

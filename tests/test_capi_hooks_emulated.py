@@ -127,7 +127,7 @@ def assemble():
     ah = (CSRC / "anomres_host.cuh").read_text()
     ms = (CSRC / "moc_stage.cuh").read_text()
     fns = ["int alloc_plane(", "void build_axis(", "void build_ghost_proto(", "void fill_moc(", "int launch_moc_save(", "int launch_moc(", "int moc_limit(", "int launch_ghosts(", "int launch_propagate(spruce_domain *d, int from_state)\n{", "int derive_to(",
-           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int ms_feed(", "int ah_post(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(", "bool dev_subcycles(",
+           "int read_reductions(", "int reset_reductions(", "double bits_to_double(", "int exchange_plane(", "int after_module_propagate(", "int ms_feed(", "int ah_post(", "int launch_op(", "int dc_post(", "int fh_pre(", "int fh_iterate(", "int src_post(", "int bo_post(", "int tc_derive(", "int tc_iterate(", "int rl_launch(", "int rl_iterate(", "bool dev_subcycles(",
            "int exchange_planes4(", "PvArgs pv_args(", "int pv_substeps(",
            "int evolved_slot(int var)\n{", "const double *materialise_var(", "int visc_needs_dt_plane(", "int visc_refresh_dt(", "int visc_term(", "int prepare_rhs_modules(", "int av_iterate("]
     one_liners = {"double bits_to_double(", "int visc_needs_dt_plane(", "int visc_refresh_dt("}
@@ -947,3 +947,10 @@ def test_planned_subcycles_stop_before_anything_changes(emu, stopped):
     for k, v in enumerate(EV):
         assert same_bits(dev["planes"][k], dev["before"][k]), v
     assert not dev["avg"].any() and not dev["sat"].any() and not dev["rad"].any()
+
+
+def test_fused_conduction_planes_equal_the_three_derive_passes(emu):
+    """k_tc_derive (temp, b_hat_x, b_hat_y in one pass) against three derive_to passes, bit for bit, ghost cells included"""
+    for xb, yb in ((("periodic", "periodic"), ("fixed", "open")), (("reflect", "open"), ("fixed", "fixed"))):
+        _, _, h, _, _ = make_pair(emu, xb, yb, 22, 19)
+        assert emu.cemu_tc_derive_mismatches(h) == 0
