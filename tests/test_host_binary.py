@@ -2,6 +2,7 @@
 C ABI) against the UNMODIFIED reference binary (oracle/_ref/run) on the same .state / .config files:
 mhd.out and end.state must be byte-identical for ideal MHD, and numerically within 1e-9 for runs with libm-dependent
 modules.  Both programs end a completed run with SIGABRT (exit status 134), as the reference does on purpose."""
+import os
 import subprocess
 from pathlib import Path
 
@@ -16,10 +17,11 @@ ROOT = Path(__file__).resolve().parents[1]
 OURS = ROOT / "spruce_b200" / "bin" / "run"
 
 
-def run_ours(state, cfg_text, out_dir):
+def run_ours(state, cfg_text, out_dir, env=None):
     out_dir.mkdir(parents=True, exist_ok=True)
     (out_dir / "run.config").write_text(cfg_text)
-    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out_dir), "-s", str(state)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    r = subprocess.run([str(OURS), "-m", "input", "-o", str(out_dir), "-s", str(state)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600,
+                       env=None if env is None else dict(os.environ, **env))
     assert r.returncode in (-6, 134), r.stderr.decode()[-2000:]
     assert "Simulation successfully reached max simulation time or iterations" in r.stderr.decode()
     return r.stdout.decode()
@@ -165,6 +167,27 @@ def test_run_binary_matches_reference_files(name, tmp_path):
                 assert all(k in fb[-1] and np.count_nonzero(fb[-1][k]) for k in ("viscous_heating", "viscous_force_x", "viscous_force_y", "viscous_force_z"))
         if name == "loop_solar_modules":
             assert "Thermal Subcycles" in stdout and "Radiative Subcycles" in stdout
+
+
+@pytest.mark.xfail(reason="written after round 2's GPU budget was spent; CPU-checked (tests/test_capi_hooks_emulated.py::test_planned_subcycles_*), first device run", strict=False)
+@pytest.mark.parametrize("name,every", [("loop_solar_modules", 1), ("example_state_solar_modules", 3)])
+def test_run_binary_with_the_device_resident_subcycle_plan_writes_the_same_files(name, every, tmp_path):
+    """SPRUCE_DEVICE_SUBCYCLES=1: the solar module set through the drop-in binary with the sub-cycle counts planned on the device -- with an output every
+    step (one-step batches) and every third step (batches inside which no step waits for the host) -- must write the files of the host-driven run byte for byte and print
+    the same sub-cycle counts"""
+    if not OURS.exists():
+        subprocess.run(["make", "-C", str(ROOT / "spruce_b200" / "host")], check=True)
+    gen, ckw, _ = CASES[name]
+    s = gen()
+    state = tmp_path / "in.state"
+    refrun.write_state(state, s["planes"], s["ion_mass"], s["adiabatic_index"])
+    # a stdout line with module messages makes the shell look after every step: only the every-step case prints
+    cfg = refrun.ideal_mhd_config(**dict(ckw, std_out_interval=1 if every == 1 else -1, iter_output_interval=every, max_iterations=6))
+    outs = [run_ours(state, cfg, tmp_path / tag, env={"SPRUCE_DEVICE_SUBCYCLES": on, "SPRUCE_TC_BUDGET": "2"}) for tag, on in (("host", "0"), ("plan", "1"))]
+    for fname in ("mhd.out", "end.state"):
+        assert (tmp_path / "plan" / fname).read_bytes() == (tmp_path / "host" / fname).read_bytes(), fname
+    pick = lambda text: [ln for ln in text.splitlines() if "Subcycles" in ln]
+    assert pick(outs[0]) == pick(outs[1]) and (every != 1 or pick(outs[0]))
 
 
 def _n_gpus():
