@@ -440,6 +440,12 @@ def test_thermal_conduction_on_slabs_equals_the_whole_domain_with_and_without_fa
         assert emu.cemu_run_slabs((C.c_void_p * world)(*hs), C.c_int(world), C.c_int(3), vp(p)) == 0
         got = gather(emu, hs, cuts, ny, 4)
         assert same_bits(got, whole), "thermal energy on %d slabs (fast %d): %s" % (world, int(fast), mismatch(got, whole))
+    # the plan-driven form (SPRUCE_DEVICE_SUBCYCLES): 5 sub-cycles enqueued on every slab, 2 planned -- the skipped stages still take part in the halo exchanges
+    hs, cuts, keep = make_slabs(emu, s, o, xb, yb, nx, ny, world)
+    p = np.array([float(sat), 1.0, 1.0e-4, float(code), 2.0, step, 1.0, 5.0])
+    assert emu.cemu_run_slabs((C.c_void_p * world)(*hs), C.c_int(world), C.c_int(4), vp(p)) == 0
+    got = gather(emu, hs, cuts, ny, 4)
+    assert same_bits(got, whole), "thermal energy on %d slabs (device-resident plan): %s" % (world, mismatch(got, whole))
     assert not np.array_equal(whole, o.get("thermal_energy"))
     o.close()
 
