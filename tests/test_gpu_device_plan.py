@@ -152,3 +152,22 @@ def test_euler_batch_that_stops_at_max_time_keeps_the_primary_state(zfull):
             assert same_bits(a.grid(v), b.grid(v)), (n_batch, v)
         b.close()
     a.close()
+
+
+@pytest.mark.parametrize("args", [("128", "96", "4", "rk2", "periodic", "p2p", "tcsat,rl,ah"), ("96", "80", "3", "euler", "reflect", "p2p", "tc,rl")])
+@pytest.mark.parametrize("budget", ["1", "6"])
+def test_device_plan_on_two_slabs_equals_one_gpu(args, budget):
+    """the plan-driven module steps on 2 slabs (the reduction words all-gathered over peer memory before the planning thread, skipped sub-cycle stages still taking part in the
+    halo exchanges, a stop for a larger budget taken by both ranks at the same step) == the plan-driven run on one GPU, bit for bit (scripts/mgpu_check.py)"""
+    import subprocess
+    import sys
+    import torch
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        str(root / "scripts" / "mgpu_check.py"), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300,
+                       env=dict(os.environ, SPRUCE_DEVICE_SUBCYCLES="1", SPRUCE_TC_BUDGET=budget))
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "IDENTICAL" in out, out[-3000:]
