@@ -36,7 +36,7 @@ RUNS = {
 }
 
 
-def sanitize(tool, name, tmp_path, gpus=1, relaxed=False):
+def sanitize(tool, name, tmp_path, gpus=1, relaxed=False, extra_env=None):
     if not Path(SANITIZER).exists():
         pytest.skip("compute-sanitizer is not installed")
     gen, ckw = RUNS[name]
@@ -49,7 +49,7 @@ def sanitize(tool, name, tmp_path, gpus=1, relaxed=False):
     cmd = [SANITIZER, "--tool", tool, "--error-exitcode", "99", "--target-processes", "all", str(OURS), "-m", "input", "-o", str(out), "-s", str(state), "-r", "1.0e-6"]
     if gpus > 1:
         cmd += ["-g", str(gpus)]
-    env = dict(os.environ, SPRUCE_NVTX="0", **({"SPRUCE_ARITH": "relaxed"} if relaxed else {}))
+    env = dict(os.environ, SPRUCE_NVTX="0", **({"SPRUCE_ARITH": "relaxed"} if relaxed else {}), **(extra_env or {}))
     if time.monotonic() - T0 > BUDGET_S:
         pytest.skip("the sanitizer runs of this file have used their %d s" % BUDGET_S)
     p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, start_new_session=True)      # its own process group: a timeout takes the tool AND the binary down
@@ -87,6 +87,12 @@ def test_racecheck_clean(name, relaxed, tmp_path):
 @pytest.mark.parametrize("name", [n for n in RUNS if n not in ("ot_2d_rk2", "ot_zfull_rk2")])
 def test_memcheck_clean(name, tmp_path):
     sanitize("memcheck", name, tmp_path)
+
+
+@FIRST_RUN
+def test_memcheck_clean_with_the_device_resident_subcycle_plan(tmp_path):
+    """the solar module set planned on the device (k_sub_plan, plan-driven k_tc_stage / k_rl, k_tc_derive); a budget of 1 also takes the stop-and-enqueue-again path"""
+    sanitize("memcheck", "loop_walls_euler_modules", tmp_path, extra_env={"SPRUCE_DEVICE_SUBCYCLES": "1", "SPRUCE_TC_BUDGET": "1"})
 
 
 @FIRST_RUN
