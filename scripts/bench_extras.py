@@ -90,7 +90,7 @@ def clean_env():
     return {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC_") and not k.startswith("TORCH_NCCL_")}
 
 
-def conduction_workload(n_gpus, size, steps, limit_s):
+def conduction_workload(n_gpus, size, steps, limit_s, device_plan=False):
     """BASELINE.json configs[4] / SURVEY 8d cfg-C (MHD + thermal conduction) through bench.py's own --workload mhd_tc leg, as a bounded side measurement"""
     cmd = [sys.executable]
     if n_gpus > 1:
@@ -98,7 +98,7 @@ def conduction_workload(n_gpus, size, steps, limit_s):
     cmd += [str(ROOT / "bench.py"), "--gpus", str(n_gpus), "--steps", str(steps), "--warmup", "3", "--workload", "mhd_tc", "--size", str(size), "--no-extra", "--no-cpu-baseline"]
     try:
         remaining(limit_s, least_s=45)                  # a whole bench.py process: not worth starting with less
-        rc, so, se = run_bounded(cmd, limit_s, env=clean_env())
+        rc, so, se = run_bounded(cmd, limit_s, env=dict(clean_env(), **({"SPRUCE_DEVICE_SUBCYCLES": "1"} if device_plan else {})))
         lines = [ln for ln in so.decode(errors="replace").splitlines() if ln.startswith("{")]
         if not lines:
             return {"error": "rc %s: %s" % (rc, se.decode(errors="replace")[-300:])}
@@ -141,6 +141,8 @@ def mode_single(tmp):
         out["device_plan_solar_modules"] = json.loads(so.decode()) if rc == 0 else {"error": se.decode(errors="replace")[-300:]}
     except Exception as e:
         out["device_plan_solar_modules"] = {"error": repr(e)[:300]}
+    # the conduction workload once more with the device-resident sub-cycle plan, if the budget still allows a whole bench.py process
+    out["conduction_workload_4096_device_plan"] = conduction_workload(1, 4096, 10, 100, device_plan=True)
     return out
 
 
@@ -168,6 +170,8 @@ def mode_ranks_all(tmp, n_gpus):
         out["dropin_binary_ranks"] = {"error": repr(e)[:300]}
     # cfg-C: 16384^2 needs the memory of >= 4 GPUs' slabs to stay small next to the enclosing run's; 8192^2 below that
     out["conduction_workload"] = conduction_workload(n_gpus, 16384 if n_gpus >= 4 else 8192, 5, 160)
+    # the same with the device-resident sub-cycle plan (no rank waits for its host inside a batch), if the budget still allows it; its parity_vs_1gpu is the plan's slab check
+    out["conduction_workload_device_plan"] = conduction_workload(n_gpus, 16384 if n_gpus >= 4 else 8192, 5, 120, device_plan=True)
     return out
 
 
