@@ -114,6 +114,7 @@ struct spruce_domain {
     double ms_frac_tc = 1.0, ms_frac_rl = 1.0, ms_frac_ah = 0.5, ms_frac_pv = 0.0;
     std::vector<SourceTerm> sources;
     TcParams tc{}; int tc_integrator = 0; double tc_epsilon = 0.0; int tc_nsub = 0; bool tc_planes_valid = false;
+    bool tc_two_pass = true; double *tc_pass[3] = {nullptr, nullptr, nullptr};      // SPRUCE_TC_TWO_PASS=0: saturated conduction evaluates the coefficient at five points per cell (k_tc_coef off)
     RlParams rl{}; int rl_nsub = 0;
     double *heating = nullptr;
     // diagnostic planes of output_to_file = true (thermalconduction.cpp:226-237, radiativelosses.cpp:172-179)
@@ -672,9 +673,22 @@ int tc_iterate(spruce_domain *d, double dt, bool dev = false)
         }
     }
     int sub = 0;
+    const bool two_pass = d->tc.flux_saturation && d->tc_two_pass;
+    if (two_pass) for (int k = 0; k < 3; k++) if (!d->tc_pass[k] && (rc = alloc_plane(d, &d->tc_pass[k]))) return rc;
     auto stage = [&](const double *Tin, double *Tout, int mode, int half, double *Kst) -> int {
         TcStageArgs A{};
         A.F = TcFields{Tin, d->Pset.p[E_N], bhx, bhy};
+        if (two_pass) {                                  // saturation coefficient and raw flux of this temperature plane, once per cell (k_tc_coef)
+            TcCoefArgs K{};
+            K.F = A.F; K.C = d->tc; K.coef = d->tc_pass[0]; K.rx = d->tc_pass[1]; K.ry = d->tc_pass[2]; K.fast = d->fast_interior ? 1 : 0;
+            const int halo1 = d->cfg.n_ranks > 1 ? 1 : 0;                // a slab differentiates the coefficient across its edges: one halo row per side
+            K.row_off = -halo1;
+            if (dev) { K.plan = d->plan; K.sub = sub; }
+            const dim3 gridk((d->P.ny + 127) / 128, d->P.nx + 2 * halo1);
+            k_tc_coef<<<gridk, 128, 0, d->stream>>>(d->P, K);
+            d->launches++;
+            A.S.coef = K.coef; A.S.rx = K.rx; A.S.ry = K.ry;
+        }
         A.C = d->tc; A.e_base = e; A.e_out = e; A.T_out = Tout; A.K_store = Kst; A.K1 = K1; A.K2 = K2; A.K3 = K3; A.mode = mode; A.c = half ? 0.5 * dts : dts;
         A.fast = d->fast_interior ? 1 : 0;
         if (dev) { A.plan = d->plan; A.sub = sub; A.half = half; }
@@ -1514,6 +1528,7 @@ int spruce_domain_create(const spruce_config *cfg, spruce_domain **out)
     if (const char *fc = getenv("SPRUCE_FUSED_CTL")) d->fuse_ctl_enabled = atoi(fc) != 0;
     if (const char *fi = getenv("SPRUCE_FAST_INTERIOR")) d->fast_interior = atoi(fi) != 0;
     if (const char *ds = getenv("SPRUCE_DEVICE_SUBCYCLES")) d->dev_sub = atoi(ds) != 0;
+    if (const char *tp = getenv("SPRUCE_TC_TWO_PASS")) d->tc_two_pass = atoi(tp) != 0;
     if (const char *tb = getenv("SPRUCE_TC_BUDGET")) { const int v = atoi(tb); if (v >= 1) d->tc_budget = v; }      // the first advance's budget
     if (const char *tl = getenv("SPRUCE_TIMELINE")) d->timeline_steps = atoi(tl);
     if (const char *sl = getenv("SPRUCE_STATIC_LISTS")) d->static_lists = atoi(sl) != 0;

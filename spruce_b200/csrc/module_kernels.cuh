@@ -190,9 +190,12 @@ __device__ __noinline__ double tc_coefficient(const DomainParams &P, const TcPar
     return (fm != 0.0) ? sfm / fm : 1.0;
 }
 
+// planes of the two-pass form of saturated conduction (k_tc_coef below): saturation coefficient and raw field-aligned flux of every cell, for the temperature plane F.T
+struct TcSat { const double *coef = nullptr, *rx = nullptr, *ry = nullptr; };
+
 // thermalEnergyDerivative at one cell (thermalconduction.cpp:114-132)
 template <bool FAST = false>
-__device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j)
+__device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C, const TcFields &F, int r, int j, const TcSat S = TcSat())
 {
     auto T = [&](int a, int b) { return rdT<FAST>(P, F.T, a, b); };
     auto BX = [&](int a, int b) { return rdT<FAST>(P, F.bhx, a, b); };
@@ -214,6 +217,15 @@ __device__ double tc_energy_derivative(const DomainParams &P, const TcParams &C,
     const double tty = ((p15 * (5.0 / 2.0)) * Ty) * bg + p25 * ((t1y + t2y) + t3y);
     double out = (((p25 * bg) * (bxx + byy)) + (bhx * ttx + bhy * tty)) * C.kappa;
     if (C.flux_saturation) {
+        if (S.coef) {
+            // two-pass form: every cell's coefficient and raw flux were written by k_tc_coef (the same functions, evaluated once per cell instead of at each of the five
+            // points of every neighbour's stencil); saturationTerms (thermalconduction.cpp:211-224) differentiates the plane
+            auto CP = [&](int a, int b) { return rdT<FAST>(P, S.coef, a, b); };
+            const double coef = CP(r, j), rx = rdT<FAST>(P, S.rx, r, j), ry = rdT<FAST>(P, S.ry, r, j);
+            const double mask = (FAST || is_interior(P, r, j)) ? 1.0 : 0.0;
+            const double add = (mask * -1.0) * (Dx<FAST>(P, CP, r, j) * rx + Dy<FAST>(P, CP, r, j) * ry);
+            return coef * out + add;
+        }
         auto CO = [&](int a, int b) { return tc_coefficient<FAST>(P, C, F, a, b); };
         if (FAST) {
             // the general form below evaluates the coefficient seven times (the centre once by itself and once inside each derivative) and the centre's raw flux twice;
@@ -288,7 +300,27 @@ struct TcStageArgs {
     int fast;                  // deep-interior cells take the FAST instance (SPRUCE_FAST_INTERIOR, default on; same results bit for bit)
     const SubPlan *plan;       // device-resident plan (or null): sub-cycle `sub` runs only below plan->tc_nsub, c = plan->tc_dts (times 0.5 when `half`)
     int sub, half;
+    TcSat S;                   // two-pass form of saturated conduction (or nulls)
 };
+
+// first pass of the two-pass form: saturation coefficient (tc_coefficient's body) and raw flux of every cell of the plane -- ghost cells (no flux: coefficient 1) and, on a
+// slab, one halo row per side included (row_off = -1), which the neighbours' temperature rows make computable
+struct TcCoefArgs { TcFields F; TcParams C; double *coef, *rx, *ry; int fast, row_off; const SubPlan *plan; int sub; };
+__global__ void __launch_bounds__(128) k_tc_coef(const __grid_constant__ DomainParams P, const __grid_constant__ TcCoefArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)blockIdx.y + A.row_off;
+    if (j >= P.ny || (A.plan && A.sub >= A.plan->tc_nsub)) return;
+    const ptrdiff_t off = (ptrdiff_t)r * (ptrdiff_t)P.pitch + j;
+    const bool fast = A.fast && deep_interior(P, r, j);
+    double fx, fy;
+    if (fast) tc_raw_flux<true>(P, A.C, A.F, r, j, &fx, &fy); else tc_raw_flux<false>(P, A.C, A.F, r, j, &fx, &fy);
+    A.rx[off] = fx; A.ry[off] = fy;
+    const double fm = sqrt(fx * fx + fy * fy);
+    if (fast) tc_saturate<true>(P, A.F, r, j, &fx, &fy); else tc_saturate<false>(P, A.F, r, j, &fx, &fy);
+    const double sfm = sqrt(fx * fx + fy * fy);
+    A.coef[off] = (fm != 0.0) ? sfm / fm : 1.0;
+}
 
 __global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ DomainParams P, const __grid_constant__ TcStageArgs A)
 {
@@ -304,7 +336,7 @@ __global__ void __launch_bounds__(128) k_tc_stage(const __grid_constant__ Domain
     const bool in = is_interior(P, r, j);
     const double mask = in ? 1.0 : 0.0;
     double dE = 0.0;                                                    // ghost cells: multiplied by mask = 0
-    if (in) dE = (A.fast && deep_interior(P, r, j)) ? tc_energy_derivative<true>(P, A.C, A.F, r, j) : tc_energy_derivative<false>(P, A.C, A.F, r, j);
+    if (in) dE = (A.fast && deep_interior(P, r, j)) ? tc_energy_derivative<true>(P, A.C, A.F, r, j, A.S) : tc_energy_derivative<false>(P, A.C, A.F, r, j, A.S);
     if (A.K_store) A.K_store[off] = dE;
     const double e0 = A.e_base[off];
     double e1;

@@ -960,3 +960,26 @@ def test_fused_conduction_planes_equal_the_three_derive_passes(emu):
     for xb, yb in ((("periodic", "periodic"), ("fixed", "open")), (("reflect", "open"), ("fixed", "fixed"))):
         _, _, h, _, _ = make_pair(emu, xb, yb, 22, 19)
         assert emu.cemu_tc_derive_mismatches(h) == 0
+
+
+@pytest.mark.parametrize("integ", ["euler", "rk2", "rk4"])
+@pytest.mark.parametrize("fast", [1, 0])
+@pytest.mark.parametrize("xb,yb", [(("periodic", "periodic"), ("periodic", "periodic")), (("periodic", "periodic"), ("fixed", "open")), (("reflect", "open"), ("fixed", "fixed")),
+                                   (("fixed", "open"), ("reflect", "open"))])
+def test_two_pass_saturated_conduction_equals_the_five_point_form(emu, xb, yb, integ, fast):
+    """k_tc_coef + the plane-differentiating saturated branch (default) against the form that evaluates the coefficient at five points per cell (SPRUCE_TC_TWO_PASS=0): thermal
+    energy and both output planes after tc_iterate bit for bit, FAST instances on and off"""
+    res = []
+    for two_pass in (1, 0):
+        s, o, h, step, _ = make_pair(emu, xb, yb, 22, 19)
+        emu.cemu_set_fast_interior(h, C.c_int(fast))
+        emu.cemu_set_two_pass(h, C.c_int(two_pass))
+        avg, satp = np.zeros(22 * 19), np.zeros(22 * 19)
+        assert emu.cemu_thermal_conduction(h, C.c_int(1), C.c_double(1.0), C.c_double(1.0e-4), C.c_int({"euler": 0, "rk2": 1, "rk4": 2}[integ]), C.c_int(3), C.c_double(step), vp(avg), vp(satp)) == 0
+        e = np.zeros((22, 19))
+        emu.cemu_get(h, C.c_int(4), vp(e))
+        res.append((e, avg, satp, np.ascontiguousarray(o.get("thermal_energy")).copy()))
+        o.close()
+    for a, b, name in zip(res[0][:3], res[1][:3], ("thermal energy", "thermal_conduction plane", "flux_saturation plane")):
+        assert same_bits(a, b), "%s: %s" % (name, mismatch(a.reshape(22, 19), b.reshape(22, 19)))
+    assert not same_bits(res[0][0], res[0][3])

@@ -16,19 +16,19 @@ pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="written after round 2's
 FLOORS = dict(density_min=1.0e7, temp_min=1.0e4, thermal_energy_min=1.0e-6)
 
 
-def run_both(make, steps):
+def run_both(make, steps, switch="SPRUCE_FAST_INTERIOR"):
     from spruce_b200.domain import PlasmaDomain  # noqa: F401
     out = []
     for fast in ("1", "0"):
-        old = os.environ.get("SPRUCE_FAST_INTERIOR")
-        os.environ["SPRUCE_FAST_INTERIOR"] = fast
+        old = os.environ.get(switch)
+        os.environ[switch] = fast
         try:
             d = make()
         finally:
             if old is None:
-                os.environ.pop("SPRUCE_FAST_INTERIOR", None)
+                os.environ.pop(switch, None)
             else:
-                os.environ["SPRUCE_FAST_INTERIOR"] = old
+                os.environ[switch] = old
         dts = np.asarray(d.advance(steps))
         planes = {v: d.grid(v).copy() for v in d.EVOLVED}
         d.close()
@@ -51,6 +51,23 @@ def test_thermal_conduction_fast_equals_general(xb, yb, sat, integ):
         d.set_thermal_conduction(flux_saturation=sat, integrator=integ, epsilon=0.1, dt_subcycle_min=1.0e-4)
         return d
     dts, planes = run_both(make, 3)
+    assert np.all(np.isfinite(planes["thermal_energy"]))
+
+
+@pytest.mark.parametrize("xb,yb", [(("periodic", "periodic"), ("fixed", "open")), (("reflect", "open"), ("periodic", "periodic")), (("fixed", "fixed"), ("fixed", "fixed"))])
+@pytest.mark.parametrize("integ", ["euler", "rk2", "rk4"])
+def test_saturated_conduction_two_pass_equals_the_five_point_form(xb, yb, integ):
+    """SPRUCE_TC_TWO_PASS (default 1): the saturation coefficient and raw flux of every cell written once by k_tc_coef and differentiated as a plane, against the form that
+    evaluates the coefficient at five points per cell (the one the round-2 strict tests validated): same step sizes, same planes, bit for bit"""
+    from spruce_b200.domain import PlasmaDomain
+    s = synthetic.stratified_loop(150, 140, bump=0.5)
+
+    def make():
+        d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], xb=xb, yb=yb, integrator="rk2", **FLOORS)
+        d.set_thermal_conduction(flux_saturation=True, integrator=integ, epsilon=0.1, dt_subcycle_min=1.0e-4)
+        d.set_module_output_to_file("thermal_conduction")
+        return d
+    dts, planes = run_both(make, 3, switch="SPRUCE_TC_TWO_PASS")
     assert np.all(np.isfinite(planes["thermal_energy"]))
 
 
