@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the secondary paths on one GPU (device-timed): two-fluid RK2 step, MHD + thermal conduction, MHD + physical viscosity -- each as shipped
-and (key suffix " [general instances]") with SPRUCE_FAST_INTERIOR=0, i.e. the wrapping, range-testing stencil instances for every cell.
+and (key suffix " [general instances]") with SPRUCE_FAST_INTERIOR=0, i.e. the wrapping, range-testing stencil instances for every cell; saturated conduction also
+with SPRUCE_TC_TWO_PASS=0 (" [five-point coefficient]").
 usage: module_perf.py [size]"""
 import json, os, sys, time
 import numpy as np
@@ -50,4 +51,15 @@ for name, setup in (("mhd only", lambda d: None),
                 e["subcycles_last_step"] = d.subcycles(k)
         out["%s %d^2%s" % (name, n, "" if fast == "1" else " [general instances]")] = e
         d.close()
+# saturated conduction with the coefficient evaluated at five points per cell (SPRUCE_TC_TWO_PASS=0) next to the two-pass form timed above
+try:
+    os.environ["SPRUCE_FAST_INTERIOR"] = "1"; os.environ["SPRUCE_TC_TWO_PASS"] = "0"
+    d = PlasmaDomain(s["planes"], s["ion_mass"], s["adiabatic_index"], **KW)
+    d.set_thermal_conduction(flux_saturation=True, integrator="rk2", epsilon=0.1, dt_subcycle_min=1.0e-4)
+    ms = timed(d, 10)
+    out["mhd + thermal_conduction (saturated, rk2) %d^2 [five-point coefficient]" % n] = dict(ms_per_step=ms, cell_updates_per_s=n * n / ms * 1e3, subcycles_last_step=d.subcycles("thermal_conduction"))
+    d.close()
+except Exception as e:                                                 # a side measurement: the others stand
+    out["five-point coefficient"] = {"error": repr(e)[:200]}
+os.environ.pop("SPRUCE_TC_TWO_PASS", None)
 print(json.dumps(out, indent=1))
