@@ -483,6 +483,7 @@ def emit(args, r, world):
         line["config"]["workload"] = ("OT-%d + thermal conduction: the same grid with temp = T0 (1 + 0.1 sin kx sin ky), ideal MHD RK2 + thermal_conduction "
                                       "(unsaturated, euler sub-cycles, epsilon 0.1, weakening_factor 1e-3) (BASELINE.json configs[4], SURVEY 8d cfg-C)" % args.size)
         line["config"]["thermal_conduction_subcycles_last_step"] = r.get("tc_subcycles")
+        line["config"]["device_resident_subcycle_plan"] = os.environ.get("SPRUCE_DEVICE_SUBCYCLES", "0") not in ("", "0")      # opt-in, read by spruce_domain_create
         line["roofline"]["note"] = "stage-kernel roofline is not meaningful for this workload (the step also runs the conduction sub-cycles); value is whole-step throughput"
     print(json.dumps(line))
 

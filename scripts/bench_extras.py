@@ -104,7 +104,7 @@ def conduction_workload(n_gpus, size, steps, limit_s, device_plan=False):
             return {"error": "rc %s: %s" % (rc, se.decode(errors="replace")[-300:])}
         l = json.loads(lines[-1])
         return {"workload": l["config"]["workload"], "n_gpus": l["n_gpus"], "size": size, "steps": steps, "value": l["value"], "unit": l["unit"], "ms_per_step": l["ms_per_step"],
-                "thermal_conduction_subcycles_last_step": l["config"].get("thermal_conduction_subcycles_last_step"), "e2e_value": (l.get("e2e") or {}).get("value"),
+                "thermal_conduction_subcycles_last_step": l["config"].get("thermal_conduction_subcycles_last_step"), "device_resident_subcycle_plan": l["config"].get("device_resident_subcycle_plan"), "e2e_value": (l.get("e2e") or {}).get("value"),
                 "parity_vs_1gpu": l.get("parity_vs_1gpu")}
     except Exception as e:
         return {"error": repr(e)[:300]}
